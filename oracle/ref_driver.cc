@@ -1,0 +1,308 @@
+// oracle/ref_driver.cc -- TEST INFRASTRUCTURE (never linked into the product).
+//
+// Drives the UNMODIFIED GetFEM reference (oracle/_ref/libgetfem.so, built from
+// /root/reference/src by oracle/Makefile) through its own public API
+//   getfem::regular_unit_mesh            (src/getfem_regular_meshes.cc:237-284)
+//   getfem::mesh_fem / mesh_im           (src/getfem_mesh_fem.cc, getfem_mesh_im.cc)
+//   getfem::ga_workspace::add_expression / assembly
+//                                        (src/getfem_generic_assembly_workspace.cc:545-600, 791-936)
+//   getfem::model::assembly + bricks     (src/getfem_models.cc:2330, 6102-6136;
+//                                         src/getfem_nonlinear_elasticity.cc:2301-2325)
+// and dumps, as .npy files, (a) every INPUT the device path needs (node
+// coordinates, connectivity, dof table, reference tables at the quadrature
+// points) read through the reference's accessors and (b) the reference RESULT
+// (tangent as CSC jc/ir/pr via gmm::csc_matrix::init_with, residual vector).
+// It is also the CPU baseline timer (mode=time).
+//
+// usage: gf_ref_driver key=value ...
+//   dim=3 n=4 gt=pk|qk k=2 q=3 im=4 | imname="IM_TETRAHEDRON(5)"
+//   family=laplace|elast|svk|nh_ciarlet|nh_bonet|mass  lambda=1 mu=1 a=1
+//   u=smooth|random|zero  out=DIR  mode=dump|time|model  threads=T reps=R
+#include "getfem/getfem_regular_meshes.h"
+#include "getfem/getfem_mesh_fem.h"
+#include "getfem/getfem_mesh_im.h"
+#include "getfem/getfem_generic_assembly.h"
+#include "getfem/getfem_models.h"
+#include "getfem/getfem_nonlinear_elasticity.h"
+#include "getfem/getfem_omp.h"
+#include "getfem/getfem_accumulated_distro.h"
+#include "gmm/gmm_kernel.h"
+#include <chrono>
+#include <cstdio>
+#include <cstdint>
+#include <fstream>
+#include <map>
+#include <random>
+#include <string>
+#include <sys/stat.h>
+
+using getfem::size_type;
+using getfem::scalar_type;
+using bgeot::base_node;
+
+// ---------------------------------------------------------------- npy writer
+static void write_npy(const std::string &path, const char *descr, size_t itemsize,
+                      const std::vector<size_t> &shape, const void *data) {
+  std::string hdr = "{'descr': '";
+  hdr += descr;
+  hdr += "', 'fortran_order': False, 'shape': (";
+  size_t tot = 1;
+  for (size_t i = 0; i < shape.size(); ++i) {
+    hdr += std::to_string(shape[i]);
+    if (shape.size() == 1 || i + 1 < shape.size()) hdr += ",";
+    if (i + 1 < shape.size()) hdr += " ";
+    tot *= shape[i];
+  }
+  hdr += "), }";
+  size_t len = 10 + hdr.size() + 1;
+  size_t pad = (64 - len % 64) % 64;
+  hdr.append(pad, ' ');
+  hdr += "\n";
+  std::ofstream f(path, std::ios::binary);
+  const unsigned char magic[8] = {0x93, 'N', 'U', 'M', 'P', 'Y', 1, 0};
+  f.write((const char *)magic, 8);
+  uint16_t hl = (uint16_t)hdr.size();
+  f.write((const char *)&hl, 2);
+  f.write(hdr.data(), hdr.size());
+  f.write((const char *)data, tot * itemsize);
+}
+static void npy_f64(const std::string &p, const std::vector<size_t> &s, const std::vector<double> &v) {
+  write_npy(p, "<f8", 8, s, v.data());
+}
+static void npy_i64(const std::string &p, const std::vector<size_t> &s, const std::vector<int64_t> &v) {
+  write_npy(p, "<i8", 8, s, v.data());
+}
+static void npy_i32(const std::string &p, const std::vector<size_t> &s, const std::vector<int32_t> &v) {
+  write_npy(p, "<i4", 4, s, v.data());
+}
+
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int main(int argc, char **argv) {
+  std::map<std::string, std::string> a;
+  for (int i = 1; i < argc; ++i) {
+    std::string s(argv[i]);
+    size_t e = s.find('=');
+    if (e == std::string::npos) { std::fprintf(stderr, "bad arg %s\n", argv[i]); return 2; }
+    a[s.substr(0, e)] = s.substr(e + 1);
+  }
+  auto geti = [&](const char *k, long d) { return a.count(k) ? std::stol(a[k]) : d; };
+  auto getd = [&](const char *k, double d) { return a.count(k) ? std::stod(a[k]) : d; };
+  auto gets = [&](const char *k, const char *d) { return a.count(k) ? a[k] : std::string(d); };
+
+  const int dim = (int)geti("dim", 3), n = (int)geti("n", 2), K = (int)geti("k", 1);
+  const int Q = (int)geti("q", 1), imdeg = (int)geti("im", 2);
+  const int nx = (int)geti("nx", n), ny = (int)geti("ny", n), nz = (int)geti("nz", n);
+  const std::string gt = gets("gt", "pk"), family = gets("family", "laplace");
+  const std::string umode = gets("u", "random"), out = gets("out", ""), mode = gets("mode", "dump");
+  const double lambda = getd("lambda", 1.0), mu = getd("mu", 1.0), acoef = getd("a", 1.0);
+  const int threads = (int)geti("threads", 1), reps = (int)geti("reps", 3);
+  const double uamp = getd("uamp", 0.02);
+
+  // ---- mesh / fem / im through the reference's own constructors
+  getfem::mesh m;
+  std::vector<size_type> ns;
+  ns.push_back(nx); if (dim > 1) ns.push_back(ny); if (dim > 2) ns.push_back(nz);
+  bgeot::pgeometric_trans pgt =
+      gt == "pk" ? bgeot::simplex_geotrans(dim, 1) : bgeot::parallelepiped_geotrans(dim, 1);
+  double t0 = now_s();
+  getfem::regular_unit_mesh(m, ns, pgt);
+  double t_mesh = now_s() - t0;
+  getfem::mesh_fem mf(m, getfem::dim_type(Q));
+  mf.set_classical_finite_element(getfem::dim_type(K));
+  getfem::mesh_im mim(m);
+  if (a.count("imname")) mim.set_integration_method(getfem::int_method_descriptor(a["imname"]));
+  else mim.set_integration_method(getfem::dim_type(imdeg));
+  t0 = now_s();
+  const size_type ndof = mf.nb_dof();  // triggers enumerate_dof (src/getfem_mesh_fem.cc:320-446)
+  double t_enum = now_s() - t0;
+  const size_type ne = m.convex_index().card();
+  const size_type cv0 = m.convex_index().first_true();
+  getfem::pfem pf = mf.fem_of_element(cv0);
+  getfem::pintegration_method pim = mim.int_method_of_element(cv0);
+  getfem::papprox_integration pai = pim->approx_method();
+  const size_type nq = pai->nb_points_on_convex();
+  const size_type nd = pf->nb_dof(cv0), ng = pgt->nb_points();
+
+  // ---- expression of the family (the brick strings of the reference)
+  std::string expr;
+  if (family == "laplace") expr = "a*Grad_u.Grad_Test_u";  // generic elliptic, scalar a
+  else if (family == "laplace_vec") expr = "a*Grad_u:Grad_Test_u";
+  else if (family == "mass") expr = "a*u.Test_u";
+  else if (family == "elast")  // src/getfem_models.cc:6112-6113
+    expr = "(Div_u*((lambda)*Id(meshdim))+(2*(mu))*Sym(Grad_u)):Grad_Test_u";
+  else {
+    std::string law = family == "svk" ? "Saint_Venant_Kirchhoff"
+                    : family == "nh_ciarlet" ? "Compressible_Neo_Hookean_Ciarlet"
+                    : family == "nh_bonet" ? "Compressible_Neo_Hookean_Bonet" : "";
+    if (law.empty()) { std::fprintf(stderr, "unknown family %s\n", family.c_str()); return 2; }
+    // src/getfem_nonlinear_elasticity.cc:2319-2320
+    expr = "((Id(meshdim)+Grad_u)*(" + law + "_PK2(Grad_u,params))):Grad_Test_u";
+  }
+  if (a.count("expr")) expr = a["expr"];
+
+  // ---- state vector
+  std::vector<double> U(ndof, 0.0);
+  if (umode == "random") {
+    std::mt19937_64 rng(12345);
+    std::uniform_real_distribution<double> d(-1.0, 1.0);
+    for (auto &v : U) v = d(rng);
+  } else if (umode == "smooth") {
+    // u_k(x) = amp * sin(2 pi x_{(k+1) mod dim}) * cos(pi x_k)   
+    for (size_type d = 0; d < ndof; ++d) {
+      base_node P = mf.point_of_basic_dof(d);
+      int k = int(d % Q);
+      double xk = P[k % dim], xn = P[(k + 1) % dim];
+      U[d] = uamp * std::sin(2 * M_PI * xn) * std::cos(M_PI * xk);
+    }
+  }
+  if (a.count("uscale")) for (auto &v : U) v *= getd("uscale", 1.0);
+
+  // constants are BORROWED by the workspace (generic_assembly.h:277): keep them alive
+  const std::vector<double> c_a{acoef}, c_lambda{lambda}, c_mu{mu}, c_params{lambda, mu};
+  auto setup_ws = [&](getfem::ga_workspace &ws, const getfem::mesh_region &rg) {
+    ws.add_fem_variable("u", mf, gmm::sub_interval(0, ndof), U);
+    if (family == "laplace" || family == "laplace_vec" || family == "mass")
+      ws.add_fixed_size_constant("a", c_a);
+    else if (family == "elast") {
+      ws.add_fixed_size_constant("lambda", c_lambda);
+      ws.add_fixed_size_constant("mu", c_mu);
+    } else
+      ws.add_fixed_size_constant("params", c_params);
+    ws.add_expression(expr, mim, rg);
+  };
+
+  std::printf("{\"dim\": %d, \"ne\": %zu, \"ndof\": %zu, \"nd\": %zu, \"ng\": %zu, \"nq\": %zu, "
+              "\"fem\": \"%s\", \"im\": \"%s\", \"t_mesh\": %.4f, \"t_enum\": %.4f",
+              dim, ne, ndof, nd, ng, nq, getfem::name_of_fem(pf).c_str(),
+              getfem::name_of_int_method(pim).c_str(), t_mesh, t_enum);
+
+  if (mode == "time") {
+    // direct ga_workspace path, 1 thread (ws.assembly is single-threaded by design)
+    double best2 = 1e300, best1 = 1e300;
+    size_type nnz = 0;
+    for (int r = 0; r < reps + 1; ++r) {   // first pass = warm-up (precomp caches)
+      getfem::ga_workspace ws;
+      setup_ws(ws, getfem::mesh_region::all_convexes());
+      getfem::model_real_sparse_matrix Kmat(ndof, ndof);
+      ws.set_assembled_matrix(Kmat);
+      t0 = now_s(); ws.assembly(2); double t2 = now_s() - t0;
+      t0 = now_s(); ws.assembly(1); double t1 = now_s() - t0;
+      if (r > 0) { best2 = std::min(best2, t2); best1 = std::min(best1, t1); }
+      nnz = gmm::nnz(Kmat);
+    }
+    std::printf(", \"t_asm2\": %.6f, \"t_asm1\": %.6f, \"nnz\": %zu, \"threads\": 1}\n", best2, best1, nnz);
+    return 0;
+  }
+  if (mode == "omp") {
+    // The reference's own OpenMP scheme (src/getfem/getfem_accumulated_distro.h:157-224,
+    // src/getfem_models.cc:2686-2722): per-thread workspaces on the thread's slice of the
+    // region, per-thread matrix/vector copies, summed afterwards.
+    getfem::set_num_threads(threads);
+    double best = 1e300; size_type nnz = 0;
+    for (int r = 0; r < reps + 1; ++r) {
+      getfem::model_real_sparse_matrix Kmat(ndof, ndof);
+      std::vector<double> R(ndof, 0.0);
+      t0 = now_s();
+      {
+        getfem::accumulated_distro<getfem::model_real_sparse_matrix> Kd(Kmat);
+        getfem::accumulated_distro<std::vector<double>> Rd(R);
+        GETFEM_OMP_PARALLEL(
+          getfem::ga_workspace ws;
+          setup_ws(ws, getfem::mesh_region::all_convexes());
+          ws.set_assembled_matrix(Kd);
+          ws.assembly(2);
+          ws.set_assembled_vector(Rd);
+          ws.assembly(1);
+        )
+      }
+      double t = now_s() - t0;
+      if (r > 0) best = std::min(best, t);
+      nnz = gmm::nnz(Kmat);
+    }
+    std::printf(", \"t_asm21\": %.6f, \"nnz\": %zu, \"threads\": %d}\n", best, nnz, threads);
+    return 0;
+  }
+
+  // ---- dump mode: reference result
+  getfem::ga_workspace ws;
+  setup_ws(ws, getfem::mesh_region::all_convexes());
+  getfem::model_real_sparse_matrix Kmat(ndof, ndof);
+  ws.set_assembled_matrix(Kmat);
+  t0 = now_s(); ws.assembly(2); double t2 = now_s() - t0;
+  t0 = now_s(); ws.assembly(1); double t1 = now_s() - t0;
+  std::vector<double> R(ws.assembled_vector().begin(), ws.assembled_vector().end());
+  gmm::csc_matrix<double> C;
+  C.init_with(Kmat);
+  const size_type nnz = C.jc[ndof];
+  std::printf(", \"t_asm2\": %.6f, \"t_asm1\": %.6f, \"nnz\": %zu, \"expr\": \"%s\"}\n", t2, t1, nnz, expr.c_str());
+  if (out.empty()) return 0;
+  mkdir(out.c_str(), 0755);
+
+  // mesh: points in point-id order, connectivity in convex order
+  GMM_ASSERT1(m.convex_index().card() == m.convex_index().last_true() + 1, "non-contiguous convex ids");
+  const size_type npts = m.points_index().last_true() + 1;
+  std::vector<double> pts(npts * dim);
+  for (size_type p = 0; p < npts; ++p)
+    for (int d = 0; d < dim; ++d) pts[p * dim + d] = m.points()[p][d];
+  std::vector<int32_t> conn(ne * ng);
+  std::vector<int64_t> edof(ne * nd);
+  for (size_type cv = 0; cv < ne; ++cv) {
+    for (size_type i = 0; i < ng; ++i) conn[cv * ng + i] = int32_t(m.ind_points_of_convex(cv)[i]);
+    const auto &ct = mf.ind_scalar_basic_dof_of_element(cv);
+    for (size_type i = 0; i < nd; ++i) edof[cv * nd + i] = int64_t(ct[i]);
+  }
+  npy_f64(out + "/pts.npy", {npts, size_t(dim)}, pts);
+  npy_i32(out + "/conn.npy", {ne, ng}, conn);
+  npy_i64(out + "/elem_dof.npy", {ne, nd}, edof);
+  std::vector<double> dxyz(ndof * dim);
+  for (size_type d = 0; d < ndof; ++d) {
+    base_node P = mf.point_of_basic_dof(d);
+    for (int c = 0; c < dim; ++c) dxyz[d * dim + c] = P[c];
+  }
+  npy_f64(out + "/dof_xyz.npy", {ndof, size_t(dim)}, dxyz);
+
+  // reference tables at the volume quadrature points
+  bgeot::pstored_point_tab pspt = pai->pintegration_points();
+  getfem::pfem_precomp pfp = getfem::fem_precomp(pf, pspt, 0);
+  bgeot::pgeotrans_precomp pgp = bgeot::geotrans_precomp(pgt, pspt, 0);
+  std::vector<double> w(nq), xq(nq * dim), gtg(nq * ng * dim), phi(nq * nd), gphi(nq * nd * dim);
+  for (size_type q = 0; q < nq; ++q) {
+    w[q] = pai->coeff(q);
+    for (int d = 0; d < dim; ++d) xq[q * dim + d] = (*pspt)[q][d];
+    const bgeot::base_matrix &pc = pgp->grad(q);  // ng x P
+    for (size_type i = 0; i < ng; ++i)
+      for (int d = 0; d < dim; ++d) gtg[(q * ng + i) * dim + d] = pc(i, d);
+    const bgeot::base_tensor &v = pfp->val(q);    // (nd, target_dim)
+    const bgeot::base_tensor &g = pfp->grad(q);   // (nd, target_dim, P) first index fastest
+    for (size_type i = 0; i < nd; ++i) {
+      phi[q * nd + i] = v[i];
+      for (int d = 0; d < dim; ++d) gphi[(q * nd + i) * dim + d] = g[i + nd * d];
+    }
+  }
+  npy_f64(out + "/quad_w.npy", {nq}, w);
+  npy_f64(out + "/quad_x.npy", {nq, size_t(dim)}, xq);
+  npy_f64(out + "/gt_grad.npy", {nq, ng, size_t(dim)}, gtg);
+  npy_f64(out + "/phi.npy", {nq, nd}, phi);
+  npy_f64(out + "/gphi.npy", {nq, nd, size_t(dim)}, gphi);
+  // reference-element node coordinates of the fem
+  std::vector<double> rnodes(nd * dim);
+  for (size_type i = 0; i < nd; ++i)
+    for (int d = 0; d < dim; ++d) rnodes[i * dim + d] = pf->node_of_dof(cv0, i)[d];
+  npy_f64(out + "/ref_nodes.npy", {nd, size_t(dim)}, rnodes);
+
+  npy_f64(out + "/U.npy", {ndof}, U);
+  std::vector<int64_t> jc(ndof + 1), ir(nnz);
+  std::vector<double> pr(nnz);
+  for (size_type j = 0; j <= ndof; ++j) jc[j] = C.jc[j];
+  for (size_type k = 0; k < nnz; ++k) { ir[k] = C.ir[k]; pr[k] = C.pr[k]; }
+  npy_i64(out + "/K_jc.npy", {ndof + 1}, jc);
+  npy_i64(out + "/K_ir.npy", {nnz}, ir);
+  npy_f64(out + "/K_pr.npy", {nnz}, pr);
+  npy_f64(out + "/R.npy", {ndof}, R);
+  std::vector<double> par = {lambda, mu, acoef};
+  npy_f64(out + "/params.npy", {3}, par);
+  return 0;
+}
