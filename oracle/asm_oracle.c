@@ -1,0 +1,339 @@
+/* oracle/asm_oracle.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C, single-threaded CPU restatement of GetFEM's generic weak-form
+ * assembly for the expression families this repository accelerates.  It is the
+ * CHECKER for the CUDA path (tests/, __graft_entry__.smoke(), bench.py's
+ * cpu_baseline leg); nothing in getfem_b200/ may link, import or call it.
+ *
+ * Parity pinning: this file is validated against the UNMODIFIED reference
+ * (oracle/_ref/libgetfem.so driven by oracle/ref_driver.cc) and against the
+ * golden fixtures in tests/golden/ generated from it (tests/test_oracle.py):
+ * CSC pattern identical, values to 1e-13 relative Frobenius.
+ *
+ * What it follows (paths relative to /root/reference/src):
+ *   element loop, Gauss loop, weight = J*w_q ....... getfem_generic_assembly_compile_and_exec.cc:8789-8866
+ *   K = G*pc, J = |det K|, B = K^{-T} .............. bgeot_geometric_trans.cc:270-288, 321-355, 374-413
+ *   grad(phi) = grad_ref(phi) * B^T ................ getfem_fem.cc:85-90, 160-168
+ *   local coefficients coeff[node*Q+q] ............. getfem_mesh_fem.h:662-689
+ *   Grad_u at the point ............................ compile_and_exec.cc:692-747
+ *   integrands ................. getfem_models.cc:6112-6113,
+ *                                                    getfem_nonlinear_elasticity.cc:612-702, 1781-1827, 1945-1994
+ *   elem += coeff*t; finalize with ninf, threshold . compile_and_exec.cc:5359-5481
+ *   add_elem_matrix: sorted column merge, drop
+ *        |v| <= 1e-14*ninf ......................... compile_and_exec.cc:4853-4936
+ *   vector assembly V[dof] += elem ................. compile_and_exec.cc:4669-4735
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+enum { GFO_LAPLACE = 0, GFO_ELAST = 1, GFO_SVK = 2, GFO_NH_CIARLET = 3, GFO_NH_BONET = 4, GFO_MASS = 5 };
+
+typedef struct { int64_t c; double e; } entry_t; /* gmm::elt_rsvector_ (gmm_vector.h:913-932) */
+typedef struct { entry_t *v; int64_t n, cap; } col_t;
+
+typedef struct gfo_result {
+  int64_t ndof, nnz;
+  col_t *cols;
+  double *R;
+} gfo_result;
+
+static void col_insert(col_t *col, int64_t pos, entry_t ev) {
+  if (col->n == col->cap) {
+    col->cap = col->cap ? 2 * col->cap : 16;
+    col->v = (entry_t *)realloc(col->v, (size_t)col->cap * sizeof(entry_t));
+  }
+  memmove(col->v + pos + 1, col->v + pos, (size_t)(col->n - pos) * sizeof(entry_t));
+  col->v[pos] = ev;
+  col->n++;
+}
+
+/* add_elem_matrix (compile_and_exec.cc:4853-4936): rows visited in ascending dof order,
+   binary search from the last position, add in place or shifting insert. */
+static void add_elem_matrix(col_t *K, int s1, int s2, const int64_t *dofs1, const int64_t *dofs2,
+                            const double *elem, double threshold, int *sort) {
+  for (int i = 0; i < s1; ++i) { /* insertion sort of the row dofs */
+    int j = i;
+    while (j > 0 && dofs1[i] < dofs1[sort[j - 1]]) { sort[j] = sort[j - 1]; j--; }
+    sort[j] = i;
+  }
+  for (int c = 0; c < s2; ++c) {
+    col_t *col = &K[dofs2[c]];
+    const double *it = elem + (size_t)c * s1;
+    int64_t ind = 0;
+    for (int kk = 0; kk < s1; ++kk) {
+      int k = sort[kk];
+      entry_t ev; ev.e = it[k];
+      if (fabs(ev.e) > threshold) {
+        ev.c = dofs1[k];
+        int64_t count = col->n - ind;
+        while (count > 0) {
+          int64_t step = count / 2, l = ind + step;
+          if (col->v[l].c < ev.c) { ind = l + 1; count -= step + 1; } else count = step;
+        }
+        if (ind != col->n && col->v[ind].c == ev.c) col->v[ind].e += ev.e;
+        else col_insert(col, ind, ev);
+        ++ind;
+      }
+    }
+  }
+}
+
+static double det3(const double *K, int N) { /* K column-major N x N */
+  if (N == 1) return K[0];
+  if (N == 2) return K[0] * K[3] - K[1] * K[2];
+  return K[0] * (K[4] * K[8] - K[5] * K[7]) - K[3] * (K[1] * K[8] - K[2] * K[7]) +
+         K[6] * (K[1] * K[5] - K[2] * K[4]);
+}
+/* Ainv = A^{-1}, column-major; returns det */
+static double inv3(const double *A, double *Ai, int N) {
+  double d = det3(A, N);
+  if (N == 1) { Ai[0] = 1.0 / A[0]; return d; }
+  if (N == 2) {
+    Ai[0] = A[3] / d; Ai[1] = -A[1] / d; Ai[2] = -A[2] / d; Ai[3] = A[0] / d;
+    return d;
+  }
+#define A_(i, j) A[(i) + 3 * (j)]
+  Ai[0] = (A_(1, 1) * A_(2, 2) - A_(1, 2) * A_(2, 1)) / d;
+  Ai[1] = -(A_(1, 0) * A_(2, 2) - A_(1, 2) * A_(2, 0)) / d;
+  Ai[2] = (A_(1, 0) * A_(2, 1) - A_(1, 1) * A_(2, 0)) / d;
+  Ai[3] = -(A_(0, 1) * A_(2, 2) - A_(0, 2) * A_(2, 1)) / d;
+  Ai[4] = (A_(0, 0) * A_(2, 2) - A_(0, 2) * A_(2, 0)) / d;
+  Ai[5] = -(A_(0, 0) * A_(2, 1) - A_(0, 1) * A_(2, 0)) / d;
+  Ai[6] = (A_(0, 1) * A_(1, 2) - A_(0, 2) * A_(1, 1)) / d;
+  Ai[7] = -(A_(0, 0) * A_(1, 2) - A_(0, 2) * A_(1, 0)) / d;
+  Ai[8] = (A_(0, 0) * A_(1, 1) - A_(0, 1) * A_(1, 0)) / d;
+#undef A_
+  return d;
+}
+
+/* Hyperelastic PK2 stress S (N x N col-major) and dS(i,j,k,l) = dS_ij/d(Grad_u)_kl
+   (first index fastest), as the registered GWFL operators compute them. */
+static void hyper_law(int family, const double *Gu, const double *par, double *S, double *dS) {
+  const int N = 3;
+  double lambda = par[0], mu = par[1];
+  double E[9], F[9];
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) {
+      double s = 0;
+      for (int k = 0; k < N; ++k) s += Gu[k + N * i] * Gu[k + N * j]; /* (Gu^T Gu)(i,j) */
+      E[i + N * j] = 0.5 * (s + Gu[i + N * j] + Gu[j + N * i]);
+      F[i + N * j] = Gu[i + N * j] + (i == j ? 1.0 : 0.0);
+    }
+  if (family == GFO_SVK) { /* getfem_nonlinear_elasticity.cc:1945-1994 */
+    double trE = E[0] + E[4] + E[8];
+    for (int j = 0; j < N; ++j)
+      for (int i = 0; i < N; ++i) S[i + N * j] = 2 * mu * E[i + N * j] + (i == j ? lambda * trE : 0.0);
+    double *it = dS;
+    for (int l = 0; l < N; ++l)
+      for (int k = 0; k < N; ++k)
+        for (int j = 0; j < N; ++j)
+          for (int i = 0; i < N; ++i, ++it) {
+            double v = 0;
+            if (i == j && k == l) v += lambda;
+            if (i == j) v += lambda * Gu[k + N * l];
+            if (i == k && j == l) v += mu;
+            if (i == l && j == k) v += mu;
+            if (i == l) v += mu * Gu[k + N * j];
+            if (l == j) v += mu * Gu[k + N * i];
+            *it = v;
+          }
+    return;
+  }
+  /* Neo_Hookean_hyperelastic_law (cc:612-702), through AHL_wrapper_sigma (cc:1781-1827) */
+  int bonet = family == GFO_NH_BONET;
+  double detF = det3(F, N);
+  double C[9], Ci[9];
+  for (int i = 0; i < 9; ++i) C[i] = 2 * E[i];
+  C[0] += 1; C[4] += 1; C[8] += 1;
+  double i3 = inv3(C, Ci, N);
+  double di3[9];
+  for (int i = 0; i < 9; ++i) di3[i] = Ci[i] * i3; /* compute_di3 (cc:132-140) */
+  double cs = bonet ? (lambda / 2 * log(i3) - mu) / i3 : lambda / 2 - lambda / (2 * i3) - mu / i3;
+  for (int i = 0; i < 9; ++i) S[i] = cs * di3[i];
+  S[0] += mu; S[4] += mu; S[8] += mu; /* mu * grad_i1 = mu * Id */
+  if (detF <= 0) for (int i = 0; i < 9; ++i) S[i] += 1e200 * C[i];
+  double c1, c2;
+  if (bonet) { double lg = log(i3); c1 = (lambda * lg - 2 * mu) / i3; c2 = (lambda + 2 * mu - lambda * lg) / (i3 * i3); }
+  else { c1 = lambda - (lambda + 2 * mu) / i3; c2 = (lambda + 2 * mu) / (i3 * i3); }
+  double A4[81];
+  double hd = i3 / 2;
+#define CI(i, j) Ci[(i) + 3 * (j)]
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j)
+      for (int k = 0; k < N; ++k)
+        for (int l = 0; l < N; ++l) { /* compute_ddi3 (cc:142-152) */
+          double dd = hd * (CI(j, i) * CI(l, k) - CI(j, k) * CI(l, i) + CI(i, j) * CI(l, k) - CI(i, k) * CI(l, j));
+          A4[i + 3 * j + 9 * k + 27 * l] = c1 * dd + c2 * di3[i + 3 * j] * di3[k + 3 * l];
+        }
+#undef CI
+  double *it = dS;
+  for (int l = 0; l < N; ++l)
+    for (int k = 0; k < N; ++k)
+      for (int j = 0; j < N; ++j)
+        for (int i = 0; i < N; ++i, ++it) {
+          double v = 0;
+          for (int m = 0; m < N; ++m) v += A4[i + 3 * j + 9 * m + 27 * l] * F[k + N * m];
+          *it = v;
+        }
+}
+
+/* pts: npts x dim (row-major), conn: ne x ng, elem_dof: ne x nd (dof of component 0),
+   gt_grad: nq x ng x dim, phi: nq x nd, gphi: nq x nd x dim.  order_mask: bit0 residual, bit1 tangent. */
+gfo_result *gfo_assemble(int dim, int64_t ne, int ng, const double *pts, const int32_t *conn, int nd, int Q,
+                         const int64_t *elem_dof, int64_t ndof, int nq, const double *w, const double *gt_grad,
+                         const double *phi, const double *gphi, int gt_linear, int family, const double *par,
+                         const double *U, int order_mask) {
+  const int N = dim, s1 = nd * Q;
+  gfo_result *res = (gfo_result *)calloc(1, sizeof(gfo_result));
+  res->ndof = ndof;
+  res->cols = (col_t *)calloc((size_t)ndof, sizeof(col_t));
+  res->R = (double *)calloc((size_t)ndof, sizeof(double));
+  double *elem = (double *)malloc(sizeof(double) * s1 * s1), *t = (double *)malloc(sizeof(double) * s1 * s1);
+  double *relem = (double *)malloc(sizeof(double) * s1), *Z = (double *)malloc(sizeof(double) * nd * N);
+  double *G = (double *)malloc(sizeof(double) * N * ng), *ue = (double *)malloc(sizeof(double) * s1);
+  int64_t *dofs = (int64_t *)malloc(sizeof(int64_t) * s1);
+  int *sort = (int *)malloc(sizeof(int) * s1);
+  double K[9], Ki[9], B[9], J = 0, D[81], P[9], Gu[9], S[9], dS[81];
+  const int nonlinear = family == GFO_SVK || family == GFO_NH_CIARLET || family == GFO_NH_BONET;
+
+  for (int64_t cv = 0; cv < ne; ++cv) {
+    for (int i = 0; i < ng; ++i) /* points_of_convex: G is N x ng column-major */
+      for (int d = 0; d < N; ++d) G[d + N * i] = pts[(size_t)conn[cv * ng + i] * dim + d];
+    for (int i = 0; i < nd; ++i)
+      for (int q = 0; q < Q; ++q) {
+        dofs[i * Q + q] = elem_dof[cv * nd + i] + q; /* populate_dofs_vector (cc:5008-5029) */
+        ue[i * Q + q] = U ? U[dofs[i * Q + q]] : 0.0;
+      }
+    memset(elem, 0, sizeof(double) * s1 * s1);
+    memset(relem, 0, sizeof(double) * s1);
+    for (int ipt = 0; ipt < nq; ++ipt) {
+      if (ipt == 0 || !gt_linear) {
+        const double *pc = gt_grad + (size_t)ipt * ng * N; /* ng x P, row i = node */
+        for (int r = 0; r < N; ++r)
+          for (int c = 0; c < N; ++c) {
+            double s = 0;
+            for (int i = 0; i < ng; ++i) s += G[r + N * i] * pc[i * N + c];
+            K[r + N * c] = s;
+          }
+        J = fabs(inv3(K, Ki, N));
+        for (int r = 0; r < N; ++r)
+          for (int c = 0; c < N; ++c) B[r + N * c] = Ki[c + N * r]; /* B = K^{-T} */
+      }
+      double coeff = J * w[ipt];
+      if (w[ipt] == 0.0) continue; /* disabled points contribute coeff = 0 (cc:8852-8854) */
+      const double *g = gphi + (size_t)ipt * nd * N;
+      for (int i = 0; i < nd; ++i)
+        for (int n = 0; n < N; ++n) {
+          double s = 0;
+          for (int p = 0; p < N; ++p) s += g[i * N + p] * B[n + N * p];
+          Z[i * N + n] = s;
+        }
+      if (family == GFO_MASS) {
+        const double *ph = phi + (size_t)ipt * nd;
+        for (int j = 0; j < nd; ++j)
+          for (int b = 0; b < Q; ++b)
+            for (int i = 0; i < nd; ++i) elem[(i * Q + b) + s1 * (j * Q + b)] += coeff * par[0] * ph[i] * ph[j];
+        for (int b = 0; b < Q; ++b) {
+          double uh = 0;
+          for (int i = 0; i < nd; ++i) uh += ue[i * Q + b] * ph[i];
+          for (int i = 0; i < nd; ++i) relem[i * Q + b] += coeff * par[0] * uh * ph[i];
+        }
+        continue;
+      }
+      /* Grad_u(q, n) = sum_i u(i,q) Z(i,n)   (cc:692-747) */
+      for (int q = 0; q < Q; ++q)
+        for (int n = 0; n < N; ++n) {
+          double s = 0;
+          for (int i = 0; i < nd; ++i) s += ue[i * Q + q] * Z[i * N + n];
+          Gu[q + Q * n] = s;
+        }
+      /* material tangent D(alpha,n,beta,l) and flux P(alpha,n) of the family */
+      memset(D, 0, sizeof(D));
+      memset(P, 0, sizeof(P));
+#define D_(a, n, b, l) D[(a) + Q * ((n) + N * ((b) + Q * (l)))]
+      if (family == GFO_LAPLACE) {
+        for (int a = 0; a < Q; ++a)
+          for (int n = 0; n < N; ++n) { D_(a, n, a, n) = par[0]; P[a + Q * n] = par[0] * Gu[a + Q * n]; }
+      } else if (family == GFO_ELAST) {
+        double lambda = par[0], mu = par[1], tr = 0;
+        for (int a = 0; a < N; ++a) tr += Gu[a + Q * a];
+        for (int a = 0; a < Q; ++a)
+          for (int n = 0; n < N; ++n) {
+            P[a + Q * n] = mu * (Gu[a + Q * n] + Gu[n + Q * a]) + (a == n ? lambda * tr : 0.0);
+            for (int b = 0; b < Q; ++b)
+              for (int l = 0; l < N; ++l)
+                D_(a, n, b, l) = (a == n && b == l ? lambda : 0.0) + (a == l && b == n ? mu : 0.0) +
+                                 (a == b && n == l ? mu : 0.0);
+          }
+      } else if (nonlinear) {
+        hyper_law(family, Gu, par, S, dS);
+        double F[9];
+        for (int i = 0; i < 9; ++i) F[i] = Gu[i];
+        F[0] += 1; F[4] += 1; F[8] += 1;
+        for (int a = 0; a < 3; ++a)
+          for (int n = 0; n < 3; ++n) {
+            double s = 0;
+            for (int m = 0; m < 3; ++m) s += F[a + 3 * m] * S[m + 3 * n];
+            P[a + 3 * n] = s; /* (Id+Grad_u)*PK2 */
+            for (int b = 0; b < 3; ++b)
+              for (int l = 0; l < 3; ++l) {
+                double v = (a == b) ? S[l + 3 * n] : 0.0; /* Grad_Test2_u*S */
+                for (int p = 0; p < 3; ++p) v += F[a + 3 * p] * dS[p + 3 * n + 9 * b + 27 * l];
+                D_(a, n, b, l) = v;
+              }
+          }
+      }
+      /* t(i alpha, j beta) = sum_{n,l} Z(i,n) D(alpha,n,beta,l) Z(j,l);  elem += coeff*t */
+      if (order_mask & 2) {
+        for (int j = 0; j < nd; ++j)
+          for (int b = 0; b < Q; ++b)
+            for (int i = 0; i < nd; ++i)
+              for (int a = 0; a < Q; ++a) {
+                double s = 0;
+                for (int n = 0; n < N; ++n)
+                  for (int l = 0; l < N; ++l) s += Z[i * N + n] * D_(a, n, b, l) * Z[j * N + l];
+                t[(i * Q + a) + s1 * (j * Q + b)] = s;
+              }
+        for (int k = 0; k < s1 * s1; ++k) elem[k] += coeff * t[k];
+      }
+#undef D_
+      if (order_mask & 1)
+        for (int i = 0; i < nd; ++i)
+          for (int a = 0; a < Q; ++a) {
+            double s = 0;
+            for (int n = 0; n < N; ++n) s += P[a + Q * n] * Z[i * N + n];
+            relem[i * Q + a] += coeff * s;
+          }
+    }
+    if (order_mask & 2) {
+      double ninf = 0;
+      for (int k = 0; k < s1 * s1; ++k) if (fabs(elem[k]) > ninf) ninf = fabs(elem[k]);
+      if (ninf != 0.0) add_elem_matrix(res->cols, s1, s1, dofs, dofs, elem, ninf * 1e-14, sort);
+    }
+    if (order_mask & 1)
+      for (int k = 0; k < s1; ++k) res->R[dofs[k]] += relem[k];
+  }
+  res->nnz = 0;
+  for (int64_t j = 0; j < ndof; ++j) res->nnz += res->cols[j].n;
+  free(elem); free(t); free(relem); free(Z); free(G); free(ue); free(dofs); free(sort);
+  return res;
+}
+
+int64_t gfo_nnz(const gfo_result *r) { return r->nnz; }
+
+/* gmm::csc_matrix::init_with_good_format (gmm_matrix.h:545-566) */
+void gfo_get_csc(const gfo_result *r, int64_t *jc, int64_t *ir, double *pr) {
+  int64_t k = 0;
+  for (int64_t j = 0; j < r->ndof; ++j) {
+    jc[j] = k;
+    for (int64_t e = 0; e < r->cols[j].n; ++e, ++k) { ir[k] = r->cols[j].v[e].c; pr[k] = r->cols[j].v[e].e; }
+  }
+  jc[r->ndof] = k;
+}
+void gfo_get_residual(const gfo_result *r, double *R) { memcpy(R, r->R, sizeof(double) * (size_t)r->ndof); }
+void gfo_free(gfo_result *r) {
+  for (int64_t j = 0; j < r->ndof; ++j) free(r->cols[j].v);
+  free(r->cols); free(r->R); free(r);
+}

@@ -1,0 +1,76 @@
+"""ctypes binding of the plain-C assembly oracle (oracle/asm_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  Never imported by the
+getfem_b200 package (tests/test_boundaries.py enforces this).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libgfo.so")
+FAMILIES = {"laplace": 0, "elast": 1, "svk": 2, "nh_ciarlet": 3, "nh_bonet": 4, "mass": 5}
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "asm_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(_SO), exist_ok=True)
+        cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+        subprocess.check_call([cc, "-O2", "-fPIC", "-shared", "-o", _SO, src, "-lm"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        L.gfo_assemble.restype = C.c_void_p
+        L.gfo_assemble.argtypes = [C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.gfo_nnz.restype = C.c_int64
+        L.gfo_nnz.argtypes = [C.c_void_p]
+        L.gfo_get_csc.argtypes = [C.c_void_p] * 4
+        L.gfo_get_residual.argtypes = [C.c_void_p] * 2
+        L.gfo_free.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def assemble(pts, conn, elem_dof, ndof, Q, w, gt_grad, phi, gphi, gt_linear, family, params, U, order_mask=3):
+    """Returns (jc, ir, pr, R): tangent in CSC (int64 indices) and residual."""
+    pts = np.ascontiguousarray(pts, np.float64)
+    conn = np.ascontiguousarray(conn, np.int32)
+    elem_dof = np.ascontiguousarray(elem_dof, np.int64)
+    w = np.ascontiguousarray(w, np.float64)
+    gt_grad = np.ascontiguousarray(gt_grad, np.float64)
+    phi = np.ascontiguousarray(phi, np.float64)
+    gphi = np.ascontiguousarray(gphi, np.float64)
+    params = np.ascontiguousarray(params, np.float64)
+    U = np.ascontiguousarray(U, np.float64)
+    ne, ng = conn.shape
+    nd = elem_dof.shape[1]
+    L = lib()
+    h = L.gfo_assemble(pts.shape[1], ne, ng, _p(pts), _p(conn), nd, Q, _p(elem_dof), ndof, len(w), _p(w),
+                       _p(gt_grad), _p(phi), _p(gphi), int(gt_linear), FAMILIES[family], _p(params), _p(U),
+                       order_mask)
+    nnz = L.gfo_nnz(h)
+    jc = np.empty(ndof + 1, np.int64)
+    ir = np.empty(nnz, np.int64)
+    pr = np.empty(nnz, np.float64)
+    R = np.empty(ndof, np.float64)
+    L.gfo_get_csc(h, _p(jc), _p(ir), _p(pr))
+    L.gfo_get_residual(h, _p(R))
+    L.gfo_free(h)
+    return jc, ir, pr, R

@@ -1,0 +1,40 @@
+import glob
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def golden_names():
+    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    d = {k: z[k] for k in z.files}
+    d["meta"] = json.loads(bytes(d["meta"]).decode())
+    args = dict(kv.split("=") for kv in d["meta"]["driver_args"].split())
+    d["args"] = args
+    fam = args["family"]
+    d["family"] = "laplace" if fam == "laplace_vec" else fam
+    d["Q"] = int(args["q"])
+    d["gt_linear"] = args["gt"] == "pk"
+    lam, mu, a = d["params"]
+    d["fparams"] = np.array([a]) if d["family"] in ("laplace", "mass") else np.array([lam, mu])
+    return d
+
+
+def csc_to_scipy(jc, ir, pr, n):
+    import scipy.sparse as sp
+    return sp.csc_matrix((pr, ir, jc), shape=(n, n))

@@ -1,0 +1,64 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (oracle/_ref/gf_ref_driver,
+built by oracle/Makefile from /root/reference/src).  Run in the build container only:
+
+    make -C oracle && python tests/golden/make_golden.py
+
+Each fixture holds the inputs read through the reference's own accessors (mesh, dof table,
+reference tables at the quadrature points, U) and the reference result of
+ga_workspace::assembly(2) / assembly(1): tangent as CSC (K_jc, K_ir, K_pr) and residual R.
+"""
+import glob
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DRV = os.path.join(HERE, "..", "..", "oracle", "_ref", "gf_ref_driver")
+
+# name -> driver arguments.  Sizes are kept tiny: the fixtures are committed.
+CASES = {
+    # BASELINE.json configs at CPU-checkable size
+    "c1_lap2d_p1_n6": "dim=2 n=6 gt=pk k=1 q=1 im=2 family=laplace u=random",
+    "c2_lap3d_p1_n3": "dim=3 n=3 gt=pk k=1 q=1 im=2 family=laplace u=random",
+    "c3_elast3d_p2_n2": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=elast u=random lambda=1 mu=1",
+    "c4_nh_ciarlet_q2_n2": "dim=3 n=2 gt=qk k=2 q=3 im=6 family=nh_ciarlet u=smooth lambda=1 mu=1 uamp=0.02",
+    "c4b_svk_q2_n2": "dim=3 n=2 gt=qk k=2 q=3 im=6 family=svk u=smooth lambda=1 mu=1 uamp=0.02",
+    "c5_lap_q4_n1": "dim=3 n=1 gt=qk k=4 q=1 im=8 family=laplace u=random",
+    # extra coverage of the same path
+    "x_nh_bonet_p2tet_n1": "dim=3 n=1 gt=pk k=2 q=3 im=4 family=nh_bonet u=smooth lambda=1.3 mu=0.7 uamp=0.05",
+    "x_nh_ciarlet_p1tet_n2": "dim=3 n=2 gt=pk k=1 q=3 im=2 family=nh_ciarlet u=smooth lambda=1.3 mu=0.7 uamp=0.05",
+    "x_elast2d_p2_n3": "dim=2 n=3 gt=pk k=2 q=2 im=4 family=elast u=random lambda=2 mu=0.5",
+    "x_elast3d_p1_n2": "dim=3 n=2 gt=pk k=1 q=3 im=2 family=elast u=random lambda=1.3 mu=0.7",
+    "x_lap3d_q1_n3": "dim=3 n=3 gt=qk k=1 q=1 im=3 family=laplace u=random a=2.5",
+    "x_lap3d_p2_n2": "dim=3 n=2 gt=pk k=2 q=1 im=4 family=laplace u=random",
+    "x_lapvec3d_p1_n2": "dim=3 n=2 gt=pk k=1 q=3 im=2 family=laplace_vec u=random",
+    "x_lap2d_q2_n3": "dim=2 n=3 gt=qk k=2 q=1 im=4 family=laplace u=random",
+    "x_lap3d_p1_ragged": "dim=3 nx=1 ny=2 nz=3 gt=pk k=1 q=1 im=2 family=laplace u=random",
+    "x_elast3d_q2_n1": "dim=3 n=1 gt=qk k=2 q=3 im=4 family=elast u=random lambda=1 mu=1",
+}
+
+
+def main():
+    only = sys.argv[1:]
+    for name, args in CASES.items():
+        if only and name not in only:
+            continue
+        with tempfile.TemporaryDirectory() as d:
+            out = subprocess.check_output([DRV] + args.split() + ["out=" + d]).decode()
+            meta = json.loads(out.strip().splitlines()[-1])
+            arrs = {os.path.basename(f)[:-4]: np.load(f) for f in glob.glob(d + "/*.npy")}
+        meta["driver_args"] = args
+        arrs["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+        for k in ("conn", "elem_dof", "K_jc", "K_ir"):
+            arrs[k] = arrs[k].astype(np.int32)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrs)
+        print(name, meta["fem"], meta["im"], "ne", meta["ne"], "ndof", meta["ndof"], "nnz", meta["nnz"],
+              os.path.getsize(os.path.join(HERE, name + ".npz")) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
