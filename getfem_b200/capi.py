@@ -1,0 +1,227 @@
+"""ctypes binding of the C ABI declared in include/gfgpu.h (getfem_b200/libgfgpu.so).
+
+This is the only way the Python host side reaches the device: there is no CPU fallback, and a
+missing library or a missing GPU raises immediately.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgfgpu.so")
+
+GT_PK, GT_QK = 0, 1
+FEM_PK, FEM_QK = 0, 1
+LAPLACE, ELASTICITY, SVK, NEOHOOKEAN_CIARLET, NEOHOOKEAN_BONET, MASS = range(6)
+RESIDUAL, TANGENT = 1, 2
+STRATEGY_AUTO, STRATEGY_STAGED, STRATEGY_RECOMPUTE = 0, 1, 2
+
+FAMILY_BY_NAME = {
+    "laplace": LAPLACE, "elast": ELASTICITY, "elasticity": ELASTICITY, "svk": SVK,
+    "nh_ciarlet": NEOHOOKEAN_CIARLET, "nh_bonet": NEOHOOKEAN_BONET, "mass": MASS,
+}
+
+# symbol -> (restype, argtypes); kept in one table so tests can check it against include/gfgpu.h
+_P = C.c_void_p
+_PP = C.POINTER(C.c_void_p)
+_i64 = C.c_int64
+SIGNATURES = {
+    "gfgpu_last_error": (C.c_char_p, []),
+    "gfgpu_version": (C.c_int, []),
+    "gfgpu_launch_count": (_i64, []),
+    "gfgpu_ctx_create": (C.c_int, [C.c_int, _P, _PP]),
+    "gfgpu_ctx_destroy": (C.c_int, [_P]),
+    "gfgpu_ctx_synchronize": (C.c_int, [_P]),
+    "gfgpu_ctx_bytes_in_use": (_i64, [_P]),
+    "gfgpu_mesh_create": (C.c_int, [_P, C.c_int, _i64, _P, _i64, C.c_int, _P, C.c_int, _PP]),
+    "gfgpu_mesh_destroy": (C.c_int, [_P]),
+    "gfgpu_fem_create": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _i64, _PP]),
+    "gfgpu_fem_nb_dof": (_i64, [_P]),
+    "gfgpu_fem_get_elem_dof": (C.c_int, [_P, _P]),
+    "gfgpu_fem_destroy": (C.c_int, [_P]),
+    "gfgpu_tables_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _PP]),
+    "gfgpu_tables_destroy": (C.c_int, [_P]),
+    "gfgpu_term_create": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_double, C.c_int, _PP]),
+    "gfgpu_term_destroy": (C.c_int, [_P]),
+    "gfgpu_term_set_element_range": (C.c_int, [_P, _i64, _i64]),
+    "gfgpu_term_assemble_dev": (C.c_int, [_P, _P, C.c_int]),
+    "gfgpu_term_assemble_host": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "gfgpu_term_nnz": (_i64, [_P]),
+    "gfgpu_term_nb_dof": (_i64, [_P]),
+    "gfgpu_term_pattern_generation": (_i64, [_P]),
+    "gfgpu_term_csc_view": (C.c_int, [_P, _PP, _PP, _PP]),
+    "gfgpu_term_residual_view": (C.c_int, [_P, _PP]),
+    "gfgpu_term_export_csc_host": (C.c_int, [_P, _P, _P, _P]),
+    "gfgpu_term_export_residual_host": (C.c_int, [_P, _P]),
+}
+
+
+class GfgpuError(RuntimeError):
+    """Mirrors gmm::gmm_error: raised for every non-zero status of the C ABI."""
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GfgpuError("%s is missing: run `python -m getfem_b200.build` (there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise GfgpuError(lib().gfgpu_last_error().decode())
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def launch_count():
+    return int(lib().gfgpu_launch_count())
+
+
+class _Handle:
+    _destroy = None
+
+    def __init__(self):
+        self.h = C.c_void_p()
+
+    def close(self):
+        if self.h is not None and self.h.value:
+            getattr(lib(), self._destroy)(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context(_Handle):
+    _destroy = "gfgpu_ctx_destroy"
+
+    def __init__(self, device=0, stream=None):
+        super().__init__()
+        check(lib().gfgpu_ctx_create(int(device), C.c_void_p(stream or 0), C.byref(self.h)))
+        self.device = device
+
+    def synchronize(self):
+        check(lib().gfgpu_ctx_synchronize(self.h))
+
+    def bytes_in_use(self):
+        return int(lib().gfgpu_ctx_bytes_in_use(self.h))
+
+
+class DeviceMesh(_Handle):
+    _destroy = "gfgpu_mesh_destroy"
+
+    def __init__(self, ctx, pts, conn, gt_kind):
+        super().__init__()
+        pts = np.ascontiguousarray(pts, np.float64)
+        conn = np.ascontiguousarray(conn, np.int32)
+        self.ctx, self.dim, self.ne, self.ng, self.npts = ctx, pts.shape[1], conn.shape[0], conn.shape[1], pts.shape[0]
+        check(lib().gfgpu_mesh_create(ctx.h, self.dim, self.npts, ptr(pts), self.ne, self.ng, ptr(conn), int(gt_kind),
+                                      C.byref(self.h)))
+
+
+class DeviceFem(_Handle):
+    _destroy = "gfgpu_fem_destroy"
+
+    def __init__(self, ctx, mesh, fem_kind, degree, qdim, nd, elem_dof=None, ndof=0):
+        super().__init__()
+        self.ctx, self.mesh, self.qdim, self.nd = ctx, mesh, qdim, nd
+        ed = None if elem_dof is None else np.ascontiguousarray(elem_dof, np.int64)
+        check(lib().gfgpu_fem_create(ctx.h, mesh.h, int(fem_kind), int(degree), int(qdim), int(nd), ptr(ed), int(ndof),
+                                     C.byref(self.h)))
+        self.ndof = int(lib().gfgpu_fem_nb_dof(self.h))
+
+    def elem_dof(self):
+        out = np.empty((self.mesh.ne, self.nd), np.int64)
+        check(lib().gfgpu_fem_get_elem_dof(self.h, ptr(out)))
+        return out
+
+
+class DeviceTables(_Handle):
+    _destroy = "gfgpu_tables_destroy"
+
+    def __init__(self, ctx, w, gt_grad, phi, gphi):
+        super().__init__()
+        w = np.ascontiguousarray(w, np.float64)
+        gt_grad = np.ascontiguousarray(gt_grad, np.float64)
+        phi = np.ascontiguousarray(phi, np.float64)
+        gphi = np.ascontiguousarray(gphi, np.float64)
+        nq, ng, dim = gt_grad.shape
+        nd = phi.shape[1]
+        assert w.shape == (nq,) and gphi.shape == (nq, nd, dim)
+        self.nq, self.ng, self.nd, self.dim = nq, ng, nd, dim
+        check(lib().gfgpu_tables_create(ctx.h, dim, nq, ng, nd, ptr(w), ptr(gt_grad), ptr(phi), ptr(gphi),
+                                        C.byref(self.h)))
+
+
+class DeviceTerm(_Handle):
+    _destroy = "gfgpu_term_destroy"
+
+    def __init__(self, ctx, mesh, fem, tables, family, params, alpha=1.0, strategy=STRATEGY_AUTO):
+        super().__init__()
+        self.ctx, self.mesh, self.fem, self.tables = ctx, mesh, fem, tables
+        params = np.ascontiguousarray(params, np.float64)
+        fam = FAMILY_BY_NAME[family] if isinstance(family, str) else int(family)
+        check(lib().gfgpu_term_create(ctx.h, mesh.h, fem.h, tables.h, fam, ptr(params), len(params), float(alpha),
+                                      int(strategy), C.byref(self.h)))
+
+    def set_element_range(self, e0, e1):
+        check(lib().gfgpu_term_set_element_range(self.h, int(e0), int(e1)))
+
+    def assemble_dev(self, U_dev_ptr, order_mask):
+        check(lib().gfgpu_term_assemble_dev(self.h, C.c_void_p(U_dev_ptr or 0), int(order_mask)))
+
+    def assemble_host(self, U, order_mask, pr_out=None, R_out=None):
+        U = None if U is None else np.ascontiguousarray(U, np.float64)
+        check(lib().gfgpu_term_assemble_host(self.h, ptr(U), int(order_mask), ptr(pr_out), ptr(R_out)))
+
+    @property
+    def nnz(self):
+        return int(lib().gfgpu_term_nnz(self.h))
+
+    @property
+    def ndof(self):
+        return int(lib().gfgpu_term_nb_dof(self.h))
+
+    @property
+    def pattern_generation(self):
+        return int(lib().gfgpu_term_pattern_generation(self.h))
+
+    def csc_view(self):
+        jc, ir, pr = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib().gfgpu_term_csc_view(self.h, C.byref(jc), C.byref(ir), C.byref(pr)))
+        return jc.value, ir.value, pr.value
+
+    def residual_view(self):
+        r = C.c_void_p()
+        check(lib().gfgpu_term_residual_view(self.h, C.byref(r)))
+        return r.value
+
+    def export_csc(self, values=True):
+        nnz, n = self.nnz, self.ndof
+        jc = np.empty(n + 1, np.int64)
+        ir = np.empty(nnz, np.int32)
+        pr = np.empty(nnz, np.float64) if values else None
+        check(lib().gfgpu_term_export_csc_host(self.h, ptr(jc), ptr(ir), ptr(pr)))
+        return jc, ir, pr
+
+    def export_residual(self):
+        R = np.empty(self.ndof, np.float64)
+        check(lib().gfgpu_term_export_residual_host(self.h, ptr(R)))
+        return R

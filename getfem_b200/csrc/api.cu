@@ -1,0 +1,355 @@
+// api.cu -- the extern "C" boundary declared in include/gfgpu.h.
+#include <cstring>
+#include <memory>
+
+#include "common.cuh"
+
+namespace gf {
+std::atomic<int64_t> g_launches{0};
+static thread_local std::string g_err;
+}  // namespace gf
+
+#define GF_API_BEGIN try {
+#define GF_API_END                      \
+  return 0;                             \
+  }                                     \
+  catch (const std::exception &ex) {    \
+    gf::g_err = ex.what();              \
+    return 1;                           \
+  }                                     \
+  catch (...) {                         \
+    gf::g_err = "unknown error";        \
+    return 1;                           \
+  }
+
+using gf::DevBuf;
+
+extern "C" {
+
+const char *gfgpu_last_error(void) { return gf::g_err.c_str(); }
+int gfgpu_version(void) { return 100; }
+int64_t gfgpu_launch_count(void) { return gf::g_launches.load(); }
+
+int gfgpu_ctx_create(int device, void *stream, gfgpu_ctx **out) {
+  GF_API_BEGIN
+  GF_REQUIRE(out, "null output");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  GF_REQUIRE(e == cudaSuccess && ndev > 0,
+             std::string("no CUDA device: this library has no CPU fallback (") + cudaGetErrorString(e) + ")");
+  GF_REQUIRE(device >= 0 && device < ndev, "bad device index");
+  GF_CUDA(cudaSetDevice(device));
+  std::unique_ptr<gfgpu_ctx> c(new gfgpu_ctx);
+  c->device = device;
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+  } else {
+    GF_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  GF_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+  *out = c.release();
+  GF_API_END
+}
+
+int gfgpu_ctx_destroy(gfgpu_ctx *ctx) {
+  GF_API_BEGIN
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->cub_tmp) cudaFree(ctx->cub_tmp);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  GF_API_END
+}
+
+int gfgpu_ctx_synchronize(gfgpu_ctx *ctx) {
+  GF_API_BEGIN
+  GF_REQUIRE(ctx, "null context");
+  GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  GF_API_END
+}
+
+int64_t gfgpu_ctx_bytes_in_use(gfgpu_ctx *ctx) { return ctx ? ctx->bytes : 0; }
+
+int gfgpu_mesh_create(gfgpu_ctx *ctx, int dim, int64_t npts, const double *pts, int64_t ne, int ng,
+                      const int32_t *conn, int gt_kind, gfgpu_mesh **out) {
+  GF_API_BEGIN
+  GF_REQUIRE(ctx && out, "null argument");
+  GF_REQUIRE(dim == 2 || dim == 3, "mesh dimension must be 2 or 3");
+  GF_REQUIRE(npts >= 0 && ne >= 0 && ng >= dim + 1, "bad mesh sizes");
+  GF_REQUIRE(gt_kind == GFGPU_GT_PK || gt_kind == GFGPU_GT_QK, "unknown geometric transformation kind");
+  GF_REQUIRE((pts || !npts) && (conn || !ne), "null mesh arrays");
+  GF_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<gfgpu_mesh> m(new gfgpu_mesh);
+  m->ctx = ctx; m->dim = dim; m->ng = ng; m->gt_kind = gt_kind; m->npts = npts; m->ne = ne;
+  for (int64_t k = 0; k < ne * ng; ++k)
+    GF_REQUIRE(conn[k] >= 0 && conn[k] < npts, "connectivity refers to a point outside [0, npts)");
+  // AoS -> SoA on the host, then one upload
+  std::vector<double> soa((size_t)3 * npts, 0.0);
+  for (int64_t p = 0; p < npts; ++p)
+    for (int d = 0; d < dim; ++d) soa[(size_t)d * npts + p] = pts[p * dim + d];
+  m->xyz.alloc(ctx, soa.size());
+  m->xyz.upload(soa.data());
+  m->conn.alloc(ctx, (size_t)ne * ng);
+  m->conn.upload(conn);
+  GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = m.release();
+  GF_API_END
+}
+
+int gfgpu_mesh_destroy(gfgpu_mesh *m) {
+  GF_API_BEGIN
+  delete m;
+  GF_API_END
+}
+
+int gfgpu_fem_create(gfgpu_ctx *ctx, gfgpu_mesh *mesh, int fem_kind, int degree, int qdim, int nd,
+                     const int64_t *elem_dof, int64_t ndof, gfgpu_fem **out) {
+  GF_API_BEGIN
+  GF_REQUIRE(ctx && mesh && out, "null argument");
+  GF_REQUIRE(qdim >= 1 && qdim <= 3, "qdim must be 1, 2 or 3");
+  GF_REQUIRE(nd >= 1, "bad number of local dofs");
+  GF_REQUIRE(fem_kind == GFGPU_FEM_PK || fem_kind == GFGPU_FEM_QK, "unknown fem kind");
+  GF_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<gfgpu_fem> f(new gfgpu_fem);
+  f->ctx = ctx; f->mesh = mesh; f->fem_kind = fem_kind; f->degree = degree; f->qdim = qdim; f->nd = nd;
+  GF_REQUIRE(elem_dof != nullptr, "device dof enumeration is not available yet: pass the element->dof table");
+  GF_REQUIRE(ndof > 0 && ndof < (int64_t(1) << 31) - 4, "ndof out of range");
+  f->ndof = ndof;
+  std::vector<int32_t> ed((size_t)mesh->ne * nd);
+  for (size_t k = 0; k < ed.size(); ++k) {
+    GF_REQUIRE(elem_dof[k] >= 0 && elem_dof[k] + qdim <= ndof, "element dof outside [0, ndof)");
+    ed[k] = (int32_t)elem_dof[k];
+  }
+  f->edof.alloc(ctx, ed.size());
+  f->edof.upload(ed.data());
+  GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = f.release();
+  GF_API_END
+}
+
+int64_t gfgpu_fem_nb_dof(gfgpu_fem *f) { return f ? f->ndof : -1; }
+
+int gfgpu_fem_get_elem_dof(gfgpu_fem *f, int64_t *out) {
+  GF_API_BEGIN
+  GF_REQUIRE(f && out, "null argument");
+  GF_CUDA(cudaSetDevice(f->ctx->device));
+  std::vector<int32_t> ed(f->edof.n);
+  f->edof.download(ed.data());
+  GF_CUDA(cudaStreamSynchronize(f->ctx->stream));
+  for (size_t k = 0; k < ed.size(); ++k) out[k] = ed[k];
+  GF_API_END
+}
+
+int gfgpu_fem_destroy(gfgpu_fem *f) {
+  GF_API_BEGIN
+  delete f;
+  GF_API_END
+}
+
+int gfgpu_tables_create(gfgpu_ctx *ctx, int dim, int nq, int ng, int nd, const double *w, const double *gt_grad,
+                        const double *phi, const double *gphi, gfgpu_tables **out) {
+  GF_API_BEGIN
+  GF_REQUIRE(ctx && out && w && gt_grad && phi && gphi, "null argument");
+  GF_REQUIRE(nq >= 1 && ng >= 1 && nd >= 1, "bad table sizes");
+  GF_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<gfgpu_tables> t(new gfgpu_tables);
+  t->ctx = ctx; t->dim = dim; t->nq = nq; t->ng = ng; t->nd = nd;
+  t->h_w.assign(w, w + nq);
+  t->h_gt_grad.assign(gt_grad, gt_grad + (size_t)nq * ng * dim);
+  t->h_phi.assign(phi, phi + (size_t)nq * nd);
+  t->h_gphi.assign(gphi, gphi + (size_t)nq * nd * dim);
+  t->w.alloc(ctx, t->h_w.size()); t->w.upload(t->h_w.data());
+  t->gt_grad.alloc(ctx, t->h_gt_grad.size()); t->gt_grad.upload(t->h_gt_grad.data());
+  t->phi.alloc(ctx, t->h_phi.size()); t->phi.upload(t->h_phi.data());
+  t->gphi.alloc(ctx, t->h_gphi.size()); t->gphi.upload(t->h_gphi.data());
+  GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = t.release();
+  GF_API_END
+}
+
+int gfgpu_tables_destroy(gfgpu_tables *t) {
+  GF_API_BEGIN
+  delete t;
+  GF_API_END
+}
+
+int gfgpu_term_create(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem, gfgpu_tables *tab, int family,
+                      const double *params, int nparams, double alpha, int strategy, gfgpu_term **out) {
+  GF_API_BEGIN
+  GF_REQUIRE(ctx && mesh && fem && tab && out, "null argument");
+  GF_REQUIRE(fem->mesh == mesh, "the fem was built on another mesh");
+  GF_REQUIRE(tab->dim == mesh->dim && tab->ng == mesh->ng && tab->nd == fem->nd, "tables do not match mesh/fem");
+  GF_REQUIRE(family >= GFGPU_LAPLACE && family <= GFGPU_MASS, "unknown expression family");
+  const int need = (family == GFGPU_LAPLACE || family == GFGPU_MASS) ? 1 : 2;
+  GF_REQUIRE(params && nparams >= need, "missing parameters for this family");
+  if (family == GFGPU_ELASTICITY) GF_REQUIRE(fem->qdim == mesh->dim, "elasticity needs qdim == mesh dimension");
+  if (family == GFGPU_SVK || family == GFGPU_NEOHOOKEAN_CIARLET || family == GFGPU_NEOHOOKEAN_BONET)
+    GF_REQUIRE(fem->qdim == 3 && mesh->dim == 3, "finite-strain families need a 3D vector field");
+  GF_REQUIRE(strategy == GFGPU_STRATEGY_AUTO || strategy == GFGPU_STRATEGY_STAGED,
+             "strategy not available");
+  std::unique_ptr<gfgpu_term> t(new gfgpu_term);
+  t->ctx = ctx; t->mesh = mesh; t->fem = fem; t->tab = tab; t->family = family;
+  t->strategy = GFGPU_STRATEGY_STAGED;
+  for (int k = 0; k < 4; ++k) t->par[k] = k < nparams ? params[k] : 0.0;
+  t->alpha = alpha;
+  t->e0 = 0; t->e1 = mesh->ne;
+  GF_CUDA(cudaSetDevice(ctx->device));
+  t->flag.alloc(ctx, 1);
+  t->flag.zero();
+  *out = t.release();
+  GF_API_END
+}
+
+int gfgpu_term_destroy(gfgpu_term *t) {
+  GF_API_BEGIN
+  if (t) {
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+  }
+  delete t;
+  GF_API_END
+}
+
+int gfgpu_term_set_element_range(gfgpu_term *t, int64_t e0, int64_t e1) {
+  GF_API_BEGIN
+  GF_REQUIRE(t, "null term");
+  GF_REQUIRE(0 <= e0 && e0 <= e1 && e1 <= t->mesh->ne, "bad element range");
+  if (e0 != t->e0 || e1 != t->e1) {
+    t->e0 = e0; t->e1 = e1;
+    t->st_valid = false;
+    t->pat_valid = false;
+  }
+  GF_API_END
+}
+
+static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
+  gfgpu_ctx *ctx = t->ctx;
+  GF_CUDA(cudaSetDevice(ctx->device));
+  GF_REQUIRE(order_mask & (GFGPU_RESIDUAL | GFGPU_TANGENT), "order_mask selects nothing");
+  const bool do_t = order_mask & GFGPU_TANGENT, do_r = order_mask & GFGPU_RESIDUAL;
+  const int nd = t->fem->nd, Q = t->fem->qdim, s1 = nd * Q;
+  const int64_t ne = t->e1 - t->e0;
+  if (!t->st_valid) {
+    gf::build_structure(ctx, t->fem->edof.p, nd, t->e0, t->e1, t->fem->ndof, t->st);
+    t->st_valid = true;
+    t->pat_valid = false;
+  }
+  if (do_t) {
+    if (t->stage.n != (size_t)ne * s1 * s1) t->stage.alloc(ctx, (size_t)ne * s1 * s1);
+    if (t->emask.n != (size_t)ne * nd * nd) t->emask.alloc(ctx, (size_t)ne * nd * nd);
+  }
+  if (do_r) {
+    if (t->rstage.n != (size_t)ne * s1) t->rstage.alloc(ctx, (size_t)ne * s1);
+    if (t->R.n != (size_t)t->fem->ndof) t->R.alloc(ctx, t->fem->ndof);
+  }
+  gf::ElemArgs a;
+  const int64_t np = t->mesh->npts;
+  a.x = t->mesh->xyz.p; a.y = a.x + np; a.z = a.y + np;
+  a.conn = t->mesh->conn.p;
+  a.edof = t->fem->edof.p;
+  a.U = U_dev;
+  a.w = t->tab->w.p; a.gt_grad = t->tab->gt_grad.p; a.phi = t->tab->phi.p; a.gphi = t->tab->gphi.p;
+  a.nq = t->tab->nq; a.ng = t->mesh->ng; a.qc = 0;
+  a.e0 = t->e0; a.e1 = t->e1;
+  for (int k = 0; k < 4; ++k) a.par[k] = t->par[k];
+  a.alpha = t->alpha;
+  a.family = t->family;
+  a.stage = do_t ? t->stage.p : nullptr;
+  a.emask = do_t ? t->emask.p : nullptr;
+  a.rstage = do_r ? t->rstage.p : nullptr;
+  if (ne > 0) {
+    bool ok = gf::launch_elem_kernel(ctx, t->mesh->dim, Q, nd, t->mesh->gt_kind == GFGPU_GT_PK, a);
+    GF_REQUIRE(ok, "no device kernel for this (dimension, qdim, local dofs, family) combination");
+  }
+  if (do_t) {
+    // linear families: the keep masks do not depend on U, a valid pattern stays valid
+    const bool value_dependent = t->family == GFGPU_SVK || t->family == GFGPU_NEOHOOKEAN_CIARLET ||
+                                 t->family == GFGPU_NEOHOOKEAN_BONET;
+    if (!t->pat_valid) {
+      gf::build_pattern(t);
+      gf::gather_tangent(t, false);
+    } else if (!value_dependent) {
+      gf::gather_tangent(t, false);
+    } else {
+      t->flag.zero();
+      gf::gather_tangent(t, true);
+      int32_t changed = 0;
+      t->flag.download(&changed);
+      GF_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (changed) {
+        gf::build_pattern(t);
+        gf::gather_tangent(t, false);
+      }
+    }
+  }
+  if (do_r) gf::gather_residual(t);
+}
+
+int gfgpu_term_assemble_dev(gfgpu_term *t, const double *U_dev, int order_mask) {
+  GF_API_BEGIN
+  GF_REQUIRE(t, "null term");
+  term_assemble(t, U_dev, order_mask);
+  GF_API_END
+}
+
+int gfgpu_term_assemble_host(gfgpu_term *t, const double *U_host, int order_mask, double *pr_host, double *R_host) {
+  GF_API_BEGIN
+  GF_REQUIRE(t, "null term");
+  gfgpu_ctx *ctx = t->ctx;
+  GF_CUDA(cudaSetDevice(ctx->device));
+  const double *U_dev = nullptr;
+  if (U_host) {
+    if (t->Ubuf.n != (size_t)t->fem->ndof) t->Ubuf.alloc(ctx, t->fem->ndof);
+    t->Ubuf.upload(U_host);
+    U_dev = t->Ubuf.p;
+  }
+  term_assemble(t, U_dev, order_mask);
+  if ((order_mask & GFGPU_TANGENT) && pr_host) t->pr.download(pr_host);
+  if ((order_mask & GFGPU_RESIDUAL) && R_host) t->R.download(R_host);
+  GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  GF_API_END
+}
+
+int64_t gfgpu_term_nnz(gfgpu_term *t) { return (t && t->pat_valid) ? t->nnz : -1; }
+int64_t gfgpu_term_nb_dof(gfgpu_term *t) { return t ? t->fem->ndof : -1; }
+int64_t gfgpu_term_pattern_generation(gfgpu_term *t) { return t ? t->generation : -1; }
+
+int gfgpu_term_csc_view(gfgpu_term *t, const int64_t **jc, const int32_t **ir, const double **pr) {
+  GF_API_BEGIN
+  GF_REQUIRE(t && t->pat_valid, "no assembled tangent");
+  if (jc) *jc = t->jc.p;
+  if (ir) *ir = t->ir.p;
+  if (pr) *pr = t->pr.p;
+  GF_API_END
+}
+
+int gfgpu_term_residual_view(gfgpu_term *t, const double **R) {
+  GF_API_BEGIN
+  GF_REQUIRE(t && t->R.n, "no assembled residual");
+  if (R) *R = t->R.p;
+  GF_API_END
+}
+
+int gfgpu_term_export_csc_host(gfgpu_term *t, int64_t *jc, int32_t *ir, double *pr) {
+  GF_API_BEGIN
+  GF_REQUIRE(t && t->pat_valid, "no assembled tangent");
+  GF_CUDA(cudaSetDevice(t->ctx->device));
+  if (jc) t->jc.download(jc);
+  if (ir) t->ir.download(ir);
+  if (pr) t->pr.download(pr);
+  GF_CUDA(cudaStreamSynchronize(t->ctx->stream));
+  GF_API_END
+}
+
+int gfgpu_term_export_residual_host(gfgpu_term *t, double *R) {
+  GF_API_BEGIN
+  GF_REQUIRE(t && t->R.n, "no assembled residual");
+  GF_CUDA(cudaSetDevice(t->ctx->device));
+  if (R) t->R.download(R);
+  GF_CUDA(cudaStreamSynchronize(t->ctx->stream));
+  GF_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,196 @@
+// common.cuh -- shared declarations of libgfgpu (sm_100a only; no CPU fallback).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/gfgpu.h"
+
+namespace gf {
+
+struct Error : std::runtime_error {
+  explicit Error(const std::string &s) : std::runtime_error(s) {}
+};
+
+#define GF_STR2(x) #x
+#define GF_STR(x) GF_STR2(x)
+#define GF_REQUIRE(cond, msg)                                                        \
+  do {                                                                               \
+    if (!(cond)) throw gf::Error(std::string(__FILE__ ":" GF_STR(__LINE__) ": ") + (msg)); \
+  } while (0)
+#define GF_CUDA(call)                                                                \
+  do {                                                                               \
+    cudaError_t e_ = (call);                                                         \
+    if (e_ != cudaSuccess)                                                           \
+      throw gf::Error(std::string(__FILE__ ":" GF_STR(__LINE__) ": " #call ": ") + cudaGetErrorString(e_)); \
+  } while (0)
+
+extern std::atomic<int64_t> g_launches;  // kernels launched by this process (ours + CUB passes we call)
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+#define GF_LAUNCH_CHECK()             \
+  do {                                \
+    gf::count_launch();               \
+    GF_CUDA(cudaGetLastError());      \
+  } while (0)
+
+}  // namespace gf
+
+struct gfgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  int64_t bytes = 0;
+  void *cub_tmp = nullptr;  // grow-only scratch for CUB calls
+  size_t cub_tmp_bytes = 0;
+};
+
+namespace gf {
+
+// Device buffer tied to a context (cudaMalloc; sizes are large and long-lived, no pooling needed).
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  gfgpu_ctx *ctx = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }
+  void alloc(gfgpu_ctx *c, size_t count) {
+    release();
+    ctx = c;
+    n = count;
+    if (count) {
+      GF_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+      ctx->bytes += (int64_t)(count * sizeof(T));
+    }
+  }
+  void release() {
+    if (p) {
+      cudaFree(p);
+      if (ctx) ctx->bytes -= (int64_t)(n * sizeof(T));
+    }
+    p = nullptr;
+    n = 0;
+  }
+  void zero() {
+    if (n) GF_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), ctx->stream));
+  }
+  void upload(const T *h) {
+    if (n) GF_CUDA(cudaMemcpyAsync(p, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  void download(T *h) const {
+    if (n) GF_CUDA(cudaMemcpyAsync(h, p, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+};
+
+void *cub_scratch(gfgpu_ctx *ctx, size_t bytes);
+
+}  // namespace gf
+
+struct gfgpu_mesh {
+  gfgpu_ctx *ctx;
+  int dim, ng, gt_kind;
+  int64_t npts, ne;
+  gf::DevBuf<double> xyz;    // SoA: x[npts] y[npts] z[npts]
+  gf::DevBuf<int32_t> conn;  // ne x ng
+};
+
+namespace gf {
+// Structural (value-independent) part of the scatter: node pairs and their contributions.
+struct Structure {
+  int64_t e0 = 0, e1 = 0;  // element range it was built for
+  int64_t ncontrib = 0;    // (e1-e0) * nd * nd
+  int64_t npairs = 0;
+  int64_t ncolnodes = 0;
+  DevBuf<int32_t> pI, pJ;      // dof0 of row / column node of each pair (pairs sorted by (J, I))
+  DevBuf<uint32_t> cstart;     // npairs+1: contributions of pair p are csrc[cstart[p] .. cstart[p+1])
+  DevBuf<uint32_t> csrc;       // contribution id = (e-e0)*nd*nd + j*nd + i, ascending inside a pair
+  DevBuf<uint32_t> colstart;   // ncolnodes+1: pairs of column node k are [colstart[k], colstart[k+1])
+  // residual: node -> (element, local node) incidences
+  int64_t nrnodes = 0, nrinc = 0;
+  DevBuf<int32_t> rdof;        // dof0 of each touched node
+  DevBuf<uint32_t> rstart;     // nrnodes+1
+  DevBuf<uint32_t> rsrc;       // incidence id = (e-e0)*nd + i
+};
+}  // namespace gf
+
+struct gfgpu_fem {
+  gfgpu_ctx *ctx;
+  gfgpu_mesh *mesh;
+  int fem_kind, degree, qdim, nd;
+  int64_t ndof;
+  gf::DevBuf<int32_t> edof;  // ne x nd : dof of component 0
+};
+
+struct gfgpu_tables {
+  gfgpu_ctx *ctx;
+  int dim, nq, ng, nd;
+  gf::DevBuf<double> w, gt_grad, phi, gphi;
+  std::vector<double> h_w, h_gt_grad, h_phi, h_gphi;
+};
+
+struct gfgpu_term {
+  gfgpu_ctx *ctx;
+  gfgpu_mesh *mesh;
+  gfgpu_fem *fem;
+  gfgpu_tables *tab;
+  int family, strategy;
+  double par[4];
+  double alpha;
+  int64_t e0, e1;
+  // structure
+  gf::Structure st;
+  bool st_valid = false;
+  // pattern (value dependent)
+  bool pat_valid = false;
+  int64_t generation = 0;
+  int64_t nnz = 0;
+  gf::DevBuf<uint16_t> pmask;   // npairs
+  gf::DevBuf<uint32_t> prel;    // Q x npairs: offset of the pair's first kept entry inside column QJ+beta
+  gf::DevBuf<int64_t> jc;       // ndof+1
+  gf::DevBuf<int64_t> ctot;     // ndof (scratch)
+  gf::DevBuf<int32_t> ir;       // nnz
+  gf::DevBuf<double> pr;        // nnz
+  gf::DevBuf<double> R;         // ndof
+  // staging
+  gf::DevBuf<double> stage;     // ne_loc x s1 x s1
+  gf::DevBuf<uint16_t> emask;   // ne_loc x nd x nd
+  gf::DevBuf<double> rstage;    // ne_loc x s1
+  gf::DevBuf<double> Ubuf;      // ndof (host path)
+  gf::DevBuf<int32_t> flag;     // pattern-changed flag
+};
+
+namespace gf {
+
+// ---- element kernels (elem_*.cu)
+struct ElemArgs {
+  const double *x, *y, *z;
+  const int32_t *conn;
+  const int32_t *edof;
+  const double *U;
+  const double *w, *gt_grad, *phi, *gphi;
+  int nq, ng, qc;
+  int64_t e0, e1;
+  double par[4];
+  double alpha;
+  int family;
+  double *stage;
+  uint16_t *emask;
+  double *rstage;
+};
+// returns false when the (dim, Q, nd, family, affine) combination has no instantiation
+bool launch_elem_kernel(gfgpu_ctx *ctx, int dim, int Q, int nd, bool affine, const ElemArgs &a);
+
+// ---- scatter structure / pattern / gather (scatter.cu)
+void build_structure(gfgpu_ctx *ctx, const int32_t *edof, int nd, int64_t e0, int64_t e1, int64_t ndof,
+                     Structure &st);
+void build_pattern(gfgpu_term *t);
+void gather_tangent(gfgpu_term *t, bool check);
+void gather_residual(gfgpu_term *t);
+
+}  // namespace gf

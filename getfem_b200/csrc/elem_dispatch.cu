@@ -1,0 +1,23 @@
+// elem_dispatch.cu -- family -> kernel class mapping and dispatch over the instantiation files.
+#include "elem_kernel.cuh"
+namespace gf {
+bool launch_elem_inst_2d(gfgpu_ctx *, int, int, int, int, bool, const ElemArgs &);
+bool launch_elem_inst_3d_pk(gfgpu_ctx *, int, int, int, int, bool, const ElemArgs &);
+bool launch_elem_inst_3d_qk(gfgpu_ctx *, int, int, int, int, bool, const ElemArgs &);
+bool launch_elem_inst_3d_qk_hi(gfgpu_ctx *, int, int, int, int, bool, const ElemArgs &);
+
+bool launch_elem_kernel(gfgpu_ctx *ctx, int dim, int Q, int nd, bool affine, const ElemArgs &a) {
+  int fk;
+  switch (a.family) {
+    case GFGPU_LAPLACE: fk = FK_LAPLACE; break;
+    case GFGPU_MASS: fk = FK_MASS; break;
+    case GFGPU_ELASTICITY: fk = FK_ELAST; break;
+    case GFGPU_SVK: case GFGPU_NEOHOOKEAN_CIARLET: case GFGPU_NEOHOOKEAN_BONET: fk = FK_HYPER; break;
+    default: return false;
+  }
+  return launch_elem_inst_2d(ctx, dim, Q, nd, fk, affine, a) ||
+         launch_elem_inst_3d_pk(ctx, dim, Q, nd, fk, affine, a) ||
+         launch_elem_inst_3d_qk(ctx, dim, Q, nd, fk, affine, a) ||
+         launch_elem_inst_3d_qk_hi(ctx, dim, Q, nd, fk, affine, a);
+}
+}  // namespace gf

@@ -1,0 +1,397 @@
+// scatter.cu -- replaces add_elem_matrix / add_to_coeff scatter into gmm::col_matrix<rsvector>
+// (C&E.cc:4853-4936) and ga_instruction_vector_assembly_mf (C&E.cc:4669-4735) by a precomputed
+// map + deterministic gather-sum:
+//   structure : node pairs (J,I) present in the mesh graph and, per pair, the ascending list of
+//               (element, local j, local i) contributions          [value independent, per fem]
+//   pattern   : per pair a QxQ keep mask = OR over elements of "|K_e(r,c)| > 1e-14*max|K_e|"
+//               (the reference's drop rule) -> CSC jc/ir identical to gmm::csc_matrix::init_with
+//   gather    : pr[slot] = sum over the pair's contributions, ascending element id (the order the
+//               reference's sequential ga_exec adds them), no atomics.
+// CUB (radix sort / scan / select) is used for the symbolic phase only.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace gf {
+
+void *cub_scratch(gfgpu_ctx *ctx, size_t bytes) {
+  if (bytes > ctx->cub_tmp_bytes) {
+    if (ctx->cub_tmp) {
+      GF_CUDA(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->cub_tmp);
+      ctx->bytes -= (int64_t)ctx->cub_tmp_bytes;
+    }
+    size_t nb = bytes + bytes / 8 + 256;
+    GF_CUDA(cudaMalloc(&ctx->cub_tmp, nb));
+    ctx->cub_tmp_bytes = nb;
+    ctx->bytes += (int64_t)nb;
+  }
+  return ctx->cub_tmp;
+}
+
+static inline int nbits(int64_t v) {
+  int b = 1;
+  while (b < 63 && (int64_t(1) << b) <= v) ++b;
+  return b;
+}
+
+static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+// ------------------------------------------------------------------ structure
+__global__ void k_pair_keys(const int32_t *__restrict__ edof, int nd, int64_t e0, int64_t ncontrib, int bI,
+                            uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  const int nb = nd * nd;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncontrib; c += (int64_t)gridDim.x * blockDim.x) {
+    int64_t el = c / nb;
+    int r = (int)(c % nb);
+    int j = r / nd, i = r % nd;
+    const int32_t *ed = edof + (e0 + el) * nd;
+    keys[c] = ((uint64_t)(uint32_t)ed[j] << bI) | (uint64_t)(uint32_t)ed[i];
+    vals[c] = (uint32_t)c;
+  }
+}
+
+__global__ void k_node_keys(const int32_t *__restrict__ edof, int nd, int64_t e0, int64_t ninc,
+                            uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ninc; c += (int64_t)gridDim.x * blockDim.x) {
+    keys[c] = (uint32_t)edof[e0 * nd + c];
+    vals[c] = (uint32_t)c;
+  }
+}
+
+template <class K>
+__global__ void k_head_flags(const K *__restrict__ keys, int64_t n, uint8_t *__restrict__ flags) {
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x)
+    flags[s] = (s == 0 || keys[s] != keys[s - 1]) ? 1 : 0;
+}
+
+__global__ void k_pair_ids(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ cstart, int64_t npairs,
+                           int bI, int32_t *__restrict__ pI, int32_t *__restrict__ pJ, uint8_t *__restrict__ colflag) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npairs; p += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t k = keys[cstart[p]];
+    int32_t J = (int32_t)(k >> bI);
+    pI[p] = (int32_t)(k & ((uint64_t(1) << bI) - 1));
+    pJ[p] = J;
+    bool head = p == 0;
+    if (!head) head = (int32_t)(keys[cstart[p - 1]] >> bI) != J;
+    colflag[p] = head ? 1 : 0;
+  }
+}
+
+__global__ void k_node_ids(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ rstart, int64_t n,
+                           int32_t *__restrict__ rdof) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
+    rdof[p] = (int32_t)keys[rstart[p]];
+}
+
+__global__ void k_set_u32(uint32_t *p, uint32_t v) { *p = v; }
+
+// positions of set flags -> out[0..count), count returned on host
+static int64_t select_heads(gfgpu_ctx *ctx, const uint8_t *flags, int64_t n, uint32_t *out) {
+  GF_REQUIRE(n < (int64_t(1) << 32), "too many contributions for 32-bit positions");
+  DevBuf<int64_t> dcount;
+  dcount.alloc(ctx, 1);
+  cub::CountingInputIterator<uint32_t> it(0);
+  size_t tb = 0;
+  GF_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, it, flags, out, dcount.p, n, ctx->stream));
+  void *tmp = cub_scratch(ctx, tb);
+  GF_CUDA(cub::DeviceSelect::Flagged(tmp, tb, it, flags, out, dcount.p, n, ctx->stream));
+  count_launch(2);
+  int64_t h = 0;
+  dcount.download(&h);
+  GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  return h;
+}
+
+void build_structure(gfgpu_ctx *ctx, const int32_t *edof, int nd, int64_t e0, int64_t e1, int64_t ndof, Structure &st) {
+  const int64_t ne = e1 - e0;
+  const int64_t nb = (int64_t)nd * nd;
+  st.e0 = e0;
+  st.e1 = e1;
+  st.ncontrib = ne * nb;
+  GF_REQUIRE(st.ncontrib < (int64_t(1) << 32), "element block too large: (ne*nd*nd) must stay below 2^32");
+  const int bI = nbits(ndof);
+  GF_REQUIRE(2 * bI <= 64, "ndof too large");
+  cudaStream_t s = ctx->stream;
+  const int B = 256;
+  {  // ---- tangent: sort contributions by (J, I)
+    const int64_t n = st.ncontrib;
+    DevBuf<uint64_t> k0, k1;
+    DevBuf<uint32_t> v0;
+    k0.alloc(ctx, n);
+    k1.alloc(ctx, n);
+    v0.alloc(ctx, n);
+    st.csrc.alloc(ctx, n);
+    if (n) {
+      k_pair_keys<<<min(grid_for(n, B), 148 * 16), B, 0, s>>>(edof, nd, e0, n, bI, k0.p, v0.p);
+      GF_LAUNCH_CHECK();
+      // explicit in/out buffers: the sorted values land in st.csrc
+      size_t tb = 0;
+      GF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, k0.p, k1.p, v0.p, st.csrc.p, n, 0, 2 * bI, s));
+      void *tmp = cub_scratch(ctx, tb);
+      GF_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, k0.p, k1.p, v0.p, st.csrc.p, n, 0, 2 * bI, s));
+      count_launch(2 * ((2 * bI + 7) / 8) + 1);
+    }
+    v0.release();
+    k0.release();
+    DevBuf<uint8_t> flags;
+    flags.alloc(ctx, n);
+    DevBuf<uint32_t> heads;
+    heads.alloc(ctx, n + 1);
+    if (n) {
+      k_head_flags<uint64_t><<<min(grid_for(n, B), 148 * 16), B, 0, s>>>(k1.p, n, flags.p);
+      GF_LAUNCH_CHECK();
+    }
+    st.npairs = n ? select_heads(ctx, flags.p, n, heads.p) : 0;
+    st.cstart.alloc(ctx, st.npairs + 1);
+    GF_CUDA(cudaMemcpyAsync(st.cstart.p, heads.p, st.npairs * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    k_set_u32<<<1, 1, 0, s>>>(st.cstart.p + st.npairs, (uint32_t)n);
+    GF_LAUNCH_CHECK();
+    st.pI.alloc(ctx, st.npairs);
+    st.pJ.alloc(ctx, st.npairs);
+    flags.alloc(ctx, st.npairs);
+    if (st.npairs) {
+      k_pair_ids<<<min(grid_for(st.npairs, B), 148 * 16), B, 0, s>>>(k1.p, st.cstart.p, st.npairs, bI, st.pI.p, st.pJ.p,
+                                                                   flags.p);
+      GF_LAUNCH_CHECK();
+    }
+    k1.release();
+    heads.alloc(ctx, st.npairs + 1);
+    st.ncolnodes = st.npairs ? select_heads(ctx, flags.p, st.npairs, heads.p) : 0;
+    st.colstart.alloc(ctx, st.ncolnodes + 1);
+    GF_CUDA(cudaMemcpyAsync(st.colstart.p, heads.p, st.ncolnodes * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    k_set_u32<<<1, 1, 0, s>>>(st.colstart.p + st.ncolnodes, (uint32_t)st.npairs);
+    GF_LAUNCH_CHECK();
+    GF_CUDA(cudaStreamSynchronize(s));
+  }
+  {  // ---- residual: sort (element, local node) incidences by node
+    const int64_t n = ne * nd;
+    st.nrinc = n;
+    DevBuf<uint32_t> k0, k1, v0;
+    k0.alloc(ctx, n);
+    k1.alloc(ctx, n);
+    v0.alloc(ctx, n);
+    st.rsrc.alloc(ctx, n);
+    if (n) {
+      k_node_keys<<<min(grid_for(n, B), 148 * 16), B, 0, s>>>(edof, nd, e0, n, k0.p, v0.p);
+      GF_LAUNCH_CHECK();
+      size_t tb = 0;
+      GF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, k0.p, k1.p, v0.p, st.rsrc.p, n, 0, bI, s));
+      void *tmp = cub_scratch(ctx, tb);
+      GF_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, k0.p, k1.p, v0.p, st.rsrc.p, n, 0, bI, s));
+      count_launch(2 * ((bI + 7) / 8) + 1);
+    }
+    DevBuf<uint8_t> flags;
+    flags.alloc(ctx, n);
+    DevBuf<uint32_t> heads;
+    heads.alloc(ctx, n + 1);
+    if (n) {
+      k_head_flags<uint32_t><<<min(grid_for(n, B), 148 * 16), B, 0, s>>>(k1.p, n, flags.p);
+      GF_LAUNCH_CHECK();
+    }
+    st.nrnodes = n ? select_heads(ctx, flags.p, n, heads.p) : 0;
+    st.rstart.alloc(ctx, st.nrnodes + 1);
+    GF_CUDA(cudaMemcpyAsync(st.rstart.p, heads.p, st.nrnodes * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    k_set_u32<<<1, 1, 0, s>>>(st.rstart.p + st.nrnodes, (uint32_t)n);
+    GF_LAUNCH_CHECK();
+    st.rdof.alloc(ctx, st.nrnodes);
+    if (st.nrnodes) {
+      k_node_ids<<<min(grid_for(st.nrnodes, B), 148 * 16), B, 0, s>>>(k1.p, st.rstart.p, st.nrnodes, st.rdof.p);
+      GF_LAUNCH_CHECK();
+    }
+    GF_CUDA(cudaStreamSynchronize(s));
+  }
+}
+
+// ------------------------------------------------------------------ pattern
+__global__ void k_pair_masks(const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ csrc,
+                             const uint16_t *__restrict__ emask, int64_t npairs, uint16_t *__restrict__ pmask) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npairs; p += (int64_t)gridDim.x * blockDim.x) {
+    unsigned m = 0;
+    for (uint32_t s = cstart[p], e = cstart[p + 1]; s < e; ++s) m |= emask[csrc[s]];
+    pmask[p] = (uint16_t)m;
+  }
+}
+
+// one thread per column node: running counts of kept entries per component column
+template <int Q>
+__global__ void k_column_scan(const uint32_t *__restrict__ colstart, const int32_t *__restrict__ pJ,
+                              const uint16_t *__restrict__ pmask, int64_t ncol, int64_t npairs,
+                              uint32_t *__restrict__ prel, int64_t *__restrict__ ctot) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < ncol; k += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t cnt[Q];
+#pragma unroll
+    for (int b = 0; b < Q; ++b) cnt[b] = 0;
+    const uint32_t p0 = colstart[k], p1 = colstart[k + 1];
+    for (uint32_t p = p0; p < p1; ++p) {
+      unsigned m = pmask[p];
+#pragma unroll
+      for (int b = 0; b < Q; ++b) {
+        prel[(size_t)b * npairs + p] = cnt[b];
+        cnt[b] += __popc((m >> (b * Q)) & ((1u << Q) - 1));
+      }
+    }
+    const int32_t J = pJ[p0];
+#pragma unroll
+    for (int b = 0; b < Q; ++b) ctot[J + b] = cnt[b];
+  }
+}
+
+template <int Q>
+__global__ void k_fill_ir(const int32_t *__restrict__ pI, const int32_t *__restrict__ pJ,
+                          const uint16_t *__restrict__ pmask, const uint32_t *__restrict__ prel,
+                          const int64_t *__restrict__ jc, int64_t npairs, int32_t *__restrict__ ir) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npairs; p += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned m = pmask[p];
+    const int32_t I = pI[p], J = pJ[p];
+#pragma unroll
+    for (int b = 0; b < Q; ++b) {
+      int64_t pos = jc[J + b] + prel[(size_t)b * npairs + p];
+#pragma unroll
+      for (int a = 0; a < Q; ++a)
+        if (m & (1u << (b * Q + a))) ir[pos++] = I + a;
+    }
+  }
+}
+
+template <int Q>
+static void build_pattern_t(gfgpu_term *t) {
+  gfgpu_ctx *ctx = t->ctx;
+  Structure &st = t->st;
+  cudaStream_t s = ctx->stream;
+  const int B = 256;
+  const int64_t ndof = t->fem->ndof;
+  t->pmask.alloc(ctx, st.npairs);
+  t->prel.alloc(ctx, (size_t)Q * st.npairs);
+  if (t->ctot.n != (size_t)ndof + 1) t->ctot.alloc(ctx, ndof + 1);
+  if (t->jc.n != (size_t)ndof + 1) t->jc.alloc(ctx, ndof + 1);
+  t->ctot.zero();
+  if (st.npairs) {
+    k_pair_masks<<<min(grid_for(st.npairs, B), 148 * 32), B, 0, s>>>(st.cstart.p, st.csrc.p, t->emask.p, st.npairs,
+                                                                   t->pmask.p);
+    GF_LAUNCH_CHECK();
+    k_column_scan<Q><<<min(grid_for(st.ncolnodes, B), 148 * 32), B, 0, s>>>(st.colstart.p, st.pJ.p, t->pmask.p,
+                                                                          st.ncolnodes, st.npairs, t->prel.p, t->ctot.p);
+    GF_LAUNCH_CHECK();
+  }
+  size_t tb = 0;
+  GF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, t->ctot.p, t->jc.p, ndof + 1, s));
+  void *tmp = cub_scratch(ctx, tb);
+  GF_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, t->ctot.p, t->jc.p, ndof + 1, s));
+  count_launch(2);
+  int64_t nnz = 0;
+  GF_CUDA(cudaMemcpyAsync(&nnz, t->jc.p + ndof, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  GF_CUDA(cudaStreamSynchronize(s));
+  t->nnz = nnz;
+  t->ir.alloc(ctx, nnz);
+  t->pr.alloc(ctx, nnz);
+  if (st.npairs) {
+    k_fill_ir<Q><<<min(grid_for(st.npairs, B), 148 * 32), B, 0, s>>>(st.pI.p, st.pJ.p, t->pmask.p, t->prel.p, t->jc.p,
+                                                                   st.npairs, t->ir.p);
+    GF_LAUNCH_CHECK();
+  }
+  t->pat_valid = true;
+  t->generation++;
+}
+
+void build_pattern(gfgpu_term *t) {
+  switch (t->fem->qdim) {
+    case 1: build_pattern_t<1>(t); break;
+    case 2: build_pattern_t<2>(t); break;
+    case 3: build_pattern_t<3>(t); break;
+    default: GF_REQUIRE(false, "qdim must be 1, 2 or 3");
+  }
+}
+
+// ------------------------------------------------------------------ gather
+// One thread per node pair: sums the QxQ blocks of its contributions from the stage (ascending
+// element id) and writes the kept entries to their CSC slots.  With CHECK it also re-derives
+// the pair's keep mask from the fresh element masks and raises `flag` when the pattern moved.
+template <int Q, bool CHECK>
+__global__ void __launch_bounds__(256)
+k_gather(const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ csrc, const int32_t *__restrict__ pJ,
+         const uint16_t *__restrict__ pmask, const uint32_t *__restrict__ prel, const int64_t *__restrict__ jc,
+         const double *__restrict__ stage, const uint16_t *__restrict__ emask, int nd, int64_t npairs,
+         double *__restrict__ pr, int *__restrict__ flag) {
+  const int nb = nd * nd, s1 = nd * Q;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npairs; p += (int64_t)gridDim.x * blockDim.x) {
+    double acc[Q * Q];
+#pragma unroll
+    for (int m = 0; m < Q * Q; ++m) acc[m] = 0.0;
+    unsigned mnew = 0;
+    for (uint32_t s = cstart[p], e = cstart[p + 1]; s < e; ++s) {
+      const uint32_t c = csrc[s];
+      const uint32_t el = c / nb, r = c % nb;
+      const int j = r / nd, i = r % nd;
+      const double *src = stage + (size_t)el * s1 * s1 + (size_t)(j * Q) * s1 + i * Q;
+#pragma unroll
+      for (int b = 0; b < Q; ++b)
+#pragma unroll
+        for (int a = 0; a < Q; ++a) acc[b * Q + a] += src[b * s1 + a];
+      if (CHECK) mnew |= emask[c];
+    }
+    const unsigned m = pmask[p];
+    if (CHECK && mnew != m) atomicExch(flag, 1);
+    const int32_t J = pJ[p];
+#pragma unroll
+    for (int b = 0; b < Q; ++b) {
+      int64_t pos = jc[J + b] + prel[(size_t)b * npairs + p];
+#pragma unroll
+      for (int a = 0; a < Q; ++a)
+        if (m & (1u << (b * Q + a))) pr[pos++] = acc[b * Q + a];
+    }
+  }
+}
+
+template <int Q>
+static void gather_tangent_t(gfgpu_term *t, bool check) {
+  Structure &st = t->st;
+  if (!st.npairs) return;
+  const int B = 256;
+  int grid = min(grid_for(st.npairs, B), 148 * 64);
+  if (check)
+    k_gather<Q, true><<<grid, B, 0, t->ctx->stream>>>(st.cstart.p, st.csrc.p, st.pJ.p, t->pmask.p, t->prel.p, t->jc.p,
+                                                      t->stage.p, t->emask.p, t->fem->nd, st.npairs, t->pr.p,
+                                                      (int *)t->flag.p);
+  else
+    k_gather<Q, false><<<grid, B, 0, t->ctx->stream>>>(st.cstart.p, st.csrc.p, st.pJ.p, t->pmask.p, t->prel.p, t->jc.p,
+                                                       t->stage.p, t->emask.p, t->fem->nd, st.npairs, t->pr.p,
+                                                       (int *)t->flag.p);
+  GF_LAUNCH_CHECK();
+}
+
+void gather_tangent(gfgpu_term *t, bool check) {
+  switch (t->fem->qdim) {
+    case 1: gather_tangent_t<1>(t, check); break;
+    case 2: gather_tangent_t<2>(t, check); break;
+    case 3: gather_tangent_t<3>(t, check); break;
+    default: GF_REQUIRE(false, "qdim must be 1, 2 or 3");
+  }
+}
+
+// one thread per (node, component): R[dof0 + a] = sum of staged element residuals, ascending element id
+__global__ void k_gather_residual(const uint32_t *__restrict__ rstart, const uint32_t *__restrict__ rsrc,
+                                  const int32_t *__restrict__ rdof, const double *__restrict__ rstage, int Q,
+                                  int64_t nrnodes, double *__restrict__ R) {
+  const int64_t n = nrnodes * Q;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t u = idx / Q;
+    const int a = (int)(idx % Q);
+    double s = 0.0;
+    for (uint32_t k = rstart[u], e = rstart[u + 1]; k < e; ++k) s += rstage[(size_t)rsrc[k] * Q + a];
+    R[rdof[u] + a] = s;
+  }
+}
+
+void gather_residual(gfgpu_term *t) {
+  Structure &st = t->st;
+  t->R.zero();
+  if (!st.nrnodes) return;
+  const int B = 256;
+  const int Q = t->fem->qdim;
+  k_gather_residual<<<min(grid_for(st.nrnodes * Q, B), 148 * 64), B, 0, t->ctx->stream>>>(
+      st.rstart.p, st.rsrc.p, st.rdof.p, t->rstage.p, Q, st.nrnodes, t->R.p);
+  GF_LAUNCH_CHECK();
+}
+
+}  // namespace gf

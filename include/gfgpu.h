@@ -1,0 +1,145 @@
+/* gfgpu.h -- C ABI of the B200-native generic weak-form assembly path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  A GetFEM
+ * maintainer binds these from ga_workspace::assembly() (see INTEGRATION.md and
+ * getfem_b200/shim/gfgpu_getfem_shim.cc); the Python host mirror binds the same symbols
+ * through ctypes (getfem_b200/capi.py).
+ *
+ * Every entry point names the reference interface it replaces; paths are relative to the
+ * GetFEM source tree (getfem/getfem v5.5), "C&E.cc" = src/getfem_generic_assembly_compile_and_exec.cc.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; gfgpu_last_error() returns
+ *     the message of the last failure on the calling thread (the C++ shim turns it into
+ *     GMM_ASSERT1 / gmm::gmm_error, gmm_except.h:55-163);
+ *   - "_host" pointers are host memory, "_dev" pointers are device memory of the context's GPU;
+ *   - tensors follow the reference: column-major, first index fastest (bgeot_tensor.h:200-230);
+ *     local dof of a vector fem = node*Q + q (C&E.cc:5008-5020);
+ *   - the tangent is produced column-compressed like gmm::csc_matrix (gmm_matrix.h:506-566):
+ *     jc[ndof+1], ir[nnz] (rows ascending inside each column), pr[nnz].  K(r,c): r = Test_ dof,
+ *     c = Test2_ dof (C&E.cc:4837-4843).  jc is int64 because nnz exceeds 2^32 at benchmark size.
+ *   - there is no CPU fallback anywhere behind this interface.
+ */
+#ifndef GFGPU_H
+#define GFGPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gfgpu_ctx gfgpu_ctx;     /* one GPU + one stream */
+typedef struct gfgpu_mesh gfgpu_mesh;   /* SoA node coordinates + connectivity */
+typedef struct gfgpu_fem gfgpu_fem;     /* element->dof table (mesh_fem) */
+typedef struct gfgpu_tables gfgpu_tables; /* reference tables at the quadrature points */
+typedef struct gfgpu_term gfgpu_term;   /* one compiled weak-form term + its pattern */
+
+/* geometric transformation kinds (bgeot_geometric_trans.cc:600-672) */
+enum { GFGPU_GT_PK = 0 /* affine simplex, is_linear() */, GFGPU_GT_QK = 1 /* multilinear, K per Gauss point */ };
+/* Lagrange fem kinds (getfem_fem.cc:719-843, 1010-1047) */
+enum { GFGPU_FEM_PK = 0, GFGPU_FEM_QK = 1 };
+
+/* Expression families = the compiled ga_instruction chains that are replaced:
+ *   LAPLACE      "a*Grad_u.Grad_Test_u" / "a*Grad_u:Grad_Test_u"     params = {a}
+ *                (add_generic_elliptic_brick, getfem_models.cc:3943-3997)
+ *   ELASTICITY   "(Div_u*(lambda*Id(meshdim))+(2*mu)*Sym(Grad_u)):Grad_Test_u"  params = {lambda, mu}
+ *                (add_isotropic_linearized_elasticity_brick, getfem_models.cc:6102-6136)
+ *   SVK / NEOHOOKEAN_CIARLET / NEOHOOKEAN_BONET
+ *                "((Id(meshdim)+Grad_u)*(<law>_PK2(Grad_u,params))):Grad_Test_u" params = {lambda, mu}
+ *                (add_finite_strain_elasticity_brick, getfem_nonlinear_elasticity.cc:2301-2325;
+ *                 laws :1945-1994, :612-702)
+ *   MASS         "a*u.Test_u"                                        params = {a}
+ */
+enum {
+  GFGPU_LAPLACE = 0,
+  GFGPU_ELASTICITY = 1,
+  GFGPU_SVK = 2,
+  GFGPU_NEOHOOKEAN_CIARLET = 3,
+  GFGPU_NEOHOOKEAN_BONET = 4,
+  GFGPU_MASS = 5
+};
+
+/* order_mask bits of gfgpu_term_assemble_*: ga_workspace::assembly(1) and assembly(2)
+ * (getfem_generic_assembly_workspace.cc:791-936) */
+enum { GFGPU_RESIDUAL = 1, GFGPU_TANGENT = 2 };
+
+/* numeric strategies; AUTO picks RECOMPUTE for affine geometry + constant
+ * coefficient bilinear forms and STAGED otherwise */
+enum { GFGPU_STRATEGY_AUTO = 0, GFGPU_STRATEGY_STAGED = 1, GFGPU_STRATEGY_RECOMPUTE = 2 };
+
+const char *gfgpu_last_error(void);
+/* library/ABI version, and the number of kernels launched by this process so far
+ * (bench.py's gpu_launches claim is read from here) */
+int gfgpu_version(void);
+int64_t gfgpu_launch_count(void);
+
+/* ---- context.  `stream` is a cudaStream_t passed as void* (NULL = the context creates its own). */
+int gfgpu_ctx_create(int device, void *stream, gfgpu_ctx **out);
+int gfgpu_ctx_destroy(gfgpu_ctx *ctx);
+int gfgpu_ctx_synchronize(gfgpu_ctx *ctx);
+/* bytes currently allocated by the library on this context */
+int64_t gfgpu_ctx_bytes_in_use(gfgpu_ctx *ctx);
+
+/* ---- mesh.  Replaces basic_mesh::points_of_convex(cv,G) (getfem/bgeot_mesh.h:94) and
+ * mesh_structure::ind_points_of_convex (bgeot_mesh_structure.h:106): points in point-id order
+ * (npts x dim, row-major), connectivity in convex order (ne x ng, the geometric nodes in
+ * pgt->geometric_nodes() order).  Stored on device as SoA x[],y[],z[] + int32 conn. */
+int gfgpu_mesh_create(gfgpu_ctx *ctx, int dim, int64_t npts, const double *pts_host, int64_t ne, int ng,
+                      const int32_t *conn_host, int gt_kind, gfgpu_mesh **out);
+int gfgpu_mesh_destroy(gfgpu_mesh *m);
+
+/* ---- fem.  Replaces mesh_fem::ind_scalar_basic_dof_of_element (getfem_mesh_fem.h:459-461).
+ * elem_dof_host: ne x nd, global dof of COMPONENT 0 of local node i (components are consecutive),
+ * or NULL: the first-touch numbering of mesh_fem::enumerate_dof (getfem_mesh_fem.cc:320-446) is
+ * then re-derived on the device from the connectivity (classical Lagrange PK/QK of `degree`). */
+int gfgpu_fem_create(gfgpu_ctx *ctx, gfgpu_mesh *mesh, int fem_kind, int degree, int qdim, int nd,
+                     const int64_t *elem_dof_host, int64_t ndof, gfgpu_fem **out);
+int64_t gfgpu_fem_nb_dof(gfgpu_fem *f);
+int gfgpu_fem_get_elem_dof(gfgpu_fem *f, int64_t *elem_dof_host /* ne x nd */);
+int gfgpu_fem_destroy(gfgpu_fem *f);
+
+/* ---- reference tables at the nq volume quadrature points.  Replaces geotrans_precomp_::grad
+ * (bgeot_geometric_trans.h:292-345), fem_precomp_::val/grad (getfem_fem.h:653-680) and
+ * approx_integration::coeff (getfem_integration.h:155-222).
+ *   w[nq]; gt_grad[nq][ng][dim]; phi[nq][nd]; gphi[nq][nd][dim]   (row-major as written) */
+int gfgpu_tables_create(gfgpu_ctx *ctx, int dim, int nq, int ng, int nd, const double *w_host,
+                        const double *gt_grad_host, const double *phi_host, const double *gphi_host,
+                        gfgpu_tables **out);
+int gfgpu_tables_destroy(gfgpu_tables *t);
+
+/* ---- term.  Replaces ga_compile + ga_exec for one expression of a recognised family
+ * (C&E.cc:7910-8643, 8750-9047).  alpha multiplies every contribution (factor_of_variable,
+ * C&E.cc:5052,8196-8198). */
+int gfgpu_term_create(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem, gfgpu_tables *tab, int family,
+                      const double *params_host, int nparams, double alpha, int strategy, gfgpu_term **out);
+int gfgpu_term_destroy(gfgpu_term *t);
+
+/* Restrict the term to the element block [e0, e1) (mesh_region / per-rank element partition,
+ * getfem_mesh_region.cc:145-185).  Default: all elements. */
+int gfgpu_term_set_element_range(gfgpu_term *t, int64_t e0, int64_t e1);
+
+/* Assemble with the state vector resident on the device (U_dev may be NULL: zero state).
+ * Tangent: builds/validates the value-dependent pattern (add_elem_matrix drop rule,
+ * C&E.cc:4853-4936, threshold 1e-14*max|K_e| from :5380-5402,:5441-5465) then the
+ * deterministic gather-sum.  Residual: ga_instruction_vector_assembly_mf (C&E.cc:4669-4735). */
+int gfgpu_term_assemble_dev(gfgpu_term *t, const double *U_dev, int order_mask);
+/* Same through host buffers (the drop-in call): copies U host->device, assembles, copies the
+ * tangent values (nnz doubles, may be NULL) and the residual (ndof doubles, may be NULL) back. */
+int gfgpu_term_assemble_host(gfgpu_term *t, const double *U_host, int order_mask, double *pr_host,
+                             double *R_host);
+
+int64_t gfgpu_term_nnz(gfgpu_term *t);
+int64_t gfgpu_term_nb_dof(gfgpu_term *t);
+/* number of times the pattern has been (re)built; a Newton loop can watch it */
+int64_t gfgpu_term_pattern_generation(gfgpu_term *t);
+/* device views (valid until the next assemble/destroy): gmm::csc_matrix layout */
+int gfgpu_term_csc_view(gfgpu_term *t, const int64_t **jc_dev, const int32_t **ir_dev, const double **pr_dev);
+int gfgpu_term_residual_view(gfgpu_term *t, const double **R_dev);
+/* host export of the pattern / values / residual (any pointer may be NULL) */
+int gfgpu_term_export_csc_host(gfgpu_term *t, int64_t *jc_host, int32_t *ir_host, double *pr_host);
+int gfgpu_term_export_residual_host(gfgpu_term *t, double *R_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFGPU_H */

@@ -29,7 +29,7 @@ CASES = {
     "c4b_svk_q2_n2": "dim=3 n=2 gt=qk k=2 q=3 im=6 family=svk u=smooth lambda=1 mu=1 uamp=0.02",
     "c5_lap_q4_n1": "dim=3 n=1 gt=qk k=4 q=1 im=8 family=laplace u=random",
     # extra coverage of the same path
-    "x_nh_bonet_p2tet_n1": "dim=3 n=1 gt=pk k=2 q=3 im=4 family=nh_bonet u=smooth lambda=1.3 mu=0.7 uamp=0.05",
+    "x_nh_bonet_p2tet_n2": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=nh_bonet u=smooth lambda=1.3 mu=0.7 uamp=0.05",
     "x_nh_ciarlet_p1tet_n2": "dim=3 n=2 gt=pk k=1 q=3 im=2 family=nh_ciarlet u=smooth lambda=1.3 mu=0.7 uamp=0.05",
     "x_elast2d_p2_n3": "dim=2 n=3 gt=pk k=2 q=2 im=4 family=elast u=random lambda=2 mu=0.5",
     "x_elast3d_p1_n2": "dim=3 n=2 gt=pk k=1 q=3 im=2 family=elast u=random lambda=1.3 mu=0.7",
