@@ -114,17 +114,52 @@ int gfgpu_fem_create(gfgpu_ctx *ctx, gfgpu_mesh *mesh, int fem_kind, int degree,
   GF_CUDA(cudaSetDevice(ctx->device));
   std::unique_ptr<gfgpu_fem> f(new gfgpu_fem);
   f->ctx = ctx; f->mesh = mesh; f->fem_kind = fem_kind; f->degree = degree; f->qdim = qdim; f->nd = nd;
-  GF_REQUIRE(elem_dof != nullptr, "device dof enumeration is not available yet: pass the element->dof table");
-  GF_REQUIRE(ndof > 0 && ndof < (int64_t(1) << 31) - 4, "ndof out of range");
-  f->ndof = ndof;
-  std::vector<int32_t> ed((size_t)mesh->ne * nd);
-  for (size_t k = 0; k < ed.size(); ++k) {
-    GF_REQUIRE(elem_dof[k] >= 0 && elem_dof[k] + qdim <= ndof, "element dof outside [0, ndof)");
-    ed[k] = (int32_t)elem_dof[k];
+  if (elem_dof) {
+    GF_REQUIRE(ndof > 0 && ndof < (int64_t(1) << 31) - 4, "ndof out of range");
+    f->ndof = ndof;
+    std::vector<int32_t> ed((size_t)mesh->ne * nd);
+    for (size_t k = 0; k < ed.size(); ++k) {
+      GF_REQUIRE(elem_dof[k] >= 0 && elem_dof[k] + qdim <= ndof, "element dof outside [0, ndof)");
+      ed[k] = (int32_t)elem_dof[k];
+    }
+    f->edof.alloc(ctx, ed.size());
+    f->edof.upload(ed.data());
+    GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  } else {
+    // local lattice of the classical Lagrange element (getfem_fem.cc:760-763, 816-825)
+    const int N = mesh->dim;
+    GF_REQUIRE(degree >= 1 && degree <= 8, "fem degree must be in 1..8 for device enumeration");
+    const bool qk = fem_kind == GFGPU_FEM_QK;
+    GF_REQUIRE(qk == (mesh->gt_kind == GFGPU_GT_QK), "fem kind does not match the geometric transformation");
+    GF_REQUIRE(mesh->ng == (qk ? (1 << N) : N + 1), "device enumeration needs a degree-1 geometric transformation");
+    std::vector<int8_t> lat;
+    int cnt = 0;
+    if (qk) {
+      const int n1 = degree + 1;
+      int tot = 1;
+      for (int d = 0; d < N; ++d) tot *= n1;
+      for (int i = 0; i < tot; ++i) {
+        int r = i;
+        int8_t l[4] = {0, 0, 0, 0};
+        for (int d = 0; d < N; ++d) { l[d] = (int8_t)(r % n1); r /= n1; }
+        lat.insert(lat.end(), l, l + 4);
+        ++cnt;
+      }
+    } else {
+      for (int c = 0; c <= (N == 3 ? degree : 0); ++c)
+        for (int b = 0; b <= degree; ++b)
+          for (int a = 0; a <= degree; ++a)
+            if (a + b + c <= degree) {
+              int8_t l[4] = {(int8_t)(degree - a - b - c), (int8_t)a, (int8_t)b, (int8_t)c};
+              lat.insert(lat.end(), l, l + 4);
+              ++cnt;
+            }
+    }
+    GF_REQUIRE(cnt == nd, "nd does not match the classical Lagrange element of this kind/degree");
+    f->edof.alloc(ctx, (size_t)mesh->ne * nd);
+    f->ndof = gf::enumerate_dof(ctx, mesh->conn.p, mesh->ne, mesh->ng, N, qk, degree, qdim, nd, lat.data(), f->edof.p);
+    GF_REQUIRE(f->ndof < (int64_t(1) << 31) - 4, "ndof out of range");
   }
-  f->edof.alloc(ctx, ed.size());
-  f->edof.upload(ed.data());
-  GF_CUDA(cudaStreamSynchronize(ctx->stream));
   *out = f.release();
   GF_API_END
 }

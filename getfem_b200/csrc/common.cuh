@@ -186,6 +186,10 @@ struct ElemArgs {
 // returns false when the (dim, Q, nd, family, affine) combination has no instantiation
 bool launch_elem_kernel(gfgpu_ctx *ctx, int dim, int Q, int nd, bool affine, const ElemArgs &a);
 
+// ---- first-touch dof numbering (dof_enum.cu); returns ndof
+int64_t enumerate_dof(gfgpu_ctx *ctx, const int32_t *conn, int64_t ne, int ng, int N, bool qk, int k, int Q, int nd,
+                      const int8_t *lat_host, int32_t *edof_dev);
+
 // ---- scatter structure / pattern / gather (scatter.cu)
 void build_structure(gfgpu_ctx *ctx, const int32_t *edof, int nd, int64_t e0, int64_t e1, int64_t ndof,
                      Structure &st);

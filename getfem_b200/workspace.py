@@ -1,0 +1,283 @@
+"""Host-side mirror of the reference interface for the accelerated path.
+
+Same names and argument meaning as GetFEM's C++ API (the parity tests read like tests/test_assembly.cc):
+
+  mesh          regular_unit_mesh(m, nsubdiv, pgt)              src/getfem_regular_meshes.cc:237-284
+  mesh_fem      mesh_fem(m, Qdim); set_classical_finite_element(K); nb_dof();
+                ind_scalar_basic_dof_of_element(cv)              src/getfem/getfem_mesh_fem.h:459-461
+  mesh_im       mesh_im(m); set_integration_method(degree)       src/getfem/getfem_mesh_im.h
+  ga_workspace  add_fem_variable, add_fixed_size_constant, add_expression, assembly(order),
+                assembled_matrix(), assembled_vector()           src/getfem/getfem_generic_assembly.h:262-597
+
+Everything numerical happens on the device through the C ABI (capi.py); there is no CPU fallback:
+an expression that is not one of the recognised families raises, exactly like GMM_ASSERT1 would.
+"""
+import re
+
+import numpy as np
+
+from . import capi, fem_tables
+from .regular_mesh import regular_unit_mesh as _regular_unit_mesh
+
+_ctx = {}
+
+
+def default_context(device=None, stream=None):
+    """One context per (device, stream).  The device defaults to LOCAL_RANK (one process per GPU)."""
+    import os
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    key = (device, stream)
+    if key not in _ctx:
+        _ctx[key] = capi.Context(device, stream)
+    return _ctx[key]
+
+
+class mesh:
+    """getfem::mesh restricted to what the path reads: points and convex connectivity."""
+
+    def __init__(self, pts=None, conn=None, gt="GT_PK"):
+        self.pts = None if pts is None else np.ascontiguousarray(pts, np.float64)
+        self.conn = None if conn is None else np.ascontiguousarray(conn, np.int32)
+        self.gt = gt  # "GT_PK" (affine simplices) or "GT_QK" (multilinear parallelepipeds), degree 1
+        self._dev = {}
+
+    def dim(self):
+        return self.pts.shape[1]
+
+    def nb_convex(self):
+        return self.conn.shape[0]
+
+    def nb_points(self):
+        return self.pts.shape[0]
+
+    def device(self, ctx):
+        if ctx not in self._dev:
+            self._dev[ctx] = capi.DeviceMesh(ctx, self.pts, self.conn, capi.GT_PK if self.gt == "GT_PK" else capi.GT_QK)
+        return self._dev[ctx]
+
+
+def regular_unit_mesh(m, nsubdiv, pgt):
+    """pgt: 'GT_PK(N,1)' or 'GT_QK(N,1)' (name_of_geometric_trans syntax)."""
+    mt = re.fullmatch(r"GT_(PK|QK)\((\d),1\)", pgt.replace(" ", ""))
+    if not mt or int(mt.group(2)) != len(nsubdiv):
+        raise capi.GfgpuError("cannot build a regular mesh for " + pgt)
+    m.gt = "GT_" + mt.group(1)
+    m.pts, m.conn = _regular_unit_mesh(nsubdiv, "simplex" if mt.group(1) == "PK" else "parallelepiped")
+    m._dev = {}
+    return m
+
+
+class mesh_fem:
+    def __init__(self, m, Qdim=1):
+        self.linked_mesh = m
+        self.Qdim = int(Qdim)
+        self.K = None
+        self._elem_dof = None
+        self._ndof = None
+        self._dev = {}
+
+    def set_classical_finite_element(self, K):
+        self.K = int(K)
+        self._elem_dof = None
+        self._ndof = None
+        self._dev = {}
+
+    def fem_kind(self):
+        return "PK" if self.linked_mesh.gt == "GT_PK" else "QK"
+
+    def nb_basic_dof_of_element(self):
+        return fem_tables.nb_dof(self.fem_kind(), self.linked_mesh.dim(), self.K) * self.Qdim
+
+    def set_dof_table(self, elem_dof, ndof):
+        """Adopt a numbering produced elsewhere (e.g. read from the reference's mesh_fem)."""
+        self._elem_dof = np.ascontiguousarray(elem_dof, np.int64)
+        self._ndof = int(ndof)
+        self._dev = {}
+
+    def device(self, ctx):
+        if ctx not in self._dev:
+            m = self.linked_mesh
+            nd = fem_tables.nb_dof(self.fem_kind(), m.dim(), self.K)
+            kind = capi.FEM_PK if self.fem_kind() == "PK" else capi.FEM_QK
+            self._dev[ctx] = capi.DeviceFem(ctx, m.device(ctx), kind, self.K, self.Qdim, nd, self._elem_dof,
+                                            self._ndof or 0)
+            if self._ndof is None:
+                self._ndof = self._dev[ctx].ndof
+        return self._dev[ctx]
+
+    def nb_dof(self, ctx=None):
+        if self._ndof is None:
+            self.device(ctx or default_context())  # enumerate_dof on the device
+        return self._ndof
+
+    def ind_scalar_basic_dof_of_element(self, cv=None, ctx=None):
+        """Element -> dof table (component 0 of each local node); all elements when cv is None."""
+        if self._elem_dof is None:
+            self._elem_dof = self.device(ctx or default_context()).elem_dof()
+        return self._elem_dof if cv is None else self._elem_dof[cv]
+
+    def basic_dof_nodes(self, ctx=None):
+        """Physical coordinates of the node of every dof (mesh_fem::point_of_basic_dof)."""
+        m = self.linked_mesh
+        ed = self.ind_scalar_basic_dof_of_element(ctx=ctx)
+        kind = self.fem_kind()
+        X = fem_tables.ref_nodes(kind, m.dim(), self.K)
+        shp, _ = fem_tables.lagrange_tables(kind, m.dim(), 1, X)  # [nd, ng]
+        nodes = np.einsum("ig,egd->eid", shp, m.pts[m.conn])  # [ne, nd, dim]
+        out = np.zeros((self.nb_dof(ctx), m.dim()))
+        for q in range(self.Qdim):
+            out[(ed + q).reshape(-1)] = nodes.reshape(-1, m.dim())
+        return out
+
+
+class mesh_im:
+    def __init__(self, m):
+        self.linked_mesh = m
+        self.degree = None
+
+    def set_integration_method(self, degree):
+        self.degree = int(degree)
+
+
+# ---------------------------------------------------------------- expression recognition
+_ID = r"[A-Za-z_][A-Za-z_0-9]*"
+_LAWS = {
+    "Saint_Venant_Kirchhoff": "svk",
+    "Compressible_Neo_Hookean_Ciarlet": "nh_ciarlet",
+    "Compressible_Neo_Hookean_Bonet": "nh_bonet",
+}
+
+
+def _strip_outer(s):
+    while s.startswith("(") and s.endswith(")"):
+        depth = 0
+        for i, ch in enumerate(s):
+            depth += ch == "("
+            depth -= ch == ")"
+            if depth == 0 and i < len(s) - 1:
+                return s
+        s = s[1:-1]
+    return s
+
+
+def recognise(expr):
+    """Maps a GWFL string to (family, variable, constant names).  Covers the strings the reference's
+    bricks generate (getfem_models.cc:3943-3997, 6112-6113; getfem_nonlinear_elasticity.cc:2319-2320)
+    and their usual hand-written forms."""
+    s = _strip_outer(re.sub(r"\s+", "", expr))
+    m = re.fullmatch(rf"(?:\(?({_ID})\)?\*)?\(?Grad_({_ID})[.:]Grad_Test_\2\)?", s)
+    if m:
+        return "laplace", m.group(2), [m.group(1)] if m.group(1) else []
+    m = re.fullmatch(rf"\(?\(?({_ID})\)?\*Grad_({_ID})\)?[.:]Grad_Test_\2", s)
+    if m:
+        return "laplace", m.group(2), [m.group(1)]
+    m = re.fullmatch(rf"(?:\(?({_ID})\)?\*)?\(?({_ID})[.:]Test_\2\)?", s)
+    if m and not m.group(2).startswith("Grad_"):
+        return "mass", m.group(2), [m.group(1)] if m.group(1) else []
+    m = re.fullmatch(rf"\(Div_({_ID})\*\(\(?({_ID})\)?\*Id\(meshdim\)\)\+\(2\*\(?({_ID})\)?\)\*Sym\(Grad_\1\)\):Grad_Test_\1", s)
+    if m:
+        return "elast", m.group(1), [m.group(2), m.group(3)]
+    m = re.fullmatch(rf"\(?({_ID})\)?\*\(?Div_({_ID})\*Div_Test_\2\)?\+\(?2\*\(?({_ID})\)?\)?\*\(?Sym\(Grad_\2\):Grad_Test_\2\)?", s)
+    if m:
+        return "elast", m.group(2), [m.group(1), m.group(3)]
+    m = re.fullmatch(rf"\(\(Id\(meshdim\)\+Grad_({_ID})\)\*\(?({_ID})_PK2\(Grad_\1,({_ID})\)\)?\):Grad_Test_\1", s)
+    if m and m.group(2) in _LAWS:
+        return _LAWS[m.group(2)], m.group(1), [m.group(3)]
+    raise capi.GfgpuError("expression not handled by the device path (no CPU fallback): " + expr)
+
+
+class ga_workspace:
+    """Device-backed ga_workspace for one fem variable and the recognised expression families."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+        self.variables = {}   # name -> (mesh_fem, values)
+        self.constants = {}   # name -> values
+        self.terms = []       # (family, variable, params, mim, DeviceTerm or None)
+        self._K = None
+        self._R = None
+
+    # ---- declaration API (generic_assembly.h:453-470)
+    def add_fem_variable(self, name, mf, I, V):
+        self.variables[name] = (mf, V)
+
+    def add_fixed_size_constant(self, name, V):
+        self.constants[name] = np.atleast_1d(np.asarray(V, np.float64))
+
+    def add_expression(self, expr, mim, region=None, add_derivative_order=2):
+        fam, var, cnames = recognise(expr)
+        if var not in self.variables:
+            raise capi.GfgpuError("unknown variable " + var)
+        for c in cnames:
+            if c not in self.constants:
+                raise capi.GfgpuError("unknown constant " + c)
+        if fam in ("laplace", "mass"):
+            params = [float(self.constants[cnames[0]][0])] if cnames else [1.0]
+        elif fam == "elast":
+            params = [float(self.constants[cnames[0]][0]), float(self.constants[cnames[1]][0])]
+        else:
+            p = self.constants[cnames[0]]
+            if p.size != 2:
+                raise capi.GfgpuError("wrong number of parameters for the hyperelastic law")
+            params = [float(p[0]), float(p[1])]
+        if region is not None:
+            raise capi.GfgpuError("only mesh_region::all_convexes() is handled by the device path")
+        self.terms.append([fam, var, params, mim, None])
+        return len(self.terms) - 1
+
+    def nb_trees(self):
+        return len(self.terms)
+
+    # ---- device objects
+    def _term(self, k):
+        fam, var, params, mim, dev = self.terms[k]
+        if dev is None:
+            mf, _ = self.variables[var]
+            m = mf.linked_mesh
+            t = fem_tables.classical_tables(mf.fem_kind(), m.dim(), mf.K, mim.degree)
+            tab = capi.DeviceTables(self.ctx, t["quad_w"], t["gt_grad"], t["phi"], t["gphi"])
+            dev = capi.DeviceTerm(self.ctx, m.device(self.ctx), mf.device(self.ctx), tab, fam, params)
+            self.terms[k][4] = dev
+        return dev
+
+    def assembly(self, order):
+        """order 1: residual vector; order 2: tangent matrix (workspace.cc:791-936).  One term per
+        workspace is assembled on the device; several terms are summed on the host side."""
+        if order not in (1, 2):
+            raise capi.GfgpuError("only assembly orders 1 and 2 are handled by the device path")
+        if not self.terms:
+            raise capi.GfgpuError("no expression")
+        if order == 2:
+            mats = []
+        else:
+            vec = None
+        for k in range(len(self.terms)):
+            dev = self._term(k)
+            mf, V = self.variables[self.terms[k][1]]
+            U = None if V is None else np.ascontiguousarray(V, np.float64)
+            if order == 2:
+                dev.assemble_host(U, capi.TANGENT, None, None)
+                mats.append(dev.export_csc())
+            else:
+                R = np.empty(dev.ndof)
+                dev.assemble_host(U, capi.RESIDUAL, None, R)
+                vec = R if vec is None else vec + R
+        if order == 2:
+            if len(mats) == 1:
+                self._K = mats[0]
+            else:
+                import scipy.sparse as sp
+                n = self._term(0).ndof
+                S = sum(sp.csc_matrix((pr, ir, jc), shape=(n, n)) for jc, ir, pr in mats).tocsc()
+                S.sort_indices()
+                self._K = (S.indptr.astype(np.int64), S.indices.astype(np.int32), S.data)
+        else:
+            self._R = vec
+
+    def assembled_matrix(self):
+        """(jc, ir, pr): the layout of gmm::csc_matrix::init_with(K) (gmm_matrix.h:545-566)."""
+        return self._K
+
+    def assembled_vector(self):
+        return self._R

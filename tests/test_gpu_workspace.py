@@ -1,0 +1,132 @@
+"""GPU: the ga_workspace mirror end to end -- own regular mesh, DEVICE dof enumeration, own tables --
+against the reference goldens (dof numbering and CSC pattern bit-exact, values 1e-12) and, at sizes
+the oracle finishes in seconds, against the CPU oracle; plus size-independent properties."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+EXPR = {
+    "laplace": "a*Grad_u.Grad_Test_u",
+    "mass": "a*u.Test_u",
+    "elast": "(Div_u*((lambda)*Id(meshdim))+(2*(mu))*Sym(Grad_u)):Grad_Test_u",
+    "svk": "((Id(meshdim)+Grad_u)*(Saint_Venant_Kirchhoff_PK2(Grad_u,params))):Grad_Test_u",
+    "nh_ciarlet": "((Id(meshdim)+Grad_u)*(Compressible_Neo_Hookean_Ciarlet_PK2(Grad_u,params))):Grad_Test_u",
+    "nh_bonet": "((Id(meshdim)+Grad_u)*(Compressible_Neo_Hookean_Bonet_PK2(Grad_u,params))):Grad_Test_u",
+}
+
+
+def build_ws(dim, nsub, gt, k, Q, im, family, params, U=None):
+    import getfem_b200 as gf
+    m = gf.mesh()
+    gf.regular_unit_mesh(m, nsub, "GT_%s(%d,1)" % (gt, dim))
+    mf = gf.mesh_fem(m, Q)
+    mf.set_classical_finite_element(k)
+    mim = gf.mesh_im(m)
+    mim.set_integration_method(im)
+    ws = gf.ga_workspace()
+    ndof = mf.nb_dof()
+    if U is None:
+        U = np.zeros(ndof)
+    elif callable(U):
+        U = U(mf)
+    ws.add_fem_variable("u", mf, slice(0, ndof), U)
+    if family in ("laplace", "mass"):
+        ws.add_fixed_size_constant("a", [params[0]])
+    elif family == "elast":
+        ws.add_fixed_size_constant("lambda", [params[0]])
+        ws.add_fixed_size_constant("mu", [params[1]])
+    else:
+        ws.add_fixed_size_constant("params", params)
+    ws.add_expression(EXPR[family], mim)
+    return ws, mf, m, U
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_workspace_matches_reference_golden(name):
+    g = load_golden(name)
+    a = g["args"]
+    dim = int(a["dim"])
+    nsub = [int(a["n"])] * dim if "n" in a else [int(a["nx"]), int(a["ny"]), int(a["nz"])][:dim]
+    ws, mf, m, _ = build_ws(dim, nsub, "PK" if g["gt_linear"] else "QK", int(a["k"]), g["Q"], int(a["im"]),
+                            g["family"], g["fparams"], g["U"])
+    # device first-touch numbering == mesh_fem::enumerate_dof, bit for bit
+    assert mf.nb_dof() == g["meta"]["ndof"]
+    assert np.array_equal(mf.ind_scalar_basic_dof_of_element(), g["elem_dof"])
+    ws.assembly(2)
+    ws.assembly(1)
+    jc, ir, pr = ws.assembled_matrix()
+    assert np.array_equal(jc, g["K_jc"]) and np.array_equal(ir, g["K_ir"])
+    # Q4: the reference's own basis tables carry 5e-10 of round-off (see test_host_tables.py)
+    tol = 1e-8 if int(a["k"]) >= 4 else 1e-12
+    assert np.linalg.norm(pr - g["K_pr"]) / np.linalg.norm(g["K_pr"]) < tol
+    assert np.linalg.norm(ws.assembled_vector() - g["R"]) / np.linalg.norm(g["R"]) < tol
+
+
+def smooth_u(amp):
+    def f(mf):
+        X = mf.basic_dof_nodes()
+        dim = X.shape[1]
+        k = np.arange(X.shape[0]) % mf.Qdim
+        xk = X[np.arange(X.shape[0]), k % dim]
+        xn = X[np.arange(X.shape[0]), (k + 1) % dim]
+        return amp * np.sin(2 * np.pi * xn) * np.cos(np.pi * xk)
+    return f
+
+
+CASES = [  # dim, nsub, gt, k, Q, im, family, params, U
+    (3, [6, 5, 4], "PK", 2, 3, 4, "elast", [1.0, 1.0], "random"),
+    (3, [9, 9, 9], "PK", 1, 1, 2, "laplace", [1.0], "random"),
+    (2, [40, 30], "PK", 1, 1, 2, "laplace", [2.0], "random"),
+    (3, [4, 3, 3], "QK", 2, 3, 6, "nh_ciarlet", [1.0, 1.0], "smooth"),
+    (3, [3, 3, 2], "QK", 2, 3, 6, "svk", [1.3, 0.7], "smooth"),
+    (3, [4, 4, 3], "PK", 2, 3, 4, "nh_bonet", [1.3, 0.7], "smooth"),
+    (3, [2, 2, 1], "QK", 4, 1, 8, "laplace", [1.0], "random"),
+    (3, [5, 4, 3], "PK", 2, 3, 4, "mass", [1.5], "random"),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s_%s%d_q%d_%s" % (c[6], c[2], c[3], c[4], "x".join(map(str, c[1]))))
+def test_workspace_matches_oracle(case):
+    from oracle import oracle
+    from getfem_b200 import fem_tables
+    dim, nsub, gt, k, Q, im, family, params, umode = case
+    if umode == "random":
+        rng = np.random.default_rng(7)
+        U = lambda mf: rng.uniform(-1, 1, mf.nb_dof())  # noqa: E731
+    else:
+        U = smooth_u(0.03)
+    ws, mf, m, Uv = build_ws(dim, nsub, gt, k, Q, im, family, params, U)
+    ws.assembly(2)
+    ws.assembly(1)
+    jc, ir, pr = ws.assembled_matrix()
+    t = fem_tables.classical_tables(gt, dim, k, im)
+    ojc, oir, opr, oR = oracle.assemble(m.pts, m.conn, mf.ind_scalar_basic_dof_of_element(), mf.nb_dof(), Q,
+                                        t["quad_w"], t["gt_grad"], t["phi"], t["gphi"], gt == "PK", family,
+                                        params, Uv)
+    assert np.array_equal(jc, ojc) and np.array_equal(ir, oir)
+    assert np.linalg.norm(pr - opr) / np.linalg.norm(opr) < 1e-12
+    assert np.linalg.norm(ws.assembled_vector() - oR) / np.linalg.norm(oR) < 1e-12
+
+
+def test_properties_at_size():
+    """Size-independent checks on a mesh too large for the oracle to be practical in a test:
+    stencil nnz count of the P1 Laplacian (7-point: the drop rule removes the exact zeros), K*1 = 0,
+    symmetry, residual == K*u for the linear form."""
+    import scipy.sparse as sp
+    n = 40
+    rng = np.random.default_rng(3)
+    ws, mf, m, U = build_ws(3, [n, n, n], "PK", 1, 1, 2, "laplace", [1.0], lambda mf: rng.uniform(-1, 1, mf.nb_dof()))
+    ws.assembly(2)
+    ws.assembly(1)
+    jc, ir, pr = ws.assembled_matrix()
+    nd = mf.nb_dof()
+    assert nd == (n + 1) ** 3
+    assert jc[-1] == 7 * (n + 1) ** 3 - 6 * (n + 1) ** 2
+    K = sp.csc_matrix((pr, ir, jc), shape=(nd, nd))
+    assert abs(K - K.T).max() < 1e-13 * abs(K).max()
+    assert np.abs(K @ np.ones(nd)).max() < 1e-12 * abs(K).max()
+    R = ws.assembled_vector()
+    assert np.linalg.norm(K @ U - R) / np.linalg.norm(R) < 1e-12
