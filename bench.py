@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- GWFL assembly throughput on B200 (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--n 110] [--impl reference]
+
+A step = one tangent + residual assembly (ga_workspace::assembly(2) + assembly(1)) over the whole
+synthetic mesh.  Default workload = BASELINE.json configs[2], the configuration the north-star target
+is quoted on: 3D linearised isotropic elasticity, P2 tetrahedra, regular_unit_mesh n=110 -> 7 986 000
+elements, lambda = mu = 1, IM_TETRAHEDRON(5).  `value` = elements/s with every input resident in HBM;
+`e2e` = the same through gfgpu_term_assemble_host with HOST buffers (U in, CSC values + residual out).
+The symbolic phase (dof numbering, scatter structure, value-dependent pattern) is done once before the
+timed region and reported separately, like a Newton loop would amortise it.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (dim, gt, k, Q, im, family, params, default n, description)
+    "c1": (2, "PK", 1, 1, 2, "laplace", [1.0], 512, "2D Poisson P1 triangles 512x512"),
+    "c2": (3, "PK", 1, 1, 2, "laplace", [1.0], 119, "3D Laplacian P1 tetrahedra, 10.1M elements"),
+    "c3": (3, "PK", 2, 3, 4, "elast", [1.0, 1.0], 110, "3D linearised isotropic elasticity P2 tetrahedra, 7.99M elements, tangent+residual"),
+    "c4": (3, "QK", 2, 3, 6, "nh_ciarlet", [1.0, 1.0], 64, "3D Neo-Hookean (Ciarlet) Q2 hexahedra, tangent+residual"),
+    "c5": (3, "QK", 4, 1, 8, "laplace", [1.0], 48, "3D Q4 hexahedral Laplacian"),
+}
+REF_FAMILY = {"laplace": "laplace", "elast": "elast", "nh_ciarlet": "nh_ciarlet"}
+# bounded CPU sample (cells per direction) of each workload: ~10-30 s of reference CPU work
+CPU_SAMPLE_N = {"c1": 512, "c2": 40, "c3": 20, "c4": 8, "c5": 3}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def ref_driver():
+    p = os.path.join(ROOT, "oracle", "_ref", "gf_ref_driver")
+    return p if os.path.exists(p) else None
+
+
+def reference_cpu_rate(wl, n, threads, reps, warm):
+    """elements/s of the UNMODIFIED reference (oracle/_ref, its own OpenMP scheme) on a bounded sample."""
+    dim, gt, k, Q, im, family, params, _, _ = WORKLOADS[wl]
+    drv = ref_driver()
+    if drv is None:
+        return None
+    args = [drv, "dim=%d" % dim, "n=%d" % n, "gt=%s" % gt.lower(), "k=%d" % k, "q=%d" % Q, "im=%d" % im,
+            "family=%s" % REF_FAMILY[family], "u=%s" % ("smooth" if family.startswith("nh") else "random"),
+            "lambda=%g" % (params[0]), "mu=%g" % (params[1] if len(params) > 1 else 1.0), "a=%g" % params[0],
+            "mode=omp", "threads=%d" % threads, "reps=%d" % reps, "warm=%d" % warm]
+    out = subprocess.check_output(args, text=True, env=dict(os.environ, OMP_NUM_THREADS=str(threads)))
+    r = json.loads(out.strip().splitlines()[-1])
+    return {"ne": r["ne"], "nnz": r["nnz"], "t_mean": r["t_asm21_mean"], "t_best": r["t_asm21"],
+            "rate": r["ne"] / r["t_asm21_mean"], "threads": threads}
+
+
+def cpu_baseline(wl, threads=None, reps=2, warm=1):
+    nproc = os.cpu_count() or 1
+    threads = threads or min(nproc, 32)
+    n = CPU_SAMPLE_N[wl]
+    r = reference_cpu_rate(wl, n, threads, reps, warm)
+    if r is None:
+        return {"value": None, "unit": "elements/s", "cores": 0, "kind": "reference",
+                "sample": "oracle/_ref/gf_ref_driver missing"}
+    return {"value": r["rate"], "unit": "elements/s", "cores": threads, "kind": "reference",
+            "sample": "%s at n=%d (%d elements, nnz %d), ga_workspace assembly(2)+assembly(1) under the reference's "
+                      "OpenMP scheme, mean of %d after %d warm-up; host has %d cores"
+                      % (wl, n, r["ne"], r["nnz"], reps, warm, nproc),
+            "nnz_per_s": r["nnz"] / r["t_mean"]}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.workload
+    dim, gt, k, Q, im, family, params, ndef, desc = WORKLOADS[wl]
+    nproc = os.cpu_count() or 1
+    threads = min(nproc, 32)
+    n = CPU_SAMPLE_N[wl]
+    t0 = time.time()
+    r = reference_cpu_rate(wl, n, threads, args.steps, args.warmup)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/gf_ref_driver not present"}))
+        return
+    line = {
+        "impl": "reference", "metric": "assembled_elements_per_s", "value": r["rate"], "unit": "elements/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["t_mean"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: %s" % (wl, desc), "sample_n": n, "elements_per_step": r["ne"]},
+        "nnz_per_s": r["nnz"] / r["t_mean"],
+        "cpu_baseline": {"value": r["rate"], "unit": "elements/s", "cores": threads, "kind": "reference",
+                         "sample": "%s at n=%d (%d elements): each step = ga_workspace assembly(2)+assembly(1) of the "
+                                   "UNMODIFIED reference under its OpenMP scheme; host has %d cores"
+                                   % (wl, n, r["ne"], nproc)},
+        "e2e": {"value": r["rate"], "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0, help="cells per direction (default: the BASELINE size)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strategy", type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import getfem_b200 as gf
+    from getfem_b200 import capi, fem_tables
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wl = args.workload
+    dim, gt, k, Q, im, family, params, ndef, desc = WORKLOADS[wl]
+    n = args.n or ndef
+
+    stream = torch.cuda.Stream()
+    ctx = capi.Context(local, stream.cuda_stream)
+    t_setup = time.time()
+    # weak scaling: every rank assembles its own element block of a mesh that is `world` times
+    # longer in the last direction (z-slabs in the reference's convex order)
+    nsub = [n] * dim
+    nsub[-1] = n * world
+    m = gf.mesh()
+    gf.regular_unit_mesh(m, nsub, "GT_%s(%d,1)" % (gt, dim))
+    mf = gf.mesh_fem(m, Q)
+    mf.set_classical_finite_element(k)
+    dmesh = m.device(ctx)
+    dfem = mf.device(ctx)  # first-touch dof numbering on the device
+    ndof = dfem.ndof
+    t = fem_tables.classical_tables(gt, dim, k, im)
+    tab = capi.DeviceTables(ctx, t["quad_w"], t["gt_grad"], t["phi"], t["gphi"])
+    term = capi.DeviceTerm(ctx, dmesh, dfem, tab, family, params, 1.0, args.strategy)
+    ne_total = m.nb_convex()
+    per = ne_total // world
+    e0, e1 = rank * per, (rank + 1) * per if rank < world - 1 else ne_total
+    if world > 1:
+        term.set_element_range(e0, e1)
+    ne_local = e1 - e0
+    rng = np.random.default_rng(12345)
+    if family.startswith("nh") or family == "svk":
+        X = mf.basic_dof_nodes(ctx)
+        kk = np.arange(ndof) % Q
+        U_host = 0.02 * np.sin(2 * np.pi * X[np.arange(ndof), (kk + 1) % dim]) * np.cos(np.pi * X[np.arange(ndof), kk % dim])
+    else:
+        U_host = rng.uniform(-1.0, 1.0, ndof)
+    with torch.cuda.stream(stream):
+        U_dev = torch.from_numpy(U_host).to("cuda:%d" % local)
+    stream.synchronize()
+    t_setup = time.time() - t_setup
+
+    ORDER = capi.TANGENT | capi.RESIDUAL
+    t_sym = time.time()
+    term.assemble_dev(U_dev.data_ptr(), ORDER)  # builds structure + pattern, first numeric pass
+    ctx.synchronize()
+    t_sym = time.time() - t_sym
+    nnz = term.nnz
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        term.assemble_dev(U_dev.data_ptr(), ORDER)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = capi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ktimes = []
+    barrier()
+    with torch.cuda.stream(stream):
+        ev0.record()
+        for _ in range(args.steps):
+            term.assemble_dev(U_dev.data_ptr(), ORDER)
+        ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = capi.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # per-kernel device durations (events recorded inside the library on the same stream)
+    for _ in range(3):
+        term.assemble_dev(U_dev.data_ptr(), ORDER)
+        ktimes.append(term.last_timings())
+    kavg = {kname: float(np.mean([d[kname] for d in ktimes])) for kname in ktimes[0]}
+    if world > 1:
+        tms = torch.tensor([ms], device="cuda:%d" % local, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+        tot = torch.tensor([ne_local, nnz], device="cuda:%d" % local, dtype=torch.float64)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        ne_all, nnz_all = int(tot[0].item()), int(tot[1].item())
+    else:
+        ne_all, nnz_all = ne_local, nnz
+    ms_step = ms / args.steps
+    value = ne_all / (ms_step * 1e-3)
+
+    # ---- end to end through the host-buffer entry point (pinned host memory)
+    pr_host = torch.empty(nnz, dtype=torch.float64, pin_memory=True)
+    R_host = torch.empty(ndof, dtype=torch.float64, pin_memory=True)
+    U_pin = torch.from_numpy(U_host).pin_memory()
+    term.assemble_host(U_pin.numpy(), ORDER, pr_host.numpy(), R_host.numpy())  # warm-up
+    barrier()
+    te = time.time()
+    with torch.cuda.stream(stream):
+        ev0.record()
+        for _ in range(args.e2e_steps):
+            term.assemble_host(U_pin.numpy(), ORDER, pr_host.numpy(), R_host.numpy())
+        ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1) / args.e2e_steps
+    e2e_wall_ms = (time.time() - te) * 1e3 / args.e2e_steps
+    e2e_ms = max(e2e_ms, e2e_wall_ms)  # the call is synchronous: wall clock includes the copies' host side
+    if world > 1:
+        tms = torch.tensor([e2e_ms], device="cuda:%d" % local, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tms.item())
+    e2e_value = ne_all / (e2e_ms * 1e-3)
+    checks = {"pr_norm": float(np.linalg.norm(pr_host.numpy()[: min(nnz, 10_000_000)])),
+              "R_norm": float(np.linalg.norm(R_host.numpy()))}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk, pk_src = peaks()
+    # algorithmic bytes per launch: element->dof ids + node coordinates + U + residual + tangent values
+    nd = dfem.nd
+    alg_bytes = 4 * nd * ne_local + 8 * dim * m.nb_points() / world + 2 * 8 * ndof / world + 8 * nnz
+    dom = max(("elem", "gather"), key=lambda kname: kavg[kname])
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if tj.get("workload") == wl and tj.get("n") == n and tj.get("kernel") == dom:
+            traffic = tj.get("traffic_bytes_per_launch")
+    achieved = alg_bytes / (kavg[dom] * 1e-3) / 1e9
+    line = {
+        "metric": "assembled_elements_per_s", "value": value, "unit": "elements/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: %s" % (wl, desc), "n": n, "elements": ne_all, "ndof": ndof, "nnz": nnz_all,
+                   "fem": "FEM_%s(%d,%d) Q=%d" % (gt, dim, k, Q), "im": t["im"], "family": family,
+                   "order": "tangent+residual", "l2": "outputs (%.1f GB) exceed L2" % (8e-9 * nnz),
+                   "parallelism": "element blocks x%d" % world},
+        "nnz_per_s": nnz_all / (ms_step * 1e-3),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_src,
+                     "algorithmic_bytes_per_launch": alg_bytes,
+                     "step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"]},
+        "kernel_ms": kavg,
+        "e2e": {"value": e2e_value, "unit": "elements/s", "h2d_bytes_per_step": int(8 * ndof),
+                "d2h_bytes_per_step": int(8 * nnz + 8 * ndof), "ms_per_step": e2e_ms, "steps": args.e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "symbolic_s": t_sym, "setup_s": t_setup, "device_bytes": ctx.bytes_in_use(), "checks": checks,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(wl)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -47,6 +47,7 @@ SIGNATURES = {
     "gfgpu_term_set_element_range": (C.c_int, [_P, _i64, _i64]),
     "gfgpu_term_assemble_dev": (C.c_int, [_P, _P, C.c_int]),
     "gfgpu_term_assemble_host": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "gfgpu_term_last_timings": (C.c_int, [_P, _P]),
     "gfgpu_term_nnz": (_i64, [_P]),
     "gfgpu_term_nb_dof": (_i64, [_P]),
     "gfgpu_term_pattern_generation": (_i64, [_P]),
@@ -190,6 +191,12 @@ class DeviceTerm(_Handle):
     def assemble_host(self, U, order_mask, pr_out=None, R_out=None):
         U = None if U is None else np.ascontiguousarray(U, np.float64)
         check(lib().gfgpu_term_assemble_host(self.h, ptr(U), int(order_mask), ptr(pr_out), ptr(R_out)))
+
+    def last_timings(self):
+        """dict of device ms of the last assemble: elem, gather, rgather, pattern."""
+        out = np.zeros(4, np.float32)
+        check(lib().gfgpu_term_last_timings(self.h, ptr(out)))
+        return dict(zip(("elem", "gather", "rgather", "pattern"), (float(v) for v in out)))
 
     @property
     def nnz(self):

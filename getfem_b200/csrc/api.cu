@@ -233,6 +233,7 @@ int gfgpu_term_create(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem, gfgpu_ta
   GF_CUDA(cudaSetDevice(ctx->device));
   t->flag.alloc(ctx, 1);
   t->flag.zero();
+  for (int k = 0; k < 8; ++k) GF_CUDA(cudaEventCreate(&t->ev[k]));
   *out = t.release();
   GF_API_END
 }
@@ -242,6 +243,8 @@ int gfgpu_term_destroy(gfgpu_term *t) {
   if (t) {
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
+    for (int k = 0; k < 8; ++k)
+      if (t->ev[k]) cudaEventDestroy(t->ev[k]);
   }
   delete t;
   GF_API_END
@@ -294,32 +297,37 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
   a.stage = do_t ? t->stage.p : nullptr;
   a.emask = do_t ? t->emask.p : nullptr;
   a.rstage = do_r ? t->rstage.p : nullptr;
+  for (int k = 0; k < 4; ++k) t->ev_used[k] = false;
+  auto tic = [&](int k) { GF_CUDA(cudaEventRecord(t->ev[2 * k], ctx->stream)); };
+  auto toc = [&](int k) { GF_CUDA(cudaEventRecord(t->ev[2 * k + 1], ctx->stream)); t->ev_used[k] = true; };
   if (ne > 0) {
+    tic(0);
     bool ok = gf::launch_elem_kernel(ctx, t->mesh->dim, Q, nd, t->mesh->gt_kind == GFGPU_GT_PK, a);
     GF_REQUIRE(ok, "no device kernel for this (dimension, qdim, local dofs, family) combination");
+    toc(0);
   }
   if (do_t) {
     // linear families: the keep masks do not depend on U, a valid pattern stays valid
     const bool value_dependent = t->family == GFGPU_SVK || t->family == GFGPU_NEOHOOKEAN_CIARLET ||
                                  t->family == GFGPU_NEOHOOKEAN_BONET;
     if (!t->pat_valid) {
-      gf::build_pattern(t);
-      gf::gather_tangent(t, false);
+      tic(3); gf::build_pattern(t); toc(3);
+      tic(1); gf::gather_tangent(t, false); toc(1);
     } else if (!value_dependent) {
-      gf::gather_tangent(t, false);
+      tic(1); gf::gather_tangent(t, false); toc(1);
     } else {
       t->flag.zero();
-      gf::gather_tangent(t, true);
+      tic(1); gf::gather_tangent(t, true); toc(1);
       int32_t changed = 0;
       t->flag.download(&changed);
       GF_CUDA(cudaStreamSynchronize(ctx->stream));
       if (changed) {
-        gf::build_pattern(t);
-        gf::gather_tangent(t, false);
+        tic(3); gf::build_pattern(t); toc(3);
+        tic(1); gf::gather_tangent(t, false); toc(1);
       }
     }
   }
-  if (do_r) gf::gather_residual(t);
+  if (do_r) { tic(2); gf::gather_residual(t); toc(2); }
 }
 
 int gfgpu_term_assemble_dev(gfgpu_term *t, const double *U_dev, int order_mask) {
@@ -344,6 +352,18 @@ int gfgpu_term_assemble_host(gfgpu_term *t, const double *U_host, int order_mask
   if ((order_mask & GFGPU_TANGENT) && pr_host) t->pr.download(pr_host);
   if ((order_mask & GFGPU_RESIDUAL) && R_host) t->R.download(R_host);
   GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  GF_API_END
+}
+
+int gfgpu_term_last_timings(gfgpu_term *t, float *out4) {
+  GF_API_BEGIN
+  GF_REQUIRE(t && out4, "null argument");
+  GF_CUDA(cudaSetDevice(t->ctx->device));
+  GF_CUDA(cudaStreamSynchronize(t->ctx->stream));
+  for (int k = 0; k < 4; ++k) {
+    out4[k] = 0.f;
+    if (t->ev_used[k]) GF_CUDA(cudaEventElapsedTime(&out4[k], t->ev[2 * k], t->ev[2 * k + 1]));
+  }
   GF_API_END
 }
 

@@ -163,6 +163,9 @@ struct gfgpu_term {
   gf::DevBuf<double> rstage;    // ne_loc x s1
   gf::DevBuf<double> Ubuf;      // ndof (host path)
   gf::DevBuf<int32_t> flag;     // pattern-changed flag
+  // per-phase events of the last assemble: [0,1] element kernel, [2,3] gather, [4,5] residual gather, [6,7] pattern
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ev_used[4] = {false, false, false, false};
 };
 
 namespace gf {

@@ -128,6 +128,11 @@ int gfgpu_term_assemble_dev(gfgpu_term *t, const double *U_dev, int order_mask);
 int gfgpu_term_assemble_host(gfgpu_term *t, const double *U_host, int order_mask, double *pr_host,
                              double *R_host);
 
+/* Device durations (ms, CUDA events on the context's stream) of the kernels of the LAST assemble call:
+ * out[0] element/recompute kernel, out[1] tangent gather-sum, out[2] residual gather-sum,
+ * out[3] pattern (re)build (0 when the pattern was reused).  Synchronises the stream. */
+int gfgpu_term_last_timings(gfgpu_term *t, float *out4);
+
 int64_t gfgpu_term_nnz(gfgpu_term *t);
 int64_t gfgpu_term_nb_dof(gfgpu_term *t);
 /* number of times the pattern has been (re)built; a Newton loop can watch it */
