@@ -48,6 +48,7 @@ SIGNATURES = {
     "gfgpu_term_assemble_dev": (C.c_int, [_P, _P, C.c_int]),
     "gfgpu_term_assemble_host": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "gfgpu_term_last_timings": (C.c_int, [_P, _P]),
+    "gfgpu_term_strategy": (C.c_int, [_P]),
     "gfgpu_term_nnz": (_i64, [_P]),
     "gfgpu_term_nb_dof": (_i64, [_P]),
     "gfgpu_term_pattern_generation": (_i64, [_P]),
@@ -194,9 +195,13 @@ class DeviceTerm(_Handle):
 
     def last_timings(self):
         """dict of device ms of the last assemble: elem, gather, rgather, pattern."""
-        out = np.zeros(4, np.float32)
+        out = np.zeros(8, np.float32)
         check(lib().gfgpu_term_last_timings(self.h, ptr(out)))
-        return dict(zip(("elem", "gather", "rgather", "pattern"), (float(v) for v in out)))
+        return dict(zip(("elem", "gather", "rgather", "pattern", "recompute"), (float(v) for v in out[:5])))
+
+    @property
+    def strategy(self):
+        return int(lib().gfgpu_term_strategy(self.h))
 
     @property
     def nnz(self):

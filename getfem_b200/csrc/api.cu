@@ -222,18 +222,20 @@ int gfgpu_term_create(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem, gfgpu_ta
   if (family == GFGPU_ELASTICITY) GF_REQUIRE(fem->qdim == mesh->dim, "elasticity needs qdim == mesh dimension");
   if (family == GFGPU_SVK || family == GFGPU_NEOHOOKEAN_CIARLET || family == GFGPU_NEOHOOKEAN_BONET)
     GF_REQUIRE(fem->qdim == 3 && mesh->dim == 3, "finite-strain families need a 3D vector field");
-  GF_REQUIRE(strategy == GFGPU_STRATEGY_AUTO || strategy == GFGPU_STRATEGY_STAGED,
-             "strategy not available");
+  GF_REQUIRE(strategy >= GFGPU_STRATEGY_AUTO && strategy <= GFGPU_STRATEGY_RECOMPUTE, "unknown strategy");
   std::unique_ptr<gfgpu_term> t(new gfgpu_term);
   t->ctx = ctx; t->mesh = mesh; t->fem = fem; t->tab = tab; t->family = family;
-  t->strategy = GFGPU_STRATEGY_STAGED;
+  const bool rc_ok = gf::recompute_supported(t.get());
+  GF_REQUIRE(strategy != GFGPU_STRATEGY_RECOMPUTE || rc_ok,
+             "strategy RECOMPUTE needs an affine (simplex) mesh and a Laplace / elasticity / mass term");
+  t->strategy = strategy == GFGPU_STRATEGY_AUTO ? (rc_ok ? GFGPU_STRATEGY_RECOMPUTE : GFGPU_STRATEGY_STAGED) : strategy;
   for (int k = 0; k < 4; ++k) t->par[k] = k < nparams ? params[k] : 0.0;
   t->alpha = alpha;
   t->e0 = 0; t->e1 = mesh->ne;
   GF_CUDA(cudaSetDevice(ctx->device));
   t->flag.alloc(ctx, 1);
   t->flag.zero();
-  for (int k = 0; k < 8; ++k) GF_CUDA(cudaEventCreate(&t->ev[k]));
+  for (int k = 0; k < 10; ++k) GF_CUDA(cudaEventCreate(&t->ev[k]));
   *out = t.release();
   GF_API_END
 }
@@ -243,7 +245,7 @@ int gfgpu_term_destroy(gfgpu_term *t) {
   if (t) {
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
-    for (int k = 0; k < 8; ++k)
+    for (int k = 0; k < 10; ++k)
       if (t->ev[k]) cudaEventDestroy(t->ev[k]);
   }
   delete t;
@@ -258,6 +260,7 @@ int gfgpu_term_set_element_range(gfgpu_term *t, int64_t e0, int64_t e1) {
     t->e0 = e0; t->e1 = e1;
     t->st_valid = false;
     t->pat_valid = false;
+    t->rc_ready = false;
   }
   GF_API_END
 }
@@ -274,10 +277,12 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
     t->st_valid = true;
     t->pat_valid = false;
   }
-  if (do_t) {
-    if (t->stage.n != (size_t)ne * s1 * s1) t->stage.alloc(ctx, (size_t)ne * s1 * s1);
-    if (t->emask.n != (size_t)ne * nd * nd) t->emask.alloc(ctx, (size_t)ne * nd * nd);
-  }
+  const bool recompute = t->strategy == GFGPU_STRATEGY_RECOMPUTE;
+  // what the element kernel has to produce in this call
+  const bool need_masks = do_t && (!recompute || !t->pat_valid);
+  const bool need_stage = do_t && !recompute;
+  if (need_stage && t->stage.n != (size_t)ne * s1 * s1) t->stage.alloc(ctx, (size_t)ne * s1 * s1);
+  if (need_masks && t->emask.n != (size_t)ne * nd * nd) t->emask.alloc(ctx, (size_t)ne * nd * nd);
   if (do_r) {
     if (t->rstage.n != (size_t)ne * s1) t->rstage.alloc(ctx, (size_t)ne * s1);
     if (t->R.n != (size_t)t->fem->ndof) t->R.alloc(ctx, t->fem->ndof);
@@ -294,19 +299,26 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
   for (int k = 0; k < 4; ++k) a.par[k] = t->par[k];
   a.alpha = t->alpha;
   a.family = t->family;
-  a.stage = do_t ? t->stage.p : nullptr;
-  a.emask = do_t ? t->emask.p : nullptr;
+  a.stage = need_stage ? t->stage.p : nullptr;
+  a.emask = need_masks ? t->emask.p : nullptr;
   a.rstage = do_r ? t->rstage.p : nullptr;
-  for (int k = 0; k < 4; ++k) t->ev_used[k] = false;
+  for (int k = 0; k < 5; ++k) t->ev_used[k] = false;
   auto tic = [&](int k) { GF_CUDA(cudaEventRecord(t->ev[2 * k], ctx->stream)); };
   auto toc = [&](int k) { GF_CUDA(cudaEventRecord(t->ev[2 * k + 1], ctx->stream)); t->ev_used[k] = true; };
-  if (ne > 0) {
+  if (ne > 0 && (need_stage || need_masks || do_r)) {
     tic(0);
     bool ok = gf::launch_elem_kernel(ctx, t->mesh->dim, Q, nd, t->mesh->gt_kind == GFGPU_GT_PK, a);
     GF_REQUIRE(ok, "no device kernel for this (dimension, qdim, local dofs, family) combination");
     toc(0);
   }
-  if (do_t) {
+  if (do_t && recompute) {
+    if (!t->pat_valid) {
+      tic(3); gf::build_pattern(t); toc(3);
+      t->emask.release();  // constant-coefficient linear form: the pattern cannot move any more
+    }
+    if (!t->rc_ready) gf::recompute_prepare(t);
+    tic(4); gf::recompute_tangent(t); toc(4);
+  } else if (do_t) {
     // linear families: the keep masks do not depend on U, a valid pattern stays valid
     const bool value_dependent = t->family == GFGPU_SVK || t->family == GFGPU_NEOHOOKEAN_CIARLET ||
                                  t->family == GFGPU_NEOHOOKEAN_BONET;
@@ -355,17 +367,18 @@ int gfgpu_term_assemble_host(gfgpu_term *t, const double *U_host, int order_mask
   GF_API_END
 }
 
-int gfgpu_term_last_timings(gfgpu_term *t, float *out4) {
+int gfgpu_term_last_timings(gfgpu_term *t, float *out8) {
   GF_API_BEGIN
-  GF_REQUIRE(t && out4, "null argument");
+  GF_REQUIRE(t && out8, "null argument");
   GF_CUDA(cudaSetDevice(t->ctx->device));
   GF_CUDA(cudaStreamSynchronize(t->ctx->stream));
-  for (int k = 0; k < 4; ++k) {
-    out4[k] = 0.f;
-    if (t->ev_used[k]) GF_CUDA(cudaEventElapsedTime(&out4[k], t->ev[2 * k], t->ev[2 * k + 1]));
-  }
+  for (int k = 0; k < 8; ++k) out8[k] = 0.f;
+  for (int k = 0; k < 5; ++k)
+    if (t->ev_used[k]) GF_CUDA(cudaEventElapsedTime(&out8[k], t->ev[2 * k], t->ev[2 * k + 1]));
   GF_API_END
 }
+
+int gfgpu_term_strategy(gfgpu_term *t) { return t ? t->strategy : -1; }
 
 int64_t gfgpu_term_nnz(gfgpu_term *t) { return (t && t->pat_valid) ? t->nnz : -1; }
 int64_t gfgpu_term_nb_dof(gfgpu_term *t) { return t ? t->fem->ndof : -1; }

@@ -164,8 +164,13 @@ struct gfgpu_term {
   gf::DevBuf<double> Ubuf;      // ndof (host path)
   gf::DevBuf<int32_t> flag;     // pattern-changed flag
   // per-phase events of the last assemble: [0,1] element kernel, [2,3] gather, [4,5] residual gather, [6,7] pattern
-  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  bool ev_used[4] = {false, false, false, false};
+  // [2k, 2k+1], k = 0 element kernel, 1 gather, 2 residual gather, 3 pattern, 4 recompute kernel
+  cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ev_used[5] = {false, false, false, false, false};
+  // strategy RECOMPUTE
+  bool rc_ready = false;
+  gf::DevBuf<double> rc_M;      // reference tensors per (j,i)
+  gf::DevBuf<double> rc_eg;     // per-element geometry
 };
 
 namespace gf {
@@ -199,5 +204,10 @@ void build_structure(gfgpu_ctx *ctx, const int32_t *edof, int nd, int64_t e0, in
 void build_pattern(gfgpu_term *t);
 void gather_tangent(gfgpu_term *t, bool check);
 void gather_residual(gfgpu_term *t);
+
+// ---- strategy RECOMPUTE (recompute.cu)
+bool recompute_supported(const gfgpu_term *t);
+void recompute_prepare(gfgpu_term *t);
+void recompute_tangent(gfgpu_term *t);
 
 }  // namespace gf

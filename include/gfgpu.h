@@ -129,9 +129,12 @@ int gfgpu_term_assemble_host(gfgpu_term *t, const double *U_host, int order_mask
                              double *R_host);
 
 /* Device durations (ms, CUDA events on the context's stream) of the kernels of the LAST assemble call:
- * out[0] element/recompute kernel, out[1] tangent gather-sum, out[2] residual gather-sum,
- * out[3] pattern (re)build (0 when the pattern was reused).  Synchronises the stream. */
-int gfgpu_term_last_timings(gfgpu_term *t, float *out4);
+ * out[0] generic element kernel, out[1] tangent gather-sum (STAGED), out[2] residual gather-sum,
+ * out[3] pattern (re)build (0 when reused), out[4] per-nonzero tangent kernel (RECOMPUTE), out[5..7] 0.
+ * Synchronises the stream. */
+int gfgpu_term_last_timings(gfgpu_term *t, float *out8);
+/* the strategy the term actually uses (GFGPU_STRATEGY_STAGED or GFGPU_STRATEGY_RECOMPUTE) */
+int gfgpu_term_strategy(gfgpu_term *t);
 
 int64_t gfgpu_term_nnz(gfgpu_term *t);
 int64_t gfgpu_term_nb_dof(gfgpu_term *t);
