@@ -300,7 +300,7 @@ def main():
     # algorithmic bytes per launch: element->dof ids + node coordinates + U + residual + tangent values
     nd = dfem.nd
     alg_bytes = 4 * nd * ne_local + 8 * dim * m.nb_points() / world + 2 * 8 * ndof / world + 8 * nnz
-    dom = max(("elem", "gather"), key=lambda kname: kavg[kname])
+    dom = max(("elem", "gather", "recompute"), key=lambda kname: kavg[kname])
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):

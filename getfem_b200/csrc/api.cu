@@ -278,15 +278,15 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
     t->pat_valid = false;
   }
   const bool recompute = t->strategy == GFGPU_STRATEGY_RECOMPUTE;
-  // what the element kernel has to produce in this call
-  const bool need_masks = do_t && (!recompute || !t->pat_valid);
+  // what the generic element kernel has to produce in this call.  RECOMPUTE needs it only once, for
+  // the keep masks of the pattern; its residual is K^T U inside the per-nonzero kernel.
+  const bool need_masks = recompute ? !t->pat_valid : do_t;
   const bool need_stage = do_t && !recompute;
+  const bool need_rstage = do_r && !recompute;
   if (need_stage && t->stage.n != (size_t)ne * s1 * s1) t->stage.alloc(ctx, (size_t)ne * s1 * s1);
   if (need_masks && t->emask.n != (size_t)ne * nd * nd) t->emask.alloc(ctx, (size_t)ne * nd * nd);
-  if (do_r) {
-    if (t->rstage.n != (size_t)ne * s1) t->rstage.alloc(ctx, (size_t)ne * s1);
-    if (t->R.n != (size_t)t->fem->ndof) t->R.alloc(ctx, t->fem->ndof);
-  }
+  if (need_rstage && t->rstage.n != (size_t)ne * s1) t->rstage.alloc(ctx, (size_t)ne * s1);
+  if (do_r && t->R.n != (size_t)t->fem->ndof) t->R.alloc(ctx, t->fem->ndof);
   gf::ElemArgs a;
   const int64_t np = t->mesh->npts;
   a.x = t->mesh->xyz.p; a.y = a.x + np; a.z = a.y + np;
@@ -301,24 +301,27 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
   a.family = t->family;
   a.stage = need_stage ? t->stage.p : nullptr;
   a.emask = need_masks ? t->emask.p : nullptr;
-  a.rstage = do_r ? t->rstage.p : nullptr;
+  a.rstage = need_rstage ? t->rstage.p : nullptr;
   for (int k = 0; k < 5; ++k) t->ev_used[k] = false;
   auto tic = [&](int k) { GF_CUDA(cudaEventRecord(t->ev[2 * k], ctx->stream)); };
   auto toc = [&](int k) { GF_CUDA(cudaEventRecord(t->ev[2 * k + 1], ctx->stream)); t->ev_used[k] = true; };
-  if (ne > 0 && (need_stage || need_masks || do_r)) {
+  if (ne > 0 && (need_stage || need_masks || need_rstage)) {
     tic(0);
     bool ok = gf::launch_elem_kernel(ctx, t->mesh->dim, Q, nd, t->mesh->gt_kind == GFGPU_GT_PK, a);
     GF_REQUIRE(ok, "no device kernel for this (dimension, qdim, local dofs, family) combination");
     toc(0);
   }
-  if (do_t && recompute) {
+  if (recompute) {
     if (!t->pat_valid) {
       tic(3); gf::build_pattern(t); toc(3);
       t->emask.release();  // constant-coefficient linear form: the pattern cannot move any more
     }
     if (!t->rc_ready) gf::recompute_prepare(t);
-    tic(4); gf::recompute_tangent(t); toc(4);
-  } else if (do_t) {
+    if (do_r) t->R.zero();
+    tic(4); gf::recompute_assemble(t, U_dev, do_t, do_r); toc(4);
+    return;
+  }
+  if (do_t) {
     // linear families: the keep masks do not depend on U, a valid pattern stays valid
     const bool value_dependent = t->family == GFGPU_SVK || t->family == GFGPU_NEOHOOKEAN_CIARLET ||
                                  t->family == GFGPU_NEOHOOKEAN_BONET;

@@ -171,6 +171,12 @@ struct gfgpu_term {
   bool rc_ready = false;
   gf::DevBuf<double> rc_M;      // reference tensors per (j,i)
   gf::DevBuf<double> rc_eg;     // per-element geometry
+  gf::DevBuf<uint16_t> rc_cdesc; // per contribution, (J, I, element) order: incidence slot << 10 | j << 5 | i
+  gf::DevBuf<uint32_t> rc_poff;  // Q x npairs CSC offsets relative to the packet base
+  gf::DevBuf<uint32_t> rc_wcol;  // column-node packets, one warp each
+  gf::DevBuf<int64_t> rc_wbase;  // CSC position of each packet
+  int64_t rc_nw = 0;
+  int rc_cap_inc = 0, rc_cap_pairs = 0;
 };
 
 namespace gf {
@@ -208,6 +214,6 @@ void gather_residual(gfgpu_term *t);
 // ---- strategy RECOMPUTE (recompute.cu)
 bool recompute_supported(const gfgpu_term *t);
 void recompute_prepare(gfgpu_term *t);
-void recompute_tangent(gfgpu_term *t);
+void recompute_assemble(gfgpu_term *t, const double *U, bool do_t, bool do_r);
 
 }  // namespace gf

@@ -88,77 +88,223 @@ struct RcCfg {
   static constexpr int MT = RF == RF_ELAST ? N * N : RF == RF_LAPLACE ? N * (N + 1) / 2 : 1;  // table entries per (j,i)
 };
 
-// v1: one thread per node pair.
-template <int N, int Q, int ND, int RF>
+// One warp per PACKET of whole column nodes (<= 32 element incidences, packed greedily on the host).
+//   stage A  lane = (element, local column node j) incidence: copies the element geometry (B, J) into the
+//            warp's shared memory once -- 10 blocks will reuse it;
+//   stage B  the packet's contributions, in (row node, element) order, are processed 32 at a time:
+//            lane = contribution: a 16-bit descriptor (incidence slot, j, i) selects geometry and reference
+//            tensor, the QxQ block goes to a 32-slot shared buffer; then OWNER lanes (pair index mod 32)
+//            add the slots of their node pair in ascending element order (the reference's order), carry
+//            the sum across batches and, when the pair is complete, write its kept entries to their CSC
+//            slots (coalesced along the column) and their part of K^T U for the residual;
+//   stage C  lane = (column node, component): fixed-order sum of the pair parts -> R.
+// Every lane does the same amount of work in stage B whatever the valence of the nodes; no atomics, the
+// summation order is fixed, so the result is bitwise reproducible.
+struct ColArgs {
+  const uint32_t *wcol;      // nw+1: packet w owns column nodes [wcol[w], wcol[w+1])
+  const int64_t *wbase;      // nw: CSC position of the first entry of the packet
+  const uint32_t *rstart, *rsrc;
+  const int32_t *rdof;
+  const uint32_t *colstart, *cstart;
+  const uint16_t *cdesc;     // per contribution: slot << 10 | j << 5 | i
+  const int32_t *pI;
+  const uint16_t *pmask;
+  const uint32_t *poff;      // Q x npairs: position of the pair's first kept entry of column component b, relative to wbase
+  const double *eg, *Mtab, *U;
+  double lambda, mu;
+  int64_t nw, npairs;
+  int cap_inc, cap_pairs;
+  double *pr, *R;
+};
+
+template <int N, int Q, int ND, int RF, bool DO_T, bool DO_R>
 __global__ void __launch_bounds__(256)
-k_recompute_pairs(const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ csrc,
-                  const int32_t *__restrict__ pJ, const uint16_t *__restrict__ pmask,
-                  const uint32_t *__restrict__ prel, const int64_t *__restrict__ jc,
-                  const double *__restrict__ eg, const double *__restrict__ Mtab, double lambda, double mu,
-                  int64_t npairs, double *__restrict__ pr) {
+k_recompute_cols(const ColArgs a) {
   using C = RcCfg<N, RF>;
-  constexpr int NB = ND * ND, MT = C::MT, EG = C::EG;
-  __shared__ double sM[NB * MT];
-  for (int k = threadIdx.x; k < NB * MT; k += blockDim.x) sM[k] = Mtab[k];
+  constexpr int NB = ND * ND, MT = C::MT, EG = C::EG, ACC = RF == RF_ELAST ? Q * Q : 1;
+  constexpr int EGP = EG | 1;   // odd stride (in doubles): conflict-free geometry rows
+  constexpr int ITS = ACC | 1;  // odd stride of the item slots
+  extern __shared__ double sm[];
+  double *sM = sm;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, WPB = blockDim.x >> 5;
+  const size_t per_warp = (size_t)a.cap_inc * EGP + 32 * ITS + (size_t)a.cap_pairs * Q;
+  double *sG = sM + NB * MT + (size_t)warp * per_warp;
+  double *sI = sG + (size_t)a.cap_inc * EGP;
+  double *rp = sI + 32 * ITS;
+  for (int k = threadIdx.x; k < NB * MT; k += blockDim.x) sM[k] = a.Mtab[k];
   __syncthreads();
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npairs; p += (int64_t)gridDim.x * blockDim.x) {
-    double acc[RF == RF_ELAST ? Q * Q : 1];
+  for (int64_t w = (int64_t)blockIdx.x * WPB + warp; w < a.nw; w += (int64_t)gridDim.x * WPB) {
+    const uint32_t k0 = a.wcol[w], k1 = a.wcol[w + 1];
+    const uint32_t r0 = a.rstart[k0], r1 = a.rstart[k1];
+    const uint32_t p0 = a.colstart[k0], p1 = a.colstart[k1];
+    const uint32_t it0 = a.cstart[p0], nit = a.cstart[p1] - it0;
+    const int64_t base = DO_T ? a.wbase[w] : 0;
+    // ---- stage A: element geometry of the packet's incidences
+    for (uint32_t ri = r0 + lane; ri < r1; ri += 32) {
+      const uint32_t el = a.rsrc[ri] / ND;
+      const double *g = a.eg + (size_t)el * EG;
+      double *o = sG + (size_t)(ri - r0) * EGP;
 #pragma unroll
-    for (int m = 0; m < (RF == RF_ELAST ? Q * Q : 1); ++m) acc[m] = 0.0;
-    for (uint32_t s = cstart[p], e = cstart[p + 1]; s < e; ++s) {
-      const uint32_t c = csrc[s];
-      const uint32_t el = c / NB, r = c - el * NB;
-      const double *g = eg + (size_t)el * EG;
-      const double *M = sM + r * MT;
-      if (RF == RF_ELAST) {
-        double B[N * N], W[N * N];
-#pragma unroll
-        for (int k = 0; k < N * N; ++k) B[k] = g[k];
-        const double J = g[N * N];
-        // W(a,q) = sum_p B(a,p) M(p,q) ; T(a,b) = sum_q W(a,q) B(b,q)
-#pragma unroll
-        for (int q = 0; q < N; ++q)
-#pragma unroll
-          for (int a = 0; a < N; ++a) {
-            double s2 = 0;
-#pragma unroll
-            for (int pp = 0; pp < N; ++pp) s2 += B[a + N * pp] * M[pp * N + q];
-            W[a + N * q] = s2;
-          }
-        double T[N * N], tr = 0;
-#pragma unroll
-        for (int b = 0; b < N; ++b)
-#pragma unroll
-          for (int a = 0; a < N; ++a) {
-            double s2 = 0;
-#pragma unroll
-            for (int q = 0; q < N; ++q) s2 += W[a + N * q] * B[b + N * q];
-            T[a + N * b] = s2;
-            if (a == b) tr += s2;
-          }
-        const double jl = J * lambda, jm = J * mu;
-#pragma unroll
-        for (int b = 0; b < N; ++b)
-#pragma unroll
-          for (int a = 0; a < N; ++a)
-            acc[b * Q + a] += jl * T[a + N * b] + jm * T[b + N * a] + (a == b ? jm * tr : 0.0);
-      } else if (RF == RF_LAPLACE) {
-        double s2 = 0;
-#pragma unroll
-        for (int k = 0; k < MT; ++k) s2 += M[k] * g[k];
-        acc[0] += s2;
-      } else {
-        acc[0] += M[0] * g[0];
-      }
+      for (int k = 0; k < EG; ++k) o[k] = g[k];
     }
-    const unsigned m = pmask[p];
-    const int32_t J = pJ[p];
+    __syncwarp();
+    // ---- stage B
+    uint32_t pcur = p0;
+    double acc[ACC];
 #pragma unroll
-    for (int b = 0; b < Q; ++b) {
-      int64_t pos = jc[J + b] + prel[(size_t)b * npairs + p];
+    for (int m = 0; m < ACC; ++m) acc[m] = 0.0;
+    for (uint32_t t0 = 0; t0 < nit; t0 += 32) {
+      const uint32_t t = t0 + lane;
+      if (t < nit) {
+        const unsigned d = a.cdesc[(size_t)it0 + t];
+        const int i = d & 31, j = (d >> 5) & 31;
+        const double *G = sG + (size_t)(d >> 10) * EGP;
+        const double *M = sM + (j * ND + i) * MT;
+        double *o = sI + lane * ITS;
+        if (RF == RF_ELAST) {
+          double Bm[N * N], W[N * N];
 #pragma unroll
-      for (int a = 0; a < Q; ++a)
-        if (m & (1u << (b * Q + a))) pr[pos++] = RF == RF_ELAST ? acc[RF == RF_ELAST ? b * Q + a : 0] : (a == b ? acc[0] : 0.0);
+          for (int k = 0; k < N * N; ++k) Bm[k] = G[k];
+#pragma unroll
+          for (int q = 0; q < N; ++q)
+#pragma unroll
+            for (int aa = 0; aa < N; ++aa) {
+              double s2 = 0;
+#pragma unroll
+              for (int pp = 0; pp < N; ++pp) s2 += Bm[aa + N * pp] * M[pp * N + q];
+              W[aa + N * q] = s2;
+            }
+          double T[N * N], tr = 0;
+#pragma unroll
+          for (int b = 0; b < N; ++b)
+#pragma unroll
+            for (int aa = 0; aa < N; ++aa) {
+              double s2 = 0;
+#pragma unroll
+              for (int q = 0; q < N; ++q) s2 += W[aa + N * q] * Bm[b + N * q];
+              T[aa + N * b] = s2;
+              if (aa == b) tr += s2;
+            }
+          const double jl = G[N * N] * a.lambda, jm = G[N * N] * a.mu;
+#pragma unroll
+          for (int b = 0; b < N; ++b)
+#pragma unroll
+            for (int aa = 0; aa < N; ++aa)
+              o[b * Q + aa] = jl * T[aa + N * b] + jm * T[b + N * aa] + (aa == b ? jm * tr : 0.0);
+        } else if (RF == RF_LAPLACE) {
+          double s2 = 0;
+#pragma unroll
+          for (int k = 0; k < MT; ++k) s2 += M[k] * G[k];
+          o[0] = s2;
+        } else {
+          o[0] = M[0] * G[0];
+        }
+      }
+      __syncwarp();
+      // owner lanes: the pair p >= pcur with p = lane (mod 32)
+      const uint32_t p = pcur + ((lane - pcur) & 31u);
+      bool complete = false;
+      if (p < p1) {
+        const uint32_t sa = a.cstart[p] - it0, sb = a.cstart[p + 1] - it0;
+        const uint32_t lo = sa > t0 ? sa : t0, hi = sb < t0 + 32 ? sb : t0 + 32;
+        if (lo < hi) {
+          for (uint32_t s = lo; s < hi; ++s) {
+            const double *it = sI + (s - t0) * ITS;
+#pragma unroll
+            for (int m = 0; m < ACC; ++m) acc[m] += it[m];
+          }
+          complete = sb <= t0 + 32;
+        }
+        if (complete) {
+          if (DO_T) {
+            const unsigned m = a.pmask[p];
+#pragma unroll
+            for (int b = 0; b < Q; ++b) {
+              int64_t pos = base + a.poff[(size_t)b * a.npairs + p];
+#pragma unroll
+              for (int aa = 0; aa < Q; ++aa)
+                if (m & (1u << (b * Q + aa)))
+                  a.pr[pos++] = RF == RF_ELAST ? acc[RF == RF_ELAST ? b * Q + aa : 0] : (aa == b ? acc[0] : 0.0);
+            }
+          }
+          if (DO_R) {
+            const int32_t I = a.pI[p];
+            double u[Q];
+#pragma unroll
+            for (int aa = 0; aa < Q; ++aa) u[aa] = a.U ? a.U[I + aa] : 0.0;
+#pragma unroll
+            for (int b = 0; b < Q; ++b) {
+              double s2 = 0;
+              if (RF == RF_ELAST) {
+#pragma unroll
+                for (int aa = 0; aa < Q; ++aa) s2 += acc[RF == RF_ELAST ? b * Q + aa : 0] * u[aa];
+              } else {
+                s2 = acc[0] * u[b];
+              }
+              rp[(size_t)(p - p0) * Q + b] = s2;
+            }
+          }
+#pragma unroll
+          for (int m = 0; m < ACC; ++m) acc[m] = 0.0;
+        }
+      }
+      pcur += __popc(__ballot_sync(0xffffffffu, complete));
+      __syncwarp();
+    }
+    // ---- stage C
+    if (DO_R) {
+      for (uint32_t idx = lane; idx < (k1 - k0) * Q; idx += 32) {
+        const uint32_t kc = k0 + idx / Q, b = idx % Q;
+        double s2 = 0;
+        for (uint32_t pp = a.colstart[kc] - p0, pe = a.colstart[kc + 1] - p0; pp < pe; ++pp) s2 += rp[(size_t)pp * Q + b];
+        a.R[a.rdof[kc] + b] = s2;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ---- one-time plan kernels
+__global__ void k_invert_perm(const uint32_t *__restrict__ src, int64_t n, uint32_t *__restrict__ pos) {
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x)
+    pos[src[s]] = (uint32_t)s;
+}
+
+__global__ void k_col_packet(const uint32_t *__restrict__ wcol, int64_t nw, uint32_t *__restrict__ colw) {
+  for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < nw; w += (int64_t)gridDim.x * blockDim.x)
+    for (uint32_t k = wcol[w]; k < wcol[w + 1]; ++k) colw[k] = (uint32_t)w;
+}
+
+// thread per column node: contribution descriptors and packet-relative CSC offsets of its pairs
+template <int Q>
+__global__ void k_col_plan(const uint32_t *__restrict__ wcol, const uint32_t *__restrict__ colw,
+                           const uint32_t *__restrict__ colstart, const uint32_t *__restrict__ cstart,
+                           const uint32_t *__restrict__ csrc, const uint32_t *__restrict__ rstart,
+                           const uint32_t *__restrict__ rpos, const int32_t *__restrict__ pJ,
+                           const int64_t *__restrict__ jc, const uint32_t *__restrict__ prel, int nd, int64_t ncol,
+                           int64_t npairs, uint16_t *__restrict__ cdesc, uint32_t *__restrict__ poff,
+                           int64_t *__restrict__ wbase, int *__restrict__ err) {
+  const int nb = nd * nd;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < ncol; k += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t w = colw[k], kf = wcol[w];
+    const uint32_t rbase = rstart[kf];
+    const int64_t base = jc[pJ[colstart[kf]]];
+    if (k == kf) wbase[w] = base;
+    for (uint32_t p = colstart[k]; p < colstart[k + 1]; ++p) {
+      const int32_t J = pJ[p];
+      for (int b = 0; b < Q; ++b) {
+        const int64_t off = jc[J + b] + prel[(size_t)b * npairs + p] - base;
+        if (off < 0 || off >= (int64_t(1) << 32)) *err = 1;
+        poff[(size_t)b * npairs + p] = (uint32_t)off;
+      }
+      for (uint32_t s = cstart[p]; s < cstart[p + 1]; ++s) {
+        const uint32_t c = csrc[s];
+        const uint32_t el = c / nb, r = c - el * nb;
+        const uint32_t j = r / nd, i = r - j * nd;
+        const uint32_t slot = rpos[el * nd + j] - rbase;
+        if (slot > 63u) *err = 2;
+        cdesc[s] = (uint16_t)((slot << 10) | (j << 5) | i);
+      }
     }
   }
 }
@@ -227,27 +373,107 @@ void recompute_prepare(gfgpu_term *t) {
                                                      t->tab->gt_grad.p, t->e0, ne, rf, scale, t->rc_eg.p, EG);
     GF_LAUNCH_CHECK();
   }
+  // ---- column packets: whole column nodes packed greedily up to 32 element incidences per warp
+  Structure &st = t->st;
+  GF_REQUIRE(st.ncolnodes == st.nrnodes, "column nodes and incidence nodes differ");
+  GF_REQUIRE(nd <= 32, "too many local nodes for the 16-bit contribution descriptor");
+  std::vector<uint32_t> rstart(st.nrnodes + 1), colstart(st.ncolnodes + 1);
+  st.rstart.download(rstart.data());
+  st.colstart.download(colstart.data());
   GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<uint32_t> wcol;
+  wcol.reserve(st.ncolnodes / 2 + 2);
+  int cap_inc = 1, cap_pairs = 1;
+  for (int64_t k = 0; k < st.ncolnodes;) {
+    wcol.push_back((uint32_t)k);
+    int64_t k1 = k + 1;
+    while (k1 < st.ncolnodes && rstart[k1 + 1] - rstart[k] <= 32) ++k1;
+    cap_inc = std::max<int>(cap_inc, (int)(rstart[k1] - rstart[k]));
+    cap_pairs = std::max<int>(cap_pairs, (int)(colstart[k1] - colstart[k]));
+    k = k1;
+  }
+  wcol.push_back((uint32_t)st.ncolnodes);
+  GF_REQUIRE(cap_inc <= 64, "node valence above 64 elements: use strategy STAGED");
+  t->rc_nw = (int64_t)wcol.size() - 1;
+  t->rc_cap_inc = cap_inc;
+  t->rc_cap_pairs = cap_pairs;
+  t->rc_wcol.alloc(ctx, wcol.size());
+  t->rc_wcol.upload(wcol.data());
+  t->rc_wbase.alloc(ctx, t->rc_nw);
+  t->rc_cdesc.alloc(ctx, st.ncontrib);
+  t->rc_poff.alloc(ctx, (size_t)t->fem->qdim * st.npairs);
+  {
+    DevBuf<uint32_t> colw, rpos;
+    colw.alloc(ctx, st.ncolnodes);
+    rpos.alloc(ctx, st.nrinc);
+    t->flag.zero();
+    const int B = 256;
+    auto grid = [&](int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + B - 1) / B, 148 * 32)); };
+    k_invert_perm<<<grid(st.nrinc), B, 0, ctx->stream>>>(st.rsrc.p, st.nrinc, rpos.p);
+    GF_LAUNCH_CHECK();
+    k_col_packet<<<grid(t->rc_nw), B, 0, ctx->stream>>>(t->rc_wcol.p, t->rc_nw, colw.p);
+    GF_LAUNCH_CHECK();
+#define GF_PLAN(QQ)                                                                                               \
+  k_col_plan<QQ><<<grid(st.ncolnodes), B, 0, ctx->stream>>>(t->rc_wcol.p, colw.p, st.colstart.p, st.cstart.p,      \
+                                                            st.csrc.p, st.rstart.p, rpos.p, st.pJ.p, t->jc.p,      \
+                                                            t->prel.p, nd, st.ncolnodes, st.npairs, t->rc_cdesc.p, \
+                                                            t->rc_poff.p, t->rc_wbase.p, (int *)t->flag.p)
+    if (t->fem->qdim == 1) GF_PLAN(1);
+    else if (t->fem->qdim == 2) GF_PLAN(2);
+    else GF_PLAN(3);
+#undef GF_PLAN
+    GF_LAUNCH_CHECK();
+    int32_t err = 0;
+    t->flag.download(&err);
+    GF_CUDA(cudaStreamSynchronize(ctx->stream));
+    GF_REQUIRE(err == 0, "recompute plan: packet too large for the compact descriptors");
+  }
+  // the contribution list and the column-relative offsets are folded into cdesc / poff
+  t->prel.release();
   t->rc_ready = true;
 }
 
 template <int N, int Q, int ND, int RF>
-static void launch_pairs(gfgpu_term *t) {
+static void launch_cols(gfgpu_term *t, const double *U, bool do_t, bool do_r) {
+  using C = RcCfg<N, RF>;
+  constexpr int ACC = RF == RF_ELAST ? Q * Q : 1;
   Structure &st = t->st;
-  int grid = (int)std::min<int64_t>((st.npairs + 255) / 256, 148 * 64);
-  k_recompute_pairs<N, Q, ND, RF><<<grid, 256, 0, t->ctx->stream>>>(
-      st.cstart.p, st.csrc.p, st.pJ.p, t->pmask.p, t->prel.p, t->jc.p, t->rc_eg.p, t->rc_M.p, t->par[0], t->par[1],
-      st.npairs, t->pr.p);
-  GF_LAUNCH_CHECK();
+  ColArgs a;
+  a.wcol = t->rc_wcol.p; a.wbase = t->rc_wbase.p; a.rstart = st.rstart.p; a.rsrc = st.rsrc.p; a.rdof = st.rdof.p;
+  a.colstart = st.colstart.p; a.cstart = st.cstart.p; a.cdesc = t->rc_cdesc.p;
+  a.pI = st.pI.p; a.pmask = t->pmask.p; a.poff = t->rc_poff.p;
+  a.eg = t->rc_eg.p; a.Mtab = t->rc_M.p; a.U = U;
+  a.lambda = t->par[0]; a.mu = t->par[1];
+  a.nw = t->rc_nw; a.npairs = st.npairs;
+  a.cap_inc = t->rc_cap_inc; a.cap_pairs = t->rc_cap_pairs;
+  a.pr = t->pr.p; a.R = t->R.p;
+  const int WPB = 8;
+  const size_t smem = ((size_t)ND * ND * C::MT +
+                       (size_t)WPB * ((size_t)a.cap_inc * (C::EG | 1) + 32 * (ACC | 1) + (size_t)a.cap_pairs * Q)) * 8;
+  GF_REQUIRE(smem <= 220 * 1024, "packet too large for shared memory; use strategy STAGED");
+  auto launch = [&](auto kern) {
+    GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WPB * 32, smem));
+    if (occ < 1) occ = 1;
+    int64_t want = (a.nw + WPB - 1) / WPB;
+    int grid = (int)std::min<int64_t>(want, (int64_t)t->ctx->sm_count * occ);
+    kern<<<grid, WPB * 32, smem, t->ctx->stream>>>(a);
+    GF_LAUNCH_CHECK();
+  };
+  if (do_t && do_r) launch(k_recompute_cols<N, Q, ND, RF, true, true>);
+  else if (do_t) launch(k_recompute_cols<N, Q, ND, RF, true, false>);
+  else launch(k_recompute_cols<N, Q, ND, RF, false, true>);
 }
 
 #define RC_CASE(NN, QQ, NDD, RFF)                                   \
   if (N == NN && Q == QQ && nd == NDD && rf == RFF) {               \
-    launch_pairs<NN, QQ, NDD, RFF>(t);                              \
+    launch_cols<NN, QQ, NDD, RFF>(t, U, do_t, do_r);                \
     return;                                                         \
   }
 
-void recompute_tangent(gfgpu_term *t) {
+// tangent and/or residual (R = K^T U = K U, the handled forms are symmetric) in one kernel
+void recompute_assemble(gfgpu_term *t, const double *U, bool do_t, bool do_r) {
   if (!t->st.npairs) return;
   const int N = t->mesh->dim, nd = t->fem->nd, Q = t->fem->qdim, rf = rf_of(t->family);
   RC_CASE(3, 3, 10, RF_ELAST) RC_CASE(3, 3, 4, RF_ELAST) RC_CASE(3, 3, 20, RF_ELAST)
