@@ -90,16 +90,16 @@ struct RcCfg {
 
 // One warp per PACKET of whole column nodes (<= 32 element incidences, packed greedily on the host).
 //   stage A  lane = (element, local column node j) incidence: copies the element geometry (B, J) into the
-//            warp's shared memory once -- 10 blocks will reuse it;
-//   stage B  the packet's contributions, in (row node, element) order, are processed 32 at a time:
-//            lane = contribution: a 16-bit descriptor (incidence slot, j, i) selects geometry and reference
-//            tensor, the QxQ block goes to a 32-slot shared buffer; then OWNER lanes (pair index mod 32)
-//            add the slots of their node pair in ascending element order (the reference's order), carry
-//            the sum across batches and, when the pair is complete, write its kept entries to their CSC
-//            slots (coalesced along the column) and their part of K^T U for the residual;
+//            warp's shared memory once -- nd blocks reuse it; the packet's pair boundaries go to smem too;
+//   stage B  the packet's contributions are in (row node, element) order; every lane takes an EQUAL run of
+//            consecutive contributions (same work whatever the node valences).  A 16-bit descriptor
+//            (incidence slot, j, i) selects geometry and reference tensor; the QxQ block is accumulated in
+//            registers while the node pair stays the same and flushed when it changes: kept entries go to
+//            their CSC slots, and (residual) the pair's part of K^T U to shared memory.  A pair cut by a
+//            run boundary leaves a HEAD part in shared memory; the lane where the pair starts adds the
+//            following head parts in lane order (= ascending element id, the reference's order);
 //   stage C  lane = (column node, component): fixed-order sum of the pair parts -> R.
-// Every lane does the same amount of work in stage B whatever the valence of the nodes; no atomics, the
-// summation order is fixed, so the result is bitwise reproducible.
+// No atomics, fixed summation order: bitwise reproducible.
 struct ColArgs {
   const uint32_t *wcol;      // nw+1: packet w owns column nodes [wcol[w], wcol[w+1])
   const int64_t *wbase;      // nw: CSC position of the first entry of the packet
@@ -117,29 +117,43 @@ struct ColArgs {
   double *pr, *R;
 };
 
+template <int N, int Q, int ND, int RF>
+struct ColSmem {
+  using C = RcCfg<N, RF>;
+  static constexpr int ACC = RF == RF_ELAST ? Q * Q : 1;
+  static constexpr int EGP = C::EG | 1;  // odd stride (doubles): conflict-free geometry rows
+  static constexpr int HS = ACC | 1;     // odd stride of the head parts
+  // doubles per warp: geometry, head parts, residual parts, then (as uint32) pair boundaries + head pair ids
+  __host__ __device__ static size_t per_warp(int cap_inc, int cap_pairs, bool do_r) {
+    size_t d = (size_t)cap_inc * EGP + 32 * HS + (do_r ? (size_t)cap_pairs * Q : 0);
+    size_t u = (size_t)cap_pairs + 1 + 32;
+    return d + (u + 1) / 2;
+  }
+};
+
 template <int N, int Q, int ND, int RF, bool DO_T, bool DO_R>
 __global__ void __launch_bounds__(256)
 k_recompute_cols(const ColArgs a) {
   using C = RcCfg<N, RF>;
-  constexpr int NB = ND * ND, MT = C::MT, EG = C::EG, ACC = RF == RF_ELAST ? Q * Q : 1;
-  constexpr int EGP = EG | 1;   // odd stride (in doubles): conflict-free geometry rows
-  constexpr int ITS = ACC | 1;  // odd stride of the item slots
+  using S = ColSmem<N, Q, ND, RF>;
+  constexpr int NB = ND * ND, MT = C::MT, EG = C::EG, ACC = S::ACC, EGP = S::EGP, HS = S::HS;
   extern __shared__ double sm[];
   double *sM = sm;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, WPB = blockDim.x >> 5;
-  const size_t per_warp = (size_t)a.cap_inc * EGP + 32 * ITS + (size_t)a.cap_pairs * Q;
-  double *sG = sM + NB * MT + (size_t)warp * per_warp;
-  double *sI = sG + (size_t)a.cap_inc * EGP;
-  double *rp = sI + 32 * ITS;
+  double *sG = sM + NB * MT + (size_t)warp * S::per_warp(a.cap_inc, a.cap_pairs, DO_R);
+  double *sH = sG + (size_t)a.cap_inc * EGP;          // head parts, one per lane
+  double *rp = sH + 32 * HS;                          // residual parts, one per pair
+  uint32_t *scs = (uint32_t *)(rp + (DO_R ? (size_t)a.cap_pairs * Q : 0));  // pair boundaries (relative)
+  uint32_t *shid = scs + a.cap_pairs + 1;             // pair (relative) of each lane's head part, or ~0
   for (int k = threadIdx.x; k < NB * MT; k += blockDim.x) sM[k] = a.Mtab[k];
   __syncthreads();
   for (int64_t w = (int64_t)blockIdx.x * WPB + warp; w < a.nw; w += (int64_t)gridDim.x * WPB) {
     const uint32_t k0 = a.wcol[w], k1 = a.wcol[w + 1];
     const uint32_t r0 = a.rstart[k0], r1 = a.rstart[k1];
-    const uint32_t p0 = a.colstart[k0], p1 = a.colstart[k1];
-    const uint32_t it0 = a.cstart[p0], nit = a.cstart[p1] - it0;
+    const uint32_t p0 = a.colstart[k0], npk = a.colstart[k1] - p0;
+    const uint32_t it0 = a.cstart[p0];
     const int64_t base = DO_T ? a.wbase[w] : 0;
-    // ---- stage A: element geometry of the packet's incidences
+    // ---- stage A
     for (uint32_t ri = r0 + lane; ri < r1; ri += 32) {
       const uint32_t el = a.rsrc[ri] / ND;
       const double *g = a.eg + (size_t)el * EG;
@@ -147,110 +161,136 @@ k_recompute_cols(const ColArgs a) {
 #pragma unroll
       for (int k = 0; k < EG; ++k) o[k] = g[k];
     }
+    for (uint32_t q = lane; q <= npk; q += 32) scs[q] = a.cstart[p0 + q] - it0;
+    shid[lane] = 0xffffffffu;
     __syncwarp();
-    // ---- stage B
-    uint32_t pcur = p0;
+    const uint32_t nit = scs[npk];
+    // ---- stage B: equal runs of consecutive contributions
+    const uint32_t L = (nit + 31) >> 5;
+    const uint32_t tb = min(lane * L, nit), te = min(tb + L, nit);
     double acc[ACC];
 #pragma unroll
     for (int m = 0; m < ACC; ++m) acc[m] = 0.0;
-    for (uint32_t t0 = 0; t0 < nit; t0 += 32) {
-      const uint32_t t = t0 + lane;
-      if (t < nit) {
-        const unsigned d = a.cdesc[(size_t)it0 + t];
-        const int i = d & 31, j = (d >> 5) & 31;
-        const double *G = sG + (size_t)(d >> 10) * EGP;
-        const double *M = sM + (j * ND + i) * MT;
-        double *o = sI + lane * ITS;
-        if (RF == RF_ELAST) {
-          double Bm[N * N], W[N * N];
+    // flush of a COMPLETE pair sum held in acc
+    auto flush = [&](uint32_t q) {
+      const uint32_t p = p0 + q;
+      if (DO_T) {
+        const unsigned m = a.pmask[p];
 #pragma unroll
-          for (int k = 0; k < N * N; ++k) Bm[k] = G[k];
+        for (int b = 0; b < Q; ++b) {
+          double *dst = a.pr + (base + a.poff[(size_t)b * a.npairs + p]);
 #pragma unroll
-          for (int q = 0; q < N; ++q)
+          for (int aa = 0; aa < Q; ++aa)
+            if (m & (1u << (b * Q + aa)))
+              *dst++ = RF == RF_ELAST ? acc[RF == RF_ELAST ? b * Q + aa : 0] : (aa == b ? acc[0] : 0.0);
+        }
+      }
+      if (DO_R) {
+        const int32_t I = a.pI[p];
+        double u[Q];
 #pragma unroll
-            for (int aa = 0; aa < N; ++aa) {
-              double s2 = 0;
+        for (int aa = 0; aa < Q; ++aa) u[aa] = a.U ? a.U[I + aa] : 0.0;
 #pragma unroll
-              for (int pp = 0; pp < N; ++pp) s2 += Bm[aa + N * pp] * M[pp * N + q];
-              W[aa + N * q] = s2;
-            }
-          double T[N * N], tr = 0;
-#pragma unroll
-          for (int b = 0; b < N; ++b)
-#pragma unroll
-            for (int aa = 0; aa < N; ++aa) {
-              double s2 = 0;
-#pragma unroll
-              for (int q = 0; q < N; ++q) s2 += W[aa + N * q] * Bm[b + N * q];
-              T[aa + N * b] = s2;
-              if (aa == b) tr += s2;
-            }
-          const double jl = G[N * N] * a.lambda, jm = G[N * N] * a.mu;
-#pragma unroll
-          for (int b = 0; b < N; ++b)
-#pragma unroll
-            for (int aa = 0; aa < N; ++aa)
-              o[b * Q + aa] = jl * T[aa + N * b] + jm * T[b + N * aa] + (aa == b ? jm * tr : 0.0);
-        } else if (RF == RF_LAPLACE) {
+        for (int b = 0; b < Q; ++b) {
           double s2 = 0;
+          if (RF == RF_ELAST) {
 #pragma unroll
-          for (int k = 0; k < MT; ++k) s2 += M[k] * G[k];
-          o[0] = s2;
-        } else {
-          o[0] = M[0] * G[0];
+            for (int aa = 0; aa < Q; ++aa) s2 += acc[RF == RF_ELAST ? b * Q + aa : 0] * u[aa];
+          } else {
+            s2 = acc[0] * u[b];
+          }
+          rp[(size_t)q * Q + b] = s2;
         }
       }
-      __syncwarp();
-      // owner lanes: the pair p >= pcur with p = lane (mod 32)
-      const uint32_t p = pcur + ((lane - pcur) & 31u);
-      bool complete = false;
-      if (p < p1) {
-        const uint32_t sa = a.cstart[p] - it0, sb = a.cstart[p + 1] - it0;
-        const uint32_t lo = sa > t0 ? sa : t0, hi = sb < t0 + 32 ? sb : t0 + 32;
-        if (lo < hi) {
-          for (uint32_t s = lo; s < hi; ++s) {
-            const double *it = sI + (s - t0) * ITS;
+    };
+    uint32_t q = 0;           // current pair (relative)
+    uint32_t tailq = 0xffffffffu;  // pair whose first part ends my run and continues in the next lanes
+    double tail[ACC];
 #pragma unroll
-            for (int m = 0; m < ACC; ++m) acc[m] += it[m];
-          }
-          complete = sb <= t0 + 32;
-        }
-        if (complete) {
-          if (DO_T) {
-            const unsigned m = a.pmask[p];
-#pragma unroll
-            for (int b = 0; b < Q; ++b) {
-              int64_t pos = base + a.poff[(size_t)b * a.npairs + p];
-#pragma unroll
-              for (int aa = 0; aa < Q; ++aa)
-                if (m & (1u << (b * Q + aa)))
-                  a.pr[pos++] = RF == RF_ELAST ? acc[RF == RF_ELAST ? b * Q + aa : 0] : (aa == b ? acc[0] : 0.0);
-            }
-          }
-          if (DO_R) {
-            const int32_t I = a.pI[p];
-            double u[Q];
-#pragma unroll
-            for (int aa = 0; aa < Q; ++aa) u[aa] = a.U ? a.U[I + aa] : 0.0;
-#pragma unroll
-            for (int b = 0; b < Q; ++b) {
-              double s2 = 0;
-              if (RF == RF_ELAST) {
-#pragma unroll
-                for (int aa = 0; aa < Q; ++aa) s2 += acc[RF == RF_ELAST ? b * Q + aa : 0] * u[aa];
-              } else {
-                s2 = acc[0] * u[b];
-              }
-              rp[(size_t)(p - p0) * Q + b] = s2;
-            }
-          }
-#pragma unroll
-          for (int m = 0; m < ACC; ++m) acc[m] = 0.0;
-        }
+    for (int m = 0; m < ACC; ++m) tail[m] = 0.0;
+    if (tb < te) {
+      // pair containing contribution tb: largest q with scs[q] <= tb
+      uint32_t lo = 0, hi = npk;
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (scs[mid] <= tb) lo = mid; else hi = mid;
       }
-      pcur += __popc(__ballot_sync(0xffffffffu, complete));
-      __syncwarp();
+      q = lo;
     }
+    uint32_t qend = (tb < te) ? scs[q + 1] : 0;
+    for (uint32_t t = tb; t < te; ++t) {
+      const unsigned d = a.cdesc[(size_t)it0 + t];
+      const int i = d & 31, j = (d >> 5) & 31;
+      const double *G = sG + (size_t)(d >> 10) * EGP;
+      const double *M = sM + (j * ND + i) * MT;
+      if (RF == RF_ELAST) {
+        double Bm[N * N], W[N * N];
+#pragma unroll
+        for (int k = 0; k < N * N; ++k) Bm[k] = G[k];
+#pragma unroll
+        for (int qq = 0; qq < N; ++qq)
+#pragma unroll
+          for (int aa = 0; aa < N; ++aa) {
+            double s2 = 0;
+#pragma unroll
+            for (int pp = 0; pp < N; ++pp) s2 += Bm[aa + N * pp] * M[pp * N + qq];
+            W[aa + N * qq] = s2;
+          }
+        double T[N * N], tr = 0;
+#pragma unroll
+        for (int b = 0; b < N; ++b)
+#pragma unroll
+          for (int aa = 0; aa < N; ++aa) {
+            double s2 = 0;
+#pragma unroll
+            for (int qq = 0; qq < N; ++qq) s2 += W[aa + N * qq] * Bm[b + N * qq];
+            T[aa + N * b] = s2;
+            if (aa == b) tr += s2;
+          }
+        const double jl = G[N * N] * a.lambda, jm = G[N * N] * a.mu;
+#pragma unroll
+        for (int b = 0; b < N; ++b)
+#pragma unroll
+          for (int aa = 0; aa < N; ++aa)
+            acc[RF == RF_ELAST ? b * Q + aa : 0] += jl * T[aa + N * b] + jm * T[b + N * aa] + (aa == b ? jm * tr : 0.0);
+      } else if (RF == RF_LAPLACE) {
+        double s2 = 0;
+#pragma unroll
+        for (int k = 0; k < MT; ++k) s2 += M[k] * G[k];
+        acc[0] += s2;
+      } else {
+        acc[0] += M[0] * G[0];
+      }
+      if (t + 1 == qend || t + 1 == te) {  // the pair, or my run, ends here
+        const bool started_here = scs[q] >= tb, ends_here = qend <= te;
+        if (started_here && ends_here) {
+          flush(q);
+        } else if (!started_here) {  // head part of a pair that began in an earlier lane
+          shid[lane] = q;
+#pragma unroll
+          for (int m = 0; m < ACC; ++m) sH[lane * HS + m] = acc[m];
+        } else {  // began here, continues: I own it, the rest arrives as head parts
+          tailq = q;
+#pragma unroll
+          for (int m = 0; m < ACC; ++m) tail[m] = acc[m];
+        }
+#pragma unroll
+        for (int m = 0; m < ACC; ++m) acc[m] = 0.0;
+        ++q;
+        qend = (q < npk) ? scs[q + 1] : 0xffffffffu;
+      }
+    }
+    __syncwarp();
+    if (tailq != 0xffffffffu) {
+#pragma unroll
+      for (int m = 0; m < ACC; ++m) acc[m] = tail[m];
+      for (int l2 = lane + 1; l2 < 32 && shid[l2] == tailq; ++l2) {
+#pragma unroll
+        for (int m = 0; m < ACC; ++m) acc[m] += sH[l2 * HS + m];
+      }
+      flush(tailq);
+    }
+    __syncwarp();
     // ---- stage C
     if (DO_R) {
       for (uint32_t idx = lane; idx < (k1 - k0) * Q; idx += 32) {
@@ -436,7 +476,6 @@ void recompute_prepare(gfgpu_term *t) {
 template <int N, int Q, int ND, int RF>
 static void launch_cols(gfgpu_term *t, const double *U, bool do_t, bool do_r) {
   using C = RcCfg<N, RF>;
-  constexpr int ACC = RF == RF_ELAST ? Q * Q : 1;
   Structure &st = t->st;
   ColArgs a;
   a.wcol = t->rc_wcol.p; a.wbase = t->rc_wbase.p; a.rstart = st.rstart.p; a.rsrc = st.rsrc.p; a.rdof = st.rdof.p;
@@ -448,8 +487,7 @@ static void launch_cols(gfgpu_term *t, const double *U, bool do_t, bool do_r) {
   a.cap_inc = t->rc_cap_inc; a.cap_pairs = t->rc_cap_pairs;
   a.pr = t->pr.p; a.R = t->R.p;
   const int WPB = 8;
-  const size_t smem = ((size_t)ND * ND * C::MT +
-                       (size_t)WPB * ((size_t)a.cap_inc * (C::EG | 1) + 32 * (ACC | 1) + (size_t)a.cap_pairs * Q)) * 8;
+  const size_t smem = ((size_t)ND * ND * C::MT + (size_t)WPB * ColSmem<N, Q, ND, RF>::per_warp(a.cap_inc, a.cap_pairs, do_r)) * 8;
   GF_REQUIRE(smem <= 220 * 1024, "packet too large for shared memory; use strategy STAGED");
   auto launch = [&](auto kern) {
     GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
