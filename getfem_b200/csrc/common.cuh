@@ -172,7 +172,8 @@ struct gfgpu_term {
   gf::DevBuf<double> rc_M;      // reference tensors per (j,i)
   gf::DevBuf<double> rc_eg;     // per-element geometry
   gf::DevBuf<uint16_t> rc_cdesc; // per contribution, (J, I, element) order: incidence slot << 10 | j << 5 | i
-  gf::DevBuf<uint32_t> rc_poff;  // Q x npairs CSC offsets relative to the packet base
+  struct alignas(16) PairRec { uint32_t x, y, z, w; };
+  gf::DevBuf<PairRec> rc_prec;   // per pair: packed CSC offsets (relative to the packet base), keep mask, row dof
   gf::DevBuf<uint32_t> rc_wcol;  // column-node packets, one warp each
   gf::DevBuf<int64_t> rc_wbase;  // CSC position of each packet
   int64_t rc_nw = 0;

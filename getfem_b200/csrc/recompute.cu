@@ -107,9 +107,8 @@ struct ColArgs {
   const int32_t *rdof;
   const uint32_t *colstart, *cstart;
   const uint16_t *cdesc;     // per contribution: slot << 10 | j << 5 | i
-  const int32_t *pI;
-  const uint16_t *pmask;
-  const uint32_t *poff;      // Q x npairs: position of the pair's first kept entry of column component b, relative to wbase
+  const uint4 *prec;         // per pair: x = CSC offset of column component 0 (relative to wbase),
+                             //   y = (offset of component 1 - x) | keep mask << 20, z = offset of component 2 - x, w = row dof
   const double *eg, *Mtab, *U;
   double lambda, mu;
   int64_t nw, npairs;
@@ -153,13 +152,25 @@ k_recompute_cols(const ColArgs a) {
     const uint32_t p0 = a.colstart[k0], npk = a.colstart[k1] - p0;
     const uint32_t it0 = a.cstart[p0];
     const int64_t base = DO_T ? a.wbase[w] : 0;
-    // ---- stage A
-    for (uint32_t ri = r0 + lane; ri < r1; ri += 32) {
-      const uint32_t el = a.rsrc[ri] / ND;
-      const double *g = a.eg + (size_t)el * EG;
-      double *o = sG + (size_t)(ri - r0) * EGP;
+    // ---- stage A (EG/2 lanes per geometry row when EG is even: few 128-byte lines per load instruction)
+    if (EG % 2 == 0) {
+      constexpr int PARTS = EG / 2 > 0 ? EG / 2 : 1;
+      for (uint32_t idx = lane; idx < (r1 - r0) * PARTS; idx += 32) {
+        const uint32_t row = idx / PARTS, part = idx - row * PARTS;
+        const uint32_t el = a.rsrc[r0 + row] / ND;
+        const double2 v = *reinterpret_cast<const double2 *>(a.eg + (size_t)el * EG + 2 * part);
+        double *o = sG + (size_t)row * EGP + 2 * part;
+        o[0] = v.x;
+        o[1] = v.y;
+      }
+    } else {
+      for (uint32_t ri = r0 + lane; ri < r1; ri += 32) {
+        const uint32_t el = a.rsrc[ri] / ND;
+        const double *g = a.eg + (size_t)el * EG;
+        double *o = sG + (size_t)(ri - r0) * EGP;
 #pragma unroll
-      for (int k = 0; k < EG; ++k) o[k] = g[k];
+        for (int k = 0; k < EG; ++k) o[k] = g[k];
+      }
     }
     for (uint32_t q = lane; q <= npk; q += 32) scs[q] = a.cstart[p0 + q] - it0;
     shid[lane] = 0xffffffffu;
@@ -171,25 +182,41 @@ k_recompute_cols(const ColArgs a) {
     double acc[ACC];
 #pragma unroll
     for (int m = 0; m < ACC; ++m) acc[m] = 0.0;
+    // Pair metadata is fetched into registers when the lane STARTS a pair it owns, the U values one
+    // contribution later (their address depends on the row node): by the time the pair is flushed the
+    // loads have landed instead of stalling the flush.
+    uint4 rec = make_uint4(0, 0, 0, 0);  // kept packed until the flush: unpacking would wait for the load
+    double u[Q];
+    bool need_u = false;
+#pragma unroll
+    for (int b = 0; b < Q; ++b) u[b] = 0.0;
+    auto fetch_meta = [&](uint32_t qq) {
+      rec = a.prec[p0 + qq];  // one 16-byte load
+      need_u = DO_R;
+    };
+    auto fetch_u = [&]() {
+#pragma unroll
+      for (int aa = 0; aa < Q; ++aa) u[aa] = a.U ? a.U[(int32_t)rec.w + aa] : 0.0;
+      need_u = false;
+    };
     // flush of a COMPLETE pair sum held in acc
-    auto flush = [&](uint32_t q) {
-      const uint32_t p = p0 + q;
+    auto flush = [&](uint32_t qq) {
       if (DO_T) {
-        const unsigned m = a.pmask[p];
+        const uint32_t po[3] = {rec.x, rec.x + (rec.y & 0xfffffu), rec.x + rec.z};
+        const unsigned pm = rec.y >> 20;
 #pragma unroll
         for (int b = 0; b < Q; ++b) {
-          double *dst = a.pr + (base + a.poff[(size_t)b * a.npairs + p]);
+          double *dst = a.pr + (base + po[b]);
+          const unsigned mb = (pm >> (b * Q)) & ((1u << Q) - 1);
 #pragma unroll
           for (int aa = 0; aa < Q; ++aa)
-            if (m & (1u << (b * Q + aa)))
-              *dst++ = RF == RF_ELAST ? acc[RF == RF_ELAST ? b * Q + aa : 0] : (aa == b ? acc[0] : 0.0);
+            if (mb & (1u << aa))
+              dst[__popc(mb & ((1u << aa) - 1))] =
+                  RF == RF_ELAST ? acc[RF == RF_ELAST ? b * Q + aa : 0] : (aa == b ? acc[0] : 0.0);
         }
       }
       if (DO_R) {
-        const int32_t I = a.pI[p];
-        double u[Q];
-#pragma unroll
-        for (int aa = 0; aa < Q; ++aa) u[aa] = a.U ? a.U[I + aa] : 0.0;
+        if (need_u) fetch_u();
 #pragma unroll
         for (int b = 0; b < Q; ++b) {
           double s2 = 0;
@@ -199,15 +226,13 @@ k_recompute_cols(const ColArgs a) {
           } else {
             s2 = acc[0] * u[b];
           }
-          rp[(size_t)q * Q + b] = s2;
+          rp[(size_t)qq * Q + b] = s2;
         }
       }
     };
-    uint32_t q = 0;           // current pair (relative)
+    uint32_t q = 0;                // current pair (relative)
     uint32_t tailq = 0xffffffffu;  // pair whose first part ends my run and continues in the next lanes
-    double tail[ACC];
-#pragma unroll
-    for (int m = 0; m < ACC; ++m) tail[m] = 0.0;
+    unsigned dnext = 0;
     if (tb < te) {
       // pair containing contribution tb: largest q with scs[q] <= tb
       uint32_t lo = 0, hi = npk;
@@ -216,10 +241,14 @@ k_recompute_cols(const ColArgs a) {
         if (scs[mid] <= tb) lo = mid; else hi = mid;
       }
       q = lo;
+      dnext = a.cdesc[(size_t)it0 + tb];
+      if (scs[q] >= tb) fetch_meta(q);
     }
     uint32_t qend = (tb < te) ? scs[q + 1] : 0;
     for (uint32_t t = tb; t < te; ++t) {
-      const unsigned d = a.cdesc[(size_t)it0 + t];
+      const unsigned d = dnext;
+      if (t + 1 < te) dnext = a.cdesc[(size_t)it0 + t + 1];
+      if (DO_R && need_u && t > tb) fetch_u();
       const int i = d & 31, j = (d >> 5) & 31;
       const double *G = sG + (size_t)(d >> 10) * EGP;
       const double *M = sM + (j * ND + i) * MT;
@@ -269,21 +298,20 @@ k_recompute_cols(const ColArgs a) {
           shid[lane] = q;
 #pragma unroll
           for (int m = 0; m < ACC; ++m) sH[lane * HS + m] = acc[m];
-        } else {  // began here, continues: I own it, the rest arrives as head parts
+        } else {  // began here, continues: I own it (its metadata stays in registers), the rest arrives as head parts
           tailq = q;
-#pragma unroll
-          for (int m = 0; m < ACC; ++m) tail[m] = acc[m];
         }
+        if (t + 1 < te) {
 #pragma unroll
-        for (int m = 0; m < ACC; ++m) acc[m] = 0.0;
-        ++q;
-        qend = (q < npk) ? scs[q + 1] : 0xffffffffu;
+          for (int m = 0; m < ACC; ++m) acc[m] = 0.0;
+          ++q;
+          qend = scs[q + 1];
+          fetch_meta(q);
+        }
       }
     }
     __syncwarp();
-    if (tailq != 0xffffffffu) {
-#pragma unroll
-      for (int m = 0; m < ACC; ++m) acc[m] = tail[m];
+    if (tailq != 0xffffffffu) {  // acc still holds my (first) part of the pair
       for (int l2 = lane + 1; l2 < 32 && shid[l2] == tailq; ++l2) {
 #pragma unroll
         for (int m = 0; m < ACC; ++m) acc[m] += sH[l2 * HS + m];
@@ -322,8 +350,9 @@ __global__ void k_col_plan(const uint32_t *__restrict__ wcol, const uint32_t *__
                            const uint32_t *__restrict__ csrc, const uint32_t *__restrict__ rstart,
                            const uint32_t *__restrict__ rpos, const int32_t *__restrict__ pJ,
                            const int64_t *__restrict__ jc, const uint32_t *__restrict__ prel, int nd, int64_t ncol,
-                           int64_t npairs, uint16_t *__restrict__ cdesc, uint32_t *__restrict__ poff,
-                           int64_t *__restrict__ wbase, int *__restrict__ err) {
+                           int64_t npairs, const int32_t *__restrict__ pI, const uint16_t *__restrict__ pmask,
+                           uint16_t *__restrict__ cdesc, uint4 *__restrict__ prec, int64_t *__restrict__ wbase,
+                           int *__restrict__ err) {
   const int nb = nd * nd;
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < ncol; k += (int64_t)gridDim.x * blockDim.x) {
     const uint32_t w = colw[k], kf = wcol[w];
@@ -332,11 +361,14 @@ __global__ void k_col_plan(const uint32_t *__restrict__ wcol, const uint32_t *__
     if (k == kf) wbase[w] = base;
     for (uint32_t p = colstart[k]; p < colstart[k + 1]; ++p) {
       const int32_t J = pJ[p];
-      for (int b = 0; b < Q; ++b) {
-        const int64_t off = jc[J + b] + prel[(size_t)b * npairs + p] - base;
-        if (off < 0 || off >= (int64_t(1) << 32)) *err = 1;
-        poff[(size_t)b * npairs + p] = (uint32_t)off;
-      }
+      int64_t off[3] = {0, 0, 0};
+      for (int b = 0; b < Q; ++b) off[b] = jc[J + b] + prel[(size_t)b * npairs + p] - base;
+      const int64_t d1 = off[1] - off[0], d2 = off[2] - off[0];
+      if (off[0] < 0 || off[0] >= (int64_t(1) << 32) || (Q > 1 && (d1 < 0 || d1 >= (1 << 20))) ||
+          (Q > 2 && (d2 < 0 || d2 >= (int64_t(1) << 32))) || pmask[p] >= (1u << 12))
+        *err = 1;
+      prec[p] = make_uint4((uint32_t)off[0], (uint32_t)(Q > 1 ? d1 : 0) | ((uint32_t)pmask[p] << 20),
+                           (uint32_t)(Q > 2 ? d2 : 0), (uint32_t)pI[p]);
       for (uint32_t s = cstart[p]; s < cstart[p + 1]; ++s) {
         const uint32_t c = csrc[s];
         const uint32_t el = c / nb, r = c - el * nb;
@@ -441,7 +473,7 @@ void recompute_prepare(gfgpu_term *t) {
   t->rc_wcol.upload(wcol.data());
   t->rc_wbase.alloc(ctx, t->rc_nw);
   t->rc_cdesc.alloc(ctx, st.ncontrib);
-  t->rc_poff.alloc(ctx, (size_t)t->fem->qdim * st.npairs);
+  t->rc_prec.alloc(ctx, st.npairs);
   {
     DevBuf<uint32_t> colw, rpos;
     colw.alloc(ctx, st.ncolnodes);
@@ -456,8 +488,9 @@ void recompute_prepare(gfgpu_term *t) {
 #define GF_PLAN(QQ)                                                                                               \
   k_col_plan<QQ><<<grid(st.ncolnodes), B, 0, ctx->stream>>>(t->rc_wcol.p, colw.p, st.colstart.p, st.cstart.p,      \
                                                             st.csrc.p, st.rstart.p, rpos.p, st.pJ.p, t->jc.p,      \
-                                                            t->prel.p, nd, st.ncolnodes, st.npairs, t->rc_cdesc.p, \
-                                                            t->rc_poff.p, t->rc_wbase.p, (int *)t->flag.p)
+                                                            t->prel.p, nd, st.ncolnodes, st.npairs, st.pI.p,       \
+                                                            t->pmask.p, t->rc_cdesc.p, (uint4 *)t->rc_prec.p,      \
+                                                            t->rc_wbase.p, (int *)t->flag.p)
     if (t->fem->qdim == 1) GF_PLAN(1);
     else if (t->fem->qdim == 2) GF_PLAN(2);
     else GF_PLAN(3);
@@ -480,7 +513,7 @@ static void launch_cols(gfgpu_term *t, const double *U, bool do_t, bool do_r) {
   ColArgs a;
   a.wcol = t->rc_wcol.p; a.wbase = t->rc_wbase.p; a.rstart = st.rstart.p; a.rsrc = st.rsrc.p; a.rdof = st.rdof.p;
   a.colstart = st.colstart.p; a.cstart = st.cstart.p; a.cdesc = t->rc_cdesc.p;
-  a.pI = st.pI.p; a.pmask = t->pmask.p; a.poff = t->rc_poff.p;
+  a.prec = (const uint4 *)t->rc_prec.p;
   a.eg = t->rc_eg.p; a.Mtab = t->rc_M.p; a.U = U;
   a.lambda = t->par[0]; a.mu = t->par[1];
   a.nw = t->rc_nw; a.npairs = st.npairs;
