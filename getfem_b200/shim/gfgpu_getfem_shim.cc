@@ -1,0 +1,275 @@
+// gfgpu_getfem_shim.cc -- see gfgpu_getfem_shim.h.
+#include "gfgpu_getfem_shim.h"
+
+#include <chrono>
+#include <regex>
+#include <sstream>
+
+#include "getfem/getfem_fem.h"
+#include "getfem/getfem_generic_assembly_tree.h"
+#include "getfem/getfem_integration.h"
+#include "getfem/getfem_mesh_fem.h"
+#include "getfem/getfem_mesh_im.h"
+
+namespace getfem_b200 {
+
+using getfem::size_type;
+
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+#define GFGPU_CALL(call) GMM_ASSERT1((call) == 0, "gfgpu: " << gfgpu_last_error())
+
+static std::string strip(const std::string &s) {
+  std::string r;
+  for (char c : s)
+    if (c != ' ' && c != '\t' && c != '\n') r.push_back(c);
+  return r;
+}
+
+bool recognise_tree(const getfem::ga_workspace &ws, size_type itree, recognised_term &out) {
+  const getfem::ga_workspace::tree_description &td = ws.tree_info(itree);
+  if (td.order != 1 || td.operation != getfem::ga_workspace::ASSEMBLY) return false;
+  const std::string s = strip(getfem::ga_tree_to_string(*td.ptree));
+  const std::string v = td.name_test1;
+  const std::string ID = "([A-Za-z_][A-Za-z_0-9]*)";
+  const std::string I3 = "\\[\\[1,0,0\\],\\[0,1,0\\],\\[0,0,1\\]\\]", I2 = "\\[\\[1,0\\],\\[0,1\\]\\]";
+  const std::string Idm = "(?:" + I3 + "|" + I2 + ")";
+  std::smatch m;
+  auto scalar = [&](const std::string &name) {
+    GMM_ASSERT1(ws.is_constant(name) && ws.value(name).size() == 1, "gfgpu: '" << name << "' must be a scalar constant");
+    return ws.value(name)[0];
+  };
+  out.varname = v;
+  out.params.clear();
+  if (std::regex_match(s, m, std::regex("\\(" + ID + "\\*Grad_" + v + "\\)[.:]Grad_Test_" + v))) {
+    out.family = GFGPU_LAPLACE; out.params = {scalar(m[1])}; return true;
+  }
+  if (std::regex_match(s, std::regex("Grad_" + v + "[.:]Grad_Test_" + v))) {
+    out.family = GFGPU_LAPLACE; out.params = {1.0}; return true;
+  }
+  if (std::regex_match(s, m, std::regex("\\(" + ID + "\\*" + v + "\\)\\.Test_" + v))) {
+    out.family = GFGPU_MASS; out.params = {scalar(m[1])}; return true;
+  }
+  if (std::regex_match(s, std::regex(v + "\\.Test_" + v))) {
+    out.family = GFGPU_MASS; out.params = {1.0}; return true;
+  }
+  if (std::regex_match(s, m, std::regex("\\(\\(Div_" + v + "\\*\\(" + ID + "\\*" + Idm + "\\)\\)\\+\\(\\(2\\*" + ID +
+                                        "\\)\\*\\(Sym\\(Grad_" + v + "\\)\\)\\)\\):Grad_Test_" + v))) {
+    out.family = GFGPU_ELASTICITY; out.params = {scalar(m[1]), scalar(m[2])}; return true;
+  }
+  if (std::regex_match(s, m, std::regex("\\(\\(" + ID + "\\*Div_" + v + "\\)\\*Div_Test_" + v + "\\)\\+\\(\\(\\(2\\*" + ID +
+                                        "\\)\\*\\(Sym\\(Grad_" + v + "\\)\\)\\):Grad_Test_" + v + "\\)"))) {
+    out.family = GFGPU_ELASTICITY; out.params = {scalar(m[1]), scalar(m[2])}; return true;
+  }
+  if (std::regex_match(s, m, std::regex("\\(\\(" + I3 + "\\+Grad_" + v + "\\)\\*" + ID + "_PK2\\(Grad_" + v + "," + ID +
+                                        "\\)\\):Grad_Test_" + v))) {
+    const std::string law = m[1];
+    if (law == "Saint_Venant_Kirchhoff") out.family = GFGPU_SVK;
+    else if (law == "Compressible_Neo_Hookean_Ciarlet") out.family = GFGPU_NEOHOOKEAN_CIARLET;
+    else if (law == "Compressible_Neo_Hookean_Bonet") out.family = GFGPU_NEOHOOKEAN_BONET;
+    else return false;
+    const std::string pn = m[2];
+    GMM_ASSERT1(ws.is_constant(pn) && ws.value(pn).size() == 2, "gfgpu: wrong parameters for " << law);
+    out.params = {ws.value(pn)[0], ws.value(pn)[1]};
+    return true;
+  }
+  return false;
+}
+
+struct device_assembler::entry {
+  gfgpu_mesh *mesh = nullptr;
+  gfgpu_fem *fem = nullptr;
+  gfgpu_tables *tab = nullptr;
+  gfgpu_term *term = nullptr;
+  size_type ndof = 0;
+  std::vector<int64_t> jc;
+  std::vector<int32_t> ir;
+  int64_t generation = -1;
+  ~entry() {
+    gfgpu_term_destroy(term);
+    gfgpu_tables_destroy(tab);
+    gfgpu_fem_destroy(fem);
+    gfgpu_mesh_destroy(mesh);
+  }
+};
+
+device_assembler::device_assembler(int device) { GFGPU_CALL(gfgpu_ctx_create(device, nullptr, &ctx_)); }
+device_assembler::~device_assembler() {
+  cache_.clear();
+  gfgpu_ctx_destroy(ctx_);
+}
+
+// parses "FEM_PK(3,2)" / "FEM_QK(3,2)" / "GT_PK(3,1)"; returns false on anything else
+static bool parse_kind(const std::string &name, const char *prefix, bool &qk, int &dim, int &deg) {
+  std::smatch m;
+  if (!std::regex_match(name, m, std::regex(std::string(prefix) + "_(PK|QK)\\((\\d+),(\\d+)\\)"))) return false;
+  qk = m[1] == "QK";
+  dim = std::stoi(m[2]);
+  deg = std::stoi(m[3]);
+  return true;
+}
+
+void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
+  GMM_ASSERT1(order == 1 || order == 2, "gfgpu: only assembly orders 1 and 2 run on the device");
+  double t0 = now_s();
+  // ---- every order-1 tree must be a recognised family (the order-2 trees are their derivatives)
+  std::vector<std::pair<size_type, recognised_term>> terms;
+  for (size_type i = 0; i < ws.nb_trees(); ++i) {
+    const auto &td = ws.tree_info(i);
+    if (td.order == 0) continue;
+    GMM_ASSERT1(td.operation == getfem::ga_workspace::ASSEMBLY, "gfgpu: assignments are not handled");
+    if (td.order == 2) {
+      GMM_ASSERT1(td.name_test1 == td.name_test2, "gfgpu: coupled terms (" << td.name_test1 << ", " << td.name_test2
+                                                                           << ") are not handled by the device path");
+      continue;
+    }
+    recognised_term rt;
+    GMM_ASSERT1(recognise_tree(ws, i, rt), "gfgpu: expression not handled by the device path (no CPU fallback): "
+                                               << getfem::ga_tree_to_string(*td.ptree));
+    terms.emplace_back(i, rt);
+  }
+  GMM_ASSERT1(!terms.empty(), "gfgpu: nothing to assemble");
+  t_extract = t_device = t_fill = 0;
+
+  const size_type nprim = ws.nb_primary_dof() ? ws.nb_primary_dof() : 0;
+  for (auto &it : terms) {
+    const auto &td = ws.tree_info(it.first);
+    const recognised_term &rt = it.second;
+    const getfem::mesh_fem *pmf = ws.associated_mf(rt.varname);
+    GMM_ASSERT1(pmf && !pmf->is_reduced(), "gfgpu: the variable must live on a non-reduced mesh_fem");
+    const getfem::mesh_fem &mf = *pmf;
+    const getfem::mesh_im &mim = *td.mim;
+    const getfem::mesh &m = mf.linked_mesh();
+    GMM_ASSERT1(td.rg && td.rg->id() == getfem::mesh_region::all_convexes().id(),
+                "gfgpu: only mesh_region::all_convexes() is handled");
+    const gmm::sub_interval &I = ws.interval_of_variable(rt.varname);
+    const size_type ndof = mf.nb_dof();  // triggers enumerate_dof
+    GMM_ASSERT1(m.convex_index().card() > 0 && m.convex_index().card() == m.convex_index().last_true() + 1,
+                "gfgpu: convex ids must be contiguous (call mesh::optimize_structure)");
+    const size_type ne = m.convex_index().card(), cv0 = 0;
+    // uniform classical Lagrange fem / degree-1 geometric transformation / one approximate im
+    getfem::pfem pf = mf.fem_of_element(cv0);
+    bgeot::pgeometric_trans pgt = m.trans_of_convex(cv0);
+    getfem::pintegration_method pim = mim.int_method_of_element(cv0);
+    GMM_ASSERT1(pim->type() == getfem::IM_APPROX, "gfgpu: exact integration methods are not handled");
+    for (dal::bv_visitor cv(m.convex_index()); !cv.finished(); ++cv)
+      GMM_ASSERT1(mf.fem_of_element(cv) == pf && m.trans_of_convex(cv) == pgt && mim.int_method_of_element(cv) == pim,
+                  "gfgpu: mixed fems / transformations / integration methods are not handled");
+    bool fqk, gqk;
+    int fdim, fdeg, gdim, gdeg;
+    GMM_ASSERT1(parse_kind(getfem::name_of_fem(pf), "FEM", fqk, fdim, fdeg),
+                "gfgpu: fem not handled: " << getfem::name_of_fem(pf));
+    GMM_ASSERT1(parse_kind(bgeot::name_of_geometric_trans(pgt), "GT", gqk, gdim, gdeg) && gdeg == 1 && gqk == fqk,
+                "gfgpu: geometric transformation not handled: " << bgeot::name_of_geometric_trans(pgt));
+    const int dim = int(m.dim()), Q = int(mf.get_qdim());
+    const size_type nd = pf->nb_dof(cv0), ng = pgt->nb_points();
+    getfem::papprox_integration pai = pim->approx_method();
+    const size_type nq = pai->nb_points_on_convex();
+
+    std::ostringstream key;
+    key << &m << "/" << &mf << "/" << &mim << "/" << rt.family << "/" << ne << "/" << ndof << "/" << fdeg << "/"
+        << getfem::name_of_int_method(pim);
+    for (double p : rt.params) key << "/" << p;
+    std::unique_ptr<entry> &pe = cache_[key.str()];
+    if (!pe) {
+      pe.reset(new entry);
+      entry &e = *pe;
+      e.ndof = ndof;
+      // mesh (basic_mesh::points_of_convex / ind_points_of_convex)
+      const size_type npts = m.points_index().last_true() + 1;
+      std::vector<double> pts(npts * dim, 0.0);
+      for (dal::bv_visitor p(m.points_index()); !p.finished(); ++p)
+        for (int d = 0; d < dim; ++d) pts[p * dim + d] = m.points()[p][d];
+      std::vector<int32_t> conn(ne * ng);
+      std::vector<int64_t> edof(ne * nd);
+      for (size_type cv = 0; cv < ne; ++cv) {
+        for (size_type i = 0; i < ng; ++i) conn[cv * ng + i] = int32_t(m.ind_points_of_convex(cv)[i]);
+        const auto &ct = mf.ind_scalar_basic_dof_of_element(cv);
+        for (size_type i = 0; i < nd; ++i) edof[cv * nd + i] = int64_t(ct[i]);
+      }
+      // reference tables at the volume quadrature points (geotrans_precomp_ / fem_precomp_)
+      bgeot::pstored_point_tab pspt = pai->pintegration_points();
+      getfem::pfem_precomp pfp = getfem::fem_precomp(pf, pspt, 0);
+      bgeot::pgeotrans_precomp pgp = bgeot::geotrans_precomp(pgt, pspt, 0);
+      std::vector<double> w(nq), gtg(nq * ng * dim), phi(nq * nd), gphi(nq * nd * dim);
+      for (size_type q = 0; q < nq; ++q) {
+        w[q] = pai->coeff(q);
+        const bgeot::base_matrix &pc = pgp->grad(q);
+        for (size_type i = 0; i < ng; ++i)
+          for (int d = 0; d < dim; ++d) gtg[(q * ng + i) * dim + d] = pc(i, d);
+        const bgeot::base_tensor &bv = pfp->val(q), &bg = pfp->grad(q);
+        for (size_type i = 0; i < nd; ++i) {
+          phi[q * nd + i] = bv[i];
+          for (int d = 0; d < dim; ++d) gphi[(q * nd + i) * dim + d] = bg[i + nd * d];
+        }
+      }
+      GFGPU_CALL(gfgpu_mesh_create(ctx_, dim, int64_t(npts), pts.data(), int64_t(ne), int(ng), conn.data(),
+                                   gqk ? GFGPU_GT_QK : GFGPU_GT_PK, &e.mesh));
+      GFGPU_CALL(gfgpu_fem_create(ctx_, e.mesh, fqk ? GFGPU_FEM_QK : GFGPU_FEM_PK, fdeg, Q, int(nd), edof.data(),
+                                  int64_t(ndof), &e.fem));
+      GFGPU_CALL(gfgpu_tables_create(ctx_, dim, int(nq), int(ng), int(nd), w.data(), gtg.data(), phi.data(), gphi.data(),
+                                     &e.tab));
+      const double alpha = ws.factor_of_variable(rt.varname);
+      GFGPU_CALL(gfgpu_term_create(ctx_, e.mesh, e.fem, e.tab, rt.family, rt.params.data(), int(rt.params.size()),
+                                   order == 2 ? alpha * alpha : alpha, GFGPU_STRATEGY_AUTO, &e.term));
+    }
+    entry &e = *pe;
+    // the variable's values, in the fem's own numbering (the workspace interval only offsets the result)
+    const getfem::model_real_plain_vector &U = ws.value(rt.varname);
+    GMM_ASSERT1(U.size() == ndof, "gfgpu: bad size of the variable's value vector");
+    double t1 = now_s();
+    t_extract += t1 - t0;
+
+    if (order == 1) {
+      std::vector<double> R(ndof);
+      GFGPU_CALL(gfgpu_term_assemble_host(e.term, U.data(), GFGPU_RESIDUAL, nullptr, R.data()));
+      double t2 = now_s();
+      t_device += t2 - t1;
+      getfem::base_vector &V = ws.assembled_vector();
+      if (V.size() < I.first() + ndof) V.resize(std::max<size_type>(nprim, I.first() + ndof), 0.0);
+      for (size_type d = 0; d < ndof; ++d) V[I.first() + d] += R[d];
+      t_fill += now_s() - t2;
+    } else {
+      GFGPU_CALL(gfgpu_term_assemble_host(e.term, U.data(), GFGPU_TANGENT, nullptr, nullptr));
+      const int64_t nnz = gfgpu_term_nnz(e.term);
+      if (gfgpu_term_pattern_generation(e.term) != e.generation) {
+        e.jc.resize(ndof + 1);
+        e.ir.resize(size_t(nnz));
+        GFGPU_CALL(gfgpu_term_export_csc_host(e.term, e.jc.data(), e.ir.data(), nullptr));
+        e.generation = gfgpu_term_pattern_generation(e.term);
+      }
+      std::vector<double> pr((size_t)nnz, 0.0);
+      GFGPU_CALL(gfgpu_term_export_csc_host(e.term, nullptr, nullptr, pr.data()));
+      double t2 = now_s();
+      t_device += t2 - t1;
+      // fill gmm::col_matrix<rsvector>: each column is a row-sorted vector of (index, value)
+      // (gmm_vector.h:913-1030).  Empty columns take the device column as is; otherwise add.
+      getfem::model_real_sparse_matrix &K = ws.assembled_matrix();
+      const size_type need = std::max<size_type>(nprim, I.first() + ndof);
+      if (gmm::mat_nrows(K) < need || gmm::mat_ncols(K) < need) gmm::resize(K, need, need);
+      const size_type off = I.first();
+      for (size_type j = 0; j < ndof; ++j) {
+        gmm::rsvector<double> &col = K[off + j];
+        const int64_t b = e.jc[j], en = e.jc[j + 1];
+        if (col.nb_stored() == 0) {
+          col.base_resize(size_type(en - b));
+          auto itc = col.begin();
+          for (int64_t k = b; k < en; ++k, ++itc) { itc->c = off + size_type(e.ir[size_t(k)]); itc->e = pr[size_t(k)]; }
+        } else {
+          for (int64_t k = b; k < en; ++k) col.w(off + size_type(e.ir[size_t(k)]), col.r(off + size_type(e.ir[size_t(k)])) + pr[size_t(k)]);
+        }
+      }
+      t_fill += now_s() - t2;
+    }
+    t0 = now_s();
+  }
+}
+
+void assembly(getfem::ga_workspace &ws, size_type order, int device) {
+  device_assembler a(device);
+  a.assembly(ws, order);
+}
+
+}  // namespace getfem_b200

@@ -1,0 +1,56 @@
+// gfgpu_getfem_shim.h -- drop-in device path for getfem::ga_workspace::assembly().
+//
+// Compiled against the UNMODIFIED GetFEM headers (it is the code a GetFEM maintainer would add next
+// to src/getfem_generic_assembly_workspace.cc).  Everything it needs from GetFEM
+// goes through public accessors; everything it asks of the GPU goes through the C ABI of
+// include/gfgpu.h.  No CPU fallback: an expression, fem or integration method the device path does
+// not cover raises gmm::gmm_error (GMM_ASSERT1), exactly like any other unsupported GWFL construct.
+#ifndef GFGPU_GETFEM_SHIM_H
+#define GFGPU_GETFEM_SHIM_H
+
+#include <map>
+#include <memory>
+#include <string>
+
+#include "getfem/getfem_generic_assembly.h"
+#include "gfgpu.h"
+
+namespace getfem_b200 {
+
+struct recognised_term {
+  int family;             // GFGPU_LAPLACE ...
+  std::string varname;    // the fem variable (Test and Test2)
+  std::vector<double> params;
+};
+
+// Matches the ORDER-1 tree of `ws` number `itree` (as printed by ga_tree_to_string after the
+// reference's semantic analysis) against the families of include/gfgpu.h.  Returns false if unknown.
+bool recognise_tree(const getfem::ga_workspace &ws, getfem::size_type itree, recognised_term &out);
+
+// Device-side state of one (mesh, mesh_fem, mesh_im, term); reusable across Newton iterations.
+class device_assembler {
+ public:
+  explicit device_assembler(int device = 0);
+  ~device_assembler();
+  device_assembler(const device_assembler &) = delete;
+  device_assembler &operator=(const device_assembler &) = delete;
+
+  // Same contract as getfem::ga_workspace::assembly(order) for order 1 and 2
+  // (src/getfem_generic_assembly_workspace.cc:791-936): results are ADDED into
+  // ws.assembled_vector() / ws.assembled_matrix(), which are sized first if needed.
+  void assembly(getfem::ga_workspace &ws, getfem::size_type order);
+
+  // seconds spent in the last call: extraction of GetFEM data, device work, fill of the gmm containers
+  double t_extract = 0, t_device = 0, t_fill = 0;
+
+ private:
+  struct entry;
+  gfgpu_ctx *ctx_ = nullptr;
+  std::map<std::string, std::unique_ptr<entry>> cache_;
+};
+
+// One-shot convenience: getfem_b200::assembly(ws, 2) instead of ws.assembly(2).
+void assembly(getfem::ga_workspace &ws, getfem::size_type order, int device = 0);
+
+}  // namespace getfem_b200
+#endif

@@ -1,0 +1,121 @@
+// oracle/shim_test.cc -- TEST INFRASTRUCTURE.  In ONE process: the UNMODIFIED reference assembles with
+// ga_workspace::assembly() on the CPU, the drop-in shim (getfem_b200/shim) assembles the SAME workspace
+// description on the GPU through the C ABI, and the two gmm matrices / vectors are compared:
+// CSC pattern identical, relative Frobenius / l2 differences printed as JSON (tests/test_gpu_shim.py).
+#include <chrono>
+#include <cstdio>
+#include <map>
+#include <random>
+
+#include "getfem/getfem_generic_assembly.h"
+#include "getfem/getfem_mesh_fem.h"
+#include "getfem/getfem_mesh_im.h"
+#include "getfem/getfem_regular_meshes.h"
+#include "gfgpu_getfem_shim.h"
+#include "gmm/gmm_kernel.h"
+
+using getfem::size_type;
+
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int main(int argc, char **argv) {
+  std::map<std::string, std::string> a;
+  for (int i = 1; i < argc; ++i) {
+    std::string s(argv[i]);
+    size_t e = s.find('=');
+    if (e == std::string::npos) return 2;
+    a[s.substr(0, e)] = s.substr(e + 1);
+  }
+  auto geti = [&](const char *k, long d) { return a.count(k) ? std::stol(a[k]) : d; };
+  auto gets = [&](const char *k, const char *d) { return a.count(k) ? a[k] : std::string(d); };
+  const int dim = (int)geti("dim", 3), n = (int)geti("n", 4), K = (int)geti("k", 2), Q = (int)geti("q", 3);
+  const int imdeg = (int)geti("im", 4);
+  const std::string gt = gets("gt", "pk"), family = gets("family", "elast");
+  const double lambda = 1.3, mu = 0.7, acoef = 2.5;
+
+  getfem::mesh m;
+  std::vector<size_type> ns(dim, size_type(n));
+  bgeot::pgeometric_trans pgt = gt == "pk" ? bgeot::simplex_geotrans(dim, 1) : bgeot::parallelepiped_geotrans(dim, 1);
+  getfem::regular_unit_mesh(m, ns, pgt);
+  getfem::mesh_fem mf(m, getfem::dim_type(Q));
+  mf.set_classical_finite_element(getfem::dim_type(K));
+  getfem::mesh_im mim(m);
+  mim.set_integration_method(getfem::dim_type(imdeg));
+  const size_type ndof = mf.nb_dof();
+  std::vector<double> U(ndof);
+  if (family == "elast" || family == "laplace" || family == "mass") {
+    std::mt19937_64 rng(12345);
+    std::uniform_real_distribution<double> d(-1.0, 1.0);
+    for (auto &v : U) v = d(rng);
+  } else {
+    for (size_type d = 0; d < ndof; ++d) {
+      bgeot::base_node P = mf.point_of_basic_dof(d);
+      int k = int(d % Q);
+      U[d] = 0.03 * std::sin(2 * M_PI * P[(k + 1) % dim]) * std::cos(M_PI * P[k % dim]);
+    }
+  }
+  std::string expr;
+  if (family == "laplace") expr = "a*Grad_u:Grad_Test_u";
+  else if (family == "mass") expr = "a*u.Test_u";
+  else if (family == "elast") expr = "(Div_u*((lambda)*Id(meshdim))+(2*(mu))*Sym(Grad_u)):Grad_Test_u";
+  else {
+    std::string law = family == "svk" ? "Saint_Venant_Kirchhoff"
+                      : family == "nh_ciarlet" ? "Compressible_Neo_Hookean_Ciarlet" : "Compressible_Neo_Hookean_Bonet";
+    expr = "((Id(meshdim)+Grad_u)*(" + law + "_PK2(Grad_u,params))):Grad_Test_u";
+  }
+  const std::vector<double> c_a{acoef}, c_l{lambda}, c_m{mu}, c_p{lambda, mu};
+  auto setup = [&](getfem::ga_workspace &ws) {
+    ws.add_fem_variable("u", mf, gmm::sub_interval(0, ndof), U);
+    ws.add_fixed_size_constant("a", c_a);
+    ws.add_fixed_size_constant("lambda", c_l);
+    ws.add_fixed_size_constant("mu", c_m);
+    ws.add_fixed_size_constant("params", c_p);
+    ws.add_expression(expr, mim);
+  };
+  // ---- reference on the CPU
+  getfem::ga_workspace wr;
+  setup(wr);
+  double t0 = now_s();
+  wr.assembly(2);
+  double t_ref2 = now_s() - t0;
+  gmm::csc_matrix<double> Cr;
+  Cr.init_with(wr.assembled_matrix());
+  t0 = now_s();
+  wr.assembly(1);
+  double t_ref1 = now_s() - t0;
+  std::vector<double> Rr(wr.assembled_vector().begin(), wr.assembled_vector().end());
+  // ---- drop-in on the GPU (twice: the second call reuses the cached device state)
+  getfem::ga_workspace wg;
+  setup(wg);
+  getfem_b200::device_assembler dev(0);
+  t0 = now_s();
+  dev.assembly(wg, 2);
+  double t_gpu2_first = now_s() - t0;
+  gmm::csc_matrix<double> Cg;
+  Cg.init_with(wg.assembled_matrix());
+  gmm::clear(wg.assembled_matrix());
+  t0 = now_s();
+  dev.assembly(wg, 2);
+  double t_gpu2 = now_s() - t0;
+  const double te = dev.t_extract, td = dev.t_device, tf = dev.t_fill;
+  dev.assembly(wg, 1);
+  std::vector<double> Rg(wg.assembled_vector().begin(), wg.assembled_vector().end());
+
+  bool pattern_ok = Cr.nrows() == Cg.nrows() && Cr.jc.size() == Cg.jc.size() && Cr.ir.size() == Cg.ir.size();
+  if (pattern_ok)
+    for (size_t k = 0; k < Cr.jc.size() && pattern_ok; ++k) pattern_ok = Cr.jc[k] == Cg.jc[k];
+  if (pattern_ok)
+    for (size_t k = 0; k < Cr.ir.size() && pattern_ok; ++k) pattern_ok = Cr.ir[k] == Cg.ir[k];
+  double nK = 0, dK = 0, nR = 0, dR = 0;
+  if (pattern_ok)
+    for (size_t k = 0; k < Cr.pr.size(); ++k) { nK += Cr.pr[k] * Cr.pr[k]; dK += (Cr.pr[k] - Cg.pr[k]) * (Cr.pr[k] - Cg.pr[k]); }
+  for (size_type d = 0; d < ndof; ++d) { nR += Rr[d] * Rr[d]; dR += (Rr[d] - Rg[d]) * (Rr[d] - Rg[d]); }
+  std::printf("{\"family\": \"%s\", \"ne\": %zu, \"ndof\": %zu, \"nnz_ref\": %zu, \"nnz_gpu\": %zu, \"pattern_ok\": %s, "
+              "\"rel_K\": %.3e, \"rel_R\": %.3e, \"t_ref_asm2\": %.4f, \"t_ref_asm1\": %.4f, \"t_gpu_asm2_first\": %.4f, "
+              "\"t_gpu_asm2\": %.4f, \"t_extract\": %.4f, \"t_device\": %.4f, \"t_fill\": %.4f}\n",
+              family.c_str(), m.convex_index().card(), ndof, Cr.pr.size(), Cg.pr.size(), pattern_ok ? "true" : "false",
+              pattern_ok ? std::sqrt(dK / nK) : -1.0, std::sqrt(dR / nR), t_ref2, t_ref1, t_gpu2_first, t_gpu2, te, td, tf);
+  return pattern_ok ? 0 : 1;
+}
