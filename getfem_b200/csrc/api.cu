@@ -317,8 +317,8 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
       t->emask.release();  // constant-coefficient linear form: the pattern cannot move any more
     }
     if (!t->rc_ready) gf::recompute_prepare(t);
-    if (do_r) t->R.zero();
-    tic(4); gf::recompute_assemble(t, U_dev, do_t, do_r); toc(4);
+    if (do_r) { tic(2); gf::recompute_assemble(t, U_dev, false, true); toc(2); }
+    if (do_t) { tic(4); gf::recompute_assemble(t, U_dev, true, false); toc(4); }
     return;
   }
   if (do_t) {

@@ -171,13 +171,13 @@ struct gfgpu_term {
   bool rc_ready = false;
   gf::DevBuf<double> rc_M;      // reference tensors per (j,i)
   gf::DevBuf<double> rc_eg;     // per-element geometry
-  gf::DevBuf<uint16_t> rc_cdesc; // per contribution, (J, I, element) order: incidence slot << 10 | j << 5 | i
   struct alignas(16) PairRec { uint32_t x, y, z, w; };
-  gf::DevBuf<PairRec> rc_prec;   // per pair: packed CSC offsets (relative to the packet base), keep mask, row dof
-  gf::DevBuf<uint32_t> rc_wcol;  // column-node packets, one warp each
-  gf::DevBuf<int64_t> rc_wbase;  // CSC position of each packet
-  int64_t rc_nw = 0;
-  int rc_cap_inc = 0, rc_cap_pairs = 0;
+  gf::DevBuf<uint16_t> rc_dblob; // per long task (> 2 steps): descriptors of steps 0..9, [step][lane]
+  gf::DevBuf<PairRec> rc_prec;   // per (task, lane): packed CSC offsets (relative to the tile base), keep mask, row dof
+  gf::DevBuf<uint8_t> rc_hdr;    // TileHdr per tile (recompute_tiles.cu)
+  gf::DevBuf<uint32_t> rc_els;   // per tile: sorted distinct local element ids (stride rc_cap_inc)
+  int64_t rc_nt = 0, rc_ntask = 0;
+  int rc_cap_inc = 0, rc_cap_pairs = 0, rc_cap_slots = 0, rc_cap_tasks = 0, rc_cap_long = 0;
 };
 
 namespace gf {

@@ -1,0 +1,971 @@
+// recompute_tiles.cu -- strategy RECOMPUTE, tile kernel: tangent (and fused residual) of an
+// affine-geometry, constant-coefficient bilinear form assembled per NONZERO, no element matrix in HBM.
+//
+// Same mathematics as recompute.cu (reference tensors M^{ij}; SURVEY appendix B, getfem_models.cc:6112-6113,
+// bgeot_geometric_trans.h:462-468), different work decomposition:
+//
+//   tile  = a run of consecutive column nodes (<= cap_inc element incidences, <= cap_pairs node pairs).
+//           The tile's DISTINCT elements are staged once in shared memory (elasticity: sqrt(|alpha| J) B,
+//           9 doubles; Laplace: alpha a J B^T B, 6 doubles; mass: alpha a J) together with its pair records,
+//           by a producer warp (TMA bulk copies + LDGSTS gather on an mbarrier), double buffered.
+//   task  = 32 node pairs of the tile with (almost) the same number of contributions: the tile's pairs are
+//           counting-sorted by contribution count, so that one warp runs `cnt` steps with every lane busy and
+//           all lanes flush together (no divergence).  Lane = pair: the Q x Q block is accumulated in registers,
+//           one step = one (element, j, i) contribution = T += B~ M^{ji} B~^T (54 DFMA), operands from shared
+//           memory through a 16-bit descriptor (slot | j*nd+i) carried in the pair record.  Short pairs of a
+//           task are padded with a descriptor that points at an all-zero geometry slot (adds +0.0).
+//   flush = the elasticity combination lambda T + mu T^T + mu tr(T) I is applied ONCE per pair (it is linear),
+//           kept entries go straight to their CSC slots.
+//   The residual is a separate per-element kernel (r_e = K_e u_e through the same reference tensors) followed
+//   by the fixed-order per-node gather of scatter.cu.
+//
+// Every pair sums its contributions in ascending element order; results are bitwise reproducible.
+#include <cub/cub.cuh>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace gf {
+
+enum { TF_LAPLACE = 0, TF_ELAST = 1, TF_MASS = 2 };
+
+static int tf_of(int family) {
+  return family == GFGPU_LAPLACE ? TF_LAPLACE : family == GFGPU_ELASTICITY ? TF_ELAST : family == GFGPU_MASS ? TF_MASS : -1;
+}
+
+__host__ __device__ constexpr int tl_clog2(int v) {
+  int b = 0;
+  while ((1 << b) < v) ++b;
+  return b;
+}
+
+template <int N, int RF>
+struct TlCfg {
+  static constexpr int GSZ = RF == TF_ELAST ? N * N : RF == TF_LAPLACE ? N * (N + 1) / 2 : 1;  // doubles per element
+  static constexpr int MT = GSZ;                                                               // table entries per (j,i)
+  static constexpr int ACC = RF == TF_ELAST ? N * N : 1;
+};
+
+// ---------------------------------------------------------------- per-element geometry
+template <int N>
+__global__ void k_tile_geo(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+                           const int32_t *__restrict__ conn, int ng, const double *__restrict__ pc /* ng x N */,
+                           int64_t e0, int64_t ne, int rf, double scale, double *__restrict__ eg, int gsz) {
+  for (int64_t el = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; el < ne; el += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t *cv = conn + (e0 + el) * ng;
+    double K[N * N];
+#pragma unroll
+    for (int k = 0; k < N * N; ++k) K[k] = 0.0;
+    for (int i = 0; i < ng; ++i) {
+      const int32_t p = cv[i];
+      double g[3] = {x[p], y[p], N == 3 ? z[p] : 0.0};
+#pragma unroll
+      for (int c = 0; c < N; ++c)
+#pragma unroll
+        for (int r = 0; r < N; ++r) K[r + N * c] += g[r] * pc[i * N + c];
+    }
+    double B[N * N], J;  // B = K^-T, B(n,p) at n + N*p
+    if (N == 2) {
+      double d = K[0] * K[3] - K[1] * K[2], id = 1.0 / d;
+      B[0] = K[3] * id; B[2] = -K[1] * id; B[1] = -K[2] * id; B[3] = K[0] * id;
+      J = fabs(d);
+    } else {
+#define K_(i, j) K[(i) + 3 * (j)]
+      double c00 = K_(1, 1) * K_(2, 2) - K_(1, 2) * K_(2, 1);
+      double c10 = K_(1, 2) * K_(2, 0) - K_(1, 0) * K_(2, 2);
+      double c20 = K_(1, 0) * K_(2, 1) - K_(1, 1) * K_(2, 0);
+      double d = K_(0, 0) * c00 + K_(0, 1) * c10 + K_(0, 2) * c20, id = 1.0 / d;
+      B[0] = c00 * id; B[3] = c10 * id; B[6] = c20 * id;
+      B[1] = (K_(0, 2) * K_(2, 1) - K_(0, 1) * K_(2, 2)) * id;
+      B[4] = (K_(0, 0) * K_(2, 2) - K_(0, 2) * K_(2, 0)) * id;
+      B[7] = (K_(0, 1) * K_(2, 0) - K_(0, 0) * K_(2, 1)) * id;
+      B[2] = (K_(0, 1) * K_(1, 2) - K_(0, 2) * K_(1, 1)) * id;
+      B[5] = (K_(0, 2) * K_(1, 0) - K_(0, 0) * K_(1, 2)) * id;
+      B[8] = (K_(0, 0) * K_(1, 1) - K_(0, 1) * K_(1, 0)) * id;
+#undef K_
+      J = fabs(d);
+    }
+    double *o = eg + (size_t)el * gsz;
+    if (rf == TF_ELAST) {  // sqrt(|alpha| J) B : T~ = B~ M B~^T = |alpha| J B M B^T, the sign of alpha is applied at the flush
+      const double s = sqrt(fabs(scale) * J);
+#pragma unroll
+      for (int k = 0; k < N * N; ++k) o[k] = s * B[k];
+    } else if (rf == TF_LAPLACE) {  // scale*J * B^T B, upper triangle row by row
+      int k = 0;
+#pragma unroll
+      for (int p = 0; p < N; ++p)
+#pragma unroll
+        for (int q = p; q < N; ++q) {
+          double s = 0;
+#pragma unroll
+          for (int n = 0; n < N; ++n) s += B[n + N * p] * B[n + N * q];
+          o[k++] = scale * J * s;
+        }
+    } else {
+      o[0] = scale * J;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- plan
+struct alignas(16) TileHdr {
+  int64_t base;              // CSC position of the tile's first entry
+  uint32_t pair0, npairs;    // pair range (Structure order = CSC order)
+  uint32_t node0, nnodes;    // column-node range
+  uint32_t task0, ntasks;    // task range
+  uint32_t nel, n_long;      // distinct elements staged; tasks that need a descriptor blob (they come first)
+  uint32_t n_wide, r2_0;     // pairs with more than TL_INREC contributions (one task each); first blob (task units)
+  uint32_t pad0, pad1, pad2, pad3;
+};
+static_assert(sizeof(TileHdr) == 64, "TileHdr layout");
+
+__global__ void k_tile_base(TileHdr *__restrict__ hdr, int64_t nt, const int32_t *__restrict__ pJ,
+                            const int64_t *__restrict__ jc) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nt; k += (int64_t)gridDim.x * blockDim.x)
+    hdr[k].base = jc[pJ[hdr[k].pair0]];
+}
+
+// CTA per tile: sorted distinct local element ids of the tile's incidences -> els[tile*stride ..], hdr.nel
+__global__ void __launch_bounds__(128)
+k_tile_elements(TileHdr *__restrict__ hdr, const uint32_t *__restrict__ rstart, const uint32_t *__restrict__ rsrc, int nd,
+                int stride, uint32_t *__restrict__ els) {
+  extern __shared__ uint32_t sv[];  // P values + P flags
+  const int64_t tile = blockIdx.x;
+  const uint32_t n0 = hdr[tile].node0, n1 = n0 + hdr[tile].nnodes;
+  const uint32_t r0 = rstart[n0], n = rstart[n1] - r0;
+  int P = 32;
+  while (P < (int)n) P <<= 1;
+  uint32_t *flag = sv + P;
+  for (int k = threadIdx.x; k < P; k += blockDim.x) sv[k] = k < (int)n ? rsrc[r0 + k] / (uint32_t)nd : 0xffffffffu;
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1)
+    for (int stridek = size >> 1; stridek > 0; stridek >>= 1) {
+      for (int k = threadIdx.x; k < P; k += blockDim.x) {
+        const int partner = k ^ stridek;
+        if (partner > k) {
+          const bool up = (k & size) == 0;
+          const uint32_t a = sv[k], b = sv[partner];
+          if ((a > b) == up) { sv[k] = b; sv[partner] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int k = threadIdx.x; k < P; k += blockDim.x)
+    flag[k] = (sv[k] != 0xffffffffu && (k == 0 || sv[k] != sv[k - 1])) ? 1u : 0u;
+  __syncthreads();
+  // exclusive scan of the flags: each thread owns a contiguous chunk
+  __shared__ uint32_t part[128];
+  const int chunk = P / blockDim.x > 0 ? P / blockDim.x : 1;
+  const int c0 = threadIdx.x * chunk;
+  uint32_t s = 0;
+  if (c0 < P)
+    for (int k = c0; k < c0 + chunk; ++k) s += flag[k];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int k = 0; k < (int)blockDim.x; ++k) { const uint32_t v = part[k]; part[k] = run; run += v; }
+    hdr[tile].nel = run;
+  }
+  __syncthreads();
+  if (c0 < P) {
+    uint32_t pos = part[threadIdx.x];
+    for (int k = c0; k < c0 + chunk; ++k)
+      if (flag[k]) els[(size_t)tile * stride + pos++] = sv[k];
+  }
+}
+
+// Tasks of a tile, longest first:
+//   wide tasks   : one per pair with more than TL_INREC contributions (vertex-diagonal pairs): the warp spreads the
+//                  contributions over its lanes (lane l takes l, l+32, ...) and tree-reduces the accumulators;
+//   normal tasks : 32 pairs each of the remaining pairs sorted by contribution count (descending), lane = pair.
+constexpr int TL_INREC = 10;  // largest step count of a normal task = rows of a descriptor blob
+
+// CTA per tile: stable counting sort of the tile's pairs by contribution count (descending) -> sp_pair[pair0 ..],
+// number of wide pairs and of tasks that need a descriptor blob.
+__global__ void __launch_bounds__(256)
+k_tile_sort_pairs(TileHdr *__restrict__ hdr, const uint32_t *__restrict__ cstart, uint32_t *__restrict__ sp_pair,
+                  int *__restrict__ err) {
+  __shared__ uint32_t wh[8][256];
+  __shared__ uint32_t binbase[256];
+  const int64_t tile = blockIdx.x;
+  const TileHdr h = hdr[tile];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = threadIdx.x; k < 8 * 256; k += 256) (&wh[0][0])[k] = 0;
+  __syncthreads();
+  const uint32_t chunk = ((h.npairs + 8 * 32 - 1) / (8 * 32)) * 32;  // per warp, a multiple of 32
+  const uint32_t w0 = min(warp * chunk, h.npairs), w1 = min(w0 + chunk, h.npairs);
+  for (uint32_t i = w0 + lane; i < w1; i += 32) {
+    const uint32_t p = h.pair0 + i, cnt = cstart[p + 1] - cstart[p];
+    if (cnt > 255u) *err = 3;
+    atomicAdd(&wh[warp][255u - min(cnt, 255u)], 1u);
+  }
+  __syncthreads();
+  {  // thread k: total of bin k, then (after the scan over bins) the start of each warp inside the bin
+    uint32_t tot = 0;
+    for (int w = 0; w < 8; ++w) tot += wh[w][threadIdx.x];
+    binbase[threadIdx.x] = tot;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0, nwide = 0, ngt2 = 0;
+    for (int k = 0; k < 256; ++k) {  // bin k holds the pairs with 255-k contributions
+      const uint32_t v = binbase[k];
+      binbase[k] = run;
+      run += v;
+      if (255 - k > TL_INREC) nwide += v;
+      if (255 - k > 2) ngt2 += v;
+    }
+    hdr[tile].n_wide = nwide;
+    hdr[tile].n_long = nwide + (ngt2 > nwide ? (ngt2 - nwide + 31) / 32 : 0u);
+  }
+  __syncthreads();
+  {
+    uint32_t run = binbase[threadIdx.x];
+    for (int w = 0; w < 8; ++w) { const uint32_t v = wh[w][threadIdx.x]; wh[w][threadIdx.x] = run; run += v; }
+  }
+  __syncthreads();
+  uint32_t *out = sp_pair + h.pair0;
+  for (uint32_t i0 = w0; i0 < w1; i0 += 32) {
+    const uint32_t i = i0 + lane;
+    const bool act = i < w1;
+    uint32_t key = 0xffffu;
+    if (act) {
+      const uint32_t p = h.pair0 + i;
+      key = 255u - min(cstart[p + 1] - cstart[p], 255u);
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+    uint32_t b = 0;
+    if (act) b = wh[warp][key];
+    __syncwarp();
+    if (act) {
+      out[b + rank] = h.pair0 + i;
+      if (rank == 0) wh[warp][key] = b + __popc(peers);
+    }
+    __syncwarp();
+  }
+}
+
+// thread per task: owning tile
+__global__ void k_tile_task_owner(const TileHdr *__restrict__ hdr, int64_t nt, uint32_t *__restrict__ tk_tile) {
+  for (int64_t tile = blockIdx.x; tile < nt; tile += gridDim.x)
+    for (uint32_t k = threadIdx.x; k < hdr[tile].ntasks; k += blockDim.x) tk_tile[hdr[tile].task0 + k] = (uint32_t)tile;
+}
+
+// thread per (task, lane): pair record + descriptors.
+//   rec.x  = CSC offset of the column-component-0 piece (relative to the tile base, 20 bits)
+//   rec.y  = offset of the component-1 piece relative to x (20 bits) | keep mask << 20 | wide << 30 | valid << 31
+//   rec.z  = offset of the component-2 piece relative to x (20 bits) | steps of the task << 20
+//   rec.w  = descriptors of steps 0 and 1 (16 bits each)
+//   dblob  = tasks with more than 2 steps and wide tasks: descriptors as [step][lane] uint16, TL_INREC rows
+//            (640 bytes per task).  Wide task: lane l, row r = contribution r*32 + l of the pair; only lane 0 is valid.
+template <int Q>
+__global__ void k_tile_fill(const TileHdr *__restrict__ hdr, const uint32_t *__restrict__ tk_tile,
+                            const uint32_t *__restrict__ sp_pair, const uint32_t *__restrict__ els, int stride,
+                            const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ csrc,
+                            const int32_t *__restrict__ pJ, const uint16_t *__restrict__ pmask,
+                            const uint32_t *__restrict__ prel, const int64_t *__restrict__ jc, int64_t npairs, int nd,
+                            int cbits, uint32_t zslot, int64_t ntask, uint4 *__restrict__ rec,
+                            uint16_t *__restrict__ dblob, int *__restrict__ err) {
+  const uint32_t nb = nd * nd;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < ntask * 32;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t task = idx >> 5;
+    const uint32_t lane = (uint32_t)(idx & 31);
+    const uint32_t tile = tk_tile[task];
+    const TileHdr h = hdr[tile];
+    const uint32_t tkl = (uint32_t)(task - h.task0);
+    const bool wide = tkl < h.n_wide;
+    // sorted position of my pair, of the task's first (longest) pair
+    const uint32_t pos0 = wide ? tkl : h.n_wide + (tkl - h.n_wide) * 32;
+    const uint32_t pos = wide ? tkl : pos0 + lane;
+    const uint32_t pf = sp_pair[h.pair0 + pos0];
+    const uint32_t cntf = cstart[pf + 1] - cstart[pf];
+    const uint32_t steps = wide ? (cntf + 31) / 32 : cntf;
+    if (steps > (uint32_t)TL_INREC) *err = 4;
+    const uint32_t zdesc = (zslot << cbits) & 0xffffu;
+    uint32_t w0 = zdesc | (zdesc << 16);
+    uint16_t *bl = tkl < h.n_long ? dblob + ((size_t)h.r2_0 + tkl) * (TL_INREC * 32) + lane : nullptr;
+    if (!bl && steps > 2) *err = 5;
+    uint4 r = make_uint4(0, wide ? 0x40000000u : 0u, steps << 20, 0);
+    uint32_t cnt = 0, s0 = 0;
+    if (pos < h.npairs) {
+      const uint32_t p = sp_pair[h.pair0 + pos];
+      const int32_t J = pJ[p];
+      int64_t off[3] = {0, 0, 0};
+      for (int b = 0; b < Q; ++b) off[b] = jc[J + b] + prel[(size_t)b * npairs + p] - h.base;
+      const int64_t d1 = off[1] - off[0], d2 = off[2] - off[0];
+      const uint32_t m = pmask[p];
+      if (off[0] < 0 || off[0] >= (1 << 20) || (Q > 1 && (d1 < 0 || d1 >= (1 << 20))) ||
+          (Q > 2 && (d2 < 0 || d2 >= (1 << 20))) || m >= (1u << 9))
+        *err = 1;
+      r.x = (uint32_t)off[0];
+      r.y |= (uint32_t)(Q > 1 ? d1 : 0) | (m << 20) | ((!wide || lane == 0) ? 0x80000000u : 0u);
+      r.z |= (uint32_t)(Q > 2 ? d2 : 0);
+      s0 = cstart[p];
+      cnt = cstart[p + 1] - s0;
+    }
+    const uint32_t *te = els + (size_t)tile * stride;
+    for (uint32_t c = 0; c < (bl ? (uint32_t)TL_INREC : steps); ++c) {
+      const uint32_t ci = wide ? c * 32 + lane : c;  // contribution handled at step c
+      uint32_t d = zdesc;
+      if (ci < cnt && c < steps) {
+        const uint32_t ctr = csrc[s0 + ci];
+        const uint32_t el = ctr / nb, rr = ctr - el * nb;  // rr = j*nd + i
+        uint32_t lo = 0, hi = h.nel;                       // first position with te[pos] >= el
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (te[mid] < el) lo = mid + 1; else hi = mid;
+        }
+        if (lo >= h.nel || te[lo] != el) *err = 2;
+        d = (lo << cbits) | rr;
+      }
+      if (c < 2) w0 = (w0 & ~(0xffffu << (16 * c))) | (d << (16 * c));
+      if (bl) bl[c * 32] = (uint16_t)d;
+    }
+    r.w = w0;
+    rec[idx] = r;
+  }
+}
+
+// ---------------------------------------------------------------- the tangent kernel
+// Warp-specialised CTA, one per SM: TL_CW consumer warps + one producer warp, two tile buffers in shared memory.
+//   producer : per tile, one bulk async copy (TMA, mbarrier complete_tx) of the tile's pair records, one of its
+//              long-task descriptors, and an LDGSTS gather of the element geometry rows, all arriving on full[b];
+//   consumer : waits full[b], takes tasks (first one static, then a shared-memory counter, longest first), lane =
+//              pair, operands from shared memory only, kept entries stored straight to their CSC slots, then
+//              arrives on empty[b].  No __syncthreads in the steady state.
+struct TileArgs {
+  const TileHdr *hdr;
+  const uint32_t *els;
+  int els_stride;
+  const uint4 *rec;
+  const uint16_t *dblob;
+  const double *eg, *Mtab;
+  double sl, smu;  // sign(alpha) * lambda, sign(alpha) * mu (elasticity)
+  int64_t nt;
+  int zslot, cap_tasks, cap_long;
+  double *pr;
+  unsigned long long *trace;  // optional (GFGPU_TILE_TRACE): per-tile timestamps of CTA 0
+};
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long v;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
+  return v;
+}
+
+constexpr int TL_CW = 16;                        // consumer warps
+constexpr int TL_THREADS = (TL_CW + 1) * 32;     // + the producer warp
+constexpr int TL_BLOB = TL_INREC * 32 * 2;       // bytes of a long task's descriptor blob
+constexpr int TL_ROWS = 16;                      // element rows per producer lane (cap_slots <= 32 * TL_ROWS)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void ldgsts8(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ldgsts_arrive(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int N, int RF>
+struct TlSmem {  // byte offsets inside one tile buffer: pair records | long-task descriptor blobs | geometry rows
+  using C = TlCfg<N, RF>;
+  static constexpr int GSP = C::GSZ | 1;
+  __host__ __device__ static size_t blob_off(int cap_tasks) { return (size_t)cap_tasks * 512; }
+  __host__ __device__ static size_t geo_off(int cap_tasks, int cap_long) {
+    return (size_t)cap_tasks * 512 + (size_t)cap_long * TL_BLOB;
+  }
+  __host__ __device__ static size_t bytes(int cap_tasks, int cap_long, int zslot) {
+    return (geo_off(cap_tasks, cap_long) + (size_t)(zslot + 1) * GSP * 8 + 127) / 128 * 128;
+  }
+};
+
+template <int N, int Q, int ND, int RF>
+__global__ void __launch_bounds__(TL_THREADS, 1)
+k_tiles(const TileArgs a) {
+  using C = TlCfg<N, RF>;
+  using L = TlSmem<N, RF>;
+  constexpr int NB = ND * ND, MT = C::MT, GSZ = C::GSZ, GSP = GSZ | 1, ACC = C::ACC, CB = tl_clog2(NB);
+  extern __shared__ __align__(128) unsigned char smraw[];
+  __shared__ uint64_t full[2], empty[2];
+  __shared__ TileHdr s_hdr[2];
+  __shared__ unsigned s_next[2];
+  const size_t bufsz = L::bytes(a.cap_tasks, a.cap_long, a.zslot);
+  double *sM = reinterpret_cast<double *>(smraw + 2 * bufsz);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int k = tid; k < NB * MT; k += TL_THREADS) sM[k] = a.Mtab[k];
+  if (tid < 2 * GSP) {  // the all-zero geometry slot of both buffers
+    double *g = reinterpret_cast<double *>(smraw + (tid / GSP) * bufsz + L::geo_off(a.cap_tasks, a.cap_long));
+    g[a.zslot * GSP + tid % GSP] = 0.0;
+  }
+  if (tid == 0) {
+    mbar_init(&full[0], 33); mbar_init(&full[1], 33);      // 32 LDGSTS arrivals + the expect_tx arrival
+    mbar_init(&empty[0], TL_CW); mbar_init(&empty[1], TL_CW);
+  }
+  __syncthreads();
+  if (warp == TL_CW) {
+    // ================= producer =================
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    // the header and the element ids of the NEXT tile are loaded (into registers) before waiting for its buffer
+    TileHdr h;
+    uint32_t e[TL_ROWS];
+    auto fetch = [&](int64_t tile) {
+      h = a.hdr[tile];
+      const uint32_t *els = a.els + (size_t)tile * a.els_stride;
+#pragma unroll
+      for (int r = 0; r < TL_ROWS; ++r) e[r] = r * 32 + lane < (int)h.nel ? els[r * 32 + lane] : 0u;
+    };
+    if ((int64_t)blockIdx.x < a.nt) fetch(blockIdx.x);
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < a.nt; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      const unsigned long long tp0 = a.trace ? gtimer() : 0;
+      if (it >= 2) mbar_wait(&empty[b], ((it >> 1) - 1) & 1);
+      const unsigned long long tp1 = a.trace ? gtimer() : 0;
+      unsigned char *buf = smraw + b * bufsz;
+      if (lane == 0) {
+        s_hdr[b] = h;
+        s_next[b] = TL_CW;
+        const uint32_t nb1 = h.ntasks * 512u, nb2 = h.n_long * (uint32_t)TL_BLOB;
+        mbar_arrive_expect_tx(&full[b], nb1 + nb2);
+        bulk_g2s(buf, a.rec + (size_t)h.task0 * 32, nb1, &full[b], pol);
+        if (nb2) bulk_g2s(buf + L::blob_off(a.cap_tasks), a.dblob + (size_t)h.r2_0 * (TL_BLOB / 2), nb2, &full[b], pol);
+      }
+      double *g = reinterpret_cast<double *>(buf + L::geo_off(a.cap_tasks, a.cap_long));
+#pragma unroll
+      for (int r = 0; r < TL_ROWS; ++r) {
+        const uint32_t sr = r * 32 + lane;
+        if (sr < h.nel) {
+#pragma unroll
+          for (int k = 0; k < GSZ; ++k) ldgsts8(g + sr * GSP + k, a.eg + (size_t)e[r] * GSZ + k);
+        }
+      }
+      ldgsts_arrive(&full[b]);
+      const unsigned long long tp2 = a.trace ? gtimer() : 0;
+      if (tile + gridDim.x < a.nt) fetch(tile + gridDim.x);
+      if (a.trace && blockIdx.x == 0 && lane == 0 && it < 256) {
+        a.trace[it * 8 + 0] = tp0; a.trace[it * 8 + 1] = tp1; a.trace[it * 8 + 2] = tp2; a.trace[it * 8 + 3] = gtimer() + (h.nel & 0);
+      }
+    }
+    return;
+  }
+  // ================= consumers =================
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < a.nt; tile += gridDim.x, ++it) {
+    const int b = it & 1;
+    const unsigned long long tc0 = a.trace ? gtimer() : 0;
+    mbar_wait(&full[b], (it >> 1) & 1);
+    const unsigned long long tc1 = a.trace ? gtimer() : 0;
+    const unsigned char *buf = smraw + b * bufsz;
+    const uint4 *sRec = reinterpret_cast<const uint4 *>(buf) + lane;
+    const uint16_t *sBlob = reinterpret_cast<const uint16_t *>(buf + L::blob_off(a.cap_tasks)) + lane;
+    const double *sG = reinterpret_cast<const double *>(buf + L::geo_off(a.cap_tasks, a.cap_long));
+    const unsigned ntasks = s_hdr[b].ntasks;
+    double *prb = a.pr + s_hdr[b].base;
+    unsigned tk = warp;
+    while (tk < ntasks) {
+      unsigned nxt = 0;
+      if (lane == 0) nxt = atomicAdd(&s_next[b], 1u);
+      const uint4 rec = sRec[tk * 32];
+      const int steps = (int)(rec.z >> 20);
+      double acc[ACC];
+#pragma unroll
+      for (int m = 0; m < ACC; ++m) acc[m] = 0.0;
+      auto step = [&](unsigned d) {
+        const double *G = sG + (d >> CB) * GSP;
+        const double *M = sM + (d & ((1u << CB) - 1u)) * MT;
+        if (RF == TF_ELAST) {
+          double Bm[N * N];
+#pragma unroll
+          for (int k = 0; k < N * N; ++k) Bm[k] = G[k];
+#pragma unroll
+          for (int qq = 0; qq < N; ++qq) {
+            double Wq[N];  // column qq of W = B M
+#pragma unroll
+            for (int aa = 0; aa < N; ++aa) {
+              double s2 = 0;
+#pragma unroll
+              for (int pp = 0; pp < N; ++pp) s2 += Bm[aa + N * pp] * M[pp * N + qq];
+              Wq[aa] = s2;
+            }
+#pragma unroll
+            for (int b2 = 0; b2 < N; ++b2)
+#pragma unroll
+              for (int aa = 0; aa < N; ++aa) acc[RF == TF_ELAST ? aa + N * b2 : 0] += Wq[aa] * Bm[b2 + N * qq];
+          }
+        } else {
+          double s2 = acc[0];
+#pragma unroll
+          for (int k = 0; k < MT; ++k) s2 += M[k] * G[k];
+          acc[0] = s2;
+        }
+      };
+      if (steps <= 2 && !(rec.y & 0x40000000u)) {  // both descriptors travel in the record
+        step(rec.w & 0xffffu);
+        if (steps == 2) step(rec.w >> 16);
+      } else {
+        const uint16_t *bl = sBlob + tk * (TL_BLOB / 2);
+        unsigned dn = bl[0];
+        for (int c = 0; c < steps; ++c) {
+          const unsigned d = dn;
+          if (c + 1 < steps) dn = bl[(c + 1) * 32];
+          step(d);
+        }
+        if (rec.y & 0x40000000u) {  // wide task: the lanes hold parts of ONE pair; fixed-order tree sum
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+            for (int m = 0; m < ACC; ++m) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], off);
+        }
+      }
+      // ---- flush: all lanes of the task together; per column component the kept entries are compacted
+      if (rec.y >> 31) {
+        double kv[Q * Q];  // kv[b*Q + aa] = K(row component aa, column component b)
+        if (RF == TF_ELAST) {
+          double tr = 0;
+#pragma unroll
+          for (int n = 0; n < N; ++n) tr += acc[RF == TF_ELAST ? n + N * n : 0];
+#pragma unroll
+          for (int b2 = 0; b2 < Q; ++b2)
+#pragma unroll
+            for (int aa = 0; aa < Q; ++aa)
+              kv[b2 * Q + aa] = a.sl * acc[RF == TF_ELAST ? aa + N * b2 : 0] + a.smu * acc[RF == TF_ELAST ? b2 + N * aa : 0] +
+                                (aa == b2 ? a.smu * tr : 0.0);
+        } else {
+#pragma unroll
+          for (int b2 = 0; b2 < Q; ++b2)
+#pragma unroll
+            for (int aa = 0; aa < Q; ++aa) kv[b2 * Q + aa] = aa == b2 ? acc[0] : 0.0;
+        }
+        double *p0 = prb + (rec.x & 0xfffffu);
+        const unsigned pm = (rec.y >> 20) & 0x1ffu;
+#pragma unroll
+        for (int b2 = 0; b2 < Q; ++b2) {
+          double *dst = p0 + (b2 == 0 ? 0u : b2 == 1 ? (rec.y & 0xfffffu) : (rec.z & 0xfffffu));
+          const unsigned mb = (pm >> (b2 * Q)) & ((1u << Q) - 1);
+          if (Q == 3) {
+            const double v0 = kv[b2 * Q], v1 = kv[b2 * Q + (Q > 1 ? 1 : 0)], v2 = kv[b2 * Q + (Q > 2 ? 2 : 0)];
+            const int n = __popc(mb);
+            const double x0 = (mb & 1u) ? v0 : ((mb & 2u) ? v1 : v2);
+            const double x1 = ((mb & 3u) == 3u) ? v1 : v2;
+            if (n >= 1) dst[0] = x0;
+            if (n >= 2) dst[1] = x1;
+            if (n >= 3) dst[2] = v2;
+          } else {
+#pragma unroll
+            for (int aa = 0; aa < Q; ++aa)
+              if (mb & (1u << aa)) dst[__popc(mb & ((1u << aa) - 1))] = kv[b2 * Q + aa];
+          }
+        }
+      }
+      tk = __shfl_sync(0xffffffffu, nxt, 0);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[b]);
+    if (a.trace && blockIdx.x == 0 && tid == 0 && it < 256) {
+      a.trace[it * 8 + 4] = tc0; a.trace[it * 8 + 5] = tc1; a.trace[it * 8 + 6] = gtimer(); a.trace[it * 8 + 7] = ntasks;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- the residual kernel
+// Thread per element: r_e = K_e u_e without forming K_e, through the same reference tensors M_ij(p,q)
+// (uniform shared-memory reads, every thread of the warp at the same (i,j)):
+//   elasticity  V_j = B~^T u_j, S = B~^T B~,
+//               r_i = sl B~ (sum_j M_ij V_j) + smu B~ (sum_j M_ij^T V_j) + smu sum_j <M_ij, S> u_j
+//   Laplace     r_i = sum_j <Msym_ij, G> u_j ;  mass  r_i = sum_j M_ij G u_j
+// into the per-element stage; scatter.cu::gather_residual sums them per node in ascending element order
+// (replaces ga_instruction_vector_assembly_mf, C&E.cc:4669-4735).
+struct ResArgs {
+  const int32_t *edof;
+  const double *eg, *Mtab, *U;
+  double sl, smu;
+  int64_t e0, ne;
+  double *rstage;
+};
+
+template <int N, int Q, int ND, int RF>
+__global__ void __launch_bounds__(128, 1)
+k_affine_residual(const ResArgs a) {
+  using C = TlCfg<N, RF>;
+  constexpr int NB = ND * ND, MT = C::MT, GSZ = C::GSZ;
+  extern __shared__ double sM[];
+  for (int k = threadIdx.x; k < NB * MT; k += blockDim.x) sM[k] = a.Mtab[k];
+  __syncthreads();
+  for (int64_t el = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; el < a.ne; el += (int64_t)gridDim.x * blockDim.x) {
+    double G[GSZ];
+#pragma unroll
+    for (int k = 0; k < GSZ; ++k) G[k] = a.eg[(size_t)el * GSZ + k];
+    const int32_t *ed = a.edof + (a.e0 + el) * ND;
+    double u[ND][Q];
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      const int32_t dj = ed[j];
+#pragma unroll
+      for (int b = 0; b < Q; ++b) u[j][b] = a.U ? a.U[dj + b] : 0.0;
+    }
+    double *out = a.rstage + (size_t)el * ND * Q;
+    if (RF == TF_ELAST) {
+      double V[ND][N], S[N][N];
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+#pragma unroll
+        for (int q = 0; q < N; ++q) {
+          double s2 = 0;
+#pragma unroll
+          for (int b = 0; b < N; ++b) s2 += G[RF == TF_ELAST ? b + N * q : 0] * u[j][b % Q];
+          V[j][q] = s2;
+        }
+#pragma unroll
+      for (int p = 0; p < N; ++p)
+#pragma unroll
+        for (int q = 0; q < N; ++q) {
+          double s2 = 0;
+#pragma unroll
+          for (int n = 0; n < N; ++n) s2 += G[RF == TF_ELAST ? n + N * p : 0] * G[RF == TF_ELAST ? n + N * q : 0];
+          S[p][q] = s2;
+        }
+#pragma unroll 1
+      for (int i = 0; i < ND; ++i) {
+        double y[N], yt[N], t3[N];
+#pragma unroll
+        for (int n = 0; n < N; ++n) y[n] = yt[n] = t3[n] = 0.0;
+#pragma unroll
+        for (int j = 0; j < ND; ++j) {
+          const double *M = sM + (j * ND + i) * MT;  // M(p,q) = sum_k w ghat_k(i,p) ghat_k(j,q)
+          double tr = 0;
+#pragma unroll
+          for (int p = 0; p < N; ++p)
+#pragma unroll
+            for (int q = 0; q < N; ++q) {
+              const double m = M[RF == TF_ELAST ? p * N + q : 0];
+              y[p] += m * V[j][q];
+              yt[q] += m * V[j][p];
+              tr += m * S[p][q];
+            }
+#pragma unroll
+          for (int n = 0; n < N; ++n) t3[n] += tr * u[j][n % Q];
+        }
+#pragma unroll
+        for (int aa = 0; aa < N; ++aa) {
+          double s1 = 0, s2 = 0;
+#pragma unroll
+          for (int p = 0; p < N; ++p) {
+            s1 += G[RF == TF_ELAST ? aa + N * p : 0] * y[p];
+            s2 += G[RF == TF_ELAST ? aa + N * p : 0] * yt[p];
+          }
+          out[i * Q + aa % Q] = a.sl * s1 + a.smu * (s2 + t3[aa]);
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int i = 0; i < ND; ++i) {
+        double r[Q];
+#pragma unroll
+        for (int b = 0; b < Q; ++b) r[b] = 0.0;
+#pragma unroll
+        for (int j = 0; j < ND; ++j) {
+          const double *M = sM + (j * ND + i) * MT;
+          double kij = 0;
+#pragma unroll
+          for (int k = 0; k < MT; ++k) kij += M[k] * G[k];
+#pragma unroll
+          for (int b = 0; b < Q; ++b) r[b] += kij * u[j][b];
+        }
+#pragma unroll
+        for (int b = 0; b < Q; ++b) out[i * Q + b] = r[b];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- host side
+bool recompute_supported(const gfgpu_term *t) {
+  if (t->mesh->gt_kind != GFGPU_GT_PK) return false;
+  if (tf_of(t->family) < 0) return false;
+  const int N = t->mesh->dim, nd = t->fem->nd, Q = t->fem->qdim;
+  const bool ndok = N == 2 ? (nd == 3 || nd == 6 || nd == 10) : (nd == 4 || nd == 10 || nd == 20);
+  if (!ndok) return false;
+  if (t->family == GFGPU_ELASTICITY) return Q == N;
+  return Q == 1 || Q == N;
+}
+
+static int env_int(const char *name, int dflt) {
+  const char *s = getenv(name);
+  return s && *s ? atoi(s) : dflt;
+}
+
+void recompute_prepare(gfgpu_term *t) {
+  gfgpu_ctx *ctx = t->ctx;
+  cudaStream_t s = ctx->stream;
+  const int N = t->mesh->dim, nd = t->fem->nd, nq = t->tab->nq, Q = t->fem->qdim;
+  const int rf = tf_of(t->family);
+  const int MT = rf == TF_ELAST ? N * N : rf == TF_LAPLACE ? N * (N + 1) / 2 : 1;
+  const int GSZ = MT;
+  // ---- reference tensors M^{ji} from the staged tables (the same tables the reference integrates with)
+  const std::vector<double> &w = t->tab->h_w, &g = t->tab->h_gphi, &ph = t->tab->h_phi;
+  std::vector<double> M((size_t)nd * nd * MT, 0.0);
+  for (int j = 0; j < nd; ++j)
+    for (int i = 0; i < nd; ++i) {
+      double *o = M.data() + ((size_t)j * nd + i) * MT;
+      if (rf == TF_MASS) {
+        double sum = 0;
+        for (int k = 0; k < nq; ++k) sum += w[k] * ph[(size_t)k * nd + i] * ph[(size_t)k * nd + j];
+        o[0] = sum;
+        continue;
+      }
+      double full[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int k = 0; k < nq; ++k) {
+        if (w[k] == 0.0) continue;
+        const double *gi = g.data() + ((size_t)k * nd + i) * N, *gj = g.data() + ((size_t)k * nd + j) * N;
+        for (int p = 0; p < N; ++p)
+          for (int q = 0; q < N; ++q) full[p * N + q] += w[k] * gi[p] * gj[q];
+      }
+      if (rf == TF_ELAST) {
+        for (int k = 0; k < N * N; ++k) o[k] = full[k];
+      } else {  // symmetrised against G = a J B^T B (upper triangle, row by row)
+        int k = 0;
+        for (int p = 0; p < N; ++p)
+          for (int q = p; q < N; ++q) o[k++] = p == q ? full[p * N + p] : full[p * N + q] + full[q * N + p];
+      }
+    }
+  t->rc_M.alloc(ctx, M.size());
+  t->rc_M.upload(M.data());
+  // ---- per-element geometry
+  const int64_t ne = t->e1 - t->e0;
+  t->rc_eg.alloc(ctx, (size_t)ne * GSZ);
+  const double scale = t->alpha * ((rf == TF_ELAST) ? 1.0 : t->par[0]);
+  const int64_t np = t->mesh->npts;
+  const double *x = t->mesh->xyz.p;
+  if (ne) {
+    int grid = (int)std::min<int64_t>((ne + 255) / 256, 148 * 16);
+    if (N == 2)
+      k_tile_geo<2><<<grid, 256, 0, s>>>(x, x + np, x + 2 * np, t->mesh->conn.p, t->mesh->ng, t->tab->gt_grad.p, t->e0, ne,
+                                        rf, scale, t->rc_eg.p, GSZ);
+    else
+      k_tile_geo<3><<<grid, 256, 0, s>>>(x, x + np, x + 2 * np, t->mesh->conn.p, t->mesh->ng, t->tab->gt_grad.p, t->e0, ne,
+                                        rf, scale, t->rc_eg.p, GSZ);
+    GF_LAUNCH_CHECK();
+  }
+  // ---- tiles: consecutive column nodes, greedily, bounded by incidences and pairs
+  Structure &st = t->st;
+  GF_REQUIRE(st.ncolnodes == st.nrnodes, "column nodes and incidence nodes differ");
+  const int cbits = tl_clog2(nd * nd);
+  GF_REQUIRE(cbits <= 10, "too many local nodes for the 16-bit contribution descriptor");
+  const int slot_max = (1 << (16 - cbits)) - 1;  // the top slot index is the all-zero geometry
+  const int cap_inc_want = std::max(1, std::min(std::min(env_int("GFGPU_TILE_INC", 510), slot_max), 1024));
+  const int cap_pairs_want = std::max(32, std::min(env_int("GFGPU_TILE_PAIRS", 2048), 4095));
+  std::vector<uint32_t> rstart(st.nrnodes + 1), colstart(st.ncolnodes + 1);
+  st.rstart.download(rstart.data());
+  st.colstart.download(colstart.data());
+  GF_CUDA(cudaStreamSynchronize(s));
+  std::vector<TileHdr> hdr;
+  hdr.reserve(st.ncolnodes / 16 + 2);
+  int cap_inc = 1;
+  for (int64_t k = 0; k < st.ncolnodes;) {
+    int64_t k1 = k + 1;
+    while (k1 < st.ncolnodes && rstart[k1 + 1] - rstart[k] <= (uint32_t)cap_inc_want &&
+           colstart[k1 + 1] - colstart[k] <= (uint32_t)cap_pairs_want)
+      ++k1;
+    TileHdr h;
+    memset(&h, 0, sizeof h);
+    h.pair0 = colstart[k];
+    h.npairs = colstart[k1] - colstart[k];
+    h.node0 = (uint32_t)k;
+    h.nnodes = (uint32_t)(k1 - k);
+    cap_inc = std::max<int>(cap_inc, (int)(rstart[k1] - rstart[k]));
+    hdr.push_back(h);
+    k = k1;
+  }
+  GF_REQUIRE(cap_inc <= std::min(slot_max, 1024), "node valence too high for the compact tile descriptors: use strategy STAGED");
+  const int64_t nt = (int64_t)hdr.size();
+  t->rc_nt = nt;
+  t->rc_cap_inc = cap_inc;
+  t->rc_hdr.alloc(ctx, hdr.size() * sizeof(TileHdr));
+  GF_CUDA(cudaMemcpyAsync(t->rc_hdr.p, hdr.data(), hdr.size() * sizeof(TileHdr), cudaMemcpyHostToDevice, s));
+  TileHdr *dh = (TileHdr *)t->rc_hdr.p;
+  t->rc_els.alloc(ctx, (size_t)nt * cap_inc);
+  t->flag.zero();
+  {
+    int P = 32;
+    while (P < cap_inc) P <<= 1;
+    k_tile_elements<<<(unsigned)nt, 128, 2 * P * sizeof(uint32_t), s>>>(dh, st.rstart.p, st.rsrc.p, nd, cap_inc, t->rc_els.p);
+    GF_LAUNCH_CHECK();
+  }
+  DevBuf<uint32_t> sp_pair, tk_tile;
+  sp_pair.alloc(ctx, st.npairs);
+  k_tile_sort_pairs<<<(unsigned)nt, 256, 0, s>>>(dh, st.cstart.p, sp_pair.p, (int *)t->flag.p);
+  GF_LAUNCH_CHECK();
+  k_tile_base<<<(unsigned)std::min<int64_t>((nt + 255) / 256, 148 * 8), 256, 0, s>>>(dh, nt, st.pJ.p, t->jc.p);
+  GF_LAUNCH_CHECK();
+  // task ranges, blob ranges and the shared-memory capacities (host scan over the tiles)
+  GF_CUDA(cudaMemcpyAsync(hdr.data(), dh, hdr.size() * sizeof(TileHdr), cudaMemcpyDeviceToHost, s));
+  GF_CUDA(cudaStreamSynchronize(s));
+  int cap_slots = 1, cap_tasks = 1, cap_long = 1;
+  int64_t ntask = 0, nlong = 0;
+  for (TileHdr &h : hdr) {
+    h.ntasks = h.n_wide + (h.npairs - h.n_wide + 31) / 32;
+    h.task0 = (uint32_t)ntask;
+    h.r2_0 = (uint32_t)nlong;
+    ntask += h.ntasks;
+    nlong += h.n_long;
+    cap_slots = std::max<int>(cap_slots, (int)h.nel);
+    cap_tasks = std::max<int>(cap_tasks, (int)h.ntasks);
+    cap_long = std::max<int>(cap_long, (int)h.n_long);
+  }
+  GF_REQUIRE(ntask < (int64_t(1) << 31) && nlong < (int64_t(1) << 31), "too many tasks");
+  GF_REQUIRE(cap_slots <= 32 * TL_ROWS, "tile has too many distinct elements");
+  GF_CUDA(cudaMemcpyAsync(dh, hdr.data(), hdr.size() * sizeof(TileHdr), cudaMemcpyHostToDevice, s));
+  t->rc_ntask = ntask;
+  t->rc_cap_slots = cap_slots;
+  t->rc_cap_tasks = cap_tasks;
+  t->rc_cap_long = cap_long;
+  tk_tile.alloc(ctx, ntask);
+  k_tile_task_owner<<<(unsigned)std::min<int64_t>(nt, 148 * 32), 128, 0, s>>>(dh, nt, tk_tile.p);
+  GF_LAUNCH_CHECK();
+  t->rc_prec.alloc(ctx, (size_t)ntask * 32);
+  t->rc_dblob.alloc(ctx, std::max<size_t>((size_t)nlong * TL_INREC * 32, 1));
+  {
+    const int B = 256;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ntask * 32 + B - 1) / B, 148 * 64));
+#define GF_FILL(QQ)                                                                                                  \
+  k_tile_fill<QQ><<<grid, B, 0, s>>>(dh, tk_tile.p, sp_pair.p, t->rc_els.p, cap_inc, st.cstart.p, st.csrc.p,         \
+                                     st.pJ.p, t->pmask.p, t->prel.p, t->jc.p, st.npairs, nd, cbits,                 \
+                                     (uint32_t)cap_slots, ntask, (uint4 *)t->rc_prec.p, t->rc_dblob.p,              \
+                                     (int *)t->flag.p)
+    if (Q == 1) GF_FILL(1);
+    else if (Q == 2) GF_FILL(2);
+    else GF_FILL(3);
+#undef GF_FILL
+    GF_LAUNCH_CHECK();
+  }
+  int32_t err = 0;
+  t->flag.download(&err);
+  GF_CUDA(cudaStreamSynchronize(s));
+  GF_REQUIRE(err == 0, "recompute plan failed (code " + std::to_string(err) + "): tile too large for the compact records");
+  t->prel.release();  // folded into the pair records
+  t->rc_ready = true;
+}
+
+template <int N, int Q, int ND, int RF>
+static void launch_tiles(gfgpu_term *t, const double *U, bool do_t, bool do_r) {
+  using C = TlCfg<N, RF>;
+  const double sign = t->alpha < 0 ? -1.0 : 1.0;
+  if (do_r) {  // per-element residual -> stage -> fixed-order gather per node
+    const int64_t ne = t->e1 - t->e0;
+    if (t->rstage.n != (size_t)ne * ND * Q) t->rstage.alloc(t->ctx, (size_t)ne * ND * Q);
+    ResArgs r;
+    r.edof = t->fem->edof.p; r.eg = t->rc_eg.p; r.Mtab = t->rc_M.p; r.U = U;
+    r.sl = sign * t->par[0]; r.smu = sign * t->par[1];
+    r.e0 = t->e0; r.ne = ne; r.rstage = t->rstage.p;
+    const size_t smem = (size_t)ND * ND * C::MT * 8;
+    auto kern = k_affine_residual<N, Q, ND, RF>;
+    GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ne + 127) / 128, (int64_t)t->ctx->sm_count * 8));
+    kern<<<grid, 128, smem, t->ctx->stream>>>(r);
+    GF_LAUNCH_CHECK();
+    gather_residual(t);
+  }
+  if (!do_t) return;
+  using L = TlSmem<N, RF>;
+  TileArgs a;
+  a.hdr = (const TileHdr *)t->rc_hdr.p;
+  a.els = t->rc_els.p;
+  a.els_stride = t->rc_cap_inc;
+  a.rec = (const uint4 *)t->rc_prec.p;
+  a.dblob = t->rc_dblob.p;
+  a.eg = t->rc_eg.p; a.Mtab = t->rc_M.p;
+  a.sl = sign * t->par[0]; a.smu = sign * t->par[1];
+  a.nt = t->rc_nt;
+  a.zslot = t->rc_cap_slots; a.cap_tasks = t->rc_cap_tasks; a.cap_long = t->rc_cap_long;
+  a.pr = t->pr.p;
+  a.trace = nullptr;
+  DevBuf<unsigned long long> trace;
+  if (getenv("GFGPU_TILE_TRACE")) {
+    trace.alloc(t->ctx, 256 * 8);
+    trace.zero();
+    a.trace = trace.p;
+  }
+  const size_t smem = 2 * L::bytes(a.cap_tasks, a.cap_long, a.zslot) + (size_t)ND * ND * C::MT * 8;
+  GF_REQUIRE(smem <= 226 * 1024, "tile too large for shared memory; use strategy STAGED");
+  auto kern = k_tiles<N, Q, ND, RF>;
+  GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)std::min<int64_t>(a.nt, (int64_t)t->ctx->sm_count);
+  kern<<<grid, TL_THREADS, smem, t->ctx->stream>>>(a);
+  GF_LAUNCH_CHECK();
+  if (a.trace) {
+    std::vector<unsigned long long> h(256 * 8);
+    trace.download(h.data());
+    GF_CUDA(cudaStreamSynchronize(t->ctx->stream));
+    FILE *f = fopen(getenv("GFGPU_TILE_TRACE"), "w");
+    if (f) {
+      fprintf(f, "it p_wait_start p_empty_ok p_issued p_fetched c_wait_start c_full_ok c_done ntasks (ns, relative)\n");
+      const unsigned long long t0 = h[0];
+      for (int k = 0; k < 256; ++k) {
+        fprintf(f, "%d", k);
+        for (int j = 0; j < 7; ++j) fprintf(f, " %lld", (long long)(h[k * 8 + j] - t0));
+        fprintf(f, " %llu\n", h[k * 8 + 7]);
+      }
+      fclose(f);
+    }
+  }
+}
+
+#define TL_CASE(NN, QQ, NDD, RFF)                                  \
+  if (N == NN && Q == QQ && nd == NDD && rf == RFF) {              \
+    launch_tiles<NN, QQ, NDD, RFF>(t, U, do_t, do_r);              \
+    return;                                                        \
+  }
+
+// tangent and/or residual (R = K^T U = K U, the handled forms are symmetric) in one kernel
+void recompute_assemble(gfgpu_term *t, const double *U, bool do_t, bool do_r) {
+  if (!t->st.npairs) return;
+  const int N = t->mesh->dim, nd = t->fem->nd, Q = t->fem->qdim, rf = tf_of(t->family);
+  TL_CASE(3, 3, 10, TF_ELAST) TL_CASE(3, 3, 4, TF_ELAST) TL_CASE(3, 3, 20, TF_ELAST)
+  TL_CASE(3, 1, 10, TF_LAPLACE) TL_CASE(3, 1, 4, TF_LAPLACE) TL_CASE(3, 1, 20, TF_LAPLACE)
+  TL_CASE(3, 3, 10, TF_LAPLACE) TL_CASE(3, 3, 4, TF_LAPLACE) TL_CASE(3, 3, 20, TF_LAPLACE)
+  TL_CASE(3, 1, 10, TF_MASS) TL_CASE(3, 1, 4, TF_MASS) TL_CASE(3, 1, 20, TF_MASS)
+  TL_CASE(3, 3, 10, TF_MASS) TL_CASE(3, 3, 4, TF_MASS) TL_CASE(3, 3, 20, TF_MASS)
+  TL_CASE(2, 2, 3, TF_ELAST) TL_CASE(2, 2, 6, TF_ELAST) TL_CASE(2, 2, 10, TF_ELAST)
+  TL_CASE(2, 1, 3, TF_LAPLACE) TL_CASE(2, 1, 6, TF_LAPLACE) TL_CASE(2, 1, 10, TF_LAPLACE)
+  TL_CASE(2, 2, 3, TF_LAPLACE) TL_CASE(2, 2, 6, TF_LAPLACE) TL_CASE(2, 2, 10, TF_LAPLACE)
+  TL_CASE(2, 1, 3, TF_MASS) TL_CASE(2, 1, 6, TF_MASS) TL_CASE(2, 1, 10, TF_MASS)
+  TL_CASE(2, 2, 3, TF_MASS) TL_CASE(2, 2, 6, TF_MASS) TL_CASE(2, 2, 10, TF_MASS)
+  GF_REQUIRE(false, "no recompute kernel for this combination");
+}
+
+}  // namespace gf
