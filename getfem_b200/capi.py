@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgfgpu.so")
+LIB_PATH = os.environ.get("GFGPU_LIB") or os.path.join(_HERE, "libgfgpu.so")  # GFGPU_LIB: kernel-variant experiments
 
 GT_PK, GT_QK = 0, 1
 FEM_PK, FEM_QK = 0, 1

@@ -171,6 +171,8 @@ struct gfgpu_term {
   bool rc_ready = false;
   gf::DevBuf<double> rc_M;      // reference tensors per (j,i)
   gf::DevBuf<double> rc_eg;     // per-element geometry
+  gf::DevBuf<double> rc_L;      // low-rank factor of the reference Gram matrix (residual kernel)
+  int rc_rank = 0;
   struct alignas(16) PairRec { uint32_t x, y, z, w; };
   gf::DevBuf<uint16_t> rc_dblob; // per long task (> 2 steps): descriptors of steps 0..9, [step][lane]
   gf::DevBuf<PairRec> rc_prec;   // per (task, lane): packed CSC offsets (relative to the tile base), keep mask, row dof

@@ -25,6 +25,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 
 #include "common.cuh"
 
@@ -359,7 +360,10 @@ __device__ __forceinline__ unsigned long long gtimer() {
   return v;
 }
 
-constexpr int TL_CW = 16;                        // consumer warps
+#ifndef GF_TL_CW
+#define GF_TL_CW 16
+#endif
+constexpr int TL_CW = GF_TL_CW;                  // consumer warps
 constexpr int TL_THREADS = (TL_CW + 1) * 32;     // + the producer warp
 constexpr int TL_BLOB = TL_INREC * 32 * 2;       // bytes of a long task's descriptor blob
 constexpr int TL_ROWS = 16;                      // element rows per producer lane (cap_slots <= 32 * TL_ROWS)
@@ -459,7 +463,7 @@ k_tiles(const TileArgs a) {
       unsigned char *buf = smraw + b * bufsz;
       if (lane == 0) {
         s_hdr[b] = h;
-        s_next[b] = TL_CW;
+        s_next[b] = 2 * TL_CW;
         const uint32_t nb1 = h.ntasks * 512u, nb2 = h.n_long * (uint32_t)TL_BLOB;
         mbar_arrive_expect_tx(&full[b], nb1 + nb2);
         bulk_g2s(buf, a.rec + (size_t)h.task0 * 32, nb1, &full[b], pol);
@@ -496,11 +500,15 @@ k_tiles(const TileArgs a) {
     const double *sG = reinterpret_cast<const double *>(buf + L::geo_off(a.cap_tasks, a.cap_long));
     const unsigned ntasks = s_hdr[b].ntasks;
     double *prb = a.pr + s_hdr[b].base;
-    unsigned tk = warp;
+    // the next task index and its record are fetched while the current task runs
+    unsigned tk = warp, tkB = warp + TL_CW;
+    uint4 rec = make_uint4(0, 0, 0, 0);
+    if (tk < ntasks) rec = sRec[tk * 32];
     while (tk < ntasks) {
       unsigned nxt = 0;
       if (lane == 0) nxt = atomicAdd(&s_next[b], 1u);
-      const uint4 rec = sRec[tk * 32];
+      uint4 recB = make_uint4(0, 0, 0, 0);
+      if (tkB < ntasks) recB = sRec[tkB * 32];
       const int steps = (int)(rec.z >> 20);
       double acc[ACC];
 #pragma unroll
@@ -592,7 +600,9 @@ k_tiles(const TileArgs a) {
           }
         }
       }
-      tk = __shfl_sync(0xffffffffu, nxt, 0);
+      tk = tkB;
+      rec = recB;
+      tkB = __shfl_sync(0xffffffffu, nxt, 0);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[b]);
@@ -603,18 +613,21 @@ k_tiles(const TileArgs a) {
 }
 
 // ---------------------------------------------------------------- the residual kernel
-// Thread per element: r_e = K_e u_e without forming K_e, through the same reference tensors M_ij(p,q)
-// (uniform shared-memory reads, every thread of the warp at the same (i,j)):
-//   elasticity  V_j = B~^T u_j, S = B~^T B~,
-//               r_i = sl B~ (sum_j M_ij V_j) + smu B~ (sum_j M_ij^T V_j) + smu sum_j <M_ij, S> u_j
-//   Laplace     r_i = sum_j <Msym_ij, G> u_j ;  mass  r_i = sum_j M_ij G u_j
+// Thread per element: r_e = K_e u_e without forming K_e.  The reference tensors M_ij(p,q) = sum_k w_k ghat_k(i,p)
+// ghat_k(j,q) form a Gram matrix of low rank (the gradients of a degree-k element span P_{k-1}: rank 4 for P2
+// whatever the number of quadrature points), factorised once on the host, M = sum_k s_k l_k l_k^T.  Per generalised
+// point k (uniform shared-memory reads, every thread of the warp at the same entry):
+//   elasticity  Uh = sum_j u_j (x) l_k(j),  grad = Uh B~^T,  sigma = sl tr(grad) I + smu (grad + grad^T),
+//               r_i += s_k (sigma B~) l_k(i)
+//   Laplace     r_i += s_k (Uh G) l_k(i)          mass   r_i += s_k G l_k(i) sum_j l_k(j) u_j
 // into the per-element stage; scatter.cu::gather_residual sums them per node in ascending element order
 // (replaces ga_instruction_vector_assembly_mf, C&E.cc:4669-4735).
 struct ResArgs {
   const int32_t *edof;
-  const double *eg, *Mtab, *U;
+  const double *eg, *Ltab, *U;  // Ltab: rank x (sign, then nd x N (or nd) entries)
   double sl, smu;
   int64_t e0, ne;
+  int rank;
   double *rstage;
 };
 
@@ -622,95 +635,160 @@ template <int N, int Q, int ND, int RF>
 __global__ void __launch_bounds__(128, 1)
 k_affine_residual(const ResArgs a) {
   using C = TlCfg<N, RF>;
-  constexpr int NB = ND * ND, MT = C::MT, GSZ = C::GSZ;
-  extern __shared__ double sM[];
-  for (int k = threadIdx.x; k < NB * MT; k += blockDim.x) sM[k] = a.Mtab[k];
+  constexpr int GSZ = C::GSZ, LW = RF == TF_MASS ? ND : ND * N, LS = LW + 1;
+  extern __shared__ double sL[];
+  for (int k = threadIdx.x; k < a.rank * LS; k += blockDim.x) sL[k] = a.Ltab[k];
   __syncthreads();
   for (int64_t el = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; el < a.ne; el += (int64_t)gridDim.x * blockDim.x) {
     double G[GSZ];
 #pragma unroll
     for (int k = 0; k < GSZ; ++k) G[k] = a.eg[(size_t)el * GSZ + k];
     const int32_t *ed = a.edof + (a.e0 + el) * ND;
-    double u[ND][Q];
+    double u[ND][Q], r[ND][Q];
 #pragma unroll
     for (int j = 0; j < ND; ++j) {
       const int32_t dj = ed[j];
 #pragma unroll
-      for (int b = 0; b < Q; ++b) u[j][b] = a.U ? a.U[dj + b] : 0.0;
+      for (int b = 0; b < Q; ++b) {
+        u[j][b] = a.U ? a.U[dj + b] : 0.0;
+        r[j][b] = 0.0;
+      }
     }
-    double *out = a.rstage + (size_t)el * ND * Q;
-    if (RF == TF_ELAST) {
-      double V[ND][N], S[N][N];
-#pragma unroll
-      for (int j = 0; j < ND; ++j)
-#pragma unroll
-        for (int q = 0; q < N; ++q) {
-          double s2 = 0;
-#pragma unroll
-          for (int b = 0; b < N; ++b) s2 += G[RF == TF_ELAST ? b + N * q : 0] * u[j][b % Q];
-          V[j][q] = s2;
-        }
-#pragma unroll
-      for (int p = 0; p < N; ++p)
-#pragma unroll
-        for (int q = 0; q < N; ++q) {
-          double s2 = 0;
-#pragma unroll
-          for (int n = 0; n < N; ++n) s2 += G[RF == TF_ELAST ? n + N * p : 0] * G[RF == TF_ELAST ? n + N * q : 0];
-          S[p][q] = s2;
-        }
 #pragma unroll 1
-      for (int i = 0; i < ND; ++i) {
-        double y[N], yt[N], t3[N];
+    for (int k = 0; k < a.rank; ++k) {
+      const double *L = sL + k * LS;
+      const double sk = L[0];
+      ++L;
+      if (RF == TF_MASS) {
+        double c[Q];
 #pragma unroll
-        for (int n = 0; n < N; ++n) y[n] = yt[n] = t3[n] = 0.0;
+        for (int b = 0; b < Q; ++b) c[b] = 0.0;
 #pragma unroll
-        for (int j = 0; j < ND; ++j) {
-          const double *M = sM + (j * ND + i) * MT;  // M(p,q) = sum_k w ghat_k(i,p) ghat_k(j,q)
-          double tr = 0;
+        for (int j = 0; j < ND; ++j)
 #pragma unroll
-          for (int p = 0; p < N; ++p)
+          for (int b = 0; b < Q; ++b) c[b] += L[j] * u[j][b];
+        const double g = sk * G[0];
+#pragma unroll
+        for (int i = 0; i < ND; ++i)
+#pragma unroll
+          for (int b = 0; b < Q; ++b) r[i][b] += g * L[i] * c[b];
+      } else {
+        double Uh[Q][N];  // reference gradient of u at the generalised point
+#pragma unroll
+        for (int b = 0; b < Q; ++b)
+#pragma unroll
+          for (int q = 0; q < N; ++q) Uh[b][q] = 0.0;
+#pragma unroll
+        for (int j = 0; j < ND; ++j)
+#pragma unroll
+          for (int q = 0; q < N; ++q) {
+            const double l = L[RF == TF_MASS ? 0 : j * N + q];
+#pragma unroll
+            for (int b = 0; b < Q; ++b) Uh[b][q] += u[j][b] * l;
+          }
+        double P[Q][N];
+        if (RF == TF_ELAST) {
+          double gr[N][N], tr = 0;  // (scaled) physical gradient, Q == N
+#pragma unroll
+          for (int aa = 0; aa < N; ++aa)
+#pragma unroll
+            for (int bb = 0; bb < N; ++bb) {
+              double s2 = 0;
+#pragma unroll
+              for (int q = 0; q < N; ++q) s2 += Uh[aa % Q][q] * G[RF == TF_ELAST ? bb + N * q : 0];
+              gr[aa][bb] = s2;
+              if (aa == bb) tr += s2;
+            }
+          double sg[N][N];
+#pragma unroll
+          for (int aa = 0; aa < N; ++aa)
+#pragma unroll
+            for (int bb = 0; bb < N; ++bb) sg[aa][bb] = a.smu * (gr[aa][bb] + gr[bb][aa]) + (aa == bb ? a.sl * tr : 0.0);
+#pragma unroll
+          for (int aa = 0; aa < N; ++aa)
 #pragma unroll
             for (int q = 0; q < N; ++q) {
-              const double m = M[RF == TF_ELAST ? p * N + q : 0];
-              y[p] += m * V[j][q];
-              yt[q] += m * V[j][p];
-              tr += m * S[p][q];
+              double s2 = 0;
+#pragma unroll
+              for (int bb = 0; bb < N; ++bb) s2 += sg[aa][bb] * G[RF == TF_ELAST ? bb + N * q : 0];
+              P[aa % Q][q] = sk * s2;
             }
+        } else {  // Laplace: G = upper triangle of the symmetric N x N matrix alpha a J B^T B, row by row
+          double Gs[N][N];
+          {
+            int kk = 0;
 #pragma unroll
-          for (int n = 0; n < N; ++n) t3[n] += tr * u[j][n % Q];
-        }
+            for (int p = 0; p < N; ++p)
 #pragma unroll
-        for (int aa = 0; aa < N; ++aa) {
-          double s1 = 0, s2 = 0;
-#pragma unroll
-          for (int p = 0; p < N; ++p) {
-            s1 += G[RF == TF_ELAST ? aa + N * p : 0] * y[p];
-            s2 += G[RF == TF_ELAST ? aa + N * p : 0] * yt[p];
+              for (int q = p; q < N; ++q) {
+                Gs[p][q] = Gs[q][p] = G[RF == TF_LAPLACE ? kk : 0];
+                ++kk;
+              }
           }
-          out[i * Q + aa % Q] = a.sl * s1 + a.smu * (s2 + t3[aa]);
-        }
-      }
-    } else {
-#pragma unroll 1
-      for (int i = 0; i < ND; ++i) {
-        double r[Q];
 #pragma unroll
-        for (int b = 0; b < Q; ++b) r[b] = 0.0;
+          for (int b = 0; b < Q; ++b)
 #pragma unroll
-        for (int j = 0; j < ND; ++j) {
-          const double *M = sM + (j * ND + i) * MT;
-          double kij = 0;
+            for (int p = 0; p < N; ++p) {
+              double s2 = 0;
 #pragma unroll
-          for (int k = 0; k < MT; ++k) kij += M[k] * G[k];
-#pragma unroll
-          for (int b = 0; b < Q; ++b) r[b] += kij * u[j][b];
+              for (int q = 0; q < N; ++q) s2 += Gs[p][q] * Uh[b][q];
+              P[b][p] = sk * s2;
+            }
         }
 #pragma unroll
-        for (int b = 0; b < Q; ++b) out[i * Q + b] = r[b];
+        for (int i = 0; i < ND; ++i)
+#pragma unroll
+          for (int q = 0; q < N; ++q) {
+            const double l = L[RF == TF_MASS ? 0 : i * N + q];
+#pragma unroll
+            for (int b = 0; b < Q; ++b) r[i][b] += P[b][q] * l;
+          }
       }
     }
+    double *out = a.rstage + (size_t)el * ND * Q;
+#pragma unroll
+    for (int i = 0; i < ND; ++i)
+#pragma unroll
+      for (int b = 0; b < Q; ++b) out[i * Q + b] = r[i][b];
   }
+}
+
+// symmetric eigen-decomposition (cyclic Jacobi), A (m x m, row-major) -> eigenvalues in d, eigenvectors in the
+// COLUMNS of V.  m <= 60, host only.
+static void jacobi_eig(std::vector<double> &A, int m, std::vector<double> &d, std::vector<double> &V) {
+  V.assign((size_t)m * m, 0.0);
+  for (int i = 0; i < m; ++i) V[(size_t)i * m + i] = 1.0;
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    double off = 0, diag = 0;
+    for (int i = 0; i < m; ++i)
+      for (int j = 0; j < m; ++j) (i == j ? diag : off) += A[(size_t)i * m + j] * A[(size_t)i * m + j];
+    if (off <= 1e-60 || off <= 1e-34 * diag) break;
+    for (int p = 0; p < m; ++p)
+      for (int q = p + 1; q < m; ++q) {
+        const double apq = A[(size_t)p * m + q];
+        if (apq == 0.0) continue;
+        const double theta = (A[(size_t)q * m + q] - A[(size_t)p * m + p]) / (2.0 * apq);
+        const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(tt * tt + 1.0), sn = tt * c;
+        for (int k = 0; k < m; ++k) {
+          const double akp = A[(size_t)k * m + p], akq = A[(size_t)k * m + q];
+          A[(size_t)k * m + p] = c * akp - sn * akq;
+          A[(size_t)k * m + q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < m; ++k) {
+          const double apk = A[(size_t)p * m + k], aqk = A[(size_t)q * m + k];
+          A[(size_t)p * m + k] = c * apk - sn * aqk;
+          A[(size_t)q * m + k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < m; ++k) {
+          const double vkp = V[(size_t)k * m + p], vkq = V[(size_t)k * m + q];
+          V[(size_t)k * m + p] = c * vkp - sn * vkq;
+          V[(size_t)k * m + q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  d.resize(m);
+  for (int i = 0; i < m; ++i) d[i] = A[(size_t)i * m + i];
 }
 
 // ---------------------------------------------------------------- host side
@@ -765,6 +843,32 @@ void recompute_prepare(gfgpu_term *t) {
     }
   t->rc_M.alloc(ctx, M.size());
   t->rc_M.upload(M.data());
+  {  // ---- low-rank factor of the Gram matrix of the reference (gradient) functions, for the residual kernel
+    const int m = rf == TF_MASS ? nd : nd * N;
+    std::vector<double> A((size_t)m * m, 0.0), ev, V;
+    for (int k = 0; k < nq; ++k) {
+      if (w[k] == 0.0) continue;
+      const double *f = rf == TF_MASS ? ph.data() + (size_t)k * nd : g.data() + (size_t)k * nd * N;
+      for (int r = 0; r < m; ++r)
+        for (int c = 0; c < m; ++c) A[(size_t)r * m + c] += w[k] * f[r] * f[c];
+    }
+    jacobi_eig(A, m, ev, V);
+    double emax = 0;
+    for (double e : ev) emax = std::max(emax, fabs(e));
+    std::vector<double> L;
+    int rank = 0;
+    for (int k = 0; k < m; ++k) {
+      if (fabs(ev[k]) <= 1e-13 * emax) continue;
+      L.push_back(ev[k] < 0 ? -1.0 : 1.0);
+      const double sc = sqrt(fabs(ev[k]));
+      for (int r = 0; r < m; ++r) L.push_back(sc * V[(size_t)r * m + k]);
+      ++rank;
+    }
+    t->rc_rank = rank;
+    t->rc_L.alloc(ctx, std::max<size_t>(L.size(), 1));
+    t->rc_L.upload(L.data());
+    GF_CUDA(cudaStreamSynchronize(s));
+  }
   // ---- per-element geometry
   const int64_t ne = t->e1 - t->e0;
   t->rc_eg.alloc(ctx, (size_t)ne * GSZ);
@@ -889,10 +993,11 @@ static void launch_tiles(gfgpu_term *t, const double *U, bool do_t, bool do_r) {
     const int64_t ne = t->e1 - t->e0;
     if (t->rstage.n != (size_t)ne * ND * Q) t->rstage.alloc(t->ctx, (size_t)ne * ND * Q);
     ResArgs r;
-    r.edof = t->fem->edof.p; r.eg = t->rc_eg.p; r.Mtab = t->rc_M.p; r.U = U;
+    r.edof = t->fem->edof.p; r.eg = t->rc_eg.p; r.Ltab = t->rc_L.p; r.U = U;
+    r.rank = t->rc_rank;
     r.sl = sign * t->par[0]; r.smu = sign * t->par[1];
     r.e0 = t->e0; r.ne = ne; r.rstage = t->rstage.p;
-    const size_t smem = (size_t)ND * ND * C::MT * 8;
+    const size_t smem = (size_t)t->rc_rank * ((RF == TF_MASS ? ND : ND * N) + 1) * 8;
     auto kern = k_affine_residual<N, Q, ND, RF>;
     GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ne + 127) / 128, (int64_t)t->ctx->sm_count * 8));
