@@ -56,6 +56,14 @@ SIGNATURES = {
     "gfgpu_term_residual_view": (C.c_int, [_P, _PP]),
     "gfgpu_term_export_csc_host": (C.c_int, [_P, _P, _P, _P]),
     "gfgpu_term_export_residual_host": (C.c_int, [_P, _P]),
+    "gfgpu_term_halo_begin": (C.c_int, [_P, _P, _P, _P]),
+    "gfgpu_term_halo_ghost_pairs": (C.c_int, [_P, _i64, _i64, _P, _P, _P, _P]),
+    "gfgpu_term_halo_add_source": (C.c_int, [_P, C.c_int, _i64, _P, _P, _P, _i64, _i64]),
+    "gfgpu_term_halo_commit": (C.c_int, [_P, _i64, _i64]),
+    "gfgpu_term_halo_send_view": (C.c_int, [_P, _i64, _i64, _PP, _P, _PP]),
+    "gfgpu_term_halo_recv_view": (C.c_int, [_P, C.c_int, _PP, _P, _PP, _P]),
+    "gfgpu_term_halo_accumulate": (C.c_int, [_P, C.c_int]),
+    "gfgpu_term_owned_range": (C.c_int, [_P, _P, _P]),
 }
 
 
@@ -237,3 +245,61 @@ class DeviceTerm(_Handle):
         R = np.empty(self.ndof, np.float64)
         check(lib().gfgpu_term_export_residual_host(self.h, ptr(R)))
         return R
+
+    # ---- multi-GPU halo (include/gfgpu.h, "multi-GPU"); getfem_b200/halo.py drives these
+    def halo_begin(self, U_dev_ptr=None):
+        lo, hi = _i64(), _i64()
+        check(lib().gfgpu_term_halo_begin(self.h, C.c_void_p(U_dev_ptr or 0), C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def halo_ghost_pairs(self, dof_lo, dof_hi):
+        n = _i64()
+        check(lib().gfgpu_term_halo_ghost_pairs(self.h, int(dof_lo), int(dof_hi), C.byref(n), None, None, None))
+        J, I, m = np.empty(n.value, np.int32), np.empty(n.value, np.int32), np.empty(n.value, np.uint16)
+        if n.value:
+            check(lib().gfgpu_term_halo_ghost_pairs(self.h, int(dof_lo), int(dof_hi), C.byref(n), ptr(J), ptr(I), ptr(m)))
+        return J, I, m
+
+    def halo_add_source(self, src_rank, J, I, mask, r_lo, r_hi):
+        J, I = np.ascontiguousarray(J, np.int32), np.ascontiguousarray(I, np.int32)
+        mask = np.ascontiguousarray(mask, np.uint16)
+        check(lib().gfgpu_term_halo_add_source(self.h, int(src_rank), len(J), ptr(J), ptr(I), ptr(mask), int(r_lo), int(r_hi)))
+
+    def halo_commit(self, own_lo, own_hi):
+        check(lib().gfgpu_term_halo_commit(self.h, int(own_lo), int(own_hi)))
+
+    def halo_send_buffers(self, dof_lo, dof_hi, r_lo):
+        """(values of my ghost columns [dof_lo, dof_hi), residual slice [r_lo, dof_hi)) as zero-copy device tensors."""
+        pr, R, cnt = C.c_void_p(), C.c_void_p(), _i64()
+        check(lib().gfgpu_term_halo_send_view(self.h, int(dof_lo), int(dof_hi), C.byref(pr), C.byref(cnt), C.byref(R)))
+        rp = (R.value + 8 * (int(r_lo) - int(dof_lo))) if R.value else None
+        return _dev_tensor(pr.value, cnt.value, self.ctx.device), _dev_tensor(rp, int(dof_hi) - int(r_lo), self.ctx.device)
+
+    def halo_recv_buffers(self, src_rank):
+        pr, R, cnt, rc = C.c_void_p(), C.c_void_p(), _i64(), _i64()
+        check(lib().gfgpu_term_halo_recv_view(self.h, int(src_rank), C.byref(pr), C.byref(cnt), C.byref(R), C.byref(rc)))
+        return _dev_tensor(pr.value, cnt.value, self.ctx.device), _dev_tensor(R.value, rc.value, self.ctx.device)
+
+    def halo_accumulate(self, order_mask):
+        check(lib().gfgpu_term_halo_accumulate(self.h, int(order_mask)))
+
+    def ctx_synchronize(self):
+        self.ctx.synchronize()
+
+    def owned_range(self):
+        lo, hi = _i64(), _i64()
+        check(lib().gfgpu_term_owned_range(self.h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+
+class _DevArray:
+    def __init__(self, p, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (p, False), "version": 2}
+
+
+def _dev_tensor(p, n, device):
+    """Zero-copy torch view of `n` doubles of library-owned device memory (torch is plumbing: NCCL p2p on it)."""
+    import torch
+    if not p or n <= 0:
+        return torch.empty(0, dtype=torch.float64, device="cuda:%d" % device)
+    return torch.as_tensor(_DevArray(p, n), device="cuda:%d" % device)

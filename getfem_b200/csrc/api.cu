@@ -1,4 +1,6 @@
 // api.cu -- the extern "C" boundary declared in include/gfgpu.h.
+#include <algorithm>
+#include <climits>
 #include <cstring>
 #include <memory>
 
@@ -261,6 +263,9 @@ int gfgpu_term_set_element_range(gfgpu_term *t, int64_t e0, int64_t e1) {
     t->st_valid = false;
     t->pat_valid = false;
     t->rc_ready = false;
+    t->halo = false;
+    t->halo_src.clear();
+    t->vJ.release(); t->vI.release(); t->vmask.release();
   }
   GF_API_END
 }
@@ -273,7 +278,7 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
   const int nd = t->fem->nd, Q = t->fem->qdim, s1 = nd * Q;
   const int64_t ne = t->e1 - t->e0;
   if (!t->st_valid) {
-    gf::build_structure(ctx, t->fem->edof.p, nd, t->e0, t->e1, t->fem->ndof, t->st);
+    gf::build_structure(ctx, t->fem->edof.p, nd, t->e0, t->e1, t->fem->ndof, t->st, t->vJ.p, t->vI.p, (int64_t)t->vJ.n);
     t->st_valid = true;
     t->pat_valid = false;
   }
@@ -315,6 +320,7 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
     if (!t->pat_valid) {
       tic(3); gf::build_pattern(t); toc(3);
       t->emask.release();  // constant-coefficient linear form: the pattern cannot move any more
+      if (t->halo) gf::halo_build_maps(t);
     }
     if (!t->rc_ready) gf::recompute_prepare(t);
     if (do_r) { tic(2); gf::recompute_assemble(t, U_dev, false, true); toc(2); }
@@ -327,6 +333,7 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
                                  t->family == GFGPU_NEOHOOKEAN_BONET;
     if (!t->pat_valid) {
       tic(3); gf::build_pattern(t); toc(3);
+      if (t->halo) gf::halo_build_maps(t);
       tic(1); gf::gather_tangent(t, false); toc(1);
     } else if (!value_dependent) {
       tic(1); gf::gather_tangent(t, false); toc(1);
@@ -337,6 +344,7 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
       t->flag.download(&changed);
       GF_CUDA(cudaStreamSynchronize(ctx->stream));
       if (changed) {
+        GF_REQUIRE(!t->halo, "the pattern moved under a multi-GPU halo: announce the pairs again (halo_begin .. halo_commit)");
         tic(3); gf::build_pattern(t); toc(3);
         tic(1); gf::gather_tangent(t, false); toc(1);
       }
@@ -420,6 +428,160 @@ int gfgpu_term_export_residual_host(gfgpu_term *t, double *R) {
   GF_CUDA(cudaSetDevice(t->ctx->device));
   if (R) t->R.download(R);
   GF_CUDA(cudaStreamSynchronize(t->ctx->stream));
+  GF_API_END
+}
+
+
+/* ------------------------------------------------------------------ multi-GPU halo */
+int gfgpu_term_halo_begin(gfgpu_term *t, const double *U_dev, int64_t *touched_lo, int64_t *touched_hi) {
+  GF_API_BEGIN
+  GF_REQUIRE(t, "null term");
+  GF_CUDA(cudaSetDevice(t->ctx->device));
+  // forget a previous halo, then build the LOCAL structure + pattern (one tangent pass)
+  t->halo = false;
+  t->halo_src.clear();
+  t->vJ.release(); t->vI.release(); t->vmask.release();
+  t->st_valid = false; t->pat_valid = false; t->rc_ready = false;
+  term_assemble(t, U_dev, GFGPU_TANGENT);
+  // the pair records of RECOMPUTE dropped prel; the announcement below only needs pJ / pI / pmask
+  int64_t lo = 0, hi = 0;
+  if (t->st.nrnodes) {
+    int32_t first = 0, last = 0;
+    GF_CUDA(cudaMemcpyAsync(&first, t->st.rdof.p, sizeof(int32_t), cudaMemcpyDeviceToHost, t->ctx->stream));
+    GF_CUDA(cudaMemcpyAsync(&last, t->st.rdof.p + t->st.nrnodes - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, t->ctx->stream));
+    GF_CUDA(cudaStreamSynchronize(t->ctx->stream));
+    lo = first; hi = (int64_t)last + t->fem->qdim;
+  }
+  if (touched_lo) *touched_lo = lo;
+  if (touched_hi) *touched_hi = hi;
+  GF_API_END
+}
+
+int gfgpu_term_halo_ghost_pairs(gfgpu_term *t, int64_t dof_lo, int64_t dof_hi, int64_t *n, int32_t *J_host,
+                                int32_t *I_host, uint16_t *mask_host) {
+  GF_API_BEGIN
+  GF_REQUIRE(t && n && t->pat_valid, "halo_begin first");
+  GF_CUDA(cudaSetDevice(t->ctx->device));
+  gf::Structure &st = t->st;
+  // pairs are sorted by (J, I): the columns [dof_lo, dof_hi) are a contiguous range of pairs
+  std::vector<int32_t> pJ(st.npairs);
+  st.pJ.download(pJ.data());
+  GF_CUDA(cudaStreamSynchronize(t->ctx->stream));
+  const int64_t a = std::lower_bound(pJ.begin(), pJ.end(), (int32_t)std::min<int64_t>(dof_lo, INT32_MAX)) - pJ.begin();
+  const int64_t b = std::lower_bound(pJ.begin(), pJ.end(), (int32_t)std::min<int64_t>(dof_hi, INT32_MAX)) - pJ.begin();
+  *n = b - a;
+  if (J_host && I_host && mask_host && b > a) {
+    std::copy(pJ.begin() + a, pJ.begin() + b, J_host);
+    GF_CUDA(cudaMemcpyAsync(I_host, st.pI.p + a, (b - a) * sizeof(int32_t), cudaMemcpyDeviceToHost, t->ctx->stream));
+    GF_CUDA(cudaMemcpyAsync(mask_host, t->pmask.p + a, (b - a) * sizeof(uint16_t), cudaMemcpyDeviceToHost, t->ctx->stream));
+    GF_CUDA(cudaStreamSynchronize(t->ctx->stream));
+  }
+  GF_API_END
+}
+
+int gfgpu_term_halo_add_source(gfgpu_term *t, int src_rank, int64_t n, const int32_t *J_host, const int32_t *I_host,
+                               const uint16_t *mask_host, int64_t r_lo, int64_t r_hi) {
+  GF_API_BEGIN
+  GF_REQUIRE(t && (n == 0 || (J_host && I_host && mask_host)), "null argument");
+  GF_REQUIRE(t->halo_src.empty() || t->halo_src.back()->rank < src_rank, "sources must be added in ascending rank order");
+  GF_REQUIRE(0 <= r_lo && r_lo <= r_hi && r_hi <= t->fem->ndof, "bad residual range");
+  GF_CUDA(cudaSetDevice(t->ctx->device));
+  const int Q = t->fem->qdim;
+  std::unique_ptr<gfgpu_term::HaloSource> hs(new gfgpu_term::HaloSource);
+  hs->rank = src_rank; hs->n = n; hs->r_lo = r_lo; hs->r_hi = r_hi;
+  // layout of the source's segment = its CSC restricted to these columns: columns ascending, component by
+  // component, rows ascending.  The announced pairs are sorted by (J, I).
+  std::vector<uint32_t> soff((size_t)Q * std::max<int64_t>(n, 1), 0);
+  int64_t run = 0;
+  for (int64_t k = 0; k < n;) {
+    int64_t k1 = k;
+    while (k1 < n && J_host[k1] == J_host[k]) ++k1;
+    for (int b = 0; b < Q; ++b)
+      for (int64_t q = k; q < k1; ++q) {
+        GF_REQUIRE(q == k || I_host[q] > I_host[q - 1], "announced pairs are not sorted by (J, I)");
+        soff[(size_t)b * n + q] = (uint32_t)run;
+        run += __builtin_popcount((mask_host[q] >> (b * Q)) & ((1u << Q) - 1));
+      }
+    GF_REQUIRE(k1 == n || J_host[k1] > J_host[k], "announced pairs are not sorted by (J, I)");
+    k = k1;
+  }
+  GF_REQUIRE(run < (int64_t(1) << 32), "halo segment too large");
+  hs->nvals = run;
+  hs->J.alloc(t->ctx, n); hs->I.alloc(t->ctx, n); hs->mask.alloc(t->ctx, n); hs->soff.alloc(t->ctx, (size_t)Q * n);
+  hs->J.upload(J_host); hs->I.upload(I_host); hs->mask.upload(mask_host); hs->soff.upload(soff.data());
+  hs->rrecv.alloc(t->ctx, std::max<int64_t>(r_hi - r_lo, 1));
+  GF_CUDA(cudaStreamSynchronize(t->ctx->stream));
+  t->halo_src.push_back(std::move(hs));
+  GF_API_END
+}
+
+int gfgpu_term_halo_commit(gfgpu_term *t, int64_t own_lo, int64_t own_hi) {
+  GF_API_BEGIN
+  GF_REQUIRE(t, "null term");
+  GF_REQUIRE(0 <= own_lo && own_lo <= own_hi && own_hi <= t->fem->ndof, "bad owned range");
+  GF_CUDA(cudaSetDevice(t->ctx->device));
+  int64_t nv = 0;
+  for (auto &hs : t->halo_src) nv += hs->n;
+  t->vJ.alloc(t->ctx, nv); t->vI.alloc(t->ctx, nv); t->vmask.alloc(t->ctx, nv);
+  int64_t at = 0;
+  for (auto &hs : t->halo_src) {
+    if (!hs->n) continue;
+    GF_CUDA(cudaMemcpyAsync(t->vJ.p + at, hs->J.p, hs->n * sizeof(int32_t), cudaMemcpyDeviceToDevice, t->ctx->stream));
+    GF_CUDA(cudaMemcpyAsync(t->vI.p + at, hs->I.p, hs->n * sizeof(int32_t), cudaMemcpyDeviceToDevice, t->ctx->stream));
+    GF_CUDA(cudaMemcpyAsync(t->vmask.p + at, hs->mask.p, hs->n * sizeof(uint16_t), cudaMemcpyDeviceToDevice, t->ctx->stream));
+    at += hs->n;
+  }
+  t->halo = true;
+  t->own_lo = own_lo; t->own_hi = own_hi;
+  t->st_valid = false; t->pat_valid = false; t->rc_ready = false;  // rebuilt with the virtual pairs at the next assemble
+  GF_API_END
+}
+
+int gfgpu_term_halo_send_view(gfgpu_term *t, int64_t dof_lo, int64_t dof_hi, const double **pr_dev, int64_t *count,
+                              const double **R_dev) {
+  GF_API_BEGIN
+  GF_REQUIRE(t && t->halo && t->pat_valid, "assemble after halo_commit first");
+  GF_REQUIRE(0 <= dof_lo && dof_lo <= dof_hi && dof_hi <= t->fem->ndof, "bad dof range");
+  GF_CUDA(cudaSetDevice(t->ctx->device));
+  int64_t a = 0, b = 0;
+  GF_CUDA(cudaMemcpyAsync(&a, t->jc.p + dof_lo, sizeof(int64_t), cudaMemcpyDeviceToHost, t->ctx->stream));
+  GF_CUDA(cudaMemcpyAsync(&b, t->jc.p + dof_hi, sizeof(int64_t), cudaMemcpyDeviceToHost, t->ctx->stream));
+  GF_CUDA(cudaStreamSynchronize(t->ctx->stream));
+  if (pr_dev) *pr_dev = t->pr.p + a;
+  if (count) *count = b - a;
+  if (R_dev) *R_dev = t->R.n ? t->R.p + dof_lo : nullptr;
+  GF_API_END
+}
+
+int gfgpu_term_halo_recv_view(gfgpu_term *t, int src_rank, double **pr_recv_dev, int64_t *count, double **R_recv_dev,
+                              int64_t *r_count) {
+  GF_API_BEGIN
+  GF_REQUIRE(t && t->halo && t->pat_valid, "assemble after halo_commit first");
+  for (auto &hs : t->halo_src)
+    if (hs->rank == src_rank) {
+      if (pr_recv_dev) *pr_recv_dev = hs->recv.p;
+      if (count) *count = hs->nvals;
+      if (R_recv_dev) *R_recv_dev = hs->rrecv.p;
+      if (r_count) *r_count = hs->r_hi - hs->r_lo;
+      return 0;
+    }
+  GF_REQUIRE(false, "unknown halo source rank");
+  GF_API_END
+}
+
+int gfgpu_term_halo_accumulate(gfgpu_term *t, int order_mask) {
+  GF_API_BEGIN
+  GF_REQUIRE(t && t->halo && t->pat_valid, "assemble after halo_commit first");
+  GF_CUDA(cudaSetDevice(t->ctx->device));
+  gf::halo_accumulate(t, order_mask & GFGPU_TANGENT, order_mask & GFGPU_RESIDUAL);
+  GF_API_END
+}
+
+int gfgpu_term_owned_range(gfgpu_term *t, int64_t *own_lo, int64_t *own_hi) {
+  GF_API_BEGIN
+  GF_REQUIRE(t, "null term");
+  if (own_lo) *own_lo = t->halo ? t->own_lo : 0;
+  if (own_hi) *own_hi = t->halo ? t->own_hi : t->fem->ndof;
   GF_API_END
 }
 

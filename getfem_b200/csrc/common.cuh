@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -104,7 +105,8 @@ namespace gf {
 // Structural (value-independent) part of the scatter: node pairs and their contributions.
 struct Structure {
   int64_t e0 = 0, e1 = 0;  // element range it was built for
-  int64_t ncontrib = 0;    // (e1-e0) * nd * nd
+  int64_t ncontrib = 0;    // (e1-e0) * nd * nd : LOCAL contributions; ids >= ncontrib in csrc are virtual (halo)
+  int64_t nvirt = 0;       // virtual contributions: pairs announced by other ranks for columns owned here
   int64_t npairs = 0;
   int64_t ncolnodes = 0;
   DevBuf<int32_t> pI, pJ;      // dof0 of row / column node of each pair (pairs sorted by (J, I))
@@ -167,6 +169,23 @@ struct gfgpu_term {
   // [2k, 2k+1], k = 0 element kernel, 1 gather, 2 residual gather, 3 pattern, 4 recompute kernel
   cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ev_used[5] = {false, false, false, false, false};
+  // multi-GPU halo: this rank owns the columns [own_lo, own_hi); columns below own_lo are ghosts
+  // whose partial values are sent to their owners, sources are the ranks that send their parts of OUR columns
+  struct HaloSource {
+    int rank = 0;
+    int64_t n = 0, nvals = 0;            // announced pairs; values per assembly
+    int64_t r_lo = 0, r_hi = 0;          // residual range received from this source
+    gf::DevBuf<int32_t> J, I;
+    gf::DevBuf<uint16_t> mask;
+    gf::DevBuf<uint32_t> soff;           // Q x n: offset of the pair's first kept entry of component b in the source's segment
+    gf::DevBuf<int64_t> map;             // nvals: position in pr of every received value
+    gf::DevBuf<double> recv, rrecv;      // tangent values, residual slice
+  };
+  bool halo = false;
+  int64_t own_lo = 0, own_hi = 0;
+  std::vector<std::unique_ptr<HaloSource>> halo_src;
+  gf::DevBuf<int32_t> vJ, vI;            // all announced pairs, concatenated in source order
+  gf::DevBuf<uint16_t> vmask;
   // strategy RECOMPUTE
   bool rc_ready = false;
   gf::DevBuf<double> rc_M;      // reference tensors per (j,i)
@@ -209,7 +228,9 @@ int64_t enumerate_dof(gfgpu_ctx *ctx, const int32_t *conn, int64_t ne, int ng, i
 
 // ---- scatter structure / pattern / gather (scatter.cu)
 void build_structure(gfgpu_ctx *ctx, const int32_t *edof, int nd, int64_t e0, int64_t e1, int64_t ndof,
-                     Structure &st);
+                     Structure &st, const int32_t *vJ = nullptr, const int32_t *vI = nullptr, int64_t nvirt = 0);
+void halo_build_maps(gfgpu_term *t);
+void halo_accumulate(gfgpu_term *t, bool do_t, bool do_r);
 void build_pattern(gfgpu_term *t);
 void gather_tangent(gfgpu_term *t, bool check);
 void gather_residual(gfgpu_term *t);

@@ -270,7 +270,7 @@ __global__ void k_tile_fill(const TileHdr *__restrict__ hdr, const uint32_t *__r
                             const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ csrc,
                             const int32_t *__restrict__ pJ, const uint16_t *__restrict__ pmask,
                             const uint32_t *__restrict__ prel, const int64_t *__restrict__ jc, int64_t npairs, int nd,
-                            int cbits, uint32_t zslot, int64_t ntask, uint4 *__restrict__ rec,
+                            int cbits, uint32_t zslot, int64_t ntask, uint32_t nlocal, uint4 *__restrict__ rec,
                             uint16_t *__restrict__ dblob, int *__restrict__ err) {
   const uint32_t nb = nd * nd;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < ntask * 32;
@@ -314,7 +314,7 @@ __global__ void k_tile_fill(const TileHdr *__restrict__ hdr, const uint32_t *__r
     for (uint32_t c = 0; c < (bl ? (uint32_t)TL_INREC : steps); ++c) {
       const uint32_t ci = wide ? c * 32 + lane : c;  // contribution handled at step c
       uint32_t d = zdesc;
-      if (ci < cnt && c < steps) {
+      if (ci < cnt && c < steps && csrc[s0 + ci] < nlocal) {  // virtual (halo) contributions add nothing here
         const uint32_t ctr = csrc[s0 + ci];
         const uint32_t el = ctr / nb, rr = ctr - el * nb;  // rr = j*nd + i
         uint32_t lo = 0, hi = h.nel;                       // first position with te[pos] >= el
@@ -969,7 +969,8 @@ void recompute_prepare(gfgpu_term *t) {
 #define GF_FILL(QQ)                                                                                                  \
   k_tile_fill<QQ><<<grid, B, 0, s>>>(dh, tk_tile.p, sp_pair.p, t->rc_els.p, cap_inc, st.cstart.p, st.csrc.p,         \
                                      st.pJ.p, t->pmask.p, t->prel.p, t->jc.p, st.npairs, nd, cbits,                 \
-                                     (uint32_t)cap_slots, ntask, (uint4 *)t->rc_prec.p, t->rc_dblob.p,              \
+                                     (uint32_t)cap_slots, ntask, (uint32_t)st.ncontrib, (uint4 *)t->rc_prec.p,      \
+                                     t->rc_dblob.p,                                                                 \
                                      (int *)t->flag.p)
     if (Q == 1) GF_FILL(1);
     else if (Q == 2) GF_FILL(2);
@@ -981,7 +982,7 @@ void recompute_prepare(gfgpu_term *t) {
   t->flag.download(&err);
   GF_CUDA(cudaStreamSynchronize(s));
   GF_REQUIRE(err == 0, "recompute plan failed (code " + std::to_string(err) + "): tile too large for the compact records");
-  t->prel.release();  // folded into the pair records
+  if (!t->halo) t->prel.release();  // folded into the pair records
   t->rc_ready = true;
 }
 

@@ -103,19 +103,29 @@ static int64_t select_heads(gfgpu_ctx *ctx, const uint8_t *flags, int64_t n, uin
   return h;
 }
 
-void build_structure(gfgpu_ctx *ctx, const int32_t *edof, int nd, int64_t e0, int64_t e1, int64_t ndof, Structure &st) {
+__global__ void k_virtual_keys(const int32_t *__restrict__ vJ, const int32_t *__restrict__ vI, int64_t nvirt, int bI,
+                               int64_t first, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nvirt; k += (int64_t)gridDim.x * blockDim.x) {
+    keys[first + k] = ((uint64_t)(uint32_t)vJ[k] << bI) | (uint64_t)(uint32_t)vI[k];
+    vals[first + k] = (uint32_t)(first + k);
+  }
+}
+
+void build_structure(gfgpu_ctx *ctx, const int32_t *edof, int nd, int64_t e0, int64_t e1, int64_t ndof, Structure &st,
+                     const int32_t *vJ, const int32_t *vI, int64_t nvirt) {
   const int64_t ne = e1 - e0;
   const int64_t nb = (int64_t)nd * nd;
   st.e0 = e0;
   st.e1 = e1;
   st.ncontrib = ne * nb;
-  GF_REQUIRE(st.ncontrib < (int64_t(1) << 32), "element block too large: (ne*nd*nd) must stay below 2^32");
+  st.nvirt = nvirt;
+  GF_REQUIRE(st.ncontrib + nvirt < (int64_t(1) << 32), "element block too large: (ne*nd*nd) must stay below 2^32");
   const int bI = nbits(ndof);
   GF_REQUIRE(2 * bI <= 64, "ndof too large");
   cudaStream_t s = ctx->stream;
   const int B = 256;
-  {  // ---- tangent: sort contributions by (J, I)
-    const int64_t n = st.ncontrib;
+  {  // ---- tangent: sort contributions by (J, I); the virtual ones (halo) go after the local ones of their pair
+    const int64_t n = st.ncontrib + nvirt;
     DevBuf<uint64_t> k0, k1;
     DevBuf<uint32_t> v0;
     k0.alloc(ctx, n);
@@ -123,8 +133,14 @@ void build_structure(gfgpu_ctx *ctx, const int32_t *edof, int nd, int64_t e0, in
     v0.alloc(ctx, n);
     st.csrc.alloc(ctx, n);
     if (n) {
-      k_pair_keys<<<min(grid_for(n, B), 148 * 16), B, 0, s>>>(edof, nd, e0, n, bI, k0.p, v0.p);
-      GF_LAUNCH_CHECK();
+      if (st.ncontrib) {
+        k_pair_keys<<<min(grid_for(st.ncontrib, B), 148 * 16), B, 0, s>>>(edof, nd, e0, st.ncontrib, bI, k0.p, v0.p);
+        GF_LAUNCH_CHECK();
+      }
+      if (nvirt) {
+        k_virtual_keys<<<min(grid_for(nvirt, B), 148 * 16), B, 0, s>>>(vJ, vI, nvirt, bI, st.ncontrib, k0.p, v0.p);
+        GF_LAUNCH_CHECK();
+      }
       // explicit in/out buffers: the sorted values land in st.csrc
       size_t tb = 0;
       GF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, k0.p, k1.p, v0.p, st.csrc.p, n, 0, 2 * bI, s));
@@ -205,10 +221,14 @@ void build_structure(gfgpu_ctx *ctx, const int32_t *edof, int nd, int64_t e0, in
 
 // ------------------------------------------------------------------ pattern
 __global__ void k_pair_masks(const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ csrc,
-                             const uint16_t *__restrict__ emask, int64_t npairs, uint16_t *__restrict__ pmask) {
+                             const uint16_t *__restrict__ emask, int64_t npairs, uint32_t nlocal,
+                             const uint16_t *__restrict__ vmask, uint16_t *__restrict__ pmask) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npairs; p += (int64_t)gridDim.x * blockDim.x) {
     unsigned m = 0;
-    for (uint32_t s = cstart[p], e = cstart[p + 1]; s < e; ++s) m |= emask[csrc[s]];
+    for (uint32_t s = cstart[p], e = cstart[p + 1]; s < e; ++s) {
+      const uint32_t c = csrc[s];
+      m |= c < nlocal ? emask[c] : vmask[c - nlocal];  // virtual contribution: the mask announced by its rank
+    }
     pmask[p] = (uint16_t)m;
   }
 }
@@ -268,7 +288,7 @@ static void build_pattern_t(gfgpu_term *t) {
   t->ctot.zero();
   if (st.npairs) {
     k_pair_masks<<<min(grid_for(st.npairs, B), 148 * 32), B, 0, s>>>(st.cstart.p, st.csrc.p, t->emask.p, st.npairs,
-                                                                   t->pmask.p);
+                                                                   (uint32_t)st.ncontrib, t->vmask.p, t->pmask.p);
     GF_LAUNCH_CHECK();
     k_column_scan<Q><<<min(grid_for(st.ncolnodes, B), 148 * 32), B, 0, s>>>(st.colstart.p, st.pJ.p, t->pmask.p,
                                                                           st.ncolnodes, st.npairs, t->prel.p, t->ctot.p);
@@ -303,6 +323,89 @@ void build_pattern(gfgpu_term *t) {
   }
 }
 
+// ------------------------------------------------------------------ halo maps (multi-GPU)
+// thread per announced pair of one source: position in OUR pr of each value the source will send
+template <int Q>
+__global__ void k_halo_map(const int32_t *__restrict__ sJ, const int32_t *__restrict__ sI,
+                           const uint16_t *__restrict__ smask, const uint32_t *__restrict__ soff, int64_t n,
+                           const int32_t *__restrict__ pJ, const int32_t *__restrict__ pI,
+                           const uint16_t *__restrict__ pmask, const uint32_t *__restrict__ prel,
+                           const int64_t *__restrict__ jc, int64_t npairs, int64_t *__restrict__ map,
+                           int *__restrict__ err) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t J = sJ[k], I = sI[k];
+    int64_t lo = 0, hi = npairs;  // first pair >= (J, I)
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      const bool less = pJ[mid] < J || (pJ[mid] == J && pI[mid] < I);
+      if (less) lo = mid + 1; else hi = mid;
+    }
+    if (lo >= npairs || pJ[lo] != J || pI[lo] != I) { *err = 1; continue; }
+    const unsigned ms = smask[k], mm = pmask[lo];
+    if (ms & ~mm) { *err = 2; continue; }
+#pragma unroll
+    for (int b = 0; b < Q; ++b) {
+      const unsigned sb = (ms >> (b * Q)) & ((1u << Q) - 1), mb = (mm >> (b * Q)) & ((1u << Q) - 1);
+      int64_t src = soff[(size_t)b * n + k];
+      const int64_t dst = jc[J + b] + prel[(size_t)b * npairs + lo];
+#pragma unroll
+      for (int a = 0; a < Q; ++a)
+        if (sb & (1u << a)) map[src++] = dst + __popc(mb & ((1u << a) - 1));
+    }
+  }
+}
+
+__global__ void k_halo_add(const double *__restrict__ recv, const int64_t *__restrict__ map, int64_t n,
+                           double *__restrict__ pr) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+    pr[map[k]] += recv[k];
+}
+
+__global__ void k_vec_add(const double *__restrict__ src, int64_t n, double *__restrict__ dst) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+    dst[k] += src[k];
+}
+
+void halo_build_maps(gfgpu_term *t) {
+  Structure &st = t->st;
+  const int Q = t->fem->qdim;
+  cudaStream_t s = t->ctx->stream;
+  t->flag.zero();
+  for (auto &hs : t->halo_src) {
+    hs->map.alloc(t->ctx, std::max<int64_t>(hs->nvals, 1));
+    hs->recv.alloc(t->ctx, std::max<int64_t>(hs->nvals, 1));
+    if (!hs->n) continue;
+    const int grid = min(grid_for(hs->n, 256), 148 * 32);
+#define GF_MAP(QQ)                                                                                                     \
+  k_halo_map<QQ><<<grid, 256, 0, s>>>(hs->J.p, hs->I.p, hs->mask.p, hs->soff.p, hs->n, st.pJ.p, st.pI.p, t->pmask.p,   \
+                                      t->prel.p, t->jc.p, st.npairs, hs->map.p, (int *)t->flag.p)
+    if (Q == 1) GF_MAP(1);
+    else if (Q == 2) GF_MAP(2);
+    else GF_MAP(3);
+#undef GF_MAP
+    GF_LAUNCH_CHECK();
+  }
+  int32_t err = 0;
+  t->flag.download(&err);
+  GF_CUDA(cudaStreamSynchronize(s));
+  GF_REQUIRE(err == 0, "halo: an announced pair is missing from the merged pattern (code " + std::to_string(err) + ")");
+}
+
+void halo_accumulate(gfgpu_term *t, bool do_t, bool do_r) {
+  cudaStream_t s = t->ctx->stream;
+  for (auto &hs : t->halo_src) {  // ascending source rank: fixed summation order
+    if (do_t && hs->nvals) {
+      k_halo_add<<<min(grid_for(hs->nvals, 256), 148 * 32), 256, 0, s>>>(hs->recv.p, hs->map.p, hs->nvals, t->pr.p);
+      GF_LAUNCH_CHECK();
+    }
+    if (do_r && hs->r_hi > hs->r_lo) {
+      const int64_t n = hs->r_hi - hs->r_lo;
+      k_vec_add<<<min(grid_for(n, 256), 148 * 32), 256, 0, s>>>(hs->rrecv.p, n, t->R.p + hs->r_lo);
+      GF_LAUNCH_CHECK();
+    }
+  }
+}
+
 // ------------------------------------------------------------------ gather
 // One thread per node pair: sums the QxQ blocks of its contributions from the stage (ascending
 // element id) and writes the kept entries to their CSC slots.  With CHECK it also re-derives
@@ -312,7 +415,7 @@ __global__ void __launch_bounds__(256)
 k_gather(const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ csrc, const int32_t *__restrict__ pJ,
          const uint16_t *__restrict__ pmask, const uint32_t *__restrict__ prel, const int64_t *__restrict__ jc,
          const double *__restrict__ stage, const uint16_t *__restrict__ emask, int nd, int64_t npairs,
-         double *__restrict__ pr, int *__restrict__ flag) {
+         uint32_t nlocal, const uint16_t *__restrict__ vmask, double *__restrict__ pr, int *__restrict__ flag) {
   const int nb = nd * nd, s1 = nd * Q;
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npairs; p += (int64_t)gridDim.x * blockDim.x) {
     double acc[Q * Q];
@@ -321,6 +424,10 @@ k_gather(const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ csrc,
     unsigned mnew = 0;
     for (uint32_t s = cstart[p], e = cstart[p + 1]; s < e; ++s) {
       const uint32_t c = csrc[s];
+      if (c >= nlocal) {  // virtual (halo) contribution: its values arrive through gfgpu_term_halo_accumulate
+        if (CHECK) mnew |= vmask[c - nlocal];
+        continue;
+      }
       const uint32_t el = c / nb, r = c % nb;
       const int j = r / nd, i = r % nd;
       const double *src = stage + (size_t)el * s1 * s1 + (size_t)(j * Q) * s1 + i * Q;
@@ -351,12 +458,12 @@ static void gather_tangent_t(gfgpu_term *t, bool check) {
   int grid = min(grid_for(st.npairs, B), 148 * 64);
   if (check)
     k_gather<Q, true><<<grid, B, 0, t->ctx->stream>>>(st.cstart.p, st.csrc.p, st.pJ.p, t->pmask.p, t->prel.p, t->jc.p,
-                                                      t->stage.p, t->emask.p, t->fem->nd, st.npairs, t->pr.p,
-                                                      (int *)t->flag.p);
+                                                      t->stage.p, t->emask.p, t->fem->nd, st.npairs,
+                                                      (uint32_t)st.ncontrib, t->vmask.p, t->pr.p, (int *)t->flag.p);
   else
     k_gather<Q, false><<<grid, B, 0, t->ctx->stream>>>(st.cstart.p, st.csrc.p, st.pJ.p, t->pmask.p, t->prel.p, t->jc.p,
-                                                       t->stage.p, t->emask.p, t->fem->nd, st.npairs, t->pr.p,
-                                                       (int *)t->flag.p);
+                                                       t->stage.p, t->emask.p, t->fem->nd, st.npairs,
+                                                       (uint32_t)st.ncontrib, t->vmask.p, t->pr.p, (int *)t->flag.p);
   GF_LAUNCH_CHECK();
 }
 

@@ -1,0 +1,148 @@
+"""Multi-GPU halo exchange of the assembled tangent / residual (include/gfgpu.h "multi-GPU").
+
+One process per GPU; every rank assembles the element block it was given (DeviceTerm.set_element_range).
+Dofs are owned by the rank whose block touches them first, which with the reference's first-touch numbering
+(getfem_mesh_fem.cc:320-446) gives contiguous ranges [D[r], D[r+1]); the columns a rank touches below its
+range are ghosts.  Replaces the reference's MPI scheme -- every rank holds a full-size partial matrix / vector
+and MPI_SUM_SPARSE_MATRIX / MPI_SUM_VECTOR reduce them (getfem_generic_assembly_workspace.cc:855-858,
+getfem_models.cc:586,2572,2608) -- by column-owned slabs and ONE point-to-point exchange per assembly:
+
+  setup    (once)  touched ranges all-gathered -> owner bounds; every rank announces the (J, I, keep mask) pairs of
+                   its ghost columns to their owners (host mediated, pickled objects); owners merge them into
+                   their pattern (drop rule = OR of the masks);
+  exchange (every assembly)  ghost values = a contiguous slice of pr, residual = a slice of R, sent with
+                   isend/irecv (NCCL over NVLink on device tensors; gloo on CPU tensors in the tests), then the
+                   owner adds the received parts in ascending source rank: fixed order, no atomics.
+
+The term object only has to provide the halo_* methods of capi.DeviceTerm, so the protocol is tested on CPU under
+gloo with an oracle-backed term (tests/test_halo_gloo.py) and on one GPU with several terms (tests/test_gpu_halo.py).
+"""
+from dataclasses import dataclass, field
+
+
+def owner_bounds(touched_hi, ndof):
+    """D[r] = first dof owned by rank r: everything below max(hi of the lower ranks); the last rank keeps the rest."""
+    D = [0]
+    for h in touched_hi:
+        D.append(max(D[-1], int(h)))
+    D[-1] = max(D[-1], int(ndof))
+    return D
+
+
+@dataclass
+class HaloPlan:
+    rank: int
+    world: int
+    D: list
+    touched: tuple
+    sends: list = field(default_factory=list)    # (owner rank q, dof_lo, dof_hi, r_lo)
+    sources: list = field(default_factory=list)  # source ranks, ascending
+
+    @property
+    def own(self):
+        return self.D[self.rank], self.D[self.rank + 1]
+
+
+def announcements(term, rank, D, touched):
+    """{owner q: (J, I, mask, r_lo, r_hi)} for the ghost columns of `term`, and the matching send list."""
+    lo, hi = touched
+    out, sends = {}, []
+    for q in range(rank):
+        a, b = D[q], D[q + 1]
+        if b <= a or lo >= b or hi <= a:
+            continue
+        J, I, m = term.halo_ghost_pairs(a, b)
+        r_lo = max(lo, a)
+        if len(J) == 0:
+            continue
+        out[q] = (J, I, m, r_lo, b)
+        sends.append((q, a, b, r_lo))
+    return out, sends
+
+
+def merge(term, plan, incoming):
+    """incoming: {source rank: (J, I, mask, r_lo, r_hi)} announced for the columns this rank owns."""
+    for src in sorted(incoming):
+        J, I, m, r_lo, r_hi = incoming[src]
+        term.halo_add_source(src, J, I, m, r_lo, r_hi)
+        plan.sources.append(src)
+    term.halo_commit(*plan.own)
+
+
+# ---------------------------------------------------------------- torch.distributed driver (one process per GPU)
+def setup_distributed(term, U_dev_ptr=None, group=None):
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    touched = term.halo_begin(U_dev_ptr)
+    his = [None] * world
+    dist.all_gather_object(his, int(touched[1]), group=group)
+    D = owner_bounds(his, term.ndof)
+    plan = HaloPlan(rank, world, D, touched)
+    out, plan.sends = announcements(term, rank, D, touched)
+    everything = [None] * world
+    dist.all_gather_object(everything, out, group=group)
+    incoming = {src: everything[src][rank] for src in range(world) if rank in everything[src]}
+    merge(term, plan, incoming)
+    return plan
+
+
+def exchange_distributed(term, plan, order_mask, group=None):
+    """Call after term.assemble_dev(..., order_mask), on the stream the term's context was created with."""
+    import torch.distributed as dist
+    from . import capi
+    ops, keep = [], []
+    for q, a, b, r_lo in plan.sends:
+        pr, R = term.halo_send_buffers(a, b, r_lo)
+        if (order_mask & capi.TANGENT) and pr.numel():
+            ops.append(dist.P2POp(dist.isend, pr, q, group))
+        if (order_mask & capi.RESIDUAL) and R.numel():
+            ops.append(dist.P2POp(dist.isend, R, q, group))
+        keep += [pr, R]
+    for src in plan.sources:
+        pr, R = term.halo_recv_buffers(src)
+        if (order_mask & capi.TANGENT) and pr.numel():
+            ops.append(dist.P2POp(dist.irecv, pr, src, group))
+        if (order_mask & capi.RESIDUAL) and R.numel():
+            ops.append(dist.P2POp(dist.irecv, R, src, group))
+        keep += [pr, R]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    term.halo_accumulate(order_mask)
+
+
+# ---------------------------------------------------------------- in-process driver (several terms, one process)
+def setup_local(terms, U_dev_ptr=None):
+    """terms[r] plays rank r (same mesh / fem, disjoint element blocks in rank order)."""
+    world = len(terms)
+    touched = [t.halo_begin(U_dev_ptr) for t in terms]
+    D = owner_bounds([h for _, h in touched], terms[0].ndof)
+    plans, outs = [], []
+    for r, t in enumerate(terms):
+        plan = HaloPlan(r, world, D, touched[r])
+        out, plan.sends = announcements(t, r, D, touched[r])
+        plans.append(plan)
+        outs.append(out)
+    for r, t in enumerate(terms):
+        merge(t, plans[r], {src: outs[src][r] for src in range(world) if r in outs[src]})
+    return plans
+
+
+def exchange_local(terms, plans, order_mask):
+    """Copies the send slices into the owners' receive buffers (same device or host), then accumulates."""
+    for t in terms:
+        t.ctx_synchronize()
+    cuda = False
+    for r, t in enumerate(terms):
+        for q, a, b, r_lo in plans[r].sends:
+            pr, R = t.halo_send_buffers(a, b, r_lo)
+            dpr, dR = terms[q].halo_recv_buffers(r)
+            assert dpr.numel() == pr.numel() and dR.numel() == R.numel(), (dpr.numel(), pr.numel(), dR.numel(), R.numel())
+            dpr.copy_(pr)
+            dR.copy_(R)
+            cuda = cuda or pr.is_cuda
+    if cuda:
+        import torch
+        torch.cuda.synchronize()
+    for t in terms:
+        t.halo_accumulate(order_mask)

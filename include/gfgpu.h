@@ -147,6 +147,39 @@ int gfgpu_term_residual_view(gfgpu_term *t, const double **R_dev);
 int gfgpu_term_export_csc_host(gfgpu_term *t, int64_t *jc_host, int32_t *ir_host, double *pr_host);
 int gfgpu_term_export_residual_host(gfgpu_term *t, double *R_host);
 
+/* ---- multi-GPU: element blocks per rank, column-owned CSC slabs, one halo exchange per assembly.
+ * Replaces the reference's MPI scheme (per-rank partial matrices summed with MPI_SUM_SPARSE_MATRIX /
+ * MPI_SUM_VECTOR, getfem_generic_assembly_workspace.cc:855-858, getfem_models.cc:586,2572,2608) by owned slabs:
+ * dofs are owned by the rank whose element block touches them first (first-touch numbering, getfem_mesh_fem.cc:
+ * 320-446, makes these contiguous ranges [own_lo, own_hi)); a rank's columns below own_lo are ghosts.
+ *   symbolic, once (host mediated, any transport):
+ *     halo_begin        local structure + pattern of the element block; returns the dof range it touches
+ *     halo_ghost_pairs  the (column node J, row node I, keep mask) pairs of MY ghost columns in [dof_lo, dof_hi),
+ *                       sorted by (J, I), to be sent to the owner of that range (call with NULL arrays for n)
+ *     halo_add_source   pairs announced BY rank src for columns I own (ascending src), and the dof range of
+ *                       the residual slice it will send
+ *     halo_commit       declares the owned range; the next assemble rebuilds the pattern with the announced
+ *                       pairs merged in (reference drop rule = OR of the keep masks)
+ *   numeric, every assembly (device pointers, e.g. ncclSend / ncclRecv on them):
+ *     assemble_dev      local contributions; owned columns are written in the merged layout
+ *     halo_send_view    my partial values of the ghost columns [dof_lo, dof_hi): a contiguous slice of pr,
+ *                       and the matching slice of the residual
+ *     halo_recv_view    where the values of source rank src must land
+ *     halo_accumulate   owner adds the received parts in ascending source rank (fixed order, no atomics)
+ * After halo_accumulate the columns [own_lo, own_hi) of the CSC view and R[own_lo, own_hi) are complete. */
+int gfgpu_term_halo_begin(gfgpu_term *t, const double *U_dev, int64_t *touched_lo, int64_t *touched_hi);
+int gfgpu_term_halo_ghost_pairs(gfgpu_term *t, int64_t dof_lo, int64_t dof_hi, int64_t *n, int32_t *J_host,
+                                int32_t *I_host, uint16_t *mask_host);
+int gfgpu_term_halo_add_source(gfgpu_term *t, int src_rank, int64_t n, const int32_t *J_host, const int32_t *I_host,
+                               const uint16_t *mask_host, int64_t r_lo, int64_t r_hi);
+int gfgpu_term_halo_commit(gfgpu_term *t, int64_t own_lo, int64_t own_hi);
+int gfgpu_term_halo_send_view(gfgpu_term *t, int64_t dof_lo, int64_t dof_hi, const double **pr_dev, int64_t *count,
+                              const double **R_dev);
+int gfgpu_term_halo_recv_view(gfgpu_term *t, int src_rank, double **pr_recv_dev, int64_t *count, double **R_recv_dev,
+                              int64_t *r_count);
+int gfgpu_term_halo_accumulate(gfgpu_term *t, int order_mask);
+int gfgpu_term_owned_range(gfgpu_term *t, int64_t *own_lo, int64_t *own_hi);
+
 #ifdef __cplusplus
 }
 #endif
