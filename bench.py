@@ -44,6 +44,13 @@ def peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+class _DevI64:
+    """zero-copy int64 view of library-owned device memory (reads the owned nnz from the device jc)"""
+
+    def __init__(self, p, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (p, False), "version": 2}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -220,10 +227,31 @@ def main():
 
     ORDER = capi.TANGENT | capi.RESIDUAL
     t_sym = time.time()
-    term.assemble_dev(U_dev.data_ptr(), ORDER)  # builds structure + pattern, first numeric pass
+    plan = None
+    if world > 1:
+        # symbolic halo phase (once): owner bounds, ghost-pair announcements merged into the owners' patterns
+        from getfem_b200 import halo
+        with torch.cuda.stream(stream):
+            plan = halo.setup_distributed(term, U_dev.data_ptr())
+
+    def step():
+        """one tangent + residual assembly; with N > 1 it ends with the halo exchange, after which this rank's
+        owned column slab and residual slice are complete"""
+        term.assemble_dev(U_dev.data_ptr(), ORDER)
+        if plan is not None:
+            halo.exchange_distributed(term, plan, ORDER)
+
+    with torch.cuda.stream(stream):
+        step()  # builds structure + pattern, first numeric pass
     ctx.synchronize()
     t_sym = time.time() - t_sym
     nnz = term.nnz
+    nnz_owned = nnz
+    if plan is not None:
+        own_lo, own_hi = plan.own
+        jcp = term.csc_view()[0]
+        jc_t = torch.as_tensor(_DevI64(jcp, ndof + 1), device="cuda:%d" % local)
+        nnz_owned = int(jc_t[own_hi].item()) - int(jc_t[own_lo].item())
 
     def barrier():
         if world > 1:
@@ -233,8 +261,9 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()  # started before the warm-up so that it is sampling when the timed region begins
-    for _ in range(args.warmup):
-        term.assemble_dev(U_dev.data_ptr(), ORDER)
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step()
     barrier()
     if rank == 0:
         sampler.mark()
@@ -245,7 +274,7 @@ def main():
     with torch.cuda.stream(stream):
         ev0.record()
         for _ in range(args.steps):
-            term.assemble_dev(U_dev.data_ptr(), ORDER)
+            step()
         ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -260,7 +289,7 @@ def main():
         tms = torch.tensor([ms], device="cuda:%d" % local, dtype=torch.float64)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
-        tot = torch.tensor([ne_local, nnz], device="cuda:%d" % local, dtype=torch.float64)
+        tot = torch.tensor([ne_local, nnz_owned], device="cuda:%d" % local, dtype=torch.float64)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         ne_all, nnz_all = int(tot[0].item()), int(tot[1].item())
     else:
@@ -268,17 +297,39 @@ def main():
     ms_step = ms / args.steps
     value = ne_all / (ms_step * 1e-3)
 
-    # ---- end to end through the host-buffer entry point (pinned host memory)
-    pr_host = torch.empty(nnz, dtype=torch.float64, pin_memory=True)
-    R_host = torch.empty(ndof, dtype=torch.float64, pin_memory=True)
+    # ---- end to end with HOST buffers (pinned): U host->device, assembly, CSC values + residual device->host.
+    # N = 1: the drop-in call gfgpu_term_assemble_host.  N > 1: the same three phases around the halo exchange,
+    # every rank returning its OWNED column slab and residual slice.
     U_pin = torch.from_numpy(U_host).pin_memory()
-    term.assemble_host(U_pin.numpy(), ORDER, pr_host.numpy(), R_host.numpy())  # warm-up
+    if plan is None:
+        pr_host = torch.empty(nnz, dtype=torch.float64, pin_memory=True)
+        R_host = torch.empty(ndof, dtype=torch.float64, pin_memory=True)
+        h2d_bytes, d2h_bytes = 8 * ndof, 8 * nnz + 8 * ndof
+
+        def e2e_step():
+            term.assemble_host(U_pin.numpy(), ORDER, pr_host.numpy(), R_host.numpy())
+    else:
+        own_lo, own_hi = plan.own
+        jc0 = int(jc_t[own_lo].item())
+        pr_host = torch.empty(nnz_owned, dtype=torch.float64, pin_memory=True)
+        R_host = torch.empty(own_hi - own_lo, dtype=torch.float64, pin_memory=True)
+        h2d_bytes, d2h_bytes = 8 * ndof, 8 * nnz_owned + 8 * (own_hi - own_lo)
+
+        def e2e_step():
+            U_dev.copy_(U_pin, non_blocking=True)
+            step()
+            _, _, prp = term.csc_view()
+            pr_host.copy_(capi._dev_tensor(prp + 8 * jc0, nnz_owned, local), non_blocking=True)
+            R_host.copy_(capi._dev_tensor(term.residual_view() + 8 * own_lo, own_hi - own_lo, local), non_blocking=True)
+            stream.synchronize()
+    with torch.cuda.stream(stream):
+        e2e_step()  # warm-up
     barrier()
     te = time.time()
     with torch.cuda.stream(stream):
         ev0.record()
         for _ in range(args.e2e_steps):
-            term.assemble_host(U_pin.numpy(), ORDER, pr_host.numpy(), R_host.numpy())
+            e2e_step()
         ev1.record()
     barrier()
     e2e_ms = ev0.elapsed_time(ev1) / args.e2e_steps
@@ -289,7 +340,7 @@ def main():
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         e2e_ms = float(tms.item())
     e2e_value = ne_all / (e2e_ms * 1e-3)
-    checks = {"pr_norm": float(np.linalg.norm(pr_host.numpy()[: min(nnz, 10_000_000)])),
+    checks = {"pr_norm": float(np.linalg.norm(pr_host.numpy()[: min(pr_host.numel(), 10_000_000)])),
               "R_norm": float(np.linalg.norm(R_host.numpy()))}
 
     if rank != 0:
@@ -322,8 +373,8 @@ def main():
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"]},
         "kernel_ms": kavg,
-        "e2e": {"value": e2e_value, "unit": "elements/s", "h2d_bytes_per_step": int(8 * ndof),
-                "d2h_bytes_per_step": int(8 * nnz + 8 * ndof), "ms_per_step": e2e_ms, "steps": args.e2e_steps},
+        "e2e": {"value": e2e_value, "unit": "elements/s", "h2d_bytes_per_step": int(h2d_bytes),
+                "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_ms, "steps": args.e2e_steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "symbolic_s": t_sym, "setup_s": t_setup, "device_bytes": ctx.bytes_in_use(), "checks": checks,
