@@ -164,7 +164,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--n", type=int, default=0, help="cells per direction (default: the BASELINE size)")
+    ap.add_argument("--n", "--cells", dest="n", type=int, default=0, help="cells per direction (default: the BASELINE size); use --cells under torchrun")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
