@@ -198,7 +198,7 @@ struct gfgpu_term {
   gf::DevBuf<uint8_t> rc_hdr;    // TileHdr per tile (recompute_tiles.cu)
   gf::DevBuf<uint32_t> rc_els;   // per tile: sorted distinct local element ids (stride rc_cap_inc)
   int64_t rc_nt = 0, rc_ntask = 0;
-  int rc_cap_inc = 0, rc_cap_pairs = 0, rc_cap_slots = 0, rc_cap_tasks = 0, rc_cap_long = 0;
+  int rc_cap_inc = 0, rc_cap_len = 0, rc_cap_pairs = 0, rc_cap_slots = 0, rc_cap_tasks = 0, rc_cap_long = 0;
 };
 
 namespace gf {

@@ -14,8 +14,11 @@
 //           one step = one (element, j, i) contribution = T += B~ M^{ji} B~^T (54 DFMA), operands from shared
 //           memory through a 16-bit descriptor (slot | j*nd+i) carried in the pair record.  Short pairs of a
 //           task are padded with a descriptor that points at an all-zero geometry slot (adds +0.0).
-//   flush = the elasticity combination lambda T + mu T^T + mu tr(T) I is applied ONCE per pair (it is linear),
-//           kept entries go straight to their CSC slots.
+//   flush = the elasticity combination lambda T + mu T^T + mu tr(T) I is applied ONCE per pair (it is linear);
+//           kept entries are written to an image of the tile's CSC segment in shared memory (the segment of a run of
+//           column nodes is contiguous), and the finished image leaves with ONE bulk async store (TMA) per tile:
+//           full 32-byte sectors only.  Scattered 8-byte global stores made L2 fetch every partially written
+//           sector from DRAM (measured: profiles/round1_ncu_tiles_v1_c3_n110.txt and the symmetric-store experiment).
 //   The residual is a separate per-element kernel (r_e = K_e u_e through the same reference tensors) followed
 //   by the fixed-order per-node gather of scatter.cu.
 //
@@ -119,14 +122,18 @@ struct alignas(16) TileHdr {
   uint32_t task0, ntasks;    // task range
   uint32_t nel, n_long;      // distinct elements staged; tasks that need a descriptor blob (they come first)
   uint32_t n_wide, r2_0;     // pairs with more than TL_INREC contributions (one task each); first blob (task units)
-  uint32_t pad0, pad1, pad2, pad3;
+  uint32_t len;              // entries of the tile's CSC segment [base, base + len)
+  uint32_t pad1, pad2, pad3;
 };
 static_assert(sizeof(TileHdr) == 64, "TileHdr layout");
 
 __global__ void k_tile_base(TileHdr *__restrict__ hdr, int64_t nt, const int32_t *__restrict__ pJ,
-                            const int64_t *__restrict__ jc) {
-  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nt; k += (int64_t)gridDim.x * blockDim.x)
-    hdr[k].base = jc[pJ[hdr[k].pair0]];
+                            const int32_t *__restrict__ rdof, int Q, const int64_t *__restrict__ jc) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nt; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = jc[pJ[hdr[k].pair0]];
+    hdr[k].base = b;
+    hdr[k].len = (uint32_t)(jc[rdof[hdr[k].node0 + hdr[k].nnodes - 1] + Q] - b);
+  }
 }
 
 // CTA per tile: sorted distinct local element ids of the tile's incidences -> els[tile*stride ..], hdr.nel
@@ -185,69 +192,66 @@ k_tile_elements(TileHdr *__restrict__ hdr, const uint32_t *__restrict__ rstart, 
 //   normal tasks : 32 pairs each of the remaining pairs sorted by contribution count (descending), lane = pair.
 constexpr int TL_INREC = 10;  // largest step count of a normal task = rows of a descriptor blob
 
-// CTA per tile: stable counting sort of the tile's pairs by contribution count (descending) -> sp_pair[pair0 ..],
-// number of wide pairs and of tasks that need a descriptor blob.
+// CTA per tile: sort of the tile's pairs by (contribution count descending, signature, pair id) -> sp_pair[pair0 ..],
+// number of wide pairs and of tasks that need a descriptor blob.  The signature hashes the pair's sequence of local
+// node couples (j, i): pairs that are translated copies of each other (structured parts of a mesh) become neighbours,
+// so the lanes of a task mostly read the SAME reference tensor M^{ji} at every step (a shared-memory broadcast instead
+// of a 32-way gather).  Any order inside a count class is correct (the output goes through the shared-memory image,
+// so the lane order has no effect on the global stores); this one only changes bank conflicts.
+constexpr int TL_MAXPAIRS = 4096;
 __global__ void __launch_bounds__(256)
-k_tile_sort_pairs(TileHdr *__restrict__ hdr, const uint32_t *__restrict__ cstart, uint32_t *__restrict__ sp_pair,
-                  int *__restrict__ err) {
-  __shared__ uint32_t wh[8][256];
-  __shared__ uint32_t binbase[256];
+k_tile_sort_pairs(TileHdr *__restrict__ hdr, const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ csrc,
+                  uint32_t nb, uint32_t nlocal, int use_sig, uint32_t *__restrict__ sp_pair, int *__restrict__ err) {
+  __shared__ uint64_t key[TL_MAXPAIRS];
+  __shared__ uint32_t s_nwide, s_ngt2;
   const int64_t tile = blockIdx.x;
   const TileHdr h = hdr[tile];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int k = threadIdx.x; k < 8 * 256; k += 256) (&wh[0][0])[k] = 0;
-  __syncthreads();
-  const uint32_t chunk = ((h.npairs + 8 * 32 - 1) / (8 * 32)) * 32;  // per warp, a multiple of 32
-  const uint32_t w0 = min(warp * chunk, h.npairs), w1 = min(w0 + chunk, h.npairs);
-  for (uint32_t i = w0 + lane; i < w1; i += 32) {
-    const uint32_t p = h.pair0 + i, cnt = cstart[p + 1] - cstart[p];
-    if (cnt > 255u) *err = 3;
-    atomicAdd(&wh[warp][255u - min(cnt, 255u)], 1u);
+  const uint32_t n = h.npairs;
+  if (n > (uint32_t)TL_MAXPAIRS) {
+    if (threadIdx.x == 0) *err = 8;
+    return;
   }
+  uint32_t P = 32;
+  while (P < n) P <<= 1;
+  if (threadIdx.x == 0) { s_nwide = 0; s_ngt2 = 0; }
   __syncthreads();
-  {  // thread k: total of bin k, then (after the scan over bins) the start of each warp inside the bin
-    uint32_t tot = 0;
-    for (int w = 0; w < 8; ++w) tot += wh[w][threadIdx.x];
-    binbase[threadIdx.x] = tot;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t run = 0, nwide = 0, ngt2 = 0;
-    for (int k = 0; k < 256; ++k) {  // bin k holds the pairs with 255-k contributions
-      const uint32_t v = binbase[k];
-      binbase[k] = run;
-      run += v;
-      if (255 - k > TL_INREC) nwide += v;
-      if (255 - k > 2) ngt2 += v;
+  for (uint32_t k = threadIdx.x; k < P; k += blockDim.x) {
+    uint64_t v = ~0ull;
+    if (k < n) {
+      const uint32_t p = h.pair0 + k, s0 = cstart[p], cnt = cstart[p + 1] - s0;
+      if (cnt > 255u) *err = 3;
+      uint32_t sig = 0;
+      if (use_sig && cnt <= (uint32_t)TL_INREC)
+        for (uint32_t c = 0; c < cnt; ++c) {
+          const uint32_t ctr = csrc[s0 + c];
+          const uint32_t rr = ctr < nlocal ? ctr % nb : 0xffffu;
+          sig = (sig ^ rr) * 0x9E3779B1u + 0x7F4A7C15u;
+          sig ^= sig >> 15;
+        }
+      if (cnt > (uint32_t)TL_INREC) atomicAdd(&s_nwide, 1u);
+      if (cnt > 2u) atomicAdd(&s_ngt2, 1u);
+      v = ((uint64_t)(255u - min(cnt, 255u)) << 56) | ((uint64_t)(sig & 0xffffffu) << 32) | k;
     }
+    key[k] = v;
+  }
+  __syncthreads();
+  for (uint32_t size = 2; size <= P; size <<= 1)
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t k = threadIdx.x; k < P; k += blockDim.x) {
+        const uint32_t partner = k ^ stride;
+        if (partner > k) {
+          const bool up = (k & size) == 0;
+          const uint64_t a = key[k], b = key[partner];
+          if ((a > b) == up) { key[k] = b; key[partner] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) sp_pair[h.pair0 + k] = h.pair0 + (uint32_t)(key[k] & 0xffffffffu);
+  if (threadIdx.x == 0) {
+    const uint32_t nwide = s_nwide, ngt2 = s_ngt2;
     hdr[tile].n_wide = nwide;
     hdr[tile].n_long = nwide + (ngt2 > nwide ? (ngt2 - nwide + 31) / 32 : 0u);
-  }
-  __syncthreads();
-  {
-    uint32_t run = binbase[threadIdx.x];
-    for (int w = 0; w < 8; ++w) { const uint32_t v = wh[w][threadIdx.x]; wh[w][threadIdx.x] = run; run += v; }
-  }
-  __syncthreads();
-  uint32_t *out = sp_pair + h.pair0;
-  for (uint32_t i0 = w0; i0 < w1; i0 += 32) {
-    const uint32_t i = i0 + lane;
-    const bool act = i < w1;
-    uint32_t key = 0xffffu;
-    if (act) {
-      const uint32_t p = h.pair0 + i;
-      key = 255u - min(cstart[p + 1] - cstart[p], 255u);
-    }
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    const unsigned rank = __popc(peers & ((1u << lane) - 1u));
-    uint32_t b = 0;
-    if (act) b = wh[warp][key];
-    __syncwarp();
-    if (act) {
-      out[b + rank] = h.pair0 + i;
-      if (rank == 0) wh[warp][key] = b + __popc(peers);
-    }
-    __syncwarp();
   }
 }
 
@@ -349,7 +353,7 @@ struct TileArgs {
   const double *eg, *Mtab;
   double sl, smu;  // sign(alpha) * lambda, sign(alpha) * mu (elasticity)
   int64_t nt;
-  int zslot, cap_tasks, cap_long;
+  int zslot, cap_tasks, cap_long, cap_len;
   double *pr;
   unsigned long long *trace;  // optional (GFGPU_TILE_TRACE): per-tile timestamps of CTA 0
 };
@@ -397,6 +401,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
       : "memory");
 }
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void ldgsts8(void *dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
@@ -415,6 +427,9 @@ struct TlSmem {  // byte offsets inside one tile buffer: pair records | long-tas
   __host__ __device__ static size_t bytes(int cap_tasks, int cap_long, int zslot) {
     return (geo_off(cap_tasks, cap_long) + (size_t)(zslot + 1) * GSP * 8 + 127) / 128 * 128;
   }
+  // image of the tile's CSC segment: entry e lives at index (base & 1) + e so that shared and global addresses agree
+  // modulo 16 (bulk copies need 16-byte alignment on both sides)
+  __host__ __device__ static size_t out_bytes(int cap_len) { return ((size_t)(cap_len + 2) * 8 + 127) / 128 * 128; }
 };
 
 template <int N, int Q, int ND, int RF>
@@ -428,7 +443,9 @@ k_tiles(const TileArgs a) {
   __shared__ TileHdr s_hdr[2];
   __shared__ unsigned s_next[2];
   const size_t bufsz = L::bytes(a.cap_tasks, a.cap_long, a.zslot);
-  double *sM = reinterpret_cast<double *>(smraw + 2 * bufsz);
+  const size_t outsz = L::out_bytes(a.cap_len);
+  unsigned char *outraw = smraw + 2 * bufsz;
+  double *sM = reinterpret_cast<double *>(outraw + 2 * outsz);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int k = tid; k < NB * MT; k += TL_THREADS) sM[k] = a.Mtab[k];
   if (tid < 2 * GSP) {  // the all-zero geometry slot of both buffers
@@ -436,7 +453,7 @@ k_tiles(const TileArgs a) {
     g[a.zslot * GSP + tid % GSP] = 0.0;
   }
   if (tid == 0) {
-    mbar_init(&full[0], 33); mbar_init(&full[1], 33);      // 32 LDGSTS arrivals + the expect_tx arrival
+    mbar_init(&full[0], 34); mbar_init(&full[1], 34);      // 32 LDGSTS arrivals + expect_tx + "output image free"
     mbar_init(&empty[0], TL_CW); mbar_init(&empty[1], TL_CW);
   }
   __syncthreads();
@@ -454,6 +471,22 @@ k_tiles(const TileArgs a) {
       for (int r = 0; r < TL_ROWS; ++r) e[r] = r * 32 + lane < (int)h.nel ? els[r * 32 + lane] : 0u;
     };
     if ((int64_t)blockIdx.x < a.nt) fetch(blockIdx.x);
+    int4 hprev[2] = {make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};  // base (lo, hi), len of the tile in each buffer
+    auto drain = [&](int b, int4 hp) {
+      const int64_t base = (int64_t)(uint32_t)hp.x | ((int64_t)hp.y << 32);
+      const int64_t len = (uint32_t)hp.z;
+      if (lane == 0 && len) {
+        fence_async_smem();
+        const double *img = reinterpret_cast<const double *>(outraw + b * outsz);
+        const int64_t odd = base & 1, gs = base + odd, ge = (base + len) & ~int64_t(1);
+        if (odd) a.pr[base] = img[1];
+        if (ge > gs) bulk_s2g(a.pr + gs, img + 2 * odd, (uint32_t)((ge - gs) * 8));
+        if (((base + len) & 1) && base + len - 1 >= gs) a.pr[base + len - 1] = img[odd + len - 1];
+        bulk_commit();
+        bulk_wait_read0();
+      }
+      __syncwarp();
+    };
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < a.nt; tile += gridDim.x, ++it) {
       const int b = it & 1;
@@ -479,12 +512,23 @@ k_tiles(const TileArgs a) {
         }
       }
       ldgsts_arrive(&full[b]);
+      // the image of the tile that used this buffer two iterations ago is complete (empty[b] fired): send it
+      if (it >= 2) drain(b, hprev[b]);
+      if (lane == 0) mbar_arrive(&full[b]);  // output image b is free again
+      hprev[b] = make_int4((int)(h.base & 0xffffffffll), (int)(h.base >> 32), (int)h.len, 0);
       const unsigned long long tp2 = a.trace ? gtimer() : 0;
       if (tile + gridDim.x < a.nt) fetch(tile + gridDim.x);
       if (a.trace && blockIdx.x == 0 && lane == 0 && it < 256) {
         a.trace[it * 8 + 0] = tp0; a.trace[it * 8 + 1] = tp1; a.trace[it * 8 + 2] = tp2; a.trace[it * 8 + 3] = gtimer() + (h.nel & 0);
       }
     }
+    // the last two tiles of this CTA: `it` is now the number of tiles it processed
+    for (int k = it >= 2 ? it - 2 : 0; k < it; ++k) {
+      const int b = k & 1;
+      mbar_wait(&empty[b], (k >> 1) & 1);
+      drain(b, hprev[b]);
+    }
+    if (lane == 0) bulk_wait0();
     return;
   }
   // ================= consumers =================
@@ -499,7 +543,7 @@ k_tiles(const TileArgs a) {
     const uint16_t *sBlob = reinterpret_cast<const uint16_t *>(buf + L::blob_off(a.cap_tasks)) + lane;
     const double *sG = reinterpret_cast<const double *>(buf + L::geo_off(a.cap_tasks, a.cap_long));
     const unsigned ntasks = s_hdr[b].ntasks;
-    double *prb = a.pr + s_hdr[b].base;
+    double *prb = reinterpret_cast<double *>(outraw + b * outsz) + (s_hdr[b].base & 1);  // image of the CSC segment
     // the next task index and its record are fetched while the current task runs
     unsigned tk = warp, tkB = warp + TL_CW;
     uint4 rec = make_uint4(0, 0, 0, 0);
@@ -604,6 +648,7 @@ k_tiles(const TileArgs a) {
       rec = recB;
       tkB = __shfl_sync(0xffffffffu, nxt, 0);
     }
+    fence_async_smem();  // my image writes (generic proxy) before the producer's bulk store (async proxy)
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[b]);
     if (a.trace && blockIdx.x == 0 && tid == 0 && it < 256) {
@@ -892,67 +937,84 @@ void recompute_prepare(gfgpu_term *t) {
   GF_REQUIRE(cbits <= 10, "too many local nodes for the 16-bit contribution descriptor");
   const int slot_max = (1 << (16 - cbits)) - 1;  // the top slot index is the all-zero geometry
   const int cap_inc_want = std::max(1, std::min(std::min(env_int("GFGPU_TILE_INC", 510), slot_max), 1024));
-  const int cap_pairs_want = std::max(32, std::min(env_int("GFGPU_TILE_PAIRS", 2048), 4095));
   std::vector<uint32_t> rstart(st.nrnodes + 1), colstart(st.ncolnodes + 1);
   st.rstart.download(rstart.data());
   st.colstart.download(colstart.data());
   GF_CUDA(cudaStreamSynchronize(s));
+  // The pair capacity of a tile is lowered until two input buffers + two output images fit in shared memory.
+  const int GSPh = GSZ | 1;
+  const size_t smem_limit = 224 * 1024;
   std::vector<TileHdr> hdr;
-  hdr.reserve(st.ncolnodes / 16 + 2);
-  int cap_inc = 1;
-  for (int64_t k = 0; k < st.ncolnodes;) {
-    int64_t k1 = k + 1;
-    while (k1 < st.ncolnodes && rstart[k1 + 1] - rstart[k] <= (uint32_t)cap_inc_want &&
-           colstart[k1 + 1] - colstart[k] <= (uint32_t)cap_pairs_want)
-      ++k1;
-    TileHdr h;
-    memset(&h, 0, sizeof h);
-    h.pair0 = colstart[k];
-    h.npairs = colstart[k1] - colstart[k];
-    h.node0 = (uint32_t)k;
-    h.nnodes = (uint32_t)(k1 - k);
-    cap_inc = std::max<int>(cap_inc, (int)(rstart[k1] - rstart[k]));
-    hdr.push_back(h);
-    k = k1;
-  }
-  GF_REQUIRE(cap_inc <= std::min(slot_max, 1024), "node valence too high for the compact tile descriptors: use strategy STAGED");
-  const int64_t nt = (int64_t)hdr.size();
-  t->rc_nt = nt;
-  t->rc_cap_inc = cap_inc;
-  t->rc_hdr.alloc(ctx, hdr.size() * sizeof(TileHdr));
-  GF_CUDA(cudaMemcpyAsync(t->rc_hdr.p, hdr.data(), hdr.size() * sizeof(TileHdr), cudaMemcpyHostToDevice, s));
-  TileHdr *dh = (TileHdr *)t->rc_hdr.p;
-  t->rc_els.alloc(ctx, (size_t)nt * cap_inc);
-  t->flag.zero();
-  {
-    int P = 32;
-    while (P < cap_inc) P <<= 1;
-    k_tile_elements<<<(unsigned)nt, 128, 2 * P * sizeof(uint32_t), s>>>(dh, st.rstart.p, st.rsrc.p, nd, cap_inc, t->rc_els.p);
-    GF_LAUNCH_CHECK();
-  }
   DevBuf<uint32_t> sp_pair, tk_tile;
   sp_pair.alloc(ctx, st.npairs);
-  k_tile_sort_pairs<<<(unsigned)nt, 256, 0, s>>>(dh, st.cstart.p, sp_pair.p, (int *)t->flag.p);
-  GF_LAUNCH_CHECK();
-  k_tile_base<<<(unsigned)std::min<int64_t>((nt + 255) / 256, 148 * 8), 256, 0, s>>>(dh, nt, st.pJ.p, t->jc.p);
-  GF_LAUNCH_CHECK();
-  // task ranges, blob ranges and the shared-memory capacities (host scan over the tiles)
-  GF_CUDA(cudaMemcpyAsync(hdr.data(), dh, hdr.size() * sizeof(TileHdr), cudaMemcpyDeviceToHost, s));
-  GF_CUDA(cudaStreamSynchronize(s));
-  int cap_slots = 1, cap_tasks = 1, cap_long = 1;
-  int64_t ntask = 0, nlong = 0;
-  for (TileHdr &h : hdr) {
-    h.ntasks = h.n_wide + (h.npairs - h.n_wide + 31) / 32;
-    h.task0 = (uint32_t)ntask;
-    h.r2_0 = (uint32_t)nlong;
-    ntask += h.ntasks;
-    nlong += h.n_long;
-    cap_slots = std::max<int>(cap_slots, (int)h.nel);
-    cap_tasks = std::max<int>(cap_tasks, (int)h.ntasks);
-    cap_long = std::max<int>(cap_long, (int)h.n_long);
+  TileHdr *dh = nullptr;
+  int cap_inc = 1, cap_slots = 1, cap_tasks = 1, cap_long = 1, cap_len = 1;
+  int64_t ntask = 0, nlong = 0, nt = 0;
+  int cap_pairs_want = std::max(32, std::min(env_int("GFGPU_TILE_PAIRS", 1024), 4095));
+  for (;;) {
+    hdr.clear();
+    hdr.reserve(st.ncolnodes / 8 + 2);
+    cap_inc = 1;
+    for (int64_t k = 0; k < st.ncolnodes;) {
+      int64_t k1 = k + 1;
+      while (k1 < st.ncolnodes && rstart[k1 + 1] - rstart[k] <= (uint32_t)cap_inc_want &&
+             colstart[k1 + 1] - colstart[k] <= (uint32_t)cap_pairs_want)
+        ++k1;
+      TileHdr h;
+      memset(&h, 0, sizeof h);
+      h.pair0 = colstart[k];
+      h.npairs = colstart[k1] - colstart[k];
+      h.node0 = (uint32_t)k;
+      h.nnodes = (uint32_t)(k1 - k);
+      cap_inc = std::max<int>(cap_inc, (int)(rstart[k1] - rstart[k]));
+      hdr.push_back(h);
+      k = k1;
+    }
+    GF_REQUIRE(cap_inc <= std::min(slot_max, 1024), "node valence too high for the compact tile descriptors: use strategy STAGED");
+    nt = (int64_t)hdr.size();
+    t->rc_hdr.alloc(ctx, hdr.size() * sizeof(TileHdr));
+    GF_CUDA(cudaMemcpyAsync(t->rc_hdr.p, hdr.data(), hdr.size() * sizeof(TileHdr), cudaMemcpyHostToDevice, s));
+    dh = (TileHdr *)t->rc_hdr.p;
+    t->rc_els.alloc(ctx, (size_t)nt * cap_inc);
+    t->flag.zero();
+    {
+      int P = 32;
+      while (P < cap_inc) P <<= 1;
+      k_tile_elements<<<(unsigned)nt, 128, 2 * P * sizeof(uint32_t), s>>>(dh, st.rstart.p, st.rsrc.p, nd, cap_inc, t->rc_els.p);
+      GF_LAUNCH_CHECK();
+    }
+    k_tile_sort_pairs<<<(unsigned)nt, 256, 0, s>>>(dh, st.cstart.p, st.csrc.p, (uint32_t)(nd * nd), (uint32_t)st.ncontrib,
+                                                   env_int("GFGPU_TILE_SIGSORT", 1), sp_pair.p, (int *)t->flag.p);
+    GF_LAUNCH_CHECK();
+    k_tile_base<<<(unsigned)std::min<int64_t>((nt + 255) / 256, 148 * 8), 256, 0, s>>>(dh, nt, st.pJ.p, st.rdof.p, Q, t->jc.p);
+    GF_LAUNCH_CHECK();
+    // task ranges, blob ranges and the shared-memory capacities (host scan over the tiles)
+    GF_CUDA(cudaMemcpyAsync(hdr.data(), dh, hdr.size() * sizeof(TileHdr), cudaMemcpyDeviceToHost, s));
+    GF_CUDA(cudaStreamSynchronize(s));
+    cap_slots = cap_tasks = cap_long = cap_len = 1;
+    ntask = nlong = 0;
+    for (TileHdr &h : hdr) {
+      h.ntasks = h.n_wide + (h.npairs - h.n_wide + 31) / 32;
+      h.task0 = (uint32_t)ntask;
+      h.r2_0 = (uint32_t)nlong;
+      ntask += h.ntasks;
+      nlong += h.n_long;
+      cap_slots = std::max<int>(cap_slots, (int)h.nel);
+      cap_tasks = std::max<int>(cap_tasks, (int)h.ntasks);
+      cap_long = std::max<int>(cap_long, (int)h.n_long);
+      cap_len = std::max<int>(cap_len, (int)h.len);
+    }
+    const size_t in_b = ((size_t)cap_tasks * 512 + (size_t)cap_long * TL_BLOB + (size_t)(cap_slots + 1) * GSPh * 8 + 127) / 128 * 128;
+    const size_t out_b = ((size_t)(cap_len + 2) * 8 + 127) / 128 * 128;
+    const size_t need = 2 * in_b + 2 * out_b + (size_t)nd * nd * MT * 8;
+    if (need <= smem_limit && cap_slots <= 32 * TL_ROWS) break;
+    GF_REQUIRE(cap_pairs_want > 32, "a single column node does not fit the tile kernel's shared memory: use strategy STAGED");
+    cap_pairs_want = std::max(32, cap_pairs_want * 3 / 4);
   }
+  t->rc_nt = nt;
+  t->rc_cap_inc = cap_inc;
+  t->rc_cap_len = cap_len;
   GF_REQUIRE(ntask < (int64_t(1) << 31) && nlong < (int64_t(1) << 31), "too many tasks");
-  GF_REQUIRE(cap_slots <= 32 * TL_ROWS, "tile has too many distinct elements");
   GF_CUDA(cudaMemcpyAsync(dh, hdr.data(), hdr.size() * sizeof(TileHdr), cudaMemcpyHostToDevice, s));
   t->rc_ntask = ntask;
   t->rc_cap_slots = cap_slots;
@@ -1017,7 +1079,7 @@ static void launch_tiles(gfgpu_term *t, const double *U, bool do_t, bool do_r) {
   a.eg = t->rc_eg.p; a.Mtab = t->rc_M.p;
   a.sl = sign * t->par[0]; a.smu = sign * t->par[1];
   a.nt = t->rc_nt;
-  a.zslot = t->rc_cap_slots; a.cap_tasks = t->rc_cap_tasks; a.cap_long = t->rc_cap_long;
+  a.zslot = t->rc_cap_slots; a.cap_tasks = t->rc_cap_tasks; a.cap_long = t->rc_cap_long; a.cap_len = t->rc_cap_len;
   a.pr = t->pr.p;
   a.trace = nullptr;
   DevBuf<unsigned long long> trace;
@@ -1026,7 +1088,7 @@ static void launch_tiles(gfgpu_term *t, const double *U, bool do_t, bool do_r) {
     trace.zero();
     a.trace = trace.p;
   }
-  const size_t smem = 2 * L::bytes(a.cap_tasks, a.cap_long, a.zslot) + (size_t)ND * ND * C::MT * 8;
+  const size_t smem = 2 * L::bytes(a.cap_tasks, a.cap_long, a.zslot) + 2 * L::out_bytes(a.cap_len) + (size_t)ND * ND * C::MT * 8;
   GF_REQUIRE(smem <= 226 * 1024, "tile too large for shared memory; use strategy STAGED");
   auto kern = k_tiles<N, Q, ND, RF>;
   GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
