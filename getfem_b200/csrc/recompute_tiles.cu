@@ -950,7 +950,7 @@ void recompute_prepare(gfgpu_term *t) {
   TileHdr *dh = nullptr;
   int cap_inc = 1, cap_slots = 1, cap_tasks = 1, cap_long = 1, cap_len = 1;
   int64_t ntask = 0, nlong = 0, nt = 0;
-  int cap_pairs_want = std::max(32, std::min(env_int("GFGPU_TILE_PAIRS", 1024), 4095));
+  int cap_pairs_want = std::max(32, std::min(env_int("GFGPU_TILE_PAIRS", 1280), 4095));
   for (;;) {
     hdr.clear();
     hdr.reserve(st.ncolnodes / 8 + 2);
@@ -1014,6 +1014,9 @@ void recompute_prepare(gfgpu_term *t) {
   t->rc_nt = nt;
   t->rc_cap_inc = cap_inc;
   t->rc_cap_len = cap_len;
+  if (getenv("GFGPU_DEBUG"))
+    fprintf(stderr, "[gfgpu] tiles: %lld (pairs/tile <= %d), tasks %lld (long %lld), caps: incidences %d slots %d tasks %d long %d len %d\n",
+            (long long)nt, cap_pairs_want, (long long)ntask, (long long)nlong, cap_inc, cap_slots, cap_tasks, cap_long, cap_len);
   GF_REQUIRE(ntask < (int64_t(1) << 31) && nlong < (int64_t(1) << 31), "too many tasks");
   GF_CUDA(cudaMemcpyAsync(dh, hdr.data(), hdr.size() * sizeof(TileHdr), cudaMemcpyHostToDevice, s));
   t->rc_ntask = ntask;
