@@ -312,7 +312,9 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
   auto toc = [&](int k) { GF_CUDA(cudaEventRecord(t->ev[2 * k + 1], ctx->stream)); t->ev_used[k] = true; };
   if (ne > 0 && (need_stage || need_masks || need_rstage)) {
     tic(0);
-    bool ok = gf::launch_elem_kernel(ctx, t->mesh->dim, Q, nd, t->mesh->gt_kind == GFGPU_GT_PK, a);
+    const bool affine = t->mesh->gt_kind == GFGPU_GT_PK;
+    bool ok = gf::launch_sumfact_kernel(ctx, t->tab, t->mesh->dim, Q, nd, affine, a) ||
+              gf::launch_elem_kernel(ctx, t->mesh->dim, Q, nd, affine, a);
     GF_REQUIRE(ok, "no device kernel for this (dimension, qdim, local dofs, family) combination");
     toc(0);
   }

@@ -222,6 +222,9 @@ struct ElemArgs {
 // returns false when the (dim, Q, nd, family, affine) combination has no instantiation
 bool launch_elem_kernel(gfgpu_ctx *ctx, int dim, int Q, int nd, bool affine, const ElemArgs &a);
 
+// sum-factorised kernel for the scalar Laplace form on Q3/Q4 hexahedra (sumfact.cu); false = not handled, use the generic one
+bool launch_sumfact_kernel(gfgpu_ctx *ctx, const gfgpu_tables *tab, int dim, int Q, int nd, bool affine, const ElemArgs &a);
+
 // ---- first-touch dof numbering (dof_enum.cu); returns ndof
 int64_t enumerate_dof(gfgpu_ctx *ctx, const int32_t *conn, int64_t ne, int ng, int N, bool qk, int k, int Q, int nd,
                       const int8_t *lat_host, int32_t *edof_dev);

@@ -1,0 +1,281 @@
+// sumfact.cu -- sum-factorised element kernel for the scalar Laplace form on high-order hexahedra (BASELINE config 5:
+// FEM_QK(3,4), IM_GAUSS_PARALLELEPIPED(3,8), GT_QK(3,1)).  Strategy STAGED: same outputs as the generic element kernel
+// (elem_kernel.cuh: element matrix column-major in `stage`, per-block keep masks, element residual), 13x fewer flops.
+//
+// Replaces, for this family, rows 6-15 of SURVEY 8(a): K(), B() per Gauss point (bgeot_geometric_trans.cc:270-413),
+// pfp_grad_base_value (getfem_fem.cc:160-199), the per-point tensor algebra of ga_exec (C&E.cc:2769-3760) and the
+// accumulation elem += J w_q t (C&E.cc:5047-5057), which cost the reference 2 nd^2 nq N = 11.7 Mflop per Q4 element.
+//
+// A tensor-product basis phi_i = l_{i1}(x) l_{i2}(y) l_{i3}(z) on a tensor-product rule q = (q1, q2, q3) gives
+//   K_e(i, j) = sum_{a,b} sum_{q1 q2 q3} C_ab(q) X^a_{i1}(q1) X^b_{j1}(q1) Y^a_{i2}(q2) Y^b_{j2}(q2) Z^a_{i3}(q3) Z^b_{j3}(q3)
+// with C(q) = alpha a w_q J(q) B(q)^T B(q) (3x3 symmetric) and X^a = l' if a == 0 else l (Y: a == 1, Z: a == 2).
+// The three sums are done one direction at a time:
+//   1  S1[ab][q1 q2]      = sum_q3 C_ab(q) Z^a_{i3} Z^b_{j3}                       per slice (i3, j3)
+//   2  s2[ab][q1](i2, j2) = sum_q2 S1[ab][q1 q2] Y^a_{i2} Y^b_{j2}                 lane = (i2, j2), in registers
+//   3  K(i1 i2 i3, j1 j2 j3) += P_x[ab][q1][(i1, j1)] * s2                         25 accumulators per lane
+// Step 3 carries 80 % of the flops; its left operand P_x = X^a_{i1}(q1) X^b_{j1}(q1) is the same for every element,
+// lane and slice, so it travels as a KERNEL PARAMETER: with the loops unrolled every DFMA takes it straight from the
+// constant bank (c[0x0][imm]) -- no register, no shared-memory traffic, the fp64 pipe is the only unit that works.
+// (On B200 the fp64 tensor-core peak equals the fp64 FMA peak; DMMA m8n8k4 would need the K = 45 contraction padded to
+// 48 and 25 x 25 tiles padded to 32 x 32, i.e. 1.7x the flops of this formulation for the same peak.)
+//
+// The 1D tables are recovered from the full tables handed over the C ABI (partition of unity: summing phi over the other
+// two directions leaves l_{i1}(q1)) and the factorisation is VERIFIED entry by entry; when the tables are not an exact
+// tensor product (1e-13) the generic kernel is used instead -- so the result always reproduces the given tables.
+#include <cmath>
+#include <cstring>
+
+#include "elem_kernel.cuh"
+
+namespace gf {
+
+template <int ND1, int NQ1>
+struct SfTables {
+  static constexpr int NN = ND1 * ND1;
+  double px[9][NQ1][NN];  // [a*3+b][q1][i1 + ND1*j1] = X^a_{i1}(q1) X^b_{j1}(q1)
+  double py[4][NN][NQ1];  // [(a==1)*2 + (b==1)][i2 + ND1*j2][q2]
+  double pz[4][NN][NQ1];  // [(a==2)*2 + (b==2)][i3 + ND1*j3][q3]
+};
+
+struct SfArgs {
+  const double *x, *y, *z;
+  const int32_t *conn, *edof;
+  const double *U, *w, *gt_grad;
+  int64_t e0, ne;
+  double coef;  // alpha * a
+  double *stage;
+  uint16_t *emask;
+  double *rstage;
+};
+
+template <int ND1, int NQ1, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+k_sumfact_laplace(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T) {
+  constexpr int NN = ND1 * ND1, ND = ND1 * ND1 * ND1, NQ2 = NQ1 * NQ1, NQ = NQ1 * NQ1 * NQ1, NT = NW * 32;
+  extern __shared__ __align__(16) double sm[];
+  double *sK = sm;                       // ND x ND, column-major (row i + ND * column j) = the layout of the stage
+  double *sC = sK + ND * ND;             // 6 x NQ : C00 C01 C02 C11 C12 C22
+  double *sS1 = sC + 6 * NQ;             // per warp 9 x NQ2
+  double *sG = sS1 + NW * 9 * NQ2;       // 3 x 8 node coordinates
+  double *sU = sG + 24;                  // ND coefficients
+  double *sRed = sU + ND;                // NW
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // lane = (i2, j2): its 1D factors for the y direction
+  double yy[4][NQ1];
+  if (lane < NN) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int q = 0; q < NQ1; ++q) yy[c][q] = T.py[c][lane][q];
+  } else {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int q = 0; q < NQ1; ++q) yy[c][q] = 0.0;
+  }
+  for (int64_t el = blockIdx.x; el < a.ne; el += gridDim.x) {
+    const int64_t e = a.e0 + el;
+    // ---- A: gather
+    if (tid < 24) {
+      const int i = tid / 3, d = tid % 3;
+      const int32_t p = a.conn[e * 8 + i];
+      sG[d + 3 * i] = (d == 0 ? a.x : d == 1 ? a.y : a.z)[p];
+    }
+    if (a.rstage)
+      for (int i = tid; i < ND; i += NT) sU[i] = a.U ? a.U[a.edof[e * ND + i]] : 0.0;
+    __syncthreads();
+    // ---- B: metric at the Gauss points
+    for (int q = tid; q < NQ; q += NT) {
+      double geo[10];
+      geometry<3>(sG, a.gt_grad + (size_t)q * 24, 8, geo);
+      const double wq = a.w[q];
+      const double c = (wq == 0.0) ? 0.0 : a.coef * geo[9] * wq;  // zero-weight points are skipped (C&E.cc:8852)
+      int k = 0;
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int r = p; r < 3; ++r) {
+          double s = 0;
+#pragma unroll
+          for (int n = 0; n < 3; ++n) s += geo[n + 3 * p] * geo[n + 3 * r];
+          sC[(k++) * NQ + q] = c * s;
+        }
+    }
+    __syncthreads();
+    // ---- C: slices (i3, j3), one per warp
+    double *S1 = sS1 + warp * 9 * NQ2;
+    for (int sl = warp; sl < NN; sl += NW) {
+      // 1: contract the third direction
+      for (int idx = lane; idx < 9 * NQ2; idx += 32) {
+        const int ab = idx / NQ2, q12 = idx - ab * NQ2;
+        const int aa = ab / 3, bb = ab - aa * 3;
+        const int lo = aa < bb ? aa : bb, hi = aa < bb ? bb : aa;
+        const double *C = sC + (lo == 0 ? hi : lo == 1 ? 2 + hi : 5) * NQ + q12;
+        const double *pz = T.pz[(aa == 2) * 2 + (bb == 2)][sl];
+        double s = 0;
+#pragma unroll
+        for (int q3 = 0; q3 < NQ1; ++q3) s += C[q3 * NQ2] * pz[q3];
+        S1[idx] = s;
+      }
+      __syncwarp();
+      // 2 + 3: contract the second direction in registers, then the first against the constant-bank operand
+      double acc[NN];
+#pragma unroll
+      for (int m = 0; m < NN; ++m) acc[m] = 0.0;
+#pragma unroll
+      for (int ab = 0; ab < 9; ++ab) {
+        const int yc = ((ab / 3) == 1) * 2 + ((ab % 3) == 1);
+#pragma unroll
+        for (int q1 = 0; q1 < NQ1; ++q1) {
+          double s2 = 0;
+#pragma unroll
+          for (int q2 = 0; q2 < NQ1; ++q2) s2 += S1[ab * NQ2 + q1 + NQ1 * q2] * yy[yc][q2];
+#pragma unroll
+          for (int m = 0; m < NN; ++m) acc[m] += T.px[ab][q1][m] * s2;
+        }
+      }
+      if (lane < NN) {
+        const int i2 = lane % ND1, j2 = lane / ND1, i3 = sl % ND1, j3 = sl / ND1;
+        double *o = sK + (ND1 * i2 + NN * i3) + ND * (ND1 * j2 + NN * j3);
+#pragma unroll
+        for (int m = 0; m < NN; ++m) o[(m % ND1) + ND * (m / ND1)] = acc[m];
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    // ---- element residual r = K_e u_e (before the drop rule, like the quadrature form of the generic kernel)
+    if (a.rstage)
+      for (int i = tid; i < ND; i += NT) {
+        double s = 0;
+        for (int j = 0; j < ND; ++j) s += sK[i + ND * j] * sU[j];
+        a.rstage[(size_t)el * ND + i] = s;
+      }
+    // ---- D: drop rule and output (C&E.cc:4889,4898; 5380-5402)
+    if (a.stage || a.emask) {
+      double vmax = 0.0;
+      for (int k = tid; k < ND * ND; k += NT) vmax = fmax(vmax, fabs(sK[k]));
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, off));
+      if (lane == 0) sRed[warp] = vmax;
+      __syncthreads();
+      vmax = 0.0;
+#pragma unroll
+      for (int wv = 0; wv < NW; ++wv) vmax = fmax(vmax, sRed[wv]);
+      const double thr = vmax * 1e-14;
+      double *st = a.stage ? a.stage + (size_t)el * ND * ND : nullptr;
+      uint16_t *em = a.emask ? a.emask + (size_t)el * ND * ND : nullptr;
+      for (int k = tid; k < ND * ND; k += NT) {  // k = i + ND*j: the stage index and the mask index p = j*ND + i
+        const double v = sK[k];
+        const bool keep = (vmax != 0.0) && (fabs(v) > thr);
+        if (st) st[k] = keep ? v : 0.0;
+        if (em) em[k] = keep ? 1 : 0;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- host: factorise and verify the tables
+struct SfHost {
+  int nd1 = 0, nq1 = 0;
+  bool ok = false;
+  std::vector<double> l, d;  // nd1 x nq1
+};
+
+static int icbrt(int v) {
+  int r = (int)std::lround(std::cbrt((double)v));
+  return r * r * r == v ? r : 0;
+}
+
+static SfHost factorise(const gfgpu_tables *tab) {
+  SfHost h;
+  if (tab->dim != 3 || tab->ng != 8) return h;
+  const int nd1 = icbrt(tab->nd), nq1 = icbrt(tab->nq);
+  if (nd1 < 2 || nq1 < 1) return h;
+  const int nd = tab->nd, nq = tab->nq, nn = nd1 * nd1;
+  const std::vector<double> &phi = tab->h_phi, &g = tab->h_gphi;
+  h.nd1 = nd1; h.nq1 = nq1;
+  h.l.assign((size_t)nd1 * nq1, 0.0);
+  h.d.assign((size_t)nd1 * nq1, 0.0);
+  for (int q1 = 0; q1 < nq1; ++q1)  // q = (q1, 0, 0): sum over (i2, i3) by partition of unity
+    for (int i1 = 0; i1 < nd1; ++i1) {
+      double sl = 0, sd = 0;
+      for (int r = 0; r < nn; ++r) {
+        const int i = i1 + nd1 * r;
+        sl += phi[(size_t)q1 * nd + i];
+        sd += g[((size_t)q1 * nd + i) * 3 + 0];
+      }
+      h.l[(size_t)i1 * nq1 + q1] = sl;
+      h.d[(size_t)i1 * nq1 + q1] = sd;
+    }
+  double err = 0, ref = 0;
+  for (int q = 0; q < nq; ++q) {
+    const int q1 = q % nq1, q2 = (q / nq1) % nq1, q3 = q / (nq1 * nq1);
+    for (int i = 0; i < nd; ++i) {
+      const int i1 = i % nd1, i2 = (i / nd1) % nd1, i3 = i / nn;
+      const double l1 = h.l[(size_t)i1 * nq1 + q1], l2 = h.l[(size_t)i2 * nq1 + q2], l3 = h.l[(size_t)i3 * nq1 + q3];
+      const double d1 = h.d[(size_t)i1 * nq1 + q1], d2 = h.d[(size_t)i2 * nq1 + q2], d3 = h.d[(size_t)i3 * nq1 + q3];
+      const double v[4] = {l1 * l2 * l3, d1 * l2 * l3, l1 * d2 * l3, l1 * l2 * d3};
+      const double t[4] = {phi[(size_t)q * nd + i], g[((size_t)q * nd + i) * 3], g[((size_t)q * nd + i) * 3 + 1],
+                           g[((size_t)q * nd + i) * 3 + 2]};
+      for (int k = 0; k < 4; ++k) {
+        err = std::max(err, std::fabs(v[k] - t[k]));
+        ref = std::max(ref, std::fabs(t[k]));
+      }
+    }
+  }
+  h.ok = ref > 0 && err <= 1e-13 * ref;
+  return h;
+}
+
+template <int ND1, int NQ1, int NW>
+static void launch_sf(gfgpu_ctx *ctx, const SfHost &h, const SfArgs &a) {
+  constexpr int NN = ND1 * ND1, ND = ND1 * ND1 * ND1, NQ2 = NQ1 * NQ1, NQ = NQ2 * NQ1;
+  std::unique_ptr<SfTables<ND1, NQ1>> Tp(new SfTables<ND1, NQ1>);  // filled per call (host side, cheap)
+  SfTables<ND1, NQ1> &T = *Tp;
+  auto L = [&](int i, int q) { return h.l[(size_t)i * NQ1 + q]; };
+  auto D = [&](int i, int q) { return h.d[(size_t)i * NQ1 + q]; };
+  for (int aa = 0; aa < 3; ++aa)
+    for (int bb = 0; bb < 3; ++bb)
+      for (int q = 0; q < NQ1; ++q)
+        for (int m = 0; m < NN; ++m) {
+          const int i1 = m % ND1, j1 = m / ND1;
+          T.px[aa * 3 + bb][q][m] = (aa == 0 ? D(i1, q) : L(i1, q)) * (bb == 0 ? D(j1, q) : L(j1, q));
+        }
+  for (int c = 0; c < 4; ++c)
+    for (int m = 0; m < NN; ++m)
+      for (int q = 0; q < NQ1; ++q) {
+        const int i = m % ND1, j = m / ND1;
+        const double v = ((c & 2) ? D(i, q) : L(i, q)) * ((c & 1) ? D(j, q) : L(j, q));
+        T.py[c][m][q] = v;
+        T.pz[c][m][q] = v;
+      }
+  static_assert(sizeof(SfTables<ND1, NQ1>) + sizeof(SfArgs) <= 32000, "tables exceed the kernel parameter space");
+  const size_t smem = ((size_t)ND * ND + 6 * NQ + (size_t)NW * 9 * NQ2 + 24 + ND + NW + 2) * 8;
+  auto kern = k_sumfact_laplace<ND1, NQ1, NW>;
+  GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(a.ne, ctx->sm_count));
+  kern<<<grid, NW * 32, smem, ctx->stream>>>(a, T);
+  GF_LAUNCH_CHECK();
+}
+
+// returns false when this family / element / table set is not handled here (the caller then uses the generic kernel)
+bool launch_sumfact_kernel(gfgpu_ctx *ctx, const gfgpu_tables *tab, int dim, int Q, int nd, bool affine, const ElemArgs &ea) {
+  if (ea.family != GFGPU_LAPLACE || dim != 3 || Q != 1 || affine || ea.ng != 8) return false;
+  if (!(nd == 125 && ea.nq == 125) && !(nd == 64 && ea.nq == 64)) return false;
+  if (getenv("GFGPU_NO_SUMFACT")) return false;
+  const SfHost h = factorise(tab);
+  if (!h.ok) return false;
+  SfArgs a;
+  a.x = ea.x; a.y = ea.y; a.z = ea.z; a.conn = ea.conn; a.edof = ea.edof; a.U = ea.U; a.w = ea.w; a.gt_grad = ea.gt_grad;
+  a.e0 = ea.e0; a.ne = ea.e1 - ea.e0;
+  a.coef = ea.alpha * ea.par[0];
+  a.stage = ea.stage; a.emask = ea.emask; a.rstage = ea.rstage;
+  if (a.ne <= 0) return true;
+  if (h.nd1 == 5 && h.nq1 == 5) launch_sf<5, 5, 13>(ctx, h, a);
+  else if (h.nd1 == 4 && h.nq1 == 4) launch_sf<4, 4, 8>(ctx, h, a);
+  else return false;
+  return true;
+}
+
+}  // namespace gf

@@ -1,0 +1,99 @@
+"""GPU: the sum-factorised Laplace kernel for Q3/Q4 hexahedra (csrc/sumfact.cu) on DISTORTED meshes (a different
+Jacobian at every Gauss point), against the generic element kernel (GFGPU_NO_SUMFACT=1) and against the CPU oracle.
+Pattern identical, values and residual 1e-12; the reference-generated golden c5 (Q4) is covered by
+test_gpu_golden.py / test_gpu_workspace.py (its tables carry the reference's 5e-10 round-off, are not an exact tensor
+product, and therefore take the generic kernel: the factorisation check is part of the contract)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CASES = [  # k, im, nsub
+    (4, 8, [2, 2, 3]),
+    (4, 8, [1, 1, 1]),
+    (3, 6, [2, 3, 2]),
+]
+
+
+def _setup(k, im, nsub, distort=0.15):
+    import getfem_b200 as gf
+    from getfem_b200 import capi, fem_tables
+    ctx = capi.Context(0)
+    m = gf.mesh()
+    gf.regular_unit_mesh(m, nsub, "GT_QK(3,1)")
+    rng = np.random.default_rng(3)
+    h = 1.0 / max(nsub)
+    m.pts = m.pts + distort * h * rng.uniform(-1, 1, m.pts.shape)  # every hexahedron becomes genuinely trilinear
+    m._dev = {}
+    mf = gf.mesh_fem(m, 1)
+    mf.set_classical_finite_element(k)
+    dmesh, dfem = m.device(ctx), mf.device(ctx)
+    t = fem_tables.classical_tables("QK", 3, k, im)
+    tab = capi.DeviceTables(ctx, t["quad_w"], t["gt_grad"], t["phi"], t["gphi"])
+    U = rng.uniform(-1, 1, dfem.ndof)
+    return ctx, m, mf, dmesh, dfem, t, tab, U
+
+
+def _assemble(ctx, dmesh, dfem, tab, U, strategy=0):
+    from getfem_b200 import capi
+    term = capi.DeviceTerm(ctx, dmesh, dfem, tab, "laplace", [1.7], 0.5, strategy)
+    R = np.empty(dfem.ndof)
+    term.assemble_host(U, capi.TANGENT | capi.RESIDUAL, None, R)
+    jc, ir, pr = term.export_csc()
+    return jc, ir, pr, R, term.last_timings()
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "q%d-im%d-%s" % (c[0], c[1], "x".join(map(str, c[2]))))
+def test_sumfact_matches_generic_kernel_and_oracle(case):
+    from oracle import oracle
+    k, im, nsub = case
+    ctx, m, mf, dmesh, dfem, t, tab, U = _setup(k, im, nsub)
+    os.environ.pop("GFGPU_NO_SUMFACT", None)
+    jc, ir, pr, R, _ = _assemble(ctx, dmesh, dfem, tab, U)
+    os.environ["GFGPU_NO_SUMFACT"] = "1"
+    try:
+        gjc, gir, gpr, gR, _ = _assemble(ctx, dmesh, dfem, tab, U)
+    finally:
+        os.environ.pop("GFGPU_NO_SUMFACT", None)
+    assert np.array_equal(jc, gjc) and np.array_equal(ir, gir), "pattern differs from the generic kernel"
+    assert np.linalg.norm(pr - gpr) <= 1e-12 * np.linalg.norm(gpr)
+    assert np.linalg.norm(R - gR) <= 1e-12 * np.linalg.norm(gR)
+    ed = dfem.elem_dof()
+    ojc, oir, opr, oR = oracle.assemble(m.pts, m.conn, ed, dfem.ndof, 1, t["quad_w"], t["gt_grad"], t["phi"], t["gphi"],
+                                        False, "laplace", [1.7], U)
+    opr, oR = 0.5 * opr, 0.5 * oR  # the term's factor alpha = 0.5 (factor_of_variable)
+    assert np.array_equal(jc, ojc) and np.array_equal(ir, oir), "pattern differs from the oracle"
+    assert np.linalg.norm(pr - opr) <= 1e-12 * np.linalg.norm(opr)
+    assert np.linalg.norm(R - oR) <= 1e-12 * np.linalg.norm(oR)
+
+
+def test_sumfact_is_the_kernel_that_runs_and_is_faster():
+    """The factorised kernel must actually be selected for exact tensor-product tables (no silent generic path)."""
+    ctx, m, mf, dmesh, dfem, t, tab, U = _setup(4, 8, [4, 4, 4])
+    os.environ.pop("GFGPU_NO_SUMFACT", None)
+    _assemble(ctx, dmesh, dfem, tab, U)
+    *_, tm = _assemble(ctx, dmesh, dfem, tab, U)
+    os.environ["GFGPU_NO_SUMFACT"] = "1"
+    try:
+        *_, tg = _assemble(ctx, dmesh, dfem, tab, U)
+    finally:
+        os.environ.pop("GFGPU_NO_SUMFACT", None)
+    assert tm["elem"] > 0 and tg["elem"] > 3 * tm["elem"], (tm, tg)
+
+
+def test_noisy_tables_fall_back_to_the_generic_kernel():
+    """Tables that are not a tensor product to 1e-13 (e.g. the reference's own Q4 tables) must not be factorised."""
+    from getfem_b200 import capi
+    ctx, m, mf, dmesh, dfem, t, tab, U = _setup(4, 8, [1, 1, 2])
+    rng = np.random.default_rng(5)
+    noisy = capi.DeviceTables(ctx, t["quad_w"], t["gt_grad"], t["phi"] * (1 + 1e-9 * rng.standard_normal(t["phi"].shape)),
+                              t["gphi"])
+    jc, ir, pr, R, _ = _assemble(ctx, dmesh, dfem, noisy, U)
+    os.environ["GFGPU_NO_SUMFACT"] = "1"
+    try:
+        gjc, gir, gpr, gR, _ = _assemble(ctx, dmesh, dfem, noisy, U)
+    finally:
+        os.environ.pop("GFGPU_NO_SUMFACT", None)
+    assert np.array_equal(pr, gpr) and np.array_equal(R, gR), "noisy tables must take the generic kernel (bitwise equal)"
