@@ -94,12 +94,16 @@ __device__ __forceinline__ double det3cm(const double *A) {
   return A[0] * (A[4] * A[8] - A[5] * A[7]) - A[3] * (A[1] * A[8] - A[2] * A[7]) + A[6] * (A[1] * A[5] - A[2] * A[4]);
 }
 
-// Hyperelastic material point (N = Q = 3).  Gu(q,n) col-major.  Writes P (flux, 9) and D (81) to
-// (shared) memory, both multiplied by `coeff`.  law: GFGPU_SVK / NEOHOOKEAN_CIARLET / NEOHOOKEAN_BONET.
+// Hyperelastic material point (N = Q = 3), in two parts so that callers can spread the nine (l, n) slices of the
+// tangent over threads (sumfact.cu) or run them in sequence (hyper_point below).  Gu(a,n) col-major.
 //   S = PK2(E), dS(i,j,k,l) = dS_ij/dGu_kl ; P = F S ; D(a,n,b,l) = delta_ab S(l,n) + F(a,p) dS(p,n,b,l)
-__device__ inline void hyper_point(int law, const double *Gu, double lambda, double mu, double coeff, double *P,
-                                   double *D) {
-  double E[9], F[9], S[9];
+struct HyperPrep {
+  double Gu[9], F[9], S[9], Ci[9], di3[9];
+  double c1, c2, hd;
+};
+
+__device__ __forceinline__ void hyper_prep(int law, const double *Gu, double lambda, double mu, HyperPrep &h) {
+  double E[9];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -108,106 +112,133 @@ __device__ inline void hyper_point(int law, const double *Gu, double lambda, dou
 #pragma unroll
       for (int k = 0; k < 3; ++k) s += Gu[k + 3 * i] * Gu[k + 3 * j];
       E[i + 3 * j] = 0.5 * (s + Gu[i + 3 * j] + Gu[j + 3 * i]);
-      F[i + 3 * j] = Gu[i + 3 * j] + (i == j ? 1.0 : 0.0);
+      h.F[i + 3 * j] = Gu[i + 3 * j] + (i == j ? 1.0 : 0.0);
+      h.Gu[i + 3 * j] = Gu[i + 3 * j];
     }
+  h.c1 = h.c2 = h.hd = 0.0;
   if (law == GFGPU_SVK) {  // getfem_nonlinear_elasticity.cc:1945-1994
-    double trE = E[0] + E[4] + E[8];
+    const double trE = E[0] + E[4] + E[8];
 #pragma unroll
     for (int j = 0; j < 3; ++j)
 #pragma unroll
-      for (int i = 0; i < 3; ++i) S[i + 3 * j] = 2 * mu * E[i + 3 * j] + (i == j ? lambda * trE : 0.0);
+      for (int i = 0; i < 3; ++i) {
+        h.S[i + 3 * j] = 2 * mu * E[i + 3 * j] + (i == j ? lambda * trE : 0.0);
+        h.Ci[i + 3 * j] = 0.0;
+        h.di3[i + 3 * j] = 0.0;
+      }
     // (the registered GWFL operator has no det F penalty, unlike the Neo-Hookean law below)
+    return;
+  }
+  // Neo_Hookean_hyperelastic_law (:612-702) through AHL_wrapper_sigma (:1781-1827)
+  const bool bonet = law == GFGPU_NEOHOOKEAN_BONET;
+  const double detF = det3cm(h.F);
+  double C[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) C[i] = 2 * E[i];
+  C[0] += 1; C[4] += 1; C[8] += 1;
+  const double i3 = det3cm(C);
+  {
+#define C_(i, j) C[(i) + 3 * (j)]
+    h.Ci[0] = (C_(1, 1) * C_(2, 2) - C_(1, 2) * C_(2, 1)) / i3;
+    h.Ci[1] = -(C_(1, 0) * C_(2, 2) - C_(1, 2) * C_(2, 0)) / i3;
+    h.Ci[2] = (C_(1, 0) * C_(2, 1) - C_(1, 1) * C_(2, 0)) / i3;
+    h.Ci[3] = -(C_(0, 1) * C_(2, 2) - C_(0, 2) * C_(2, 1)) / i3;
+    h.Ci[4] = (C_(0, 0) * C_(2, 2) - C_(0, 2) * C_(2, 0)) / i3;
+    h.Ci[5] = -(C_(0, 0) * C_(2, 1) - C_(0, 1) * C_(2, 0)) / i3;
+    h.Ci[6] = (C_(0, 1) * C_(1, 2) - C_(0, 2) * C_(1, 1)) / i3;
+    h.Ci[7] = -(C_(0, 0) * C_(1, 2) - C_(0, 2) * C_(1, 0)) / i3;
+    h.Ci[8] = (C_(0, 0) * C_(1, 1) - C_(0, 1) * C_(1, 0)) / i3;
+#undef C_
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) h.di3[i] = h.Ci[i] * i3;  // compute_di3 (:132-140)
+  const double lg = bonet ? log(i3) : 0.0;
+  const double cs = bonet ? (lambda / 2 * lg - mu) / i3 : lambda / 2 - lambda / (2 * i3) - mu / i3;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) h.S[i] = cs * h.di3[i];
+  h.S[0] += mu; h.S[4] += mu; h.S[8] += mu;
+  if (detF <= 0) {  // :655-656
+#pragma unroll
+    for (int i = 0; i < 9; ++i) h.S[i] += 1e200 * C[i];
+  }
+  if (bonet) { h.c1 = (lambda * lg - 2 * mu) / i3; h.c2 = (lambda + 2 * mu - lambda * lg) / (i3 * i3); }
+  else { h.c1 = lambda - (lambda + 2 * mu) / i3; h.c2 = (lambda + 2 * mu) / (i3 * i3); }
+  h.hd = i3 / 2;
+}
+
+// the nine entries D(a,n,b,l), a,b = 0..2, of the slice (l, n), multiplied by coeff, written at their place in D[81]
+__device__ __forceinline__ void hyper_slice(int law, const HyperPrep &h, int l, int n, double lambda, double mu,
+                                            double coeff, double *D) {
+  const double *F = h.F, *S = h.S, *Gu = h.Gu;
+  if (law == GFGPU_SVK) {
     // D(a,n,b,l) = delta_ab S(l,n) + sum_p F(a,p) dS(p,n,b,l),
     // dS(p,n,b,l) = lambda(d_pn d_bl + d_pn Gu_bl) + mu(d_pb d_nl + d_pl d_nb + d_pl Gu_bn + d_ln Gu_bp)
-    for (int l = 0; l < 3; ++l)
-      for (int b = 0; b < 3; ++b)
-        for (int n = 0; n < 3; ++n)
-          for (int a = 0; a < 3; ++a) {
-            double v = (a == b) ? S[l + 3 * n] : 0.0;
-            double fbl = Gu[b + 3 * l] + (b == l ? 1.0 : 0.0);  // delta_bl + Gu_bl
-            v += lambda * F[a + 3 * n] * fbl;                   // p = n
-            v += mu * ((n == l ? F[a + 3 * b] : 0.0) + (n == b ? F[a + 3 * l] : 0.0) + F[a + 3 * l] * Gu[b + 3 * n]);
-            if (l == n) {
-              double s = 0;
 #pragma unroll
-              for (int p = 0; p < 3; ++p) s += F[a + 3 * p] * Gu[b + 3 * p];
-              v += mu * s;
-            }
-            D[a + 3 * (n + 3 * (b + 3 * l))] = coeff * v;
-          }
-  } else {  // Neo_Hookean_hyperelastic_law (:612-702) through AHL_wrapper_sigma (:1781-1827)
-    const bool bonet = law == GFGPU_NEOHOOKEAN_BONET;
-    double detF = det3cm(F);
-    double C[9], Ci[9];
+    for (int b = 0; b < 3; ++b)
 #pragma unroll
-    for (int i = 0; i < 9; ++i) C[i] = 2 * E[i];
-    C[0] += 1; C[4] += 1; C[8] += 1;
-    double i3 = det3cm(C);
-    {
-#define C_(i, j) C[(i) + 3 * (j)]
-      Ci[0] = (C_(1, 1) * C_(2, 2) - C_(1, 2) * C_(2, 1)) / i3;
-      Ci[1] = -(C_(1, 0) * C_(2, 2) - C_(1, 2) * C_(2, 0)) / i3;
-      Ci[2] = (C_(1, 0) * C_(2, 1) - C_(1, 1) * C_(2, 0)) / i3;
-      Ci[3] = -(C_(0, 1) * C_(2, 2) - C_(0, 2) * C_(2, 1)) / i3;
-      Ci[4] = (C_(0, 0) * C_(2, 2) - C_(0, 2) * C_(2, 0)) / i3;
-      Ci[5] = -(C_(0, 0) * C_(2, 1) - C_(0, 1) * C_(2, 0)) / i3;
-      Ci[6] = (C_(0, 1) * C_(1, 2) - C_(0, 2) * C_(1, 1)) / i3;
-      Ci[7] = -(C_(0, 0) * C_(1, 2) - C_(0, 2) * C_(1, 0)) / i3;
-      Ci[8] = (C_(0, 0) * C_(1, 1) - C_(0, 1) * C_(1, 0)) / i3;
-#undef C_
-    }
-    double di3[9];
+      for (int a = 0; a < 3; ++a) {
+        double v = (a == b) ? S[l + 3 * n] : 0.0;
+        const double fbl = Gu[b + 3 * l] + (b == l ? 1.0 : 0.0);  // delta_bl + Gu_bl
+        v += lambda * F[a + 3 * n] * fbl;                         // p = n
+        v += mu * ((n == l ? F[a + 3 * b] : 0.0) + (n == b ? F[a + 3 * l] : 0.0) + F[a + 3 * l] * Gu[b + 3 * n]);
+        if (l == n) {
+          double s = 0;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) di3[i] = Ci[i] * i3;  // compute_di3 (:132-140)
-    double lg = bonet ? log(i3) : 0.0;
-    double cs = bonet ? (lambda / 2 * lg - mu) / i3 : lambda / 2 - lambda / (2 * i3) - mu / i3;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) S[i] = cs * di3[i];
-    S[0] += mu; S[4] += mu; S[8] += mu;
-    if (detF <= 0) {  // :655-656
-#pragma unroll
-      for (int i = 0; i < 9; ++i) S[i] += 1e200 * C[i];
-    }
-    double c1, c2;
-    if (bonet) { c1 = (lambda * lg - 2 * mu) / i3; c2 = (lambda + 2 * mu - lambda * lg) / (i3 * i3); }
-    else { c1 = lambda - (lambda + 2 * mu) / i3; c2 = (lambda + 2 * mu) / (i3 * i3); }
-    const double hd = i3 / 2;
-#define CI(i, j) Ci[(i) + 3 * (j)]
-    // dS(p,n,b,l) = sum_m A(p,n,m,l) F(b,m);  A = c1*ddi3 + c2*di3 (x) di3  (:142-152, :674-692)
-    // G(p,n,b,l) held implicitly: D(a,n,b,l) = delta_ab S(l,n) + sum_p F(a,p) sum_m A(p,n,m,l) F(b,m)
-    for (int l = 0; l < 3; ++l)
-      for (int n = 0; n < 3; ++n) {
-        // T(p,m) = A(p,n,m,l)
-        double T[9];
-#pragma unroll
-        for (int p = 0; p < 3; ++p)
-#pragma unroll
-          for (int m = 0; m < 3; ++m) {
-            double dd = hd * (CI(n, p) * CI(l, m) - CI(n, m) * CI(l, p) + CI(p, n) * CI(l, m) - CI(p, m) * CI(l, n));
-            T[p + 3 * m] = c1 * dd + c2 * di3[p + 3 * n] * di3[m + 3 * l];
-          }
-        // FT(a,m) = sum_p F(a,p) T(p,m);  D(a,n,b,l) = sum_m FT(a,m) F(b,m)
-        double FT[9];
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-          for (int m = 0; m < 3; ++m) FT[a + 3 * m] = F[a] * T[3 * m] + F[a + 3] * T[1 + 3 * m] + F[a + 6] * T[2 + 3 * m];
-#pragma unroll
-        for (int b = 0; b < 3; ++b)
-#pragma unroll
-          for (int a = 0; a < 3; ++a) {
-            double v = FT[a] * F[b] + FT[a + 3] * F[b + 3] + FT[a + 6] * F[b + 6];
-            if (a == b) v += S[l + 3 * n];
-            D[a + 3 * (n + 3 * (b + 3 * l))] = coeff * v;
-          }
+          for (int p = 0; p < 3; ++p) s += F[a + 3 * p] * Gu[b + 3 * p];
+          v += mu * s;
+        }
+        D[a + 3 * (n + 3 * (b + 3 * l))] = coeff * v;
       }
-#undef CI
+    return;
   }
-  // P = F S
+#define CI(i, j) h.Ci[(i) + 3 * (j)]
+  // dS(p,n,b,l) = sum_m A(p,n,m,l) F(b,m);  A = c1*ddi3 + c2*di3 (x) di3  (:142-152, :674-692)
+  // D(a,n,b,l) = delta_ab S(l,n) + sum_p F(a,p) sum_m A(p,n,m,l) F(b,m);  T(p,m) = A(p,n,m,l)
+  double T[9];
+#pragma unroll
+  for (int p = 0; p < 3; ++p)
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      const double dd = h.hd * (CI(n, p) * CI(l, m) - CI(n, m) * CI(l, p) + CI(p, n) * CI(l, m) - CI(p, m) * CI(l, n));
+      T[p + 3 * m] = h.c1 * dd + h.c2 * h.di3[p + 3 * n] * h.di3[m + 3 * l];
+    }
+#undef CI
+  double FT[9];  // FT(a,m) = sum_p F(a,p) T(p,m)
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int m = 0; m < 3; ++m) FT[a + 3 * m] = F[a] * T[3 * m] + F[a + 3] * T[1 + 3 * m] + F[a + 6] * T[2 + 3 * m];
+#pragma unroll
+  for (int b = 0; b < 3; ++b)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      double v = FT[a] * F[b] + FT[a + 3] * F[b + 3] + FT[a + 6] * F[b + 6];
+      if (a == b) v += S[l + 3 * n];
+      D[a + 3 * (n + 3 * (b + 3 * l))] = coeff * v;
+    }
+}
+
+// P = F S (flux), multiplied by coeff
+__device__ __forceinline__ void hyper_flux(const HyperPrep &h, double coeff, double *P) {
 #pragma unroll
   for (int n = 0; n < 3; ++n)
 #pragma unroll
-    for (int a = 0; a < 3; ++a) P[a + 3 * n] = coeff * (F[a] * S[3 * n] + F[a + 3] * S[1 + 3 * n] + F[a + 6] * S[2 + 3 * n]);
+    for (int a = 0; a < 3; ++a)
+      P[a + 3 * n] = coeff * (h.F[a] * h.S[3 * n] + h.F[a + 3] * h.S[1 + 3 * n] + h.F[a + 6] * h.S[2 + 3 * n]);
+}
+
+// Writes P (flux, 9) and D (81) to (shared) memory, both multiplied by `coeff`.
+// law: GFGPU_SVK / NEOHOOKEAN_CIARLET / NEOHOOKEAN_BONET.
+__device__ inline void hyper_point(int law, const double *Gu, double lambda, double mu, double coeff, double *P,
+                                   double *D) {
+  HyperPrep h;
+  hyper_prep(law, Gu, lambda, mu, h);
+  // (l, n) fully unrolled: every index into Ci / di3 / S is then static and the 3x3 temporaries stay in registers
+#pragma unroll
+  for (int l = 0; l < 3; ++l)
+#pragma unroll
+    for (int n = 0; n < 3; ++n) hyper_slice(law, h, l, n, lambda, mu, coeff, D);
+  hyper_flux(h, coeff, P);
 }
 
 template <int DIM, int Q, int ND, int FK, bool AFFINE>

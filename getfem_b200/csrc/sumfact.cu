@@ -43,6 +43,9 @@ struct SfArgs {
   const double *U, *w, *gt_grad;
   int64_t e0, ne;
   double coef;  // alpha * a
+  const double *gphi;         // hyperelastic kernel: full gradient table [q][i][3] (Grad_u and the residual)
+  double lambda, mu, alpha;   // hyperelastic kernel
+  int law;                    // GFGPU_SVK / GFGPU_NEOHOOKEAN_*
   double *stage;
   uint16_t *emask;
   double *rstage;
@@ -175,6 +178,205 @@ k_sumfact_laplace(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T) 
   }
 }
 
+
+// ---------------------------------------------------------------- hyperelastic (vector, Q = 3) variant
+// K_e(i al, j be) = sum_q sum_{p,r} ghat_i^p(q) A^(al,p,be,r)(q) ghat_j^r(q) with the tangent pulled back to reference
+// coordinates, A^(al,p,be,r) = sum_{n,l} B(n,p) D(al,n,be,l) B(l,r) (D from hyper_point, elem_kernel.cuh): nine
+// scalar systems of the Laplace shape, one per (al, be), with a full 3x3 metric each.  Lane = (i2, j2, al); the lane
+// runs be = 0..2 in sequence (9 accumulators (i1, j1) per be).  BASELINE config 4: FEM_QK(3,2), 64 Gauss points.
+template <int ND1, int NQ1, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+k_sumfact_hyper(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T) {
+  constexpr int NN = ND1 * ND1, ND = ND1 * ND1 * ND1, S1 = 3 * ND, NQ2 = NQ1 * NQ1, NQ = NQ1 * NQ1 * NQ1, NT = NW * 32;
+  constexpr int DS = 82;  // row stride of the per-point tangent
+  static_assert(3 * NN <= 32 && NN <= NW * 32, "lane mapping");
+  extern __shared__ __align__(16) double sm[];
+  double *sK = sm;                    // S1 x S1 column-major: (i*3 + al) + S1 * (j*3 + be)
+  double *sD = sK + S1 * S1;          // NQ x DS : D(al,n,be,l) per point
+  double *sA = sD + NQ * DS;          // 81 x NQ : A^[(al + 3 be) * 9 + p*3 + r][q]
+  double *sS1 = sA + 81 * NQ;         // per warp 3 x 9 x NQ2
+  double *sP = sS1 + NW * 27 * NQ2;   // NQ x 9 : P^(al,p) = sum_n P(al,n) B(n,p)
+  double *sGeo = sP + 9 * NQ;         // NQ x 10 : B, J per point
+  double *sG = sGeo + 10 * NQ;
+  double *sU = sG + 24;
+  double *sRed = sU + S1;             // NW, then 3 x S1 partial residuals
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ln = lane % NN, lal = lane / NN;  // lane = (i2 + ND1*j2) + NN * al ; lanes >= 3*NN idle
+  const bool lact = lane < 3 * NN;
+  double yy[4][NQ1];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int q = 0; q < NQ1; ++q) yy[c][q] = lact ? T.py[c][ln][q] : 0.0;
+  for (int64_t el = blockIdx.x; el < a.ne; el += gridDim.x) {
+    const int64_t e = a.e0 + el;
+    if (tid < 24) {
+      const int i = tid / 3, d = tid % 3;
+      const int32_t p = a.conn[e * 8 + i];
+      sG[d + 3 * i] = (d == 0 ? a.x : d == 1 ? a.y : a.z)[p];
+    }
+    for (int i = tid; i < S1; i += NT) sU[i] = a.U ? a.U[a.edof[e * ND + i / 3] + i % 3] : 0.0;
+    __syncthreads();
+    // ---- B: material point at every Gauss point (thread = point).  Spreading the nine (l, n) slices of the tangent
+    // over threads (hyper_prep / hyper_slice) was measured slower: the shared prologue is most of the work.
+    for (int q = tid; q < NQ; q += NT) {
+      double *geo = sGeo + q * 10;
+      geometry<3>(sG, a.gt_grad + (size_t)q * 24, 8, geo);
+      double Gh[9];  // reference gradient of u: Gh(al,p) = sum_i u_i(al) ghat_i^p
+#pragma unroll
+      for (int k = 0; k < 9; ++k) Gh[k] = 0.0;
+      const double *g = a.gphi + (size_t)q * ND * 3;
+      for (int i = 0; i < ND; ++i) {
+        const double g0 = g[i * 3], g1 = g[i * 3 + 1], g2 = g[i * 3 + 2];
+#pragma unroll
+        for (int al = 0; al < 3; ++al) {
+          const double u = sU[i * 3 + al];
+          Gh[al] += u * g0; Gh[al + 3] += u * g1; Gh[al + 6] += u * g2;
+        }
+      }
+      double Gu[9];  // Gu(al,n) = sum_p Gh(al,p) B(n,p)
+#pragma unroll
+      for (int n = 0; n < 3; ++n)
+#pragma unroll
+        for (int al = 0; al < 3; ++al) Gu[al + 3 * n] = Gh[al] * geo[n] + Gh[al + 3] * geo[n + 3] + Gh[al + 6] * geo[n + 6];
+      const double wq = a.w[q];
+      const double coeff = (wq == 0.0) ? 0.0 : a.alpha * geo[9] * wq;  // zero-weight points are skipped (C&E.cc:8852)
+      double P[9];
+      hyper_point(a.law, Gu, a.lambda, a.mu, coeff, P, sD + (size_t)q * DS);
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int al = 0; al < 3; ++al)
+          sP[q * 9 + al + 3 * p] = P[al] * geo[3 * p] + P[al + 3] * geo[1 + 3 * p] + P[al + 6] * geo[2 + 3 * p];
+    }
+    __syncthreads();
+    // ---- B2: pull-back of the tangent: work item = (point, be, r)
+    for (int w = tid; w < NQ * 9; w += NT) {
+      const int q = w / 9, br = w % 9, be = br / 3, r = br % 3;
+      const double *geo = sGeo + q * 10;
+      const double *D = sD + (size_t)q * DS;
+      double t[9];  // t(al,n) = sum_l D(al,n,be,l) B(l,r)
+#pragma unroll
+      for (int n = 0; n < 3; ++n)
+#pragma unroll
+        for (int al = 0; al < 3; ++al) {
+          double s = 0;
+#pragma unroll
+          for (int l = 0; l < 3; ++l) s += D[al + 3 * (n + 3 * (be + 3 * l))] * geo[l + 3 * r];
+          t[al + 3 * n] = s;
+        }
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int al = 0; al < 3; ++al) {
+          const double v = geo[3 * p] * t[al] + geo[1 + 3 * p] * t[al + 3] + geo[2 + 3 * p] * t[al + 6];
+          sA[((al + 3 * be) * 9 + p * 3 + r) * NQ + q] = v;
+        }
+    }
+    __syncthreads();
+    // ---- C: slices (i3, j3), one per warp
+    double *S1w = sS1 + warp * 27 * NQ2;
+    for (int sl = warp; sl < NN; sl += NW) {
+      double acc[3][NN];
+#pragma unroll
+      for (int be = 0; be < 3; ++be)
+#pragma unroll
+        for (int m = 0; m < NN; ++m) acc[be][m] = 0.0;
+#pragma unroll
+      for (int be = 0; be < 3; ++be) {
+        for (int idx = lane; idx < 27 * NQ2; idx += 32) {  // S1[al'][ab][q1 q2] for this be
+          const int al2 = idx / (9 * NQ2), rem = idx - al2 * 9 * NQ2, ab = rem / NQ2, q12 = rem - ab * NQ2;
+          const double *A = sA + ((al2 + 3 * be) * 9 + ab) * NQ + q12;
+          const double *pz = T.pz[((ab / 3) == 2) * 2 + ((ab % 3) == 2)][sl];
+          double s = 0;
+#pragma unroll
+          for (int q3 = 0; q3 < NQ1; ++q3) s += A[q3 * NQ2] * pz[q3];
+          S1w[idx] = s;
+        }
+        __syncwarp();
+        const double *S1 = S1w + (lact ? lal : 0) * 9 * NQ2;
+#pragma unroll
+        for (int ab = 0; ab < 9; ++ab) {
+          const int yc = ((ab / 3) == 1) * 2 + ((ab % 3) == 1);
+#pragma unroll
+          for (int q1 = 0; q1 < NQ1; ++q1) {
+            double s2 = 0;
+#pragma unroll
+            for (int q2 = 0; q2 < NQ1; ++q2) s2 += S1[ab * NQ2 + q1 + NQ1 * q2] * yy[yc][q2];
+#pragma unroll
+            for (int m = 0; m < NN; ++m) acc[be][m] += T.px[ab][q1][m] * s2;
+          }
+        }
+        __syncwarp();
+      }
+      if (lact) {
+        const int i2 = ln % ND1, j2 = ln / ND1, i3 = sl % ND1, j3 = sl / ND1;
+#pragma unroll
+        for (int be = 0; be < 3; ++be)
+#pragma unroll
+          for (int m = 0; m < NN; ++m) {
+            const int i = (m % ND1) + ND1 * i2 + NN * i3, j = (m / ND1) + ND1 * j2 + NN * j3;
+            sK[(i * 3 + lal) + S1 * (j * 3 + be)] = acc[be][m];
+          }
+      }
+    }
+    __syncthreads();
+    // ---- element residual r(i al) = sum_q sum_p ghat_i^p(q) P^(al,p)(q)        (C&E.cc:4669-4735)
+    // three threads per entry, each a third of the points; the partial sums are added in a fixed order
+    if (a.rstage) {
+      double *sR = sRed + NW;
+      for (int w = tid; w < 3 * S1; w += NT) {
+        const int part = w / S1, k = w - part * S1, i = k / 3, al = k % 3;
+        const int q0 = part * NQ / 3, q1 = (part + 1) * NQ / 3;
+        double s = 0;
+        for (int q = q0; q < q1; ++q) {
+          const double *g = a.gphi + ((size_t)q * ND + i) * 3;
+          s += g[0] * sP[q * 9 + al] + g[1] * sP[q * 9 + al + 3] + g[2] * sP[q * 9 + al + 6];
+        }
+        sR[w] = s;
+      }
+      __syncthreads();
+      for (int k = tid; k < S1; k += NT) a.rstage[(size_t)el * S1 + k] = (sR[k] + sR[S1 + k]) + sR[2 * S1 + k];
+    }
+    // ---- D: drop rule and output
+    if (a.stage || a.emask) {
+      double vmax = 0.0;
+      for (int k = tid; k < S1 * S1; k += NT) vmax = fmax(vmax, fabs(sK[k]));
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, off));
+      if (lane == 0) sRed[warp] = vmax;
+      __syncthreads();
+      vmax = 0.0;
+#pragma unroll
+      for (int wv = 0; wv < NW; ++wv) vmax = fmax(vmax, sRed[wv]);
+      const double thr = vmax * 1e-14;
+      if (a.stage) {
+        double *st = a.stage + (size_t)el * S1 * S1;
+        for (int k = tid; k < S1 * S1; k += NT) {
+          const double v = sK[k];
+          st[k] = ((vmax != 0.0) && (fabs(v) > thr)) ? v : 0.0;
+        }
+      }
+      if (a.emask) {
+        uint16_t *em = a.emask + (size_t)el * ND * ND;
+        for (int p = tid; p < ND * ND; p += NT) {
+          const int j = p / ND, i = p % ND;
+          unsigned mask = 0;
+#pragma unroll
+          for (int bb = 0; bb < 3; ++bb)
+#pragma unroll
+            for (int aa = 0; aa < 3; ++aa) {
+              const double v = sK[(i * 3 + aa) + S1 * (j * 3 + bb)];
+              if ((vmax != 0.0) && (fabs(v) > thr)) mask |= 1u << (bb * 3 + aa);
+            }
+          em[p] = (uint16_t)mask;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------- host: factorise and verify the tables
 struct SfHost {
   int nd1 = 0, nq1 = 0;
@@ -228,11 +430,9 @@ static SfHost factorise(const gfgpu_tables *tab) {
   return h;
 }
 
-template <int ND1, int NQ1, int NW>
-static void launch_sf(gfgpu_ctx *ctx, const SfHost &h, const SfArgs &a) {
-  constexpr int NN = ND1 * ND1, ND = ND1 * ND1 * ND1, NQ2 = NQ1 * NQ1, NQ = NQ2 * NQ1;
-  std::unique_ptr<SfTables<ND1, NQ1>> Tp(new SfTables<ND1, NQ1>);  // filled per call (host side, cheap)
-  SfTables<ND1, NQ1> &T = *Tp;
+template <int ND1, int NQ1>
+static void fill_tables(const SfHost &h, SfTables<ND1, NQ1> &T) {
+  constexpr int NN = ND1 * ND1;
   auto L = [&](int i, int q) { return h.l[(size_t)i * NQ1 + q]; };
   auto D = [&](int i, int q) { return h.d[(size_t)i * NQ1 + q]; };
   for (int aa = 0; aa < 3; ++aa)
@@ -250,30 +450,56 @@ static void launch_sf(gfgpu_ctx *ctx, const SfHost &h, const SfArgs &a) {
         T.py[c][m][q] = v;
         T.pz[c][m][q] = v;
       }
+}
+
+template <int ND1, int NQ1, int NW>
+static void launch_sf(gfgpu_ctx *ctx, const SfHost &h, const SfArgs &a) {
+  constexpr int ND = ND1 * ND1 * ND1, NQ2 = NQ1 * NQ1, NQ = NQ2 * NQ1;
+  std::unique_ptr<SfTables<ND1, NQ1>> Tp(new SfTables<ND1, NQ1>);  // filled per call (host side, cheap)
+  fill_tables<ND1, NQ1>(h, *Tp);
   static_assert(sizeof(SfTables<ND1, NQ1>) + sizeof(SfArgs) <= 32000, "tables exceed the kernel parameter space");
   const size_t smem = ((size_t)ND * ND + 6 * NQ + (size_t)NW * 9 * NQ2 + 24 + ND + NW + 2) * 8;
   auto kern = k_sumfact_laplace<ND1, NQ1, NW>;
   GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(a.ne, ctx->sm_count));
-  kern<<<grid, NW * 32, smem, ctx->stream>>>(a, T);
+  kern<<<grid, NW * 32, smem, ctx->stream>>>(a, *Tp);
+  GF_LAUNCH_CHECK();
+}
+
+template <int ND1, int NQ1, int NW>
+static void launch_sf_hyper(gfgpu_ctx *ctx, const SfHost &h, const SfArgs &a) {
+  constexpr int ND = ND1 * ND1 * ND1, S1 = 3 * ND, NQ2 = NQ1 * NQ1, NQ = NQ2 * NQ1;
+  std::unique_ptr<SfTables<ND1, NQ1>> Tp(new SfTables<ND1, NQ1>);
+  fill_tables<ND1, NQ1>(h, *Tp);
+  const size_t smem = ((size_t)S1 * S1 + (size_t)NQ * 82 + 81 * (size_t)NQ + (size_t)NW * 27 * NQ2 + 19 * (size_t)NQ + 24 + S1 + NW +
+                       3 * S1 + 2) * 8;
+  auto kern = k_sumfact_hyper<ND1, NQ1, NW>;
+  GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(a.ne, ctx->sm_count));
+  kern<<<grid, NW * 32, smem, ctx->stream>>>(a, *Tp);
   GF_LAUNCH_CHECK();
 }
 
 // returns false when this family / element / table set is not handled here (the caller then uses the generic kernel)
 bool launch_sumfact_kernel(gfgpu_ctx *ctx, const gfgpu_tables *tab, int dim, int Q, int nd, bool affine, const ElemArgs &ea) {
-  if (ea.family != GFGPU_LAPLACE || dim != 3 || Q != 1 || affine || ea.ng != 8) return false;
-  if (!(nd == 125 && ea.nq == 125) && !(nd == 64 && ea.nq == 64)) return false;
-  if (getenv("GFGPU_NO_SUMFACT")) return false;
+  if (dim != 3 || affine || ea.ng != 8 || getenv("GFGPU_NO_SUMFACT")) return false;
+  const bool lap = ea.family == GFGPU_LAPLACE && Q == 1 && ((nd == 125 && ea.nq == 125) || (nd == 64 && ea.nq == 64));
+  const bool hyp = (ea.family == GFGPU_SVK || ea.family == GFGPU_NEOHOOKEAN_CIARLET || ea.family == GFGPU_NEOHOOKEAN_BONET) &&
+                   Q == 3 && nd == 27 && (ea.nq == 64 || ea.nq == 27);
+  if (!lap && !hyp) return false;
   const SfHost h = factorise(tab);
   if (!h.ok) return false;
   SfArgs a;
   a.x = ea.x; a.y = ea.y; a.z = ea.z; a.conn = ea.conn; a.edof = ea.edof; a.U = ea.U; a.w = ea.w; a.gt_grad = ea.gt_grad;
   a.e0 = ea.e0; a.ne = ea.e1 - ea.e0;
   a.coef = ea.alpha * ea.par[0];
+  a.gphi = ea.gphi; a.lambda = ea.par[0]; a.mu = ea.par[1]; a.alpha = ea.alpha; a.law = ea.family;
   a.stage = ea.stage; a.emask = ea.emask; a.rstage = ea.rstage;
   if (a.ne <= 0) return true;
-  if (h.nd1 == 5 && h.nq1 == 5) launch_sf<5, 5, 13>(ctx, h, a);
-  else if (h.nd1 == 4 && h.nq1 == 4) launch_sf<4, 4, 8>(ctx, h, a);
+  if (lap && h.nd1 == 5 && h.nq1 == 5) launch_sf<5, 5, 13>(ctx, h, a);
+  else if (lap && h.nd1 == 4 && h.nq1 == 4) launch_sf<4, 4, 8>(ctx, h, a);
+  else if (hyp && h.nd1 == 3 && h.nq1 == 4) launch_sf_hyper<3, 4, 9>(ctx, h, a);
+  else if (hyp && h.nd1 == 3 && h.nq1 == 3) launch_sf_hyper<3, 3, 9>(ctx, h, a);
   else return false;
   return true;
 }

@@ -17,7 +17,7 @@ CASES = [  # k, im, nsub
 ]
 
 
-def _setup(k, im, nsub, distort=0.15):
+def _setup(k, im, nsub, distort=0.15, Q=1, uscale=1.0):
     import getfem_b200 as gf
     from getfem_b200 import capi, fem_tables
     ctx = capi.Context(0)
@@ -27,18 +27,18 @@ def _setup(k, im, nsub, distort=0.15):
     h = 1.0 / max(nsub)
     m.pts = m.pts + distort * h * rng.uniform(-1, 1, m.pts.shape)  # every hexahedron becomes genuinely trilinear
     m._dev = {}
-    mf = gf.mesh_fem(m, 1)
+    mf = gf.mesh_fem(m, Q)
     mf.set_classical_finite_element(k)
     dmesh, dfem = m.device(ctx), mf.device(ctx)
     t = fem_tables.classical_tables("QK", 3, k, im)
     tab = capi.DeviceTables(ctx, t["quad_w"], t["gt_grad"], t["phi"], t["gphi"])
-    U = rng.uniform(-1, 1, dfem.ndof)
+    U = uscale * rng.uniform(-1, 1, dfem.ndof)
     return ctx, m, mf, dmesh, dfem, t, tab, U
 
 
-def _assemble(ctx, dmesh, dfem, tab, U, strategy=0):
+def _assemble(ctx, dmesh, dfem, tab, U, strategy=0, family="laplace", params=(1.7,), alpha=0.5):
     from getfem_b200 import capi
-    term = capi.DeviceTerm(ctx, dmesh, dfem, tab, "laplace", [1.7], 0.5, strategy)
+    term = capi.DeviceTerm(ctx, dmesh, dfem, tab, family, list(params), alpha, strategy)
     R = np.empty(dfem.ndof)
     term.assemble_host(U, capi.TANGENT | capi.RESIDUAL, None, R)
     jc, ir, pr = term.export_csc()
@@ -97,3 +97,36 @@ def test_noisy_tables_fall_back_to_the_generic_kernel():
     finally:
         os.environ.pop("GFGPU_NO_SUMFACT", None)
     assert np.array_equal(pr, gpr) and np.array_equal(R, gR), "noisy tables must take the generic kernel (bitwise equal)"
+
+
+HYPER = [  # family, im, nsub
+    ("nh_ciarlet", 6, [2, 2, 2]),
+    ("nh_bonet", 6, [2, 1, 2]),
+    ("svk", 6, [2, 2, 1]),
+    ("svk", 4, [1, 2, 2]),
+]
+
+
+@pytest.mark.parametrize("case", HYPER, ids=lambda c: "%s-im%d-%s" % (c[0], c[1], "x".join(map(str, c[2]))))
+def test_hyperelastic_sumfact_matches_generic_kernel_and_oracle(case):
+    """Q2 hexahedra, finite-strain laws (BASELINE config 4): factorised tangent + residual on a distorted mesh."""
+    from oracle import oracle
+    family, im, nsub = case
+    ctx, m, mf, dmesh, dfem, t, tab, U = _setup(2, im, nsub, Q=3, uscale=0.03)
+    par = (1.3, 0.8)
+    os.environ.pop("GFGPU_NO_SUMFACT", None)
+    jc, ir, pr, R, tm = _assemble(ctx, dmesh, dfem, tab, U, family=family, params=par, alpha=1.0)
+    os.environ["GFGPU_NO_SUMFACT"] = "1"
+    try:
+        gjc, gir, gpr, gR, tg = _assemble(ctx, dmesh, dfem, tab, U, family=family, params=par, alpha=1.0)
+    finally:
+        os.environ.pop("GFGPU_NO_SUMFACT", None)
+    assert np.array_equal(jc, gjc) and np.array_equal(ir, gir), "pattern differs from the generic kernel"
+    assert np.linalg.norm(pr - gpr) <= 1e-12 * np.linalg.norm(gpr)
+    assert np.linalg.norm(R - gR) <= 1e-12 * np.linalg.norm(gR)
+    ed = dfem.elem_dof()
+    ojc, oir, opr, oR = oracle.assemble(m.pts, m.conn, ed, dfem.ndof, 3, t["quad_w"], t["gt_grad"], t["phi"], t["gphi"],
+                                        False, family, list(par), U)
+    assert np.array_equal(jc, ojc) and np.array_equal(ir, oir), "pattern differs from the oracle"
+    assert np.linalg.norm(pr - opr) <= 1e-12 * np.linalg.norm(opr)
+    assert np.linalg.norm(R - oR) <= 1e-12 * np.linalg.norm(oR)
