@@ -13,13 +13,13 @@ LIB_PATH = os.environ.get("GFGPU_LIB") or os.path.join(_HERE, "libgfgpu.so")  # 
 
 GT_PK, GT_QK = 0, 1
 FEM_PK, FEM_QK = 0, 1
-LAPLACE, ELASTICITY, SVK, NEOHOOKEAN_CIARLET, NEOHOOKEAN_BONET, MASS = range(6)
+LAPLACE, ELASTICITY, SVK, NEOHOOKEAN_CIARLET, NEOHOOKEAN_BONET, MASS, SOURCE = range(7)
 RESIDUAL, TANGENT = 1, 2
 STRATEGY_AUTO, STRATEGY_STAGED, STRATEGY_RECOMPUTE = 0, 1, 2
 
 FAMILY_BY_NAME = {
     "laplace": LAPLACE, "elast": ELASTICITY, "elasticity": ELASTICITY, "svk": SVK,
-    "nh_ciarlet": NEOHOOKEAN_CIARLET, "nh_bonet": NEOHOOKEAN_BONET, "mass": MASS,
+    "nh_ciarlet": NEOHOOKEAN_CIARLET, "nh_bonet": NEOHOOKEAN_BONET, "mass": MASS, "source": SOURCE,
 }
 
 # symbol -> (restype, argtypes); kept in one table so tests can check it against include/gfgpu.h

@@ -218,8 +218,8 @@ int gfgpu_term_create(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem, gfgpu_ta
   GF_REQUIRE(ctx && mesh && fem && tab && out, "null argument");
   GF_REQUIRE(fem->mesh == mesh, "the fem was built on another mesh");
   GF_REQUIRE(tab->dim == mesh->dim && tab->ng == mesh->ng && tab->nd == fem->nd, "tables do not match mesh/fem");
-  GF_REQUIRE(family >= GFGPU_LAPLACE && family <= GFGPU_MASS, "unknown expression family");
-  const int need = (family == GFGPU_LAPLACE || family == GFGPU_MASS) ? 1 : 2;
+  GF_REQUIRE(family >= GFGPU_LAPLACE && family <= GFGPU_SOURCE, "unknown expression family");
+  const int need = family == GFGPU_SOURCE ? fem->qdim : (family == GFGPU_LAPLACE || family == GFGPU_MASS) ? 1 : 2;
   GF_REQUIRE(params && nparams >= need, "missing parameters for this family");
   if (family == GFGPU_ELASTICITY) GF_REQUIRE(fem->qdim == mesh->dim, "elasticity needs qdim == mesh dimension");
   if (family == GFGPU_SVK || family == GFGPU_NEOHOOKEAN_CIARLET || family == GFGPU_NEOHOOKEAN_BONET)
@@ -274,14 +274,25 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
   gfgpu_ctx *ctx = t->ctx;
   GF_CUDA(cudaSetDevice(ctx->device));
   GF_REQUIRE(order_mask & (GFGPU_RESIDUAL | GFGPU_TANGENT), "order_mask selects nothing");
-  const bool do_t = order_mask & GFGPU_TANGENT, do_r = order_mask & GFGPU_RESIDUAL;
+  bool do_t = order_mask & GFGPU_TANGENT;
+  const bool do_r = order_mask & GFGPU_RESIDUAL;
   const int nd = t->fem->nd, Q = t->fem->qdim, s1 = nd * Q;
   const int64_t ne = t->e1 - t->e0;
+  if (t->family == GFGPU_SOURCE && do_t) {
+    // an order-1 term has no order-2 tree (workspace.cc:545-600): the tangent is structurally empty
+    if (t->jc.n != (size_t)t->fem->ndof + 1) t->jc.alloc(ctx, t->fem->ndof + 1);
+    t->jc.zero();
+    t->nnz = 0;
+    t->pat_valid = true;
+    do_t = false;
+    if (!do_r) return;
+  }
   if (!t->st_valid) {
     gf::build_structure(ctx, t->fem->edof.p, nd, t->e0, t->e1, t->fem->ndof, t->st, t->vJ.p, t->vI.p, (int64_t)t->vJ.n);
     t->st_valid = true;
     t->pat_valid = false;
   }
+  if (t->family == GFGPU_SOURCE && t->jc.n) t->pat_valid = true;  // the (empty) pattern of an order-1 term never moves
   const bool recompute = t->strategy == GFGPU_STRATEGY_RECOMPUTE;
   // what the generic element kernel has to produce in this call.  RECOMPUTE needs it only once, for
   // the keep masks of the pattern; its residual is K^T U inside the per-nonzero kernel.

@@ -350,9 +350,15 @@ elem_kernel(const ElemArgs a) {
             if (need_gu)
               for (int r = 0; r < Q * N; ++r) P[r] = coeff * a.par[0] * Gu[r];
           } else if (FK == FK_MASS) {
-            sD[q] = coeff * a.par[0];
-            if (need_gu)
-              for (int c = 0; c < Q; ++c) P[c] = coeff * a.par[0] * Gu[c];
+            if (a.family == GFGPU_SOURCE) {  // "F.Test_u": r_e(i b) = sum_q J w_q F_b phi_i (C&E.cc:437-461, 4669-4735)
+              sD[q] = 0.0;
+              if (need_gu)
+                for (int c = 0; c < Q; ++c) P[c] = coeff * a.par[c];
+            } else {
+              sD[q] = coeff * a.par[0];
+              if (need_gu)
+                for (int c = 0; c < Q; ++c) P[c] = coeff * a.par[0] * Gu[c];
+            }
           } else if (FK == FK_ELAST) {
             sD[q] = coeff;
             if (need_gu) {

@@ -55,6 +55,21 @@ bool recognise_tree(const getfem::ga_workspace &ws, size_type itree, recognised_
   if (std::regex_match(s, std::regex(v + "\\.Test_" + v))) {
     out.family = GFGPU_MASS; out.params = {1.0}; return true;
   }
+  {  // volumic source term (add_source_term_brick, getfem_models.cc:4124-): "(-f)*Test_u", "(-f).Test_u", "-(f.Test_u)", "f.Test_u"
+    double sign = 0;
+    std::string name;
+    if (std::regex_match(s, m, std::regex("\\(-" + ID + "\\)[.*]Test_" + v))) { sign = -1; name = m[1]; }
+    else if (std::regex_match(s, m, std::regex("-\\(" + ID + "[.*]Test_" + v + "\\)"))) { sign = -1; name = m[1]; }
+    else if (std::regex_match(s, m, std::regex(ID + "[.*]Test_" + v))) { sign = 1; name = m[1]; }
+    if (sign != 0 && name != v && ws.is_constant(name) && !ws.variable_group_exists(name)) {
+      const getfem::mesh_fem *pmf = ws.associated_mf(v);
+      GMM_ASSERT1(pmf && ws.value(name).size() == pmf->get_qdim(),
+                  "gfgpu: the source term needs a fixed-size constant with qdim components");
+      out.family = GFGPU_SOURCE;
+      for (size_type k = 0; k < ws.value(name).size(); ++k) out.params.push_back(sign * ws.value(name)[k]);
+      return true;
+    }
+  }
   if (std::regex_match(s, m, std::regex("\\(\\(Div_" + v + "\\*\\(" + ID + "\\*" + Idm + "\\)\\)\\+\\(\\(2\\*" + ID +
                                         "\\)\\*\\(Sym\\(Grad_" + v + "\\)\\)\\)\\):Grad_Test_" + v))) {
     out.family = GFGPU_ELASTICITY; out.params = {scalar(m[1]), scalar(m[2])}; return true;
@@ -231,6 +246,11 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
       if (V.size() < I.first() + ndof) V.resize(std::max<size_type>(nprim, I.first() + ndof), 0.0);
       for (size_type d = 0; d < ndof; ++d) V[I.first() + d] += R[d];
       t_fill += now_s() - t2;
+    } else if (rt.family == GFGPU_SOURCE) {
+      // an order-1 term contributes nothing to the tangent; K only gets its size (workspace.cc:805-812)
+      getfem::model_real_sparse_matrix &K = ws.assembled_matrix();
+      const size_type need = std::max<size_type>(nprim, I.first() + ndof);
+      if (gmm::mat_nrows(K) < need || gmm::mat_ncols(K) < need) gmm::resize(K, need, need);
     } else {
       GFGPU_CALL(gfgpu_term_assemble_host(e.term, U.data(), GFGPU_TANGENT, nullptr, nullptr));
       const int64_t nnz = gfgpu_term_nnz(e.term);

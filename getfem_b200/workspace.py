@@ -181,6 +181,9 @@ def recognise(expr):
     m = re.fullmatch(rf"\(?({_ID})\)?\*\(?Div_({_ID})\*Div_Test_\2\)?\+\(?2\*\(?({_ID})\)?\)?\*\(?Sym\(Grad_\2\):Grad_Test_\2\)?", s)
     if m:
         return "elast", m.group(2), [m.group(1), m.group(3)]
+    m = re.fullmatch(rf"(-?)\(?({_ID})[.*]Test_({_ID})\)?", s)  # volumic source term: "-f*Test_u", "-(F.Test_u)", "F.Test_u"
+    if m and not m.group(2).startswith("Grad_") and m.group(2) != m.group(3):
+        return ("source-" if m.group(1) else "source+"), m.group(3), [m.group(2)]
     m = re.fullmatch(rf"\(\(Id\(meshdim\)\+Grad_({_ID})\)\*\(?({_ID})_PK2\(Grad_\1,({_ID})\)\)?\):Grad_Test_\1", s)
     if m and m.group(2) in _LAWS:
         return _LAWS[m.group(2)], m.group(1), [m.group(3)]
@@ -212,7 +215,14 @@ class ga_workspace:
         for c in cnames:
             if c not in self.constants:
                 raise capi.GfgpuError("unknown constant " + c)
-        if fam in ("laplace", "mass"):
+        if fam.startswith("source"):
+            mf = self.variables[var][0]
+            f = self.constants[cnames[0]]
+            if f.size != mf.Qdim:
+                raise capi.GfgpuError("the source term needs a constant of qdim components")
+            params = [(-1.0 if fam.endswith("-") else 1.0) * float(v) for v in f]
+            fam = "source"
+        elif fam in ("laplace", "mass"):
             params = [float(self.constants[cnames[0]][0])] if cnames else [1.0]
         elif fam == "elast":
             params = [float(self.constants[cnames[0]][0]), float(self.constants[cnames[1]][0])]
@@ -253,6 +263,8 @@ class ga_workspace:
         else:
             vec = None
         for k in range(len(self.terms)):
+            if order == 2 and self.terms[k][0] == "source" and len(self.terms) > 1:
+                continue  # an order-1 term has no order-2 tree (workspace.cc:545-600)
             dev = self._term(k)
             mf, V = self.variables[self.terms[k][1]]
             U = None if V is None else np.ascontiguousarray(V, np.float64)

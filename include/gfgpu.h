@@ -49,6 +49,9 @@ enum { GFGPU_FEM_PK = 0, GFGPU_FEM_QK = 1 };
  *                (add_finite_strain_elasticity_brick, getfem_nonlinear_elasticity.cc:2301-2325;
  *                 laws :1945-1994, :612-702)
  *   MASS         "a*u.Test_u"                                        params = {a}
+ *   SOURCE       "F.Test_u" (F a constant of qdim components; "-f*Test_u" passes F = -f)   params = {F_0 .. F_{qdim-1}}
+ *                (add_source_term_brick, getfem_models.cc:4124-): an order-1 term.  It has no order-2 tree: the
+ *                TANGENT bit is accepted and leaves an empty matrix (nnz = 0), as ga_workspace::assembly(2) does.
  */
 enum {
   GFGPU_LAPLACE = 0,
@@ -56,7 +59,8 @@ enum {
   GFGPU_SVK = 2,
   GFGPU_NEOHOOKEAN_CIARLET = 3,
   GFGPU_NEOHOOKEAN_BONET = 4,
-  GFGPU_MASS = 5
+  GFGPU_MASS = 5,
+  GFGPU_SOURCE = 6
 };
 
 /* order_mask bits of gfgpu_term_assemble_*: ga_workspace::assembly(1) and assembly(2)

@@ -28,7 +28,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-enum { GFO_LAPLACE = 0, GFO_ELAST = 1, GFO_SVK = 2, GFO_NH_CIARLET = 3, GFO_NH_BONET = 4, GFO_MASS = 5 };
+enum { GFO_LAPLACE = 0, GFO_ELAST = 1, GFO_SVK = 2, GFO_NH_CIARLET = 3, GFO_NH_BONET = 4, GFO_MASS = 5, GFO_SOURCE = 6 };
 
 typedef struct { int64_t c; double e; } entry_t; /* gmm::elt_rsvector_ (gmm_vector.h:913-932) */
 typedef struct { entry_t *v; int64_t n, cap; } col_t;
@@ -230,6 +230,13 @@ gfo_result *gfo_assemble(int dim, int64_t ne, int ng, const double *pts, const i
           for (int p = 0; p < N; ++p) s += g[i * N + p] * B[n + N * p];
           Z[i * N + n] = s;
         }
+      if (family == GFO_SOURCE) { /* "F.Test_u", F = par[0..Q): order 1 only (ga_instruction_vector_assembly_mf,
+                                     cc:4669-4735, fed by val_base cc:437-461); no order-2 tree, the tangent is empty */
+        const double *ph = phi + (size_t)ipt * nd;
+        for (int i = 0; i < nd; ++i)
+          for (int b = 0; b < Q; ++b) relem[i * Q + b] += coeff * par[b] * ph[i];
+        continue;
+      }
       if (family == GFO_MASS) {
         const double *ph = phi + (size_t)ipt * nd;
         for (int j = 0; j < nd; ++j)

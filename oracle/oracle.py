@@ -12,7 +12,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libgfo.so")
-FAMILIES = {"laplace": 0, "elast": 1, "svk": 2, "nh_ciarlet": 3, "nh_bonet": 4, "mass": 5}
+FAMILIES = {"laplace": 0, "elast": 1, "svk": 2, "nh_ciarlet": 3, "nh_bonet": 4, "mass": 5, "source": 6}
 
 
 def build(force=False):

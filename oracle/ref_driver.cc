@@ -16,7 +16,7 @@
 //
 // usage: gf_ref_driver key=value ...
 //   dim=3 n=4 gt=pk|qk k=2 q=3 im=4 | imname="IM_TETRAHEDRON(5)"
-//   family=laplace|elast|svk|nh_ciarlet|nh_bonet|mass  lambda=1 mu=1 a=1
+//   family=laplace|elast|svk|nh_ciarlet|nh_bonet|mass|source  lambda=1 mu=1 a=1
 //   u=smooth|random|zero  out=DIR  mode=dump|time|model  threads=T reps=R
 #include "getfem/getfem_regular_meshes.h"
 #include "getfem/getfem_mesh_fem.h"
@@ -134,6 +134,9 @@ int main(int argc, char **argv) {
   if (family == "laplace") expr = "a*Grad_u.Grad_Test_u";  // generic elliptic, scalar a
   else if (family == "laplace_vec") expr = "a*Grad_u:Grad_Test_u";
   else if (family == "mass") expr = "a*u.Test_u";
+  // volumic source term, the string of add_source_term_brick (getfem_models.cc:4124-, "-(A.Test_u)" shape):
+  // order 1 only, no tangent.  f = a * (1, 2, .., Q)
+  else if (family == "source") expr = Q == 1 ? "-f*Test_u" : "-f.Test_u";
   else if (family == "elast")  // src/getfem_models.cc:6112-6113
     expr = "(Div_u*((lambda)*Id(meshdim))+(2*(mu))*Sym(Grad_u)):Grad_Test_u";
   else {
@@ -165,10 +168,14 @@ int main(int argc, char **argv) {
 
   // constants are BORROWED by the workspace (generic_assembly.h:277): keep them alive
   const std::vector<double> c_a{acoef}, c_lambda{lambda}, c_mu{mu}, c_params{lambda, mu};
+  std::vector<double> c_f(Q);
+  for (size_type k = 0; k < size_type(Q); ++k) c_f[k] = acoef * double(k + 1);
   auto setup_ws = [&](getfem::ga_workspace &ws, const getfem::mesh_region &rg) {
     ws.add_fem_variable("u", mf, gmm::sub_interval(0, ndof), U);
     if (family == "laplace" || family == "laplace_vec" || family == "mass")
       ws.add_fixed_size_constant("a", c_a);
+    else if (family == "source")
+      ws.add_fixed_size_constant("f", c_f);
     else if (family == "elast") {
       ws.add_fixed_size_constant("lambda", c_lambda);
       ws.add_fixed_size_constant("mu", c_mu);

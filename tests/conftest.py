@@ -31,7 +31,10 @@ def load_golden(name):
     d["Q"] = int(args["q"])
     d["gt_linear"] = args["gt"] == "pk"
     lam, mu, a = d["params"]
-    d["fparams"] = np.array([a]) if d["family"] in ("laplace", "mass") else np.array([lam, mu])
+    if d["family"] == "source":  # "-f.Test_u" with f = a * (1..Q): the family integrates F.Test_u, F = -f
+        d["fparams"] = -a * np.arange(1, d["Q"] + 1, dtype=np.float64)
+    else:
+        d["fparams"] = np.array([a]) if d["family"] in ("laplace", "mass") else np.array([lam, mu])
     return d
 
 

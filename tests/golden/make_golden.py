@@ -39,6 +39,10 @@ CASES = {
     "x_lap2d_q2_n3": "dim=2 n=3 gt=qk k=2 q=1 im=4 family=laplace u=random",
     "x_lap3d_p1_ragged": "dim=3 nx=1 ny=2 nz=3 gt=pk k=1 q=1 im=2 family=laplace u=random",
     "x_elast3d_q2_n1": "dim=3 n=1 gt=qk k=2 q=3 im=4 family=elast u=random lambda=1 mu=1",
+    # volumic source term (order 1 only, empty tangent): the RHS of BASELINE config 1
+    "c1b_source2d_p1_n6": "dim=2 n=6 gt=pk k=1 q=1 im=2 family=source u=random a=1.5",
+    "x_source3d_p2vec_n2": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=source u=random a=0.5",
+    "x_source3d_q2_n2": "dim=3 n=2 gt=qk k=2 q=1 im=6 family=source u=random a=2",
 }
 
 

@@ -15,6 +15,7 @@ EXPR = {
     "svk": "((Id(meshdim)+Grad_u)*(Saint_Venant_Kirchhoff_PK2(Grad_u,params))):Grad_Test_u",
     "nh_ciarlet": "((Id(meshdim)+Grad_u)*(Compressible_Neo_Hookean_Ciarlet_PK2(Grad_u,params))):Grad_Test_u",
     "nh_bonet": "((Id(meshdim)+Grad_u)*(Compressible_Neo_Hookean_Bonet_PK2(Grad_u,params))):Grad_Test_u",
+    "source": "-f.Test_u",  # "-f*Test_u" when qdim = 1 (the strings of oracle/ref_driver.cc)
 }
 
 
@@ -33,14 +34,19 @@ def build_ws(dim, nsub, gt, k, Q, im, family, params, U=None):
     elif callable(U):
         U = U(mf)
     ws.add_fem_variable("u", mf, slice(0, ndof), U)
-    if family in ("laplace", "mass"):
+    expr = EXPR[family]
+    if family == "source":
+        ws.add_fixed_size_constant("f", [-p for p in params])  # the goldens carry F = -f
+        if Q == 1:
+            expr = "-f*Test_u"
+    elif family in ("laplace", "mass"):
         ws.add_fixed_size_constant("a", [params[0]])
     elif family == "elast":
         ws.add_fixed_size_constant("lambda", [params[0]])
         ws.add_fixed_size_constant("mu", [params[1]])
     else:
         ws.add_fixed_size_constant("params", params)
-    ws.add_expression(EXPR[family], mim)
+    ws.add_expression(expr, mim)
     return ws, mf, m, U
 
 
@@ -61,7 +67,7 @@ def test_workspace_matches_reference_golden(name):
     assert np.array_equal(jc, g["K_jc"]) and np.array_equal(ir, g["K_ir"])
     # Q4: the reference's own basis tables carry 5e-10 of round-off (see test_host_tables.py)
     tol = 1e-8 if int(a["k"]) >= 4 else 1e-12
-    assert np.linalg.norm(pr - g["K_pr"]) / np.linalg.norm(g["K_pr"]) < tol
+    assert np.linalg.norm(pr - g["K_pr"]) / max(np.linalg.norm(g["K_pr"]), 1e-300) < tol
     assert np.linalg.norm(ws.assembled_vector() - g["R"]) / np.linalg.norm(g["R"]) < tol
 
 
@@ -85,6 +91,8 @@ CASES = [  # dim, nsub, gt, k, Q, im, family, params, U
     (3, [4, 4, 3], "PK", 2, 3, 4, "nh_bonet", [1.3, 0.7], "smooth"),
     (3, [2, 2, 1], "QK", 4, 1, 8, "laplace", [1.0], "random"),
     (3, [5, 4, 3], "PK", 2, 3, 4, "mass", [1.5], "random"),
+    (2, [30, 20], "PK", 1, 1, 2, "source", [-1.5], "random"),
+    (3, [3, 2, 2], "QK", 2, 3, 6, "source", [0.5, -1.0, 2.0], "random"),
 ]
 
 
@@ -107,8 +115,45 @@ def test_workspace_matches_oracle(case):
                                         t["quad_w"], t["gt_grad"], t["phi"], t["gphi"], gt == "PK", family,
                                         params, Uv)
     assert np.array_equal(jc, ojc) and np.array_equal(ir, oir)
-    assert np.linalg.norm(pr - opr) / np.linalg.norm(opr) < 1e-12
+    assert np.linalg.norm(pr - opr) / max(np.linalg.norm(opr), 1e-300) < 1e-12
     assert np.linalg.norm(ws.assembled_vector() - oR) / np.linalg.norm(oR) < 1e-12
+
+
+def test_config1_stiffness_plus_rhs():
+    """BASELINE config 1 as the reference states it: 2D Poisson P1, stiffness AND right-hand side in one workspace
+    ("a*Grad_u.Grad_Test_u" + "-f*Test_u").  assembly(2) = K (the source term has no order-2 tree), assembly(1) =
+    K u - F; checked against the oracle term by term."""
+    import getfem_b200 as gf
+    from getfem_b200 import fem_tables
+    from oracle import oracle
+    n = 24
+    m = gf.mesh()
+    gf.regular_unit_mesh(m, [n, n], "GT_PK(2,1)")
+    mf = gf.mesh_fem(m, 1)
+    mf.set_classical_finite_element(1)
+    mim = gf.mesh_im(m)
+    mim.set_integration_method(2)
+    rng = np.random.default_rng(11)
+    U = rng.uniform(-1, 1, mf.nb_dof())
+    ws = gf.ga_workspace()
+    ws.add_fem_variable("u", mf, slice(0, mf.nb_dof()), U)
+    ws.add_fixed_size_constant("a", [1.0])
+    ws.add_fixed_size_constant("f", [3.0])
+    ws.add_expression("a*Grad_u.Grad_Test_u", mim)
+    ws.add_expression("-f*Test_u", mim)
+    ws.assembly(2)
+    ws.assembly(1)
+    jc, ir, pr = ws.assembled_matrix()
+    t = fem_tables.classical_tables("PK", 2, 1, 2)
+    args = (m.pts, m.conn, mf.ind_scalar_basic_dof_of_element(), mf.nb_dof(), 1, t["quad_w"], t["gt_grad"], t["phi"],
+            t["gphi"], True)
+    ojc, oir, opr, oR = oracle.assemble(*args, "laplace", [1.0], U)
+    sjc, sir, spr, sR = oracle.assemble(*args, "source", [-3.0], U)
+    assert sjc[-1] == 0, "a source term must not produce tangent entries"
+    assert np.array_equal(jc, ojc) and np.array_equal(ir, oir)
+    assert np.linalg.norm(pr - opr) / np.linalg.norm(opr) < 1e-12
+    assert np.linalg.norm(ws.assembled_vector() - (oR + sR)) / np.linalg.norm(oR + sR) < 1e-12
+    assert abs(sR.sum() + 3.0) < 1e-12  # integral of -f over the unit square
 
 
 def test_properties_at_size():
