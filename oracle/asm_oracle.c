@@ -28,7 +28,8 @@
 #include <stdlib.h>
 #include <string.h>
 
-enum { GFO_LAPLACE = 0, GFO_ELAST = 1, GFO_SVK = 2, GFO_NH_CIARLET = 3, GFO_NH_BONET = 4, GFO_MASS = 5, GFO_SOURCE = 6 };
+enum { GFO_LAPLACE = 0, GFO_ELAST = 1, GFO_SVK = 2, GFO_NH_CIARLET = 3, GFO_NH_BONET = 4, GFO_MASS = 5, GFO_SOURCE = 6,
+       GFO_NORMAL_SOURCE = 7 };
 
 typedef struct { int64_t c; double e; } entry_t; /* gmm::elt_rsvector_ (gmm_vector.h:913-932) */
 typedef struct { entry_t *v; int64_t n, cap; } col_t;
@@ -180,11 +181,19 @@ static void hyper_law(int family, const double *Gu, const double *par, double *S
 }
 
 /* pts: npts x dim (row-major), conn: ne x ng, elem_dof: ne x nd (dof of component 0),
-   gt_grad: nq x ng x dim, phi: nq x nd, gphi: nq x nd x dim.  order_mask: bit0 residual, bit1 tangent. */
-gfo_result *gfo_assemble(int dim, int64_t ne, int ng, const double *pts, const int32_t *conn, int nd, int Q,
-                         const int64_t *elem_dof, int64_t ndof, int nq, const double *w, const double *gt_grad,
-                         const double *phi, const double *gphi, int gt_linear, int family, const double *par,
-                         const double *U, int order_mask) {
+   gt_grad: nq x ng x dim, phi: nq x nd, gphi: nq x nd x dim.  order_mask: bit0 residual, bit1 tangent.
+   Region (mesh_region walked by mr_visitor, compile_and_exec.cc:8789): n_items items (item_cv[k], item_face[k]),
+   face -1 = the whole convex; item_cv == NULL = all convexes.  With faces the tables hold ALL integration points
+   (volume points first, then face by face: approx_integration::valid_method, getfem_integration.cc:353-368);
+   the points of face f are [face_first[f], face_first[f] + face_nq[f]) and ref_normals[f] is pgt->normals()[f].
+   On a face: Normal = B*n_ref, J *= |Normal|, Normal /= |Normal|, components below 1e-13 cleaned
+   (compile_and_exec.cc:8836-8847). */
+gfo_result *gfo_assemble_region(int dim, int64_t ne, int ng, const double *pts, const int32_t *conn, int nd, int Q,
+                                const int64_t *elem_dof, int64_t ndof, int nq, const double *w, const double *gt_grad,
+                                const double *phi, const double *gphi, int gt_linear, int family, const double *par,
+                                const double *U, int order_mask, int64_t n_items, const int32_t *item_cv,
+                                const int32_t *item_face, const int32_t *face_first, const int32_t *face_nq,
+                                const double *ref_normals) {
   const int N = dim, s1 = nd * Q;
   gfo_result *res = (gfo_result *)calloc(1, sizeof(gfo_result));
   res->ndof = ndof;
@@ -195,10 +204,15 @@ gfo_result *gfo_assemble(int dim, int64_t ne, int ng, const double *pts, const i
   double *G = (double *)malloc(sizeof(double) * N * ng), *ue = (double *)malloc(sizeof(double) * s1);
   int64_t *dofs = (int64_t *)malloc(sizeof(int64_t) * s1);
   int *sort = (int *)malloc(sizeof(int) * s1);
-  double K[9], Ki[9], B[9], J = 0, D[81], P[9], Gu[9], S[9], dS[81];
+  double K[9], Ki[9], B[9], J = 0, D[81], P[9], Gu[9], S[9], dS[81], Nrm[3] = {0, 0, 0};
   const int nonlinear = family == GFO_SVK || family == GFO_NH_CIARLET || family == GFO_NH_BONET;
+  if (!item_cv) n_items = ne;
 
-  for (int64_t cv = 0; cv < ne; ++cv) {
+  for (int64_t item = 0; item < n_items; ++item) {
+    const int64_t cv = item_cv ? item_cv[item] : item;
+    const int face = (item_cv && item_face) ? item_face[item] : -1;
+    const int first_ind = face >= 0 ? face_first[face] : 0;
+    const int nbpt = face >= 0 ? face_nq[face] : nq;
     for (int i = 0; i < ng; ++i) /* points_of_convex: G is N x ng column-major */
       for (int d = 0; d < N; ++d) G[d + N * i] = pts[(size_t)conn[cv * ng + i] * dim + d];
     for (int i = 0; i < nd; ++i)
@@ -208,8 +222,9 @@ gfo_result *gfo_assemble(int dim, int64_t ne, int ng, const double *pts, const i
       }
     memset(elem, 0, sizeof(double) * s1 * s1);
     memset(relem, 0, sizeof(double) * s1);
-    for (int ipt = 0; ipt < nq; ++ipt) {
-      if (ipt == 0 || !gt_linear) {
+    for (int ip = 0; ip < nbpt; ++ip) {
+      const int ipt = first_ind + ip;
+      if (ip == 0 || !gt_linear) {
         const double *pc = gt_grad + (size_t)ipt * ng * N; /* ng x P, row i = node */
         for (int r = 0; r < N; ++r)
           for (int c = 0; c < N; ++c) {
@@ -220,6 +235,21 @@ gfo_result *gfo_assemble(int dim, int64_t ne, int ng, const double *pts, const i
         J = fabs(inv3(K, Ki, N));
         for (int r = 0; r < N; ++r)
           for (int c = 0; c < N; ++c) B[r + N * c] = Ki[c + N * r]; /* B = K^{-T} */
+        if (face >= 0) { /* unit normal and surface Jacobian (cc:8836-8847) */
+          double nup = 0;
+          for (int r = 0; r < N; ++r) {
+            double s = 0;
+            for (int c = 0; c < N; ++c) s += B[r + N * c] * ref_normals[face * N + c];
+            Nrm[r] = s;
+            nup += s * s;
+          }
+          nup = sqrt(nup);
+          J *= nup;
+          for (int r = 0; r < N; ++r) {
+            Nrm[r] /= nup;
+            if (fabs(Nrm[r]) < 1e-13) Nrm[r] = 0.0; /* gmm::clean */
+          }
+        }
       }
       double coeff = J * w[ipt];
       if (w[ipt] == 0.0) continue; /* disabled points contribute coeff = 0 (cc:8852-8854) */
@@ -235,6 +265,16 @@ gfo_result *gfo_assemble(int dim, int64_t ne, int ng, const double *pts, const i
         const double *ph = phi + (size_t)ipt * nd;
         for (int i = 0; i < nd; ++i)
           for (int b = 0; b < Q; ++b) relem[i * Q + b] += coeff * par[b] * ph[i];
+        continue;
+      }
+      if (family == GFO_NORMAL_SOURCE) { /* "(Reshape(A,qdim,meshdim)*Normal).Test_u" / "((g).Normal)*Test_u"
+                                            (getfem_models.cc:4290-4299): A(b,n) = par[b + Q*n] */
+        const double *ph = phi + (size_t)ipt * nd;
+        for (int b = 0; b < Q; ++b) {
+          double an = 0;
+          for (int n = 0; n < N; ++n) an += par[b + Q * n] * Nrm[n];
+          for (int i = 0; i < nd; ++i) relem[i * Q + b] += coeff * an * ph[i];
+        }
         continue;
       }
       if (family == GFO_MASS) {
@@ -326,6 +366,14 @@ gfo_result *gfo_assemble(int dim, int64_t ne, int ng, const double *pts, const i
   for (int64_t j = 0; j < ndof; ++j) res->nnz += res->cols[j].n;
   free(elem); free(t); free(relem); free(Z); free(G); free(ue); free(dofs); free(sort);
   return res;
+}
+
+gfo_result *gfo_assemble(int dim, int64_t ne, int ng, const double *pts, const int32_t *conn, int nd, int Q,
+                         const int64_t *elem_dof, int64_t ndof, int nq, const double *w, const double *gt_grad,
+                         const double *phi, const double *gphi, int gt_linear, int family, const double *par,
+                         const double *U, int order_mask) {
+  return gfo_assemble_region(dim, ne, ng, pts, conn, nd, Q, elem_dof, ndof, nq, w, gt_grad, phi, gphi, gt_linear, family,
+                             par, U, order_mask, ne, NULL, NULL, NULL, NULL, NULL);
 }
 
 int64_t gfo_nnz(const gfo_result *r) { return r->nnz; }

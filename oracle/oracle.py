@@ -12,7 +12,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libgfo.so")
-FAMILIES = {"laplace": 0, "elast": 1, "svk": 2, "nh_ciarlet": 3, "nh_bonet": 4, "mass": 5, "source": 6}
+FAMILIES = {"laplace": 0, "elast": 1, "svk": 2, "nh_ciarlet": 3, "nh_bonet": 4, "mass": 5, "source": 6,
+            "nsource": 7}
 
 
 def build(force=False):
@@ -35,6 +36,8 @@ def lib():
         L.gfo_assemble.argtypes = [C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                    C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.gfo_assemble_region.restype = C.c_void_p
+        L.gfo_assemble_region.argtypes = L.gfo_assemble.argtypes + [C.c_int64] + [C.c_void_p] * 5
         L.gfo_nnz.restype = C.c_int64
         L.gfo_nnz.argtypes = [C.c_void_p]
         L.gfo_get_csc.argtypes = [C.c_void_p] * 4
@@ -48,8 +51,12 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def assemble(pts, conn, elem_dof, ndof, Q, w, gt_grad, phi, gphi, gt_linear, family, params, U, order_mask=3):
-    """Returns (jc, ir, pr, R): tangent in CSC (int64 indices) and residual."""
+def assemble(pts, conn, elem_dof, ndof, Q, w, gt_grad, phi, gphi, gt_linear, family, params, U, order_mask=3,
+             region=None, nq=None):
+    """Returns (jc, ir, pr, R): tangent in CSC (int64 indices) and residual.
+    region = None (all convexes) or a dict: items_cv, items_f (face -1 = whole convex) and, when faces are used,
+    face_first, face_nq, ref_normals -- the tables then cover ALL integration points and nq is the number of
+    volume points."""
     pts = np.ascontiguousarray(pts, np.float64)
     conn = np.ascontiguousarray(conn, np.int32)
     elem_dof = np.ascontiguousarray(elem_dof, np.int64)
@@ -62,9 +69,22 @@ def assemble(pts, conn, elem_dof, ndof, Q, w, gt_grad, phi, gphi, gt_linear, fam
     ne, ng = conn.shape
     nd = elem_dof.shape[1]
     L = lib()
-    h = L.gfo_assemble(pts.shape[1], ne, ng, _p(pts), _p(conn), nd, Q, _p(elem_dof), ndof, len(w), _p(w),
-                       _p(gt_grad), _p(phi), _p(gphi), int(gt_linear), FAMILIES[family], _p(params), _p(U),
-                       order_mask)
+    if region is None:
+        h = L.gfo_assemble(pts.shape[1], ne, ng, _p(pts), _p(conn), nd, Q, _p(elem_dof), ndof, len(w), _p(w),
+                           _p(gt_grad), _p(phi), _p(gphi), int(gt_linear), FAMILIES[family], _p(params), _p(U),
+                           order_mask)
+    else:
+        icv = np.ascontiguousarray(region["items_cv"], np.int32)
+        ifc = np.ascontiguousarray(region.get("items_f", np.full(len(icv), -1)), np.int32)
+        faces = bool((ifc >= 0).any())
+        ff = np.ascontiguousarray(region["face_first"], np.int32) if faces else None
+        fn = np.ascontiguousarray(region["face_nq"], np.int32) if faces else None
+        rn = np.ascontiguousarray(region["ref_normals"], np.float64) if faces else None
+        h = L.gfo_assemble_region(pts.shape[1], ne, ng, _p(pts), _p(conn), nd, Q, _p(elem_dof), ndof,
+                                  len(w) if nq is None else nq, _p(w), _p(gt_grad), _p(phi), _p(gphi),
+                                  int(gt_linear), FAMILIES[family], _p(params), _p(U), order_mask, len(icv), _p(icv),
+                                  _p(ifc), _p(ff) if faces else None, _p(fn) if faces else None,
+                                  _p(rn) if faces else None)
     nnz = L.gfo_nnz(h)
     jc = np.empty(ndof + 1, np.int64)
     ir = np.empty(nnz, np.int64)

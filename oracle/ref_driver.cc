@@ -17,6 +17,8 @@
 // usage: gf_ref_driver key=value ...
 //   dim=3 n=4 gt=pk|qk k=2 q=3 im=4 | imname="IM_TETRAHEDRON(5)"
 //   family=laplace|elast|svk|nh_ciarlet|nh_bonet|mass|source  lambda=1 mu=1 a=1
+//   family=nsource (normal source term, getfem_models.cc:4290-4299; boundary regions only)
+//   region=all|outer|xmax|zmin|half   (outer faces / faces on x=1 / on z=0 (last coord) / convexes with barycentre x<0.5)
 //   u=smooth|random|zero  out=DIR  mode=dump|time|model  threads=T reps=R
 #include "getfem/getfem_regular_meshes.h"
 #include "getfem/getfem_mesh_fem.h"
@@ -129,6 +131,31 @@ int main(int argc, char **argv) {
   const size_type nq = pai->nb_points_on_convex();
   const size_type nd = pf->nb_dof(cv0), ng = pgt->nb_points();
 
+  // ---- integration region (mesh_region of convexes or of faces, getfem_mesh_region.h)
+  const std::string rgname = gets("region", "all");
+  getfem::mesh_region rg_all = getfem::mesh_region::all_convexes();
+  getfem::mesh_region rg_sel;
+  if (rgname != "all") {
+    if (rgname == "half") {
+      for (dal::bv_visitor cv(m.convex_index()); !cv.finished(); ++cv) {
+        double bx = 0;
+        for (size_type i = 0; i < ng; ++i) bx += m.points_of_convex(cv)[i][0];
+        if (bx / double(ng) < 0.5) rg_sel.add(cv);
+      }
+    } else {
+      getfem::mesh_region outer;
+      getfem::outer_faces_of_mesh(m, outer);
+      for (getfem::mr_visitor v(outer); !v.finished(); ++v) {
+        base_node un = m.normal_of_face_of_convex(v.cv(), v.f());
+        un /= gmm::vect_norm2(un);
+        bool keep = rgname == "outer" || (rgname == "xmax" && un[0] > 0.999) ||
+                    (rgname == "zmin" && un[dim - 1] < -0.999);
+        if (keep) rg_sel.add(v.cv(), v.f());
+      }
+    }
+  }
+  const getfem::mesh_region &rg_use = rgname == "all" ? rg_all : rg_sel;
+
   // ---- expression of the family (the brick strings of the reference)
   std::string expr;
   if (family == "laplace") expr = "a*Grad_u.Grad_Test_u";  // generic elliptic, scalar a
@@ -137,6 +164,9 @@ int main(int argc, char **argv) {
   // volumic source term, the string of add_source_term_brick (getfem_models.cc:4124-, "-(A.Test_u)" shape):
   // order 1 only, no tangent.  f = a * (1, 2, .., Q)
   else if (family == "source") expr = Q == 1 ? "-f*Test_u" : "-f.Test_u";
+  // normal source term brick (getfem_models.cc:4290-4299): data g of meshdim (scalar u) or Q x meshdim (vector u)
+  else if (family == "nsource")
+    expr = Q == 1 ? "((g).Normal)*Test_u" : "(Reshape(g,qdim(u),meshdim)*Normal).Test_u";
   else if (family == "elast")  // src/getfem_models.cc:6112-6113
     expr = "(Div_u*((lambda)*Id(meshdim))+(2*(mu))*Sym(Grad_u)):Grad_Test_u";
   else {
@@ -170,12 +200,16 @@ int main(int argc, char **argv) {
   const std::vector<double> c_a{acoef}, c_lambda{lambda}, c_mu{mu}, c_params{lambda, mu};
   std::vector<double> c_f(Q);
   for (size_type k = 0; k < size_type(Q); ++k) c_f[k] = acoef * double(k + 1);
+  std::vector<double> c_g(size_t(Q) * dim);
+  for (size_t k = 0; k < c_g.size(); ++k) c_g[k] = acoef * (0.5 + 0.37 * double(k)) * ((k % 3) == 1 ? -1.0 : 1.0);
   auto setup_ws = [&](getfem::ga_workspace &ws, const getfem::mesh_region &rg) {
     ws.add_fem_variable("u", mf, gmm::sub_interval(0, ndof), U);
     if (family == "laplace" || family == "laplace_vec" || family == "mass")
       ws.add_fixed_size_constant("a", c_a);
     else if (family == "source")
       ws.add_fixed_size_constant("f", c_f);
+    else if (family == "nsource")
+      ws.add_fixed_size_constant("g", c_g);
     else if (family == "elast") {
       ws.add_fixed_size_constant("lambda", c_lambda);
       ws.add_fixed_size_constant("mu", c_mu);
@@ -195,7 +229,7 @@ int main(int argc, char **argv) {
     size_type nnz = 0;
     for (int r = 0; r < reps + 1; ++r) {   // first pass = warm-up (precomp caches)
       getfem::ga_workspace ws;
-      setup_ws(ws, getfem::mesh_region::all_convexes());
+      setup_ws(ws, rg_use);
       getfem::model_real_sparse_matrix Kmat(ndof, ndof);
       ws.set_assembled_matrix(Kmat);
       t0 = now_s(); ws.assembly(2); double t2 = now_s() - t0;
@@ -220,7 +254,7 @@ int main(int argc, char **argv) {
         getfem::accumulated_distro<std::vector<double>> Rd(R);
         GETFEM_OMP_PARALLEL(
           getfem::ga_workspace ws;
-          setup_ws(ws, getfem::mesh_region::all_convexes());
+          setup_ws(ws, rg_use);
           ws.set_assembled_matrix(Kd);
           ws.assembly(2);
           ws.set_assembled_vector(Rd);
@@ -238,7 +272,7 @@ int main(int argc, char **argv) {
 
   // ---- dump mode: reference result
   getfem::ga_workspace ws;
-  setup_ws(ws, getfem::mesh_region::all_convexes());
+  setup_ws(ws, rg_use);
   getfem::model_real_sparse_matrix Kmat(ndof, ndof);
   ws.set_assembled_matrix(Kmat);
   t0 = now_s(); ws.assembly(2); double t2 = now_s() - t0;
@@ -303,6 +337,50 @@ int main(int argc, char **argv) {
     for (int d = 0; d < dim; ++d) rnodes[i * dim + d] = pf->node_of_dof(cv0, i)[d];
   npy_f64(out + "/ref_nodes.npy", {nd, size_t(dim)}, rnodes);
 
+  // region items in mr_visitor order (the order ga_exec walks them, C&E.cc:8789): face -1 = the whole convex
+  if (rgname != "all") {
+    std::vector<int32_t> icv, ifc;
+    for (getfem::mr_visitor v(rg_use, m); !v.finished(); ++v) {
+      icv.push_back(int32_t(v.cv()));
+      ifc.push_back(v.f() == getfem::short_type(-1) ? -1 : int32_t(v.f()));
+    }
+    npy_i32(out + "/items_cv.npy", {icv.size()}, icv);
+    npy_i32(out + "/items_f.npy", {ifc.size()}, ifc);
+  }
+  { // tables at ALL integration points (volume points first, then the points of face 0, 1, ...:
+    // approx_integration::valid_method, getfem_integration.cc:353-368) + reference normals of the faces
+    const size_type nqa = pai->nb_points(), nf = pgt->structure()->nb_faces();
+    std::vector<double> aw(nqa), ax(nqa * dim), agtg(nqa * ng * dim), aphi(nqa * nd), agphi(nqa * nd * dim);
+    for (size_type q = 0; q < nqa; ++q) {
+      aw[q] = pai->coeff(q);
+      for (int d = 0; d < dim; ++d) ax[q * dim + d] = (*pspt)[q][d];
+      const bgeot::base_matrix &pc = pgp->grad(q);
+      for (size_type i = 0; i < ng; ++i)
+        for (int d = 0; d < dim; ++d) agtg[(q * ng + i) * dim + d] = pc(i, d);
+      const bgeot::base_tensor &v = pfp->val(q);
+      const bgeot::base_tensor &g = pfp->grad(q);
+      for (size_type i = 0; i < nd; ++i) {
+        aphi[q * nd + i] = v[i];
+        for (int d = 0; d < dim; ++d) agphi[(q * nd + i) * dim + d] = g[i + nd * d];
+      }
+    }
+    std::vector<int32_t> ff(nf), fn(nf);
+    std::vector<double> rn(nf * dim);
+    for (size_type f = 0; f < nf; ++f) {
+      ff[f] = int32_t(pai->ind_first_point_on_face(getfem::short_type(f)));
+      fn[f] = int32_t(pai->nb_points_on_face(getfem::short_type(f)));
+      for (int d = 0; d < dim; ++d) rn[f * dim + d] = pgt->normals()[f][d];
+    }
+    npy_f64(out + "/all_w.npy", {nqa}, aw);
+    npy_f64(out + "/all_x.npy", {nqa, size_t(dim)}, ax);
+    npy_f64(out + "/all_gt_grad.npy", {nqa, ng, size_t(dim)}, agtg);
+    npy_f64(out + "/all_phi.npy", {nqa, nd}, aphi);
+    npy_f64(out + "/all_gphi.npy", {nqa, nd, size_t(dim)}, agphi);
+    npy_i32(out + "/face_first.npy", {nf}, ff);
+    npy_i32(out + "/face_nq.npy", {nf}, fn);
+    npy_f64(out + "/ref_normals.npy", {nf, size_t(dim)}, rn);
+  }
+
   npy_f64(out + "/U.npy", {ndof}, U);
   std::vector<int64_t> jc(ndof + 1), ir(nnz);
   std::vector<double> pr(nnz);
@@ -314,5 +392,6 @@ int main(int argc, char **argv) {
   npy_f64(out + "/R.npy", {ndof}, R);
   std::vector<double> par = {lambda, mu, acoef};
   npy_f64(out + "/params.npy", {3}, par);
+  npy_f64(out + "/gdata.npy", {c_g.size()}, c_g);
   return 0;
 }

@@ -33,8 +33,18 @@ def load_golden(name):
     lam, mu, a = d["params"]
     if d["family"] == "source":  # "-f.Test_u" with f = a * (1..Q): the family integrates F.Test_u, F = -f
         d["fparams"] = -a * np.arange(1, d["Q"] + 1, dtype=np.float64)
+    elif d["family"] == "nsource":  # "(Reshape(g,qdim,meshdim)*Normal).Test_u": A(b,n) = g[b + Q*n]
+        d["fparams"] = d["gdata"].astype(np.float64)
     else:
         d["fparams"] = np.array([a]) if d["family"] in ("laplace", "mass") else np.array([lam, mu])
+    # mesh regions: items in mr_visitor order; with faces the tables cover ALL integration points
+    d["region"] = None
+    d["tables"] = (d["quad_w"], d["gt_grad"], d["phi"], d["gphi"])
+    if "items_cv" in d:
+        d["region"] = {"items_cv": d["items_cv"], "items_f": d["items_f"]}
+        if (d["items_f"] >= 0).any():
+            d["region"].update(face_first=d["face_first"], face_nq=d["face_nq"], ref_normals=d["ref_normals"])
+            d["tables"] = (d["all_w"], d["all_gt_grad"], d["all_phi"], d["all_gphi"])
     return d
 
 

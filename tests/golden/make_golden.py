@@ -43,6 +43,18 @@ CASES = {
     "c1b_source2d_p1_n6": "dim=2 n=6 gt=pk k=1 q=1 im=2 family=source u=random a=1.5",
     "x_source3d_p2vec_n2": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=source u=random a=0.5",
     "x_source3d_q2_n2": "dim=3 n=2 gt=qk k=2 q=1 im=6 family=source u=random a=2",
+    # mesh regions: boundary faces (unit normal, surface Jacobian, C&E.cc:8827-8848) with the
+    # Neumann / normal source / boundary mass (Robin, Dirichlet penalisation) terms, and sub-regions of convexes
+    "r_mass3d_p2vec_outer": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=mass region=outer u=random a=1.5",
+    "r_source3d_p2vec_xmax": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=source region=xmax u=random a=0.5",
+    "r_nsource3d_p2vec_outer": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=nsource region=outer u=random a=0.8",
+    "r_nsource2d_p1_outer": "dim=2 n=4 gt=pk k=1 q=1 im=2 family=nsource region=outer u=random a=1.2",
+    "r_mass2d_p2_outer": "dim=2 n=3 gt=pk k=2 q=1 im=4 family=mass region=outer u=random a=2",
+    "r_mass3d_q2_zmin": "dim=3 n=2 gt=qk k=2 q=1 im=6 family=mass region=zmin u=random a=1.5",
+    "r_nsource3d_q2vec_outer": "dim=3 n=2 gt=qk k=2 q=3 im=6 family=nsource region=outer u=random a=0.7",
+    "r_elast3d_p2_half": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=elast region=half u=random lambda=1 mu=1",
+    "r_lap3d_p1_half": "dim=3 n=4 gt=pk k=1 q=1 im=2 family=laplace region=half u=random",
+    "r_nh_ciarlet_q2_half": "dim=3 n=2 gt=qk k=2 q=3 im=6 family=nh_ciarlet region=half u=smooth lambda=1 mu=1 uamp=0.02",
 }
 
 
@@ -59,6 +71,10 @@ def main():
         arrs["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
         for k in ("conn", "elem_dof", "K_jc", "K_ir"):
             arrs[k] = arrs[k].astype(np.int32)
+        if "region=" not in args:  # the all-point tables and face data only travel with the region fixtures
+            for k in ("all_w", "all_x", "all_gt_grad", "all_phi", "all_gphi", "face_first", "face_nq", "ref_normals",
+                      "gdata"):
+                arrs.pop(k, None)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrs)
         print(name, meta["fem"], meta["im"], "ne", meta["ne"], "ndof", meta["ndof"], "nnz", meta["nnz"],
               os.path.getsize(os.path.join(HERE, name + ".npz")) // 1024, "KiB")

@@ -11,8 +11,10 @@ from oracle import oracle
 def test_oracle_matches_reference(name):
     g = load_golden(name)
     ndof = g["meta"]["ndof"]
-    jc, ir, pr, R = oracle.assemble(g["pts"], g["conn"], g["elem_dof"], ndof, g["Q"], g["quad_w"], g["gt_grad"],
-                                    g["phi"], g["gphi"], g["gt_linear"], g["family"], g["fparams"], g["U"])
+    w, gt_grad, phi, gphi = g["tables"]
+    jc, ir, pr, R = oracle.assemble(g["pts"], g["conn"], g["elem_dof"], ndof, g["Q"], w, gt_grad, phi, gphi,
+                                    g["gt_linear"], g["family"], g["fparams"], g["U"], region=g["region"],
+                                    nq=g["meta"]["nq"])
     assert np.array_equal(jc, g["K_jc"]), "column pointers differ (pattern not bit-exact)"
     assert np.array_equal(ir, g["K_ir"]), "row indices differ (pattern not bit-exact)"
     rel = np.linalg.norm(pr - g["K_pr"]) / max(np.linalg.norm(g["K_pr"]), 1e-300)
