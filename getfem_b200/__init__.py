@@ -8,5 +8,5 @@ shim/            C++ drop-in for the real GetFEM (compiled against its headers, 
 """
 from . import capi, fem_tables  # noqa: F401
 from .capi import GfgpuError  # noqa: F401
-from .workspace import (default_context, ga_workspace, mesh, mesh_fem, mesh_im,  # noqa: F401
-                        regular_unit_mesh)
+from .workspace import (default_context, ga_workspace, mesh, mesh_fem, mesh_im, mesh_region,  # noqa: F401
+                        outer_faces_of_mesh, regular_unit_mesh)

@@ -13,13 +13,14 @@ LIB_PATH = os.environ.get("GFGPU_LIB") or os.path.join(_HERE, "libgfgpu.so")  # 
 
 GT_PK, GT_QK = 0, 1
 FEM_PK, FEM_QK = 0, 1
-LAPLACE, ELASTICITY, SVK, NEOHOOKEAN_CIARLET, NEOHOOKEAN_BONET, MASS, SOURCE = range(7)
+LAPLACE, ELASTICITY, SVK, NEOHOOKEAN_CIARLET, NEOHOOKEAN_BONET, MASS, SOURCE, NORMAL_SOURCE = range(8)
 RESIDUAL, TANGENT = 1, 2
 STRATEGY_AUTO, STRATEGY_STAGED, STRATEGY_RECOMPUTE = 0, 1, 2
 
 FAMILY_BY_NAME = {
     "laplace": LAPLACE, "elast": ELASTICITY, "elasticity": ELASTICITY, "svk": SVK,
     "nh_ciarlet": NEOHOOKEAN_CIARLET, "nh_bonet": NEOHOOKEAN_BONET, "mass": MASS, "source": SOURCE,
+    "nsource": NORMAL_SOURCE, "normal_source": NORMAL_SOURCE,
 }
 
 # symbol -> (restype, argtypes); kept in one table so tests can check it against include/gfgpu.h
@@ -41,9 +42,11 @@ SIGNATURES = {
     "gfgpu_fem_get_elem_dof": (C.c_int, [_P, _P]),
     "gfgpu_fem_destroy": (C.c_int, [_P]),
     "gfgpu_tables_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _PP]),
+    "gfgpu_tables_set_faces": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "gfgpu_tables_destroy": (C.c_int, [_P]),
     "gfgpu_term_create": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_double, C.c_int, _PP]),
     "gfgpu_term_destroy": (C.c_int, [_P]),
+    "gfgpu_term_set_region": (C.c_int, [_P, _i64, _P, _P]),
     "gfgpu_term_set_element_range": (C.c_int, [_P, _i64, _i64]),
     "gfgpu_term_assemble_dev": (C.c_int, [_P, _P, C.c_int]),
     "gfgpu_term_assemble_host": (C.c_int, [_P, _P, C.c_int, _P, _P]),
@@ -179,6 +182,28 @@ class DeviceTables(_Handle):
         check(lib().gfgpu_tables_create(ctx.h, dim, nq, ng, nd, ptr(w), ptr(gt_grad), ptr(phi), ptr(gphi),
                                         C.byref(self.h)))
 
+    def set_faces(self, normals, w, gt_grad, phi, gphi):
+        """Tables at the face points: normals [nf, dim], w [nf, nqf], gt_grad [nf, nqf, ng, dim], phi [nf, nqf, nd],
+        gphi [nf, nqf, nd, dim]."""
+        normals = np.ascontiguousarray(normals, np.float64)
+        w = np.ascontiguousarray(w, np.float64)
+        gt_grad = np.ascontiguousarray(gt_grad, np.float64)
+        phi = np.ascontiguousarray(phi, np.float64)
+        gphi = np.ascontiguousarray(gphi, np.float64)
+        nf, nqf = w.shape
+        assert normals.shape == (nf, self.dim) and gt_grad.shape == (nf, nqf, self.ng, self.dim)
+        assert phi.shape == (nf, nqf, self.nd) and gphi.shape == (nf, nqf, self.nd, self.dim)
+        check(lib().gfgpu_tables_set_faces(self.h, nf, nqf, ptr(normals), ptr(w), ptr(gt_grad), ptr(phi), ptr(gphi)))
+
+    def set_faces_from_all_points(self, face_first, face_nq, normals, w, gt_grad, phi, gphi):
+        """Same from tables over ALL integration points of an approx_integration (volume points, then face after
+        face): the points of face f are [face_first[f], face_first[f] + face_nq[f])."""
+        face_first, face_nq = np.asarray(face_first), np.asarray(face_nq)
+        if len(set(int(v) for v in face_nq)) != 1:
+            raise GfgpuError("the faces of the integration method carry different numbers of points")
+        idx = np.array([np.arange(f0, f0 + n) for f0, n in zip(face_first, face_nq)])
+        self.set_faces(normals, np.asarray(w)[idx], np.asarray(gt_grad)[idx], np.asarray(phi)[idx], np.asarray(gphi)[idx])
+
 
 class DeviceTerm(_Handle):
     _destroy = "gfgpu_term_destroy"
@@ -190,6 +215,16 @@ class DeviceTerm(_Handle):
         fam = FAMILY_BY_NAME[family] if isinstance(family, str) else int(family)
         check(lib().gfgpu_term_create(ctx.h, mesh.h, fem.h, tables.h, fam, ptr(params), len(params), float(alpha),
                                       int(strategy), C.byref(self.h)))
+
+    def set_region(self, cv, face=None):
+        """Integrate over the items (cv[k], face[k]) in mr_visitor order; face None / -1 = whole convexes;
+        cv None = back to all convexes."""
+        if cv is None:
+            check(lib().gfgpu_term_set_region(self.h, 0, None, None))
+            return
+        cv = np.ascontiguousarray(cv, np.int32)
+        fc = None if face is None else np.ascontiguousarray(face, np.int32)
+        check(lib().gfgpu_term_set_region(self.h, len(cv), ptr(cv), ptr(fc)))
 
     def set_element_range(self, e0, e1):
         check(lib().gfgpu_term_set_element_range(self.h, int(e0), int(e1)))

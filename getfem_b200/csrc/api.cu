@@ -206,6 +206,27 @@ int gfgpu_tables_create(gfgpu_ctx *ctx, int dim, int nq, int ng, int nd, const d
   GF_API_END
 }
 
+int gfgpu_tables_set_faces(gfgpu_tables *t, int nf, int nqf, const double *normals, const double *w,
+                           const double *gt_grad, const double *phi, const double *gphi) {
+  GF_API_BEGIN
+  GF_REQUIRE(t && normals && w && gt_grad && phi && gphi, "null argument");
+  GF_REQUIRE(nf >= 1 && nf <= GFGPU_MAX_FACES && nqf >= 1, "bad face table sizes");
+  gfgpu_ctx *ctx = t->ctx;
+  GF_CUDA(cudaSetDevice(ctx->device));
+  const size_t np = (size_t)nf * nqf;
+  t->nf = nf; t->nqf = nqf;
+  std::vector<double> hn((size_t)nf * 3, 0.0);
+  for (int f = 0; f < nf; ++f)
+    for (int d = 0; d < t->dim; ++d) hn[f * 3 + d] = normals[f * t->dim + d];
+  t->fnormal.alloc(ctx, hn.size()); t->fnormal.upload(hn.data());
+  t->fw.alloc(ctx, np); t->fw.upload(w);
+  t->fgt_grad.alloc(ctx, np * t->ng * t->dim); t->fgt_grad.upload(gt_grad);
+  t->fphi.alloc(ctx, np * t->nd); t->fphi.upload(phi);
+  t->fgphi.alloc(ctx, np * t->nd * t->dim); t->fgphi.upload(gphi);
+  GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  GF_API_END
+}
+
 int gfgpu_tables_destroy(gfgpu_tables *t) {
   GF_API_BEGIN
   delete t;
@@ -218,8 +239,10 @@ int gfgpu_term_create(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem, gfgpu_ta
   GF_REQUIRE(ctx && mesh && fem && tab && out, "null argument");
   GF_REQUIRE(fem->mesh == mesh, "the fem was built on another mesh");
   GF_REQUIRE(tab->dim == mesh->dim && tab->ng == mesh->ng && tab->nd == fem->nd, "tables do not match mesh/fem");
-  GF_REQUIRE(family >= GFGPU_LAPLACE && family <= GFGPU_SOURCE, "unknown expression family");
-  const int need = family == GFGPU_SOURCE ? fem->qdim : (family == GFGPU_LAPLACE || family == GFGPU_MASS) ? 1 : 2;
+  GF_REQUIRE(family >= GFGPU_LAPLACE && family <= GFGPU_NORMAL_SOURCE, "unknown expression family");
+  const int need = family == GFGPU_SOURCE ? fem->qdim
+                   : family == GFGPU_NORMAL_SOURCE ? fem->qdim * mesh->dim
+                   : (family == GFGPU_LAPLACE || family == GFGPU_MASS) ? 1 : 2;
   GF_REQUIRE(params && nparams >= need, "missing parameters for this family");
   if (family == GFGPU_ELASTICITY) GF_REQUIRE(fem->qdim == mesh->dim, "elasticity needs qdim == mesh dimension");
   if (family == GFGPU_SVK || family == GFGPU_NEOHOOKEAN_CIARLET || family == GFGPU_NEOHOOKEAN_BONET)
@@ -231,7 +254,8 @@ int gfgpu_term_create(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem, gfgpu_ta
   GF_REQUIRE(strategy != GFGPU_STRATEGY_RECOMPUTE || rc_ok,
              "strategy RECOMPUTE needs an affine (simplex) mesh and a Laplace / elasticity / mass term");
   t->strategy = strategy == GFGPU_STRATEGY_AUTO ? (rc_ok ? GFGPU_STRATEGY_RECOMPUTE : GFGPU_STRATEGY_STAGED) : strategy;
-  for (int k = 0; k < 4; ++k) t->par[k] = k < nparams ? params[k] : 0.0;
+  t->strategy_asked = strategy;
+  for (int k = 0; k < GFGPU_MAX_PARAMS; ++k) t->par[k] = k < nparams ? params[k] : 0.0;
   t->alpha = alpha;
   t->e0 = 0; t->e1 = mesh->ne;
   GF_CUDA(cudaSetDevice(ctx->device));
@@ -254,19 +278,81 @@ int gfgpu_term_destroy(gfgpu_term *t) {
   GF_API_END
 }
 
+static void term_forget_symbolic(gfgpu_term *t) {
+  t->st_valid = false;
+  t->pat_valid = false;
+  t->rc_ready = false;
+  t->halo = false;
+  t->halo_src.clear();
+  t->vJ.release(); t->vI.release(); t->vmask.release();
+}
+
 int gfgpu_term_set_element_range(gfgpu_term *t, int64_t e0, int64_t e1) {
   GF_API_BEGIN
   GF_REQUIRE(t, "null term");
-  GF_REQUIRE(0 <= e0 && e0 <= e1 && e1 <= t->mesh->ne, "bad element range");
+  GF_REQUIRE(0 <= e0 && e0 <= e1 && e1 <= t->nb_items(), "bad element range");
   if (e0 != t->e0 || e1 != t->e1) {
     t->e0 = e0; t->e1 = e1;
-    t->st_valid = false;
-    t->pat_valid = false;
-    t->rc_ready = false;
-    t->halo = false;
-    t->halo_src.clear();
-    t->vJ.release(); t->vI.release(); t->vmask.release();
+    term_forget_symbolic(t);
   }
+  GF_API_END
+}
+
+int gfgpu_term_set_region(gfgpu_term *t, int64_t n_items, const int32_t *cv, const int32_t *face) {
+  GF_API_BEGIN
+  GF_REQUIRE(t, "null term");
+  GF_REQUIRE(n_items >= 0 && (cv || n_items == 0), "bad region");
+  gfgpu_ctx *ctx = t->ctx;
+  GF_CUDA(cudaSetDevice(ctx->device));
+  term_forget_symbolic(t);
+  t->stage.release(); t->emask.release(); t->rstage.release();
+  if (!cv) {  // back to all convexes
+    t->region = t->region_faces = false;
+    t->n_items = 0;
+    t->r_conn.release(); t->r_edof.release(); t->r_face.release();
+    t->strategy = t->strategy_asked == GFGPU_STRATEGY_AUTO
+                      ? (gf::recompute_supported(t) ? GFGPU_STRATEGY_RECOMPUTE : GFGPU_STRATEGY_STAGED)
+                      : t->strategy_asked;
+    t->e0 = 0; t->e1 = t->mesh->ne;
+    return 0;
+  }
+  const int ng = t->mesh->ng, nd = t->fem->nd;
+  int nfaces = 0;
+  for (int64_t k = 0; k < n_items; ++k) {
+    GF_REQUIRE(cv[k] >= 0 && cv[k] < t->mesh->ne, "region refers to a convex outside the mesh");
+    GF_REQUIRE(k == 0 || cv[k] > cv[k - 1] || (cv[k] == cv[k - 1] && face && face[k] > face[k - 1]),
+               "region items must come in mr_visitor order (ascending convex, then face)");
+    if (face && face[k] >= 0) ++nfaces;
+  }
+  GF_REQUIRE(nfaces == 0 || nfaces == n_items, "a region must hold either convexes or faces, not both");
+  if (nfaces) {
+    GF_REQUIRE(t->tab->nf > 0, "a region of faces needs gfgpu_tables_set_faces");
+    GF_REQUIRE(t->strategy_asked != GFGPU_STRATEGY_RECOMPUTE, "regions of faces use strategy STAGED");
+    for (int64_t k = 0; k < n_items; ++k) GF_REQUIRE(face[k] < t->tab->nf, "face number outside the reference element");
+  } else {
+    GF_REQUIRE(t->family != GFGPU_NORMAL_SOURCE, "the normal source term needs a region of faces");
+  }
+  // region-ordered copies of the connectivity and dof rows (built on the host: a region is set once)
+  std::vector<int32_t> hc((size_t)t->mesh->ne * ng), hd((size_t)t->mesh->ne * nd);
+  t->mesh->conn.download(hc.data());
+  t->fem->edof.download(hd.data());
+  GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<int32_t> rc((size_t)n_items * ng), rd((size_t)n_items * nd);
+  std::vector<int8_t> rf((size_t)n_items);
+  for (int64_t k = 0; k < n_items; ++k) {
+    std::copy(hc.begin() + (size_t)cv[k] * ng, hc.begin() + (size_t)(cv[k] + 1) * ng, rc.begin() + (size_t)k * ng);
+    std::copy(hd.begin() + (size_t)cv[k] * nd, hd.begin() + (size_t)(cv[k] + 1) * nd, rd.begin() + (size_t)k * nd);
+    rf[k] = (int8_t)(nfaces ? face[k] : -1);
+  }
+  t->r_conn.alloc(ctx, rc.size()); t->r_conn.upload(rc.data());
+  t->r_edof.alloc(ctx, rd.size()); t->r_edof.upload(rd.data());
+  if (nfaces) { t->r_face.alloc(ctx, rf.size()); t->r_face.upload(rf.data()); } else t->r_face.release();
+  GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  t->region = true;
+  t->region_faces = nfaces > 0;
+  t->n_items = n_items;
+  if (nfaces) t->strategy = GFGPU_STRATEGY_STAGED;
+  t->e0 = 0; t->e1 = n_items;
   GF_API_END
 }
 
@@ -278,7 +364,9 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
   const bool do_r = order_mask & GFGPU_RESIDUAL;
   const int nd = t->fem->nd, Q = t->fem->qdim, s1 = nd * Q;
   const int64_t ne = t->e1 - t->e0;
-  if (t->family == GFGPU_SOURCE && do_t) {
+  const bool order1_only = t->family == GFGPU_SOURCE || t->family == GFGPU_NORMAL_SOURCE;
+  GF_REQUIRE(t->family != GFGPU_NORMAL_SOURCE || t->region_faces, "the normal source term needs a region of faces");
+  if (order1_only && do_t) {
     // an order-1 term has no order-2 tree (workspace.cc:545-600): the tangent is structurally empty
     if (t->jc.n != (size_t)t->fem->ndof + 1) t->jc.alloc(ctx, t->fem->ndof + 1);
     t->jc.zero();
@@ -288,11 +376,11 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
     if (!do_r) return;
   }
   if (!t->st_valid) {
-    gf::build_structure(ctx, t->fem->edof.p, nd, t->e0, t->e1, t->fem->ndof, t->st, t->vJ.p, t->vI.p, (int64_t)t->vJ.n);
+    gf::build_structure(ctx, t->edof_p(), nd, t->e0, t->e1, t->fem->ndof, t->st, t->vJ.p, t->vI.p, (int64_t)t->vJ.n);
     t->st_valid = true;
     t->pat_valid = false;
   }
-  if (t->family == GFGPU_SOURCE && t->jc.n) t->pat_valid = true;  // the (empty) pattern of an order-1 term never moves
+  if (order1_only && t->jc.n) t->pat_valid = true;  // the (empty) pattern of an order-1 term never moves
   const bool recompute = t->strategy == GFGPU_STRATEGY_RECOMPUTE;
   // what the generic element kernel has to produce in this call.  RECOMPUTE needs it only once, for
   // the keep masks of the pattern; its residual is K^T U inside the per-nonzero kernel.
@@ -306,25 +394,29 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
   gf::ElemArgs a;
   const int64_t np = t->mesh->npts;
   a.x = t->mesh->xyz.p; a.y = a.x + np; a.z = a.y + np;
-  a.conn = t->mesh->conn.p;
-  a.edof = t->fem->edof.p;
+  a.conn = t->conn_p();
+  a.edof = t->edof_p();
   a.U = U_dev;
   a.w = t->tab->w.p; a.gt_grad = t->tab->gt_grad.p; a.phi = t->tab->phi.p; a.gphi = t->tab->gphi.p;
   a.nq = t->tab->nq; a.ng = t->mesh->ng; a.qc = 0;
   a.e0 = t->e0; a.e1 = t->e1;
-  for (int k = 0; k < 4; ++k) a.par[k] = t->par[k];
+  for (int k = 0; k < GFGPU_MAX_PARAMS; ++k) a.par[k] = t->par[k];
   a.alpha = t->alpha;
   a.family = t->family;
   a.stage = need_stage ? t->stage.p : nullptr;
   a.emask = need_masks ? t->emask.p : nullptr;
   a.rstage = need_rstage ? t->rstage.p : nullptr;
+  a.face = t->region_faces ? t->r_face.p : nullptr;
+  a.fw = t->tab->fw.p; a.fgt_grad = t->tab->fgt_grad.p; a.fphi = t->tab->fphi.p; a.fgphi = t->tab->fgphi.p;
+  a.fnormal = t->tab->fnormal.p;
+  a.nqf = t->tab->nqf;
   for (int k = 0; k < 5; ++k) t->ev_used[k] = false;
   auto tic = [&](int k) { GF_CUDA(cudaEventRecord(t->ev[2 * k], ctx->stream)); };
   auto toc = [&](int k) { GF_CUDA(cudaEventRecord(t->ev[2 * k + 1], ctx->stream)); t->ev_used[k] = true; };
   if (ne > 0 && (need_stage || need_masks || need_rstage)) {
     tic(0);
     const bool affine = t->mesh->gt_kind == GFGPU_GT_PK;
-    bool ok = gf::launch_sumfact_kernel(ctx, t->tab, t->mesh->dim, Q, nd, affine, a) ||
+    bool ok = (!t->region_faces && gf::launch_sumfact_kernel(ctx, t->tab, t->mesh->dim, Q, nd, affine, a)) ||
               gf::launch_elem_kernel(ctx, t->mesh->dim, Q, nd, affine, a);
     GF_REQUIRE(ok, "no device kernel for this (dimension, qdim, local dofs, family) combination");
     toc(0);

@@ -134,6 +134,9 @@ struct gfgpu_tables {
   int dim, nq, ng, nd;
   gf::DevBuf<double> w, gt_grad, phi, gphi;
   std::vector<double> h_w, h_gt_grad, h_phi, h_gphi;
+  // face points (gfgpu_tables_set_faces): nf faces with nqf points each, tables laid out face after face
+  int nf = 0, nqf = 0;
+  gf::DevBuf<double> fw, fgt_grad, fphi, fgphi, fnormal;  // fnormal: nf x 3
 };
 
 struct gfgpu_term {
@@ -141,10 +144,19 @@ struct gfgpu_term {
   gfgpu_mesh *mesh;
   gfgpu_fem *fem;
   gfgpu_tables *tab;
-  int family, strategy;
-  double par[4];
+  int family, strategy, strategy_asked = 0;
+  double par[GFGPU_MAX_PARAMS];
   double alpha;
   int64_t e0, e1;
+  // mesh region (gfgpu_term_set_region): the term then runs over `n_items` items (convex, face) through region-ordered
+  // copies of the connectivity and dof tables, so that every kernel keeps addressing rows [e0, e1)
+  bool region = false, region_faces = false;
+  int64_t n_items = 0;
+  gf::DevBuf<int32_t> r_conn, r_edof;
+  gf::DevBuf<int8_t> r_face;
+  const int32_t *conn_p() const { return region ? r_conn.p : mesh->conn.p; }
+  const int32_t *edof_p() const { return region ? r_edof.p : fem->edof.p; }
+  int64_t nb_items() const { return region ? n_items : mesh->ne; }
   // structure
   gf::Structure st;
   bool st_valid = false;
@@ -212,9 +224,13 @@ struct ElemArgs {
   const double *w, *gt_grad, *phi, *gphi;
   int nq, ng, qc;
   int64_t e0, e1;
-  double par[4];
+  double par[GFGPU_MAX_PARAMS];
   double alpha;
   int family;
+  // boundary faces: face of every item (nullptr = volume integration), tables at the face points, reference normals
+  const int8_t *face;
+  const double *fw, *fgt_grad, *fphi, *fgphi, *fnormal;  // fnormal: nf x 3
+  int nqf;
   double *stage;
   uint16_t *emask;
   double *rstage;

@@ -10,7 +10,7 @@ bool launch_elem_kernel(gfgpu_ctx *ctx, int dim, int Q, int nd, bool affine, con
   int fk;
   switch (a.family) {
     case GFGPU_LAPLACE: fk = FK_LAPLACE; break;
-    case GFGPU_MASS: case GFGPU_SOURCE: fk = FK_MASS; break;  // the source term is the flux part of the mass kernel
+    case GFGPU_MASS: case GFGPU_SOURCE: case GFGPU_NORMAL_SOURCE: fk = FK_MASS; break;  // source terms = the flux part of the mass kernel
     case GFGPU_ELASTICITY: fk = FK_ELAST; break;
     case GFGPU_SVK: case GFGPU_NEOHOOKEAN_CIARLET: case GFGPU_NEOHOOKEAN_BONET: fk = FK_HYPER; break;
     default: return false;

@@ -14,6 +14,8 @@
 //   C  K_e(i a, j b) += Z(i,n) D(a,n,b,l) Z(j,l)  in registers; r_e(i a) += P(a,n) Z(i,n)
 //   D  ninf = max|K_e|, entries <= 1e-14*ninf are not inserted (C&E.cc:4889,4898; 5380-5402):
 //        written as 0 to the stage and flagged 0 in the per-block keep mask.
+// Boundary-face items (mesh regions of faces, C&E.cc:8827-8848): the tables are those of the face's points, the weight
+// is J |B n_ref| w_q and the unit normal B n_ref / |B n_ref| (components below 1e-13 cleaned) is kept beside B and J.
 // The Gauss points are processed in chunks of qc so that any (nd, nq) fits shared memory.
 #pragma once
 #include "common.cuh"
@@ -33,7 +35,7 @@ struct ElemCfg {
   static constexpr bool SCALAR = (FK == FK_LAPLACE || FK == FK_MASS);
   static constexpr int DSZ = FK == FK_HYPER ? (Q * N * Q * N) : 1;
   static constexpr int ACC = SCALAR ? 1 : Q * Q;
-  static constexpr int GEO = N * N + 1;
+  static constexpr int GEO = N * N + 1 + N;  // B, J, unit normal (faces)
   __host__ __device__ static constexpr int per_q() { return GEO + ND * N + Q * N + DSZ + Q * N; }
   __host__ __device__ static int slot_doubles(int ng, int qc) { return N * ng + S1 + GEO + qc * per_q() + 8; }
 };
@@ -69,9 +71,12 @@ __device__ __forceinline__ double inv_transpose(const double *K, double *B) {
   }
 }
 
-// geo[0..N*N) = B (col-major), geo[N*N] = J, from G (N x ng col-major) and pc (ng x N row-major)
+// geo[0..N*N) = B (col-major), geo[N*N] = J, from G (N x ng col-major) and pc (ng x N row-major).
+// nref != nullptr (boundary face): Normal = B n_ref, J *= |Normal|, Normal /= |Normal|, gmm::clean(Normal, 1e-13)
+// (C&E.cc:8836-8847) -> geo[N*N+1 ..).
 template <int N>
-__device__ __forceinline__ void geometry(const double *G, const double *pc, int ng, double *geo) {
+__device__ __forceinline__ void geometry(const double *G, const double *pc, int ng, double *geo,
+                                         const double *nref = nullptr) {
   double K[N * N];
 #pragma unroll
   for (int k = 0; k < N * N; ++k) K[k] = 0.0;
@@ -87,6 +92,24 @@ __device__ __forceinline__ void geometry(const double *G, const double *pc, int 
   double J = inv_transpose<N>(K, B);
 #pragma unroll
   for (int k = 0; k < N * N; ++k) geo[k] = B[k];
+  if (nref) {
+    double nr[N], nup = 0.0;
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+      double s = 0;
+#pragma unroll
+      for (int c = 0; c < N; ++c) s += B[r + N * c] * nref[c];
+      nr[r] = s;
+      nup += s * s;
+    }
+    nup = sqrt(nup);
+    J *= nup;
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+      const double v = nr[r] / nup;
+      geo[N * N + 1 + r] = fabs(v) < 1e-13 ? 0.0 : v;
+    }
+  }
   geo[N * N] = J;
 }
 
@@ -248,7 +271,7 @@ elem_kernel(const ElemArgs a) {
   constexpr int N = C::N, S1 = C::S1, NB = C::NB, TPE = C::TPE, EPB = C::EPB, GEO = C::GEO;
   extern __shared__ double sm[];
   const int slot = threadIdx.x / TPE, lt = threadIdx.x % TPE;
-  const int ng = a.ng, qc = a.qc, nq = a.nq;
+  const int ng = a.ng, qc = a.qc, nq = a.face ? a.nqf : a.nq;
   double *sG = sm + (size_t)slot * C::slot_doubles(ng, qc);
   double *sU = sG + N * ng;
   double *sGeoA = sU + S1;
@@ -268,6 +291,13 @@ elem_kernel(const ElemArgs a) {
     const int64_t el = base + slot;
     const bool active = el < ne;
     const int64_t e = a.e0 + el;
+    // tables of this item: the volume points, or the points of its face
+    const int face = (a.face && active) ? a.face[e] : -1;
+    const double *nref = face >= 0 ? a.fnormal + face * 3 : nullptr;
+    const double *tw = face >= 0 ? a.fw + (size_t)face * nq : a.w;
+    const double *tgt = face >= 0 ? a.fgt_grad + (size_t)face * nq * ng * N : a.gt_grad;
+    const double *tphi = face >= 0 ? a.fphi + (size_t)face * nq * ND : a.phi;
+    const double *tgphi = face >= 0 ? a.fgphi + (size_t)face * nq * ND * N : a.gphi;
     // ---- A: gather
     if (active) {
       for (int idx = lt; idx < N * ng; idx += TPE) {
@@ -281,7 +311,7 @@ elem_kernel(const ElemArgs a) {
       }
     }
     __syncthreads();
-    if (AFFINE && active && lt == 0) geometry<N>(sG, a.gt_grad, ng, sGeoA);
+    if (AFFINE && active && lt == 0) geometry<N>(sG, tgt, ng, sGeoA, nref);
 
     double acc[C::BPT][C::ACC];
     double racc[C::RPT];
@@ -296,14 +326,14 @@ elem_kernel(const ElemArgs a) {
       const int qn = min(qc, nq - q0);
       // ---- B1: geometry per Gauss point
       if (!AFFINE && active)
-        for (int q = lt; q < qn; q += TPE) geometry<N>(sG, a.gt_grad + (size_t)(q0 + q) * ng * N, ng, sGeo + q * GEO);
+        for (int q = lt; q < qn; q += TPE) geometry<N>(sG, tgt + (size_t)(q0 + q) * ng * N, ng, sGeo + q * GEO, nref);
       __syncthreads();
       // ---- B2: Z
       if (active)
         for (int idx = lt; idx < qn * ND; idx += TPE) {
           int q = idx / ND, i = idx % ND;
           const double *B = AFFINE ? sGeoA : sGeo + q * GEO;
-          const double *g = a.gphi + ((size_t)(q0 + q) * ND + i) * N;
+          const double *g = tgphi + ((size_t)(q0 + q) * ND + i) * N;
           double gl[N];
 #pragma unroll
           for (int p = 0; p < N; ++p) gl[p] = g[p];
@@ -321,7 +351,7 @@ elem_kernel(const ElemArgs a) {
         if (FK == FK_MASS) {
           for (int idx = lt; idx < qn * Q; idx += TPE) {
             int q = idx / Q, c = idx % Q;
-            const double *ph = a.phi + (size_t)(q0 + q) * ND;
+            const double *ph = tphi + (size_t)(q0 + q) * ND;
             double s = 0;
             for (int i = 0; i < ND; ++i) s += sU[i * Q + c] * ph[i];
             sGu[q * Q * N + c] = s;
@@ -340,7 +370,7 @@ elem_kernel(const ElemArgs a) {
       // ---- B4: material point
       if (active)
         for (int q = lt; q < qn; q += TPE) {
-          const double wq = a.w[q0 + q];
+          const double wq = tw[q0 + q];
           const double J = AFFINE ? sGeoA[N * N] : sGeo[q * GEO + N * N];
           const double coeff = (wq == 0.0) ? 0.0 : a.alpha * J * wq;  // zero-weight points are skipped (C&E.cc:8852)
           const double *Gu = sGu + q * Q * N;
@@ -354,6 +384,15 @@ elem_kernel(const ElemArgs a) {
               sD[q] = 0.0;
               if (need_gu)
                 for (int c = 0; c < Q; ++c) P[c] = coeff * a.par[c];
+            } else if (a.family == GFGPU_NORMAL_SOURCE) {  // "(A*Normal).Test_u", A(b,n) = par[b + Q n] (getfem_models.cc:4290-4299)
+              sD[q] = 0.0;
+              const double *nrm = (AFFINE ? sGeoA : sGeo + q * GEO) + N * N + 1;
+              if (need_gu)
+                for (int c = 0; c < Q; ++c) {
+                  double an = 0;
+                  for (int n = 0; n < N; ++n) an += a.par[c + Q * n] * nrm[n];
+                  P[c] = coeff * an;
+                }
             } else {
               sD[q] = coeff * a.par[0];
               if (need_gu)
@@ -395,7 +434,7 @@ elem_kernel(const ElemArgs a) {
                 for (int n = 0; n < N; ++n) s += Zi[n] * Zj[n];
                 acc[k][0] += sD[q] * s;
               } else if (FK == FK_MASS) {
-                const double *ph = a.phi + (size_t)(q0 + q) * ND;
+                const double *ph = tphi + (size_t)(q0 + q) * ND;
                 acc[k][0] += sD[q] * ph[i] * ph[j];
               } else if (FK == FK_ELAST) {
                 double zi[N], zj[N], s = 0;
@@ -436,7 +475,7 @@ elem_kernel(const ElemArgs a) {
             const int i = idx / Q, c = idx % Q;
             double s = 0;
             if (FK == FK_MASS) {
-              for (int q = 0; q < qn; ++q) s += sP[q * Q * N + c] * a.phi[(size_t)(q0 + q) * ND + i];
+              for (int q = 0; q < qn; ++q) s += sP[q * Q * N + c] * tphi[(size_t)(q0 + q) * ND + i];
             } else {
               for (int q = 0; q < qn; ++q) {
                 const double *Zi = sZ + (q * ND + i) * N;
@@ -512,7 +551,8 @@ void launch_elem_t(gfgpu_ctx *ctx, ElemArgs a) {
   GF_REQUIRE(fixed + (size_t)C::EPB * C::per_q() * 8 <= 200 * 1024, "element too large for shared memory");
   int qc = (int)((budget > fixed ? budget - fixed : 0) / ((size_t)C::EPB * C::per_q() * 8));
   if (qc < 1) qc = 1;
-  if (qc > a.nq) qc = a.nq;
+  const int nq_used = a.face ? a.nqf : a.nq;
+  if (qc > nq_used) qc = nq_used;
   a.qc = qc;
   const size_t smem = (size_t)C::EPB * C::slot_doubles(a.ng, qc) * 8;
   GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -923,10 +923,10 @@ void recompute_prepare(gfgpu_term *t) {
   if (ne) {
     int grid = (int)std::min<int64_t>((ne + 255) / 256, 148 * 16);
     if (N == 2)
-      k_tile_geo<2><<<grid, 256, 0, s>>>(x, x + np, x + 2 * np, t->mesh->conn.p, t->mesh->ng, t->tab->gt_grad.p, t->e0, ne,
+      k_tile_geo<2><<<grid, 256, 0, s>>>(x, x + np, x + 2 * np, t->conn_p(), t->mesh->ng, t->tab->gt_grad.p, t->e0, ne,
                                         rf, scale, t->rc_eg.p, GSZ);
     else
-      k_tile_geo<3><<<grid, 256, 0, s>>>(x, x + np, x + 2 * np, t->mesh->conn.p, t->mesh->ng, t->tab->gt_grad.p, t->e0, ne,
+      k_tile_geo<3><<<grid, 256, 0, s>>>(x, x + np, x + 2 * np, t->conn_p(), t->mesh->ng, t->tab->gt_grad.p, t->e0, ne,
                                         rf, scale, t->rc_eg.p, GSZ);
     GF_LAUNCH_CHECK();
   }
@@ -1059,7 +1059,7 @@ static void launch_tiles(gfgpu_term *t, const double *U, bool do_t, bool do_r) {
     const int64_t ne = t->e1 - t->e0;
     if (t->rstage.n != (size_t)ne * ND * Q) t->rstage.alloc(t->ctx, (size_t)ne * ND * Q);
     ResArgs r;
-    r.edof = t->fem->edof.p; r.eg = t->rc_eg.p; r.Ltab = t->rc_L.p; r.U = U;
+    r.edof = t->edof_p(); r.eg = t->rc_eg.p; r.Ltab = t->rc_L.p; r.U = U;
     r.rank = t->rc_rank;
     r.sl = sign * t->par[0]; r.smu = sign * t->par[1];
     r.e0 = t->e0; r.ne = ne; r.rstage = t->rstage.p;

@@ -171,6 +171,87 @@ def parallelepiped_rule(N, degree):
     return "IM_GAUSS_PARALLELEPIPED(%d,%d)" % (N, degree), X, W
 
 
+# ---------------------------------------------------------------- faces of the reference elements
+def face_dir_points(gt_kind, N):
+    """cvr->dir_points_of_face(f) of the reference simplex / parallelepiped (bgeot_convex_ref.cc): [nf, N, N] (N points
+    of dimension N per face) and the reference normals pgt->normals() [nf, N].
+    Simplex: face 0 is the oblique face (points e_1..e_N, unit normal (1..1)/sqrt(N)), face f >= 1 is x_{f-1} = 0
+    (origin, then the e_j, j != f-1; normal -e_{f-1}).  Parallelepiped: face 2d is x_d = 1, face 2d+1 is x_d = 0
+    (base point, then base + e_j, j != d; normals +-e_d)."""
+    I = np.eye(N)
+    pts, nrm = [], []
+    if gt_kind == "PK":
+        pts.append(I.copy())
+        nrm.append(np.full(N, 1.0 / math.sqrt(N)))
+        for f in range(N):
+            pts.append(np.array([np.zeros(N)] + [I[j] for j in range(N) if j != f]))
+            nrm.append(-I[f])
+    else:
+        for d in range(N):
+            for side in (1.0, 0.0):
+                base = side * I[d]
+                pts.append(np.array([base] + [base + I[j] for j in range(N) if j != d]))
+                nrm.append(I[d] if side else -I[d])
+    return np.array(pts), np.array(nrm)
+
+
+def _face_rule(gt_kind, N, im_name):
+    """The (N-1)-dimensional method the reference puts on every face (getfem_im_list.h im_desc_face_meth;
+    IM_PRODUCT of Gauss rules for parallelepipeds, getfem_integration.cc:620-647)."""
+    if gt_kind == "QK":
+        deg = int(im_name.split(",")[1].rstrip(")"))
+        if N == 2:
+            x, w = gauss_1d(deg // 2 + 1)
+            return x[:, None], w
+        _, X, w = parallelepiped_rule(N - 1, deg)
+        return X, w
+    if im_name == "IM_TRIANGLE(2)":
+        x, w = gauss_1d(2)
+        return x[:, None], w
+    if im_name == "IM_TRIANGLE(4)":
+        x, w = gauss_1d(3)
+        return x[:, None], w
+    if im_name == "IM_TETRAHEDRON(2)":
+        _, X, w = simplex_rule(2, 2)
+        return X, w
+    if im_name == "IM_TETRAHEDRON(5)":  # IM_TRIANGLE(5): Radon's 7 points
+        s15 = math.sqrt(15.0)
+        a, b = (6.0 + s15) / 21.0, (9.0 - 2.0 * s15) / 21.0  # 0.4701.., 0.0597..
+        c, d = (6.0 - s15) / 21.0, (9.0 + 2.0 * s15) / 21.0  # 0.1012.., 0.7974..
+        X = [(1.0 / 3.0, 1.0 / 3.0), (a, a), (b, a), (a, b), (c, c), (d, c), (c, d)]
+        w = [9.0 / 80.0] + [(155.0 + s15) / 2400.0] * 3 + [(155.0 - s15) / 2400.0] * 3
+        return np.array(X), np.array(w)
+    raise NotImplementedError("no face method for " + im_name)
+
+
+def face_rule_points(gt_kind, N, im_name):
+    """Points [nf, nqf, N] and weights [nf, nqf] of the face part of the approx_integration, as
+    approx_integration::add_method_on_face builds them (getfem_integration.cc:320-351): pt = P0 + sum_j (P_{j+1} - P0)
+    xi_j, weight = w * sqrt(det(A^T A))."""
+    P, nrm = face_dir_points(gt_kind, N)
+    xi, w = _face_rule(gt_kind, N, im_name)
+    X = np.empty((P.shape[0], xi.shape[0], N))
+    W = np.empty((P.shape[0], xi.shape[0]))
+    for f in range(P.shape[0]):
+        A = (P[f, 1:] - P[f, 0]).T  # N x (N-1)
+        det = math.sqrt(abs(np.linalg.det(A.T @ A)))
+        X[f] = P[f, 0][None, :] + xi @ A.T
+        W[f] = w * det
+    return X, W, nrm
+
+
+def classical_face_tables(gt_kind, N, fem_degree, im_degree):
+    """Face tables for gfgpu_tables_set_faces: normals [nf, N], w [nf, nqf], gt_grad [nf, nqf, ng, N], phi, gphi."""
+    name = (simplex_rule(N, im_degree) if gt_kind == "PK" else parallelepiped_rule(N, im_degree))[0]
+    X, W, nrm = face_rule_points(gt_kind, N, name)
+    nf, nqf = W.shape
+    flat = X.reshape(nf * nqf, N)
+    _, gt_grad = lagrange_tables(gt_kind, N, 1, flat)
+    phi, gphi = lagrange_tables(gt_kind, N, fem_degree, flat)
+    return {"normals": nrm, "quad_x": X, "quad_w": W, "gt_grad": gt_grad.reshape(nf, nqf, -1, N),
+            "phi": phi.reshape(nf, nqf, -1), "gphi": gphi.reshape(nf, nqf, -1, N)}
+
+
 def classical_tables(gt_kind, N, fem_degree, im_degree):
     """All tables one (geotrans, fem, im) triple needs.  gt_kind 'PK' (simplices, affine) or 'QK'."""
     name, X, w = simplex_rule(N, im_degree) if gt_kind == "PK" else parallelepiped_rule(N, im_degree)

@@ -70,6 +70,23 @@ bool recognise_tree(const getfem::ga_workspace &ws, size_type itree, recognised_
       return true;
     }
   }
+  {  // normal source term (add_normal_source_term_brick, getfem_models.cc:4290-4299), on regions of faces:
+     // "(g.Normal)*Test_u" (scalar u, g of meshdim components) / "(Reshape(g,Q,N)*Normal).Test_u" (A(b,n) = g[b + Q n])
+    double sign = 0;
+    std::string name;
+    if (std::regex_match(s, m, std::regex("\\(" + ID + "\\.Normal\\)\\*Test_" + v))) { sign = 1; name = m[1]; }
+    else if (std::regex_match(s, m, std::regex("\\(-\\(" + ID + "\\.Normal\\)\\)\\*Test_" + v))) { sign = -1; name = m[1]; }
+    else if (std::regex_match(s, m, std::regex("\\(Reshape\\(" + ID + ",\\d+,\\d+\\)\\*Normal\\)\\.Test_" + v))) { sign = 1; name = m[1]; }
+    else if (std::regex_match(s, m, std::regex("\\(-\\(Reshape\\(" + ID + ",\\d+,\\d+\\)\\*Normal\\)\\)\\.Test_" + v))) { sign = -1; name = m[1]; }
+    if (sign != 0 && ws.is_constant(name)) {
+      const getfem::mesh_fem *pmf = ws.associated_mf(v);
+      GMM_ASSERT1(pmf && ws.value(name).size() == size_type(pmf->get_qdim()) * pmf->linked_mesh().dim(),
+                  "gfgpu: the normal source term needs a fixed-size constant with qdim x meshdim components");
+      out.family = GFGPU_NORMAL_SOURCE;
+      for (size_type k = 0; k < ws.value(name).size(); ++k) out.params.push_back(sign * ws.value(name)[k]);
+      return true;
+    }
+  }
   if (std::regex_match(s, m, std::regex("\\(\\(Div_" + v + "\\*\\(" + ID + "\\*" + Idm + "\\)\\)\\+\\(\\(2\\*" + ID +
                                         "\\)\\*\\(Sym\\(Grad_" + v + "\\)\\)\\)\\):Grad_Test_" + v))) {
     out.family = GFGPU_ELASTICITY; out.params = {scalar(m[1]), scalar(m[2])}; return true;
@@ -157,8 +174,22 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     const getfem::mesh_fem &mf = *pmf;
     const getfem::mesh_im &mim = *td.mim;
     const getfem::mesh &m = mf.linked_mesh();
-    GMM_ASSERT1(td.rg && td.rg->id() == getfem::mesh_region::all_convexes().id(),
-                "gfgpu: only mesh_region::all_convexes() is handled");
+    // integration region in mr_visitor order (the order ga_exec walks it, C&E.cc:8789): all convexes, a set of
+    // convexes, or a set of faces
+    GMM_ASSERT1(td.rg, "gfgpu: no region");
+    const bool all_cv = td.rg->id() == getfem::mesh_region::all_convexes().id();
+    std::vector<int32_t> rg_cv, rg_f;
+    size_type rg_faces = 0;
+    if (!all_cv) {
+      for (getfem::mr_visitor v(*td.rg, m); !v.finished(); ++v) {
+        rg_cv.push_back(int32_t(v.cv()));
+        const bool isf = v.f() != getfem::short_type(-1);
+        rg_f.push_back(isf ? int32_t(v.f()) : -1);
+        rg_faces += isf;
+      }
+      GMM_ASSERT1(!rg_cv.empty(), "gfgpu: empty region");
+      GMM_ASSERT1(rg_faces == 0 || rg_faces == rg_cv.size(), "gfgpu: a region must hold either convexes or faces");
+    }
     const gmm::sub_interval &I = ws.interval_of_variable(rt.varname);
     const size_type ndof = mf.nb_dof();  // triggers enumerate_dof
     GMM_ASSERT1(m.convex_index().card() > 0 && m.convex_index().card() == m.convex_index().last_true() + 1,
@@ -187,6 +218,14 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     key << &m << "/" << &mf << "/" << &mim << "/" << rt.family << "/" << ne << "/" << ndof << "/" << fdeg << "/"
         << getfem::name_of_int_method(pim);
     for (double p : rt.params) key << "/" << p;
+    if (!all_cv) {  // the region's content is part of the key (FNV-1a over the items)
+      uint64_t h = 1469598103934665603ull;
+      for (size_t k = 0; k < rg_cv.size(); ++k) {
+        h = (h ^ uint64_t(uint32_t(rg_cv[k]))) * 1099511628211ull;
+        h = (h ^ uint64_t(uint32_t(rg_f[k]))) * 1099511628211ull;
+      }
+      key << "/rg" << rg_cv.size() << ":" << h;
+    }
     std::unique_ptr<entry> &pe = cache_[key.str()];
     if (!pe) {
       pe.reset(new entry);
@@ -226,9 +265,36 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
                                   int64_t(ndof), &e.fem));
       GFGPU_CALL(gfgpu_tables_create(ctx_, dim, int(nq), int(ng), int(nd), w.data(), gtg.data(), phi.data(), gphi.data(),
                                      &e.tab));
+      if (rg_faces) {
+        // tables at the face points (they follow the volume points in the method's point table, face after face:
+        // approx_integration::valid_method, getfem_integration.cc:353-368) and the reference normals
+        const size_type nf = pgt->structure()->nb_faces(), nqf = pai->nb_points_on_face(0);
+        std::vector<double> fn(nf * dim), fw(nf * nqf), fgtg(nf * nqf * ng * dim), fphi(nf * nqf * nd), fgphi(nf * nqf * nd * dim);
+        for (size_type f = 0; f < nf; ++f) {
+          GMM_ASSERT1(pai->nb_points_on_face(getfem::short_type(f)) == nqf,
+                      "gfgpu: faces with different numbers of integration points are not handled");
+          for (int d = 0; d < dim; ++d) fn[f * dim + d] = pgt->normals()[f][d];
+          for (size_type q = 0; q < nqf; ++q) {
+            const size_type ip = pai->ind_first_point_on_face(getfem::short_type(f)) + q, o = f * nqf + q;
+            fw[o] = pai->coeff(ip);
+            const bgeot::base_matrix &pc = pgp->grad(ip);
+            for (size_type i = 0; i < ng; ++i)
+              for (int d = 0; d < dim; ++d) fgtg[(o * ng + i) * dim + d] = pc(i, d);
+            const bgeot::base_tensor &bv = pfp->val(ip), &bg = pfp->grad(ip);
+            for (size_type i = 0; i < nd; ++i) {
+              fphi[o * nd + i] = bv[i];
+              for (int d = 0; d < dim; ++d) fgphi[(o * nd + i) * dim + d] = bg[i + nd * d];
+            }
+          }
+        }
+        GFGPU_CALL(gfgpu_tables_set_faces(e.tab, int(nf), int(nqf), fn.data(), fw.data(), fgtg.data(), fphi.data(),
+                                          fgphi.data()));
+      }
       const double alpha = ws.factor_of_variable(rt.varname);
       GFGPU_CALL(gfgpu_term_create(ctx_, e.mesh, e.fem, e.tab, rt.family, rt.params.data(), int(rt.params.size()),
                                    order == 2 ? alpha * alpha : alpha, GFGPU_STRATEGY_AUTO, &e.term));
+      if (!all_cv)
+        GFGPU_CALL(gfgpu_term_set_region(e.term, int64_t(rg_cv.size()), rg_cv.data(), rg_faces ? rg_f.data() : nullptr));
     }
     entry &e = *pe;
     // the variable's values, in the fem's own numbering (the workspace interval only offsets the result)
@@ -246,7 +312,7 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
       if (V.size() < I.first() + ndof) V.resize(std::max<size_type>(nprim, I.first() + ndof), 0.0);
       for (size_type d = 0; d < ndof; ++d) V[I.first() + d] += R[d];
       t_fill += now_s() - t2;
-    } else if (rt.family == GFGPU_SOURCE) {
+    } else if (rt.family == GFGPU_SOURCE || rt.family == GFGPU_NORMAL_SOURCE) {
       // an order-1 term contributes nothing to the tangent; K only gets its size (workspace.cc:805-812)
       getfem::model_real_sparse_matrix &K = ws.assembled_matrix();
       const size_type need = std::max<size_type>(nprim, I.first() + ndof);

@@ -6,6 +6,7 @@ Same names and argument meaning as GetFEM's C++ API (the parity tests read like 
   mesh_fem      mesh_fem(m, Qdim); set_classical_finite_element(K); nb_dof();
                 ind_scalar_basic_dof_of_element(cv)              src/getfem/getfem_mesh_fem.h:459-461
   mesh_im       mesh_im(m); set_integration_method(degree)       src/getfem/getfem_mesh_im.h
+  mesh_region   add(cv[, f]), is_only_faces(); outer_faces_of_mesh(m)   src/getfem/getfem_mesh_region.h, getfem_mesh.h:629-645
   ga_workspace  add_fem_variable, add_fixed_size_constant, add_expression, assembly(order),
                 assembled_matrix(), assembled_vector()           src/getfem/getfem_generic_assembly.h:262-597
 
@@ -55,6 +56,60 @@ class mesh:
         if ctx not in self._dev:
             self._dev[ctx] = capi.DeviceMesh(ctx, self.pts, self.conn, capi.GT_PK if self.gt == "GT_PK" else capi.GT_QK)
         return self._dev[ctx]
+
+    def face_local_nodes(self):
+        """Local geometric nodes of every face of the (degree-1) reference convex: [nf, nodes per face].
+        Simplex: face f holds every vertex but vertex f (bgeot_convex_structure.cc simplex_structure); parallelepiped
+        (node ix + 2 iy + 4 iz): face 2d is x_d = 1, face 2d+1 is x_d = 0 -- the numbering of fem_tables.face_dir_points."""
+        N, ng = self.dim(), self.conn.shape[1]
+        if self.gt == "GT_PK":
+            return np.array([[v for v in range(ng) if v != f] for f in range(N + 1)])
+        out = []
+        for d in range(N):
+            for side in (1, 0):
+                out.append([v for v in range(ng) if ((v >> d) & 1) == side])
+        return np.array(out)
+
+    def points_of_face_of_convex(self, cv, f):
+        return self.pts[self.conn[cv][self.face_local_nodes()[f]]]
+
+
+class mesh_region:
+    """getfem::mesh_region restricted to what the path reads: a set of convexes or of (convex, face) pairs, walked in
+    mr_visitor order (ascending convex, then ascending face; getfem_mesh_region.h)."""
+
+    def __init__(self):
+        self._items = set()
+
+    def add(self, cv, f=-1):
+        self._items.add((int(cv), int(f)))
+
+    def is_only_faces(self):
+        return bool(self._items) and all(f >= 0 for _, f in self._items)
+
+    def is_only_convexes(self):
+        return all(f < 0 for _, f in self._items)
+
+    def items(self):
+        """(cv [n], face [n]) int32 arrays in visitor order."""
+        it = sorted(self._items)
+        return np.array([c for c, _ in it], np.int32), np.array([f for _, f in it], np.int32)
+
+    def __len__(self):
+        return len(self._items)
+
+
+def outer_faces_of_mesh(m):
+    """getfem::outer_faces_of_mesh (getfem_mesh.h:629-645): the faces that belong to one convex only."""
+    fl = m.face_local_nodes()  # [nf, nv]
+    nf = fl.shape[0]
+    keys = np.sort(m.conn[:, fl], axis=2).reshape(-1, fl.shape[1])  # [ne*nf, nv] sorted vertex ids
+    _, inv, cnt = np.unique(keys, axis=0, return_inverse=True, return_counts=True)
+    outer = np.nonzero(cnt[inv.reshape(-1)] == 1)[0]
+    rg = mesh_region()
+    for k in outer:
+        rg.add(k // nf, k % nf)
+    return rg
 
 
 def regular_unit_mesh(m, nsubdiv, pgt):
@@ -181,6 +236,13 @@ def recognise(expr):
     m = re.fullmatch(rf"\(?({_ID})\)?\*\(?Div_({_ID})\*Div_Test_\2\)?\+\(?2\*\(?({_ID})\)?\)?\*\(?Sym\(Grad_\2\):Grad_Test_\2\)?", s)
     if m:
         return "elast", m.group(2), [m.group(1), m.group(3)]
+    # normal source term (add_normal_source_term_brick, getfem_models.cc:4290-4299)
+    m = re.fullmatch(rf"(-?)\(?\(\(?({_ID})\)?\.Normal\)\*Test_({_ID})\)?", s)
+    if m:
+        return ("nsource-" if m.group(1) else "nsource+"), m.group(3), [m.group(2)]
+    m = re.fullmatch(rf"(-?)\(?\(Reshape\(({_ID}),qdim\(({_ID})\),meshdim\)\*Normal\)\.Test_\3\)?", s)
+    if m:
+        return ("nsource-" if m.group(1) else "nsource+"), m.group(3), [m.group(2)]
     m = re.fullmatch(rf"(-?)\(?({_ID})[.*]Test_({_ID})\)?", s)  # volumic source term: "-f*Test_u", "-(F.Test_u)", "F.Test_u"
     if m and not m.group(2).startswith("Grad_") and m.group(2) != m.group(3):
         return ("source-" if m.group(1) else "source+"), m.group(3), [m.group(2)]
@@ -215,7 +277,14 @@ class ga_workspace:
         for c in cnames:
             if c not in self.constants:
                 raise capi.GfgpuError("unknown constant " + c)
-        if fam.startswith("source"):
+        if fam.startswith("nsource"):
+            mf = self.variables[var][0]
+            g = self.constants[cnames[0]]
+            if g.size != mf.Qdim * mf.linked_mesh.dim():
+                raise capi.GfgpuError("the normal source term needs a constant of qdim x meshdim components")
+            params = [(-1.0 if fam.endswith("-") else 1.0) * float(v) for v in g.reshape(-1)]
+            fam = "nsource"
+        elif fam.startswith("source"):
             mf = self.variables[var][0]
             f = self.constants[cnames[0]]
             if f.size != mf.Qdim:
@@ -232,8 +301,13 @@ class ga_workspace:
                 raise capi.GfgpuError("wrong number of parameters for the hyperelastic law")
             params = [float(p[0]), float(p[1])]
         if region is not None:
-            raise capi.GfgpuError("only mesh_region::all_convexes() is handled by the device path")
-        self.terms.append([fam, var, params, mim, None])
+            if not isinstance(region, mesh_region) or not len(region):
+                raise capi.GfgpuError("the region must be a non-empty mesh_region (or None for all convexes)")
+            if not (region.is_only_faces() or region.is_only_convexes()):
+                raise capi.GfgpuError("a region must hold either convexes or faces, not both")
+        if fam == "nsource" and (region is None or not region.is_only_faces()):
+            raise capi.GfgpuError("Normal is only defined on a region of faces")
+        self.terms.append([fam, var, params, mim, None, region])
         return len(self.terms) - 1
 
     def nb_trees(self):
@@ -241,13 +315,19 @@ class ga_workspace:
 
     # ---- device objects
     def _term(self, k):
-        fam, var, params, mim, dev = self.terms[k]
+        fam, var, params, mim, dev, region = self.terms[k]
         if dev is None:
             mf, _ = self.variables[var]
             m = mf.linked_mesh
             t = fem_tables.classical_tables(mf.fem_kind(), m.dim(), mf.K, mim.degree)
             tab = capi.DeviceTables(self.ctx, t["quad_w"], t["gt_grad"], t["phi"], t["gphi"])
+            if region is not None and region.is_only_faces():
+                ft = fem_tables.classical_face_tables(mf.fem_kind(), m.dim(), mf.K, mim.degree)
+                tab.set_faces(ft["normals"], ft["quad_w"], ft["gt_grad"], ft["phi"], ft["gphi"])
             dev = capi.DeviceTerm(self.ctx, m.device(self.ctx), mf.device(self.ctx), tab, fam, params)
+            if region is not None:
+                cv, fc = region.items()
+                dev.set_region(cv, fc if region.is_only_faces() else None)
             self.terms[k][4] = dev
         return dev
 
@@ -263,7 +343,7 @@ class ga_workspace:
         else:
             vec = None
         for k in range(len(self.terms)):
-            if order == 2 and self.terms[k][0] == "source" and len(self.terms) > 1:
+            if order == 2 and self.terms[k][0] in ("source", "nsource") and len(self.terms) > 1:
                 continue  # an order-1 term has no order-2 tree (workspace.cc:545-600)
             dev = self._term(k)
             mf, V = self.variables[self.terms[k][1]]

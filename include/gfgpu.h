@@ -52,6 +52,11 @@ enum { GFGPU_FEM_PK = 0, GFGPU_FEM_QK = 1 };
  *   SOURCE       "F.Test_u" (F a constant of qdim components; "-f*Test_u" passes F = -f)   params = {F_0 .. F_{qdim-1}}
  *                (add_source_term_brick, getfem_models.cc:4124-): an order-1 term.  It has no order-2 tree: the
  *                TANGENT bit is accepted and leaves an empty matrix (nnz = 0), as ga_workspace::assembly(2) does.
+ *   NORMAL_SOURCE "(Reshape(A,qdim(u),meshdim)*Normal).Test_u" / "((g).Normal)*Test_u": A(b,n) = params[b + qdim*n]
+ *                (add_normal_source_term_brick, getfem_models.cc:4280-4299): order 1, boundary-face regions only
+ *                (the unit normal exists on faces, C&E.cc:8836-8847).
+ * Every family can be integrated over a mesh region (gfgpu_term_set_region): MASS on boundary faces is the Robin /
+ * Dirichlet-penalisation matrix, SOURCE on faces the Neumann load.
  */
 enum {
   GFGPU_LAPLACE = 0,
@@ -60,8 +65,11 @@ enum {
   GFGPU_NEOHOOKEAN_CIARLET = 3,
   GFGPU_NEOHOOKEAN_BONET = 4,
   GFGPU_MASS = 5,
-  GFGPU_SOURCE = 6
+  GFGPU_SOURCE = 6,
+  GFGPU_NORMAL_SOURCE = 7
 };
+#define GFGPU_MAX_PARAMS 12 /* parameters kept per term (NORMAL_SOURCE: qdim x dim <= 9) */
+#define GFGPU_MAX_FACES 6   /* faces of a reference element (simplices: dim+1, parallelepipeds: 2*dim) */
 
 /* order_mask bits of gfgpu_term_assemble_*: ga_workspace::assembly(1) and assembly(2)
  * (getfem_generic_assembly_workspace.cc:791-936) */
@@ -109,6 +117,14 @@ int gfgpu_fem_destroy(gfgpu_fem *f);
 int gfgpu_tables_create(gfgpu_ctx *ctx, int dim, int nq, int ng, int nd, const double *w_host,
                         const double *gt_grad_host, const double *phi_host, const double *gphi_host,
                         gfgpu_tables **out);
+/* Tables at the points of the element FACES, for integration over boundary regions.  Replaces the face part of
+ * approx_integration (ind_first_point_on_face / nb_points_on_face, getfem_integration.h:170-186: the points of face f
+ * follow the volume points, face after face, getfem_integration.cc:353-368) and pgt->normals()
+ * (bgeot_geometric_trans.h:141).  nf faces with nqf points each (the classical rules carry the same method on every face):
+ *   normals[nf][dim] (reference normals as the reference stores them, not necessarily unit);
+ *   w[nf][nqf]; gt_grad[nf][nqf][ng][dim]; phi[nf][nqf][nd]; gphi[nf][nqf][nd][dim] */
+int gfgpu_tables_set_faces(gfgpu_tables *t, int nf, int nqf, const double *normals_host, const double *w_host,
+                           const double *gt_grad_host, const double *phi_host, const double *gphi_host);
 int gfgpu_tables_destroy(gfgpu_tables *t);
 
 /* ---- term.  Replaces ga_compile + ga_exec for one expression of a recognised family
@@ -118,8 +134,17 @@ int gfgpu_term_create(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem, gfgpu_ta
                       const double *params_host, int nparams, double alpha, int strategy, gfgpu_term **out);
 int gfgpu_term_destroy(gfgpu_term *t);
 
-/* Restrict the term to the element block [e0, e1) (mesh_region / per-rank element partition,
- * getfem_mesh_region.cc:145-185).  Default: all elements. */
+/* Integrate over a mesh region (getfem::mesh_region, getfem_mesh_region.h; walked by mr_visitor in ga_exec,
+ * C&E.cc:8789-8866): n_items items (cv_host[k], face_host[k]) in the visitor's order (ascending convex, then face).
+ * face_host == NULL or face -1: the whole convex; face >= 0: that face of the convex -- the weight becomes
+ * J * |B n_ref| * w_q and the unit normal B n_ref / |B n_ref| (C&E.cc:8836-8847); needs gfgpu_tables_set_faces.
+ * A region is either all convexes or all faces.  Each item is one "element" of the reference's loop: its element
+ * matrix goes through the drop rule on its own.  Face regions use strategy STAGED.
+ * n_items = 0 with cv_host == NULL removes the region (all convexes again). */
+int gfgpu_term_set_region(gfgpu_term *t, int64_t n_items, const int32_t *cv_host, const int32_t *face_host);
+
+/* Restrict the term to the block [e0, e1) of its elements -- of its region's items when a region is set -- (per-rank
+ * element partition, getfem_mesh_region.cc:145-185).  Default: everything. */
 int gfgpu_term_set_element_range(gfgpu_term *t, int64_t e0, int64_t e1);
 
 /* Assemble with the state vector resident on the device (U_dev may be NULL: zero state).

@@ -32,7 +32,7 @@ int main(int argc, char **argv) {
   auto gets = [&](const char *k, const char *d) { return a.count(k) ? a[k] : std::string(d); };
   const int dim = (int)geti("dim", 3), n = (int)geti("n", 4), K = (int)geti("k", 2), Q = (int)geti("q", 3);
   const int imdeg = (int)geti("im", 4);
-  const std::string gt = gets("gt", "pk"), family = gets("family", "elast");
+  const std::string gt = gets("gt", "pk"), family = gets("family", "elast"), rgname = gets("region", "all");
   const double lambda = 1.3, mu = 0.7, acoef = 2.5;
 
   getfem::mesh m;
@@ -45,7 +45,7 @@ int main(int argc, char **argv) {
   mim.set_integration_method(getfem::dim_type(imdeg));
   const size_type ndof = mf.nb_dof();
   std::vector<double> U(ndof);
-  if (family == "elast" || family == "laplace" || family == "mass" || family == "source") {
+  if (family == "elast" || family == "laplace" || family == "mass" || family == "source" || family == "nsource") {
     std::mt19937_64 rng(12345);
     std::uniform_real_distribution<double> d(-1.0, 1.0);
     for (auto &v : U) v = d(rng);
@@ -60,6 +60,7 @@ int main(int argc, char **argv) {
   if (family == "laplace") expr = "a*Grad_u:Grad_Test_u";
   else if (family == "mass") expr = "a*u.Test_u";
   else if (family == "source") expr = Q == 1 ? "-f*Test_u" : "-(f.Test_u)";
+  else if (family == "nsource") expr = Q == 1 ? "((g).Normal)*Test_u" : "-(Reshape(g,qdim(u),meshdim)*Normal).Test_u";
   else if (family == "elast") expr = "(Div_u*((lambda)*Id(meshdim))+(2*(mu))*Sym(Grad_u)):Grad_Test_u";
   else {
     std::string law = family == "svk" ? "Saint_Venant_Kirchhoff"
@@ -69,6 +70,27 @@ int main(int argc, char **argv) {
   const std::vector<double> c_a{acoef}, c_l{lambda}, c_m{mu}, c_p{lambda, mu};
   std::vector<double> c_f(Q);
   for (int k = 0; k < Q; ++k) c_f[k] = 0.75 * (k + 1);
+  std::vector<double> c_g(size_t(Q) * dim);
+  for (size_t k = 0; k < c_g.size(); ++k) c_g[k] = 0.4 + 0.3 * double(k) * ((k & 1) ? -1.0 : 1.0);
+  // region: all convexes, the outer faces, the faces on x = 1, or the convexes with barycentre x < 0.5
+  getfem::mesh_region rg_sel;
+  if (rgname == "half") {
+    for (dal::bv_visitor cv(m.convex_index()); !cv.finished(); ++cv) {
+      double bx = 0;
+      for (size_type i = 0; i < pgt->nb_points(); ++i) bx += m.points_of_convex(cv)[i][0];
+      if (bx / double(pgt->nb_points()) < 0.5) rg_sel.add(cv);
+    }
+  } else if (rgname != "all") {
+    getfem::mesh_region outer;
+    getfem::outer_faces_of_mesh(m, outer);
+    for (getfem::mr_visitor v(outer); !v.finished(); ++v) {
+      bgeot::base_node un = m.normal_of_face_of_convex(v.cv(), v.f());
+      un /= gmm::vect_norm2(un);
+      if (rgname == "outer" || (rgname == "xmax" && un[0] > 0.999)) rg_sel.add(v.cv(), v.f());
+    }
+  }
+  const getfem::mesh_region rg_all = getfem::mesh_region::all_convexes();
+  const getfem::mesh_region &rg = rgname == "all" ? rg_all : rg_sel;
   auto setup = [&](getfem::ga_workspace &ws) {
     ws.add_fem_variable("u", mf, gmm::sub_interval(0, ndof), U);
     ws.add_fixed_size_constant("a", c_a);
@@ -76,7 +98,8 @@ int main(int argc, char **argv) {
     ws.add_fixed_size_constant("mu", c_m);
     ws.add_fixed_size_constant("params", c_p);
     ws.add_fixed_size_constant("f", c_f);
-    ws.add_expression(expr, mim);
+    ws.add_fixed_size_constant("g", c_g);
+    ws.add_expression(expr, mim, rg);
   };
   // ---- reference on the CPU
   getfem::ga_workspace wr;

@@ -51,3 +51,22 @@ def load_golden(name):
 def csc_to_scipy(jc, ir, pr, n):
     import scipy.sparse as sp
     return sp.csc_matrix((pr, ir, jc), shape=(n, n))
+
+
+def make_region(m, name):
+    """The regions of oracle/ref_driver.cc (region=outer|xmax|zmin|half) on the Python mirror of the mesh."""
+    import getfem_b200 as gf
+    if name in (None, "all"):
+        return None
+    rg = gf.mesh_region()
+    if name == "half":  # convexes whose barycentre has x < 0.5
+        for cv in np.nonzero(m.pts[m.conn][:, :, 0].mean(1) < 0.5)[0]:
+            rg.add(cv)
+        return rg
+    cvs, fcs = gf.outer_faces_of_mesh(m).items()
+    for cv, f in zip(cvs, fcs):
+        P = m.points_of_face_of_convex(cv, f)
+        if name == "outer" or (name == "xmax" and (abs(P[:, 0] - 1.0) < 1e-12).all()) or \
+                (name == "zmin" and (abs(P[:, -1]) < 1e-12).all()):
+            rg.add(cv, f)
+    return rg

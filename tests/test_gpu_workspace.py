@@ -16,10 +16,11 @@ EXPR = {
     "nh_ciarlet": "((Id(meshdim)+Grad_u)*(Compressible_Neo_Hookean_Ciarlet_PK2(Grad_u,params))):Grad_Test_u",
     "nh_bonet": "((Id(meshdim)+Grad_u)*(Compressible_Neo_Hookean_Bonet_PK2(Grad_u,params))):Grad_Test_u",
     "source": "-f.Test_u",  # "-f*Test_u" when qdim = 1 (the strings of oracle/ref_driver.cc)
+    "nsource": "(Reshape(g,qdim(u),meshdim)*Normal).Test_u",  # "((g).Normal)*Test_u" when qdim = 1
 }
 
 
-def build_ws(dim, nsub, gt, k, Q, im, family, params, U=None):
+def build_ws(dim, nsub, gt, k, Q, im, family, params, U=None, region=None):
     import getfem_b200 as gf
     m = gf.mesh()
     gf.regular_unit_mesh(m, nsub, "GT_%s(%d,1)" % (gt, dim))
@@ -39,6 +40,10 @@ def build_ws(dim, nsub, gt, k, Q, im, family, params, U=None):
         ws.add_fixed_size_constant("f", [-p for p in params])  # the goldens carry F = -f
         if Q == 1:
             expr = "-f*Test_u"
+    elif family == "nsource":
+        ws.add_fixed_size_constant("g", params)
+        if Q == 1:
+            expr = "((g).Normal)*Test_u"
     elif family in ("laplace", "mass"):
         ws.add_fixed_size_constant("a", [params[0]])
     elif family == "elast":
@@ -46,7 +51,10 @@ def build_ws(dim, nsub, gt, k, Q, im, family, params, U=None):
         ws.add_fixed_size_constant("mu", [params[1]])
     else:
         ws.add_fixed_size_constant("params", params)
-    ws.add_expression(expr, mim)
+    from conftest import make_region
+    rg = make_region(m, region)
+    ws.add_expression(expr, mim, rg)
+    ws.region = rg
     return ws, mf, m, U
 
 
@@ -57,7 +65,7 @@ def test_workspace_matches_reference_golden(name):
     dim = int(a["dim"])
     nsub = [int(a["n"])] * dim if "n" in a else [int(a["nx"]), int(a["ny"]), int(a["nz"])][:dim]
     ws, mf, m, _ = build_ws(dim, nsub, "PK" if g["gt_linear"] else "QK", int(a["k"]), g["Q"], int(a["im"]),
-                            g["family"], g["fparams"], g["U"])
+                            g["family"], g["fparams"], g["U"], a.get("region"))
     # device first-touch numbering == mesh_fem::enumerate_dof, bit for bit
     assert mf.nb_dof() == g["meta"]["ndof"]
     assert np.array_equal(mf.ind_scalar_basic_dof_of_element(), g["elem_dof"])
@@ -93,30 +101,71 @@ CASES = [  # dim, nsub, gt, k, Q, im, family, params, U
     (3, [5, 4, 3], "PK", 2, 3, 4, "mass", [1.5], "random"),
     (2, [30, 20], "PK", 1, 1, 2, "source", [-1.5], "random"),
     (3, [3, 2, 2], "QK", 2, 3, 6, "source", [0.5, -1.0, 2.0], "random"),
+    # mesh regions: boundary faces (Robin / penalisation mass, Neumann source, normal source) and sub-regions of convexes
+    (3, [5, 4, 3], "PK", 2, 3, 4, "mass", [1.5], "random", "outer"),
+    (3, [6, 5, 4], "PK", 2, 3, 4, "source", [0.5, -1.0, 2.0], "random", "xmax"),
+    (3, [5, 4, 4], "PK", 2, 3, 4, "nsource", [0.3, -0.2, 0.9, 1.1, 0.4, -0.7, 0.6, 0.1, -1.3], "random", "outer"),
+    (2, [30, 20], "PK", 1, 1, 2, "nsource", [0.8, -0.4], "random", "outer"),
+    (2, [12, 9], "PK", 2, 2, 4, "mass", [2.0], "random", "outer"),
+    (3, [4, 3, 3], "QK", 2, 1, 6, "mass", [1.5], "random", "zmin"),
+    (3, [3, 3, 2], "QK", 2, 3, 6, "nsource", [0.3, -0.2, 0.9, 1.1, 0.4, -0.7, 0.6, 0.1, -1.3], "random", "outer"),
+    (2, [9, 7], "QK", 2, 1, 4, "mass", [1.0], "random", "outer"),
+    (3, [6, 5, 4], "PK", 2, 3, 4, "elast", [1.0, 1.0], "random", "half"),
+    (3, [9, 9, 9], "PK", 1, 1, 2, "laplace", [1.0], "random", "half"),
+    (3, [4, 3, 3], "QK", 2, 3, 6, "nh_ciarlet", [1.0, 1.0], "smooth", "half"),
+    (3, [2, 2, 1], "QK", 4, 1, 8, "laplace", [1.0], "random", "half"),
 ]
 
 
-@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s_%s%d_q%d_%s" % (c[6], c[2], c[3], c[4], "x".join(map(str, c[1]))))
+def oracle_region(rg, t, ft):
+    """Region + all-point tables in the oracle's layout (volume points, then face after face)."""
+    if rg is None:
+        return None, (t["quad_w"], t["gt_grad"], t["phi"], t["gphi"])
+    cv, fc = rg.items()
+    if not rg.is_only_faces():
+        return {"items_cv": cv, "items_f": fc}, (t["quad_w"], t["gt_grad"], t["phi"], t["gphi"])
+    nq = len(t["quad_w"])
+    nf, nqf = ft["quad_w"].shape
+    reg = {"items_cv": cv, "items_f": fc, "face_first": nq + nqf * np.arange(nf), "face_nq": np.full(nf, nqf),
+           "ref_normals": ft["normals"]}
+    cat = lambda a, b: np.concatenate([a, b.reshape((nf * nqf,) + a.shape[1:])])  # noqa: E731
+    return reg, (cat(t["quad_w"], ft["quad_w"]), cat(t["gt_grad"], ft["gt_grad"]), cat(t["phi"], ft["phi"]),
+                 cat(t["gphi"], ft["gphi"]))
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s_%s%d_q%d_%s%s" % (c[6], c[2], c[3], c[4], "x".join(map(str, c[1])),
+                                                                           "_" + c[9] if len(c) > 9 else ""))
 def test_workspace_matches_oracle(case):
     from oracle import oracle
     from getfem_b200 import fem_tables
-    dim, nsub, gt, k, Q, im, family, params, umode = case
+    dim, nsub, gt, k, Q, im, family, params, umode = case[:9]
+    region = case[9] if len(case) > 9 else None
     if umode == "random":
         rng = np.random.default_rng(7)
         U = lambda mf: rng.uniform(-1, 1, mf.nb_dof())  # noqa: E731
     else:
         U = smooth_u(0.03)
-    ws, mf, m, Uv = build_ws(dim, nsub, gt, k, Q, im, family, params, U)
+    ws, mf, m, Uv = build_ws(dim, nsub, gt, k, Q, im, family, params, U, region)
     ws.assembly(2)
     ws.assembly(1)
     jc, ir, pr = ws.assembled_matrix()
     t = fem_tables.classical_tables(gt, dim, k, im)
+    ft = fem_tables.classical_face_tables(gt, dim, k, im) if region in ("outer", "xmax", "zmin") else None
+    reg, (w, gtg, phi, gphi) = oracle_region(ws.region, t, ft)
     ojc, oir, opr, oR = oracle.assemble(m.pts, m.conn, mf.ind_scalar_basic_dof_of_element(), mf.nb_dof(), Q,
-                                        t["quad_w"], t["gt_grad"], t["phi"], t["gphi"], gt == "PK", family,
-                                        params, Uv)
+                                        w, gtg, phi, gphi, gt == "PK", family, params, Uv, region=reg,
+                                        nq=len(t["quad_w"]))
     assert np.array_equal(jc, ojc) and np.array_equal(ir, oir)
     assert np.linalg.norm(pr - opr) / max(np.linalg.norm(opr), 1e-300) < 1e-12
     assert np.linalg.norm(ws.assembled_vector() - oR) / np.linalg.norm(oR) < 1e-12
+    if family == "nsource" and region == "outer" and Q == dim:
+        # divergence theorem on the closed boundary: sum_i int (A n)_b phi_i = int (A n)_b = 0 for a constant A
+        assert np.abs(ws.assembled_vector().reshape(-1, Q).sum(0)).max() < 1e-12
+    if family == "mass" and region == "outer" and Q == 1:
+        # 1^T M 1 = measure of the boundary of the unit square / cube
+        import scipy.sparse as sp
+        M = sp.csc_matrix((pr, ir, jc), shape=(mf.nb_dof(),) * 2)
+        assert abs(M.sum() / params[0] - 2 * dim) < 1e-11
 
 
 def test_config1_stiffness_plus_rhs():

@@ -44,6 +44,33 @@ def test_tables_match_reference(name):
     assert np.abs(t["gphi"].sum(1)).max() < 1e-11
 
 
+@pytest.mark.parametrize("name", [n for n in golden_names() if n.startswith("r_")])
+def test_regions_and_face_tables_match_reference(name):
+    """mesh_region items in mr_visitor order (outer_faces_of_mesh + the driver's selections) and the face part of the
+    integration method (points, weights, reference normals, basis tables) against the reference's dumps."""
+    import getfem_b200 as gf
+    from conftest import make_region
+    g = load_golden(name)
+    a = g["args"]
+    N, k = int(a["dim"]), int(a["k"])
+    kind = "PK" if g["gt_linear"] else "QK"
+    m = gf.mesh()
+    gf.regular_unit_mesh(m, _subdiv(a), "GT_%s(%d,1)" % (kind, N))
+    cv, fc = make_region(m, a["region"]).items()
+    assert np.array_equal(cv, g["items_cv"]) and np.array_equal(fc, g["items_f"])
+    t = fem_tables.classical_face_tables(kind, N, k, int(a["im"]))
+    idx = np.array([np.arange(f0, f0 + n) for f0, n in zip(g["face_first"], g["face_nq"])])
+    assert np.array_equal(t["normals"], g["ref_normals"])
+    assert np.abs(t["quad_x"] - g["all_x"][idx]).max() < 2e-15
+    assert np.abs(t["quad_w"] - g["all_w"][idx]).max() < 2e-15
+    assert np.abs(t["gt_grad"] - g["all_gt_grad"][idx]).max() < 2e-15
+    assert np.abs(t["phi"] - g["all_phi"][idx]).max() < 5e-14
+    assert np.abs(t["gphi"] - g["all_gphi"][idx]).max() < 5e-14
+    # the face weights sum to the measure of the reference face
+    area = {("PK", 2): [2 ** 0.5, 1, 1], ("PK", 3): [3 ** 0.5 / 2, 0.5, 0.5, 0.5]}.get((kind, N), [1.0] * (2 * N))
+    assert np.abs(t["quad_w"].sum(1) - np.array(area)).max() < 1e-14
+
+
 def test_cubature_exactness():
     # IM_TETRAHEDRON(5): exact to degree 5 on the reference tetrahedron; int x^a y^b z^c = a!b!c!/(a+b+c+3)!
     from math import factorial as f
@@ -62,6 +89,9 @@ def test_cubature_exactness():
     ("Grad_u:Grad_Test_u", "laplace"),
     ("(a*Grad_p).Grad_Test_p", "laplace"),
     ("a*u.Test_u", "mass"),
+    ("((g).Normal)*Test_u", "nsource+"),
+    ("(Reshape(g,qdim(u),meshdim)*Normal).Test_u", "nsource+"),
+    ("-f*Test_u", "source-"),
     ("(Div_u*((lambda)*Id(meshdim))+(2*(mu))*Sym(Grad_u)):Grad_Test_u", "elast"),
     ("lambda*Div_u*Div_Test_u + 2*mu*Sym(Grad_u):Grad_Test_u", "elast"),
     ("((Id(meshdim)+Grad_u)*(Compressible_Neo_Hookean_Ciarlet_PK2(Grad_u,params))):Grad_Test_u", "nh_ciarlet"),
