@@ -25,6 +25,15 @@ CASES = [
     "dim=3 n=2 gt=qk k=4 q=1 im=8 family=laplace",      # config 5 (reduced); tables come from the reference itself
     "dim=2 n=48 gt=pk k=1 q=1 im=2 family=source",      # the RHS of config 1: "-f*Test_u" (order 1 only, empty tangent)
     "dim=3 n=4 gt=pk k=2 q=3 im=4 family=source",       # "-(f.Test_u)", vector
+    # mesh regions read from td.rg: boundary faces and sub-regions of convexes
+    "dim=3 n=4 gt=pk k=2 q=3 im=4 family=mass region=outer",     # Robin / Dirichlet penalisation matrix
+    "dim=3 n=4 gt=pk k=2 q=3 im=4 family=source region=xmax",    # Neumann load
+    "dim=3 n=4 gt=pk k=2 q=3 im=4 family=nsource region=outer",  # "-(Reshape(g,qdim(u),meshdim)*Normal).Test_u"
+    "dim=2 n=24 gt=pk k=1 q=1 im=2 family=nsource region=outer", # "((g).Normal)*Test_u"
+    "dim=3 n=3 gt=qk k=2 q=1 im=6 family=mass region=outer",
+    "dim=3 n=3 gt=qk k=2 q=3 im=6 family=nsource region=xmax",
+    "dim=3 n=6 gt=pk k=2 q=3 im=4 family=elast region=half",
+    "dim=3 n=3 gt=qk k=2 q=3 im=6 family=nh_ciarlet region=half",
 ]
 
 
