@@ -59,6 +59,16 @@ SIGNATURES = {
     "gfgpu_term_residual_view": (C.c_int, [_P, _PP]),
     "gfgpu_term_export_csc_host": (C.c_int, [_P, _P, _P, _P]),
     "gfgpu_term_export_residual_host": (C.c_int, [_P, _P]),
+    "gfgpu_matrix_create": (C.c_int, [_P, _i64, _i64, _PP]),
+    "gfgpu_matrix_destroy": (C.c_int, [_P]),
+    "gfgpu_matrix_clear": (C.c_int, [_P, C.c_int]),
+    "gfgpu_matrix_add_term": (C.c_int, [_P, _P, C.c_double, _i64, _i64]),
+    "gfgpu_matrix_nnz": (_i64, [_P]),
+    "gfgpu_matrix_pattern_generation": (_i64, [_P]),
+    "gfgpu_matrix_csc_view": (C.c_int, [_P, _PP, _PP, _PP]),
+    "gfgpu_matrix_export_csc_host": (C.c_int, [_P, _P, _P, _P]),
+    "gfgpu_matrix_mult_dev": (C.c_int, [_P, C.c_int, C.c_double, _P, C.c_double, _P]),
+    "gfgpu_matrix_mult_host": (C.c_int, [_P, C.c_int, C.c_double, _P, C.c_double, _P]),
     "gfgpu_term_halo_begin": (C.c_int, [_P, _P, _P, _P]),
     "gfgpu_term_halo_ghost_pairs": (C.c_int, [_P, _i64, _i64, _P, _P, _P, _P]),
     "gfgpu_term_halo_add_source": (C.c_int, [_P, C.c_int, _i64, _P, _P, _P, _i64, _i64]),
@@ -325,6 +335,55 @@ class DeviceTerm(_Handle):
         lo, hi = _i64(), _i64()
         check(lib().gfgpu_term_owned_range(self.h, C.byref(lo), C.byref(hi)))
         return lo.value, hi.value
+
+
+class DeviceMatrix(_Handle):
+    """The workspace-level tangent on the device: the sum of terms at their variable offsets (gfgpu_matrix_*)."""
+    _destroy = "gfgpu_matrix_destroy"
+
+    def __init__(self, ctx, nrows, ncols=None):
+        super().__init__()
+        self.ctx, self.nrows, self.ncols = ctx, int(nrows), int(nrows if ncols is None else ncols)
+        check(lib().gfgpu_matrix_create(ctx.h, self.nrows, self.ncols, C.byref(self.h)))
+
+    def clear(self, keep_pattern=False):
+        check(lib().gfgpu_matrix_clear(self.h, 1 if keep_pattern else 0))
+
+    def add_term(self, term, alpha=1.0, row_off=0, col_off=0):
+        check(lib().gfgpu_matrix_add_term(self.h, term.h, float(alpha), int(row_off), int(col_off)))
+
+    @property
+    def nnz(self):
+        return int(lib().gfgpu_matrix_nnz(self.h))
+
+    @property
+    def pattern_generation(self):
+        return int(lib().gfgpu_matrix_pattern_generation(self.h))
+
+    def csc_view(self):
+        jc, ir, pr = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib().gfgpu_matrix_csc_view(self.h, C.byref(jc), C.byref(ir), C.byref(pr)))
+        return jc.value, ir.value, pr.value
+
+    def export_csc(self):
+        nnz = self.nnz
+        jc = np.empty(self.ncols + 1, np.int64)
+        ir = np.empty(nnz, np.int32)
+        pr = np.empty(nnz, np.float64)
+        check(lib().gfgpu_matrix_export_csc_host(self.h, ptr(jc), ptr(ir), ptr(pr)))
+        return jc, ir, pr
+
+    def mult(self, x, transposed=False, alpha=1.0, beta=0.0, y=None):
+        """y = beta*y + alpha*K x (or K^T x) through host buffers."""
+        x = np.ascontiguousarray(x, np.float64)
+        nout = self.ncols if transposed else self.nrows
+        y = np.zeros(nout) if y is None else np.ascontiguousarray(y, np.float64).copy()
+        check(lib().gfgpu_matrix_mult_host(self.h, 1 if transposed else 0, float(alpha), ptr(x), float(beta), ptr(y)))
+        return y
+
+    def mult_dev(self, x_dev_ptr, y_dev_ptr, transposed=False, alpha=1.0, beta=0.0):
+        check(lib().gfgpu_matrix_mult_dev(self.h, 1 if transposed else 0, float(alpha), C.c_void_p(x_dev_ptr), float(beta),
+                                          C.c_void_p(y_dev_ptr)))
 
 
 class _DevArray:

@@ -9,6 +9,7 @@
 namespace gf {
 std::atomic<int64_t> g_launches{0};
 static thread_local std::string g_err;
+void set_last_error(const std::string &s) { g_err = s; }
 }  // namespace gf
 
 #define GF_API_BEGIN try {

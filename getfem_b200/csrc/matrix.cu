@@ -1,0 +1,386 @@
+// matrix.cu -- the workspace-level tangent kept on the device.
+//
+// ga_workspace::assembly(2) adds EVERY order-2 tree into one gmm::col_matrix<rsvector> (workspace.cc:791-936), a model
+// then sums brick matrices into its tangent and forms residuals of linear bricks as K*u (getfem_models.cc:2536-2620,
+// 2753-2900).  Here the terms' CSC slabs are accumulated into ONE device CSC:
+//   pattern  = union of the terms' patterns at their (row, column) offsets -- an entry an element matrix inserted stays
+//              stored even when a later term cancels it, like rsvector::w / add_elem_matrix (C&E.cc:4853-4936);
+//   values   = sum over the terms in the order they were added; inside one term every (row, column) occurs once, so a
+//              term is added by one kernel without atomics: results are bitwise reproducible;
+//   products = y = K^T x (gather per column) and y = K x (gather per row through a row-sorted permutation built once per
+//              pattern), fixed summation order, no atomics.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+struct gfgpu_matrix {
+  gfgpu_ctx *ctx = nullptr;
+  int64_t nrows = 0, ncols = 0, nnz = 0;
+  int64_t generation = 0;       // pattern generation
+  gf::DevBuf<int64_t> jc;       // ncols + 1
+  gf::DevBuf<int32_t> ir;       // nnz, ascending inside a column
+  gf::DevBuf<double> pr;        // nnz
+  gf::DevBuf<int64_t> cnt;      // ncols + 1 scratch
+  gf::DevBuf<int32_t> flag;
+  // row-major view for y = K x: entries sorted by (row, column)
+  int64_t csr_generation = -1;
+  gf::DevBuf<int64_t> rp;       // nrows + 1
+  gf::DevBuf<uint32_t> rperm;   // nnz: entry index
+  gf::DevBuf<int32_t> rcol;     // nnz: column of that entry
+};
+
+namespace gf {
+
+static inline int mgrid(int64_t n, int block, int cap = 148 * 32) {
+  int64_t g = (n + block - 1) / block;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(g, cap));
+}
+
+// first position in [lo, hi) with ir[pos] >= row
+__device__ __forceinline__ int64_t lower_row(const int32_t *__restrict__ ir, int64_t lo, int64_t hi, int32_t row) {
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (ir[mid] < row) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// warp per term column: how many of its rows are missing from the matrix column
+__global__ void k_mat_missing(const int64_t *__restrict__ tjc, const int32_t *__restrict__ tir, int64_t tn, int64_t row_off,
+                              int64_t col_off, const int64_t *__restrict__ jc, const int32_t *__restrict__ ir,
+                              int64_t *__restrict__ cnt /* per matrix column: stored + missing */, int32_t *__restrict__ any) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t j = w0; j < tn; j += nw) {
+    const int64_t a = tjc[j], b = tjc[j + 1], c = col_off + j;
+    const int64_t lo = jc ? jc[c] : 0, hi = jc ? jc[c + 1] : 0;
+    int miss = 0;
+    for (int64_t k = a + lane; k < b; k += 32) {
+      const int32_t r = (int32_t)(row_off + tir[k]);
+      const int64_t p = lower_row(ir, lo, hi, r);
+      if (p >= hi || ir[p] != r) ++miss;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) miss += __shfl_xor_sync(0xffffffffu, miss, o);
+    if (lane == 0 && miss) {
+      cnt[c] = (hi - lo) + miss;
+      *any = 1;
+    }
+  }
+}
+
+__global__ void k_mat_counts(const int64_t *__restrict__ jc, int64_t n, int64_t *__restrict__ cnt) {
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+    cnt[j] = jc ? jc[j + 1] - jc[j] : 0;
+}
+
+// thread per matrix column: merge the old column with the term column (both row-sorted) into the new layout
+__global__ void k_mat_merge(const int64_t *__restrict__ ojc, const int32_t *__restrict__ oir, const double *__restrict__ opr,
+                            const int64_t *__restrict__ tjc, const int32_t *__restrict__ tir, int64_t tn, int64_t row_off,
+                            int64_t col_off, const int64_t *__restrict__ njc, int64_t ncols, int32_t *__restrict__ nir,
+                            double *__restrict__ npr) {
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncols; c += (int64_t)gridDim.x * blockDim.x) {
+    int64_t a = ojc ? ojc[c] : 0;
+    const int64_t ae = ojc ? ojc[c + 1] : 0;
+    const int64_t j = c - col_off;
+    int64_t b = (j >= 0 && j < tn) ? tjc[j] : 0;
+    const int64_t be = (j >= 0 && j < tn) ? tjc[j + 1] : 0;
+    int64_t o = njc[c];
+    while (a < ae || b < be) {
+      const int32_t ra = a < ae ? oir[a] : INT32_MAX;
+      const int32_t rb = b < be ? (int32_t)(row_off + tir[b]) : INT32_MAX;
+      if (ra <= rb) {
+        nir[o] = ra; npr[o] = opr[a]; ++a;
+        if (ra == rb) ++b;
+      } else {
+        nir[o] = rb; npr[o] = 0.0; ++b;
+      }
+      ++o;
+    }
+  }
+}
+
+// warp per term column: pr[pos(row, column)] += alpha * value.  Every (row, column) occurs once per term: no conflicts.
+__global__ void k_mat_add(const int64_t *__restrict__ tjc, const int32_t *__restrict__ tir, const double *__restrict__ tpr,
+                          int64_t tn, double alpha, int64_t row_off, int64_t col_off, const int64_t *__restrict__ jc,
+                          const int32_t *__restrict__ ir, double *__restrict__ pr, int32_t *__restrict__ err) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t j = w0; j < tn; j += nw) {
+    const int64_t a = tjc[j], b = tjc[j + 1], c = col_off + j;
+    const int64_t lo = jc[c], hi = jc[c + 1];
+    // the term's rows ascend with k: the search restarts from the previous hit of this lane
+    int64_t from = lo;
+    for (int64_t k = a + lane; k < b; k += 32) {
+      const int32_t r = (int32_t)(row_off + tir[k]);
+      const int64_t p = lower_row(ir, from, hi, r);
+      if (p >= hi || ir[p] != r) { *err = 1; continue; }
+      pr[p] += alpha * tpr[k];
+      from = p + 1;
+    }
+  }
+}
+
+// y[col] = beta*y[col] + alpha * sum_k pr[k] x[ir[k]]   (K^T x), warp per column, fixed lane tree
+__global__ void k_mat_tmult(const int64_t *__restrict__ jc, const int32_t *__restrict__ ir, const double *__restrict__ pr,
+                            int64_t ncols, const double *__restrict__ x, double alpha, double beta, double *__restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = w0; c < ncols; c += nw) {
+    double s = 0.0;
+    for (int64_t k = jc[c] + lane; k < jc[c + 1]; k += 32) s += pr[k] * x[ir[k]];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) y[c] = (beta == 0.0 ? 0.0 : beta * y[c]) + alpha * s;
+  }
+}
+
+// y[row] = beta*y[row] + alpha * sum over the row's entries (ascending column) pr[e] x[col(e)]
+__global__ void k_mat_mult(const int64_t *__restrict__ rp, const uint32_t *__restrict__ rperm, const int32_t *__restrict__ rcol,
+                           const double *__restrict__ pr, int64_t nrows, const double *__restrict__ x, double alpha,
+                           double beta, double *__restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = w0; r < nrows; r += nw) {
+    double s = 0.0;
+    for (int64_t k = rp[r] + lane; k < rp[r + 1]; k += 32) s += pr[rperm[k]] * x[rcol[k]];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) y[r] = (beta == 0.0 ? 0.0 : beta * y[r]) + alpha * s;
+  }
+}
+
+__global__ void k_mat_entry_cols(const int64_t *__restrict__ jc, int64_t ncols, int32_t *__restrict__ col, uint32_t *__restrict__ idx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = w0; c < ncols; c += nw)
+    for (int64_t k = jc[c] + lane; k < jc[c + 1]; k += 32) { col[k] = (int32_t)c; idx[k] = (uint32_t)k; }
+}
+
+__global__ void k_mat_row_hist(const int32_t *__restrict__ ir, int64_t nnz, unsigned long long *__restrict__ cnt) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&cnt[ir[k]], 1ull);  // integer counts: the order of the additions does not matter
+}
+
+static void scan_counts(gfgpu_ctx *ctx, int64_t *cnt, int64_t *out, int64_t n) {
+  size_t tb = 0;
+  GF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, out, n, ctx->stream));
+  void *tmp = cub_scratch(ctx, tb);
+  GF_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, out, n, ctx->stream));
+  count_launch(2);
+}
+
+static void mat_add(gfgpu_matrix *m, const int64_t *tjc, const int32_t *tir, const double *tpr, int64_t tn, int64_t tnnz,
+                    double alpha, int64_t row_off, int64_t col_off) {
+  gfgpu_ctx *ctx = m->ctx;
+  cudaStream_t s = ctx->stream;
+  if (!tn || !tnnz) return;
+  const int B = 256;
+  // ---- symbolic: does the matrix already store every (row, column) of the term?
+  if (m->cnt.n != (size_t)m->ncols + 1) m->cnt.alloc(ctx, m->ncols + 1);
+  m->flag.zero();
+  k_mat_counts<<<mgrid(m->ncols, B), B, 0, s>>>(m->jc.n ? m->jc.p : nullptr, m->ncols, m->cnt.p);
+  GF_LAUNCH_CHECK();
+  GF_CUDA(cudaMemsetAsync(m->cnt.p + m->ncols, 0, sizeof(int64_t), s));
+  k_mat_missing<<<mgrid(tn * 32, B), B, 0, s>>>(tjc, tir, tn, row_off, col_off, m->jc.n ? m->jc.p : nullptr, m->ir.p, m->cnt.p,
+                                               m->flag.p);
+  GF_LAUNCH_CHECK();
+  int32_t grow = 0;
+  m->flag.download(&grow);
+  GF_CUDA(cudaStreamSynchronize(s));
+  if (grow) {
+    DevBuf<int64_t> njc;
+    njc.alloc(ctx, m->ncols + 1);
+    scan_counts(ctx, m->cnt.p, njc.p, m->ncols + 1);
+    int64_t nnz = 0;
+    GF_CUDA(cudaMemcpyAsync(&nnz, njc.p + m->ncols, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    GF_CUDA(cudaStreamSynchronize(s));
+    DevBuf<int32_t> nir;
+    DevBuf<double> npr;
+    nir.alloc(ctx, nnz);
+    npr.alloc(ctx, nnz);
+    k_mat_merge<<<mgrid(m->ncols, 128), 128, 0, s>>>(m->jc.n ? m->jc.p : nullptr, m->ir.p, m->pr.p, tjc, tir, tn, row_off, col_off,
+                                                    njc.p, m->ncols, nir.p, npr.p);
+    GF_LAUNCH_CHECK();
+    GF_CUDA(cudaStreamSynchronize(s));
+    std::swap(m->jc.p, njc.p); std::swap(m->jc.n, njc.n); std::swap(m->jc.ctx, njc.ctx);
+    std::swap(m->ir.p, nir.p); std::swap(m->ir.n, nir.n); std::swap(m->ir.ctx, nir.ctx);
+    std::swap(m->pr.p, npr.p); std::swap(m->pr.n, npr.n); std::swap(m->pr.ctx, npr.ctx);
+    m->nnz = nnz;
+    m->generation++;
+  }
+  // ---- numeric
+  m->flag.zero();
+  k_mat_add<<<mgrid(tn * 32, B), B, 0, s>>>(tjc, tir, tpr, tn, alpha, row_off, col_off, m->jc.p, m->ir.p, m->pr.p, m->flag.p);
+  GF_LAUNCH_CHECK();
+  int32_t err = 0;
+  m->flag.download(&err);
+  GF_CUDA(cudaStreamSynchronize(s));
+  GF_REQUIRE(err == 0, "internal error: a term entry has no slot in the matrix pattern");
+}
+
+static void mat_build_csr(gfgpu_matrix *m) {
+  if (m->csr_generation == m->generation) return;
+  gfgpu_ctx *ctx = m->ctx;
+  cudaStream_t s = ctx->stream;
+  GF_REQUIRE(m->nnz < (int64_t(1) << 31) - 1, "y = K x needs nnz < 2^31 (use the transposed product, or split the matrix)");
+  const int B = 256;
+  const int64_t nnz = m->nnz;
+  DevBuf<int32_t> col0, key1;
+  DevBuf<uint32_t> idx0;
+  col0.alloc(ctx, nnz); idx0.alloc(ctx, nnz); key1.alloc(ctx, nnz);
+  m->rperm.alloc(ctx, nnz); m->rcol.alloc(ctx, nnz); m->rp.alloc(ctx, m->nrows + 1);
+  k_mat_entry_cols<<<mgrid(m->ncols * 32, B), B, 0, s>>>(m->jc.p, m->ncols, col0.p, idx0.p);
+  GF_LAUNCH_CHECK();
+  int bits = 1;
+  while (bits < 31 && (int64_t(1) << bits) < m->nrows) ++bits;
+  // stable sort by row: inside a row the entries keep their CSC order = ascending column
+  size_t tb = 0;
+  GF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, m->ir.p, key1.p, idx0.p, m->rperm.p, (int)nnz, 0, bits, s));
+  void *tmp = cub_scratch(ctx, tb);
+  GF_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, m->ir.p, key1.p, idx0.p, m->rperm.p, (int)nnz, 0, bits, s));
+  GF_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, m->ir.p, key1.p, col0.p, m->rcol.p, (int)nnz, 0, bits, s));
+  count_launch(4);
+  DevBuf<int64_t> cnt;
+  cnt.alloc(ctx, m->nrows + 1);
+  cnt.zero();
+  k_mat_row_hist<<<mgrid(nnz, B), B, 0, s>>>(m->ir.p, nnz, (unsigned long long *)cnt.p);
+  GF_LAUNCH_CHECK();
+  scan_counts(ctx, cnt.p, m->rp.p, m->nrows + 1);
+  GF_CUDA(cudaStreamSynchronize(s));
+  m->csr_generation = m->generation;
+}
+
+}  // namespace gf
+
+namespace gf { void set_last_error(const std::string &); }  // api.cu
+
+#define GFM_BEGIN try {
+#define GFM_END                                  \
+  return 0;                                      \
+  }                                              \
+  catch (const std::exception &ex) {             \
+    gf::set_last_error(ex.what());               \
+    return 1;                                    \
+  }                                              \
+  catch (...) {                                  \
+    gf::set_last_error("unknown error");         \
+    return 1;                                    \
+  }
+
+extern "C" {
+
+int gfgpu_matrix_create(gfgpu_ctx *ctx, int64_t nrows, int64_t ncols, gfgpu_matrix **out) {
+  GFM_BEGIN
+  GF_REQUIRE(ctx && out, "null argument");
+  GF_REQUIRE(nrows >= 0 && ncols >= 0 && nrows < (int64_t(1) << 31) - 4 && ncols < (int64_t(1) << 31) - 4, "bad matrix sizes");
+  GF_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<gfgpu_matrix> m(new gfgpu_matrix);
+  m->ctx = ctx; m->nrows = nrows; m->ncols = ncols;
+  m->flag.alloc(ctx, 1);
+  *out = m.release();
+  GFM_END
+}
+
+int gfgpu_matrix_destroy(gfgpu_matrix *m) {
+  GFM_BEGIN
+  if (m) {
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+  }
+  delete m;
+  GFM_END
+}
+
+int gfgpu_matrix_clear(gfgpu_matrix *m, int keep_pattern) {
+  GFM_BEGIN
+  GF_REQUIRE(m, "null matrix");
+  GF_CUDA(cudaSetDevice(m->ctx->device));
+  if (keep_pattern) {
+    m->pr.zero();
+  } else {
+    m->jc.release(); m->ir.release(); m->pr.release();
+    m->nnz = 0;
+    m->generation++;
+  }
+  GFM_END
+}
+
+int gfgpu_matrix_add_term(gfgpu_matrix *m, gfgpu_term *t, double alpha, int64_t row_off, int64_t col_off) {
+  GFM_BEGIN
+  GF_REQUIRE(m && t, "null argument");
+  GF_REQUIRE(m->ctx == t->ctx, "matrix and term live on different contexts");
+  GF_REQUIRE(t->pat_valid, "the term has no assembled tangent");
+  const int64_t n = t->fem->ndof;
+  GF_REQUIRE(row_off >= 0 && col_off >= 0 && row_off + n <= m->nrows && col_off + n <= m->ncols, "the term does not fit the matrix");
+  GF_CUDA(cudaSetDevice(m->ctx->device));
+  gf::mat_add(m, t->jc.p, t->ir.p, t->pr.p, n, t->nnz, alpha, row_off, col_off);
+  GFM_END
+}
+
+int64_t gfgpu_matrix_nnz(gfgpu_matrix *m) { return m ? m->nnz : -1; }
+int64_t gfgpu_matrix_pattern_generation(gfgpu_matrix *m) { return m ? m->generation : -1; }
+
+int gfgpu_matrix_csc_view(gfgpu_matrix *m, const int64_t **jc, const int32_t **ir, const double **pr) {
+  GFM_BEGIN
+  GF_REQUIRE(m, "null matrix");
+  if (jc) *jc = m->jc.p;
+  if (ir) *ir = m->ir.p;
+  if (pr) *pr = m->pr.p;
+  GFM_END
+}
+
+int gfgpu_matrix_export_csc_host(gfgpu_matrix *m, int64_t *jc, int32_t *ir, double *pr) {
+  GFM_BEGIN
+  GF_REQUIRE(m, "null matrix");
+  GF_CUDA(cudaSetDevice(m->ctx->device));
+  if (jc) {
+    if (m->jc.n) m->jc.download(jc);
+    else for (int64_t k = 0; k <= m->ncols; ++k) jc[k] = 0;
+  }
+  if (ir) m->ir.download(ir);
+  if (pr) m->pr.download(pr);
+  GF_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  GFM_END
+}
+
+int gfgpu_matrix_mult_dev(gfgpu_matrix *m, int transposed, double alpha, const double *x_dev, double beta, double *y_dev) {
+  GFM_BEGIN
+  GF_REQUIRE(m && x_dev && y_dev, "null argument");
+  GF_CUDA(cudaSetDevice(m->ctx->device));
+  cudaStream_t s = m->ctx->stream;
+  const int B = 256;
+  const int64_t nout = transposed ? m->ncols : m->nrows;
+  if (!m->nnz) {  // empty matrix: y = beta * y
+    if (beta == 0.0) GF_CUDA(cudaMemsetAsync(y_dev, 0, nout * sizeof(double), s));
+    else GF_REQUIRE(beta == 1.0, "empty matrix: only beta = 0 or 1 is handled");
+    return 0;
+  }
+  if (transposed) {
+    gf::k_mat_tmult<<<gf::mgrid(m->ncols * 32, B), B, 0, s>>>(m->jc.p, m->ir.p, m->pr.p, m->ncols, x_dev, alpha, beta, y_dev);
+    GF_LAUNCH_CHECK();
+  } else {
+    gf::mat_build_csr(m);
+    gf::k_mat_mult<<<gf::mgrid(m->nrows * 32, B), B, 0, s>>>(m->rp.p, m->rperm.p, m->rcol.p, m->pr.p, m->nrows, x_dev, alpha, beta, y_dev);
+    GF_LAUNCH_CHECK();
+  }
+  GFM_END
+}
+
+int gfgpu_matrix_mult_host(gfgpu_matrix *m, int transposed, double alpha, const double *x_host, double beta, double *y_host) {
+  GFM_BEGIN
+  GF_REQUIRE(m && x_host && y_host, "null argument");
+  gfgpu_ctx *ctx = m->ctx;
+  GF_CUDA(cudaSetDevice(ctx->device));
+  const int64_t nin = transposed ? m->nrows : m->ncols, nout = transposed ? m->ncols : m->nrows;
+  gf::DevBuf<double> x, y;
+  x.alloc(ctx, nin); y.alloc(ctx, nout);
+  x.upload(x_host);
+  if (beta != 0.0) y.upload(y_host); else y.zero();
+  GF_REQUIRE(gfgpu_matrix_mult_dev(m, transposed, alpha, x.p, beta, y.p) == 0, gfgpu_last_error());
+  y.download(y_host);
+  GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  GFM_END
+}
+
+}  // extern "C"

@@ -28,11 +28,59 @@ static std::string strip(const std::string &s) {
   return r;
 }
 
+static bool recognise_string(const getfem::ga_workspace &ws, const std::string &v, const std::string &s, recognised_term &out);
+
 bool recognise_tree(const getfem::ga_workspace &ws, size_type itree, recognised_term &out) {
   const getfem::ga_workspace::tree_description &td = ws.tree_info(itree);
   if (td.order != 1 || td.operation != getfem::ga_workspace::ASSEMBLY) return false;
-  const std::string s = strip(getfem::ga_tree_to_string(*td.ptree));
-  const std::string v = td.name_test1;
+  return recognise_string(ws, td.name_test1, strip(getfem::ga_tree_to_string(*td.ptree)), out);
+}
+
+// removes parentheses that enclose the whole string
+static std::string strip_outer(std::string s) {
+  for (;;) {
+    if (s.size() < 2 || s.front() != '(' || s.back() != ')') return s;
+    int depth = 0;
+    bool encloses = true;
+    for (size_t i = 0; i < s.size(); ++i) {
+      if (s[i] == '(') ++depth;
+      else if (s[i] == ')') --depth;
+      if (depth == 0 && i + 1 < s.size()) { encloses = false; break; }
+    }
+    if (!encloses) return s;
+    s = s.substr(1, s.size() - 2);
+  }
+}
+
+static bool recognise_sum(const getfem::ga_workspace &ws, const std::string &v, const std::string &s0,
+                          std::vector<recognised_term> &out) {
+  const std::string s = strip_outer(s0);
+  recognised_term rt;
+  if (recognise_string(ws, v, s, rt) || recognise_string(ws, v, s0, rt)) { out.push_back(rt); return true; }
+  int depth = 0;  // LAST top-level '+': add_tree builds ((A)+(B))+(C)
+  size_t at = std::string::npos;
+  for (size_t i = 0; i < s.size(); ++i) {
+    if (s[i] == '(' || s[i] == '[') ++depth;
+    else if (s[i] == ')' || s[i] == ']') --depth;
+    else if (s[i] == '+' && depth == 0 && i > 0) at = i;
+  }
+  if (at == std::string::npos) return false;
+  return recognise_sum(ws, v, s.substr(0, at), out) && recognise_sum(ws, v, s.substr(at + 1), out);
+}
+
+bool recognise_tree_sum(const getfem::ga_workspace &ws, size_type itree, std::vector<recognised_term> &out) {
+  const getfem::ga_workspace::tree_description &td = ws.tree_info(itree);
+  if (td.order != 1 || td.operation != getfem::ga_workspace::ASSEMBLY) return false;
+  out.clear();
+  if (!recognise_sum(ws, td.name_test1, strip(getfem::ga_tree_to_string(*td.ptree)), out)) return false;
+  size_t bilinear = 0;
+  for (const recognised_term &rt : out) bilinear += rt.family != GFGPU_SOURCE && rt.family != GFGPU_NORMAL_SOURCE;
+  GMM_ASSERT1(bilinear <= 1, "gfgpu: several bilinear forms summed on one region are thresholded together by the reference "
+                             "(C&E.cc:4889); give them distinct regions or one expression family");
+  return true;
+}
+
+static bool recognise_string(const getfem::ga_workspace &ws, const std::string &v, const std::string &s, recognised_term &out) {
   const std::string ID = "([A-Za-z_][A-Za-z_0-9]*)";
   const std::string I3 = "\\[\\[1,0,0\\],\\[0,1,0\\],\\[0,0,1\\]\\]", I2 = "\\[\\[1,0\\],\\[0,1\\]\\]";
   const std::string Idm = "(?:" + I3 + "|" + I2 + ")";
@@ -116,9 +164,6 @@ struct device_assembler::entry {
   gfgpu_tables *tab = nullptr;
   gfgpu_term *term = nullptr;
   size_type ndof = 0;
-  std::vector<int64_t> jc;
-  std::vector<int32_t> ir;
-  int64_t generation = -1;
   ~entry() {
     gfgpu_term_destroy(term);
     gfgpu_tables_destroy(tab);
@@ -157,15 +202,28 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
                                                                            << ") are not handled by the device path");
       continue;
     }
-    recognised_term rt;
-    GMM_ASSERT1(recognise_tree(ws, i, rt), "gfgpu: expression not handled by the device path (no CPU fallback): "
-                                               << getfem::ga_tree_to_string(*td.ptree));
-    terms.emplace_back(i, rt);
+    std::vector<recognised_term> rts;
+    GMM_ASSERT1(recognise_tree_sum(ws, i, rts), "gfgpu: expression not handled by the device path (no CPU fallback): "
+                                                    << getfem::ga_tree_to_string(*td.ptree));
+    for (const recognised_term &rt : rts) terms.emplace_back(i, rt);
   }
   GMM_ASSERT1(!terms.empty(), "gfgpu: nothing to assemble");
   t_extract = t_device = t_fill = 0;
 
   const size_type nprim = ws.nb_primary_dof() ? ws.nb_primary_dof() : 0;
+  // order 2: every tree adds into ONE tangent (workspace.cc:791-936) -- accumulated on the device at the variables'
+  // intervals (gfgpu_matrix_*), downloaded once
+  size_type need_all = nprim;
+  for (auto &it : terms) {
+    const getfem::mesh_fem *pmf = ws.associated_mf(it.second.varname);
+    GMM_ASSERT1(pmf, "gfgpu: the variable must be a fem variable");
+    need_all = std::max<size_type>(need_all, ws.interval_of_variable(it.second.varname).first() + pmf->nb_dof());
+  }
+  struct matrix_guard {
+    gfgpu_matrix *m = nullptr;
+    ~matrix_guard() { gfgpu_matrix_destroy(m); }
+  } dK;
+  if (order == 2) GFGPU_CALL(gfgpu_matrix_create(ctx_, int64_t(need_all), int64_t(need_all), &dK.m));
   for (auto &it : terms) {
     const auto &td = ws.tree_info(it.first);
     const recognised_term &rt = it.second;
@@ -319,37 +377,37 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
       if (gmm::mat_nrows(K) < need || gmm::mat_ncols(K) < need) gmm::resize(K, need, need);
     } else {
       GFGPU_CALL(gfgpu_term_assemble_host(e.term, U.data(), GFGPU_TANGENT, nullptr, nullptr));
-      const int64_t nnz = gfgpu_term_nnz(e.term);
-      if (gfgpu_term_pattern_generation(e.term) != e.generation) {
-        e.jc.resize(ndof + 1);
-        e.ir.resize(size_t(nnz));
-        GFGPU_CALL(gfgpu_term_export_csc_host(e.term, e.jc.data(), e.ir.data(), nullptr));
-        e.generation = gfgpu_term_pattern_generation(e.term);
-      }
-      std::vector<double> pr((size_t)nnz, 0.0);
-      GFGPU_CALL(gfgpu_term_export_csc_host(e.term, nullptr, nullptr, pr.data()));
-      double t2 = now_s();
-      t_device += t2 - t1;
-      // fill gmm::col_matrix<rsvector>: each column is a row-sorted vector of (index, value)
-      // (gmm_vector.h:913-1030).  Empty columns take the device column as is; otherwise add.
-      getfem::model_real_sparse_matrix &K = ws.assembled_matrix();
-      const size_type need = std::max<size_type>(nprim, I.first() + ndof);
-      if (gmm::mat_nrows(K) < need || gmm::mat_ncols(K) < need) gmm::resize(K, need, need);
-      const size_type off = I.first();
-      for (size_type j = 0; j < ndof; ++j) {
-        gmm::rsvector<double> &col = K[off + j];
-        const int64_t b = e.jc[j], en = e.jc[j + 1];
-        if (col.nb_stored() == 0) {
-          col.base_resize(size_type(en - b));
-          auto itc = col.begin();
-          for (int64_t k = b; k < en; ++k, ++itc) { itc->c = off + size_type(e.ir[size_t(k)]); itc->e = pr[size_t(k)]; }
-        } else {
-          for (int64_t k = b; k < en; ++k) col.w(off + size_type(e.ir[size_t(k)]), col.r(off + size_type(e.ir[size_t(k)])) + pr[size_t(k)]);
-        }
-      }
-      t_fill += now_s() - t2;
+      GFGPU_CALL(gfgpu_matrix_add_term(dK.m, e.term, 1.0, int64_t(I.first()), int64_t(I.first())));
+      t_device += now_s() - t1;
     }
     t0 = now_s();
+  }
+  if (order == 2) {
+    double t1 = now_s();
+    const int64_t nnz = gfgpu_matrix_nnz(dK.m);
+    std::vector<int64_t> jc(need_all + 1);
+    std::vector<int32_t> ir((size_t)nnz);
+    std::vector<double> pr((size_t)nnz);
+    GFGPU_CALL(gfgpu_matrix_export_csc_host(dK.m, jc.data(), ir.data(), pr.data()));
+    double t2 = now_s();
+    t_device += t2 - t1;
+    // fill gmm::col_matrix<rsvector>: each column is a row-sorted vector of (index, value) (gmm_vector.h:913-1030).
+    // Empty columns take the device column as is; otherwise add (accumulate-into-aliased-K, workspace.cc:805-812).
+    getfem::model_real_sparse_matrix &K = ws.assembled_matrix();
+    if (gmm::mat_nrows(K) < need_all || gmm::mat_ncols(K) < need_all) gmm::resize(K, need_all, need_all);
+    for (size_type j = 0; j < need_all; ++j) {
+      const int64_t b = jc[j], en = jc[j + 1];
+      if (b == en) continue;
+      gmm::rsvector<double> &col = K[j];
+      if (col.nb_stored() == 0) {
+        col.base_resize(size_type(en - b));
+        auto itc = col.begin();
+        for (int64_t k = b; k < en; ++k, ++itc) { itc->c = size_type(ir[size_t(k)]); itc->e = pr[size_t(k)]; }
+      } else {
+        for (int64_t k = b; k < en; ++k) col.w(size_type(ir[size_t(k)]), col.r(size_type(ir[size_t(k)])) + pr[size_t(k)]);
+      }
+    }
+    t_fill += now_s() - t2;
   }
 }
 

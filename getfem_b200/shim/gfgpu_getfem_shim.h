@@ -26,6 +26,11 @@ struct recognised_term {
 // Matches the ORDER-1 tree of `ws` number `itree` (as printed by ga_tree_to_string after the
 // reference's semantic analysis) against the families of include/gfgpu.h.  Returns false if unknown.
 bool recognise_tree(const getfem::ga_workspace &ws, getfem::size_type itree, recognised_term &out);
+// ga_workspace::add_tree SUMS the expressions that share (mim, region, test variables) into one tree
+// (getfem_generic_assembly_workspace.cc:472-493): this splits such a tree "(A)+(B)" into its recognised summands.
+// At most one summand may carry a tangent: the reference thresholds the element matrix of the SUM
+// (C&E.cc:4889,4898), which two separately assembled bilinear forms would not reproduce.
+bool recognise_tree_sum(const getfem::ga_workspace &ws, getfem::size_type itree, std::vector<recognised_term> &out);
 
 // Device-side state of one (mesh, mesh_fem, mesh_im, term); reusable across Newton iterations.
 class device_assembler {

@@ -262,6 +262,7 @@ class ga_workspace:
         self.terms = []       # (family, variable, params, mim, DeviceTerm or None)
         self._K = None
         self._R = None
+        self._Kdev = None
 
     # ---- declaration API (generic_assembly.h:453-470)
     def add_fem_variable(self, name, mf, I, V):
@@ -307,6 +308,16 @@ class ga_workspace:
                 raise capi.GfgpuError("a region must hold either convexes or faces, not both")
         if fam == "nsource" and (region is None or not region.is_only_faces()):
             raise capi.GfgpuError("Normal is only defined on a region of faces")
+        # ga_workspace::add_tree sums the expressions that share (mim, region, test variable) into ONE tree
+        # (workspace.cc:472-493): their element matrices are thresholded together (C&E.cc:4889).  Two bilinear forms on
+        # one region would therefore not reproduce the reference's pattern when assembled separately: refuse.
+        if fam not in ("source", "nsource"):
+            key = None if region is None else frozenset(region._items)
+            for f2, v2, _, mim2, _, rg2 in self.terms:
+                if f2 not in ("source", "nsource") and v2 == var and mim2 is mim and \
+                        (None if rg2 is None else frozenset(rg2._items)) == key:
+                    raise capi.GfgpuError("several bilinear forms on one region are thresholded together by the reference; "
+                                          "not handled by the device path")
         self.terms.append([fam, var, params, mim, None, region])
         return len(self.terms) - 1
 
@@ -332,40 +343,41 @@ class ga_workspace:
         return dev
 
     def assembly(self, order):
-        """order 1: residual vector; order 2: tangent matrix (workspace.cc:791-936).  One term per
-        workspace is assembled on the device; several terms are summed on the host side."""
+        """order 1: residual vector; order 2: tangent matrix (workspace.cc:791-936).  Every term is assembled on the
+        device; the tangents are accumulated there into one matrix (capi.DeviceMatrix) and exported once."""
         if order not in (1, 2):
             raise capi.GfgpuError("only assembly orders 1 and 2 are handled by the device path")
         if not self.terms:
             raise capi.GfgpuError("no expression")
         if order == 2:
-            mats = []
+            # every order-2 tree adds into ONE matrix (workspace.cc:791-936): accumulated on the device
+            n = self._term(0).ndof
+            if self._Kdev is None:
+                self._Kdev = capi.DeviceMatrix(self.ctx, n)
+            self._Kdev.clear(keep_pattern=False)
         else:
             vec = None
         for k in range(len(self.terms)):
-            if order == 2 and self.terms[k][0] in ("source", "nsource") and len(self.terms) > 1:
+            if order == 2 and self.terms[k][0] in ("source", "nsource"):
                 continue  # an order-1 term has no order-2 tree (workspace.cc:545-600)
             dev = self._term(k)
             mf, V = self.variables[self.terms[k][1]]
             U = None if V is None else np.ascontiguousarray(V, np.float64)
             if order == 2:
                 dev.assemble_host(U, capi.TANGENT, None, None)
-                mats.append(dev.export_csc())
+                self._Kdev.add_term(dev, 1.0, 0, 0)
             else:
                 R = np.empty(dev.ndof)
                 dev.assemble_host(U, capi.RESIDUAL, None, R)
                 vec = R if vec is None else vec + R
         if order == 2:
-            if len(mats) == 1:
-                self._K = mats[0]
-            else:
-                import scipy.sparse as sp
-                n = self._term(0).ndof
-                S = sum(sp.csc_matrix((pr, ir, jc), shape=(n, n)) for jc, ir, pr in mats).tocsc()
-                S.sort_indices()
-                self._K = (S.indptr.astype(np.int64), S.indices.astype(np.int32), S.data)
+            self._K = self._Kdev.export_csc()
         else:
             self._R = vec
+
+    def assembled_matrix_device(self):
+        """The device-resident tangent of the last assembly(2) (capi.DeviceMatrix): csc_view(), mult(), ..."""
+        return self._Kdev
 
     def assembled_matrix(self):
         """(jc, ir, pr): the layout of gmm::csc_matrix::init_with(K) (gmm_matrix.h:545-566)."""

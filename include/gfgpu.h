@@ -33,6 +33,7 @@ typedef struct gfgpu_mesh gfgpu_mesh;   /* SoA node coordinates + connectivity *
 typedef struct gfgpu_fem gfgpu_fem;     /* element->dof table (mesh_fem) */
 typedef struct gfgpu_tables gfgpu_tables; /* reference tables at the quadrature points */
 typedef struct gfgpu_term gfgpu_term;   /* one compiled weak-form term + its pattern */
+typedef struct gfgpu_matrix gfgpu_matrix; /* the workspace-level tangent: sum of terms, resident on the device */
 
 /* geometric transformation kinds (bgeot_geometric_trans.cc:600-672) */
 enum { GFGPU_GT_PK = 0 /* affine simplex, is_linear() */, GFGPU_GT_QK = 1 /* multilinear, K per Gauss point */ };
@@ -175,6 +176,27 @@ int gfgpu_term_residual_view(gfgpu_term *t, const double **R_dev);
 /* host export of the pattern / values / residual (any pointer may be NULL) */
 int gfgpu_term_export_csc_host(gfgpu_term *t, int64_t *jc_host, int32_t *ir_host, double *pr_host);
 int gfgpu_term_export_residual_host(gfgpu_term *t, double *R_host);
+
+/* ---- workspace-level tangent on the device.  ga_workspace::assembly(2) adds every order-2 tree
+ * into ONE gmm::col_matrix<rsvector> at the variables' intervals (getfem_generic_assembly_workspace.cc:791-936;
+ * add_elem_matrix C&E.cc:4853-4936); a model sums brick matrices into its tangent and forms the residual of linear bricks
+ * as K*u (getfem_models.cc:2536-2620, 2753-2900).  gfgpu_matrix is that container, kept in HBM:
+ *   add_term   K(row_off + r, col_off + c) += alpha * term(r, c) over the term's stored entries.  The pattern is the UNION
+ *              of what was added (an entry stays stored even if a later term cancels it, like rsvector); values are summed
+ *              in the order of the calls; no atomics, bitwise reproducible.  The term must have an assembled tangent.
+ *   clear      keep_pattern != 0: zero the values (next Newton iteration); 0: forget the pattern as well
+ *   mult       y = beta*y + alpha*K x (transposed == 0) or alpha*K^T x (transposed != 0), fixed summation order
+ *   export / view: gmm::csc_matrix layout (gmm_matrix.h:545-566), like the term-level calls. */
+int gfgpu_matrix_create(gfgpu_ctx *ctx, int64_t nrows, int64_t ncols, gfgpu_matrix **out);
+int gfgpu_matrix_destroy(gfgpu_matrix *m);
+int gfgpu_matrix_clear(gfgpu_matrix *m, int keep_pattern);
+int gfgpu_matrix_add_term(gfgpu_matrix *m, gfgpu_term *t, double alpha, int64_t row_off, int64_t col_off);
+int64_t gfgpu_matrix_nnz(gfgpu_matrix *m);
+int64_t gfgpu_matrix_pattern_generation(gfgpu_matrix *m);
+int gfgpu_matrix_csc_view(gfgpu_matrix *m, const int64_t **jc_dev, const int32_t **ir_dev, const double **pr_dev);
+int gfgpu_matrix_export_csc_host(gfgpu_matrix *m, int64_t *jc_host, int32_t *ir_host, double *pr_host);
+int gfgpu_matrix_mult_dev(gfgpu_matrix *m, int transposed, double alpha, const double *x_dev, double beta, double *y_dev);
+int gfgpu_matrix_mult_host(gfgpu_matrix *m, int transposed, double alpha, const double *x_host, double beta, double *y_host);
 
 /* ---- multi-GPU: element blocks per rank, column-owned CSC slabs, one halo exchange per assembly.
  * Replaces the reference's MPI scheme (per-rank partial matrices summed with MPI_SUM_SPARSE_MATRIX /

@@ -69,6 +69,8 @@ def assemble(pts, conn, elem_dof, ndof, Q, w, gt_grad, phi, gphi, gt_linear, fam
     ne, ng = conn.shape
     nd = elem_dof.shape[1]
     L = lib()
+    if region is None and nq is not None:  # all-point tables were passed: the volume points come first
+        w, gt_grad, phi, gphi = (np.ascontiguousarray(t[:nq]) for t in (w, gt_grad, phi, gphi))
     if region is None:
         h = L.gfo_assemble(pts.shape[1], ne, ng, _p(pts), _p(conn), nd, Q, _p(elem_dof), ndof, len(w), _p(w),
                            _p(gt_grad), _p(phi), _p(gphi), int(gt_linear), FAMILIES[family], _p(params), _p(U),

@@ -19,6 +19,9 @@
 //   family=laplace|elast|svk|nh_ciarlet|nh_bonet|mass|source  lambda=1 mu=1 a=1
 //   family=nsource (normal source term, getfem_models.cc:4290-4299; boundary regions only)
 //   region=all|outer|xmax|zmin|half   (outer faces / faces on x=1 / on z=0 (last coord) / convexes with barycentre x<0.5)
+//   family2=.. region2=.. a2=..  family3=.. region3=.. a3=..   further expressions of the SAME workspace (linear
+//       families laplace|mass|source|nsource|elast with constants a2/f2/g2/lambda2/mu2 ...): every tree adds into the one
+//       K / V, as a model's bricks do
 //   u=smooth|random|zero  out=DIR  mode=dump|time|model  threads=T reps=R
 #include "getfem/getfem_regular_meshes.h"
 #include "getfem/getfem_mesh_fem.h"
@@ -34,6 +37,7 @@
 #include <cstdint>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <random>
 #include <string>
 #include <sys/stat.h>
@@ -135,7 +139,7 @@ int main(int argc, char **argv) {
   const std::string rgname = gets("region", "all");
   getfem::mesh_region rg_all = getfem::mesh_region::all_convexes();
   getfem::mesh_region rg_sel;
-  if (rgname != "all") {
+  auto make_region = [&](const std::string &rgname, getfem::mesh_region &rg_sel) {
     if (rgname == "half") {
       for (dal::bv_visitor cv(m.convex_index()); !cv.finished(); ++cv) {
         double bx = 0;
@@ -153,8 +157,36 @@ int main(int argc, char **argv) {
         if (keep) rg_sel.add(v.cv(), v.f());
       }
     }
-  }
+  };
+  if (rgname != "all") make_region(rgname, rg_sel);
   const getfem::mesh_region &rg_use = rgname == "all" ? rg_all : rg_sel;
+  // further expressions of the same workspace
+  struct extra_term { std::string family, region, expr, sfx; getfem::mesh_region rg; std::vector<double> c_a, c_f, c_g, c_l, c_m; };
+  std::vector<std::unique_ptr<extra_term>> extras;
+  for (int t = 2; t <= 4; ++t) {
+    const std::string sfx = std::to_string(t);
+    if (!a.count("family" + sfx)) continue;
+    std::unique_ptr<extra_term> e(new extra_term);
+    e->family = a["family" + sfx];
+    e->region = a.count("region" + sfx) ? a["region" + sfx] : "all";
+    e->sfx = sfx;
+    if (e->region != "all") make_region(e->region, e->rg);
+    const double ac = a.count("a" + sfx) ? std::stod(a["a" + sfx]) : 1.0;
+    e->c_a = {ac};
+    e->c_l = {a.count("lambda" + sfx) ? std::stod(a["lambda" + sfx]) : 1.0};
+    e->c_m = {a.count("mu" + sfx) ? std::stod(a["mu" + sfx]) : 1.0};
+    for (int k = 0; k < Q; ++k) e->c_f.push_back(ac * double(k + 1));
+    for (int k = 0; k < Q * dim; ++k) e->c_g.push_back(ac * (0.5 + 0.37 * double(k)) * ((k % 3) == 1 ? -1.0 : 1.0));
+    if (e->family == "laplace") e->expr = "a" + sfx + "*Grad_u:Grad_Test_u";
+    else if (e->family == "mass") e->expr = "a" + sfx + "*u.Test_u";
+    else if (e->family == "source") e->expr = Q == 1 ? "-f" + sfx + "*Test_u" : "-f" + sfx + ".Test_u";
+    else if (e->family == "nsource")
+      e->expr = Q == 1 ? "((g" + sfx + ").Normal)*Test_u" : "(Reshape(g" + sfx + ",qdim(u),meshdim)*Normal).Test_u";
+    else if (e->family == "elast")
+      e->expr = "(Div_u*((lambda" + sfx + ")*Id(meshdim))+(2*(mu" + sfx + "))*Sym(Grad_u)):Grad_Test_u";
+    else { std::fprintf(stderr, "family%s=%s not handled\n", sfx.c_str(), e->family.c_str()); return 2; }
+    extras.push_back(std::move(e));
+  }
 
   // ---- expression of the family (the brick strings of the reference)
   std::string expr;
@@ -216,6 +248,15 @@ int main(int argc, char **argv) {
     } else
       ws.add_fixed_size_constant("params", c_params);
     ws.add_expression(expr, mim, rg);
+    for (auto &e : extras) {
+      ws.add_fixed_size_constant("a" + e->sfx, e->c_a);
+      ws.add_fixed_size_constant("f" + e->sfx, e->c_f);
+      ws.add_fixed_size_constant("g" + e->sfx, e->c_g);
+      ws.add_fixed_size_constant("lambda" + e->sfx, e->c_l);
+      ws.add_fixed_size_constant("mu" + e->sfx, e->c_m);
+      if (e->region == "all") ws.add_expression(e->expr, mim, getfem::mesh_region::all_convexes());
+      else ws.add_expression(e->expr, mim, e->rg);
+    }
   };
 
   std::printf("{\"dim\": %d, \"ne\": %zu, \"ndof\": %zu, \"nd\": %zu, \"ng\": %zu, \"nq\": %zu, "
@@ -346,6 +387,18 @@ int main(int argc, char **argv) {
     }
     npy_i32(out + "/items_cv.npy", {icv.size()}, icv);
     npy_i32(out + "/items_f.npy", {ifc.size()}, ifc);
+  }
+  for (auto &e : extras) {
+    if (e->region != "all") {
+      std::vector<int32_t> icv, ifc;
+      for (getfem::mr_visitor v(e->rg, m); !v.finished(); ++v) {
+        icv.push_back(int32_t(v.cv()));
+        ifc.push_back(v.f() == getfem::short_type(-1) ? -1 : int32_t(v.f()));
+      }
+      npy_i32(out + "/items" + e->sfx + "_cv.npy", {icv.size()}, icv);
+      npy_i32(out + "/items" + e->sfx + "_f.npy", {ifc.size()}, ifc);
+    }
+    npy_f64(out + "/gdata" + e->sfx + ".npy", {e->c_g.size()}, e->c_g);
   }
   { // tables at ALL integration points (volume points first, then the points of face 0, 1, ...:
     // approx_integration::valid_method, getfem_integration.cc:353-368) + reference normals of the faces

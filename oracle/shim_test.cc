@@ -89,6 +89,8 @@ int main(int argc, char **argv) {
       if (rgname == "outer" || (rgname == "xmax" && un[0] > 0.999)) rg_sel.add(v.cv(), v.f());
     }
   }
+  getfem::mesh_region rg_outer;
+  getfem::outer_faces_of_mesh(m, rg_outer);
   const getfem::mesh_region rg_all = getfem::mesh_region::all_convexes();
   const getfem::mesh_region &rg = rgname == "all" ? rg_all : rg_sel;
   auto setup = [&](getfem::ga_workspace &ws) {
@@ -100,6 +102,11 @@ int main(int argc, char **argv) {
     ws.add_fixed_size_constant("f", c_f);
     ws.add_fixed_size_constant("g", c_g);
     ws.add_expression(expr, mim, rg);
+    if (a.count("model")) {  // a model-like workspace: + Robin mass on the outer faces + Neumann load + volumic source
+      ws.add_expression("a*u.Test_u", mim, rg_outer);
+      ws.add_expression(Q == 1 ? "-((g).Normal)*Test_u" : "-(Reshape(g,qdim(u),meshdim)*Normal).Test_u", mim, rg_outer);
+      ws.add_expression(Q == 1 ? "-f*Test_u" : "-(f.Test_u)", mim);
+    }
   };
   // ---- reference on the CPU
   getfem::ga_workspace wr;

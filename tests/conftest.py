@@ -37,6 +37,27 @@ def load_golden(name):
         d["fparams"] = d["gdata"].astype(np.float64)
     else:
         d["fparams"] = np.array([a]) if d["family"] in ("laplace", "mass") else np.array([lam, mu])
+    # further expressions of the same workspace (family2.., make_golden "m_*"): (family, parameters, region, region name)
+    d["extra_terms"] = []
+    for t in (2, 3, 4):
+        ft = args.get("family%d" % t)
+        if not ft:
+            continue
+        at = float(args.get("a%d" % t, 1.0))
+        if ft == "source":
+            fp = -at * np.arange(1, d["Q"] + 1, dtype=np.float64)
+        elif ft == "nsource":
+            fp = d["gdata%d" % t].astype(np.float64)
+        elif ft == "elast":
+            fp = np.array([float(args.get("lambda%d" % t, 1.0)), float(args.get("mu%d" % t, 1.0))])
+        else:
+            fp = np.array([at])
+        rg = None
+        if "items%d_cv" % t in d:
+            rg = {"items_cv": d["items%d_cv" % t], "items_f": d["items%d_f" % t]}
+            if (rg["items_f"] >= 0).any():
+                rg.update(face_first=d["face_first"], face_nq=d["face_nq"], ref_normals=d["ref_normals"])
+        d["extra_terms"].append((ft, fp, rg, args.get("region%d" % t, "all")))
     # mesh regions: items in mr_visitor order; with faces the tables cover ALL integration points
     d["region"] = None
     d["tables"] = (d["quad_w"], d["gt_grad"], d["phi"], d["gphi"])
@@ -45,6 +66,8 @@ def load_golden(name):
         if (d["items_f"] >= 0).any():
             d["region"].update(face_first=d["face_first"], face_nq=d["face_nq"], ref_normals=d["ref_normals"])
             d["tables"] = (d["all_w"], d["all_gt_grad"], d["all_phi"], d["all_gphi"])
+    if any(rg is not None and "face_first" in rg for _, _, rg, _ in d["extra_terms"]):
+        d["tables"] = (d["all_w"], d["all_gt_grad"], d["all_phi"], d["all_gphi"])
     return d
 
 
@@ -70,3 +93,18 @@ def make_region(m, name):
                 (name == "zmin" and (abs(P[:, -1]) < 1e-12).all()):
             rg.add(cv, f)
     return rg
+
+
+def csc_sum(mats, n):
+    """Sum of CSC matrices (jc, ir, pr) with the UNION pattern: stored entries stay stored even when they are or become
+    exactly zero (what adding into gmm::col_matrix<rsvector> does; scipy's + would drop them).  Terms are added in order."""
+    keys = np.concatenate([np.repeat(np.arange(n, dtype=np.int64), np.diff(jc)) * n + np.asarray(ir, np.int64)
+                           for jc, ir, _ in mats])
+    vals = np.concatenate([pr for _, _, pr in mats])
+    uk, inv = np.unique(keys, return_inverse=True)
+    out = np.zeros(len(uk))
+    np.add.at(out, inv, vals)
+    cols = uk // n
+    jc = np.zeros(n + 1, np.int64)
+    np.add.at(jc, cols + 1, 1)
+    return np.cumsum(jc), (uk % n).astype(np.int64), out

@@ -54,6 +54,15 @@ CASES = {
     "r_nsource3d_q2vec_outer": "dim=3 n=2 gt=qk k=2 q=3 im=6 family=nsource region=outer u=random a=0.7",
     "r_elast3d_p2_half": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=elast region=half u=random lambda=1 mu=1",
     "r_lap3d_p1_half": "dim=3 n=4 gt=pk k=1 q=1 im=2 family=laplace region=half u=random",
+    # several expressions in ONE workspace (what a model's bricks add up to): stiffness + Robin boundary mass + Neumann
+    # load + normal source; K = sum of the order-2 trees (union pattern), V = sum of the order-1 trees
+    "m_elast_robin_neumann_p2": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=elast u=random lambda=1.2 mu=0.8 "
+                                "family2=mass region2=outer a2=3.5 family3=source region3=xmax a3=0.6 "
+                                "family4=nsource region4=zmin a4=0.9",
+    "m_poisson_rhs_robin_2d": "dim=2 n=6 gt=pk k=1 q=1 im=2 family=laplace u=random a=1.3 family2=source a2=2.0 "
+                              "family3=mass region3=outer a3=5.0 family4=nsource region4=outer a4=0.7",
+    "m_lap_q2_robin": "dim=3 n=2 gt=qk k=2 q=1 im=6 family=laplace u=random a=0.9 family2=mass region2=zmin a2=4.0 "
+                      "family3=source a3=1.1",
     "r_nh_ciarlet_q2_half": "dim=3 n=2 gt=qk k=2 q=3 im=6 family=nh_ciarlet region=half u=smooth lambda=1 mu=1 uamp=0.02",
 }
 
@@ -71,7 +80,7 @@ def main():
         arrs["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
         for k in ("conn", "elem_dof", "K_jc", "K_ir"):
             arrs[k] = arrs[k].astype(np.int32)
-        if "region=" not in args:  # the all-point tables and face data only travel with the region fixtures
+        if "region" not in args:  # the all-point tables and face data only travel with the region fixtures
             for k in ("all_w", "all_x", "all_gt_grad", "all_phi", "all_gphi", "face_first", "face_nq", "ref_normals",
                       "gdata"):
                 arrs.pop(k, None)

@@ -34,6 +34,11 @@ CASES = [
     "dim=3 n=3 gt=qk k=2 q=3 im=6 family=nsource region=xmax",
     "dim=3 n=6 gt=pk k=2 q=3 im=4 family=elast region=half",
     "dim=3 n=3 gt=qk k=2 q=3 im=6 family=nh_ciarlet region=half",
+    # model-like workspaces: stiffness + Robin boundary mass + normal source + volumic source, ONE tangent accumulated
+    # on the device (gfgpu_matrix_*) and downloaded once
+    "dim=3 n=4 gt=pk k=2 q=3 im=4 family=elast model=1",
+    "dim=2 n=24 gt=pk k=1 q=1 im=2 family=laplace model=1",
+    "dim=3 n=3 gt=qk k=2 q=3 im=6 family=nh_ciarlet model=1",
 ]
 
 

@@ -8,19 +8,42 @@ from conftest import golden_names, load_golden
 
 pytestmark = pytest.mark.gpu
 
-EXPR = {
-    "laplace": "a*Grad_u.Grad_Test_u",
-    "mass": "a*u.Test_u",
-    "elast": "(Div_u*((lambda)*Id(meshdim))+(2*(mu))*Sym(Grad_u)):Grad_Test_u",
-    "svk": "((Id(meshdim)+Grad_u)*(Saint_Venant_Kirchhoff_PK2(Grad_u,params))):Grad_Test_u",
-    "nh_ciarlet": "((Id(meshdim)+Grad_u)*(Compressible_Neo_Hookean_Ciarlet_PK2(Grad_u,params))):Grad_Test_u",
-    "nh_bonet": "((Id(meshdim)+Grad_u)*(Compressible_Neo_Hookean_Bonet_PK2(Grad_u,params))):Grad_Test_u",
-    "source": "-f.Test_u",  # "-f*Test_u" when qdim = 1 (the strings of oracle/ref_driver.cc)
-    "nsource": "(Reshape(g,qdim(u),meshdim)*Normal).Test_u",  # "((g).Normal)*Test_u" when qdim = 1
+EXPR = {  # {s}: suffix of the constants' names when several expressions share a workspace
+    "laplace": "a{s}*Grad_u.Grad_Test_u",
+    "mass": "a{s}*u.Test_u",
+    "elast": "(Div_u*((lambda{s})*Id(meshdim))+(2*(mu{s}))*Sym(Grad_u)):Grad_Test_u",
+    "svk": "((Id(meshdim)+Grad_u)*(Saint_Venant_Kirchhoff_PK2(Grad_u,params{s}))):Grad_Test_u",
+    "nh_ciarlet": "((Id(meshdim)+Grad_u)*(Compressible_Neo_Hookean_Ciarlet_PK2(Grad_u,params{s}))):Grad_Test_u",
+    "nh_bonet": "((Id(meshdim)+Grad_u)*(Compressible_Neo_Hookean_Bonet_PK2(Grad_u,params{s}))):Grad_Test_u",
+    "source": "-f{s}.Test_u",  # "-f*Test_u" when qdim = 1 (the strings of oracle/ref_driver.cc)
+    "nsource": "(Reshape(g{s},qdim(u),meshdim)*Normal).Test_u",  # "((g).Normal)*Test_u" when qdim = 1
 }
 
 
-def build_ws(dim, nsub, gt, k, Q, im, family, params, U=None, region=None):
+def add_term(ws, mim, m, Q, family, params, region, sfx=""):
+    from conftest import make_region
+    expr = EXPR[family].format(s=sfx)
+    if family == "source":
+        ws.add_fixed_size_constant("f" + sfx, [-p for p in params])  # the goldens carry F = -f
+        if Q == 1:
+            expr = "-f%s*Test_u" % sfx
+    elif family == "nsource":
+        ws.add_fixed_size_constant("g" + sfx, params)
+        if Q == 1:
+            expr = "((g%s).Normal)*Test_u" % sfx
+    elif family in ("laplace", "mass"):
+        ws.add_fixed_size_constant("a" + sfx, [params[0]])
+    elif family == "elast":
+        ws.add_fixed_size_constant("lambda" + sfx, [params[0]])
+        ws.add_fixed_size_constant("mu" + sfx, [params[1]])
+    else:
+        ws.add_fixed_size_constant("params" + sfx, params)
+    rg = make_region(m, region)
+    ws.add_expression(expr, mim, rg)
+    return rg
+
+
+def build_ws(dim, nsub, gt, k, Q, im, family, params, U=None, region=None, extra=()):
     import getfem_b200 as gf
     m = gf.mesh()
     gf.regular_unit_mesh(m, nsub, "GT_%s(%d,1)" % (gt, dim))
@@ -35,26 +58,9 @@ def build_ws(dim, nsub, gt, k, Q, im, family, params, U=None, region=None):
     elif callable(U):
         U = U(mf)
     ws.add_fem_variable("u", mf, slice(0, ndof), U)
-    expr = EXPR[family]
-    if family == "source":
-        ws.add_fixed_size_constant("f", [-p for p in params])  # the goldens carry F = -f
-        if Q == 1:
-            expr = "-f*Test_u"
-    elif family == "nsource":
-        ws.add_fixed_size_constant("g", params)
-        if Q == 1:
-            expr = "((g).Normal)*Test_u"
-    elif family in ("laplace", "mass"):
-        ws.add_fixed_size_constant("a", [params[0]])
-    elif family == "elast":
-        ws.add_fixed_size_constant("lambda", [params[0]])
-        ws.add_fixed_size_constant("mu", [params[1]])
-    else:
-        ws.add_fixed_size_constant("params", params)
-    from conftest import make_region
-    rg = make_region(m, region)
-    ws.add_expression(expr, mim, rg)
-    ws.region = rg
+    ws.region = add_term(ws, mim, m, Q, family, params, region)
+    for t, (fam2, fp2, _, rgname2) in enumerate(extra):
+        add_term(ws, mim, m, Q, fam2, list(fp2), rgname2, str(t + 2))
     return ws, mf, m, U
 
 
@@ -65,7 +71,7 @@ def test_workspace_matches_reference_golden(name):
     dim = int(a["dim"])
     nsub = [int(a["n"])] * dim if "n" in a else [int(a["nx"]), int(a["ny"]), int(a["nz"])][:dim]
     ws, mf, m, _ = build_ws(dim, nsub, "PK" if g["gt_linear"] else "QK", int(a["k"]), g["Q"], int(a["im"]),
-                            g["family"], g["fparams"], g["U"], a.get("region"))
+                            g["family"], g["fparams"], g["U"], a.get("region"), g["extra_terms"])
     # device first-touch numbering == mesh_fem::enumerate_dof, bit for bit
     assert mf.nb_dof() == g["meta"]["ndof"]
     assert np.array_equal(mf.ind_scalar_basic_dof_of_element(), g["elem_dof"])

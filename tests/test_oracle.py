@@ -15,6 +15,15 @@ def test_oracle_matches_reference(name):
     jc, ir, pr, R = oracle.assemble(g["pts"], g["conn"], g["elem_dof"], ndof, g["Q"], w, gt_grad, phi, gphi,
                                     g["gt_linear"], g["family"], g["fparams"], g["U"], region=g["region"],
                                     nq=g["meta"]["nq"])
+    if g["extra_terms"]:  # several expressions in one workspace: every tree adds into the same K / V
+        from conftest import csc_sum
+        mats = [(jc, ir, pr)]
+        for fam, fp, rg, _ in g["extra_terms"]:
+            jc2, ir2, pr2, R2 = oracle.assemble(g["pts"], g["conn"], g["elem_dof"], ndof, g["Q"], w, gt_grad, phi, gphi,
+                                                g["gt_linear"], fam, fp, g["U"], region=rg, nq=g["meta"]["nq"])
+            mats.append((jc2, ir2, pr2))
+            R = R + R2
+        jc, ir, pr = csc_sum(mats, ndof)
     assert np.array_equal(jc, g["K_jc"]), "column pointers differ (pattern not bit-exact)"
     assert np.array_equal(ir, g["K_ir"]), "row indices differ (pattern not bit-exact)"
     rel = np.linalg.norm(pr - g["K_pr"]) / max(np.linalg.norm(g["K_pr"]), 1e-300)
