@@ -32,6 +32,10 @@ WORKLOADS = {
     "c4": (3, "QK", 2, 3, 6, "nh_ciarlet", [1.0, 1.0], 64, "3D Neo-Hookean (Ciarlet) Q2 hexahedra, tangent+residual"),
     "c5": (3, "QK", 4, 1, 8, "laplace", [1.0], 48, "3D Q4 hexahedral Laplacian"),
 }
+# algorithmic fp64 flops per element (FMA = 2), SURVEY 8(d): c2 K/inverse/gradients/K_e of a P1 tetrahedron (c1: the 2D
+# analogue); c3 constant-coefficient elasticity through reference tensors; c4 tangent with the 3-of-9 gradient sparsity;
+# c5 sum-factorised Q4 matrix assembly.  The kernels' own operation counts are in DESIGN.md section 3.
+ALG_FLOPS = {"c1": 0.12e3, "c2": 0.3e3, "c3": 20e3, "c4": 1.5e6, "c5": 2.0e6}
 REF_FAMILY = {"laplace": "laplace", "elast": "elast", "nh_ciarlet": "nh_ciarlet"}
 # bounded CPU sample (cells per direction) of each workload: ~10-30 s of reference CPU work
 CPU_SAMPLE_N = {"c1": 512, "c2": 40, "c3": 20, "c4": 8, "c5": 3}
@@ -359,6 +363,8 @@ def main():
         if tj.get("workload") == wl and tj.get("n") == n and tj.get("kernel") == dom:
             traffic = tj.get("traffic_bytes_per_launch")
     achieved = alg_bytes / (kavg[dom] * 1e-3) / 1e9
+    fp64_peak = ctx.measure_fp64_peak()  # TFLOP/s, DFMA probe on this device (outside every timed region)
+    fp64_ach = ALG_FLOPS[wl] * ne_local / (kavg[dom] * 1e-3) / 1e12
     line = {
         "metric": "assembled_elements_per_s", "value": value, "unit": "elements/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -372,6 +378,10 @@ def main():
                      "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_src,
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"]},
+        "roofline_fp64": {"bound": "fp64", "kernel": dom, "achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                          "frac": fp64_ach / fp64_peak, "peak_source": "measured (gfgpu_ctx_measure_fp64_peak, DFMA probe)",
+                          "algorithmic_flops_per_element": ALG_FLOPS[wl],
+                          "step_frac": ALG_FLOPS[wl] * ne_local / (ms_step * 1e-3) / 1e12 / fp64_peak},
         "kernel_ms": kavg,
         "e2e": {"value": e2e_value, "unit": "elements/s", "h2d_bytes_per_step": int(h2d_bytes),
                 "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_ms, "steps": args.e2e_steps},

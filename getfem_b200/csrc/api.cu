@@ -27,6 +27,22 @@ void set_last_error(const std::string &s) { g_err = s; }
 
 using gf::DevBuf;
 
+namespace gf {
+// fp64 FMA throughput probe: 8 independent accumulator chains per thread, operands in registers
+__global__ void __launch_bounds__(256) k_dfma_probe(double *out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 123.456) out[0] = s;  // never true: keeps the chains alive
+}
+}  // namespace gf
+
 extern "C" {
 
 const char *gfgpu_last_error(void) { return gf::g_err.c_str(); }
@@ -74,6 +90,34 @@ int gfgpu_ctx_synchronize(gfgpu_ctx *ctx) {
 }
 
 int64_t gfgpu_ctx_bytes_in_use(gfgpu_ctx *ctx) { return ctx ? ctx->bytes : 0; }
+
+int gfgpu_ctx_measure_fp64_peak(gfgpu_ctx *ctx, double *tflops) {
+  GF_API_BEGIN
+  GF_REQUIRE(ctx && tflops, "null argument");
+  GF_CUDA(cudaSetDevice(ctx->device));
+  DevBuf<double> out;
+  out.alloc(ctx, 1);
+  cudaEvent_t e0, e1;
+  GF_CUDA(cudaEventCreate(&e0));
+  GF_CUDA(cudaEventCreate(&e1));
+  const int grid = ctx->sm_count * 8, iters = 4096;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {  // first pass = warm-up
+    GF_CUDA(cudaEventRecord(e0, ctx->stream));
+    gf::k_dfma_probe<<<grid, 256, 0, ctx->stream>>>(out.p, iters, 0.999999, 1e-9);
+    GF_LAUNCH_CHECK();
+    GF_CUDA(cudaEventRecord(e1, ctx->stream));
+    GF_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    GF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = 2.0 * 64.0 * iters * 256.0 * grid / (ms * 1e-3) / 1e12;
+    if (rep > 0) best = std::max(best, tf);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops = best;
+  GF_API_END
+}
 
 int gfgpu_mesh_create(gfgpu_ctx *ctx, int dim, int64_t npts, const double *pts, int64_t ne, int ng,
                       const int32_t *conn, int gt_kind, gfgpu_mesh **out) {

@@ -202,6 +202,8 @@ struct gfgpu_term {
   bool rc_ready = false;
   gf::DevBuf<double> rc_M;      // reference tensors per (j,i)
   gf::DevBuf<double> rc_eg;     // per-element geometry
+  gf::DevBuf<double> rc_tgeo;   // per tile: the geometry rows of its distinct elements, in slot order (one bulk copy per tile)
+  int rc_geo_rows = 0;
   gf::DevBuf<double> rc_L;      // low-rank factor of the reference Gram matrix (residual kernel)
   int rc_rank = 0;
   struct alignas(16) PairRec { uint32_t x, y, z, w; };

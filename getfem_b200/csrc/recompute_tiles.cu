@@ -186,6 +186,21 @@ k_tile_elements(TileHdr *__restrict__ hdr, const uint32_t *__restrict__ rstart, 
   }
 }
 
+// CTA per tile: the geometry rows of the tile's distinct elements, copied once into a contiguous per-tile blob so that
+// the tangent kernel stages them with ONE bulk copy (the LDGSTS gather of 8-byte pieces kept the producer warp busy for
+// 1.4 us per tile and cost ~700 shared-memory wavefronts: profiles/round1_tile_trace_producer.txt)
+__global__ void __launch_bounds__(128)
+k_tile_gather_geo(const TileHdr *__restrict__ hdr, const uint32_t *__restrict__ els, int els_stride,
+                  const double *__restrict__ eg, int gsz, int gsp /* padded row length, as in shared memory */,
+                  int rows_stride, double *__restrict__ tgeo) {
+  const int64_t tile = blockIdx.x;
+  const uint32_t nel = hdr[tile].nel;
+  const uint32_t *te = els + (size_t)tile * els_stride;
+  double *o = tgeo + (size_t)tile * rows_stride * gsp;
+  for (uint32_t k = threadIdx.x; k < nel * (uint32_t)gsz; k += blockDim.x)
+    o[(k / gsz) * gsp + k % gsz] = eg[(size_t)te[k / gsz] * gsz + k % gsz];
+}
+
 // Tasks of a tile, longest first:
 //   wide tasks   : one per pair with more than TL_INREC contributions (vertex-diagonal pairs): the warp spreads the
 //                  contributions over its lanes (lane l takes l, l+32, ...) and tree-reduces the accumulators;
@@ -346,11 +361,11 @@ __global__ void k_tile_fill(const TileHdr *__restrict__ hdr, const uint32_t *__r
 //              arrives on empty[b].  No __syncthreads in the steady state.
 struct TileArgs {
   const TileHdr *hdr;
-  const uint32_t *els;
-  int els_stride;
+  const double *tgeo;   // per tile: geo_rows rows of GSP doubles (the tile's distinct elements, slot order; zero padded)
+  int geo_rows;
   const uint4 *rec;
   const uint16_t *dblob;
-  const double *eg, *Mtab;
+  const double *Mtab;
   double sl, smu;  // sign(alpha) * lambda, sign(alpha) * mu (elasticity)
   int64_t nt;
   int zslot, cap_tasks, cap_long, cap_len;
@@ -453,7 +468,7 @@ k_tiles(const TileArgs a) {
     g[a.zslot * GSP + tid % GSP] = 0.0;
   }
   if (tid == 0) {
-    mbar_init(&full[0], 34); mbar_init(&full[1], 34);      // 32 LDGSTS arrivals + expect_tx + "output image free"
+    mbar_init(&full[0], 2); mbar_init(&full[1], 2);        // expect_tx (three bulk copies) + "output image free"
     mbar_init(&empty[0], TL_CW); mbar_init(&empty[1], TL_CW);
   }
   __syncthreads();
@@ -463,13 +478,7 @@ k_tiles(const TileArgs a) {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     // the header and the element ids of the NEXT tile are loaded (into registers) before waiting for its buffer
     TileHdr h;
-    uint32_t e[TL_ROWS];
-    auto fetch = [&](int64_t tile) {
-      h = a.hdr[tile];
-      const uint32_t *els = a.els + (size_t)tile * a.els_stride;
-#pragma unroll
-      for (int r = 0; r < TL_ROWS; ++r) e[r] = r * 32 + lane < (int)h.nel ? els[r * 32 + lane] : 0u;
-    };
+    auto fetch = [&](int64_t tile) { h = a.hdr[tile]; };
     if ((int64_t)blockIdx.x < a.nt) fetch(blockIdx.x);
     int4 hprev[2] = {make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};  // base (lo, hi), len of the tile in each buffer
     auto drain = [&](int b, int4 hp) {
@@ -498,20 +507,15 @@ k_tiles(const TileArgs a) {
         s_hdr[b] = h;
         s_next[b] = 2 * TL_CW;
         const uint32_t nb1 = h.ntasks * 512u, nb2 = h.n_long * (uint32_t)TL_BLOB;
-        mbar_arrive_expect_tx(&full[b], nb1 + nb2);
+        // geometry rows: a whole number of 16-byte units (the blob is zero padded, a spare row may land on the zero slot)
+        const uint32_t nb3 = (h.nel * (uint32_t)(GSP * 8) + 15u) & ~15u;
+        mbar_arrive_expect_tx(&full[b], nb1 + nb2 + nb3);
         bulk_g2s(buf, a.rec + (size_t)h.task0 * 32, nb1, &full[b], pol);
         if (nb2) bulk_g2s(buf + L::blob_off(a.cap_tasks), a.dblob + (size_t)h.r2_0 * (TL_BLOB / 2), nb2, &full[b], pol);
+        if (nb3) bulk_g2s(buf + L::geo_off(a.cap_tasks, a.cap_long), a.tgeo + (size_t)tile * a.geo_rows * GSP, nb3, &full[b], pol);
       }
-      double *g = reinterpret_cast<double *>(buf + L::geo_off(a.cap_tasks, a.cap_long));
-#pragma unroll
-      for (int r = 0; r < TL_ROWS; ++r) {
-        const uint32_t sr = r * 32 + lane;
-        if (sr < h.nel) {
-#pragma unroll
-          for (int k = 0; k < GSZ; ++k) ldgsts8(g + sr * GSP + k, a.eg + (size_t)e[r] * GSZ + k);
-        }
-      }
-      ldgsts_arrive(&full[b]);
+      const unsigned long long tpa = a.trace ? gtimer() : 0;
+      const unsigned long long tpb = tpa;
       // the image of the tile that used this buffer two iterations ago is complete (empty[b] fired): send it
       if (it >= 2) drain(b, hprev[b]);
       if (lane == 0) mbar_arrive(&full[b]);  // output image b is free again
@@ -519,7 +523,8 @@ k_tiles(const TileArgs a) {
       const unsigned long long tp2 = a.trace ? gtimer() : 0;
       if (tile + gridDim.x < a.nt) fetch(tile + gridDim.x);
       if (a.trace && blockIdx.x == 0 && lane == 0 && it < 256) {
-        a.trace[it * 8 + 0] = tp0; a.trace[it * 8 + 1] = tp1; a.trace[it * 8 + 2] = tp2; a.trace[it * 8 + 3] = gtimer() + (h.nel & 0);
+        a.trace[it * 12 + 0] = tp0; a.trace[it * 12 + 1] = tp1; a.trace[it * 12 + 2] = tp2; a.trace[it * 12 + 3] = gtimer() + (h.nel & 0);
+        a.trace[it * 12 + 8] = tpa; a.trace[it * 12 + 9] = tpb; a.trace[it * 12 + 10] = h.nel; a.trace[it * 12 + 11] = h.len;
       }
     }
     // the last two tiles of this CTA: `it` is now the number of tiles it processed
@@ -652,7 +657,7 @@ k_tiles(const TileArgs a) {
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[b]);
     if (a.trace && blockIdx.x == 0 && tid == 0 && it < 256) {
-      a.trace[it * 8 + 4] = tc0; a.trace[it * 8 + 5] = tc1; a.trace[it * 8 + 6] = gtimer(); a.trace[it * 8 + 7] = ntasks;
+      a.trace[it * 12 + 4] = tc0; a.trace[it * 12 + 5] = tc1; a.trace[it * 12 + 6] = gtimer(); a.trace[it * 12 + 7] = ntasks;
     }
   }
 }
@@ -1048,6 +1053,20 @@ void recompute_prepare(gfgpu_term *t) {
   GF_CUDA(cudaStreamSynchronize(s));
   GF_REQUIRE(err == 0, "recompute plan failed (code " + std::to_string(err) + "): tile too large for the compact records");
   if (!t->halo) t->prel.release();  // folded into the pair records
+  // ---- per-tile geometry blobs (one bulk copy per tile in the tangent kernel); the element lists are then done with
+  {
+    int rows = cap_slots + 1;
+    if ((rows * GSPh) & 1) ++rows;  // every tile's blob starts on a 16-byte boundary (bulk copy source alignment)
+    t->rc_geo_rows = rows;
+    t->rc_tgeo.alloc(ctx, (size_t)nt * rows * GSPh);
+    t->rc_tgeo.zero();
+    if (nt) {
+      k_tile_gather_geo<<<(unsigned)nt, 128, 0, s>>>(dh, t->rc_els.p, cap_inc, t->rc_eg.p, GSZ, GSPh, rows, t->rc_tgeo.p);
+      GF_LAUNCH_CHECK();
+    }
+    GF_CUDA(cudaStreamSynchronize(s));
+    t->rc_els.release();
+  }
   t->rc_ready = true;
 }
 
@@ -1075,11 +1094,11 @@ static void launch_tiles(gfgpu_term *t, const double *U, bool do_t, bool do_r) {
   using L = TlSmem<N, RF>;
   TileArgs a;
   a.hdr = (const TileHdr *)t->rc_hdr.p;
-  a.els = t->rc_els.p;
-  a.els_stride = t->rc_cap_inc;
+  a.tgeo = t->rc_tgeo.p;
+  a.geo_rows = t->rc_geo_rows;
   a.rec = (const uint4 *)t->rc_prec.p;
   a.dblob = t->rc_dblob.p;
-  a.eg = t->rc_eg.p; a.Mtab = t->rc_M.p;
+  a.Mtab = t->rc_M.p;
   a.sl = sign * t->par[0]; a.smu = sign * t->par[1];
   a.nt = t->rc_nt;
   a.zslot = t->rc_cap_slots; a.cap_tasks = t->rc_cap_tasks; a.cap_long = t->rc_cap_long; a.cap_len = t->rc_cap_len;
@@ -1087,7 +1106,7 @@ static void launch_tiles(gfgpu_term *t, const double *U, bool do_t, bool do_r) {
   a.trace = nullptr;
   DevBuf<unsigned long long> trace;
   if (getenv("GFGPU_TILE_TRACE")) {
-    trace.alloc(t->ctx, 256 * 8);
+    trace.alloc(t->ctx, 256 * 12);
     trace.zero();
     a.trace = trace.p;
   }
@@ -1099,17 +1118,18 @@ static void launch_tiles(gfgpu_term *t, const double *U, bool do_t, bool do_r) {
   kern<<<grid, TL_THREADS, smem, t->ctx->stream>>>(a);
   GF_LAUNCH_CHECK();
   if (a.trace) {
-    std::vector<unsigned long long> h(256 * 8);
+    std::vector<unsigned long long> h(256 * 12);
     trace.download(h.data());
     GF_CUDA(cudaStreamSynchronize(t->ctx->stream));
     FILE *f = fopen(getenv("GFGPU_TILE_TRACE"), "w");
     if (f) {
-      fprintf(f, "it p_wait_start p_empty_ok p_issued p_fetched c_wait_start c_full_ok c_done ntasks (ns, relative)\n");
+      fprintf(f, "it p_wait_start p_empty_ok p_issued p_fetched c_wait_start c_full_ok c_done ntasks p_tma_issued p_ldgsts_issued nel len (ns, relative)\n");
       const unsigned long long t0 = h[0];
       for (int k = 0; k < 256; ++k) {
         fprintf(f, "%d", k);
-        for (int j = 0; j < 7; ++j) fprintf(f, " %lld", (long long)(h[k * 8 + j] - t0));
-        fprintf(f, " %llu\n", h[k * 8 + 7]);
+        for (int j = 0; j < 7; ++j) fprintf(f, " %lld", (long long)(h[k * 12 + j] - t0));
+        fprintf(f, " %llu %lld %lld %llu %llu\n", h[k * 12 + 7], (long long)(h[k * 12 + 8] - t0), (long long)(h[k * 12 + 9] - t0),
+                h[k * 12 + 10], h[k * 12 + 11]);
       }
       fclose(f);
     }
