@@ -123,7 +123,8 @@ struct alignas(16) TileHdr {
   uint32_t nel, n_long;      // distinct elements staged; tasks that need a descriptor blob (they come first)
   uint32_t n_wide, r2_0;     // pairs with more than TL_INREC contributions (one task each); first blob (task units)
   uint32_t len;              // entries of the tile's CSC segment [base, base + len)
-  uint32_t pad1, pad2, pad3;
+  uint32_t nitems;           // lane items of the normal tasks (an item = up to TL_KG pairs sharing column node + element list)
+  uint32_t pad2, pad3;
 };
 static_assert(sizeof(TileHdr) == 64, "TileHdr layout");
 
@@ -214,11 +215,30 @@ constexpr int TL_INREC = 10;  // largest step count of a normal task = rows of a
 // of a 32-way gather).  Any order inside a count class is correct (the output goes through the shared-memory image,
 // so the lane order has no effect on the global stores); this one only changes bank conflicts.
 constexpr int TL_MAXPAIRS = 4096;
+#ifndef GF_TL_KG
+#define GF_TL_KG 1
+#endif
+constexpr int TL_KG = GF_TL_KG;  // pairs per lane item
+
+// element identity of contribution `ctr` (virtual halo contributions are unique: they never make two pairs equal)
+__device__ __forceinline__ uint32_t tl_elem_of(uint32_t ctr, uint32_t nb, uint32_t nlocal) {
+  return ctr < nlocal ? ctr / nb : (0x80000000u | ctr);
+}
+
+// CTA per tile.  Phase 1 sorts the tile's pairs by (contribution count descending, hash of (column node, element list), pair
+// id): pairs of ONE column node that are fed by the SAME elements become neighbours and are cut into ITEMS of up to TL_KG
+// pairs -- a lane item: the geometry row of a step is loaded once and serves all its pairs.  Phase 2 sorts the items by
+// (count descending, members descending, joint signature of their (j, i) sequences, position): items that are translated copies of each other
+// (structured parts of a mesh) become neighbours, so the lanes of a task mostly read the SAME reference tensor at a step.
+// Outputs: sp_pair (phase-1 order), it_head (per item: members << 16 | position of its first pair in sp_pair), the number
+// of wide pairs (more than TL_INREC contributions: one task each, they come first), of items, of long tasks.
 __global__ void __launch_bounds__(256)
 k_tile_sort_pairs(TileHdr *__restrict__ hdr, const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ csrc,
-                  uint32_t nb, uint32_t nlocal, int use_sig, uint32_t *__restrict__ sp_pair, int *__restrict__ err) {
+                  const int32_t *__restrict__ pJ, uint32_t nb, uint32_t nlocal, int use_sig, uint32_t *__restrict__ sp_pair,
+                  uint32_t *__restrict__ it_head, int *__restrict__ err) {
   __shared__ uint64_t key[TL_MAXPAIRS];
-  __shared__ uint32_t s_nwide, s_ngt2;
+  __shared__ uint8_t same[TL_MAXPAIRS];
+  __shared__ uint32_t s_nwide, s_nitems, s_nit_gt2;
   const int64_t tile = blockIdx.x;
   const TileHdr h = hdr[tile];
   const uint32_t n = h.npairs;
@@ -228,45 +248,104 @@ k_tile_sort_pairs(TileHdr *__restrict__ hdr, const uint32_t *__restrict__ cstart
   }
   uint32_t P = 32;
   while (P < n) P <<= 1;
-  if (threadIdx.x == 0) { s_nwide = 0; s_ngt2 = 0; }
+  if (threadIdx.x == 0) { s_nwide = 0; s_nitems = 0; s_nit_gt2 = 0; }
   __syncthreads();
+  auto bitonic = [&]() {
+    for (uint32_t size = 2; size <= P; size <<= 1)
+      for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+        for (uint32_t k = threadIdx.x; k < P; k += blockDim.x) {
+          const uint32_t partner = k ^ stride;
+          if (partner > k) {
+            const bool up = (k & size) == 0;
+            const uint64_t a = key[k], b = key[partner];
+            if ((a > b) == up) { key[k] = b; key[partner] = a; }
+          }
+        }
+        __syncthreads();
+      }
+  };
+  // ---- phase 1
   for (uint32_t k = threadIdx.x; k < P; k += blockDim.x) {
     uint64_t v = ~0ull;
     if (k < n) {
       const uint32_t p = h.pair0 + k, s0 = cstart[p], cnt = cstart[p + 1] - s0;
       if (cnt > 255u) *err = 3;
-      uint32_t sig = 0;
-      if (use_sig && cnt <= (uint32_t)TL_INREC)
+      uint32_t hh = (uint32_t)pJ[p] * 0x85EBCA6Bu;
+      if (cnt <= (uint32_t)TL_INREC)
         for (uint32_t c = 0; c < cnt; ++c) {
-          const uint32_t ctr = csrc[s0 + c];
-          const uint32_t rr = ctr < nlocal ? ctr % nb : 0xffffu;
-          sig = (sig ^ rr) * 0x9E3779B1u + 0x7F4A7C15u;
-          sig ^= sig >> 15;
+          hh = (hh ^ tl_elem_of(csrc[s0 + c], nb, nlocal)) * 0x9E3779B1u + 0x7F4A7C15u;
+          hh ^= hh >> 15;
         }
       if (cnt > (uint32_t)TL_INREC) atomicAdd(&s_nwide, 1u);
-      if (cnt > 2u) atomicAdd(&s_ngt2, 1u);
-      v = ((uint64_t)(255u - min(cnt, 255u)) << 56) | ((uint64_t)(sig & 0xffffffu) << 32) | k;
+      v = ((uint64_t)(255u - min(cnt, 255u)) << 56) | ((uint64_t)(hh & 0xffffffu) << 32) | k;
     }
     key[k] = v;
   }
   __syncthreads();
-  for (uint32_t size = 2; size <= P; size <<= 1)
-    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-      for (uint32_t k = threadIdx.x; k < P; k += blockDim.x) {
-        const uint32_t partner = k ^ stride;
-        if (partner > k) {
-          const bool up = (k & size) == 0;
-          const uint64_t a = key[k], b = key[partner];
-          if ((a > b) == up) { key[k] = b; key[partner] = a; }
-        }
-      }
-      __syncthreads();
+  bitonic();
+  const uint32_t nwide = s_nwide;
+  // same[pos]: the pair at pos continues the run of its predecessor (same column node, same element list)
+  for (uint32_t pos = threadIdx.x; pos < n; pos += blockDim.x) {
+    bool sm = false;
+    if (TL_KG > 1 && pos > nwide) {
+      const uint32_t p = h.pair0 + (uint32_t)(key[pos] & 0xffffffffu), q = h.pair0 + (uint32_t)(key[pos - 1] & 0xffffffffu);
+      const uint32_t sp = cstart[p], sq = cstart[q], cnt = cstart[p + 1] - sp;
+      sm = cnt == cstart[q + 1] - sq && pJ[p] == pJ[q];
+      for (uint32_t c = 0; sm && c < cnt; ++c)
+        sm = tl_elem_of(csrc[sp + c], nb, nlocal) == tl_elem_of(csrc[sq + c], nb, nlocal);
     }
-  for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) sp_pair[h.pair0 + k] = h.pair0 + (uint32_t)(key[k] & 0xffffffffu);
+    same[pos] = sm ? 1 : 0;
+    sp_pair[h.pair0 + pos] = h.pair0 + (uint32_t)(key[pos] & 0xffffffffu);
+  }
+  __syncthreads();
+  // ---- phase 2: item heads
+  uint64_t mykey[TL_MAXPAIRS / 256];
+#pragma unroll
+  for (int r = 0; r < TL_MAXPAIRS / 256; ++r) {
+    const uint32_t pos = threadIdx.x + r * 256;
+    uint64_t v = ~0ull;
+    if (pos < n && pos >= nwide) {
+      uint32_t back = 0;
+      while (same[pos - back]) ++back;  // same[nwide] == 0 stops the walk
+      if (back % TL_KG == 0) {
+        uint32_t m = 1;
+        while (m < (uint32_t)TL_KG && pos + m < n && same[pos + m]) ++m;
+        const uint32_t p0 = h.pair0 + (uint32_t)(key[pos] & 0xffffffffu);
+        const uint32_t cnt = cstart[p0 + 1] - cstart[p0];
+        uint32_t sig = m;
+        if (use_sig)
+          for (uint32_t g = 0; g < m; ++g) {
+            const uint32_t p = h.pair0 + (uint32_t)(key[pos + g] & 0xffffffffu), s0 = cstart[p];
+            for (uint32_t c = 0; c < cnt; ++c) {
+              const uint32_t ctr = csrc[s0 + c];
+              const uint32_t rr = ctr < nlocal ? ctr % nb : 0xffffu;
+              sig = (sig ^ rr) * 0x9E3779B1u + 0x7F4A7C15u;
+              sig ^= sig >> 15;
+            }
+          }
+        atomicAdd(&s_nitems, 1u);
+        if (cnt > 2u) atomicAdd(&s_nit_gt2, 1u);
+        // items with the same number of members share tasks: a task then runs exactly the members its lanes have
+        v = ((uint64_t)(255u - min(cnt, 255u)) << 56) | ((uint64_t)((uint32_t)TL_KG - m) << 52) |
+            ((uint64_t)(sig & 0xfffffu) << 32) | (m << 16) | pos;
+      }
+    }
+    mykey[r] = v;
+  }
+  __syncthreads();  // every thread has read the phase-1 keys it needs
+#pragma unroll
+  for (int r = 0; r < TL_MAXPAIRS / 256; ++r) {
+    const uint32_t pos = threadIdx.x + r * 256;
+    if (pos < P) key[pos] = mykey[r];
+  }
+  __syncthreads();
+  bitonic();
+  const uint32_t nitems = s_nitems;
+  for (uint32_t k = threadIdx.x; k < nitems; k += blockDim.x) it_head[h.pair0 + k] = (uint32_t)(key[k] & 0xffffffffu);
   if (threadIdx.x == 0) {
-    const uint32_t nwide = s_nwide, ngt2 = s_ngt2;
     hdr[tile].n_wide = nwide;
-    hdr[tile].n_long = nwide + (ngt2 > nwide ? (ngt2 - nwide + 31) / 32 : 0u);
+    hdr[tile].nitems = nitems;
+    hdr[tile].n_long = nwide + (s_nit_gt2 + 31) / 32;
   }
 }
 
@@ -276,16 +355,19 @@ __global__ void k_tile_task_owner(const TileHdr *__restrict__ hdr, int64_t nt, u
     for (uint32_t k = threadIdx.x; k < hdr[tile].ntasks; k += blockDim.x) tk_tile[hdr[tile].task0 + k] = (uint32_t)tile;
 }
 
-// thread per (task, lane): pair record + descriptors.
+// thread per (task, lane): the TL_KG pair records of the lane's item + descriptors.
+//   rec[(task*TL_KG + g)*32 + lane], g = member of the item:
 //   rec.x  = CSC offset of the column-component-0 piece (relative to the tile base, 20 bits)
 //   rec.y  = offset of the component-1 piece relative to x (20 bits) | keep mask << 20 | wide << 30 | valid << 31
 //   rec.z  = offset of the component-2 piece relative to x (20 bits) | steps of the task << 20
-//   rec.w  = descriptors of steps 0 and 1 (16 bits each)
-//   dblob  = tasks with more than 2 steps and wide tasks: descriptors as [step][lane] uint16, TL_INREC rows
-//            (640 bytes per task).  Wide task: lane l, row r = contribution r*32 + l of the pair; only lane 0 is valid.
+//   rec.w  = descriptors of steps 0 and 1 (16 bits each): element slot << cbits | (j*nd + i)
+//   dblob  = tasks with more than 2 steps and wide tasks: descriptors as [member][step][lane] uint16, TL_INREC rows per
+//            member.  Wide task: lane l, row r = contribution r*32 + l of the pair; only lane 0 / member 0 is valid.
+//   The members of an item share their element list: at every step their descriptors carry the same slot.
 template <int Q>
 __global__ void k_tile_fill(const TileHdr *__restrict__ hdr, const uint32_t *__restrict__ tk_tile,
-                            const uint32_t *__restrict__ sp_pair, const uint32_t *__restrict__ els, int stride,
+                            const uint32_t *__restrict__ sp_pair, const uint32_t *__restrict__ it_head,
+                            const uint32_t *__restrict__ els, int stride,
                             const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ csrc,
                             const int32_t *__restrict__ pJ, const uint16_t *__restrict__ pmask,
                             const uint32_t *__restrict__ prel, const int64_t *__restrict__ jc, int64_t npairs, int nd,
@@ -300,55 +382,68 @@ __global__ void k_tile_fill(const TileHdr *__restrict__ hdr, const uint32_t *__r
     const TileHdr h = hdr[tile];
     const uint32_t tkl = (uint32_t)(task - h.task0);
     const bool wide = tkl < h.n_wide;
-    // sorted position of my pair, of the task's first (longest) pair
-    const uint32_t pos0 = wide ? tkl : h.n_wide + (tkl - h.n_wide) * 32;
-    const uint32_t pos = wide ? tkl : pos0 + lane;
-    const uint32_t pf = sp_pair[h.pair0 + pos0];
+    // position (in sp_pair) of the first pair of my item and of the task's first (longest) item
+    uint32_t pos = tkl, members = 1, posf = tkl;
+    bool exists = true;
+    if (!wide) {
+      const uint32_t t0 = (tkl - h.n_wide) * 32, tl = t0 + lane;
+      posf = it_head[h.pair0 + t0] & 0xffffu;
+      exists = tl < h.nitems;
+      if (exists) {
+        const uint32_t ih = it_head[h.pair0 + tl];
+        pos = ih & 0xffffu;
+        members = (ih >> 16) & 0xffu;
+      }
+    }
+    const uint32_t pf = sp_pair[h.pair0 + posf];
     const uint32_t cntf = cstart[pf + 1] - cstart[pf];
     const uint32_t steps = wide ? (cntf + 31) / 32 : cntf;
     if (steps > (uint32_t)TL_INREC) *err = 4;
+    if (members > (uint32_t)TL_KG) *err = 6;
     const uint32_t zdesc = (zslot << cbits) & 0xffffu;
-    uint32_t w0 = zdesc | (zdesc << 16);
-    uint16_t *bl = tkl < h.n_long ? dblob + ((size_t)h.r2_0 + tkl) * (TL_INREC * 32) + lane : nullptr;
-    if (!bl && steps > 2) *err = 5;
-    uint4 r = make_uint4(0, wide ? 0x40000000u : 0u, steps << 20, 0);
-    uint32_t cnt = 0, s0 = 0;
-    if (pos < h.npairs) {
-      const uint32_t p = sp_pair[h.pair0 + pos];
-      const int32_t J = pJ[p];
-      int64_t off[3] = {0, 0, 0};
-      for (int b = 0; b < Q; ++b) off[b] = jc[J + b] + prel[(size_t)b * npairs + p] - h.base;
-      const int64_t d1 = off[1] - off[0], d2 = off[2] - off[0];
-      const uint32_t m = pmask[p];
-      if (off[0] < 0 || off[0] >= (1 << 20) || (Q > 1 && (d1 < 0 || d1 >= (1 << 20))) ||
-          (Q > 2 && (d2 < 0 || d2 >= (1 << 20))) || m >= (1u << 9))
-        *err = 1;
-      r.x = (uint32_t)off[0];
-      r.y |= (uint32_t)(Q > 1 ? d1 : 0) | (m << 20) | ((!wide || lane == 0) ? 0x80000000u : 0u);
-      r.z |= (uint32_t)(Q > 2 ? d2 : 0);
-      s0 = cstart[p];
-      cnt = cstart[p + 1] - s0;
-    }
     const uint32_t *te = els + (size_t)tile * stride;
-    for (uint32_t c = 0; c < (bl ? (uint32_t)TL_INREC : steps); ++c) {
-      const uint32_t ci = wide ? c * 32 + lane : c;  // contribution handled at step c
-      uint32_t d = zdesc;
-      if (ci < cnt && c < steps && csrc[s0 + ci] < nlocal) {  // virtual (halo) contributions add nothing here
-        const uint32_t ctr = csrc[s0 + ci];
-        const uint32_t el = ctr / nb, rr = ctr - el * nb;  // rr = j*nd + i
-        uint32_t lo = 0, hi = h.nel;                       // first position with te[pos] >= el
-        while (lo < hi) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (te[mid] < el) lo = mid + 1; else hi = mid;
-        }
-        if (lo >= h.nel || te[lo] != el) *err = 2;
-        d = (lo << cbits) | rr;
+    for (int g = 0; g < TL_KG; ++g) {
+      uint32_t w0 = zdesc | (zdesc << 16);
+      uint16_t *bl = tkl < h.n_long ? dblob + (((size_t)h.r2_0 + tkl) * TL_KG + g) * (TL_INREC * 32) + lane : nullptr;
+      if (!bl && steps > 2) *err = 5;
+      uint4 r = make_uint4(0, wide ? 0x40000000u : 0u, steps << 20, 0);
+      uint32_t cnt = 0, s0 = 0;
+      if (exists && (uint32_t)g < members && pos + g < h.npairs) {
+        const uint32_t p = sp_pair[h.pair0 + pos + g];
+        const int32_t J = pJ[p];
+        int64_t off[3] = {0, 0, 0};
+        for (int b = 0; b < Q; ++b) off[b] = jc[J + b] + prel[(size_t)b * npairs + p] - h.base;
+        const int64_t d1 = off[1] - off[0], d2 = off[2] - off[0];
+        const uint32_t m = pmask[p];
+        if (off[0] < 0 || off[0] >= (1 << 20) || (Q > 1 && (d1 < 0 || d1 >= (1 << 20))) ||
+            (Q > 2 && (d2 < 0 || d2 >= (1 << 20))) || m >= (1u << 9))
+          *err = 1;
+        r.x = (uint32_t)off[0];
+        r.y |= (uint32_t)(Q > 1 ? d1 : 0) | (m << 20) | ((!wide || lane == 0) ? 0x80000000u : 0u);
+        r.z |= (uint32_t)(Q > 2 ? d2 : 0);
+        s0 = cstart[p];
+        cnt = cstart[p + 1] - s0;
       }
-      if (c < 2) w0 = (w0 & ~(0xffffu << (16 * c))) | (d << (16 * c));
-      if (bl) bl[c * 32] = (uint16_t)d;
+      for (uint32_t c = 0; c < (bl ? (uint32_t)TL_INREC : steps); ++c) {
+        const uint32_t ci = wide ? c * 32 + lane : c;  // contribution handled at step c
+        uint32_t d = zdesc;
+        if (ci < cnt && c < steps && csrc[s0 + ci] < nlocal) {  // virtual (halo) contributions add nothing here
+          const uint32_t ctr = csrc[s0 + ci];
+          const uint32_t el = ctr / nb, rr = ctr - el * nb;  // rr = j*nd + i
+          uint32_t lo = 0, hi = h.nel;                       // first position with te[pos] >= el
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (te[mid] < el) lo = mid + 1; else hi = mid;
+          }
+          if (lo >= h.nel || te[lo] != el) *err = 2;
+          d = (lo << cbits) | rr;
+        }
+        if (c < 2) w0 = (w0 & ~(0xffffu << (16 * c))) | (d << (16 * c));
+        if (bl) bl[c * 32] = (uint16_t)d;
+      }
+      r.w = w0;
+      rec[((size_t)task * TL_KG + g) * 32 + lane] = r;
     }
-    r.w = w0;
-    rec[idx] = r;
   }
 }
 
@@ -380,7 +475,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 
 #ifndef GF_TL_CW
-#define GF_TL_CW 16
+#define GF_TL_CW 11
 #endif
 constexpr int TL_CW = GF_TL_CW;                  // consumer warps
 constexpr int TL_THREADS = (TL_CW + 1) * 32;     // + the producer warp
@@ -435,9 +530,9 @@ template <int N, int RF>
 struct TlSmem {  // byte offsets inside one tile buffer: pair records | long-task descriptor blobs | geometry rows
   using C = TlCfg<N, RF>;
   static constexpr int GSP = C::GSZ | 1;
-  __host__ __device__ static size_t blob_off(int cap_tasks) { return (size_t)cap_tasks * 512; }
+  __host__ __device__ static size_t blob_off(int cap_tasks) { return (size_t)cap_tasks * 512 * TL_KG; }
   __host__ __device__ static size_t geo_off(int cap_tasks, int cap_long) {
-    return (size_t)cap_tasks * 512 + (size_t)cap_long * TL_BLOB;
+    return (size_t)cap_tasks * 512 * TL_KG + (size_t)cap_long * TL_BLOB * TL_KG;
   }
   __host__ __device__ static size_t bytes(int cap_tasks, int cap_long, int zslot) {
     return (geo_off(cap_tasks, cap_long) + (size_t)(zslot + 1) * GSP * 8 + 127) / 128 * 128;
@@ -506,12 +601,12 @@ k_tiles(const TileArgs a) {
       if (lane == 0) {
         s_hdr[b] = h;
         s_next[b] = 2 * TL_CW;
-        const uint32_t nb1 = h.ntasks * 512u, nb2 = h.n_long * (uint32_t)TL_BLOB;
+        const uint32_t nb1 = h.ntasks * 512u * TL_KG, nb2 = h.n_long * (uint32_t)(TL_BLOB * TL_KG);
         // geometry rows: a whole number of 16-byte units (the blob is zero padded, a spare row may land on the zero slot)
         const uint32_t nb3 = (h.nel * (uint32_t)(GSP * 8) + 15u) & ~15u;
         mbar_arrive_expect_tx(&full[b], nb1 + nb2 + nb3);
-        bulk_g2s(buf, a.rec + (size_t)h.task0 * 32, nb1, &full[b], pol);
-        if (nb2) bulk_g2s(buf + L::blob_off(a.cap_tasks), a.dblob + (size_t)h.r2_0 * (TL_BLOB / 2), nb2, &full[b], pol);
+        bulk_g2s(buf, a.rec + (size_t)h.task0 * 32 * TL_KG, nb1, &full[b], pol);
+        if (nb2) bulk_g2s(buf + L::blob_off(a.cap_tasks), a.dblob + (size_t)h.r2_0 * (TL_BLOB / 2) * TL_KG, nb2, &full[b], pol);
         if (nb3) bulk_g2s(buf + L::geo_off(a.cap_tasks, a.cap_long), a.tgeo + (size_t)tile * a.geo_rows * GSP, nb3, &full[b], pol);
       }
       const unsigned long long tpa = a.trace ? gtimer() : 0;
@@ -549,108 +644,153 @@ k_tiles(const TileArgs a) {
     const double *sG = reinterpret_cast<const double *>(buf + L::geo_off(a.cap_tasks, a.cap_long));
     const unsigned ntasks = s_hdr[b].ntasks;
     double *prb = reinterpret_cast<double *>(outraw + b * outsz) + (s_hdr[b].base & 1);  // image of the CSC segment
-    // the next task index and its record are fetched while the current task runs
+    // the next task index and its first record are fetched while the current task runs
     unsigned tk = warp, tkB = warp + TL_CW;
-    uint4 rec = make_uint4(0, 0, 0, 0);
-    if (tk < ntasks) rec = sRec[tk * 32];
+    uint4 rec0 = make_uint4(0, 0, 0, 0);
+    if (tk < ntasks) rec0 = sRec[tk * (32 * TL_KG)];
     while (tk < ntasks) {
       unsigned nxt = 0;
       if (lane == 0) nxt = atomicAdd(&s_next[b], 1u);
       uint4 recB = make_uint4(0, 0, 0, 0);
-      if (tkB < ntasks) recB = sRec[tkB * 32];
-      const int steps = (int)(rec.z >> 20);
-      double acc[ACC];
+      if (tkB < ntasks) recB = sRec[tkB * (32 * TL_KG)];
+      uint4 rec[TL_KG];
+      rec[0] = rec0;
 #pragma unroll
-      for (int m = 0; m < ACC; ++m) acc[m] = 0.0;
-      auto step = [&](unsigned d) {
-        const double *G = sG + (d >> CB) * GSP;
-        const double *M = sM + (d & ((1u << CB) - 1u)) * MT;
+      for (int g = 1; g < TL_KG; ++g) rec[g] = sRec[(tk * TL_KG + g) * 32];
+      // members in use by some lane of this task (warp uniform): the members of an item are contiguous from 0
+      int kmax = 1;
+#pragma unroll
+      for (int g = 1; g < TL_KG; ++g)
+        if (__any_sync(0xffffffffu, rec[g].y >> 31)) kmax = g + 1;
+      const int steps = (int)(rec0.z >> 20);
+      double acc[TL_KG][ACC];
+#pragma unroll
+      for (int g = 0; g < TL_KG; ++g)
+#pragma unroll
+        for (int m = 0; m < ACC; ++m) acc[g][m] = 0.0;
+      // one step: the geometry row (slot of member 0's descriptor: the members share their element list) is loaded once
+      auto step = [&](const unsigned (&d)[TL_KG]) {
+        const double *G = sG + (d[0] >> CB) * GSP;
         if (RF == TF_ELAST) {
           double Bm[N * N];
 #pragma unroll
           for (int k = 0; k < N * N; ++k) Bm[k] = G[k];
 #pragma unroll
-          for (int qq = 0; qq < N; ++qq) {
-            double Wq[N];  // column qq of W = B M
+          for (int g = 0; g < TL_KG; ++g) {
+            if (g < kmax) {
+              const double *M = sM + (d[g] & ((1u << CB) - 1u)) * MT;
 #pragma unroll
-            for (int aa = 0; aa < N; ++aa) {
-              double s2 = 0;
+              for (int qq = 0; qq < N; ++qq) {
+                double Wq[N];  // column qq of W = B M
 #pragma unroll
-              for (int pp = 0; pp < N; ++pp) s2 += Bm[aa + N * pp] * M[pp * N + qq];
-              Wq[aa] = s2;
+                for (int aa = 0; aa < N; ++aa) {
+                  double s2 = 0;
+#pragma unroll
+                  for (int pp = 0; pp < N; ++pp) s2 += Bm[aa + N * pp] * M[pp * N + qq];
+                  Wq[aa] = s2;
+                }
+#pragma unroll
+                for (int b2 = 0; b2 < N; ++b2)
+#pragma unroll
+                  for (int aa = 0; aa < N; ++aa) acc[g][RF == TF_ELAST ? aa + N * b2 : 0] += Wq[aa] * Bm[b2 + N * qq];
+              }
             }
-#pragma unroll
-            for (int b2 = 0; b2 < N; ++b2)
-#pragma unroll
-              for (int aa = 0; aa < N; ++aa) acc[RF == TF_ELAST ? aa + N * b2 : 0] += Wq[aa] * Bm[b2 + N * qq];
           }
         } else {
-          double s2 = acc[0];
+          double Gv[MT];
 #pragma unroll
-          for (int k = 0; k < MT; ++k) s2 += M[k] * G[k];
-          acc[0] = s2;
+          for (int k = 0; k < MT; ++k) Gv[k] = G[k];
+#pragma unroll
+          for (int g = 0; g < TL_KG; ++g) {
+            if (g < kmax) {
+              const double *M = sM + (d[g] & ((1u << CB) - 1u)) * MT;
+              double s2 = acc[g][0];
+#pragma unroll
+              for (int k = 0; k < MT; ++k) s2 += M[k] * Gv[k];
+              acc[g][0] = s2;
+            }
+          }
         }
       };
-      if (steps <= 2 && !(rec.y & 0x40000000u)) {  // both descriptors travel in the record
-        step(rec.w & 0xffffu);
-        if (steps == 2) step(rec.w >> 16);
-      } else {
-        const uint16_t *bl = sBlob + tk * (TL_BLOB / 2);
-        unsigned dn = bl[0];
-        for (int c = 0; c < steps; ++c) {
-          const unsigned d = dn;
-          if (c + 1 < steps) dn = bl[(c + 1) * 32];
+      const bool wide = rec0.y & 0x40000000u;
+      if (steps <= 2 && !wide) {  // both descriptors travel in the records
+        unsigned d[TL_KG];
+#pragma unroll
+        for (int g = 0; g < TL_KG; ++g) d[g] = rec[g].w & 0xffffu;
+        step(d);
+        if (steps == 2) {
+#pragma unroll
+          for (int g = 0; g < TL_KG; ++g) d[g] = rec[g].w >> 16;
           step(d);
         }
-        if (rec.y & 0x40000000u) {  // wide task: the lanes hold parts of ONE pair; fixed-order tree sum
+      } else {
+        const uint16_t *bl = sBlob + tk * (TL_KG * (TL_BLOB / 2));
+        unsigned dn[TL_KG];
+#pragma unroll
+        for (int g = 0; g < TL_KG; ++g) dn[g] = g < kmax ? bl[g * (TL_BLOB / 2)] : 0u;
+        for (int c = 0; c < steps; ++c) {
+          unsigned d[TL_KG];
+#pragma unroll
+          for (int g = 0; g < TL_KG; ++g) d[g] = dn[g];
+          if (c + 1 < steps) {
+#pragma unroll
+            for (int g = 0; g < TL_KG; ++g)
+              if (g < kmax) dn[g] = bl[g * (TL_BLOB / 2) + (c + 1) * 32];
+          }
+          step(d);
+        }
+        if (wide) {  // wide task: the lanes hold parts of ONE pair; fixed-order tree sum
 #pragma unroll
           for (int off = 16; off > 0; off >>= 1)
 #pragma unroll
-            for (int m = 0; m < ACC; ++m) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], off);
+            for (int m = 0; m < ACC; ++m) acc[0][m] += __shfl_xor_sync(0xffffffffu, acc[0][m], off);
         }
       }
       // ---- flush: all lanes of the task together; per column component the kept entries are compacted
-      if (rec.y >> 31) {
-        double kv[Q * Q];  // kv[b*Q + aa] = K(row component aa, column component b)
-        if (RF == TF_ELAST) {
-          double tr = 0;
 #pragma unroll
-          for (int n = 0; n < N; ++n) tr += acc[RF == TF_ELAST ? n + N * n : 0];
+      for (int g = 0; g < TL_KG; ++g) {
+        if (g < kmax && (rec[g].y >> 31)) {
+          double kv[Q * Q];  // kv[b*Q + aa] = K(row component aa, column component b)
+          if (RF == TF_ELAST) {
+            double tr = 0;
 #pragma unroll
-          for (int b2 = 0; b2 < Q; ++b2)
+            for (int n = 0; n < N; ++n) tr += acc[g][RF == TF_ELAST ? n + N * n : 0];
 #pragma unroll
-            for (int aa = 0; aa < Q; ++aa)
-              kv[b2 * Q + aa] = a.sl * acc[RF == TF_ELAST ? aa + N * b2 : 0] + a.smu * acc[RF == TF_ELAST ? b2 + N * aa : 0] +
-                                (aa == b2 ? a.smu * tr : 0.0);
-        } else {
+            for (int b2 = 0; b2 < Q; ++b2)
 #pragma unroll
-          for (int b2 = 0; b2 < Q; ++b2)
-#pragma unroll
-            for (int aa = 0; aa < Q; ++aa) kv[b2 * Q + aa] = aa == b2 ? acc[0] : 0.0;
-        }
-        double *p0 = prb + (rec.x & 0xfffffu);
-        const unsigned pm = (rec.y >> 20) & 0x1ffu;
-#pragma unroll
-        for (int b2 = 0; b2 < Q; ++b2) {
-          double *dst = p0 + (b2 == 0 ? 0u : b2 == 1 ? (rec.y & 0xfffffu) : (rec.z & 0xfffffu));
-          const unsigned mb = (pm >> (b2 * Q)) & ((1u << Q) - 1);
-          if (Q == 3) {
-            const double v0 = kv[b2 * Q], v1 = kv[b2 * Q + (Q > 1 ? 1 : 0)], v2 = kv[b2 * Q + (Q > 2 ? 2 : 0)];
-            const int n = __popc(mb);
-            const double x0 = (mb & 1u) ? v0 : ((mb & 2u) ? v1 : v2);
-            const double x1 = ((mb & 3u) == 3u) ? v1 : v2;
-            if (n >= 1) dst[0] = x0;
-            if (n >= 2) dst[1] = x1;
-            if (n >= 3) dst[2] = v2;
+              for (int aa = 0; aa < Q; ++aa)
+                kv[b2 * Q + aa] = a.sl * acc[g][RF == TF_ELAST ? aa + N * b2 : 0] + a.smu * acc[g][RF == TF_ELAST ? b2 + N * aa : 0] +
+                                  (aa == b2 ? a.smu * tr : 0.0);
           } else {
 #pragma unroll
-            for (int aa = 0; aa < Q; ++aa)
-              if (mb & (1u << aa)) dst[__popc(mb & ((1u << aa) - 1))] = kv[b2 * Q + aa];
+            for (int b2 = 0; b2 < Q; ++b2)
+#pragma unroll
+              for (int aa = 0; aa < Q; ++aa) kv[b2 * Q + aa] = aa == b2 ? acc[g][0] : 0.0;
+          }
+          double *p0 = prb + (rec[g].x & 0xfffffu);
+          const unsigned pm = (rec[g].y >> 20) & 0x1ffu;
+#pragma unroll
+          for (int b2 = 0; b2 < Q; ++b2) {
+            double *dst = p0 + (b2 == 0 ? 0u : b2 == 1 ? (rec[g].y & 0xfffffu) : (rec[g].z & 0xfffffu));
+            const unsigned mb = (pm >> (b2 * Q)) & ((1u << Q) - 1);
+            if (Q == 3) {
+              const double v0 = kv[b2 * Q], v1 = kv[b2 * Q + (Q > 1 ? 1 : 0)], v2 = kv[b2 * Q + (Q > 2 ? 2 : 0)];
+              const int n = __popc(mb);
+              const double x0 = (mb & 1u) ? v0 : ((mb & 2u) ? v1 : v2);
+              const double x1 = ((mb & 3u) == 3u) ? v1 : v2;
+              if (n >= 1) dst[0] = x0;
+              if (n >= 2) dst[1] = x1;
+              if (n >= 3) dst[2] = v2;
+            } else {
+#pragma unroll
+              for (int aa = 0; aa < Q; ++aa)
+                if (mb & (1u << aa)) dst[__popc(mb & ((1u << aa) - 1))] = kv[b2 * Q + aa];
+            }
           }
         }
       }
       tk = tkB;
-      rec = recB;
+      rec0 = recB;
       tkB = __shfl_sync(0xffffffffu, nxt, 0);
     }
     fence_async_smem();  // my image writes (generic proxy) before the producer's bulk store (async proxy)
@@ -950,8 +1090,9 @@ void recompute_prepare(gfgpu_term *t) {
   const int GSPh = GSZ | 1;
   const size_t smem_limit = 224 * 1024;
   std::vector<TileHdr> hdr;
-  DevBuf<uint32_t> sp_pair, tk_tile;
+  DevBuf<uint32_t> sp_pair, it_head, tk_tile;
   sp_pair.alloc(ctx, st.npairs);
+  it_head.alloc(ctx, st.npairs);
   TileHdr *dh = nullptr;
   int cap_inc = 1, cap_slots = 1, cap_tasks = 1, cap_long = 1, cap_len = 1;
   int64_t ntask = 0, nlong = 0, nt = 0;
@@ -988,8 +1129,9 @@ void recompute_prepare(gfgpu_term *t) {
       k_tile_elements<<<(unsigned)nt, 128, 2 * P * sizeof(uint32_t), s>>>(dh, st.rstart.p, st.rsrc.p, nd, cap_inc, t->rc_els.p);
       GF_LAUNCH_CHECK();
     }
-    k_tile_sort_pairs<<<(unsigned)nt, 256, 0, s>>>(dh, st.cstart.p, st.csrc.p, (uint32_t)(nd * nd), (uint32_t)st.ncontrib,
-                                                   env_int("GFGPU_TILE_SIGSORT", 1), sp_pair.p, (int *)t->flag.p);
+    k_tile_sort_pairs<<<(unsigned)nt, 256, 0, s>>>(dh, st.cstart.p, st.csrc.p, st.pJ.p, (uint32_t)(nd * nd),
+                                                   (uint32_t)st.ncontrib, env_int("GFGPU_TILE_SIGSORT", 1), sp_pair.p,
+                                                   it_head.p, (int *)t->flag.p);
     GF_LAUNCH_CHECK();
     k_tile_base<<<(unsigned)std::min<int64_t>((nt + 255) / 256, 148 * 8), 256, 0, s>>>(dh, nt, st.pJ.p, st.rdof.p, Q, t->jc.p);
     GF_LAUNCH_CHECK();
@@ -999,7 +1141,7 @@ void recompute_prepare(gfgpu_term *t) {
     cap_slots = cap_tasks = cap_long = cap_len = 1;
     ntask = nlong = 0;
     for (TileHdr &h : hdr) {
-      h.ntasks = h.n_wide + (h.npairs - h.n_wide + 31) / 32;
+      h.ntasks = h.n_wide + (h.nitems + 31) / 32;
       h.task0 = (uint32_t)ntask;
       h.r2_0 = (uint32_t)nlong;
       ntask += h.ntasks;
@@ -1009,7 +1151,7 @@ void recompute_prepare(gfgpu_term *t) {
       cap_long = std::max<int>(cap_long, (int)h.n_long);
       cap_len = std::max<int>(cap_len, (int)h.len);
     }
-    const size_t in_b = ((size_t)cap_tasks * 512 + (size_t)cap_long * TL_BLOB + (size_t)(cap_slots + 1) * GSPh * 8 + 127) / 128 * 128;
+    const size_t in_b = ((size_t)cap_tasks * 512 * TL_KG + (size_t)cap_long * TL_BLOB * TL_KG + (size_t)(cap_slots + 1) * GSPh * 8 + 127) / 128 * 128;
     const size_t out_b = ((size_t)(cap_len + 2) * 8 + 127) / 128 * 128;
     const size_t need = 2 * in_b + 2 * out_b + (size_t)nd * nd * MT * 8;
     if (need <= smem_limit && cap_slots <= 32 * TL_ROWS) break;
@@ -1031,13 +1173,13 @@ void recompute_prepare(gfgpu_term *t) {
   tk_tile.alloc(ctx, ntask);
   k_tile_task_owner<<<(unsigned)std::min<int64_t>(nt, 148 * 32), 128, 0, s>>>(dh, nt, tk_tile.p);
   GF_LAUNCH_CHECK();
-  t->rc_prec.alloc(ctx, (size_t)ntask * 32);
-  t->rc_dblob.alloc(ctx, std::max<size_t>((size_t)nlong * TL_INREC * 32, 1));
+  t->rc_prec.alloc(ctx, (size_t)ntask * 32 * TL_KG);
+  t->rc_dblob.alloc(ctx, std::max<size_t>((size_t)nlong * TL_INREC * 32 * TL_KG, 1));
   {
     const int B = 256;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ntask * 32 + B - 1) / B, 148 * 64));
 #define GF_FILL(QQ)                                                                                                  \
-  k_tile_fill<QQ><<<grid, B, 0, s>>>(dh, tk_tile.p, sp_pair.p, t->rc_els.p, cap_inc, st.cstart.p, st.csrc.p,         \
+  k_tile_fill<QQ><<<grid, B, 0, s>>>(dh, tk_tile.p, sp_pair.p, it_head.p, t->rc_els.p, cap_inc, st.cstart.p, st.csrc.p, \
                                      st.pJ.p, t->pmask.p, t->prel.p, t->jc.p, st.npairs, nd, cbits,                 \
                                      (uint32_t)cap_slots, ntask, (uint32_t)st.ncontrib, (uint4 *)t->rc_prec.p,      \
                                      t->rc_dblob.p,                                                                 \

@@ -193,7 +193,7 @@ def color_slots(normal, els):
     return slot_of
 
 
-def simulate_groups(st, KG=3, max_tiles=60, sort="sig"):
+def simulate_groups(st, KG=3, max_tiles=60, sort="sig", same_column=True):
     """Variant F: a lane owns up to KG pairs of ONE column node that have the same element list; the geometry row of a
     step is loaded once and reused for the KG pairs.  Returns wavefronts per pair-contribution (G, M), stores per pair."""
     tl = tiles(st)
@@ -217,7 +217,7 @@ def simulate_groups(st, KG=3, max_tiles=60, sort="sig"):
             if len(c) > INREC:
                 continue
             el, rr = c // NB, c % NB
-            groups.setdefault((int(st["pJ"][p]), tuple(int(e) for e in el)), []).append((rr, p))
+            groups.setdefault((int(st["pJ"][p]) if same_column else -1, tuple(int(e) for e in el)), []).append((rr, p))
         items = []
         for (J, el), lst in groups.items():
             for a in range(0, len(lst), KG):
@@ -279,9 +279,10 @@ def main():
     edof = np.load(d + "/elem_dof.npy")
     st = build(edof)
     if len(sys.argv) > 2 and sys.argv[2] == "groups":
-        for KG in (1, 2, 3, 4):
-            for srt in ("sig", "elem"):
-                print(KG, srt, simulate_groups(st, KG, sort=srt))
+        for sc in (True, False):
+            for KG in (1, 2, 3, 4, 6):
+                r = simulate_groups(st, KG, sort="sig", same_column=sc)
+                print("same_column", sc, "KG", KG, {k: round(v, 2) for k, v in r.items()})
         return
     names = sys.argv[2:] or list(VARIANTS)
     print("%-26s %8s %8s %8s %8s %8s %10s" % ("variant", "G wf/ld", "M wf/ld", "sum/step", "rows/half", "wf/store", "total wf"))
