@@ -188,12 +188,22 @@ static void hyper_law(int family, const double *Gu, const double *par, double *S
    the points of face f are [face_first[f], face_first[f] + face_nq[f]) and ref_normals[f] is pgt->normals()[f].
    On a face: Normal = B*n_ref, J *= |Normal|, Normal /= |Normal|, components below 1e-13 cleaned
    (compile_and_exec.cc:8836-8847). */
-gfo_result *gfo_assemble_region(int dim, int64_t ne, int ng, const double *pts, const int32_t *conn, int nd, int Q,
+/* Fem-data coefficients (ga_workspace::add_fem_constant, generic_assembly.h:465; evaluated at the Gauss point by
+   ga_instruction_val, compile_and_exec.cc:636-690): nfields > 0 replaces par[0 .. nfields) by the value at the point of a
+   field on a data mesh_fem with nd_d local dofs (d_edof: ne x nd_d, dof of component 0; d_phi: its basis at every
+   integration point, same point order as the other tables); the SOURCE family reads one field of Q components. */
+gfo_result *gfo_assemble_fields(int dim, int64_t ne, int ng, const double *pts, const int32_t *conn, int nd, int Q,
                                 const int64_t *elem_dof, int64_t ndof, int nq, const double *w, const double *gt_grad,
-                                const double *phi, const double *gphi, int gt_linear, int family, const double *par,
+                                const double *phi, const double *gphi, int gt_linear, int family, const double *par_in,
                                 const double *U, int order_mask, int64_t n_items, const int32_t *item_cv,
                                 const int32_t *item_face, const int32_t *face_first, const int32_t *face_nq,
-                                const double *ref_normals) {
+                                const double *ref_normals, int nfields, int nd_d, const int64_t *d_edof,
+                                const double *d_phi, const double *d_vals0, const double *d_vals1) {
+  double par[16];
+  for (int k = 0; k < 16; ++k) par[k] = 0.0;
+  { int np = family == GFO_SOURCE ? Q : family == GFO_NORMAL_SOURCE ? Q * dim
+             : (family == GFO_LAPLACE || family == GFO_MASS) ? 1 : 2;
+    for (int k = 0; k < np; ++k) par[k] = par_in[k]; }
   const int N = dim, s1 = nd * Q;
   gfo_result *res = (gfo_result *)calloc(1, sizeof(gfo_result));
   res->ndof = ndof;
@@ -253,6 +263,18 @@ gfo_result *gfo_assemble_region(int dim, int64_t ne, int ng, const double *pts, 
       }
       double coeff = J * w[ipt];
       if (w[ipt] == 0.0) continue; /* disabled points contribute coeff = 0 (cc:8852-8854) */
+      if (nfields > 0) { /* coefficient fields at the point */
+        const double *dp = d_phi + (size_t)ipt * nd_d;
+        const int ncomp = family == GFO_SOURCE ? Q : 1;
+        for (int k = 0; k < (family == GFO_SOURCE ? 1 : nfields); ++k) {
+          const double *vals = k == 0 ? d_vals0 : d_vals1;
+          for (int b = 0; b < ncomp; ++b) {
+            double v = 0;
+            for (int i = 0; i < nd_d; ++i) v += vals[d_edof[cv * nd_d + i] + b] * dp[i];
+            par[k + b] = v;
+          }
+        }
+      }
       const double *g = gphi + (size_t)ipt * nd * N;
       for (int i = 0; i < nd; ++i)
         for (int n = 0; n < N; ++n) {
@@ -366,6 +388,17 @@ gfo_result *gfo_assemble_region(int dim, int64_t ne, int ng, const double *pts, 
   for (int64_t j = 0; j < ndof; ++j) res->nnz += res->cols[j].n;
   free(elem); free(t); free(relem); free(Z); free(G); free(ue); free(dofs); free(sort);
   return res;
+}
+
+gfo_result *gfo_assemble_region(int dim, int64_t ne, int ng, const double *pts, const int32_t *conn, int nd, int Q,
+                                const int64_t *elem_dof, int64_t ndof, int nq, const double *w, const double *gt_grad,
+                                const double *phi, const double *gphi, int gt_linear, int family, const double *par,
+                                const double *U, int order_mask, int64_t n_items, const int32_t *item_cv,
+                                const int32_t *item_face, const int32_t *face_first, const int32_t *face_nq,
+                                const double *ref_normals) {
+  return gfo_assemble_fields(dim, ne, ng, pts, conn, nd, Q, elem_dof, ndof, nq, w, gt_grad, phi, gphi, gt_linear, family, par,
+                             U, order_mask, n_items, item_cv, item_face, face_first, face_nq, ref_normals, 0, 0, NULL, NULL,
+                             NULL, NULL);
 }
 
 gfo_result *gfo_assemble(int dim, int64_t ne, int ng, const double *pts, const int32_t *conn, int nd, int Q,

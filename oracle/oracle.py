@@ -38,6 +38,8 @@ def lib():
                                    C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.gfo_assemble_region.restype = C.c_void_p
         L.gfo_assemble_region.argtypes = L.gfo_assemble.argtypes + [C.c_int64] + [C.c_void_p] * 5
+        L.gfo_assemble_fields.restype = C.c_void_p
+        L.gfo_assemble_fields.argtypes = L.gfo_assemble_region.argtypes + [C.c_int, C.c_int] + [C.c_void_p] * 4
         L.gfo_nnz.restype = C.c_int64
         L.gfo_nnz.argtypes = [C.c_void_p]
         L.gfo_get_csc.argtypes = [C.c_void_p] * 4
@@ -52,11 +54,13 @@ def _p(a):
 
 
 def assemble(pts, conn, elem_dof, ndof, Q, w, gt_grad, phi, gphi, gt_linear, family, params, U, order_mask=3,
-             region=None, nq=None):
+             region=None, nq=None, fields=None):
     """Returns (jc, ir, pr, R): tangent in CSC (int64 indices) and residual.
     region = None (all convexes) or a dict: items_cv, items_f (face -1 = whole convex) and, when faces are used,
     face_first, face_nq, ref_normals -- the tables then cover ALL integration points and nq is the number of
-    volume points."""
+    volume points.
+    fields = None or a dict: d_elem_dof [ne, nd_d], d_phi [points, nd_d] (same point order as the other tables),
+    vals = [values of field 0 (, field 1)]: fem-data coefficients replacing params[0 .. len(vals))."""
     pts = np.ascontiguousarray(pts, np.float64)
     conn = np.ascontiguousarray(conn, np.int32)
     elem_dof = np.ascontiguousarray(elem_dof, np.int64)
@@ -69,9 +73,30 @@ def assemble(pts, conn, elem_dof, ndof, Q, w, gt_grad, phi, gphi, gt_linear, fam
     ne, ng = conn.shape
     nd = elem_dof.shape[1]
     L = lib()
-    if region is None and nq is not None:  # all-point tables were passed: the volume points come first
+    if fields is not None:
+        ded = np.ascontiguousarray(fields["d_elem_dof"], np.int64)
+        dphi = np.ascontiguousarray(fields["d_phi"], np.float64)
+        vals = [np.ascontiguousarray(v, np.float64) for v in fields["vals"]]
+        assert dphi.shape[0] == len(w), "the data fem's table must cover the same points as the other tables"
+        icv = ifc = ff = fn = rn = None
+        if region is not None:
+            icv = np.ascontiguousarray(region["items_cv"], np.int32)
+            ifc = np.ascontiguousarray(region.get("items_f", np.full(len(icv), -1)), np.int32)
+            if (ifc >= 0).any():
+                ff = np.ascontiguousarray(region["face_first"], np.int32)
+                fn = np.ascontiguousarray(region["face_nq"], np.int32)
+                rn = np.ascontiguousarray(region["ref_normals"], np.float64)
+        pp = lambda a: None if a is None else _p(a)  # noqa: E731
+        h = L.gfo_assemble_fields(pts.shape[1], ne, ng, _p(pts), _p(conn), nd, Q, _p(elem_dof), ndof,
+                                  len(w) if nq is None else nq, _p(w), _p(gt_grad), _p(phi), _p(gphi), int(gt_linear),
+                                  FAMILIES[family], _p(params), _p(U), order_mask, ne if icv is None else len(icv), pp(icv),
+                                  pp(ifc), pp(ff), pp(fn), pp(rn), len(vals), ded.shape[1], _p(ded), _p(dphi), _p(vals[0]),
+                                  _p(vals[1]) if len(vals) > 1 else None)
+    elif region is None and nq is not None:  # all-point tables were passed: the volume points come first
         w, gt_grad, phi, gphi = (np.ascontiguousarray(t[:nq]) for t in (w, gt_grad, phi, gphi))
-    if region is None:
+    if fields is not None:
+        pass
+    elif region is None:
         h = L.gfo_assemble(pts.shape[1], ne, ng, _p(pts), _p(conn), nd, Q, _p(elem_dof), ndof, len(w), _p(w),
                            _p(gt_grad), _p(phi), _p(gphi), int(gt_linear), FAMILIES[family], _p(params), _p(U),
                            order_mask)

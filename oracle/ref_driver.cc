@@ -22,6 +22,8 @@
 //   family2=.. region2=.. a2=..  family3=.. region3=.. a3=..   further expressions of the SAME workspace (linear
 //       families laplace|mass|source|nsource|elast with constants a2/f2/g2/lambda2/mu2 ...): every tree adds into the one
 //       K / V, as a model's bricks do
+//   coef=fem kd=1   the coefficients (a | lambda, mu | f) are fem data on a classical mesh_fem of degree kd
+//                   (ws.add_fem_constant) instead of fixed-size constants: heterogeneous material / distributed load
 //   u=smooth|random|zero  out=DIR  mode=dump|time|model  threads=T reps=R
 #include "getfem/getfem_regular_meshes.h"
 #include "getfem/getfem_mesh_fem.h"
@@ -232,11 +234,39 @@ int main(int argc, char **argv) {
   const std::vector<double> c_a{acoef}, c_lambda{lambda}, c_mu{mu}, c_params{lambda, mu};
   std::vector<double> c_f(Q);
   for (size_type k = 0; k < size_type(Q); ++k) c_f[k] = acoef * double(k + 1);
+  // fem-data coefficients (coef=fem): scalar fields on mf_d, the source term's field on mf_dq (qdim Q)
+  const bool coef_fem = gets("coef", "const") == "fem";
+  const int kd = (int)geti("kd", 1);
+  getfem::mesh_fem mf_d(m, 1), mf_dq(m, getfem::dim_type(Q));
+  mf_d.set_classical_finite_element(getfem::dim_type(kd));
+  mf_dq.set_classical_finite_element(getfem::dim_type(kd));
+  std::vector<double> d_a, d_l, d_m, d_f;
+  if (coef_fem) {
+    d_a.resize(mf_d.nb_dof()); d_l.resize(mf_d.nb_dof()); d_m.resize(mf_d.nb_dof()); d_f.resize(mf_dq.nb_dof());
+    for (size_type d = 0; d < mf_d.nb_dof(); ++d) {
+      base_node P = mf_d.point_of_basic_dof(d);
+      const double x0 = P[0], x1 = P[1], x2 = dim > 2 ? P[2] : 0.0;
+      d_a[d] = acoef * (1.0 + 0.3 * std::sin(1.7 * x0 + 0.9 * x1 + 0.4 * x2));
+      d_l[d] = lambda * (1.0 + 0.25 * std::cos(1.1 * x0 - 0.7 * x1 + 0.3 * x2));
+      d_m[d] = mu * (1.0 + 0.2 * std::cos(1.3 * x0 - x1));
+    }
+    for (size_type d = 0; d < mf_dq.nb_dof(); ++d) {
+      base_node P = mf_dq.point_of_basic_dof(d);
+      d_f[d] = acoef * double(d % Q + 1) * (1.0 + 0.5 * P[0] - 0.25 * P[dim - 1]);
+    }
+  }
   std::vector<double> c_g(size_t(Q) * dim);
   for (size_t k = 0; k < c_g.size(); ++k) c_g[k] = acoef * (0.5 + 0.37 * double(k)) * ((k % 3) == 1 ? -1.0 : 1.0);
   auto setup_ws = [&](getfem::ga_workspace &ws, const getfem::mesh_region &rg) {
     ws.add_fem_variable("u", mf, gmm::sub_interval(0, ndof), U);
-    if (family == "laplace" || family == "laplace_vec" || family == "mass")
+    if (coef_fem && (family == "laplace" || family == "laplace_vec" || family == "mass"))
+      ws.add_fem_constant("a", mf_d, d_a);
+    else if (coef_fem && family == "source")
+      ws.add_fem_constant("f", mf_dq, d_f);
+    else if (coef_fem && family == "elast") {
+      ws.add_fem_constant("lambda", mf_d, d_l);
+      ws.add_fem_constant("mu", mf_d, d_m);
+    } else if (family == "laplace" || family == "laplace_vec" || family == "mass")
       ws.add_fixed_size_constant("a", c_a);
     else if (family == "source")
       ws.add_fixed_size_constant("f", c_f);
@@ -387,6 +417,25 @@ int main(int argc, char **argv) {
     }
     npy_i32(out + "/items_cv.npy", {icv.size()}, icv);
     npy_i32(out + "/items_f.npy", {ifc.size()}, ifc);
+  }
+  if (coef_fem) {  // the data fems: dof tables, basis values at ALL integration points, nodal values
+    const getfem::mesh_fem &mfx = family == "source" ? mf_dq : mf_d;
+    getfem::pfem pfd = mfx.fem_of_element(cv0);
+    const size_type ndd = pfd->nb_dof(cv0), nqa = pai->nb_points();
+    std::vector<int64_t> ded(ne * ndd);
+    for (size_type cv = 0; cv < ne; ++cv) {
+      const auto &ct = mfx.ind_scalar_basic_dof_of_element(cv);
+      for (size_type i = 0; i < ndd; ++i) ded[cv * ndd + i] = int64_t(ct[i]);
+    }
+    getfem::pfem_precomp pfpd = getfem::fem_precomp(pfd, pai->pintegration_points(), 0);
+    std::vector<double> dphi(nqa * ndd);
+    for (size_type q = 0; q < nqa; ++q)
+      for (size_type i = 0; i < ndd; ++i) dphi[q * ndd + i] = pfpd->val(q)[i];
+    npy_i64(out + "/d_elem_dof.npy", {ne, ndd}, ded);
+    npy_f64(out + "/d_phi.npy", {nqa, ndd}, dphi);
+    if (family == "source") npy_f64(out + "/d_vals0.npy", {d_f.size()}, d_f);
+    else if (family == "elast") { npy_f64(out + "/d_vals0.npy", {d_l.size()}, d_l); npy_f64(out + "/d_vals1.npy", {d_m.size()}, d_m); }
+    else npy_f64(out + "/d_vals0.npy", {d_a.size()}, d_a);
   }
   for (auto &e : extras) {
     if (e->region != "all") {

@@ -37,6 +37,14 @@ def load_golden(name):
         d["fparams"] = d["gdata"].astype(np.float64)
     else:
         d["fparams"] = np.array([a]) if d["family"] in ("laplace", "mass") else np.array([lam, mu])
+    # fem-data coefficients (coef=fem): the fields replace the leading parameters; the data fem's basis table covers ALL
+    # integration points, so the all-point tables are used with it
+    d["fields"] = None
+    if args.get("coef") == "fem":
+        vals = [d["d_vals0"].astype(np.float64)] + ([d["d_vals1"].astype(np.float64)] if "d_vals1" in d else [])
+        if d["family"] == "source":
+            vals = [-vals[0]]  # "-f.Test_u": the family integrates F = -f
+        d["fields"] = {"d_elem_dof": d["d_elem_dof"], "d_phi": d["d_phi"], "vals": vals, "kd": int(args.get("kd", 1))}
     # further expressions of the same workspace (family2.., make_golden "m_*"): (family, parameters, region, region name)
     d["extra_terms"] = []
     for t in (2, 3, 4):
@@ -66,7 +74,7 @@ def load_golden(name):
         if (d["items_f"] >= 0).any():
             d["region"].update(face_first=d["face_first"], face_nq=d["face_nq"], ref_normals=d["ref_normals"])
             d["tables"] = (d["all_w"], d["all_gt_grad"], d["all_phi"], d["all_gphi"])
-    if any(rg is not None and "face_first" in rg for _, _, rg, _ in d["extra_terms"]):
+    if d["fields"] is not None or any(rg is not None and "face_first" in rg for _, _, rg, _ in d["extra_terms"]):
         d["tables"] = (d["all_w"], d["all_gt_grad"], d["all_phi"], d["all_gphi"])
     return d
 

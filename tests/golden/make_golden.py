@@ -63,6 +63,16 @@ CASES = {
                               "family3=mass region3=outer a3=5.0 family4=nsource region4=outer a4=0.7",
     "m_lap_q2_robin": "dim=3 n=2 gt=qk k=2 q=1 im=6 family=laplace u=random a=0.9 family2=mass region2=zmin a2=4.0 "
                       "family3=source a3=1.1",
+    # fem-data coefficients (ws.add_fem_constant): heterogeneous material, distributed loads
+    "f_lap3d_p2_coefp1": "dim=3 n=2 gt=pk k=2 q=1 im=4 family=laplace u=random a=1.3 coef=fem kd=1",
+    "f_elast3d_p2_coefp1": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=elast u=random lambda=1.2 mu=0.8 coef=fem kd=1",
+    "f_elast2d_p2_coefp2": "dim=2 n=3 gt=pk k=2 q=2 im=4 family=elast u=random lambda=2 mu=0.5 coef=fem kd=2",
+    "f_source3d_p2vec_coefp2": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=source u=random a=0.5 coef=fem kd=2",
+    "f_source2d_p1_coefp1": "dim=2 n=6 gt=pk k=1 q=1 im=2 family=source u=random a=1.5 coef=fem kd=1",
+    "f_mass3d_q2_coefq1": "dim=3 n=2 gt=qk k=2 q=1 im=6 family=mass u=random a=1.5 coef=fem kd=1",
+    "f_lap3d_q2_coefq2": "dim=3 n=2 gt=qk k=2 q=1 im=6 family=laplace u=random a=0.7 coef=fem kd=2",
+    "f_source3d_p2vec_xmax_coefp1": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=source region=xmax u=random a=0.5 coef=fem kd=1",
+    "f_mass3d_p2_outer_coefp1": "dim=3 n=2 gt=pk k=2 q=1 im=4 family=mass region=outer u=random a=2.5 coef=fem kd=1",
     "r_nh_ciarlet_q2_half": "dim=3 n=2 gt=qk k=2 q=3 im=6 family=nh_ciarlet region=half u=smooth lambda=1 mu=1 uamp=0.02",
 }
 
@@ -80,7 +90,9 @@ def main():
         arrs["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
         for k in ("conn", "elem_dof", "K_jc", "K_ir"):
             arrs[k] = arrs[k].astype(np.int32)
-        if "region" not in args:  # the all-point tables and face data only travel with the region fixtures
+        if "coef=fem" in args:  # keep the all-point tables: the data fem's basis table covers all points
+            arrs["d_elem_dof"] = arrs["d_elem_dof"].astype(np.int32)
+        elif "region" not in args:  # the all-point tables and face data only travel with the region fixtures
             for k in ("all_w", "all_x", "all_gt_grad", "all_phi", "all_gphi", "face_first", "face_nq", "ref_normals",
                       "gdata"):
                 arrs.pop(k, None)

@@ -14,7 +14,7 @@ def test_oracle_matches_reference(name):
     w, gt_grad, phi, gphi = g["tables"]
     jc, ir, pr, R = oracle.assemble(g["pts"], g["conn"], g["elem_dof"], ndof, g["Q"], w, gt_grad, phi, gphi,
                                     g["gt_linear"], g["family"], g["fparams"], g["U"], region=g["region"],
-                                    nq=g["meta"]["nq"])
+                                    nq=g["meta"]["nq"], fields=g["fields"])
     if g["extra_terms"]:  # several expressions in one workspace: every tree adds into the same K / V
         from conftest import csc_sum
         mats = [(jc, ir, pr)]
