@@ -48,6 +48,8 @@ SIGNATURES = {
     "gfgpu_term_create": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_double, C.c_int, _PP]),
     "gfgpu_term_destroy": (C.c_int, [_P]),
     "gfgpu_term_set_region": (C.c_int, [_P, _i64, _P, _P]),
+    "gfgpu_term_set_fields": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
+    "gfgpu_term_update_field": (C.c_int, [_P, C.c_int, _P]),
     "gfgpu_term_set_element_range": (C.c_int, [_P, _i64, _i64]),
     "gfgpu_term_assemble_dev": (C.c_int, [_P, _P, C.c_int]),
     "gfgpu_term_assemble_host": (C.c_int, [_P, _P, C.c_int, _P, _P]),
@@ -242,6 +244,24 @@ class DeviceTerm(_Handle):
         cv = np.ascontiguousarray(cv, np.int32)
         fc = None if face is None else np.ascontiguousarray(face, np.int32)
         check(lib().gfgpu_term_set_region(self.h, len(cv), ptr(cv), ptr(fc)))
+
+    def set_fields(self, data_fem, phi, vals, phi_faces=None):
+        """Fem-data coefficients: vals = [values of field 0 (, field 1)] on data_fem (a DeviceFem of the same mesh);
+        phi [nq, nd_d] = its basis at the volume points, phi_faces [nf, nqf, nd_d] at the face points."""
+        if data_fem is None:
+            check(lib().gfgpu_term_set_fields(self.h, 0, None, None, None, None, None))
+            self._dfem = None
+            return
+        phi = np.ascontiguousarray(phi, np.float64)
+        pf = None if phi_faces is None else np.ascontiguousarray(phi_faces, np.float64)
+        v = [np.ascontiguousarray(x, np.float64) for x in vals]
+        assert phi.shape[1] == data_fem.nd and all(len(x) == data_fem.ndof for x in v)
+        check(lib().gfgpu_term_set_fields(self.h, len(v), data_fem.h, ptr(phi), ptr(pf), ptr(v[0]),
+                                          ptr(v[1]) if len(v) > 1 else None))
+        self._dfem = data_fem  # keep it alive
+
+    def update_field(self, k, vals):
+        check(lib().gfgpu_term_update_field(self.h, int(k), ptr(np.ascontiguousarray(vals, np.float64))))
 
     def set_element_range(self, e0, e1):
         check(lib().gfgpu_term_set_element_range(self.h, int(e0), int(e1)))

@@ -332,6 +332,58 @@ static void term_forget_symbolic(gfgpu_term *t) {
   t->vJ.release(); t->vI.release(); t->vmask.release();
 }
 
+int gfgpu_term_set_fields(gfgpu_term *t, int nfields, gfgpu_fem *dfem, const double *phi, const double *phi_faces,
+                          const double *vals0, const double *vals1) {
+  GF_API_BEGIN
+  GF_REQUIRE(t, "null term");
+  gfgpu_ctx *ctx = t->ctx;
+  GF_CUDA(cudaSetDevice(ctx->device));
+  term_forget_symbolic(t);
+  t->stage.release(); t->emask.release(); t->rstage.release();
+  t->r_dedof_valid = false;
+  if (nfields == 0) {
+    t->nfields = 0; t->dfem = nullptr;
+    t->dphi.release(); t->dfphi.release(); t->dvals[0].release(); t->dvals[1].release(); t->r_dedof.release();
+    if (!t->region_faces)
+      t->strategy = t->strategy_asked == GFGPU_STRATEGY_AUTO
+                        ? (gf::recompute_supported(t) ? GFGPU_STRATEGY_RECOMPUTE : GFGPU_STRATEGY_STAGED)
+                        : t->strategy_asked;
+    return 0;
+  }
+  GF_REQUIRE(dfem && phi && vals0, "null argument");
+  GF_REQUIRE(dfem->mesh == t->mesh, "the data fem was built on another mesh");
+  const int fam = t->family;
+  const int maxf = (fam == GFGPU_LAPLACE || fam == GFGPU_MASS || fam == GFGPU_SOURCE) ? 1 : fam == GFGPU_ELASTICITY ? 2 : 0;
+  GF_REQUIRE(maxf > 0, "fem-data coefficients are handled for the Laplace, mass, elasticity and source families");
+  GF_REQUIRE(nfields >= 1 && nfields <= maxf, "wrong number of coefficient fields for this family");
+  GF_REQUIRE(nfields < 2 || vals1, "null argument");
+  GF_REQUIRE(dfem->qdim == (fam == GFGPU_SOURCE ? t->fem->qdim : 1),
+             "the data fem must be scalar (the source term's: qdim of the variable)");
+  GF_REQUIRE(t->strategy_asked != GFGPU_STRATEGY_RECOMPUTE, "fem-data coefficients use strategy STAGED");
+  const int ndd = dfem->nd, nq = t->tab->nq;
+  t->dphi.alloc(ctx, (size_t)nq * ndd); t->dphi.upload(phi);
+  if (phi_faces) {
+    GF_REQUIRE(t->tab->nf > 0, "face tables of the data fem need gfgpu_tables_set_faces first");
+    t->dfphi.alloc(ctx, (size_t)t->tab->nf * t->tab->nqf * ndd); t->dfphi.upload(phi_faces);
+  } else t->dfphi.release();
+  t->dvals[0].alloc(ctx, dfem->ndof); t->dvals[0].upload(vals0);
+  if (nfields > 1) { t->dvals[1].alloc(ctx, dfem->ndof); t->dvals[1].upload(vals1); } else t->dvals[1].release();
+  GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  t->nfields = nfields; t->dfem = dfem;
+  t->strategy = GFGPU_STRATEGY_STAGED;
+  GF_API_END
+}
+
+int gfgpu_term_update_field(gfgpu_term *t, int k, const double *vals) {
+  GF_API_BEGIN
+  GF_REQUIRE(t && vals && k >= 0 && k < t->nfields, "no such coefficient field");
+  GF_CUDA(cudaSetDevice(t->ctx->device));
+  t->dvals[k].upload(vals);
+  GF_CUDA(cudaStreamSynchronize(t->ctx->stream));
+  t->pat_valid = false;  // the drop rule looks at the values
+  GF_API_END
+}
+
 int gfgpu_term_set_element_range(gfgpu_term *t, int64_t e0, int64_t e1) {
   GF_API_BEGIN
   GF_REQUIRE(t, "null term");
@@ -354,10 +406,13 @@ int gfgpu_term_set_region(gfgpu_term *t, int64_t n_items, const int32_t *cv, con
   if (!cv) {  // back to all convexes
     t->region = t->region_faces = false;
     t->n_items = 0;
+    t->h_items_cv.clear();
+    t->r_dedof_valid = false;
     t->r_conn.release(); t->r_edof.release(); t->r_face.release();
-    t->strategy = t->strategy_asked == GFGPU_STRATEGY_AUTO
-                      ? (gf::recompute_supported(t) ? GFGPU_STRATEGY_RECOMPUTE : GFGPU_STRATEGY_STAGED)
-                      : t->strategy_asked;
+    if (!t->nfields)
+      t->strategy = t->strategy_asked == GFGPU_STRATEGY_AUTO
+                        ? (gf::recompute_supported(t) ? GFGPU_STRATEGY_RECOMPUTE : GFGPU_STRATEGY_STAGED)
+                        : t->strategy_asked;
     t->e0 = 0; t->e1 = t->mesh->ne;
     return 0;
   }
@@ -396,6 +451,8 @@ int gfgpu_term_set_region(gfgpu_term *t, int64_t n_items, const int32_t *cv, con
   t->region = true;
   t->region_faces = nfaces > 0;
   t->n_items = n_items;
+  t->h_items_cv.assign(cv, cv + n_items);
+  t->r_dedof_valid = false;
   if (nfaces) t->strategy = GFGPU_STRATEGY_STAGED;
   t->e0 = 0; t->e1 = n_items;
   GF_API_END
@@ -455,13 +512,34 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
   a.fw = t->tab->fw.p; a.fgt_grad = t->tab->fgt_grad.p; a.fphi = t->tab->fphi.p; a.fgphi = t->tab->fgphi.p;
   a.fnormal = t->tab->fnormal.p;
   a.nqf = t->tab->nqf;
+  a.nfields = t->nfields; a.nd_d = 0;
+  a.dedof = nullptr; a.dphi = a.dfphi = a.dvals0 = a.dvals1 = nullptr;
+  if (t->nfields) {
+    GF_REQUIRE(!t->region_faces || t->dfphi.n, "a region of faces needs the data fem's basis at the face points");
+    if (t->region && !t->r_dedof_valid) {  // region-ordered copy of the data fem's dof rows
+      const int ndd = t->dfem->nd;
+      std::vector<int32_t> hd((size_t)t->mesh->ne * ndd), rd((size_t)t->n_items * ndd);
+      t->dfem->edof.download(hd.data());
+      GF_CUDA(cudaStreamSynchronize(ctx->stream));
+      for (int64_t k = 0; k < t->n_items; ++k)
+        std::copy(hd.begin() + (size_t)t->h_items_cv[k] * ndd, hd.begin() + (size_t)(t->h_items_cv[k] + 1) * ndd,
+                  rd.begin() + (size_t)k * ndd);
+      t->r_dedof.alloc(ctx, rd.size());
+      t->r_dedof.upload(rd.data());
+      GF_CUDA(cudaStreamSynchronize(ctx->stream));
+      t->r_dedof_valid = true;
+    }
+    a.nd_d = t->dfem->nd;
+    a.dedof = t->region ? t->r_dedof.p : t->dfem->edof.p;
+    a.dphi = t->dphi.p; a.dfphi = t->dfphi.p; a.dvals0 = t->dvals[0].p; a.dvals1 = t->dvals[1].p;
+  }
   for (int k = 0; k < 5; ++k) t->ev_used[k] = false;
   auto tic = [&](int k) { GF_CUDA(cudaEventRecord(t->ev[2 * k], ctx->stream)); };
   auto toc = [&](int k) { GF_CUDA(cudaEventRecord(t->ev[2 * k + 1], ctx->stream)); t->ev_used[k] = true; };
   if (ne > 0 && (need_stage || need_masks || need_rstage)) {
     tic(0);
     const bool affine = t->mesh->gt_kind == GFGPU_GT_PK;
-    bool ok = (!t->region_faces && gf::launch_sumfact_kernel(ctx, t->tab, t->mesh->dim, Q, nd, affine, a)) ||
+    bool ok = (!t->region_faces && !t->nfields && gf::launch_sumfact_kernel(ctx, t->tab, t->mesh->dim, Q, nd, affine, a)) ||
               gf::launch_elem_kernel(ctx, t->mesh->dim, Q, nd, affine, a);
     GF_REQUIRE(ok, "no device kernel for this (dimension, qdim, local dofs, family) combination");
     toc(0);

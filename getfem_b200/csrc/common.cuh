@@ -154,6 +154,13 @@ struct gfgpu_term {
   int64_t n_items = 0;
   gf::DevBuf<int32_t> r_conn, r_edof;
   gf::DevBuf<int8_t> r_face;
+  std::vector<int32_t> h_items_cv;
+  // fem-data coefficients (gfgpu_term_set_fields): the leading `nfields` parameters are fields on `dfem`
+  int nfields = 0;
+  gfgpu_fem *dfem = nullptr;
+  gf::DevBuf<double> dphi, dfphi, dvals[2];   // basis of the data fem at the volume / face points; nodal values
+  gf::DevBuf<int32_t> r_dedof;                 // region-ordered copy of the data fem's dof rows
+  bool r_dedof_valid = false;
   const int32_t *conn_p() const { return region ? r_conn.p : mesh->conn.p; }
   const int32_t *edof_p() const { return region ? r_edof.p : fem->edof.p; }
   int64_t nb_items() const { return region ? n_items : mesh->ne; }
@@ -233,6 +240,10 @@ struct ElemArgs {
   const int8_t *face;
   const double *fw, *fgt_grad, *fphi, *fgphi, *fnormal;  // fnormal: nf x 3
   int nqf;
+  // fem-data coefficients: values at the Gauss point = sum_i vals[dedof[e][i] (+ component)] * dphi[q][i]
+  int nfields, nd_d;
+  const int32_t *dedof;
+  const double *dphi, *dfphi, *dvals0, *dvals1;
   double *stage;
   uint16_t *emask;
   double *rstage;

@@ -36,7 +36,7 @@ struct ElemCfg {
   static constexpr int DSZ = FK == FK_HYPER ? (Q * N * Q * N) : 1;
   static constexpr int ACC = SCALAR ? 1 : Q * Q;
   static constexpr int GEO = N * N + 1 + N;  // B, J, unit normal (faces)
-  __host__ __device__ static constexpr int per_q() { return GEO + ND * N + Q * N + DSZ + Q * N; }
+  __host__ __device__ static constexpr int per_q() { return GEO + ND * N + Q * N + DSZ + Q * N + 2; }  // + (lambda, mu) at the point
   __host__ __device__ static int slot_doubles(int ng, int qc) { return N * ng + S1 + GEO + qc * per_q() + 8; }
 };
 
@@ -280,11 +280,11 @@ elem_kernel(const ElemArgs a) {
   double *sGu = sZ + qc * ND * N;
   double *sD = sGu + qc * Q * N;
   double *sP = sD + qc * C::DSZ;
-  double *sRed = sP + qc * Q * N;
+  double *sLM = sP + qc * Q * N;  // Lame coefficients at the Gauss points (constants, or fem-data fields)
+  double *sRed = sLM + 2 * qc;
   const bool do_t = a.stage != nullptr || a.emask != nullptr;
   const bool do_r = a.rstage != nullptr;
   const bool need_gu = do_r || FK == FK_HYPER;
-  const double lambda = a.par[0], mu = a.par[1];
   const int64_t ne = a.e1 - a.e0;
 
   for (int64_t base = (int64_t)blockIdx.x * EPB; base < ne; base += (int64_t)gridDim.x * EPB) {
@@ -375,15 +375,44 @@ elem_kernel(const ElemArgs a) {
           const double coeff = (wq == 0.0) ? 0.0 : a.alpha * J * wq;  // zero-weight points are skipped (C&E.cc:8852)
           const double *Gu = sGu + q * Q * N;
           double *P = sP + q * Q * N;
+          // parameters at the point: constants, or fem-data fields (ga_instruction_val on the data fem, C&E.cc:636-690)
+          double par0 = a.par[0], par1 = a.par[1], fsrc[Q];
+#pragma unroll
+          for (int c = 0; c < Q; ++c) fsrc[c] = a.par[c];
+          if (a.nfields) {
+            const double *dp = (face >= 0 ? a.dfphi + ((size_t)face * nq + q0 + q) * a.nd_d : a.dphi + (size_t)(q0 + q) * a.nd_d);
+            const int32_t *dd = a.dedof + e * a.nd_d;
+            if (a.family == GFGPU_SOURCE) {
+#pragma unroll
+              for (int c = 0; c < Q; ++c) fsrc[c] = 0.0;
+              for (int i = 0; i < a.nd_d; ++i) {
+                const double ph = dp[i];
+                const double *v = a.dvals0 + dd[i];
+#pragma unroll
+                for (int c = 0; c < Q; ++c) fsrc[c] += v[c] * ph;
+              }
+            } else {
+              double v0 = 0.0, v1 = 0.0;
+              for (int i = 0; i < a.nd_d; ++i) {
+                v0 += a.dvals0[dd[i]] * dp[i];
+                if (a.nfields > 1) v1 += a.dvals1[dd[i]] * dp[i];
+              }
+              par0 = v0;
+              if (a.nfields > 1) par1 = v1;
+            }
+          }
+          const double lambda = par0, mu = par1;
+          sLM[2 * q] = lambda;
+          sLM[2 * q + 1] = mu;
           if (FK == FK_LAPLACE) {
-            sD[q] = coeff * a.par[0];
+            sD[q] = coeff * par0;
             if (need_gu)
-              for (int r = 0; r < Q * N; ++r) P[r] = coeff * a.par[0] * Gu[r];
+              for (int r = 0; r < Q * N; ++r) P[r] = coeff * par0 * Gu[r];
           } else if (FK == FK_MASS) {
             if (a.family == GFGPU_SOURCE) {  // "F.Test_u": r_e(i b) = sum_q J w_q F_b phi_i (C&E.cc:437-461, 4669-4735)
               sD[q] = 0.0;
               if (need_gu)
-                for (int c = 0; c < Q; ++c) P[c] = coeff * a.par[c];
+                for (int c = 0; c < Q; ++c) P[c] = coeff * fsrc[c];
             } else if (a.family == GFGPU_NORMAL_SOURCE) {  // "(A*Normal).Test_u", A(b,n) = par[b + Q n] (getfem_models.cc:4290-4299)
               sD[q] = 0.0;
               const double *nrm = (AFFINE ? sGeoA : sGeo + q * GEO) + N * N + 1;
@@ -394,9 +423,9 @@ elem_kernel(const ElemArgs a) {
                   P[c] = coeff * an;
                 }
             } else {
-              sD[q] = coeff * a.par[0];
+              sD[q] = coeff * par0;
               if (need_gu)
-                for (int c = 0; c < Q; ++c) P[c] = coeff * a.par[0] * Gu[c];
+                for (int c = 0; c < Q; ++c) P[c] = coeff * par0 * Gu[c];
             }
           } else if (FK == FK_ELAST) {
             sD[q] = coeff;
@@ -440,7 +469,7 @@ elem_kernel(const ElemArgs a) {
                 double zi[N], zj[N], s = 0;
 #pragma unroll
                 for (int n = 0; n < N; ++n) { zi[n] = Zi[n]; zj[n] = Zj[n]; s += zi[n] * zj[n]; }
-                const double c = sD[q];
+                const double c = sD[q], lambda = sLM[2 * q], mu = sLM[2 * q + 1];
 #pragma unroll
                 for (int bb = 0; bb < Q; ++bb)
 #pragma unroll

@@ -259,6 +259,7 @@ class ga_workspace:
         self.ctx = ctx or default_context()
         self.variables = {}   # name -> (mesh_fem, values)
         self.constants = {}   # name -> values
+        self.fem_constants = {}   # name -> (mesh_fem, nodal values): ga_workspace::add_fem_constant
         self.terms = []       # (family, variable, params, mim, DeviceTerm or None)
         self._K = None
         self._R = None
@@ -271,13 +272,36 @@ class ga_workspace:
     def add_fixed_size_constant(self, name, V):
         self.constants[name] = np.atleast_1d(np.asarray(V, np.float64))
 
+    def add_fem_constant(self, name, mf, V):
+        """Fem data (generic_assembly.h:465): a coefficient or load given by nodal values on a mesh_fem."""
+        V = np.ascontiguousarray(V, np.float64)
+        self.fem_constants[name] = (mf, V)
+
     def add_expression(self, expr, mim, region=None, add_derivative_order=2):
         fam, var, cnames = recognise(expr)
         if var not in self.variables:
             raise capi.GfgpuError("unknown variable " + var)
         for c in cnames:
-            if c not in self.constants:
+            if c not in self.constants and c not in self.fem_constants:
                 raise capi.GfgpuError("unknown constant " + c)
+        # fem-data coefficients: the leading parameters of the family given as fields on one data mesh_fem
+        fields = None
+        nfem = [c in self.fem_constants for c in cnames]
+        if any(nfem):
+            if fam.startswith("nsource") or fam not in ("laplace", "mass", "elast", "source-", "source+"):
+                raise capi.GfgpuError("fem-data coefficients are not handled for this expression")
+            if not nfem[0] or (len(nfem) > 1 and nfem[1] and not nfem[0]):
+                raise capi.GfgpuError("a fem-data second coefficient needs a fem-data first coefficient")
+            names = [c for c, f in zip(cnames, nfem) if f]
+            mfd = self.fem_constants[names[0]][0]
+            if any(self.fem_constants[c][0] is not mfd for c in names):
+                raise capi.GfgpuError("the fem-data coefficients of one term must live on the same mesh_fem")
+            if mfd.linked_mesh is not self.variables[var][0].linked_mesh:
+                raise capi.GfgpuError("the data mesh_fem must be defined on the mesh of the variable")
+            sign = -1.0 if fam == "source-" else 1.0
+            fields = (mfd, [sign * self.fem_constants[c][1] for c in names])
+            for c in names:  # placeholders: the parameter slots of the fields are ignored by the device term
+                self.constants.setdefault(c, np.ones(self.variables[var][0].Qdim if fam.startswith("source") else 1))
         if fam.startswith("nsource"):
             mf = self.variables[var][0]
             g = self.constants[cnames[0]]
@@ -313,12 +337,16 @@ class ga_workspace:
         # one region would therefore not reproduce the reference's pattern when assembled separately: refuse.
         if fam not in ("source", "nsource"):
             key = None if region is None else frozenset(region._items)
-            for f2, v2, _, mim2, _, rg2 in self.terms:
+            for f2, v2, _, mim2, _, rg2, _ in self.terms:
                 if f2 not in ("source", "nsource") and v2 == var and mim2 is mim and \
                         (None if rg2 is None else frozenset(rg2._items)) == key:
                     raise capi.GfgpuError("several bilinear forms on one region are thresholded together by the reference; "
                                           "not handled by the device path")
-        self.terms.append([fam, var, params, mim, None, region])
+        if fields is not None:
+            want = self.variables[var][0].Qdim if fam == "source" else 1
+            if fields[0].Qdim != want:
+                raise capi.GfgpuError("the data mesh_fem must have qdim %d for this term" % want)
+        self.terms.append([fam, var, params, mim, None, region, fields])
         return len(self.terms) - 1
 
     def nb_trees(self):
@@ -326,7 +354,7 @@ class ga_workspace:
 
     # ---- device objects
     def _term(self, k):
-        fam, var, params, mim, dev, region = self.terms[k]
+        fam, var, params, mim, dev, region, fields = self.terms[k]
         if dev is None:
             mf, _ = self.variables[var]
             m = mf.linked_mesh
@@ -339,6 +367,15 @@ class ga_workspace:
             if region is not None:
                 cv, fc = region.items()
                 dev.set_region(cv, fc if region.is_only_faces() else None)
+            if fields is not None:
+                mfd, vals = fields
+                kind = mfd.fem_kind()
+                phi = fem_tables.lagrange_tables(kind, m.dim(), mfd.K, t["quad_x"])[0]
+                pf = None
+                if region is not None and region.is_only_faces():
+                    X = ft["quad_x"]
+                    pf = fem_tables.lagrange_tables(kind, m.dim(), mfd.K, X.reshape(-1, m.dim()))[0].reshape(X.shape[0], X.shape[1], -1)
+                dev.set_fields(mfd.device(self.ctx), phi, vals, pf)
             self.terms[k][4] = dev
         return dev
 

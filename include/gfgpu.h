@@ -147,6 +147,20 @@ int gfgpu_term_destroy(gfgpu_term *t);
  * n_items = 0 with cv_host == NULL removes the region (all convexes again). */
 int gfgpu_term_set_region(gfgpu_term *t, int64_t n_items, const int32_t *cv_host, const int32_t *face_host);
 
+/* Fem-data coefficients: the leading `nfields` parameters of the family become FIELDS on a data mesh_fem instead of
+ * constants -- ga_workspace::add_fem_constant (generic_assembly.h:465), evaluated at every Gauss point by
+ * ga_instruction_val on the data fem (C&E.cc:636-690): "a*Grad_u.Grad_Test_u" with a heterogeneous a(x), lambda(x) / mu(x)
+ * of the elasticity brick, the distributed load F(x) of add_source_term_brick (getfem_models.cc:4124-).
+ *   LAPLACE, MASS: 1 field (a), scalar data fem; ELASTICITY: 1 or 2 (lambda[, mu]), scalar data fem;
+ *   SOURCE: 1 field of qdim components (data fem of the variable's qdim), vals0 already carrying the sign of the expression.
+ *   data_fem: a gfgpu_fem on the same mesh; phi_host[nq][nd_d]: its basis at the volume quadrature points
+ *   (fem_precomp_::val); phi_faces_host[nf][nqf][nd_d] (or NULL): the same at the face points, for regions of faces;
+ *   vals*_host: nodal values (data_fem ndof).  nfields = 0 removes the fields.  Such terms use strategy STAGED.
+ * update_field replaces the nodal values of field k (same data fem), e.g. between load steps. */
+int gfgpu_term_set_fields(gfgpu_term *t, int nfields, gfgpu_fem *data_fem, const double *phi_host,
+                          const double *phi_faces_host, const double *vals0_host, const double *vals1_host);
+int gfgpu_term_update_field(gfgpu_term *t, int k, const double *vals_host);
+
 /* Restrict the term to the block [e0, e1) of its elements -- of its region's items when a region is set -- (per-rank
  * element partition, getfem_mesh_region.cc:145-185).  Default: everything. */
 int gfgpu_term_set_element_range(gfgpu_term *t, int64_t e0, int64_t e1);

@@ -20,9 +20,25 @@ EXPR = {  # {s}: suffix of the constants' names when several expressions share a
 }
 
 
-def add_term(ws, mim, m, Q, family, params, region, sfx=""):
+def add_term(ws, mim, m, Q, family, params, region, sfx="", fields=None):
     from conftest import make_region
+    import getfem_b200 as gf
     expr = EXPR[family].format(s=sfx)
+    if fields is not None:  # fem-data coefficients on a classical data fem of degree kd: (kd, [nodal values ...], dof table)
+        kd, vals, ded = fields
+        mfd = gf.mesh_fem(m, Q if family == "source" else 1)
+        mfd.set_classical_finite_element(kd)
+        if ded is not None:
+            assert np.array_equal(mfd.ind_scalar_basic_dof_of_element(), ded), "data fem numbering differs from the reference"
+        names = {"laplace": ["a"], "mass": ["a"], "elast": ["lambda", "mu"], "source": ["f"]}[family]
+        for nm, v in zip(names, vals):
+            ws.add_fem_constant(nm + sfx, mfd, v(mfd) if callable(v) else v)
+        if family == "source" and Q == 1:
+            expr = "-f%s*Test_u" % sfx
+        rg = make_region(m, region)
+        ws.add_expression(expr, mim, rg)
+        ws.data_fem = mfd
+        return rg
     if family == "source":
         ws.add_fixed_size_constant("f" + sfx, [-p for p in params])  # the goldens carry F = -f
         if Q == 1:
@@ -43,7 +59,7 @@ def add_term(ws, mim, m, Q, family, params, region, sfx=""):
     return rg
 
 
-def build_ws(dim, nsub, gt, k, Q, im, family, params, U=None, region=None, extra=()):
+def build_ws(dim, nsub, gt, k, Q, im, family, params, U=None, region=None, extra=(), fields=None):
     import getfem_b200 as gf
     m = gf.mesh()
     gf.regular_unit_mesh(m, nsub, "GT_%s(%d,1)" % (gt, dim))
@@ -58,7 +74,7 @@ def build_ws(dim, nsub, gt, k, Q, im, family, params, U=None, region=None, extra
     elif callable(U):
         U = U(mf)
     ws.add_fem_variable("u", mf, slice(0, ndof), U)
-    ws.region = add_term(ws, mim, m, Q, family, params, region)
+    ws.region = add_term(ws, mim, m, Q, family, params, region, fields=fields)
     for t, (fam2, fp2, _, rgname2) in enumerate(extra):
         add_term(ws, mim, m, Q, fam2, list(fp2), rgname2, str(t + 2))
     return ws, mf, m, U
@@ -71,7 +87,10 @@ def test_workspace_matches_reference_golden(name):
     dim = int(a["dim"])
     nsub = [int(a["n"])] * dim if "n" in a else [int(a["nx"]), int(a["ny"]), int(a["nz"])][:dim]
     ws, mf, m, _ = build_ws(dim, nsub, "PK" if g["gt_linear"] else "QK", int(a["k"]), g["Q"], int(a["im"]),
-                            g["family"], g["fparams"], g["U"], a.get("region"), g["extra_terms"])
+                            g["family"], g["fparams"], g["U"], a.get("region"), g["extra_terms"],
+                            None if g["fields"] is None else
+                            (g["fields"]["kd"], [(-v if g["family"] == "source" else v) for v in g["fields"]["vals"]],
+                             g["fields"]["d_elem_dof"]))
     # device first-touch numbering == mesh_fem::enumerate_dof, bit for bit
     assert mf.nb_dof() == g["meta"]["ndof"]
     assert np.array_equal(mf.ind_scalar_basic_dof_of_element(), g["elem_dof"])
@@ -120,7 +139,36 @@ CASES = [  # dim, nsub, gt, k, Q, im, family, params, U
     (3, [9, 9, 9], "PK", 1, 1, 2, "laplace", [1.0], "random", "half"),
     (3, [4, 3, 3], "QK", 2, 3, 6, "nh_ciarlet", [1.0, 1.0], "smooth", "half"),
     (3, [2, 2, 1], "QK", 4, 1, 8, "laplace", [1.0], "random", "half"),
+    # fem-data coefficients (add_fem_constant) on a data fem of degree kd (last entry), volume and boundary regions
+    (3, [5, 4, 3], "PK", 2, 1, 4, "laplace", [1.0], "random", None, 1),
+    (3, [5, 4, 3], "PK", 2, 3, 4, "elast", [1.0, 1.0], "random", None, 2),
+    (2, [14, 11], "PK", 2, 2, 4, "elast", [1.0, 1.0], "random", "half", 1),
+    (3, [5, 4, 3], "PK", 2, 3, 4, "source", [1.0, 1.0, 1.0], "random", None, 2),
+    (3, [5, 4, 3], "PK", 2, 3, 4, "source", [1.0, 1.0, 1.0], "random", "xmax", 1),
+    (3, [5, 4, 3], "PK", 2, 1, 4, "mass", [1.0], "random", "outer", 2),
+    (3, [3, 3, 2], "QK", 2, 1, 6, "laplace", [1.0], "random", None, 2),
+    (3, [3, 3, 2], "QK", 2, 3, 6, "source", [1.0, 1.0, 1.0], "random", "zmin", 1),
 ]
+
+
+def field_functions(family, Q):
+    """Analytic coefficient fields sampled at the data fem's dof nodes."""
+    def scal(c0, kx, ky, kz):
+        def f(mfd):
+            X = mfd.basic_dof_nodes()
+            z = X[:, 2] if X.shape[1] > 2 else 0.0
+            return c0 * (1.0 + 0.3 * np.sin(kx * X[:, 0] + ky * X[:, 1] + kz * z))
+        return f
+
+    def vec(mfd):
+        X = mfd.basic_dof_nodes()
+        comp = np.arange(X.shape[0]) % Q
+        return 0.7 * (comp + 1) * (1.0 + 0.5 * X[:, 0] - 0.25 * X[:, -1])
+    if family == "source":
+        return [vec]
+    if family == "elast":
+        return [scal(1.2, 1.1, -0.7, 0.3), scal(0.8, 1.3, -1.0, 0.0)]
+    return [scal(1.3, 1.7, 0.9, 0.4)]
 
 
 def oracle_region(rg, t, ft):
@@ -139,35 +187,45 @@ def oracle_region(rg, t, ft):
                  cat(t["gphi"], ft["gphi"]))
 
 
-@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s_%s%d_q%d_%s%s" % (c[6], c[2], c[3], c[4], "x".join(map(str, c[1])),
-                                                                           "_" + c[9] if len(c) > 9 else ""))
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s_%s%d_q%d_%s%s%s" % (
+    c[6], c[2], c[3], c[4], "x".join(map(str, c[1])), "_" + c[9] if len(c) > 9 and c[9] else "",
+    "_coefk%d" % c[10] if len(c) > 10 else ""))
 def test_workspace_matches_oracle(case):
     from oracle import oracle
     from getfem_b200 import fem_tables
     dim, nsub, gt, k, Q, im, family, params, umode = case[:9]
     region = case[9] if len(case) > 9 else None
+    kd = case[10] if len(case) > 10 else None
     if umode == "random":
         rng = np.random.default_rng(7)
         U = lambda mf: rng.uniform(-1, 1, mf.nb_dof())  # noqa: E731
     else:
         U = smooth_u(0.03)
-    ws, mf, m, Uv = build_ws(dim, nsub, gt, k, Q, im, family, params, U, region)
+    fields = None if kd is None else (kd, field_functions(family, Q), None)
+    ws, mf, m, Uv = build_ws(dim, nsub, gt, k, Q, im, family, params, U, region, fields=fields)
     ws.assembly(2)
     ws.assembly(1)
     jc, ir, pr = ws.assembled_matrix()
     t = fem_tables.classical_tables(gt, dim, k, im)
     ft = fem_tables.classical_face_tables(gt, dim, k, im) if region in ("outer", "xmax", "zmin") else None
     reg, (w, gtg, phi, gphi) = oracle_region(ws.region, t, ft)
+    ofields = None
+    if kd is not None:  # the data fem's basis at the same points as the other tables; "-f.Test_u" integrates F = -f
+        mfd = ws.data_fem
+        X = t["quad_x"] if ft is None else np.concatenate([t["quad_x"], ft["quad_x"].reshape(-1, dim)])
+        vals = [fn(mfd) for fn in field_functions(family, Q)]
+        ofields = {"d_elem_dof": mfd.ind_scalar_basic_dof_of_element(), "d_phi": fem_tables.lagrange_tables(gt, dim, kd, X)[0],
+                   "vals": [-v for v in vals] if family == "source" else vals}
     ojc, oir, opr, oR = oracle.assemble(m.pts, m.conn, mf.ind_scalar_basic_dof_of_element(), mf.nb_dof(), Q,
                                         w, gtg, phi, gphi, gt == "PK", family, params, Uv, region=reg,
-                                        nq=len(t["quad_w"]))
+                                        nq=len(t["quad_w"]), fields=ofields)
     assert np.array_equal(jc, ojc) and np.array_equal(ir, oir)
     assert np.linalg.norm(pr - opr) / max(np.linalg.norm(opr), 1e-300) < 1e-12
     assert np.linalg.norm(ws.assembled_vector() - oR) / np.linalg.norm(oR) < 1e-12
     if family == "nsource" and region == "outer" and Q == dim:
         # divergence theorem on the closed boundary: sum_i int (A n)_b phi_i = int (A n)_b = 0 for a constant A
         assert np.abs(ws.assembled_vector().reshape(-1, Q).sum(0)).max() < 1e-12
-    if family == "mass" and region == "outer" and Q == 1:
+    if family == "mass" and region == "outer" and Q == 1 and kd is None:
         # 1^T M 1 = measure of the boundary of the unit square / cube
         import scipy.sparse as sp
         M = sp.csc_matrix((pr, ir, jc), shape=(mf.nb_dof(),) * 2)
