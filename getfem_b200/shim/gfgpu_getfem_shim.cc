@@ -85,12 +85,19 @@ static bool recognise_string(const getfem::ga_workspace &ws, const std::string &
   const std::string I3 = "\\[\\[1,0,0\\],\\[0,1,0\\],\\[0,0,1\\]\\]", I2 = "\\[\\[1,0\\],\\[0,1\\]\\]";
   const std::string Idm = "(?:" + I3 + "|" + I2 + ")";
   std::smatch m;
-  auto scalar = [&](const std::string &name) {
-    GMM_ASSERT1(ws.is_constant(name) && ws.value(name).size() == 1, "gfgpu: '" << name << "' must be a scalar constant");
-    return ws.value(name)[0];
-  };
   out.varname = v;
   out.params.clear();
+  out.field_names.clear();
+  out.field_sign = 1.0;
+  auto scalar = [&](const std::string &name) {
+    GMM_ASSERT1(ws.is_constant(name), "gfgpu: '" << name << "' must be a constant");
+    if (ws.associated_mf(name)) {  // fem data: a field on its mesh_fem (add_fem_constant)
+      out.field_names.push_back(name);
+      return 1.0;
+    }
+    GMM_ASSERT1(ws.value(name).size() == 1, "gfgpu: '" << name << "' must be a scalar constant");
+    return ws.value(name)[0];
+  };
   if (std::regex_match(s, m, std::regex("\\(" + ID + "\\*Grad_" + v + "\\)[.:]Grad_Test_" + v))) {
     out.family = GFGPU_LAPLACE; out.params = {scalar(m[1])}; return true;
   }
@@ -111,9 +118,16 @@ static bool recognise_string(const getfem::ga_workspace &ws, const std::string &
     else if (std::regex_match(s, m, std::regex(ID + "[.*]Test_" + v))) { sign = 1; name = m[1]; }
     if (sign != 0 && name != v && ws.is_constant(name) && !ws.variable_group_exists(name)) {
       const getfem::mesh_fem *pmf = ws.associated_mf(v);
+      out.family = GFGPU_SOURCE;
+      if (const getfem::mesh_fem *pmd = ws.associated_mf(name)) {  // distributed load: fem data of the variable's qdim
+        GMM_ASSERT1(pmf && pmd->get_qdim() == pmf->get_qdim(), "gfgpu: the load's mesh_fem must have the qdim of the variable");
+        out.field_names.push_back(name);
+        out.field_sign = sign;
+        out.params.assign(pmf->get_qdim(), 0.0);
+        return true;
+      }
       GMM_ASSERT1(pmf && ws.value(name).size() == pmf->get_qdim(),
                   "gfgpu: the source term needs a fixed-size constant with qdim components");
-      out.family = GFGPU_SOURCE;
       for (size_type k = 0; k < ws.value(name).size(); ++k) out.params.push_back(sign * ws.value(name)[k]);
       return true;
     }
@@ -137,10 +151,14 @@ static bool recognise_string(const getfem::ga_workspace &ws, const std::string &
   }
   if (std::regex_match(s, m, std::regex("\\(\\(Div_" + v + "\\*\\(" + ID + "\\*" + Idm + "\\)\\)\\+\\(\\(2\\*" + ID +
                                         "\\)\\*\\(Sym\\(Grad_" + v + "\\)\\)\\)\\):Grad_Test_" + v))) {
+    GMM_ASSERT1(ws.associated_mf(m[1]) || !ws.associated_mf(m[2]),
+                "gfgpu: a fem-data mu needs a fem-data lambda (fields replace the LEADING parameters)");
     out.family = GFGPU_ELASTICITY; out.params = {scalar(m[1]), scalar(m[2])}; return true;
   }
   if (std::regex_match(s, m, std::regex("\\(\\(" + ID + "\\*Div_" + v + "\\)\\*Div_Test_" + v + "\\)\\+\\(\\(\\(2\\*" + ID +
                                         "\\)\\*\\(Sym\\(Grad_" + v + "\\)\\)\\):Grad_Test_" + v + "\\)"))) {
+    GMM_ASSERT1(ws.associated_mf(m[1]) || !ws.associated_mf(m[2]),
+                "gfgpu: a fem-data mu needs a fem-data lambda (fields replace the LEADING parameters)");
     out.family = GFGPU_ELASTICITY; out.params = {scalar(m[1]), scalar(m[2])}; return true;
   }
   if (std::regex_match(s, m, std::regex("\\(\\(" + I3 + "\\+Grad_" + v + "\\)\\*" + ID + "_PK2\\(Grad_" + v + "," + ID +
@@ -161,12 +179,15 @@ static bool recognise_string(const getfem::ga_workspace &ws, const std::string &
 struct device_assembler::entry {
   gfgpu_mesh *mesh = nullptr;
   gfgpu_fem *fem = nullptr;
+  gfgpu_fem *dfem = nullptr;  // data fem of the fem-data coefficients
+  bool used = false;
   gfgpu_tables *tab = nullptr;
   gfgpu_term *term = nullptr;
   size_type ndof = 0;
   ~entry() {
     gfgpu_term_destroy(term);
     gfgpu_tables_destroy(tab);
+    gfgpu_fem_destroy(dfem);
     gfgpu_fem_destroy(fem);
     gfgpu_mesh_destroy(mesh);
   }
@@ -276,6 +297,7 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     key << &m << "/" << &mf << "/" << &mim << "/" << rt.family << "/" << ne << "/" << ndof << "/" << fdeg << "/"
         << getfem::name_of_int_method(pim);
     for (double p : rt.params) key << "/" << p;
+    for (const std::string &fn : rt.field_names) key << "/field:" << fn << "@" << ws.associated_mf(fn);
     if (!all_cv) {  // the region's content is part of the key (FNV-1a over the items)
       uint64_t h = 1469598103934665603ull;
       for (size_t k = 0; k < rg_cv.size(); ++k) {
@@ -353,8 +375,56 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
                                    order == 2 ? alpha * alpha : alpha, GFGPU_STRATEGY_AUTO, &e.term));
       if (!all_cv)
         GFGPU_CALL(gfgpu_term_set_region(e.term, int64_t(rg_cv.size()), rg_cv.data(), rg_faces ? rg_f.data() : nullptr));
+      if (!rt.field_names.empty()) {
+        // fem-data coefficients: the data mesh_fem's dof table and its basis at the same points (fem_precomp_::val)
+        const getfem::mesh_fem *pmd = ws.associated_mf(rt.field_names[0]);
+        for (const std::string &fn : rt.field_names)
+          GMM_ASSERT1(ws.associated_mf(fn) == pmd, "gfgpu: the fem-data coefficients of one term must share their mesh_fem");
+        GMM_ASSERT1(&pmd->linked_mesh() == &m && !pmd->is_reduced(), "gfgpu: the data mesh_fem must be a non-reduced fem of the same mesh");
+        getfem::pfem pfd = pmd->fem_of_element(cv0);
+        for (dal::bv_visitor cv(m.convex_index()); !cv.finished(); ++cv)
+          GMM_ASSERT1(pmd->fem_of_element(cv) == pfd, "gfgpu: mixed data fems are not handled");
+        bool dqk; int ddim, ddeg;
+        GMM_ASSERT1(parse_kind(getfem::name_of_fem(pfd), "FEM", dqk, ddim, ddeg) && dqk == fqk,
+                    "gfgpu: data fem not handled: " << getfem::name_of_fem(pfd));
+        const size_type ndd = pfd->nb_dof(cv0);
+        std::vector<int64_t> ded(ne * ndd);
+        for (size_type cv = 0; cv < ne; ++cv) {
+          const auto &ct = pmd->ind_scalar_basic_dof_of_element(cv);
+          for (size_type i = 0; i < ndd; ++i) ded[cv * ndd + i] = int64_t(ct[i]);
+        }
+        GFGPU_CALL(gfgpu_fem_create(ctx_, e.mesh, dqk ? GFGPU_FEM_QK : GFGPU_FEM_PK, ddeg, int(pmd->get_qdim()), int(ndd),
+                                    ded.data(), int64_t(pmd->nb_dof()), &e.dfem));
+        getfem::pfem_precomp pfpd = getfem::fem_precomp(pfd, pspt, 0);
+        std::vector<double> dphi(nq * ndd), dfphi;
+        for (size_type q = 0; q < nq; ++q)
+          for (size_type i = 0; i < ndd; ++i) dphi[q * ndd + i] = pfpd->val(q)[i];
+        if (rg_faces) {
+          const size_type nf = pgt->structure()->nb_faces(), nqf = pai->nb_points_on_face(0);
+          dfphi.resize(nf * nqf * ndd);
+          for (size_type f = 0; f < nf; ++f)
+            for (size_type q = 0; q < nqf; ++q)
+              for (size_type i = 0; i < ndd; ++i)
+                dfphi[((f * nqf) + q) * ndd + i] = pfpd->val(pai->ind_first_point_on_face(getfem::short_type(f)) + q)[i];
+        }
+        std::vector<std::vector<double>> vals;
+        for (const std::string &fn : rt.field_names) {
+          vals.emplace_back(ws.value(fn).begin(), ws.value(fn).end());
+          for (double &x : vals.back()) x *= rt.field_sign;
+        }
+        GFGPU_CALL(gfgpu_term_set_fields(e.term, int(vals.size()), e.dfem, dphi.data(), rg_faces ? dfphi.data() : nullptr,
+                                         vals[0].data(), vals.size() > 1 ? vals[1].data() : nullptr));
+      }
     }
     entry &e = *pe;
+    if (!rt.field_names.empty() && e.used) {  // cached device term: the data may have changed since the last assembly
+      for (size_t k = 0; k < rt.field_names.size(); ++k) {
+        std::vector<double> vals(ws.value(rt.field_names[k]).begin(), ws.value(rt.field_names[k]).end());
+        for (double &x : vals) x *= rt.field_sign;
+        GFGPU_CALL(gfgpu_term_update_field(e.term, int(k), vals.data()));
+      }
+    }
+    e.used = true;
     // the variable's values, in the fem's own numbering (the workspace interval only offsets the result)
     const getfem::model_real_plain_vector &U = ws.value(rt.varname);
     GMM_ASSERT1(U.size() == ndof, "gfgpu: bad size of the variable's value vector");

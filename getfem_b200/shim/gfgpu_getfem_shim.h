@@ -21,6 +21,10 @@ struct recognised_term {
   int family;             // GFGPU_LAPLACE ...
   std::string varname;    // the fem variable (Test and Test2)
   std::vector<double> params;
+  // fem-data coefficients (ga_workspace::add_fem_constant): names of the leading parameters that are fields on a data
+  // mesh_fem; `field_sign` multiplies their nodal values (the source term's "-f")
+  std::vector<std::string> field_names;
+  double field_sign = 1.0;
 };
 
 // Matches the ORDER-1 tree of `ws` number `itree` (as printed by ga_tree_to_string after the

@@ -93,13 +93,36 @@ int main(int argc, char **argv) {
   getfem::outer_faces_of_mesh(m, rg_outer);
   const getfem::mesh_region rg_all = getfem::mesh_region::all_convexes();
   const getfem::mesh_region &rg = rgname == "all" ? rg_all : rg_sel;
+  // coef=fem: the coefficients / the load are fem data on classical mesh_fems of degree kd (add_fem_constant)
+  const bool coef_fem = gets("coef", "const") == "fem";
+  getfem::mesh_fem mf_d(m, 1), mf_dq(m, getfem::dim_type(Q));
+  mf_d.set_classical_finite_element(getfem::dim_type(geti("kd", 1)));
+  mf_dq.set_classical_finite_element(getfem::dim_type(geti("kd", 1)));
+  std::vector<double> d_a(mf_d.nb_dof()), d_l(mf_d.nb_dof()), d_m(mf_d.nb_dof()), d_f(mf_dq.nb_dof());
+  for (size_type d = 0; d < mf_d.nb_dof(); ++d) {
+    bgeot::base_node P = mf_d.point_of_basic_dof(d);
+    d_a[d] = acoef * (1.0 + 0.3 * std::sin(1.7 * P[0] + 0.9 * P[1]));
+    d_l[d] = lambda * (1.0 + 0.25 * std::cos(1.1 * P[0] - 0.7 * P[1]));
+    d_m[d] = mu * (1.0 + 0.2 * std::cos(1.3 * P[0] - P[dim - 1]));
+  }
+  for (size_type d = 0; d < mf_dq.nb_dof(); ++d) {
+    bgeot::base_node P = mf_dq.point_of_basic_dof(d);
+    d_f[d] = 0.75 * double(d % Q + 1) * (1.0 + 0.5 * P[0] - 0.25 * P[dim - 1]);
+  }
   auto setup = [&](getfem::ga_workspace &ws) {
     ws.add_fem_variable("u", mf, gmm::sub_interval(0, ndof), U);
-    ws.add_fixed_size_constant("a", c_a);
-    ws.add_fixed_size_constant("lambda", c_l);
-    ws.add_fixed_size_constant("mu", c_m);
+    if (coef_fem) {
+      ws.add_fem_constant("a", mf_d, d_a);
+      ws.add_fem_constant("lambda", mf_d, d_l);
+      ws.add_fem_constant("mu", mf_d, d_m);
+      ws.add_fem_constant("f", mf_dq, d_f);
+    } else {
+      ws.add_fixed_size_constant("a", c_a);
+      ws.add_fixed_size_constant("lambda", c_l);
+      ws.add_fixed_size_constant("mu", c_m);
+      ws.add_fixed_size_constant("f", c_f);
+    }
     ws.add_fixed_size_constant("params", c_p);
-    ws.add_fixed_size_constant("f", c_f);
     ws.add_fixed_size_constant("g", c_g);
     ws.add_expression(expr, mim, rg);
     if (a.count("model")) {  // a model-like workspace: + Robin mass on the outer faces + Neumann load + volumic source

@@ -39,6 +39,13 @@ CASES = [
     "dim=3 n=4 gt=pk k=2 q=3 im=4 family=elast model=1",
     "dim=2 n=24 gt=pk k=1 q=1 im=2 family=laplace model=1",
     "dim=3 n=3 gt=qk k=2 q=3 im=6 family=nh_ciarlet model=1",
+    # fem-data coefficients read from the workspace (add_fem_constant): heterogeneous material, distributed load
+    "dim=3 n=4 gt=pk k=2 q=3 im=4 family=elast coef=fem kd=1",
+    "dim=3 n=4 gt=pk k=2 q=1 im=4 family=laplace coef=fem kd=2",
+    "dim=3 n=4 gt=pk k=2 q=3 im=4 family=source coef=fem kd=2",
+    "dim=3 n=4 gt=pk k=2 q=3 im=4 family=source region=xmax coef=fem kd=1",
+    "dim=3 n=3 gt=qk k=2 q=1 im=6 family=mass region=outer coef=fem kd=1",
+    "dim=3 n=4 gt=pk k=2 q=3 im=4 family=elast model=1 coef=fem kd=1",
 ]
 
 
