@@ -36,6 +36,7 @@ SIGNATURES = {
     "gfgpu_ctx_synchronize": (C.c_int, [_P]),
     "gfgpu_ctx_bytes_in_use": (_i64, [_P]),
     "gfgpu_ctx_measure_fp64_peak": (C.c_int, [_P, _P]),
+    "gfgpu_ctx_measure_dmma_peak": (C.c_int, [_P, _P]),
     "gfgpu_mesh_create": (C.c_int, [_P, C.c_int, _i64, _P, _i64, C.c_int, _P, C.c_int, _PP]),
     "gfgpu_mesh_destroy": (C.c_int, [_P]),
     "gfgpu_fem_create": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _i64, _PP]),
@@ -148,6 +149,12 @@ class Context(_Handle):
 
     def bytes_in_use(self):
         return int(lib().gfgpu_ctx_bytes_in_use(self.h))
+
+    def measure_dmma_peak(self):
+        """fp64 tensor-core (mma.sync m8n8k4) peak in TFLOP/s measured on this device."""
+        v = C.c_double()
+        check(lib().gfgpu_ctx_measure_dmma_peak(self.h, C.byref(v)))
+        return float(v.value)
 
     def measure_fp64_peak(self):
         """fp64 FMA peak in TFLOP/s measured on this device (DFMA chains in registers)."""

@@ -480,7 +480,6 @@ __device__ __forceinline__ unsigned long long gtimer() {
 constexpr int TL_CW = GF_TL_CW;                  // consumer warps
 constexpr int TL_THREADS = (TL_CW + 1) * 32;     // + the producer warp
 constexpr int TL_BLOB = TL_INREC * 32 * 2;       // bytes of a long task's descriptor blob
-constexpr int TL_ROWS = 16;                      // element rows per producer lane (cap_slots <= 32 * TL_ROWS)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -519,12 +518,6 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void ldgsts8(void *dst, const void *src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void ldgsts_arrive(uint64_t *bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 template <int N, int RF>
 struct TlSmem {  // byte offsets inside one tile buffer: pair records | long-task descriptor blobs | geometry rows
@@ -1154,7 +1147,7 @@ void recompute_prepare(gfgpu_term *t) {
     const size_t in_b = ((size_t)cap_tasks * 512 * TL_KG + (size_t)cap_long * TL_BLOB * TL_KG + (size_t)(cap_slots + 1) * GSPh * 8 + 127) / 128 * 128;
     const size_t out_b = ((size_t)(cap_len + 2) * 8 + 127) / 128 * 128;
     const size_t need = 2 * in_b + 2 * out_b + (size_t)nd * nd * MT * 8;
-    if (need <= smem_limit && cap_slots <= 32 * TL_ROWS) break;
+    if (need <= smem_limit) break;
     GF_REQUIRE(cap_pairs_want > 32, "a single column node does not fit the tile kernel's shared memory: use strategy STAGED");
     cap_pairs_want = std::max(32, cap_pairs_want * 3 / 4);
   }

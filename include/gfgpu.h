@@ -95,6 +95,9 @@ int64_t gfgpu_ctx_bytes_in_use(gfgpu_ctx *ctx);
 /* measured fp64 FMA peak of the device (TFLOP/s, FMA = 2 flops; register-resident DFMA chains on every SM, best of 3
  * after a warm-up): the denominator of the fp64 roofline bench.py reports (MEASURED_PEAKS.json has no fp64 figure) */
 int gfgpu_ctx_measure_fp64_peak(gfgpu_ctx *ctx, double *tflops);
+/* the same for the fp64 tensor-core path (mma.sync m8n8k4 f64 chains): the evidence behind keeping the sum-factorised
+ * Q4 contraction on the FMA pipe */
+int gfgpu_ctx_measure_dmma_peak(gfgpu_ctx *ctx, double *tflops);
 
 /* ---- mesh.  Replaces basic_mesh::points_of_convex(cv,G) (getfem/bgeot_mesh.h:94) and
  * mesh_structure::ind_points_of_convex (bgeot_mesh_structure.h:106): points in point-id order
