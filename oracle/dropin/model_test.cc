@@ -1,0 +1,144 @@
+// oracle/dropin/model_test.cc -- TEST INFRASTRUCTURE.  Drop-in at the MODEL level: a getfem::model built from the
+// reference's own bricks (add_isotropic_linearized_elasticity_brick, add_generic_elliptic_brick, add_source_term_brick on
+// a volume and on a Neumann boundary, add_linear_term for a Robin condition, add_finite_strain_elasticity_brick) is
+// assembled twice by model::assembly(BUILD_ALL) in ONE process, against ONE library (oracle/_ref/libgetfem_gfgpu.so =
+// the unmodified reference objects + the dispatch patch of INTEGRATION.md section 2): once through the reference's
+// ga_exec, once through the device path.  The model's tangent matrix and right-hand side must agree: CSC pattern
+// identical, values / rhs to 1e-12 (tests/test_gpu_dropin.py).
+#include <cstdio>
+#include <map>
+#include <random>
+
+#include "getfem/getfem_models.h"
+#include "getfem/getfem_nonlinear_elasticity.h"
+#include "getfem/getfem_regular_meshes.h"
+#include "gmm/gmm_kernel.h"
+
+namespace getfem_b200 {
+void gfgpu_enable(bool on);
+long gfgpu_device_calls();
+long gfgpu_reference_calls();
+}  // namespace getfem_b200
+
+using getfem::size_type;
+
+int main(int argc, char **argv) {
+  std::map<std::string, std::string> a;
+  for (int i = 1; i < argc; ++i) {
+    std::string s(argv[i]);
+    size_t e = s.find('=');
+    if (e == std::string::npos) return 2;
+    a[s.substr(0, e)] = s.substr(e + 1);
+  }
+  auto geti = [&](const char *k, long d) { return a.count(k) ? std::stol(a[k]) : d; };
+  auto gets = [&](const char *k, const char *d) { return a.count(k) ? a[k] : std::string(d); };
+  const std::string kind = gets("model", "elasticity");
+  const int dim = (int)geti("dim", 3), n = (int)geti("n", 4), K = (int)geti("k", 2);
+  const bool qk = gets("gt", "pk") == "qk";
+  const int Q = kind == "poisson" ? 1 : dim;
+
+  getfem::mesh m;
+  std::vector<size_type> ns(dim, size_type(n));
+  getfem::regular_unit_mesh(m, ns, qk ? bgeot::parallelepiped_geotrans(dim, 1) : bgeot::simplex_geotrans(dim, 1));
+  // boundary regions: 1 = Neumann (x = 1), 2 = Robin (the other outer faces)
+  getfem::mesh_region outer;
+  getfem::outer_faces_of_mesh(m, outer);
+  for (getfem::mr_visitor v(outer); !v.finished(); ++v) {
+    bgeot::base_node un = m.normal_of_face_of_convex(v.cv(), v.f());
+    un /= gmm::vect_norm2(un);
+    m.region(un[0] > 0.999 ? 1 : 2).add(v.cv(), v.f());
+  }
+  getfem::mesh_fem mf(m, getfem::dim_type(Q));
+  mf.set_classical_finite_element(getfem::dim_type(K));
+  getfem::mesh_im mim(m);
+  mim.set_integration_method(getfem::dim_type(qk ? 2 * K + 2 : 2 * K));
+  getfem::mesh_fem mf_d(m, 1);  // fem data: heterogeneous coefficient
+  mf_d.set_classical_finite_element(1);
+
+  auto assemble = [&](bool device, gmm::csc_matrix<double> &C, std::vector<double> &rhs) {
+  // a FRESH model per path: model::assembly caches the matrices of linear bricks
+  getfem::model md;
+  md.add_fem_variable("u", mf);
+  const size_type ndof = mf.nb_dof();
+  std::vector<double> U(ndof);
+  if (kind == "finite_strain") {
+    for (size_type d = 0; d < ndof; ++d) {
+      bgeot::base_node P = mf.point_of_basic_dof(d);
+      int k = int(d % Q);
+      U[d] = 0.03 * std::sin(2 * M_PI * P[(k + 1) % dim]) * std::cos(M_PI * P[k % dim]);
+    }
+  } else {
+    std::mt19937_64 rng(4321);
+    std::uniform_real_distribution<double> dist(-1.0, 1.0);
+    for (auto &v : U) v = dist(rng);
+  }
+  gmm::copy(U, md.set_real_variable("u"));
+
+  std::vector<double> F(Q), G(Q);
+  for (int k = 0; k < Q; ++k) { F[k] = 0.5 * (k + 1); G[k] = -0.3 * (k + 2); }
+  md.add_initialized_fixed_size_data("F", F);
+  md.add_initialized_fixed_size_data("G", G);
+  md.add_initialized_scalar_data("robin", 7.5);
+  if (kind == "elasticity") {
+    md.add_initialized_scalar_data("lambda", 1.3);
+    md.add_initialized_scalar_data("mu", 0.7);
+    getfem::add_isotropic_linearized_elasticity_brick(md, mim, "u", "lambda", "mu");
+  } else if (kind == "poisson") {
+    std::vector<double> A(mf_d.nb_dof());
+    for (size_type d = 0; d < mf_d.nb_dof(); ++d) {
+      bgeot::base_node P = mf_d.point_of_basic_dof(d);
+      A[d] = 1.0 + 0.4 * std::sin(2.0 * P[0] + P[1]);
+    }
+    md.add_initialized_fem_data("a", mf_d, A);
+    getfem::add_generic_elliptic_brick(md, mim, "u", "a");
+  } else {
+    std::vector<double> params{1.3, 0.7};
+    md.add_initialized_fixed_size_data("params", params);
+    getfem::add_finite_strain_elasticity_brick(md, mim, "Saint_Venant_Kirchhoff", "u", "params");
+  }
+  getfem::add_source_term_brick(md, mim, "u", "F");          // volumic load
+  getfem::add_source_term_brick(md, mim, "u", "G", 1);       // Neumann load on x = 1
+  getfem::add_linear_term(md, mim, "robin*u.Test_u", 2);     // Robin condition on the rest of the boundary
+
+    getfem_b200::gfgpu_enable(device);
+    md.assembly(getfem::model::BUILD_ALL);
+    C.init_with(md.real_tangent_matrix());
+    rhs.assign(md.real_rhs().begin(), md.real_rhs().end());
+    getfem_b200::gfgpu_enable(false);
+  };
+  gmm::csc_matrix<double> Cr, Cg;
+  std::vector<double> Rr, Rg;
+  assemble(false, Cr, Rr);
+  const long ref_calls = getfem_b200::gfgpu_reference_calls();
+  assemble(true, Cg, Rg);
+  const long dev_calls = getfem_b200::gfgpu_device_calls();
+
+  // Model level: the bricks copy the workspace matrices with gmm::copy, which drops entries that are EXACTLY zero
+  // (gmm_blas.h copy of sparse vectors).  An entry that cancels to round-off (1e-17) in one path and to 0.0 in the other is
+  // therefore stored by one model tangent only: the comparison is made over the union of the two patterns, and the entries
+  // present on one side only are reported with their magnitude (they must be round-off).
+  const size_t nc = Cr.jc.size() - 1;
+  double nK = 0, dK = 0, nR = 0, dR = 0, maxK = 0, max_only = 0;
+  size_t n_only = 0;
+  bool sizes_ok = Cr.jc.size() == Cg.jc.size();
+  for (size_t j = 0; sizes_ok && j < nc; ++j) {
+    size_t a0 = Cr.jc[j], a1 = Cr.jc[j + 1], b0 = Cg.jc[j], b1 = Cg.jc[j + 1];
+    while (a0 < a1 || b0 < b1) {
+      const size_t ra = a0 < a1 ? Cr.ir[a0] : size_t(-1), rb = b0 < b1 ? Cg.ir[b0] : size_t(-1);
+      double va = 0, vb = 0;
+      if (ra <= rb) va = Cr.pr[a0++];
+      if (rb <= ra) vb = Cg.pr[b0++];
+      if (ra != rb) { ++n_only; max_only = std::max(max_only, std::max(std::fabs(va), std::fabs(vb))); }
+      nK += va * va; dK += (va - vb) * (va - vb);
+      maxK = std::max(maxK, std::fabs(va));
+    }
+  }
+  for (size_t d = 0; d < Rr.size(); ++d) { nR += Rr[d] * Rr[d]; dR += (Rr[d] - Rg[d]) * (Rr[d] - Rg[d]); }
+  std::printf("{\"model\": \"%s\", \"ne\": %zu, \"ndof\": %zu, \"nnz_ref\": %zu, \"nnz_gpu\": %zu, \"entries_on_one_side_only\": %zu, "
+              "\"max_one_sided_rel\": %.3e, \"rel_K\": %.3e, \"rel_rhs\": %.3e, \"reference_workspace_calls\": %ld, "
+              "\"device_workspace_calls\": %ld}\n",
+              kind.c_str(), m.convex_index().card(), size_t(mf.nb_dof()), Cr.pr.size(), Cg.pr.size(), n_only,
+              maxK > 0 ? max_only / maxK : 0.0, sizes_ok && nK > 0 ? std::sqrt(dK / nK) : -1.0, nR > 0 ? std::sqrt(dR / nR) : 0.0,
+              ref_calls, dev_calls);
+  return sizes_ok ? 0 : 1;
+}

@@ -1,0 +1,64 @@
+// oracle/dropin/ws_dispatch.cc -- TEST INFRASTRUCTURE: the reference-side patch of INTEGRATION.md section 2, as real code.
+//
+// Defines ga_workspace::assembly (getfem_generic_assembly_workspace.cc:791 in the reference): when the device path is
+// enabled it prepares K / V exactly as the reference does before ga_exec (workspace.cc:803-848: an OWNED matrix / vector is
+// cleared and resized to nb_prim_dof, an aliased one is trusted and accumulated into) and hands the workspace to the shim;
+// otherwise it calls the reference's own implementation (renamed by ws_reference_renamed.cc).  With this library in place
+// of libgetfem.so, model::assembly, the bricks and every asm_* wrapper run on the GPU unchanged.
+#include <cstdio>
+#include <cstdlib>
+
+#include "getfem/getfem_generic_assembly.h"
+#include "getfem/getfem_generic_assembly_tree.h"
+#include "getfem/getfem_models.h"
+#include "gfgpu_getfem_shim.h"
+
+namespace getfem_b200 {
+void reference_assembly(getfem::ga_workspace &ws, getfem::size_type order, bool condensation);
+static bool g_enabled = false;
+static long g_device_calls = 0, g_reference_calls = 0;
+void gfgpu_enable(bool on) { g_enabled = on; }
+long gfgpu_device_calls() { return g_device_calls; }
+long gfgpu_reference_calls() { return g_reference_calls; }
+}  // namespace getfem_b200
+
+namespace getfem {
+void ga_workspace::assembly(size_type order, bool condensation) {
+  if (!getfem_b200::g_enabled || condensation || (order != 1 && order != 2)) {
+    ++getfem_b200::g_reference_calls;
+    getfem_b200::reference_assembly(*this, order, condensation);
+    return;
+  }
+  if (std::getenv("GFGPU_DRYRUN")) {  // CPU debugging aid: what would be sent to the device, then the reference path
+    for (size_type i = 0; i < nb_trees(); ++i) {
+      const tree_description &td = tree_info(i);
+      std::vector<getfem_b200::recognised_term> rts;
+      bool ok = false;
+      std::string why;
+      try { ok = td.order == 1 ? getfem_b200::recognise_tree_sum(*this, i, rts) : true; } catch (const std::exception &ex) { why = ex.what(); }
+      std::fprintf(stderr, "[gfgpu dryrun] order %d (assembly order %d) region %ld: %s -> %s %s\n", int(td.order), int(order),
+                   long(td.rg->id()), ga_tree_to_string(*td.ptree).c_str(), td.order == 1 ? (ok ? "recognised" : "NOT recognised") : "-",
+                   why.c_str());
+    }
+    getfem_b200::reference_assembly(*this, order, condensation);
+    return;
+  }
+  const ga_workspace *w = this;
+  while (w->parent_workspace) w = w->parent_workspace;
+  if (w->md) w->md->nb_dof();  // actualize_sizes, as the reference does first
+  if (order == 2 && K.use_count()) {
+    gmm::clear(*K);
+    gmm::resize(*K, nb_prim_dof, nb_prim_dof);
+  }
+  if (order == 1) {
+    if (V.use_count()) {
+      gmm::clear(*V);
+      gmm::resize(*V, nb_prim_dof);
+    } else
+      GMM_ASSERT1(V->size() == nb_prim_dof, "Wrong size of assembled vector in workspace");
+  }
+  static thread_local getfem_b200::device_assembler dev(0);
+  ++getfem_b200::g_device_calls;
+  dev.assembly(*this, order);  // throws gmm::gmm_error when the workspace is not covered: no silent CPU fallback
+}
+}  // namespace getfem

@@ -1,0 +1,44 @@
+"""GPU: drop-in at the MODEL level.  oracle/_ref/model_test links ONE library, libgetfem_gfgpu.so = the unmodified reference
+objects + the dispatch patch of INTEGRATION.md section 2 (oracle/dropin/ws_dispatch.cc defines ga_workspace::assembly; the
+reference's own body is kept, renamed, by compiling its translation unit from /root/reference/src with one preprocessor
+rename).  A getfem::model made of the reference's bricks (linearised elasticity / generic elliptic with fem-data
+coefficient / finite-strain elasticity + volumic source + Neumann source on a boundary region + Robin linear term) is
+assembled by model::assembly(BUILD_ALL) once through the reference's ga_exec and once through the device path: tangent
+and right-hand side within 1e-12.  (At this level the bricks copy the workspace matrices with gmm::copy, which drops
+EXACT zeros: an entry that cancels to 1e-17 in one path and to 0.0 in the other is stored on one side only -- those
+entries are counted and must be round-off; the workspace-level CSC pattern itself is checked bit for bit in
+test_gpu_shim.py / test_gpu_golden.py.)"""
+import json
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(ROOT, "oracle", "_ref", "model_test")
+
+CASES = [
+    "model=elasticity dim=3 n=4 gt=pk k=2",
+    "model=elasticity dim=2 n=12 gt=pk k=2",
+    "model=elasticity dim=3 n=3 gt=qk k=2",
+    "model=poisson dim=2 n=24 gt=pk k=1",
+    "model=poisson dim=3 n=5 gt=pk k=2",
+    "model=poisson dim=3 n=3 gt=qk k=2",
+    "model=finite_strain dim=3 n=3 gt=pk k=2",
+    "model=finite_strain dim=3 n=3 gt=qk k=2",
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_model_assembly_runs_on_the_device_unchanged(case):
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN] + case.split(), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["device_workspace_calls"] >= 4, r  # every brick's workspace went through the device path
+    assert r["max_one_sided_rel"] < 1e-14, r
+    assert 0 <= r["rel_K"] < 1e-12, r
+    assert r["rel_rhs"] < 1e-12, r
