@@ -68,8 +68,70 @@ static bool recognise_sum(const getfem::ga_workspace &ws, const std::string &v, 
   return recognise_sum(ws, v, s.substr(0, at), out) && recognise_sum(ws, v, s.substr(at + 1), out);
 }
 
+// number of top-level summands of a printed tree: "(A)+(B)" -> 2
+static size_t count_top_level_summands(const std::string &s0) {
+  const std::string s = strip_outer(s0);
+  int depth = 0;
+  size_t n = 1;
+  for (size_t i = 0; i < s.size(); ++i) {
+    if (s[i] == '(' || s[i] == '[') ++depth;
+    else if (s[i] == ')' || s[i] == ']') --depth;
+    else if (s[i] == '+' && depth == 0 && i > 0) ++n;
+  }
+  return n;
+}
+
+// ORDER-2 trees written directly with Test_ / Test2_ (no order-1 tree): the legacy asm_* wrappers of getfem_assembling.h --
+// "Test_u:Test2_u" (asm_mass_matrix :695-720), "Grad_Test_u:Grad_Test2_u" (asm_stiffness_matrix_for_homogeneous_laplacian
+// :1108-1131), "((lambda*Div_Test_u)*Id(meshdim)+(2*mu)*Sym(Grad_Test_u)):Grad_Test2_u" (asm_stiffness_matrix_for_*linear_
+// elasticity :972-1048).  The handled forms are symmetric: Test_ and Test2_ may come in either order.
+static bool recognise_order2_string(const getfem::ga_workspace &ws, const std::string &v, const std::string &s0,
+                                    recognised_term &out) {
+  const std::string s = strip_outer(s0);
+  const std::string ID = "([A-Za-z_][A-Za-z_0-9]*)", T = "Test2?_" + v;
+  const std::string I3 = "\\[\\[1,0,0\\],\\[0,1,0\\],\\[0,0,1\\]\\]", I2 = "\\[\\[1,0\\],\\[0,1\\]\\]";
+  const std::string Idm = "(?:" + I3 + "|" + I2 + ")";
+  std::smatch m;
+  out.varname = v;
+  out.params.clear();
+  out.field_names.clear();
+  out.field_sign = 1.0;
+  auto coef = [&](const std::string &name) {
+    GMM_ASSERT1(ws.is_constant(name), "gfgpu: '" << name << "' must be a constant");
+    if (ws.associated_mf(name)) { out.field_names.push_back(name); return 1.0; }
+    GMM_ASSERT1(ws.value(name).size() == 1, "gfgpu: '" << name << "' must be a scalar constant");
+    return ws.value(name)[0];
+  };
+  auto both_tests = [&](const std::string &str) {  // exactly one Test_v and one Test2_v
+    return str.find("Test_" + v) != std::string::npos && str.find("Test2_" + v) != std::string::npos;
+  };
+  if (!both_tests(s)) return false;
+  if (std::regex_match(s, std::regex(T + "[.:]" + T))) { out.family = GFGPU_MASS; out.params = {1.0}; return true; }
+  if (std::regex_match(s, m, std::regex("\\(" + ID + "\\*" + T + "\\)[.:]" + T))) {
+    out.family = GFGPU_MASS; out.params = {coef(m[1])}; return true;
+  }
+  if (std::regex_match(s, std::regex("Grad_" + T + "[.:]Grad_" + T))) { out.family = GFGPU_LAPLACE; out.params = {1.0}; return true; }
+  if (std::regex_match(s, m, std::regex("\\(" + ID + "\\*Grad_" + T + "\\)[.:]Grad_" + T))) {
+    out.family = GFGPU_LAPLACE; out.params = {coef(m[1])}; return true;
+  }
+  if (std::regex_match(s, m, std::regex("\\(\\(\\(" + ID + "\\*Div_" + T + "\\)\\*" + Idm + "\\)\\+\\(\\(2\\*" + ID +
+                                        "\\)\\*\\(Sym\\(Grad_" + T + "\\)\\)\\)\\):Grad_" + T))) {
+    GMM_ASSERT1(ws.associated_mf(m[1]) || !ws.associated_mf(m[2]),
+                "gfgpu: a fem-data mu needs a fem-data lambda (fields replace the LEADING parameters)");
+    out.family = GFGPU_ELASTICITY; out.params = {coef(m[1]), coef(m[2])}; return true;
+  }
+  return false;
+}
+
 bool recognise_tree_sum(const getfem::ga_workspace &ws, size_type itree, std::vector<recognised_term> &out) {
   const getfem::ga_workspace::tree_description &td = ws.tree_info(itree);
+  if (td.order == 2 && td.operation == getfem::ga_workspace::ASSEMBLY && td.name_test1 == td.name_test2) {
+    recognised_term rt;
+    out.clear();
+    if (!recognise_order2_string(ws, td.name_test1, strip(getfem::ga_tree_to_string(*td.ptree)), rt)) return false;
+    out.push_back(rt);
+    return true;
+  }
   if (td.order != 1 || td.operation != getfem::ga_workspace::ASSEMBLY) return false;
   out.clear();
   if (!recognise_sum(ws, td.name_test1, strip(getfem::ga_tree_to_string(*td.ptree)), out)) return false;
@@ -221,6 +283,32 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     if (td.order == 2) {
       GMM_ASSERT1(td.name_test1 == td.name_test2, "gfgpu: coupled terms (" << td.name_test1 << ", " << td.name_test2
                                                                            << ") are not handled by the device path");
+      // the derivative of an order-1 tree of the same (mim, region, variable) -- or a bilinear form written directly
+      // with Test_ / Test2_ (the asm_* wrappers)
+      size_type i1 = size_type(-1);
+      for (size_type j = 0; j < ws.nb_trees(); ++j) {
+        const auto &t1 = ws.tree_info(j);
+        if (t1.order == 1 && t1.mim == td.mim && t1.rg == td.rg && t1.name_test1 == td.name_test1) i1 = j;
+      }
+      if (i1 != size_type(-1)) {
+        // a direct order-2 expression on the same region would have been SUMMED into this tree by add_tree: the number of
+        // top-level summands must be that of the order-1 tree minus its source terms
+        std::vector<recognised_term> r1;
+        GMM_ASSERT1(recognise_tree_sum(ws, i1, r1), "gfgpu: expression not handled by the device path (no CPU fallback): "
+                                                        << getfem::ga_tree_to_string(*ws.tree_info(i1).ptree));
+        size_t nsrc = 0;
+        for (const recognised_term &rt : r1) nsrc += rt.family == GFGPU_SOURCE || rt.family == GFGPU_NORMAL_SOURCE;
+        const size_t n1 = count_top_level_summands(strip(getfem::ga_tree_to_string(*ws.tree_info(i1).ptree)));
+        const size_t n2 = count_top_level_summands(strip(getfem::ga_tree_to_string(*td.ptree)));
+        GMM_ASSERT1(n2 + nsrc == n1, "gfgpu: a tangent tree that mixes derived and directly written terms is not handled: "
+                                         << getfem::ga_tree_to_string(*td.ptree));
+        continue;
+      }
+      if (order != 2) continue;  // a directly written bilinear form contributes to the matrix only
+      std::vector<recognised_term> r2;
+      GMM_ASSERT1(recognise_tree_sum(ws, i, r2), "gfgpu: expression not handled by the device path (no CPU fallback): "
+                                                     << getfem::ga_tree_to_string(*td.ptree));
+      for (const recognised_term &rt : r2) terms.emplace_back(i, rt);
       continue;
     }
     std::vector<recognised_term> rts;

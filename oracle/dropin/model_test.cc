@@ -9,6 +9,7 @@
 #include <map>
 #include <random>
 
+#include "getfem/getfem_assembling.h"
 #include "getfem/getfem_models.h"
 #include "getfem/getfem_nonlinear_elasticity.h"
 #include "getfem/getfem_regular_meshes.h"
@@ -35,7 +36,7 @@ int main(int argc, char **argv) {
   const std::string kind = gets("model", "elasticity");
   const int dim = (int)geti("dim", 3), n = (int)geti("n", 4), K = (int)geti("k", 2);
   const bool qk = gets("gt", "pk") == "qk";
-  const int Q = kind == "poisson" ? 1 : dim;
+  const int Q = (kind == "poisson" || kind == "asm_laplacian") ? 1 : dim;
 
   getfem::mesh m;
   std::vector<size_type> ns(dim, size_type(n));
@@ -55,6 +56,40 @@ int main(int argc, char **argv) {
   getfem::mesh_fem mf_d(m, 1);  // fem data: heterogeneous coefficient
   mf_d.set_classical_finite_element(1);
 
+  if (kind.rfind("asm_", 0) == 0) {
+    // the legacy asm_* wrappers (getfem_assembling.h): thin layers over ga_workspace, written with Test / Test2 directly
+    std::vector<double> LAMBDA(mf_d.nb_dof()), MU(mf_d.nb_dof());
+    for (size_type d = 0; d < mf_d.nb_dof(); ++d) {
+      bgeot::base_node P = mf_d.point_of_basic_dof(d);
+      LAMBDA[d] = 1.3 * (1.0 + 0.25 * std::cos(1.1 * P[0] - 0.7 * P[1]));
+      MU[d] = 0.7 * (1.0 + 0.2 * std::cos(1.3 * P[0] - P[dim - 1]));
+    }
+    auto run = [&](bool device, gmm::csc_matrix<double> &C) {
+      getfem_b200::gfgpu_enable(device);
+      getfem::model_real_sparse_matrix M(mf.nb_dof(), mf.nb_dof());
+      if (kind == "asm_mass") getfem::asm_mass_matrix(M, mim, mf);
+      else if (kind == "asm_laplacian") getfem::asm_stiffness_matrix_for_homogeneous_laplacian(M, mim, mf);
+      else if (kind == "asm_elasticity") getfem::asm_stiffness_matrix_for_linear_elasticity(M, mim, mf, mf_d, LAMBDA, MU);
+      else if (kind == "asm_mass_boundary") getfem::asm_mass_matrix(M, mim, mf, m.region(2));
+      else GMM_ASSERT1(false, "unknown asm_ case");
+      C.init_with(M);
+      getfem_b200::gfgpu_enable(false);
+    };
+    gmm::csc_matrix<double> Cr, Cg;
+    run(false, Cr);
+    run(true, Cg);
+    bool pattern_ok = Cr.jc.size() == Cg.jc.size() && Cr.ir.size() == Cg.ir.size();
+    for (size_t k = 0; pattern_ok && k < Cr.jc.size(); ++k) pattern_ok = Cr.jc[k] == Cg.jc[k];
+    for (size_t k = 0; pattern_ok && k < Cr.ir.size(); ++k) pattern_ok = Cr.ir[k] == Cg.ir[k];
+    double nK = 0, dK = 0;
+    if (pattern_ok)
+      for (size_t k = 0; k < Cr.pr.size(); ++k) { nK += Cr.pr[k] * Cr.pr[k]; dK += (Cr.pr[k] - Cg.pr[k]) * (Cr.pr[k] - Cg.pr[k]); }
+    std::printf("{\"model\": \"%s\", \"ndof\": %zu, \"nnz_ref\": %zu, \"nnz_gpu\": %zu, \"pattern_ok\": %s, \"rel_K\": %.3e, "
+                "\"device_workspace_calls\": %ld}\n",
+                kind.c_str(), size_t(mf.nb_dof()), Cr.pr.size(), Cg.pr.size(), pattern_ok ? "true" : "false",
+                pattern_ok && nK > 0 ? std::sqrt(dK / nK) : -1.0, getfem_b200::gfgpu_device_calls());
+    return pattern_ok ? 0 : 1;
+  }
   auto assemble = [&](bool device, gmm::csc_matrix<double> &C, std::vector<double> &rhs) {
   // a FRESH model per path: model::assembly caches the matrices of linear bricks
   getfem::model md;

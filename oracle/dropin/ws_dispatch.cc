@@ -35,9 +35,9 @@ void ga_workspace::assembly(size_type order, bool condensation) {
       std::vector<getfem_b200::recognised_term> rts;
       bool ok = false;
       std::string why;
-      try { ok = td.order == 1 ? getfem_b200::recognise_tree_sum(*this, i, rts) : true; } catch (const std::exception &ex) { why = ex.what(); }
+      try { ok = td.order >= 1 ? getfem_b200::recognise_tree_sum(*this, i, rts) : true; } catch (const std::exception &ex) { why = ex.what(); }
       std::fprintf(stderr, "[gfgpu dryrun] order %d (assembly order %d) region %ld: %s -> %s %s\n", int(td.order), int(order),
-                   long(td.rg->id()), ga_tree_to_string(*td.ptree).c_str(), td.order == 1 ? (ok ? "recognised" : "NOT recognised") : "-",
+                   long(td.rg->id()), ga_tree_to_string(*td.ptree).c_str(), ok ? "recognised" : "NOT recognised",
                    why.c_str());
     }
     getfem_b200::reference_assembly(*this, order, condensation);

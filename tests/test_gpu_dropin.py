@@ -42,3 +42,27 @@ def test_model_assembly_runs_on_the_device_unchanged(case):
     assert r["max_one_sided_rel"] < 1e-14, r
     assert 0 <= r["rel_K"] < 1e-12, r
     assert r["rel_rhs"] < 1e-12, r
+
+
+ASM_CASES = [
+    "model=asm_mass dim=3 n=4 gt=pk k=2",                # asm_mass_matrix                                  "Test_u1:Test2_u1"
+    "model=asm_mass_boundary dim=3 n=4 gt=pk k=2",       # asm_mass_matrix on a boundary region
+    "model=asm_laplacian dim=3 n=5 gt=pk k=2",           # asm_stiffness_matrix_for_homogeneous_laplacian  "Grad_Test_u:Grad_Test2_u"
+    "model=asm_laplacian dim=3 n=3 gt=qk k=2",
+    "model=asm_elasticity dim=3 n=4 gt=pk k=2",          # asm_stiffness_matrix_for_linear_elasticity (fem-data lambda, mu)
+    "model=asm_elasticity dim=2 n=10 gt=pk k=2",
+]
+
+
+@pytest.mark.parametrize("case", ASM_CASES)
+def test_legacy_asm_wrappers_run_on_the_device_unchanged(case):
+    """The asm_* functions of getfem_assembling.h are thin layers over ga_workspace written with Test_ / Test2_ directly:
+    with the patched library they run on the device; CSC pattern identical, values 1e-12."""
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN] + case.split(), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["device_workspace_calls"] >= 1, r
+    assert r["pattern_ok"] and r["nnz_ref"] == r["nnz_gpu"]
+    assert 0 <= r["rel_K"] < 1e-12, r
