@@ -182,6 +182,9 @@ struct gfgpu_term {
   gf::DevBuf<double> stage;     // ne_loc x s1 x s1
   gf::DevBuf<uint16_t> emask;   // ne_loc x nd x nd
   gf::DevBuf<double> rstage;    // ne_loc x s1
+  // Q = 1 entry-wise gather (scatter.cu): stage index of every single-contribution entry, list of the other pairs
+  gf::DevBuf<uint32_t> g1_src, g1_multi;
+  int64_t g1_nmulti = 0, g1_generation = -1;
   gf::DevBuf<double> Ubuf;      // ndof (host path)
   gf::DevBuf<int32_t> flag;     // pattern-changed flag
   // per-phase events of the last assemble: [0,1] element kernel, [2,3] gather, [4,5] residual gather, [6,7] pattern

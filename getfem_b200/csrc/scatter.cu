@@ -450,10 +450,85 @@ k_gather(const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ csrc,
   }
 }
 
+// ---- scalar fems (Q = 1), linear forms: most node pairs of a high-order element have ONE contribution (both nodes interior
+// to the same element), and for Q = 1 the contribution id IS the index of the value in the stage (nb = nd^2 = s1^2).  Such
+// entries are copied entry-wise through a 4-byte source index (20 B of traffic per entry instead of ~34 B of pair
+// metadata); the pairs with several contributions (or halo parts) keep the ordered per-pair sum.
+__global__ void k_g1_build(const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ csrc, const int32_t *__restrict__ pJ,
+                           const uint16_t *__restrict__ pmask, const uint32_t *__restrict__ prel, const int64_t *__restrict__ jc,
+                           int64_t npairs, uint32_t nlocal, uint32_t *__restrict__ src, uint32_t *__restrict__ multi,
+                           unsigned long long *__restrict__ nmulti) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npairs; p += (int64_t)gridDim.x * blockDim.x) {
+    if (!(pmask[p] & 1u)) continue;  // dropped entry: no slot
+    const int64_t pos = jc[pJ[p]] + prel[p];
+    const uint32_t s0 = cstart[p], cnt = cstart[p + 1] - s0;
+    if (cnt == 1 && csrc[s0] < nlocal) {
+      src[pos] = csrc[s0];
+    } else {
+      src[pos] = 0xffffffffu;
+      multi[atomicAdd(nmulti, 1ull)] = (uint32_t)p;  // any order: every listed pair is summed on its own
+    }
+  }
+}
+
+__global__ void k_g1_copy(const uint32_t *__restrict__ src, const double *__restrict__ stage, int64_t nnz, double *__restrict__ pr) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t s = src[k];
+    if (s != 0xffffffffu) pr[k] = stage[s];
+  }
+}
+
+__global__ void k_g1_multi(const uint32_t *__restrict__ multi, int64_t nmulti, const uint32_t *__restrict__ cstart,
+                           const uint32_t *__restrict__ csrc, const int32_t *__restrict__ pJ, const uint32_t *__restrict__ prel,
+                           const int64_t *__restrict__ jc, const double *__restrict__ stage, uint32_t nlocal,
+                           double *__restrict__ pr) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nmulti; k += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t p = multi[k];
+    double acc = 0.0;
+    for (uint32_t s = cstart[p], e = cstart[p + 1]; s < e; ++s) {
+      const uint32_t c = csrc[s];
+      if (c < nlocal) acc += stage[c];  // ascending element id; virtual (halo) parts arrive through halo_accumulate
+    }
+    pr[jc[pJ[p]] + prel[p]] = acc;
+  }
+}
+
+static bool gather_tangent_q1_fast(gfgpu_term *t) {
+  Structure &st = t->st;
+  gfgpu_ctx *ctx = t->ctx;
+  if (t->nnz >= (int64_t(1) << 32) - 1 || st.ncontrib >= (int64_t(1) << 32) - 1 || st.npairs >= (int64_t(1) << 32) - 1) return false;
+  if (t->fem->nd < 27) return false;  // low-order elements: few single-contribution pairs, the pair kernel is as good
+  const int B = 256;
+  if (t->g1_generation != t->generation) {
+    t->g1_src.alloc(ctx, t->nnz);
+    t->g1_multi.alloc(ctx, st.npairs);
+    DevBuf<int64_t> cnt;
+    cnt.alloc(ctx, 1);
+    cnt.zero();
+    k_g1_build<<<min(grid_for(st.npairs, B), 148 * 64), B, 0, ctx->stream>>>(st.cstart.p, st.csrc.p, st.pJ.p, t->pmask.p, t->prel.p,
+                                                                          t->jc.p, st.npairs, (uint32_t)st.ncontrib, t->g1_src.p,
+                                                                          t->g1_multi.p, (unsigned long long *)cnt.p);
+    GF_LAUNCH_CHECK();
+    cnt.download(&t->g1_nmulti);
+    GF_CUDA(cudaStreamSynchronize(ctx->stream));
+    t->g1_generation = t->generation;
+  }
+  k_g1_copy<<<min(grid_for(t->nnz, B), 148 * 64), B, 0, ctx->stream>>>(t->g1_src.p, t->stage.p, t->nnz, t->pr.p);
+  GF_LAUNCH_CHECK();
+  if (t->g1_nmulti) {
+    k_g1_multi<<<min(grid_for(t->g1_nmulti, B), 148 * 64), B, 0, ctx->stream>>>(t->g1_multi.p, t->g1_nmulti, st.cstart.p, st.csrc.p,
+                                                                              st.pJ.p, t->prel.p, t->jc.p, t->stage.p,
+                                                                              (uint32_t)st.ncontrib, t->pr.p);
+    GF_LAUNCH_CHECK();
+  }
+  return true;
+}
+
 template <int Q>
 static void gather_tangent_t(gfgpu_term *t, bool check) {
   Structure &st = t->st;
   if (!st.npairs) return;
+  if (Q == 1 && !check && gather_tangent_q1_fast(t)) return;
   const int B = 256;
   int grid = min(grid_for(st.npairs, B), 148 * 64);
   if (check)

@@ -12,6 +12,7 @@
 #include "getfem/getfem_assembling.h"
 #include "getfem/getfem_models.h"
 #include "getfem/getfem_nonlinear_elasticity.h"
+#include "getfem/getfem_omp.h"
 #include "getfem/getfem_regular_meshes.h"
 #include "gmm/gmm_kernel.h"
 
@@ -36,6 +37,8 @@ int main(int argc, char **argv) {
   const std::string kind = gets("model", "elasticity");
   const int dim = (int)geti("dim", 3), n = (int)geti("n", 4), K = (int)geti("k", 2);
   const bool qk = gets("gt", "pk") == "qk";
+  // threads > 1: the bricks' GETFEM_OMP_PARALLEL blocks slice the regions; the patch leaves that regime on the reference path
+  if (geti("threads", 1) > 1) getfem::set_num_threads(int(geti("threads", 1)));
   const int Q = (kind == "poisson" || kind == "asm_laplacian") ? 1 : dim;
 
   getfem::mesh m;

@@ -11,6 +11,7 @@
 #include "getfem/getfem_generic_assembly.h"
 #include "getfem/getfem_generic_assembly_tree.h"
 #include "getfem/getfem_models.h"
+#include "getfem/getfem_omp.h"
 #include "gfgpu_getfem_shim.h"
 
 namespace getfem_b200 {
@@ -24,7 +25,12 @@ long gfgpu_reference_calls() { return g_reference_calls; }
 
 namespace getfem {
 void ga_workspace::assembly(size_type order, bool condensation) {
-  if (!getfem_b200::g_enabled || condensation || (order != 1 && order != 2)) {
+  // inside GETFEM_OMP_PARALLEL with SEVERAL partitions every thread assembles its slice of the region into a private
+  // copy (getfem_accumulated_distro.h:157-224): that regime stays on the reference path.
+  // With one partition (the library default, partition_master's constructor calls set_num_threads(1), getfem_omp.cc:236)
+  // the slice is the whole region although me_is_multithreaded_now() is true inside the bricks' parallel blocks.
+  const bool sliced = getfem::me_is_multithreaded_now() && getfem::partition_master::get().get_nb_partitions() > 1;
+  if (!getfem_b200::g_enabled || condensation || (order != 1 && order != 2) || sliced) {
     ++getfem_b200::g_reference_calls;
     getfem_b200::reference_assembly(*this, order, condensation);
     return;

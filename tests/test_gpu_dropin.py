@@ -66,3 +66,17 @@ def test_legacy_asm_wrappers_run_on_the_device_unchanged(case):
     assert r["device_workspace_calls"] >= 1, r
     assert r["pattern_ok"] and r["nnz_ref"] == r["nnz_gpu"]
     assert 0 <= r["rel_K"] < 1e-12, r
+
+
+def test_sliced_regions_stay_on_the_reference_path():
+    """With several OpenMP partitions every thread of a brick's GETFEM_OMP_PARALLEL block assembles its slice of the
+    region into a private copy (getfem_accumulated_distro.h:157-224): the dispatch patch must leave that regime to the
+    reference (no device call, same result), instead of assembling the whole region once per thread."""
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN] + "model=elasticity dim=3 n=4 gt=pk k=2 threads=3".split(), capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["device_workspace_calls"] == 0 and r["reference_workspace_calls"] > 0, r
+    assert r["entries_on_one_side_only"] == 0 and r["rel_K"] < 1e-13 and r["rel_rhs"] < 1e-13, r
