@@ -395,6 +395,10 @@ def main():
         "clocks": clocks,
         "symbolic_s": t_sym, "setup_s": t_setup, "device_bytes": ctx.bytes_in_use(), "checks": checks,
     }
+    if kavg["recompute"] > 0 and kavg["rgather"] > 0 and not os.environ.get("GFGPU_NO_OVERLAP"):
+        # tile kernel + residual path: the residual kernels run on the library's side stream NEXT to the tile kernel
+        line["kernel_ms_note"] = ("rgather = span of the residual path on the side stream (it overlaps the tile kernel: "
+                                  "not additive); recompute = tile kernel on the main stream")
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(wl)
     print(json.dumps(line))

@@ -82,6 +82,9 @@ int gfgpu_ctx_create(int device, void *stream, gfgpu_ctx **out) {
     c->own_stream = true;
   }
   GF_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+  GF_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  GF_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  GF_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   *out = c.release();
   GF_API_END
 }
@@ -92,6 +95,9 @@ int gfgpu_ctx_destroy(gfgpu_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->cub_tmp) cudaFree(ctx->cub_tmp);
+  if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   GF_API_END
@@ -595,6 +601,35 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
       if (t->halo) gf::halo_build_maps(t);
     }
     if (!t->rc_ready) gf::recompute_prepare(t);
+    if (do_r && do_t && t->rc_cols) {  // column kernel: tangent and R = K U in one pass
+      tic(4); gf::recompute_assemble(t, U_dev, true, true); toc(4);
+      return;
+    }
+    static const bool no_overlap = getenv("GFGPU_NO_OVERLAP") != nullptr;
+    if (do_r && do_t && ctx->stream2 && !no_overlap) {
+      // The tile kernel is a persistent 1-CTA-per-SM kernel bound by the shared-memory pipe; the residual path (a latency
+      // bound per-element kernel + an HBM bound gather) runs NEXT to it on the side stream: fork after everything queued so
+      // far, tile kernel first (its CTAs take their SMs), residual kernels into the registers / thread slots that are left
+      // (64-thread blocks: 238 registers x 64 fit beside 106 x 384), join before anything that follows.
+      GF_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+      GF_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+      tic(4); gf::recompute_assemble(t, U_dev, true, false); toc(4);
+      cudaStream_t s0 = ctx->stream;
+      ctx->stream = ctx->stream2;
+      t->rc_res_block = 64;
+      try {
+        tic(2); gf::recompute_assemble(t, U_dev, false, true); toc(2);
+      } catch (...) {
+        ctx->stream = s0;
+        t->rc_res_block = 128;
+        throw;
+      }
+      ctx->stream = s0;
+      t->rc_res_block = 128;
+      GF_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream2));
+      GF_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+      return;
+    }
     if (do_r) { tic(2); gf::recompute_assemble(t, U_dev, false, true); toc(2); }
     if (do_t) { tic(4); gf::recompute_assemble(t, U_dev, true, false); toc(4); }
     return;

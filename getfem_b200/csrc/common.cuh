@@ -47,6 +47,9 @@ struct gfgpu_ctx {
   int64_t bytes = 0;
   void *cub_tmp = nullptr;  // grow-only scratch for CUB calls
   size_t cub_tmp_bytes = 0;
+  // side stream: the residual path of strategy RECOMPUTE runs next to the tile kernel (fork / join through these events)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace gf {
@@ -223,6 +226,13 @@ struct gfgpu_term {
   gf::DevBuf<uint32_t> rc_els;   // per tile: sorted distinct local element ids (stride rc_cap_inc)
   int64_t rc_nt = 0, rc_ntask = 0;
   int rc_cap_inc = 0, rc_cap_len = 0, rc_cap_pairs = 0, rc_cap_slots = 0, rc_cap_tasks = 0, rc_cap_long = 0;
+  int rc_res_block = 128;         // threads per block of k_affine_residual (64 when it has to fit next to the tile kernel)
+  // column kernel (recompute_cols.cu): low-order scalar-coefficient forms, thread per column node
+  bool rc_cols = false;
+  int rc_cmaxq = 0;               // most pairs in one column
+  gf::DevBuf<int64_t> rc_cgoff;   // per group of 32 column nodes: first ELL row
+  gf::DevBuf<double> rc_cell;     // warp-transposed incidence records: geometry row, j and pair slots
+  int64_t rc_cngroups = 0;
 };
 
 namespace gf {
@@ -274,5 +284,9 @@ void gather_residual(gfgpu_term *t);
 bool recompute_supported(const gfgpu_term *t);
 void recompute_prepare(gfgpu_term *t);
 void recompute_assemble(gfgpu_term *t, const double *U, bool do_t, bool do_r);
+// column kernel for low-order Laplace / mass forms (recompute_cols.cu)
+bool recompute_cols_wanted(const gfgpu_term *t);
+bool recompute_cols_prepare(gfgpu_term *t, const std::vector<uint32_t> &colstart, const std::vector<uint32_t> &rstart);
+void recompute_cols_tangent(gfgpu_term *t, const double *U, bool with_r);
 
 }  // namespace gf

@@ -1079,6 +1079,11 @@ void recompute_prepare(gfgpu_term *t) {
   st.rstart.download(rstart.data());
   st.colstart.download(colstart.data());
   GF_CUDA(cudaStreamSynchronize(s));
+  t->rc_cols = false;
+  if (recompute_cols_wanted(t) && recompute_cols_prepare(t, colstart, rstart)) {  // low-order scalar forms: no tile plan at all
+    t->rc_ready = true;
+    return;
+  }
   // The pair capacity of a tile is lowered until two input buffers + two output images fit in shared memory.
   const int GSPh = GSZ | 1;
   const size_t smem_limit = 224 * 1024;
@@ -1209,7 +1214,8 @@ template <int N, int Q, int ND, int RF>
 static void launch_tiles(gfgpu_term *t, const double *U, bool do_t, bool do_r) {
   using C = TlCfg<N, RF>;
   const double sign = t->alpha < 0 ? -1.0 : 1.0;
-  if (do_r) {  // per-element residual -> stage -> fixed-order gather per node
+  const bool fused_r = do_r && do_t && t->rc_cols;  // the column kernel forms R = K U next to the tangent
+  if (do_r && !fused_r) {  // per-element residual -> stage -> fixed-order gather per node
     const int64_t ne = t->e1 - t->e0;
     if (t->rstage.n != (size_t)ne * ND * Q) t->rstage.alloc(t->ctx, (size_t)ne * ND * Q);
     ResArgs r;
@@ -1220,12 +1226,17 @@ static void launch_tiles(gfgpu_term *t, const double *U, bool do_t, bool do_r) {
     const size_t smem = (size_t)t->rc_rank * ((RF == TF_MASS ? ND : ND * N) + 1) * 8;
     auto kern = k_affine_residual<N, Q, ND, RF>;
     GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ne + 127) / 128, (int64_t)t->ctx->sm_count * 8));
-    kern<<<grid, 128, smem, t->ctx->stream>>>(r);
+    const int rb = t->rc_res_block;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ne + rb - 1) / rb, (int64_t)t->ctx->sm_count * 8 * (128 / rb)));
+    kern<<<grid, rb, smem, t->ctx->stream>>>(r);
     GF_LAUNCH_CHECK();
     gather_residual(t);
   }
   if (!do_t) return;
+  if (t->rc_cols) {
+    recompute_cols_tangent(t, U, fused_r);
+    return;
+  }
   using L = TlSmem<N, RF>;
   TileArgs a;
   a.hdr = (const TileHdr *)t->rc_hdr.p;

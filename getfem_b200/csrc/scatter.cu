@@ -511,6 +511,22 @@ static bool gather_tangent_q1_fast(gfgpu_term *t) {
     GF_LAUNCH_CHECK();
     cnt.download(&t->g1_nmulti);
     GF_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (t->g1_nmulti > 1) {  // the list was filled through an atomic counter: back to pair (= CSC) order, for the locality of k_g1_multi
+      DevBuf<uint32_t> sorted;
+      sorted.alloc(ctx, t->g1_nmulti);
+      size_t tb = 0;
+      GF_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, t->g1_multi.p, sorted.p, (int64_t)t->g1_nmulti, 0, 32, ctx->stream));
+      void *tmp = cub_scratch(ctx, tb);
+      GF_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tb, t->g1_multi.p, sorted.p, (int64_t)t->g1_nmulti, 0, 32, ctx->stream));
+      count_launch(4);
+      GF_CUDA(cudaStreamSynchronize(ctx->stream));
+      t->g1_multi.release();
+      std::swap(t->g1_multi.p, sorted.p);
+      std::swap(t->g1_multi.n, sorted.n);
+      std::swap(t->g1_multi.ctx, sorted.ctx);
+    } else if (!t->g1_nmulti) {
+      t->g1_multi.release();
+    }
     t->g1_generation = t->generation;
   }
   k_g1_copy<<<min(grid_for(t->nnz, B), 148 * 64), B, 0, ctx->stream>>>(t->g1_src.p, t->stage.p, t->nnz, t->pr.p);
