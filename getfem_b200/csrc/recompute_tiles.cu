@@ -936,6 +936,95 @@ k_affine_residual(const ResArgs a) {
   }
 }
 
+// Elasticity (Q == N), one LANE PER (element, component): lane a holds u_a(j), r_a(i) (2 x ND doubles instead of 2 x ND x N:
+// ~100 registers instead of 238, so that 4x more warps are resident -- the thread-per-element kernel is latency bound at 12 %
+// occupancy -- and several blocks fit NEXT to the tile kernel on the side stream).  The three lanes of an element sit in
+// one warp (32 / N elements per warp, the last 32 % N lanes idle) and exchange the rows of the scaled gradient with
+// shuffles (sigma couples the components); the loads of U and the stores of r become N-lane contiguous pieces.
+template <int N, int ND>
+__global__ void __launch_bounds__(128, (ND <= 10 ? 3 : 1))
+k_affine_residual_split(const ResArgs a) {
+  constexpr int LW = ND * N, LS = LW + 1, EPW = 32 / N;  // elements per warp
+  extern __shared__ double sL[];
+  for (int k = threadIdx.x; k < a.rank * LS; k += blockDim.x) sL[k] = a.Ltab[k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, le = lane / N, c = lane % N;  // local element, component
+  const bool lane_ok = le < EPW;
+  const int base = le * N;  // first lane of my element
+  const int64_t wpb = blockDim.x >> 5, nwarps = (int64_t)gridDim.x * wpb;
+  const int64_t ngroups = (a.ne + EPW - 1) / EPW;
+  for (int64_t g = blockIdx.x * wpb + (threadIdx.x >> 5); g < ngroups; g += nwarps) {
+    const int64_t el = g * EPW + le;
+    const bool live = lane_ok && el < a.ne;  // idle lanes run along on element 0 of the group's range (shuffles need them converged)
+    const int64_t e = live ? el : g * EPW;
+    double G[N * N];
+#pragma unroll
+    for (int k = 0; k < N * N; ++k) G[k] = a.eg[(size_t)e * (N * N) + k];
+    const int32_t *ed = a.edof + (a.e0 + e) * ND;
+    double u[ND], r[ND];
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      u[j] = a.U ? a.U[ed[j] + c] : 0.0;
+      r[j] = 0.0;
+    }
+#pragma unroll 1
+    for (int k = 0; k < a.rank; ++k) {
+      const double *L = sL + k * LS;
+      const double sk = L[0];
+      ++L;
+      double Uh[N];  // row c of the reference gradient of u at the generalised point
+#pragma unroll
+      for (int q = 0; q < N; ++q) Uh[q] = 0.0;
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+#pragma unroll
+        for (int q = 0; q < N; ++q) Uh[q] += u[j] * L[j * N + q];
+      double grc[N];  // row c of the (scaled) physical gradient
+#pragma unroll
+      for (int bb = 0; bb < N; ++bb) {
+        double s2 = 0;
+#pragma unroll
+        for (int q = 0; q < N; ++q) s2 += Uh[q] * G[bb + N * q];
+        grc[bb] = s2;
+      }
+      // column c of the gradient (gr[bb][c]) and the trace come from the other lanes of the element
+      double tr = 0, sg[N];
+#pragma unroll
+      for (int bb = 0; bb < N; ++bb) {
+        double col = 0, dg = 0;  // gr[bb][c], gr[bb][bb]
+#pragma unroll
+        for (int x = 0; x < N; ++x) {
+          const double v = __shfl_sync(0xffffffffu, grc[x], base + bb);  // gr[bb][x]
+          if (x == c) col = v;
+          if (x == bb) dg = v;
+        }
+        tr += dg;
+        sg[bb] = a.smu * (grc[bb] + col);
+      }
+#pragma unroll
+      for (int bb = 0; bb < N; ++bb)
+        if (bb == c) sg[bb] += a.sl * tr;
+      double P[N];
+#pragma unroll
+      for (int q = 0; q < N; ++q) {
+        double s2 = 0;
+#pragma unroll
+        for (int bb = 0; bb < N; ++bb) s2 += sg[bb] * G[bb + N * q];
+        P[q] = sk * s2;
+      }
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+#pragma unroll
+        for (int q = 0; q < N; ++q) r[i] += P[q] * L[i * N + q];
+    }
+    if (live) {
+      double *out = a.rstage + (size_t)el * ND * N + c;
+#pragma unroll
+      for (int i = 0; i < ND; ++i) out[i * N] = r[i];
+    }
+  }
+}
+
 // symmetric eigen-decomposition (cyclic Jacobi), A (m x m, row-major) -> eigenvalues in d, eigenvectors in the
 // COLUMNS of V.  m <= 60, host only.
 static void jacobi_eig(std::vector<double> &A, int m, std::vector<double> &d, std::vector<double> &V) {
@@ -1227,9 +1316,24 @@ static void launch_tiles(gfgpu_term *t, const double *U, bool do_t, bool do_r) {
     auto kern = k_affine_residual<N, Q, ND, RF>;
     GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int rb = t->rc_res_block;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ne + rb - 1) / rb, (int64_t)t->ctx->sm_count * 8 * (128 / rb)));
-    kern<<<grid, rb, smem, t->ctx->stream>>>(r);
-    GF_LAUNCH_CHECK();
+    static const bool no_split = getenv("GFGPU_NO_RSPLIT") != nullptr;
+    bool launched = false;
+    if constexpr (RF == TF_ELAST) {
+      if (!no_split) {  // lane per (element, component)
+        auto ks = k_affine_residual_split<N, ND>;
+        GF_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t groups = (ne + 32 / N - 1) / (32 / N), wpb = rb / 32;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((groups + wpb - 1) / wpb, (int64_t)t->ctx->sm_count * 16 * (128 / rb)));
+        ks<<<grid, rb, smem, t->ctx->stream>>>(r);
+        GF_LAUNCH_CHECK();
+        launched = true;
+      }
+    }
+    if (!launched) {
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ne + rb - 1) / rb, (int64_t)t->ctx->sm_count * 8 * (128 / rb)));
+      kern<<<grid, rb, smem, t->ctx->stream>>>(r);
+      GF_LAUNCH_CHECK();
+    }
     gather_residual(t);
   }
   if (!do_t) return;
