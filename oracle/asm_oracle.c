@@ -409,6 +409,10 @@ gfo_result *gfo_assemble(int dim, int64_t ne, int ng, const double *pts, const i
                              par, U, order_mask, ne, NULL, NULL, NULL, NULL, NULL);
 }
 
+/* the material point alone, for the derivative check of tests/test_oracle.py (the restatement of
+   abstract_hyperelastic_law::test_derivatives, getfem_nonlinear_elasticity.cc:298-347) */
+void gfo_hyper_law(int family, const double *Gu, const double *par, double *S, double *dS) { hyper_law(family, Gu, par, S, dS); }
+
 int64_t gfo_nnz(const gfo_result *r) { return r->nnz; }
 
 /* gmm::csc_matrix::init_with_good_format (gmm_matrix.h:545-566) */

@@ -45,12 +45,23 @@ def lib():
         L.gfo_get_csc.argtypes = [C.c_void_p] * 4
         L.gfo_get_residual.argtypes = [C.c_void_p] * 2
         L.gfo_free.argtypes = [C.c_void_p]
+        L.gfo_hyper_law.argtypes = [C.c_int] + [C.c_void_p] * 4
         _lib = L
     return _lib
 
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def hyper_law(family, grad_u, params):
+    """(S, dS): PK2 stress (3x3) and dS[i,j,k,l] = dS_ij / d(Grad_u)_kl of the law behind `family` at one point."""
+    Gu = np.asfortranarray(grad_u, dtype=np.float64)  # the oracle's tensors are column-major
+    par = np.ascontiguousarray(params, np.float64)
+    S = np.zeros((3, 3), order="F")
+    dS = np.zeros((3, 3, 3, 3), order="F")
+    lib().gfo_hyper_law(FAMILIES[family], _p(Gu), _p(par), _p(S), _p(dS))
+    return np.array(S), np.array(dS)
 
 
 def assemble(pts, conn, elem_dof, ndof, Q, w, gt_grad, phi, gphi, gt_linear, family, params, U, order_mask=3,

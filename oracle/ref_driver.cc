@@ -24,11 +24,17 @@
 //       K / V, as a model's bricks do
 //   coef=fem kd=1   the coefficients (a | lambda, mu | f) are fem data on a classical mesh_fem of degree kd
 //                   (ws.add_fem_constant) instead of fixed-size constants: heterogeneous material / distributed load
-//   u=smooth|random|zero  out=DIR  mode=dump|time|model  threads=T reps=R
+//   u=smooth|random|zero  out=DIR  mode=dump|time|model|crosscheck|lawcheck  threads=T reps=R
+//   mode=crosscheck  the reference's own old-vs-new comparison (tests/test_assembly.cc:279-349, 773-881): the tangent of the
+//                    GWFL expression against the LEGACY generic_assembly string of the same form (an independent code path,
+//                    getfem_assembling_tensors.cc), tolerance 1e-10 there; families laplace | elast | mass, constant coefficients
+//   mode=lawcheck    abstract_hyperelastic_law::test_derivatives (getfem_nonlinear_elasticity.cc:298-347) for the laws behind
+//                    the families svk | nh_ciarlet | nh_bonet
 #include "getfem/getfem_regular_meshes.h"
 #include "getfem/getfem_mesh_fem.h"
 #include "getfem/getfem_mesh_im.h"
 #include "getfem/getfem_generic_assembly.h"
+#include "getfem/getfem_assembling.h"
 #include "getfem/getfem_models.h"
 #include "getfem/getfem_nonlinear_elasticity.h"
 #include "getfem/getfem_omp.h"
@@ -294,6 +300,50 @@ int main(int argc, char **argv) {
               dim, ne, ndof, nd, ng, nq, getfem::name_of_fem(pf).c_str(),
               getfem::name_of_int_method(pim).c_str(), t_mesh, t_enum);
 
+  if (mode == "lawcheck") {
+    bgeot::base_vector bp(2);
+    bp[0] = lambda; bp[1] = mu;
+    bool ok = true;
+    std::string what;
+    const double hfd = getd("h", 1e-8);  // step of the finite difference (no call site in the reference fixes one)
+    try {
+      if (family == "svk") getfem::SaintVenant_Kirchhoff_hyperelastic_law().test_derivatives(3, hfd, bp);
+      else if (family == "nh_ciarlet") getfem::Neo_Hookean_hyperelastic_law(false).test_derivatives(3, hfd, bp);
+      else if (family == "nh_bonet") getfem::Neo_Hookean_hyperelastic_law(true).test_derivatives(3, hfd, bp);
+      else { ok = false; what = "no law for this family"; }
+    } catch (const std::exception &ex) { ok = false; what = ex.what(); }
+    std::printf(", \"lawcheck\": %s, \"what\": \"%s\"}\n", ok ? "true" : "false", what.c_str());
+    return ok ? 0 : 1;
+  }
+  if (mode == "crosscheck") {
+    getfem::ga_workspace ws;
+    setup_ws(ws, rg_use);
+    getfem::model_real_sparse_matrix Knew(ndof, ndof), Kold(ndof, ndof);
+    ws.set_assembled_matrix(Knew);
+    ws.assembly(2);
+    std::string old;
+    std::vector<double> LAMBDA(1, lambda), MU(1, mu);
+    if (family == "laplace" || family == "laplace_vec")
+      old = Q == 1 ? "M$1(#1,#1)+=sym(comp(Grad(#1).Grad(#1))(:,i,:,i))" : "M$1(#1,#1)+=sym(comp(vGrad(#1).vGrad(#1))(:,i,j,:,i,j))";
+    else if (family == "mass")
+      old = Q == 1 ? "M$1(#1,#1)+=sym(comp(Base(#1).Base(#1)))" : "M$1(#1,#1)+=sym(comp(vBase(#1).vBase(#1))(:,i,:,i))";
+    else if (family == "elast")  // old_asm_stiffness_matrix_for_homogeneous_linear_elasticity, tests/test_assembly.cc:319-336
+      old = "lambda=data$1(1); mu=data$2(1); t=comp(vGrad(#1).vGrad(#1));"
+            "M(#1,#1)+= sym(t(:,i,j,:,i,j).mu(1)+ t(:,j,i,:,i,j).mu(1)+ t(:,i,i,:,j,j).lambda(1))";
+    GMM_ASSERT1(!old.empty(), "crosscheck: families laplace | mass | elast");
+    getfem::generic_assembly assem(old);
+    assem.push_mi(mim);
+    assem.push_mf(mf);
+    if (family == "elast") { assem.push_data(LAMBDA); assem.push_data(MU); }
+    assem.push_mat(Kold);
+    assem.assembly(rg_use);
+    if (family != "elast") gmm::scale(Kold, acoef);  // the legacy strings carry no coefficient
+    const double nn = gmm::mat_euclidean_norm(Knew);
+    gmm::add(gmm::scaled(Knew, -1.0), Kold);
+    const double dd = gmm::mat_euclidean_norm(Kold);
+    std::printf(", \"cross_rel\": %.3e, \"norm\": %.6e}\n", dd / nn, nn);
+    return 0;
+  }
   if (mode == "time") {
     // direct ga_workspace path, 1 thread (ws.assembly is single-threaded by design)
     double best2 = 1e300, best1 = 1e300;

@@ -42,3 +42,69 @@ def test_oracle_penalty_branch_detF_negative():
     _, _, pr, R = oracle.assemble(g["pts"], g["conn"], g["elem_dof"], g["meta"]["ndof"], 3, g["quad_w"], g["gt_grad"],
                                   g["phi"], g["gphi"], True, "nh_ciarlet", g["fparams"], U)
     assert np.abs(R).max() > 1e190
+
+
+@pytest.mark.parametrize("family", ["svk", "nh_ciarlet", "nh_bonet"])
+def test_oracle_law_derivatives(family):
+    """The reference's own check of its hyperelastic laws, abstract_hyperelastic_law::test_derivatives
+    (getfem_nonlinear_elasticity.cc:298-347: 100 random states, dsigma.DE against sigma(E+DE)-sigma(E), 1.5e-4 relative),
+    restated on the oracle's material point in the variable the GWFL operators use (Grad_u).  A central difference keeps the
+    truncation error below the reference's tolerance for every sample."""
+    rng = np.random.default_rng(7)
+    par = np.array([1.3, 0.7])
+    h, done = 1e-6, 0
+    while done < 100:
+        Gu = 0.4 * rng.uniform(-1, 1, (3, 3))
+        if np.linalg.det(np.eye(3) + Gu) < 0.2:
+            continue
+        D = rng.uniform(-1, 1, (3, 3))
+        S, dS = oracle.hyper_law(family, Gu, par)
+        Sp, _ = oracle.hyper_law(family, Gu + h * D, par)
+        Sm, _ = oracle.hyper_law(family, Gu - h * D, par)
+        fd = (Sp - Sm) / (2 * h)
+        an = np.einsum("ijkl,kl->ij", dS, D)
+        assert np.abs(an - fd).max() <= 1.5e-4 * np.abs(an).max(), (family, done)
+        assert np.abs(S - S.T).max() <= 1e-13 * max(np.abs(S).max(), 1.0)  # PK2 is symmetric
+        done += 1
+
+
+_DRIVER = None
+
+
+def _ref_driver():
+    import os
+    from conftest import ROOT
+    p = os.path.join(ROOT, "oracle", "_ref", "gf_ref_driver")
+    if not os.path.exists(p):
+        pytest.skip("oracle/_ref/gf_ref_driver not built (needs the reference sources)")
+    return p
+
+
+@pytest.mark.parametrize("case", [
+    "family=laplace dim=3 n=3 k=1 q=1 im=2", "family=laplace dim=2 n=6 k=1 q=1 im=2 a=0.7",
+    "family=laplace_vec dim=3 n=2 k=1 q=3 im=2", "family=laplace dim=3 n=2 gt=qk k=2 q=1 im=6",
+    "family=elast dim=3 n=3 k=2 q=3 im=4 lambda=1.3 mu=0.7", "family=elast dim=2 n=5 k=2 q=2 im=4",
+    "family=elast dim=3 n=2 gt=qk k=2 q=3 im=6", "family=mass dim=3 n=3 k=2 q=1 im=4 a=2.5", "family=mass dim=2 n=4 k=1 q=2 im=2",
+])
+def test_reference_old_vs_new_assembly(case):
+    """The reference's own cross-check for this path (tests/test_assembly.cc:279-349, 773-881, tolerance 1e-10): the GWFL
+    expression the golden fixtures are generated from against the LEGACY generic_assembly string of the same form, an
+    independent code path of the reference (getfem_assembling_tensors.cc).  Pins the fixture generator, hence the oracle."""
+    import json
+    import subprocess
+    out = subprocess.run([_ref_driver()] + case.split() + ["mode=crosscheck"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-1500:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["cross_rel"] < 1e-10, r
+
+
+@pytest.mark.parametrize("family", ["svk", "nh_ciarlet", "nh_bonet"])
+def test_reference_law_derivative_check(family):
+    """abstract_hyperelastic_law::test_derivatives run on the reference's own laws (the ones the golden fixtures of the
+    finite-strain families were generated with)."""
+    import json
+    import subprocess
+    out = subprocess.run([_ref_driver(), "family=" + family, "dim=3", "n=1", "gt=qk", "k=2", "q=3", "im=6", "mode=lawcheck"],
+                         capture_output=True, text=True, timeout=300)
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert out.returncode == 0 and r["lawcheck"], r
