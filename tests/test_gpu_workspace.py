@@ -124,6 +124,12 @@ CASES = [  # dim, nsub, gt, k, Q, im, family, params, U
     (3, [4, 4, 3], "PK", 2, 3, 4, "nh_bonet", [1.3, 0.7], "smooth"),
     (3, [2, 2, 1], "QK", 4, 1, 8, "laplace", [1.0], "random"),
     (3, [5, 4, 3], "PK", 2, 3, 4, "mass", [1.5], "random"),
+    # low-order scalar-coefficient forms: the column kernel (csrc/recompute_cols.cu) with every (table size, qdim) pair
+    (3, [6, 5, 4], "PK", 1, 1, 2, "mass", [1.5], "random"),
+    (3, [4, 4, 3], "PK", 1, 3, 2, "mass", [0.8], "random"),
+    (2, [12, 9], "PK", 1, 2, 2, "mass", [2.0], "random"),
+    (2, [10, 8], "PK", 1, 2, 2, "laplace", [0.7], "random"),
+    (3, [4, 3, 5], "PK", 1, 3, 2, "laplace", [1.1], "random"),
     (2, [30, 20], "PK", 1, 1, 2, "source", [-1.5], "random"),
     (3, [3, 2, 2], "QK", 2, 3, 6, "source", [0.5, -1.0, 2.0], "random"),
     # mesh regions: boundary faces (Robin / penalisation mass, Neumann source, normal source) and sub-regions of convexes
