@@ -600,7 +600,7 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
       t->emask.release();  // constant-coefficient linear form: the pattern cannot move any more
       if (t->halo) gf::halo_build_maps(t);
     }
-    if (!t->rc_ready) gf::recompute_prepare(t);
+    if (!t->rc_ready && t->st.npairs) gf::recompute_prepare(t);  // nothing to plan for an empty element range
     if (do_r && do_t && t->rc_cols) {  // column kernel: tangent and R = K U in one pass
       tic(4); gf::recompute_assemble(t, U_dev, true, true); toc(4);
       return;

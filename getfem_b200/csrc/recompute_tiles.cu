@@ -1394,7 +1394,10 @@ static void launch_tiles(gfgpu_term *t, const double *U, bool do_t, bool do_r) {
 
 // tangent and/or residual (R = K^T U = K U, the handled forms are symmetric) in one kernel
 void recompute_assemble(gfgpu_term *t, const double *U, bool do_t, bool do_r) {
-  if (!t->st.npairs) return;
+  if (!t->st.npairs) {  // no element in the range (empty region / a rank without elements): empty tangent, ZERO residual
+    if (do_r) t->R.zero();
+    return;
+  }
   const int N = t->mesh->dim, nd = t->fem->nd, Q = t->fem->qdim, rf = tf_of(t->family);
   TL_CASE(3, 3, 10, TF_ELAST) TL_CASE(3, 3, 4, TF_ELAST) TL_CASE(3, 3, 20, TF_ELAST)
   TL_CASE(3, 1, 10, TF_LAPLACE) TL_CASE(3, 1, 4, TF_LAPLACE) TL_CASE(3, 1, 20, TF_LAPLACE)
