@@ -333,6 +333,7 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     ~matrix_guard() { gfgpu_matrix_destroy(m); }
   } dK;
   if (order == 2) GFGPU_CALL(gfgpu_matrix_create(ctx_, int64_t(need_all), int64_t(need_all), &dK.m));
+  size_type n_added = 0;  // tangents accumulated into dK
   for (auto &it : terms) {
     const auto &td = ws.tree_info(it.first);
     const recognised_term &rt = it.second;
@@ -354,7 +355,7 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
         rg_f.push_back(isf ? int32_t(v.f()) : -1);
         rg_faces += isf;
       }
-      GMM_ASSERT1(!rg_cv.empty(), "gfgpu: empty region");
+      if (rg_cv.empty()) continue;  // an empty region assembles nothing: ga_exec walks zero elements (C&E.cc:8789-8866)
       GMM_ASSERT1(rg_faces == 0 || rg_faces == rg_cv.size(), "gfgpu: a region must hold either convexes or faces");
     }
     const gmm::sub_interval &I = ws.interval_of_variable(rt.varname);
@@ -536,9 +537,15 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     } else {
       GFGPU_CALL(gfgpu_term_assemble_host(e.term, U.data(), GFGPU_TANGENT, nullptr, nullptr));
       GFGPU_CALL(gfgpu_matrix_add_term(dK.m, e.term, 1.0, int64_t(I.first()), int64_t(I.first())));
+      ++n_added;
       t_device += now_s() - t1;
     }
     t0 = now_s();
+  }
+  if (order == 2 && n_added == 0) {  // only order-1 terms / empty regions: K just gets its size (workspace.cc:805-812)
+    getfem::model_real_sparse_matrix &K = ws.assembled_matrix();
+    if (gmm::mat_nrows(K) < need_all || gmm::mat_ncols(K) < need_all) gmm::resize(K, need_all, need_all);
+    return;
   }
   if (order == 2) {
     double t1 = now_s();

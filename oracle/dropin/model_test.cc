@@ -137,6 +137,10 @@ int main(int argc, char **argv) {
   getfem::add_source_term_brick(md, mim, "u", "F");          // volumic load
   getfem::add_source_term_brick(md, mim, "u", "G", 1);       // Neumann load on x = 1
   getfem::add_linear_term(md, mim, "robin*u.Test_u", 2);     // Robin condition on the rest of the boundary
+  if (geti("empty_region", 0)) {  // bricks on regions without any element: ga_exec walks nothing, the device path must do the same
+    getfem::add_source_term_brick(md, mim, "u", "G", 77);
+    getfem::add_linear_term(md, mim, "robin*u.Test_u", 78);
+  }
 
     getfem_b200::gfgpu_enable(device);
     md.assembly(getfem::model::BUILD_ALL);
