@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
 bench.py's cpu_baseline / --impl reference legs.  Never imported by the
-getfem_b200 package (tests/test_boundaries.py enforces this).
+getfem_b200 package (tests/test_abi.py::test_product_never_imports_oracle enforces this).
 """
 import ctypes as C
 import os
