@@ -1,5 +1,8 @@
 // gfgpu_getfem_shim.cc -- see gfgpu_getfem_shim.h.
 #include "gfgpu_getfem_shim.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include <chrono>
 #include <regex>
@@ -556,23 +559,35 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     GFGPU_CALL(gfgpu_matrix_export_csc_host(dK.m, jc.data(), ir.data(), pr.data()));
     double t2 = now_s();
     t_device += t2 - t1;
-    // fill gmm::col_matrix<rsvector>: each column is a row-sorted vector of (index, value) (gmm_vector.h:913-1030).
-    // Empty columns take the device column as is; otherwise add (accumulate-into-aliased-K, workspace.cc:805-812).
     getfem::model_real_sparse_matrix &K = ws.assembled_matrix();
     if (gmm::mat_nrows(K) < need_all || gmm::mat_ncols(K) < need_all) gmm::resize(K, need_all, need_all);
-    for (size_type j = 0; j < need_all; ++j) {
-      const int64_t b = jc[j], en = jc[j + 1];
-      if (b == en) continue;
-      gmm::rsvector<double> &col = K[j];
-      if (col.nb_stored() == 0) {
-        col.base_resize(size_type(en - b));
-        auto itc = col.begin();
-        for (int64_t k = b; k < en; ++k, ++itc) { itc->c = size_type(ir[size_t(k)]); itc->e = pr[size_t(k)]; }
-      } else {
-        for (int64_t k = b; k < en; ++k) col.w(size_type(ir[size_t(k)]), col.r(size_type(ir[size_t(k)])) + pr[size_t(k)]);
-      }
-    }
+    fill_col_matrix(K, need_all, jc.data(), ir.data(), pr.data());
     t_fill += now_s() - t2;
+  }
+}
+
+// CSC -> gmm::col_matrix<rsvector>: each column is a row-sorted vector of (index, value) (gmm_vector.h:913-1030).  Empty columns
+// take the device column as is; otherwise the values are added (accumulate-into-aliased-K, workspace.cc:805-812).  Columns are
+// independent objects, so the loop runs on the host cores when OpenMP is on and we are not already inside a parallel region
+// (the bricks' GETFEM_OMP_PARALLEL blocks): at benchmark size this fill, not the device, is what a drop-in caller waits for.
+void fill_col_matrix(getfem::model_real_sparse_matrix &K, size_type ncols, const int64_t *jc, const int32_t *ir, const double *pr) {
+  const long n = long(ncols);
+  int nt = 1;
+#ifdef _OPENMP
+  if (!omp_in_parallel() && n >= 4096) nt = std::max(1, std::min(omp_get_num_procs(), 32));
+#endif
+#pragma omp parallel for schedule(static, 512) num_threads(nt) if (nt > 1)
+  for (long j = 0; j < n; ++j) {
+    const int64_t b = jc[j], en = jc[j + 1];
+    if (b == en) continue;
+    gmm::rsvector<double> &col = K[size_type(j)];
+    if (col.nb_stored() == 0) {
+      col.base_resize(size_type(en - b));
+      auto itc = col.begin();
+      for (int64_t k = b; k < en; ++k, ++itc) { itc->c = size_type(ir[size_t(k)]); itc->e = pr[size_t(k)]; }
+    } else {
+      for (int64_t k = b; k < en; ++k) col.w(size_type(ir[size_t(k)]), col.r(size_type(ir[size_t(k)])) + pr[size_t(k)]);
+    }
   }
 }
 

@@ -58,6 +58,11 @@ class device_assembler {
   std::map<std::string, std::unique_ptr<entry>> cache_;
 };
 
+// Adds a CSC matrix (jc[ncols+1], ir, pr: gmm::csc_matrix layout, rows ascending inside a column) into K, column by column
+// (OpenMP over the columns when available); K must already have at least ncols columns.
+void fill_col_matrix(getfem::model_real_sparse_matrix &K, getfem::size_type ncols, const int64_t *jc, const int32_t *ir,
+                     const double *pr);
+
 // One-shot convenience: getfem_b200::assembly(ws, 2) instead of ws.assembly(2).
 void assembly(getfem::ga_workspace &ws, getfem::size_type order, int device = 0);
 

@@ -104,3 +104,21 @@ def test_expression_recognition(expr, fam):
 def test_unknown_expression_raises_not_falls_back():
     with pytest.raises(capi.GfgpuError, match="no CPU fallback"):
         recognise("Det(Grad_u)*Test_u")
+
+
+def test_shim_fill_of_the_gmm_matrix():
+    """Host end of the drop-in, CPU only: getfem_b200::fill_col_matrix (device CSC -> gmm::col_matrix<rsvector>, OpenMP over
+    the columns) gives exactly what gmm's own element-wise accumulation gives, for fresh columns and for columns that
+    already hold entries (oracle/fill_test.cc, linked with the unmodified reference)."""
+    import json
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "oracle", "_ref", "fill_test")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/fill_test not built (needs the reference sources)")
+    for env in ({}, {"OMP_THREAD_LIMIT": "1"}):
+        out = subprocess.run([exe, "30000"], capture_output=True, text=True, timeout=300, env=dict(os.environ, **env))
+        assert out.returncode == 0, out.stdout + out.stderr[-1000:]
+        r = json.loads(out.stdout.strip().splitlines()[-1])
+        assert r["same"] and r["sorted"] and r["nnz"] > 0
