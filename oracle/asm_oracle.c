@@ -29,7 +29,7 @@
 #include <string.h>
 
 enum { GFO_LAPLACE = 0, GFO_ELAST = 1, GFO_SVK = 2, GFO_NH_CIARLET = 3, GFO_NH_BONET = 4, GFO_MASS = 5, GFO_SOURCE = 6,
-       GFO_NORMAL_SOURCE = 7 };
+       GFO_NORMAL_SOURCE = 7, GFO_MOONEY_RIVLIN = 8 /* Compressible_Mooney_Rivlin_PK2, params (C10, C01, D1) */ };
 
 typedef struct { int64_t c; double e; } entry_t; /* gmm::elt_rsvector_ (gmm_vector.h:913-932) */
 typedef struct { entry_t *v; int64_t n, cap; } col_t;
@@ -142,8 +142,6 @@ static void hyper_law(int family, const double *Gu, const double *par, double *S
           }
     return;
   }
-  /* Neo_Hookean_hyperelastic_law (cc:612-702), through AHL_wrapper_sigma (cc:1781-1827) */
-  int bonet = family == GFO_NH_BONET;
   double detF = det3(F, N);
   double C[9], Ci[9];
   for (int i = 0; i < 9; ++i) C[i] = 2 * E[i];
@@ -151,6 +149,53 @@ static void hyper_law(int family, const double *Gu, const double *par, double *S
   double i3 = inv3(C, Ci, N);
   double di3[9];
   for (int i = 0; i < 9; ++i) di3[i] = Ci[i] * i3; /* compute_di3 (cc:132-140) */
+  double A4[81];
+#define CI(i, j) Ci[(i) + 3 * (j)]
+#define T4(T, i, j, k, l) T[(i) + 3 * (j) + 9 * (k) + 27 * (l)]
+  if (family == GFO_MOONEY_RIVLIN) {
+    /* Mooney_Rivlin_hyperelastic_law(compressible, !neohookean) (cc:503-607) on the invariants of C (compute_invariants,
+       cc:45-262): W = C10 (j1 - 3) + C01 (j2 - 3) + D1 (sqrt|i3| - 1)^2, j1 = i1 i3^(-1/3), j2 = i2 i3^(-2/3) */
+    const double c10 = par[0], c01 = par[1], d1 = par[2];
+    double i1 = C[0] + C[4] + C[8], ff = 0;
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) ff += C[i + N * j] * C[j + N * i]; /* frobenius_product_trans(C, C) */
+    const double i2 = (i1 * i1 - ff) / 2;
+    double di1[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, di2[9], dd3[81], ddi2[81];
+    for (int i = 0; i < 9; ++i) di2[i] = i1 * di1[i] - C[i]; /* compute_di2 (cc:95-102) */
+    for (int i = 0; i < 81; ++i) ddi2[i] = 0;
+    for (int i = 0; i < N; ++i)
+      for (int k = 0; k < N; ++k) T4(ddi2, i, i, k, k) += 1.0; /* compute_ddi2 (cc:104-115) */
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) { T4(ddi2, i, j, j, i) -= 0.5; T4(ddi2, j, i, j, i) -= 0.5; }
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j)
+        for (int k = 0; k < N; ++k)
+          for (int l = 0; l < N; ++l) /* compute_ddi3 (cc:142-152) */
+            T4(dd3, i, j, k, l) = i3 / 2 * (CI(j, i) * CI(l, k) - CI(j, k) * CI(l, i) + CI(i, j) * CI(l, k) - CI(i, k) * CI(l, j));
+    const double p13 = pow(fabs(i3), -1.0 / 3.0), p23 = pow(fabs(i3), -2.0 / 3.0);
+    const double k1 = 1.0 / (3 * i3), k2 = 4 * k1 * k1 * i1;          /* compute_ddj1 (cc:176-196) */
+    const double m1 = 2.0 / (3 * i3), m2 = 5 * m1 * m1 * i2 / 2;      /* compute_ddj2 (cc:219-240) */
+    const double dw3 = d1 - d1 / sqrt(fabs(i3)), a22 = d1 / (2 * pow(fabs(i3), 1.5));
+    for (int i = 0; i < 9; ++i) {
+      const double dj1 = (di1[i] - i1 / (3 * i3) * di3[i]) * p13;     /* compute_dj1 (cc:169-174) */
+      const double dj2 = (di2[i] - 2 * i2 / (3 * i3) * di3[i]) * p23; /* compute_dj2 (cc:212-217) */
+      S[i] = 2 * c10 * dj1 + 2 * c01 * dj2 + 2 * dw3 * di3[i];
+    }
+    if (detF <= 0) for (int i = 0; i < 9; ++i) S[i] += 1e200 * C[i];
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j)
+        for (int k = 0; k < N; ++k)
+          for (int l = 0; l < N; ++l) {
+            const double d3ij = di3[i + 3 * j], d3kl = di3[k + 3 * l];
+            const double ddj1 = (-i1 * k1 * T4(dd3, i, j, k, l) + d3ij * d3kl * k2 -
+                                 (di1[i + 3 * j] * d3kl + di1[k + 3 * l] * d3ij) * k1) * p13;
+            const double ddj2 = (T4(ddi2, i, j, k, l) - i2 * m1 * T4(dd3, i, j, k, l) + d3ij * d3kl * m2 -
+                                 (di2[i + 3 * j] * d3kl + di2[k + 3 * l] * d3ij) * m1) * p23;
+            T4(A4, i, j, k, l) = 4 * c10 * ddj1 + 4 * c01 * ddj2 + 4 * dw3 * T4(dd3, i, j, k, l) + 4 * a22 * d3ij * d3kl;
+          }
+  } else {
+  /* Neo_Hookean_hyperelastic_law (cc:612-702), through AHL_wrapper_sigma (cc:1781-1827) */
+  int bonet = family == GFO_NH_BONET;
   double cs = bonet ? (lambda / 2 * log(i3) - mu) / i3 : lambda / 2 - lambda / (2 * i3) - mu / i3;
   for (int i = 0; i < 9; ++i) S[i] = cs * di3[i];
   S[0] += mu; S[4] += mu; S[8] += mu; /* mu * grad_i1 = mu * Id */
@@ -158,9 +203,7 @@ static void hyper_law(int family, const double *Gu, const double *par, double *S
   double c1, c2;
   if (bonet) { double lg = log(i3); c1 = (lambda * lg - 2 * mu) / i3; c2 = (lambda + 2 * mu - lambda * lg) / (i3 * i3); }
   else { c1 = lambda - (lambda + 2 * mu) / i3; c2 = (lambda + 2 * mu) / (i3 * i3); }
-  double A4[81];
   double hd = i3 / 2;
-#define CI(i, j) Ci[(i) + 3 * (j)]
   for (int i = 0; i < N; ++i)
     for (int j = 0; j < N; ++j)
       for (int k = 0; k < N; ++k)
@@ -168,7 +211,9 @@ static void hyper_law(int family, const double *Gu, const double *par, double *S
           double dd = hd * (CI(j, i) * CI(l, k) - CI(j, k) * CI(l, i) + CI(i, j) * CI(l, k) - CI(i, k) * CI(l, j));
           A4[i + 3 * j + 9 * k + 27 * l] = c1 * dd + c2 * di3[i + 3 * j] * di3[k + 3 * l];
         }
+  }
 #undef CI
+#undef T4
   double *it = dS;
   for (int l = 0; l < N; ++l)
     for (int k = 0; k < N; ++k)
@@ -202,7 +247,7 @@ gfo_result *gfo_assemble_fields(int dim, int64_t ne, int ng, const double *pts, 
   double par[16];
   for (int k = 0; k < 16; ++k) par[k] = 0.0;
   { int np = family == GFO_SOURCE ? Q : family == GFO_NORMAL_SOURCE ? Q * dim
-             : (family == GFO_LAPLACE || family == GFO_MASS) ? 1 : 2;
+             : (family == GFO_LAPLACE || family == GFO_MASS) ? 1 : family == GFO_MOONEY_RIVLIN ? 3 : 2;
     for (int k = 0; k < np; ++k) par[k] = par_in[k]; }
   const int N = dim, s1 = nd * Q;
   gfo_result *res = (gfo_result *)calloc(1, sizeof(gfo_result));
@@ -215,7 +260,7 @@ gfo_result *gfo_assemble_fields(int dim, int64_t ne, int ng, const double *pts, 
   int64_t *dofs = (int64_t *)malloc(sizeof(int64_t) * s1);
   int *sort = (int *)malloc(sizeof(int) * s1);
   double K[9], Ki[9], B[9], J = 0, D[81], P[9], Gu[9], S[9], dS[81], Nrm[3] = {0, 0, 0};
-  const int nonlinear = family == GFO_SVK || family == GFO_NH_CIARLET || family == GFO_NH_BONET;
+  const int nonlinear = family == GFO_SVK || family == GFO_NH_CIARLET || family == GFO_NH_BONET || family == GFO_MOONEY_RIVLIN;
   if (!item_cv) n_items = ne;
 
   for (int64_t item = 0; item < n_items; ++item) {

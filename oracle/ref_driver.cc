@@ -16,7 +16,7 @@
 //
 // usage: gf_ref_driver key=value ...
 //   dim=3 n=4 gt=pk|qk k=2 q=3 im=4 | imname="IM_TETRAHEDRON(5)"
-//   family=laplace|elast|svk|nh_ciarlet|nh_bonet|mass|source  lambda=1 mu=1 a=1
+//   family=laplace|elast|svk|nh_ciarlet|nh_bonet|mooney_rivlin|mass|source  lambda=1 mu=1 a=1   (mooney_rivlin: C10=lambda C01=mu D1=a)
 //   family=nsource (normal source term, getfem_models.cc:4290-4299; boundary regions only)
 //   region=all|outer|xmax|zmin|half   (outer faces / faces on x=1 / on z=0 (last coord) / convexes with barycentre x<0.5)
 //   family2=.. region2=.. a2=..  family3=.. region3=.. a3=..   further expressions of the SAME workspace (linear
@@ -212,7 +212,8 @@ int main(int argc, char **argv) {
   else {
     std::string law = family == "svk" ? "Saint_Venant_Kirchhoff"
                     : family == "nh_ciarlet" ? "Compressible_Neo_Hookean_Ciarlet"
-                    : family == "nh_bonet" ? "Compressible_Neo_Hookean_Bonet" : "";
+                    : family == "nh_bonet" ? "Compressible_Neo_Hookean_Bonet"
+                    : family == "mooney_rivlin" ? "Compressible_Mooney_Rivlin" : "";
     if (law.empty()) { std::fprintf(stderr, "unknown family %s\n", family.c_str()); return 2; }
     // src/getfem_nonlinear_elasticity.cc:2319-2320
     expr = "((Id(meshdim)+Grad_u)*(" + law + "_PK2(Grad_u,params))):Grad_Test_u";
@@ -237,7 +238,9 @@ int main(int argc, char **argv) {
   if (a.count("uscale")) for (auto &v : U) v *= getd("uscale", 1.0);
 
   // constants are BORROWED by the workspace (generic_assembly.h:277): keep them alive
-  const std::vector<double> c_a{acoef}, c_lambda{lambda}, c_mu{mu}, c_params{lambda, mu};
+  const std::vector<double> c_a{acoef}, c_lambda{lambda}, c_mu{mu};
+  // the laws' parameter vector: (lambda, mu); Compressible_Mooney_Rivlin takes (C10, C01, D1), passed as lambda= mu= a=
+  const std::vector<double> c_params = family == "mooney_rivlin" ? std::vector<double>{lambda, mu, acoef} : std::vector<double>{lambda, mu};
   std::vector<double> c_f(Q);
   for (size_type k = 0; k < size_type(Q); ++k) c_f[k] = acoef * double(k + 1);
   // fem-data coefficients (coef=fem): scalar fields on mf_d, the source term's field on mf_dq (qdim Q)
@@ -310,6 +313,11 @@ int main(int argc, char **argv) {
       if (family == "svk") getfem::SaintVenant_Kirchhoff_hyperelastic_law().test_derivatives(3, hfd, bp);
       else if (family == "nh_ciarlet") getfem::Neo_Hookean_hyperelastic_law(false).test_derivatives(3, hfd, bp);
       else if (family == "nh_bonet") getfem::Neo_Hookean_hyperelastic_law(true).test_derivatives(3, hfd, bp);
+      else if (family == "mooney_rivlin") {
+        bgeot::base_vector b3(3);
+        b3[0] = lambda; b3[1] = mu; b3[2] = acoef;
+        getfem::Mooney_Rivlin_hyperelastic_law(true, false).test_derivatives(3, hfd, b3);
+      }
       else { ok = false; what = "no law for this family"; }
     } catch (const std::exception &ex) { ok = false; what = ex.what(); }
     std::printf(", \"lawcheck\": %s, \"what\": \"%s\"}\n", ok ? "true" : "false", what.c_str());

@@ -16,8 +16,10 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-def golden_names():
-    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz")))
+def golden_names(oracle_only=False):
+    names = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    # "o_*": oracle-only fixtures (a family the oracle restates and pins before the device implements it)
+    return names if oracle_only else [n for n in names if not n.startswith("o_")]
 
 
 def load_golden(name):
@@ -36,7 +38,8 @@ def load_golden(name):
     elif d["family"] == "nsource":  # "(Reshape(g,qdim,meshdim)*Normal).Test_u": A(b,n) = g[b + Q*n]
         d["fparams"] = d["gdata"].astype(np.float64)
     else:
-        d["fparams"] = np.array([a]) if d["family"] in ("laplace", "mass") else np.array([lam, mu])
+        d["fparams"] = (np.array([a]) if d["family"] in ("laplace", "mass") else
+                        np.array([lam, mu, a]) if d["family"] == "mooney_rivlin" else np.array([lam, mu]))
     # fem-data coefficients (coef=fem): the fields replace the leading parameters; the data fem's basis table covers ALL
     # integration points, so the all-point tables are used with it
     d["fields"] = None

@@ -74,6 +74,10 @@ CASES = {
     "f_source3d_p2vec_xmax_coefp1": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=source region=xmax u=random a=0.5 coef=fem kd=1",
     "f_mass3d_p2_outer_coefp1": "dim=3 n=2 gt=pk k=2 q=1 im=4 family=mass region=outer u=random a=2.5 coef=fem kd=1",
     "r_nh_ciarlet_q2_half": "dim=3 n=2 gt=qk k=2 q=3 im=6 family=nh_ciarlet region=half u=smooth lambda=1 mu=1 uamp=0.02",
+    # ORACLE-ONLY fixtures (prefix o_: not yet a device family; tests/conftest.py keeps them out of the GPU parametrisations).
+    # Compressible Mooney-Rivlin (the law of the reference's tests/nonlinear_elastostatic.cc), C10 = lambda, C01 = mu, D1 = a
+    "o_mooney_rivlin_q2_n2": "dim=3 n=2 gt=qk k=2 q=3 im=6 family=mooney_rivlin u=smooth lambda=0.8 mu=0.3 a=2.0 uamp=0.03",
+    "o_mooney_rivlin_p2tet_n2": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=mooney_rivlin u=smooth lambda=1.1 mu=0.2 a=1.5 uamp=0.05",
 }
 
 
