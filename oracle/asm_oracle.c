@@ -29,7 +29,9 @@
 #include <string.h>
 
 enum { GFO_LAPLACE = 0, GFO_ELAST = 1, GFO_SVK = 2, GFO_NH_CIARLET = 3, GFO_NH_BONET = 4, GFO_MASS = 5, GFO_SOURCE = 6,
-       GFO_NORMAL_SOURCE = 7, GFO_MOONEY_RIVLIN = 8 /* Compressible_Mooney_Rivlin_PK2, params (C10, C01, D1) */ };
+       GFO_NORMAL_SOURCE = 7, GFO_MOONEY_RIVLIN = 8 /* Compressible_Mooney_Rivlin_PK2, params (C10, C01, D1) */,
+       GFO_CIARLET_GEYMONAT = 9 /* Ciarlet_Geymonat_PK2, params (lambda, mu, a) */,
+       GFO_BLATZ_KO = 10 /* Generalized_Blatz_Ko_PK2, params (a, b, c, d, n) */ };
 
 typedef struct { int64_t c; double e; } entry_t; /* gmm::elt_rsvector_ (gmm_vector.h:913-932) */
 typedef struct { entry_t *v; int64_t n, cap; } col_t;
@@ -193,6 +195,58 @@ static void hyper_law(int family, const double *Gu, const double *par, double *S
                                  (di2[i + 3 * j] * d3kl + di2[k + 3 * l] * d3ij) * m1) * p23;
             T4(A4, i, j, k, l) = 4 * c10 * ddj1 + 4 * c01 * ddj2 + 4 * dw3 * T4(dd3, i, j, k, l) + 4 * a22 * d3ij * d3kl;
           }
+  } else if (family == GFO_CIARLET_GEYMONAT) {
+    /* Ciarlet_Geymonat_hyperelastic_law (cc:817-888): W = a i1(C) + b i2(C) + c i3(C) - d/2 log i3(C) + e */
+    const double a = par[2], b = par[1] / 2 - par[2], c = par[0] / 4 - par[1] / 2 + par[2], d = par[0] / 2 + par[1];
+    const double trC = C[0] + C[4] + C[8], b2 = 2 * b;
+    for (int i = 0; i < 9; ++i) S[i] = -2 * b * C[i];
+    for (int i = 0; i < N; ++i) S[i + N * i] += 2 * (a + b * trC);
+    if (detF <= 0) for (int i = 0; i < 9; ++i) S[i] += 1e200 * C[i];
+    else for (int i = 0; i < 9; ++i) S[i] += Ci[i] * (2 * c * i3 - d);
+    for (int i = 0; i < 81; ++i) A4[i] = 0;
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) {
+        T4(A4, i, i, j, j) += 2 * b2;
+        T4(A4, i, j, i, j) -= b2;
+        T4(A4, i, j, j, i) -= b2;
+        for (int k = 0; k < N; ++k)
+          for (int l = 0; l < N; ++l)
+            T4(A4, i, j, k, l) += (CI(i, k) * CI(l, j) + CI(i, l) * CI(k, j)) * (d - 2 * i3 * c) + CI(i, j) * CI(k, l) * i3 * c * 4;
+      }
+  } else if (family == GFO_BLATZ_KO) {
+    /* generalized_Blatz_Ko_hyperelastic_law (cc:706-815): W = (a i1 + b sqrt|i3| + c i2 / i3 + d)^n on the invariants of C */
+    const double a = par[0], b = par[1], c = par[2], d = par[3], n = par[4];
+    double i1 = C[0] + C[4] + C[8], ff = 0;
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) ff += C[i + N * j] * C[j + N * i];
+    const double i2 = (i1 * i1 - ff) / 2;
+    double di1[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, di2[9];
+    for (int i = 0; i < 9; ++i) di2[i] = i1 * di1[i] - C[i];
+    const double z = a * i1 + b * sqrt(fabs(i3)) + c * i2 / i3 + d, nz = n * pow(z, n - 1.);
+    const double w1 = nz * a, w2 = nz * c / i3, y = b / (2. * sqrt(fabs(i3))) - c * i2 / (i3 * i3), w3 = nz * y;
+    for (int i = 0; i < 9; ++i) S[i] = 2 * (w1 * di1[i] + w2 * di2[i] + w3 * di3[i]);
+    if (detF <= 0) for (int i = 0; i < 9; ++i) S[i] += 1e200 * C[i];
+    const double nnz = n * (n - 1.) * pow(z, n - 2.);
+    double A[3][3];
+    A[0][0] = nnz * a * a;
+    A[1][0] = A[0][1] = nnz * a * c / i3;
+    A[2][0] = A[0][2] = nnz * a * y;
+    A[1][1] = nnz * c * c / (i3 * i3);
+    A[2][1] = A[1][2] = nnz * y * c / i3 - nz * c / (i3 * i3);
+    A[2][2] = nnz * y * y + nz * (2. * c * i2 / pow(i3, 3.) - b / (4. * pow(i3, 1.5)));
+    const double *dv[3] = {di1, di2, di3};
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j)
+        for (int k = 0; k < N; ++k)
+          for (int l = 0; l < N; ++l) {
+            double v = 0; /* 4 w2 ddi2 + 4 w3 ddi3 (ddi1 = 0), compute_ddi2 / compute_ddi3 (cc:104-115, 142-152) */
+            double dd2 = (i == j && k == l ? 1.0 : 0.0) - (j == k && i == l ? 0.5 : 0.0) - (i == k && j == l ? 0.5 : 0.0);
+            double dd3 = i3 / 2 * (CI(j, i) * CI(l, k) - CI(j, k) * CI(l, i) + CI(i, j) * CI(l, k) - CI(i, k) * CI(l, j));
+            v = 4 * w2 * dd2 + 4 * w3 * dd3;
+            for (int p = 0; p < 3; ++p)
+              for (int q = 0; q < 3; ++q) v += 4. * A[p][q] * dv[p][i + 3 * j] * dv[q][k + 3 * l];
+            T4(A4, i, j, k, l) = v;
+          }
   } else {
   /* Neo_Hookean_hyperelastic_law (cc:612-702), through AHL_wrapper_sigma (cc:1781-1827) */
   int bonet = family == GFO_NH_BONET;
@@ -247,7 +301,8 @@ gfo_result *gfo_assemble_fields(int dim, int64_t ne, int ng, const double *pts, 
   double par[16];
   for (int k = 0; k < 16; ++k) par[k] = 0.0;
   { int np = family == GFO_SOURCE ? Q : family == GFO_NORMAL_SOURCE ? Q * dim
-             : (family == GFO_LAPLACE || family == GFO_MASS) ? 1 : family == GFO_MOONEY_RIVLIN ? 3 : 2;
+             : (family == GFO_LAPLACE || family == GFO_MASS) ? 1
+             : (family == GFO_MOONEY_RIVLIN || family == GFO_CIARLET_GEYMONAT) ? 3 : family == GFO_BLATZ_KO ? 5 : 2;
     for (int k = 0; k < np; ++k) par[k] = par_in[k]; }
   const int N = dim, s1 = nd * Q;
   gfo_result *res = (gfo_result *)calloc(1, sizeof(gfo_result));
@@ -260,7 +315,8 @@ gfo_result *gfo_assemble_fields(int dim, int64_t ne, int ng, const double *pts, 
   int64_t *dofs = (int64_t *)malloc(sizeof(int64_t) * s1);
   int *sort = (int *)malloc(sizeof(int) * s1);
   double K[9], Ki[9], B[9], J = 0, D[81], P[9], Gu[9], S[9], dS[81], Nrm[3] = {0, 0, 0};
-  const int nonlinear = family == GFO_SVK || family == GFO_NH_CIARLET || family == GFO_NH_BONET || family == GFO_MOONEY_RIVLIN;
+  const int nonlinear = family == GFO_SVK || family == GFO_NH_CIARLET || family == GFO_NH_BONET || family == GFO_MOONEY_RIVLIN ||
+                        family == GFO_CIARLET_GEYMONAT || family == GFO_BLATZ_KO;
   if (!item_cv) n_items = ne;
 
   for (int64_t item = 0; item < n_items; ++item) {

@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libgfo.so")
 FAMILIES = {"laplace": 0, "elast": 1, "svk": 2, "nh_ciarlet": 3, "nh_bonet": 4, "mass": 5, "source": 6,
-            "nsource": 7, "mooney_rivlin": 8}
+            "nsource": 7, "mooney_rivlin": 8, "ciarlet_geymonat": 9, "blatz_ko": 10}
 
 
 def build(force=False):

@@ -47,6 +47,7 @@
 #include <map>
 #include <memory>
 #include <random>
+#include <sstream>
 #include <string>
 #include <sys/stat.h>
 
@@ -213,7 +214,9 @@ int main(int argc, char **argv) {
     std::string law = family == "svk" ? "Saint_Venant_Kirchhoff"
                     : family == "nh_ciarlet" ? "Compressible_Neo_Hookean_Ciarlet"
                     : family == "nh_bonet" ? "Compressible_Neo_Hookean_Bonet"
-                    : family == "mooney_rivlin" ? "Compressible_Mooney_Rivlin" : "";
+                    : family == "mooney_rivlin" ? "Compressible_Mooney_Rivlin"
+                    : family == "ciarlet_geymonat" ? "Ciarlet_Geymonat"
+                    : family == "blatz_ko" ? "Generalized_Blatz_Ko" : "";
     if (law.empty()) { std::fprintf(stderr, "unknown family %s\n", family.c_str()); return 2; }
     // src/getfem_nonlinear_elasticity.cc:2319-2320
     expr = "((Id(meshdim)+Grad_u)*(" + law + "_PK2(Grad_u,params))):Grad_Test_u";
@@ -240,7 +243,13 @@ int main(int argc, char **argv) {
   // constants are BORROWED by the workspace (generic_assembly.h:277): keep them alive
   const std::vector<double> c_a{acoef}, c_lambda{lambda}, c_mu{mu};
   // the laws' parameter vector: (lambda, mu); Compressible_Mooney_Rivlin takes (C10, C01, D1), passed as lambda= mu= a=
-  const std::vector<double> c_params = family == "mooney_rivlin" ? std::vector<double>{lambda, mu, acoef} : std::vector<double>{lambda, mu};
+  std::vector<double> c_params = (family == "mooney_rivlin" || family == "ciarlet_geymonat") ? std::vector<double>{lambda, mu, acoef}
+                                                                                             : std::vector<double>{lambda, mu};
+  if (a.count("params")) {  // params=p0,p1,...: the law's whole parameter vector (Generalized_Blatz_Ko takes five)
+    c_params.clear();
+    std::stringstream ss(a["params"]);
+    for (std::string tok; std::getline(ss, tok, ',');) c_params.push_back(std::stod(tok));
+  }
   std::vector<double> c_f(Q);
   for (size_type k = 0; k < size_type(Q); ++k) c_f[k] = acoef * double(k + 1);
   // fem-data coefficients (coef=fem): scalar fields on mf_d, the source term's field on mf_dq (qdim Q)
@@ -317,6 +326,14 @@ int main(int argc, char **argv) {
         bgeot::base_vector b3(3);
         b3[0] = lambda; b3[1] = mu; b3[2] = acoef;
         getfem::Mooney_Rivlin_hyperelastic_law(true, false).test_derivatives(3, hfd, b3);
+      } else if (family == "ciarlet_geymonat") {
+        bgeot::base_vector b3(3);
+        b3[0] = lambda; b3[1] = mu; b3[2] = acoef;
+        getfem::Ciarlet_Geymonat_hyperelastic_law().test_derivatives(3, hfd, b3);
+      } else if (family == "blatz_ko") {
+        bgeot::base_vector b5(5);
+        b5[0] = 1.0; b5[1] = 1.0; b5[2] = 1.5; b5[3] = -0.5; b5[4] = 1.5;  // the law's own default set (cc:810-815)
+        getfem::generalized_Blatz_Ko_hyperelastic_law().test_derivatives(3, hfd, b5);
       }
       else { ok = false; what = "no law for this family"; }
     } catch (const std::exception &ex) { ok = false; what = ex.what(); }
@@ -552,6 +569,7 @@ int main(int argc, char **argv) {
   npy_f64(out + "/R.npy", {ndof}, R);
   std::vector<double> par = {lambda, mu, acoef};
   npy_f64(out + "/params.npy", {3}, par);
+  npy_f64(out + "/lawparams.npy", {c_params.size()}, c_params);
   npy_f64(out + "/gdata.npy", {c_g.size()}, c_g);
   return 0;
 }

@@ -39,7 +39,7 @@ def load_golden(name):
         d["fparams"] = d["gdata"].astype(np.float64)
     else:
         d["fparams"] = (np.array([a]) if d["family"] in ("laplace", "mass") else
-                        np.array([lam, mu, a]) if d["family"] == "mooney_rivlin" else np.array([lam, mu]))
+                        d["lawparams"].astype(np.float64) if "lawparams" in d else np.array([lam, mu]))
     # fem-data coefficients (coef=fem): the fields replace the leading parameters; the data fem's basis table covers ALL
     # integration points, so the all-point tables are used with it
     d["fields"] = None

@@ -78,6 +78,10 @@ CASES = {
     # Compressible Mooney-Rivlin (the law of the reference's tests/nonlinear_elastostatic.cc), C10 = lambda, C01 = mu, D1 = a
     "o_mooney_rivlin_q2_n2": "dim=3 n=2 gt=qk k=2 q=3 im=6 family=mooney_rivlin u=smooth lambda=0.8 mu=0.3 a=2.0 uamp=0.03",
     "o_mooney_rivlin_p2tet_n2": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=mooney_rivlin u=smooth lambda=1.1 mu=0.2 a=1.5 uamp=0.05",
+    # Ciarlet-Geymonat (lambda, mu, a) and generalized Blatz-Ko (a, b, c, d, n: the law's default set), the other laws of
+    # add_finite_strain_elasticity_brick (getfem_nonlinear_elasticity.cc:2276-2290)
+    "o_ciarlet_geymonat_q2_n2": "dim=3 n=2 gt=qk k=2 q=3 im=6 family=ciarlet_geymonat u=smooth lambda=1.3 mu=0.7 a=0.25 uamp=0.03",
+    "o_blatz_ko_p2tet_n2": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=blatz_ko u=smooth params=1.0,1.0,1.5,-0.5,1.5 uamp=0.04",
 }
 
 

@@ -44,14 +44,15 @@ def test_oracle_penalty_branch_detF_negative():
     assert np.abs(R).max() > 1e190
 
 
-@pytest.mark.parametrize("family", ["svk", "nh_ciarlet", "nh_bonet", "mooney_rivlin"])
+@pytest.mark.parametrize("family", ["svk", "nh_ciarlet", "nh_bonet", "mooney_rivlin", "ciarlet_geymonat", "blatz_ko"])
 def test_oracle_law_derivatives(family):
     """The reference's own check of its hyperelastic laws, abstract_hyperelastic_law::test_derivatives
     (getfem_nonlinear_elasticity.cc:298-347: 100 random states, dsigma.DE against sigma(E+DE)-sigma(E), 1.5e-4 relative),
     restated on the oracle's material point in the variable the GWFL operators use (Grad_u).  A central difference keeps the
     truncation error below the reference's tolerance for every sample."""
     rng = np.random.default_rng(7)
-    par = np.array([1.3, 0.7]) if family != "mooney_rivlin" else np.array([0.8, 0.3, 2.0])
+    par = {"mooney_rivlin": np.array([0.8, 0.3, 2.0]), "ciarlet_geymonat": np.array([1.3, 0.7, 0.25]),
+           "blatz_ko": np.array([1.0, 1.0, 1.5, -0.5, 1.5])}.get(family, np.array([1.3, 0.7]))
     h, done = 1e-6, 0
     while done < 100:
         Gu = 0.4 * rng.uniform(-1, 1, (3, 3))
@@ -98,13 +99,14 @@ def test_reference_old_vs_new_assembly(case):
     assert r["cross_rel"] < 1e-10, r
 
 
-@pytest.mark.parametrize("family", ["svk", "nh_ciarlet", "nh_bonet", "mooney_rivlin"])
+@pytest.mark.parametrize("family", ["svk", "nh_ciarlet", "nh_bonet", "mooney_rivlin", "ciarlet_geymonat", "blatz_ko"])
 def test_reference_law_derivative_check(family):
     """abstract_hyperelastic_law::test_derivatives run on the reference's own laws (the ones the golden fixtures of the
     finite-strain families were generated with)."""
     import json
     import subprocess
-    out = subprocess.run([_ref_driver(), "family=" + family, "dim=3", "n=1", "gt=qk", "k=2", "q=3", "im=6", "mode=lawcheck"],
+    out = subprocess.run([_ref_driver(), "family=" + family, "dim=3", "n=1", "gt=qk", "k=2", "q=3", "im=6", "mode=lawcheck",
+                          "lambda=1.3", "mu=0.7", "a=0.25"],
                          capture_output=True, text=True, timeout=300)
     r = json.loads(out.stdout.strip().splitlines()[-1])
     assert out.returncode == 0 and r["lawcheck"], r
