@@ -5,6 +5,9 @@
 #endif
 
 #include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <regex>
 #include <sstream>
 
@@ -126,12 +129,116 @@ static bool recognise_order2_string(const getfem::ga_workspace &ws, const std::s
   return false;
 }
 
+// ---------------------------------------------------------------- recognition by probe
+// The reference's own tests write ONE bilinear form in many algebraically equivalent ways (tests/test_assembly.cc:777-866:
+// "lambda*Div_Test_u*Div_Test2_u + mu*(Grad_Test_u'+Grad_Test_u):Grad_Test2_u", "lambda*Trace(..)*Trace(..) + ...", ...); their
+// analysed trees all print differently.  When no printed normal form matches a directly written order-2 tree, the form is
+// identified NUMERICALLY: the tree's expression and the normal forms of the families are assembled by the reference's own
+// interpreter on the first TWO convexes of the region (a symbolic-phase cost of microseconds, not a fallback: every other element
+// of the region is assembled on the device), and the element matrices are fitted:  K = a M (mass), a L (Laplace),
+// lambda D + mu S (elasticity).  A fit to 1e-11 of |K| is a recognition; anything else (non-constant coefficient, another
+// form, a nonlinear tangent) is not.  The probe runs at every assembly, so constants may change between calls.
+static void (*g_reference_assembly)(getfem::ga_workspace &, size_type) = nullptr;
+void set_reference_assembly(void (*f)(getfem::ga_workspace &, size_type)) { g_reference_assembly = f; }
+
+static bool probe_matrix(const getfem::ga_workspace &ws, const std::string &v, const getfem::mesh_fem &mf, const getfem::mesh_im &mim,
+                         const getfem::mesh_region &rg, const std::string &expr, std::vector<double> &dense,
+                         const std::vector<size_type> &dofs) {
+  try {
+    getfem::ga_workspace w2(ws, getfem::ga_workspace::inherit::ALL);  // sees the variables and constants of the caller
+    w2.add_expression(expr, mim, rg, 2);
+    getfem::model_real_sparse_matrix K(ws.nb_primary_dof() ? ws.nb_primary_dof() : mf.nb_dof(),
+                                       ws.nb_primary_dof() ? ws.nb_primary_dof() : mf.nb_dof());
+    w2.set_assembled_matrix(K);
+    if (g_reference_assembly) g_reference_assembly(w2, 2); else w2.assembly(2);
+    const size_type off = ws.interval_of_variable(v).first();
+    dense.assign(dofs.size() * dofs.size(), 0.0);
+    for (size_t c = 0; c < dofs.size(); ++c)
+      for (size_t r = 0; r < dofs.size(); ++r) dense[r + dofs.size() * c] = K(off + dofs[r], off + dofs[c]);
+    return true;
+  } catch (const std::exception &) { return false; }
+}
+
+// a fitted coefficient carries the round-off of the fit (1e-14 relative): 12 significant digits, and exact zeros
+static double snap_coefficient(double x, double scale) {
+  if (std::fabs(x) <= 1e-12 * scale) return 0.0;
+  char b[40];
+  std::snprintf(b, sizeof b, "%.12g", x);
+  return std::strtod(b, nullptr);
+}
+
+static bool recognise_by_probe(const getfem::ga_workspace &ws, size_type itree, recognised_term &out) {
+  const getfem::ga_workspace::tree_description &td = ws.tree_info(itree);
+  const std::string v = td.name_test1;
+  const getfem::mesh_fem *pmf = ws.associated_mf(v);
+  if (!pmf || pmf->is_reduced() || !td.mim || !td.rg) return false;
+  const getfem::mesh &m = pmf->linked_mesh();
+  const size_type Q = pmf->get_qdim(), N = m.dim();
+  getfem::mesh_region rg2;
+  std::vector<size_type> dofs;
+  size_type ncv = 0;
+  for (getfem::mr_visitor it(*td.rg, m); !it.finished() && ncv < 2; ++it) {
+    if (it.f() != getfem::short_type(-1)) return false;  // face regions: printed forms only
+    rg2.add(it.cv());
+    for (size_type d : pmf->ind_basic_dof_of_element(it.cv())) dofs.push_back(d);
+    ++ncv;
+  }
+  if (!ncv) return false;
+  std::sort(dofs.begin(), dofs.end());
+  dofs.erase(std::unique(dofs.begin(), dofs.end()), dofs.end());
+  std::vector<double> K, A, B;
+  if (!probe_matrix(ws, v, *pmf, *td.mim, rg2, getfem::ga_tree_to_string(*td.ptree), K, dofs)) return false;
+  double nK = 0;
+  for (double x : K) nK += x * x;
+  if (nK == 0) return false;
+  const std::string T1 = "Test_" + v, T2 = "Test2_" + v;
+  auto fit1 = [&](const std::vector<double> &X, double &a) {  // K = a X ?
+    double xx = 0, xk = 0;
+    for (size_t k = 0; k < K.size(); ++k) { xx += X[k] * X[k]; xk += X[k] * K[k]; }
+    if (xx == 0) return false;
+    a = xk / xx;
+    double r = 0;
+    for (size_t k = 0; k < K.size(); ++k) r += (K[k] - a * X[k]) * (K[k] - a * X[k]);
+    return r <= 1e-22 * nK;
+  };
+  out.varname = v;
+  out.field_names.clear();
+  out.field_sign = 1.0;
+  double a = 0;
+  if (probe_matrix(ws, v, *pmf, *td.mim, rg2, Q == 1 ? T1 + "*" + T2 : T1 + "." + T2, A, dofs) && fit1(A, a)) {
+    out.family = GFGPU_MASS; out.params = {snap_coefficient(a, std::fabs(a))}; return true;
+  }
+  if (probe_matrix(ws, v, *pmf, *td.mim, rg2, Q == 1 ? "Grad_" + T1 + ".Grad_" + T2 : "Grad_" + T1 + ":Grad_" + T2, A, dofs) && fit1(A, a)) {
+    out.family = GFGPU_LAPLACE; out.params = {snap_coefficient(a, std::fabs(a))}; return true;
+  }
+  if (Q == N && Q > 1 && probe_matrix(ws, v, *pmf, *td.mim, rg2, "Div_" + T1 + "*Div_" + T2, A, dofs) &&
+      probe_matrix(ws, v, *pmf, *td.mim, rg2, "(Grad_" + T1 + "'+Grad_" + T1 + "):Grad_" + T2, B, dofs)) {
+    double aa = 0, ab = 0, bb = 0, ak = 0, bk = 0;  // normal equations of K = lambda A + mu B
+    for (size_t k = 0; k < K.size(); ++k) { aa += A[k] * A[k]; ab += A[k] * B[k]; bb += B[k] * B[k]; ak += A[k] * K[k]; bk += B[k] * K[k]; }
+    const double det = aa * bb - ab * ab;
+    if (det > 1e-12 * aa * bb) {
+      const double lam = (ak * bb - bk * ab) / det, mu = (bk * aa - ak * ab) / det;
+      double r = 0;
+      for (size_t k = 0; k < K.size(); ++k) { const double d = K[k] - lam * A[k] - mu * B[k]; r += d * d; }
+      if (r <= 1e-22 * nK) {
+        const double sc = std::max(std::fabs(lam), std::fabs(mu));
+        out.family = GFGPU_ELASTICITY;
+        out.params = {snap_coefficient(lam, sc), snap_coefficient(mu, sc)};
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
 bool recognise_tree_sum(const getfem::ga_workspace &ws, size_type itree, std::vector<recognised_term> &out) {
   const getfem::ga_workspace::tree_description &td = ws.tree_info(itree);
   if (td.order == 2 && td.operation == getfem::ga_workspace::ASSEMBLY && td.name_test1 == td.name_test2) {
     recognised_term rt;
     out.clear();
-    if (!recognise_order2_string(ws, td.name_test1, strip(getfem::ga_tree_to_string(*td.ptree)), rt)) return false;
+    if (!recognise_order2_string(ws, td.name_test1, strip(getfem::ga_tree_to_string(*td.ptree)), rt) &&
+        !recognise_by_probe(ws, itree, rt))
+      return false;
     out.push_back(rt);
     return true;
   }

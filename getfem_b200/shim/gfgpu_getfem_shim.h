@@ -36,6 +36,10 @@ bool recognise_tree(const getfem::ga_workspace &ws, getfem::size_type itree, rec
 // (C&E.cc:4889,4898), which two separately assembled bilinear forms would not reproduce.
 bool recognise_tree_sum(const getfem::ga_workspace &ws, getfem::size_type itree, std::vector<recognised_term> &out);
 
+// Recognition by probe (see the .cc) assembles a few normal forms on two convexes with the reference's interpreter.  Inside a
+// library whose ga_workspace::assembly IS the dispatch patch, give it the body of the reference here (the dispatch patch of INTEGRATION.md section 2 does).
+void set_reference_assembly(void (*f)(getfem::ga_workspace &, getfem::size_type));
+
 // Device-side state of one (mesh, mesh_fem, mesh_im, term); reusable across Newton iterations.
 class device_assembler {
  public:

@@ -39,7 +39,7 @@ int main(int argc, char **argv) {
   const bool qk = gets("gt", "pk") == "qk";
   // threads > 1: the bricks' GETFEM_OMP_PARALLEL blocks slice the regions; the patch leaves that regime on the reference path
   if (geti("threads", 1) > 1) getfem::set_num_threads(int(geti("threads", 1)));
-  const int Q = (kind == "poisson" || kind == "asm_laplacian") ? 1 : dim;
+  const int Q = kind == "expr" ? (int)geti("q", dim) : (kind == "poisson" || kind == "asm_laplacian") ? 1 : dim;
 
   getfem::mesh m;
   std::vector<size_type> ns(dim, size_type(n));
@@ -59,6 +59,40 @@ int main(int argc, char **argv) {
   getfem::mesh_fem mf_d(m, 1);  // fem data: heterogeneous coefficient
   mf_d.set_classical_finite_element(1);
 
+  if (kind == "expr") {
+    // one bilinear form written directly with Test_ / Test2_, in any of the algebraically equivalent spellings of the
+    // reference's own tests (tests/test_assembly.cc:777-866, lambda = 3, mu = 2 there): reference path against device path
+    const std::string expr = gets("expr", "Grad_Test_u:Grad_Test2_u");
+    std::vector<double> U(mf.nb_dof(), 0.0), LAMBDA(1, 3.0), MU(1, 2.0), A(1, 1.7);
+    auto run = [&](bool device, gmm::csc_matrix<double> &C) {
+      getfem_b200::gfgpu_enable(device);
+      getfem::ga_workspace ws;
+      ws.add_fem_variable("u", mf, gmm::sub_interval(0, mf.nb_dof()), U);
+      ws.add_fixed_size_constant("lambda", LAMBDA);
+      ws.add_fixed_size_constant("mu", MU);
+      ws.add_fixed_size_constant("a", A);
+      ws.add_expression(expr, mim);
+      getfem::model_real_sparse_matrix M(mf.nb_dof(), mf.nb_dof());
+      ws.set_assembled_matrix(M);
+      ws.assembly(2);
+      C.init_with(M);
+      getfem_b200::gfgpu_enable(false);
+    };
+    gmm::csc_matrix<double> Cr, Cg;
+    run(false, Cr);
+    run(true, Cg);
+    bool pattern_ok = Cr.jc.size() == Cg.jc.size() && Cr.ir.size() == Cg.ir.size();
+    for (size_t k = 0; pattern_ok && k < Cr.jc.size(); ++k) pattern_ok = Cr.jc[k] == Cg.jc[k];
+    for (size_t k = 0; pattern_ok && k < Cr.ir.size(); ++k) pattern_ok = Cr.ir[k] == Cg.ir[k];
+    double nK = 0, dK = 0;
+    if (pattern_ok)
+      for (size_t k = 0; k < Cr.pr.size(); ++k) { nK += Cr.pr[k] * Cr.pr[k]; dK += (Cr.pr[k] - Cg.pr[k]) * (Cr.pr[k] - Cg.pr[k]); }
+    std::printf("{\"model\": \"expr\", \"ndof\": %zu, \"nnz_ref\": %zu, \"nnz_gpu\": %zu, \"pattern_ok\": %s, \"rel_K\": %.3e, "
+                "\"device_workspace_calls\": %ld}\n",
+                size_t(mf.nb_dof()), Cr.pr.size(), Cg.pr.size(), pattern_ok ? "true" : "false",
+                pattern_ok && nK > 0 ? std::sqrt(dK / nK) : -1.0, getfem_b200::gfgpu_device_calls());
+    return pattern_ok ? 0 : 1;
+  }
   if (kind.rfind("asm_", 0) == 0) {
     // the legacy asm_* wrappers (getfem_assembling.h): thin layers over ga_workspace, written with Test / Test2 directly
     std::vector<double> LAMBDA(mf_d.nb_dof()), MU(mf_d.nb_dof());

@@ -18,7 +18,11 @@ namespace getfem_b200 {
 void reference_assembly(getfem::ga_workspace &ws, getfem::size_type order, bool condensation);
 static bool g_enabled = false;
 static long g_device_calls = 0, g_reference_calls = 0;
-void gfgpu_enable(bool on) { g_enabled = on; }
+static void reference_order(getfem::ga_workspace &ws, getfem::size_type order) { reference_assembly(ws, order, false); }
+void gfgpu_enable(bool on) {
+  g_enabled = on;
+  set_reference_assembly(&reference_order);  // the probe of the shim's recogniser must not re-enter the dispatch
+}
 long gfgpu_device_calls() { return g_device_calls; }
 long gfgpu_reference_calls() { return g_reference_calls; }
 }  // namespace getfem_b200
@@ -42,8 +46,14 @@ void ga_workspace::assembly(size_type order, bool condensation) {
       bool ok = false;
       std::string why;
       try { ok = td.order >= 1 ? getfem_b200::recognise_tree_sum(*this, i, rts) : true; } catch (const std::exception &ex) { why = ex.what(); }
-      std::fprintf(stderr, "[gfgpu dryrun] order %d (assembly order %d) region %ld: %s -> %s %s\n", int(td.order), int(order),
-                   long(td.rg->id()), ga_tree_to_string(*td.ptree).c_str(), ok ? "recognised" : "NOT recognised",
+      std::string fam;
+      for (const auto &rt : rts) {
+        fam += " family " + std::to_string(rt.family) + " (";
+        for (double p : rt.params) { char b[40]; std::snprintf(b, sizeof b, " %.12g", p); fam += b; }
+        fam += " )";
+      }
+      std::fprintf(stderr, "[gfgpu dryrun] order %d (assembly order %d) region %ld: %s -> %s%s %s\n", int(td.order), int(order),
+                   long(td.rg->id()), ga_tree_to_string(*td.ptree).c_str(), ok ? "recognised" : "NOT recognised", fam.c_str(),
                    why.c_str());
     }
     getfem_b200::reference_assembly(*this, order, condensation);

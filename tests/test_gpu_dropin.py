@@ -80,3 +80,25 @@ def test_sliced_regions_stay_on_the_reference_path():
     r = json.loads(out.stdout.strip().splitlines()[-1])
     assert r["device_workspace_calls"] == 0 and r["reference_workspace_calls"] > 0, r
     assert r["entries_on_one_side_only"] == 0 and r["rel_K"] < 1e-13 and r["rel_rhs"] < 1e-13, r
+
+
+PROBE_CASES = [  # spellings of tests/test_assembly.cc:812-866 that only recognition BY PROBE covers (tests/test_shim_probe.py, CPU)
+    ("dim=3 n=3 gt=pk k=2", "lambda*Div_Test_u*Div_Test2_u + mu*(Grad_Test_u'+Grad_Test_u):Grad_Test2_u"),
+    ("dim=2 n=8 gt=pk k=2", "lambda*Trace(Grad_Test_u)*Trace(Grad_Test2_u) +mu*(Grad_Test_u'(:,1)+Grad_Test_u(:,1)):Grad_Test2_u(:,1)"
+                            "+mu*(Grad_Test_u'(:,2)+Grad_Test_u(:,2)):Grad_Test2_u(:,2)"),
+    ("dim=3 n=3 gt=pk k=2 q=1", "Grad_Test_u(1)*Grad_Test2_u(1) + Grad_Test_u(2)*Grad_Test2_u(2) + Grad_Test_u(3)*Grad_Test2_u(3)"),
+]
+
+
+@pytest.mark.xfail(strict=False, reason="written after the GPU minutes of round 1 were spent: the recognition is verified on CPU "
+                                        "(tests/test_shim_probe.py), the device run of these spellings is still to be observed")
+@pytest.mark.parametrize("mesh,expr", PROBE_CASES)
+def test_equivalent_spellings_run_on_the_device(mesh, expr):
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN, "model=expr"] + mesh.split() + ["expr=" + expr], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["device_workspace_calls"] >= 1, r
+    assert r["pattern_ok"] and r["nnz_ref"] == r["nnz_gpu"]
+    assert 0 <= r["rel_K"] < 1e-12, r

@@ -1,0 +1,77 @@
+"""CPU: recognition BY PROBE in the C++ shim (getfem_b200/shim/gfgpu_getfem_shim.cc::recognise_by_probe).  The reference's own
+tests write one bilinear form in many algebraically equivalent ways (tests/test_assembly.cc:777-866, lambda = 3, mu = 2); the
+shim identifies such a directly written order-2 tree numerically, from the reference's interpreter on two convexes, and sends
+the FAMILY to the device.  Here, without a GPU: the dispatch patch in GFGPU_DRYRUN mode prints what it would send (family and
+fitted parameters) for each spelling, and says "NOT recognised" for forms outside the families."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+BIN = os.path.join(ROOT, "oracle", "_ref", "model_test")
+LAPLACE, ELASTICITY, MASS = 0, 1, 5
+EL = "mu*(Grad_Test_u'+Grad_Test_u):Grad_Test2_u"
+
+CASES = [  # (mesh args, expression, family, parameters)
+    ("dim=3 n=2 gt=pk k=2", "(lambda*Trace(Grad_Test_u)*Id(qdim(u)) + mu*(Grad_Test_u'+Grad_Test_u)):Grad_Test2_u", ELASTICITY, (3, 2)),
+    ("dim=3 n=2 gt=pk k=2", "lambda*Div_Test_u*Div_Test2_u + " + EL, ELASTICITY, (3, 2)),
+    ("dim=3 n=2 gt=pk k=2", "lambda*((Grad_Test2_u@Grad_Test_u):Id(meshdim)):Id(meshdim) + " + EL, ELASTICITY, (3, 2)),
+    ("dim=3 n=2 gt=pk k=2", "lambda*Id(meshdim)@Id(meshdim)*Grad_Test_u:Grad_Test2_u + " + EL, ELASTICITY, (3, 2)),
+    ("dim=3 n=2 gt=pk k=2", "lambda*(Id(meshdim)*Id(meshdim))@Id(meshdim)*Grad_Test_u:Grad_Test2_u + " + EL, ELASTICITY, (3, 2)),
+    ("dim=3 n=2 gt=pk k=2", "lambda*Trace(Grad_Test_u)*Trace(Grad_Test2_u) +mu*(Grad_Test_u'(:,1)+Grad_Test_u(:,1)):Grad_Test2_u(:,1)"
+     "+mu*(Grad_Test_u'(:,2)+Grad_Test_u(:,2)):Grad_Test2_u(:,2)+mu*(Grad_Test_u'(:,3)+Grad_Test_u(:,3)):Grad_Test2_u(:,3)", ELASTICITY, (3, 2)),
+    ("dim=3 n=2 gt=pk k=2", "lambda*Trace(Grad_Test_u)*Trace(Grad_Test2_u) + mu*(Grad_Test_u'(1,:)+Grad_Test_u(1,:)):Grad_Test2_u(1,:)"
+     "+ mu*(Grad_Test_u'(2,:)+Grad_Test_u(2,:)):Grad_Test2_u(2,:)+mu*(Grad_Test_u'(3,:)+Grad_Test_u(3,:)):Grad_Test2_u(3,:)", ELASTICITY, (3, 2)),
+    ("dim=2 n=4 gt=pk k=2", "lambda*Trace(Grad_Test_u)*Trace(Grad_Test2_u) +mu*(Grad_Test_u'(:,1)+Grad_Test_u(:,1)):Grad_Test2_u(:,1)"
+     "+mu*(Grad_Test_u'(:,2)+Grad_Test_u(:,2)):Grad_Test2_u(:,2)", ELASTICITY, (3, 2)),
+    ("dim=3 n=2 gt=qk k=2", "lambda*Div_Test_u*Div_Test2_u + " + EL, ELASTICITY, (3, 2)),
+    ("dim=3 n=2 gt=pk k=2", "2*mu*Sym(Grad_Test_u):Sym(Grad_Test2_u)", ELASTICITY, (0, 2)),
+    # scalar forms (q=1)
+    ("dim=3 n=2 gt=pk k=2 q=1", "Grad_Test_u(1)*Grad_Test2_u(1) + Grad_Test_u(2)*Grad_Test2_u(2) + Grad_Test_u(3)*Grad_Test2_u(3)", LAPLACE, (1,)),
+    ("dim=3 n=2 gt=pk k=2 q=1", "[Grad_Test_u(1); Grad_Test_u(3); Grad_Test_u(2)].[Grad_Test2_u(1); Grad_Test2_u(3); Grad_Test2_u(2)]", LAPLACE, (1,)),
+    ("dim=2 n=4 gt=pk k=1 q=1", "a*[Grad_Test_u(2); Grad_Test_u(1)].[Grad_Test2_u(2); Grad_Test2_u(1)]", LAPLACE, (1.7,)),
+    ("dim=3 n=2 gt=pk k=2 q=1", "Test2_u*(a*Test_u)*2", MASS, (3.4,)),
+    # vector Laplace and vector mass
+    ("dim=3 n=2 gt=pk k=1", "a*(Grad_Test_u(1,:).Grad_Test2_u(1,:) + Grad_Test_u(2,:).Grad_Test2_u(2,:) + Grad_Test_u(3,:).Grad_Test2_u(3,:))", LAPLACE, (1.7,)),
+    ("dim=2 n=4 gt=pk k=2", "Test_u(1)*Test2_u(1) + Test_u(2)*Test2_u(2)", MASS, (1,)),
+]
+
+NOT_FAMILIES = [
+    ("dim=3 n=2 gt=pk k=2", "Grad_Test_u(1,:).Grad_Test2_u(1,:)"),                     # one row of the gradient only
+    ("dim=3 n=2 gt=pk k=2", "lambda*Div_Test_u*Div_Test2_u"),                           # no shear part: see the test
+    ("dim=3 n=2 gt=pk k=2 q=1", "X(1)*Grad_Test_u.Grad_Test2_u"),                       # a coefficient that varies in space
+    ("dim=3 n=2 gt=pk k=2 q=1", "Grad_Test_u(1)*Grad_Test2_u(1) + 2*Grad_Test_u(2)*Grad_Test2_u(2) + Grad_Test_u(3)*Grad_Test2_u(3)"),  # anisotropic
+]
+
+
+def _dryrun(mesh, expr):
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN, "model=expr"] + mesh.split() + ["expr=" + expr], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, GFGPU_DRYRUN="1"))
+    assert out.returncode == 0, out.stderr[-1500:]
+    lines = [l for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun] order 2")]
+    assert len(lines) == 1, out.stderr[-1500:]
+    return lines[0]
+
+
+@pytest.mark.parametrize("mesh,expr,family,params", CASES)
+def test_equivalent_spellings_are_recognised(mesh, expr, family, params):
+    line = _dryrun(mesh, expr)
+    m = re.search(r"-> recognised family (\d+) \(([^)]*)\)", line)
+    assert m, line
+    assert int(m.group(1)) == family, line
+    got = [float(x) for x in m.group(2).split()]
+    assert len(got) == len(params) and all(abs(g - p) <= 1e-9 * max(1.0, abs(p)) for g, p in zip(got, params)), line
+
+
+@pytest.mark.parametrize("mesh,expr", NOT_FAMILIES)
+def test_other_forms_are_not_recognised(mesh, expr):
+    line = _dryrun(mesh, expr)
+    if "lambda*Div_Test_u*Div_Test2_u" == expr:  # a pure volumetric form IS lambda D + 0 S: elasticity with mu snapped to 0
+        assert "-> recognised family 1 ( 3 0 )" in line, line
+        return
+    assert "NOT recognised" in line, line
