@@ -167,8 +167,40 @@ static double snap_coefficient(double x, double scale) {
   return std::strtod(b, nullptr);
 }
 
+// the order-1 tree `expr` (a linear form in Test_v at the current state) assembled on the probe region -> values on `dofs`
+static bool probe_vector(const getfem::ga_workspace &ws, const std::string &v, const getfem::mesh_fem &mf, const getfem::mesh_im &mim,
+                         const getfem::mesh_region &rg, const std::string &expr, std::vector<double> &vec,
+                         const std::vector<size_type> &dofs) {
+  try {
+    getfem::ga_workspace w2(ws, getfem::ga_workspace::inherit::ALL);
+    w2.add_expression(expr, mim, rg, 1);
+    getfem::base_vector V(ws.nb_primary_dof() ? ws.nb_primary_dof() : mf.nb_dof());
+    w2.set_assembled_vector(V);
+    if (g_reference_assembly) g_reference_assembly(w2, 1); else w2.assembly(1);
+    const size_type off = ws.interval_of_variable(v).first();
+    vec.resize(dofs.size());
+    for (size_t r = 0; r < dofs.size(); ++r) vec[r] = V[off + dofs[r]];
+    return true;
+  } catch (const std::exception &) { return false; }
+}
+
 static bool recognise_by_probe(const getfem::ga_workspace &ws, size_type itree, recognised_term &out) {
-  const getfem::ga_workspace::tree_description &td = ws.tree_info(itree);
+  const getfem::ga_workspace::tree_description &td0 = ws.tree_info(itree);
+  // an order-1 tree is identified through its derivative (the order-2 tree of the same mim / region / variable, added by
+  // add_expression with the default derivative order): the bilinear form K is probed there, and the order-1 tree itself must
+  // then be the linear form K u at the current state, nothing else (no load mixed in)
+  size_type i2 = itree;
+  if (td0.order == 1) {
+    i2 = size_type(-1);
+    for (size_type j = 0; j < ws.nb_trees(); ++j) {
+      const auto &t2 = ws.tree_info(j);
+      if (t2.order == 2 && t2.mim == td0.mim && t2.rg == td0.rg && t2.name_test1 == td0.name_test1 &&
+          t2.name_test2 == td0.name_test1)
+        i2 = j;
+    }
+    if (i2 == size_type(-1)) return false;
+  }
+  const getfem::ga_workspace::tree_description &td = ws.tree_info(i2);
   const std::string v = td.name_test1;
   const getfem::mesh_fem *pmf = ws.associated_mf(v);
   if (!pmf || pmf->is_reduced() || !td.mim || !td.rg) return false;
@@ -191,6 +223,20 @@ static bool recognise_by_probe(const getfem::ga_workspace &ws, size_type itree, 
   double nK = 0;
   for (double x : K) nK += x * x;
   if (nK == 0) return false;
+  if (td0.order == 1) {
+    std::vector<double> r;
+    if (!probe_vector(ws, v, *pmf, *td.mim, rg2, getfem::ga_tree_to_string(*td0.ptree), r, dofs)) return false;
+    const getfem::model_real_plain_vector &Uv = ws.value(v);
+    double nr = 0, dr = 0, nu = 0;
+    for (size_t a = 0; a < dofs.size(); ++a) {
+      double ku = 0;
+      for (size_t b = 0; b < dofs.size(); ++b) ku += K[a + dofs.size() * b] * Uv[dofs[b]];
+      nr += r[a] * r[a];
+      dr += (r[a] - ku) * (r[a] - ku);
+      nu += Uv[dofs[a]] * Uv[dofs[a]];
+    }
+    if (dr > 1e-22 * std::max(nr, nK * nu)) return false;
+  }
   const std::string T1 = "Test_" + v, T2 = "Test2_" + v;
   auto fit1 = [&](const std::vector<double> &X, double &a) {  // K = a X ?
     double xx = 0, xk = 0;
@@ -204,6 +250,7 @@ static bool recognise_by_probe(const getfem::ga_workspace &ws, size_type itree, 
   out.varname = v;
   out.field_names.clear();
   out.field_sign = 1.0;
+  out.by_probe = true;
   double a = 0;
   if (probe_matrix(ws, v, *pmf, *td.mim, rg2, Q == 1 ? T1 + "*" + T2 : T1 + "." + T2, A, dofs) && fit1(A, a)) {
     out.family = GFGPU_MASS; out.params = {snap_coefficient(a, std::fabs(a))}; return true;
@@ -244,7 +291,13 @@ bool recognise_tree_sum(const getfem::ga_workspace &ws, size_type itree, std::ve
   }
   if (td.order != 1 || td.operation != getfem::ga_workspace::ASSEMBLY) return false;
   out.clear();
-  if (!recognise_sum(ws, td.name_test1, strip(getfem::ga_tree_to_string(*td.ptree)), out)) return false;
+  if (!recognise_sum(ws, td.name_test1, strip(getfem::ga_tree_to_string(*td.ptree)), out)) {
+    recognised_term rt;
+    out.clear();
+    if (!recognise_by_probe(ws, itree, rt)) return false;
+    out.push_back(rt);
+    return true;
+  }
   size_t bilinear = 0;
   for (const recognised_term &rt : out) bilinear += rt.family != GFGPU_SOURCE && rt.family != GFGPU_NORMAL_SOURCE;
   GMM_ASSERT1(bilinear <= 1, "gfgpu: several bilinear forms summed on one region are thresholded together by the reference "
@@ -406,6 +459,7 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
         std::vector<recognised_term> r1;
         GMM_ASSERT1(recognise_tree_sum(ws, i1, r1), "gfgpu: expression not handled by the device path (no CPU fallback): "
                                                         << getfem::ga_tree_to_string(*ws.tree_info(i1).ptree));
+        if (r1.size() == 1 && r1[0].by_probe) continue;  // the probe checked K against THIS tree and r = K u against the order-1 tree
         size_t nsrc = 0;
         for (const recognised_term &rt : r1) nsrc += rt.family == GFGPU_SOURCE || rt.family == GFGPU_NORMAL_SOURCE;
         const size_t n1 = count_top_level_summands(strip(getfem::ga_tree_to_string(*ws.tree_info(i1).ptree)));

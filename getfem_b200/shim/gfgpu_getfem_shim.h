@@ -25,6 +25,7 @@ struct recognised_term {
   // mesh_fem; `field_sign` multiplies their nodal values (the source term's "-f")
   std::vector<std::string> field_names;
   double field_sign = 1.0;
+  bool by_probe = false;  // identified numerically (recognise_by_probe), not from a printed normal form
 };
 
 // Matches the ORDER-1 tree of `ws` number `itree` (as printed by ga_tree_to_string after the

@@ -64,6 +64,12 @@ int main(int argc, char **argv) {
     // reference's own tests (tests/test_assembly.cc:777-866, lambda = 3, mu = 2 there): reference path against device path
     const std::string expr = gets("expr", "Grad_Test_u:Grad_Test2_u");
     std::vector<double> U(mf.nb_dof(), 0.0), LAMBDA(1, 3.0), MU(1, 2.0), A(1, 1.7);
+    {
+      std::mt19937_64 rng(99);
+      std::uniform_real_distribution<double> dist(-1.0, 1.0);
+      for (auto &x : U) x = dist(rng);
+    }
+    std::vector<double> Vr, Vg;
     auto run = [&](bool device, gmm::csc_matrix<double> &C) {
       getfem_b200::gfgpu_enable(device);
       getfem::ga_workspace ws;
@@ -76,11 +82,15 @@ int main(int argc, char **argv) {
       ws.set_assembled_matrix(M);
       ws.assembly(2);
       C.init_with(M);
+      ws.assembly(1);  // an expression written in u (not in Test2_u) also has a residual
+      (device ? Vg : Vr).assign(ws.assembled_vector().begin(), ws.assembled_vector().end());
       getfem_b200::gfgpu_enable(false);
     };
     gmm::csc_matrix<double> Cr, Cg;
     run(false, Cr);
     run(true, Cg);
+    double nV = 0, dV = 0;
+    for (size_t k = 0; k < Vr.size() && k < Vg.size(); ++k) { nV += Vr[k] * Vr[k]; dV += (Vr[k] - Vg[k]) * (Vr[k] - Vg[k]); }
     bool pattern_ok = Cr.jc.size() == Cg.jc.size() && Cr.ir.size() == Cg.ir.size();
     for (size_t k = 0; pattern_ok && k < Cr.jc.size(); ++k) pattern_ok = Cr.jc[k] == Cg.jc[k];
     for (size_t k = 0; pattern_ok && k < Cr.ir.size(); ++k) pattern_ok = Cr.ir[k] == Cg.ir[k];
@@ -88,9 +98,10 @@ int main(int argc, char **argv) {
     if (pattern_ok)
       for (size_t k = 0; k < Cr.pr.size(); ++k) { nK += Cr.pr[k] * Cr.pr[k]; dK += (Cr.pr[k] - Cg.pr[k]) * (Cr.pr[k] - Cg.pr[k]); }
     std::printf("{\"model\": \"expr\", \"ndof\": %zu, \"nnz_ref\": %zu, \"nnz_gpu\": %zu, \"pattern_ok\": %s, \"rel_K\": %.3e, "
-                "\"device_workspace_calls\": %ld}\n",
+                "\"rel_V\": %.3e, \"norm_V\": %.3e, \"device_workspace_calls\": %ld}\n",
                 size_t(mf.nb_dof()), Cr.pr.size(), Cg.pr.size(), pattern_ok ? "true" : "false",
-                pattern_ok && nK > 0 ? std::sqrt(dK / nK) : -1.0, getfem_b200::gfgpu_device_calls());
+                pattern_ok && nK > 0 ? std::sqrt(dK / nK) : -1.0, nV > 0 ? std::sqrt(dV / nV) : 0.0, std::sqrt(nV),
+                getfem_b200::gfgpu_device_calls());
     return pattern_ok ? 0 : 1;
   }
   if (kind.rfind("asm_", 0) == 0) {

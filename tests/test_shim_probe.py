@@ -53,7 +53,7 @@ def _dryrun(mesh, expr):
     out = subprocess.run([BIN, "model=expr"] + mesh.split() + ["expr=" + expr], capture_output=True, text=True, timeout=300,
                          env=dict(os.environ, GFGPU_DRYRUN="1"))
     assert out.returncode == 0, out.stderr[-1500:]
-    lines = [l for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun] order 2")]
+    lines = [l for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun] order 2 (assembly order 2)")]
     assert len(lines) == 1, out.stderr[-1500:]
     return lines[0]
 
@@ -75,3 +75,52 @@ def test_other_forms_are_not_recognised(mesh, expr):
         assert "-> recognised family 1 ( 3 0 )" in line, line
         return
     assert "NOT recognised" in line, line
+
+
+EU = "mu*(Grad_u'+Grad_u):Grad_Test_u"
+DERIVED_CASES = [  # written in u: an order-1 tree (identified through its derivative, and checked to be K u) and its tangent
+    ("dim=3 n=2 gt=pk k=2", "lambda*Div_u*Div_Test_u + " + EU, ELASTICITY, (3, 2)),
+    ("dim=3 n=2 gt=pk k=2", "lambda*Trace(Grad_u)*Trace(Grad_Test_u) + mu*(Grad_u'(:,1)+Grad_u(:,1)):Grad_Test_u(:,1)"
+     "+mu*(Grad_u'(:,2)+Grad_u(:,2)):Grad_Test_u(:,2)+mu*(Grad_u'(:,3)+Grad_u(:,3)):Grad_Test_u(:,3)", ELASTICITY, (3, 2)),
+    ("dim=2 n=4 gt=qk k=2", "(lambda*Trace(Grad_u)*Id(qdim(u)) + mu*(Grad_u'+Grad_u)):Grad_Test_u", ELASTICITY, (3, 2)),
+    # the potentials of tests/test_assembly.cc:777-803: order 0, differentiated twice by add_expression
+    ("dim=3 n=2 gt=pk k=2 q=1", "(Grad_u:Grad_u)/2", LAPLACE, (1,)),
+    ("dim=3 n=2 gt=pk k=2 q=1", "sqr(Norm(Grad_u))/2", LAPLACE, (1,)),
+    ("dim=3 n=2 gt=pk k=2 q=1", "Norm_sqr(Grad_u)/2", LAPLACE, (1,)),
+    ("dim=3 n=2 gt=pk k=2 q=1", "a*(sqr(Grad_u(1)) + sqr(Grad_u(2)) + sqr(Grad_u(3)))/2", LAPLACE, (1.7,)),
+    ("dim=2 n=4 gt=pk k=1 q=1", "([Grad_u(2); Grad_u(1)].[Grad_u(2); Grad_u(1)])/2", LAPLACE, (1,)),
+    ("dim=2 n=4 gt=pk k=2 q=1", "a*u*u/2", MASS, (1.7,)),
+]
+
+
+@pytest.mark.parametrize("mesh,expr,family,params", DERIVED_CASES)
+def test_derived_spellings_are_recognised(mesh, expr, family, params):
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN, "model=expr"] + mesh.split() + ["expr=" + expr], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, GFGPU_DRYRUN="1"))
+    assert out.returncode == 0, out.stderr[-1500:]
+    seen = set()
+    for line in out.stderr.splitlines():
+        m = re.match(r"\[gfgpu dryrun\] order ([12]) \(assembly order ([12])\)", line)
+        if not m:
+            continue
+        r = re.search(r"-> recognised family (\d+) \(([^)]*)\)", line)
+        assert r, line
+        got = [float(x) for x in r.group(2).split()]
+        assert int(r.group(1)) == family and len(got) == len(params), line
+        assert all(abs(g - p) <= 1e-9 * max(1.0, abs(p)) for g, p in zip(got, params)), line
+        seen.add((int(m.group(1)), int(m.group(2))))
+    assert seen == {(1, 1), (1, 2), (2, 1), (2, 2)}, (seen, out.stderr[-800:])
+
+
+def test_a_load_mixed_into_the_tree_is_not_taken_for_the_linear_form():
+    """r = K u must hold for the order-1 tree: with a source term summed into the same tree the printed forms decide (they
+    split the sum) or the expression is refused -- the probe alone never accepts it."""
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    expr = "lambda*Trace(Grad_u)*Trace(Grad_Test_u) + mu*(Grad_u'+Grad_u):Grad_Test_u + [1;2;3].Test_u"
+    out = subprocess.run([BIN, "model=expr", "dim=3", "n=2", "gt=pk", "k=2", "expr=" + expr], capture_output=True, text=True,
+                         timeout=300, env=dict(os.environ, GFGPU_DRYRUN="1"))
+    lines = [l for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun] order 1")]
+    assert lines and all("NOT recognised" in l for l in lines), out.stderr[-1500:]
