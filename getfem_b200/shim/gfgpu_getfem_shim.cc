@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <regex>
 #include <sstream>
 
@@ -167,6 +168,35 @@ static double snap_coefficient(double x, double scale) {
   return std::strtod(b, nullptr);
 }
 
+// Two probe items say nothing about the REST of the region unless the form is the same everywhere: the probe is only allowed on
+// expressions whose leaves are the variable itself and FIXED-SIZE constants.  Fem data (a piecewise material!), im_data, other
+// variables, the position X, the normal, element sizes, interpolate / elementary transformations ... are left to the printed
+// normal forms (which handle fem-data coefficients and normal loads explicitly) or refused.
+static bool probe_is_safe(const getfem::ga_workspace &ws, const std::string &v, const std::string &printed) {
+  static const char *forbidden[] = {"X", "Normal", "element_size", "element_K", "element_B", "Interpolate", "Interpolate_filter",
+                                    "Interpolate_derivative", "Elementary", "Elementary_transformation", "Secondary_domain",
+                                    "Secondary_Domain", "Xfem_plus", "Xfem_minus", "Cross_product", "Print"};
+  static const char *prefixes[] = {"Test2_", "Test_", "Grad_", "Hess_", "Div_", "Previous_", "Old_"};
+  static const std::regex ident("[A-Za-z_][A-Za-z_0-9]*");
+  for (auto it = std::sregex_iterator(printed.begin(), printed.end(), ident); it != std::sregex_iterator(); ++it) {
+    std::string tok = it->str();
+    for (const char *f : forbidden)
+      if (tok == f) return false;
+    for (bool again = true; again;) {
+      again = false;
+      for (const char *p : prefixes) {
+        const size_t n = std::strlen(p);
+        if (tok.size() > n && tok.compare(0, n, p) == 0) { tok = tok.substr(n); again = true; }
+      }
+    }
+    if (tok == v) continue;
+    if (ws.variable_group_exists(tok)) return false;
+    if (!ws.variable_exists(tok)) continue;  // a function or operator name
+    if (!ws.is_constant(tok) || ws.associated_mf(tok) || ws.associated_im_data(tok)) return false;
+  }
+  return true;
+}
+
 // the order-1 tree `expr` (a linear form in Test_v at the current state) assembled on the probe region -> values on `dofs`
 static bool probe_vector(const getfem::ga_workspace &ws, const std::string &v, const getfem::mesh_fem &mf, const getfem::mesh_im &mim,
                          const getfem::mesh_region &rg, const std::string &expr, std::vector<double> &vec,
@@ -184,6 +214,59 @@ static bool probe_vector(const getfem::ga_workspace &ws, const std::string &v, c
   } catch (const std::exception &) { return false; }
 }
 
+// An order-1 tree without any derivative tree does not depend on the unknowns: a load.  Whatever its spelling, a CONSTANT load is
+// r = sum_b F_b int Test_v(b): F is fitted on the first two items (convexes or faces) of the region and the tree becomes the
+// SOURCE family; a load that varies in space, or with the normal of non-coplanar faces, does not fit.
+static bool recognise_load_by_probe(const getfem::ga_workspace &ws, size_type itree, recognised_term &out) {
+  const getfem::ga_workspace::tree_description &td = ws.tree_info(itree);
+  const std::string v = td.name_test1;
+  for (size_type j = 0; j < ws.nb_trees(); ++j) {  // a coupling tangent (Test_v, Test2_w) means the tree depends on w: not a load
+    const auto &t2 = ws.tree_info(j);
+    if (t2.order == 2 && t2.mim == td.mim && t2.rg == td.rg && (t2.name_test1 == v || t2.name_test2 == v)) return false;
+  }
+  const getfem::mesh_fem *pmf = ws.associated_mf(v);
+  if (!pmf || pmf->is_reduced() || !td.mim || !td.rg) return false;
+  if (!probe_is_safe(ws, v, getfem::ga_tree_to_string(*td.ptree))) return false;
+  const getfem::mesh &m = pmf->linked_mesh();
+  const size_type Q = pmf->get_qdim();
+  getfem::mesh_region rg2;
+  std::vector<size_type> dofs;
+  size_type nit = 0;
+  for (getfem::mr_visitor it(*td.rg, m); !it.finished() && nit < 2; ++it, ++nit) {
+    if (it.f() != getfem::short_type(-1)) rg2.add(it.cv(), it.f()); else rg2.add(it.cv());
+    for (size_type d : pmf->ind_basic_dof_of_element(it.cv())) dofs.push_back(d);
+  }
+  if (!nit) return false;
+  std::sort(dofs.begin(), dofs.end());
+  dofs.erase(std::unique(dofs.begin(), dofs.end()), dofs.end());
+  std::vector<double> r, t, fit(dofs.size(), 0.0), F(Q, 0.0);
+  if (!probe_vector(ws, v, *pmf, *td.mim, rg2, getfem::ga_tree_to_string(*td.ptree), r, dofs)) return false;
+  double nr = 0;
+  for (double x : r) nr += x * x;
+  if (nr == 0) return false;
+  for (size_type b = 0; b < Q; ++b) {  // the component templates have disjoint supports: independent one-parameter fits
+    const std::string e = Q == 1 ? "Test_" + v : "Test_" + v + "(" + std::to_string(b + 1) + ")";
+    if (!probe_vector(ws, v, *pmf, *td.mim, rg2, e, t, dofs)) return false;
+    double tt = 0, tr = 0;
+    for (size_t k = 0; k < t.size(); ++k) { tt += t[k] * t[k]; tr += t[k] * r[k]; }
+    if (tt == 0) return false;
+    F[b] = tr / tt;
+    for (size_t k = 0; k < t.size(); ++k) fit[k] += F[b] * t[k];
+  }
+  double dr = 0, sc = 0;
+  for (size_t k = 0; k < r.size(); ++k) dr += (r[k] - fit[k]) * (r[k] - fit[k]);
+  if (dr > 1e-22 * nr) return false;
+  for (double f : F) sc = std::max(sc, std::fabs(f));
+  out.varname = v;
+  out.field_names.clear();
+  out.field_sign = 1.0;
+  out.by_probe = true;
+  out.family = GFGPU_SOURCE;
+  out.params.clear();
+  for (double f : F) out.params.push_back(snap_coefficient(f, sc));
+  return true;
+}
+
 static bool recognise_by_probe(const getfem::ga_workspace &ws, size_type itree, recognised_term &out) {
   const getfem::ga_workspace::tree_description &td0 = ws.tree_info(itree);
   // an order-1 tree is identified through its derivative (the order-2 tree of the same mim / region / variable, added by
@@ -198,12 +281,15 @@ static bool recognise_by_probe(const getfem::ga_workspace &ws, size_type itree, 
           t2.name_test2 == td0.name_test1)
         i2 = j;
     }
-    if (i2 == size_type(-1)) return false;
+    if (i2 == size_type(-1)) return recognise_load_by_probe(ws, itree, out);
   }
   const getfem::ga_workspace::tree_description &td = ws.tree_info(i2);
   const std::string v = td.name_test1;
   const getfem::mesh_fem *pmf = ws.associated_mf(v);
   if (!pmf || pmf->is_reduced() || !td.mim || !td.rg) return false;
+  if (!probe_is_safe(ws, v, getfem::ga_tree_to_string(*td.ptree)) ||
+      !probe_is_safe(ws, v, getfem::ga_tree_to_string(*td0.ptree)))
+    return false;
   const getfem::mesh &m = pmf->linked_mesh();
   const size_type Q = pmf->get_qdim(), N = m.dim();
   getfem::mesh_region rg2;

@@ -69,7 +69,8 @@ int main(int argc, char **argv) {
       std::uniform_real_distribution<double> dist(-1.0, 1.0);
       for (auto &x : U) x = dist(rng);
     }
-    std::vector<double> Vr, Vg;
+    std::vector<double> Vr, Vg, C0(mf_d.nb_dof(), 1.0);
+    C0.back() = 5.0;
     auto run = [&](bool device, gmm::csc_matrix<double> &C) {
       getfem_b200::gfgpu_enable(device);
       getfem::ga_workspace ws;
@@ -77,7 +78,9 @@ int main(int argc, char **argv) {
       ws.add_fixed_size_constant("lambda", LAMBDA);
       ws.add_fixed_size_constant("mu", MU);
       ws.add_fixed_size_constant("a", A);
-      ws.add_expression(expr, mim);
+      ws.add_fem_constant("c0", mf_d, C0);  // a material that is 1 on the first convexes and 5 in a far corner
+      if (a.count("region")) ws.add_expression(expr, mim, m.region(size_type(geti("region", 1))));
+      else ws.add_expression(expr, mim);
       getfem::model_real_sparse_matrix M(mf.nb_dof(), mf.nb_dof());
       ws.set_assembled_matrix(M);
       ws.assembly(2);

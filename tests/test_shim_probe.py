@@ -124,3 +124,44 @@ def test_a_load_mixed_into_the_tree_is_not_taken_for_the_linear_form():
                          timeout=300, env=dict(os.environ, GFGPU_DRYRUN="1"))
     lines = [l for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun] order 1")]
     assert lines and all("NOT recognised" in l for l in lines), out.stderr[-1500:]
+
+
+SOURCE = 6
+LOAD_CASES = [  # constant loads in spellings the printed forms do not know -> family SOURCE with the fitted F
+    ("dim=3 n=2 gt=pk k=2", "-(a*[1;2;3]).Test_u", (-1.7, -3.4, -5.1)),
+    ("dim=3 n=2 gt=pk k=2", "Test_u(2)*lambda - mu*Test_u(1)", (-2, 3, 0)),
+    ("dim=2 n=4 gt=pk k=1 q=1", "(a/2)*Test_u*2", (1.7,)),
+    ("dim=3 n=2 gt=qk k=2 region=1", "[0;mu;-lambda].Test_u*2", (0, 4, -6)),   # a Neumann load on the faces x = 1
+]
+REFUSED = [  # the probe sees two items only: anything that may vary over the region is not its business
+    ("dim=3 n=2 gt=pk k=2", "X(1)*Test_u(1)"),
+    ("dim=3 n=2 gt=pk k=2 region=2", "Test_u.(lambda*Normal)*2"),                 # normal load on a non-planar boundary
+    ("dim=3 n=2 gt=pk k=2 q=1", "Grad_Test_u.(c0*Grad_Test2_u)*2"),               # fem-data material: constant on the probe convexes only
+    ("dim=3 n=2 gt=pk k=2 q=1", "c0*Test_u*3"),                                   # fem-data load
+]
+
+
+@pytest.mark.parametrize("mesh,expr,F", LOAD_CASES)
+def test_constant_loads_are_recognised(mesh, expr, F):
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN, "model=expr"] + mesh.split() + ["expr=" + expr], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, GFGPU_DRYRUN="1"))
+    assert out.returncode == 0, out.stderr[-1500:]
+    lines = [l for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun] order 1")]
+    assert lines, out.stderr[-1500:]
+    for line in lines:
+        r = re.search(r"-> recognised family (\d+) \(([^)]*)\)", line)
+        assert r and int(r.group(1)) == SOURCE, line
+        got = [float(x) for x in r.group(2).split()]
+        assert len(got) == len(F) and all(abs(g - f) <= 1e-9 * max(1.0, abs(f)) for g, f in zip(got, F)), line
+
+
+@pytest.mark.parametrize("mesh,expr", REFUSED)
+def test_the_probe_refuses_what_may_vary_over_the_region(mesh, expr):
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN, "model=expr"] + mesh.split() + ["expr=" + expr], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, GFGPU_DRYRUN="1"))
+    lines = [l for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun] order")]
+    assert lines and all("NOT recognised" in l for l in lines), out.stderr[-1500:]
