@@ -56,6 +56,7 @@ SIGNATURES = {
     "gfgpu_term_assemble_host": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "gfgpu_term_last_timings": (C.c_int, [_P, _P]),
     "gfgpu_term_strategy": (C.c_int, [_P]),
+    "gfgpu_term_kernel_kind": (C.c_int, [_P]),
     "gfgpu_term_nnz": (_i64, [_P]),
     "gfgpu_term_nb_dof": (_i64, [_P]),
     "gfgpu_term_pattern_generation": (_i64, [_P]),
@@ -289,6 +290,11 @@ class DeviceTerm(_Handle):
     @property
     def strategy(self):
         return int(lib().gfgpu_term_strategy(self.h))
+
+    @property
+    def kernel_kind(self):
+        """0 generic element kernel, 1 general tile kernel, 2 column kernel, 3 class-uniform tile kernel."""
+        return int(lib().gfgpu_term_kernel_kind(self.h))
 
     @property
     def nnz(self):

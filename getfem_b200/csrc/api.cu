@@ -697,6 +697,11 @@ int gfgpu_term_last_timings(gfgpu_term *t, float *out8) {
 }
 
 int gfgpu_term_strategy(gfgpu_term *t) { return t ? t->strategy : -1; }
+int gfgpu_term_kernel_kind(gfgpu_term *t) {
+  if (!t) return -1;
+  if (t->strategy != GFGPU_STRATEGY_RECOMPUTE || !t->rc_ready) return 0;
+  return t->rc_cols ? 2 : t->rc_uni ? 3 : 1;
+}
 
 int64_t gfgpu_term_nnz(gfgpu_term *t) { return (t && t->pat_valid) ? t->nnz : -1; }
 int64_t gfgpu_term_nb_dof(gfgpu_term *t) { return t ? t->fem->ndof : -1; }

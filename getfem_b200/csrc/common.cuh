@@ -233,6 +233,15 @@ struct gfgpu_term {
   gf::DevBuf<int64_t> rc_cgoff;   // per group of 32 column nodes: first ELL row
   gf::DevBuf<double> rc_cell;     // warp-transposed incidence records: geometry row, j and pair slots
   int64_t rc_cngroups = 0;
+  // class-uniform tile kernel (recompute_uniform.cu): columns with translated copies run in lock step, one per lane
+  bool rc_uni = false;
+  gf::DevBuf<uint8_t> ru_tiles;    // UTile per tile (+ one sentinel)
+  gf::DevBuf<uint32_t> ru_cta;     // first tile of every CTA
+  gf::DevBuf<uint32_t> ru_prog;    // per (class, sub-range) programs
+  gf::DevBuf<uint32_t> ru_ld;      // per chunk of 32 class members: CSC base and element strip positions of every lane
+  gf::DevBuf<double> ru_eg;        // per-element geometry, component-major, strip order
+  int64_t ru_nepad = 0, ru_ntiles = 0, ru_ntasks = 0;
+  int ru_grid = 0, ru_nbuf = 0, ru_imgcap = 0;
 };
 
 namespace gf {
@@ -288,5 +297,8 @@ void recompute_assemble(gfgpu_term *t, const double *U, bool do_t, bool do_r);
 bool recompute_cols_wanted(const gfgpu_term *t);
 bool recompute_cols_prepare(gfgpu_term *t, const std::vector<uint32_t> &colstart, const std::vector<uint32_t> &rstart);
 void recompute_cols_tangent(gfgpu_term *t, const double *U, bool with_r);
+// class-uniform tile kernel (recompute_uniform.cu); prepare returns false when the term keeps the general tile kernel
+bool uniform_prepare(gfgpu_term *t);
+void uniform_tangent(gfgpu_term *t);
 
 }  // namespace gf

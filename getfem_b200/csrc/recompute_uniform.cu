@@ -1,0 +1,726 @@
+// recompute_uniform.cu -- strategy RECOMPUTE, class-uniform tile kernel: the per-nonzero tangent of an affine-geometry,
+// constant-coefficient bilinear form on meshes with translated structure.
+//
+// Same mathematics and the same CSC pattern as recompute_tiles.cu (reference tensors M^{ji}, T = B~ M^{ji} B~^T per
+// contribution; replaces ga_exec + add_elem_matrix, C&E.cc:8750-8870 / 4853-4936); what changes is WHO does a contribution:
+//
+//   lane  = a column node.  A tile is up to 32 column nodes of one CLASS (uniform_plan.h: word-for-word equal descriptors,
+//           i.e. translated copies of one node): at every step the 32 lanes handle the SAME local couple (j, i) of 32
+//           DIFFERENT elements, so the reference tensor M^{ji} is one shared-memory broadcast (16-byte loads, 5 per step)
+//           and the program -- which pairs, which steps, where the results go -- is stored once per class instead of once
+//           per (pair, lane): the 16-byte pair records and descriptor blobs of the general kernel (8 GB on BASELINE
+//           config 3) shrink to 4 bytes per (column, incident element) + 8 bytes per column.
+//   task  = up to 3 node pairs of the column that are fed by the same elements (a P2 edge midside node and the two vertices
+//           of its edge; a vertex and the midside node towards it, ...): the geometry row B~_e of a step is loaded ONCE into
+//           registers and applied to all of them -- register-level operand reuse.
+//   B~_e  = read straight from global memory, coalesced: the geometry table is stored component-major in STRIP ORDER
+//           (elements sorted by (rank in the incidence list of their first node, class position of that node)), so the
+//           elements the 32 lanes need at a step are consecutive: one 256-byte line pair per component, no shared-memory
+//           staging, no bank conflicts.  The table is read from L2 (0.6 GB for config 3), L1 keeps the rows of the tiles in
+//           flight.
+//   image = per tile, the CSC segments of its columns in shared memory (one row per lane, stride = 2 mod 16 doubles);
+//           when the last task of a tile has stored its results the finishing warp sends every row with one bulk async
+//           store (TMA, full 16-byte units; the odd first / last entries go out as single stores).  Several tiles are in
+//           flight per CTA (ring of image buffers), tasks are handed out through one shared-memory counter, longest first.
+//
+// Columns whose class is small simply run with few active lanes; terms whose columns mostly have no translated copies
+// (unstructured meshes) keep the general tile kernel (recompute_tiles.cu).  Every pair still sums its contributions in a
+// fixed order (ascending element): bitwise reproducible, no atomics on data.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "common.cuh"
+#include "tile_common.cuh"
+#include "uniform_plan.h"
+
+namespace gf {
+
+static inline int ugrid(int64_t n, int block, int cap = 148 * 16) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>((n + block - 1) / block, cap));
+}
+static int uenv_int(const char *name, int dflt) {
+  const char *s = getenv(name);
+  return s && *s ? atoi(s) : dflt;
+}
+
+// ---------------------------------------------------------------- column descriptors
+struct UIn {
+  const uint32_t *colstart, *cstart, *csrc, *rstart, *rsrc;
+  const int32_t *rdof;
+  const uint16_t *pmask;
+  const uint32_t *prel;
+  const int64_t *jc;
+  int64_t npairs;
+  uint32_t nlocal;
+  int nd, Q;
+};
+
+// the descriptor words of column node k (uniform_plan.h), in order; false when an incidence is missing (corrupt structure)
+template <class F>
+__device__ __forceinline__ bool ut_col_words(const UIn &in, int64_t k, F &&f) {
+  const uint32_t p0 = in.colstart[k], p1 = in.colstart[k + 1], r0 = in.rstart[k], r1 = in.rstart[k + 1];
+  const int32_t J = in.rdof[k];
+  const int64_t j0 = in.jc[J];
+  f(p1 - p0);
+  f(r1 - r0);
+  for (int b = 0; b < in.Q; ++b) f((uint32_t)(in.jc[J + b + 1] - j0));
+  const uint32_t nb = (uint32_t)(in.nd * in.nd);
+  bool ok = true;
+  for (uint32_t p = p0; p < p1; ++p) {
+    const uint32_t s0 = in.cstart[p], s1 = in.cstart[p + 1];
+    uint32_t cntl = 0;
+    while (s0 + cntl < s1 && in.csrc[s0 + cntl] < in.nlocal) ++cntl;  // the virtual (halo) contributions come last
+    f((uint32_t)in.pmask[p] | (cntl << 16));
+    for (int b = 0; b < in.Q; ++b) f(in.prel[(size_t)b * in.npairs + p]);
+    for (uint32_t s = s0; s < s0 + cntl; ++s) {
+      const uint32_t c = in.csrc[s], el = c / nb, rr = c - el * nb, key = el * (uint32_t)in.nd + rr / (uint32_t)in.nd;
+      uint32_t lo = r0, hi = r1;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (in.rsrc[mid] < key) lo = mid + 1; else hi = mid;
+      }
+      if (lo >= r1 || in.rsrc[lo] != key) ok = false;
+      f(((lo - r0) << 16) | rr);
+    }
+  }
+  return ok;
+}
+
+__global__ void k_ut_hash(const UIn in, int64_t ncol, uint64_t *__restrict__ h1, uint64_t *__restrict__ h2,
+                          uint32_t *__restrict__ dlen, uint32_t *__restrict__ ids, int *__restrict__ err) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < ncol; k += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t a = 0x9E3779B97F4A7C15ull, b = 0xC2B2AE3D27D4EB4Full;
+    uint32_t n = 0;
+    const bool ok = ut_col_words(in, k, [&](uint32_t w) {
+      a = (a ^ w) * 0x100000001B3ull;
+      a ^= a >> 29;
+      b = (b + w) * 0xD6E8FEB86659FD93ull;
+      b ^= b >> 32;
+      ++n;
+    });
+    if (!ok) atomicExch(err, 21);
+    const uint32_t r = in.rstart[k + 1] - in.rstart[k];
+    if (r > 0xffffu || in.colstart[k + 1] - in.colstart[k] > 0xffffu) atomicExch(err, 22);
+    h1[k] = a;
+    h2[k] = b;
+    dlen[k] = n;
+    ids[k] = (uint32_t)k;
+  }
+}
+
+// sorted position s starts a class when (h1, h2) differ from the position before
+__global__ void k_ut_class_flags(const uint64_t *__restrict__ h1s, const uint64_t *__restrict__ h2,
+                                 const uint32_t *__restrict__ scol, int64_t ncol, uint8_t *__restrict__ flags) {
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < ncol; s += (int64_t)gridDim.x * blockDim.x)
+    flags[s] = (s == 0 || h1s[s] != h1s[s - 1] || h2[scol[s]] != h2[scol[s - 1]]) ? 1 : 0;
+}
+
+__global__ void k_ut_leader_len(const uint32_t *__restrict__ cls_start, const uint32_t *__restrict__ scol,
+                                const uint32_t *__restrict__ dlen, int64_t ncls, uint32_t *__restrict__ out) {
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncls; c += (int64_t)gridDim.x * blockDim.x)
+    out[c] = dlen[scol[cls_start[c]]];
+}
+
+__global__ void k_ut_leader_desc(const UIn in, const uint32_t *__restrict__ cls_start, const uint32_t *__restrict__ scol,
+                                 int64_t ncls, uint32_t dw, uint32_t *__restrict__ desc) {
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncls; c += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t *o = desc + (size_t)c * dw;
+    uint32_t n = 0;
+    ut_col_words(in, scol[cls_start[c]], [&](uint32_t w) {
+      if (n < dw) o[n] = w;
+      ++n;
+    });
+  }
+}
+
+__global__ void k_ut_inverse(const uint32_t *__restrict__ scol, int64_t ncol, uint32_t *__restrict__ sp) {
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < ncol; s += (int64_t)gridDim.x * blockDim.x)
+    sp[scol[s]] = (uint32_t)s;
+}
+
+// strip order of the elements: key = (rank of the element in the incidence list of its local node 0, class position of
+// that node).  Translated copies of an element then sit next to each other, in the order of the lanes that use them.
+__global__ void k_ut_elem_key(const int32_t *__restrict__ edof, int nd, int64_t e0, int64_t ne,
+                              const int32_t *__restrict__ rdof, int64_t ncol, const uint32_t *__restrict__ rstart,
+                              const uint32_t *__restrict__ rsrc, const uint32_t *__restrict__ sp,
+                              uint64_t *__restrict__ keys, uint32_t *__restrict__ ids, int *__restrict__ err) {
+  for (int64_t el = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; el < ne; el += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t dof = edof[(e0 + el) * nd];
+    int64_t lo = 0, hi = ncol;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (rdof[mid] < dof) lo = mid + 1; else hi = mid;
+    }
+    uint64_t key = ~0ull;
+    if (lo < ncol && rdof[lo] == dof) {
+      const uint32_t r0 = rstart[lo], r1 = rstart[lo + 1], want = (uint32_t)el * (uint32_t)nd;
+      uint32_t a = r0, b = r1;
+      while (a < b) {
+        const uint32_t mid = (a + b) >> 1;
+        if (rsrc[mid] < want) a = mid + 1; else b = mid;
+      }
+      if (a < r1 && rsrc[a] == want) key = ((uint64_t)(a - r0) << 32) | sp[lo];
+    }
+    if (key == ~0ull) atomicExch(err, 23);
+    keys[el] = key;
+    ids[el] = (uint32_t)el;
+  }
+}
+
+__global__ void k_ut_scatter_pos(const uint32_t *__restrict__ order, int64_t ne, uint32_t *__restrict__ epos) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < ne; i += (int64_t)gridDim.x * blockDim.x)
+    epos[order[i]] = (uint32_t)i;
+}
+
+__global__ void k_ut_eg_soa(const double *__restrict__ eg, int gsz, int64_t ne, const uint32_t *__restrict__ epos,
+                            int64_t nepad, double *__restrict__ out) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < ne * gsz; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t el = idx / gsz;
+    const int c = (int)(idx - el * gsz);
+    out[(size_t)c * nepad + epos[el]] = eg[idx];
+  }
+}
+
+// thread per (chunk, lane): the lane data of the chunk's tiles -- CSC base of the lane's column (two 32-bit halves) and the
+// strip position of every element of its incidence list -- after checking that the column's descriptor IS the leader's
+struct UChunk {
+  uint32_t pos0, cls, ld, nmem;
+};
+__global__ void k_ut_lane_data(const UIn in, const UChunk *__restrict__ chunks, int64_t nchunks,
+                               const uint32_t *__restrict__ scol, const uint32_t *__restrict__ desc, uint32_t dw,
+                               const uint32_t *__restrict__ epos, uint32_t *__restrict__ ld, int *__restrict__ err) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < nchunks * 32; idx += (int64_t)gridDim.x * blockDim.x) {
+    const UChunk ch = chunks[idx >> 5];
+    const uint32_t lane = (uint32_t)(idx & 31);
+    uint32_t *o = ld + ch.ld;
+    const uint32_t m = desc[(size_t)ch.cls * dw + 1];
+    if (lane >= ch.nmem) {
+      o[lane] = 0; o[32 + lane] = 0;
+      for (uint32_t r = 0; r < m; ++r) o[64 + r * 32 + lane] = 0;
+      continue;
+    }
+    const int64_t k = scol[ch.pos0 + lane];
+    const uint32_t *L = desc + (size_t)ch.cls * dw;
+    uint32_t n = 0;
+    bool same = true;
+    const bool ok = ut_col_words(in, k, [&](uint32_t w) {
+      if (n >= dw || L[n] != w) same = false;
+      ++n;
+    });
+    if (!ok || !same) atomicExch(err, 24);
+    const int64_t jc = in.jc[in.rdof[k]];
+    o[lane] = (uint32_t)(jc & 0xffffffffll);
+    o[32 + lane] = (uint32_t)(jc >> 32);
+    const uint32_t r0 = in.rstart[k];
+    for (uint32_t r = 0; r < m; ++r) o[64 + r * 32 + lane] = epos[in.rsrc[r0 + r] / (uint32_t)in.nd];
+  }
+}
+
+// ---------------------------------------------------------------- the tangent kernel
+struct alignas(16) UTile {
+  uint32_t prog, ld, task0;
+  uint16_t nmem, ntasks;
+};
+static_assert(sizeof(UTile) == 16, "UTile layout");
+
+struct UArgs {
+  const UTile *tiles;      // ntiles + 1 (the last one only carries the total number of tasks)
+  const uint32_t *cta_t0;  // grid + 1: tiles of CTA c are [cta_t0[c], cta_t0[c+1])
+  const uint32_t *prog, *ld;
+  const double *eg;        // [GSZ][nepad], strip order
+  int64_t nepad;
+  const double *Mtab;
+  double sl, smu;
+  double *pr;
+  int nbuf, imgcap;        // image buffers per CTA; doubles per buffer
+};
+
+constexpr int UT_WARPS = 12, UT_THREADS = UT_WARPS * 32, UT_MAXBUF = 8;
+
+template <int N, int Q, int ND, int RF>
+__global__ void __launch_bounds__(UT_THREADS, 1)
+k_utiles(const UArgs a) {
+  using C = TlCfg<N, RF>;
+  constexpr int NB = ND * ND, MT = C::MT, MTP = (MT + 1) & ~1, GSZ = C::GSZ, ACC = C::ACC, KG = uplan::KGU;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  __shared__ unsigned s_next, s_done[UT_MAXBUF];
+  __shared__ volatile unsigned s_freed[UT_MAXBUF];
+  double *sM = reinterpret_cast<double *>(smraw);
+  double *img0 = sM + ((NB * MTP + 15) & ~15);
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int k = tid; k < NB * MTP; k += UT_THREADS) sM[k] = (k % MTP) < MT ? a.Mtab[(k / MTP) * MT + k % MTP] : 0.0;
+  if (tid < UT_MAXBUF) { s_done[tid] = 0; s_freed[tid] = 0; }
+  if (tid == 0) s_next = 0;
+  __syncthreads();
+  const uint32_t t0 = a.cta_t0[blockIdx.x], t1 = a.cta_t0[blockIdx.x + 1];
+  const uint32_t taskbase = a.tiles[t0].task0, ntot = a.tiles[t1].task0 - taskbase;
+  uint32_t cur = t0;
+  for (;;) {
+    unsigned tk = 0;
+    if (lane == 0) tk = atomicAdd(&s_next, 1u);
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    if (tk >= ntot) break;
+    const uint32_t gt = taskbase + tk;
+    while (__ldg(&a.tiles[cur + 1].task0) <= gt) ++cur;
+    const uint4 tw = __ldg(reinterpret_cast<const uint4 *>(a.tiles + cur));
+    const uint32_t nmem = tw.w & 0xffffu, ntasks = tw.w >> 16;
+    const uint32_t g = gt - tw.z, lt = cur - t0;
+    const int b = (int)(lt % (uint32_t)a.nbuf);
+    const unsigned need = lt / (uint32_t)a.nbuf;
+    const uint32_t *P = a.prog + tw.x;
+    const uint32_t *T = P + __ldg(P + uplan::HDR + g);
+    const uint32_t tw0 = __ldg(T);
+    const int npairs = (int)(tw0 & 0xffu), nsteps = (int)(tw0 >> 8);
+    const uint32_t *PR = T + 1, *ST = T + 1 + 4 * npairs;
+    const uint32_t le = min((uint32_t)lane, nmem - 1u);
+    const uint32_t *ldp = a.ld + tw.y;
+    const uint32_t *lpos = ldp + 64 + le;
+    const uint32_t jclo = __ldg(ldp + le);
+
+    double acc[KG][ACC];
+#pragma unroll
+    for (int p = 0; p < KG; ++p)
+#pragma unroll
+      for (int m = 0; m < ACC; ++m) acc[p][m] = 0.0;
+
+    if (nsteps > 0) {
+      // software pipeline: the geometry row of step s+1 and the strip position of step s+2 are in flight during step s
+      uint32_t sw0 = __ldg(ST), sw1 = __ldg(ST + 1);
+      uint32_t nw0 = 0, nw1 = 0, npos = 0;
+      double G[GSZ];
+      {
+        const uint32_t pos = __ldg(lpos + (sw0 & 0xffffu) * 32u);
+#pragma unroll
+        for (int c = 0; c < GSZ; ++c) G[c] = __ldg(a.eg + (size_t)c * a.nepad + pos);
+      }
+      if (nsteps > 1) {
+        nw0 = __ldg(ST + 2); nw1 = __ldg(ST + 3);
+        npos = __ldg(lpos + (nw0 & 0xffffu) * 32u);
+      }
+      for (int s = 0; s < nsteps; ++s) {
+        double Gn[GSZ];
+        uint32_t mw0 = 0, mw1 = 0, mpos = 0;
+        if (s + 1 < nsteps) {
+#pragma unroll
+          for (int c = 0; c < GSZ; ++c) Gn[c] = __ldg(a.eg + (size_t)c * a.nepad + npos);
+          if (s + 2 < nsteps) {
+            mw0 = __ldg(ST + 2 * (s + 2)); mw1 = __ldg(ST + 2 * (s + 2) + 1);
+            mpos = __ldg(lpos + (mw0 & 0xffffu) * 32u);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < GSZ; ++c) Gn[c] = 0.0;
+        }
+        const uint32_t code[3] = {sw0 >> 16, sw1 & 0xffffu, sw1 >> 16};
+#pragma unroll
+        for (int p = 0; p < KG; ++p) {
+          if (p < npairs) {
+            double M[MTP];
+            const double2 *M2 = reinterpret_cast<const double2 *>(sM + code[p] * MTP);
+#pragma unroll
+            for (int q = 0; q < MTP / 2; ++q) {
+              const double2 v = M2[q];
+              M[2 * q] = v.x;
+              M[2 * q + 1] = v.y;
+            }
+            if (RF == TF_ELAST) {
+#pragma unroll
+              for (int qq = 0; qq < N; ++qq) {
+                double Wq[N];  // column qq of W = B~ M
+#pragma unroll
+                for (int aa = 0; aa < N; ++aa) {
+                  double s2 = 0;
+#pragma unroll
+                  for (int pp = 0; pp < N; ++pp) s2 += G[RF == TF_ELAST ? aa + N * pp : 0] * M[RF == TF_ELAST ? pp * N + qq : 0];
+                  Wq[aa] = s2;
+                }
+#pragma unroll
+                for (int b2 = 0; b2 < N; ++b2)
+#pragma unroll
+                  for (int aa = 0; aa < N; ++aa)
+                    acc[p][RF == TF_ELAST ? aa + N * b2 : 0] += Wq[aa] * G[RF == TF_ELAST ? b2 + N * qq : 0];
+              }
+            } else {
+              double s2 = acc[p][0];
+#pragma unroll
+              for (int k = 0; k < MT; ++k) s2 += M[k] * G[k];
+              acc[p][0] = s2;
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < GSZ; ++c) G[c] = Gn[c];
+        sw0 = nw0; sw1 = nw1;
+        nw0 = mw0; nw1 = mw1; npos = mpos;
+      }
+    }
+    // ---- the image buffer of this tile is free once the tile that used it before has left
+    while (s_freed[b] < need) __nanosleep(40);
+    const uint32_t rowstride = __ldg(P);
+    double *row = img0 + (size_t)b * a.imgcap + (size_t)lane * rowstride;
+    uint32_t par[3];
+#pragma unroll
+    for (int pc = 0; pc < 3; ++pc) par[pc] = (jclo + __ldg(P + 2 + 3 * pc)) & 1u;
+#pragma unroll
+    for (int p = 0; p < KG; ++p) {
+      if (p < npairs) {
+        const uint32_t pw = __ldg(PR + 4 * p);
+        double kv[Q * Q];  // kv[b2*Q + aa] = K(row component aa, column component b2)
+        if (RF == TF_ELAST) {
+          double tr = 0;
+#pragma unroll
+          for (int n = 0; n < N; ++n) tr += acc[p][RF == TF_ELAST ? n + N * n : 0];
+#pragma unroll
+          for (int b2 = 0; b2 < Q; ++b2)
+#pragma unroll
+            for (int aa = 0; aa < Q; ++aa)
+              kv[b2 * Q + aa] = a.sl * acc[p][RF == TF_ELAST ? aa + N * b2 : 0] + a.smu * acc[p][RF == TF_ELAST ? b2 + N * aa : 0] +
+                                (aa == b2 ? a.smu * tr : 0.0);
+        } else {
+#pragma unroll
+          for (int b2 = 0; b2 < Q; ++b2)
+#pragma unroll
+            for (int aa = 0; aa < Q; ++aa) kv[b2 * Q + aa] = aa == b2 ? acc[p][0] : 0.0;
+        }
+        if ((uint32_t)lane < nmem) {
+#pragma unroll
+          for (int b2 = 0; b2 < Q; ++b2) {
+            const uint32_t piece = (pw >> (16 + 2 * b2)) & 3u;
+            double *dst = row + __ldg(PR + 4 * p + 1 + b2) + (piece == 0 ? par[0] : piece == 1 ? par[1] : par[2]);
+            const unsigned mb = (pw >> (b2 * Q)) & ((1u << Q) - 1);
+            if (Q == 3) {
+              const double v0 = kv[b2 * Q], v1 = kv[b2 * Q + (Q > 1 ? 1 : 0)], v2 = kv[b2 * Q + (Q > 2 ? 2 : 0)];
+              const int n = __popc(mb);
+              const double x0 = (mb & 1u) ? v0 : ((mb & 2u) ? v1 : v2);
+              const double x1 = ((mb & 3u) == 3u) ? v1 : v2;
+              if (n >= 1) dst[0] = x0;
+              if (n >= 2) dst[1] = x1;
+              if (n >= 3) dst[2] = v2;
+            } else {
+#pragma unroll
+              for (int aa = 0; aa < Q; ++aa)
+                if (mb & (1u << aa)) dst[__popc(mb & ((1u << aa) - 1))] = kv[b2 * Q + aa];
+            }
+          }
+        }
+      }
+    }
+    // ---- my stores (generic proxy) before the bulk store (async proxy) of whoever finishes the tile
+    fence_async_smem();
+    __syncwarp();
+    unsigned last = 0;
+    if (lane == 0) {
+      __threadfence_block();
+      last = atomicAdd(&s_done[b], 1u) == ntasks - 1u ? 1u : 0u;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      __threadfence_block();
+      fence_async_smem();
+      if ((uint32_t)lane < nmem) {
+        const int64_t jc = (int64_t)(((uint64_t)__ldg(ldp + 32 + le) << 32) | jclo);
+        const uint32_t npieces = __ldg(P + 1);
+        for (uint32_t pc = 0; pc < npieces; ++pc) {
+          const int64_t len = __ldg(P + 3 + 3 * pc);
+          if (!len) continue;
+          const int64_t gstart = jc + __ldg(P + 2 + 3 * pc);
+          const int64_t odd = gstart & 1, gs = gstart + odd, ge = (gstart + len) & ~int64_t(1);
+          const double *src = row + __ldg(P + 4 + 3 * pc) + odd;  // entry e of the piece sits at src[e]
+          if (odd) a.pr[gstart] = src[0];
+          if (ge > gs) bulk_s2g(a.pr + gs, src + odd, (uint32_t)((ge - gs) * 8));
+          if (((gstart + len) & 1) && gstart + len - 1 >= gs) a.pr[gstart + len - 1] = src[len - 1];
+        }
+        bulk_commit();
+        bulk_wait_read0();
+      }
+      __syncwarp();
+      if (lane == 0) {
+        s_done[b] = 0;
+        __threadfence_block();
+        s_freed[b] = need + 1u;
+      }
+    }
+  }
+  bulk_wait0();
+}
+
+// ---------------------------------------------------------------- host side
+static int64_t ut_select_heads(gfgpu_ctx *ctx, const uint8_t *flags, int64_t n, uint32_t *out) {
+  DevBuf<int64_t> dcount;
+  dcount.alloc(ctx, 1);
+  cub::CountingInputIterator<uint32_t> it(0);
+  size_t tb = 0;
+  GF_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, it, flags, out, dcount.p, n, ctx->stream));
+  void *tmp = cub_scratch(ctx, tb);
+  GF_CUDA(cub::DeviceSelect::Flagged(tmp, tb, it, flags, out, dcount.p, n, ctx->stream));
+  count_launch(2);
+  int64_t h = 0;
+  dcount.download(&h);
+  GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  return h;
+}
+
+// Builds the class-uniform plan of term t.  false = the term keeps the general tile kernel (GFGPU_UNIFORM=0, or too few of
+// its columns have translated copies).  GFGPU_UNIFORM=2 forces the uniform kernel whatever the class sizes (tests).
+bool uniform_prepare(gfgpu_term *t) {
+  const int mode = uenv_int("GFGPU_UNIFORM", 1);
+  t->rc_uni = false;
+  if (!mode) return false;
+  gfgpu_ctx *ctx = t->ctx;
+  cudaStream_t s = ctx->stream;
+  Structure &st = t->st;
+  const int64_t ncol = st.ncolnodes, ne = t->e1 - t->e0;
+  const int nd = t->fem->nd, Q = t->fem->qdim, N = t->mesh->dim;
+  const int rf = tf_of(t->family);
+  const int GSZ = rf == TF_ELAST ? N * N : rf == TF_LAPLACE ? N * (N + 1) / 2 : 1;
+  if (!ncol || !ne || ncol >= (int64_t(1) << 32) || ne >= (int64_t(1) << 32)) return false;
+  const int B = 256;
+  UIn in;
+  in.colstart = st.colstart.p; in.cstart = st.cstart.p; in.csrc = st.csrc.p; in.rstart = st.rstart.p; in.rsrc = st.rsrc.p;
+  in.rdof = st.rdof.p; in.pmask = t->pmask.p; in.prel = t->prel.p; in.jc = t->jc.p;
+  in.npairs = st.npairs; in.nlocal = (uint32_t)st.ncontrib; in.nd = nd; in.Q = Q;
+  GF_REQUIRE(t->prel.n == (size_t)Q * st.npairs, "uniform plan: the pattern offsets are gone");
+  t->flag.zero();
+  // ---- classes: hash of the descriptor, sort, run heads
+  DevBuf<uint64_t> h1, h2, h1s;
+  DevBuf<uint32_t> dlen, ids, scol;
+  h1.alloc(ctx, ncol); h2.alloc(ctx, ncol); h1s.alloc(ctx, ncol);
+  dlen.alloc(ctx, ncol); ids.alloc(ctx, ncol); scol.alloc(ctx, ncol);
+  k_ut_hash<<<ugrid(ncol, B), B, 0, s>>>(in, ncol, h1.p, h2.p, dlen.p, ids.p, (int *)t->flag.p);
+  GF_LAUNCH_CHECK();
+  {
+    size_t tb = 0;
+    GF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, h1.p, h1s.p, ids.p, scol.p, ncol, 0, 64, s));
+    void *tmp = cub_scratch(ctx, tb);
+    GF_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, h1.p, h1s.p, ids.p, scol.p, ncol, 0, 64, s));
+    count_launch(17);
+  }
+  DevBuf<uint8_t> flags;
+  flags.alloc(ctx, ncol);
+  k_ut_class_flags<<<ugrid(ncol, B), B, 0, s>>>(h1s.p, h2.p, scol.p, ncol, flags.p);
+  GF_LAUNCH_CHECK();
+  DevBuf<uint32_t> cls_start;
+  cls_start.alloc(ctx, ncol + 1);
+  const int64_t ncls = ut_select_heads(ctx, flags.p, ncol, cls_start.p);
+  flags.release(); h1.release(); h1s.release(); h2.release(); ids.release();
+  {
+    int32_t err = 0;
+    t->flag.download(&err);
+    GF_CUDA(cudaStreamSynchronize(s));
+    GF_REQUIRE(err == 0, "uniform plan: corrupt structure (code " + std::to_string(err) + ")");
+  }
+  const int64_t max_classes = (int64_t)uenv_int("GFGPU_UT_MAXCLASSES", 60000);
+  if (mode != 2 && (ncls > max_classes || ncls * 8 > ncol)) return false;
+  std::vector<uint32_t> h_cls(ncls + 1);
+  GF_CUDA(cudaMemcpyAsync(h_cls.data(), cls_start.p, ncls * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  GF_CUDA(cudaStreamSynchronize(s));
+  h_cls[ncls] = (uint32_t)ncol;
+  if (mode != 2) {  // columns in classes of at least 16 members
+    int64_t covered = 0;
+    for (int64_t c = 0; c < ncls; ++c)
+      if (h_cls[c + 1] - h_cls[c] >= 16u) covered += h_cls[c + 1] - h_cls[c];
+    if (covered * 10 < ncol * 9) return false;
+  }
+  // ---- leaders' descriptors -> host -> programs
+  DevBuf<uint32_t> llen;
+  llen.alloc(ctx, ncls);
+  GF_CUDA(cudaMemcpyAsync(cls_start.p + ncls, &h_cls[ncls], sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  k_ut_leader_len<<<ugrid(ncls, B), B, 0, s>>>(cls_start.p, scol.p, dlen.p, ncls, llen.p);
+  GF_LAUNCH_CHECK();
+  std::vector<uint32_t> h_llen(ncls);
+  llen.download(h_llen.data());
+  GF_CUDA(cudaStreamSynchronize(s));
+  uint32_t dw = 0;
+  for (uint32_t v : h_llen) dw = std::max(dw, v);
+  GF_REQUIRE((size_t)ncls * dw < (size_t(1) << 31), "uniform plan: descriptors too large");
+  DevBuf<uint32_t> desc;
+  desc.alloc(ctx, (size_t)ncls * dw);
+  k_ut_leader_desc<<<ugrid(ncls, 64), 64, 0, s>>>(in, cls_start.p, scol.p, ncls, dw, desc.p);
+  GF_LAUNCH_CHECK();
+  std::vector<uint32_t> h_desc((size_t)ncls * dw), h_scol(ncol);
+  desc.download(h_desc.data());
+  scol.download(h_scol.data());
+  GF_CUDA(cudaStreamSynchronize(s));
+  dlen.release(); llen.release();
+
+  const int nbuf = std::max(1, std::min(uenv_int("GFGPU_UT_NBUF", 3), UT_MAXBUF));
+  const int img_bytes = std::max(8192, std::min(uenv_int("GFGPU_UT_IMG", 40960), 200 * 1024));
+  const uint32_t row_cap = (uint32_t)(img_bytes / 8 / 32);
+  const int task_cap = std::max(1, uenv_int("GFGPU_UT_TASKCAP", 16));
+  std::vector<uint32_t> prog;
+  std::vector<uplan::ClassPlan> cplan(ncls);
+  uint32_t max_stride = 2;
+  for (int64_t c = 0; c < ncls; ++c) {
+    std::string err;
+    const bool ok = uplan::build_class(h_desc.data() + (size_t)c * dw, h_llen[c], Q, nd, row_cap, task_cap, prog, cplan[c], err);
+    GF_REQUIRE(ok, "uniform plan: " + err);
+    for (const uplan::Sub &sb : cplan[c].subs) max_stride = std::max(max_stride, sb.rowstride);
+    GF_REQUIRE(prog.size() < (size_t(1) << 31), "uniform plan: programs too large");
+  }
+  // ---- chunks of 32 class members, in the order of their first column; tiles = chunk x sub-range
+  struct HChunk { uint32_t pos0, cls, nmem, first; };
+  std::vector<HChunk> hch;
+  hch.reserve(ncol / 32 + ncls + 1);
+  for (int64_t c = 0; c < ncls; ++c)
+    for (uint32_t p = h_cls[c]; p < h_cls[c + 1]; p += 32)
+      hch.push_back({p, (uint32_t)c, std::min<uint32_t>(32u, h_cls[c + 1] - p), h_scol[p]});
+  std::sort(hch.begin(), hch.end(), [](const HChunk &x, const HChunk &y) { return x.first < y.first; });
+  std::vector<UChunk> chunks(hch.size());
+  std::vector<UTile> tiles;
+  std::vector<uint64_t> wsum;
+  tiles.reserve(hch.size() * 2 + 1);
+  uint64_t ldw = 0, wtot = 0, ntask = 0;
+  for (size_t q = 0; q < hch.size(); ++q) {
+    const uplan::ClassPlan &cp = cplan[hch[q].cls];
+    GF_REQUIRE(ldw < (uint64_t(1) << 32), "uniform plan: lane data too large");
+    chunks[q] = {hch[q].pos0, hch[q].cls, (uint32_t)ldw, hch[q].nmem};
+    for (const uplan::Sub &sb : cp.subs) {
+      UTile tl;
+      tl.prog = sb.prog; tl.ld = (uint32_t)ldw; tl.task0 = (uint32_t)ntask;
+      tl.nmem = (uint16_t)hch[q].nmem; tl.ntasks = (uint16_t)sb.ntasks;
+      tiles.push_back(tl);
+      wtot += sb.weight;
+      wsum.push_back(wtot);
+      ntask += sb.ntasks;
+    }
+    ldw += 64 + 32 * (uint64_t)cp.m;
+  }
+  GF_REQUIRE(ntask < (uint64_t(1) << 32) && tiles.size() < (size_t(1) << 31), "uniform plan: too many tasks");
+  const int64_t ntiles = (int64_t)tiles.size();
+  {
+    UTile sentinel;
+    sentinel.prog = 0; sentinel.ld = 0; sentinel.task0 = (uint32_t)ntask; sentinel.nmem = 1; sentinel.ntasks = 0;
+    tiles.push_back(sentinel);
+  }
+  const int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * std::max(1, uenv_int("GFGPU_UT_CTAS_PER_SM", 1)));
+  std::vector<uint32_t> cta_t0(grid + 1, 0);
+  {
+    size_t tpos = 0;
+    for (int c = 1; c < grid; ++c) {
+      const uint64_t target = wtot * (uint64_t)c / (uint64_t)grid;
+      while (tpos < (size_t)ntiles && wsum[tpos] <= target) ++tpos;
+      cta_t0[c] = (uint32_t)std::max<size_t>(tpos, cta_t0[c - 1]);
+    }
+    cta_t0[grid] = (uint32_t)ntiles;
+  }
+  t->ru_tiles.alloc(ctx, tiles.size() * sizeof(UTile));
+  GF_CUDA(cudaMemcpyAsync(t->ru_tiles.p, tiles.data(), tiles.size() * sizeof(UTile), cudaMemcpyHostToDevice, s));
+  t->ru_cta.alloc(ctx, cta_t0.size());
+  t->ru_cta.upload(cta_t0.data());
+  t->ru_prog.alloc(ctx, std::max<size_t>(prog.size(), 1));
+  GF_CUDA(cudaMemcpyAsync(t->ru_prog.p, prog.data(), prog.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  DevBuf<uint8_t> dchunks;
+  dchunks.alloc(ctx, chunks.size() * sizeof(UChunk));
+  GF_CUDA(cudaMemcpyAsync(dchunks.p, chunks.data(), chunks.size() * sizeof(UChunk), cudaMemcpyHostToDevice, s));
+  // ---- strip order of the elements, geometry table component-major in that order
+  DevBuf<uint32_t> sp, epos;
+  sp.alloc(ctx, ncol);
+  epos.alloc(ctx, ne);
+  k_ut_inverse<<<ugrid(ncol, B), B, 0, s>>>(scol.p, ncol, sp.p);
+  GF_LAUNCH_CHECK();
+  {
+    DevBuf<uint64_t> k0, k1;
+    DevBuf<uint32_t> v0, v1;
+    k0.alloc(ctx, ne); k1.alloc(ctx, ne); v0.alloc(ctx, ne); v1.alloc(ctx, ne);
+    k_ut_elem_key<<<ugrid(ne, B), B, 0, s>>>(t->edof_p(), nd, t->e0, ne, st.rdof.p, ncol, st.rstart.p, st.rsrc.p, sp.p,
+                                           k0.p, v0.p, (int *)t->flag.p);
+    GF_LAUNCH_CHECK();
+    size_t tb = 0;
+    GF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, k0.p, k1.p, v0.p, v1.p, ne, 0, 64, s));
+    void *tmp = cub_scratch(ctx, tb);
+    GF_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, k0.p, k1.p, v0.p, v1.p, ne, 0, 64, s));
+    count_launch(17);
+    k_ut_scatter_pos<<<ugrid(ne, B), B, 0, s>>>(v1.p, ne, epos.p);
+    GF_LAUNCH_CHECK();
+    GF_CUDA(cudaStreamSynchronize(s));
+  }
+  sp.release();
+  const int64_t nepad = (ne + 31) / 32 * 32;
+  t->ru_nepad = nepad;
+  t->ru_eg.alloc(ctx, (size_t)nepad * GSZ);
+  t->ru_eg.zero();
+  k_ut_eg_soa<<<ugrid(ne * GSZ, B), B, 0, s>>>(t->rc_eg.p, GSZ, ne, epos.p, nepad, t->ru_eg.p);
+  GF_LAUNCH_CHECK();
+  // ---- lane data (with the check that every member really has its leader's descriptor)
+  t->ru_ld.alloc(ctx, std::max<uint64_t>(ldw, 1));
+  k_ut_lane_data<<<ugrid((int64_t)chunks.size() * 32, B), B, 0, s>>>(in, (const UChunk *)dchunks.p, (int64_t)chunks.size(),
+                                                                  scol.p, desc.p, dw, epos.p, t->ru_ld.p, (int *)t->flag.p);
+  GF_LAUNCH_CHECK();
+  {
+    int32_t err = 0;
+    t->flag.download(&err);
+    GF_CUDA(cudaStreamSynchronize(s));
+    GF_REQUIRE(err == 0, "uniform plan failed (code " + std::to_string(err) + ")");
+  }
+  t->ru_grid = grid;
+  t->ru_nbuf = nbuf;
+  t->ru_imgcap = (int)(32 * max_stride);
+  t->ru_ntiles = ntiles;
+  t->ru_ntasks = (int64_t)ntask;
+  if (getenv("GFGPU_DEBUG")) {
+    int64_t big = 0;
+    for (int64_t c = 0; c < ncls; ++c)
+      if (h_cls[c + 1] - h_cls[c] >= 32u) ++big;
+    fprintf(stderr,
+            "[gfgpu] uniform tiles: %lld columns in %lld classes (%lld with >= 32 members), %lld chunks, %lld tiles, %llu tasks, "
+            "programs %.1f KB, lane data %.1f MB, image %d B x %d, grid %d\n",
+            (long long)ncol, (long long)ncls, (long long)big, (long long)chunks.size(), (long long)ntiles,
+            (unsigned long long)ntask, prog.size() * 4 / 1024.0, ldw * 4 / 1048576.0, t->ru_imgcap * 8, nbuf, grid);
+  }
+  if (!t->halo) t->prel.release();
+  t->rc_uni = true;
+  return true;
+}
+
+template <int N, int Q, int ND, int RF>
+static void launch_utiles(gfgpu_term *t) {
+  using C = TlCfg<N, RF>;
+  constexpr int MTP = (C::MT + 1) & ~1;
+  const double sign = t->alpha < 0 ? -1.0 : 1.0;
+  UArgs a;
+  a.tiles = (const UTile *)t->ru_tiles.p;
+  a.cta_t0 = t->ru_cta.p;
+  a.prog = t->ru_prog.p;
+  a.ld = t->ru_ld.p;
+  a.eg = t->ru_eg.p;
+  a.nepad = t->ru_nepad;
+  a.Mtab = t->rc_M.p;
+  a.sl = sign * t->par[0]; a.smu = sign * t->par[1];
+  a.pr = t->pr.p;
+  a.nbuf = t->ru_nbuf;
+  a.imgcap = t->ru_imgcap;
+  const size_t smem = (size_t)((ND * ND * MTP + 15) & ~15) * 8 + (size_t)a.nbuf * a.imgcap * 8;
+  GF_REQUIRE(smem <= 226 * 1024, "uniform tiles: image buffers too large for shared memory (GFGPU_UT_IMG / GFGPU_UT_NBUF)");
+  auto kern = k_utiles<N, Q, ND, RF>;
+  GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<t->ru_grid, UT_THREADS, smem, t->ctx->stream>>>(a);
+  GF_LAUNCH_CHECK();
+}
+
+#define UT_CASE(NN, QQ, NDD, RFF)                     \
+  if (N == NN && Q == QQ && nd == NDD && rf == RFF) { \
+    launch_utiles<NN, QQ, NDD, RFF>(t);               \
+    return;                                           \
+  }
+
+void uniform_tangent(gfgpu_term *t) {
+  const int N = t->mesh->dim, nd = t->fem->nd, Q = t->fem->qdim, rf = tf_of(t->family);
+  UT_CASE(3, 3, 10, TF_ELAST) UT_CASE(3, 3, 4, TF_ELAST) UT_CASE(3, 3, 20, TF_ELAST)
+  UT_CASE(3, 1, 10, TF_LAPLACE) UT_CASE(3, 1, 4, TF_LAPLACE) UT_CASE(3, 1, 20, TF_LAPLACE)
+  UT_CASE(3, 3, 10, TF_LAPLACE) UT_CASE(3, 3, 4, TF_LAPLACE) UT_CASE(3, 3, 20, TF_LAPLACE)
+  UT_CASE(3, 1, 10, TF_MASS) UT_CASE(3, 1, 4, TF_MASS) UT_CASE(3, 1, 20, TF_MASS)
+  UT_CASE(3, 3, 10, TF_MASS) UT_CASE(3, 3, 4, TF_MASS) UT_CASE(3, 3, 20, TF_MASS)
+  UT_CASE(2, 2, 3, TF_ELAST) UT_CASE(2, 2, 6, TF_ELAST) UT_CASE(2, 2, 10, TF_ELAST)
+  UT_CASE(2, 1, 3, TF_LAPLACE) UT_CASE(2, 1, 6, TF_LAPLACE) UT_CASE(2, 1, 10, TF_LAPLACE)
+  UT_CASE(2, 2, 3, TF_LAPLACE) UT_CASE(2, 2, 6, TF_LAPLACE) UT_CASE(2, 2, 10, TF_LAPLACE)
+  UT_CASE(2, 1, 3, TF_MASS) UT_CASE(2, 1, 6, TF_MASS) UT_CASE(2, 1, 10, TF_MASS)
+  UT_CASE(2, 2, 3, TF_MASS) UT_CASE(2, 2, 6, TF_MASS) UT_CASE(2, 2, 10, TF_MASS)
+  GF_REQUIRE(false, "no uniform tile kernel for this combination");
+}
+
+}  // namespace gf

@@ -172,7 +172,13 @@ static double snap_coefficient(double x, double scale) {
 // expressions whose leaves are the variable itself and FIXED-SIZE constants.  Fem data (a piecewise material!), im_data, other
 // variables, the position X, the normal, element sizes, interpolate / elementary transformations ... are left to the printed
 // normal forms (which handle fem-data coefficients and normal loads explicitly) or refused.
-static bool probe_is_safe(const getfem::ga_workspace &ws, const std::string &v, const std::string &printed) {
+// `unknown_allowed` = false also refuses the variable itself WITHOUT a Test_ / Test2_ prefix: a bilinear form or a load that
+// contains the unknown depends on the state, and a numerical fit at ONE state (zero on the probe convexes, say, at the first
+// Newton step) would take a nonlinear form such as (1+u*u)*Grad_u.Grad_Test_u for a Laplacian.  Only the order-1 tree of a
+// derived pair may contain the unknown: its derivative -- checked with unknown_allowed = false -- is then state independent, so
+// the tree is affine in u, and the r = K u check at the current state leaves no room for a constant part.
+static bool probe_is_safe(const getfem::ga_workspace &ws, const std::string &v, const std::string &printed,
+                          bool unknown_allowed) {
   static const char *forbidden[] = {"X", "Normal", "element_size", "element_K", "element_B", "Interpolate", "Interpolate_filter",
                                     "Interpolate_derivative", "Elementary", "Elementary_transformation", "Secondary_domain",
                                     "Secondary_Domain", "Xfem_plus", "Xfem_minus", "Cross_product", "Print"};
@@ -182,14 +188,22 @@ static bool probe_is_safe(const getfem::ga_workspace &ws, const std::string &v, 
     std::string tok = it->str();
     for (const char *f : forbidden)
       if (tok == f) return false;
+    bool is_test = false;
     for (bool again = true; again;) {
       again = false;
       for (const char *p : prefixes) {
         const size_t n = std::strlen(p);
-        if (tok.size() > n && tok.compare(0, n, p) == 0) { tok = tok.substr(n); again = true; }
+        if (tok.size() > n && tok.compare(0, n, p) == 0) {
+          is_test = is_test || p[0] == 'T';
+          tok = tok.substr(n);
+          again = true;
+        }
       }
     }
-    if (tok == v) continue;
+    if (tok == v) {
+      if (!is_test && !unknown_allowed) return false;
+      continue;
+    }
     if (ws.variable_group_exists(tok)) return false;
     if (!ws.variable_exists(tok)) continue;  // a function or operator name
     if (!ws.is_constant(tok) || ws.associated_mf(tok) || ws.associated_im_data(tok)) return false;
@@ -226,7 +240,7 @@ static bool recognise_load_by_probe(const getfem::ga_workspace &ws, size_type it
   }
   const getfem::mesh_fem *pmf = ws.associated_mf(v);
   if (!pmf || pmf->is_reduced() || !td.mim || !td.rg) return false;
-  if (!probe_is_safe(ws, v, getfem::ga_tree_to_string(*td.ptree))) return false;
+  if (!probe_is_safe(ws, v, getfem::ga_tree_to_string(*td.ptree), false)) return false;
   const getfem::mesh &m = pmf->linked_mesh();
   const size_type Q = pmf->get_qdim();
   getfem::mesh_region rg2;
@@ -287,8 +301,8 @@ static bool recognise_by_probe(const getfem::ga_workspace &ws, size_type itree, 
   const std::string v = td.name_test1;
   const getfem::mesh_fem *pmf = ws.associated_mf(v);
   if (!pmf || pmf->is_reduced() || !td.mim || !td.rg) return false;
-  if (!probe_is_safe(ws, v, getfem::ga_tree_to_string(*td.ptree)) ||
-      !probe_is_safe(ws, v, getfem::ga_tree_to_string(*td0.ptree)))
+  if (!probe_is_safe(ws, v, getfem::ga_tree_to_string(*td.ptree), false) ||
+      !probe_is_safe(ws, v, getfem::ga_tree_to_string(*td0.ptree), td0.order == 1))
     return false;
   const getfem::mesh &m = pmf->linked_mesh();
   const size_type Q = pmf->get_qdim(), N = m.dim();

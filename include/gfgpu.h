@@ -185,6 +185,10 @@ int gfgpu_term_assemble_host(gfgpu_term *t, const double *U_host, int order_mask
 int gfgpu_term_last_timings(gfgpu_term *t, float *out8);
 /* the strategy the term actually uses (GFGPU_STRATEGY_STAGED or GFGPU_STRATEGY_RECOMPUTE) */
 int gfgpu_term_strategy(gfgpu_term *t);
+/* which tangent kernel the last plan of the term selected: 0 = generic element kernel + gather-sum (STAGED, or RECOMPUTE not
+ * planned yet), 1 = general per-nonzero tile kernel, 2 = column kernel (low-order scalar forms), 3 = class-uniform tile kernel
+ * (meshes with translated structure).  Diagnostic: the choice never changes results beyond round-off. */
+int gfgpu_term_kernel_kind(gfgpu_term *t);
 
 int64_t gfgpu_term_nnz(gfgpu_term *t);
 int64_t gfgpu_term_nb_dof(gfgpu_term *t);
