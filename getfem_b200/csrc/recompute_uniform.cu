@@ -177,12 +177,13 @@ __global__ void k_ut_scatter_pos(const uint32_t *__restrict__ order, int64_t ne,
     epos[order[i]] = (uint32_t)i;
 }
 
-__global__ void k_ut_eg_soa(const double *__restrict__ eg, int gsz, int64_t ne, const uint32_t *__restrict__ epos,
-                            int64_t nepad, double *__restrict__ out) {
+__global__ void k_ut_eg_blocked(const double *__restrict__ eg, int gsz, int64_t ne, const uint32_t *__restrict__ epos,
+                                double *__restrict__ out) {
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < ne * gsz; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t el = idx / gsz;
     const int c = (int)(idx - el * gsz);
-    out[(size_t)c * nepad + epos[el]] = eg[idx];
+    const uint32_t pos = epos[el];
+    out[(size_t)(pos >> 5) * (gsz * 32) + c * 32 + (pos & 31u)] = eg[idx];
   }
 }
 
@@ -223,24 +224,74 @@ __global__ void k_ut_lane_data(const UIn in, const UChunk *__restrict__ chunks, 
 
 // ---------------------------------------------------------------- the tangent kernel
 struct alignas(16) UTile {
-  uint32_t prog, ld, task0;
-  uint16_t nmem, ntasks;
+  uint32_t prog, ld;  // program (8-byte units), lane data (words)
+  uint32_t nmem, pad;
 };
 static_assert(sizeof(UTile) == 16, "UTile layout");
 
 struct UArgs {
-  const UTile *tiles;      // ntiles + 1 (the last one only carries the total number of tasks)
+  const UTile *tiles;
   const uint32_t *cta_t0;  // grid + 1: tiles of CTA c are [cta_t0[c], cta_t0[c+1])
-  const uint32_t *prog, *ld;
-  const double *eg;        // [GSZ][nepad], strip order
-  int64_t nepad;
+  const uint2 *prog;
+  const uint32_t *ld;
+  const double *eg;        // strip order, blocked: [strip position / 32][GSZ][strip position % 32]
   const double *Mtab;
   double sl, smu;
   double *pr;
-  int nbuf, imgcap;        // image buffers per CTA; doubles per buffer
+  int imgcap;              // doubles per image buffer (one per team)
 };
 
-constexpr int UT_WARPS = 12, UT_THREADS = UT_WARPS * 32, UT_MAXBUF = 8;
+// A CTA = UT_TEAMS teams of UT_TW warps (one per SM sub-partition); a team runs one tile at a time: every warp its task (the
+// plan packs the tile's groups into UT_TW tasks), team barrier, every warp sends UT_ROWS rows of the image, team barrier.
+// No spinning, no atomics on data; the teams are independent, so one team's flush overlaps the others' arithmetic.
+constexpr int UT_TW = 4, UT_TEAMS = 3, UT_WARPS = UT_TW * UT_TEAMS, UT_THREADS = UT_WARPS * 32, UT_ROWS = 32 / UT_TW, UT_RB = 4;
+
+__device__ __forceinline__ void team_barrier(int team) {
+  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(UT_TW * 32) : "memory");
+}
+
+// flush of a tile image: warp wq sends rows [wq*UT_ROWS, (wq+1)*UT_ROWS) -- the CSC segments of these columns -- as 16-byte
+// units, 32 lanes side by side (coalesced; full sectors except at the two ends of a row), UT_RB rows in flight together.
+// Kept out of line: its address registers must not weigh on the allocation of the arithmetic loop.
+__device__ __noinline__ void ut_flush_rows(const double *img, double *pr, uint32_t rowstride, uint32_t nmem, int wq, int lane,
+                                           uint32_t jclo, uint32_t jchi, uint32_t npieces, uint2 pc0, uint2 pc1, uint2 pc2) {
+  for (uint32_t pc = 0; pc < npieces; ++pc) {
+    const uint2 pw = pc == 0 ? pc0 : pc == 1 ? pc1 : pc2;
+    const int64_t len = pw.y & 0xffffu;
+    if (!len) continue;
+    const uint32_t pbase = pw.y >> 16;
+    const int maxun = (int)((len + 1) >> 1);
+#pragma unroll 1
+    for (int r0 = 0; r0 < UT_ROWS; r0 += UT_RB) {
+      const double2 *s2[UT_RB];
+      double2 *d2[UT_RB];
+      int nun[UT_RB];
+#pragma unroll
+      for (int r = 0; r < UT_RB; ++r) {
+        const uint32_t k = (uint32_t)(wq * UT_ROWS + r0 + r);
+        const uint32_t lo = __shfl_sync(0xffffffffu, jclo, k), hi = __shfl_sync(0xffffffffu, jchi, k);
+        const int64_t gstart = (int64_t)(((uint64_t)hi << 32) | lo) + pw.x;
+        const int64_t odd = gstart & 1, gs = gstart + odd, ge = (gstart + len) & ~int64_t(1);
+        const double *src = img + (size_t)k * rowstride + pbase + odd;  // entry e of the piece sits at src[e]
+        const bool live = k < nmem;
+        if (live && odd && lane == 0) pr[gstart] = src[0];
+        if (live && ((gstart + len) & 1) && gstart + len - 1 >= gs && lane == 31) pr[gstart + len - 1] = src[len - 1];
+        s2[r] = reinterpret_cast<const double2 *>(src + odd);
+        d2[r] = reinterpret_cast<double2 *>(pr + gs);
+        nun[r] = live ? (int)((ge - gs) >> 1) : 0;
+      }
+      for (int u = lane; u < maxun; u += 32) {
+        double2 v[UT_RB];
+#pragma unroll
+        for (int r = 0; r < UT_RB; ++r)
+          if (u < nun[r]) v[r] = s2[r][u];
+#pragma unroll
+        for (int r = 0; r < UT_RB; ++r)
+          if (u < nun[r]) d2[r][u] = v[r];
+      }
+    }
+  }
+}
 
 template <int N, int Q, int ND, int RF>
 __global__ void __launch_bounds__(UT_THREADS, 1)
@@ -248,159 +299,84 @@ k_utiles(const UArgs a) {
   using C = TlCfg<N, RF>;
   constexpr int NB = ND * ND, MT = C::MT, MTP = (MT + 1) & ~1, GSZ = C::GSZ, ACC = C::ACC, KG = uplan::KGU;
   extern __shared__ __align__(128) unsigned char smraw[];
-  __shared__ unsigned s_next, s_done[UT_MAXBUF];
-  __shared__ volatile unsigned s_freed[UT_MAXBUF];
+  __shared__ unsigned s_next, s_tile[UT_TEAMS];
   double *sM = reinterpret_cast<double *>(smraw);
-  double *img0 = sM + ((NB * MTP + 15) & ~15);
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, team = warp / UT_TW, wq = warp % UT_TW;
+  double *img = sM + ((NB * MTP + 15) & ~15) + (size_t)team * a.imgcap;
   for (int k = tid; k < NB * MTP; k += UT_THREADS) sM[k] = (k % MTP) < MT ? a.Mtab[(k / MTP) * MT + k % MTP] : 0.0;
-  if (tid < UT_MAXBUF) { s_done[tid] = 0; s_freed[tid] = 0; }
-  if (tid == 0) s_next = 0;
+  if (tid == 0) s_next = UT_TEAMS;
+  if (tid < UT_TEAMS) s_tile[tid] = tid;  // the first tile of every team
   __syncthreads();
-  const uint32_t t0 = a.cta_t0[blockIdx.x], t1 = a.cta_t0[blockIdx.x + 1];
-  const uint32_t taskbase = a.tiles[t0].task0, ntot = a.tiles[t1].task0 - taskbase;
-  uint32_t cur = t0;
+  const uint32_t t0 = a.cta_t0[blockIdx.x], ntl = a.cta_t0[blockIdx.x + 1] - t0;
   for (;;) {
-    unsigned tk = 0;
-    if (lane == 0) tk = atomicAdd(&s_next, 1u);
-    tk = __shfl_sync(0xffffffffu, tk, 0);
-    if (tk >= ntot) break;
-    const uint32_t gt = taskbase + tk;
-    while (__ldg(&a.tiles[cur + 1].task0) <= gt) ++cur;
-    const uint4 tw = __ldg(reinterpret_cast<const uint4 *>(a.tiles + cur));
-    const uint32_t nmem = tw.w & 0xffffu, ntasks = tw.w >> 16;
-    const uint32_t g = gt - tw.z, lt = cur - t0;
-    const int b = (int)(lt % (uint32_t)a.nbuf);
-    const unsigned need = lt / (uint32_t)a.nbuf;
-    const uint32_t *P = a.prog + tw.x;
-    const uint32_t *T = P + __ldg(P + uplan::HDR + g);
-    const uint32_t tw0 = __ldg(T);
-    const int npairs = (int)(tw0 & 0xffu), nsteps = (int)(tw0 >> 8);
-    const uint32_t *PR = T + 1, *ST = T + 1 + 4 * npairs;
+    const uint32_t lt = s_tile[team];
+    if (lt >= ntl) break;
+    const uint4 tw = __ldg(reinterpret_cast<const uint4 *>(a.tiles + t0 + lt));
+    const uint32_t nmem = tw.z;
+    const uint2 *P = a.prog + tw.x;
+    const uint2 h0 = __ldg(P), tr = __ldg(P + uplan::HDR_UNITS + wq);
+    const uint2 pc0 = __ldg(P + 1), pc1 = __ldg(P + 2), pc2 = __ldg(P + 3);
+    const uint32_t rowstride = h0.x, npieces = h0.y & 0xffu;
     const uint32_t le = min((uint32_t)lane, nmem - 1u);
     const uint32_t *ldp = a.ld + tw.y;
     const uint32_t *lpos = ldp + 64 + le;
-    const uint32_t jclo = __ldg(ldp + le);
+    const uint32_t jclo = __ldg(ldp + le), jchi = __ldg(ldp + 32 + le);
+    double *row = img + (size_t)lane * rowstride;
+    const uint32_t par0 = (jclo + pc0.x) & 1u, par1 = (jclo + pc1.x) & 1u, par2 = (jclo + pc2.x) & 1u;
 
-    double acc[KG][ACC];
+    if (tr.y > tr.x) {
+      double acc[KG][ACC];
 #pragma unroll
-    for (int p = 0; p < KG; ++p)
+      for (int p = 0; p < KG; ++p)
 #pragma unroll
-      for (int m = 0; m < ACC; ++m) acc[p][m] = 0.0;
+        for (int m = 0; m < ACC; ++m) acc[p][m] = 0.0;
+      // instruction stream [tr.x, tr.y) with a three-deep software pipeline: while instruction ip runs, the geometry row of
+      // ip+1, the strip position of ip+2 and the instruction word ip+3 are in flight
+      uint32_t ip = tr.x;
+      const uint32_t ipl = tr.y - 1u;
+      auto fetch = [&](uint32_t k) { return __ldg(P + min(k, ipl)); };  // past the end: the final FLUSH again (no loads follow)
+      auto is_step = [](const uint2 &I) { return (I.x & uplan::OP_FLUSH) == 0u; };
+      auto load_pos = [&](const uint2 &I) { return __ldg(lpos + (I.x & 0xfffu) * 32u); };
+      auto load_g = [&](double (&G)[GSZ], uint32_t pos) {
+        const double *gp = a.eg + (size_t)(pos >> 5) * (GSZ * 32) + (pos & 31u);
+#pragma unroll
+        for (int c = 0; c < GSZ; ++c) G[c] = __ldg(gp + c * 32);
+      };
+      uint2 I0 = fetch(ip), I1 = fetch(ip + 1), I2 = fetch(ip + 2);
+      double GA[GSZ], GB[GSZ];
+#pragma unroll
+      for (int c = 0; c < GSZ; ++c) GA[c] = GB[c] = 0.0;
+      uint32_t pos1 = 0;
+      if (is_step(I0)) load_g(GA, load_pos(I0));
+      if (is_step(I1)) pos1 = load_pos(I1);
 
-    if (nsteps > 0) {
-      // software pipeline: the geometry row of step s+1 and the strip position of step s+2 are in flight during step s
-      uint32_t sw0 = __ldg(ST), sw1 = __ldg(ST + 1);
-      uint32_t nw0 = 0, nw1 = 0, npos = 0;
-      double G[GSZ];
-      {
-        const uint32_t pos = __ldg(lpos + (sw0 & 0xffffu) * 32u);
-#pragma unroll
-        for (int c = 0; c < GSZ; ++c) G[c] = __ldg(a.eg + (size_t)c * a.nepad + pos);
-      }
-      if (nsteps > 1) {
-        nw0 = __ldg(ST + 2); nw1 = __ldg(ST + 3);
-        npos = __ldg(lpos + (nw0 & 0xffffu) * 32u);
-      }
-      for (int s = 0; s < nsteps; ++s) {
-        double Gn[GSZ];
-        uint32_t mw0 = 0, mw1 = 0, mpos = 0;
-        if (s + 1 < nsteps) {
-#pragma unroll
-          for (int c = 0; c < GSZ; ++c) Gn[c] = __ldg(a.eg + (size_t)c * a.nepad + npos);
-          if (s + 2 < nsteps) {
-            mw0 = __ldg(ST + 2 * (s + 2)); mw1 = __ldg(ST + 2 * (s + 2) + 1);
-            mpos = __ldg(lpos + (mw0 & 0xffffu) * 32u);
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < GSZ; ++c) Gn[c] = 0.0;
-        }
-        const uint32_t code[3] = {sw0 >> 16, sw1 & 0xffffu, sw1 >> 16};
-#pragma unroll
-        for (int p = 0; p < KG; ++p) {
-          if (p < npairs) {
-            double M[MTP];
-            const double2 *M2 = reinterpret_cast<const double2 *>(sM + code[p] * MTP);
-#pragma unroll
-            for (int q = 0; q < MTP / 2; ++q) {
-              const double2 v = M2[q];
-              M[2 * q] = v.x;
-              M[2 * q + 1] = v.y;
-            }
-            if (RF == TF_ELAST) {
-#pragma unroll
-              for (int qq = 0; qq < N; ++qq) {
-                double Wq[N];  // column qq of W = B~ M
-#pragma unroll
-                for (int aa = 0; aa < N; ++aa) {
-                  double s2 = 0;
-#pragma unroll
-                  for (int pp = 0; pp < N; ++pp) s2 += G[RF == TF_ELAST ? aa + N * pp : 0] * M[RF == TF_ELAST ? pp * N + qq : 0];
-                  Wq[aa] = s2;
-                }
-#pragma unroll
-                for (int b2 = 0; b2 < N; ++b2)
-#pragma unroll
-                  for (int aa = 0; aa < N; ++aa)
-                    acc[p][RF == TF_ELAST ? aa + N * b2 : 0] += Wq[aa] * G[RF == TF_ELAST ? b2 + N * qq : 0];
-              }
-            } else {
-              double s2 = acc[p][0];
-#pragma unroll
-              for (int k = 0; k < MT; ++k) s2 += M[k] * G[k];
-              acc[p][0] = s2;
-            }
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < GSZ; ++c) G[c] = Gn[c];
-        sw0 = nw0; sw1 = nw1;
-        nw0 = mw0; nw1 = mw1; npos = mpos;
-      }
-    }
-    // ---- the image buffer of this tile is free once the tile that used it before has left
-    while (s_freed[b] < need) __nanosleep(40);
-    const uint32_t rowstride = __ldg(P);
-    double *row = img0 + (size_t)b * a.imgcap + (size_t)lane * rowstride;
-    uint32_t par[3];
-#pragma unroll
-    for (int pc = 0; pc < 3; ++pc) par[pc] = (jclo + __ldg(P + 2 + 3 * pc)) & 1u;
-#pragma unroll
-    for (int p = 0; p < KG; ++p) {
-      if (p < npairs) {
-        const uint32_t pw = __ldg(PR + 4 * p);
+      auto flush_pair = [&](double (&A)[ACC], const uint2 &I) {
         double kv[Q * Q];  // kv[b2*Q + aa] = K(row component aa, column component b2)
         if (RF == TF_ELAST) {
-          double tr = 0;
+          double trc = 0;
 #pragma unroll
-          for (int n = 0; n < N; ++n) tr += acc[p][RF == TF_ELAST ? n + N * n : 0];
+          for (int n = 0; n < N; ++n) trc += A[RF == TF_ELAST ? n + N * n : 0];
 #pragma unroll
           for (int b2 = 0; b2 < Q; ++b2)
 #pragma unroll
             for (int aa = 0; aa < Q; ++aa)
-              kv[b2 * Q + aa] = a.sl * acc[p][RF == TF_ELAST ? aa + N * b2 : 0] + a.smu * acc[p][RF == TF_ELAST ? b2 + N * aa : 0] +
-                                (aa == b2 ? a.smu * tr : 0.0);
+              kv[b2 * Q + aa] = a.sl * A[RF == TF_ELAST ? aa + N * b2 : 0] + a.smu * A[RF == TF_ELAST ? b2 + N * aa : 0] +
+                                (aa == b2 ? a.smu * trc : 0.0);
         } else {
 #pragma unroll
           for (int b2 = 0; b2 < Q; ++b2)
 #pragma unroll
-            for (int aa = 0; aa < Q; ++aa) kv[b2 * Q + aa] = aa == b2 ? acc[p][0] : 0.0;
+            for (int aa = 0; aa < Q; ++aa) kv[b2 * Q + aa] = aa == b2 ? A[0] : 0.0;
         }
         if ((uint32_t)lane < nmem) {
 #pragma unroll
           for (int b2 = 0; b2 < Q; ++b2) {
-            const uint32_t piece = (pw >> (16 + 2 * b2)) & 3u;
-            double *dst = row + __ldg(PR + 4 * p + 1 + b2) + (piece == 0 ? par[0] : piece == 1 ? par[1] : par[2]);
-            const unsigned mb = (pw >> (b2 * Q)) & ((1u << Q) - 1);
-            if (Q == 3) {
-              const double v0 = kv[b2 * Q], v1 = kv[b2 * Q + (Q > 1 ? 1 : 0)], v2 = kv[b2 * Q + (Q > 2 ? 2 : 0)];
-              const int n = __popc(mb);
-              const double x0 = (mb & 1u) ? v0 : ((mb & 2u) ? v1 : v2);
-              const double x1 = ((mb & 3u) == 3u) ? v1 : v2;
-              if (n >= 1) dst[0] = x0;
-              if (n >= 2) dst[1] = x1;
-              if (n >= 3) dst[2] = v2;
+            const uint32_t piece = (I.x >> (9 + 2 * b2)) & 3u;
+            double *dst = row + ((I.y >> (10 * b2)) & 0x3ffu) + (piece == 0 ? par0 : piece == 1 ? par1 : par2);
+            const unsigned mb = (I.x >> (b2 * Q)) & ((1u << Q) - 1);
+            if (mb == (1u << Q) - 1) {  // the mask is the same for every lane: the common case takes no selects
+#pragma unroll
+              for (int aa = 0; aa < Q; ++aa) dst[aa] = kv[b2 * Q + aa];
             } else {
 #pragma unroll
               for (int aa = 0; aa < Q; ++aa)
@@ -408,45 +384,75 @@ k_utiles(const UArgs a) {
             }
           }
         }
-      }
-    }
-    // ---- my stores (generic proxy) before the bulk store (async proxy) of whoever finishes the tile
-    fence_async_smem();
-    __syncwarp();
-    unsigned last = 0;
-    if (lane == 0) {
-      __threadfence_block();
-      last = atomicAdd(&s_done[b], 1u) == ntasks - 1u ? 1u : 0u;
-    }
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) {
-      __threadfence_block();
-      fence_async_smem();
-      if ((uint32_t)lane < nmem) {
-        const int64_t jc = (int64_t)(((uint64_t)__ldg(ldp + 32 + le) << 32) | jclo);
-        const uint32_t npieces = __ldg(P + 1);
-        for (uint32_t pc = 0; pc < npieces; ++pc) {
-          const int64_t len = __ldg(P + 3 + 3 * pc);
-          if (!len) continue;
-          const int64_t gstart = jc + __ldg(P + 2 + 3 * pc);
-          const int64_t odd = gstart & 1, gs = gstart + odd, ge = (gstart + len) & ~int64_t(1);
-          const double *src = row + __ldg(P + 4 + 3 * pc) + odd;  // entry e of the piece sits at src[e]
-          if (odd) a.pr[gstart] = src[0];
-          if (ge > gs) bulk_s2g(a.pr + gs, src + odd, (uint32_t)((ge - gs) * 8));
-          if (((gstart + len) & 1) && gstart + len - 1 >= gs) a.pr[gstart + len - 1] = src[len - 1];
+#pragma unroll
+        for (int m = 0; m < ACC; ++m) A[m] = 0.0;
+      };
+
+      auto phase = [&](double (&Gc)[GSZ], double (&Gn)[GSZ]) {
+        const uint2 I3 = fetch(ip + 3);
+        uint32_t pos2 = 0;
+        if (is_step(I2)) pos2 = load_pos(I2);
+        if (is_step(I1)) load_g(Gn, pos1);
+        if (is_step(I0)) {
+          const int npairs = (int)((I0.x >> 28) & 3u);
+          const uint32_t code[3] = {(I0.x >> 12) & 0x3ffu, I0.y & 0x3ffu, (I0.y >> 10) & 0x3ffu};
+#pragma unroll
+          for (int p = 0; p < KG; ++p) {
+            if (p < npairs) {
+              double M[MTP];
+              const double2 *M2 = reinterpret_cast<const double2 *>(sM + code[p] * MTP);
+#pragma unroll
+              for (int q = 0; q < MTP / 2; ++q) {
+                const double2 v = M2[q];
+                M[2 * q] = v.x;
+                M[2 * q + 1] = v.y;
+              }
+              if (RF == TF_ELAST) {
+#pragma unroll
+                for (int qq = 0; qq < N; ++qq) {
+                  double Wq[N];  // column qq of W = B~ M
+#pragma unroll
+                  for (int aa = 0; aa < N; ++aa) {
+                    double s2 = Gc[RF == TF_ELAST ? aa : 0] * M[RF == TF_ELAST ? qq : 0];
+#pragma unroll
+                    for (int pp = 1; pp < N; ++pp) s2 += Gc[RF == TF_ELAST ? aa + N * pp : 0] * M[RF == TF_ELAST ? pp * N + qq : 0];
+                    Wq[aa] = s2;
+                  }
+#pragma unroll
+                  for (int b2 = 0; b2 < N; ++b2)
+#pragma unroll
+                    for (int aa = 0; aa < N; ++aa)
+                      acc[p][RF == TF_ELAST ? aa + N * b2 : 0] += Wq[aa] * Gc[RF == TF_ELAST ? b2 + N * qq : 0];
+                }
+              } else {
+                double s2 = acc[p][0];
+#pragma unroll
+                for (int k = 0; k < MT; ++k) s2 += M[k] * Gc[k];
+                acc[p][0] = s2;
+              }
+            }
+          }
+        } else {
+          const uint32_t slot = (I0.x >> 15) & 3u;
+          if (slot == 0) flush_pair(acc[0], I0);
+          else if (slot == 1) flush_pair(acc[1], I0);
+          else flush_pair(acc[2], I0);
         }
-        bulk_commit();
-        bulk_wait_read0();
-      }
-      __syncwarp();
-      if (lane == 0) {
-        s_done[b] = 0;
-        __threadfence_block();
-        s_freed[b] = need + 1u;
+        I0 = I1; I1 = I2; I2 = I3;
+        pos1 = pos2;
+      };
+      for (;;) {
+        phase(GA, GB);
+        if (++ip > ipl) break;
+        phase(GB, GA);
+        if (++ip > ipl) break;
       }
     }
+    team_barrier(team);  // the image of the tile is complete
+    if (wq == 0 && lane == 0) s_tile[team] = atomicAdd(&s_next, 1u);  // everybody has read the old value before the barrier
+    ut_flush_rows(img, a.pr, rowstride, nmem, wq, lane, jclo, jchi, npieces, pc0, pc1, pc2);
+    team_barrier(team);  // the image may be overwritten; s_tile[team] is the next tile
   }
-  bulk_wait0();
 }
 
 // ---------------------------------------------------------------- host side
@@ -548,19 +554,20 @@ bool uniform_prepare(gfgpu_term *t) {
   GF_CUDA(cudaStreamSynchronize(s));
   dlen.release(); llen.release();
 
-  const int nbuf = std::max(1, std::min(uenv_int("GFGPU_UT_NBUF", 3), UT_MAXBUF));
-  const int img_bytes = std::max(8192, std::min(uenv_int("GFGPU_UT_IMG", 40960), 200 * 1024));
+  const int img_bytes = std::max(8192, std::min(uenv_int("GFGPU_UT_IMG", 51200), 200 * 1024));
   const uint32_t row_cap = (uint32_t)(img_bytes / 8 / 32);
-  const int task_cap = std::max(1, uenv_int("GFGPU_UT_TASKCAP", 16));
+  const int group_cap = std::max(1, uenv_int("GFGPU_UT_TASKCAP", 24));  // contributions per group of pairs
   std::vector<uint32_t> prog;
   std::vector<uplan::ClassPlan> cplan(ncls);
   uint32_t max_stride = 2;
   for (int64_t c = 0; c < ncls; ++c) {
     std::string err;
-    const bool ok = uplan::build_class(h_desc.data() + (size_t)c * dw, h_llen[c], Q, nd, row_cap, task_cap, prog, cplan[c], err);
+    const bool ok = uplan::build_class(h_desc.data() + (size_t)c * dw, h_llen[c], Q, nd, row_cap, group_cap, UT_TW, prog,
+                                       cplan[c], err);
     GF_REQUIRE(ok, "uniform plan: " + err);
     for (const uplan::Sub &sb : cplan[c].subs) max_stride = std::max(max_stride, sb.rowstride);
     GF_REQUIRE(prog.size() < (size_t(1) << 31), "uniform plan: programs too large");
+    GF_REQUIRE(cplan[c].m <= 4096, "uniform plan: column valence beyond the instruction format");
   }
   // ---- chunks of 32 class members, in the order of their first column; tiles = chunk x sub-range
   struct HChunk { uint32_t pos0, cls, nmem, first; };
@@ -581,8 +588,8 @@ bool uniform_prepare(gfgpu_term *t) {
     chunks[q] = {hch[q].pos0, hch[q].cls, (uint32_t)ldw, hch[q].nmem};
     for (const uplan::Sub &sb : cp.subs) {
       UTile tl;
-      tl.prog = sb.prog; tl.ld = (uint32_t)ldw; tl.task0 = (uint32_t)ntask;
-      tl.nmem = (uint16_t)hch[q].nmem; tl.ntasks = (uint16_t)sb.ntasks;
+      tl.prog = sb.prog; tl.ld = (uint32_t)ldw;
+      tl.nmem = hch[q].nmem; tl.pad = 0;
       tiles.push_back(tl);
       wtot += sb.weight;
       wsum.push_back(wtot);
@@ -592,11 +599,6 @@ bool uniform_prepare(gfgpu_term *t) {
   }
   GF_REQUIRE(ntask < (uint64_t(1) << 32) && tiles.size() < (size_t(1) << 31), "uniform plan: too many tasks");
   const int64_t ntiles = (int64_t)tiles.size();
-  {
-    UTile sentinel;
-    sentinel.prog = 0; sentinel.ld = 0; sentinel.task0 = (uint32_t)ntask; sentinel.nmem = 1; sentinel.ntasks = 0;
-    tiles.push_back(sentinel);
-  }
   const int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * std::max(1, uenv_int("GFGPU_UT_CTAS_PER_SM", 1)));
   std::vector<uint32_t> cta_t0(grid + 1, 0);
   {
@@ -644,7 +646,7 @@ bool uniform_prepare(gfgpu_term *t) {
   t->ru_nepad = nepad;
   t->ru_eg.alloc(ctx, (size_t)nepad * GSZ);
   t->ru_eg.zero();
-  k_ut_eg_soa<<<ugrid(ne * GSZ, B), B, 0, s>>>(t->rc_eg.p, GSZ, ne, epos.p, nepad, t->ru_eg.p);
+  k_ut_eg_blocked<<<ugrid(ne * GSZ, B), B, 0, s>>>(t->rc_eg.p, GSZ, ne, epos.p, t->ru_eg.p);
   GF_LAUNCH_CHECK();
   // ---- lane data (with the check that every member really has its leader's descriptor)
   t->ru_ld.alloc(ctx, std::max<uint64_t>(ldw, 1));
@@ -658,7 +660,7 @@ bool uniform_prepare(gfgpu_term *t) {
     GF_REQUIRE(err == 0, "uniform plan failed (code " + std::to_string(err) + ")");
   }
   t->ru_grid = grid;
-  t->ru_nbuf = nbuf;
+  t->ru_nbuf = UT_TEAMS;
   t->ru_imgcap = (int)(32 * max_stride);
   t->ru_ntiles = ntiles;
   t->ru_ntasks = (int64_t)ntask;
@@ -670,7 +672,7 @@ bool uniform_prepare(gfgpu_term *t) {
             "[gfgpu] uniform tiles: %lld columns in %lld classes (%lld with >= 32 members), %lld chunks, %lld tiles, %llu tasks, "
             "programs %.1f KB, lane data %.1f MB, image %d B x %d, grid %d\n",
             (long long)ncol, (long long)ncls, (long long)big, (long long)chunks.size(), (long long)ntiles,
-            (unsigned long long)ntask, prog.size() * 4 / 1024.0, ldw * 4 / 1048576.0, t->ru_imgcap * 8, nbuf, grid);
+            (unsigned long long)ntask, prog.size() * 4 / 1024.0, ldw * 4 / 1048576.0, t->ru_imgcap * 8, UT_TEAMS, grid);
   }
   if (!t->halo) t->prel.release();
   t->rc_uni = true;
@@ -685,16 +687,14 @@ static void launch_utiles(gfgpu_term *t) {
   UArgs a;
   a.tiles = (const UTile *)t->ru_tiles.p;
   a.cta_t0 = t->ru_cta.p;
-  a.prog = t->ru_prog.p;
+  a.prog = (const uint2 *)t->ru_prog.p;
   a.ld = t->ru_ld.p;
   a.eg = t->ru_eg.p;
-  a.nepad = t->ru_nepad;
   a.Mtab = t->rc_M.p;
   a.sl = sign * t->par[0]; a.smu = sign * t->par[1];
   a.pr = t->pr.p;
-  a.nbuf = t->ru_nbuf;
   a.imgcap = t->ru_imgcap;
-  const size_t smem = (size_t)((ND * ND * MTP + 15) & ~15) * 8 + (size_t)a.nbuf * a.imgcap * 8;
+  const size_t smem = (size_t)((ND * ND * MTP + 15) & ~15) * 8 + (size_t)UT_TEAMS * a.imgcap * 8;
   GF_REQUIRE(smem <= 226 * 1024, "uniform tiles: image buffers too large for shared memory (GFGPU_UT_IMG / GFGPU_UT_NBUF)");
   auto kern = k_utiles<N, Q, ND, RF>;
   GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

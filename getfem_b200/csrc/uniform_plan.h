@@ -9,16 +9,16 @@
 // through ONE program built here from the descriptor of the class leader; what differs between the lanes -- the CSC
 // base jc[J] and the elements of the incidence list -- is per-lane data.
 //
-// Program of a (class, sub-range of its pairs), 32-bit words:
-//   [0] row stride of the tile image (doubles per lane)     [1] pieces (1 .. Q)
-//   [2+3b ..] piece b: first entry relative to jc[J], entries, position inside the lane's image row (even)
-//   [11] tasks       [12 + g] offset of task g's record (from the program start)
-//   task record: [pairs | steps << 8]
-//                per pair : [keep mask | piece of component 0 << 16 | of component 1 << 18 | of component 2 << 20]
-//                           [offset of the pair's first kept entry of component b inside the row, parity excluded] x 3
-//                per step : [rank | code of pair 0 << 16] [code of pair 1 | code of pair 2 << 16]
-// A task = up to KGU pairs of the column that are fed by the SAME elements: the geometry row of a step is loaded once
-// and serves all of them (register-level operand reuse).
+// Program of a (class, sub-range of its pairs): an array of 8-byte units (two 32-bit words each)
+//   unit 0            : [row stride of the tile image (doubles per lane)] [pieces (1 .. Q) | tasks << 8]
+//   unit 1 + b, b < 3 : piece b: [first entry relative to jc[J]] [entries | position inside the lane's image row (even) << 16]
+//   unit 4 + t        : task t: [first instruction] [one past its last instruction]   (unit indices from the program start)
+//   then the instruction stream.  A task is a sequence of GROUPS; a group = up to KGU node pairs of the column that are fed by
+//   the SAME elements (the geometry row of a step is loaded once and serves all of them: register-level operand reuse):
+//     STEP   x = rank of the element (bits 0-11) | code j*nd+i of pair 0 (12-21) | pairs of the group (28-29) | 0 << 30
+//            y = code of pair 1 (0-9) | code of pair 2 (10-19)
+//     FLUSH  x = keep mask (0-8) | piece of component 0, 1, 2 (9-10, 11-12, 13-14) | pair of the group (15-16) | 1 << 30
+//            y = offset of the pair's first kept entry of component 0 | 1 << 10 | 2 << 20 inside the row (parity excluded)
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -29,11 +29,12 @@
 namespace gf {
 namespace uplan {
 
-constexpr int KGU = 3;   // pairs per task
-constexpr int HDR = 12;  // header words in front of the task offset table
+constexpr int KGU = 3;         // pairs per group
+constexpr int HDR_UNITS = 4;   // units in front of the task table
+constexpr uint32_t OP_FLUSH = 1u << 30;
 
 struct Sub {
-  uint32_t prog;    // word offset of the program
+  uint32_t prog;    // unit offset of the program
   uint32_t ntasks;
   uint32_t weight;  // cost estimate of one tile running this program (arbitrary units)
   uint32_t rowstride;
@@ -56,13 +57,16 @@ struct PairD {
   const uint32_t *codes;
 };
 
-// Appends the programs of one class to `prog`.  row_cap = largest row stride that fits the image buffers,
-// task_cap = contributions per task above which a group of pairs is cut.  Returns false with `err` set on failure.
-inline bool build_class(const uint32_t *d, size_t dlen, int Q, int nd, uint32_t row_cap, int task_cap,
+// Appends the programs of one class to `prog` (8-byte units as pairs of words).  row_cap = largest row stride that fits the
+// image buffers, group_cap = contributions above which a group of pairs is cut, ntasks = tasks per tile = warps of the team
+// that runs a tile (the groups are packed into them longest-processing-time first; a task may be empty).  Returns false with
+// `err` set on failure.
+inline bool build_class(const uint32_t *d, size_t dlen, int Q, int nd, uint32_t row_cap, int group_cap, int ntasks,
                         std::vector<uint32_t> &prog, ClassPlan &out, std::string &err) {
   if (dlen < (size_t)(2 + Q)) { err = "short descriptor"; return false; }
   const uint32_t np = d[0];
   out.m = (int)d[1];
+  if (d[1] > 4096u || nd * nd > 1024) { err = "column valence / element size beyond the instruction format"; return false; }
   uint32_t coloff[4] = {0, 0, 0, 0};
   for (int b = 0; b < Q; ++b) coloff[b + 1] = d[2 + b];
   std::vector<PairD> pr(np);
@@ -112,69 +116,88 @@ inline bool build_class(const uint32_t *d, size_t dlen, int Q, int nd, uint32_t 
     }
     const uint32_t rowlen = layout(a, e, pc, npc);
     const uint32_t stride = row_stride_for(rowlen);
-    if (stride > row_cap) { err = "a single node pair does not fit the tile image"; return false; }
+    if (stride > row_cap || stride > 1023u) { err = "a single node pair does not fit the tile image"; return false; }
+    for (int b = 0; b < npc; ++b)
+      if (pc[b].len > 0xffffu) { err = "column too long for the instruction format"; return false; }
     // ---- groups of pairs with the same element list
-    std::map<std::vector<uint16_t>, std::vector<uint32_t>> groups;
+    std::map<std::vector<uint16_t>, std::vector<uint32_t>> bylist;
     for (uint32_t p = a; p < e; ++p) {
       std::vector<uint16_t> key(pr[p].cntl);
       for (uint32_t c = 0; c < pr[p].cntl; ++c) key[c] = (uint16_t)(pr[p].codes[c] >> 16);
-      groups[key].push_back(p);
+      bylist[key].push_back(p);
     }
-    struct Task { std::vector<uint32_t> pairs; uint32_t steps, weight; };
-    std::vector<Task> tasks;
-    for (auto &g : groups) {
+    struct Group { std::vector<uint32_t> pairs; uint32_t steps, weight; };
+    std::vector<Group> groups;
+    uint32_t wtot = 0, wmax = 0;
+    for (auto &g : bylist) {
       const uint32_t steps = (uint32_t)g.first.size();
-      if (steps > 0xffffffu) { err = "too many contributions in one pair"; return false; }
-      int cs = steps ? task_cap / (int)steps : KGU;
+      int cs = steps ? group_cap / (int)steps : KGU;
       cs = std::max(1, std::min(KGU, cs));
       for (size_t q = 0; q < g.second.size(); q += cs) {
-        Task t;
+        Group t;
         t.steps = steps;
         for (size_t k = q; k < std::min(g.second.size(), q + cs); ++k) t.pairs.push_back(g.second[k]);
-        t.weight = 8u + (uint32_t)t.pairs.size() * (steps * 6u + 3u) + steps * 2u;
-        tasks.push_back(t);
+        t.weight = (uint32_t)t.pairs.size() * (steps * 6u + 4u) + steps * 2u;
+        wtot += t.weight;
+        wmax = std::max(wmax, t.weight);
+        groups.push_back(t);
       }
     }
-    std::stable_sort(tasks.begin(), tasks.end(), [](const Task &x, const Task &y) { return x.weight > y.weight; });
-    if (tasks.size() > 0xffffu) { err = "too many tasks in one tile"; return false; }
+    // ---- tasks: longest-processing-time packing of the groups into bins of about task_weight
+    std::stable_sort(groups.begin(), groups.end(), [](const Group &x, const Group &y) { return x.weight > y.weight; });
+    (void)wmax;
+    const size_t nbins = (size_t)std::max(1, ntasks);  // one task per warp of the team that runs the tile (some may be empty)
+    std::vector<std::vector<size_t>> bins(nbins);
+    std::vector<uint32_t> binw(nbins, 0);
+    for (size_t g = 0; g < groups.size(); ++g) {
+      size_t best = 0;
+      for (size_t k = 1; k < nbins; ++k)
+        if (binw[k] < binw[best]) best = k;
+      bins[best].push_back(g);
+      binw[best] += groups[g].weight;
+    }
+    std::vector<size_t> order(nbins);
+    for (size_t k = 0; k < nbins; ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return binw[x] > binw[y]; });
+    if (nbins > 0xffffu) { err = "too many tasks in one tile"; return false; }
     // ---- emit
     Sub sub;
-    sub.prog = (uint32_t)prog.size();
-    sub.ntasks = (uint32_t)tasks.size();
+    sub.prog = (uint32_t)(prog.size() / 2);
+    sub.ntasks = (uint32_t)nbins;
     sub.rowstride = stride;
-    sub.weight = 0;
+    sub.weight = *std::max_element(binw.begin(), binw.end()) + 60u;  // a tile lasts as long as its longest task (+ flush)
     const size_t base = prog.size();
-    prog.resize(base + HDR + tasks.size(), 0u);
+    prog.resize(base + 2 * (HDR_UNITS + nbins), 0u);
     prog[base + 0] = stride;
-    prog[base + 1] = (uint32_t)npc;
+    prog[base + 1] = (uint32_t)npc | ((uint32_t)nbins << 8);
     for (int b = 0; b < 3; ++b) {
-      prog[base + 2 + 3 * b] = pc[b].goff;
-      prog[base + 3 + 3 * b] = b < npc ? pc[b].len : 0u;
-      prog[base + 4 + 3 * b] = pc[b].pbase;
+      prog[base + 2 * (1 + b)] = pc[b].goff;
+      prog[base + 2 * (1 + b) + 1] = (b < npc ? pc[b].len : 0u) | (pc[b].pbase << 16);
     }
-    prog[base + 11] = (uint32_t)tasks.size();
-    for (size_t g = 0; g < tasks.size(); ++g) {
-      const Task &t = tasks[g];
-      prog[base + HDR + g] = (uint32_t)(prog.size() - base);
-      sub.weight += t.weight;
-      prog.push_back((uint32_t)t.pairs.size() | (t.steps << 8));
-      for (uint32_t p : t.pairs) {
-        uint32_t w0 = pr[p].mask, off[3] = {0, 0, 0};
-        for (int b = 0; b < Q; ++b) {
-          const int piece = npc == 1 ? 0 : b;
-          w0 |= (uint32_t)piece << (16 + 2 * b);
-          off[b] = pc[piece].pbase + (coloff[b] + pr[p].prel[b] - pc[piece].goff);
+    for (size_t t = 0; t < nbins; ++t) {
+      prog[base + 2 * (HDR_UNITS + t)] = (uint32_t)((prog.size() - base) / 2);
+      for (size_t gi : bins[order[t]]) {
+        const Group &g = groups[gi];
+        for (uint32_t s = 0; s < g.steps; ++s) {
+          uint32_t code[KGU] = {0, 0, 0};
+          for (size_t k = 0; k < g.pairs.size(); ++k) code[k] = pr[g.pairs[k]].codes[s] & 0xffffu;
+          const uint32_t rank = pr[g.pairs[0]].codes[s] >> 16;
+          prog.push_back(rank | (code[0] << 12) | ((uint32_t)g.pairs.size() << 28));
+          prog.push_back(code[1] | (code[2] << 10));
         }
-        prog.push_back(w0);
-        prog.push_back(off[0]); prog.push_back(off[1]); prog.push_back(off[2]);
+        for (size_t k = 0; k < g.pairs.size(); ++k) {
+          const uint32_t p = g.pairs[k];
+          uint32_t x = OP_FLUSH | pr[p].mask | ((uint32_t)k << 15), off[3] = {0, 0, 0};
+          for (int b = 0; b < Q; ++b) {
+            const int piece = npc == 1 ? 0 : b;
+            x |= (uint32_t)piece << (9 + 2 * b);
+            off[b] = pc[piece].pbase + (coloff[b] + pr[p].prel[b] - pc[piece].goff);
+          }
+          prog.push_back(x);
+          prog.push_back(off[0] | (off[1] << 10) | (off[2] << 20));
+        }
       }
-      for (uint32_t s = 0; s < t.steps; ++s) {
-        uint32_t code[KGU] = {0, 0, 0};
-        for (size_t k = 0; k < t.pairs.size(); ++k) code[k] = pr[t.pairs[k]].codes[s] & 0xffffu;
-        const uint32_t rank = pr[t.pairs[0]].codes[s] >> 16;
-        prog.push_back(rank | (code[0] << 16));
-        prog.push_back(code[1] | (code[2] << 16));
-      }
+      prog[base + 2 * (HDR_UNITS + t) + 1] = (uint32_t)((prog.size() - base) / 2);
     }
     out.subs.push_back(sub);
     a = e;

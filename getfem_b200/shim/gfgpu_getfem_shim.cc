@@ -144,9 +144,11 @@ void set_reference_assembly(void (*f)(getfem::ga_workspace &, size_type)) { g_re
 
 static bool probe_matrix(const getfem::ga_workspace &ws, const std::string &v, const getfem::mesh_fem &mf, const getfem::mesh_im &mim,
                          const getfem::mesh_region &rg, const std::string &expr, std::vector<double> &dense,
-                         const std::vector<size_type> &dofs) {
+                         const std::vector<size_type> &dofs, const getfem::model_real_plain_vector *private_state = nullptr) {
   try {
     getfem::ga_workspace w2(ws, getfem::ga_workspace::inherit::ALL);  // sees the variables and constants of the caller
+    // a PRIVATE state of the unknown shadows the caller's (own variables are looked up first, workspace.cc:328-339)
+    if (private_state) w2.add_fem_variable(v, mf, ws.interval_of_variable(v), *private_state);
     w2.add_expression(expr, mim, rg, 2);
     getfem::model_real_sparse_matrix K(ws.nb_primary_dof() ? ws.nb_primary_dof() : mf.nb_dof(),
                                        ws.nb_primary_dof() ? ws.nb_primary_dof() : mf.nb_dof());
@@ -301,9 +303,22 @@ static bool recognise_by_probe(const getfem::ga_workspace &ws, size_type itree, 
   const std::string v = td.name_test1;
   const getfem::mesh_fem *pmf = ws.associated_mf(v);
   if (!pmf || pmf->is_reduced() || !td.mim || !td.rg) return false;
-  if (!probe_is_safe(ws, v, getfem::ga_tree_to_string(*td.ptree), false) ||
-      !probe_is_safe(ws, v, getfem::ga_tree_to_string(*td0.ptree), td0.order == 1))
+  // the tangent tree may mention the unknown and still be state independent (sqr(Norm(Grad_u))/2 differentiates into
+  // Norm(Grad_u)*Derivative_1_Norm(..)): such a tree is then probed at TWO private random states, never at the caller's
+  const bool k_mentions_u = !probe_is_safe(ws, v, getfem::ga_tree_to_string(*td.ptree), false);
+  if (!probe_is_safe(ws, v, getfem::ga_tree_to_string(*td.ptree), true) ||
+      !probe_is_safe(ws, v, getfem::ga_tree_to_string(*td0.ptree), true))
     return false;
+  if (k_mentions_u && td0.order != 1) {
+    // asked about the tangent tree itself: fine when it is the derivative of an order-1 tree (same two-state check below);
+    // a DIRECTLY written "bilinear" form that mentions the unknown has a state-dependent coefficient
+    bool derived = false;
+    for (size_type j = 0; j < ws.nb_trees() && !derived; ++j) {
+      const auto &t1 = ws.tree_info(j);
+      derived = t1.order == 1 && t1.mim == td.mim && t1.rg == td.rg && t1.name_test1 == v;
+    }
+    if (!derived) return false;
+  }
   const getfem::mesh &m = pmf->linked_mesh();
   const size_type Q = pmf->get_qdim(), N = m.dim();
   getfem::mesh_region rg2;
@@ -319,10 +334,32 @@ static bool recognise_by_probe(const getfem::ga_workspace &ws, size_type itree, 
   std::sort(dofs.begin(), dofs.end());
   dofs.erase(std::unique(dofs.begin(), dofs.end()), dofs.end());
   std::vector<double> K, A, B;
-  if (!probe_matrix(ws, v, *pmf, *td.mim, rg2, getfem::ga_tree_to_string(*td.ptree), K, dofs)) return false;
+  if (k_mentions_u) {
+    getfem::model_real_plain_vector Ua(pmf->nb_dof()), Ub(pmf->nb_dof());
+    uint64_t sd = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&sd]() {  // splitmix64 -> (-1, 1)
+      sd += 0x9E3779B97F4A7C15ull;
+      uint64_t z = sd;
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      z ^= z >> 31;
+      return double(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+    };
+    for (double &x : Ua) x = rnd();
+    for (double &x : Ub) x = 3.0 * rnd();
+    std::vector<double> Kb;
+    if (!probe_matrix(ws, v, *pmf, *td.mim, rg2, getfem::ga_tree_to_string(*td.ptree), K, dofs, &Ua) ||
+        !probe_matrix(ws, v, *pmf, *td.mim, rg2, getfem::ga_tree_to_string(*td.ptree), Kb, dofs, &Ub))
+      return false;
+    double na = 0, dab = 0;
+    for (size_t k = 0; k < K.size(); ++k) { na += K[k] * K[k]; dab += (K[k] - Kb[k]) * (K[k] - Kb[k]); }
+    if (!(dab <= 1e-22 * na)) return false;  // the tangent moves with the state (or is not finite): a nonlinear form
+  } else if (!probe_matrix(ws, v, *pmf, *td.mim, rg2, getfem::ga_tree_to_string(*td.ptree), K, dofs)) {
+    return false;
+  }
   double nK = 0;
   for (double x : K) nK += x * x;
-  if (nK == 0) return false;
+  if (!(nK > 0)) return false;
   if (td0.order == 1) {
     std::vector<double> r;
     if (!probe_vector(ws, v, *pmf, *td.mim, rg2, getfem::ga_tree_to_string(*td0.ptree), r, dofs)) return false;
@@ -501,7 +538,23 @@ static bool recognise_string(const getfem::ga_workspace &ws, const std::string &
   return false;
 }
 
+// A cached device term mirrors a getfem::mesh / mesh_fem / mesh_im.  It registers as a context dependent of the three
+// (getfem_context.h): mesh::translation / transformation / refinement, set_finite_element, set_integration_method ... all
+// touch() their dependents, and the destruction of any of them invalidates the context -- either way the entry is dropped at
+// the next lookup, so moved nodes or a new object at a recycled address never meet stale device data.
+struct context_watcher : public getfem::context_dependencies {
+  mutable bool stale = false;
+  void update_from_context() const override { stale = true; }
+  bool still_valid() const {
+    if (!is_context_valid()) return false;
+    context_check();
+    return !stale && is_context_valid();
+  }
+};
+
 struct device_assembler::entry {
+  context_watcher watch;
+  uint64_t last_use = 0;
   gfgpu_mesh *mesh = nullptr;
   gfgpu_fem *fem = nullptr;
   gfgpu_fem *dfem = nullptr;  // data fem of the fem-data coefficients
@@ -539,6 +592,18 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
   double t0 = now_s();
   // ---- every order-1 tree must be a recognised family (the order-2 trees are their derivatives)
   std::vector<std::pair<size_type, recognised_term>> terms;
+  // recognition (with its probe assemblies) runs once per tree and call, whoever asks
+  std::map<size_type, std::pair<bool, std::vector<recognised_term>>> memo;
+  auto recognise_memo = [&](size_type i, std::vector<recognised_term> &out) {
+    auto it = memo.find(i);
+    if (it == memo.end()) {
+      std::vector<recognised_term> r;
+      const bool ok = recognise_tree_sum(ws, i, r);
+      it = memo.emplace(i, std::make_pair(ok, std::move(r))).first;
+    }
+    out = it->second.second;
+    return it->second.first;
+  };
   for (size_type i = 0; i < ws.nb_trees(); ++i) {
     const auto &td = ws.tree_info(i);
     if (td.order == 0) continue;
@@ -557,7 +622,7 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
         // a direct order-2 expression on the same region would have been SUMMED into this tree by add_tree: the number of
         // top-level summands must be that of the order-1 tree minus its source terms
         std::vector<recognised_term> r1;
-        GMM_ASSERT1(recognise_tree_sum(ws, i1, r1), "gfgpu: expression not handled by the device path (no CPU fallback): "
+        GMM_ASSERT1(recognise_memo(i1, r1), "gfgpu: expression not handled by the device path (no CPU fallback): "
                                                         << getfem::ga_tree_to_string(*ws.tree_info(i1).ptree));
         if (r1.size() == 1 && r1[0].by_probe) continue;  // the probe checked K against THIS tree and r = K u against the order-1 tree
         size_t nsrc = 0;
@@ -570,15 +635,23 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
       }
       if (order != 2) continue;  // a directly written bilinear form contributes to the matrix only
       std::vector<recognised_term> r2;
-      GMM_ASSERT1(recognise_tree_sum(ws, i, r2), "gfgpu: expression not handled by the device path (no CPU fallback): "
+      GMM_ASSERT1(recognise_memo(i, r2), "gfgpu: expression not handled by the device path (no CPU fallback): "
                                                      << getfem::ga_tree_to_string(*td.ptree));
       for (const recognised_term &rt : r2) terms.emplace_back(i, rt);
       continue;
     }
     std::vector<recognised_term> rts;
-    GMM_ASSERT1(recognise_tree_sum(ws, i, rts), "gfgpu: expression not handled by the device path (no CPU fallback): "
-                                                    << getfem::ga_tree_to_string(*td.ptree));
-    for (const recognised_term &rt : rts) terms.emplace_back(i, rt);
+    GMM_ASSERT1(recognise_memo(i, rts), "gfgpu: expression not handled by the device path (no CPU fallback): "
+                                            << getfem::ga_tree_to_string(*td.ptree));
+    bool has_derivative = false;  // only the order-2 trees that exist are assembled (workspace.cc:791-936)
+    for (size_type j = 0; j < ws.nb_trees() && !has_derivative; ++j) {
+      const auto &t2 = ws.tree_info(j);
+      has_derivative = t2.order == 2 && t2.mim == td.mim && t2.rg == td.rg && t2.name_test1 == td.name_test1;
+    }
+    for (recognised_term &rt : rts) {
+      rt.no_tangent = order == 2 && !has_derivative;
+      terms.emplace_back(i, rt);
+    }
   }
   GMM_ASSERT1(!terms.empty(), "gfgpu: nothing to assemble");
   t_extract = t_device = t_fill = 0;
@@ -632,9 +705,6 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     bgeot::pgeometric_trans pgt = m.trans_of_convex(cv0);
     getfem::pintegration_method pim = mim.int_method_of_element(cv0);
     GMM_ASSERT1(pim->type() == getfem::IM_APPROX, "gfgpu: exact integration methods are not handled");
-    for (dal::bv_visitor cv(m.convex_index()); !cv.finished(); ++cv)
-      GMM_ASSERT1(mf.fem_of_element(cv) == pf && m.trans_of_convex(cv) == pgt && mim.int_method_of_element(cv) == pim,
-                  "gfgpu: mixed fems / transformations / integration methods are not handled");
     bool fqk, gqk;
     int fdim, fdeg, gdim, gdeg;
     GMM_ASSERT1(parse_kind(getfem::name_of_fem(pf), "FEM", fqk, fdim, fdeg),
@@ -649,7 +719,11 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     std::ostringstream key;
     key << &m << "/" << &mf << "/" << &mim << "/" << rt.family << "/" << ne << "/" << ndof << "/" << fdeg << "/"
         << getfem::name_of_int_method(pim);
-    for (double p : rt.params) key << "/" << p;
+    {  // parameters bit for bit (a load that changes by 1e-9 is another term), and the family's own scale stays 1:
+       // factor_of_variable enters at gfgpu_matrix_add_term for order 2 only, like the reference (C&E.cc:5359-5418 vs 4669-4735)
+      char hb[40];
+      for (double p : rt.params) { std::snprintf(hb, sizeof hb, "/%a", p); key << hb; }
+    }
     for (const std::string &fn : rt.field_names) key << "/field:" << fn << "@" << ws.associated_mf(fn);
     if (!all_cv) {  // the region's content is part of the key (FNV-1a over the items)
       uint64_t h = 1469598103934665603ull;
@@ -659,11 +733,28 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
       }
       key << "/rg" << rg_cv.size() << ":" << h;
     }
+    {  // drop what the context says is stale, and the least recently used entries beyond the cache bound
+      auto it = cache_.find(key.str());
+      if (it != cache_.end() && !it->second->watch.still_valid()) cache_.erase(it);
+      const size_t cache_max = 12;
+      while (cache_.size() >= cache_max && cache_.find(key.str()) == cache_.end()) {
+        auto lru = cache_.begin();
+        for (auto jt = cache_.begin(); jt != cache_.end(); ++jt)
+          if (jt->second->last_use < lru->second->last_use) lru = jt;
+        cache_.erase(lru);
+      }
+    }
     std::unique_ptr<entry> &pe = cache_[key.str()];
     if (!pe) {
       pe.reset(new entry);
       entry &e = *pe;
       e.ndof = ndof;
+      e.watch.add_dependency(m);
+      e.watch.add_dependency(mf);
+      e.watch.add_dependency(mim);
+      for (dal::bv_visitor cv(m.convex_index()); !cv.finished(); ++cv)  // once per entry: a change touches the context
+        GMM_ASSERT1(mf.fem_of_element(cv) == pf && m.trans_of_convex(cv) == pgt && mim.int_method_of_element(cv) == pim,
+                    "gfgpu: mixed fems / transformations / integration methods are not handled");
       // mesh (basic_mesh::points_of_convex / ind_points_of_convex)
       const size_type npts = m.points_index().last_true() + 1;
       std::vector<double> pts(npts * dim, 0.0);
@@ -723,9 +814,8 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
         GFGPU_CALL(gfgpu_tables_set_faces(e.tab, int(nf), int(nqf), fn.data(), fw.data(), fgtg.data(), fphi.data(),
                                           fgphi.data()));
       }
-      const double alpha = ws.factor_of_variable(rt.varname);
-      GFGPU_CALL(gfgpu_term_create(ctx_, e.mesh, e.fem, e.tab, rt.family, rt.params.data(), int(rt.params.size()),
-                                   order == 2 ? alpha * alpha : alpha, GFGPU_STRATEGY_AUTO, &e.term));
+      GFGPU_CALL(gfgpu_term_create(ctx_, e.mesh, e.fem, e.tab, rt.family, rt.params.data(), int(rt.params.size()), 1.0,
+                                   GFGPU_STRATEGY_AUTO, &e.term));
       if (!all_cv)
         GFGPU_CALL(gfgpu_term_set_region(e.term, int64_t(rg_cv.size()), rg_cv.data(), rg_faces ? rg_f.data() : nullptr));
       if (!rt.field_names.empty()) {
@@ -778,6 +868,7 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
       }
     }
     e.used = true;
+    e.last_use = ++use_clock_;
     // the variable's values, in the fem's own numbering (the workspace interval only offsets the result)
     const getfem::model_real_plain_vector &U = ws.value(rt.varname);
     GMM_ASSERT1(U.size() == ndof, "gfgpu: bad size of the variable's value vector");
@@ -793,14 +884,15 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
       if (V.size() < I.first() + ndof) V.resize(std::max<size_type>(nprim, I.first() + ndof), 0.0);
       for (size_type d = 0; d < ndof; ++d) V[I.first() + d] += R[d];
       t_fill += now_s() - t2;
-    } else if (rt.family == GFGPU_SOURCE || rt.family == GFGPU_NORMAL_SOURCE) {
+    } else if (rt.family == GFGPU_SOURCE || rt.family == GFGPU_NORMAL_SOURCE || rt.no_tangent) {
       // an order-1 term contributes nothing to the tangent; K only gets its size (workspace.cc:805-812)
       getfem::model_real_sparse_matrix &K = ws.assembled_matrix();
       const size_type need = std::max<size_type>(nprim, I.first() + ndof);
       if (gmm::mat_nrows(K) < need || gmm::mat_ncols(K) < need) gmm::resize(K, need, need);
     } else {
       GFGPU_CALL(gfgpu_term_assemble_host(e.term, U.data(), GFGPU_TANGENT, nullptr, nullptr));
-      GFGPU_CALL(gfgpu_matrix_add_term(dK.m, e.term, 1.0, int64_t(I.first()), int64_t(I.first())));
+      const double alpha = ws.factor_of_variable(rt.varname);  // alpha1 * alpha2 of the matrix assembly instructions
+      GFGPU_CALL(gfgpu_matrix_add_term(dK.m, e.term, alpha * alpha, int64_t(I.first()), int64_t(I.first())));
       ++n_added;
       t_device += now_s() - t1;
     }

@@ -26,6 +26,9 @@ struct recognised_term {
   std::vector<std::string> field_names;
   double field_sign = 1.0;
   bool by_probe = false;  // identified numerically (recognise_by_probe), not from a printed normal form
+  // assembly(2) on a workspace whose expression was added WITHOUT derivative trees (add_expression(.., order 1)): the reference
+  // assembles the order-2 trees that exist and nothing else, so this order-1 term must not contribute its family's tangent
+  bool no_tangent = false;
 };
 
 // Matches the ORDER-1 tree of `ws` number `itree` (as printed by ga_tree_to_string after the
@@ -60,7 +63,8 @@ class device_assembler {
  private:
   struct entry;
   gfgpu_ctx *ctx_ = nullptr;
-  std::map<std::string, std::unique_ptr<entry>> cache_;
+  std::map<std::string, std::unique_ptr<entry>> cache_;  // bounded (LRU); entries die with the getfem objects they mirror
+  uint64_t use_clock_ = 0;
 };
 
 // Adds a CSC matrix (jc[ncols+1], ir, pr: gmm::csc_matrix layout, rows ascending inside a column) into K, column by column

@@ -69,6 +69,11 @@ int main(int argc, char **argv) {
       std::uniform_real_distribution<double> dist(-1.0, 1.0);
       for (auto &x : U) x = dist(rng);
     }
+    if (a.count("uzero")) {  // state that vanishes on the first dofs (the probe convexes) or everywhere (uzero=-1)
+      const long nz = geti("uzero", -1);
+      for (size_t k = 0; k < U.size(); ++k)
+        if (nz < 0 || long(k) < nz) U[k] = 0.0;
+    }
     std::vector<double> Vr, Vg, C0(mf_d.nb_dof(), 1.0);
     C0.back() = 5.0;
     auto run = [&](bool device, gmm::csc_matrix<double> &C) {

@@ -165,3 +165,34 @@ def test_the_probe_refuses_what_may_vary_over_the_region(mesh, expr):
                          env=dict(os.environ, GFGPU_DRYRUN="1"))
     lines = [l for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun] order")]
     assert lines and all("NOT recognised" in l for l in lines), out.stderr[-1500:]
+
+
+NONLINEAR = [  # forms that contain the unknown: a numerical fit at ONE state says nothing
+    ("dim=2 n=4 gt=pk k=1 q=1", "(1+u*u)*Grad_u.Grad_Test_u"),
+    ("dim=2 n=4 gt=pk k=1 q=1", "u*u*u*Test_u+Grad_u.Grad_Test_u"),
+    ("dim=2 n=4 gt=pk k=1 q=1", "u*Test_u*Test2_u"),       # a "bilinear form" whose coefficient is the state
+]
+
+
+@pytest.mark.parametrize("uzero", ["4", "-1", None])
+@pytest.mark.parametrize("mesh,expr", NONLINEAR)
+def test_state_dependent_forms_are_refused_whatever_the_state(mesh, expr, uzero):
+    """with u = 0 on the probe convexes (uzero=4: the first two triangles) or everywhere (the first Newton step) the old
+    probe fitted a plain Laplacian / a constant load; the structural check refuses the tree before any fit"""
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    args = [BIN, "model=expr"] + mesh.split() + ["expr=" + expr] + (["uzero=" + uzero] if uzero else [])
+    out = subprocess.run(args, capture_output=True, text=True, timeout=300, env=dict(os.environ, GFGPU_DRYRUN="1"))
+    lines = [l for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun] order")]
+    assert lines and all("NOT recognised" in l for l in lines), out.stderr[-1500:]
+
+
+def test_a_load_written_with_the_unknown_is_not_a_constant_load():
+    """order-1-only tree u*Test_u (added without derivatives it would look like a load): u locally constant must not fit SOURCE"""
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN, "model=expr", "dim=2", "n=4", "gt=pk", "k=1", "q=1", "expr=u*Test_u", "uzero=-1"],
+                         capture_output=True, text=True, timeout=300, env=dict(os.environ, GFGPU_DRYRUN="1"))
+    lines = [l for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun] order")]
+    # u*Test_u has a derivative tree (mass), so it is the derived route: recognised as MASS with r = M u checked, never as a load
+    assert lines and not any("recognised family 6" in l for l in lines), out.stderr[-1500:]
