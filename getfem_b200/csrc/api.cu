@@ -748,6 +748,10 @@ int gfgpu_term_export_residual_host(gfgpu_term *t, double *R) {
 int gfgpu_term_halo_begin(gfgpu_term *t, const double *U_dev, int64_t *touched_lo, int64_t *touched_hi) {
   GF_API_BEGIN
   GF_REQUIRE(t, "null term");
+  // the halo is driven by the tangent's ghost columns; a load has none, and its interface contributions would be lost silently
+  GF_REQUIRE(t->family != GFGPU_SOURCE && t->family != GFGPU_NORMAL_SOURCE,
+             "halo: order-1-only terms (source / normal source) have no tangent to announce -- assemble the load on every rank's "
+             "element range and sum the residual slices of the interface dofs yourself, or add it on one rank over the whole region");
   GF_CUDA(cudaSetDevice(t->ctx->device));
   // forget a previous halo, then build the LOCAL structure + pattern (one tangent pass)
   t->halo = false;

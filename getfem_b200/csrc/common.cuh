@@ -241,7 +241,7 @@ struct gfgpu_term {
   gf::DevBuf<uint32_t> ru_ld;      // per chunk of 32 class members: CSC base and element strip positions of every lane
   gf::DevBuf<double> ru_eg;        // per-element geometry, component-major, strip order
   int64_t ru_nepad = 0, ru_ntiles = 0, ru_ntasks = 0;
-  int ru_grid = 0, ru_nbuf = 0, ru_imgcap = 0;
+  int ru_grid = 0, ru_nbuf = 0, ru_imgcap = 0, ru_kg = 3, ru_tw = 4;
 };
 
 namespace gf {

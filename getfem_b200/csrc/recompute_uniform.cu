@@ -194,7 +194,7 @@ struct UChunk {
 };
 __global__ void k_ut_lane_data(const UIn in, const UChunk *__restrict__ chunks, int64_t nchunks,
                                const uint32_t *__restrict__ scol, const uint32_t *__restrict__ desc, uint32_t dw,
-                               const uint32_t *__restrict__ epos, uint32_t *__restrict__ ld, int *__restrict__ err) {
+                               const uint32_t *__restrict__ epos, int gsz, uint32_t *__restrict__ ld, int *__restrict__ err) {
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < nchunks * 32; idx += (int64_t)gridDim.x * blockDim.x) {
     const UChunk ch = chunks[idx >> 5];
     const uint32_t lane = (uint32_t)(idx & 31);
@@ -218,7 +218,10 @@ __global__ void k_ut_lane_data(const UIn in, const UChunk *__restrict__ chunks, 
     o[lane] = (uint32_t)(jc & 0xffffffffll);
     o[32 + lane] = (uint32_t)(jc >> 32);
     const uint32_t r0 = in.rstart[k];
-    for (uint32_t r = 0; r < m; ++r) o[64 + r * 32 + lane] = epos[in.rsrc[r0 + r] / (uint32_t)in.nd];
+    for (uint32_t r = 0; r < m; ++r) {  // byte offset of the element's entry in the blocked geometry table
+      const uint32_t pos = epos[in.rsrc[r0 + r] / (uint32_t)in.nd];
+      o[64 + r * 32 + lane] = ((pos >> 5) * (uint32_t)(gsz * 32) + (pos & 31u)) * 8u;
+    }
   }
 }
 
@@ -244,84 +247,120 @@ struct UArgs {
 // A CTA = UT_TEAMS teams of UT_TW warps (one per SM sub-partition); a team runs one tile at a time: every warp its task (the
 // plan packs the tile's groups into UT_TW tasks), team barrier, every warp sends UT_ROWS rows of the image, team barrier.
 // No spinning, no atomics on data; the teams are independent, so one team's flush overlaps the others' arithmetic.
-constexpr int UT_TW = 4, UT_TEAMS = 3, UT_WARPS = UT_TW * UT_TEAMS, UT_THREADS = UT_WARPS * 32, UT_ROWS = 32 / UT_TW, UT_RB = 4;
 
-__device__ __forceinline__ void team_barrier(int team) {
-  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(UT_TW * 32) : "memory");
+
+__device__ __forceinline__ void team_barrier(int team, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(nthreads) : "memory");
 }
 
-// flush of a tile image: warp wq sends rows [wq*UT_ROWS, (wq+1)*UT_ROWS) -- the CSC segments of these columns -- as 16-byte
-// units, 32 lanes side by side (coalesced; full sectors except at the two ends of a row), UT_RB rows in flight together.
+// flush of a tile image: warp wq sends rows [wq*UT_ROWS, (wq+1)*UT_ROWS) -- the CSC segments of these columns.  Four lanes per
+// row (8 rows side by side), 16-byte units: every store instruction writes 8 runs of 64 contiguous bytes (full sectors except at
+// the two ends of a row); the odd first / last entry of a row goes out as a single 8-byte store of lane 0 / 1 of its quad.
 // Kept out of line: its address registers must not weigh on the allocation of the arithmetic loop.
-__device__ __noinline__ void ut_flush_rows(const double *img, double *pr, uint32_t rowstride, uint32_t nmem, int wq, int lane,
-                                           uint32_t jclo, uint32_t jchi, uint32_t npieces, uint2 pc0, uint2 pc1, uint2 pc2) {
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+// program words are shared by every tile of a class: ask L1 to keep them (the geometry rows stream through the same cache)
+__device__ __forceinline__ uint2 ldg_keep_u2(const uint2 *p) {
+  uint2 v;
+#ifdef GF_UT_NO_EVICT_LAST
+  v = __ldg(p);
+#else
+  asm volatile("ld.global.nc.L1::evict_last.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+#endif
+  return v;
+}
+template <int ROWS>  // rows per warp (32 / warps of a team): 32 / ROWS lanes per row
+__device__ __noinline__ void ut_flush_rows(uint32_t img_s /* shared address of the image */, double *pr, uint32_t rowstride,
+                                           uint32_t nmem, int wq, int lane, uint32_t jclo, uint32_t jchi, uint32_t npieces,
+                                           uint2 pc0, uint2 pc1, uint2 pc2) {
+  constexpr int LPR = 32 / ROWS;  // lanes per row
+  const uint32_t k = (uint32_t)(wq * ROWS + lane / LPR), sub = (uint32_t)(lane % LPR);
+  const uint32_t lo = __shfl_sync(0xffffffffu, jclo, k), hi = __shfl_sync(0xffffffffu, jchi, k);
+  const int64_t jc = (int64_t)(((uint64_t)hi << 32) | lo);
+  if (k >= nmem) return;
   for (uint32_t pc = 0; pc < npieces; ++pc) {
     const uint2 pw = pc == 0 ? pc0 : pc == 1 ? pc1 : pc2;
-    const int64_t len = pw.y & 0xffffu;
+    const uint32_t len = pw.y & 0xffffu;
     if (!len) continue;
-    const uint32_t pbase = pw.y >> 16;
-    const int maxun = (int)((len + 1) >> 1);
-#pragma unroll 1
-    for (int r0 = 0; r0 < UT_ROWS; r0 += UT_RB) {
-      const double2 *s2[UT_RB];
-      double2 *d2[UT_RB];
-      int nun[UT_RB];
-#pragma unroll
-      for (int r = 0; r < UT_RB; ++r) {
-        const uint32_t k = (uint32_t)(wq * UT_ROWS + r0 + r);
-        const uint32_t lo = __shfl_sync(0xffffffffu, jclo, k), hi = __shfl_sync(0xffffffffu, jchi, k);
-        const int64_t gstart = (int64_t)(((uint64_t)hi << 32) | lo) + pw.x;
-        const int64_t odd = gstart & 1, gs = gstart + odd, ge = (gstart + len) & ~int64_t(1);
-        const double *src = img + (size_t)k * rowstride + pbase + odd;  // entry e of the piece sits at src[e]
-        const bool live = k < nmem;
-        if (live && odd && lane == 0) pr[gstart] = src[0];
-        if (live && ((gstart + len) & 1) && gstart + len - 1 >= gs && lane == 31) pr[gstart + len - 1] = src[len - 1];
-        s2[r] = reinterpret_cast<const double2 *>(src + odd);
-        d2[r] = reinterpret_cast<double2 *>(pr + gs);
-        nun[r] = live ? (int)((ge - gs) >> 1) : 0;
-      }
-      for (int u = lane; u < maxun; u += 32) {
-        double2 v[UT_RB];
-#pragma unroll
-        for (int r = 0; r < UT_RB; ++r)
-          if (u < nun[r]) v[r] = s2[r][u];
-#pragma unroll
-        for (int r = 0; r < UT_RB; ++r)
-          if (u < nun[r]) d2[r][u] = v[r];
-      }
+    const int64_t gstart = jc + pw.x;
+    const uint32_t odd = (uint32_t)(gstart & 1), tail = (odd + len) & 1u;
+    const uint32_t src = img_s + (k * rowstride + (pw.y >> 16) + odd) * 8u;  // entry e of the piece sits at src + 8 e
+    double *g = pr + gstart;
+    if (sub == 0 && odd) g[0] = lds_f64(src);
+    if (sub == 1 && tail && len - 1u >= odd) g[len - 1u] = lds_f64(src + (len - 1u) * 8u);
+    const int nun = (int)(len - odd - tail) >> 1;  // aligned 16-byte units, the first one at entry `odd`
+    double2 *d2 = reinterpret_cast<double2 *>(g + odd);
+    const uint32_t s2 = src + odd * 8u;
+    int u = (int)sub;
+    for (; u + 3 * LPR < nun; u += 4 * LPR) {
+      const double2 v0 = lds_f64x2(s2 + u * 16u), v1 = lds_f64x2(s2 + (u + LPR) * 16u), v2 = lds_f64x2(s2 + (u + 2 * LPR) * 16u),
+                    v3 = lds_f64x2(s2 + (u + 3 * LPR) * 16u);
+      d2[u] = v0; d2[u + LPR] = v1; d2[u + 2 * LPR] = v2; d2[u + 3 * LPR] = v3;
     }
+    for (; u < nun; u += LPR) d2[u] = lds_f64x2(s2 + u * 16u);
   }
 }
 
-template <int N, int Q, int ND, int RF>
-__global__ void __launch_bounds__(UT_THREADS, 1)
+template <int N, int Q, int ND, int RF, int KG, int UT_TW, int TEAMS>
+__global__ void __launch_bounds__(TEAMS * UT_TW * 32, 1)
 k_utiles(const UArgs a) {
+  constexpr int UT_TEAMS = TEAMS, UT_THREADS = TEAMS * UT_TW * 32, UT_ROWS = 32 / UT_TW;
   using C = TlCfg<N, RF>;
-  constexpr int NB = ND * ND, MT = C::MT, MTP = (MT + 1) & ~1, GSZ = C::GSZ, ACC = C::ACC, KG = uplan::KGU;
+  constexpr int NB = ND * ND, MT = C::MT, MTP = (MT + 1) & ~1, GSZ = C::GSZ, ACC = C::ACC;
   extern __shared__ __align__(128) unsigned char smraw[];
-  __shared__ unsigned s_next, s_tile[UT_TEAMS];
   double *sM = reinterpret_cast<double *>(smraw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, team = warp / UT_TW, wq = warp % UT_TW;
   double *img = sM + ((NB * MTP + 15) & ~15) + (size_t)team * a.imgcap;
   for (int k = tid; k < NB * MTP; k += UT_THREADS) sM[k] = (k % MTP) < MT ? a.Mtab[(k / MTP) * MT + k % MTP] : 0.0;
-  if (tid == 0) s_next = UT_TEAMS;
-  if (tid < UT_TEAMS) s_tile[tid] = tid;  // the first tile of every team
   __syncthreads();
   const uint32_t t0 = a.cta_t0[blockIdx.x], ntl = a.cta_t0[blockIdx.x + 1] - t0;
-  for (;;) {
-    const uint32_t lt = s_tile[team];
-    if (lt >= ntl) break;
-    const uint4 tw = __ldg(reinterpret_cast<const uint4 *>(a.tiles + t0 + lt));
+  const uint32_t sM_s = smem_u32(sM);
+  // Tiles go to the teams round robin, so the NEXT tile of a team is known from the start: its record is loaded while the
+  // current tile runs, its program header / task range / lane words while the current image is flushed (a cold chain of five
+  // dependent loads per tile cost 17 % of the kernel: profiles/round2_ncu_utiles_v5_c3_n110.txt)
+  struct Meta {
+    uint4 tw;
+    uint2 h0, tr, pc0, pc1, pc2;
+    uint32_t jclo, jchi;
+  };
+  auto load_tw = [&](uint32_t lt) { return __ldg(reinterpret_cast<const uint4 *>(a.tiles + t0 + min(lt, ntl - 1u))); };
+  auto load_meta = [&](Meta &m) {
+    const uint2 *P = a.prog + m.tw.x;
+    m.h0 = __ldg(P);
+    m.tr = __ldg(P + uplan::HDR_UNITS + wq);
+    m.pc0 = __ldg(P + 1); m.pc1 = __ldg(P + 2); m.pc2 = __ldg(P + 3);
+    const uint32_t le = min((uint32_t)lane, m.tw.z - 1u);
+    m.jclo = __ldg(a.ld + m.tw.y + le);
+    m.jchi = __ldg(a.ld + m.tw.y + 32 + le);
+  };
+  if (ntl == 0) return;
+  Meta cur;
+  cur.tw = load_tw((uint32_t)team);
+  load_meta(cur);
+  for (uint32_t lt = (uint32_t)team; lt < ntl; lt += UT_TEAMS) {
+    Meta nxt;
+    nxt.tw = load_tw(lt + UT_TEAMS);
+    const uint4 tw = cur.tw;
     const uint32_t nmem = tw.z;
     const uint2 *P = a.prog + tw.x;
-    const uint2 h0 = __ldg(P), tr = __ldg(P + uplan::HDR_UNITS + wq);
-    const uint2 pc0 = __ldg(P + 1), pc1 = __ldg(P + 2), pc2 = __ldg(P + 3);
+    const uint2 h0 = cur.h0, tr = cur.tr, pc0 = cur.pc0, pc1 = cur.pc1, pc2 = cur.pc2;
     const uint32_t rowstride = h0.x, npieces = h0.y & 0xffu;
     const uint32_t le = min((uint32_t)lane, nmem - 1u);
     const uint32_t *ldp = a.ld + tw.y;
     const uint32_t *lpos = ldp + 64 + le;
-    const uint32_t jclo = __ldg(ldp + le), jchi = __ldg(ldp + 32 + le);
-    double *row = img + (size_t)lane * rowstride;
+    const uint32_t jclo = cur.jclo, jchi = cur.jchi;
+    const uint32_t row_s = smem_u32(img) + (uint32_t)lane * rowstride * 8u;  // shared address of the lane's image row
     const uint32_t par0 = (jclo + pc0.x) & 1u, par1 = (jclo + pc1.x) & 1u, par2 = (jclo + pc2.x) & 1u;
 
     if (tr.y > tr.x) {
@@ -334,11 +373,13 @@ k_utiles(const UArgs a) {
       // ip+1, the strip position of ip+2 and the instruction word ip+3 are in flight
       uint32_t ip = tr.x;
       const uint32_t ipl = tr.y - 1u;
-      auto fetch = [&](uint32_t k) { return __ldg(P + min(k, ipl)); };  // past the end: the final FLUSH again (no loads follow)
-      auto is_step = [](const uint2 &I) { return (I.x & uplan::OP_FLUSH) == 0u; };
-      auto load_pos = [&](const uint2 &I) { return __ldg(lpos + (I.x & 0xfffu) * 32u); };
-      auto load_g = [&](double (&G)[GSZ], uint32_t pos) {
-        const double *gp = a.eg + (size_t)(pos >> 5) * (GSZ * 32) + (pos & 31u);
+      auto fetch = [&](uint32_t k) { return ldg_keep_u2(P + min(k, ipl)); };  // past the end: the final FLUSH again (no loads follow)
+      auto is_step = [](const uint2 &I) { return (int)I.x >= 0; };
+      auto load_pos = [&](const uint2 &I) {  // byte offset of the lane's element of that rank in the geometry table
+        return __ldg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(lpos) + (I.x & 0x7ff80u)));
+      };
+      auto load_g = [&](double (&G)[GSZ], uint32_t off) {
+        const double *gp = reinterpret_cast<const double *>(reinterpret_cast<const char *>(a.eg) + off);
 #pragma unroll
         for (int c = 0; c < GSZ; ++c) G[c] = __ldg(gp + c * 32);
       };
@@ -350,42 +391,45 @@ k_utiles(const UArgs a) {
       if (is_step(I0)) load_g(GA, load_pos(I0));
       if (is_step(I1)) pos1 = load_pos(I1);
 
-      auto flush_pair = [&](double (&A)[ACC], const uint2 &I) {
+      auto flush_pair = [&](const double (&A)[ACC], const uint2 &I) {
+        if ((uint32_t)lane >= nmem) return;
         double kv[Q * Q];  // kv[b2*Q + aa] = K(row component aa, column component b2)
         if (RF == TF_ELAST) {
-          double trc = 0;
+          double trc = A[0];
 #pragma unroll
-          for (int n = 0; n < N; ++n) trc += A[RF == TF_ELAST ? n + N * n : 0];
+          for (int n = 1; n < N; ++n) trc += A[RF == TF_ELAST ? n + N * n : 0];
+          trc *= a.smu;
 #pragma unroll
           for (int b2 = 0; b2 < Q; ++b2)
 #pragma unroll
-            for (int aa = 0; aa < Q; ++aa)
-              kv[b2 * Q + aa] = a.sl * A[RF == TF_ELAST ? aa + N * b2 : 0] + a.smu * A[RF == TF_ELAST ? b2 + N * aa : 0] +
-                                (aa == b2 ? a.smu * trc : 0.0);
+            for (int aa = 0; aa < Q; ++aa) {
+              const double v = a.sl * A[RF == TF_ELAST ? aa + N * b2 : 0] + a.smu * A[RF == TF_ELAST ? b2 + N * aa : 0];
+              kv[b2 * Q + aa] = aa == b2 ? v + trc : v;
+            }
         } else {
 #pragma unroll
           for (int b2 = 0; b2 < Q; ++b2)
 #pragma unroll
             for (int aa = 0; aa < Q; ++aa) kv[b2 * Q + aa] = aa == b2 ? A[0] : 0.0;
         }
-        if ((uint32_t)lane < nmem) {
+        if (I.x & (1u << 17)) {  // no local contribution (a pair announced by another rank): zeros
 #pragma unroll
-          for (int b2 = 0; b2 < Q; ++b2) {
-            const uint32_t piece = (I.x >> (9 + 2 * b2)) & 3u;
-            double *dst = row + ((I.y >> (10 * b2)) & 0x3ffu) + (piece == 0 ? par0 : piece == 1 ? par1 : par2);
-            const unsigned mb = (I.x >> (b2 * Q)) & ((1u << Q) - 1);
-            if (mb == (1u << Q) - 1) {  // the mask is the same for every lane: the common case takes no selects
-#pragma unroll
-              for (int aa = 0; aa < Q; ++aa) dst[aa] = kv[b2 * Q + aa];
-            } else {
-#pragma unroll
-              for (int aa = 0; aa < Q; ++aa)
-                if (mb & (1u << aa)) dst[__popc(mb & ((1u << aa) - 1))] = kv[b2 * Q + aa];
-            }
-          }
+          for (int k = 0; k < Q * Q; ++k) kv[k] = 0.0;
         }
 #pragma unroll
-        for (int m = 0; m < ACC; ++m) A[m] = 0.0;
+        for (int b2 = 0; b2 < Q; ++b2) {
+          const uint32_t piece = (I.x >> (9 + 2 * b2)) & 3u;
+          const uint32_t dst = row_s + ((((I.y >> (10 * b2)) & 0x3ffu) + (piece == 0 ? par0 : piece == 1 ? par1 : par2)) << 3);
+          const unsigned mb = (I.x >> (b2 * Q)) & ((1u << Q) - 1);
+          if (mb == (1u << Q) - 1) {  // the mask is the same for every lane: the common case takes no selects
+#pragma unroll
+            for (int aa = 0; aa < Q; ++aa) sts_f64(dst + 8 * aa, kv[b2 * Q + aa]);
+          } else {
+#pragma unroll
+            for (int aa = 0; aa < Q; ++aa)
+              if (mb & (1u << aa)) sts_f64(dst + 8 * __popc(mb & ((1u << aa) - 1)), kv[b2 * Q + aa]);
+          }
+        }
       };
 
       auto phase = [&](double (&Gc)[GSZ], double (&Gn)[GSZ]) {
@@ -394,16 +438,22 @@ k_utiles(const UArgs a) {
         if (is_step(I2)) pos2 = load_pos(I2);
         if (is_step(I1)) load_g(Gn, pos1);
         if (is_step(I0)) {
-          const int npairs = (int)((I0.x >> 28) & 3u);
-          const uint32_t code[3] = {(I0.x >> 12) & 0x3ffu, I0.y & 0x3ffu, (I0.y >> 10) & 0x3ffu};
+          const int npairs = (int)((I0.x >> 29) & 3u);
+          const uint32_t code[3] = {(I0.x >> 19) & 0x3ffu, I0.y & 0x3ffu, (I0.y >> 10) & 0x3ffu};
+          if (I0.x & 1u) {  // first step of a group: its accumulators start from zero (a flush leaves them alone)
+#pragma unroll
+            for (int p = 0; p < KG; ++p)
+#pragma unroll
+              for (int m = 0; m < ACC; ++m) acc[p][m] = 0.0;
+          }
 #pragma unroll
           for (int p = 0; p < KG; ++p) {
             if (p < npairs) {
               double M[MTP];
-              const double2 *M2 = reinterpret_cast<const double2 *>(sM + code[p] * MTP);
+              const uint32_t ma = sM_s + code[p] * (MTP * 8);
 #pragma unroll
               for (int q = 0; q < MTP / 2; ++q) {
-                const double2 v = M2[q];
+                const double2 v = lds_f64x2(ma + q * 16);
                 M[2 * q] = v.x;
                 M[2 * q + 1] = v.y;
               }
@@ -434,9 +484,9 @@ k_utiles(const UArgs a) {
           }
         } else {
           const uint32_t slot = (I0.x >> 15) & 3u;
-          if (slot == 0) flush_pair(acc[0], I0);
-          else if (slot == 1) flush_pair(acc[1], I0);
-          else flush_pair(acc[2], I0);
+          if (KG == 1 || slot == 0) flush_pair(acc[0], I0);
+          else if (KG == 2 || slot == 1) flush_pair(acc[KG > 1 ? 1 : 0], I0);
+          else flush_pair(acc[KG > 2 ? 2 : 0], I0);
         }
         I0 = I1; I1 = I2; I2 = I3;
         pos1 = pos2;
@@ -448,10 +498,11 @@ k_utiles(const UArgs a) {
         if (++ip > ipl) break;
       }
     }
-    team_barrier(team);  // the image of the tile is complete
-    if (wq == 0 && lane == 0) s_tile[team] = atomicAdd(&s_next, 1u);  // everybody has read the old value before the barrier
-    ut_flush_rows(img, a.pr, rowstride, nmem, wq, lane, jclo, jchi, npieces, pc0, pc1, pc2);
-    team_barrier(team);  // the image may be overwritten; s_tile[team] is the next tile
+    team_barrier(team, UT_TW * 32);  // the image of the tile is complete
+    load_meta(nxt);      // in flight during the flush
+    ut_flush_rows<UT_ROWS>(smem_u32(img), a.pr, rowstride, nmem, wq, lane, jclo, jchi, npieces, pc0, pc1, pc2);
+    team_barrier(team, UT_TW * 32);  // the image may be overwritten
+    cur = nxt;
   }
 }
 
@@ -554,7 +605,13 @@ bool uniform_prepare(gfgpu_term *t) {
   GF_CUDA(cudaStreamSynchronize(s));
   dlen.release(); llen.release();
 
-  const int img_bytes = std::max(8192, std::min(uenv_int("GFGPU_UT_IMG", 51200), 200 * 1024));
+  // kernel variant: pairs per group (accumulator sets per lane) / warps per team / teams per CTA
+  int kg = 3, tw = 4, teams = 3;
+  if (const char *v = getenv("GFGPU_UT_VARIANT")) {
+    if (sscanf(v, "%d,%d,%d", &kg, &tw, &teams) != 3) kg = 3, tw = 4, teams = 3;
+  }
+  GF_REQUIRE(kg >= 1 && kg <= 3 && (tw == 4 || tw == 8) && teams >= 2 && teams <= 4, "GFGPU_UT_VARIANT: kg,tw,teams out of range");
+  const int img_bytes = std::max(8192, std::min(uenv_int("GFGPU_UT_IMG", teams == 4 ? 45056 : 51200), 200 * 1024));
   const uint32_t row_cap = (uint32_t)(img_bytes / 8 / 32);
   const int group_cap = std::max(1, uenv_int("GFGPU_UT_TASKCAP", 24));  // contributions per group of pairs
   std::vector<uint32_t> prog;
@@ -562,7 +619,7 @@ bool uniform_prepare(gfgpu_term *t) {
   uint32_t max_stride = 2;
   for (int64_t c = 0; c < ncls; ++c) {
     std::string err;
-    const bool ok = uplan::build_class(h_desc.data() + (size_t)c * dw, h_llen[c], Q, nd, row_cap, group_cap, UT_TW, prog,
+    const bool ok = uplan::build_class(h_desc.data() + (size_t)c * dw, h_llen[c], Q, nd, row_cap, group_cap, tw, kg, prog,
                                        cplan[c], err);
     GF_REQUIRE(ok, "uniform plan: " + err);
     for (const uplan::Sub &sb : cplan[c].subs) max_stride = std::max(max_stride, sb.rowstride);
@@ -644,6 +701,7 @@ bool uniform_prepare(gfgpu_term *t) {
   sp.release();
   const int64_t nepad = (ne + 31) / 32 * 32;
   t->ru_nepad = nepad;
+  GF_REQUIRE((size_t)nepad * GSZ * 8 < (size_t(1) << 32), "uniform plan: geometry table beyond 32-bit byte offsets");
   t->ru_eg.alloc(ctx, (size_t)nepad * GSZ);
   t->ru_eg.zero();
   k_ut_eg_blocked<<<ugrid(ne * GSZ, B), B, 0, s>>>(t->rc_eg.p, GSZ, ne, epos.p, t->ru_eg.p);
@@ -651,7 +709,7 @@ bool uniform_prepare(gfgpu_term *t) {
   // ---- lane data (with the check that every member really has its leader's descriptor)
   t->ru_ld.alloc(ctx, std::max<uint64_t>(ldw, 1));
   k_ut_lane_data<<<ugrid((int64_t)chunks.size() * 32, B), B, 0, s>>>(in, (const UChunk *)dchunks.p, (int64_t)chunks.size(),
-                                                                  scol.p, desc.p, dw, epos.p, t->ru_ld.p, (int *)t->flag.p);
+                                                                  scol.p, desc.p, dw, epos.p, GSZ, t->ru_ld.p, (int *)t->flag.p);
   GF_LAUNCH_CHECK();
   {
     int32_t err = 0;
@@ -660,7 +718,9 @@ bool uniform_prepare(gfgpu_term *t) {
     GF_REQUIRE(err == 0, "uniform plan failed (code " + std::to_string(err) + ")");
   }
   t->ru_grid = grid;
-  t->ru_nbuf = UT_TEAMS;
+  t->ru_nbuf = teams;
+  t->ru_kg = kg;
+  t->ru_tw = tw;
   t->ru_imgcap = (int)(32 * max_stride);
   t->ru_ntiles = ntiles;
   t->ru_ntasks = (int64_t)ntask;
@@ -672,15 +732,16 @@ bool uniform_prepare(gfgpu_term *t) {
             "[gfgpu] uniform tiles: %lld columns in %lld classes (%lld with >= 32 members), %lld chunks, %lld tiles, %llu tasks, "
             "programs %.1f KB, lane data %.1f MB, image %d B x %d, grid %d\n",
             (long long)ncol, (long long)ncls, (long long)big, (long long)chunks.size(), (long long)ntiles,
-            (unsigned long long)ntask, prog.size() * 4 / 1024.0, ldw * 4 / 1048576.0, t->ru_imgcap * 8, UT_TEAMS, grid);
+            (unsigned long long)ntask, prog.size() * 4 / 1024.0, ldw * 4 / 1048576.0, t->ru_imgcap * 8, teams, grid);
+    fprintf(stderr, "[gfgpu] uniform tiles: variant kg %d, %d warps per team, %d teams\n", kg, tw, teams);
   }
   if (!t->halo) t->prel.release();
   t->rc_uni = true;
   return true;
 }
 
-template <int N, int Q, int ND, int RF>
-static void launch_utiles(gfgpu_term *t) {
+template <int N, int Q, int ND, int RF, int KG, int TW, int TEAMS>
+static void launch_utiles_t(gfgpu_term *t) {
   using C = TlCfg<N, RF>;
   constexpr int MTP = (C::MT + 1) & ~1;
   const double sign = t->alpha < 0 ? -1.0 : 1.0;
@@ -694,12 +755,25 @@ static void launch_utiles(gfgpu_term *t) {
   a.sl = sign * t->par[0]; a.smu = sign * t->par[1];
   a.pr = t->pr.p;
   a.imgcap = t->ru_imgcap;
-  const size_t smem = (size_t)((ND * ND * MTP + 15) & ~15) * 8 + (size_t)UT_TEAMS * a.imgcap * 8;
-  GF_REQUIRE(smem <= 226 * 1024, "uniform tiles: image buffers too large for shared memory (GFGPU_UT_IMG / GFGPU_UT_NBUF)");
-  auto kern = k_utiles<N, Q, ND, RF>;
+  const size_t smem = (size_t)((ND * ND * MTP + 15) & ~15) * 8 + (size_t)TEAMS * a.imgcap * 8;
+  GF_REQUIRE(smem <= 226 * 1024, "uniform tiles: image buffers too large for shared memory (GFGPU_UT_IMG / GFGPU_UT_VARIANT)");
+  auto kern = k_utiles<N, Q, ND, RF, KG, TW, TEAMS>;
   GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<t->ru_grid, UT_THREADS, smem, t->ctx->stream>>>(a);
+  kern<<<t->ru_grid, TEAMS * TW * 32, smem, t->ctx->stream>>>(a);
   GF_LAUNCH_CHECK();
+}
+
+// kernel variants (GFGPU_UT_VARIANT=kg,tw,teams): the default everywhere; the experimental ones only for BASELINE config 3
+template <int N, int Q, int ND, int RF>
+static void launch_utiles(gfgpu_term *t) {
+  const int kg = t->ru_kg, tw = t->ru_tw, teams = t->ru_nbuf;
+  if (kg == 3 && tw == 4 && teams == 3) return launch_utiles_t<N, Q, ND, RF, 3, 4, 3>(t);
+  if constexpr (N == 3 && Q == 3 && ND == 10 && RF == TF_ELAST) {
+#define UT_VAR(K, W, T) if (kg == K && tw == W && teams == T) return launch_utiles_t<N, Q, ND, RF, K, W, T>(t);
+    UT_VAR(1, 8, 3) UT_VAR(2, 8, 2) UT_VAR(1, 8, 2) UT_VAR(2, 4, 3) UT_VAR(1, 4, 3) UT_VAR(2, 8, 3) UT_VAR(3, 8, 2)
+#undef UT_VAR
+  }
+  GF_REQUIRE(false, "uniform tiles: this GFGPU_UT_VARIANT is not compiled");
 }
 
 #define UT_CASE(NN, QQ, NDD, RFF)                     \

@@ -15,9 +15,11 @@
 //   unit 4 + t        : task t: [first instruction] [one past its last instruction]   (unit indices from the program start)
 //   then the instruction stream.  A task is a sequence of GROUPS; a group = up to KGU node pairs of the column that are fed by
 //   the SAME elements (the geometry row of a step is loaded once and serves all of them: register-level operand reuse):
-//     STEP   x = rank of the element (bits 0-11) | code j*nd+i of pair 0 (12-21) | pairs of the group (28-29) | 0 << 30
+//     STEP   x = first step of its group (bit 0) | rank of the element (bits 7-18, so that x & 0x7ff80 is the byte offset of
+//                the rank's row of strip positions in the lane data) | code j*nd+i of pair 0 (19-28) | pairs of the group (29-30)
 //            y = code of pair 1 (0-9) | code of pair 2 (10-19)
-//     FLUSH  x = keep mask (0-8) | piece of component 0, 1, 2 (9-10, 11-12, 13-14) | pair of the group (15-16) | 1 << 30
+//     FLUSH  x = keep mask (0-8) | piece of component 0, 1, 2 (9-10, 11-12, 13-14) | pair of the group (15-16) |
+//                the pair has no local contribution: store zeros (17) | 1 << 31
 //            y = offset of the pair's first kept entry of component 0 | 1 << 10 | 2 << 20 inside the row (parity excluded)
 #pragma once
 #include <algorithm>
@@ -29,9 +31,9 @@
 namespace gf {
 namespace uplan {
 
-constexpr int KGU = 3;         // pairs per group
+constexpr int KGU = 3;         // most pairs per group
 constexpr int HDR_UNITS = 4;   // units in front of the task table
-constexpr uint32_t OP_FLUSH = 1u << 30;
+constexpr uint32_t OP_FLUSH = 1u << 31;
 
 struct Sub {
   uint32_t prog;    // unit offset of the program
@@ -61,12 +63,13 @@ struct PairD {
 // image buffers, group_cap = contributions above which a group of pairs is cut, ntasks = tasks per tile = warps of the team
 // that runs a tile (the groups are packed into them longest-processing-time first; a task may be empty).  Returns false with
 // `err` set on failure.
-inline bool build_class(const uint32_t *d, size_t dlen, int Q, int nd, uint32_t row_cap, int group_cap, int ntasks,
+inline bool build_class(const uint32_t *d, size_t dlen, int Q, int nd, uint32_t row_cap, int group_cap, int ntasks, int kg,
                         std::vector<uint32_t> &prog, ClassPlan &out, std::string &err) {
+  kg = std::max(1, std::min(kg, KGU));  // pairs per group (the kernel variant's accumulator sets)
   if (dlen < (size_t)(2 + Q)) { err = "short descriptor"; return false; }
   const uint32_t np = d[0];
   out.m = (int)d[1];
-  if (d[1] > 4096u || nd * nd > 1024) { err = "column valence / element size beyond the instruction format"; return false; }
+  if (d[1] > 4095u || nd * nd > 1024) { err = "column valence / element size beyond the instruction format"; return false; }
   uint32_t coloff[4] = {0, 0, 0, 0};
   for (int b = 0; b < Q; ++b) coloff[b + 1] = d[2 + b];
   std::vector<PairD> pr(np);
@@ -131,8 +134,8 @@ inline bool build_class(const uint32_t *d, size_t dlen, int Q, int nd, uint32_t 
     uint32_t wtot = 0, wmax = 0;
     for (auto &g : bylist) {
       const uint32_t steps = (uint32_t)g.first.size();
-      int cs = steps ? group_cap / (int)steps : KGU;
-      cs = std::max(1, std::min(KGU, cs));
+      int cs = steps ? group_cap / (int)steps : kg;
+      cs = std::max(1, std::min(kg, cs));
       for (size_t q = 0; q < g.second.size(); q += cs) {
         Group t;
         t.steps = steps;
@@ -182,12 +185,12 @@ inline bool build_class(const uint32_t *d, size_t dlen, int Q, int nd, uint32_t 
           uint32_t code[KGU] = {0, 0, 0};
           for (size_t k = 0; k < g.pairs.size(); ++k) code[k] = pr[g.pairs[k]].codes[s] & 0xffffu;
           const uint32_t rank = pr[g.pairs[0]].codes[s] >> 16;
-          prog.push_back(rank | (code[0] << 12) | ((uint32_t)g.pairs.size() << 28));
+          prog.push_back((s == 0 ? 1u : 0u) | (rank << 7) | (code[0] << 19) | ((uint32_t)g.pairs.size() << 29));
           prog.push_back(code[1] | (code[2] << 10));
         }
         for (size_t k = 0; k < g.pairs.size(); ++k) {
           const uint32_t p = g.pairs[k];
-          uint32_t x = OP_FLUSH | pr[p].mask | ((uint32_t)k << 15), off[3] = {0, 0, 0};
+          uint32_t x = OP_FLUSH | pr[p].mask | ((uint32_t)k << 15) | (g.steps == 0 ? 1u << 17 : 0u), off[3] = {0, 0, 0};
           for (int b = 0; b < Q; ++b) {
             const int piece = npc == 1 ? 0 : b;
             x |= (uint32_t)piece << (9 + 2 * b);

@@ -128,6 +128,27 @@ int main(int argc, char **argv) {
   double t0 = now_s();
   getfem::regular_unit_mesh(m, ns, pgt);
   double t_mesh = now_s() - t0;
+  // noise=<amp>: every node moved by amp * h * uniform(-1, 1) per direction (seeded), the mesh rebuilt convex by convex with
+  // add_convex_by_points like regular_unit_mesh does (src/getfem_regular_meshes.cc:237-284), so the numbering is unchanged:
+  // distorted simplices (every element its own K, B, J) and non-affine GT_QK cells (geometry at every Gauss point)
+  const double noise = getd("noise", 0.0);
+  if (noise > 0) {
+    std::vector<bgeot::base_node> np(m.points_index().last_true() + 1);
+    std::mt19937_64 rng(777);
+    std::uniform_real_distribution<double> dist(-1.0, 1.0);
+    for (dal::bv_visitor i(m.points_index()); !i.finished(); ++i) {
+      np[i] = m.points()[i];
+      for (int d = 0; d < dim; ++d) np[i][d] += noise * dist(rng) / double(ns[d]);
+    }
+    getfem::mesh m2;
+    for (dal::bv_visitor cv(m.convex_index()); !cv.finished(); ++cv) {
+      std::vector<bgeot::base_node> cp;
+      for (size_type i : m.ind_points_of_convex(cv)) cp.push_back(np[i]);
+      m2.add_convex_by_points(m.trans_of_convex(cv), cp.begin());
+    }
+    m.clear();
+    m.copy_from(m2);
+  }
   getfem::mesh_fem mf(m, getfem::dim_type(Q));
   mf.set_classical_finite_element(getfem::dim_type(K));
   getfem::mesh_im mim(m);

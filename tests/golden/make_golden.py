@@ -74,6 +74,27 @@ CASES = {
     "f_source3d_p2vec_xmax_coefp1": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=source region=xmax u=random a=0.5 coef=fem kd=1",
     "f_mass3d_p2_outer_coefp1": "dim=3 n=2 gt=pk k=2 q=1 im=4 family=mass region=outer u=random a=2.5 coef=fem kd=1",
     "r_nh_ciarlet_q2_half": "dim=3 n=2 gt=qk k=2 q=3 im=6 family=nh_ciarlet region=half u=smooth lambda=1 mu=1 uamp=0.02",
+    # DISTORTED meshes (noise=amp: every node moved by amp*h*uniform(-1,1)): every simplex has its own K / B / J, every GT_QK
+    # cell is non-affine (geometry evaluated at every Gauss point, C&E.cc:8789-8866), boundary normals vary face by face
+    "d_elast3d_p2_n3": "dim=3 n=3 gt=pk k=2 q=3 im=4 family=elast u=random lambda=1.3 mu=0.7 noise=0.2",
+    "d_lap3d_p1_n3": "dim=3 n=3 gt=pk k=1 q=1 im=2 family=laplace u=random a=1.7 noise=0.2",
+    "d_lap3d_p2_n2": "dim=3 n=2 gt=pk k=2 q=1 im=4 family=laplace u=random noise=0.2",
+    "d_elast2d_p2_n4": "dim=2 n=4 gt=pk k=2 q=2 im=4 family=elast u=random lambda=2 mu=0.5 noise=0.2",
+    "d_mass3d_p2vec_n2": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=mass u=random a=1.5 noise=0.2",
+    "d_lap3d_q2_n2": "dim=3 n=2 gt=qk k=2 q=1 im=6 family=laplace u=random a=0.9 noise=0.15",
+    "d_lap_q4_n1": "dim=3 n=1 gt=qk k=4 q=1 im=8 family=laplace u=random noise=0.15",
+    "d_lap_q4_n2": "dim=3 nx=2 ny=1 nz=1 gt=qk k=4 q=1 im=8 family=laplace u=random noise=0.15",
+    "d_elast3d_q2_n2": "dim=3 n=2 gt=qk k=2 q=3 im=6 family=elast u=random lambda=1 mu=1 noise=0.15",
+    "d_nh_ciarlet_q2_n2": "dim=3 n=2 gt=qk k=2 q=3 im=6 family=nh_ciarlet u=smooth lambda=1 mu=1 uamp=0.02 noise=0.15",
+    "d_svk_q2_n2": "dim=3 n=2 gt=qk k=2 q=3 im=6 family=svk u=smooth lambda=1 mu=1 uamp=0.02 noise=0.15",
+    "d_nh_bonet_p2tet_n2": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=nh_bonet u=smooth lambda=1.3 mu=0.7 uamp=0.05 noise=0.2",
+    "d_source3d_p2vec_n2": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=source u=random a=0.5 noise=0.2",
+    "d_mass3d_p2vec_outer": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=mass region=outer u=random a=1.5 noise=0.2",
+    "d_nsource3d_q2vec_outer": "dim=3 n=2 gt=qk k=2 q=3 im=6 family=nsource region=outer u=random a=0.7 noise=0.15",
+    "d_elast3d_p2_half": "dim=3 n=2 gt=pk k=2 q=3 im=4 family=elast region=half u=random lambda=1 mu=1 noise=0.2",
+    # mid-size fixtures of the two headline configurations (values checked beyond n = 2)
+    "c3_elast3d_p2_n8": "dim=3 n=8 gt=pk k=2 q=3 im=4 family=elast u=random lambda=1 mu=1",
+    "c4_nh_ciarlet_q2_n4": "dim=3 n=4 gt=qk k=2 q=3 im=6 family=nh_ciarlet u=smooth lambda=1 mu=1 uamp=0.02",
     # ORACLE-ONLY fixtures (prefix o_: not yet a device family; tests/conftest.py keeps them out of the GPU parametrisations).
     # Compressible Mooney-Rivlin (the law of the reference's tests/nonlinear_elastostatic.cc), C10 = lambda, C01 = mu, D1 = a
     "o_mooney_rivlin_q2_n2": "dim=3 n=2 gt=qk k=2 q=3 im=6 family=mooney_rivlin u=smooth lambda=0.8 mu=0.3 a=2.0 uamp=0.03",

@@ -101,3 +101,22 @@ def test_exchange_is_deterministic():
         outs.append([(t.export_csc()[2], t.export_residual()) for t in terms])
     for (p0, r0), (p1, r1) in zip(*outs):
         assert np.array_equal(p0, p1) and np.array_equal(r0, r1)
+
+
+def test_halo_with_the_uniform_tile_kernel(monkeypatch):
+    """the class-uniform kernel under a halo: ghost columns are computed like owned ones, virtual pairs write zeros"""
+    monkeypatch.setenv("GFGPU_UNIFORM", "2")
+    monkeypatch.setenv("GFGPU_COLS", "0")
+    test_owned_slabs_match_single_term((3, [4, 3, 6], "PK", 2, 3, 4, "elast", [1.3, 0.7], 0, 3))
+    test_owned_slabs_match_single_term((3, [3, 3, 4], "PK", 1, 1, 2, "laplace", [2.0], 0, 2))
+
+
+def test_halo_refuses_load_terms_loudly():
+    """a source term has no tangent to announce; its interface contributions used to be dropped silently"""
+    from getfem_b200 import capi
+    ctx, m, mk, U_dev, ndof, keep = _setup(3, [3, 3, 4], "PK", 2, 3, 4, "elast", [1.0, 1.0], 0)
+    dmesh, dfem, tab = keep
+    t = capi.DeviceTerm(ctx, dmesh, dfem, tab, "source", [1.0, 2.0, 3.0], 1.0, 0)
+    t.set_element_range(0, m.nb_convex() // 2)
+    with pytest.raises(capi.GfgpuError, match="order-1-only"):
+        t.halo_begin(U_dev.data_ptr())

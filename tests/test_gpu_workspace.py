@@ -59,10 +59,13 @@ def add_term(ws, mim, m, Q, family, params, region, sfx="", fields=None):
     return rg
 
 
-def build_ws(dim, nsub, gt, k, Q, im, family, params, U=None, region=None, extra=(), fields=None):
+def build_ws(dim, nsub, gt, k, Q, im, family, params, U=None, region=None, extra=(), fields=None, pts=None):
     import getfem_b200 as gf
     m = gf.mesh()
     gf.regular_unit_mesh(m, nsub, "GT_%s(%d,1)" % (gt, dim))
+    if pts is not None:  # distorted fixture: same numbering (the reference re-adds the convexes in order), moved nodes
+        assert pts.shape == m.pts.shape and np.abs(pts - m.pts).max() < 0.5 / min(nsub)
+        m.pts = np.ascontiguousarray(pts, np.float64)
     mf = gf.mesh_fem(m, Q)
     mf.set_classical_finite_element(k)
     mim = gf.mesh_im(m)
@@ -90,7 +93,8 @@ def test_workspace_matches_reference_golden(name):
                             g["family"], g["fparams"], g["U"], a.get("region"), g["extra_terms"],
                             None if g["fields"] is None else
                             (g["fields"]["kd"], [(-v if g["family"] == "source" else v) for v in g["fields"]["vals"]],
-                             g["fields"]["d_elem_dof"]))
+                             g["fields"]["d_elem_dof"]),
+                            pts=g["pts"] if "noise" in a else None)
     # device first-touch numbering == mesh_fem::enumerate_dof, bit for bit
     assert mf.nb_dof() == g["meta"]["ndof"]
     assert np.array_equal(mf.ind_scalar_basic_dof_of_element(), g["elem_dof"])
