@@ -81,6 +81,13 @@ SIGNATURES = {
     "gfgpu_term_halo_send_view": (C.c_int, [_P, _i64, _i64, _PP, _P, _PP]),
     "gfgpu_term_halo_recv_view": (C.c_int, [_P, C.c_int, _PP, _P, _PP, _P]),
     "gfgpu_term_halo_accumulate": (C.c_int, [_P, C.c_int]),
+    "gfgpu_term_halo_add_send": (C.c_int, [_P, C.c_int, _i64, _i64, _i64]),
+    "gfgpu_term_halo_exchange": (C.c_int, [_P, _P, C.c_int]),
+    "gfgpu_comm_unique_id": (C.c_int, [_P, C.c_int]),
+    "gfgpu_comm_create": (C.c_int, [_P, C.c_int, C.c_int, _P, _PP]),
+    "gfgpu_comm_destroy": (C.c_int, [_P]),
+    "gfgpu_comm_rank": (C.c_int, [_P]),
+    "gfgpu_comm_size": (C.c_int, [_P]),
     "gfgpu_term_owned_range": (C.c_int, [_P, _P, _P]),
 }
 
@@ -368,6 +375,13 @@ class DeviceTerm(_Handle):
     def halo_accumulate(self, order_mask):
         check(lib().gfgpu_term_halo_accumulate(self.h, int(order_mask)))
 
+    def halo_add_send(self, owner_rank, dof_lo, dof_hi, r_lo):
+        check(lib().gfgpu_term_halo_add_send(self.h, int(owner_rank), int(dof_lo), int(dof_hi), int(r_lo)))
+
+    def halo_exchange(self, comm, order_mask):
+        """the exchange inside the library: one ncclGroup of sends / receives on the context's stream + accumulation"""
+        check(lib().gfgpu_term_halo_exchange(self.h, comm.h, int(order_mask)))
+
     def ctx_synchronize(self):
         self.ctx.synchronize()
 
@@ -375,6 +389,36 @@ class DeviceTerm(_Handle):
         lo, hi = _i64(), _i64()
         check(lib().gfgpu_term_owned_range(self.h, C.byref(lo), C.byref(hi)))
         return lo.value, hi.value
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """rendezvous id of a new communicator (rank 0 creates it, every rank passes it to Communicator)"""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    check(lib().gfgpu_comm_unique_id(buf, COMM_ID_BYTES))
+    return bytes(buf.raw)
+
+
+class Communicator(_Handle):
+    """gfgpu_comm: NCCL communicator of the ranks that share an assembly (one process per GPU)."""
+    _destroy = "gfgpu_comm_destroy"
+
+    def __init__(self, ctx, nranks, rank, unique_id):
+        super().__init__()
+        assert len(unique_id) == COMM_ID_BYTES
+        self.ctx = ctx
+        buf = C.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        check(lib().gfgpu_comm_create(ctx.h, int(nranks), int(rank), buf, C.byref(self.h)))
+
+    @property
+    def rank(self):
+        return int(lib().gfgpu_comm_rank(self.h))
+
+    @property
+    def size(self):
+        return int(lib().gfgpu_comm_size(self.h))
 
 
 class DeviceMatrix(_Handle):

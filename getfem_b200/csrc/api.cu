@@ -756,6 +756,7 @@ int gfgpu_term_halo_begin(gfgpu_term *t, const double *U_dev, int64_t *touched_l
   // forget a previous halo, then build the LOCAL structure + pattern (one tangent pass)
   t->halo = false;
   t->halo_src.clear();
+  t->halo_sends.clear();
   t->vJ.release(); t->vI.release(); t->vmask.release();
   t->st_valid = false; t->pat_valid = false; t->rc_ready = false;
   term_assemble(t, U_dev, GFGPU_TANGENT);

@@ -208,6 +208,14 @@ struct gfgpu_term {
   };
   bool halo = false;
   int64_t own_lo = 0, own_hi = 0;
+  // what this rank sends at every exchange (gfgpu_term_halo_add_send): ghost columns [dof_lo, dof_hi) of rank `owner`,
+  // residual slice [r_lo, dof_hi); pr_off / pr_cnt = that slice of pr under the current pattern
+  struct HaloSend {
+    int owner = 0;
+    int64_t dof_lo = 0, dof_hi = 0, r_lo = 0, pr_off = 0, pr_cnt = 0;
+  };
+  std::vector<HaloSend> halo_sends;
+  int64_t halo_sends_generation = -1;
   std::vector<std::unique_ptr<HaloSource>> halo_src;
   gf::DevBuf<int32_t> vJ, vI;            // all announced pairs, concatenated in source order
   gf::DevBuf<uint16_t> vmask;

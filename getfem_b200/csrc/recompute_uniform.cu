@@ -242,6 +242,7 @@ struct UArgs {
   double sl, smu;
   double *pr;
   int imgcap;              // doubles per image buffer (one per team)
+  int dbg;                 // experiments (GFGPU_UT_DBG): 1 = no flush of the images, 2 = no arithmetic, 4 = no team barriers
 };
 
 // A CTA = UT_TEAMS teams of UT_TW warps (one per SM sub-partition); a team runs one tile at a time: every warp its task (the
@@ -312,6 +313,58 @@ __device__ __noinline__ void ut_flush_rows(uint32_t img_s /* shared address of t
   }
 }
 
+// asynchronous copies global -> shared without registers (LDGSTS): the warp's next instruction stream and, a few steps
+// ahead, the strip positions of the elements it is going to need
+__device__ __forceinline__ void cp_async16(uint32_t dst_s, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_s), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst_s, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_s), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NLEFT>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NLEFT) : "memory"); }
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+constexpr int UT_SB = 64;  // units of a task's instruction stream (one 16-byte asynchronous copy per lane); the plan enforces it
+constexpr int UT_PR = 8;   // slots of a warp's ring of strip positions
+constexpr int UT_PD = 6;   // a step's strip positions are requested UT_PD instructions ahead
+constexpr int UT_WS = 2 * UT_SB * 8 + UT_PR * 128;  // bytes of shared memory per warp: two stream buffers + the ring
+
+// asynchronous flush: lane r < ROWS of warp wq sends row wq*ROWS + r with one bulk async store (TMA) per piece; nobody waits
+// here -- the copies read the image while the team already computes the first group of its next tile
+template <int ROWS>
+__device__ __noinline__ void ut_flush_rows_bulk(const double *img, double *pr, uint32_t rowstride, uint32_t nmem, int wq, int lane,
+                                                uint32_t jclo, uint32_t jchi, uint32_t npieces, uint2 pc0, uint2 pc1, uint2 pc2) {
+  const uint32_t k = (uint32_t)(wq * ROWS + (lane % ROWS));
+  const uint32_t lo = __shfl_sync(0xffffffffu, jclo, k), hi = __shfl_sync(0xffffffffu, jchi, k);
+  const int64_t jc = (int64_t)(((uint64_t)hi << 32) | lo);
+  fence_async_smem();
+  if (lane < ROWS && k < nmem) {
+    for (uint32_t pc = 0; pc < npieces; ++pc) {
+      const uint2 pw = pc == 0 ? pc0 : pc == 1 ? pc1 : pc2;
+      const int64_t len = pw.y & 0xffffu;
+      if (!len) continue;
+      const int64_t gstart = jc + pw.x;
+      const int64_t odd = gstart & 1, gs = gstart + odd, ge = (gstart + len) & ~int64_t(1);
+      const double *src = img + (size_t)k * rowstride + (pw.y >> 16) + odd;  // entry e of the piece sits at src[e]
+      if (odd) pr[gstart] = src[0];
+      if (ge > gs) bulk_s2g(pr + gs, src + odd, (uint32_t)((ge - gs) * 8));
+      if (((gstart + len) & 1) && gstart + len - 1 >= gs) pr[gstart + len - 1] = src[len - 1];
+    }
+    bulk_commit();
+  }
+}
+
 template <int N, int Q, int ND, int RF, int KG, int UT_TW, int TEAMS>
 __global__ void __launch_bounds__(TEAMS * UT_TW * 32, 1)
 k_utiles(const UArgs a) {
@@ -322,13 +375,17 @@ k_utiles(const UArgs a) {
   double *sM = reinterpret_cast<double *>(smraw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, team = warp / UT_TW, wq = warp % UT_TW;
   double *img = sM + ((NB * MTP + 15) & ~15) + (size_t)team * a.imgcap;
+  // per-warp scratch behind the images: instruction streams of the current / next tile, ring of strip positions
+  const uint32_t ws_s = smem_u32(sM + ((NB * MTP + 15) & ~15) + (size_t)UT_TEAMS * a.imgcap) + (uint32_t)warp * UT_WS;
+  const uint32_t ring_s = ws_s + 2 * UT_SB * 8 + (uint32_t)lane * 4u;
   for (int k = tid; k < NB * MTP; k += UT_THREADS) sM[k] = (k % MTP) < MT ? a.Mtab[(k / MTP) * MT + k % MTP] : 0.0;
   __syncthreads();
   const uint32_t t0 = a.cta_t0[blockIdx.x], ntl = a.cta_t0[blockIdx.x + 1] - t0;
   const uint32_t sM_s = smem_u32(sM);
-  // Tiles go to the teams round robin, so the NEXT tile of a team is known from the start: its record is loaded while the
-  // current tile runs, its program header / task range / lane words while the current image is flushed (a cold chain of five
-  // dependent loads per tile cost 17 % of the kernel: profiles/round2_ncu_utiles_v5_c3_n110.txt)
+  // Tiles go to the teams round robin, so the tiles a team will run are known from the start: the record of tile k+2, the
+  // program header / task range / CSC base of tile k+1 are loaded while tile k runs, and the instruction stream of tile k+1
+  // is copied to shared memory during the flush of tile k (a cold chain of dependent loads per tile, then per instruction,
+  // kept every warp waiting for 85 % of its time: profiles/round2_ncu_utiles_v6_c3_n110.txt)
   struct Meta {
     uint4 tw;
     uint2 h0, tr, pc0, pc1, pc2;
@@ -344,52 +401,75 @@ k_utiles(const UArgs a) {
     m.jclo = __ldg(a.ld + m.tw.y + le);
     m.jchi = __ldg(a.ld + m.tw.y + 32 + le);
   };
-  if (ntl == 0) return;
+  auto stream_copy = [&](const Meta &m, int buf) {  // the task's units [tr.x, tr.x + UT_SB): tr.x is even (16-byte source)
+    cp_async16(ws_s + (uint32_t)buf * (UT_SB * 8) + (uint32_t)lane * 16u, a.prog + m.tw.x + m.tr.x + 2 * lane);
+    cp_async_commit();
+  };
+  if (ntl == 0 || (uint32_t)team >= ntl) return;
   Meta cur;
   cur.tw = load_tw((uint32_t)team);
   load_meta(cur);
-  for (uint32_t lt = (uint32_t)team; lt < ntl; lt += UT_TEAMS) {
+  stream_copy(cur, 0);
+  uint4 tw1 = load_tw((uint32_t)team + UT_TEAMS);
+  int it = 0;
+  for (uint32_t lt = (uint32_t)team; lt < ntl; lt += UT_TEAMS, ++it) {
     Meta nxt;
-    nxt.tw = load_tw(lt + UT_TEAMS);
+    nxt.tw = tw1;
+    load_meta(nxt);                       // tile lt + TEAMS: header, task range, CSC base (in flight during this tile)
+    tw1 = load_tw(lt + 2 * UT_TEAMS);     // record of tile lt + 2 TEAMS
     const uint4 tw = cur.tw;
     const uint32_t nmem = tw.z;
-    const uint2 *P = a.prog + tw.x;
-    const uint2 h0 = cur.h0, tr = cur.tr, pc0 = cur.pc0, pc1 = cur.pc1, pc2 = cur.pc2;
-    const uint32_t rowstride = h0.x, npieces = h0.y & 0xffu;
+    const uint2 tr = cur.tr, pc0 = cur.pc0, pc1 = cur.pc1, pc2 = cur.pc2;
+    const uint32_t rowstride = cur.h0.x, npieces = cur.h0.y & 0xffu;
     const uint32_t le = min((uint32_t)lane, nmem - 1u);
-    const uint32_t *ldp = a.ld + tw.y;
-    const uint32_t *lpos = ldp + 64 + le;
+    const char *lpos = reinterpret_cast<const char *>(a.ld + tw.y + 64 + le);
     const uint32_t jclo = cur.jclo, jchi = cur.jchi;
     const uint32_t row_s = smem_u32(img) + (uint32_t)lane * rowstride * 8u;  // shared address of the lane's image row
     const uint32_t par0 = (jclo + pc0.x) & 1u, par1 = (jclo + pc1.x) & 1u, par2 = (jclo + pc2.x) & 1u;
+    const uint32_t sb_s = ws_s + (uint32_t)(it & 1) * (UT_SB * 8);  // my instruction stream, unit u at sb_s + 8 u
+    cp_async_wait<0>();  // the stream of this tile (requested during the previous one) has landed
+    __syncwarp();
 
-    if (tr.y > tr.x) {
+    const uint32_t nu = (a.dbg & 2) ? 0u : tr.y - tr.x;  // units of my task
+    // bulk flush (a.dbg & 8): the image may be overwritten once every warp's bulk stores of the previous tile have read it:
+    // checked as late as possible, before the first store of the task
+    bool img_ok = !(a.dbg & 8);
+    auto image_ready = [&]() {
+      if (!img_ok) {
+        bulk_wait_read0();
+        team_barrier(team, UT_TW * 32);
+        img_ok = true;
+      }
+    };
+    if (nu) {
       double acc[KG][ACC];
 #pragma unroll
       for (int p = 0; p < KG; ++p)
 #pragma unroll
         for (int m = 0; m < ACC; ++m) acc[p][m] = 0.0;
-      // instruction stream [tr.x, tr.y) with a three-deep software pipeline: while instruction ip runs, the geometry row of
-      // ip+1, the strip position of ip+2 and the instruction word ip+3 are in flight
-      uint32_t ip = tr.x;
-      const uint32_t ipl = tr.y - 1u;
-      auto fetch = [&](uint32_t k) { return ldg_keep_u2(P + min(k, ipl)); };  // past the end: the final FLUSH again (no loads follow)
+      auto unit = [&](uint32_t u) { return lds_u2(sb_s + min(u, nu - 1u) * 8u); };  // past the end: the final FLUSH again
       auto is_step = [](const uint2 &I) { return (int)I.x >= 0; };
-      auto load_pos = [&](const uint2 &I) {  // byte offset of the lane's element of that rank in the geometry table
-        return __ldg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(lpos) + (I.x & 0x7ff80u)));
+      // strip position of unit u's element -> ring slot u % UT_PR (one group per unit, also for a FLUSH: the count stays aligned)
+      auto request_pos = [&](uint32_t u) {
+        const uint2 I = unit(u);
+        if (u < nu && is_step(I)) cp_async4(ring_s + (u % UT_PR) * 128u, lpos + (I.x & 0x7ff80u));
+        cp_async_commit();
       };
-      auto load_g = [&](double (&G)[GSZ], uint32_t off) {
+      auto load_g = [&](double (&G)[GSZ], uint32_t u) {  // geometry row of unit u: its strip position has landed in the ring
+        const uint32_t off = lds_u32(ring_s + (u % UT_PR) * 128u);
         const double *gp = reinterpret_cast<const double *>(reinterpret_cast<const char *>(a.eg) + off);
 #pragma unroll
         for (int c = 0; c < GSZ; ++c) G[c] = __ldg(gp + c * 32);
       };
-      uint2 I0 = fetch(ip), I1 = fetch(ip + 1), I2 = fetch(ip + 2);
+#pragma unroll
+      for (int d = 0; d < UT_PD; ++d) request_pos((uint32_t)d);
       double GA[GSZ], GB[GSZ];
 #pragma unroll
       for (int c = 0; c < GSZ; ++c) GA[c] = GB[c] = 0.0;
-      uint32_t pos1 = 0;
-      if (is_step(I0)) load_g(GA, load_pos(I0));
-      if (is_step(I1)) pos1 = load_pos(I1);
+      uint2 I0 = unit(0), I1 = unit(1);
+      cp_async_wait<UT_PD - 1>();  // position of unit 0
+      if (is_step(I0)) load_g(GA, 0);
+      uint32_t ip = 0;
 
       auto flush_pair = [&](const double (&A)[ACC], const uint2 &I) {
         if ((uint32_t)lane >= nmem) return;
@@ -432,11 +512,11 @@ k_utiles(const UArgs a) {
         }
       };
 
+      // one instruction: while unit ip runs, the geometry row of ip+1 is loaded and the strip position of ip+UT_PD requested
       auto phase = [&](double (&Gc)[GSZ], double (&Gn)[GSZ]) {
-        const uint2 I3 = fetch(ip + 3);
-        uint32_t pos2 = 0;
-        if (is_step(I2)) pos2 = load_pos(I2);
-        if (is_step(I1)) load_g(Gn, pos1);
+        request_pos(ip + UT_PD);
+        cp_async_wait<UT_PD - 1>();  // position of unit ip + 1
+        if (ip + 1 < nu && is_step(I1)) load_g(Gn, ip + 1);
         if (is_step(I0)) {
           const int npairs = (int)((I0.x >> 29) & 3u);
           const uint32_t code[3] = {(I0.x >> 19) & 0x3ffu, I0.y & 0x3ffu, (I0.y >> 10) & 0x3ffu};
@@ -483,27 +563,38 @@ k_utiles(const UArgs a) {
             }
           }
         } else {
+          image_ready();
           const uint32_t slot = (I0.x >> 15) & 3u;
           if (KG == 1 || slot == 0) flush_pair(acc[0], I0);
           else if (KG == 2 || slot == 1) flush_pair(acc[KG > 1 ? 1 : 0], I0);
           else flush_pair(acc[KG > 2 ? 2 : 0], I0);
         }
-        I0 = I1; I1 = I2; I2 = I3;
-        pos1 = pos2;
+        I0 = I1;
+        I1 = unit(ip + 2);
       };
+      // (a geometry row TWO instructions ahead, three register buffers in rotation, was tried: slower -- the extra 18
+      // registers cost more than the longer prefetch distance brought: profiles/round2_utiles_experiments.txt)
       for (;;) {
         phase(GA, GB);
-        if (++ip > ipl) break;
+        if (++ip >= nu) break;
         phase(GB, GA);
-        if (++ip > ipl) break;
+        if (++ip >= nu) break;
       }
     }
-    team_barrier(team, UT_TW * 32);  // the image of the tile is complete
-    load_meta(nxt);      // in flight during the flush
-    ut_flush_rows<UT_ROWS>(smem_u32(img), a.pr, rowstride, nmem, wq, lane, jclo, jchi, npieces, pc0, pc1, pc2);
-    team_barrier(team, UT_TW * 32);  // the image may be overwritten
+    image_ready();  // (a task without a flush)
+    if (!(a.dbg & 4)) team_barrier(team, UT_TW * 32);  // the image of the tile is complete
+    cp_async_wait<0>();              // (my ring requests past the end of the task)
+    stream_copy(nxt, (it + 1) & 1);  // lands during the flush
+    if (a.dbg & 8) {
+      ut_flush_rows_bulk<UT_ROWS>(img, a.pr, rowstride, nmem, wq, lane, jclo, jchi, npieces, pc0, pc1, pc2);
+    } else {
+      if (!(a.dbg & 1)) ut_flush_rows<UT_ROWS>(smem_u32(img), a.pr, rowstride, nmem, wq, lane, jclo, jchi, npieces, pc0, pc1, pc2);
+      if (!(a.dbg & 4)) team_barrier(team, UT_TW * 32);  // the image may be overwritten
+    }
     cur = nxt;
   }
+  cp_async_wait<0>();
+  bulk_wait0();
 }
 
 // ---------------------------------------------------------------- host side
@@ -525,7 +616,11 @@ static int64_t ut_select_heads(gfgpu_ctx *ctx, const uint8_t *flags, int64_t n, 
 // Builds the class-uniform plan of term t.  false = the term keeps the general tile kernel (GFGPU_UNIFORM=0, or too few of
 // its columns have translated copies).  GFGPU_UNIFORM=2 forces the uniform kernel whatever the class sizes (tests).
 bool uniform_prepare(gfgpu_term *t) {
-  const int mode = uenv_int("GFGPU_UNIFORM", 1);
+  // 0 (default): general tile kernel.  1: this kernel when most columns have translated copies.  2: always (tests).
+  // Measured on BASELINE config 3 (profiles/round2_utiles_experiments.txt): 10.4 ms against 8.6 ms for the general kernel --
+  // 27 % less DRAM traffic and 9 GB less device memory, but the per-tile interpretation (team barriers, image flush, short
+  // instruction streams) leaves the fp64 pipe idle 74 % of the time; it stays an opt-in until that is solved.
+  const int mode = uenv_int("GFGPU_UNIFORM", 0);
   t->rc_uni = false;
   if (!mode) return false;
   gfgpu_ctx *ctx = t->ctx;
@@ -619,9 +714,13 @@ bool uniform_prepare(gfgpu_term *t) {
   uint32_t max_stride = 2;
   for (int64_t c = 0; c < ncls; ++c) {
     std::string err;
-    const bool ok = uplan::build_class(h_desc.data() + (size_t)c * dw, h_llen[c], Q, nd, row_cap, group_cap, tw, kg, prog,
+    const bool ok = uplan::build_class(h_desc.data() + (size_t)c * dw, h_llen[c], Q, nd, row_cap, group_cap, tw, kg, UT_SB, prog,
                                        cplan[c], err);
-    GF_REQUIRE(ok, "uniform plan: " + err);
+    if (!ok) {  // a column the uniform kernel's formats cannot hold: the term keeps the general tile kernel
+      if (getenv("GFGPU_DEBUG")) fprintf(stderr, "[gfgpu] uniform tiles: not used (%s)\n", err.c_str());
+      GF_REQUIRE(mode != 2, "uniform plan: " + err);
+      return false;
+    }
     for (const uplan::Sub &sb : cplan[c].subs) max_stride = std::max(max_stride, sb.rowstride);
     GF_REQUIRE(prog.size() < (size_t(1) << 31), "uniform plan: programs too large");
     GF_REQUIRE(cplan[c].m <= 4096, "uniform plan: column valence beyond the instruction format");
@@ -671,6 +770,7 @@ bool uniform_prepare(gfgpu_term *t) {
   GF_CUDA(cudaMemcpyAsync(t->ru_tiles.p, tiles.data(), tiles.size() * sizeof(UTile), cudaMemcpyHostToDevice, s));
   t->ru_cta.alloc(ctx, cta_t0.size());
   t->ru_cta.upload(cta_t0.data());
+  prog.resize(prog.size() + 2 * UT_SB + 4, 0u);  // a stream copy always reads UT_SB units
   t->ru_prog.alloc(ctx, std::max<size_t>(prog.size(), 1));
   GF_CUDA(cudaMemcpyAsync(t->ru_prog.p, prog.data(), prog.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
   DevBuf<uint8_t> dchunks;
@@ -755,7 +855,8 @@ static void launch_utiles_t(gfgpu_term *t) {
   a.sl = sign * t->par[0]; a.smu = sign * t->par[1];
   a.pr = t->pr.p;
   a.imgcap = t->ru_imgcap;
-  const size_t smem = (size_t)((ND * ND * MTP + 15) & ~15) * 8 + (size_t)TEAMS * a.imgcap * 8;
+  a.dbg = uenv_int("GFGPU_UT_DBG", 0);
+  const size_t smem = (size_t)((ND * ND * MTP + 15) & ~15) * 8 + (size_t)TEAMS * a.imgcap * 8 + (size_t)TEAMS * TW * UT_WS;
   GF_REQUIRE(smem <= 226 * 1024, "uniform tiles: image buffers too large for shared memory (GFGPU_UT_IMG / GFGPU_UT_VARIANT)");
   auto kern = k_utiles<N, Q, ND, RF, KG, TW, TEAMS>;
   GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -64,7 +64,7 @@ struct PairD {
 // that runs a tile (the groups are packed into them longest-processing-time first; a task may be empty).  Returns false with
 // `err` set on failure.
 inline bool build_class(const uint32_t *d, size_t dlen, int Q, int nd, uint32_t row_cap, int group_cap, int ntasks, int kg,
-                        std::vector<uint32_t> &prog, ClassPlan &out, std::string &err) {
+                        int max_units, std::vector<uint32_t> &prog, ClassPlan &out, std::string &err) {
   kg = std::max(1, std::min(kg, KGU));  // pairs per group (the kernel variant's accumulator sets)
   if (dlen < (size_t)(2 + Q)) { err = "short descriptor"; return false; }
   const uint32_t np = d[0];
@@ -164,6 +164,7 @@ inline bool build_class(const uint32_t *d, size_t dlen, int Q, int nd, uint32_t 
     std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return binw[x] > binw[y]; });
     if (nbins > 0xffffu) { err = "too many tasks in one tile"; return false; }
     // ---- emit
+    if ((prog.size() / 2) & 1) { prog.push_back(0u); prog.push_back(0u); }  // programs start on 16 bytes
     Sub sub;
     sub.prog = (uint32_t)(prog.size() / 2);
     sub.ntasks = (uint32_t)nbins;
@@ -178,6 +179,7 @@ inline bool build_class(const uint32_t *d, size_t dlen, int Q, int nd, uint32_t 
       prog[base + 2 * (1 + b) + 1] = (b < npc ? pc[b].len : 0u) | (pc[b].pbase << 16);
     }
     for (size_t t = 0; t < nbins; ++t) {
+      if (((prog.size() - base) / 2) & 1) { prog.push_back(0u); prog.push_back(0u); }  // streams start on 16 bytes
       prog[base + 2 * (HDR_UNITS + t)] = (uint32_t)((prog.size() - base) / 2);
       for (size_t gi : bins[order[t]]) {
         const Group &g = groups[gi];
@@ -201,6 +203,10 @@ inline bool build_class(const uint32_t *d, size_t dlen, int Q, int nd, uint32_t 
         }
       }
       prog[base + 2 * (HDR_UNITS + t) + 1] = (uint32_t)((prog.size() - base) / 2);
+      if (prog[base + 2 * (HDR_UNITS + t) + 1] - prog[base + 2 * (HDR_UNITS + t)] > (uint32_t)max_units) {
+        err = "a task is longer than the kernel's instruction buffer";
+        return false;
+      }
     }
     out.subs.push_back(sub);
     a = e;

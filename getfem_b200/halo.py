@@ -86,6 +86,28 @@ def setup_distributed(term, U_dev_ptr=None, group=None):
     return plan
 
 
+def make_communicator(ctx, group=None):
+    """gfgpu communicator (NCCL, created inside the C ABI) over the ranks of a torch.distributed group: rank 0's
+    ncclGetUniqueId travels through the group's object broadcast, the exchange itself never touches torch."""
+    import torch.distributed as dist
+    from . import capi
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    return capi.Communicator(ctx, world, rank, box[0])
+
+
+def register_sends(term, plan):
+    """tells the library what this rank sends at every exchange (gfgpu_term_halo_add_send)"""
+    for q, a, b, r_lo in plan.sends:
+        term.halo_add_send(q, a, b, r_lo)
+
+
+def exchange_nccl(term, comm, order_mask):
+    """Call after term.assemble_dev(..., order_mask): gfgpu_term_halo_exchange, asynchronous on the context's stream."""
+    term.halo_exchange(comm, order_mask)
+
+
 def exchange_distributed(term, plan, order_mask, group=None):
     """Call after term.assemble_dev(..., order_mask), on the stream the term's context was created with."""
     import torch.distributed as dist

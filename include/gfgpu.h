@@ -255,6 +255,28 @@ int gfgpu_term_halo_recv_view(gfgpu_term *t, int src_rank, double **pr_recv_dev,
 int gfgpu_term_halo_accumulate(gfgpu_term *t, int order_mask);
 int gfgpu_term_owned_range(gfgpu_term *t, int64_t *own_lo, int64_t *own_hi);
 
+/* ---- the exchange inside the library: NCCL over NVLink, one communicator per process (one process per GPU).
+ * Replaces MPI_SUM_SPARSE_MATRIX / MPI_SUM_VECTOR of src/getfem/getfem_config.h:214-341 (used by
+ * getfem_generic_assembly_workspace.cc:855-858) with point-to-point slices between neighbouring element blocks.
+ *   gfgpu_comm_unique_id   rank 0 creates the rendezvous id (GFGPU_COMM_ID_BYTES bytes) and hands it to the other ranks by any
+ *                          means (MPI_Bcast, torch.distributed, a file): ncclGetUniqueId
+ *   gfgpu_comm_create      collective over the ranks: ncclCommInitRank on the context's device
+ *   gfgpu_term_halo_add_send  after halo_commit: this rank's ghost columns [dof_lo, dof_hi) belong to rank `owner`; it will
+ *                          send them and the residual slice [r_lo, dof_hi) at every exchange
+ *   gfgpu_term_halo_exchange  after gfgpu_term_assemble_dev, on the same stream, asynchronous: ONE ncclGroup with the sends to
+ *                          the owners and the receives from the sources, then halo_accumulate.  The owned slab and residual
+ *                          slice are complete when the stream reaches the end of it.
+ * NCCL is loaded at run time (libnccl.so.2); without it these calls fail with a message, nothing else is affected. */
+#define GFGPU_COMM_ID_BYTES 128
+typedef struct gfgpu_comm gfgpu_comm;
+int gfgpu_comm_unique_id(char *id_out, int capacity);
+int gfgpu_comm_create(gfgpu_ctx *ctx, int nranks, int rank, const char *id, gfgpu_comm **out);
+int gfgpu_comm_destroy(gfgpu_comm *c);
+int gfgpu_comm_rank(gfgpu_comm *c);
+int gfgpu_comm_size(gfgpu_comm *c);
+int gfgpu_term_halo_add_send(gfgpu_term *t, int owner_rank, int64_t dof_lo, int64_t dof_hi, int64_t r_lo);
+int gfgpu_term_halo_exchange(gfgpu_term *t, gfgpu_comm *c, int order_mask);
+
 #ifdef __cplusplus
 }
 #endif

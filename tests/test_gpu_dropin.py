@@ -90,8 +90,6 @@ PROBE_CASES = [  # spellings of tests/test_assembly.cc:812-866 that only recogni
 ]
 
 
-@pytest.mark.xfail(strict=False, reason="written after the GPU minutes of round 1 were spent: the recognition is verified on CPU "
-                                        "(tests/test_shim_probe.py), the device run of these spellings is still to be observed")
 @pytest.mark.parametrize("mesh,expr", PROBE_CASES)
 def test_equivalent_spellings_run_on_the_device(mesh, expr):
     if not os.path.exists(BIN):

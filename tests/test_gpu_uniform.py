@@ -100,10 +100,13 @@ def test_uniform_equals_general_tile_kernel(dim, n, k, Q, family, params, im):
     assert np.array_equal(pr1, pr2)
 
 
-def test_uniform_engages_by_default_on_a_regular_mesh():
-    """n = 20: most columns sit in classes of >= 16 translated copies, the default plan takes the uniform kernel"""
-    jc, ir, pr, dev, ws = _mirror_term(3, 20, 2, 3, "elast", [1.0, 1.0], 4)
-    assert dev.kernel_kind == 3
+def test_uniform_engages_on_a_regular_mesh_when_asked():
+    """GFGPU_UNIFORM=1, n = 20: most columns sit in classes of >= 16 translated copies, the plan takes the uniform kernel;
+    on the tiny goldens the same setting keeps the general kernel (coverage rule)"""
+    with env(GFGPU_UNIFORM=1):
+        jc, ir, pr, dev, ws = _mirror_term(3, 20, 2, 3, "elast", [1.0, 1.0], 4)
+        assert dev.kernel_kind == 3
+        assert _mirror_term(3, 3, 2, 3, "elast", [1.0, 1.0], 4)[3].kernel_kind == 1
     with env(GFGPU_UNIFORM=0):
         jc0, ir0, pr0, d0, _ = _mirror_term(3, 20, 2, 3, "elast", [1.0, 1.0], 4)
         assert d0.kernel_kind == 1
