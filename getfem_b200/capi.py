@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("GFGPU_LIB") or os.path.join(_HERE, "libgfgpu.so")  # 
 GT_PK, GT_QK = 0, 1
 FEM_PK, FEM_QK = 0, 1
 LAPLACE, ELASTICITY, SVK, NEOHOOKEAN_CIARLET, NEOHOOKEAN_BONET, MASS, SOURCE, NORMAL_SOURCE = range(8)
+MOONEY_RIVLIN, CIARLET_GEYMONAT, BLATZ_KO = 8, 9, 10
 RESIDUAL, TANGENT = 1, 2
 STRATEGY_AUTO, STRATEGY_STAGED, STRATEGY_RECOMPUTE = 0, 1, 2
 
@@ -21,6 +22,7 @@ FAMILY_BY_NAME = {
     "laplace": LAPLACE, "elast": ELASTICITY, "elasticity": ELASTICITY, "svk": SVK,
     "nh_ciarlet": NEOHOOKEAN_CIARLET, "nh_bonet": NEOHOOKEAN_BONET, "mass": MASS, "source": SOURCE,
     "nsource": NORMAL_SOURCE, "normal_source": NORMAL_SOURCE,
+    "mooney_rivlin": MOONEY_RIVLIN, "ciarlet_geymonat": CIARLET_GEYMONAT, "blatz_ko": BLATZ_KO,
 }
 
 # symbol -> (restype, argtypes); kept in one table so tests can check it against include/gfgpu.h

@@ -334,13 +334,15 @@ int gfgpu_term_create(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem, gfgpu_ta
   GF_REQUIRE(ctx && mesh && fem && tab && out, "null argument");
   GF_REQUIRE(fem->mesh == mesh, "the fem was built on another mesh");
   GF_REQUIRE(tab->dim == mesh->dim && tab->ng == mesh->ng && tab->nd == fem->nd, "tables do not match mesh/fem");
-  GF_REQUIRE(family >= GFGPU_LAPLACE && family <= GFGPU_NORMAL_SOURCE, "unknown expression family");
+  GF_REQUIRE(family >= GFGPU_LAPLACE && family <= GFGPU_BLATZ_KO, "unknown expression family");
   const int need = family == GFGPU_SOURCE ? fem->qdim
                    : family == GFGPU_NORMAL_SOURCE ? fem->qdim * mesh->dim
-                   : (family == GFGPU_LAPLACE || family == GFGPU_MASS) ? 1 : 2;
+                   : (family == GFGPU_LAPLACE || family == GFGPU_MASS) ? 1
+                   : (family == GFGPU_MOONEY_RIVLIN || family == GFGPU_CIARLET_GEYMONAT) ? 3
+                   : family == GFGPU_BLATZ_KO ? 5 : 2;
   GF_REQUIRE(params && nparams >= need, "missing parameters for this family");
   if (family == GFGPU_ELASTICITY) GF_REQUIRE(fem->qdim == mesh->dim, "elasticity needs qdim == mesh dimension");
-  if (family == GFGPU_SVK || family == GFGPU_NEOHOOKEAN_CIARLET || family == GFGPU_NEOHOOKEAN_BONET)
+  if (family == GFGPU_SVK || family == GFGPU_NEOHOOKEAN_CIARLET || family == GFGPU_NEOHOOKEAN_BONET || family >= GFGPU_MOONEY_RIVLIN)
     GF_REQUIRE(fem->qdim == 3 && mesh->dim == 3, "finite-strain families need a 3D vector field");
   GF_REQUIRE(strategy >= GFGPU_STRATEGY_AUTO && strategy <= GFGPU_STRATEGY_RECOMPUTE, "unknown strategy");
   std::unique_ptr<gfgpu_term> t(new gfgpu_term);
@@ -637,7 +639,7 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
   if (do_t) {
     // linear families: the keep masks do not depend on U, a valid pattern stays valid
     const bool value_dependent = t->family == GFGPU_SVK || t->family == GFGPU_NEOHOOKEAN_CIARLET ||
-                                 t->family == GFGPU_NEOHOOKEAN_BONET;
+                                 t->family == GFGPU_NEOHOOKEAN_BONET || t->family >= GFGPU_MOONEY_RIVLIN;
     if (!t->pat_valid) {
       tic(3); gf::build_pattern(t); toc(3);
       if (t->halo) gf::halo_build_maps(t);

@@ -12,7 +12,8 @@ bool launch_elem_kernel(gfgpu_ctx *ctx, int dim, int Q, int nd, bool affine, con
     case GFGPU_LAPLACE: fk = FK_LAPLACE; break;
     case GFGPU_MASS: case GFGPU_SOURCE: case GFGPU_NORMAL_SOURCE: fk = FK_MASS; break;  // source terms = the flux part of the mass kernel
     case GFGPU_ELASTICITY: fk = FK_ELAST; break;
-    case GFGPU_SVK: case GFGPU_NEOHOOKEAN_CIARLET: case GFGPU_NEOHOOKEAN_BONET: fk = FK_HYPER; break;
+    case GFGPU_SVK: case GFGPU_NEOHOOKEAN_CIARLET: case GFGPU_NEOHOOKEAN_BONET:
+    case GFGPU_MOONEY_RIVLIN: case GFGPU_CIARLET_GEYMONAT: case GFGPU_BLATZ_KO: fk = FK_HYPER; break;
     default: return false;
   }
   return launch_elem_inst_2d(ctx, dim, Q, nd, fk, affine, a) ||

@@ -264,6 +264,138 @@ __device__ inline void hyper_point(int law, const double *Gu, double lambda, dou
   hyper_flux(h, coeff, P);
 }
 
+// The laws of add_finite_strain_elasticity_brick written on the invariants of C = F^T F (getfem_nonlinear_elasticity.cc:
+// 2276-2290): compressible Mooney-Rivlin (:503-607, the law of the reference's tests/nonlinear_elastostatic.cc; invariants
+// j1, j2, i3 and their derivatives from compute_invariants, :45-262), Ciarlet-Geymonat (:817-888), generalized Blatz-Ko
+// (:706-815).  Their second derivative has one shape,
+//   A(i,j,k,l) = alpha ddi3(i,j,k,l) + gamma ddi2(i,j,k,l) + sum_pq beta_pq dv_p(i,j) dv_q(k,l),   dv = (Id, di2, di3),
+// with scalar coefficients per law; PK2 and the tangent dS(i,j,k,l) = sum_m A(i,j,m,l) F(k,m) then go through
+// AHL_wrapper_sigma (:1781-1827) exactly like the Neo-Hookean laws above.  par: Mooney-Rivlin (C10, C01, D1),
+// Ciarlet-Geymonat (lambda, mu, a), Blatz-Ko (a, b, c, d, n).  Writes P = coeff F S (9) and D (81) like hyper_point.
+__device__ inline void inv_law_point(int law, const double *Gu, const double *par, double coeff, double *P, double *D) {
+  double F[9], C[9], Ci[9], S[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) s += Gu[k + 3 * i] * Gu[k + 3 * j];
+      C[i + 3 * j] = s + Gu[i + 3 * j] + Gu[j + 3 * i] + (i == j ? 1.0 : 0.0);  // 2 E + Id
+      F[i + 3 * j] = Gu[i + 3 * j] + (i == j ? 1.0 : 0.0);
+    }
+  const double detF = det3cm(F), i3 = det3cm(C);
+  {
+#define C_(i, j) C[(i) + 3 * (j)]
+    Ci[0] = (C_(1, 1) * C_(2, 2) - C_(1, 2) * C_(2, 1)) / i3;
+    Ci[1] = -(C_(1, 0) * C_(2, 2) - C_(1, 2) * C_(2, 0)) / i3;
+    Ci[2] = (C_(1, 0) * C_(2, 1) - C_(1, 1) * C_(2, 0)) / i3;
+    Ci[3] = -(C_(0, 1) * C_(2, 2) - C_(0, 2) * C_(2, 1)) / i3;
+    Ci[4] = (C_(0, 0) * C_(2, 2) - C_(0, 2) * C_(2, 0)) / i3;
+    Ci[5] = -(C_(0, 0) * C_(2, 1) - C_(0, 1) * C_(2, 0)) / i3;
+    Ci[6] = (C_(0, 1) * C_(1, 2) - C_(0, 2) * C_(1, 1)) / i3;
+    Ci[7] = -(C_(0, 0) * C_(1, 2) - C_(0, 2) * C_(1, 0)) / i3;
+    Ci[8] = (C_(0, 0) * C_(1, 1) - C_(0, 1) * C_(1, 0)) / i3;
+#undef C_
+  }
+  const double i1 = C[0] + C[4] + C[8];
+  double ff = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) ff += C[i + 3 * j] * C[j + 3 * i];
+  const double i2 = (i1 * i1 - ff) / 2;
+  // dv_1 = Id, dv_2 = di2 = i1 Id - C (compute_di2, :95-102), dv_3 = di3 = i3 C^-1 (compute_di3, :132-140)
+  double alpha = 0, gamma = 0, b11 = 0, b12 = 0, b13 = 0, b22 = 0, b23 = 0, b33 = 0;
+  double s1 = 0, s2 = 0, s3 = 0;  // S = 2 (s1 Id + s2 di2 + s3 di3)
+  if (law == GFGPU_MOONEY_RIVLIN) {
+    const double c10 = par[0], c01 = par[1], d1 = par[2];
+    const double p13 = pow(fabs(i3), -1.0 / 3.0), p23 = pow(fabs(i3), -2.0 / 3.0);
+    const double k1 = 1.0 / (3 * i3), k2 = 4 * k1 * k1 * i1;      // compute_ddj1 (:176-196)
+    const double m1 = 2.0 / (3 * i3), m2 = 5 * m1 * m1 * i2 / 2;  // compute_ddj2 (:219-240)
+    const double dw3 = d1 - d1 / sqrt(fabs(i3)), a22 = d1 / (2 * pow(fabs(i3), 1.5));
+    s1 = c10 * p13;                                              // dj1 = (di1 - i1/(3 i3) di3) p13 (:169-174)
+    s2 = c01 * p23;                                              // dj2 = (di2 - 2 i2/(3 i3) di3) p23 (:212-217)
+    s3 = -c10 * p13 * i1 / (3 * i3) - c01 * p23 * 2 * i2 / (3 * i3) + dw3;
+    alpha = -4 * c10 * p13 * i1 * k1 - 4 * c01 * p23 * i2 * m1 + 4 * dw3;
+    gamma = 4 * c01 * p23;
+    b13 = -4 * c10 * p13 * k1;
+    b23 = -4 * c01 * p23 * m1;
+    b33 = 4 * c10 * p13 * k2 + 4 * c01 * p23 * m2 + 4 * a22;
+  } else if (law == GFGPU_CIARLET_GEYMONAT) {
+    // W = a i1 + b i2 + c i3 - d/2 log i3 + e (:817-888): S = -2 b C + 2 (a + b tr C) Id + C^-1 (2 c i3 - d)
+    const double a = par[2], b = par[1] / 2 - par[2], c = par[0] / 4 - par[1] / 2 + par[2], d = par[0] / 2 + par[1];
+    s1 = a;  // 2 a Id + 2 b (i1 Id - C) = 2 (a + b tr C) Id - 2 b C
+    s2 = b;
+    s3 = detF <= 0 ? 0.0 : (2 * c * i3 - d) / (2 * i3);  // the penalty REPLACES this part when det F <= 0 (:848-851)
+    alpha = -2 * (d - 2 * i3 * c) / i3;
+    gamma = 4 * b;
+    b33 = 2 * d / (i3 * i3);
+  } else {  // generalized Blatz-Ko (:706-815): W = (a i1 + b sqrt|i3| + c i2 / i3 + d)^n
+    const double a = par[0], b = par[1], c = par[2], d = par[3], n = par[4];
+    const double z = a * i1 + b * sqrt(fabs(i3)) + c * i2 / i3 + d, nz = n * pow(z, n - 1.);
+    const double y = b / (2. * sqrt(fabs(i3))) - c * i2 / (i3 * i3);
+    s1 = nz * a; s2 = nz * c / i3; s3 = nz * y;
+    const double nnz = n * (n - 1.) * pow(z, n - 2.);
+    alpha = 4 * s3;
+    gamma = 4 * s2;
+    b11 = 4 * nnz * a * a;
+    b12 = 4 * nnz * a * c / i3;
+    b13 = 4 * nnz * a * y;
+    b22 = 4 * nnz * c * c / (i3 * i3);
+    b23 = 4 * (nnz * y * c / i3 - nz * c / (i3 * i3));
+    b33 = 4 * (nnz * y * y + nz * (2. * c * i2 / (i3 * i3 * i3) - b / (4. * pow(i3, 1.5))));
+  }
+  double di2[9], di3[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    di2[i] = ((i % 4) == 0 ? i1 : 0.0) - C[i];
+    di3[i] = Ci[i] * i3;
+    S[i] = 2 * (((i % 4) == 0 ? s1 : 0.0) + s2 * di2[i] + s3 * di3[i]);
+  }
+  if (detF <= 0) {  // the reference's penalty on inverted elements
+#pragma unroll
+    for (int i = 0; i < 9; ++i) S[i] += 1e200 * C[i];
+  }
+  const double hd = i3 / 2;
+#define CI(i, j) Ci[(i) + 3 * (j)]
+#pragma unroll
+  for (int l = 0; l < 3; ++l)
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+      double T[9];  // T(p,m) = A(p,n,m,l)
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          const double dd3 = hd * (CI(n, p) * CI(l, m) - CI(n, m) * CI(l, p) + CI(p, n) * CI(l, m) - CI(p, m) * CI(l, n));
+          const double dd2 = (p == n && m == l ? 1.0 : 0.0) - (n == m && p == l ? 0.5 : 0.0) - (p == m && n == l ? 0.5 : 0.0);
+          const double u1 = p == n ? 1.0 : 0.0, u2 = di2[p + 3 * n], u3 = di3[p + 3 * n];
+          const double v1 = m == l ? 1.0 : 0.0, v2 = di2[m + 3 * l], v3 = di3[m + 3 * l];
+          T[p + 3 * m] = alpha * dd3 + gamma * dd2 + b11 * u1 * v1 + b12 * (u1 * v2 + u2 * v1) + b13 * (u1 * v3 + u3 * v1) +
+                         b22 * u2 * v2 + b23 * (u2 * v3 + u3 * v2) + b33 * u3 * v3;
+        }
+      double FT[9];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int m = 0; m < 3; ++m) FT[a + 3 * m] = F[a] * T[3 * m] + F[a + 3] * T[1 + 3 * m] + F[a + 6] * T[2 + 3 * m];
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          double v = FT[a] * F[b] + FT[a + 3] * F[b + 3] + FT[a + 6] * F[b + 6];
+          if (a == b) v += S[l + 3 * n];
+          D[a + 3 * (n + 3 * (b + 3 * l))] = coeff * v;
+        }
+    }
+#undef CI
+#pragma unroll
+  for (int n = 0; n < 3; ++n)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) P[a + 3 * n] = coeff * (F[a] * S[3 * n] + F[a + 3] * S[1 + 3 * n] + F[a + 6] * S[2 + 3 * n]);
+}
+
 template <int DIM, int Q, int ND, int FK, bool AFFINE>
 __global__ void __launch_bounds__(ElemCfg<DIM, Q, ND, FK, AFFINE>::THREADS)
 elem_kernel(const ElemArgs a) {
@@ -443,7 +575,8 @@ elem_kernel(const ElemArgs a) {
             } else {
               double gul[9];
               for (int r = 0; r < 9; ++r) gul[r] = Gu[r % (Q * N)];
-              hyper_point(a.family, gul, lambda, mu, coeff, P, sD + q * C::DSZ);
+              if (a.family >= GFGPU_MOONEY_RIVLIN) inv_law_point(a.family, gul, a.par, coeff, P, sD + q * C::DSZ);
+              else hyper_point(a.family, gul, lambda, mu, coeff, P, sD + q * C::DSZ);
             }
           }
         }

@@ -529,10 +529,14 @@ static bool recognise_string(const getfem::ga_workspace &ws, const std::string &
     if (law == "Saint_Venant_Kirchhoff") out.family = GFGPU_SVK;
     else if (law == "Compressible_Neo_Hookean_Ciarlet") out.family = GFGPU_NEOHOOKEAN_CIARLET;
     else if (law == "Compressible_Neo_Hookean_Bonet") out.family = GFGPU_NEOHOOKEAN_BONET;
+    else if (law == "Compressible_Mooney_Rivlin") out.family = GFGPU_MOONEY_RIVLIN;
+    else if (law == "Ciarlet_Geymonat") out.family = GFGPU_CIARLET_GEYMONAT;
+    else if (law == "Generalized_Blatz_Ko") out.family = GFGPU_BLATZ_KO;
     else return false;
     const std::string pn = m[2];
-    GMM_ASSERT1(ws.is_constant(pn) && ws.value(pn).size() == 2, "gfgpu: wrong parameters for " << law);
-    out.params = {ws.value(pn)[0], ws.value(pn)[1]};
+    const size_type np = out.family == GFGPU_BLATZ_KO ? 5 : out.family >= GFGPU_MOONEY_RIVLIN ? 3 : 2;
+    GMM_ASSERT1(ws.is_constant(pn) && ws.value(pn).size() == np, "gfgpu: wrong parameters for " << law);
+    out.params.assign(ws.value(pn).begin(), ws.value(pn).end());
     return true;
   }
   return false;
@@ -653,10 +657,20 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
       terms.emplace_back(i, rt);
     }
   }
-  GMM_ASSERT1(!terms.empty(), "gfgpu: nothing to assemble");
   t_extract = t_device = t_fill = 0;
-
   const size_type nprim = ws.nb_primary_dof() ? ws.nb_primary_dof() : 0;
+  if (terms.empty()) {
+    // no tree of this order (assembly(1) of a workspace that only holds directly written bilinear forms, say): the
+    // reference runs an empty instruction list and only sizes its result (workspace.cc:805-826)
+    if (order == 1) {
+      getfem::base_vector &V = ws.assembled_vector();
+      if (V.size() < nprim) V.resize(nprim, 0.0);
+    } else {
+      getfem::model_real_sparse_matrix &K = ws.assembled_matrix();
+      if (gmm::mat_nrows(K) < nprim || gmm::mat_ncols(K) < nprim) gmm::resize(K, nprim, nprim);
+    }
+    return;
+  }
   // order 2: every tree adds into ONE tangent (workspace.cc:791-936) -- accumulated on the device at the variables'
   // intervals (gfgpu_matrix_*), downloaded once
   size_type need_all = nprim;

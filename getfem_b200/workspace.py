@@ -201,6 +201,9 @@ _LAWS = {
     "Saint_Venant_Kirchhoff": "svk",
     "Compressible_Neo_Hookean_Ciarlet": "nh_ciarlet",
     "Compressible_Neo_Hookean_Bonet": "nh_bonet",
+    "Compressible_Mooney_Rivlin": "mooney_rivlin",
+    "Ciarlet_Geymonat": "ciarlet_geymonat",
+    "Generalized_Blatz_Ko": "blatz_ko",
 }
 
 

@@ -67,7 +67,15 @@ enum {
   GFGPU_NEOHOOKEAN_BONET = 4,
   GFGPU_MASS = 5,
   GFGPU_SOURCE = 6,
-  GFGPU_NORMAL_SOURCE = 7
+  GFGPU_NORMAL_SOURCE = 7,
+  /* the other laws of add_finite_strain_elasticity_brick (getfem_nonlinear_elasticity.cc:2276-2290), same expression
+   * "((Id(meshdim)+Grad_u)*(<law>_PK2(Grad_u,params))):Grad_Test_u", 3D vector fields:
+   *   MOONEY_RIVLIN     Compressible_Mooney_Rivlin_PK2 (:503-607), params (C10, C01, D1)
+   *   CIARLET_GEYMONAT  Ciarlet_Geymonat_PK2 (:817-888), params (lambda, mu, a)
+   *   BLATZ_KO          Generalized_Blatz_Ko_PK2 (:706-815), params (a, b, c, d, n) */
+  GFGPU_MOONEY_RIVLIN = 8,
+  GFGPU_CIARLET_GEYMONAT = 9,
+  GFGPU_BLATZ_KO = 10
 };
 #define GFGPU_MAX_PARAMS 12 /* parameters kept per term (NORMAL_SOURCE: qdim x dim <= 9) */
 #define GFGPU_MAX_FACES 6   /* faces of a reference element (simplices: dim+1, parallelepipeds: 2*dim) */

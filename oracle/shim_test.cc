@@ -64,10 +64,17 @@ int main(int argc, char **argv) {
   else if (family == "elast") expr = "(Div_u*((lambda)*Id(meshdim))+(2*(mu))*Sym(Grad_u)):Grad_Test_u";
   else {
     std::string law = family == "svk" ? "Saint_Venant_Kirchhoff"
-                      : family == "nh_ciarlet" ? "Compressible_Neo_Hookean_Ciarlet" : "Compressible_Neo_Hookean_Bonet";
+                      : family == "nh_ciarlet" ? "Compressible_Neo_Hookean_Ciarlet"
+                      : family == "mooney_rivlin" ? "Compressible_Mooney_Rivlin"
+                      : family == "ciarlet_geymonat" ? "Ciarlet_Geymonat"
+                      : family == "blatz_ko" ? "Generalized_Blatz_Ko" : "Compressible_Neo_Hookean_Bonet";
     expr = "((Id(meshdim)+Grad_u)*(" + law + "_PK2(Grad_u,params))):Grad_Test_u";
   }
-  const std::vector<double> c_a{acoef}, c_l{lambda}, c_m{mu}, c_p{lambda, mu};
+  const std::vector<double> c_a{acoef}, c_l{lambda}, c_m{mu};
+  const std::vector<double> c_p = family == "mooney_rivlin" ? std::vector<double>{0.8, 0.3, 2.0}             // C10, C01, D1
+                                  : family == "ciarlet_geymonat" ? std::vector<double>{lambda, mu, 0.25}     // lambda, mu, a
+                                  : family == "blatz_ko" ? std::vector<double>{1.0, 1.0, 1.5, -0.5, 1.5}      // a, b, c, d, n
+                                                         : std::vector<double>{lambda, mu};
   std::vector<double> c_f(Q);
   for (int k = 0; k < Q; ++k) c_f[k] = 0.75 * (k + 1);
   std::vector<double> c_g(size_t(Q) * dim);

@@ -18,8 +18,8 @@ def pytest_configure(config):
 
 def golden_names(oracle_only=False):
     names = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz")))
-    # "o_*": oracle-only fixtures (a family the oracle restates and pins before the device implements it)
-    return names if oracle_only else [n for n in names if not n.startswith("o_")]
+    # "o_*": the laws the oracle restated and pinned first (round 1); they are device families since round 2
+    return names
 
 
 def load_golden(name):

@@ -21,6 +21,9 @@ CASES = [
     "dim=3 n=3 gt=qk k=2 q=3 im=6 family=nh_ciarlet",   # config 4 (reduced)
     "dim=3 n=3 gt=qk k=2 q=3 im=6 family=svk",
     "dim=3 n=4 gt=pk k=2 q=3 im=4 family=nh_bonet",
+    "dim=3 n=3 gt=qk k=2 q=3 im=6 family=mooney_rivlin",   # the other laws of add_finite_strain_elasticity_brick
+    "dim=3 n=3 gt=pk k=2 q=3 im=4 family=ciarlet_geymonat",
+    "dim=3 n=3 gt=pk k=2 q=3 im=4 family=blatz_ko",
     "dim=3 n=5 gt=pk k=2 q=3 im=4 family=mass",
     "dim=3 n=2 gt=qk k=4 q=1 im=8 family=laplace",      # config 5 (reduced); tables come from the reference itself
     "dim=2 n=48 gt=pk k=1 q=1 im=2 family=source",      # the RHS of config 1: "-f*Test_u" (order 1 only, empty tangent)

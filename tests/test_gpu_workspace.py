@@ -15,6 +15,9 @@ EXPR = {  # {s}: suffix of the constants' names when several expressions share a
     "svk": "((Id(meshdim)+Grad_u)*(Saint_Venant_Kirchhoff_PK2(Grad_u,params{s}))):Grad_Test_u",
     "nh_ciarlet": "((Id(meshdim)+Grad_u)*(Compressible_Neo_Hookean_Ciarlet_PK2(Grad_u,params{s}))):Grad_Test_u",
     "nh_bonet": "((Id(meshdim)+Grad_u)*(Compressible_Neo_Hookean_Bonet_PK2(Grad_u,params{s}))):Grad_Test_u",
+    "mooney_rivlin": "((Id(meshdim)+Grad_u)*(Compressible_Mooney_Rivlin_PK2(Grad_u,params{s}))):Grad_Test_u",
+    "ciarlet_geymonat": "((Id(meshdim)+Grad_u)*(Ciarlet_Geymonat_PK2(Grad_u,params{s}))):Grad_Test_u",
+    "blatz_ko": "((Id(meshdim)+Grad_u)*(Generalized_Blatz_Ko_PK2(Grad_u,params{s}))):Grad_Test_u",
     "source": "-f{s}.Test_u",  # "-f*Test_u" when qdim = 1 (the strings of oracle/ref_driver.cc)
     "nsource": "(Reshape(g{s},qdim(u),meshdim)*Normal).Test_u",  # "((g).Normal)*Test_u" when qdim = 1
 }
