@@ -700,7 +700,13 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     std::vector<int32_t> rg_cv, rg_f;
     size_type rg_faces = 0;
     if (!all_cv) {
-      for (getfem::mr_visitor v(*td.rg, m); !v.finished(); ++v) {
+      // Inside GETFEM_OMP_PARALLEL with several partitions mr_visitor walks only the calling thread's slice
+      // (getfem_mesh_region.cc:186-200, 503-540).  The device assembles the WHOLE region in one call (made by thread 0 alone,
+      // see the dispatch patch): a private copy of the region with partitioning prohibited (getfem_mesh_region.cc:219-221)
+      // gives the full item list in the same order, without touching the shared object.
+      getfem::mesh_region rg_whole(td.rg->from_mesh(m));
+      rg_whole.prohibit_partitioning();
+      for (getfem::mr_visitor v(rg_whole, m); !v.finished(); ++v) {
         rg_cv.push_back(int32_t(v.cv()));
         const bool isf = v.f() != getfem::short_type(-1);
         rg_f.push_back(isf ? int32_t(v.f()) : -1);

@@ -325,9 +325,9 @@ class ga_workspace:
             params = [float(self.constants[cnames[0]][0]), float(self.constants[cnames[1]][0])]
         else:
             p = self.constants[cnames[0]]
-            if p.size != 2:
+            if p.size != {"mooney_rivlin": 3, "ciarlet_geymonat": 3, "blatz_ko": 5}.get(fam, 2):
                 raise capi.GfgpuError("wrong number of parameters for the hyperelastic law")
-            params = [float(p[0]), float(p[1])]
+            params = [float(v) for v in p]
         if region is not None:
             if not isinstance(region, mesh_region) or not len(region):
                 raise capi.GfgpuError("the region must be a non-empty mesh_region (or None for all convexes)")

@@ -5,6 +5,7 @@
 // cleared and resized to nb_prim_dof, an aliased one is trusted and accumulated into) and hands the workspace to the shim;
 // otherwise it calls the reference's own implementation (renamed by ws_reference_renamed.cc).  With this library in place
 // of libgetfem.so, model::assembly, the bricks and every asm_* wrapper run on the GPU unchanged.
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 
@@ -18,6 +19,7 @@ namespace getfem_b200 {
 void reference_assembly(getfem::ga_workspace &ws, getfem::size_type order, bool condensation);
 static bool g_enabled = false;
 static long g_device_calls = 0, g_reference_calls = 0;
+static std::atomic<long> g_skipped_calls{0};  // threads other than 0 of a sliced assembly (they contribute zeros)
 static void reference_order(getfem::ga_workspace &ws, getfem::size_type order) { reference_assembly(ws, order, false); }
 void gfgpu_enable(bool on) {
   g_enabled = on;
@@ -25,16 +27,16 @@ void gfgpu_enable(bool on) {
 }
 long gfgpu_device_calls() { return g_device_calls; }
 long gfgpu_reference_calls() { return g_reference_calls; }
+long gfgpu_skipped_calls() { return g_skipped_calls.load(); }
 }  // namespace getfem_b200
 
 namespace getfem {
 void ga_workspace::assembly(size_type order, bool condensation) {
   // inside GETFEM_OMP_PARALLEL with SEVERAL partitions every thread assembles its slice of the region into a private
-  // copy (getfem_accumulated_distro.h:157-224): that regime stays on the reference path.
-  // With one partition (the library default, partition_master's constructor calls set_num_threads(1), getfem_omp.cc:236)
+  // copy (getfem_accumulated_distro.h:157-224).  With one partition (the library default, partition_master's constructor calls set_num_threads(1), getfem_omp.cc:236)
   // the slice is the whole region although me_is_multithreaded_now() is true inside the bricks' parallel blocks.
   const bool sliced = getfem::me_is_multithreaded_now() && getfem::partition_master::get().get_nb_partitions() > 1;
-  if (!getfem_b200::g_enabled || condensation || (order != 1 && order != 2) || sliced) {
+  if (!getfem_b200::g_enabled || condensation || (order != 1 && order != 2)) {
     ++getfem_b200::g_reference_calls;
     getfem_b200::reference_assembly(*this, order, condensation);
     return;
@@ -72,6 +74,14 @@ void ga_workspace::assembly(size_type order, bool condensation) {
       gmm::resize(*V, nb_prim_dof);
     } else
       GMM_ASSERT1(V->size() == nb_prim_dof, "Wrong size of assembled vector in workspace");
+  }
+  if (sliced && getfem::partition_master::get().get_current_partition() != 0) {
+    // under several OpenMP partitions every thread of a brick's GETFEM_OMP_PARALLEL block holds a private,
+    // zero-initialised copy of the result (accumulated_distro::get(), getfem_accumulated_distro.h:157-224) that the block
+    // sums afterwards.  Thread 0 assembles the whole region on the device (the shim walks the region with partitioning
+    // prohibited); the other threads contribute their zeros.
+    ++getfem_b200::g_skipped_calls;
+    return;
   }
   static thread_local getfem_b200::device_assembler dev(0);
   ++getfem_b200::g_device_calls;
