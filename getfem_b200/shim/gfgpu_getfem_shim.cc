@@ -575,8 +575,20 @@ struct device_assembler::entry {
   }
 };
 
+struct device_assembler::tangent_cache {
+  size_type n = 0;
+  gfgpu_matrix *m = nullptr;
+  std::string sig;          // the terms and intervals accumulated last time
+  int64_t gen = -1;         // pattern generation of the host copy below
+  std::vector<int64_t> jc;
+  std::vector<int32_t> ir;
+  std::vector<double> pr;
+  ~tangent_cache() { gfgpu_matrix_destroy(m); }
+};
+
 device_assembler::device_assembler(int device) { GFGPU_CALL(gfgpu_ctx_create(device, nullptr, &ctx_)); }
 device_assembler::~device_assembler() {
+  tangent_.reset();
   cache_.clear();
   gfgpu_ctx_destroy(ctx_);
 }
@@ -679,11 +691,22 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     GMM_ASSERT1(pmf, "gfgpu: the variable must be a fem variable");
     need_all = std::max<size_type>(need_all, ws.interval_of_variable(it.second.varname).first() + pmf->nb_dof());
   }
-  struct matrix_guard {
-    gfgpu_matrix *m = nullptr;
-    ~matrix_guard() { gfgpu_matrix_destroy(m); }
-  } dK;
-  if (order == 2) GFGPU_CALL(gfgpu_matrix_create(ctx_, int64_t(need_all), int64_t(need_all), &dK.m));
+  // The workspace tangent lives on the device across calls (a Newton loop, a time loop): same size -> the matrix is
+  // zeroed with its pattern kept, the terms are added again, and as long as gfgpu_matrix_pattern_generation does not move
+  // only the VALUES come back to the host (jc / ir, 8.8 GB for BASELINE config 3, are downloaded once).
+  struct { gfgpu_matrix *m = nullptr; } dK;
+  std::string terms_sig;
+  struct pending_add { gfgpu_term *term; double alpha; int64_t off; };
+  std::vector<pending_add> pending_adds;
+  if (order == 2) {
+    if (tangent_ && tangent_->n != need_all) tangent_.reset();
+    if (!tangent_) {
+      tangent_.reset(new tangent_cache);
+      tangent_->n = need_all;
+      GFGPU_CALL(gfgpu_matrix_create(ctx_, int64_t(need_all), int64_t(need_all), &tangent_->m));
+    }
+    dK.m = tangent_->m;
+  }
   size_type n_added = 0;  // tangents accumulated into dK
   for (auto &it : terms) {
     const auto &td = ws.tree_info(it.first);
@@ -912,7 +935,8 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     } else {
       GFGPU_CALL(gfgpu_term_assemble_host(e.term, U.data(), GFGPU_TANGENT, nullptr, nullptr));
       const double alpha = ws.factor_of_variable(rt.varname);  // alpha1 * alpha2 of the matrix assembly instructions
-      GFGPU_CALL(gfgpu_matrix_add_term(dK.m, e.term, alpha * alpha, int64_t(I.first()), int64_t(I.first())));
+      terms_sig += key.str() + "@" + std::to_string(I.first()) + ";";
+      pending_adds.push_back({e.term, alpha * alpha, int64_t(I.first())});
       ++n_added;
       t_device += now_s() - t1;
     }
@@ -925,16 +949,27 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
   }
   if (order == 2) {
     double t1 = now_s();
-    const int64_t nnz = gfgpu_matrix_nnz(dK.m);
-    std::vector<int64_t> jc(need_all + 1);
-    std::vector<int32_t> ir((size_t)nnz);
-    std::vector<double> pr((size_t)nnz);
-    GFGPU_CALL(gfgpu_matrix_export_csc_host(dK.m, jc.data(), ir.data(), pr.data()));
+    tangent_cache &tc = *tangent_;
+    // same terms at the same places as last time: zero the values, keep the pattern (and the host copy of jc / ir)
+    GFGPU_CALL(gfgpu_matrix_clear(tc.m, tc.sig == terms_sig ? 1 : 0));
+    if (tc.sig != terms_sig) { tc.sig = terms_sig; tc.gen = -1; }
+    for (const pending_add &pa : pending_adds) GFGPU_CALL(gfgpu_matrix_add_term(tc.m, pa.term, pa.alpha, pa.off, pa.off));
+    const int64_t nnz = gfgpu_matrix_nnz(tc.m);
+    tc.pr.resize((size_t)nnz);
+    if (tc.gen != gfgpu_matrix_pattern_generation(tc.m) || tc.ir.size() != (size_t)nnz) {
+      tc.jc.resize(need_all + 1);
+      tc.ir.resize((size_t)nnz);
+      GFGPU_CALL(gfgpu_matrix_export_csc_host(tc.m, tc.jc.data(), tc.ir.data(), tc.pr.data()));
+      tc.gen = gfgpu_matrix_pattern_generation(tc.m);
+      ++pattern_downloads;
+    } else {
+      GFGPU_CALL(gfgpu_matrix_export_csc_host(tc.m, nullptr, nullptr, tc.pr.data()));
+    }
     double t2 = now_s();
     t_device += t2 - t1;
     getfem::model_real_sparse_matrix &K = ws.assembled_matrix();
     if (gmm::mat_nrows(K) < need_all || gmm::mat_ncols(K) < need_all) gmm::resize(K, need_all, need_all);
-    fill_col_matrix(K, need_all, jc.data(), ir.data(), pr.data());
+    fill_col_matrix(K, need_all, tc.jc.data(), tc.ir.data(), tc.pr.data());
     t_fill += now_s() - t2;
   }
 }

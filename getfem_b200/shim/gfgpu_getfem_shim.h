@@ -59,9 +59,14 @@ class device_assembler {
 
   // seconds spent in the last call: extraction of GetFEM data, device work, fill of the gmm containers
   double t_extract = 0, t_device = 0, t_fill = 0;
+  // how many times the pattern (jc, ir) of the workspace tangent had to be downloaded: 1 for a Newton / time loop whose
+  // pattern does not move (the values alone travel afterwards)
+  long pattern_downloads = 0;
 
  private:
   struct entry;
+  struct tangent_cache;
+  std::unique_ptr<tangent_cache> tangent_;  // the workspace tangent, resident on the device between calls
   gfgpu_ctx *ctx_ = nullptr;
   std::map<std::string, std::unique_ptr<entry>> cache_;  // bounded (LRU); entries die with the getfem objects they mirror
   uint64_t use_clock_ = 0;

@@ -62,3 +62,6 @@ def test_shim_matches_reference_in_process(case):
     assert r["pattern_ok"] and r["nnz_ref"] == r["nnz_gpu"]
     assert 0 <= r["rel_K"] < 1e-12, r
     assert r["rel_R"] < 1e-12, r
+    # the workspace tangent stays on the device between calls: the second assembly(2) downloads values only, bit-identical
+    assert r["second_call_same"], r
+    assert r["pattern_downloads"] == (0 if r["nnz_ref"] == 0 else 1), r
