@@ -56,6 +56,8 @@ SIGNATURES = {
     "gfgpu_term_set_element_range": (C.c_int, [_P, _i64, _i64]),
     "gfgpu_term_assemble_dev": (C.c_int, [_P, _P, C.c_int]),
     "gfgpu_term_assemble_host": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "gfgpu_term_potential_dev": (C.c_int, [_P, _P, _P]),
+    "gfgpu_term_potential_host": (C.c_int, [_P, _P, _P]),
     "gfgpu_term_last_timings": (C.c_int, [_P, _P]),
     "gfgpu_term_strategy": (C.c_int, [_P]),
     "gfgpu_term_kernel_kind": (C.c_int, [_P]),
@@ -289,6 +291,13 @@ class DeviceTerm(_Handle):
     def assemble_host(self, U, order_mask, pr_out=None, R_out=None):
         U = None if U is None else np.ascontiguousarray(U, np.float64)
         check(lib().gfgpu_term_assemble_host(self.h, ptr(U), int(order_mask), ptr(pr_out), ptr(R_out)))
+
+    def potential_host(self, U):
+        """order 0: the term's potential at the state U (ga_workspace::assembly(0) / assembled_potential())"""
+        U = None if U is None else np.ascontiguousarray(U, np.float64)
+        E = C.c_double()
+        check(lib().gfgpu_term_potential_host(self.h, ptr(U), C.byref(E)))
+        return E.value
 
     def last_timings(self):
         """dict of device ms of the last assemble: elem, gather, rgather, pattern."""

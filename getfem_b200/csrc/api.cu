@@ -662,6 +662,36 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
   if (do_r) { tic(2); gf::gather_residual(t); toc(2); }
 }
 
+}  // extern "C"
+namespace gf {
+double term_potential(gfgpu_term *t, const double *U_dev);  // potential.cu
+void term_assemble_for_potential(gfgpu_term *t, const double *U_dev) { term_assemble(t, U_dev, GFGPU_RESIDUAL); }
+}  // namespace gf
+extern "C" {
+
+int gfgpu_term_potential_dev(gfgpu_term *t, const double *U_dev, double *E_host) {
+  GF_API_BEGIN
+  GF_REQUIRE(t && E_host, "null argument");
+  GF_CUDA(cudaSetDevice(t->ctx->device));
+  *E_host = gf::term_potential(t, U_dev);
+  GF_API_END
+}
+
+int gfgpu_term_potential_host(gfgpu_term *t, const double *U_host, double *E_host) {
+  GF_API_BEGIN
+  GF_REQUIRE(t && E_host, "null argument");
+  gfgpu_ctx *ctx = t->ctx;
+  GF_CUDA(cudaSetDevice(ctx->device));
+  const double *U_dev = nullptr;
+  if (U_host) {
+    if (t->Ubuf.n != (size_t)t->fem->ndof) t->Ubuf.alloc(ctx, t->fem->ndof);
+    t->Ubuf.upload(U_host);
+    U_dev = t->Ubuf.p;
+  }
+  *E_host = gf::term_potential(t, U_dev);
+  GF_API_END
+}
+
 int gfgpu_term_assemble_dev(gfgpu_term *t, const double *U_dev, int order_mask) {
   GF_API_BEGIN
   GF_REQUIRE(t, "null term");

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <regex>
 #include <sstream>
 
@@ -353,13 +354,13 @@ static bool recognise_by_probe(const getfem::ga_workspace &ws, size_type itree, 
       return false;
     double na = 0, dab = 0;
     for (size_t k = 0; k < K.size(); ++k) { na += K[k] * K[k]; dab += (K[k] - Kb[k]) * (K[k] - Kb[k]); }
-    if (!(dab <= 1e-22 * na)) return false;  // the tangent moves with the state (or is not finite): a nonlinear form
+    if (!(dab <= 1e-22 * na) || !std::isfinite(na) || na > 1e150) return false;  // the tangent moves with the state (or is not finite): a nonlinear form
   } else if (!probe_matrix(ws, v, *pmf, *td.mim, rg2, getfem::ga_tree_to_string(*td.ptree), K, dofs)) {
     return false;
   }
   double nK = 0;
   for (double x : K) nK += x * x;
-  if (!(nK > 0)) return false;
+  if (!(nK > 0) || !std::isfinite(nK) || nK > 1e150) return false;  // (a law's 1e200 penalty on an inverted probe state is no fit)
   if (td0.order == 1) {
     std::vector<double> r;
     if (!probe_vector(ws, v, *pmf, *td.mim, rg2, getfem::ga_tree_to_string(*td0.ptree), r, dofs)) return false;
@@ -523,8 +524,11 @@ static bool recognise_string(const getfem::ga_workspace &ws, const std::string &
                 "gfgpu: a fem-data mu needs a fem-data lambda (fields replace the LEADING parameters)");
     out.family = GFGPU_ELASTICITY; out.params = {scalar(m[1]), scalar(m[2])}; return true;
   }
+  // the brick's form (Id+Grad_u)*<law>_PK2(Grad_u,params):Grad_Test_u, or the first variation of the law's registered
+  // potential, Derivative_1_<law>_potential(Grad_u,params):Grad_Test_u -- the same linear form (dW/dF = F S)
   if (std::regex_match(s, m, std::regex("\\(\\(" + I3 + "\\+Grad_" + v + "\\)\\*" + ID + "_PK2\\(Grad_" + v + "," + ID +
-                                        "\\)\\):Grad_Test_" + v))) {
+                                        "\\)\\):Grad_Test_" + v)) ||
+      std::regex_match(s, m, std::regex("\\(?Derivative_1_" + ID + "_potential\\(Grad_" + v + "," + ID + "\\)\\)?:Grad_Test_" + v))) {
     const std::string law = m[1];
     if (law == "Saint_Venant_Kirchhoff") out.family = GFGPU_SVK;
     else if (law == "Compressible_Neo_Hookean_Ciarlet") out.family = GFGPU_NEOHOOKEAN_CIARLET;
@@ -603,8 +607,74 @@ static bool parse_kind(const std::string &name, const char *prefix, bool &qk, in
   return true;
 }
 
+// the order-0 expression `expr` assembled by the reference's interpreter on the probe region at a PRIVATE state
+static bool probe_scalar(const getfem::ga_workspace &ws, const std::string &v, const getfem::mesh_fem &mf,
+                         const getfem::mesh_im &mim, const getfem::mesh_region &rg, const std::string &expr,
+                         const getfem::model_real_plain_vector &state, double &E) {
+  try {
+    getfem::ga_workspace w2(ws, getfem::ga_workspace::inherit::ALL);
+    w2.add_fem_variable(v, mf, ws.interval_of_variable(v), state);
+    w2.add_expression(expr, mim, rg, 0);
+    if (g_reference_assembly) g_reference_assembly(w2, 0); else w2.assembly(0);
+    E = w2.assembled_potential();
+    return true;
+  } catch (const std::exception &) { return false; }
+}
+
+// Order-0 tree number `itree`: a law's registered potential "<law>_potential(Grad_u,params)" (getfem_nonlinear_elasticity.cc:
+// 2050-2150), or a potential whose first variation -- the order-1 tree add_expression derived from it -- is a recognised
+// quadratic or linear family; then P(u) = 1/2 u^T K u + c (or F.u + c) and c = P(0) is checked to vanish on the first two
+// convexes with the reference's interpreter at a private zero state.
+static bool recognise_potential(const getfem::ga_workspace &ws, size_type itree,
+                                const std::function<bool(size_type, std::vector<recognised_term> &)> &recognise_order1,
+                                recognised_term &out) {
+  const getfem::ga_workspace::tree_description &td = ws.tree_info(itree);
+  const std::string printed = strip(getfem::ga_tree_to_string(*td.ptree));
+  std::smatch m;
+  static const std::string ID = "([A-Za-z_][A-Za-z_0-9]*)";
+  if (std::regex_match(printed, m, std::regex("\\(?" + ID + "_potential\\(Grad_" + ID + "," + ID + "\\)\\)?"))) {
+    const std::string law = m[1], pn = m[3];
+    out.varname = m[2];
+    if (law == "Saint_Venant_Kirchhoff") out.family = GFGPU_SVK;
+    else if (law == "Compressible_Neo_Hookean_Ciarlet") out.family = GFGPU_NEOHOOKEAN_CIARLET;
+    else if (law == "Compressible_Neo_Hookean_Bonet") out.family = GFGPU_NEOHOOKEAN_BONET;
+    else if (law == "Compressible_Mooney_Rivlin") out.family = GFGPU_MOONEY_RIVLIN;
+    else if (law == "Ciarlet_Geymonat") out.family = GFGPU_CIARLET_GEYMONAT;
+    else if (law == "Generalized_Blatz_Ko") out.family = GFGPU_BLATZ_KO;
+    else return false;
+    const size_type np = out.family == GFGPU_BLATZ_KO ? 5 : out.family >= GFGPU_MOONEY_RIVLIN ? 3 : 2;
+    if (!ws.variable_exists(pn) || !ws.is_constant(pn) || ws.value(pn).size() != np) return false;
+    out.params.assign(ws.value(pn).begin(), ws.value(pn).end());
+    return true;
+  }
+  for (size_type j = 0; j < ws.nb_trees(); ++j) {
+    const auto &t1 = ws.tree_info(j);
+    if (t1.order != 1 || t1.mim != td.mim || t1.rg != td.rg) continue;
+    std::vector<recognised_term> r1;
+    if (!recognise_order1(j, r1) || r1.size() != 1) continue;
+    const int f = r1[0].family;
+    if (f != GFGPU_LAPLACE && f != GFGPU_ELASTICITY && f != GFGPU_MASS && f != GFGPU_SOURCE && f != GFGPU_NORMAL_SOURCE) continue;
+    const std::string v = t1.name_test1;
+    const getfem::mesh_fem *pmf = ws.associated_mf(v);
+    if (!pmf || pmf->is_reduced() || !td.mim || !td.rg) continue;
+    const getfem::mesh &msh = pmf->linked_mesh();
+    getfem::mesh_region rg2;
+    size_type nit = 0;
+    for (getfem::mr_visitor it(*td.rg, msh); !it.finished() && nit < 2; ++it, ++nit) {
+      if (it.f() != getfem::short_type(-1)) rg2.add(it.cv(), it.f()); else rg2.add(it.cv());
+    }
+    if (!nit) continue;
+    getfem::model_real_plain_vector zero(pmf->nb_dof(), 0.0);
+    double c = 1;
+    if (!probe_scalar(ws, v, *pmf, *td.mim, rg2, getfem::ga_tree_to_string(*td.ptree), zero, c) || c != 0.0) continue;
+    out = r1[0];
+    return true;
+  }
+  return false;
+}
+
 void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
-  GMM_ASSERT1(order == 1 || order == 2, "gfgpu: only assembly orders 1 and 2 run on the device");
+  GMM_ASSERT1(order <= 2, "gfgpu: assembly orders 0, 1 and 2 run on the device");
   double t0 = now_s();
   // ---- every order-1 tree must be a recognised family (the order-2 trees are their derivatives)
   std::vector<std::pair<size_type, recognised_term>> terms;
@@ -622,6 +692,14 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
   };
   for (size_type i = 0; i < ws.nb_trees(); ++i) {
     const auto &td = ws.tree_info(i);
+    if (order == 0) {  // only the order-0 trees contribute to assembled_potential() (workspace.cc:791-803)
+      if (td.order != 0) continue;
+      recognised_term rt;
+      GMM_ASSERT1(recognise_potential(ws, i, recognise_memo, rt),
+                  "gfgpu: potential not handled by the device path (no CPU fallback): " << getfem::ga_tree_to_string(*td.ptree));
+      terms.emplace_back(i, rt);
+      continue;
+    }
     if (td.order == 0) continue;
     GMM_ASSERT1(td.operation == getfem::ga_workspace::ASSEMBLY, "gfgpu: assignments are not handled");
     if (td.order == 2) {
@@ -671,6 +749,7 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
   }
   t_extract = t_device = t_fill = 0;
   const size_type nprim = ws.nb_primary_dof() ? ws.nb_primary_dof() : 0;
+  if (terms.empty() && order == 0) return;  // nothing adds to the potential
   if (terms.empty()) {
     // no tree of this order (assembly(1) of a workspace that only holds directly written bilinear forms, say): the
     // reference runs an empty instruction list and only sizes its result (workspace.cc:805-826)
@@ -918,7 +997,12 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     double t1 = now_s();
     t_extract += t1 - t0;
 
-    if (order == 1) {
+    if (order == 0) {
+      double E = 0;
+      GFGPU_CALL(gfgpu_term_potential_host(e.term, U.data(), &E));
+      ws.assembled_potential() += E;
+      t_device += now_s() - t1;
+    } else if (order == 1) {
       std::vector<double> R(ndof);
       GFGPU_CALL(gfgpu_term_assemble_host(e.term, U.data(), GFGPU_RESIDUAL, nullptr, R.data()));
       double t2 = now_s();

@@ -186,6 +186,16 @@ int gfgpu_term_assemble_dev(gfgpu_term *t, const double *U_dev, int order_mask);
 int gfgpu_term_assemble_host(gfgpu_term *t, const double *U_host, int order_mask, double *pr_host,
                              double *R_host);
 
+/* Order 0: the scalar ga_workspace::assembly(0) accumulates into assembled_potential() (workspace.cc:791-803,
+ * ga_instruction_scalar_assembly, C&E.cc:4628-4640) for the term's POTENTIAL:
+ *   LAPLACE / ELASTICITY / MASS   1/2 u^T K u   (the quadratic form whose first variation is the family's residual)
+ *   SOURCE / NORMAL_SOURCE        the linear form itself, F.u
+ *   finite-strain families        int W(E(Grad_u)) with the law's strain energy ("<law>_potential(Grad_u,params)",
+ *                                 AHL_wrapper_potential, getfem_nonlinear_elasticity.cc:1841-1928; 1e200 where det F <= 0)
+ * Synchronises the stream; the value comes back through E_host. */
+int gfgpu_term_potential_dev(gfgpu_term *t, const double *U_dev, double *E_host);
+int gfgpu_term_potential_host(gfgpu_term *t, const double *U_host, double *E_host);
+
 /* Device durations (ms, CUDA events on the context's stream) of the kernels of the LAST assemble call:
  * out[0] generic element kernel, out[1] tangent gather-sum (STAGED), out[2] residual gather-sum,
  * out[3] pattern (re)build (0 when reused), out[4] per-nonzero tangent kernel (RECOMPUTE), out[5..7] 0.

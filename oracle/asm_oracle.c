@@ -279,6 +279,51 @@ static void hyper_law(int family, const double *Gu, const double *par, double *S
         }
 }
 
+/* Strain energy of the law at Grad_u ("<law>_potential(Grad_u,params)": AHL_wrapper_potential, cc:1841-1928, calls
+   strain_energy(E, params, det(Id + Grad_u)): SVK cc:1996-2003, Neo-Hookean cc:612-632, Mooney-Rivlin cc:503-527,
+   Ciarlet-Geymonat cc:817-836, Blatz-Ko cc:706-721) */
+static double hyper_energy(int family, const double *Gu, const double *par) {
+  const int N = 3;
+  double E[9], F[9], C[9];
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) {
+      double s = 0;
+      for (int k = 0; k < N; ++k) s += Gu[k + N * i] * Gu[k + N * j];
+      E[i + N * j] = 0.5 * (s + Gu[i + N * j] + Gu[j + N * i]);
+      C[i + N * j] = 2 * E[i + N * j] + (i == j ? 1.0 : 0.0);
+      F[i + N * j] = Gu[i + N * j] + (i == j ? 1.0 : 0.0);
+    }
+  if (family == GFO_SVK) {
+    double tr = E[0] + E[4] + E[8], n2 = 0;
+    for (int i = 0; i < 9; ++i) n2 += E[i] * E[i];
+    return tr * tr * par[0] / 2 + n2 * par[1];
+  }
+  if (det3(F, N) <= 0) return 1e200;
+  double i1 = C[0] + C[4] + C[8], i3 = det3(C, N), ff = 0, n2 = 0;
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) { ff += C[i + N * j] * C[j + N * i]; n2 += C[i + N * j] * C[i + N * j]; }
+  double i2 = (i1 * i1 - ff) / 2;
+  if (family == GFO_NH_CIARLET || family == GFO_NH_BONET) {
+    double lg = log(i3), W = par[1] / 2 * (i1 - 3.0 - lg);
+    return W + (family == GFO_NH_BONET ? par[0] / 8 * lg * lg : par[0] / 4 * (i3 - 1.0 - lg));
+  }
+  if (family == GFO_MOONEY_RIVLIN) {
+    double j1 = i1 * pow(fabs(i3), -1.0 / 3.0), j2 = i2 * pow(fabs(i3), -2.0 / 3.0), s = sqrt(fabs(i3)) - 1.0;
+    return par[0] * (j1 - 3.0) + par[1] * (j2 - 3.0) + par[2] * s * s;
+  }
+  if (family == GFO_CIARLET_GEYMONAT) {
+    double a = par[2], b = par[1] / 2 - par[2], c = par[0] / 4 - par[1] / 2 + par[2], d = par[0] / 2 + par[1];
+    double e = -(3.0 * (a + b) + c);
+    return a * i1 + b * (i1 * i1 - n2) / 2 + c * i3 - d * log(i3) / 2 + e;
+  }
+  return pow(par[0] * i1 + par[1] * sqrt(fabs(i3)) + par[2] * i2 / i3 + par[3], par[4]);
+}
+
+/* order 0 of the last gfo_assemble* call made with order_mask bit 2 (finite-strain families; the quadratic and linear
+   families take 1/2 u.R and u.R from the residual, see oracle.py) */
+static double g_last_potential = 0.0;
+double gfo_last_potential(void) { return g_last_potential; }
+
 /* pts: npts x dim (row-major), conn: ne x ng, elem_dof: ne x nd (dof of component 0),
    gt_grad: nq x ng x dim, phi: nq x nd, gphi: nq x nd x dim.  order_mask: bit0 residual, bit1 tangent.
    Region (mesh_region walked by mr_visitor, compile_and_exec.cc:8789): n_items items (item_cv[k], item_face[k]),
@@ -318,6 +363,7 @@ gfo_result *gfo_assemble_fields(int dim, int64_t ne, int ng, const double *pts, 
   const int nonlinear = family == GFO_SVK || family == GFO_NH_CIARLET || family == GFO_NH_BONET || family == GFO_MOONEY_RIVLIN ||
                         family == GFO_CIARLET_GEYMONAT || family == GFO_BLATZ_KO;
   if (!item_cv) n_items = ne;
+  if (order_mask & 4) g_last_potential = 0.0;
 
   for (int64_t item = 0; item < n_items; ++item) {
     const int64_t cv = item_cv ? item_cv[item] : item;
@@ -438,6 +484,7 @@ gfo_result *gfo_assemble_fields(int dim, int64_t ne, int ng, const double *pts, 
                                  (a == b && n == l ? mu : 0.0);
           }
       } else if (nonlinear) {
+        if (order_mask & 4) g_last_potential += coeff * hyper_energy(family, Gu, par);
         hyper_law(family, Gu, par, S, dS);
         double F[9];
         for (int i = 0; i < 9; ++i) F[i] = Gu[i];

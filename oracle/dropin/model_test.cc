@@ -69,12 +69,14 @@ int main(int argc, char **argv) {
       std::uniform_real_distribution<double> dist(-1.0, 1.0);
       for (auto &x : U) x = dist(rng);
     }
+    if (a.count("uscale")) for (auto &x : U) x *= std::stod(a["uscale"]);
     if (a.count("uzero")) {  // state that vanishes on the first dofs (the probe convexes) or everywhere (uzero=-1)
       const long nz = geti("uzero", -1);
       for (size_t k = 0; k < U.size(); ++k)
         if (nz < 0 || long(k) < nz) U[k] = 0.0;
     }
-    std::vector<double> Vr, Vg, C0(mf_d.nb_dof(), 1.0);
+    std::vector<double> Vr, Vg, C0(mf_d.nb_dof(), 1.0), PARAMS{1.3, 0.7};
+    double Er = 0, Eg = 0;
     C0.back() = 5.0;
     auto run = [&](bool device, gmm::csc_matrix<double> &C) {
       getfem_b200::gfgpu_enable(device);
@@ -83,6 +85,7 @@ int main(int argc, char **argv) {
       ws.add_fixed_size_constant("lambda", LAMBDA);
       ws.add_fixed_size_constant("mu", MU);
       ws.add_fixed_size_constant("a", A);
+      ws.add_fixed_size_constant("params", PARAMS);
       ws.add_fem_constant("c0", mf_d, C0);  // a material that is 1 on the first convexes and 5 in a far corner
       if (a.count("region")) ws.add_expression(expr, mim, m.region(size_type(geti("region", 1))));
       else ws.add_expression(expr, mim);
@@ -92,6 +95,12 @@ int main(int argc, char **argv) {
       C.init_with(M);
       ws.assembly(1);  // an expression written in u (not in Test2_u) also has a residual
       (device ? Vg : Vr).assign(ws.assembled_vector().begin(), ws.assembled_vector().end());
+      bool has0 = false;  // the potential, when the expression has an order-0 tree
+      for (size_type i = 0; i < ws.nb_trees(); ++i) has0 = has0 || ws.tree_info(i).order == 0;
+      if (has0) {
+        ws.assembly(0);
+        (device ? Eg : Er) = ws.assembled_potential();
+      }
       getfem_b200::gfgpu_enable(false);
     };
     gmm::csc_matrix<double> Cr, Cg;
@@ -106,9 +115,9 @@ int main(int argc, char **argv) {
     if (pattern_ok)
       for (size_t k = 0; k < Cr.pr.size(); ++k) { nK += Cr.pr[k] * Cr.pr[k]; dK += (Cr.pr[k] - Cg.pr[k]) * (Cr.pr[k] - Cg.pr[k]); }
     std::printf("{\"model\": \"expr\", \"ndof\": %zu, \"nnz_ref\": %zu, \"nnz_gpu\": %zu, \"pattern_ok\": %s, \"rel_K\": %.3e, "
-                "\"rel_V\": %.3e, \"norm_V\": %.3e, \"device_workspace_calls\": %ld}\n",
+                "\"rel_V\": %.3e, \"norm_V\": %.3e, \"E_ref\": %.17g, \"E_gpu\": %.17g, \"device_workspace_calls\": %ld}\n",
                 size_t(mf.nb_dof()), Cr.pr.size(), Cg.pr.size(), pattern_ok ? "true" : "false",
-                pattern_ok && nK > 0 ? std::sqrt(dK / nK) : -1.0, nV > 0 ? std::sqrt(dV / nV) : 0.0, std::sqrt(nV),
+                pattern_ok && nK > 0 ? std::sqrt(dK / nK) : -1.0, nV > 0 ? std::sqrt(dV / nV) : 0.0, std::sqrt(nV), Er, Eg,
                 getfem_b200::gfgpu_device_calls());
     return pattern_ok ? 0 : 1;
   }

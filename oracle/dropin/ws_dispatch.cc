@@ -36,7 +36,7 @@ void ga_workspace::assembly(size_type order, bool condensation) {
   // copy (getfem_accumulated_distro.h:157-224).  With one partition (the library default, partition_master's constructor calls set_num_threads(1), getfem_omp.cc:236)
   // the slice is the whole region although me_is_multithreaded_now() is true inside the bricks' parallel blocks.
   const bool sliced = getfem::me_is_multithreaded_now() && getfem::partition_master::get().get_nb_partitions() > 1;
-  if (!getfem_b200::g_enabled || condensation || (order != 1 && order != 2)) {
+  if (!getfem_b200::g_enabled || condensation || order > 2) {
     ++getfem_b200::g_reference_calls;
     getfem_b200::reference_assembly(*this, order, condensation);
     return;
@@ -67,6 +67,10 @@ void ga_workspace::assembly(size_type order, bool condensation) {
   if (order == 2 && K.use_count()) {
     gmm::clear(*K);
     gmm::resize(*K, nb_prim_dof, nb_prim_dof);
+  }
+  if (order == 0) {  // the scalar result: a one-entry tensor set to zero (C&E.cc:8067, 8733)
+    assemb_t.adjust_sizes(1);
+    assemb_t[0] = 0.0;
   }
   if (order == 1) {
     if (V.use_count()) {

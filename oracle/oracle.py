@@ -64,6 +64,20 @@ def hyper_law(family, grad_u, params):
     return np.array(S), np.array(dS)
 
 
+def potential(pts, conn, elem_dof, ndof, Q, w, gt_grad, phi, gphi, gt_linear, family, params, U, region=None, nq=None):
+    """Order 0 (ga_workspace::assembly(0), assembled_potential()): the potential whose first variation is the family's
+    order-1 form.  Quadratic forms: 1/2 u.R with R = K u; linear forms: u.R; finite-strain laws: int W (asm_oracle.c
+    hyper_energy, accumulated by the element loop under order_mask bit 2)."""
+    hyper = family in ("svk", "nh_ciarlet", "nh_bonet", "mooney_rivlin", "ciarlet_geymonat", "blatz_ko")
+    _, _, _, R = assemble(pts, conn, elem_dof, ndof, Q, w, gt_grad, phi, gphi, gt_linear, family, params, U,
+                          order_mask=5 if hyper else 1, region=region, nq=nq)
+    if hyper:
+        lib().gfo_last_potential.restype = C.c_double
+        return float(lib().gfo_last_potential())
+    d = float(np.dot(np.asarray(U, np.float64), R))
+    return d if family in ("source", "nsource") else 0.5 * d
+
+
 def assemble(pts, conn, elem_dof, ndof, Q, w, gt_grad, phi, gphi, gt_linear, family, params, U, order_mask=3,
              region=None, nq=None, fields=None):
     """Returns (jc, ir, pr, R): tangent in CSC (int64 indices) and residual.

@@ -333,6 +333,26 @@ int main(int argc, char **argv) {
               dim, ne, ndof, nd, ng, nq, getfem::name_of_fem(pf).c_str(),
               getfem::name_of_int_method(pim).c_str(), t_mesh, t_enum);
 
+  if (mode == "potential") {
+    // order 0: ga_workspace::assembly(0) of the POTENTIAL whose first variation is the family's order-1 form
+    // (workspace.cc:791-803; the laws' potentials are the registered "<law>_potential" operators, nonlinear_elasticity.cc:2050-2150)
+    std::string pexpr;
+    if (family == "laplace" || family == "laplace_vec") pexpr = "a*Norm_sqr(Grad_u)/2";
+    else if (family == "mass") pexpr = "a*Norm_sqr(u)/2";
+    else if (family == "elast") pexpr = "lambda*sqr(Div_u)/2 + mu*Norm_sqr(Sym(Grad_u))";
+    else if (family == "source") pexpr = Q == 1 ? "-f*u" : "-f.u";
+    else if (family == "nsource") pexpr = Q == 1 ? "((g).Normal)*u" : "(Reshape(g,qdim(u),meshdim)*Normal).u";
+    else pexpr = expr.substr(expr.find("*(") + 2, expr.find("_PK2") - expr.find("*(") - 2) + "_potential(Grad_u,params)";
+    const std::string keep = expr;
+    expr = pexpr;
+    extras.clear();
+    getfem::ga_workspace ws0;
+    setup_ws(ws0, rgname == "all" ? rg_all : rg_sel);
+    ws0.assembly(0);
+    expr = keep;
+    std::printf(", \"potential_expr\": \"%s\", \"potential\": %.17g}\n", pexpr.c_str(), ws0.assembled_potential());
+    return 0;
+  }
   if (mode == "lawcheck") {
     bgeot::base_vector bp(2);
     bp[0] = lambda; bp[1] = mu;

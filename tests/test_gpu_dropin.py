@@ -102,3 +102,24 @@ def test_equivalent_spellings_run_on_the_device(mesh, expr):
     assert r["device_workspace_calls"] >= 1, r
     assert r["pattern_ok"] and r["nnz_ref"] == r["nnz_gpu"]
     assert 0 <= r["rel_K"] < 1e-12, r
+
+
+POTENTIALS = [  # order 0 through the dispatch patch: ws.assembly(0) / assembled_potential() on the device
+    ("dim=3 n=3 gt=pk k=2 q=1", "(Grad_u:Grad_u)/2"),                              # tests/test_assembly.cc:777-803
+    ("dim=2 n=8 gt=pk k=2 q=1", "a*u*u/2"),
+    ("dim=3 n=2 gt=qk k=2 uscale=0.02", "Compressible_Neo_Hookean_Ciarlet_potential(Grad_u,params)"),
+    ("dim=3 n=2 gt=pk k=2 uscale=0.02", "Saint_Venant_Kirchhoff_potential(Grad_u,params)"),
+]
+
+
+@pytest.mark.parametrize("mesh,expr", POTENTIALS)
+def test_potentials_run_on_the_device(mesh, expr):
+    """north_star: assembly(order 0/1/2).  The potential, its residual and its tangent against the reference."""
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN, "model=expr"] + mesh.split() + ["expr=" + expr], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["device_workspace_calls"] >= 3, r
+    assert r["pattern_ok"] and r["rel_K"] < 1e-12 and r["rel_V"] < 1e-12, r
+    assert r["E_ref"] != 0 and abs(r["E_gpu"] - r["E_ref"]) <= 1e-12 * abs(r["E_ref"]), r

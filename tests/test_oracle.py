@@ -110,3 +110,21 @@ def test_reference_law_derivative_check(family):
                          capture_output=True, text=True, timeout=300)
     r = json.loads(out.stdout.strip().splitlines()[-1])
     assert out.returncode == 0 and r["lawcheck"], r
+
+
+def _potentials():
+    import json
+    import os
+    from conftest import GOLDEN
+    return json.load(open(os.path.join(GOLDEN, "potentials.json")))
+
+
+@pytest.mark.parametrize("name", sorted(_potentials()))
+def test_oracle_potential_matches_reference(name):
+    """order 0: ga_workspace::assembly(0) of the UNMODIFIED reference (tests/golden/make_potentials.py) against the oracle"""
+    g = load_golden(name)
+    w, gt_grad, phi, gphi = g["tables"]
+    E = oracle.potential(g["pts"], g["conn"], g["elem_dof"], g["meta"]["ndof"], g["Q"], w, gt_grad, phi, gphi,
+                         g["gt_linear"], g["family"], g["fparams"], g["U"], region=g["region"], nq=g["meta"]["nq"])
+    ref = _potentials()[name]["potential"]
+    assert abs(E - ref) <= 1e-12 * max(abs(ref), 1e-300), (E, ref)
