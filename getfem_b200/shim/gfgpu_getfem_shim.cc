@@ -12,6 +12,7 @@
 #include <functional>
 #include <regex>
 #include <sstream>
+#include <tuple>
 
 #include "getfem/getfem_fem.h"
 #include "getfem/getfem_generic_assembly_tree.h"
@@ -821,8 +822,43 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     const size_type ndof = mf.nb_dof();  // triggers enumerate_dof
     GMM_ASSERT1(m.convex_index().card() > 0 && m.convex_index().card() == m.convex_index().last_true() + 1,
                 "gfgpu: convex ids must be contiguous (call mesh::optimize_structure)");
-    const size_type ne = m.convex_index().card(), cv0 = 0;
-    // uniform classical Lagrange fem / degree-1 geometric transformation / one approximate im
+    const size_type ne_mesh = m.convex_index().card();
+    // Non-uniform meshes (C&E.cc:5902-5936, the is_uniform() == false path): the convexes are grouped by (fem, geometric
+    // transformation, integration method); every group is a device term of its own -- own compact mesh, dof rows and
+    // tables -- and the groups' tangents meet in the workspace matrix (gfgpu_matrix_add_term: union pattern, summed values),
+    // their residuals in V.  A uniform mesh is one group and takes exactly the path it always took.
+    std::vector<std::vector<size_type>> groups;
+    {
+      std::map<std::tuple<const void *, const void *, const void *>, size_t> gid;
+      for (size_type cv = 0; cv < ne_mesh; ++cv) {
+        if (!mf.convex_index().is_in(cv) || !mim.convex_index().is_in(cv)) continue;  // no fem / no im: not assembled
+        const auto k = std::make_tuple((const void *)mf.fem_of_element(cv).get(), (const void *)m.trans_of_convex(cv).get(),
+                                       (const void *)mim.int_method_of_element(cv).get());
+        auto it = gid.find(k);
+        if (it == gid.end()) { it = gid.emplace(k, groups.size()).first; groups.emplace_back(); }
+        groups[it->second].push_back(cv);
+      }
+    }
+    std::vector<int32_t> local_of(ne_mesh, -1);
+    for (size_t ig = 0; ig < groups.size(); ++ig) {
+    const std::vector<size_type> &gcv = groups[ig];
+    const bool whole_mesh = groups.size() == 1 && gcv.size() == ne_mesh;
+    for (size_t k = 0; k < gcv.size(); ++k) local_of[gcv[k]] = int32_t(k);
+    // the region restricted to this group, in the group's local numbering (visitor order kept)
+    std::vector<int32_t> grg_cv, grg_f;
+    if (!all_cv) {
+      for (size_t k = 0; k < rg_cv.size(); ++k) {
+        const size_type cv = size_type(rg_cv[k]);
+        if (cv < ne_mesh && local_of[cv] >= 0 && std::binary_search(gcv.begin(), gcv.end(), cv)) {
+          grg_cv.push_back(local_of[cv]);
+          grg_f.push_back(rg_f[k]);
+        }
+      }
+      if (grg_cv.empty()) continue;
+    }
+    const bool use_region = !all_cv;
+    const size_type ne = gcv.size(), cv0 = gcv[0];
+    // within a group: one classical Lagrange fem / degree-1 geometric transformation / approximate im
     getfem::pfem pf = mf.fem_of_element(cv0);
     bgeot::pgeometric_trans pgt = m.trans_of_convex(cv0);
     getfem::pintegration_method pim = mim.int_method_of_element(cv0);
@@ -840,20 +876,25 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
 
     std::ostringstream key;
     key << &m << "/" << &mf << "/" << &mim << "/" << rt.family << "/" << ne << "/" << ndof << "/" << fdeg << "/"
-        << getfem::name_of_int_method(pim);
+        << getfem::name_of_int_method(pim) << "/g" << ig << "of" << groups.size() << "@" << cv0;
     {  // parameters bit for bit (a load that changes by 1e-9 is another term), and the family's own scale stays 1:
        // factor_of_variable enters at gfgpu_matrix_add_term for order 2 only, like the reference (C&E.cc:5359-5418 vs 4669-4735)
       char hb[40];
       for (double p : rt.params) { std::snprintf(hb, sizeof hb, "/%a", p); key << hb; }
     }
     for (const std::string &fn : rt.field_names) key << "/field:" << fn << "@" << ws.associated_mf(fn);
-    if (!all_cv) {  // the region's content is part of the key (FNV-1a over the items)
+    if (use_region) {  // the region's content is part of the key (FNV-1a over the items)
       uint64_t h = 1469598103934665603ull;
-      for (size_t k = 0; k < rg_cv.size(); ++k) {
-        h = (h ^ uint64_t(uint32_t(rg_cv[k]))) * 1099511628211ull;
-        h = (h ^ uint64_t(uint32_t(rg_f[k]))) * 1099511628211ull;
+      for (size_t k = 0; k < grg_cv.size(); ++k) {
+        h = (h ^ uint64_t(uint32_t(grg_cv[k]))) * 1099511628211ull;
+        h = (h ^ uint64_t(uint32_t(grg_f[k]))) * 1099511628211ull;
       }
-      key << "/rg" << rg_cv.size() << ":" << h;
+      key << "/rg" << grg_cv.size() << ":" << h;
+    }
+    if (!whole_mesh) {  // ... and so is the group's convex list
+      uint64_t h = 1469598103934665603ull;
+      for (size_type cv : gcv) h = (h ^ uint64_t(cv)) * 1099511628211ull;
+      key << "/cv" << h;
     }
     {  // drop what the context says is stale, and the least recently used entries beyond the cache bound
       auto it = cache_.find(key.str());
@@ -874,9 +915,6 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
       e.watch.add_dependency(m);
       e.watch.add_dependency(mf);
       e.watch.add_dependency(mim);
-      for (dal::bv_visitor cv(m.convex_index()); !cv.finished(); ++cv)  // once per entry: a change touches the context
-        GMM_ASSERT1(mf.fem_of_element(cv) == pf && m.trans_of_convex(cv) == pgt && mim.int_method_of_element(cv) == pim,
-                    "gfgpu: mixed fems / transformations / integration methods are not handled");
       // mesh (basic_mesh::points_of_convex / ind_points_of_convex)
       const size_type npts = m.points_index().last_true() + 1;
       std::vector<double> pts(npts * dim, 0.0);
@@ -884,10 +922,11 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
         for (int d = 0; d < dim; ++d) pts[p * dim + d] = m.points()[p][d];
       std::vector<int32_t> conn(ne * ng);
       std::vector<int64_t> edof(ne * nd);
-      for (size_type cv = 0; cv < ne; ++cv) {
-        for (size_type i = 0; i < ng; ++i) conn[cv * ng + i] = int32_t(m.ind_points_of_convex(cv)[i]);
+      for (size_type k = 0; k < ne; ++k) {  // the group's convexes, in ascending order
+        const size_type cv = gcv[k];
+        for (size_type i = 0; i < ng; ++i) conn[k * ng + i] = int32_t(m.ind_points_of_convex(cv)[i]);
         const auto &ct = mf.ind_scalar_basic_dof_of_element(cv);
-        for (size_type i = 0; i < nd; ++i) edof[cv * nd + i] = int64_t(ct[i]);
+        for (size_type i = 0; i < nd; ++i) edof[k * nd + i] = int64_t(ct[i]);
       }
       // reference tables at the volume quadrature points (geotrans_precomp_ / fem_precomp_)
       bgeot::pstored_point_tab pspt = pai->pintegration_points();
@@ -938,8 +977,8 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
       }
       GFGPU_CALL(gfgpu_term_create(ctx_, e.mesh, e.fem, e.tab, rt.family, rt.params.data(), int(rt.params.size()), 1.0,
                                    GFGPU_STRATEGY_AUTO, &e.term));
-      if (!all_cv)
-        GFGPU_CALL(gfgpu_term_set_region(e.term, int64_t(rg_cv.size()), rg_cv.data(), rg_faces ? rg_f.data() : nullptr));
+      if (use_region)
+        GFGPU_CALL(gfgpu_term_set_region(e.term, int64_t(grg_cv.size()), grg_cv.data(), rg_faces ? grg_f.data() : nullptr));
       if (!rt.field_names.empty()) {
         // fem-data coefficients: the data mesh_fem's dof table and its basis at the same points (fem_precomp_::val)
         const getfem::mesh_fem *pmd = ws.associated_mf(rt.field_names[0]);
@@ -947,16 +986,16 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
           GMM_ASSERT1(ws.associated_mf(fn) == pmd, "gfgpu: the fem-data coefficients of one term must share their mesh_fem");
         GMM_ASSERT1(&pmd->linked_mesh() == &m && !pmd->is_reduced(), "gfgpu: the data mesh_fem must be a non-reduced fem of the same mesh");
         getfem::pfem pfd = pmd->fem_of_element(cv0);
-        for (dal::bv_visitor cv(m.convex_index()); !cv.finished(); ++cv)
-          GMM_ASSERT1(pmd->fem_of_element(cv) == pfd, "gfgpu: mixed data fems are not handled");
+        for (size_type cv : gcv)
+          GMM_ASSERT1(pmd->fem_of_element(cv) == pfd, "gfgpu: the data fem must be uniform on a group of like convexes");
         bool dqk; int ddim, ddeg;
         GMM_ASSERT1(parse_kind(getfem::name_of_fem(pfd), "FEM", dqk, ddim, ddeg) && dqk == fqk,
                     "gfgpu: data fem not handled: " << getfem::name_of_fem(pfd));
         const size_type ndd = pfd->nb_dof(cv0);
         std::vector<int64_t> ded(ne * ndd);
-        for (size_type cv = 0; cv < ne; ++cv) {
-          const auto &ct = pmd->ind_scalar_basic_dof_of_element(cv);
-          for (size_type i = 0; i < ndd; ++i) ded[cv * ndd + i] = int64_t(ct[i]);
+        for (size_type k = 0; k < ne; ++k) {
+          const auto &ct = pmd->ind_scalar_basic_dof_of_element(gcv[k]);
+          for (size_type i = 0; i < ndd; ++i) ded[k * ndd + i] = int64_t(ct[i]);
         }
         GFGPU_CALL(gfgpu_fem_create(ctx_, e.mesh, dqk ? GFGPU_FEM_QK : GFGPU_FEM_PK, ddeg, int(pmd->get_qdim()), int(ndd),
                                     ded.data(), int64_t(pmd->nb_dof()), &e.dfem));
@@ -1025,6 +1064,7 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
       t_device += now_s() - t1;
     }
     t0 = now_s();
+    }  // groups of like convexes
   }
   if (order == 2 && n_added == 0) {  // only order-1 terms / empty regions: K just gets its size (workspace.cc:805-812)
     getfem::model_real_sparse_matrix &K = ws.assembled_matrix();

@@ -43,6 +43,18 @@ int main(int argc, char **argv) {
   mf.set_classical_finite_element(getfem::dim_type(K));
   getfem::mesh_im mim(m);
   mim.set_integration_method(getfem::dim_type(imdeg));
+  if (geti("mixed", 0)) {
+    // a NON-UNIFORM mesh_fem / mesh_im (C&E.cc:5902-5936): the convexes whose barycentre has x < 0.5 get degree K-1 and a
+    // lower integration method; the device path assembles one term per group of like convexes
+    dal::bit_vector low;
+    for (dal::bv_visitor cv(m.convex_index()); !cv.finished(); ++cv) {
+      double bx = 0;
+      for (size_type i = 0; i < pgt->nb_points(); ++i) bx += m.points_of_convex(cv)[i][0];
+      if (bx / double(pgt->nb_points()) < 0.5) low.add(cv);
+    }
+    mf.set_classical_finite_element(low, getfem::dim_type(K - 1));
+    mim.set_integration_method(low, getfem::dim_type(imdeg - 2));
+  }
   const size_type ndof = mf.nb_dof();
   std::vector<double> U(ndof);
   if (family == "elast" || family == "laplace" || family == "mass" || family == "source" || family == "nsource") {

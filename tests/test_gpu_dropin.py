@@ -81,7 +81,9 @@ def test_multithreaded_models_run_on_the_device(case):
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     r = json.loads(out.stdout.strip().splitlines()[-1])
     assert r["device_workspace_calls"] > 0, r
-    assert r["entries_on_one_side_only"] == 0 and r["rel_K"] < 1e-12 and r["rel_rhs"] < 1e-12, r
+    # (entries that cancel to round-off on one side and to 0.0 on the other are stored by one model tangent only: the
+    # bricks' gmm::copy drops exact zeros -- same criterion as the single-thread model test above)
+    assert r["max_one_sided_rel"] < 1e-14 and r["rel_K"] < 1e-12 and r["rel_rhs"] < 1e-12, r
 
 
 PROBE_CASES = [  # spellings of tests/test_assembly.cc:812-866 that only recognition BY PROBE covers (tests/test_shim_probe.py, CPU)

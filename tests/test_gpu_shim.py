@@ -49,6 +49,13 @@ CASES = [
     "dim=3 n=4 gt=pk k=2 q=3 im=4 family=source region=xmax coef=fem kd=1",
     "dim=3 n=3 gt=qk k=2 q=1 im=6 family=mass region=outer coef=fem kd=1",
     "dim=3 n=4 gt=pk k=2 q=3 im=4 family=elast model=1 coef=fem kd=1",
+    # non-uniform mesh_fem / mesh_im (first slice): P1 + P2 (Q1 + Q2) convexes with two integration
+    # methods in one mesh; one device term per group of like convexes, merged in the workspace tangent
+    "dim=3 n=4 gt=pk k=2 q=3 im=4 family=elast mixed=1",
+    "dim=2 n=8 gt=pk k=2 q=1 im=4 family=laplace mixed=1",
+    "dim=3 n=3 gt=qk k=2 q=3 im=6 family=nh_ciarlet mixed=1",
+    "dim=3 n=4 gt=pk k=2 q=3 im=4 family=mass region=outer mixed=1",
+    "dim=3 n=4 gt=pk k=2 q=3 im=4 family=elast region=half mixed=1",
 ]
 
 
