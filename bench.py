@@ -196,6 +196,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--strategy", type=int, default=0)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = a mesh N times longer (per-GPU work fixed), strong = the same mesh split N ways")
     ap.add_argument("--torch-exchange", action="store_true", help="N > 1: halo exchange through torch.distributed P2P instead of the library's own NCCL group")
     ap.add_argument("--no-extra", action="store_true", help="skip the one-line summaries of the other BASELINE configurations")
     args = ap.parse_args()
@@ -225,7 +227,8 @@ def main():
     # weak scaling: every rank assembles its own element block of a mesh that is `world` times
     # longer in the last direction (z-slabs in the reference's convex order)
     nsub = [n] * dim
-    nsub[-1] = n * world
+    if args.scaling == "weak":
+        nsub[-1] = n * world
     m = gf.mesh()
     gf.regular_unit_mesh(m, nsub, "GT_%s(%d,1)" % (gt, dim))
     mf = gf.mesh_fem(m, Q)
@@ -359,8 +362,11 @@ def main():
         R_host = torch.empty(own_hi - own_lo, dtype=torch.float64, pin_memory=True)
         h2d_bytes, d2h_bytes = 8 * ndof, 8 * nnz_owned + 8 * (own_hi - own_lo)
 
+        t_lo, t_hi = plan.touched  # the dofs this rank's element block touches: nothing else is uploaded
+        h2d_bytes = 8 * (t_hi - t_lo)
+
         def e2e_step():
-            U_dev.copy_(U_pin, non_blocking=True)
+            U_dev[t_lo:t_hi].copy_(U_pin[t_lo:t_hi], non_blocking=True)
             step()
             _, _, prp = term.csc_view()
             pr_host.copy_(capi._dev_tensor(prp + 8 * jc0, nnz_owned, local), non_blocking=True)
@@ -387,6 +393,23 @@ def main():
     checks = {"pr_norm": float(np.linalg.norm(pr_host.numpy()[: min(pr_host.numel(), 10_000_000)])),
               "R_norm": float(np.linalg.norm(R_host.numpy()))}
 
+    multi = None
+    if world > 1:
+        # parity of THIS multi-GPU path (same processes, same communicator) at a size every rank can also assemble alone, and
+        # the checksum of every rank's owned slab of the timed run
+        nchk = {"c1": 64, "c2": 16, "c3": 10, "c4": 4, "c5": 2}[wl]
+        chk_sub = [nchk] * dim
+        chk_sub[-1] = nchk * world
+        with torch.cuda.stream(stream):
+            mine = halo.selfcheck_distributed(ctx, dim, chk_sub, gt, k, Q, im, family, params, comm)
+        mine["slab_checksum"] = float(pr_host.numpy().sum())
+        mine["slab_nnz"] = int(nnz_owned)
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+        multi = {"check_mesh": chk_sub, "exchange": "library ncclSend/ncclRecv group" if comm is not None else "torch.distributed P2P",
+                 "pattern_ok": all(r["pattern_ok"] for r in allr),
+                 "max_rel_K": max(r.get("rel_K", 0.0) for r in allr), "max_rel_R": max(r.get("rel_R", 0.0) for r in allr),
+                 "ranks": allr}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -408,7 +431,7 @@ def main():
     line = {
         "metric": "assembled_elements_per_s", "value": value, "unit": "elements/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s: %s" % (wl, desc), "n": n, "elements": ne_all, "ndof": ndof, "nnz": nnz_all,
                    "fem": "FEM_%s(%d,%d) Q=%d" % (gt, dim, k, Q), "im": t["im"], "family": family,
                    "order": "tangent+residual", "l2": "outputs (%.1f GB) exceed L2" % (8e-9 * nnz),
@@ -432,6 +455,8 @@ def main():
         "clocks": clocks,
         "symbolic_s": t_sym, "setup_s": t_setup, "device_bytes": ctx.bytes_in_use(), "checks": checks,
     }
+    if multi is not None:
+        line["multi_gpu_check"] = multi
     if k_alone is not None:
         # tile kernel + residual path: the residual kernels run on the library's side stream NEXT to the tile kernel
         line["kernel_ms_note"] = ("rgather = span of the residual path on the side stream (it overlaps the tile kernel: "

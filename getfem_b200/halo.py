@@ -168,3 +168,52 @@ def exchange_local(terms, plans, order_mask):
         torch.cuda.synchronize()
     for t in terms:
         t.halo_accumulate(order_mask)
+
+
+def selfcheck_distributed(ctx, dim, nsub, gt, k, Q, im, family, params, comm=None, group=None):
+    """Parity of the REAL multi-GPU path at a size every rank can also assemble alone: element blocks + halo exchange
+    against the single-GPU assembly of the same mesh.  Returns this rank's figures (pattern of the owned slab bit-exact,
+    relative errors of its values and of the residual slice); bench.py gathers them on rank 0."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from . import capi, fem_tables
+    from .workspace import mesh as Mesh, mesh_fem as MeshFem, regular_unit_mesh
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    m = Mesh()
+    regular_unit_mesh(m, nsub, "GT_%s(%d,1)" % (gt, dim))
+    mf = MeshFem(m, Q)
+    mf.set_classical_finite_element(k)
+    dmesh, dfem = m.device(ctx), mf.device(ctx)
+    t = fem_tables.classical_tables(gt, dim, k, im)
+    tab = capi.DeviceTables(ctx, t["quad_w"], t["gt_grad"], t["phi"], t["gphi"])
+    ndof = dfem.ndof
+    U = np.random.default_rng(7).uniform(-1, 1, ndof) * (0.02 if family in ("svk", "nh_ciarlet", "nh_bonet") else 1.0)
+    U_dev = torch.from_numpy(U).to("cuda:%d" % ctx.device)
+    order = capi.TANGENT | capi.RESIDUAL
+    full = capi.DeviceTerm(ctx, dmesh, dfem, tab, family, params, 1.0, 0)
+    full.assemble_dev(U_dev.data_ptr(), order)
+    jc, ir, pr = full.export_csc()
+    R = full.export_residual()
+    ne = m.nb_convex()
+    term = capi.DeviceTerm(ctx, dmesh, dfem, tab, family, params, 1.0, 0)
+    term.set_element_range(rank * ne // world, (rank + 1) * ne // world)
+    plan = setup_distributed(term, U_dev.data_ptr(), group)
+    if comm is not None:
+        register_sends(term, plan)
+    term.assemble_dev(U_dev.data_ptr(), order)
+    if comm is not None:
+        exchange_nccl(term, comm, order)
+    else:
+        exchange_distributed(term, plan, order, group)
+    ctx.synchronize()
+    lo, hi = term.owned_range()
+    tjc, tir, tpr = term.export_csc()
+    tR = term.export_residual()
+    a, b, A, B = tjc[lo], tjc[hi], jc[lo], jc[hi]
+    ok = bool(np.array_equal(tjc[lo:hi + 1] - a, jc[lo:hi + 1] - A) and b - a == B - A and np.array_equal(tir[a:b], ir[A:B]))
+    out = {"rank": rank, "own": [int(lo), int(hi)], "pattern_ok": ok, "elements": int(ne), "ndof": int(ndof)}
+    if ok and hi > lo:
+        out["rel_K"] = float(np.linalg.norm(tpr[a:b] - pr[A:B]) / max(np.linalg.norm(pr[A:B]), 1e-300))
+        out["rel_R"] = float(np.linalg.norm(tR[lo:hi] - R[lo:hi]) / max(np.linalg.norm(R[lo:hi]), 1e-300))
+    return out

@@ -19,6 +19,7 @@
 #include "getfem/getfem_integration.h"
 #include "getfem/getfem_mesh_fem.h"
 #include "getfem/getfem_mesh_im.h"
+#include "getfem/getfem_omp.h"
 
 namespace getfem_b200 {
 
@@ -804,16 +805,24 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     size_type rg_faces = 0;
     if (!all_cv) {
       // Inside GETFEM_OMP_PARALLEL with several partitions mr_visitor walks only the calling thread's slice
-      // (getfem_mesh_region.cc:186-200, 503-540).  The device assembles the WHOLE region in one call (made by thread 0 alone,
-      // see the dispatch patch): a private copy of the region with partitioning prohibited (getfem_mesh_region.cc:219-221)
-      // gives the full item list in the same order, without touching the shared object.
-      getfem::mesh_region rg_whole(td.rg->from_mesh(m));
-      rg_whole.prohibit_partitioning();
-      for (getfem::mr_visitor v(rg_whole, m); !v.finished(); ++v) {
-        rg_cv.push_back(int32_t(v.cv()));
-        const bool isf = v.f() != getfem::short_type(-1);
-        rg_f.push_back(isf ? int32_t(v.f()) : -1);
-        rg_faces += isf;
+      // (getfem_mesh_region.cc:186-200, 503-540), and a copy of a mesh-owned region SHARES its implementation (operator=,
+      // getfem_mesh_region.cc:100-106), partition caches included.  The device assembles the WHOLE region in one call (made by
+      // the thread of partition 0 alone, see the dispatch patch): there the item list is rebuilt from the membership test,
+      // which ignores the partition -- ascending convexes, whole convex first, then faces: the visitor's order.
+      if (getfem::me_is_multithreaded_now() && getfem::partition_master::get().get_nb_partitions() > 1) {
+        for (dal::bv_visitor cv(m.convex_index()); !cv.finished(); ++cv) {
+          if (td.rg->is_in(cv, getfem::short_type(-1), m)) { rg_cv.push_back(int32_t(cv)); rg_f.push_back(-1); }
+          const getfem::short_type nf = m.structure_of_convex(cv)->nb_faces();
+          for (getfem::short_type f = 0; f < nf; ++f)
+            if (td.rg->is_in(cv, f, m)) { rg_cv.push_back(int32_t(cv)); rg_f.push_back(int32_t(f)); ++rg_faces; }
+        }
+      } else {
+        for (getfem::mr_visitor v(*td.rg, m); !v.finished(); ++v) {
+          rg_cv.push_back(int32_t(v.cv()));
+          const bool isf = v.f() != getfem::short_type(-1);
+          rg_f.push_back(isf ? int32_t(v.f()) : -1);
+          rg_faces += isf;
+        }
       }
       if (rg_cv.empty()) continue;  // an empty region assembles nothing: ga_exec walks zero elements (C&E.cc:8789-8866)
       GMM_ASSERT1(rg_faces == 0 || rg_faces == rg_cv.size(), "gfgpu: a region must hold either convexes or faces");

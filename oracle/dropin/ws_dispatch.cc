@@ -85,10 +85,24 @@ void ga_workspace::assembly(size_type order, bool condensation) {
     // sums afterwards.  Thread 0 assembles the whole region on the device (the shim walks the region with partitioning
     // prohibited); the other threads contribute their zeros.
     ++getfem_b200::g_skipped_calls;
+    if (std::getenv("GFGPU_TRACE"))
+      std::fprintf(stderr, "[gfgpu trace] skipped order %d partition %d\n", int(order),
+                   int(getfem::partition_master::get().get_current_partition()));
     return;
   }
   static thread_local getfem_b200::device_assembler dev(0);
   ++getfem_b200::g_device_calls;
   dev.assembly(*this, order);  // throws gmm::gmm_error when the workspace is not covered: no silent CPU fallback
+  if (std::getenv("GFGPU_TRACE")) {
+    double nk = 0, nv = 0;
+    if (order == 2)
+      for (size_type j = 0; j < gmm::mat_ncols(*K); ++j)
+        for (auto it = (*K)[j].begin(); it != (*K)[j].end(); ++it) nk += it->e * it->e;
+    if (order == 1) for (double x : *V) nv += x * x;
+    std::fprintf(stderr, "[gfgpu trace] device call order %d partition %d/%d trees %d |K|^2 %.17g |V|^2 %.17g owned K %d V %d\n",
+                 int(order), int(getfem::partition_master::get().get_current_partition()),
+                 int(getfem::partition_master::get().get_nb_partitions()), int(nb_trees()), nk, nv, int(K.use_count()),
+                 int(V.use_count()));
+  }
 }
 }  // namespace getfem
