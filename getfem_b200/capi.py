@@ -78,6 +78,10 @@ SIGNATURES = {
     "gfgpu_matrix_export_csc_host": (C.c_int, [_P, _P, _P, _P]),
     "gfgpu_matrix_mult_dev": (C.c_int, [_P, C.c_int, C.c_double, _P, C.c_double, _P]),
     "gfgpu_matrix_mult_host": (C.c_int, [_P, C.c_int, C.c_double, _P, C.c_double, _P]),
+    "gfgpu_matrix_apply_dof_constraints": (C.c_int, [_P, _i64, _P, _P, _P, _P, C.c_int]),
+    "gfgpu_matrix_export_csr_dev": (C.c_int, [_P, _P, _P, _P]),
+    "gfgpu_matrix_cg_dev": (C.c_int, [_P, _P, _P, C.c_double, C.c_int, _P, _P]),
+    "gfgpu_term_residual_add_dev": (C.c_int, [_P, C.c_double, _P, _i64]),
     "gfgpu_term_halo_begin": (C.c_int, [_P, _P, _P, _P]),
     "gfgpu_term_halo_ghost_pairs": (C.c_int, [_P, _i64, _i64, _P, _P, _P, _P]),
     "gfgpu_term_halo_add_source": (C.c_int, [_P, C.c_int, _i64, _P, _P, _P, _i64, _i64]),
@@ -344,6 +348,10 @@ class DeviceTerm(_Handle):
         check(lib().gfgpu_term_export_csc_host(self.h, ptr(jc), ptr(ir), ptr(pr)))
         return jc, ir, pr
 
+    def residual_add_dev(self, rhs_dev_ptr, alpha=1.0, row_off=0):
+        """rhs[row_off + i] += alpha R_i on the device (the model's rrhs, getfem_models.cc:2553-2570)."""
+        check(lib().gfgpu_term_residual_add_dev(self.h, float(alpha), C.c_void_p(rhs_dev_ptr), int(row_off)))
+
     def export_residual(self):
         R = np.empty(self.ndof, np.float64)
         check(lib().gfgpu_term_export_residual_host(self.h, ptr(R)))
@@ -432,6 +440,9 @@ class Communicator(_Handle):
         return int(lib().gfgpu_comm_size(self.h))
 
 
+MODEL_LINEAR, MODEL_SYMMETRIC, BUILD_MATRIX = 1, 2, 4
+
+
 class DeviceMatrix(_Handle):
     """The workspace-level tangent on the device: the sum of terms at their variable offsets (gfgpu_matrix_*)."""
     _destroy = "gfgpu_matrix_destroy"
@@ -479,6 +490,31 @@ class DeviceMatrix(_Handle):
     def mult_dev(self, x_dev_ptr, y_dev_ptr, transposed=False, alpha=1.0, beta=0.0):
         check(lib().gfgpu_matrix_mult_dev(self.h, 1 if transposed else 0, float(alpha), C.c_void_p(x_dev_ptr), float(beta),
                                           C.c_void_p(y_dev_ptr)))
+
+    def apply_dof_constraints(self, dofs, values, rhs_dev_ptr=None, present=None, linear=True, symmetric=True,
+                              build_matrix=True):
+        """Dirichlet conditions with simplification on the resident tangent and a device right-hand side
+        (model::real_dof_constraints, getfem_models.cc:2806-2871)."""
+        dofs = np.ascontiguousarray(dofs, np.int64)
+        values = np.ascontiguousarray(values, np.float64)
+        assert dofs.shape == values.shape
+        pres = None if present is None else np.ascontiguousarray(present, np.float64)
+        flags = (MODEL_LINEAR if linear else 0) | (MODEL_SYMMETRIC if symmetric else 0) | (BUILD_MATRIX if build_matrix else 0)
+        check(lib().gfgpu_matrix_apply_dof_constraints(self.h, dofs.size, ptr(dofs), ptr(values),
+                                                       None if pres is None else ptr(pres),
+                                                       None if rhs_dev_ptr is None else C.c_void_p(rhs_dev_ptr), flags))
+
+    def export_csr_dev(self, rowptr_dev_ptr, col_dev_ptr, val_dev_ptr):
+        """CSR (int64 row pointers, int32 columns, values) into caller-owned device buffers: the solver hand-off."""
+        vp = lambda p: None if p is None else C.c_void_p(p)  # noqa: E731
+        check(lib().gfgpu_matrix_export_csr_dev(self.h, vp(rowptr_dev_ptr), vp(col_dev_ptr), vp(val_dev_ptr)))
+
+    def cg_dev(self, b_dev_ptr, x_dev_ptr, rtol=1e-10, max_iter=10000):
+        """Jacobi-preconditioned CG on the device; returns (iterations, relative residual)."""
+        it, rr = C.c_int(0), C.c_double(0.0)
+        check(lib().gfgpu_matrix_cg_dev(self.h, C.c_void_p(b_dev_ptr), C.c_void_p(x_dev_ptr), float(rtol), int(max_iter),
+                                        C.byref(it), C.byref(rr)))
+        return it.value, rr.value
 
 
 class _DevArray:

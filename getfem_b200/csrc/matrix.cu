@@ -9,6 +9,8 @@
 //              term is added by one kernel without atomics: results are bitwise reproducible;
 //   products = y = K^T x (gather per column) and y = K x (gather per row through a row-sorted permutation built once per
 //              pattern), fixed summation order, no atomics.
+#include <algorithm>
+#include <cmath>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -219,6 +221,123 @@ static void mat_add(gfgpu_matrix *m, const int64_t *tjc, const int32_t *tir, con
   GF_REQUIRE(err == 0, "internal error: a term entry has no slot in the matrix pattern");
 }
 
+// ---------------------------------------------------------------- model-level algebra on the resident tangent
+// Dirichlet conditions with simplification (model::add_Dirichlet_condition_with_simplification ->
+// real_dof_constraints, getfem_models.cc:2806-2871): rows (and, for a symmetric model, columns) of the constrained dofs
+// are cleared and their diagonal set to 1.  mark[dof] = 1 + position in the constraint list, 0 = free.
+__global__ void k_mat_mark(const int64_t *__restrict__ dof, int64_t n, int32_t *__restrict__ mark) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+    mark[dof[k]] = (int32_t)k + 1;
+}
+
+// warp per column: entries in constrained rows -> 0; a constrained column of a symmetric model -> 0; diagonal -> 1
+__global__ void k_mat_constrain(const int64_t *__restrict__ jc, const int32_t *__restrict__ ir, double *__restrict__ pr,
+                                int64_t ncols, const int32_t *__restrict__ mark, int symmetric, int32_t *__restrict__ flag) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = w0; c < ncols; c += nw) {
+    const bool cc = mark[c] != 0;
+    bool diag = false;
+    for (int64_t k = jc[c] + lane; k < jc[c + 1]; k += 32) {
+      const int32_t r = ir[k];
+      if (cc && r == c) { pr[k] = 1.0; diag = true; }
+      else if (mark[r] || (cc && symmetric)) pr[k] = 0.0;
+    }
+    if (cc && !__any_sync(0xffffffffu, diag) && lane == 0) atomicExch(flag, 1);
+  }
+}
+
+// rhs[dof[k]] = go[k] (linear model) or += go[k] - pr[k] (nonlinear: the Newton increment goes to the prescribed value)
+__global__ void k_rhs_constrain(const int64_t *__restrict__ dof, const double *__restrict__ go, const double *__restrict__ prv,
+                                int64_t n, int linear, double *__restrict__ rhs) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    if (linear) rhs[dof[k]] = go[k];
+    else rhs[dof[k]] += go[k] - prv[k];
+  }
+}
+
+__global__ void k_axpy_off(const double *__restrict__ x, int64_t n, double alpha, double *__restrict__ y) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) y[k] += alpha * x[k];
+}
+
+__global__ void k_scatter_vals(const int64_t *__restrict__ dof, const double *__restrict__ v, int64_t n, double *__restrict__ out) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) out[dof[k]] = v[k];
+}
+
+// CSR hand-off: values (and int32 row pointers when they fit) in row-major order for a device solver
+__global__ void k_csr_vals(const uint32_t *__restrict__ rperm, const double *__restrict__ pr, int64_t nnz, double *__restrict__ val) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) val[k] = pr[rperm[k]];
+}
+
+// ---- Jacobi-preconditioned conjugate gradient on the resident matrix (symmetric positive definite tangent).  The point is
+// the hand-off: K, the residual and the solution never leave the device.  Scalars live in device memory (sc[]):
+// 0 rz, 1 pq, 2 rz_new, 3 rr; reductions are two-stage with a fixed order (bitwise reproducible).
+constexpr int CG_PARTS = 148 * 4;
+__global__ void __launch_bounds__(256) k_dot_part(const double *__restrict__ x, const double *__restrict__ y, int64_t n, double *__restrict__ part) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) s += x[k] * y[k];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(256) k_dot_final(const double *__restrict__ part, int np, double *__restrict__ out) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int k = threadIdx.x; k < np; k += 256) s += part[k];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+__global__ void k_mat_diag_inv(const int64_t *__restrict__ jc, const int32_t *__restrict__ ir, const double *__restrict__ pr,
+                               int64_t ncols, double *__restrict__ dinv) {
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncols; c += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = lower_row(ir, jc[c], jc[c + 1], (int32_t)c);
+    const double d = (k < jc[c + 1] && ir[k] == c) ? pr[k] : 0.0;
+    dinv[c] = d != 0.0 ? 1.0 / d : 1.0;
+  }
+}
+__global__ void k_cg_init(const double *__restrict__ b, const double *__restrict__ dinv, int64_t n, double *__restrict__ r,
+                          double *__restrict__ z, double *__restrict__ p) {  // r = b - q (q = K x0 already in r's place: r holds K x0)
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const double rk = b[k] - r[k];
+    r[k] = rk;
+    z[k] = dinv[k] * rk;
+    p[k] = z[k];
+  }
+}
+__global__ void k_cg_step1(const double *__restrict__ sc, const double *__restrict__ p, const double *__restrict__ q,
+                           const double *__restrict__ dinv, int64_t n, double *__restrict__ x, double *__restrict__ r,
+                           double *__restrict__ z) {
+  const double alpha = sc[1] != 0.0 ? sc[0] / sc[1] : 0.0;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    x[k] += alpha * p[k];
+    const double rk = r[k] - alpha * q[k];
+    r[k] = rk;
+    z[k] = dinv[k] * rk;
+  }
+}
+__global__ void k_cg_step2(double *__restrict__ sc, const double *__restrict__ z, int64_t n, double *__restrict__ p) {
+  const double beta = sc[0] != 0.0 ? sc[2] / sc[0] : 0.0;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) p[k] = z[k] + beta * p[k];
+}
+__global__ void k_cg_roll(double *sc) { sc[0] = sc[2]; }
+
+static void dot_dev(gfgpu_ctx *ctx, const double *x, const double *y, int64_t n, double *part, double *out) {
+  k_dot_part<<<CG_PARTS, 256, 0, ctx->stream>>>(x, y, n, part);
+  GF_LAUNCH_CHECK();
+  k_dot_final<<<1, 256, 0, ctx->stream>>>(part, CG_PARTS, out);
+  GF_LAUNCH_CHECK();
+}
+
 static void mat_build_csr(gfgpu_matrix *m) {
   if (m->csr_generation == m->generation) return;
   gfgpu_ctx *ctx = m->ctx;
@@ -380,6 +499,161 @@ int gfgpu_matrix_mult_host(gfgpu_matrix *m, int transposed, double alpha, const 
   GF_REQUIRE(gfgpu_matrix_mult_dev(m, transposed, alpha, x.p, beta, y.p) == 0, gfgpu_last_error());
   y.download(y_host);
   GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  GFM_END
+}
+
+int gfgpu_matrix_apply_dof_constraints(gfgpu_matrix *m, int64_t n, const int64_t *dof_host, const double *go_host,
+                                       const double *pr_host, double *rhs_dev, int flags) {
+  GFM_BEGIN
+  GF_REQUIRE(m && m->nrows == m->ncols, "dof constraints need a square matrix");
+  GF_REQUIRE(n >= 0 && (n == 0 || (dof_host && go_host)), "null argument");
+  const bool linear = flags & GFGPU_MODEL_LINEAR, symmetric = flags & GFGPU_MODEL_SYMMETRIC, do_m = flags & GFGPU_BUILD_MATRIX;
+  GF_REQUIRE(linear || !rhs_dev || pr_host, "a nonlinear model needs the present values of the constrained dofs");
+  if (!n) return 0;
+  gfgpu_ctx *ctx = m->ctx;
+  GF_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const int B = 256;
+  for (int64_t k = 0; k < n; ++k) GF_REQUIRE(dof_host[k] >= 0 && dof_host[k] < m->nrows, "constrained dof out of range");
+  gf::DevBuf<int64_t> dof;
+  gf::DevBuf<double> go, prv;
+  dof.alloc(ctx, n); go.alloc(ctx, n);
+  dof.upload(dof_host); go.upload(go_host);
+  if (pr_host) { prv.alloc(ctx, n); prv.upload(pr_host); }
+  if (rhs_dev) {
+    if (linear && symmetric) {  // rhs -= K(:, SI) go, with the matrix as it is BEFORE the rows and columns are cleared
+      double nrm = 0;
+      for (int64_t k = 0; k < n; ++k) nrm += go_host[k] * go_host[k];
+      if (nrm > 0) {
+        GF_REQUIRE(do_m, "Rhs only for a symmetric linear problem with dof constraint not allowed");  // models.cc:2843-2845
+        gf::DevBuf<double> full;
+        full.alloc(ctx, m->ncols);
+        full.zero();
+        gf::k_scatter_vals<<<gf::mgrid(n, B), B, 0, s>>>(dof.p, go.p, n, full.p);
+        GF_LAUNCH_CHECK();
+        GF_REQUIRE(gfgpu_matrix_mult_dev(m, 0, -1.0, full.p, 1.0, rhs_dev) == 0, gfgpu_last_error());
+        GF_CUDA(cudaStreamSynchronize(s));
+      }
+    }
+    gf::k_rhs_constrain<<<gf::mgrid(n, B), B, 0, s>>>(dof.p, go.p, prv.p, n, linear ? 1 : 0, rhs_dev);
+    GF_LAUNCH_CHECK();
+  }
+  if (do_m) {
+    // the diagonal slots of the constrained dofs must exist: add them to the pattern (alpha = 0) if some are missing
+    {
+      std::vector<int64_t> sd(dof_host, dof_host + n);
+      std::sort(sd.begin(), sd.end());
+      sd.erase(std::unique(sd.begin(), sd.end()), sd.end());
+      std::vector<int64_t> tjc(m->ncols + 1, 0);
+      std::vector<int32_t> tir(sd.size());
+      std::vector<double> tpr(sd.size(), 0.0);
+      for (size_t k = 0; k < sd.size(); ++k) { tjc[sd[k] + 1] = 1; tir[k] = (int32_t)sd[k]; }
+      for (int64_t c = 0; c < m->ncols; ++c) tjc[c + 1] += tjc[c];
+      gf::DevBuf<int64_t> djc; gf::DevBuf<int32_t> dir; gf::DevBuf<double> dpr;
+      djc.alloc(ctx, tjc.size()); dir.alloc(ctx, tir.size()); dpr.alloc(ctx, tpr.size());
+      djc.upload(tjc.data()); dir.upload(tir.data()); dpr.upload(tpr.data());
+      gf::mat_add(m, djc.p, dir.p, dpr.p, m->ncols, (int64_t)sd.size(), 0.0, 0, 0);
+    }
+    gf::DevBuf<int32_t> mark;
+    mark.alloc(ctx, m->nrows);
+    mark.zero();
+    gf::k_mat_mark<<<gf::mgrid(n, B), B, 0, s>>>(dof.p, n, mark.p);
+    GF_LAUNCH_CHECK();
+    m->flag.zero();
+    gf::k_mat_constrain<<<gf::mgrid(m->ncols * 32, B), B, 0, s>>>(m->jc.p, m->ir.p, m->pr.p, m->ncols, mark.p, symmetric ? 1 : 0,
+                                                                 m->flag.p);
+    GF_LAUNCH_CHECK();
+    int32_t err = 0;
+    m->flag.download(&err);
+    GF_CUDA(cudaStreamSynchronize(s));
+    GF_REQUIRE(err == 0, "internal error: a constrained dof has no diagonal slot");
+  }
+  GF_CUDA(cudaStreamSynchronize(s));
+  GFM_END
+}
+
+int gfgpu_matrix_export_csr_dev(gfgpu_matrix *m, int64_t *rowptr_dev, int32_t *col_dev, double *val_dev) {
+  GFM_BEGIN
+  GF_REQUIRE(m, "null matrix");
+  GF_CUDA(cudaSetDevice(m->ctx->device));
+  cudaStream_t s = m->ctx->stream;
+  if (!m->nnz) {
+    if (rowptr_dev) GF_CUDA(cudaMemsetAsync(rowptr_dev, 0, (m->nrows + 1) * sizeof(int64_t), s));
+    return 0;
+  }
+  gf::mat_build_csr(m);
+  if (rowptr_dev) GF_CUDA(cudaMemcpyAsync(rowptr_dev, m->rp.p, (m->nrows + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+  if (col_dev) GF_CUDA(cudaMemcpyAsync(col_dev, m->rcol.p, m->nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+  if (val_dev) {
+    gf::k_csr_vals<<<gf::mgrid(m->nnz, 256), 256, 0, s>>>(m->rperm.p, m->pr.p, m->nnz, val_dev);
+    GF_LAUNCH_CHECK();
+  }
+  GFM_END
+}
+
+int gfgpu_matrix_cg_dev(gfgpu_matrix *m, const double *b_dev, double *x_dev, double rtol, int max_iter, int *iters_out,
+                        double *relres_out) {
+  GFM_BEGIN
+  GF_REQUIRE(m && b_dev && x_dev && m->nrows == m->ncols && m->nnz, "cg needs a non-empty square matrix and device vectors");
+  gfgpu_ctx *ctx = m->ctx;
+  GF_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const int64_t n = m->nrows;
+  const int B = 256, G = gf::mgrid(n, B);
+  gf::DevBuf<double> r, z, p, q, dinv, part, sc;
+  r.alloc(ctx, n); z.alloc(ctx, n); p.alloc(ctx, n); q.alloc(ctx, n); dinv.alloc(ctx, n);
+  part.alloc(ctx, gf::CG_PARTS); sc.alloc(ctx, 4);
+  // K is symmetric here: K x is formed as K^T x (a gather per column, no row-major copy of the matrix)
+  auto apply = [&](const double *x, double *y) {
+    gf::k_mat_tmult<<<gf::mgrid(n * 32, B), B, 0, s>>>(m->jc.p, m->ir.p, m->pr.p, n, x, 1.0, 0.0, y);
+    GF_LAUNCH_CHECK();
+  };
+  gf::k_mat_diag_inv<<<G, B, 0, s>>>(m->jc.p, m->ir.p, m->pr.p, n, dinv.p);
+  GF_LAUNCH_CHECK();
+  apply(x_dev, r.p);
+  gf::k_cg_init<<<G, B, 0, s>>>(b_dev, dinv.p, n, r.p, z.p, p.p);
+  GF_LAUNCH_CHECK();
+  gf::dot_dev(ctx, r.p, z.p, n, part.p, sc.p + 0);
+  gf::dot_dev(ctx, b_dev, b_dev, n, part.p, sc.p + 3);
+  double h[4];
+  sc.download(h);
+  GF_CUDA(cudaStreamSynchronize(s));
+  const double bb = h[3] > 0 ? h[3] : 1.0;
+  int it = 0;
+  double rr = bb;
+  const int check_every = 8;
+  while (it < max_iter) {
+    apply(p.p, q.p);
+    gf::dot_dev(ctx, p.p, q.p, n, part.p, sc.p + 1);
+    gf::k_cg_step1<<<G, B, 0, s>>>(sc.p, p.p, q.p, dinv.p, n, x_dev, r.p, z.p);
+    GF_LAUNCH_CHECK();
+    gf::dot_dev(ctx, r.p, z.p, n, part.p, sc.p + 2);
+    gf::k_cg_step2<<<G, B, 0, s>>>(sc.p, z.p, n, p.p);
+    GF_LAUNCH_CHECK();
+    gf::k_cg_roll<<<1, 1, 0, s>>>(sc.p);
+    GF_LAUNCH_CHECK();
+    ++it;
+    if (it % check_every == 0 || it == max_iter) {  // the only host round trip: one scalar every few iterations
+      gf::dot_dev(ctx, r.p, r.p, n, part.p, sc.p + 3);
+      sc.download(h);
+      GF_CUDA(cudaStreamSynchronize(s));
+      rr = h[3];
+      if (!(rr == rr)) break;
+      if (rr <= rtol * rtol * bb) break;
+    }
+  }
+  if (iters_out) *iters_out = it;
+  if (relres_out) *relres_out = std::sqrt(rr / bb);
+  GFM_END
+}
+
+int gfgpu_term_residual_add_dev(gfgpu_term *t, double alpha, double *rhs_dev, int64_t row_off) {
+  GFM_BEGIN
+  GF_REQUIRE(t && rhs_dev && t->R.n, "no assembled residual");
+  GF_REQUIRE(row_off >= 0, "bad offset");
+  GF_CUDA(cudaSetDevice(t->ctx->device));
+  gf::k_axpy_off<<<gf::mgrid((int64_t)t->R.n, 256), 256, 0, t->ctx->stream>>>(t->R.p, (int64_t)t->R.n, alpha, rhs_dev + row_off);
+  GF_LAUNCH_CHECK();
   GFM_END
 }
 

@@ -188,7 +188,8 @@ def selfcheck_distributed(ctx, dim, nsub, gt, k, Q, im, family, params, comm=Non
     t = fem_tables.classical_tables(gt, dim, k, im)
     tab = capi.DeviceTables(ctx, t["quad_w"], t["gt_grad"], t["phi"], t["gphi"])
     ndof = dfem.ndof
-    U = np.random.default_rng(7).uniform(-1, 1, ndof) * (0.02 if family in ("svk", "nh_ciarlet", "nh_bonet") else 1.0)
+    # finite strain laws: nodal noise well below the cell size, so that det(I + Grad_u) stays positive on every cell
+    U = np.random.default_rng(7).uniform(-1, 1, ndof) * (0.05 / max(nsub) if family in ("svk", "nh_ciarlet", "nh_bonet") else 1.0)
     U_dev = torch.from_numpy(U).to("cuda:%d" % ctx.device)
     order = capi.TANGENT | capi.RESIDUAL
     full = capi.DeviceTerm(ctx, dmesh, dfem, tab, family, params, 1.0, 0)

@@ -239,6 +239,27 @@ int gfgpu_matrix_csc_view(gfgpu_matrix *m, const int64_t **jc_dev, const int32_t
 int gfgpu_matrix_export_csc_host(gfgpu_matrix *m, int64_t *jc_host, int32_t *ir_host, double *pr_host);
 int gfgpu_matrix_mult_dev(gfgpu_matrix *m, int transposed, double alpha, const double *x_dev, double beta, double *y_dev);
 int gfgpu_matrix_mult_host(gfgpu_matrix *m, int transposed, double alpha, const double *x_host, double beta, double *y_host);
+/* Model-level algebra on the resident tangent, so that assemble -> constrain -> solve needs no copy of K to the host.
+ *   apply_dof_constraints  Dirichlet conditions "with simplification" (model::real_dof_constraints,
+ *              getfem_models.cc:2806-2871) for the n dofs dof_host[] with prescribed values go_host[]:
+ *              rhs_dev != NULL (BUILD_RHS): linear + symmetric model: rhs -= K(:, SI) go (with K as it is before the
+ *              clearing, refused without GFGPU_BUILD_MATRIX like models.cc:2843-2845), then rhs[SI] = go; nonlinear
+ *              model: rhs[SI] += go - pr_host (present values of those dofs);
+ *              GFGPU_BUILD_MATRIX: rows SI cleared, columns SI too for a symmetric model, K(i, i) = 1.  The entries stay
+ *              in the pattern as explicit zeros (the pattern generation moves only if a diagonal slot was missing).
+ *   export_csr_dev  hand-off to a device solver: row pointers (nrows + 1), columns and values in row-major order, ascending
+ *              columns inside a row, written into caller-owned DEVICE buffers (any may be NULL); needs nnz < 2^31.
+ *   cg_dev     Jacobi-preconditioned conjugate gradient for a symmetric positive definite K: x_dev holds the initial guess
+ *              and receives the solution, stops at |r| <= rtol |b| or max_iter; deterministic reductions.
+ *   gfgpu_term_residual_add_dev  rhs_dev[row_off + i] += alpha R_i: the model's rrhs accumulated on the device
+ *              (getfem_models.cc:2553-2570). */
+enum { GFGPU_MODEL_LINEAR = 1, GFGPU_MODEL_SYMMETRIC = 2, GFGPU_BUILD_MATRIX = 4 };
+int gfgpu_matrix_apply_dof_constraints(gfgpu_matrix *m, int64_t n, const int64_t *dof_host, const double *go_host,
+                                       const double *pr_host, double *rhs_dev, int flags);
+int gfgpu_matrix_export_csr_dev(gfgpu_matrix *m, int64_t *rowptr_dev, int32_t *col_dev, double *val_dev);
+int gfgpu_matrix_cg_dev(gfgpu_matrix *m, const double *b_dev, double *x_dev, double rtol, int max_iter, int *iters_out,
+                        double *relres_out);
+int gfgpu_term_residual_add_dev(gfgpu_term *t, double alpha, double *rhs_dev, int64_t row_off);
 
 /* ---- multi-GPU: element blocks per rank, column-owned CSC slabs, one halo exchange per assembly.
  * Replaces the reference's MPI scheme (per-rank partial matrices summed with MPI_SUM_SPARSE_MATRIX /
