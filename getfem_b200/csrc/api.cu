@@ -510,9 +510,27 @@ int gfgpu_term_set_region(gfgpu_term *t, int64_t n_items, const int32_t *cv, con
   GF_API_END
 }
 
+// The pattern check of a value-dependent tangent, deferred: if the last gather found entries outside the pattern, the
+// pattern is rebuilt from the masks of that same pass and the (still staged) element matrices are gathered again.
+static void term_settle(gfgpu_term *t) {
+  if (!t || !t->flag_pending) return;
+  gfgpu_ctx *ctx = t->ctx;
+  GF_CUDA(cudaSetDevice(ctx->device));
+  t->flag_pending = false;
+  int32_t changed = 0;
+  t->flag.download(&changed);
+  GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (changed) {
+    GF_REQUIRE(!t->halo, "the pattern moved under a multi-GPU halo: announce the pairs again (halo_begin .. halo_commit)");
+    gf::build_pattern(t);
+    gf::gather_tangent(t, false);
+  }
+}
+
 static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
   gfgpu_ctx *ctx = t->ctx;
   GF_CUDA(cudaSetDevice(ctx->device));
+  term_settle(t);  // before the stage of the previous pass is overwritten
   GF_REQUIRE(order_mask & (GFGPU_RESIDUAL | GFGPU_TANGENT), "order_mask selects nothing");
   bool do_t = order_mask & GFGPU_TANGENT;
   const bool do_r = order_mask & GFGPU_RESIDUAL;
@@ -538,7 +556,10 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
   const bool recompute = t->strategy == GFGPU_STRATEGY_RECOMPUTE;
   // what the generic element kernel has to produce in this call.  RECOMPUTE needs it only once, for
   // the keep masks of the pattern; its residual is K^T U inside the per-nonzero kernel.
-  const bool need_masks = recompute ? !t->pat_valid : do_t;
+  // linear families: the keep masks do not depend on U, so a valid pattern needs no masks (and none are written)
+  const bool value_dependent = t->family == GFGPU_SVK || t->family == GFGPU_NEOHOOKEAN_CIARLET ||
+                               t->family == GFGPU_NEOHOOKEAN_BONET || t->family >= GFGPU_MOONEY_RIVLIN;
+  const bool need_masks = recompute ? !t->pat_valid : (do_t && (!t->pat_valid || value_dependent));
   const bool need_stage = do_t && !recompute;
   const bool need_rstage = do_r && !recompute;
   if (need_stage && t->stage.n != (size_t)ne * s1 * s1) t->stage.alloc(ctx, (size_t)ne * s1 * s1);
@@ -637,9 +658,6 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
     return;
   }
   if (do_t) {
-    // linear families: the keep masks do not depend on U, a valid pattern stays valid
-    const bool value_dependent = t->family == GFGPU_SVK || t->family == GFGPU_NEOHOOKEAN_CIARLET ||
-                                 t->family == GFGPU_NEOHOOKEAN_BONET || t->family >= GFGPU_MOONEY_RIVLIN;
     if (!t->pat_valid) {
       tic(3); gf::build_pattern(t); toc(3);
       if (t->halo) gf::halo_build_maps(t);
@@ -647,16 +665,12 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
     } else if (!value_dependent) {
       tic(1); gf::gather_tangent(t, false); toc(1);
     } else {
+      // value-dependent keep masks: the gather compares them with the pattern and raises a DEVICE flag.  No host round
+      // trip here: the flag is read lazily (term_settle) by whoever consumes the tangent next, or by the next assembly.
       t->flag.zero();
       tic(1); gf::gather_tangent(t, true); toc(1);
-      int32_t changed = 0;
-      t->flag.download(&changed);
-      GF_CUDA(cudaStreamSynchronize(ctx->stream));
-      if (changed) {
-        GF_REQUIRE(!t->halo, "the pattern moved under a multi-GPU halo: announce the pairs again (halo_begin .. halo_commit)");
-        tic(3); gf::build_pattern(t); toc(3);
-        tic(1); gf::gather_tangent(t, false); toc(1);
-      }
+      t->flag_pending = true;
+      if (t->halo) term_settle(t);  // the exchange that follows reads pr at once
     }
   }
   if (do_r) { tic(2); gf::gather_residual(t); toc(2); }
@@ -666,6 +680,7 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
 namespace gf {
 double term_potential(gfgpu_term *t, const double *U_dev);  // potential.cu
 void term_assemble_for_potential(gfgpu_term *t, const double *U_dev) { term_assemble(t, U_dev, GFGPU_RESIDUAL); }
+void term_settle_pending(gfgpu_term *t) { term_settle(t); }
 }  // namespace gf
 extern "C" {
 
@@ -711,6 +726,7 @@ int gfgpu_term_assemble_host(gfgpu_term *t, const double *U_host, int order_mask
     U_dev = t->Ubuf.p;
   }
   term_assemble(t, U_dev, order_mask);
+  term_settle(t);
   if ((order_mask & GFGPU_TANGENT) && pr_host) t->pr.download(pr_host);
   if ((order_mask & GFGPU_RESIDUAL) && R_host) t->R.download(R_host);
   GF_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -735,13 +751,18 @@ int gfgpu_term_kernel_kind(gfgpu_term *t) {
   return t->rc_cols ? 2 : t->rc_uni ? 3 : 1;
 }
 
-int64_t gfgpu_term_nnz(gfgpu_term *t) { return (t && t->pat_valid) ? t->nnz : -1; }
+static bool settle_quiet(gfgpu_term *t) {
+  try { term_settle(t); } catch (const std::exception &e) { gf::set_last_error(e.what()); return false; }
+  return true;
+}
+int64_t gfgpu_term_nnz(gfgpu_term *t) { return (t && settle_quiet(t) && t->pat_valid) ? t->nnz : -1; }
 int64_t gfgpu_term_nb_dof(gfgpu_term *t) { return t ? t->fem->ndof : -1; }
-int64_t gfgpu_term_pattern_generation(gfgpu_term *t) { return t ? t->generation : -1; }
+int64_t gfgpu_term_pattern_generation(gfgpu_term *t) { return (t && settle_quiet(t)) ? t->generation : -1; }
 
 int gfgpu_term_csc_view(gfgpu_term *t, const int64_t **jc, const int32_t **ir, const double **pr) {
   GF_API_BEGIN
   GF_REQUIRE(t && t->pat_valid, "no assembled tangent");
+  term_settle(t);
   if (jc) *jc = t->jc.p;
   if (ir) *ir = t->ir.p;
   if (pr) *pr = t->pr.p;
@@ -759,6 +780,7 @@ int gfgpu_term_export_csc_host(gfgpu_term *t, int64_t *jc, int32_t *ir, double *
   GF_API_BEGIN
   GF_REQUIRE(t && t->pat_valid, "no assembled tangent");
   GF_CUDA(cudaSetDevice(t->ctx->device));
+  term_settle(t);
   if (jc) t->jc.download(jc);
   if (ir) t->ir.download(ir);
   if (pr) t->pr.download(pr);

@@ -190,6 +190,7 @@ struct gfgpu_term {
   int64_t g1_nmulti = 0, g1_generation = -1;
   gf::DevBuf<double> Ubuf;      // ndof (host path)
   gf::DevBuf<int32_t> flag;     // pattern-changed flag
+  bool flag_pending = false;    // a value-dependent gather raised (or not) the flag; nobody has read it yet (api.cu term_settle)
   // per-phase events of the last assemble: [0,1] element kernel, [2,3] gather, [4,5] residual gather, [6,7] pattern
   // [2k, 2k+1], k = 0 element kernel, 1 gather, 2 residual gather, 3 pattern, 4 recompute kernel
   cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -307,6 +308,7 @@ bool recompute_cols_prepare(gfgpu_term *t, const std::vector<uint32_t> &colstart
 void recompute_cols_tangent(gfgpu_term *t, const double *U, bool with_r);
 // class-uniform tile kernel (recompute_uniform.cu); prepare returns false when the term keeps the general tile kernel
 bool uniform_prepare(gfgpu_term *t);
+void term_settle_pending(gfgpu_term *t);  // api.cu: deferred pattern check of a value-dependent tangent
 void uniform_tangent(gfgpu_term *t);
 
 }  // namespace gf

@@ -430,6 +430,7 @@ int gfgpu_matrix_add_term(gfgpu_matrix *m, gfgpu_term *t, double alpha, int64_t 
   GF_REQUIRE(m && t, "null argument");
   GF_REQUIRE(m->ctx == t->ctx, "matrix and term live on different contexts");
   GF_REQUIRE(t->pat_valid, "the term has no assembled tangent");
+  gf::term_settle_pending(t);
   const int64_t n = t->fem->ndof;
   GF_REQUIRE(row_off >= 0 && col_off >= 0 && row_off + n <= m->nrows && col_off + n <= m->ncols, "the term does not fit the matrix");
   GF_CUDA(cudaSetDevice(m->ctx->device));

@@ -35,6 +35,8 @@ struct SfTables {
   double px[9][NQ1][NN];  // [a*3+b][q1][i1 + ND1*j1] = X^a_{i1}(q1) X^b_{j1}(q1)
   double py[4][NN][NQ1];  // [(a==1)*2 + (b==1)][i2 + ND1*j2][q2]
   double pz[4][NN][NQ1];  // [(a==2)*2 + (b==2)][i3 + ND1*j3][q3]
+  double l1[ND1][NQ1];    // the 1D basis and its derivative at the 1D points
+  double d1[ND1][NQ1];
 };
 
 struct SfArgs {
@@ -377,6 +379,262 @@ k_sumfact_hyper(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T) {
   }
 }
 
+// ---------------------------------------------------------------- hyperelastic variant, two elements in flight
+// Same mathematics and outputs as k_sumfact_hyper.  The profile of that kernel (profiles/round2_ncu_sumfact_hyper_v1_c4.txt)
+// shows one CTA per SM walking through serial phases: 15 % of the warp samples sit at the barrier behind the material-point
+// phase (64 threads of 288 busy), the contraction phase is latency bound at 9 warps.  Here the CTA is WARP SPECIALISED:
+//   material group (3 warps)  : element n+1 -- gather, material point per Gauss point, pull-back of the tangent into
+//                               sA[(n+1) & 1], flux into sP[(n+1) & 1], element residual;
+//   contraction group (9 warps): element n  -- slices of the sum-factorised contraction from sA[n & 1], drop rule, output.
+// The two groups meet only at named barriers (full[b] / empty[b], bar.arrive + bar.sync, no __syncthreads).
+// K_e is symmetric for a hyperelastic law (major symmetry of D): only the slices (i3 <= j3) are contracted, the others
+// are their mirror images -- 18 (slice, beta) tasks instead of 27, two per warp.
+// Grad_u and the residual use the 1D tables (products of three 1D values) instead of the full gradient table in global
+// memory: with 222 KB of shared memory the L1 that served that table is gone.
+template <int ND1, int NQ1>
+__global__ void __launch_bounds__(384, 1)
+k_sumfact_hyper_ws(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T) {
+  constexpr int NN = ND1 * ND1, ND = ND1 * ND1 * ND1, S1 = 3 * ND, NQ2 = NQ1 * NQ1, NQ = NQ1 * NQ1 * NQ1;
+  constexpr int NWC = 9, NTC = NWC * 32, NTM = 96;
+  constexpr int DS = 82;
+  constexpr int NSL = ND1 * (ND1 + 1) / 2, NTASK = NSL * 3;
+  static_assert(ND1 == 3 && 3 * NN <= 32 && NQ2 <= 32, "lane mapping");
+  extern __shared__ __align__(16) double sm[];
+  double *sK = sm;                          // S1 x S1 column-major
+  double *sA = sK + S1 * S1;                // 2 x 81 x NQ
+  double *sD = sA + 2 * 81 * NQ;            // NQ x DS
+  double *sS1 = sD + NQ * DS;               // per contraction warp 27 x NQ2
+  double *sP = sS1 + NWC * 27 * NQ2;        // 2 x NQ x 9
+  double *sGeo = sP + 2 * 9 * NQ;           // NQ x 10
+  double *sG = sGeo + 10 * NQ;              // 24
+  double *sU = sG + 24;                     // S1
+  double *sRed = sU + S1;                   // NWC
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // named barriers: 1 material group, 2 contraction group, 3 + b full[b], 5 + b empty[b]
+  auto bar_sync = [](int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); };
+  auto bar_arrive = [](int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); };
+
+  if (warp >= NWC) {
+    // ================= material group =================
+    const int mt = tid - NTC;
+    int it = 0;
+    for (int64_t el = blockIdx.x; el < a.ne; el += gridDim.x, ++it) {
+      const int b = it & 1;
+      const int64_t e = a.e0 + el;
+      double *sAb = sA + b * 81 * NQ, *sPb = sP + b * 9 * NQ;
+      if (mt < 24) {
+        const int i = mt / 3, d = mt % 3;
+        const int32_t p = a.conn[e * 8 + i];
+        sG[d + 3 * i] = (d == 0 ? a.x : d == 1 ? a.y : a.z)[p];
+      }
+      for (int i = mt; i < S1; i += NTM) sU[i] = a.U ? a.U[a.edof[e * ND + i / 3] + i % 3] : 0.0;
+      bar_sync(5 + b, 384);  // the contraction group has finished with sA[b], sP[b] (element it - 2)
+      bar_sync(1, NTM);
+      for (int q = mt; q < NQ; q += NTM) {
+        double *geo = sGeo + q * 10;
+        geometry<3>(sG, a.gt_grad + (size_t)q * 24, 8, geo);
+        const int q1 = q % NQ1, q2 = (q / NQ1) % NQ1, q3 = q / NQ2;
+        double lx[ND1], dx[ND1];
+#pragma unroll
+        for (int i = 0; i < ND1; ++i) { lx[i] = T.l1[i][q1]; dx[i] = T.d1[i][q1]; }
+        double Gh[9];  // reference gradient of u: Gh(al,p) = sum_i u_i(al) ghat_i^p
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Gh[k] = 0.0;
+#pragma unroll
+        for (int i3 = 0; i3 < ND1; ++i3) {
+          const double lz = T.l1[i3][q3], dz = T.d1[i3][q3];
+#pragma unroll
+          for (int i2 = 0; i2 < ND1; ++i2) {
+            const double ly = T.l1[i2][q2], dy = T.d1[i2][q2];
+            const double w0 = ly * lz, w1 = dy * lz, w2 = ly * dz;
+            const double *u = sU + (ND1 * i2 + NN * i3) * 3;
+#pragma unroll
+            for (int al = 0; al < 3; ++al) {
+              double t0 = 0, t1 = 0;
+#pragma unroll
+              for (int i1 = 0; i1 < ND1; ++i1) { t0 += u[i1 * 3 + al] * dx[i1]; t1 += u[i1 * 3 + al] * lx[i1]; }
+              Gh[al] += t0 * w0; Gh[al + 3] += t1 * w1; Gh[al + 6] += t1 * w2;
+            }
+          }
+        }
+        double Gu[9];
+#pragma unroll
+        for (int n = 0; n < 3; ++n)
+#pragma unroll
+          for (int al = 0; al < 3; ++al) Gu[al + 3 * n] = Gh[al] * geo[n] + Gh[al + 3] * geo[n + 3] + Gh[al + 6] * geo[n + 6];
+        const double wq = a.w[q];
+        const double coeff = (wq == 0.0) ? 0.0 : a.alpha * geo[9] * wq;  // zero-weight points are skipped (C&E.cc:8852)
+        double P[9];
+        hyper_point(a.law, Gu, a.lambda, a.mu, coeff, P, sD + (size_t)q * DS);
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+          for (int al = 0; al < 3; ++al)
+            sPb[q * 9 + al + 3 * p] = P[al] * geo[3 * p] + P[al + 3] * geo[1 + 3 * p] + P[al + 6] * geo[2 + 3 * p];
+      }
+      bar_sync(1, NTM);
+      for (int w = mt; w < NQ * 9; w += NTM) {  // pull-back of the tangent: work item = (point, be, r)
+        const int q = w / 9, br = w % 9, be = br / 3, r = br % 3;
+        const double *geo = sGeo + q * 10;
+        const double *D = sD + (size_t)q * DS;
+        double t[9];
+#pragma unroll
+        for (int n = 0; n < 3; ++n)
+#pragma unroll
+          for (int al = 0; al < 3; ++al) {
+            double s2 = 0;
+#pragma unroll
+            for (int l = 0; l < 3; ++l) s2 += D[al + 3 * (n + 3 * (be + 3 * l))] * geo[l + 3 * r];
+            t[al + 3 * n] = s2;
+          }
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+          for (int al = 0; al < 3; ++al) {
+            const double v = geo[3 * p] * t[al] + geo[1 + 3 * p] * t[al + 3] + geo[2 + 3 * p] * t[al + 6];
+            sAb[((al + 3 * be) * 9 + p * 3 + r) * NQ + q] = v;
+          }
+      }
+      __threadfence_block();
+      bar_arrive(3 + b, 384);  // sA[b] is complete (sP[b] was complete at the barrier above)
+      // element residual r(i al) = sum_q sum_p ghat_i^p(q) P^(al,p)(q)   (C&E.cc:4669-4735), thread per entry
+      if (a.rstage)
+        for (int k = mt; k < S1; k += NTM) {
+          const int i = k / 3, al = k % 3, i1 = i % ND1, i2 = (i / ND1) % ND1, i3 = i / NN;
+          double acc0 = 0, acc1 = 0;  // two interleaved chains (even / odd planes), added in a fixed order
+          for (int q3 = 0; q3 < NQ1; ++q3) {
+            const double lz = T.l1[i3][q3], dz = T.d1[i3][q3];
+            double sq = 0;
+            for (int q2 = 0; q2 < NQ1; ++q2) {
+              const double ly = T.l1[i2][q2], dy = T.d1[i2][q2];
+              const double w0 = ly * lz, w1 = dy * lz, w2 = ly * dz;
+              const double *Pq = sPb + (size_t)(NQ1 * q2 + NQ2 * q3) * 9 + al;
+#pragma unroll
+              for (int q1 = 0; q1 < NQ1; ++q1)
+                sq += (T.d1[i1][q1] * w0) * Pq[q1 * 9] + (T.l1[i1][q1] * w1) * Pq[q1 * 9 + 3] + (T.l1[i1][q1] * w2) * Pq[q1 * 9 + 6];
+            }
+            if (q3 & 1) acc1 += sq; else acc0 += sq;
+          }
+          a.rstage[(size_t)el * S1 + k] = acc0 + acc1;
+        }
+    }
+    // the contraction group arrived once more than this group waited on each empty barrier: settle the balance
+    bar_sync(5 + (it & 1), 384);
+    bar_sync(5 + ((it + 1) & 1), 384);
+    return;
+  }
+
+  // ================= contraction group =================
+  const int ln = lane % NN, lal = lane / NN;  // lane = (i2 + ND1*j2) + NN * al ; lanes >= 3*NN idle
+  const bool lact = lane < 3 * NN;
+  double yy[4][NQ1];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int q = 0; q < NQ1; ++q) yy[c][q] = lact ? T.py[c][ln][q] : 0.0;
+  bar_arrive(5, 384);  // both buffers start empty
+  bar_arrive(6, 384);
+  double *S1w = sS1 + warp * 27 * NQ2;
+  int it = 0;
+  for (int64_t el = blockIdx.x; el < a.ne; el += gridDim.x, ++it) {
+    const int b = it & 1;
+    const double *sAb = sA + b * 81 * NQ;
+    bar_sync(3 + b, 384);
+    for (int task = warp; task < NTASK; task += NWC) {
+      const int be = task % 3, sidx = task / 3;
+      // slice (i3 <= j3): sidx 0..5 -> (0,0) (0,1) (0,2) (1,1) (1,2) (2,2)
+      const int i3 = sidx < 3 ? 0 : sidx < 5 ? 1 : 2, j3 = sidx < 3 ? sidx : sidx < 5 ? sidx - 2 : 2;
+      const int sl = i3 + ND1 * j3;
+      double pzr[4][NQ1];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int q = 0; q < NQ1; ++q) pzr[c][q] = T.pz[c][sl][q];
+      // 1: contract the third direction; lane = (q1, q2), the 27 (al', ab) combinations unrolled
+      if (lane < NQ2) {
+#pragma unroll
+        for (int al2 = 0; al2 < 3; ++al2)
+#pragma unroll
+          for (int ab = 0; ab < 9; ++ab) {
+            const double *A = sAb + ((al2 + 3 * be) * 9 + ab) * NQ + lane;
+            const int cz = ((ab / 3) == 2) * 2 + ((ab % 3) == 2);
+            double s2 = 0;
+#pragma unroll
+            for (int q3 = 0; q3 < NQ1; ++q3) s2 += A[q3 * NQ2] * pzr[cz][q3];
+            S1w[(al2 * 9 + ab) * NQ2 + lane] = s2;
+          }
+      }
+      __syncwarp();
+      // 2 + 3: second direction in registers, first against the constant-bank operand
+      double acc[NN];
+#pragma unroll
+      for (int m = 0; m < NN; ++m) acc[m] = 0.0;
+      const double *S1l = S1w + (lact ? lal : 0) * 9 * NQ2;
+#pragma unroll
+      for (int ab = 0; ab < 9; ++ab) {
+        const int yc = ((ab / 3) == 1) * 2 + ((ab % 3) == 1);
+#pragma unroll
+        for (int q1 = 0; q1 < NQ1; ++q1) {
+          double s2 = 0;
+#pragma unroll
+          for (int q2 = 0; q2 < NQ1; ++q2) s2 += S1l[ab * NQ2 + q1 + NQ1 * q2] * yy[yc][q2];
+#pragma unroll
+          for (int m = 0; m < NN; ++m) acc[m] += T.px[ab][q1][m] * s2;
+        }
+      }
+      __syncwarp();
+      if (lact) {
+        const int i2 = ln % ND1, j2 = ln / ND1;
+#pragma unroll
+        for (int m = 0; m < NN; ++m) {
+          const int i = (m % ND1) + ND1 * i2 + NN * i3, j = (m / ND1) + ND1 * j2 + NN * j3;
+          sK[(i * 3 + lal) + S1 * (j * 3 + be)] = acc[m];
+          if (i3 != j3) sK[(j * 3 + be) + S1 * (i * 3 + lal)] = acc[m];  // the mirror slice (j3, i3)
+        }
+      }
+    }
+    __threadfence_block();
+    bar_arrive(5 + b, 384);  // sA[b] may be refilled
+    bar_sync(2, NTC);
+    // ---- drop rule and output (C&E.cc:4889,4898; 5380-5402)
+    if (a.stage || a.emask) {
+      double vmax = 0.0;
+      for (int k = tid; k < S1 * S1; k += NTC) vmax = fmax(vmax, fabs(sK[k]));
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, off));
+      if (lane == 0) sRed[warp] = vmax;
+      bar_sync(2, NTC);
+      vmax = 0.0;
+#pragma unroll
+      for (int wv = 0; wv < NWC; ++wv) vmax = fmax(vmax, sRed[wv]);
+      const double thr = vmax * 1e-14;
+      if (a.stage) {
+        double *st = a.stage + (size_t)el * S1 * S1;
+        for (int k = tid; k < S1 * S1; k += NTC) {
+          const double v = sK[k];
+          st[k] = ((vmax != 0.0) && (fabs(v) > thr)) ? v : 0.0;
+        }
+      }
+      if (a.emask) {
+        uint16_t *em = a.emask + (size_t)el * ND * ND;
+        for (int p = tid; p < ND * ND; p += NTC) {
+          const int j = p / ND, i = p % ND;
+          unsigned mask = 0;
+#pragma unroll
+          for (int bb = 0; bb < 3; ++bb)
+#pragma unroll
+            for (int aa = 0; aa < 3; ++aa) {
+              const double v = sK[(i * 3 + aa) + S1 * (j * 3 + bb)];
+              if ((vmax != 0.0) && (fabs(v) > thr)) mask |= 1u << (bb * 3 + aa);
+            }
+          em[p] = (uint16_t)mask;
+        }
+      }
+    }
+    bar_sync(2, NTC);  // sK and sRed are free for the next element
+  }
+}
+
 // ---------------------------------------------------------------- host: factorise and verify the tables
 struct SfHost {
   int nd1 = 0, nq1 = 0;
@@ -450,6 +708,8 @@ static void fill_tables(const SfHost &h, SfTables<ND1, NQ1> &T) {
         T.py[c][m][q] = v;
         T.pz[c][m][q] = v;
       }
+  for (int i = 0; i < ND1; ++i)
+    for (int q = 0; q < NQ1; ++q) { T.l1[i][q] = L(i, q); T.d1[i][q] = D(i, q); }
 }
 
 template <int ND1, int NQ1, int NW>
@@ -471,6 +731,17 @@ static void launch_sf_hyper(gfgpu_ctx *ctx, const SfHost &h, const SfArgs &a) {
   constexpr int ND = ND1 * ND1 * ND1, S1 = 3 * ND, NQ2 = NQ1 * NQ1, NQ = NQ2 * NQ1;
   std::unique_ptr<SfTables<ND1, NQ1>> Tp(new SfTables<ND1, NQ1>);
   fill_tables<ND1, NQ1>(h, *Tp);
+  static const bool v1 = getenv("GFGPU_SF_HYPER_V1") != nullptr;  // the serial-phase kernel, kept for the A/B in profiles/
+  if (!v1) {
+    const size_t smem2 = ((size_t)S1 * S1 + 2 * 81 * (size_t)NQ + (size_t)NQ * 82 + 9 * 27 * (size_t)NQ2 + 2 * 9 * (size_t)NQ +
+                          10 * (size_t)NQ + 24 + S1 + 9 + 2) * 8;
+    auto kern2 = k_sumfact_hyper_ws<ND1, NQ1>;
+    GF_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    const int grid2 = (int)std::max<int64_t>(1, std::min<int64_t>(a.ne, ctx->sm_count));
+    kern2<<<grid2, 384, smem2, ctx->stream>>>(a, *Tp);
+    GF_LAUNCH_CHECK();
+    return;
+  }
   const size_t smem = ((size_t)S1 * S1 + (size_t)NQ * 82 + 81 * (size_t)NQ + (size_t)NW * 27 * NQ2 + 19 * (size_t)NQ + 24 + S1 + NW +
                        3 * S1 + 2) * 8;
   auto kern = k_sumfact_hyper<ND1, NQ1, NW>;

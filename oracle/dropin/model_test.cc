@@ -5,6 +5,7 @@
 // the unmodified reference objects + the dispatch patch of INTEGRATION.md section 2): once through the reference's
 // ga_exec, once through the device path.  The model's tangent matrix and right-hand side must agree: CSC pattern
 // identical, values / rhs to 1e-12 (tests/test_gpu_dropin.py).
+#include <chrono>
 #include <cstdio>
 #include <map>
 #include <random>
@@ -20,6 +21,8 @@ namespace getfem_b200 {
 void gfgpu_enable(bool on);
 long gfgpu_device_calls();
 long gfgpu_reference_calls();
+void gfgpu_last_timings(double *t3);
+long gfgpu_pattern_downloads();
 }  // namespace getfem_b200
 
 using getfem::size_type;
@@ -39,7 +42,7 @@ int main(int argc, char **argv) {
   const bool qk = gets("gt", "pk") == "qk";
   // threads > 1: the bricks' GETFEM_OMP_PARALLEL blocks slice the regions; the patch leaves that regime on the reference path
   if (geti("threads", 1) > 1) getfem::set_num_threads(int(geti("threads", 1)));
-  const int Q = kind == "expr" ? (int)geti("q", dim) : (kind == "poisson" || kind == "asm_laplacian") ? 1 : dim;
+  const int Q = kind == "expr" ? (int)geti("q", dim) : kind == "timing" ? dim : (kind == "poisson" || kind == "asm_laplacian") ? 1 : dim;
 
   getfem::mesh m;
   std::vector<size_type> ns(dim, size_type(n));
@@ -120,6 +123,78 @@ int main(int argc, char **argv) {
                 pattern_ok && nK > 0 ? std::sqrt(dK / nK) : -1.0, nV > 0 ? std::sqrt(dV / nV) : 0.0, std::sqrt(nV), Er, Eg,
                 getfem_b200::gfgpu_device_calls());
     return pattern_ok ? 0 : 1;
+  }
+  if (kind == "timing") {
+    // The REAL drop-in, timed: ga_workspace::assembly(2) (+ assembly(1)) of the C3 form through libgetfem_gfgpu.so, wall
+    // clock around the reference's own call, host containers in and out (model_real_sparse_matrix = col_matrix<rsvector>).
+    // reps device calls on one workspace (a Newton / time loop: the pattern is downloaded once), then, with ref=1, the
+    // reference's own ga_exec on the same workspace -- the same-configuration ratio of INTEGRATION.md.
+    const int reps = (int)geti("reps", 3);
+    std::vector<double> U(mf.nb_dof()), LAMBDA(1, 1.0), MU(1, 1.0);
+    {
+      std::mt19937_64 rng(99);
+      std::uniform_real_distribution<double> dist(-1.0, 1.0);
+      for (auto &x : U) x = dist(rng);
+    }
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    getfem::ga_workspace ws;
+    ws.add_fem_variable("u", mf, gmm::sub_interval(0, mf.nb_dof()), U);
+    ws.add_fixed_size_constant("lambda", LAMBDA);
+    ws.add_fixed_size_constant("mu", MU);
+    ws.add_expression(gets("expr", "lambda*Div_u*Div_Test_u + mu*(Grad_u+Grad_u'):Grad_Test_u"), mim);
+    std::vector<double> t2(reps), t1(reps), tx(reps), td(reps), tf(reps);
+    double chk = 0, chkv = 0;
+    size_t nnz = 0;
+    getfem_b200::gfgpu_enable(true);
+    {
+      getfem::model_real_sparse_matrix M(mf.nb_dof(), mf.nb_dof());
+      ws.set_assembled_matrix(M);
+      for (int r = 0; r < reps; ++r) {
+        gmm::clear(M);
+        double a0 = now();
+        ws.assembly(2);
+        t2[r] = now() - a0;
+        double t3[3];
+        getfem_b200::gfgpu_last_timings(t3);
+        tx[r] = t3[0]; td[r] = t3[1]; tf[r] = t3[2];
+        a0 = now();
+        ws.assembly(1);
+        t1[r] = now() - a0;
+      }
+      nnz = gmm::nnz(M);
+      for (size_type j = 0; j < gmm::mat_ncols(M); ++j)
+        for (auto it = M[j].begin(); it != M[j].end(); ++it) chk += it->e * it->e;
+      for (double x : ws.assembled_vector()) chkv += x * x;
+    }
+    const long downloads = getfem_b200::gfgpu_pattern_downloads();
+    getfem_b200::gfgpu_enable(false);
+    double tr2 = -1, tr1 = -1, chkr = 0, chkrv = 0;
+    if (geti("ref", 0)) {
+      getfem::model_real_sparse_matrix M(mf.nb_dof(), mf.nb_dof());
+      ws.set_assembled_matrix(M);
+      double a0 = now();
+      ws.assembly(2);
+      tr2 = now() - a0;
+      a0 = now();
+      ws.assembly(1);
+      tr1 = now() - a0;
+      for (size_type j = 0; j < gmm::mat_ncols(M); ++j)
+        for (auto it = M[j].begin(); it != M[j].end(); ++it) chkr += it->e * it->e;
+      for (double x : ws.assembled_vector()) chkrv += x * x;
+    }
+    auto lst = [&](const std::vector<double> &v) {
+      std::string o = "[";
+      for (size_t k = 0; k < v.size(); ++k) { char b[32]; std::snprintf(b, sizeof b, "%s%.4f", k ? ", " : "", v[k]); o += b; }
+      return o + "]";
+    };
+    std::printf("{\"model\": \"timing\", \"n\": %d, \"elements\": %zu, \"ndof\": %zu, \"nnz\": %zu, \"assembly2_s\": %s, "
+                "\"assembly1_s\": %s, \"extract_s\": %s, \"device_s\": %s, \"fill_s\": %s, \"pattern_downloads\": %ld, "
+                "\"norm_K\": %.15e, \"norm_V\": %.15e, \"ref_assembly2_s\": %.4f, \"ref_assembly1_s\": %.4f, "
+                "\"ref_norm_K\": %.15e, \"ref_norm_V\": %.15e, \"device_workspace_calls\": %ld}\n",
+                n, size_t(m.convex_index().card()), size_t(mf.nb_dof()), nnz, lst(t2).c_str(), lst(t1).c_str(), lst(tx).c_str(),
+                lst(td).c_str(), lst(tf).c_str(), downloads, std::sqrt(chk), std::sqrt(chkv), tr2, tr1, std::sqrt(chkr),
+                std::sqrt(chkrv), getfem_b200::gfgpu_device_calls());
+    return 0;
   }
   if (kind.rfind("asm_", 0) == 0) {
     // the legacy asm_* wrappers (getfem_assembling.h): thin layers over ga_workspace, written with Test / Test2 directly

@@ -28,6 +28,17 @@ void gfgpu_enable(bool on) {
 long gfgpu_device_calls() { return g_device_calls; }
 long gfgpu_reference_calls() { return g_reference_calls; }
 long gfgpu_skipped_calls() { return g_skipped_calls.load(); }
+static device_assembler &thread_assembler() {
+  static thread_local device_assembler dev(0);
+  return dev;
+}
+// seconds of the calling thread's last device call: extraction of the GetFEM data, device work, fill of the gmm containers;
+// and how many times it had to download the pattern of the workspace tangent
+void gfgpu_last_timings(double *t3) {
+  device_assembler &d = thread_assembler();
+  t3[0] = d.t_extract; t3[1] = d.t_device; t3[2] = d.t_fill;
+}
+long gfgpu_pattern_downloads() { return thread_assembler().pattern_downloads; }
 }  // namespace getfem_b200
 
 namespace getfem {
@@ -90,7 +101,7 @@ void ga_workspace::assembly(size_type order, bool condensation) {
                    int(getfem::partition_master::get().get_current_partition()));
     return;
   }
-  static thread_local getfem_b200::device_assembler dev(0);
+  getfem_b200::device_assembler &dev = getfem_b200::thread_assembler();
   ++getfem_b200::g_device_calls;
   dev.assembly(*this, order);  // throws gmm::gmm_error when the workspace is not covered: no silent CPU fallback
   if (std::getenv("GFGPU_TRACE")) {
