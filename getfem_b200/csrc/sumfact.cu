@@ -108,8 +108,12 @@ k_sumfact_laplace(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T) 
     }
     __syncthreads();
     // ---- C: slices (i3, j3), one per warp
+    // K_e is symmetric (C is): only the slices (i3 <= j3) are contracted, the others are their mirror images
     double *S1 = sS1 + warp * 9 * NQ2;
-    for (int sl = warp; sl < NN; sl += NW) {
+    for (int task = warp; task < ND1 * (ND1 + 1) / 2; task += NW) {
+      int i3 = 0, rem = task;  // task -> (i3 <= j3), rows of the upper triangle
+      while (rem >= ND1 - i3) { rem -= ND1 - i3; ++i3; }
+      const int j3 = i3 + rem, sl = i3 + ND1 * j3;
       // 1: contract the third direction
       for (int idx = lane; idx < 9 * NQ2; idx += 32) {
         const int ab = idx / NQ2, q12 = idx - ab * NQ2;
@@ -140,10 +144,15 @@ k_sumfact_laplace(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T) 
         }
       }
       if (lane < NN) {
-        const int i2 = lane % ND1, j2 = lane / ND1, i3 = sl % ND1, j3 = sl / ND1;
+        const int i2 = lane % ND1, j2 = lane / ND1;
         double *o = sK + (ND1 * i2 + NN * i3) + ND * (ND1 * j2 + NN * j3);
 #pragma unroll
         for (int m = 0; m < NN; ++m) o[(m % ND1) + ND * (m / ND1)] = acc[m];
+        if (i3 != j3) {  // the mirror slice (j3, i3): K(j, i) = K(i, j)
+          double *ot = sK + (ND1 * j2 + NN * j3) + ND * (ND1 * i2 + NN * i3);
+#pragma unroll
+          for (int m = 0; m < NN; ++m) ot[(m / ND1) + ND * (m % ND1)] = acc[m];
+        }
       }
       __syncwarp();
     }
@@ -396,17 +405,19 @@ __global__ void __launch_bounds__(384, 1)
 k_sumfact_hyper_ws(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T) {
   constexpr int NN = ND1 * ND1, ND = ND1 * ND1 * ND1, S1 = 3 * ND, NQ2 = NQ1 * NQ1, NQ = NQ1 * NQ1 * NQ1;
   constexpr int NWC = 9, NTC = NWC * 32, NTM = 96;
-  constexpr int DS = 82;
+  // strides chosen for the shared-memory banks: lanes = Gauss points read / write sD and sGeo (odd strides), the three
+  // components al' of S1 sit 2 doubles apart modulo 16 (they are read by the three lane groups of a warp at once)
+  constexpr int DS = 81, GS = 11, SS = 9 * NQ2 + 2;
   constexpr int NSL = ND1 * (ND1 + 1) / 2, NTASK = NSL * 3;
   static_assert(ND1 == 3 && 3 * NN <= 32 && NQ2 <= 32, "lane mapping");
   extern __shared__ __align__(16) double sm[];
   double *sK = sm;                          // S1 x S1 column-major
   double *sA = sK + S1 * S1;                // 2 x 81 x NQ
   double *sD = sA + 2 * 81 * NQ;            // NQ x DS
-  double *sS1 = sD + NQ * DS;               // per contraction warp 27 x NQ2
-  double *sP = sS1 + NWC * 27 * NQ2;        // 2 x NQ x 9
-  double *sGeo = sP + 2 * 9 * NQ;           // NQ x 10
-  double *sG = sGeo + 10 * NQ;              // 24
+  double *sS1 = sD + NQ * DS;               // per contraction warp 3 x SS
+  double *sP = sS1 + NWC * 3 * SS;          // 2 x NQ x 9
+  double *sGeo = sP + 2 * 9 * NQ;           // NQ x GS
+  double *sG = sGeo + GS * NQ;              // 24
   double *sU = sG + 24;                     // S1
   double *sRed = sU + S1;                   // NWC
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -431,7 +442,7 @@ k_sumfact_hyper_ws(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T)
       bar_sync(5 + b, 384);  // the contraction group has finished with sA[b], sP[b] (element it - 2)
       bar_sync(1, NTM);
       for (int q = mt; q < NQ; q += NTM) {
-        double *geo = sGeo + q * 10;
+        double *geo = sGeo + q * GS;
         geometry<3>(sG, a.gt_grad + (size_t)q * 24, 8, geo);
         const int q1 = q % NQ1, q2 = (q / NQ1) % NQ1, q3 = q / NQ2;
         double lx[ND1], dx[ND1];
@@ -474,8 +485,8 @@ k_sumfact_hyper_ws(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T)
       }
       bar_sync(1, NTM);
       for (int w = mt; w < NQ * 9; w += NTM) {  // pull-back of the tangent: work item = (point, be, r)
-        const int q = w / 9, br = w % 9, be = br / 3, r = br % 3;
-        const double *geo = sGeo + q * 10;
+        const int q = w % NQ, br = w / NQ, be = br / 3, r = br % 3;  // lanes = consecutive points
+        const double *geo = sGeo + q * GS;
         const double *D = sD + (size_t)q * DS;
         double t[9];
 #pragma unroll
@@ -534,7 +545,7 @@ k_sumfact_hyper_ws(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T)
     for (int q = 0; q < NQ1; ++q) yy[c][q] = lact ? T.py[c][ln][q] : 0.0;
   bar_arrive(5, 384);  // both buffers start empty
   bar_arrive(6, 384);
-  double *S1w = sS1 + warp * 27 * NQ2;
+  double *S1w = sS1 + warp * 3 * SS;
   int it = 0;
   for (int64_t el = blockIdx.x; el < a.ne; el += gridDim.x, ++it) {
     const int b = it & 1;
@@ -561,7 +572,7 @@ k_sumfact_hyper_ws(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T)
             double s2 = 0;
 #pragma unroll
             for (int q3 = 0; q3 < NQ1; ++q3) s2 += A[q3 * NQ2] * pzr[cz][q3];
-            S1w[(al2 * 9 + ab) * NQ2 + lane] = s2;
+            S1w[al2 * SS + ab * NQ2 + lane] = s2;
           }
       }
       __syncwarp();
@@ -569,7 +580,7 @@ k_sumfact_hyper_ws(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T)
       double acc[NN];
 #pragma unroll
       for (int m = 0; m < NN; ++m) acc[m] = 0.0;
-      const double *S1l = S1w + (lact ? lal : 0) * 9 * NQ2;
+      const double *S1l = S1w + (lact ? lal : 0) * SS;
 #pragma unroll
       for (int ab = 0; ab < 9; ++ab) {
         const int yc = ((ab / 3) == 1) * 2 + ((ab % 3) == 1);
@@ -733,8 +744,8 @@ static void launch_sf_hyper(gfgpu_ctx *ctx, const SfHost &h, const SfArgs &a) {
   fill_tables<ND1, NQ1>(h, *Tp);
   static const bool v1 = getenv("GFGPU_SF_HYPER_V1") != nullptr;  // the serial-phase kernel, kept for the A/B in profiles/
   if (!v1) {
-    const size_t smem2 = ((size_t)S1 * S1 + 2 * 81 * (size_t)NQ + (size_t)NQ * 82 + 9 * 27 * (size_t)NQ2 + 2 * 9 * (size_t)NQ +
-                          10 * (size_t)NQ + 24 + S1 + 9 + 2) * 8;
+    const size_t smem2 = ((size_t)S1 * S1 + 2 * 81 * (size_t)NQ + (size_t)NQ * 81 + 9 * 3 * (9 * (size_t)NQ2 + 2) + 2 * 9 * (size_t)NQ +
+                          11 * (size_t)NQ + 24 + S1 + 9 + 2) * 8;
     auto kern2 = k_sumfact_hyper_ws<ND1, NQ1>;
     GF_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     const int grid2 = (int)std::max<int64_t>(1, std::min<int64_t>(a.ne, ctx->sm_count));
@@ -767,8 +778,8 @@ bool launch_sumfact_kernel(gfgpu_ctx *ctx, const gfgpu_tables *tab, int dim, int
   a.gphi = ea.gphi; a.lambda = ea.par[0]; a.mu = ea.par[1]; a.alpha = ea.alpha; a.law = ea.family;
   a.stage = ea.stage; a.emask = ea.emask; a.rstage = ea.rstage;
   if (a.ne <= 0) return true;
-  if (lap && h.nd1 == 5 && h.nq1 == 5) launch_sf<5, 5, 13>(ctx, h, a);
-  else if (lap && h.nd1 == 4 && h.nq1 == 4) launch_sf<4, 4, 8>(ctx, h, a);
+  if (lap && h.nd1 == 5 && h.nq1 == 5) launch_sf<5, 5, 15>(ctx, h, a);  // one warp per slice (i3 <= j3)
+  else if (lap && h.nd1 == 4 && h.nq1 == 4) launch_sf<4, 4, 10>(ctx, h, a);
   else if (hyp && h.nd1 == 3 && h.nq1 == 4) launch_sf_hyper<3, 4, 9>(ctx, h, a);
   else if (hyp && h.nd1 == 3 && h.nq1 == 3) launch_sf_hyper<3, 3, 9>(ctx, h, a);
   else return false;
