@@ -315,7 +315,7 @@ class DeviceTerm(_Handle):
 
     @property
     def kernel_kind(self):
-        """0 generic element kernel, 1 general tile kernel, 2 column kernel, 3 class-uniform tile kernel."""
+        """0 generic element kernel, 1 general tile kernel, 2 column kernel, 3 class-uniform tile kernel, 4 direct mode."""
         return int(lib().gfgpu_term_kernel_kind(self.h))
 
     @property

@@ -560,7 +560,16 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
   const bool value_dependent = t->family == GFGPU_SVK || t->family == GFGPU_NEOHOOKEAN_CIARLET ||
                                t->family == GFGPU_NEOHOOKEAN_BONET || t->family >= GFGPU_MOONEY_RIVLIN;
   const bool need_masks = recompute ? !t->pat_valid : (do_t && (!t->pat_valid || value_dependent));
-  const bool need_stage = do_t && !recompute;
+  // direct mode: a scalar sum-factorised kernel under a fixed pattern writes its entries straight to their CSC slots
+  // (scatter.cu direct_prepare): no element matrix in HBM, no gather -- only the ordered sums of the shared entries
+  bool direct = false;
+  if (!recompute && do_t && Q == 1 && t->pat_valid && !value_dependent && !t->region_faces && !t->nfields && ne > 0 &&
+      !getenv("GFGPU_NO_DIRECT")) {
+    gf::ElemArgs probe;
+    probe.family = t->family; probe.ng = t->mesh->ng; probe.nq = t->tab->nq;
+    if (gf::sumfact_kind(t->tab, t->mesh->dim, Q, nd, t->mesh->gt_kind == GFGPU_GT_PK, probe) == 1) direct = gf::direct_prepare(t);
+  }
+  const bool need_stage = do_t && !recompute && !direct;
   const bool need_rstage = do_r && !recompute;
   if (need_stage && t->stage.n != (size_t)ne * s1 * s1) t->stage.alloc(ctx, (size_t)ne * s1 * s1);
   if (need_masks && t->emask.n != (size_t)ne * nd * nd) t->emask.alloc(ctx, (size_t)ne * nd * nd);
@@ -581,6 +590,7 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
   a.stage = need_stage ? t->stage.p : nullptr;
   a.emask = need_masks ? t->emask.p : nullptr;
   a.rstage = need_rstage ? t->rstage.p : nullptr;
+  if (direct) { a.slot = t->dslot.p; a.kloc = t->dkloc.p; a.pr = t->pr.p; a.mstage = t->mstage.p; a.nnz32 = (uint32_t)t->nnz; }
   a.face = t->region_faces ? t->r_face.p : nullptr;
   a.fw = t->tab->fw.p; a.fgt_grad = t->tab->fgt_grad.p; a.fphi = t->tab->fphi.p; a.fgphi = t->tab->fgphi.p;
   a.fnormal = t->tab->fnormal.p;
@@ -609,11 +619,11 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
   for (int k = 0; k < 5; ++k) t->ev_used[k] = false;
   auto tic = [&](int k) { GF_CUDA(cudaEventRecord(t->ev[2 * k], ctx->stream)); };
   auto toc = [&](int k) { GF_CUDA(cudaEventRecord(t->ev[2 * k + 1], ctx->stream)); t->ev_used[k] = true; };
-  if (ne > 0 && (need_stage || need_masks || need_rstage)) {
+  if (ne > 0 && (need_stage || need_masks || need_rstage || direct)) {
     tic(0);
     const bool affine = t->mesh->gt_kind == GFGPU_GT_PK;
     bool ok = (!t->region_faces && !t->nfields && gf::launch_sumfact_kernel(ctx, t->tab, t->mesh->dim, Q, nd, affine, a)) ||
-              gf::launch_elem_kernel(ctx, t->mesh->dim, Q, nd, affine, a);
+              (!direct && gf::launch_elem_kernel(ctx, t->mesh->dim, Q, nd, affine, a));  // only sumfact.cu knows the direct mode
     GF_REQUIRE(ok, "no device kernel for this (dimension, qdim, local dofs, family) combination");
     toc(0);
   }
@@ -662,6 +672,8 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
       tic(3); gf::build_pattern(t); toc(3);
       if (t->halo) gf::halo_build_maps(t);
       tic(1); gf::gather_tangent(t, false); toc(1);
+    } else if (direct) {
+      tic(1); gf::direct_finish(t); toc(1);
     } else if (!value_dependent) {
       tic(1); gf::gather_tangent(t, false); toc(1);
     } else {
@@ -747,6 +759,7 @@ int gfgpu_term_last_timings(gfgpu_term *t, float *out8) {
 int gfgpu_term_strategy(gfgpu_term *t) { return t ? t->strategy : -1; }
 int gfgpu_term_kernel_kind(gfgpu_term *t) {
   if (!t) return -1;
+  if (t->strategy != GFGPU_STRATEGY_RECOMPUTE && t->direct_ok == 1 && t->d_generation == t->generation) return 4;
   if (t->strategy != GFGPU_STRATEGY_RECOMPUTE || !t->rc_ready) return 0;
   return t->rc_cols ? 2 : t->rc_uni ? 3 : 1;
 }

@@ -188,6 +188,13 @@ struct gfgpu_term {
   // Q = 1 entry-wise gather (scatter.cu): stage index of every single-contribution entry, list of the other pairs
   gf::DevBuf<uint32_t> g1_src, g1_multi;
   int64_t g1_nmulti = 0, g1_generation = -1;
+  // Q = 1 direct mode: slot of every local contribution; compact stage + offsets of the multi-contribution entries
+  gf::DevBuf<uint32_t> dslot, moff, dmpos;
+  int64_t d_nmulti = 0;
+  gf::DevBuf<uint16_t> dkloc;   // local index of the entry that goes to dslot[.] (slots sorted ascending inside an element)
+  gf::DevBuf<double> mstage;
+  int64_t d_generation = -1;
+  int direct_ok = 0;  // 0 unknown, 1 yes, -1 no
   gf::DevBuf<double> Ubuf;      // ndof (host path)
   gf::DevBuf<int32_t> flag;     // pattern-changed flag
   bool flag_pending = false;    // a value-dependent gather raised (or not) the flag; nobody has read it yet (api.cu term_settle)
@@ -278,12 +285,20 @@ struct ElemArgs {
   double *stage;
   uint16_t *emask;
   double *rstage;
+  // direct mode (sum-factorised scalar kernels): every element entry goes straight to its CSC slot (slot < nnz32), to its
+  // place in the compact stage of the multi-contribution entries (slot - nnz32), or nowhere (0xffffffff: not in the pattern)
+  const uint32_t *slot = nullptr;
+  const uint16_t *kloc = nullptr;
+  double *pr = nullptr, *mstage = nullptr;
+  uint32_t nnz32 = 0;
 };
 // returns false when the (dim, Q, nd, family, affine) combination has no instantiation
 bool launch_elem_kernel(gfgpu_ctx *ctx, int dim, int Q, int nd, bool affine, const ElemArgs &a);
 
 // sum-factorised kernel for the scalar Laplace form on Q3/Q4 hexahedra (sumfact.cu); false = not handled, use the generic one
 bool launch_sumfact_kernel(gfgpu_ctx *ctx, const gfgpu_tables *tab, int dim, int Q, int nd, bool affine, const ElemArgs &a);
+// 0: not handled by sumfact.cu, 1: scalar Laplace kernel (supports the direct mode), 2: hyperelastic kernel
+int sumfact_kind(const gfgpu_tables *tab, int dim, int Q, int nd, bool affine, const ElemArgs &a);
 
 // ---- first-touch dof numbering (dof_enum.cu); returns ndof
 int64_t enumerate_dof(gfgpu_ctx *ctx, const int32_t *conn, int64_t ne, int ng, int N, bool qk, int k, int Q, int nd,
@@ -296,6 +311,9 @@ void halo_build_maps(gfgpu_term *t);
 void halo_accumulate(gfgpu_term *t, bool do_t, bool do_r);
 void build_pattern(gfgpu_term *t);
 void gather_tangent(gfgpu_term *t, bool check);
+// direct mode (Q = 1): slots of every local contribution, built once per pattern; false = not applicable (index range)
+bool direct_prepare(gfgpu_term *t);
+void direct_finish(gfgpu_term *t);  // ordered sums of the multi-contribution entries
 void gather_residual(gfgpu_term *t);
 
 // ---- strategy RECOMPUTE (recompute.cu)

@@ -493,11 +493,29 @@ __global__ void k_g1_multi(const uint32_t *__restrict__ multi, int64_t nmulti, c
   }
 }
 
+static void g1_prepare(gfgpu_term *t);
 static bool gather_tangent_q1_fast(gfgpu_term *t) {
   Structure &st = t->st;
   gfgpu_ctx *ctx = t->ctx;
   if (t->nnz >= (int64_t(1) << 32) - 1 || st.ncontrib >= (int64_t(1) << 32) - 1 || st.npairs >= (int64_t(1) << 32) - 1) return false;
   if (t->fem->nd < 27) return false;  // low-order elements: few single-contribution pairs, the pair kernel is as good
+  const int B = 256;
+  g1_prepare(t);
+  k_g1_copy<<<min(grid_for(t->nnz, B), 148 * 64), B, 0, ctx->stream>>>(t->g1_src.p, t->stage.p, t->nnz, t->pr.p);
+  GF_LAUNCH_CHECK();
+  if (t->g1_nmulti) {
+    k_g1_multi<<<min(grid_for(t->g1_nmulti, B), 148 * 64), B, 0, ctx->stream>>>(t->g1_multi.p, t->g1_nmulti, st.cstart.p, st.csrc.p,
+                                                                              st.pJ.p, t->prel.p, t->jc.p, t->stage.p,
+                                                                              (uint32_t)st.ncontrib, t->pr.p);
+    GF_LAUNCH_CHECK();
+  }
+  return true;
+}
+
+// single-contribution sources and the list of the other pairs, once per pattern
+static void g1_prepare(gfgpu_term *t) {
+  Structure &st = t->st;
+  gfgpu_ctx *ctx = t->ctx;
   const int B = 256;
   if (t->g1_generation != t->generation) {
     t->g1_src.alloc(ctx, t->nnz);
@@ -529,15 +547,172 @@ static bool gather_tangent_q1_fast(gfgpu_term *t) {
     }
     t->g1_generation = t->generation;
   }
-  k_g1_copy<<<min(grid_for(t->nnz, B), 148 * 64), B, 0, ctx->stream>>>(t->g1_src.p, t->stage.p, t->nnz, t->pr.p);
+}
+
+// ---- direct mode (Q = 1, sum-factorised element kernels): the element kernel writes every entry straight to its CSC slot.
+// A fixed pattern fixes the destination of every local contribution c (= its index in the stage, Q = 1):
+//   single-contribution pair  -> slot[c] = position in pr (a plain store from the element kernel, no stage, no gather);
+//   pair with several contributions (or halo parts) -> slot[c] = nnz + place in a compact stage; the ordered sum
+//     (ascending element id, as everywhere) is a small second pass over those pairs only;
+//   pair outside the pattern -> 0xffffffff.
+__global__ void k_slot_single(const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ csrc, const int32_t *__restrict__ pJ,
+                              const uint16_t *__restrict__ pmask, const uint32_t *__restrict__ prel, const int64_t *__restrict__ jc,
+                              int64_t npairs, uint32_t nlocal, uint32_t *__restrict__ slot) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npairs; p += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t s0 = cstart[p], s1 = cstart[p + 1];
+    if (!(pmask[p] & 1u)) {
+      for (uint32_t s = s0; s < s1; ++s)
+        if (csrc[s] < nlocal) slot[csrc[s]] = 0xffffffffu;
+    } else if (s1 - s0 == 1 && csrc[s0] < nlocal) {
+      slot[csrc[s0]] = (uint32_t)(jc[pJ[p]] + prel[p]);
+    }
+  }
+}
+__global__ void k_slot_multi_count(const uint32_t *__restrict__ multi, int64_t nmulti, const uint32_t *__restrict__ cstart,
+                                   const uint32_t *__restrict__ csrc, uint32_t nlocal, uint32_t *__restrict__ cnt) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k <= nmulti; k += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t n = 0;
+    if (k < nmulti) {
+      const uint32_t p = multi[k];
+      for (uint32_t s = cstart[p], e = cstart[p + 1]; s < e; ++s) n += csrc[s] < nlocal;
+    }
+    cnt[k] = n;
+  }
+}
+__global__ void k_slot_multi(const uint32_t *__restrict__ multi, int64_t nmulti, const uint32_t *__restrict__ moff,
+                             const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ csrc, uint32_t nlocal, uint32_t nnz,
+                             uint32_t *__restrict__ slot) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nmulti; k += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t p = multi[k];
+    uint32_t o = nnz + moff[k];
+    for (uint32_t s = cstart[p], e = cstart[p + 1]; s < e; ++s)
+      if (csrc[s] < nlocal) slot[csrc[s]] = o++;
+  }
+}
+// (the pair id is replaced by the CSC position once the slots are built: the sum then needs no pair metadata at all)
+__global__ void k_multi_pos(uint32_t *__restrict__ multi, int64_t nmulti, const int32_t *__restrict__ pJ,
+                            const uint32_t *__restrict__ prel, const int64_t *__restrict__ jc) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nmulti; k += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t p = multi[k];
+    multi[k] = (uint32_t)(jc[pJ[p]] + prel[p]);
+  }
+}
+__global__ void k_multi_sum(const uint32_t *__restrict__ mpos, int64_t nmulti, const uint32_t *__restrict__ moff,
+                            const double *__restrict__ mstage, double *__restrict__ pr) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nmulti; k += (int64_t)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (uint32_t o = moff[k], e = moff[k + 1]; o < e; ++o) acc += mstage[o];  // ascending element id
+    pr[mpos[k]] = acc;
+  }
+}
+
+// CTA per element: its nb slots sorted ascending, with the local index k of each (uint16).  Scattered 8-byte stores in
+// LOCAL order cost the element kernel 2x its whole run time (profiles/round2_c5_direct_experiments.txt: the rows a column
+// receives from one element are runs of 4 in local order, unaligned to the 32-byte sectors); in DESTINATION order the same
+// stores are long contiguous runs -- an interior column of a Q4 element is one 1000-byte segment of pr.
+template <int IPT>
+__global__ void __launch_bounds__(512) k_slot_sort(uint32_t *__restrict__ slot, uint16_t *__restrict__ kloc, int nb) {
+  using Sort = cub::BlockRadixSort<uint32_t, 512, IPT, uint32_t>;
+  extern __shared__ __align__(16) unsigned char sort_raw[];
+  typename Sort::TempStorage &tmp = *reinterpret_cast<typename Sort::TempStorage *>(sort_raw);
+  uint32_t keys[IPT], vals[IPT];
+  uint32_t *sl = slot + (size_t)blockIdx.x * nb;
+  uint16_t *kl = kloc + (size_t)blockIdx.x * nb;
+#pragma unroll
+  for (int r = 0; r < IPT; ++r) {
+    const int k = threadIdx.x * IPT + r;
+    keys[r] = k < nb ? sl[k] : 0xffffffffu;
+    vals[r] = (uint32_t)k;
+  }
+  Sort(tmp).Sort(keys, vals);
+#pragma unroll
+  for (int r = 0; r < IPT; ++r) {
+    const int k = threadIdx.x * IPT + r;
+    if (k < nb) { sl[k] = keys[r]; kl[k] = (uint16_t)vals[r]; }
+  }
+}
+
+bool direct_prepare(gfgpu_term *t) {
+  Structure &st = t->st;
+  gfgpu_ctx *ctx = t->ctx;
+  if (t->d_generation == t->generation) return t->direct_ok == 1;
+  t->d_generation = t->generation;
+  t->direct_ok = -1;
+  if (t->fem->qdim != 1 || !st.npairs) return false;
+  if (t->nnz >= (int64_t(1) << 32) - 1 || st.ncontrib >= (int64_t(1) << 32) - 1 || st.npairs >= (int64_t(1) << 32) - 1) return false;
+  const int B = 256;
+  g1_prepare(t);
+  // places of the multi-contribution entries in the compact stage
+  int64_t total = 0;
+  if (t->g1_nmulti) {
+    DevBuf<uint32_t> cnt;
+    cnt.alloc(ctx, t->g1_nmulti + 1);
+    t->moff.alloc(ctx, t->g1_nmulti + 1);
+    k_slot_multi_count<<<min(grid_for(t->g1_nmulti + 1, B), 148 * 64), B, 0, ctx->stream>>>(t->g1_multi.p, t->g1_nmulti, st.cstart.p,
+                                                                                         st.csrc.p, (uint32_t)st.ncontrib, cnt.p);
+    GF_LAUNCH_CHECK();
+    size_t tb = 0;
+    GF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, t->moff.p, (int64_t)t->g1_nmulti + 1, ctx->stream));
+    void *tmp = cub_scratch(ctx, tb);
+    GF_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, cnt.p, t->moff.p, (int64_t)t->g1_nmulti + 1, ctx->stream));
+    count_launch(2);
+    uint32_t tot32 = 0;
+    GF_CUDA(cudaMemcpyAsync(&tot32, t->moff.p + t->g1_nmulti, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GF_CUDA(cudaStreamSynchronize(ctx->stream));
+    total = tot32;
+  }
+  if (t->nnz + total >= (int64_t(1) << 32) - 1) return false;
+  t->dslot.alloc(ctx, st.ncontrib);
+  GF_CUDA(cudaMemsetAsync(t->dslot.p, 0xff, (size_t)st.ncontrib * sizeof(uint32_t), ctx->stream));
+  k_slot_single<<<min(grid_for(st.npairs, B), 148 * 64), B, 0, ctx->stream>>>(st.cstart.p, st.csrc.p, st.pJ.p, t->pmask.p, t->prel.p,
+                                                                           t->jc.p, st.npairs, (uint32_t)st.ncontrib, t->dslot.p);
   GF_LAUNCH_CHECK();
   if (t->g1_nmulti) {
-    k_g1_multi<<<min(grid_for(t->g1_nmulti, B), 148 * 64), B, 0, ctx->stream>>>(t->g1_multi.p, t->g1_nmulti, st.cstart.p, st.csrc.p,
-                                                                              st.pJ.p, t->prel.p, t->jc.p, t->stage.p,
-                                                                              (uint32_t)st.ncontrib, t->pr.p);
+    k_slot_multi<<<min(grid_for(t->g1_nmulti, B), 148 * 64), B, 0, ctx->stream>>>(t->g1_multi.p, t->g1_nmulti, t->moff.p, st.cstart.p,
+                                                                               st.csrc.p, (uint32_t)st.ncontrib, (uint32_t)t->nnz,
+                                                                               t->dslot.p);
     GF_LAUNCH_CHECK();
   }
+  {  // destination order inside every element
+    const int nb = t->fem->nd * t->fem->nd;
+    const int64_t nel = st.ncontrib / nb;
+    GF_REQUIRE(nb <= 65536, "direct mode: element matrices above 65536 entries are not handled");
+    t->dkloc.alloc(ctx, st.ncontrib);
+    auto launch = [&](auto kern, size_t smem) {
+      GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<(unsigned)nel, 512, smem, ctx->stream>>>(t->dslot.p, t->dkloc.p, nb);
+    };
+    if (nb <= 512 * 8) launch(k_slot_sort<8>, sizeof(cub::BlockRadixSort<uint32_t, 512, 8, uint32_t>::TempStorage));
+    else if (nb <= 512 * 31) launch(k_slot_sort<31>, sizeof(cub::BlockRadixSort<uint32_t, 512, 31, uint32_t>::TempStorage));
+    else return false;
+    GF_LAUNCH_CHECK();
+  }
+  t->mstage.alloc(ctx, std::max<int64_t>(total, 1));
+  // the full stage and the entry-wise sources are not needed while the pattern stands; the list of the shared pairs
+  // becomes the list of their CSC positions (dmpos)
+  t->dmpos.release();
+  if (t->g1_nmulti) {
+    k_multi_pos<<<min(grid_for(t->g1_nmulti, B), 148 * 64), B, 0, ctx->stream>>>(t->g1_multi.p, t->g1_nmulti, st.pJ.p, t->prel.p, t->jc.p);
+    GF_LAUNCH_CHECK();
+    std::swap(t->dmpos.p, t->g1_multi.p);
+    std::swap(t->dmpos.n, t->g1_multi.n);
+    std::swap(t->dmpos.ctx, t->g1_multi.ctx);
+  }
+  t->d_nmulti = t->g1_nmulti;
+  t->g1_src.release();
+  t->g1_multi.release();
+  t->g1_generation = -1;
+  t->stage.release();
+  GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  t->direct_ok = 1;
   return true;
+}
+
+void direct_finish(gfgpu_term *t) {
+  if (!t->d_nmulti) return;
+  const int B = 256;
+  k_multi_sum<<<min(grid_for(t->d_nmulti, B), 148 * 64), B, 0, t->ctx->stream>>>(t->dmpos.p, t->d_nmulti, t->moff.p, t->mstage.p, t->pr.p);
+  GF_LAUNCH_CHECK();
 }
 
 template <int Q>

@@ -51,15 +51,32 @@ struct SfArgs {
   double *stage;
   uint16_t *emask;
   double *rstage;
+  const uint32_t *slot;  // direct mode (common.cuh ElemArgs): destinations of the element's entries, ascending
+  const uint16_t *kloc;  // ... and which entry goes there
+  double *pr, *mstage;
+  uint32_t nnz32;
 };
 
+// K_e is symmetric (C is): only the slices (i3 <= j3) are contracted and only they are STORED -- the shared-memory image
+// of K_e is its upper block triangle (ND1 (ND1+1)/2 blocks of NN x NN: 75 KB instead of 125 KB for Q4), which lets TWO CTAs
+// share an SM: while one is in its output phase (HBM latency) the other contracts.  kt(i, j) addresses K(i, j) in that image.
+template <int ND1>
+__device__ __forceinline__ int sf_tri(int a3, int b3) { return a3 * ND1 - (a3 * (a3 - 1)) / 2 + (b3 - a3); }  // a3 <= b3
+template <int ND1>
+__device__ __forceinline__ int sf_kt(int i, int j) {
+  constexpr int NN = ND1 * ND1;
+  const int i3 = i / NN, i12 = i - i3 * NN, j3 = j / NN, j12 = j - j3 * NN;
+  return i3 <= j3 ? sf_tri<ND1>(i3, j3) * NN * NN + i12 + NN * j12 : sf_tri<ND1>(j3, i3) * NN * NN + j12 + NN * i12;
+}
+
 template <int ND1, int NQ1, int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
+__global__ void __launch_bounds__(NW * 32, 2)
 k_sumfact_laplace(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T) {
   constexpr int NN = ND1 * ND1, ND = ND1 * ND1 * ND1, NQ2 = NQ1 * NQ1, NQ = NQ1 * NQ1 * NQ1, NT = NW * 32;
+  constexpr int NSL = ND1 * (ND1 + 1) / 2, BL = NN * NN;
   extern __shared__ __align__(16) double sm[];
-  double *sK = sm;                       // ND x ND, column-major (row i + ND * column j) = the layout of the stage
-  double *sC = sK + ND * ND;             // 6 x NQ : C00 C01 C02 C11 C12 C22
+  double *sK = sm;                       // NSL blocks (i3 <= j3) of NN x NN: row (i1,i2) + NN * column (j1,j2)
+  double *sC = sK + NSL * BL;            // 6 x NQ : C00 C01 C02 C11 C12 C22
   double *sS1 = sC + 6 * NQ;             // per warp 9 x NQ2
   double *sG = sS1 + NW * 9 * NQ2;       // 3 x 8 node coordinates
   double *sU = sG + 24;                  // ND coefficients
@@ -100,17 +117,16 @@ k_sumfact_laplace(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T) 
       for (int p = 0; p < 3; ++p)
 #pragma unroll
         for (int r = p; r < 3; ++r) {
-          double s = 0;
+          double s2 = 0;
 #pragma unroll
-          for (int n = 0; n < 3; ++n) s += geo[n + 3 * p] * geo[n + 3 * r];
-          sC[(k++) * NQ + q] = c * s;
+          for (int n = 0; n < 3; ++n) s2 += geo[n + 3 * p] * geo[n + 3 * r];
+          sC[(k++) * NQ + q] = c * s2;
         }
     }
     __syncthreads();
-    // ---- C: slices (i3, j3), one per warp
-    // K_e is symmetric (C is): only the slices (i3 <= j3) are contracted, the others are their mirror images
+    // ---- C: slices (i3 <= j3), one per warp and round
     double *S1 = sS1 + warp * 9 * NQ2;
-    for (int task = warp; task < ND1 * (ND1 + 1) / 2; task += NW) {
+    for (int task = warp; task < NSL; task += NW) {
       int i3 = 0, rem = task;  // task -> (i3 <= j3), rows of the upper triangle
       while (rem >= ND1 - i3) { rem -= ND1 - i3; ++i3; }
       const int j3 = i3 + rem, sl = i3 + ND1 * j3;
@@ -121,10 +137,10 @@ k_sumfact_laplace(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T) 
         const int lo = aa < bb ? aa : bb, hi = aa < bb ? bb : aa;
         const double *C = sC + (lo == 0 ? hi : lo == 1 ? 2 + hi : 5) * NQ + q12;
         const double *pz = T.pz[(aa == 2) * 2 + (bb == 2)][sl];
-        double s = 0;
+        double s2 = 0;
 #pragma unroll
-        for (int q3 = 0; q3 < NQ1; ++q3) s += C[q3 * NQ2] * pz[q3];
-        S1[idx] = s;
+        for (int q3 = 0; q3 < NQ1; ++q3) s2 += C[q3 * NQ2] * pz[q3];
+        S1[idx] = s2;
       }
       __syncwarp();
       // 2 + 3: contract the second direction in registers, then the first against the constant-bank operand
@@ -145,14 +161,9 @@ k_sumfact_laplace(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T) 
       }
       if (lane < NN) {
         const int i2 = lane % ND1, j2 = lane / ND1;
-        double *o = sK + (ND1 * i2 + NN * i3) + ND * (ND1 * j2 + NN * j3);
+        double *o = sK + task * BL + ND1 * i2 + NN * (ND1 * j2);
 #pragma unroll
-        for (int m = 0; m < NN; ++m) o[(m % ND1) + ND * (m / ND1)] = acc[m];
-        if (i3 != j3) {  // the mirror slice (j3, i3): K(j, i) = K(i, j)
-          double *ot = sK + (ND1 * j2 + NN * j3) + ND * (ND1 * i2 + NN * i3);
-#pragma unroll
-          for (int m = 0; m < NN; ++m) ot[(m / ND1) + ND * (m % ND1)] = acc[m];
-        }
+        for (int m = 0; m < NN; ++m) o[(m % ND1) + NN * (m / ND1)] = acc[m];
       }
       __syncwarp();
     }
@@ -160,14 +171,19 @@ k_sumfact_laplace(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T) 
     // ---- element residual r = K_e u_e (before the drop rule, like the quadrature form of the generic kernel)
     if (a.rstage)
       for (int i = tid; i < ND; i += NT) {
-        double s = 0;
-        for (int j = 0; j < ND; ++j) s += sK[i + ND * j] * sU[j];
-        a.rstage[(size_t)el * ND + i] = s;
+        const int i3 = i / NN, i12 = i - i3 * NN;
+        double s2 = 0;
+        for (int j3 = 0; j3 < ND1; ++j3) {
+          const double *Kb = i3 <= j3 ? sK + sf_tri<ND1>(i3, j3) * BL + i12 : sK + sf_tri<ND1>(j3, i3) * BL + NN * i12;
+          const int st = i3 <= j3 ? NN : 1;
+          for (int j12 = 0; j12 < NN; ++j12) s2 += Kb[st * j12] * sU[j12 + NN * j3];
+        }
+        a.rstage[(size_t)el * ND + i] = s2;
       }
     // ---- D: drop rule and output (C&E.cc:4889,4898; 5380-5402)
-    if (a.stage || a.emask) {
+    if (a.stage || a.emask || a.slot) {
       double vmax = 0.0;
-      for (int k = tid; k < ND * ND; k += NT) vmax = fmax(vmax, fabs(sK[k]));
+      for (int k = tid; k < NSL * BL; k += NT) vmax = fmax(vmax, fabs(sK[k]));
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, off));
       if (lane == 0) sRed[warp] = vmax;
@@ -178,11 +194,39 @@ k_sumfact_laplace(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T) 
       const double thr = vmax * 1e-14;
       double *st = a.stage ? a.stage + (size_t)el * ND * ND : nullptr;
       uint16_t *em = a.emask ? a.emask + (size_t)el * ND * ND : nullptr;
-      for (int k = tid; k < ND * ND; k += NT) {  // k = i + ND*j: the stage index and the mask index p = j*ND + i
-        const double v = sK[k];
-        const bool keep = (vmax != 0.0) && (fabs(v) > thr);
-        if (st) st[k] = keep ? v : 0.0;
-        if (em) em[k] = keep ? 1 : 0;
+      if (a.slot) {
+        // direct mode: the pattern is fixed, every entry has its destination -- a CSC slot of pr (single-contribution
+        // entries: 77 % on Q4), or a place in the compact stage of the shared entries; no element matrix goes to HBM.
+        // Destination order: consecutive threads, consecutive addresses (entries outside the pattern sort last).
+        const uint32_t *sl = a.slot + (size_t)el * ND * ND;
+        const uint16_t *kl = a.kloc + (size_t)el * ND * ND;
+        for (int k0 = tid; k0 < ND * ND; k0 += 8 * NT) {
+          uint32_t u[8];
+          uint16_t kk[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int k = k0 + r * NT;
+            u[r] = k < ND * ND ? __ldcs(sl + k) : 0xffffffffu;
+            kk[r] = k < ND * ND ? __ldcs(kl + k) : (uint16_t)0;
+          }
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            if (u[r] != 0xffffffffu) {
+              const int kq = kk[r], j = kq / ND, i = kq - j * ND;
+              const double v = sK[sf_kt<ND1>(i, j)];
+              const bool keep = (vmax != 0.0) && (fabs(v) > thr);
+              if (u[r] < a.nnz32) a.pr[u[r]] = keep ? v : 0.0;
+              else a.mstage[u[r] - a.nnz32] = keep ? v : 0.0;
+            }
+        }
+      } else {
+        for (int k = tid; k < ND * ND; k += NT) {  // k = i + ND*j: the stage index and the mask index p = j*ND + i
+          const int j = k / ND, i = k - j * ND;
+          const double v = sK[sf_kt<ND1>(i, j)];
+          const bool keep = (vmax != 0.0) && (fabs(v) > thr);
+          if (st) st[k] = keep ? v : 0.0;
+          if (em) em[k] = keep ? 1 : 0;
+        }
       }
     }
     __syncthreads();
@@ -729,10 +773,10 @@ static void launch_sf(gfgpu_ctx *ctx, const SfHost &h, const SfArgs &a) {
   std::unique_ptr<SfTables<ND1, NQ1>> Tp(new SfTables<ND1, NQ1>);  // filled per call (host side, cheap)
   fill_tables<ND1, NQ1>(h, *Tp);
   static_assert(sizeof(SfTables<ND1, NQ1>) + sizeof(SfArgs) <= 32000, "tables exceed the kernel parameter space");
-  const size_t smem = ((size_t)ND * ND + 6 * NQ + (size_t)NW * 9 * NQ2 + 24 + ND + NW + 2) * 8;
+  const size_t smem = ((size_t)(ND1 * (ND1 + 1) / 2) * ND1 * ND1 * ND1 * ND1 + 6 * NQ + (size_t)NW * 9 * NQ2 + 24 + ND + NW + 2) * 8;
   auto kern = k_sumfact_laplace<ND1, NQ1, NW>;
   GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(a.ne, ctx->sm_count));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(a.ne, 2 * (int64_t)ctx->sm_count));  // two CTAs per SM
   kern<<<grid, NW * 32, smem, ctx->stream>>>(a, *Tp);
   GF_LAUNCH_CHECK();
 }
@@ -757,18 +801,30 @@ static void launch_sf_hyper(gfgpu_ctx *ctx, const SfHost &h, const SfArgs &a) {
                        3 * S1 + 2) * 8;
   auto kern = k_sumfact_hyper<ND1, NQ1, NW>;
   GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(a.ne, ctx->sm_count));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(a.ne, 2 * (int64_t)ctx->sm_count));  // two CTAs per SM
   kern<<<grid, NW * 32, smem, ctx->stream>>>(a, *Tp);
   GF_LAUNCH_CHECK();
 }
 
-// returns false when this family / element / table set is not handled here (the caller then uses the generic kernel)
-bool launch_sumfact_kernel(gfgpu_ctx *ctx, const gfgpu_tables *tab, int dim, int Q, int nd, bool affine, const ElemArgs &ea) {
-  if (dim != 3 || affine || ea.ng != 8 || getenv("GFGPU_NO_SUMFACT")) return false;
+static int sumfact_shape(int dim, int Q, int nd, bool affine, const ElemArgs &ea) {
+  if (dim != 3 || affine || ea.ng != 8 || getenv("GFGPU_NO_SUMFACT")) return 0;
   const bool lap = ea.family == GFGPU_LAPLACE && Q == 1 && ((nd == 125 && ea.nq == 125) || (nd == 64 && ea.nq == 64));
   const bool hyp = (ea.family == GFGPU_SVK || ea.family == GFGPU_NEOHOOKEAN_CIARLET || ea.family == GFGPU_NEOHOOKEAN_BONET) &&
                    Q == 3 && nd == 27 && (ea.nq == 64 || ea.nq == 27);
-  if (!lap && !hyp) return false;
+  return lap ? 1 : hyp ? 2 : 0;
+}
+
+int sumfact_kind(const gfgpu_tables *tab, int dim, int Q, int nd, bool affine, const ElemArgs &ea) {
+  const int k = sumfact_shape(dim, Q, nd, affine, ea);
+  if (!k) return 0;
+  return factorise(tab).ok ? k : 0;
+}
+
+// returns false when this family / element / table set is not handled here (the caller then uses the generic kernel)
+bool launch_sumfact_kernel(gfgpu_ctx *ctx, const gfgpu_tables *tab, int dim, int Q, int nd, bool affine, const ElemArgs &ea) {
+  const int kind = sumfact_shape(dim, Q, nd, affine, ea);
+  if (!kind) return false;
+  const bool lap = kind == 1, hyp = kind == 2;
   const SfHost h = factorise(tab);
   if (!h.ok) return false;
   SfArgs a;
@@ -777,9 +833,11 @@ bool launch_sumfact_kernel(gfgpu_ctx *ctx, const gfgpu_tables *tab, int dim, int
   a.coef = ea.alpha * ea.par[0];
   a.gphi = ea.gphi; a.lambda = ea.par[0]; a.mu = ea.par[1]; a.alpha = ea.alpha; a.law = ea.family;
   a.stage = ea.stage; a.emask = ea.emask; a.rstage = ea.rstage;
+  a.slot = lap ? ea.slot : nullptr; a.kloc = ea.kloc; a.pr = ea.pr; a.mstage = ea.mstage; a.nnz32 = ea.nnz32;
+  GF_REQUIRE(!ea.slot || lap, "the direct mode is a feature of the scalar sum-factorised kernel");
   if (a.ne <= 0) return true;
-  if (lap && h.nd1 == 5 && h.nq1 == 5) launch_sf<5, 5, 15>(ctx, h, a);  // one warp per slice (i3 <= j3)
-  else if (lap && h.nd1 == 4 && h.nq1 == 4) launch_sf<4, 4, 10>(ctx, h, a);
+  if (lap && h.nd1 == 5 && h.nq1 == 5) launch_sf<5, 5, 8>(ctx, h, a);  // 15 slices (i3 <= j3) in two rounds of 8 warps, two CTAs per SM
+  else if (lap && h.nd1 == 4 && h.nq1 == 4) launch_sf<4, 4, 5>(ctx, h, a);
   else if (hyp && h.nd1 == 3 && h.nq1 == 4) launch_sf_hyper<3, 4, 9>(ctx, h, a);
   else if (hyp && h.nd1 == 3 && h.nq1 == 3) launch_sf_hyper<3, 3, 9>(ctx, h, a);
   else return false;

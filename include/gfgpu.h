@@ -205,7 +205,9 @@ int gfgpu_term_last_timings(gfgpu_term *t, float *out8);
 int gfgpu_term_strategy(gfgpu_term *t);
 /* which tangent kernel the last plan of the term selected: 0 = generic element kernel + gather-sum (STAGED, or RECOMPUTE not
  * planned yet), 1 = general per-nonzero tile kernel, 2 = column kernel (low-order scalar forms), 3 = class-uniform tile kernel
- * (meshes with translated structure).  Diagnostic: the choice never changes results beyond round-off. */
+ * (meshes with translated structure), 4 = STAGED in direct mode (scalar sum-factorised element kernel under a fixed pattern:
+ * entries go straight from the element kernel to their CSC slots, no element matrix in HBM).  Diagnostic: the choice never
+ * changes results beyond round-off. */
 int gfgpu_term_kernel_kind(gfgpu_term *t);
 
 int64_t gfgpu_term_nnz(gfgpu_term *t);

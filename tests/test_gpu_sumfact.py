@@ -130,3 +130,64 @@ def test_hyperelastic_sumfact_matches_generic_kernel_and_oracle(case):
     assert np.array_equal(jc, ojc) and np.array_equal(ir, oir), "pattern differs from the oracle"
     assert np.linalg.norm(pr - opr) <= 1e-12 * np.linalg.norm(opr)
     assert np.linalg.norm(R - oR) <= 1e-12 * np.linalg.norm(oR)
+
+
+@pytest.mark.parametrize("case", [(4, 8, [2, 2, 3]), (3, 6, [2, 3, 2])], ids=["q4", "q3"])
+def test_direct_mode_repeats_the_staged_pass_bit_for_bit(case):
+    """From the second assembly on (fixed pattern) the scalar sum-factorised kernel writes its entries straight to their CSC
+    slots and only the shared entries go through a compact stage (kernel_kind 4): same bits as the staged first pass, also
+    after the state changes, and the same as with the direct mode switched off."""
+    from getfem_b200 import capi
+    k, im, nsub = case
+    ctx, m, mf, dmesh, dfem, t, tab, U = _setup(k, im, nsub)
+    os.environ.pop("GFGPU_NO_SUMFACT", None)
+    order = capi.TANGENT | capi.RESIDUAL
+
+    def passes(direct):
+        if direct:
+            os.environ.pop("GFGPU_NO_DIRECT", None)
+        else:
+            os.environ["GFGPU_NO_DIRECT"] = "1"
+        try:
+            term = capi.DeviceTerm(ctx, dmesh, dfem, tab, "laplace", [1.7], 0.5, 0)
+            out = []
+            for Uk in (U, U, 0.3 * U[::-1].copy(), None):
+                R = np.empty(dfem.ndof)
+                term.assemble_host(Uk, order, None, R)
+                jc, ir, pr = term.export_csc()
+                out.append((jc, ir, pr, R, term.kernel_kind))
+            term.assemble_host(U, capi.TANGENT, None, None)  # tangent alone
+            out.append(term.export_csc() + (None, term.kernel_kind))
+            return out
+        finally:
+            os.environ.pop("GFGPU_NO_DIRECT", None)
+
+    d, s = passes(True), passes(False)
+    assert [o[4] for o in d] == [0, 4, 4, 4, 4] and [o[4] for o in s] == [0, 0, 0, 0, 0]
+    for a, b in zip(d, s):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        assert a[3] is None or np.array_equal(a[3], b[3])
+    assert np.array_equal(d[0][2], d[1][2]) and np.array_equal(d[0][3], d[1][3])
+    assert not d[3][3].any()  # zero state: zero residual
+
+
+def test_direct_mode_follows_a_new_region():
+    """changing the element range invalidates the pattern: one staged pass, then direct again with the new slots"""
+    from getfem_b200 import capi
+    ctx, m, mf, dmesh, dfem, t, tab, U = _setup(4, 8, [2, 2, 3])
+    term = capi.DeviceTerm(ctx, dmesh, dfem, tab, "laplace", [1.0], 1.0, 0)
+    ref = capi.DeviceTerm(ctx, dmesh, dfem, tab, "laplace", [1.0], 1.0, 0)
+    ne = m.nb_convex()
+    for e0, e1 in ((0, ne), (2, ne - 3), (0, 5)):
+        term.set_element_range(e0, e1)
+        for _ in range(3):
+            term.assemble_host(U, capi.TANGENT, None, None)
+        assert term.kernel_kind == 4
+        os.environ["GFGPU_NO_DIRECT"] = "1"
+        try:
+            ref.set_element_range(e0, e1)
+            ref.assemble_host(U, capi.TANGENT, None, None)
+        finally:
+            os.environ.pop("GFGPU_NO_DIRECT", None)
+        for x, y in zip(term.export_csc(), ref.export_csc()):
+            assert np.array_equal(x, y)
