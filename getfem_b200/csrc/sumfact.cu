@@ -69,11 +69,17 @@ __device__ __forceinline__ int sf_kt(int i, int j) {
   return i3 <= j3 ? sf_tri<ND1>(i3, j3) * NN * NN + i12 + NN * j12 : sf_tri<ND1>(j3, i3) * NN * NN + j12 + NN * i12;
 }
 
-template <int ND1, int NQ1, int NW>
-__global__ void __launch_bounds__(NW * 32, 2)
+// DMMA: the last contraction on the fp64 tensor core instead (north_star asks for the A/B): per slice
+//   acc(m, n) = sum_k px[k][m] s2[k][n],  m = (i1, j1) 25 -> 32,  n = (i2, j2) 25 -> 32,  k = (ab, q1) 45 -> 48,
+// as 4 x 4 x 12 mma.sync.m8n8k4.f64; the A fragments (the constant table px, zero padded) sit in shared memory in fragment
+// order, the B fragment s2[k][n] is formed by the lane that owns it, accumulators in registers.  1.75x the multiply-adds
+// of the FMA formulation for a pipe that peaks 9 % higher (api.cu fp64 probes): measured in profiles/round2_c5_dmma_ab.txt.
+template <int ND1, int NQ1, int NW, int OCC, bool DMMA>
+__global__ void __launch_bounds__(NW * 32, OCC)
 k_sumfact_laplace(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T) {
   constexpr int NN = ND1 * ND1, ND = ND1 * ND1 * ND1, NQ2 = NQ1 * NQ1, NQ = NQ1 * NQ1 * NQ1, NT = NW * 32;
   constexpr int NSL = ND1 * (ND1 + 1) / 2, BL = NN * NN;
+  constexpr int KT = (9 * NQ1 + 3) / 4, MT = (NN + 7) / 8;  // k-steps and m / n tiles of the DMMA variant
   extern __shared__ __align__(16) double sm[];
   double *sK = sm;                       // NSL blocks (i3 <= j3) of NN x NN: row (i1,i2) + NN * column (j1,j2)
   double *sC = sK + NSL * BL;            // 6 x NQ : C00 C01 C02 C11 C12 C22
@@ -81,7 +87,18 @@ k_sumfact_laplace(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T) 
   double *sG = sS1 + NW * 9 * NQ2;       // 3 x 8 node coordinates
   double *sU = sG + 24;                  // ND coefficients
   double *sRed = sU + ND;                // NW
+  double *sAf = sRed + NW + (NW & 1);    // DMMA: KT x MT x 32 A fragments
+  double *sPy = sAf + (DMMA ? KT * MT * 32 : 0);  // DMMA: 4 x NN x NQ1
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (DMMA) {
+    for (int idx = tid; idx < KT * MT * 32; idx += NT) {
+      const int ln = idx & 31, mt = (idx >> 5) % MT, kt = idx / (32 * MT);
+      const int k = 4 * kt + (ln & 3), m = 8 * mt + (ln >> 2);
+      sAf[idx] = (k < 9 * NQ1 && m < NN) ? T.px[k / NQ1][k % NQ1][m] : 0.0;
+    }
+    for (int idx = tid; idx < 4 * NN * NQ1; idx += NT) sPy[idx] = T.py[idx / (NN * NQ1)][(idx / NQ1) % NN][idx % NQ1];
+    __syncthreads();
+  }
   // lane = (i2, j2): its 1D factors for the y direction
   double yy[4][NQ1];
   if (lane < NN) {
@@ -143,6 +160,51 @@ k_sumfact_laplace(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T) 
         S1[idx] = s2;
       }
       __syncwarp();
+      if (DMMA) {
+        double cf[MT][MT][2];  // [m tile][n tile]: C(row = lane >> 2, column = 2 (lane & 3) + {0, 1})
+#pragma unroll
+        for (int x = 0; x < MT; ++x)
+#pragma unroll
+          for (int y = 0; y < MT; ++y) cf[x][y][0] = cf[x][y][1] = 0.0;
+#pragma unroll 1
+        for (int kt = 0; kt < KT; ++kt) {
+          const int k = 4 * kt + (lane & 3);
+          const bool kok = k < 9 * NQ1;
+          const int ab = kok ? k / NQ1 : 0, q1 = kok ? k % NQ1 : 0;
+          const int yc = ((ab / 3) == 1) * 2 + ((ab % 3) == 1);
+          double s1v[NQ1];
+#pragma unroll
+          for (int q2 = 0; q2 < NQ1; ++q2) s1v[q2] = S1[ab * NQ2 + q1 + NQ1 * q2];
+          double af[MT];
+#pragma unroll
+          for (int x = 0; x < MT; ++x) af[x] = sAf[(kt * MT + x) * 32 + lane];
+#pragma unroll
+          for (int y = 0; y < MT; ++y) {
+            const int n = 8 * y + (lane >> 2);
+            double bf = 0.0;  // B(row = lane & 3, column = lane >> 2) = s2[k][n]
+            if (kok && n < NN) {
+              const double *pyv = sPy + (yc * NN + n) * NQ1;
+#pragma unroll
+              for (int q2 = 0; q2 < NQ1; ++q2) bf += s1v[q2] * pyv[q2];
+            }
+#pragma unroll
+            for (int x = 0; x < MT; ++x)
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                           : "+d"(cf[x][y][0]), "+d"(cf[x][y][1])
+                           : "d"(af[x]), "d"(bf));
+          }
+        }
+        double *o = sK + task * BL;
+#pragma unroll
+        for (int x = 0; x < MT; ++x)
+#pragma unroll
+          for (int y = 0; y < MT; ++y)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int m = 8 * x + (lane >> 2), n = 8 * y + 2 * (lane & 3) + h;
+              if (m < NN && n < NN) o[(m % ND1) + ND1 * (n % ND1) + NN * ((m / ND1) + ND1 * (n / ND1))] = cf[x][y][h];
+            }
+      } else {
       // 2 + 3: contract the second direction in registers, then the first against the constant-bank operand
       double acc[NN];
 #pragma unroll
@@ -164,6 +226,7 @@ k_sumfact_laplace(const SfArgs a, const __grid_constant__ SfTables<ND1, NQ1> T) 
         double *o = sK + task * BL + ND1 * i2 + NN * (ND1 * j2);
 #pragma unroll
         for (int m = 0; m < NN; ++m) o[(m % ND1) + NN * (m / ND1)] = acc[m];
+      }
       }
       __syncwarp();
     }
@@ -767,16 +830,18 @@ static void fill_tables(const SfHost &h, SfTables<ND1, NQ1> &T) {
     for (int q = 0; q < NQ1; ++q) { T.l1[i][q] = L(i, q); T.d1[i][q] = D(i, q); }
 }
 
-template <int ND1, int NQ1, int NW>
+template <int ND1, int NQ1, int NW, int OCC, bool DMMA>
 static void launch_sf(gfgpu_ctx *ctx, const SfHost &h, const SfArgs &a) {
-  constexpr int ND = ND1 * ND1 * ND1, NQ2 = NQ1 * NQ1, NQ = NQ2 * NQ1;
+  constexpr int ND = ND1 * ND1 * ND1, NN = ND1 * ND1, NQ2 = NQ1 * NQ1, NQ = NQ2 * NQ1;
+  constexpr int KT = (9 * NQ1 + 3) / 4, MT = (NN + 7) / 8;
   std::unique_ptr<SfTables<ND1, NQ1>> Tp(new SfTables<ND1, NQ1>);  // filled per call (host side, cheap)
   fill_tables<ND1, NQ1>(h, *Tp);
   static_assert(sizeof(SfTables<ND1, NQ1>) + sizeof(SfArgs) <= 32000, "tables exceed the kernel parameter space");
-  const size_t smem = ((size_t)(ND1 * (ND1 + 1) / 2) * ND1 * ND1 * ND1 * ND1 + 6 * NQ + (size_t)NW * 9 * NQ2 + 24 + ND + NW + 2) * 8;
-  auto kern = k_sumfact_laplace<ND1, NQ1, NW>;
+  const size_t smem = ((size_t)(ND1 * (ND1 + 1) / 2) * NN * NN + 6 * NQ + (size_t)NW * 9 * NQ2 + 24 + ND + NW + 2 +
+                       (DMMA ? KT * MT * 32 + 4 * NN * NQ1 : 0)) * 8;
+  auto kern = k_sumfact_laplace<ND1, NQ1, NW, OCC, DMMA>;
   GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(a.ne, 2 * (int64_t)ctx->sm_count));  // two CTAs per SM
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(a.ne, OCC * (int64_t)ctx->sm_count));
   kern<<<grid, NW * 32, smem, ctx->stream>>>(a, *Tp);
   GF_LAUNCH_CHECK();
 }
@@ -836,8 +901,15 @@ bool launch_sumfact_kernel(gfgpu_ctx *ctx, const gfgpu_tables *tab, int dim, int
   a.slot = lap ? ea.slot : nullptr; a.kloc = ea.kloc; a.pr = ea.pr; a.mstage = ea.mstage; a.nnz32 = ea.nnz32;
   GF_REQUIRE(!ea.slot || lap, "the direct mode is a feature of the scalar sum-factorised kernel");
   if (a.ne <= 0) return true;
-  if (lap && h.nd1 == 5 && h.nq1 == 5) launch_sf<5, 5, 8>(ctx, h, a);  // 15 slices (i3 <= j3) in two rounds of 8 warps, two CTAs per SM
-  else if (lap && h.nd1 == 4 && h.nq1 == 4) launch_sf<4, 4, 5>(ctx, h, a);
+  // GFGPU_SF_VARIANT (A/B of profiles/round2_c5_dmma_ab.txt): 0 = FMA pipe, two CTAs of 8 warps per SM (default);
+  // 1 = FMA pipe, one CTA of 15 warps; 2 = fp64 tensor core (mma.sync.m8n8k4), one CTA of 15 warps; 3 = DMMA, 2 x 8 warps
+  const int variant = getenv("GFGPU_SF_VARIANT") ? atoi(getenv("GFGPU_SF_VARIANT")) : 0;
+  if (lap && h.nd1 == 5 && h.nq1 == 5) {  // 15 slices (i3 <= j3)
+    if (variant == 1) launch_sf<5, 5, 15, 1, false>(ctx, h, a);
+    else if (variant == 2) launch_sf<5, 5, 15, 1, true>(ctx, h, a);
+    else if (variant == 3) launch_sf<5, 5, 8, 2, true>(ctx, h, a);
+    else launch_sf<5, 5, 8, 2, false>(ctx, h, a);
+  } else if (lap && h.nd1 == 4 && h.nq1 == 4) launch_sf<4, 4, 5, 2, false>(ctx, h, a);
   else if (hyp && h.nd1 == 3 && h.nq1 == 4) launch_sf_hyper<3, 4, 9>(ctx, h, a);
   else if (hyp && h.nd1 == 3 && h.nq1 == 3) launch_sf_hyper<3, 3, 9>(ctx, h, a);
   else return false;

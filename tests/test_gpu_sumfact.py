@@ -191,3 +191,21 @@ def test_direct_mode_follows_a_new_region():
             os.environ.pop("GFGPU_NO_DIRECT", None)
         for x, y in zip(term.export_csc(), ref.export_csc()):
             assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_kernel_variants_of_the_last_contraction_agree(variant):
+    """GFGPU_SF_VARIANT: 1 = FMA pipe with one 15-warp CTA per SM, 2 / 3 = the last contraction on the fp64 tensor core
+    (mma.sync.m8n8k4.f64, K 45 -> 48, tiles 25 -> 32).  Same pattern, values to 1e-13 of the default kernel."""
+    ctx, m, mf, dmesh, dfem, t, tab, U = _setup(4, 8, [2, 2, 3])
+    os.environ.pop("GFGPU_NO_SUMFACT", None)
+    os.environ.pop("GFGPU_SF_VARIANT", None)
+    jc, ir, pr, R, _ = _assemble(ctx, dmesh, dfem, tab, U)
+    os.environ["GFGPU_SF_VARIANT"] = str(variant)
+    try:
+        vjc, vir, vpr, vR, _ = _assemble(ctx, dmesh, dfem, tab, U)
+    finally:
+        os.environ.pop("GFGPU_SF_VARIANT", None)
+    assert np.array_equal(jc, vjc) and np.array_equal(ir, vir)
+    assert np.linalg.norm(pr - vpr) <= 1e-13 * np.linalg.norm(pr)
+    assert np.linalg.norm(R - vR) <= 1e-13 * np.linalg.norm(R)
