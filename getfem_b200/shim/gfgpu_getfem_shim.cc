@@ -11,6 +11,7 @@
 #include <cstring>
 #include <functional>
 #include <regex>
+#include <set>
 #include <sstream>
 #include <tuple>
 
@@ -562,6 +563,13 @@ struct context_watcher : public getfem::context_dependencies {
   }
 };
 
+// the convexes of (mesh, mesh_fem, mesh_im) grouped by (fem, geometric transformation, integration method): an O(ne) walk
+// of GetFEM's per-convex tables, done once and kept until one of the three objects says it changed
+struct device_assembler::grouping {
+  context_watcher watch;
+  std::vector<std::vector<size_type>> groups;
+};
+
 struct device_assembler::entry {
   context_watcher watch;
   uint64_t last_use = 0;
@@ -675,19 +683,65 @@ static bool recognise_potential(const getfem::ga_workspace &ws, size_type itree,
   return false;
 }
 
+// What a recognition result depends on, as a string: the printed tree, where it is integrated, and for every name the
+// tree mentions that the workspace knows -- a variable: its mesh_fem and interval; a fixed-size constant: its values bit
+// for bit; fem / im data: the object it lives on (the values travel at every call anyway).
+static std::string recognition_key(const getfem::ga_workspace &ws, size_type i) {
+  const auto &td = ws.tree_info(i);
+  const std::string ts = getfem::ga_tree_to_string(*td.ptree);
+  std::ostringstream k;
+  k << ts << "|" << (const void *)td.mim << "|" << (td.rg ? long(td.rg->id()) : -2L) << "|" << td.name_test1 << "|" << td.name_test2
+    << "|" << int(td.order) << "|" << int(td.operation);
+  if (td.mim) k << "|dim" << int(td.mim->linked_mesh().dim()) << "|ne" << td.mim->linked_mesh().convex_index().card();
+  static const std::regex ident("[A-Za-z_][A-Za-z0-9_]*");
+  static const char *prefixes[] = {"", "Grad_", "Hess_", "Div_", "Test_", "Test2_", "Grad_Test_", "Grad_Test2_", "Hess_Test_",
+                                   "Hess_Test2_", "Div_Test_", "Div_Test2_"};
+  std::set<std::string> seen;
+  for (std::sregex_iterator it(ts.begin(), ts.end(), ident), end; it != end; ++it) {
+    const std::string tok = it->str();
+    for (const char *pre : prefixes) {
+      const size_t lp = std::strlen(pre);
+      if (tok.size() <= lp || tok.compare(0, lp, pre) != 0) continue;
+      const std::string name = tok.substr(lp);
+      if (!ws.variable_exists(name) || !seen.insert(name).second) continue;
+      k << "|" << name << ":";
+      if (const getfem::mesh_fem *pmf = ws.associated_mf(name)) {
+        k << "mf" << (const void *)pmf << "q" << int(pmf->get_qdim()) << "n" << pmf->nb_dof();
+        if (!ws.is_constant(name)) k << "@" << ws.interval_of_variable(name).first();
+      } else if (ws.associated_im_data(name)) {
+        k << "imd" << (const void *)ws.associated_im_data(name);
+      } else {
+        char hb[40];
+        for (double v : ws.value(name)) { std::snprintf(hb, sizeof hb, "%a,", v); k << hb; }
+      }
+    }
+  }
+  return k.str();
+}
+
 void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
   GMM_ASSERT1(order <= 2, "gfgpu: assembly orders 0, 1 and 2 run on the device");
   double t0 = now_s();
   // ---- every order-1 tree must be a recognised family (the order-2 trees are their derivatives)
   std::vector<std::pair<size_type, recognised_term>> terms;
   // recognition (with its probe assemblies) runs once per tree and call, whoever asks
+  // ... and, across calls, once per (printed tree, integration method, region, variables, VALUES of the constants it names):
+  // a Newton or time loop re-assembles the same workspace, and a probe costs two small reference assemblies whose set-up
+  // walks the whole mesh (0.4 s per call on a 660 000-element mesh before this memo).  Anything the recognised
+  // parameters were read from is part of the key, so a constant that changes is recognised again.
   std::map<size_type, std::pair<bool, std::vector<recognised_term>>> memo;
   auto recognise_memo = [&](size_type i, std::vector<recognised_term> &out) {
     auto it = memo.find(i);
     if (it == memo.end()) {
-      std::vector<recognised_term> r;
-      const bool ok = recognise_tree_sum(ws, i, r);
-      it = memo.emplace(i, std::make_pair(ok, std::move(r))).first;
+      const std::string key = recognition_key(ws, i);
+      auto pit = recognised_.find(key);
+      if (pit == recognised_.end()) {
+        std::vector<recognised_term> r;
+        const bool ok = recognise_tree_sum(ws, i, r);
+        if (recognised_.size() >= 64) recognised_.clear();
+        pit = recognised_.emplace(key, std::make_pair(ok, std::move(r))).first;
+      }
+      it = memo.emplace(i, pit->second).first;
     }
     out = it->second.second;
     return it->second.first;
@@ -750,6 +804,11 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     }
   }
   t_extract = t_device = t_fill = 0;
+  static const bool trace_t = std::getenv("GFGPU_TRACE_TIMING") != nullptr;
+  auto mark = [&](const char *what) {
+    if (trace_t) std::fprintf(stderr, "[gfgpu timing] order %d %-28s %.4f s since the call began\n", int(order), what, now_s() - t0);
+  };
+  mark("trees recognised");
   const size_type nprim = ws.nb_primary_dof() ? ws.nb_primary_dof() : 0;
   if (terms.empty() && order == 0) return;  // nothing adds to the potential
   if (terms.empty()) {
@@ -827,8 +886,10 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
       if (rg_cv.empty()) continue;  // an empty region assembles nothing: ga_exec walks zero elements (C&E.cc:8789-8866)
       GMM_ASSERT1(rg_faces == 0 || rg_faces == rg_cv.size(), "gfgpu: a region must hold either convexes or faces");
     }
+    mark("region walked");
     const gmm::sub_interval &I = ws.interval_of_variable(rt.varname);
     const size_type ndof = mf.nb_dof();  // triggers enumerate_dof
+    mark("nb_dof");
     GMM_ASSERT1(m.convex_index().card() > 0 && m.convex_index().card() == m.convex_index().last_true() + 1,
                 "gfgpu: convex ids must be contiguous (call mesh::optimize_structure)");
     const size_type ne_mesh = m.convex_index().card();
@@ -836,29 +897,43 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     // transformation, integration method); every group is a device term of its own -- own compact mesh, dof rows and
     // tables -- and the groups' tangents meet in the workspace matrix (gfgpu_matrix_add_term: union pattern, summed values),
     // their residuals in V.  A uniform mesh is one group and takes exactly the path it always took.
-    std::vector<std::vector<size_type>> groups;
-    {
+    std::ostringstream gkey;
+    gkey << &m << "/" << &mf << "/" << &mim;
+    std::unique_ptr<grouping> &pg = groupings_[gkey.str()];
+    if (pg && !pg->watch.still_valid()) pg.reset();
+    if (!pg) {
+      if (groupings_.size() > 16) {  // bounded: drop everything but the slot being filled
+        for (auto jt = groupings_.begin(); jt != groupings_.end();) jt = (&jt->second == &pg) ? std::next(jt) : groupings_.erase(jt);
+      }
+      pg.reset(new grouping);
+      pg->watch.add_dependency(m);
+      pg->watch.add_dependency(mf);
+      pg->watch.add_dependency(mim);
       std::map<std::tuple<const void *, const void *, const void *>, size_t> gid;
       for (size_type cv = 0; cv < ne_mesh; ++cv) {
         if (!mf.convex_index().is_in(cv) || !mim.convex_index().is_in(cv)) continue;  // no fem / no im: not assembled
         const auto k = std::make_tuple((const void *)mf.fem_of_element(cv).get(), (const void *)m.trans_of_convex(cv).get(),
                                        (const void *)mim.int_method_of_element(cv).get());
         auto it = gid.find(k);
-        if (it == gid.end()) { it = gid.emplace(k, groups.size()).first; groups.emplace_back(); }
-        groups[it->second].push_back(cv);
+        if (it == gid.end()) { it = gid.emplace(k, pg->groups.size()).first; pg->groups.emplace_back(); }
+        pg->groups[it->second].push_back(cv);
       }
     }
-    std::vector<int32_t> local_of(ne_mesh, -1);
+    mark("convex groups");
+    const std::vector<std::vector<size_type>> &groups = pg->groups;
+    std::vector<int32_t> local_of(groups.size() == 1 && groups[0].size() == ne_mesh ? 0 : ne_mesh, -1);
     for (size_t ig = 0; ig < groups.size(); ++ig) {
     const std::vector<size_type> &gcv = groups[ig];
     const bool whole_mesh = groups.size() == 1 && gcv.size() == ne_mesh;
-    for (size_t k = 0; k < gcv.size(); ++k) local_of[gcv[k]] = int32_t(k);
+    if (!whole_mesh) for (size_t k = 0; k < gcv.size(); ++k) local_of[gcv[k]] = int32_t(k);
     // the region restricted to this group, in the group's local numbering (visitor order kept)
     std::vector<int32_t> grg_cv, grg_f;
     if (!all_cv) {
       for (size_t k = 0; k < rg_cv.size(); ++k) {
         const size_type cv = size_type(rg_cv[k]);
-        if (cv < ne_mesh && local_of[cv] >= 0 && std::binary_search(gcv.begin(), gcv.end(), cv)) {
+        if (whole_mesh) {
+          if (cv < ne_mesh) { grg_cv.push_back(int32_t(cv)); grg_f.push_back(rg_f[k]); }
+        } else if (cv < ne_mesh && local_of[cv] >= 0 && std::binary_search(gcv.begin(), gcv.end(), cv)) {
           grg_cv.push_back(local_of[cv]);
           grg_f.push_back(rg_f[k]);
         }
@@ -916,6 +991,7 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
         cache_.erase(lru);
       }
     }
+    mark("cache looked up");
     std::unique_ptr<entry> &pe = cache_[key.str()];
     if (!pe) {
       pe.reset(new entry);
@@ -1042,6 +1118,7 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     // the variable's values, in the fem's own numbering (the workspace interval only offsets the result)
     const getfem::model_real_plain_vector &U = ws.value(rt.varname);
     GMM_ASSERT1(U.size() == ndof, "gfgpu: bad size of the variable's value vector");
+    mark("entry ready");
     double t1 = now_s();
     t_extract += t1 - t0;
 

@@ -65,10 +65,13 @@ class device_assembler {
 
  private:
   struct entry;
+  struct grouping;
   struct tangent_cache;
   std::unique_ptr<tangent_cache> tangent_;  // the workspace tangent, resident on the device between calls
   gfgpu_ctx *ctx_ = nullptr;
   std::map<std::string, std::unique_ptr<entry>> cache_;  // bounded (LRU); entries die with the getfem objects they mirror
+  std::map<std::string, std::pair<bool, std::vector<recognised_term>>> recognised_;  // recognition results across calls
+  std::map<std::string, std::unique_ptr<grouping>> groupings_;  // convex groups per (mesh, mesh_fem, mesh_im)
   uint64_t use_clock_ = 0;
 };
 
