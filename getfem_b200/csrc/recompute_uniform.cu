@@ -385,7 +385,7 @@ k_utiles(const UArgs a) {
   // Tiles go to the teams round robin, so the tiles a team will run are known from the start: the record of tile k+2, the
   // program header / task range / CSC base of tile k+1 are loaded while tile k runs, and the instruction stream of tile k+1
   // is copied to shared memory during the flush of tile k (a cold chain of dependent loads per tile, then per instruction,
-  // kept every warp waiting for 85 % of its time: profiles/round2_ncu_utiles_v6_c3_n110.txt)
+  // kept every warp waiting for 85 % of its time: profiles/round2_ncu_utiles_v5_flush_4_lanes_per_row_c3_n110.txt)
   struct Meta {
     uint4 tw;
     uint2 h0, tr, pc0, pc1, pc2;
