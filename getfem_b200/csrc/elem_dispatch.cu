@@ -5,6 +5,7 @@ bool launch_elem_inst_2d(gfgpu_ctx *, int, int, int, int, bool, const ElemArgs &
 bool launch_elem_inst_3d_pk(gfgpu_ctx *, int, int, int, int, bool, const ElemArgs &);
 bool launch_elem_inst_3d_qk(gfgpu_ctx *, int, int, int, int, bool, const ElemArgs &);
 bool launch_elem_inst_3d_qk_hi(gfgpu_ctx *, int, int, int, int, bool, const ElemArgs &);
+bool launch_elem_inst_pk4(gfgpu_ctx *, int, int, int, int, bool, const ElemArgs &);
 
 bool launch_elem_kernel(gfgpu_ctx *ctx, int dim, int Q, int nd, bool affine, const ElemArgs &a) {
   int fk;
@@ -19,6 +20,7 @@ bool launch_elem_kernel(gfgpu_ctx *ctx, int dim, int Q, int nd, bool affine, con
   return launch_elem_inst_2d(ctx, dim, Q, nd, fk, affine, a) ||
          launch_elem_inst_3d_pk(ctx, dim, Q, nd, fk, affine, a) ||
          launch_elem_inst_3d_qk(ctx, dim, Q, nd, fk, affine, a) ||
-         launch_elem_inst_3d_qk_hi(ctx, dim, Q, nd, fk, affine, a);
+         launch_elem_inst_3d_qk_hi(ctx, dim, Q, nd, fk, affine, a) ||
+         launch_elem_inst_pk4(ctx, dim, Q, nd, fk, affine, a);
 }
 }  // namespace gf

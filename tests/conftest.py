@@ -16,9 +16,13 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-def golden_names(oracle_only=False):
+def golden_names(oracle_only=False, mirror=False):
     names = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz")))
     # "o_*": the laws the oracle restated and pinned first (round 1); they are device families since round 2
+    # "p4_*": P4 simplices reach the device with the REFERENCE's tables (C ABI, C++ shim); the Python mirror has no
+    # degree-8 simplex cubature of its own, so the tests that regenerate tables in Python skip them
+    if mirror:
+        names = [n for n in names if not n.startswith("p4_")]
     return names
 
 

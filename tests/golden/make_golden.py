@@ -95,6 +95,12 @@ CASES = {
     # mid-size fixtures of the two headline configurations (values checked beyond n = 2)
     "c3_elast3d_p2_n8": "dim=3 n=8 gt=pk k=2 q=3 im=4 family=elast u=random lambda=1 mu=1",
     "c4_nh_ciarlet_q2_n4": "dim=3 n=4 gt=qk k=2 q=3 im=6 family=nh_ciarlet u=smooth lambda=1 mu=1 uamp=0.02",
+    # P4 simplices (the degree of the reference's published table, contrib/opt_assembly/opt_assembly.cc:704-712), distorted
+    "p4_lap3d_n1": "dim=3 n=1 gt=pk k=4 q=1 im=8 family=laplace u=random a=1.3 noise=0.15",
+    "p4_elast3d_n1": "dim=3 n=1 gt=pk k=4 q=3 im=8 family=elast u=random lambda=1.3 mu=0.7 noise=0.15",
+    "p4_svk3d_n1": "dim=3 n=1 gt=pk k=4 q=3 im=8 family=svk u=smooth lambda=1 mu=1 uamp=0.03",
+    "p4_elast2d_n3": "dim=2 n=3 gt=pk k=4 q=2 im=8 family=elast u=random lambda=1.3 mu=0.7 noise=0.15",
+    "p4_mass2d_n2": "dim=2 n=2 gt=pk k=4 q=1 im=8 family=mass u=random a=0.8",
     # ORACLE-ONLY fixtures (prefix o_: not yet a device family; tests/conftest.py keeps them out of the GPU parametrisations).
     # Compressible Mooney-Rivlin (the law of the reference's tests/nonlinear_elastostatic.cc), C10 = lambda, C01 = mu, D1 = a
     "o_mooney_rivlin_q2_n2": "dim=3 n=2 gt=qk k=2 q=3 im=6 family=mooney_rivlin u=smooth lambda=0.8 mu=0.3 a=2.0 uamp=0.03",

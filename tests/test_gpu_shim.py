@@ -56,6 +56,12 @@ CASES = [
     "dim=3 n=3 gt=qk k=2 q=3 im=6 family=nh_ciarlet mixed=1",
     "dim=3 n=4 gt=pk k=2 q=3 im=4 family=mass region=outer mixed=1",
     "dim=3 n=4 gt=pk k=2 q=3 im=4 family=elast region=half mixed=1",
+    # P4 simplices (the degree of the reference's published table, contrib/opt_assembly/opt_assembly.cc:704-712)
+    "dim=3 n=2 gt=pk k=4 q=3 im=8 family=elast",
+    "dim=3 n=2 gt=pk k=4 q=1 im=8 family=laplace",
+    "dim=2 n=6 gt=pk k=4 q=2 im=8 family=elast",
+    "dim=3 n=2 gt=pk k=4 q=3 im=8 family=svk",
+    "dim=3 n=2 gt=pk k=4 q=3 im=8 family=mass region=outer",
 ]
 
 

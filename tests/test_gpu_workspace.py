@@ -86,7 +86,7 @@ def build_ws(dim, nsub, gt, k, Q, im, family, params, U=None, region=None, extra
     return ws, mf, m, U
 
 
-@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("name", golden_names(mirror=True))
 def test_workspace_matches_reference_golden(name):
     g = load_golden(name)
     a = g["args"]

@@ -14,7 +14,7 @@ def _subdiv(a):
     return [int(a["n"])] * dim if "n" in a else [int(a["nx"]), int(a["ny"]), int(a["nz"])][:dim]
 
 
-@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("name", golden_names(mirror=True))
 def test_regular_mesh_matches_reference_bit_for_bit(name):
     g = load_golden(name)
     pts, conn = regular_unit_mesh(_subdiv(g["args"]), "simplex" if g["gt_linear"] else "parallelepiped")
@@ -26,7 +26,7 @@ def test_regular_mesh_matches_reference_bit_for_bit(name):
         assert np.array_equal(pts, g["pts"])  # coordinates identical to the last bit
 
 
-@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("name", golden_names(mirror=True))
 def test_tables_match_reference(name):
     g = load_golden(name)
     a = g["args"]
