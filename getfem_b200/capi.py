@@ -82,6 +82,14 @@ SIGNATURES = {
     "gfgpu_matrix_export_csr_dev": (C.c_int, [_P, _P, _P, _P]),
     "gfgpu_matrix_cg_dev": (C.c_int, [_P, _P, _P, C.c_double, C.c_int, _P, _P]),
     "gfgpu_term_residual_add_dev": (C.c_int, [_P, C.c_double, _P, _i64]),
+    "gfgpu_rect_create": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_double, C.c_double, _PP]),
+    "gfgpu_rect_destroy": (C.c_int, [_P]),
+    "gfgpu_rect_assemble_dev": (C.c_int, [_P]),
+    "gfgpu_rect_nnz": (_i64, [_P]),
+    "gfgpu_rect_export_csc_host": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "gfgpu_rect_mult_dev": (C.c_int, [_P, C.c_int, C.c_double, _P, C.c_double, _P]),
+    "gfgpu_rect_mult_host": (C.c_int, [_P, C.c_int, C.c_double, _P, C.c_double, _P]),
+    "gfgpu_matrix_add_rect": (C.c_int, [_P, _P, C.c_int, C.c_double, _i64, _i64]),
     "gfgpu_term_halo_begin": (C.c_int, [_P, _P, _P, _P]),
     "gfgpu_term_halo_ghost_pairs": (C.c_int, [_P, _i64, _i64, _P, _P, _P, _P]),
     "gfgpu_term_halo_add_source": (C.c_int, [_P, C.c_int, _i64, _P, _P, _P, _i64, _i64]),
@@ -491,6 +499,9 @@ class DeviceMatrix(_Handle):
         check(lib().gfgpu_matrix_mult_dev(self.h, 1 if transposed else 0, float(alpha), C.c_void_p(x_dev_ptr), float(beta),
                                           C.c_void_p(y_dev_ptr)))
 
+    def add_rect(self, rect, transposed=False, alpha=1.0, row_off=0, col_off=0):
+        check(lib().gfgpu_matrix_add_rect(self.h, rect.h, 1 if transposed else 0, float(alpha), int(row_off), int(col_off)))
+
     def apply_dof_constraints(self, dofs, values, rhs_dev_ptr=None, present=None, linear=True, symmetric=True,
                               build_matrix=True):
         """Dirichlet conditions with simplification on the resident tangent and a device right-hand side
@@ -515,6 +526,43 @@ class DeviceMatrix(_Handle):
         check(lib().gfgpu_matrix_cg_dev(self.h, C.c_void_p(b_dev_ptr), C.c_void_p(x_dev_ptr), float(rtol), int(max_iter),
                                         C.byref(it), C.byref(rr)))
         return it.value, rr.value
+
+
+RECT_DIV_PRESSURE = 0
+
+
+class DeviceRect(_Handle):
+    """A coupled bilinear term (gfgpu_rect_*): Test on `fem_rows`, Test2 on `fem_cols`; the block and its transpose."""
+    _destroy = "gfgpu_rect_destroy"
+
+    def __init__(self, ctx, mesh, fem_rows, tab_rows, fem_cols, tab_cols, family=RECT_DIV_PRESSURE, coef=1.0, alpha=1.0):
+        super().__init__()
+        self.ctx, self.nrows, self.ncols = ctx, fem_rows.ndof, fem_cols.ndof
+        self._keep = (mesh, fem_rows, tab_rows, fem_cols, tab_cols)
+        check(lib().gfgpu_rect_create(ctx.h, mesh.h, fem_rows.h, tab_rows.h, fem_cols.h, tab_cols.h, int(family), float(coef),
+                                      float(alpha), C.byref(self.h)))
+
+    def assemble(self):
+        check(lib().gfgpu_rect_assemble_dev(self.h))
+
+    @property
+    def nnz(self):
+        return int(lib().gfgpu_rect_nnz(self.h))
+
+    def export_csc(self, transposed=False):
+        nnz = max(self.nnz, 0)  # (-1 before the first assembly: the call below then reports it)
+        jc = np.empty((self.nrows if transposed else self.ncols) + 1, np.int64)
+        ir = np.empty(nnz, np.int32)
+        pr = np.empty(nnz, np.float64)
+        check(lib().gfgpu_rect_export_csc_host(self.h, 1 if transposed else 0, ptr(jc), ptr(ir), ptr(pr)))
+        return jc, ir, pr
+
+    def mult(self, x, transposed=False, alpha=1.0, beta=0.0, y=None):
+        x = np.ascontiguousarray(x, np.float64)
+        nout = self.ncols if transposed else self.nrows
+        y = np.zeros(nout) if y is None else np.ascontiguousarray(y, np.float64).copy()
+        check(lib().gfgpu_rect_mult_host(self.h, 1 if transposed else 0, float(alpha), ptr(x), float(beta), ptr(y)))
+        return y
 
 
 class _DevArray:

@@ -142,6 +142,29 @@ struct gfgpu_tables {
   gf::DevBuf<double> fw, fgt_grad, fphi, fgphi, fnormal;  // fnormal: nf x 3
 };
 
+// A COUPLED bilinear term: test functions on one fem (rows), trial functions on another (columns), same mesh and
+// quadrature -- the off-diagonal blocks of mixed formulations (rect.cu).
+struct gfgpu_rect {
+  gfgpu_ctx *ctx;
+  gfgpu_mesh *mesh;
+  gfgpu_fem *fr, *fc;       // row / column fem
+  gfgpu_tables *tr, *tc;    // their tables at the SAME quadrature points
+  int family;
+  double coef, alpha;
+  int64_t nrows, ncols, ne;
+  int sr, sc;               // local rows / columns of the element matrix: nd * qdim
+  bool pat_valid = false;
+  int64_t nnz = 0, generation = 0, nkept = 0;
+  gf::DevBuf<double> stage;      // ne x sr x sc element matrices, column-major, thresholded
+  gf::DevBuf<uint8_t> keep;      // ... and which entries the drop rule keeps
+  gf::DevBuf<uint32_t> perm;     // kept contributions sorted by (column, row), ascending element inside an entry
+  gf::DevBuf<uint32_t> seg;      // nnz + 1: entry -> range in perm
+  gf::DevBuf<int64_t> jc, jct;   // CSC of the block (ncols + 1) and of its transpose (nrows + 1)
+  gf::DevBuf<int32_t> ir, irt;
+  gf::DevBuf<double> pr, prt;
+  gf::DevBuf<uint32_t> tperm;    // entry k of the transpose = entry tperm[k] of the block
+};
+
 struct gfgpu_term {
   gfgpu_ctx *ctx;
   gfgpu_mesh *mesh;

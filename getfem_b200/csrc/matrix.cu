@@ -658,4 +658,17 @@ int gfgpu_term_residual_add_dev(gfgpu_term *t, double alpha, double *rhs_dev, in
   GFM_END
 }
 
+int gfgpu_matrix_add_rect(gfgpu_matrix *m, gfgpu_rect *r, int transposed, double alpha, int64_t row_off, int64_t col_off) {
+  GFM_BEGIN
+  GF_REQUIRE(m && r, "null argument");
+  GF_REQUIRE(m->ctx == r->ctx, "matrix and term live on different contexts");
+  GF_REQUIRE(r->pat_valid, "the coupled term has no assembled block");
+  const int64_t nr = transposed ? r->ncols : r->nrows, nc = transposed ? r->nrows : r->ncols;
+  GF_REQUIRE(row_off >= 0 && col_off >= 0 && row_off + nr <= m->nrows && col_off + nc <= m->ncols, "the block does not fit the matrix");
+  GF_CUDA(cudaSetDevice(m->ctx->device));
+  if (transposed) gf::mat_add(m, r->jct.p, r->irt.p, r->prt.p, nc, r->nnz, alpha, row_off, col_off);
+  else gf::mat_add(m, r->jc.p, r->ir.p, r->pr.p, nc, r->nnz, alpha, row_off, col_off);
+  GFM_END
+}
+
 }  // extern "C"

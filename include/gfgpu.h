@@ -263,6 +263,32 @@ int gfgpu_matrix_cg_dev(gfgpu_matrix *m, const double *b_dev, double *x_dev, dou
                         double *relres_out);
 int gfgpu_term_residual_add_dev(gfgpu_term *t, double alpha, double *rhs_dev, int64_t row_off);
 
+/* ---- coupled bilinear terms: Test on one fem (rows), Test2 on another (columns) -- the off-diagonal blocks of mixed
+ * formulations.  ga_workspace::assembly(2) adds an order-2 tree whose test functions belong to two variables into the block
+ * (interval of Test's variable) x (interval of Test2's variable), element matrix by element matrix through add_elem_matrix and
+ * its drop rule (C&E.cc:4853-4936, 5380-5402); the incompressibility bricks add "-p*Div_Test_u - Test_p*Div_u"
+ * (getfem_models.cc, add_linear_incompressibility).
+ *   create      both fems on `mesh`, both table sets at the SAME quadrature points (gfgpu_tables_create twice with the same
+ *               w / gt_grad).  GFGPU_RECT_DIV_PRESSURE: block(row (i,a), column j) = alpha * coef * int psi_j d(phi_i)/dx_a,
+ *               rows on a vector fem (qdim = mesh dimension), columns on a scalar fem.
+ *   assemble    element matrices, drop rule per element matrix, pattern on the first call (an entry exists iff one of its
+ *               contributions is kept), ordered sums; bitwise reproducible.
+ *   export      gmm::csc_matrix layout of the block (transposed == 0: nrows = row fem dofs) or of its transpose (the tree
+ *               with the test functions swapped).
+ *   mult        y = beta y + alpha B x (transposed == 0) or alpha B^T x: the residual parts R_u = B p, R_p = B^T u.
+ *   gfgpu_matrix_add_rect   K(row_off.., col_off..) += alpha * block (or its transpose), union pattern like add_term. */
+enum { GFGPU_RECT_DIV_PRESSURE = 0 };
+typedef struct gfgpu_rect gfgpu_rect;
+int gfgpu_rect_create(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem_rows, gfgpu_tables *tab_rows, gfgpu_fem *fem_cols,
+                      gfgpu_tables *tab_cols, int family, double coef, double alpha, gfgpu_rect **out);
+int gfgpu_rect_destroy(gfgpu_rect *r);
+int gfgpu_rect_assemble_dev(gfgpu_rect *r);
+int64_t gfgpu_rect_nnz(gfgpu_rect *r);
+int gfgpu_rect_export_csc_host(gfgpu_rect *r, int transposed, int64_t *jc_host, int32_t *ir_host, double *pr_host);
+int gfgpu_rect_mult_dev(gfgpu_rect *r, int transposed, double alpha, const double *x_dev, double beta, double *y_dev);
+int gfgpu_rect_mult_host(gfgpu_rect *r, int transposed, double alpha, const double *x_host, double beta, double *y_host);
+int gfgpu_matrix_add_rect(gfgpu_matrix *m, gfgpu_rect *r, int transposed, double alpha, int64_t row_off, int64_t col_off);
+
 /* ---- multi-GPU: element blocks per rank, column-owned CSC slabs, one halo exchange per assembly.
  * Replaces the reference's MPI scheme (per-rank partial matrices summed with MPI_SUM_SPARSE_MATRIX /
  * MPI_SUM_VECTOR, getfem_generic_assembly_workspace.cc:855-858, getfem_models.cc:586,2572,2608) by owned slabs:

@@ -146,3 +146,50 @@ def assemble(pts, conn, elem_dof, ndof, Q, w, gt_grad, phi, gphi, gt_linear, fam
     L.gfo_get_residual(h, _p(R))
     L.gfo_free(h)
     return jc, ir, pr, R
+
+
+def rect_div_pressure(pts, conn, edof_r, Qr, edof_c, quad_w, gt_grad, gphi_r, phi_c, coef=1.0):
+    """TEST INFRASTRUCTURE: numpy restatement of a coupled order-2 tree "-(Test2_p*Div_Test_u)" up to its sign and factor:
+    block(row (i,a), column j) = coef * int psi_j d(phi_i)/dx_a over every convex, element matrix by element matrix through
+    the reference's drop rule (|v| > 1e-14 max|E| per element matrix, C&E.cc:4889,4898,5380-5402; an entry is stored iff one
+    of its contributions is kept, sums in ascending convex order like add_elem_matrix, C&E.cc:4853-4936).
+    Geometry as ga_exec does it: K = G^T pc(q), J = |det K|, B = K^-T (bgeot_geometric_trans.cc:270-413).
+    Returns (jc, ir, pr) of the (ndof_r x ndof_c) block in gmm::csc_matrix layout."""
+    pts = np.asarray(pts, float)
+    ne, ng = conn.shape
+    N = pts.shape[1]
+    nq, ndr = gphi_r.shape[0], gphi_r.shape[1]
+    ndc = phi_c.shape[1]
+    nrows = int(edof_r.max()) + Qr
+    ncols = int(edof_c.max()) + 1
+    entries = {}
+    for e in range(ne):
+        G = pts[conn[e]]  # ng x N
+        E = np.zeros((ndr * Qr, ndc))
+        for q in range(nq):
+            if quad_w[q] == 0.0:
+                continue
+            K = G.T @ gt_grad[q]  # N x N
+            J = abs(np.linalg.det(K))
+            B = np.linalg.inv(K).T
+            dphi = gphi_r[q] @ B.T  # ndr x N : d phi_i / d x_a
+            for i in range(ndr):
+                for a in range(Qr):
+                    E[i * Qr + a, :] += quad_w[q] * J * dphi[i, a] * phi_c[q]
+        E *= coef
+        vmax = np.abs(E).max()
+        for i in range(ndr):
+            for a in range(Qr):
+                for j in range(ndc):
+                    v = E[i * Qr + a, j]
+                    if vmax != 0.0 and abs(v) > 1e-14 * vmax:
+                        key = (int(edof_c[e, j]), int(edof_r[e, i]) + a)
+                        entries[key] = entries.get(key, 0.0) + v
+    keys = sorted(entries)
+    jc = np.zeros(ncols + 1, np.int64)
+    for c, _ in keys:
+        jc[c + 1] += 1
+    jc = np.cumsum(jc)
+    ir = np.array([r for _, r in keys], np.int32)
+    pr = np.array([entries[k] for k in keys])
+    return jc, ir, pr
