@@ -40,6 +40,8 @@ static std::string strip(const std::string &s) {
 }
 
 static bool recognise_string(const getfem::ga_workspace &ws, const std::string &v, const std::string &s, recognised_term &out);
+static bool recognise_coupled(const getfem::ga_workspace &ws, const std::string &s0, int order, const std::string &test1,
+                              const std::string &test2, recognised_term &out);
 
 bool recognise_tree(const getfem::ga_workspace &ws, size_type itree, recognised_term &out) {
   const getfem::ga_workspace::tree_description &td = ws.tree_info(itree);
@@ -68,6 +70,7 @@ static bool recognise_sum(const getfem::ga_workspace &ws, const std::string &v, 
   const std::string s = strip_outer(s0);
   recognised_term rt;
   if (recognise_string(ws, v, s, rt) || recognise_string(ws, v, s0, rt)) { out.push_back(rt); return true; }
+  if (recognise_coupled(ws, s, 1, v, "", rt) || recognise_coupled(ws, s0, 1, v, "", rt)) { out.push_back(rt); return true; }
   int depth = 0;  // LAST top-level '+': add_tree builds ((A)+(B))+(C)
   size_t at = std::string::npos;
   for (size_t i = 0; i < s.size(); ++i) {
@@ -419,8 +422,67 @@ static bool recognise_by_probe(const getfem::ga_workspace &ws, size_type itree, 
   return false;
 }
 
+// COUPLED div-pressure parts, as the reference prints them after its semantic analysis (the incompressibility bricks add
+// "-p*Div_Test_u - Test_p*Div_u", getfem_models.cc add_linear_incompressibility; oracle/ref_coupled.cc prints the trees):
+//   order 2 (Test_u, Test2_p)  "(-Test2_p)*Div_Test_u"     order 2 (Test_p, Test2_u)  "-(Test_p*Div_Test2_u)"
+//   order 1  Test_u            "(-p)*Div_Test_u"           order 1  Test_p            "-(Test_p*Div_u)"
+// and the same without the minus signs.  u must be a vector fem variable of the mesh dimension, p a scalar one.
+static bool recognise_coupled(const getfem::ga_workspace &ws, const std::string &s0, int order, const std::string &test1,
+                              const std::string &test2, recognised_term &out) {
+  const std::string s = strip_outer(s0), ID = "([A-Za-z_][A-Za-z_0-9]*)";
+  std::smatch m;
+  // capture 1 = the scalar variable (A), capture 2 = the vector variable (B)
+  std::string A, B;
+  bool found = false;
+  if (order == 2) {
+    const std::vector<std::pair<std::string, double>> fu = {{"\\(-Test2_" + ID + "\\)\\*Div_Test_" + ID, -1.0},
+                                                            {"-\\(Test2_" + ID + "\\*Div_Test_" + ID + "\\)", -1.0},
+                                                            {"Test2_" + ID + "\\*Div_Test_" + ID, 1.0}};
+    const std::vector<std::pair<std::string, double>> fp = {{"-\\(Test_" + ID + "\\*Div_Test2_" + ID + "\\)", -1.0},
+                                                            {"\\(-Test_" + ID + "\\)\\*Div_Test2_" + ID, -1.0},
+                                                            {"Test_" + ID + "\\*Div_Test2_" + ID, 1.0}};
+    for (const auto &f : fu)
+      if (!found && std::regex_match(s, m, std::regex(f.first))) { A = m[1]; B = m[2]; out.sign = f.second; out.transposed = false; found = true; }
+    for (const auto &f : fp)
+      if (!found && std::regex_match(s, m, std::regex(f.first))) { A = m[1]; B = m[2]; out.sign = f.second; out.transposed = true; found = true; }
+    if (!found) return false;
+    if (out.transposed ? (test1 != A || test2 != B) : (test1 != B || test2 != A)) return false;
+  } else {
+    const std::vector<std::pair<std::string, double>> fu = {{"\\(-" + ID + "\\)\\*Div_Test_" + ID, -1.0},
+                                                            {"-\\(" + ID + "\\*Div_Test_" + ID + "\\)", -1.0},
+                                                            {ID + "\\*Div_Test_" + ID, 1.0}};
+    const std::vector<std::pair<std::string, double>> fp = {{"-\\(Test_" + ID + "\\*Div_" + ID + "\\)", -1.0},
+                                                            {"\\(-Test_" + ID + "\\)\\*Div_" + ID, -1.0},
+                                                            {"Test_" + ID + "\\*Div_" + ID, 1.0}};
+    for (const auto &f : fu)
+      if (!found && std::regex_match(s, m, std::regex(f.first))) { A = m[1]; B = m[2]; out.sign = f.second; out.transposed = false; found = true; }
+    for (const auto &f : fp)
+      if (!found && std::regex_match(s, m, std::regex(f.first))) { A = m[1]; B = m[2]; out.sign = f.second; out.transposed = true; found = true; }
+    if (!found) return false;
+    if (test1 != (out.transposed ? A : B)) return false;
+  }
+  if (A == B || !ws.variable_exists(A) || !ws.variable_exists(B) || ws.is_constant(A) || ws.is_constant(B)) return false;
+  const getfem::mesh_fem *mfp = ws.associated_mf(A), *mfu = ws.associated_mf(B);
+  if (!mfp || !mfu || &mfp->linked_mesh() != &mfu->linked_mesh()) return false;
+  if (mfp->get_qdim() != 1 || mfu->get_qdim() != mfu->linked_mesh().dim()) return false;
+  out.family = GFGPU_SHIM_COUPLED_DIV;
+  out.varname = test1;
+  out.varname_u = B;
+  out.varname_p = A;
+  out.params.clear();
+  out.field_names.clear();
+  return true;
+}
+
 bool recognise_tree_sum(const getfem::ga_workspace &ws, size_type itree, std::vector<recognised_term> &out) {
   const getfem::ga_workspace::tree_description &td = ws.tree_info(itree);
+  if (td.order == 2 && td.operation == getfem::ga_workspace::ASSEMBLY && td.name_test1 != td.name_test2) {
+    recognised_term rt;
+    out.clear();
+    if (!recognise_coupled(ws, strip(getfem::ga_tree_to_string(*td.ptree)), 2, td.name_test1, td.name_test2, rt)) return false;
+    out.push_back(rt);
+    return true;
+  }
   if (td.order == 2 && td.operation == getfem::ga_workspace::ASSEMBLY && td.name_test1 == td.name_test2) {
     recognised_term rt;
     out.clear();
@@ -440,7 +502,8 @@ bool recognise_tree_sum(const getfem::ga_workspace &ws, size_type itree, std::ve
     return true;
   }
   size_t bilinear = 0;
-  for (const recognised_term &rt : out) bilinear += rt.family != GFGPU_SOURCE && rt.family != GFGPU_NORMAL_SOURCE;
+  for (const recognised_term &rt : out)
+    bilinear += rt.family != GFGPU_SOURCE && rt.family != GFGPU_NORMAL_SOURCE && rt.family != GFGPU_SHIM_COUPLED_DIV;
   GMM_ASSERT1(bilinear <= 1, "gfgpu: several bilinear forms summed on one region are thresholded together by the reference "
                              "(C&E.cc:4889); give them distinct regions or one expression family");
   return true;
@@ -570,6 +633,25 @@ struct device_assembler::grouping {
   std::vector<std::vector<size_type>> groups;
 };
 
+// device side of a coupled term: one mesh, the two fems and their tables at the integration method's points, the block
+struct device_assembler::rect_entry {
+  context_watcher watch;
+  gfgpu_mesh *mesh = nullptr;
+  gfgpu_fem *fu = nullptr, *fp = nullptr;
+  gfgpu_tables *tu = nullptr, *tp = nullptr;
+  gfgpu_rect *rect = nullptr;
+  bool assembled = false;
+  size_type nu = 0, np = 0;
+  ~rect_entry() {
+    gfgpu_rect_destroy(rect);
+    gfgpu_tables_destroy(tu);
+    gfgpu_tables_destroy(tp);
+    gfgpu_fem_destroy(fu);
+    gfgpu_fem_destroy(fp);
+    gfgpu_mesh_destroy(mesh);
+  }
+};
+
 struct device_assembler::entry {
   context_watcher watch;
   uint64_t last_use = 0;
@@ -604,6 +686,7 @@ device_assembler::device_assembler(int device) { GFGPU_CALL(gfgpu_ctx_create(dev
 device_assembler::~device_assembler() {
   tangent_.reset();
   cache_.clear();
+  rect_cache_.clear();
   gfgpu_ctx_destroy(ctx_);
 }
 
@@ -683,6 +766,98 @@ static bool recognise_potential(const getfem::ga_workspace &ws, size_type itree,
   return false;
 }
 
+// Device objects of a coupled div-pressure term between the vector variable `vu` and the scalar variable `vp` (same mesh,
+// one classical Lagrange fem each on every convex, one approximate integration method), created once and watched through
+// GetFEM's context_dependencies like every other cached entry.
+device_assembler::rect_entry &device_assembler::coupled_entry(getfem::ga_workspace &ws, const getfem::mesh_im &mim,
+                                                             const std::string &vu, const std::string &vp) {
+  const getfem::mesh_fem *pmu = ws.associated_mf(vu), *pmp = ws.associated_mf(vp);
+  GMM_ASSERT1(pmu && pmp && !pmu->is_reduced() && !pmp->is_reduced(), "gfgpu: coupled terms need two non-reduced fem variables");
+  const getfem::mesh_fem &mfu = *pmu, &mfp = *pmp;
+  const getfem::mesh &m = mfu.linked_mesh();
+  GMM_ASSERT1(&mfp.linked_mesh() == &m && &mim.linked_mesh() == &m, "gfgpu: coupled variables must share the mesh");
+  std::ostringstream key;
+  key << &m << "/" << &mfu << "/" << &mfp << "/" << &mim << "/" << mfu.nb_dof() << "/" << mfp.nb_dof();
+  std::unique_ptr<rect_entry> &pe = rect_cache_[key.str()];
+  if (pe && !pe->watch.still_valid()) pe.reset();
+  if (pe) return *pe;
+  if (rect_cache_.size() > 8) {
+    for (auto jt = rect_cache_.begin(); jt != rect_cache_.end();) jt = (&jt->second == &pe) ? std::next(jt) : rect_cache_.erase(jt);
+  }
+  pe.reset(new rect_entry);
+  rect_entry &e = *pe;
+  e.watch.add_dependency(m);
+  e.watch.add_dependency(mfu);
+  e.watch.add_dependency(mfp);
+  e.watch.add_dependency(mim);
+  const size_type ne = m.convex_index().card();
+  GMM_ASSERT1(ne > 0 && ne == m.convex_index().last_true() + 1, "gfgpu: convex ids must be contiguous (call mesh::optimize_structure)");
+  const size_type cv0 = 0;
+  getfem::pfem pfu = mfu.fem_of_element(cv0), pfp = mfp.fem_of_element(cv0);
+  bgeot::pgeometric_trans pgt = m.trans_of_convex(cv0);
+  getfem::pintegration_method pim = mim.int_method_of_element(cv0);
+  for (size_type cv = 0; cv < ne; ++cv)
+    GMM_ASSERT1(mfu.convex_index().is_in(cv) && mfp.convex_index().is_in(cv) && mim.convex_index().is_in(cv) &&
+                    mfu.fem_of_element(cv) == pfu && mfp.fem_of_element(cv) == pfp && m.trans_of_convex(cv) == pgt &&
+                    mim.int_method_of_element(cv) == pim,
+                "gfgpu: coupled terms are handled on uniform meshes (one fem per variable, one integration method)");
+  GMM_ASSERT1(pim->type() == getfem::IM_APPROX, "gfgpu: exact integration methods are not handled");
+  bool uqk, pqk, gqk;
+  int udim, udeg, pdim, pdeg, gdim, gdeg;
+  GMM_ASSERT1(parse_kind(getfem::name_of_fem(pfu), "FEM", uqk, udim, udeg) && parse_kind(getfem::name_of_fem(pfp), "FEM", pqk, pdim, pdeg),
+              "gfgpu: fem not handled: " << getfem::name_of_fem(pfu) << " / " << getfem::name_of_fem(pfp));
+  GMM_ASSERT1(parse_kind(bgeot::name_of_geometric_trans(pgt), "GT", gqk, gdim, gdeg) && gdeg == 1 && gqk == uqk && gqk == pqk,
+              "gfgpu: geometric transformation not handled: " << bgeot::name_of_geometric_trans(pgt));
+  const int dim = int(m.dim());
+  const size_type ndu = pfu->nb_dof(cv0), ndp = pfp->nb_dof(cv0), ng = pgt->nb_points();
+  getfem::papprox_integration pai = pim->approx_method();
+  const size_type nq = pai->nb_points_on_convex();
+  e.nu = mfu.nb_dof();
+  e.np = mfp.nb_dof();
+  const size_type npts = m.points_index().last_true() + 1;
+  std::vector<double> pts(npts * dim, 0.0);
+  for (dal::bv_visitor p(m.points_index()); !p.finished(); ++p)
+    for (int d = 0; d < dim; ++d) pts[p * dim + d] = m.points()[p][d];
+  std::vector<int32_t> conn(ne * ng);
+  std::vector<int64_t> edu(ne * ndu), edp(ne * ndp);
+  for (size_type cv = 0; cv < ne; ++cv) {
+    for (size_type i = 0; i < ng; ++i) conn[cv * ng + i] = int32_t(m.ind_points_of_convex(cv)[i]);
+    const auto &cu = mfu.ind_scalar_basic_dof_of_element(cv);
+    for (size_type i = 0; i < ndu; ++i) edu[cv * ndu + i] = int64_t(cu[i]);
+    const auto &cp = mfp.ind_scalar_basic_dof_of_element(cv);
+    for (size_type i = 0; i < ndp; ++i) edp[cv * ndp + i] = int64_t(cp[i]);
+  }
+  bgeot::pstored_point_tab pspt = pai->pintegration_points();
+  bgeot::pgeotrans_precomp pgp = bgeot::geotrans_precomp(pgt, pspt, 0);
+  std::vector<double> w(nq), gtg(nq * ng * dim);
+  for (size_type q = 0; q < nq; ++q) {
+    w[q] = pai->coeff(q);
+    const bgeot::base_matrix &pc = pgp->grad(q);
+    for (size_type i = 0; i < ng; ++i)
+      for (int d = 0; d < dim; ++d) gtg[(q * ng + i) * dim + d] = pc(i, d);
+  }
+  auto tables = [&](getfem::pfem pf, size_type nd, gfgpu_tables **out) {
+    getfem::pfem_precomp pfp2 = getfem::fem_precomp(pf, pspt, 0);
+    std::vector<double> phi(nq * nd), gphi(nq * nd * dim);
+    for (size_type q = 0; q < nq; ++q) {
+      const bgeot::base_tensor &bv = pfp2->val(q), &bg = pfp2->grad(q);
+      for (size_type i = 0; i < nd; ++i) {
+        phi[q * nd + i] = bv[i];
+        for (int d = 0; d < dim; ++d) gphi[(q * nd + i) * dim + d] = bg[i + nd * d];
+      }
+    }
+    GFGPU_CALL(gfgpu_tables_create(ctx_, dim, int(nq), int(ng), int(nd), w.data(), gtg.data(), phi.data(), gphi.data(), out));
+  };
+  GFGPU_CALL(gfgpu_mesh_create(ctx_, dim, int64_t(npts), pts.data(), int64_t(ne), int(ng), conn.data(), gqk ? GFGPU_GT_QK : GFGPU_GT_PK,
+                               &e.mesh));
+  GFGPU_CALL(gfgpu_fem_create(ctx_, e.mesh, uqk ? GFGPU_FEM_QK : GFGPU_FEM_PK, udeg, dim, int(ndu), edu.data(), int64_t(e.nu), &e.fu));
+  GFGPU_CALL(gfgpu_fem_create(ctx_, e.mesh, pqk ? GFGPU_FEM_QK : GFGPU_FEM_PK, pdeg, 1, int(ndp), edp.data(), int64_t(e.np), &e.fp));
+  tables(pfu, ndu, &e.tu);
+  tables(pfp, ndp, &e.tp);
+  GFGPU_CALL(gfgpu_rect_create(ctx_, e.mesh, e.fu, e.tu, e.fp, e.tp, GFGPU_RECT_DIV_PRESSURE, 1.0, 1.0, &e.rect));
+  return e;
+}
+
 // What a recognition result depends on, as a string: the printed tree, where it is integrated, and for every name the
 // tree mentions that the workspace knows -- a variable: its mesh_fem and interval; a fixed-size constant: its values bit
 // for bit; fem / im data: the object it lives on (the values travel at every call anyway).
@@ -758,9 +933,17 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     }
     if (td.order == 0) continue;
     GMM_ASSERT1(td.operation == getfem::ga_workspace::ASSEMBLY, "gfgpu: assignments are not handled");
+    if (td.order == 2 && td.name_test1 != td.name_test2) {
+      // a coupled tree: the block (interval of Test's variable) x (interval of Test2's variable)
+      if (order != 2) continue;
+      std::vector<recognised_term> rc;
+      GMM_ASSERT1(recognise_memo(i, rc), "gfgpu: coupled term (" << td.name_test1 << ", " << td.name_test2
+                                             << ") not handled by the device path (no CPU fallback): "
+                                             << getfem::ga_tree_to_string(*td.ptree));
+      for (const recognised_term &rt : rc) terms.emplace_back(i, rt);
+      continue;
+    }
     if (td.order == 2) {
-      GMM_ASSERT1(td.name_test1 == td.name_test2, "gfgpu: coupled terms (" << td.name_test1 << ", " << td.name_test2
-                                                                           << ") are not handled by the device path");
       // the derivative of an order-1 tree of the same (mim, region, variable) -- or a bilinear form written directly
       // with Test_ / Test2_ (the asm_* wrappers)
       size_type i1 = size_type(-1);
@@ -776,7 +959,8 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
                                                         << getfem::ga_tree_to_string(*ws.tree_info(i1).ptree));
         if (r1.size() == 1 && r1[0].by_probe) continue;  // the probe checked K against THIS tree and r = K u against the order-1 tree
         size_t nsrc = 0;
-        for (const recognised_term &rt : r1) nsrc += rt.family == GFGPU_SOURCE || rt.family == GFGPU_NORMAL_SOURCE;
+        for (const recognised_term &rt : r1)  // (a coupled residual part has no derivative with respect to its own test variable)
+          nsrc += rt.family == GFGPU_SOURCE || rt.family == GFGPU_NORMAL_SOURCE || rt.family == GFGPU_SHIM_COUPLED_DIV;
         const size_t n1 = count_top_level_summands(strip(getfem::ga_tree_to_string(*ws.tree_info(i1).ptree)));
         const size_t n2 = count_top_level_summands(strip(getfem::ga_tree_to_string(*td.ptree)));
         GMM_ASSERT1(n2 + nsrc == n1, "gfgpu: a tangent tree that mixes derived and directly written terms is not handled: "
@@ -799,6 +983,8 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
       has_derivative = t2.order == 2 && t2.mim == td.mim && t2.rg == td.rg && t2.name_test1 == td.name_test1;
     }
     for (recognised_term &rt : rts) {
+      // the coupled part of a residual has its tangent in the order-2 trees of the OTHER variable pair (handled above)
+      if (rt.family == GFGPU_SHIM_COUPLED_DIV && order == 2) continue;
       rt.no_tangent = order == 2 && !has_derivative;
       terms.emplace_back(i, rt);
     }
@@ -827,16 +1013,19 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
   // intervals (gfgpu_matrix_*), downloaded once
   size_type need_all = nprim;
   for (auto &it : terms) {
-    const getfem::mesh_fem *pmf = ws.associated_mf(it.second.varname);
-    GMM_ASSERT1(pmf, "gfgpu: the variable must be a fem variable");
-    need_all = std::max<size_type>(need_all, ws.interval_of_variable(it.second.varname).first() + pmf->nb_dof());
+    for (const std::string &vn : {it.second.varname, it.second.varname_u, it.second.varname_p}) {
+      if (vn.empty()) continue;
+      const getfem::mesh_fem *pmf = ws.associated_mf(vn);
+      GMM_ASSERT1(pmf, "gfgpu: the variable must be a fem variable");
+      need_all = std::max<size_type>(need_all, ws.interval_of_variable(vn).first() + pmf->nb_dof());
+    }
   }
   // The workspace tangent lives on the device across calls (a Newton loop, a time loop): same size -> the matrix is
   // zeroed with its pattern kept, the terms are added again, and as long as gfgpu_matrix_pattern_generation does not move
   // only the VALUES come back to the host (jc / ir, 8.8 GB for BASELINE config 3, are downloaded once).
   struct { gfgpu_matrix *m = nullptr; } dK;
   std::string terms_sig;
-  struct pending_add { gfgpu_term *term; double alpha; int64_t off; };
+  struct pending_add { gfgpu_term *term; double alpha; int64_t off; gfgpu_rect *rect = nullptr; int transposed = 0; int64_t coff = 0; };
   std::vector<pending_add> pending_adds;
   if (order == 2) {
     if (tangent_ && tangent_->n != need_all) tangent_.reset();
@@ -851,6 +1040,48 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
   for (auto &it : terms) {
     const auto &td = ws.tree_info(it.first);
     const recognised_term &rt = it.second;
+    if (rt.family == GFGPU_SHIM_COUPLED_DIV) {
+      GMM_ASSERT1(td.rg && td.rg->id() == getfem::mesh_region::all_convexes().id(),
+                  "gfgpu: coupled terms are handled on the whole mesh (no region)");
+      GMM_ASSERT1(!(getfem::me_is_multithreaded_now() && getfem::partition_master::get().get_nb_partitions() > 1) ||
+                      getfem::partition_master::get().get_current_partition() == 0, "gfgpu: internal error (partition)");
+      rect_entry &re = coupled_entry(ws, *td.mim, rt.varname_u, rt.varname_p);
+      const gmm::sub_interval &Iu = ws.interval_of_variable(rt.varname_u), &Ip = ws.interval_of_variable(rt.varname_p);
+      double t1 = now_s();
+      t_extract += t1 - t0;
+      if (!re.assembled) {  // a constant-coefficient linear block: its values never change
+        GFGPU_CALL(gfgpu_rect_assemble_dev(re.rect));
+        re.assembled = true;
+      }
+      if (order == 2) {
+        // rows = Test's variable, columns = Test2's: (u, p) is the block, (p, u) its transpose
+        const int64_t roff = int64_t(rt.transposed ? Ip.first() : Iu.first()), coff = int64_t(rt.transposed ? Iu.first() : Ip.first());
+        pending_add pa{nullptr, rt.sign * ws.factor_of_variable(rt.varname_u) * ws.factor_of_variable(rt.varname_p), roff};
+        pa.rect = re.rect; pa.transposed = rt.transposed ? 1 : 0; pa.coff = coff;
+        std::ostringstream sg;
+        sg << "rect" << (const void *)re.rect << (rt.transposed ? "T" : "N") << "@" << roff << "," << coff << "*" << rt.sign << ";";
+        terms_sig += sg.str();
+        pending_adds.push_back(pa);
+        ++n_added;
+        t_device += now_s() - t1;
+      } else if (order == 1) {
+        // residual parts: sign * B p into u's interval, sign * B^T u into p's
+        const getfem::model_real_plain_vector &X = ws.value(rt.transposed ? rt.varname_u : rt.varname_p);
+        const size_type nout = rt.transposed ? re.np : re.nu;
+        GMM_ASSERT1(X.size() == (rt.transposed ? re.nu : re.np), "gfgpu: bad size of a coupled variable's value vector");
+        std::vector<double> y(nout, 0.0);
+        GFGPU_CALL(gfgpu_rect_mult_host(re.rect, rt.transposed ? 1 : 0, rt.sign, X.data(), 0.0, y.data()));
+        double t2 = now_s();
+        t_device += t2 - t1;
+        const size_type off = rt.transposed ? Ip.first() : Iu.first();
+        getfem::base_vector &V = ws.assembled_vector();
+        if (V.size() < off + nout) V.resize(std::max<size_type>(nprim, off + nout), 0.0);
+        for (size_type d = 0; d < nout; ++d) V[off + d] += y[d];
+        t_fill += now_s() - t2;
+      }
+      t0 = now_s();
+      continue;
+    }
     const getfem::mesh_fem *pmf = ws.associated_mf(rt.varname);
     GMM_ASSERT1(pmf && !pmf->is_reduced(), "gfgpu: the variable must live on a non-reduced mesh_fem");
     const getfem::mesh_fem &mf = *pmf;
@@ -1145,7 +1376,7 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
       GFGPU_CALL(gfgpu_term_assemble_host(e.term, U.data(), GFGPU_TANGENT, nullptr, nullptr));
       const double alpha = ws.factor_of_variable(rt.varname);  // alpha1 * alpha2 of the matrix assembly instructions
       terms_sig += key.str() + "@" + std::to_string(I.first()) + ";";
-      pending_adds.push_back({e.term, alpha * alpha, int64_t(I.first())});
+      pending_adds.push_back(pending_add{e.term, alpha * alpha, int64_t(I.first())});
       ++n_added;
       t_device += now_s() - t1;
     }
@@ -1163,7 +1394,13 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     // same terms at the same places as last time: zero the values, keep the pattern (and the host copy of jc / ir)
     GFGPU_CALL(gfgpu_matrix_clear(tc.m, tc.sig == terms_sig ? 1 : 0));
     if (tc.sig != terms_sig) { tc.sig = terms_sig; tc.gen = -1; }
-    for (const pending_add &pa : pending_adds) GFGPU_CALL(gfgpu_matrix_add_term(tc.m, pa.term, pa.alpha, pa.off, pa.off));
+    for (const pending_add &pa : pending_adds) {
+      if (pa.rect) {
+        GFGPU_CALL(gfgpu_matrix_add_rect(tc.m, pa.rect, pa.transposed, pa.alpha, pa.off, pa.coff));
+      } else {
+        GFGPU_CALL(gfgpu_matrix_add_term(tc.m, pa.term, pa.alpha, pa.off, pa.off));
+      }
+    }
     const int64_t nnz = gfgpu_matrix_nnz(tc.m);
     tc.pr.resize((size_t)nnz);
     if (tc.gen != gfgpu_matrix_pattern_generation(tc.m) || tc.ir.size() != (size_t)nnz) {

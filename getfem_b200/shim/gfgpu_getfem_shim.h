@@ -29,7 +29,15 @@ struct recognised_term {
   // assembly(2) on a workspace whose expression was added WITHOUT derivative trees (add_expression(.., order 1)): the reference
   // assembles the order-2 trees that exist and nothing else, so this order-1 term must not contribute its family's tangent
   bool no_tangent = false;
+  // COUPLED div-pressure parts (family GFGPU_SHIM_COUPLED_DIV, a shim-level tag): the block B(row dof of the vector variable
+  // `varname_u`, column dof of the scalar variable `varname_p`) = int psi_p div(phi_u), with factor `sign`.
+  //   order 2: `transposed` = false for the tree (Test_u, Test2_p), true for (Test_p, Test2_u);
+  //   order 1: `transposed` = false for the residual part of u, sign * B p; true for the part of p, sign * B^T u.
+  std::string varname_u, varname_p;
+  bool transposed = false;
+  double sign = 1.0;
 };
+enum { GFGPU_SHIM_COUPLED_DIV = 1000 };
 
 // Matches the ORDER-1 tree of `ws` number `itree` (as printed by ga_tree_to_string after the
 // reference's semantic analysis) against the families of include/gfgpu.h.  Returns false if unknown.
@@ -65,11 +73,14 @@ class device_assembler {
 
  private:
   struct entry;
+  struct rect_entry;
   struct grouping;
   struct tangent_cache;
   std::unique_ptr<tangent_cache> tangent_;  // the workspace tangent, resident on the device between calls
   gfgpu_ctx *ctx_ = nullptr;
   std::map<std::string, std::unique_ptr<entry>> cache_;  // bounded (LRU); entries die with the getfem objects they mirror
+  std::map<std::string, std::unique_ptr<rect_entry>> rect_cache_;  // coupled terms: two fems on one mesh
+  rect_entry &coupled_entry(getfem::ga_workspace &ws, const getfem::mesh_im &mim, const std::string &vu, const std::string &vp);
   std::map<std::string, std::pair<bool, std::vector<recognised_term>>> recognised_;  // recognition results across calls
   std::map<std::string, std::unique_ptr<grouping>> groupings_;  // convex groups per (mesh, mesh_fem, mesh_im)
   uint64_t use_clock_ = 0;

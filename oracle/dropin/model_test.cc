@@ -61,6 +61,8 @@ int main(int argc, char **argv) {
   mim.set_integration_method(getfem::dim_type(qk ? 2 * K + 2 : 2 * K));
   getfem::mesh_fem mf_d(m, 1);  // fem data: heterogeneous coefficient
   mf_d.set_classical_finite_element(1);
+  getfem::mesh_fem mf_p(m, 1);  // pressure of the mixed formulation
+  mf_p.set_classical_finite_element(getfem::dim_type(K > 1 ? K - 1 : 1));
 
   if (kind == "expr") {
     // one bilinear form written directly with Test_ / Test2_, in any of the algebraically equivalent spellings of the
@@ -79,12 +81,20 @@ int main(int argc, char **argv) {
         if (nz < 0 || long(k) < nz) U[k] = 0.0;
     }
     std::vector<double> Vr, Vg, C0(mf_d.nb_dof(), 1.0), PARAMS{1.3, 0.7};
+    const bool with_p = geti("pvar", 0) != 0;
+    std::vector<double> Pv(mf_p.nb_dof());
+    {
+      std::mt19937_64 rng(7);
+      std::uniform_real_distribution<double> dist(-1.0, 1.0);
+      for (auto &x : Pv) x = dist(rng);
+    }
     double Er = 0, Eg = 0;
     C0.back() = 5.0;
     auto run = [&](bool device, gmm::csc_matrix<double> &C) {
       getfem_b200::gfgpu_enable(device);
       getfem::ga_workspace ws;
       ws.add_fem_variable("u", mf, gmm::sub_interval(0, mf.nb_dof()), U);
+      if (with_p) ws.add_fem_variable("p", mf_p, gmm::sub_interval(mf.nb_dof(), mf_p.nb_dof()), Pv);  // mixed forms
       ws.add_fixed_size_constant("lambda", LAMBDA);
       ws.add_fixed_size_constant("mu", MU);
       ws.add_fixed_size_constant("a", A);
@@ -92,7 +102,8 @@ int main(int argc, char **argv) {
       ws.add_fem_constant("c0", mf_d, C0);  // a material that is 1 on the first convexes and 5 in a far corner
       if (a.count("region")) ws.add_expression(expr, mim, m.region(size_type(geti("region", 1))));
       else ws.add_expression(expr, mim);
-      getfem::model_real_sparse_matrix M(mf.nb_dof(), mf.nb_dof());
+      const size_type ntot = mf.nb_dof() + (with_p ? mf_p.nb_dof() : 0);
+      getfem::model_real_sparse_matrix M(ntot, ntot);
       ws.set_assembled_matrix(M);
       ws.assembly(2);
       C.init_with(M);
@@ -254,10 +265,21 @@ int main(int argc, char **argv) {
   md.add_initialized_fixed_size_data("F", F);
   md.add_initialized_fixed_size_data("G", G);
   md.add_initialized_scalar_data("robin", 7.5);
-  if (kind == "elasticity") {
-    md.add_initialized_scalar_data("lambda", 1.3);
+  if (kind == "elasticity" || kind == "incompressible") {
+    md.add_initialized_scalar_data("lambda", kind == "incompressible" ? 0.0 : 1.3);
     md.add_initialized_scalar_data("mu", 0.7);
     getfem::add_isotropic_linearized_elasticity_brick(md, mim, "u", "lambda", "mu");
+    if (kind == "incompressible") {
+      // mixed formulation: a pressure on a scalar fem of one degree less, coupled trees (Test_u, Test2_p) and (Test_p, Test2_u)
+      // (add_linear_incompressibility, getfem_models.cc:6373-6409: "-p*Div_Test_u-Test_p*Div_u")
+      md.add_fem_variable("p", mf_p);
+      std::vector<double> P(mf_p.nb_dof());
+      std::mt19937_64 rng(99);
+      std::uniform_real_distribution<double> dist(-1.0, 1.0);
+      for (auto &v : P) v = dist(rng);
+      gmm::copy(P, md.set_real_variable("p"));
+      getfem::add_linear_incompressibility(md, mim, "u", "p");
+    }
   } else if (kind == "poisson") {
     std::vector<double> A(mf_d.nb_dof());
     for (size_type d = 0; d < mf_d.nb_dof(); ++d) {

@@ -28,6 +28,12 @@ CASES = [
     "model=poisson dim=3 n=3 gt=qk k=2",
     "model=finite_strain dim=3 n=3 gt=pk k=2",
     "model=finite_strain dim=3 n=3 gt=qk k=2",
+    # mixed formulation: add_linear_incompressibility (getfem_models.cc:6373-6409) -- coupled trees (Test_u, Test2_p) and
+    # (Test_p, Test2_u) go to the device as one rectangular block and its transpose (gfgpu_rect_*)
+    "model=incompressible dim=3 n=3 gt=pk k=2",
+    "model=incompressible dim=2 n=8 gt=pk k=2",
+    "model=incompressible dim=3 n=2 gt=qk k=2",
+    "model=incompressible dim=3 n=2 gt=pk k=3",
 ]
 
 
@@ -125,3 +131,27 @@ def test_potentials_run_on_the_device(mesh, expr):
     assert r["device_workspace_calls"] >= 3, r
     assert r["pattern_ok"] and r["rel_K"] < 1e-12 and r["rel_V"] < 1e-12, r
     assert r["E_ref"] != 0 and abs(r["E_gpu"] - r["E_ref"]) <= 1e-12 * abs(r["E_ref"]), r
+
+
+COUPLED = [  # workspaces with two fem variables: u (vector, degree k) and p (scalar, degree k - 1), model_test pvar=1
+    ("dim=3 n=3 gt=pk k=2", "-p*Div_Test_u - Test_p*Div_u"),
+    ("dim=2 n=6 gt=qk k=2", "p*Div_Test_u + Test_p*Div_u"),
+    ("dim=3 n=2 gt=qk k=2", "-p*Div_Test_u - Test_p*Div_u"),
+    # the mixed part summed with a bilinear form of u in ONE expression: the order-1 tree of u is "(elasticity)+((-p)*Div_Test_u)"
+    ("dim=3 n=3 gt=pk k=2", "lambda*Div_u*Div_Test_u + mu*(Grad_u+Grad_u'):Grad_Test_u - p*Div_Test_u - Test_p*Div_u"),
+    ("dim=2 n=8 gt=pk k=2", "mu*Grad_u:Grad_Test_u - p*Div_Test_u - Test_p*Div_u"),  # Stokes
+]
+
+
+@pytest.mark.parametrize("mesh,expr", COUPLED)
+def test_coupled_trees_run_on_the_device(mesh, expr):
+    """Mixed formulations: the trees (Test_u, Test2_p) and (Test_p, Test2_u) are one rectangular block and its transpose on the
+    device (gfgpu_rect_*), their residual parts B p and B^T u; workspace matrix pattern identical, values and residual 1e-12."""
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN, "model=expr", "pvar=1"] + mesh.split() + ["expr=" + expr], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["device_workspace_calls"] >= 2, r
+    assert r["pattern_ok"] and r["nnz_ref"] == r["nnz_gpu"], r
+    assert 0 <= r["rel_K"] < 1e-12 and r["rel_V"] < 1e-12 and r["norm_V"] > 0, r

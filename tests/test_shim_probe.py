@@ -196,3 +196,18 @@ def test_a_load_written_with_the_unknown_is_not_a_constant_load():
     lines = [l for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun] order")]
     # u*Test_u has a derivative tree (mass), so it is the derived route: recognised as MASS with r = M u checked, never as a load
     assert lines and not any("recognised family 6" in l for l in lines), out.stderr[-1500:]
+
+
+def test_coupled_trees_of_the_incompressibility_brick_are_recognised():
+    """CPU (dry run of the dispatch patch): the four trees of "-p*Div_Test_u-Test_p*Div_u" as the reference prints them are
+    matched as coupled div-pressure parts (shim tag 1000); nothing is left to the "not recognised" path."""
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN, "model=incompressible", "dim=3", "n=2", "gt=pk", "k=2"], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, GFGPU_DRYRUN="1"))
+    assert out.returncode == 0, out.stderr[-1500:]
+    lines = [l for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun]")]
+    assert not [l for l in lines if "NOT recognised" in l], lines
+    coupled = [l for l in lines if "family 1000" in l]
+    forms = {l.split(": ", 1)[1].split(" -> ")[0] for l in coupled}
+    assert forms == {"-(Test_p*Div_u)", "-(Test_p*Div_Test2_u)", "(-p)*Div_Test_u", "(-Test2_p)*Div_Test_u"}, forms
