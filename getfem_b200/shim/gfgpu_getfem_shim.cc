@@ -4,6 +4,7 @@
 #include <omp.h>
 #endif
 
+#include <cctype>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -71,14 +72,18 @@ static bool recognise_sum(const getfem::ga_workspace &ws, const std::string &v, 
   recognised_term rt;
   if (recognise_string(ws, v, s, rt) || recognise_string(ws, v, s0, rt)) { out.push_back(rt); return true; }
   if (recognise_coupled(ws, s, 1, v, "", rt) || recognise_coupled(ws, s0, 1, v, "", rt)) { out.push_back(rt); return true; }
-  int depth = 0;  // LAST top-level '+': add_tree builds ((A)+(B))+(C)
+  int depth = 0;  // LAST top-level '+' or binary '-': add_tree builds ((A)+(B))+(C), a written "A - B" prints as (A)-(B)
   size_t at = std::string::npos;
   for (size_t i = 0; i < s.size(); ++i) {
     if (s[i] == '(' || s[i] == '[') ++depth;
     else if (s[i] == ')' || s[i] == ']') --depth;
     else if (s[i] == '+' && depth == 0 && i > 0) at = i;
+    else if (s[i] == '-' && depth == 0 && i > 0 && (s[i - 1] == ')' || s[i - 1] == ']' || std::isalnum((unsigned char)s[i - 1]) || s[i - 1] == '_'))
+      at = i;
   }
   if (at == std::string::npos) return false;
+  if (s[at] == '-')  // X - Y = X + (-(Y)): the right part is recognised in its negated spelling
+    return recognise_sum(ws, v, s.substr(0, at), out) && recognise_sum(ws, v, "-(" + strip_outer(s.substr(at + 1)) + ")", out);
   return recognise_sum(ws, v, s.substr(0, at), out) && recognise_sum(ws, v, s.substr(at + 1), out);
 }
 
@@ -91,6 +96,8 @@ static size_t count_top_level_summands(const std::string &s0) {
     if (s[i] == '(' || s[i] == '[') ++depth;
     else if (s[i] == ')' || s[i] == ']') --depth;
     else if (s[i] == '+' && depth == 0 && i > 0) ++n;
+    else if (s[i] == '-' && depth == 0 && i > 0 && (s[i - 1] == ')' || s[i - 1] == ']' || std::isalnum((unsigned char)s[i - 1]) || s[i - 1] == '_'))
+      ++n;  // binary minus
   }
   return n;
 }
@@ -586,6 +593,14 @@ static bool recognise_string(const getfem::ga_workspace &ws, const std::string &
   }
   if (std::regex_match(s, m, std::regex("\\(\\(" + ID + "\\*Div_" + v + "\\)\\*Div_Test_" + v + "\\)\\+\\(\\(\\(2\\*" + ID +
                                         "\\)\\*\\(Sym\\(Grad_" + v + "\\)\\)\\):Grad_Test_" + v + "\\)"))) {
+    GMM_ASSERT1(ws.associated_mf(m[1]) || !ws.associated_mf(m[2]),
+                "gfgpu: a fem-data mu needs a fem-data lambda (fields replace the LEADING parameters)");
+    out.family = GFGPU_ELASTICITY; out.params = {scalar(m[1]), scalar(m[2])}; return true;
+  }
+  // "lambda*Div_u*Div_Test_u + mu*(Grad_u+Grad_u'):Grad_Test_u" (the spelling of the reference's tests, tests/test_assembly.cc:812):
+  // mu (grad u + grad u^T) : grad v = 2 mu eps(u) : grad v
+  if (std::regex_match(s, m, std::regex("\\(\\(" + ID + "\\*Div_" + v + "\\)\\*Div_Test_" + v + "\\)\\+\\(\\(" + ID + "\\*\\(Grad_" + v +
+                                        "\\+\\(Grad_" + v + "'\\)\\)\\):Grad_Test_" + v + "\\)"))) {
     GMM_ASSERT1(ws.associated_mf(m[1]) || !ws.associated_mf(m[2]),
                 "gfgpu: a fem-data mu needs a fem-data lambda (fields replace the LEADING parameters)");
     out.family = GFGPU_ELASTICITY; out.params = {scalar(m[1]), scalar(m[2])}; return true;
