@@ -18,6 +18,7 @@
 
 #include "getfem/getfem_fem.h"
 #include "getfem/getfem_generic_assembly_tree.h"
+#include "getfem/getfem_im_data.h"
 #include "getfem/getfem_integration.h"
 #include "getfem/getfem_mesh_fem.h"
 #include "getfem/getfem_mesh_im.h"
@@ -119,7 +120,7 @@ static bool recognise_order2_string(const getfem::ga_workspace &ws, const std::s
   out.field_sign = 1.0;
   auto coef = [&](const std::string &name) {
     GMM_ASSERT1(ws.is_constant(name), "gfgpu: '" << name << "' must be a constant");
-    if (ws.associated_mf(name)) { out.field_names.push_back(name); return 1.0; }
+    if (ws.associated_mf(name) || ws.associated_im_data(name)) { out.field_names.push_back(name); return 1.0; }  // fem data / im data: a field
     GMM_ASSERT1(ws.value(name).size() == 1, "gfgpu: '" << name << "' must be a scalar constant");
     return ws.value(name)[0];
   };
@@ -137,7 +138,7 @@ static bool recognise_order2_string(const getfem::ga_workspace &ws, const std::s
   }
   if (std::regex_match(s, m, std::regex("\\(\\(\\(" + ID + "\\*Div_" + T + "\\)\\*" + Idm + "\\)\\+\\(\\(2\\*" + ID +
                                         "\\)\\*\\(Sym\\(Grad_" + T + "\\)\\)\\)\\):Grad_" + T))) {
-    GMM_ASSERT1(ws.associated_mf(m[1]) || !ws.associated_mf(m[2]),
+    GMM_ASSERT1((ws.associated_mf(m[1]) || ws.associated_im_data(m[1])) || !(ws.associated_mf(m[2]) || ws.associated_im_data(m[2])),
                 "gfgpu: a fem-data mu needs a fem-data lambda (fields replace the LEADING parameters)");
     out.family = GFGPU_ELASTICITY; out.params = {coef(m[1]), coef(m[2])}; return true;
   }
@@ -527,7 +528,7 @@ static bool recognise_string(const getfem::ga_workspace &ws, const std::string &
   out.field_sign = 1.0;
   auto scalar = [&](const std::string &name) {
     GMM_ASSERT1(ws.is_constant(name), "gfgpu: '" << name << "' must be a constant");
-    if (ws.associated_mf(name)) {  // fem data: a field on its mesh_fem (add_fem_constant)
+    if (ws.associated_mf(name) || ws.associated_im_data(name)) {  // fem data (add_fem_constant) or im data (add_im_data): a field
       out.field_names.push_back(name);
       return 1.0;
     }
@@ -562,6 +563,13 @@ static bool recognise_string(const getfem::ga_workspace &ws, const std::string &
         out.params.assign(pmf->get_qdim(), 0.0);
         return true;
       }
+      if (const getfem::im_data *pid = ws.associated_im_data(name)) {  // the load stored per Gauss point
+        GMM_ASSERT1(pmf && pid->nb_tensor_elem() == pmf->get_qdim(), "gfgpu: the load's im_data must have qdim components");
+        out.field_names.push_back(name);
+        out.field_sign = sign;
+        out.params.assign(pmf->get_qdim(), 0.0);
+        return true;
+      }
       GMM_ASSERT1(pmf && ws.value(name).size() == pmf->get_qdim(),
                   "gfgpu: the source term needs a fixed-size constant with qdim components");
       for (size_type k = 0; k < ws.value(name).size(); ++k) out.params.push_back(sign * ws.value(name)[k]);
@@ -587,13 +595,13 @@ static bool recognise_string(const getfem::ga_workspace &ws, const std::string &
   }
   if (std::regex_match(s, m, std::regex("\\(\\(Div_" + v + "\\*\\(" + ID + "\\*" + Idm + "\\)\\)\\+\\(\\(2\\*" + ID +
                                         "\\)\\*\\(Sym\\(Grad_" + v + "\\)\\)\\)\\):Grad_Test_" + v))) {
-    GMM_ASSERT1(ws.associated_mf(m[1]) || !ws.associated_mf(m[2]),
+    GMM_ASSERT1((ws.associated_mf(m[1]) || ws.associated_im_data(m[1])) || !(ws.associated_mf(m[2]) || ws.associated_im_data(m[2])),
                 "gfgpu: a fem-data mu needs a fem-data lambda (fields replace the LEADING parameters)");
     out.family = GFGPU_ELASTICITY; out.params = {scalar(m[1]), scalar(m[2])}; return true;
   }
   if (std::regex_match(s, m, std::regex("\\(\\(" + ID + "\\*Div_" + v + "\\)\\*Div_Test_" + v + "\\)\\+\\(\\(\\(2\\*" + ID +
                                         "\\)\\*\\(Sym\\(Grad_" + v + "\\)\\)\\):Grad_Test_" + v + "\\)"))) {
-    GMM_ASSERT1(ws.associated_mf(m[1]) || !ws.associated_mf(m[2]),
+    GMM_ASSERT1((ws.associated_mf(m[1]) || ws.associated_im_data(m[1])) || !(ws.associated_mf(m[2]) || ws.associated_im_data(m[2])),
                 "gfgpu: a fem-data mu needs a fem-data lambda (fields replace the LEADING parameters)");
     out.family = GFGPU_ELASTICITY; out.params = {scalar(m[1]), scalar(m[2])}; return true;
   }
@@ -601,7 +609,7 @@ static bool recognise_string(const getfem::ga_workspace &ws, const std::string &
   // mu (grad u + grad u^T) : grad v = 2 mu eps(u) : grad v
   if (std::regex_match(s, m, std::regex("\\(\\(" + ID + "\\*Div_" + v + "\\)\\*Div_Test_" + v + "\\)\\+\\(\\(" + ID + "\\*\\(Grad_" + v +
                                         "\\+\\(Grad_" + v + "'\\)\\)\\):Grad_Test_" + v + "\\)"))) {
-    GMM_ASSERT1(ws.associated_mf(m[1]) || !ws.associated_mf(m[2]),
+    GMM_ASSERT1((ws.associated_mf(m[1]) || ws.associated_im_data(m[1])) || !(ws.associated_mf(m[2]) || ws.associated_im_data(m[2])),
                 "gfgpu: a fem-data mu needs a fem-data lambda (fields replace the LEADING parameters)");
     out.family = GFGPU_ELASTICITY; out.params = {scalar(m[1]), scalar(m[2])}; return true;
   }
@@ -677,6 +685,8 @@ struct device_assembler::entry {
   gfgpu_tables *tab = nullptr;
   gfgpu_term *term = nullptr;
   size_type ndof = 0;
+  std::vector<size_type> imd_map;  // im_data coefficients: index in the im_data of (element of the group, Gauss point)
+  size_type imd_qd = 0;
   ~entry() {
     gfgpu_term_destroy(term);
     gfgpu_tables_destroy(tab);
@@ -1212,7 +1222,8 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
       char hb[40];
       for (double p : rt.params) { std::snprintf(hb, sizeof hb, "/%a", p); key << hb; }
     }
-    for (const std::string &fn : rt.field_names) key << "/field:" << fn << "@" << ws.associated_mf(fn);
+    for (const std::string &fn : rt.field_names)
+      key << "/field:" << fn << "@" << (const void *)ws.associated_mf(fn) << "/" << (const void *)ws.associated_im_data(fn);
     if (use_region) {  // the region's content is part of the key (FNV-1a over the items)
       uint64_t h = 1469598103934665603ull;
       for (size_t k = 0; k < grg_cv.size(); ++k) {
@@ -1310,7 +1321,41 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
                                    GFGPU_STRATEGY_AUTO, &e.term));
       if (use_region)
         GFGPU_CALL(gfgpu_term_set_region(e.term, int64_t(grg_cv.size()), grg_cv.data(), rg_faces ? grg_f.data() : nullptr));
-      if (!rt.field_names.empty()) {
+      if (!rt.field_names.empty() && ws.associated_im_data(rt.field_names[0])) {
+        // im data (ga_workspace::add_im_data): one value per Gauss point, read by ga_exec as U[filtered_index_of_point(cv, q)]
+        // (C&E.cc:134-165).  On the device it is a field on a synthetic discontinuous "fem" with one dof per Gauss point and the
+        // identity as basis table: the kernels' field evaluation sum_i vals[dof_i] phi_i(q) then returns the stored value.
+        const getfem::im_data *pid = ws.associated_im_data(rt.field_names[0]);
+        for (const std::string &fn : rt.field_names)
+          GMM_ASSERT1(ws.associated_im_data(fn) == pid, "gfgpu: the im_data coefficients of one term must share their im_data object");
+        GMM_ASSERT1(&pid->linked_mesh_im() == &mim, "gfgpu: im data have to be used on their original integration method");
+        GMM_ASSERT1(!rg_faces, "gfgpu: im_data coefficients are handled in volume terms");
+        const size_type qd = pid->nb_tensor_elem();
+        GMM_ASSERT1(qd >= 1 && qd <= 3, "gfgpu: scalar or vector im_data only");
+        std::vector<int64_t> ded(ne * nq);
+        e.imd_map.resize(ne * nq);
+        for (size_type k = 0; k < ne; ++k)
+          for (size_type q = 0; q < nq; ++q) {
+            ded[k * nq + q] = int64_t((k * nq + q) * qd);
+            const size_type ip = pid->filtered_index_of_point(gcv[k], q);
+            GMM_ASSERT1(ip != size_type(-1), "gfgpu: im data with no data on an integration point of the region");
+            e.imd_map[k * nq + q] = ip;
+          }
+        e.imd_qd = qd;
+        GFGPU_CALL(gfgpu_fem_create(ctx_, e.mesh, fqk ? GFGPU_FEM_QK : GFGPU_FEM_PK, 0, int(qd), int(nq), ded.data(),
+                                    int64_t(ne * nq * qd), &e.dfem));
+        std::vector<double> ident(nq * nq, 0.0);
+        for (size_type q = 0; q < nq; ++q) ident[q * nq + q] = 1.0;
+        std::vector<std::vector<double>> vals;
+        for (const std::string &fn : rt.field_names) {
+          const getfem::model_real_plain_vector &src = ws.value(fn);
+          vals.emplace_back(ne * nq * qd);
+          for (size_type k = 0; k < ne * nq; ++k)
+            for (size_type c = 0; c < qd; ++c) vals.back()[k * qd + c] = rt.field_sign * src[e.imd_map[k] * qd + c];
+        }
+        GFGPU_CALL(gfgpu_term_set_fields(e.term, int(vals.size()), e.dfem, ident.data(), nullptr, vals[0].data(),
+                                         vals.size() > 1 ? vals[1].data() : nullptr));
+      } else if (!rt.field_names.empty()) {
         // fem-data coefficients: the data mesh_fem's dof table and its basis at the same points (fem_precomp_::val)
         const getfem::mesh_fem *pmd = ws.associated_mf(rt.field_names[0]);
         for (const std::string &fn : rt.field_names)
@@ -1354,8 +1399,16 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     entry &e = *pe;
     if (!rt.field_names.empty() && e.used) {  // cached device term: the data may have changed since the last assembly
       for (size_t k = 0; k < rt.field_names.size(); ++k) {
-        std::vector<double> vals(ws.value(rt.field_names[k]).begin(), ws.value(rt.field_names[k]).end());
-        for (double &x : vals) x *= rt.field_sign;
+        std::vector<double> vals;
+        const getfem::model_real_plain_vector &src = ws.value(rt.field_names[k]);
+        if (!e.imd_map.empty()) {  // im data: into the device order (element of the group, Gauss point)
+          vals.resize(e.imd_map.size() * e.imd_qd);
+          for (size_t j = 0; j < e.imd_map.size(); ++j)
+            for (size_type c = 0; c < e.imd_qd; ++c) vals[j * e.imd_qd + c] = rt.field_sign * src[e.imd_map[j] * e.imd_qd + c];
+        } else {
+          vals.assign(src.begin(), src.end());
+          for (double &x : vals) x *= rt.field_sign;
+        }
         GFGPU_CALL(gfgpu_term_update_field(e.term, int(k), vals.data()));
       }
     }

@@ -10,6 +10,7 @@
 #include "getfem/getfem_generic_assembly.h"
 #include "getfem/getfem_mesh_fem.h"
 #include "getfem/getfem_mesh_im.h"
+#include "getfem/getfem_im_data.h"
 #include "getfem/getfem_regular_meshes.h"
 #include "gfgpu_getfem_shim.h"
 #include "gmm/gmm_kernel.h"
@@ -128,9 +129,39 @@ int main(int argc, char **argv) {
     bgeot::base_node P = mf_dq.point_of_basic_dof(d);
     d_f[d] = 0.75 * double(d % Q + 1) * (1.0 + 0.5 * P[0] - 0.25 * P[dim - 1]);
   }
+  // coef=imd: the same coefficient fields stored per Gauss point in im_data objects (ga_workspace::add_im_data)
+  const bool coef_imd = gets("coef", "const") == "imd";
+  getfem::im_data imd_s(mim), imd_v(mim);
+  {
+    bgeot::multi_index ts(1);  // (multi_index(n) makes n ZERO entries)
+    ts[0] = size_type(Q);
+    imd_v.set_tensor_size(ts);
+  }
+  std::vector<double> i_a, i_l, i_m, i_f;
+  if (coef_imd) {
+    i_a.resize(imd_s.nb_index()); i_l.resize(imd_s.nb_index()); i_m.resize(imd_s.nb_index());
+    i_f.resize(imd_v.nb_index() * Q);
+    for (dal::bv_visitor cv(m.convex_index()); !cv.finished(); ++cv) {
+      getfem::papprox_integration pai2 = mim.int_method_of_element(cv)->approx_method();
+      bgeot::pgeometric_trans pgt2 = m.trans_of_convex(cv);
+      for (size_type q = 0; q < pai2->nb_points_on_convex(); ++q) {
+        bgeot::base_node P = pgt2->transform(pai2->point(q), m.points_of_convex(cv));
+        const size_type is = imd_s.index_of_point(cv, q), iv = imd_v.index_of_point(cv, q);
+        i_a[is] = acoef * (1.0 + 0.3 * std::sin(1.7 * P[0] + 0.9 * P[1]));
+        i_l[is] = lambda * (1.0 + 0.25 * std::cos(1.1 * P[0] - 0.7 * P[1]));
+        i_m[is] = mu * (1.0 + 0.2 * std::cos(1.3 * P[0] - P[dim - 1]));
+        for (int c = 0; c < Q; ++c) i_f[iv * Q + c] = 0.75 * double(c + 1) * (1.0 + 0.5 * P[0] - 0.25 * P[dim - 1]);
+      }
+    }
+  }
   auto setup = [&](getfem::ga_workspace &ws) {
     ws.add_fem_variable("u", mf, gmm::sub_interval(0, ndof), U);
-    if (coef_fem) {
+    if (coef_imd) {
+      ws.add_im_data("a", imd_s, i_a);
+      ws.add_im_data("lambda", imd_s, i_l);
+      ws.add_im_data("mu", imd_s, i_m);
+      ws.add_im_data("f", imd_v, i_f);
+    } else if (coef_fem) {
       ws.add_fem_constant("a", mf_d, d_a);
       ws.add_fem_constant("lambda", mf_d, d_l);
       ws.add_fem_constant("mu", mf_d, d_m);

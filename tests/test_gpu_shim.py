@@ -56,6 +56,14 @@ CASES = [
     "dim=3 n=3 gt=qk k=2 q=3 im=6 family=nh_ciarlet mixed=1",
     "dim=3 n=4 gt=pk k=2 q=3 im=4 family=mass region=outer mixed=1",
     "dim=3 n=4 gt=pk k=2 q=3 im=4 family=elast region=half mixed=1",
+    # im_data coefficients (ga_workspace::add_im_data): one value per Gauss point, read on the device as a field on a synthetic
+    # one-dof-per-Gauss-point fem
+    "dim=3 n=4 gt=pk k=2 q=3 im=4 family=elast coef=imd",
+    "dim=3 n=4 gt=pk k=2 q=1 im=4 family=laplace coef=imd",
+    "dim=3 n=3 gt=qk k=2 q=1 im=6 family=mass coef=imd",
+    "dim=3 n=4 gt=pk k=2 q=3 im=4 family=source coef=imd",
+    "dim=2 n=12 gt=pk k=1 q=1 im=2 family=source coef=imd",
+    "dim=3 n=4 gt=pk k=2 q=3 im=4 family=elast region=half coef=imd",
     # P4 simplices (the degree of the reference's published table, contrib/opt_assembly/opt_assembly.cc:704-712)
     "dim=3 n=2 gt=pk k=4 q=3 im=8 family=elast",
     "dim=3 n=2 gt=pk k=4 q=1 im=8 family=laplace",
