@@ -49,6 +49,8 @@ SIGNATURES = {
     "gfgpu_tables_set_faces": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "gfgpu_tables_destroy": (C.c_int, [_P]),
     "gfgpu_term_create": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_double, C.c_int, _PP]),
+    "gfgpu_term_create_jit": (C.c_int, [_P, _P, _P, _P, C.c_char_p, C.c_char_p, _P, C.c_int, C.c_double, C.c_int, _PP]),
+    "gfgpu_jit_check": (C.c_int, [C.c_int, C.c_char_p, C.c_char_p]),
     "gfgpu_term_destroy": (C.c_int, [_P]),
     "gfgpu_term_set_region": (C.c_int, [_P, _i64, _P, _P]),
     "gfgpu_term_set_fields": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
@@ -265,6 +267,19 @@ class DeviceTerm(_Handle):
         fam = FAMILY_BY_NAME[family] if isinstance(family, str) else int(family)
         check(lib().gfgpu_term_create(ctx.h, mesh.h, fem.h, tables.h, fam, ptr(params), len(params), float(alpha),
                                       int(strategy), C.byref(self.h)))
+
+    @classmethod
+    def jit(cls, ctx, mesh, fem, tables, form1, form2, params=(), alpha=1.0, value_dependent=True):
+        """A JIT term (gfgpu_term_create_jit): the order-1 / order-2 forms of a scalar variable as C expressions in
+        u, gu, par[k], tv, tg, t2v, t2g; compiled with NVRTC at the first assembly."""
+        self = cls.__new__(cls)
+        _Handle.__init__(self)
+        self.ctx, self.mesh, self.fem, self.tables = ctx, mesh, fem, tables
+        params = np.ascontiguousarray(params, np.float64)
+        check(lib().gfgpu_term_create_jit(ctx.h, mesh.h, fem.h, tables.h, form1.encode(), form2.encode(),
+                                          ptr(params) if len(params) else None, len(params), float(alpha),
+                                          1 if value_dependent else 0, C.byref(self.h)))
+        return self
 
     def set_region(self, cv, face=None):
         """Integrate over the items (cv[k], face[k]) in mr_visitor order; face None / -1 = whole convexes;
@@ -529,6 +544,11 @@ class DeviceMatrix(_Handle):
 
 
 RECT_DIV_PRESSURE = 0
+
+
+def jit_check(dim, form1, form2):
+    """Compile the two forms of a JIT term with NVRTC (no GPU needed); raises GfgpuError with the compiler log."""
+    check(lib().gfgpu_jit_check(int(dim), form1.encode(), form2.encode()))
 
 
 class DeviceRect(_Handle):

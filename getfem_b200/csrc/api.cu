@@ -363,11 +363,46 @@ int gfgpu_term_create(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem, gfgpu_ta
   GF_API_END
 }
 
+int gfgpu_term_create_jit(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem, gfgpu_tables *tab, const char *form1, const char *form2,
+                          const double *params, int nparams, double alpha, int value_dependent, gfgpu_term **out) {
+  GF_API_BEGIN
+  GF_REQUIRE(ctx && mesh && fem && tab && form1 && form2 && out, "null argument");
+  GF_REQUIRE(fem->mesh == mesh, "the fem was built on another mesh");
+  GF_REQUIRE(tab->dim == mesh->dim && tab->ng == mesh->ng && tab->nd == fem->nd, "tables do not match mesh/fem");
+  GF_REQUIRE(fem->qdim == 1, "JIT terms: scalar variables");
+  GF_REQUIRE(mesh->dim == 2 || mesh->dim == 3, "JIT terms: 2D and 3D meshes");
+  GF_REQUIRE(nparams >= 0 && nparams <= GFGPU_MAX_PARAMS && (nparams == 0 || params), "bad parameters");
+  std::unique_ptr<gfgpu_term> t(new gfgpu_term);
+  t->ctx = ctx; t->mesh = mesh; t->fem = fem; t->tab = tab; t->family = GFGPU_JIT;
+  t->strategy = GFGPU_STRATEGY_STAGED;
+  t->strategy_asked = GFGPU_STRATEGY_STAGED;
+  for (int k = 0; k < GFGPU_MAX_PARAMS; ++k) t->par[k] = k < nparams ? params[k] : 0.0;
+  t->alpha = alpha;
+  t->e0 = 0; t->e1 = mesh->ne;
+  t->jit_form1 = form1; t->jit_form2 = form2;
+  t->jit_value_dependent = value_dependent != 0;
+  GF_CUDA(cudaSetDevice(ctx->device));
+  t->flag.alloc(ctx, 1);
+  t->flag.zero();
+  for (int k = 0; k < 10; ++k) GF_CUDA(cudaEventCreate(&t->ev[k]));
+  *out = t.release();
+  GF_API_END
+}
+
+int gfgpu_jit_check(int dim, const char *form1, const char *form2) {
+  GF_API_BEGIN
+  GF_REQUIRE(form1 && form2 && (dim == 2 || dim == 3), "bad argument");
+  const std::string log = gf::jit_check_source(dim, form1, form2);
+  GF_REQUIRE(log.empty(), "the integrand does not compile (NVRTC):\n" + log);
+  GF_API_END
+}
+
 int gfgpu_term_destroy(gfgpu_term *t) {
   GF_API_BEGIN
   if (t) {
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
+    if (t->jit_kernel) gf::jit_release(t);
     for (int k = 0; k < 10; ++k)
       if (t->ev[k]) cudaEventDestroy(t->ev[k]);
   }
@@ -557,8 +592,9 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
   // what the generic element kernel has to produce in this call.  RECOMPUTE needs it only once, for
   // the keep masks of the pattern; its residual is K^T U inside the per-nonzero kernel.
   // linear families: the keep masks do not depend on U, so a valid pattern needs no masks (and none are written)
-  const bool value_dependent = t->family == GFGPU_SVK || t->family == GFGPU_NEOHOOKEAN_CIARLET ||
-                               t->family == GFGPU_NEOHOOKEAN_BONET || t->family >= GFGPU_MOONEY_RIVLIN;
+  const bool value_dependent = t->family == GFGPU_JIT ? t->jit_value_dependent
+                               : (t->family == GFGPU_SVK || t->family == GFGPU_NEOHOOKEAN_CIARLET ||
+                                  t->family == GFGPU_NEOHOOKEAN_BONET || t->family >= GFGPU_MOONEY_RIVLIN);
   const bool need_masks = recompute ? !t->pat_valid : (do_t && (!t->pat_valid || value_dependent));
   // direct mode: a scalar sum-factorised kernel under a fixed pattern writes its entries straight to their CSC slots
   // (scatter.cu direct_prepare): no element matrix in HBM, no gather -- only the ordered sums of the shared entries
@@ -622,7 +658,12 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
   if (ne > 0 && (need_stage || need_masks || need_rstage || direct)) {
     tic(0);
     const bool affine = t->mesh->gt_kind == GFGPU_GT_PK;
-    bool ok = (!t->region_faces && !t->nfields && gf::launch_sumfact_kernel(ctx, t->tab, t->mesh->dim, Q, nd, affine, a)) ||
+    if (t->family == GFGPU_JIT) {
+      GF_REQUIRE(!t->region_faces && !t->nfields, "JIT terms: volume integration, constant parameters");
+      gf::launch_jit_kernel(t, a);
+    }
+    bool ok = t->family == GFGPU_JIT ||
+              (!t->region_faces && !t->nfields && gf::launch_sumfact_kernel(ctx, t->tab, t->mesh->dim, Q, nd, affine, a)) ||
               (!direct && gf::launch_elem_kernel(ctx, t->mesh->dim, Q, nd, affine, a));  // only sumfact.cu knows the direct mode
     GF_REQUIRE(ok, "no device kernel for this (dimension, qdim, local dofs, family) combination");
     toc(0);

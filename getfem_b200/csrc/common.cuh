@@ -219,6 +219,11 @@ struct gfgpu_term {
   int64_t d_generation = -1;
   int direct_ok = 0;  // 0 unknown, 1 yes, -1 no
   gf::DevBuf<double> Ubuf;      // ndof (host path)
+  // JIT family (jit.cu): the two forms as C expressions, the compiled kernel, the parameters on the device
+  std::string jit_form1, jit_form2;
+  void *jit_kernel = nullptr;
+  gf::DevBuf<double> jit_par;
+  bool jit_value_dependent = true;
   gf::DevBuf<int32_t> flag;     // pattern-changed flag
   bool flag_pending = false;    // a value-dependent gather raised (or not) the flag; nobody has read it yet (api.cu term_settle)
   // per-phase events of the last assemble: [0,1] element kernel, [2,3] gather, [4,5] residual gather, [6,7] pattern
@@ -349,6 +354,9 @@ bool recompute_cols_prepare(gfgpu_term *t, const std::vector<uint32_t> &colstart
 void recompute_cols_tangent(gfgpu_term *t, const double *U, bool with_r);
 // class-uniform tile kernel (recompute_uniform.cu); prepare returns false when the term keeps the general tile kernel
 bool uniform_prepare(gfgpu_term *t);
+void launch_jit_kernel(gfgpu_term *t, const ElemArgs &a);  // jit.cu
+void jit_release(gfgpu_term *t);
+std::string jit_check_source(int N, const std::string &form1, const std::string &form2);
 void term_settle_pending(gfgpu_term *t);  // api.cu: deferred pattern check of a value-dependent tangent
 void uniform_tangent(gfgpu_term *t);
 

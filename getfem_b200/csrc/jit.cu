@@ -1,0 +1,329 @@
+// jit.cu -- the NVRTC route: an element kernel compiled at run time around a per-Gauss-point integrand given as SOURCE.
+//
+// The families of elem_kernel.cuh are closed forms picked by recognition.  A GWFL expression that is none of them still
+// has, after the reference's own analysis and symbolic differentiation, an order-1 tree that is LINEAR in the test function
+// and an order-2 tree that is BILINEAR in (Test, Test2) (C&E.cc:8750-9047 interprets exactly those trees).  For a scalar
+// variable such a tree is, at a Gauss point, a function of (u, Grad u, constants) applied to tau = (Test_u, Grad_Test_u)
+// [and tau2]: the host translates the tree into a C expression (getfem_b200/shim: jit_translate) and this module wraps it:
+//     r(tau)        = form1(u, gu, par, tv, tg)                       linear in (tv, tg)
+//     k(tau, tau2)  = form2(u, gu, par, tv, tg, t2v, t2g)             bilinear
+// The kernel evaluates the forms with UNIT probes (tv = 1 or tg = e_k: literal constants, so the compiler folds each call
+// into the coefficient it extracts), which gives the N+1 coefficients c_a and the (N+1)^2 coefficients C_ab of
+//     r_e(i)    = sum_q w_q J sum_a c_a(q) T_a(phi_i)(q),        T_0 = value, T_k = d/dx_k
+//     K_e(i,j)  = sum_q w_q J sum_ab C_ab(q) T_a(phi_i)(q) T_b(phi_j)(q)
+// and writes the SAME stage / keep masks / element residuals as the generic kernel (drop rule included), so the pattern
+// builder, the gather and everything downstream are unchanged.  NVRTC and the driver API are resolved with dlopen:
+// libgfgpu.so has no link dependency on them, and a process that never creates a JIT term never loads them.
+#include <dlfcn.h>
+
+#include <mutex>
+#include <sstream>
+
+#include "common.cuh"
+
+namespace gf {
+
+// ---- minimal driver / NVRTC surface (types as the headers declare them: opaque pointers and ints)
+typedef struct CUmod_st *CUmodule_t;
+typedef struct CUfunc_st *CUfunction_t;
+typedef struct _nvrtcProgram *nvrtcProgram_t;
+struct JitApi {
+  void *hn = nullptr, *hc = nullptr;
+  int (*CreateProgram)(nvrtcProgram_t *, const char *, const char *, int, const char *const *, const char *const *) = nullptr;
+  int (*CompileProgram)(nvrtcProgram_t, int, const char *const *) = nullptr;
+  int (*GetProgramLogSize)(nvrtcProgram_t, size_t *) = nullptr;
+  int (*GetProgramLog)(nvrtcProgram_t, char *) = nullptr;
+  int (*GetCUBINSize)(nvrtcProgram_t, size_t *) = nullptr;
+  int (*GetCUBIN)(nvrtcProgram_t, char *) = nullptr;
+  int (*DestroyProgram)(nvrtcProgram_t *) = nullptr;
+  int (*ModuleLoadData)(CUmodule_t *, const void *) = nullptr;
+  int (*ModuleGetFunction)(CUfunction_t *, CUmodule_t, const char *) = nullptr;
+  int (*ModuleUnload)(CUmodule_t) = nullptr;
+  int (*FuncSetAttribute)(CUfunction_t, int, int) = nullptr;
+  int (*LaunchKernel)(CUfunction_t, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, cudaStream_t, void **,
+                      void **) = nullptr;
+};
+
+static JitApi &jit_api(bool need_driver = true) {
+  static JitApi a;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    for (const char *n : {"libnvrtc.so.12", "libnvrtc.so"})
+      if (!a.hn) a.hn = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    for (const char *n : {"libcuda.so.1", "libcuda.so"})
+      if (!a.hc) a.hc = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+#define GF_SYM(h, field, name) a.field = reinterpret_cast<decltype(a.field)>(dlsym(h, name))
+    if (a.hn) {
+      GF_SYM(a.hn, CreateProgram, "nvrtcCreateProgram");
+      GF_SYM(a.hn, CompileProgram, "nvrtcCompileProgram");
+      GF_SYM(a.hn, GetProgramLogSize, "nvrtcGetProgramLogSize");
+      GF_SYM(a.hn, GetProgramLog, "nvrtcGetProgramLog");
+      GF_SYM(a.hn, GetCUBINSize, "nvrtcGetCUBINSize");
+      GF_SYM(a.hn, GetCUBIN, "nvrtcGetCUBIN");
+      GF_SYM(a.hn, DestroyProgram, "nvrtcDestroyProgram");
+    }
+    if (a.hc) {
+      GF_SYM(a.hc, ModuleLoadData, "cuModuleLoadData");
+      GF_SYM(a.hc, ModuleGetFunction, "cuModuleGetFunction");
+      GF_SYM(a.hc, ModuleUnload, "cuModuleUnload");
+      GF_SYM(a.hc, FuncSetAttribute, "cuFuncSetAttribute");
+      GF_SYM(a.hc, LaunchKernel, "cuLaunchKernel");
+    }
+#undef GF_SYM
+  });
+  GF_REQUIRE(a.hn && a.CreateProgram && a.CompileProgram && a.GetCUBIN && a.GetCUBINSize && a.GetProgramLog && a.GetProgramLogSize &&
+                 a.DestroyProgram,
+             "NVRTC (libnvrtc.so.12) could not be loaded: JIT terms need it");
+  GF_REQUIRE(!need_driver || (a.hc && a.ModuleLoadData && a.ModuleGetFunction && a.LaunchKernel && a.FuncSetAttribute && a.ModuleUnload),
+             "the CUDA driver library (libcuda.so.1) could not be loaded: JIT terms need it");
+  return a;
+}
+
+// ---- the kernel template.  GF_N (2 or 3), GF_FORM1, GF_FORM2 are defined on the NVRTC command line / prepended.
+static const char *kJitSource = R"GFJIT(
+struct vec { double v[GF_N]; };
+__device__ __forceinline__ vec operator+(vec a, vec b) { vec r; for (int k = 0; k < GF_N; ++k) r.v[k] = a.v[k] + b.v[k]; return r; }
+__device__ __forceinline__ vec operator-(vec a, vec b) { vec r; for (int k = 0; k < GF_N; ++k) r.v[k] = a.v[k] - b.v[k]; return r; }
+__device__ __forceinline__ vec operator-(vec a) { vec r; for (int k = 0; k < GF_N; ++k) r.v[k] = -a.v[k]; return r; }
+__device__ __forceinline__ vec operator*(double s, vec a) { vec r; for (int k = 0; k < GF_N; ++k) r.v[k] = s * a.v[k]; return r; }
+__device__ __forceinline__ vec operator*(vec a, double s) { vec r; for (int k = 0; k < GF_N; ++k) r.v[k] = a.v[k] * s; return r; }
+__device__ __forceinline__ vec operator/(vec a, double s) { vec r; for (int k = 0; k < GF_N; ++k) r.v[k] = a.v[k] / s; return r; }
+__device__ __forceinline__ double dot(vec a, vec b) { double s = 0; for (int k = 0; k < GF_N; ++k) s += a.v[k] * b.v[k]; return s; }
+__device__ __forceinline__ double dot(double a, double b) { return a * b; }
+__device__ __forceinline__ vec dot(double a, vec b) { return a * b; }
+__device__ __forceinline__ vec dot(vec a, double b) { return a * b; }
+__device__ __forceinline__ double normsqr(vec a) { return dot(a, a); }
+__device__ __forceinline__ double normsqr(double a) { return a * a; }
+__device__ __forceinline__ double gnorm(vec a) { return sqrt(dot(a, a)); }
+__device__ __forceinline__ double gnorm(double a) { return fabs(a); }
+__device__ __forceinline__ vec mkvec(double a, double b, double c) { vec r; r.v[0] = a; r.v[1] = b; if (GF_N > 2) r.v[GF_N - 1] = c; return r; }
+__device__ __forceinline__ vec unit(int k) { vec r; for (int j = 0; j < GF_N; ++j) r.v[j] = j == k ? 1.0 : 0.0; return r; }
+__device__ __forceinline__ double sqr(double x) { return x * x; }
+__device__ __forceinline__ double pos_part(double x) { return x > 0 ? x : 0.0; }
+__device__ __forceinline__ double neg_part(double x) { return x < 0 ? -x : 0.0; }
+__device__ __forceinline__ double half_sqr_pos_part(double x) { return x > 0 ? 0.5 * x * x : 0.0; }
+__device__ __forceinline__ double half_sqr_neg_part(double x) { return x < 0 ? 0.5 * x * x : 0.0; }
+__device__ __forceinline__ double Heaviside(double x) { return x < 0 ? 0.0 : 1.0; }
+__device__ __forceinline__ double sign(double x) { return x < 0 ? -1.0 : (x > 0 ? 1.0 : 0.0); }
+
+__device__ __forceinline__ double gf_form1(double u, vec gu, const double *par, double tv, vec tg) { return GF_FORM1; }
+__device__ __forceinline__ double gf_form2(double u, vec gu, const double *par, double tv, vec tg, double t2v, vec t2g) {
+  return GF_FORM2;
+}
+
+extern "C" __global__ void __launch_bounds__(128)
+gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z, const int *__restrict__ conn,
+            const int *__restrict__ edof, const double *__restrict__ U, const double *__restrict__ w, const double *__restrict__ gt_grad,
+            const double *__restrict__ phi, const double *__restrict__ gphi, const double *__restrict__ par, int ng, int nq, int nd,
+            long long e0, long long ne, double alpha, double *__restrict__ stage, unsigned short *__restrict__ emask,
+            double *__restrict__ rstage) {
+  constexpr int N = GF_N, NA = GF_N + 1;
+  extern __shared__ double sm[];
+  double *sG = sm;                       // N x ng
+  double *sU = sG + N * ng;              // nd
+  double *sT = sU + nd;                  // nq x nd x NA : value and physical gradient of every basis function
+  double *sC1 = sT + (size_t)nq * nd * NA;   // nq x NA      (w J folded in)
+  double *sC2 = sC1 + (size_t)nq * NA;       // nq x NA x NA
+  double *sK = sC2 + (size_t)nq * NA * NA;   // nd x nd
+  __shared__ double sRed[4];
+  const int tid = threadIdx.x;
+  for (long long el = blockIdx.x; el < ne; el += gridDim.x) {
+    const long long e = e0 + el;
+    for (int k = tid; k < N * ng; k += blockDim.x) {
+      const int i = k / N, d = k % N;
+      const int p = conn[e * ng + i];
+      sG[d + N * i] = (d == 0 ? x : d == 1 ? y : z)[p];
+    }
+    for (int i = tid; i < nd; i += blockDim.x) sU[i] = U ? U[edof[e * nd + i]] : 0.0;
+    __syncthreads();
+    // per Gauss point: K = G pc(q), J = |det K|, B = K^-T; T_a(phi_i); the state; the coefficients of the two forms
+    for (int q = tid; q < nq; q += blockDim.x) {
+      double K[N * N], B[N * N];
+      for (int k = 0; k < N * N; ++k) K[k] = 0.0;
+      const double *pc = gt_grad + (size_t)q * ng * N;
+      for (int i = 0; i < ng; ++i)
+        for (int c = 0; c < N; ++c)
+          for (int r = 0; r < N; ++r) K[r + N * c] += sG[r + N * i] * pc[i * N + c];
+      double J;
+      if (N == 2) {
+        const double d = K[0] * K[3] - K[1] * K[2], id = 1.0 / d;
+        B[0] = K[3] * id; B[2] = -K[1] * id; B[1] = -K[2] * id; B[3] = K[0] * id;
+        J = fabs(d);
+      } else {
+        const double c00 = K[4] * K[8] - K[7] * K[5], c10 = K[7] * K[2] - K[1] * K[8], c20 = K[1] * K[5] - K[4] * K[2];
+        const double d = K[0] * c00 + K[3] * c10 + K[6] * c20, id = 1.0 / d;
+        B[0] = c00 * id; B[3] = c10 * id; B[6] = c20 * id;
+        B[1] = (K[6] * K[5] - K[3] * K[8]) * id; B[4] = (K[0] * K[8] - K[6] * K[2]) * id; B[7] = (K[3] * K[2] - K[0] * K[5]) * id;
+        B[2] = (K[3] * K[7] - K[6] * K[4]) * id; B[5] = (K[6] * K[1] - K[0] * K[7]) * id; B[8] = (K[0] * K[4] - K[3] * K[1]) * id;
+        J = fabs(d);
+      }
+      double uq = 0.0;
+      vec guq;
+      for (int k = 0; k < N; ++k) guq.v[k] = 0.0;
+      double *T = sT + (size_t)q * nd * NA;
+      for (int i = 0; i < nd; ++i) {
+        const double *g = gphi + ((size_t)q * nd + i) * N;
+        const double ph = phi[(size_t)q * nd + i];
+        T[i * NA] = ph;
+        uq += sU[i] * ph;
+        for (int k = 0; k < N; ++k) {
+          double s = 0.0;
+          for (int p = 0; p < N; ++p) s += B[k + N * p] * g[p];  // (B ghat)_k
+          T[i * NA + 1 + k] = s;
+          guq.v[k] += sU[i] * s;
+        }
+      }
+      const double wq = w[q];
+      const double cw = wq == 0.0 ? 0.0 : alpha * J * wq;  // zero-weight points are skipped (C&E.cc:8852)
+      vec zero;
+      for (int k = 0; k < N; ++k) zero.v[k] = 0.0;
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        const double tv = a == 0 ? 1.0 : 0.0;
+        const vec tg = a == 0 ? zero : unit(a - 1);
+        sC1[q * NA + a] = cw == 0.0 ? 0.0 : cw * gf_form1(uq, guq, par, tv, tg);
+#pragma unroll
+        for (int b = 0; b < NA; ++b) {
+          const double t2v = b == 0 ? 1.0 : 0.0;
+          const vec t2g = b == 0 ? zero : unit(b - 1);
+          sC2[(q * NA + a) * NA + b] = cw == 0.0 ? 0.0 : cw * gf_form2(uq, guq, par, tv, tg, t2v, t2g);
+        }
+      }
+    }
+    __syncthreads();
+    if (rstage)
+      for (int i = tid; i < nd; i += blockDim.x) {
+        double s = 0.0;
+        for (int q = 0; q < nq; ++q) {
+          const double *T = sT + ((size_t)q * nd + i) * NA;
+          for (int a = 0; a < NA; ++a) s += sC1[q * NA + a] * T[a];
+        }
+        rstage[(size_t)el * nd + i] = s;
+      }
+    if (stage || emask) {
+      double vmax = 0.0;
+      for (int k = tid; k < nd * nd; k += blockDim.x) {  // k = i + nd * j (row i = Test, column j = Test2)
+        const int i = k % nd, j = k / nd;
+        double s = 0.0;
+        for (int q = 0; q < nq; ++q) {
+          const double *Ti = sT + ((size_t)q * nd + i) * NA, *Tj = sT + ((size_t)q * nd + j) * NA, *C = sC2 + (size_t)q * NA * NA;
+          for (int a = 0; a < NA; ++a) {
+            double t = 0.0;
+            for (int b = 0; b < NA; ++b) t += C[a * NA + b] * Tj[b];
+            s += Ti[a] * t;
+          }
+        }
+        sK[k] = s;
+        vmax = fmax(vmax, fabs(s));
+      }
+      for (int off = 16; off > 0; off >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, off));
+      if ((tid & 31) == 0) sRed[tid >> 5] = vmax;
+      __syncthreads();
+      vmax = fmax(fmax(sRed[0], sRed[1]), fmax(sRed[2], sRed[3]));
+      const double thr = vmax * 1e-14;  // the drop rule of add_elem_matrix (C&E.cc:4889,4898)
+      for (int k = tid; k < nd * nd; k += blockDim.x) {
+        const double v = sK[k];
+        const bool keep = (vmax != 0.0) && (fabs(v) > thr);
+        if (stage) stage[(size_t)el * nd * nd + k] = keep ? v : 0.0;
+        if (emask) emask[(size_t)el * nd * nd + k] = keep ? 1 : 0;
+      }
+    }
+    __syncthreads();
+  }
+}
+)GFJIT";
+
+struct JitKernel {
+  CUmodule_t mod = nullptr;
+  CUfunction_t fn = nullptr;
+  std::string log;
+  ~JitKernel() {
+    if (mod) jit_api().ModuleUnload(mod);
+  }
+};
+
+void jit_release(gfgpu_term *t) {
+  delete static_cast<JitKernel *>(t->jit_kernel);
+  t->jit_kernel = nullptr;
+}
+
+static JitKernel *jit_compile(gfgpu_term *t) {
+  JitApi &api = jit_api();
+  const int N = t->mesh->dim;
+  std::string src = "#define GF_N " + std::to_string(N) + "\n#define GF_FORM1 (" + t->jit_form1 + ")\n#define GF_FORM2 (" + t->jit_form2 +
+                    ")\n" + kJitSource;
+  nvrtcProgram_t prog = nullptr;
+  GF_REQUIRE(api.CreateProgram(&prog, src.c_str(), "gfgpu_jit.cu", 0, nullptr, nullptr) == 0, "nvrtcCreateProgram failed");
+  const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+  const int rc = api.CompileProgram(prog, 3, opts);
+  size_t ls = 0;
+  api.GetProgramLogSize(prog, &ls);
+  std::string log(ls > 0 ? ls : 1, '\0');
+  if (ls > 1) api.GetProgramLog(prog, &log[0]);
+  if (rc != 0) {
+    api.DestroyProgram(&prog);
+    throw Error("the integrand does not compile (NVRTC):\n" + log + "\n--- form1: " + t->jit_form1 + "\n--- form2: " + t->jit_form2);
+  }
+  size_t cs = 0;
+  GF_REQUIRE(api.GetCUBINSize(prog, &cs) == 0 && cs > 0, "nvrtcGetCUBINSize failed");
+  std::vector<char> cubin(cs);
+  GF_REQUIRE(api.GetCUBIN(prog, cubin.data()) == 0, "nvrtcGetCUBIN failed");
+  api.DestroyProgram(&prog);
+  std::unique_ptr<JitKernel> k(new JitKernel);
+  k->log = log;
+  GF_CUDA(cudaFree(0));  // the runtime's primary context is the driver's current context from here on
+  int r = api.ModuleLoadData(&k->mod, cubin.data());
+  GF_REQUIRE(r == 0, "cuModuleLoadData failed for the JIT kernel (error " + std::to_string(r) + ")");
+  r = api.ModuleGetFunction(&k->fn, k->mod, "gf_jit_elem");
+  GF_REQUIRE(r == 0, "cuModuleGetFunction failed for the JIT kernel");
+  return k.release();
+}
+
+// compile-only check (no GPU needed): used by the CPU tests and by gfgpu_term_create_jit to fail early
+std::string jit_check_source(int N, const std::string &form1, const std::string &form2) {
+  JitApi &api = jit_api(false);
+  std::string src = "#define GF_N " + std::to_string(N) + "\n#define GF_FORM1 (" + form1 + ")\n#define GF_FORM2 (" + form2 + ")\n" + kJitSource;
+  nvrtcProgram_t prog = nullptr;
+  if (api.CreateProgram(&prog, src.c_str(), "gfgpu_jit.cu", 0, nullptr, nullptr) != 0) return "nvrtcCreateProgram failed";
+  const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17"};
+  const int rc = api.CompileProgram(prog, 2, opts);
+  size_t ls = 0;
+  api.GetProgramLogSize(prog, &ls);
+  std::string log(ls > 0 ? ls : 1, '\0');
+  if (ls > 1) api.GetProgramLog(prog, &log[0]);
+  api.DestroyProgram(&prog);
+  return rc == 0 ? std::string() : log;
+}
+
+void launch_jit_kernel(gfgpu_term *t, const ElemArgs &a) {
+  gfgpu_ctx *ctx = t->ctx;
+  if (!t->jit_kernel) t->jit_kernel = jit_compile(t);
+  JitKernel *k = static_cast<JitKernel *>(t->jit_kernel);
+  JitApi &api = jit_api();
+  const int N = t->mesh->dim, NA = N + 1, nd = t->fem->nd, nq = a.nq, ng = a.ng;
+  GF_REQUIRE(t->fem->qdim == 1, "JIT terms: scalar variables");
+  const size_t smem = ((size_t)N * ng + nd + (size_t)nq * nd * NA + (size_t)nq * NA + (size_t)nq * NA * NA + (size_t)nd * nd + 2) * 8;
+  GF_REQUIRE(smem <= 220 * 1024, "JIT terms: element too large for the run-time kernel (nq x nd x (N+1) doubles of shared memory)");
+  if (t->jit_par.n != (size_t)GFGPU_MAX_PARAMS) {
+    t->jit_par.alloc(ctx, GFGPU_MAX_PARAMS);
+  }
+  t->jit_par.upload(t->par);
+  GF_REQUIRE(api.FuncSetAttribute(k->fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)smem) == 0,
+             "cuFuncSetAttribute failed for the JIT kernel");
+  long long e0 = a.e0, ne = a.e1 - a.e0;
+  if (ne <= 0) return;
+  int ing = ng, inq = nq, ind = nd;
+  double alpha = a.alpha;
+  const double *par = t->jit_par.p;
+  const double *x = a.x, *y = a.y, *z = a.z, *U = a.U, *w = a.w, *gt = a.gt_grad, *phi = a.phi, *gphi = a.gphi;
+  const int32_t *conn = a.conn, *edof = a.edof;
+  double *stage = a.stage, *rstage = a.rstage;
+  uint16_t *emask = a.emask;
+  void *params[] = {&x, &y, &z, &conn, &edof, &U, &w, &gt, &phi, &gphi, &par, &ing, &inq, &ind, &e0, &ne, &alpha, &stage, &emask, &rstage};
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ne, (long long)ctx->sm_count * 4));
+  const int r = api.LaunchKernel(k->fn, grid, 1, 1, 128, 1, 1, (unsigned)smem, ctx->stream, params, nullptr);
+  GF_REQUIRE(r == 0, "cuLaunchKernel failed for the JIT kernel (error " + std::to_string(r) + ")");
+  count_launch(1);
+}
+
+}  // namespace gf

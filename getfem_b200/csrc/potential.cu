@@ -131,6 +131,7 @@ void term_assemble_for_potential(gfgpu_term *t, const double *U_dev);  // api.cu
 double term_potential(gfgpu_term *t, const double *U_dev) {
   gfgpu_ctx *ctx = t->ctx;
   const int fam = t->family;
+  GF_REQUIRE(fam != GFGPU_JIT, "JIT terms carry no order-0 form: the potential is not available");
   const bool hyper = fam == GFGPU_SVK || fam == GFGPU_NEOHOOKEAN_CIARLET || fam == GFGPU_NEOHOOKEAN_BONET || fam >= GFGPU_MOONEY_RIVLIN;
   if (!hyper) {
     GF_REQUIRE(U_dev, "the potential of a linear or quadratic form needs the state vector");

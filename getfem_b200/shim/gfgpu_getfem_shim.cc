@@ -431,7 +431,7 @@ static bool recognise_by_probe(const getfem::ga_workspace &ws, size_type itree, 
 }
 
 // COUPLED div-pressure parts, as the reference prints them after its semantic analysis (the incompressibility bricks add
-// "-p*Div_Test_u - Test_p*Div_u", getfem_models.cc add_linear_incompressibility; oracle/ref_coupled.cc prints the trees):
+// "-p*Div_Test_u - Test_p*Div_u", getfem_models.cc add_linear_incompressibility; the test driver ref_coupled.cc prints the trees):
 //   order 2 (Test_u, Test2_p)  "(-Test2_p)*Div_Test_u"     order 2 (Test_p, Test2_u)  "-(Test_p*Div_Test2_u)"
 //   order 1  Test_u            "(-p)*Div_Test_u"           order 1  Test_p            "-(Test_p*Div_u)"
 // and the same without the minus signs.  u must be a vector fem variable of the mesh dimension, p a scalar one.

@@ -75,7 +75,8 @@ enum {
    *   BLATZ_KO          Generalized_Blatz_Ko_PK2 (:706-815), params (a, b, c, d, n) */
   GFGPU_MOONEY_RIVLIN = 8,
   GFGPU_CIARLET_GEYMONAT = 9,
-  GFGPU_BLATZ_KO = 10
+  GFGPU_BLATZ_KO = 10,
+  GFGPU_JIT = 11 /* gfgpu_term_create_jit: the integrand is given as source and compiled at run time (NVRTC) */
 };
 #define GFGPU_MAX_PARAMS 12 /* parameters kept per term (NORMAL_SOURCE: qdim x dim <= 9) */
 #define GFGPU_MAX_FACES 6   /* faces of a reference element (simplices: dim+1, parallelepipeds: 2*dim) */
@@ -195,6 +196,24 @@ int gfgpu_term_assemble_host(gfgpu_term *t, const double *U_host, int order_mask
  * Synchronises the stream; the value comes back through E_host. */
 int gfgpu_term_potential_dev(gfgpu_term *t, const double *U_dev, double *E_host);
 int gfgpu_term_potential_host(gfgpu_term *t, const double *U_host, double *E_host);
+
+/* JIT terms (the NVRTC route, csrc/jit.cu): a SCALAR variable and an integrand that is none of the families above.  After the
+ * reference's analysis and symbolic differentiation the order-1 tree of an expression is linear in the test function and the
+ * order-2 tree bilinear in (Test, Test2) (ga_exec interprets exactly those trees, C&E.cc:8750-9047); the caller hands them over
+ * as C expressions in the identifiers
+ *     u (double), gu (vec, Grad_u), par[k] (the term's parameters), tv / tg (Test_u / Grad_Test_u), t2v / t2g (Test2)
+ * with the helpers dot(a,b), normsqr(v), gnorm(v), mkvec(a,b,c), sqr, pos_part, neg_part, Heaviside, sign and the CUDA math
+ * library.  form1 must be linear in (tv, tg), form2 bilinear in (tv, tg) x (t2v, t2g): the kernel extracts their coefficients
+ * with unit probes.  Example, "(1+sqr(u))*Grad_u.Grad_Test_u + sin(u)*Test_u":
+ *     form1 = "(1.0+sqr(u))*dot(gu,tg) + sin(u)*tv"
+ *     form2 = "(2.0*u*t2v)*dot(gu,tg) + (1.0+sqr(u))*dot(t2g,tg) + cos(u)*t2v*tv"
+ * The kernel is compiled on first use for sm_100a; a form that does not compile raises with the NVRTC log.  value_dependent != 0:
+ * the keep masks are re-derived at every assembly (the tangent's pattern may move with u).  Output, pattern, gather, regions of
+ * convexes, gfgpu_matrix_add_term: as for every other STAGED term.  Not handled: faces, fem-data fields, order 0.
+ * gfgpu_jit_check compiles the two forms without a GPU and returns 0 if they compile (the log goes to gfgpu_last_error). */
+int gfgpu_term_create_jit(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem, gfgpu_tables *tab, const char *form1, const char *form2,
+                          const double *params, int nparams, double alpha, int value_dependent, gfgpu_term **out);
+int gfgpu_jit_check(int dim, const char *form1, const char *form2);
 
 /* Device durations (ms, CUDA events on the context's stream) of the kernels of the LAST assemble call:
  * out[0] generic element kernel, out[1] tangent gather-sum (STAGED), out[2] residual gather-sum,
