@@ -51,6 +51,7 @@ SIGNATURES = {
     "gfgpu_term_create": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_double, C.c_int, _PP]),
     "gfgpu_term_create_jit": (C.c_int, [_P, _P, _P, _P, C.c_char_p, C.c_char_p, _P, C.c_int, C.c_double, C.c_int, _PP]),
     "gfgpu_jit_check": (C.c_int, [C.c_int, C.c_char_p, C.c_char_p]),
+    "gfgpu_term_set_params": (C.c_int, [_P, _P, C.c_int]),
     "gfgpu_term_destroy": (C.c_int, [_P]),
     "gfgpu_term_set_region": (C.c_int, [_P, _i64, _P, _P]),
     "gfgpu_term_set_fields": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
@@ -280,6 +281,10 @@ class DeviceTerm(_Handle):
                                           ptr(params) if len(params) else None, len(params), float(alpha),
                                           1 if value_dependent else 0, C.byref(self.h)))
         return self
+
+    def set_params(self, params):
+        params = np.ascontiguousarray(params, np.float64)
+        check(lib().gfgpu_term_set_params(self.h, ptr(params), len(params)))
 
     def set_region(self, cv, face=None):
         """Integrate over the items (cv[k], face[k]) in mr_visitor order; face None / -1 = whole convexes;

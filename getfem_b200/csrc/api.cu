@@ -389,6 +389,14 @@ int gfgpu_term_create_jit(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem, gfgp
   GF_API_END
 }
 
+int gfgpu_term_set_params(gfgpu_term *t, const double *params, int nparams) {
+  GF_API_BEGIN
+  GF_REQUIRE(t && nparams >= 0 && nparams <= GFGPU_MAX_PARAMS && (nparams == 0 || params), "bad parameters");
+  GF_REQUIRE(t->family == GFGPU_JIT, "parameters can be replaced on JIT terms (the closed-form families fold them into their plans)");
+  for (int k = 0; k < nparams; ++k) t->par[k] = params[k];
+  GF_API_END
+}
+
 int gfgpu_jit_check(int dim, const char *form1, const char *form2) {
   GF_API_BEGIN
   GF_REQUIRE(form1 && form2 && (dim == 2 || dim == 3), "bad argument");

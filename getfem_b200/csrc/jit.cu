@@ -103,6 +103,27 @@ __device__ __forceinline__ double pos_part(double x) { return x > 0 ? x : 0.0; }
 __device__ __forceinline__ double neg_part(double x) { return x < 0 ? -x : 0.0; }
 __device__ __forceinline__ double half_sqr_pos_part(double x) { return x > 0 ? 0.5 * x * x : 0.0; }
 __device__ __forceinline__ double half_sqr_neg_part(double x) { return x < 0 ? 0.5 * x * x : 0.0; }
+__device__ __forceinline__ double sqr_pos_part(double x) { return x > 0 ? x * x : 0.0; }
+__device__ __forceinline__ double sqr_neg_part(double x) { return x < 0 ? x * x : 0.0; }
+// first derivatives of the predefined scalar functions, under the names the reference's symbolic differentiation gives them
+__device__ __forceinline__ double DER_PDFUNC_SQRT(double t) { return 0.5 / sqrt(t); }
+__device__ __forceinline__ double DER_PDFUNC1_POW(double t, double e) { return e * pow(t, e - 1.0); }
+__device__ __forceinline__ double DER_PDFUNC2_POW(double t, double e) { return pow(t, e) * log(fabs(t)); }
+__device__ __forceinline__ double DER_PDFUNC_LOG(double t) { return 1.0 / t; }
+__device__ __forceinline__ double DER_PDFUNC_LOG10(double t) { return 1.0 / (t * log(10.0)); }
+__device__ __forceinline__ double DER_PDFUNC_TANH(double t) { const double h = tanh(t); return 1.0 - h * h; }
+__device__ __forceinline__ double DER_PDFUNC_ASINH(double t) { return 1.0 / sqrt(t * t + 1.0); }
+__device__ __forceinline__ double DER_PDFUNC_ACOSH(double t) { return 1.0 / sqrt(t * t - 1.0); }
+__device__ __forceinline__ double DER_PDFUNC_ATANH(double t) { return 1.0 / (1.0 - t * t); }
+__device__ __forceinline__ double DER_PDFUNC_COS(double t) { return -sin(t); }
+__device__ __forceinline__ double DER_PDFUNC_TAN(double t) { const double h = tan(t); return 1.0 + h * h; }
+__device__ __forceinline__ double DER_PDFUNC_ASIN(double t) { return 1.0 / sqrt(1.0 - t * t); }
+__device__ __forceinline__ double DER_PDFUNC_ACOS(double t) { return -1.0 / sqrt(1.0 - t * t); }
+__device__ __forceinline__ double DER_PDFUNC_ATAN(double t) { return 1.0 / (1.0 + t * t); }
+__device__ __forceinline__ double DER_PDFUNC1_ATAN2(double t, double v) { return v / (t * t + v * v); }
+__device__ __forceinline__ double DER_PDFUNC2_ATAN2(double t, double v) { return -t / (t * t + v * v); }
+__device__ __forceinline__ double DER_PDFUNC_ERF(double t) { return exp(-t * t) * 1.1283791670955126; }
+__device__ __forceinline__ double DER_PDFUNC_ERFC(double t) { return -exp(-t * t) * 1.1283791670955126; }
 __device__ __forceinline__ double Heaviside(double x) { return x < 0 ? 0.0 : 1.0; }
 __device__ __forceinline__ double sign(double x) { return x < 0 ? -1.0 : (x > 0 ? 1.0 : 0.0); }
 

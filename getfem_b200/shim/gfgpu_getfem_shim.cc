@@ -430,6 +430,176 @@ static bool recognise_by_probe(const getfem::ga_workspace &ws, size_type itree, 
   return false;
 }
 
+// ---------------------------------------------------------------- the NVRTC route: tree -> C expression
+// For a SCALAR fem variable v an analysed tree is, at a Gauss point, an expression in u = v, gu = Grad_v, scalar constants
+// and the test functions; Test_v / Grad_Test_v (and Test2) become the probe arguments tv / tg (t2v / t2g) of
+// gfgpu_term_create_jit.  Every value is a scalar (rank 0) or a vector of the mesh dimension (rank 1); anything else --
+// matrices, X, Normal, other variables, fem or im data, interpolate transformations -- is refused, and the caller then
+// reports the expression as not handled.  (ga_exec evaluates the same tree with tensors whose leading dimensions index
+// the test functions, C&E.cc:2769-3760; for a scalar variable the contraction pattern reduces to these ranks.)
+struct jit_value { std::string code; int rank; };
+
+static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node &n, const std::string &v, int N,
+                     std::vector<std::string> &params, jit_value &out) {
+  using namespace getfem;
+  if (!n) return false;
+  auto num = [](double x) { char b[48]; std::snprintf(b, sizeof b, "(%.17g)", x); std::string r(b);
+                            if (r.find_first_of(".eEn") == std::string::npos) r.insert(r.size() - 1, ".0"); return r; };
+  auto child = [&](size_t k, jit_value &o) { return k < n->children.size() && jit_emit(ws, n->children[k], v, N, params, o); };
+  switch (n->node_type) {
+    case GA_NODE_ZERO: {
+      const size_t sz = n->tensor().size();
+      if (sz == 1) { out = {"(0.0)", 0}; return true; }
+      if (sz == size_t(N) && n->tensor().sizes().size() == 1) { out = {"mkvec(0.0,0.0,0.0)", 1}; return true; }
+      return false;
+    }
+    case GA_NODE_CONSTANT: {
+      const base_tensor &t = n->tensor();
+      if (n->test_function_type != 0 && n->test_function_type != size_type(-1)) return false;
+      if (t.size() == 1) { out = {num(t[0]), 0}; return true; }
+      if (t.size() == size_t(N) && t.sizes().size() == 1) {
+        out = {"mkvec(" + num(t[0]) + "," + num(t[1]) + "," + (N > 2 ? num(t[2]) : std::string("0.0")) + ")", 1};
+        return true;
+      }
+      return false;
+    }
+    case GA_NODE_VAL: {
+      if (n->name == v) { out = {"u", 0}; return true; }
+      if (!ws.variable_exists(n->name) || !ws.is_constant(n->name) || ws.associated_mf(n->name) || ws.associated_im_data(n->name)) return false;
+      if (ws.value(n->name).size() != 1) return false;  // scalar fixed-size constants
+      size_t k = 0;
+      while (k < params.size() && params[k] != n->name) ++k;
+      if (k == params.size()) params.push_back(n->name);
+      if (params.size() > size_t(GFGPU_MAX_PARAMS)) return false;
+      out = {"par[" + std::to_string(k) + "]", 0};
+      return true;
+    }
+    case GA_NODE_GRAD:
+      if (n->name != v) return false;
+      out = {"gu", 1};
+      return true;
+    case GA_NODE_VAL_TEST:
+      if (n->name != v) return false;
+      out = {n->test_function_type == 2 ? "t2v" : "tv", 0};
+      return n->test_function_type == 1 || n->test_function_type == 2;
+    case GA_NODE_GRAD_TEST:
+      if (n->name != v) return false;
+      out = {n->test_function_type == 2 ? "t2g" : "tg", 1};
+      return n->test_function_type == 1 || n->test_function_type == 2;
+    case GA_NODE_OP: {
+      jit_value a, b;
+      switch (n->op_type) {
+        case GA_UNARY_MINUS:
+          if (!child(0, a)) return false;
+          out = {"(-" + a.code + ")", a.rank};
+          return true;
+        case GA_QUOTE:  // the transpose of a scalar or of a vector contracted afterwards: unchanged
+          if (!child(0, a)) return false;
+          out = a;
+          return true;
+        case GA_PLUS: case GA_MINUS:
+          if (!child(0, a) || !child(1, b) || a.rank != b.rank) return false;
+          out = {"(" + a.code + (n->op_type == GA_PLUS ? "+" : "-") + b.code + ")", a.rank};
+          return true;
+        case GA_MULT:
+          if (!child(0, a) || !child(1, b) || (a.rank && b.rank)) return false;
+          out = {"(" + a.code + "*" + b.code + ")", a.rank + b.rank};
+          return true;
+        case GA_DOTMULT:  // componentwise: a product as soon as one side is a scalar (the differentiation writes f'(u).*Test2_u)
+          if (!child(0, a) || !child(1, b) || (a.rank && b.rank)) return false;
+          out = {"(" + a.code + "*" + b.code + ")", a.rank + b.rank};
+          return true;
+        case GA_DIV: case GA_DOTDIV:
+          if (!child(0, a) || !child(1, b) || b.rank) return false;
+          out = {"(" + a.code + "/" + b.code + ")", a.rank};
+          return true;
+        case GA_DOT: case GA_COLON:
+          if (!child(0, a) || !child(1, b)) return false;
+          out = {"dot(" + a.code + "," + b.code + ")", (a.rank && b.rank) ? 0 : a.rank + b.rank};
+          return true;
+        default: return false;
+      }
+    }
+    case GA_NODE_PARAMS: {
+      if (n->children.empty()) return false;
+      const pga_tree_node &f = n->children[0];
+      if (f->node_type == GA_NODE_PREDEF_FUNC) {
+        static const std::map<std::string, std::string> fn = {
+            {"sqrt", "sqrt"}, {"sqr", "sqr"}, {"pow", "pow"}, {"exp", "exp"}, {"log", "log"}, {"log10", "log10"}, {"sinh", "sinh"},
+            {"cosh", "cosh"}, {"tanh", "tanh"}, {"asinh", "asinh"}, {"acosh", "acosh"}, {"atanh", "atanh"}, {"sin", "sin"},
+            {"cos", "cos"}, {"tan", "tan"}, {"asin", "asin"}, {"acos", "acos"}, {"atan", "atan"}, {"atan2", "atan2"}, {"erf", "erf"},
+            {"erfc", "erfc"}, {"Heaviside", "Heaviside"}, {"sign", "sign"}, {"abs", "fabs"}, {"pos_part", "pos_part"},
+            {"neg_part", "neg_part"}, {"sqr_pos_part", "sqr_pos_part"}, {"sqr_neg_part", "sqr_neg_part"},
+            {"half_sqr_pos_part", "half_sqr_pos_part"}, {"half_sqr_neg_part", "half_sqr_neg_part"}, {"max", "fmax"}, {"min", "fmin"},
+            {"DER_PDFUNC_SQRT", "DER_PDFUNC_SQRT"}, {"DER_PDFUNC1_POW", "DER_PDFUNC1_POW"}, {"DER_PDFUNC2_POW", "DER_PDFUNC2_POW"},
+            {"DER_PDFUNC_LOG", "DER_PDFUNC_LOG"}, {"DER_PDFUNC_LOG10", "DER_PDFUNC_LOG10"}, {"DER_PDFUNC_TANH", "DER_PDFUNC_TANH"},
+            {"DER_PDFUNC_ASINH", "DER_PDFUNC_ASINH"}, {"DER_PDFUNC_ACOSH", "DER_PDFUNC_ACOSH"}, {"DER_PDFUNC_ATANH", "DER_PDFUNC_ATANH"},
+            {"DER_PDFUNC_COS", "DER_PDFUNC_COS"}, {"DER_PDFUNC_TAN", "DER_PDFUNC_TAN"}, {"DER_PDFUNC_ASIN", "DER_PDFUNC_ASIN"},
+            {"DER_PDFUNC_ACOS", "DER_PDFUNC_ACOS"}, {"DER_PDFUNC_ATAN", "DER_PDFUNC_ATAN"}, {"DER_PDFUNC1_ATAN2", "DER_PDFUNC1_ATAN2"},
+            {"DER_PDFUNC2_ATAN2", "DER_PDFUNC2_ATAN2"}, {"DER_PDFUNC_ERF", "DER_PDFUNC_ERF"}, {"DER_PDFUNC_ERFC", "DER_PDFUNC_ERFC"}};
+        auto it = fn.find(f->name);
+        if (it == fn.end() || n->children.size() < 2 || n->children.size() > 3) return false;
+        std::string code = it->second + "(";
+        for (size_t k = 1; k < n->children.size(); ++k) {
+          jit_value a;
+          if (!child(k, a) || a.rank) return false;
+          code += (k > 1 ? "," : "") + a.code;
+        }
+        out = {code + ")", 0};
+        return true;
+      }
+      if (f->node_type == GA_NODE_OPERATOR && (f->name == "Norm_sqr" || f->name == "Norm") && n->children.size() == 2) {
+        jit_value a;
+        if (!child(1, a)) return false;
+        out = {(f->name == "Norm" ? "gnorm(" : "normsqr(") + a.code + ")", 0};
+        return true;
+      }
+      // component access of a vector: Grad_u(2)
+      if (n->children.size() == 2 && n->children[1]->node_type == GA_NODE_CONSTANT && n->children[1]->tensor().size() == 1) {
+        jit_value a;
+        if (!child(0, a) || a.rank != 1) return false;
+        const int k = int(n->children[1]->tensor()[0]);
+        if (k < 1 || k > N) return false;
+        out = {"(" + a.code + ").v[" + std::to_string(k - 1) + "]", 0};
+        return true;
+      }
+      return false;
+    }
+    default: return false;
+  }
+}
+
+// Translates the order-1 tree `i1` of the scalar variable v (and the order-2 tree on (v, v) with the same integration method and
+// region, if there is one) into a JIT term.  Returns false when something in the trees is outside the translator's language.
+static bool recognise_jit(const getfem::ga_workspace &ws, size_type i1, recognised_term &out) {
+  const auto &td = ws.tree_info(i1);
+  if (td.order != 1 || td.operation != getfem::ga_workspace::ASSEMBLY) return false;
+  const std::string &v = td.name_test1;
+  const getfem::mesh_fem *pmf = ws.associated_mf(v);
+  if (!pmf || pmf->get_qdim() != 1 || ws.is_constant(v)) return false;
+  const int N = int(pmf->linked_mesh().dim());
+  if (N != 2 && N != 3) return false;
+  std::vector<std::string> params;
+  jit_value f1, f2{"(0.0)", 0};
+  if (!td.ptree || !jit_emit(ws, td.ptree->root, v, N, params, f1) || f1.rank != 0) return false;
+  for (size_type j = 0; j < ws.nb_trees(); ++j) {
+    const auto &t2 = ws.tree_info(j);
+    if (t2.order == 2 && t2.mim == td.mim && t2.rg == td.rg && t2.name_test1 == v && t2.name_test2 == v) {
+      if (!t2.ptree || !jit_emit(ws, t2.ptree->root, v, N, params, f2) || f2.rank != 0) return false;
+    } else if (t2.order == 2 && t2.mim == td.mim && t2.rg == td.rg && (t2.name_test1 == v) != (t2.name_test2 == v)) {
+      return false;  // coupled to another variable: not this route
+    }
+  }
+  out = recognised_term();
+  out.family = GFGPU_JIT;
+  out.varname = v;
+  out.jit_form1 = f1.code;
+  out.jit_form2 = f2.code;
+  out.jit_params = params;
+  for (const std::string &pn : params) out.params.push_back(ws.value(pn)[0]);
+  return true;
+}
+
 // COUPLED div-pressure parts, as the reference prints them after its semantic analysis (the incompressibility bricks add
 // "-p*Div_Test_u - Test_p*Div_u", getfem_models.cc add_linear_incompressibility; the test driver ref_coupled.cc prints the trees):
 //   order 2 (Test_u, Test2_p)  "(-Test2_p)*Div_Test_u"     order 2 (Test_p, Test2_u)  "-(Test_p*Div_Test2_u)"
@@ -505,7 +675,9 @@ bool recognise_tree_sum(const getfem::ga_workspace &ws, size_type itree, std::ve
   if (!recognise_sum(ws, td.name_test1, strip(getfem::ga_tree_to_string(*td.ptree)), out)) {
     recognised_term rt;
     out.clear();
-    if (!recognise_by_probe(ws, itree, rt)) return false;
+    bool probed = false;
+    try { probed = recognise_by_probe(ws, itree, rt); } catch (const gmm::gmm_error &) { probed = false; }
+    if (!probed && !recognise_jit(ws, itree, rt)) return false;  // last resort: the NVRTC route (scalar variables)
     out.push_back(rt);
     return true;
   }
@@ -983,6 +1155,7 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
         GMM_ASSERT1(recognise_memo(i1, r1), "gfgpu: expression not handled by the device path (no CPU fallback): "
                                                         << getfem::ga_tree_to_string(*ws.tree_info(i1).ptree));
         if (r1.size() == 1 && r1[0].by_probe) continue;  // the probe checked K against THIS tree and r = K u against the order-1 tree
+        if (r1.size() == 1 && r1[0].family == GFGPU_JIT) continue;  // the JIT term carries this very tree as its second form
         size_t nsrc = 0;
         for (const recognised_term &rt : r1)  // (a coupled residual part has no derivative with respect to its own test variable)
           nsrc += rt.family == GFGPU_SOURCE || rt.family == GFGPU_NORMAL_SOURCE || rt.family == GFGPU_SHIM_COUPLED_DIV;
@@ -1220,7 +1393,8 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     {  // parameters bit for bit (a load that changes by 1e-9 is another term), and the family's own scale stays 1:
        // factor_of_variable enters at gfgpu_matrix_add_term for order 2 only, like the reference (C&E.cc:5359-5418 vs 4669-4735)
       char hb[40];
-      for (double p : rt.params) { std::snprintf(hb, sizeof hb, "/%a", p); key << hb; }
+      if (rt.family == GFGPU_JIT) key << "/jit:" << rt.jit_form1 << "|" << rt.jit_form2;  // parameters are refreshed at every call
+      else for (double p : rt.params) { std::snprintf(hb, sizeof hb, "/%a", p); key << hb; }
     }
     for (const std::string &fn : rt.field_names)
       key << "/field:" << fn << "@" << (const void *)ws.associated_mf(fn) << "/" << (const void *)ws.associated_im_data(fn);
@@ -1317,8 +1491,15 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
         GFGPU_CALL(gfgpu_tables_set_faces(e.tab, int(nf), int(nqf), fn.data(), fw.data(), fgtg.data(), fphi.data(),
                                           fgphi.data()));
       }
-      GFGPU_CALL(gfgpu_term_create(ctx_, e.mesh, e.fem, e.tab, rt.family, rt.params.data(), int(rt.params.size()), 1.0,
-                                   GFGPU_STRATEGY_AUTO, &e.term));
+      if (rt.family == GFGPU_JIT) {
+        GMM_ASSERT1(!rg_faces, "gfgpu: run-time compiled terms are volume terms");
+        const bool vdep = rt.jit_form2.find("u") != std::string::npos;  // "u" or "gu" in the tangent: its pattern may move
+        GFGPU_CALL(gfgpu_term_create_jit(ctx_, e.mesh, e.fem, e.tab, rt.jit_form1.c_str(), rt.jit_form2.c_str(), rt.params.data(),
+                                         int(rt.params.size()), 1.0, vdep ? 1 : 0, &e.term));
+      } else {
+        GFGPU_CALL(gfgpu_term_create(ctx_, e.mesh, e.fem, e.tab, rt.family, rt.params.data(), int(rt.params.size()), 1.0,
+                                     GFGPU_STRATEGY_AUTO, &e.term));
+      }
       if (use_region)
         GFGPU_CALL(gfgpu_term_set_region(e.term, int64_t(grg_cv.size()), grg_cv.data(), rg_faces ? grg_f.data() : nullptr));
       if (!rt.field_names.empty() && ws.associated_im_data(rt.field_names[0])) {
@@ -1412,6 +1593,8 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
         GFGPU_CALL(gfgpu_term_update_field(e.term, int(k), vals.data()));
       }
     }
+    if (rt.family == GFGPU_JIT && !rt.params.empty())  // the constants of the expression as they are NOW
+      GFGPU_CALL(gfgpu_term_set_params(e.term, rt.params.data(), int(rt.params.size())));
     e.used = true;
     e.last_use = ++use_clock_;
     // the variable's values, in the fem's own numbering (the workspace interval only offsets the result)

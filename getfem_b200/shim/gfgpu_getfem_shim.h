@@ -36,6 +36,10 @@ struct recognised_term {
   std::string varname_u, varname_p;
   bool transposed = false;
   double sign = 1.0;
+  // JIT terms (family GFGPU_JIT, the NVRTC route): the order-1 / order-2 trees translated into C expressions
+  // (include/gfgpu.h, gfgpu_term_create_jit) and the names of the scalar constants behind par[k]
+  std::string jit_form1, jit_form2;
+  std::vector<std::string> jit_params;
 };
 enum { GFGPU_SHIM_COUPLED_DIV = 1000 };
 

@@ -214,6 +214,8 @@ int gfgpu_term_potential_host(gfgpu_term *t, const double *U_host, double *E_hos
 int gfgpu_term_create_jit(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem, gfgpu_tables *tab, const char *form1, const char *form2,
                           const double *params, int nparams, double alpha, int value_dependent, gfgpu_term **out);
 int gfgpu_jit_check(int dim, const char *form1, const char *form2);
+/* new values of par[] for the next assemblies of a JIT term (constants of the expression may change between calls) */
+int gfgpu_term_set_params(gfgpu_term *t, const double *params, int nparams);
 
 /* Device durations (ms, CUDA events on the context's stream) of the kernels of the LAST assemble call:
  * out[0] generic element kernel, out[1] tangent gather-sum (STAGED), out[2] residual gather-sum,

@@ -155,3 +155,28 @@ def test_coupled_trees_run_on_the_device(mesh, expr):
     assert r["device_workspace_calls"] >= 2, r
     assert r["pattern_ok"] and r["nnz_ref"] == r["nnz_gpu"], r
     assert 0 <= r["rel_K"] < 1e-12 and r["rel_V"] < 1e-12 and r["norm_V"] > 0, r
+
+
+JIT = [  # expressions of a SCALAR variable that are none of the closed-form families: the NVRTC route
+    ("dim=3 n=3 gt=pk k=2 q=1", "(1+sqr(u))*Grad_u.Grad_Test_u + sin(u)*Test_u"),                       # nonlinear diffusion + reaction
+    ("dim=2 n=8 gt=pk k=2 q=1", "a*exp(u)*Grad_u.Grad_Test_u + a*Norm_sqr(Grad_u)*Test_u"),
+    ("dim=3 n=2 gt=qk k=2 q=1", "pow(1+Norm_sqr(Grad_u),0.75)*Grad_u.Grad_Test_u - a*Test_u"),          # p-Laplacian-like, trilinear hexahedra
+    ("dim=3 n=3 gt=pk k=1 q=1", "sqrt(1+Norm_sqr(Grad_u))*Test_u + Grad_u(1)*Test_u"),                   # minimal-surface-like + advection
+    ("dim=2 n=6 gt=qk k=2 q=1", "Grad_u.Grad_Test_u/(1+sqr(u)) + tanh(u)*Test_u"),
+    ("dim=3 n=3 gt=pk k=2 q=1", "([1,2,3].Grad_u)*Test_u + 0.1*Grad_u.Grad_Test_u"),                     # linear advection-diffusion: unsymmetric tangent
+]
+
+
+@pytest.mark.parametrize("mesh,expr", JIT)
+def test_general_scalar_expressions_run_on_the_device(mesh, expr):
+    """The reference's own order-1 and order-2 trees (after its symbolic differentiation) are translated into C expressions
+    and compiled at run time around a generic element kernel (NVRTC): workspace tangent pattern identical to ga_exec's,
+    values and residual 1e-12, in one process."""
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN, "model=expr"] + mesh.split() + ["expr=" + expr], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["device_workspace_calls"] >= 2, r
+    assert r["pattern_ok"] and r["nnz_ref"] == r["nnz_gpu"], r
+    assert 0 <= r["rel_K"] < 1e-12 and r["rel_V"] < 1e-12 and r["norm_V"] > 0, r

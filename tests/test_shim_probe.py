@@ -47,6 +47,17 @@ NOT_FAMILIES = [
 ]
 
 
+def _dryrun_order1(mesh, expr):
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN, "model=expr"] + mesh.split() + ["expr=" + expr], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, GFGPU_DRYRUN="1"))
+    assert out.returncode == 0, out.stderr[-1500:]
+    lines = [l for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun] order 1 (assembly order 2)")]
+    assert len(lines) == 1, out.stderr[-1500:]
+    return lines[0]
+
+
 def _dryrun(mesh, expr):
     if not os.path.exists(BIN):
         pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
@@ -184,7 +195,9 @@ def test_state_dependent_forms_are_refused_whatever_the_state(mesh, expr, uzero)
     args = [BIN, "model=expr"] + mesh.split() + ["expr=" + expr] + (["uzero=" + uzero] if uzero else [])
     out = subprocess.run(args, capture_output=True, text=True, timeout=300, env=dict(os.environ, GFGPU_DRYRUN="1"))
     lines = [l for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun] order")]
-    assert lines and all("NOT recognised" in l for l in lines), out.stderr[-1500:]
+    # never a constant-coefficient family fitted at one state: either refused, or (scalar variable, round 2) the tree itself
+    # translated for the NVRTC route -- family 11, which evaluates the state at every Gauss point
+    assert lines and all("NOT recognised" in l or "recognised family 11 " in l for l in lines), out.stderr[-1500:]
 
 
 def test_a_load_written_with_the_unknown_is_not_a_constant_load():
@@ -211,3 +224,27 @@ def test_coupled_trees_of_the_incompressibility_brick_are_recognised():
     coupled = [l for l in lines if "family 1000" in l]
     forms = {l.split(": ", 1)[1].split(" -> ")[0] for l in coupled}
     assert forms == {"-(Test_p*Div_u)", "-(Test_p*Div_Test2_u)", "(-p)*Div_Test_u", "(-Test2_p)*Div_Test_u"}, forms
+
+
+JIT_EXPRS = [
+    "(1+sqr(u))*Grad_u.Grad_Test_u + sin(u)*Test_u",
+    "a*exp(u)*Grad_u.Grad_Test_u + a*Norm_sqr(Grad_u)*Test_u",
+    "pow(1+Norm_sqr(Grad_u),0.75)*Grad_u.Grad_Test_u - a*Test_u",
+    "sqrt(1+Norm_sqr(Grad_u))*Test_u + Grad_u(1)*Test_u",
+    "([1,2,3].Grad_u)*Test_u + 0.1*Grad_u.Grad_Test_u",
+]
+
+
+@pytest.mark.parametrize("expr", JIT_EXPRS)
+def test_general_scalar_expressions_take_the_nvrtc_route(expr):
+    """CPU (dry run): an expression of a scalar variable that no normal form and no probe covers is translated from the
+    reference's analysed trees into a JIT term (family 11); constants it names become par[k]."""
+    line = _dryrun_order1("dim=3 n=2 gt=pk k=2 q=1", expr)
+    assert "recognised family 11" in line, line
+
+
+def test_the_nvrtc_route_refuses_what_it_cannot_express():
+    """vector variables, X, other variables: no silent approximation -- the tree is reported as not recognised"""
+    for mesh, expr in (("dim=3 n=2 gt=pk k=2", "sqr(Norm(u))*Grad_u:Grad_Test_u"), ("dim=3 n=2 gt=pk k=2 q=1", "X(1)*sin(u)*Test_u")):
+        line = _dryrun_order1(mesh, expr)
+        assert "NOT recognised" in line, line
