@@ -50,7 +50,7 @@ SIGNATURES = {
     "gfgpu_tables_destroy": (C.c_int, [_P]),
     "gfgpu_term_create": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_double, C.c_int, _PP]),
     "gfgpu_term_create_jit": (C.c_int, [_P, _P, _P, _P, C.c_char_p, C.c_char_p, _P, C.c_int, C.c_double, C.c_int, _PP]),
-    "gfgpu_jit_check": (C.c_int, [C.c_int, C.c_char_p, C.c_char_p]),
+    "gfgpu_jit_check": (C.c_int, [C.c_int, C.c_int, C.c_char_p, C.c_char_p]),
     "gfgpu_term_set_params": (C.c_int, [_P, _P, C.c_int]),
     "gfgpu_term_destroy": (C.c_int, [_P]),
     "gfgpu_term_set_region": (C.c_int, [_P, _i64, _P, _P]),
@@ -551,9 +551,9 @@ class DeviceMatrix(_Handle):
 RECT_DIV_PRESSURE = 0
 
 
-def jit_check(dim, form1, form2):
+def jit_check(dim, form1, form2, qdim=1):
     """Compile the two forms of a JIT term with NVRTC (no GPU needed); raises GfgpuError with the compiler log."""
-    check(lib().gfgpu_jit_check(int(dim), form1.encode(), form2.encode()))
+    check(lib().gfgpu_jit_check(int(dim), int(qdim), form1.encode(), form2.encode()))
 
 
 class DeviceRect(_Handle):

@@ -369,8 +369,8 @@ int gfgpu_term_create_jit(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem, gfgp
   GF_REQUIRE(ctx && mesh && fem && tab && form1 && form2 && out, "null argument");
   GF_REQUIRE(fem->mesh == mesh, "the fem was built on another mesh");
   GF_REQUIRE(tab->dim == mesh->dim && tab->ng == mesh->ng && tab->nd == fem->nd, "tables do not match mesh/fem");
-  GF_REQUIRE(fem->qdim == 1, "JIT terms: scalar variables");
   GF_REQUIRE(mesh->dim == 2 || mesh->dim == 3, "JIT terms: 2D and 3D meshes");
+  GF_REQUIRE(fem->qdim == 1 || fem->qdim == mesh->dim, "JIT terms: scalar variables, or vector variables of the mesh dimension");
   GF_REQUIRE(nparams >= 0 && nparams <= GFGPU_MAX_PARAMS && (nparams == 0 || params), "bad parameters");
   std::unique_ptr<gfgpu_term> t(new gfgpu_term);
   t->ctx = ctx; t->mesh = mesh; t->fem = fem; t->tab = tab; t->family = GFGPU_JIT;
@@ -397,10 +397,10 @@ int gfgpu_term_set_params(gfgpu_term *t, const double *params, int nparams) {
   GF_API_END
 }
 
-int gfgpu_jit_check(int dim, const char *form1, const char *form2) {
+int gfgpu_jit_check(int dim, int qdim, const char *form1, const char *form2) {
   GF_API_BEGIN
-  GF_REQUIRE(form1 && form2 && (dim == 2 || dim == 3), "bad argument");
-  const std::string log = gf::jit_check_source(dim, form1, form2);
+  GF_REQUIRE(form1 && form2 && (dim == 2 || dim == 3) && (qdim == 1 || qdim == dim), "bad argument");
+  const std::string log = gf::jit_check_source(dim, qdim, form1, form2);
   GF_REQUIRE(log.empty(), "the integrand does not compile (NVRTC):\n" + log);
   GF_API_END
 }

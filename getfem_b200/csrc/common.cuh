@@ -356,7 +356,7 @@ void recompute_cols_tangent(gfgpu_term *t, const double *U, bool with_r);
 bool uniform_prepare(gfgpu_term *t);
 void launch_jit_kernel(gfgpu_term *t, const ElemArgs &a);  // jit.cu
 void jit_release(gfgpu_term *t);
-std::string jit_check_source(int N, const std::string &form1, const std::string &form2);
+std::string jit_check_source(int N, int Q, const std::string &form1, const std::string &form2);
 void term_settle_pending(gfgpu_term *t);  // api.cu: deferred pattern check of a value-dependent tangent
 void uniform_tangent(gfgpu_term *t);
 

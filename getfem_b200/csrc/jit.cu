@@ -127,6 +127,47 @@ __device__ __forceinline__ double DER_PDFUNC_ERFC(double t) { return -exp(-t * t
 __device__ __forceinline__ double Heaviside(double x) { return x < 0 ? 0.0 : 1.0; }
 __device__ __forceinline__ double sign(double x) { return x < 0 ? -1.0 : (x > 0 ? 1.0 : 0.0); }
 
+// matrices of the mesh dimension: m[c][k] (for Grad_u: component c, direction k, the GWFL convention)
+struct mat { double m[GF_N][GF_N]; };
+__device__ __forceinline__ mat operator+(mat a, mat b) { mat r; for (int i = 0; i < GF_N; ++i) for (int j = 0; j < GF_N; ++j) r.m[i][j] = a.m[i][j] + b.m[i][j]; return r; }
+__device__ __forceinline__ mat operator-(mat a, mat b) { mat r; for (int i = 0; i < GF_N; ++i) for (int j = 0; j < GF_N; ++j) r.m[i][j] = a.m[i][j] - b.m[i][j]; return r; }
+__device__ __forceinline__ mat operator-(mat a) { mat r; for (int i = 0; i < GF_N; ++i) for (int j = 0; j < GF_N; ++j) r.m[i][j] = -a.m[i][j]; return r; }
+__device__ __forceinline__ mat operator*(double s, mat a) { mat r; for (int i = 0; i < GF_N; ++i) for (int j = 0; j < GF_N; ++j) r.m[i][j] = s * a.m[i][j]; return r; }
+__device__ __forceinline__ mat operator*(mat a, double s) { return s * a; }
+__device__ __forceinline__ mat operator/(mat a, double s) { mat r; for (int i = 0; i < GF_N; ++i) for (int j = 0; j < GF_N; ++j) r.m[i][j] = a.m[i][j] / s; return r; }
+__device__ __forceinline__ mat operator*(mat a, mat b) {
+  mat r;
+  for (int i = 0; i < GF_N; ++i) for (int j = 0; j < GF_N; ++j) { double t = 0; for (int k = 0; k < GF_N; ++k) t += a.m[i][k] * b.m[k][j]; r.m[i][j] = t; }
+  return r;
+}
+__device__ __forceinline__ vec operator*(mat a, vec b) { vec r; for (int i = 0; i < GF_N; ++i) { double t = 0; for (int k = 0; k < GF_N; ++k) t += a.m[i][k] * b.v[k]; r.v[i] = t; } return r; }
+__device__ __forceinline__ mat dot(mat a, mat b) { return a * b; }          // contraction of the last index with the first
+__device__ __forceinline__ vec dot(mat a, vec b) { return a * b; }
+__device__ __forceinline__ vec dot(vec a, mat b) { vec r; for (int j = 0; j < GF_N; ++j) { double t = 0; for (int k = 0; k < GF_N; ++k) t += a.v[k] * b.m[k][j]; r.v[j] = t; } return r; }
+__device__ __forceinline__ mat dot(double a, mat b) { return a * b; }
+__device__ __forceinline__ mat dot(mat a, double b) { return b * a; }
+__device__ __forceinline__ double ddot(mat a, mat b) { double t = 0; for (int i = 0; i < GF_N; ++i) for (int j = 0; j < GF_N; ++j) t += a.m[i][j] * b.m[i][j]; return t; }
+__device__ __forceinline__ double ddot(vec a, vec b) { return dot(a, b); }
+__device__ __forceinline__ double ddot(double a, double b) { return a * b; }
+__device__ __forceinline__ mat transp(mat a) { mat r; for (int i = 0; i < GF_N; ++i) for (int j = 0; j < GF_N; ++j) r.m[i][j] = a.m[j][i]; return r; }
+__device__ __forceinline__ vec transp(vec a) { return a; }
+__device__ __forceinline__ double transp(double a) { return a; }
+__device__ __forceinline__ double trace(mat a) { double t = 0; for (int i = 0; i < GF_N; ++i) t += a.m[i][i]; return t; }
+__device__ __forceinline__ mat sym(mat a) { return 0.5 * (a + transp(a)); }
+__device__ __forceinline__ mat skew(mat a) { return 0.5 * (a - transp(a)); }
+__device__ __forceinline__ mat deviator(mat a) { mat r = a; const double t = trace(a) / GF_N; for (int i = 0; i < GF_N; ++i) r.m[i][i] -= t; return r; }
+__device__ __forceinline__ double normsqr(mat a) { return ddot(a, a); }
+__device__ __forceinline__ double gnorm(mat a) { return sqrt(ddot(a, a)); }
+__device__ __forceinline__ mat outer(vec a, vec b) { mat r; for (int i = 0; i < GF_N; ++i) for (int j = 0; j < GF_N; ++j) r.m[i][j] = a.v[i] * b.v[j]; return r; }
+// mkmat takes the entries COLUMN-major, like GetFEM stores a constant matrix (first index fastest)
+__device__ __forceinline__ mat mkmat(double a0, double a1, double a2, double a3, double a4, double a5, double a6, double a7, double a8) {
+  const double a[9] = {a0, a1, a2, a3, a4, a5, a6, a7, a8};
+  mat r;
+  for (int j = 0; j < GF_N; ++j) for (int i = 0; i < GF_N; ++i) r.m[i][j] = a[i + GF_N * j];
+  return r;
+}
+
+#if GF_Q == 1
 __device__ __forceinline__ double gf_form1(double u, vec gu, const double *par, double tv, vec tg) { return GF_FORM1; }
 __device__ __forceinline__ double gf_form2(double u, vec gu, const double *par, double tv, vec tg, double t2v, vec t2g) {
   return GF_FORM2;
@@ -252,6 +293,152 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
     __syncthreads();
   }
 }
+#else  // ---------------------------------------------------------------- vector variable, qdim = mesh dimension
+__device__ __forceinline__ double gf_form1(vec u, mat gu, const double *par, vec tv, mat tg) { return GF_FORM1; }
+__device__ __forceinline__ double gf_form2(vec u, mat gu, const double *par, vec tv, mat tg, vec t2v, mat t2g) { return GF_FORM2; }
+
+// probe slot s = c * (N+1) + a: a = 0 -> the value of component c, a = 1 + k -> d/dx_k of component c
+__device__ __forceinline__ void gf_probe(int s, vec &tv, mat &tg) {
+  const int c = s / (GF_N + 1), a = s % (GF_N + 1);
+  for (int i = 0; i < GF_N; ++i) { tv.v[i] = 0.0; for (int j = 0; j < GF_N; ++j) tg.m[i][j] = 0.0; }
+  if (a == 0) tv.v[c] = 1.0; else tg.m[c][a - 1] = 1.0;
+}
+
+extern "C" __global__ void __launch_bounds__(128)
+gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z, const int *__restrict__ conn,
+            const int *__restrict__ edof, const double *__restrict__ U, const double *__restrict__ w, const double *__restrict__ gt_grad,
+            const double *__restrict__ phi, const double *__restrict__ gphi, const double *__restrict__ par, int ng, int nq, int nd,
+            long long e0, long long ne, double alpha, double *__restrict__ stage, unsigned short *__restrict__ emask,
+            double *__restrict__ rstage) {
+  constexpr int N = GF_N, NA = GF_N + 1, Q = GF_N, NS = Q * NA;
+  extern __shared__ double sm[];
+  const int s1 = nd * Q;
+  double *sG = sm;                               // N x ng
+  double *sU = sG + N * ng;                      // nd x Q
+  double *sT = sU + s1;                          // nq x nd x NA
+  double *sS = sT + (size_t)nq * nd * NA;        // nq x (Q + Q*N + 1): state u, Grad u, weight w J alpha
+  double *sC1 = sS + (size_t)nq * (Q + Q * N + 1);   // nq x NS
+  double *sC2 = sC1 + (size_t)nq * NS;           // nq x NS x NS
+  double *sK = sC2 + (size_t)nq * NS * NS;       // s1 x s1
+  __shared__ double sRed[4];
+  const int tid = threadIdx.x;
+  for (long long el = blockIdx.x; el < ne; el += gridDim.x) {
+    const long long e = e0 + el;
+    for (int k = tid; k < N * ng; k += blockDim.x) {
+      const int i = k / N, d = k % N;
+      const int p = conn[e * ng + i];
+      sG[d + N * i] = (d == 0 ? x : d == 1 ? y : z)[p];
+    }
+    for (int k = tid; k < s1; k += blockDim.x) sU[k] = U ? U[edof[e * nd + k / Q] + k % Q] : 0.0;
+    __syncthreads();
+    for (int q = tid; q < nq; q += blockDim.x) {
+      double K[N * N], B[N * N];
+      for (int k = 0; k < N * N; ++k) K[k] = 0.0;
+      const double *pc = gt_grad + (size_t)q * ng * N;
+      for (int i = 0; i < ng; ++i)
+        for (int c = 0; c < N; ++c)
+          for (int r = 0; r < N; ++r) K[r + N * c] += sG[r + N * i] * pc[i * N + c];
+      double J;
+      if (N == 2) {
+        const double d = K[0] * K[3] - K[1] * K[2], id = 1.0 / d;
+        B[0] = K[3] * id; B[2] = -K[1] * id; B[1] = -K[2] * id; B[3] = K[0] * id;
+        J = fabs(d);
+      } else {
+        const double c00 = K[4] * K[8] - K[7] * K[5], c10 = K[7] * K[2] - K[1] * K[8], c20 = K[1] * K[5] - K[4] * K[2];
+        const double d = K[0] * c00 + K[3] * c10 + K[6] * c20, id = 1.0 / d;
+        B[0] = c00 * id; B[3] = c10 * id; B[6] = c20 * id;
+        B[1] = (K[6] * K[5] - K[3] * K[8]) * id; B[4] = (K[0] * K[8] - K[6] * K[2]) * id; B[7] = (K[3] * K[2] - K[0] * K[5]) * id;
+        B[2] = (K[3] * K[7] - K[6] * K[4]) * id; B[5] = (K[6] * K[1] - K[0] * K[7]) * id; B[8] = (K[0] * K[4] - K[3] * K[1]) * id;
+        J = fabs(d);
+      }
+      double *S = sS + (size_t)q * (Q + Q * N + 1);
+      for (int k = 0; k < Q + Q * N; ++k) S[k] = 0.0;
+      double *T = sT + (size_t)q * nd * NA;
+      for (int i = 0; i < nd; ++i) {
+        const double *g = gphi + ((size_t)q * nd + i) * N;
+        const double ph = phi[(size_t)q * nd + i];
+        T[i * NA] = ph;
+        for (int c = 0; c < Q; ++c) S[c] += sU[i * Q + c] * ph;
+        for (int k = 0; k < N; ++k) {
+          double t = 0.0;
+          for (int p = 0; p < N; ++p) t += B[k + N * p] * g[p];
+          T[i * NA + 1 + k] = t;
+          for (int c = 0; c < Q; ++c) S[Q + c * N + k] += sU[i * Q + c] * t;  // Grad_u(c, k)
+        }
+      }
+      const double wq = w[q];
+      S[Q + Q * N] = wq == 0.0 ? 0.0 : alpha * J * wq;  // zero-weight points are skipped (C&E.cc:8852)
+    }
+    __syncthreads();
+    // coefficients of the two forms: work item = (Gauss point, probe slot of Test)
+    for (int it = tid; it < nq * NS; it += blockDim.x) {
+      const int q = it / NS, s = it % NS;
+      const double *S = sS + (size_t)q * (Q + Q * N + 1);
+      const double cw = S[Q + Q * N];
+      vec uq; mat guq;
+      for (int c = 0; c < Q; ++c) { uq.v[c] = S[c]; for (int k = 0; k < N; ++k) guq.m[c][k] = S[Q + c * N + k]; }
+      vec tv, t2v; mat tg, t2g;
+      gf_probe(s, tv, tg);
+      sC1[q * NS + s] = cw == 0.0 ? 0.0 : cw * gf_form1(uq, guq, par, tv, tg);
+      for (int s2 = 0; s2 < NS; ++s2) {
+        gf_probe(s2, t2v, t2g);
+        sC2[((size_t)q * NS + s) * NS + s2] = cw == 0.0 ? 0.0 : cw * gf_form2(uq, guq, par, tv, tg, t2v, t2g);
+      }
+    }
+    __syncthreads();
+    if (rstage)
+      for (int k = tid; k < s1; k += blockDim.x) {
+        const int i = k / Q, c = k % Q;
+        double r = 0.0;
+        for (int q = 0; q < nq; ++q) {
+          const double *T = sT + ((size_t)q * nd + i) * NA;
+          for (int a = 0; a < NA; ++a) r += sC1[q * NS + c * NA + a] * T[a];
+        }
+        rstage[(size_t)el * s1 + k] = r;
+      }
+    if (stage || emask) {
+      double vmax = 0.0;
+      for (int k = tid; k < s1 * s1; k += blockDim.x) {  // k = row + s1 * column, row = i*Q + c (Test), column = j*Q + d (Test2)
+        const int row = k % s1, col = k / s1, i = row / Q, c = row % Q, j = col / Q, d = col % Q;
+        double r = 0.0;
+        for (int q = 0; q < nq; ++q) {
+          const double *Ti = sT + ((size_t)q * nd + i) * NA, *Tj = sT + ((size_t)q * nd + j) * NA;
+          const double *C = sC2 + ((size_t)q * NS + c * NA) * NS + d * NA;
+          for (int a = 0; a < NA; ++a) {
+            double t = 0.0;
+            for (int b = 0; b < NA; ++b) t += C[a * NS + b] * Tj[b];
+            r += Ti[a] * t;
+          }
+        }
+        sK[k] = r;
+        vmax = fmax(vmax, fabs(r));
+      }
+      for (int off = 16; off > 0; off >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, off));
+      if ((tid & 31) == 0) sRed[tid >> 5] = vmax;
+      __syncthreads();
+      vmax = fmax(fmax(sRed[0], sRed[1]), fmax(sRed[2], sRed[3]));
+      const double thr = vmax * 1e-14;  // the drop rule of add_elem_matrix (C&E.cc:4889,4898)
+      if (stage)
+        for (int k = tid; k < s1 * s1; k += blockDim.x) {
+          const double v = sK[k];
+          stage[(size_t)el * s1 * s1 + k] = ((vmax != 0.0) && (fabs(v) > thr)) ? v : 0.0;
+        }
+      if (emask)
+        for (int p = tid; p < nd * nd; p += blockDim.x) {  // per node pair: bit (d*Q + c) = entry (row component c, column component d)
+          const int j = p / nd, i = p % nd;
+          unsigned mask = 0;
+          for (int d = 0; d < Q; ++d)
+            for (int c = 0; c < Q; ++c) {
+              const double v = sK[(i * Q + c) + s1 * (j * Q + d)];
+              if ((vmax != 0.0) && (fabs(v) > thr)) mask |= 1u << (d * Q + c);
+            }
+          emask[(size_t)el * nd * nd + p] = (unsigned short)mask;
+        }
+    }
+    __syncthreads();
+  }
+}
+#endif
 )GFJIT";
 
 struct JitKernel {
@@ -271,8 +458,8 @@ void jit_release(gfgpu_term *t) {
 static JitKernel *jit_compile(gfgpu_term *t) {
   JitApi &api = jit_api();
   const int N = t->mesh->dim;
-  std::string src = "#define GF_N " + std::to_string(N) + "\n#define GF_FORM1 (" + t->jit_form1 + ")\n#define GF_FORM2 (" + t->jit_form2 +
-                    ")\n" + kJitSource;
+  std::string src = "#define GF_N " + std::to_string(N) + "\n#define GF_Q " + std::to_string(t->fem->qdim) + "\n#define GF_FORM1 (" +
+                    t->jit_form1 + ")\n#define GF_FORM2 (" + t->jit_form2 + ")\n" + kJitSource;
   nvrtcProgram_t prog = nullptr;
   GF_REQUIRE(api.CreateProgram(&prog, src.c_str(), "gfgpu_jit.cu", 0, nullptr, nullptr) == 0, "nvrtcCreateProgram failed");
   const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
@@ -301,9 +488,10 @@ static JitKernel *jit_compile(gfgpu_term *t) {
 }
 
 // compile-only check (no GPU needed): used by the CPU tests and by gfgpu_term_create_jit to fail early
-std::string jit_check_source(int N, const std::string &form1, const std::string &form2) {
+std::string jit_check_source(int N, int Q, const std::string &form1, const std::string &form2) {
   JitApi &api = jit_api(false);
-  std::string src = "#define GF_N " + std::to_string(N) + "\n#define GF_FORM1 (" + form1 + ")\n#define GF_FORM2 (" + form2 + ")\n" + kJitSource;
+  std::string src = "#define GF_N " + std::to_string(N) + "\n#define GF_Q " + std::to_string(Q) + "\n#define GF_FORM1 (" + form1 +
+                    ")\n#define GF_FORM2 (" + form2 + ")\n" + kJitSource;
   nvrtcProgram_t prog = nullptr;
   if (api.CreateProgram(&prog, src.c_str(), "gfgpu_jit.cu", 0, nullptr, nullptr) != 0) return "nvrtcCreateProgram failed";
   const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17"};
@@ -322,8 +510,12 @@ void launch_jit_kernel(gfgpu_term *t, const ElemArgs &a) {
   JitKernel *k = static_cast<JitKernel *>(t->jit_kernel);
   JitApi &api = jit_api();
   const int N = t->mesh->dim, NA = N + 1, nd = t->fem->nd, nq = a.nq, ng = a.ng;
-  GF_REQUIRE(t->fem->qdim == 1, "JIT terms: scalar variables");
-  const size_t smem = ((size_t)N * ng + nd + (size_t)nq * nd * NA + (size_t)nq * NA + (size_t)nq * NA * NA + (size_t)nd * nd + 2) * 8;
+  const int Q = t->fem->qdim;
+  GF_REQUIRE(Q == 1 || Q == N, "JIT terms: scalar variables, or vector variables of the mesh dimension");
+  const size_t NS = (size_t)Q * NA, s1 = (size_t)nd * Q;
+  const size_t smem = Q == 1 ? ((size_t)N * ng + nd + (size_t)nq * nd * NA + (size_t)nq * NA + (size_t)nq * NA * NA + (size_t)nd * nd + 2) * 8
+                             : ((size_t)N * ng + s1 + (size_t)nq * nd * NA + (size_t)nq * (Q + Q * N + 1) + (size_t)nq * NS +
+                                (size_t)nq * NS * NS + s1 * s1 + 2) * 8;
   GF_REQUIRE(smem <= 220 * 1024, "JIT terms: element too large for the run-time kernel (nq x nd x (N+1) doubles of shared memory)");
   if (t->jit_par.n != (size_t)GFGPU_MAX_PARAMS) {
     t->jit_par.alloc(ctx, GFGPU_MAX_PARAMS);

@@ -437,34 +437,42 @@ static bool recognise_by_probe(const getfem::ga_workspace &ws, size_type itree, 
 // matrices, X, Normal, other variables, fem or im data, interpolate transformations -- is refused, and the caller then
 // reports the expression as not handled.  (ga_exec evaluates the same tree with tensors whose leading dimensions index
 // the test functions, C&E.cc:2769-3760; for a scalar variable the contraction pattern reduces to these ranks.)
-struct jit_value { std::string code; int rank; };
+struct jit_value { std::string code; int rank; };  // rank 0 scalar, 1 vector of the mesh dimension, 2 matrix N x N
 
-static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node &n, const std::string &v, int N,
+static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node &n, const std::string &v, int N, int Q,
                      std::vector<std::string> &params, jit_value &out) {
   using namespace getfem;
   if (!n) return false;
   auto num = [](double x) { char b[48]; std::snprintf(b, sizeof b, "(%.17g)", x); std::string r(b);
                             if (r.find_first_of(".eEn") == std::string::npos) r.insert(r.size() - 1, ".0"); return r; };
-  auto child = [&](size_t k, jit_value &o) { return k < n->children.size() && jit_emit(ws, n->children[k], v, N, params, o); };
+  auto child = [&](size_t k, jit_value &o) { return k < n->children.size() && jit_emit(ws, n->children[k], v, N, Q, params, o); };
+  const int rv = Q == 1 ? 0 : 1;  // rank of the variable's value; its gradient has one more
+  auto tensor_const = [&](const base_tensor &t, jit_value &o) {
+    if (t.size() == 1) { o = {num(t[0]), 0}; return true; }
+    if (t.sizes().size() == 1 && t.size() == size_t(N)) {
+      o = {"mkvec(" + num(t[0]) + "," + num(t[1]) + "," + (N > 2 ? num(t[2]) : std::string("0.0")) + ")", 1};
+      return true;
+    }
+    if (t.sizes().size() == 2 && t.sizes()[0] == size_type(N) && t.sizes()[1] == size_type(N)) {  // first index fastest
+      std::string c = "mkmat(";
+      for (int k = 0; k < 9; ++k) c += (k ? "," : "") + (k < N * N ? num(t[k]) : std::string("0.0"));
+      o = {c + ")", 2};
+      return true;
+    }
+    return false;
+  };
   switch (n->node_type) {
     case GA_NODE_ZERO: {
-      const size_t sz = n->tensor().size();
-      if (sz == 1) { out = {"(0.0)", 0}; return true; }
-      if (sz == size_t(N) && n->tensor().sizes().size() == 1) { out = {"mkvec(0.0,0.0,0.0)", 1}; return true; }
-      return false;
-    }
-    case GA_NODE_CONSTANT: {
-      const base_tensor &t = n->tensor();
       if (n->test_function_type != 0 && n->test_function_type != size_type(-1)) return false;
-      if (t.size() == 1) { out = {num(t[0]), 0}; return true; }
-      if (t.size() == size_t(N) && t.sizes().size() == 1) {
-        out = {"mkvec(" + num(t[0]) + "," + num(t[1]) + "," + (N > 2 ? num(t[2]) : std::string("0.0")) + ")", 1};
-        return true;
-      }
-      return false;
+      base_tensor z = n->tensor();
+      for (auto &x : z) x = 0.0;
+      return tensor_const(z, out);
     }
+    case GA_NODE_CONSTANT:
+      if (n->test_function_type != 0 && n->test_function_type != size_type(-1)) return false;
+      return tensor_const(n->tensor(), out);
     case GA_NODE_VAL: {
-      if (n->name == v) { out = {"u", 0}; return true; }
+      if (n->name == v) { out = {"u", rv}; return true; }
       if (!ws.variable_exists(n->name) || !ws.is_constant(n->name) || ws.associated_mf(n->name) || ws.associated_im_data(n->name)) return false;
       if (ws.value(n->name).size() != 1) return false;  // scalar fixed-size constants
       size_t k = 0;
@@ -476,15 +484,23 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
     }
     case GA_NODE_GRAD:
       if (n->name != v) return false;
-      out = {"gu", 1};
+      out = {"gu", rv + 1};
+      return true;
+    case GA_NODE_DIVERG:
+      if (n->name != v || Q == 1) return false;
+      out = {"trace(gu)", 0};
       return true;
     case GA_NODE_VAL_TEST:
       if (n->name != v) return false;
-      out = {n->test_function_type == 2 ? "t2v" : "tv", 0};
+      out = {n->test_function_type == 2 ? "t2v" : "tv", rv};
       return n->test_function_type == 1 || n->test_function_type == 2;
     case GA_NODE_GRAD_TEST:
       if (n->name != v) return false;
-      out = {n->test_function_type == 2 ? "t2g" : "tg", 1};
+      out = {n->test_function_type == 2 ? "t2g" : "tg", rv + 1};
+      return n->test_function_type == 1 || n->test_function_type == 2;
+    case GA_NODE_DIVERG_TEST:
+      if (n->name != v || Q == 1) return false;
+      out = {n->test_function_type == 2 ? "trace(t2g)" : "trace(tg)", 0};
       return n->test_function_type == 1 || n->test_function_type == 2;
     case GA_NODE_OP: {
       jit_value a, b;
@@ -493,18 +509,28 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
           if (!child(0, a)) return false;
           out = {"(-" + a.code + ")", a.rank};
           return true;
-        case GA_QUOTE:  // the transpose of a scalar or of a vector contracted afterwards: unchanged
+        case GA_QUOTE:
           if (!child(0, a)) return false;
-          out = a;
+          out = {"transp(" + a.code + ")", a.rank};
+          return true;
+        case GA_TRACE:
+          if (!child(0, a) || a.rank != 2) return false;
+          out = {"trace(" + a.code + ")", 0};
+          return true;
+        case GA_SYM: case GA_SKEW: case GA_DEVIATOR:
+          if (!child(0, a) || a.rank != 2) return false;
+          out = {std::string(n->op_type == GA_SYM ? "sym(" : n->op_type == GA_SKEW ? "skew(" : "deviator(") + a.code + ")", 2};
           return true;
         case GA_PLUS: case GA_MINUS:
           if (!child(0, a) || !child(1, b) || a.rank != b.rank) return false;
           out = {"(" + a.code + (n->op_type == GA_PLUS ? "+" : "-") + b.code + ")", a.rank};
           return true;
         case GA_MULT:
-          if (!child(0, a) || !child(1, b) || (a.rank && b.rank)) return false;
-          out = {"(" + a.code + "*" + b.code + ")", a.rank + b.rank};
-          return true;
+          if (!child(0, a) || !child(1, b)) return false;
+          if (a.rank == 0 || b.rank == 0) { out = {"(" + a.code + "*" + b.code + ")", a.rank + b.rank}; return true; }
+          if (a.rank == 2 && b.rank == 1) { out = {"(" + a.code + "*" + b.code + ")", 1}; return true; }
+          if (a.rank == 2 && b.rank == 2) { out = {"(" + a.code + "*" + b.code + ")", 2}; return true; }
+          return false;
         case GA_DOTMULT:  // componentwise: a product as soon as one side is a scalar (the differentiation writes f'(u).*Test2_u)
           if (!child(0, a) || !child(1, b) || (a.rank && b.rank)) return false;
           out = {"(" + a.code + "*" + b.code + ")", a.rank + b.rank};
@@ -513,9 +539,17 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
           if (!child(0, a) || !child(1, b) || b.rank) return false;
           out = {"(" + a.code + "/" + b.code + ")", a.rank};
           return true;
-        case GA_DOT: case GA_COLON:
+        case GA_DOT:  // contraction of the last index of a with the first of b
           if (!child(0, a) || !child(1, b)) return false;
-          out = {"dot(" + a.code + "," + b.code + ")", (a.rank && b.rank) ? 0 : a.rank + b.rank};
+          out = {"dot(" + a.code + "," + b.code + ")", (a.rank && b.rank) ? a.rank + b.rank - 2 : a.rank + b.rank};
+          return true;
+        case GA_COLON:
+          if (!child(0, a) || !child(1, b) || a.rank != b.rank) return false;
+          out = {"ddot(" + a.code + "," + b.code + ")", 0};
+          return true;
+        case GA_TMULT:
+          if (!child(0, a) || !child(1, b) || a.rank != 1 || b.rank != 1) return false;
+          out = {"outer(" + a.code + "," + b.code + ")", 2};
           return true;
         default: return false;
       }
@@ -554,13 +588,20 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
         out = {(f->name == "Norm" ? "gnorm(" : "normsqr(") + a.code + ")", 0};
         return true;
       }
-      // component access of a vector: Grad_u(2)
-      if (n->children.size() == 2 && n->children[1]->node_type == GA_NODE_CONSTANT && n->children[1]->tensor().size() == 1) {
-        jit_value a;
-        if (!child(0, a) || a.rank != 1) return false;
-        const int k = int(n->children[1]->tensor()[0]);
-        if (k < 1 || k > N) return false;
-        out = {"(" + a.code + ").v[" + std::to_string(k - 1) + "]", 0};
+      // component access: v(i) of a vector, M(i,j) of a matrix, with constant indices
+      auto index = [&](size_t k, int &o) {
+        if (k >= n->children.size() || n->children[k]->node_type != GA_NODE_CONSTANT || n->children[k]->tensor().size() != 1) return false;
+        o = int(n->children[k]->tensor()[0]);
+        return o >= 1 && o <= N;
+      };
+      jit_value a;
+      int i1 = 0, i2 = 0;
+      if (n->children.size() == 2 && index(1, i1) && child(0, a) && a.rank == 1) {
+        out = {"(" + a.code + ").v[" + std::to_string(i1 - 1) + "]", 0};
+        return true;
+      }
+      if (n->children.size() == 3 && index(1, i1) && index(2, i2) && child(0, a) && a.rank == 2) {
+        out = {"(" + a.code + ").m[" + std::to_string(i1 - 1) + "][" + std::to_string(i2 - 1) + "]", 0};
         return true;
       }
       return false;
@@ -576,16 +617,16 @@ static bool recognise_jit(const getfem::ga_workspace &ws, size_type i1, recognis
   if (td.order != 1 || td.operation != getfem::ga_workspace::ASSEMBLY) return false;
   const std::string &v = td.name_test1;
   const getfem::mesh_fem *pmf = ws.associated_mf(v);
-  if (!pmf || pmf->get_qdim() != 1 || ws.is_constant(v)) return false;
-  const int N = int(pmf->linked_mesh().dim());
-  if (N != 2 && N != 3) return false;
+  if (!pmf || ws.is_constant(v)) return false;
+  const int N = int(pmf->linked_mesh().dim()), Q = int(pmf->get_qdim());
+  if ((N != 2 && N != 3) || (Q != 1 && Q != N)) return false;
   std::vector<std::string> params;
   jit_value f1, f2{"(0.0)", 0};
-  if (!td.ptree || !jit_emit(ws, td.ptree->root, v, N, params, f1) || f1.rank != 0) return false;
+  if (!td.ptree || !jit_emit(ws, td.ptree->root, v, N, Q, params, f1) || f1.rank != 0) return false;
   for (size_type j = 0; j < ws.nb_trees(); ++j) {
     const auto &t2 = ws.tree_info(j);
     if (t2.order == 2 && t2.mim == td.mim && t2.rg == td.rg && t2.name_test1 == v && t2.name_test2 == v) {
-      if (!t2.ptree || !jit_emit(ws, t2.ptree->root, v, N, params, f2) || f2.rank != 0) return false;
+      if (!t2.ptree || !jit_emit(ws, t2.ptree->root, v, N, Q, params, f2) || f2.rank != 0) return false;
     } else if (t2.order == 2 && t2.mim == td.mim && t2.rg == td.rg && (t2.name_test1 == v) != (t2.name_test2 == v)) {
       return false;  // coupled to another variable: not this route
     }
@@ -684,6 +725,14 @@ bool recognise_tree_sum(const getfem::ga_workspace &ws, size_type itree, std::ve
   size_t bilinear = 0;
   for (const recognised_term &rt : out)
     bilinear += rt.family != GFGPU_SOURCE && rt.family != GFGPU_NORMAL_SOURCE && rt.family != GFGPU_SHIM_COUPLED_DIV;
+  if (bilinear > 1) {  // the reference thresholds the element matrix of the SUM: one run-time compiled term does exactly that
+    recognised_term rt;
+    if (recognise_jit(ws, itree, rt)) {
+      out.clear();
+      out.push_back(rt);
+      return true;
+    }
+  }
   GMM_ASSERT1(bilinear <= 1, "gfgpu: several bilinear forms summed on one region are thresholded together by the reference "
                              "(C&E.cc:4889); give them distinct regions or one expression family");
   return true;

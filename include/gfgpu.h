@@ -197,7 +197,9 @@ int gfgpu_term_assemble_host(gfgpu_term *t, const double *U_host, int order_mask
 int gfgpu_term_potential_dev(gfgpu_term *t, const double *U_dev, double *E_host);
 int gfgpu_term_potential_host(gfgpu_term *t, const double *U_host, double *E_host);
 
-/* JIT terms (the NVRTC route, csrc/jit.cu): a SCALAR variable and an integrand that is none of the families above.  After the
+/* JIT terms (the NVRTC route, csrc/jit.cu): a scalar variable -- or a vector variable of the mesh dimension, for which u / tv
+ * are vec, gu / tg are mat (m[c][k] = d u_c / d x_k) and the helpers trace, transp, sym, skew, deviator, ddot, outer, mkmat apply --
+ * and an integrand that is none of the families above.  After the
  * reference's analysis and symbolic differentiation the order-1 tree of an expression is linear in the test function and the
  * order-2 tree bilinear in (Test, Test2) (ga_exec interprets exactly those trees, C&E.cc:8750-9047); the caller hands them over
  * as C expressions in the identifiers
@@ -213,7 +215,7 @@ int gfgpu_term_potential_host(gfgpu_term *t, const double *U_host, double *E_hos
  * gfgpu_jit_check compiles the two forms without a GPU and returns 0 if they compile (the log goes to gfgpu_last_error). */
 int gfgpu_term_create_jit(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem, gfgpu_tables *tab, const char *form1, const char *form2,
                           const double *params, int nparams, double alpha, int value_dependent, gfgpu_term **out);
-int gfgpu_jit_check(int dim, const char *form1, const char *form2);
+int gfgpu_jit_check(int dim, int qdim, const char *form1, const char *form2);
 /* new values of par[] for the next assemblies of a JIT term (constants of the expression may change between calls) */
 int gfgpu_term_set_params(gfgpu_term *t, const double *params, int nparams);
 

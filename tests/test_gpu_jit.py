@@ -116,3 +116,33 @@ def test_jit_errors_are_loud():
     term = capi.DeviceTerm.jit(ctx, dmesh, dfem, tab, "nonsense(u)*tv", "0.0", [], 1.0)
     with pytest.raises(capi.GfgpuError, match="does not compile"):
         term.assemble_host(U, capi.TANGENT, None, None)
+
+
+@pytest.mark.parametrize("mesh", [("PK", 3, 2, 4, [2, 2, 2], 0.15), ("PK", 2, 2, 4, [4, 3], 0.15), ("QK", 3, 1, 3, [2, 3, 2], 0.1)],
+                         ids=lambda c: "%s%dd-k%d" % (c[0], c[1], c[2]))
+def test_jit_vector_variable_reproduces_the_elasticity_family(mesh):
+    """vector variable: u / tv are vec, gu / tg are mat; lambda div u div v + mu (grad u + grad u^T) : grad v is the ELASTICITY
+    family: identical pattern, values and residual 1e-13"""
+    import getfem_b200 as gf
+    from getfem_b200 import capi, fem_tables
+    gt, dim, k, im, nsub, distort = mesh
+    ctx = capi.Context(0)
+    m = gf.mesh()
+    gf.regular_unit_mesh(m, nsub, "GT_%s(%d,1)" % (gt, dim))
+    rng = np.random.default_rng(2)
+    m.pts = m.pts + distort / max(nsub) * rng.uniform(-1, 1, m.pts.shape)
+    m._dev = {}
+    mf = gf.mesh_fem(m, dim)
+    mf.set_classical_finite_element(k)
+    dmesh, dfem = m.device(ctx), mf.device(ctx)
+    t = fem_tables.classical_tables(gt, dim, k, im)
+    tab = capi.DeviceTables(ctx, t["quad_w"], t["gt_grad"], t["phi"], t["gphi"])
+    U = rng.uniform(-1, 1, dfem.ndof)
+    ref = capi.DeviceTerm(ctx, dmesh, dfem, tab, "elast", [1.3, 0.7], 1.0, capi.STRATEGY_STAGED)
+    jc, ir, pr, R = _run(ref, U, dfem.ndof)
+    f1 = "par[0]*trace(gu)*trace(tg) + par[1]*ddot(gu+transp(gu),tg)"
+    f2 = "par[0]*trace(t2g)*trace(tg) + par[1]*ddot(t2g+transp(t2g),tg)"
+    jit = capi.DeviceTerm.jit(ctx, dmesh, dfem, tab, f1, f2, [1.3, 0.7], 1.0, value_dependent=False)
+    jjc, jir, jpr, jR = _run(jit, U, dfem.ndof)
+    assert np.array_equal(jc, jjc) and np.array_equal(ir, jir)
+    assert np.linalg.norm(pr - jpr) <= 1e-13 * np.linalg.norm(pr) and np.linalg.norm(R - jR) <= 1e-13 * np.linalg.norm(R)

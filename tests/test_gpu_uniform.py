@@ -35,7 +35,8 @@ def _recompute_goldens():
     for n in golden_names():
         g = load_golden(n)
         faces = g["region"] is not None and "face_first" in g["region"]
-        if g["gt_linear"] and g["family"] in ("laplace", "elast", "mass") and not faces and g["fields"] is None and not g["extra_terms"]:
+        if (g["gt_linear"] and g["family"] in ("laplace", "elast", "mass") and not faces and g["fields"] is None and not g["extra_terms"]
+                and int(g["args"]["k"]) <= 3):  # the per-nonzero kernels are instantiated up to P3
             out.append(n)
     return out
 
