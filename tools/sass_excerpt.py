@@ -12,7 +12,7 @@ import sys
 obj, pat = sys.argv[1], sys.argv[2]
 out = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
 blocks = re.split(r"\n\s*Function : ", out)
-KEYS = ["UBLKCP", "UTMACMDFLUSH", "SYNCS", "LDGSTS", "LDGDEPBAR", "DEPBAR", "BAR.SYNC", "DFMA", "DMUL", "DADD", "LDS", "STS", "LDG",
+KEYS = ["UBLKCP", "UTMACMDFLUSH", "SYNCS", "LDGSTS", "LDGDEPBAR", "DEPBAR", "BAR.SYNC", "BAR.ARV", "DMMA", "DFMA", "DMUL", "DADD", "LDS", "STS", "LDG",
         "STG", "SHFL", "ATOMS", "ATOMG", "RED", "NANOSLEEP", "LDC", "ULDC", "R2UR", "BRA", "CALL"]
 for b in blocks[1:]:
     name = b.split("\n", 1)[0].strip()
@@ -29,7 +29,7 @@ for b in blocks[1:]:
     print("arch    : sm_%s   instructions: %d" % (arch.group(1) if arch else "?", len(ins)))
     print("counts  :", "  ".join("%s %d" % (k, cnt[k]) for k in KEYS if cnt[k]))
     lines = [l for l in b.splitlines() if re.search(r"/\*[0-9a-f]{4}\*/", l)]
-    for tag in ("UBLKCP", "SYNCS", "LDGSTS", "BAR.SYNC", "DFMA"):
+    for tag in ("UBLKCP", "SYNCS", "LDGSTS", "BAR.SYNC", "BAR.ARV", "DMMA", "DFMA"):
         idx = next((k for k, l in enumerate(lines) if tag in l), None)
         if idx is not None:
             print("first %s:" % tag)
