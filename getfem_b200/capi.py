@@ -46,6 +46,7 @@ SIGNATURES = {
     "gfgpu_fem_get_elem_dof": (C.c_int, [_P, _P]),
     "gfgpu_fem_destroy": (C.c_int, [_P]),
     "gfgpu_tables_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _PP]),
+    "gfgpu_tables_set_gt_values": (C.c_int, [_P, _P, _P]),
     "gfgpu_tables_set_faces": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "gfgpu_tables_destroy": (C.c_int, [_P]),
     "gfgpu_term_create": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_double, C.c_int, _PP]),
@@ -234,6 +235,16 @@ class DeviceTables(_Handle):
         self.nq, self.ng, self.nd, self.dim = nq, ng, nd, dim
         check(lib().gfgpu_tables_create(ctx.h, dim, nq, ng, nd, ptr(w), ptr(gt_grad), ptr(phi), ptr(gphi),
                                         C.byref(self.h)))
+
+    def set_gt_values(self, gt_val, face_gt_val=None):
+        """[nq, ng] shape values of the geometric transformation at the volume points (the position X in JIT integrands);
+        face_gt_val [nf, nqf, ng]: the same at the face points (after set_faces)"""
+        gt_val = np.ascontiguousarray(gt_val, np.float64)
+        assert gt_val.shape == (self.nq, self.ng)
+        if face_gt_val is not None:
+            face_gt_val = np.ascontiguousarray(face_gt_val, np.float64)
+            assert face_gt_val.ndim == 3 and face_gt_val.shape[2] == self.ng
+        check(lib().gfgpu_tables_set_gt_values(self.h, ptr(gt_val), ptr(face_gt_val) if face_gt_val is not None else None))
 
     def set_faces(self, normals, w, gt_grad, phi, gphi):
         """Tables at the face points: normals [nf, dim], w [nf, nqf], gt_grad [nf, nqf, ng, dim], phi [nf, nqf, nd],

@@ -301,6 +301,21 @@ int gfgpu_tables_create(gfgpu_ctx *ctx, int dim, int nq, int ng, int nd, const d
   GF_API_END
 }
 
+int gfgpu_tables_set_gt_values(gfgpu_tables *t, const double *gt_val, const double *face_gt_val) {
+  GF_API_BEGIN
+  GF_REQUIRE(t && gt_val, "null argument");
+  GF_CUDA(cudaSetDevice(t->ctx->device));
+  t->gt_val.alloc(t->ctx, (size_t)t->nq * t->ng);
+  t->gt_val.upload(gt_val);
+  if (face_gt_val) {
+    GF_REQUIRE(t->nf > 0, "face values need the face tables first (gfgpu_tables_set_faces)");
+    t->fgt_val.alloc(t->ctx, (size_t)t->nf * t->nqf * t->ng);
+    t->fgt_val.upload(face_gt_val);
+  }
+  GF_CUDA(cudaStreamSynchronize(t->ctx->stream));
+  GF_API_END
+}
+
 int gfgpu_tables_set_faces(gfgpu_tables *t, int nf, int nqf, const double *normals, const double *w,
                            const double *gt_grad, const double *phi, const double *gphi) {
   GF_API_BEGIN
@@ -667,7 +682,7 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
     tic(0);
     const bool affine = t->mesh->gt_kind == GFGPU_GT_PK;
     if (t->family == GFGPU_JIT) {
-      GF_REQUIRE(!t->region_faces && !t->nfields, "JIT terms: volume integration, constant parameters");
+      GF_REQUIRE(!t->nfields, "JIT terms: constant parameters");
       gf::launch_jit_kernel(t, a);
     }
     bool ok = t->family == GFGPU_JIT ||

@@ -136,6 +136,8 @@ struct gfgpu_tables {
   gfgpu_ctx *ctx;
   int dim, nq, ng, nd;
   gf::DevBuf<double> w, gt_grad, phi, gphi;
+  gf::DevBuf<double> gt_val;  // nq x ng shape values of the geometric transformation (gfgpu_tables_set_gt_values): the position X
+  gf::DevBuf<double> fgt_val;  // nf x nqf x ng: the same at the face points
   std::vector<double> h_w, h_gt_grad, h_phi, h_gphi;
   // face points (gfgpu_tables_set_faces): nf faces with nqf points each, tables laid out face after face
   int nf = 0, nqf = 0;

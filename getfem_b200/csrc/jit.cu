@@ -16,6 +16,7 @@
 // libgfgpu.so has no link dependency on them, and a process that never creates a JIT term never loads them.
 #include <dlfcn.h>
 
+#include <cctype>
 #include <mutex>
 #include <sstream>
 
@@ -168,15 +169,17 @@ __device__ __forceinline__ mat mkmat(double a0, double a1, double a2, double a3,
 }
 
 #if GF_Q == 1
-__device__ __forceinline__ double gf_form1(double u, vec gu, const double *par, double tv, vec tg) { return GF_FORM1; }
-__device__ __forceinline__ double gf_form2(double u, vec gu, const double *par, double tv, vec tg, double t2v, vec t2g) {
+__device__ __forceinline__ double gf_form1(double u, vec gu, vec X, vec Normal, const double *par, double tv, vec tg) { return GF_FORM1; }
+__device__ __forceinline__ double gf_form2(double u, vec gu, vec X, vec Normal, const double *par, double tv, vec tg, double t2v, vec t2g) {
   return GF_FORM2;
 }
 
 extern "C" __global__ void __launch_bounds__(128)
 gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z, const int *__restrict__ conn,
             const int *__restrict__ edof, const double *__restrict__ U, const double *__restrict__ w, const double *__restrict__ gt_grad,
-            const double *__restrict__ phi, const double *__restrict__ gphi, const double *__restrict__ par, int ng, int nq, int nd,
+            const double *__restrict__ phi, const double *__restrict__ gphi, const double *__restrict__ gt_val,
+            const signed char *__restrict__ face, const double *__restrict__ fnormal,
+            const double *__restrict__ par, int ng, int nq, int nd,
             long long e0, long long ne, double alpha, double *__restrict__ stage, unsigned short *__restrict__ emask,
             double *__restrict__ rstage) {
   constexpr int N = GF_N, NA = GF_N + 1;
@@ -191,6 +194,12 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
   const int tid = threadIdx.x;
   for (long long el = blockIdx.x; el < ne; el += gridDim.x) {
     const long long e = e0 + el;
+    // tables of this item: the volume points, or (boundary faces, C&E.cc:8827-8848) the nq points of its face -- the face
+    // tables are laid out face after face
+    const int fc = face ? face[e] : 0;
+    const double *wE = w + (size_t)fc * nq, *gtE = gt_grad + (size_t)fc * nq * ng * N, *phiE = phi + (size_t)fc * nq * nd;
+    const double *gphiE = gphi + (size_t)fc * nq * nd * N, *gtvE = gt_val ? gt_val + (size_t)fc * nq * ng : nullptr;
+    const double *nref = face ? fnormal + fc * 3 : nullptr;
     for (int k = tid; k < N * ng; k += blockDim.x) {
       const int i = k / N, d = k % N;
       const int p = conn[e * ng + i];
@@ -202,7 +211,7 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
     for (int q = tid; q < nq; q += blockDim.x) {
       double K[N * N], B[N * N];
       for (int k = 0; k < N * N; ++k) K[k] = 0.0;
-      const double *pc = gt_grad + (size_t)q * ng * N;
+      const double *pc = gtE + (size_t)q * ng * N;
       for (int i = 0; i < ng; ++i)
         for (int c = 0; c < N; ++c)
           for (int r = 0; r < N; ++r) K[r + N * c] += sG[r + N * i] * pc[i * N + c];
@@ -219,13 +228,27 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
         B[2] = (K[3] * K[7] - K[6] * K[4]) * id; B[5] = (K[6] * K[1] - K[0] * K[7]) * id; B[8] = (K[0] * K[4] - K[3] * K[1]) * id;
         J = fabs(d);
       }
+      vec Nq;
+      for (int k = 0; k < N; ++k) Nq.v[k] = 0.0;
+      if (nref) {  // unit normal = B n_ref / |B n_ref|, J *= |B n_ref|, gmm::clean(Normal, 1e-13) (C&E.cc:8836-8847)
+        double nup = 0.0;
+        for (int r = 0; r < N; ++r) {
+          double t = 0.0;
+          for (int c = 0; c < N; ++c) t += B[r + N * c] * nref[c];
+          Nq.v[r] = t;
+          nup += t * t;
+        }
+        nup = sqrt(nup);
+        J *= nup;
+        for (int r = 0; r < N; ++r) { const double t = Nq.v[r] / nup; Nq.v[r] = fabs(t) < 1e-13 ? 0.0 : t; }
+      }
       double uq = 0.0;
       vec guq;
       for (int k = 0; k < N; ++k) guq.v[k] = 0.0;
       double *T = sT + (size_t)q * nd * NA;
       for (int i = 0; i < nd; ++i) {
-        const double *g = gphi + ((size_t)q * nd + i) * N;
-        const double ph = phi[(size_t)q * nd + i];
+        const double *g = gphiE + ((size_t)q * nd + i) * N;
+        const double ph = phiE[(size_t)q * nd + i];
         T[i * NA] = ph;
         uq += sU[i] * ph;
         for (int k = 0; k < N; ++k) {
@@ -235,20 +258,24 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
           guq.v[k] += sU[i] * s;
         }
       }
-      const double wq = w[q];
+      const double wq = wE[q];
       const double cw = wq == 0.0 ? 0.0 : alpha * J * wq;  // zero-weight points are skipped (C&E.cc:8852)
-      vec zero;
+      vec zero, Xq;
       for (int k = 0; k < N; ++k) zero.v[k] = 0.0;
+      Xq = zero;
+      if (gtvE)
+        for (int i = 0; i < ng; ++i)
+          for (int k = 0; k < N; ++k) Xq.v[k] += sG[k + N * i] * gtvE[(size_t)q * ng + i];
 #pragma unroll
       for (int a = 0; a < NA; ++a) {
         const double tv = a == 0 ? 1.0 : 0.0;
         const vec tg = a == 0 ? zero : unit(a - 1);
-        sC1[q * NA + a] = cw == 0.0 ? 0.0 : cw * gf_form1(uq, guq, par, tv, tg);
+        sC1[q * NA + a] = cw == 0.0 ? 0.0 : cw * gf_form1(uq, guq, Xq, Nq, par, tv, tg);
 #pragma unroll
         for (int b = 0; b < NA; ++b) {
           const double t2v = b == 0 ? 1.0 : 0.0;
           const vec t2g = b == 0 ? zero : unit(b - 1);
-          sC2[(q * NA + a) * NA + b] = cw == 0.0 ? 0.0 : cw * gf_form2(uq, guq, par, tv, tg, t2v, t2g);
+          sC2[(q * NA + a) * NA + b] = cw == 0.0 ? 0.0 : cw * gf_form2(uq, guq, Xq, Nq, par, tv, tg, t2v, t2g);
         }
       }
     }
@@ -294,8 +321,8 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
   }
 }
 #else  // ---------------------------------------------------------------- vector variable, qdim = mesh dimension
-__device__ __forceinline__ double gf_form1(vec u, mat gu, const double *par, vec tv, mat tg) { return GF_FORM1; }
-__device__ __forceinline__ double gf_form2(vec u, mat gu, const double *par, vec tv, mat tg, vec t2v, mat t2g) { return GF_FORM2; }
+__device__ __forceinline__ double gf_form1(vec u, mat gu, vec X, vec Normal, const double *par, vec tv, mat tg) { return GF_FORM1; }
+__device__ __forceinline__ double gf_form2(vec u, mat gu, vec X, vec Normal, const double *par, vec tv, mat tg, vec t2v, mat t2g) { return GF_FORM2; }
 
 // probe slot s = c * (N+1) + a: a = 0 -> the value of component c, a = 1 + k -> d/dx_k of component c
 __device__ __forceinline__ void gf_probe(int s, vec &tv, mat &tg) {
@@ -307,7 +334,9 @@ __device__ __forceinline__ void gf_probe(int s, vec &tv, mat &tg) {
 extern "C" __global__ void __launch_bounds__(128)
 gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z, const int *__restrict__ conn,
             const int *__restrict__ edof, const double *__restrict__ U, const double *__restrict__ w, const double *__restrict__ gt_grad,
-            const double *__restrict__ phi, const double *__restrict__ gphi, const double *__restrict__ par, int ng, int nq, int nd,
+            const double *__restrict__ phi, const double *__restrict__ gphi, const double *__restrict__ gt_val,
+            const signed char *__restrict__ face, const double *__restrict__ fnormal,
+            const double *__restrict__ par, int ng, int nq, int nd,
             long long e0, long long ne, double alpha, double *__restrict__ stage, unsigned short *__restrict__ emask,
             double *__restrict__ rstage) {
   constexpr int N = GF_N, NA = GF_N + 1, Q = GF_N, NS = Q * NA;
@@ -316,14 +345,21 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
   double *sG = sm;                               // N x ng
   double *sU = sG + N * ng;                      // nd x Q
   double *sT = sU + s1;                          // nq x nd x NA
-  double *sS = sT + (size_t)nq * nd * NA;        // nq x (Q + Q*N + 1): state u, Grad u, weight w J alpha
-  double *sC1 = sS + (size_t)nq * (Q + Q * N + 1);   // nq x NS
+  constexpr int SS = Q + Q * N + 1 + 2 * N;      // per point: u, Grad u, weight w J alpha, position X, unit normal
+  double *sS = sT + (size_t)nq * nd * NA;        // nq x SS
+  double *sC1 = sS + (size_t)nq * SS;            // nq x NS
   double *sC2 = sC1 + (size_t)nq * NS;           // nq x NS x NS
   double *sK = sC2 + (size_t)nq * NS * NS;       // s1 x s1
   __shared__ double sRed[4];
   const int tid = threadIdx.x;
   for (long long el = blockIdx.x; el < ne; el += gridDim.x) {
     const long long e = e0 + el;
+    // tables of this item: the volume points, or (boundary faces, C&E.cc:8827-8848) the nq points of its face -- the face
+    // tables are laid out face after face
+    const int fc = face ? face[e] : 0;
+    const double *wE = w + (size_t)fc * nq, *gtE = gt_grad + (size_t)fc * nq * ng * N, *phiE = phi + (size_t)fc * nq * nd;
+    const double *gphiE = gphi + (size_t)fc * nq * nd * N, *gtvE = gt_val ? gt_val + (size_t)fc * nq * ng : nullptr;
+    const double *nref = face ? fnormal + fc * 3 : nullptr;
     for (int k = tid; k < N * ng; k += blockDim.x) {
       const int i = k / N, d = k % N;
       const int p = conn[e * ng + i];
@@ -334,7 +370,7 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
     for (int q = tid; q < nq; q += blockDim.x) {
       double K[N * N], B[N * N];
       for (int k = 0; k < N * N; ++k) K[k] = 0.0;
-      const double *pc = gt_grad + (size_t)q * ng * N;
+      const double *pc = gtE + (size_t)q * ng * N;
       for (int i = 0; i < ng; ++i)
         for (int c = 0; c < N; ++c)
           for (int r = 0; r < N; ++r) K[r + N * c] += sG[r + N * i] * pc[i * N + c];
@@ -351,12 +387,30 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
         B[2] = (K[3] * K[7] - K[6] * K[4]) * id; B[5] = (K[6] * K[1] - K[0] * K[7]) * id; B[8] = (K[0] * K[4] - K[3] * K[1]) * id;
         J = fabs(d);
       }
-      double *S = sS + (size_t)q * (Q + Q * N + 1);
-      for (int k = 0; k < Q + Q * N; ++k) S[k] = 0.0;
+      vec Nq;
+      for (int k = 0; k < N; ++k) Nq.v[k] = 0.0;
+      if (nref) {  // unit normal = B n_ref / |B n_ref|, J *= |B n_ref|, gmm::clean(Normal, 1e-13) (C&E.cc:8836-8847)
+        double nup = 0.0;
+        for (int r = 0; r < N; ++r) {
+          double t = 0.0;
+          for (int c = 0; c < N; ++c) t += B[r + N * c] * nref[c];
+          Nq.v[r] = t;
+          nup += t * t;
+        }
+        nup = sqrt(nup);
+        J *= nup;
+        for (int r = 0; r < N; ++r) { const double t = Nq.v[r] / nup; Nq.v[r] = fabs(t) < 1e-13 ? 0.0 : t; }
+      }
+      double *S = sS + (size_t)q * SS;
+      for (int k = 0; k < SS; ++k) S[k] = 0.0;
+      if (gtvE)
+        for (int i = 0; i < ng; ++i)
+          for (int k = 0; k < N; ++k) S[Q + Q * N + 1 + k] += sG[k + N * i] * gtvE[(size_t)q * ng + i];
+      for (int k = 0; k < N; ++k) S[Q + Q * N + 1 + N + k] = Nq.v[k];
       double *T = sT + (size_t)q * nd * NA;
       for (int i = 0; i < nd; ++i) {
-        const double *g = gphi + ((size_t)q * nd + i) * N;
-        const double ph = phi[(size_t)q * nd + i];
+        const double *g = gphiE + ((size_t)q * nd + i) * N;
+        const double ph = phiE[(size_t)q * nd + i];
         T[i * NA] = ph;
         for (int c = 0; c < Q; ++c) S[c] += sU[i * Q + c] * ph;
         for (int k = 0; k < N; ++k) {
@@ -366,23 +420,24 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
           for (int c = 0; c < Q; ++c) S[Q + c * N + k] += sU[i * Q + c] * t;  // Grad_u(c, k)
         }
       }
-      const double wq = w[q];
+      const double wq = wE[q];
       S[Q + Q * N] = wq == 0.0 ? 0.0 : alpha * J * wq;  // zero-weight points are skipped (C&E.cc:8852)
     }
     __syncthreads();
     // coefficients of the two forms: work item = (Gauss point, probe slot of Test)
     for (int it = tid; it < nq * NS; it += blockDim.x) {
       const int q = it / NS, s = it % NS;
-      const double *S = sS + (size_t)q * (Q + Q * N + 1);
+      const double *S = sS + (size_t)q * SS;
       const double cw = S[Q + Q * N];
-      vec uq; mat guq;
+      vec uq, Xq, Nq; mat guq;
+      for (int k = 0; k < N; ++k) { Xq.v[k] = S[Q + Q * N + 1 + k]; Nq.v[k] = S[Q + Q * N + 1 + N + k]; }
       for (int c = 0; c < Q; ++c) { uq.v[c] = S[c]; for (int k = 0; k < N; ++k) guq.m[c][k] = S[Q + c * N + k]; }
       vec tv, t2v; mat tg, t2g;
       gf_probe(s, tv, tg);
-      sC1[q * NS + s] = cw == 0.0 ? 0.0 : cw * gf_form1(uq, guq, par, tv, tg);
+      sC1[q * NS + s] = cw == 0.0 ? 0.0 : cw * gf_form1(uq, guq, Xq, Nq, par, tv, tg);
       for (int s2 = 0; s2 < NS; ++s2) {
         gf_probe(s2, t2v, t2g);
-        sC2[((size_t)q * NS + s) * NS + s2] = cw == 0.0 ? 0.0 : cw * gf_form2(uq, guq, par, tv, tg, t2v, t2g);
+        sC2[((size_t)q * NS + s) * NS + s2] = cw == 0.0 ? 0.0 : cw * gf_form2(uq, guq, Xq, Nq, par, tv, tg, t2v, t2g);
       }
     }
     __syncthreads();
@@ -509,12 +564,12 @@ void launch_jit_kernel(gfgpu_term *t, const ElemArgs &a) {
   if (!t->jit_kernel) t->jit_kernel = jit_compile(t);
   JitKernel *k = static_cast<JitKernel *>(t->jit_kernel);
   JitApi &api = jit_api();
-  const int N = t->mesh->dim, NA = N + 1, nd = t->fem->nd, nq = a.nq, ng = a.ng;
+  const int N = t->mesh->dim, NA = N + 1, nd = t->fem->nd, nq = a.face ? a.nqf : a.nq, ng = a.ng;
   const int Q = t->fem->qdim;
   GF_REQUIRE(Q == 1 || Q == N, "JIT terms: scalar variables, or vector variables of the mesh dimension");
   const size_t NS = (size_t)Q * NA, s1 = (size_t)nd * Q;
   const size_t smem = Q == 1 ? ((size_t)N * ng + nd + (size_t)nq * nd * NA + (size_t)nq * NA + (size_t)nq * NA * NA + (size_t)nd * nd + 2) * 8
-                             : ((size_t)N * ng + s1 + (size_t)nq * nd * NA + (size_t)nq * (Q + Q * N + 1) + (size_t)nq * NS +
+                             : ((size_t)N * ng + s1 + (size_t)nq * nd * NA + (size_t)nq * (Q + Q * N + 1 + 2 * N) + (size_t)nq * NS +
                                 (size_t)nq * NS * NS + s1 * s1 + 2) * 8;
   GF_REQUIRE(smem <= 220 * 1024, "JIT terms: element too large for the run-time kernel (nq x nd x (N+1) doubles of shared memory)");
   if (t->jit_par.n != (size_t)GFGPU_MAX_PARAMS) {
@@ -529,10 +584,35 @@ void launch_jit_kernel(gfgpu_term *t, const ElemArgs &a) {
   double alpha = a.alpha;
   const double *par = t->jit_par.p;
   const double *x = a.x, *y = a.y, *z = a.z, *U = a.U, *w = a.w, *gt = a.gt_grad, *phi = a.phi, *gphi = a.gphi;
+  const double *gtv = t->tab->gt_val.n ? t->tab->gt_val.p : nullptr;
+  const signed char *face = reinterpret_cast<const signed char *>(a.face);
+  const double *fnormal = a.fnormal;
+  if (face) {  // boundary faces: the kernel indexes the face tables by the item's face
+    w = a.fw; gt = a.fgt_grad; phi = a.fphi; gphi = a.fgphi;
+    gtv = t->tab->fgt_val.n ? t->tab->fgt_val.p : nullptr;
+  }
+  auto mentions_X = [](const std::string &f) {
+    for (size_t k = 0; k < f.size(); ++k)
+      if (f[k] == 'X' && (k == 0 || !(isalnum((unsigned char)f[k - 1]) || f[k - 1] == '_')) &&
+          (k + 1 == f.size() || !(isalnum((unsigned char)f[k + 1]) || f[k + 1] == '_')))
+        return true;
+    return false;
+  };
+  auto mentions = [](const std::string &f, const std::string &id) {
+    for (size_t k = f.find(id); k != std::string::npos; k = f.find(id, k + 1))
+      if ((k == 0 || !(isalnum((unsigned char)f[k - 1]) || f[k - 1] == '_')) &&
+          (k + id.size() == f.size() || !(isalnum((unsigned char)f[k + id.size()]) || f[k + id.size()] == '_')))
+        return true;
+    return false;
+  };
+  GF_REQUIRE(gtv || !(mentions_X(t->jit_form1) || mentions_X(t->jit_form2)),
+             "the integrand mentions the position X: give the tables the geometric transformation's values (gfgpu_tables_set_gt_values)");
+  GF_REQUIRE(face || !(mentions(t->jit_form1, "Normal") || mentions(t->jit_form2, "Normal")),
+             "the integrand mentions the unit normal: the term must be restricted to a region of faces (gfgpu_term_set_region)");
   const int32_t *conn = a.conn, *edof = a.edof;
   double *stage = a.stage, *rstage = a.rstage;
   uint16_t *emask = a.emask;
-  void *params[] = {&x, &y, &z, &conn, &edof, &U, &w, &gt, &phi, &gphi, &par, &ing, &inq, &ind, &e0, &ne, &alpha, &stage, &emask, &rstage};
+  void *params[] = {&x, &y, &z, &conn, &edof, &U, &w, &gt, &phi, &gphi, &gtv, &face, &fnormal, &par, &ing, &inq, &ind, &e0, &ne, &alpha, &stage, &emask, &rstage};
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ne, (long long)ctx->sm_count * 4));
   const int r = api.LaunchKernel(k->fn, grid, 1, 1, 128, 1, 1, (unsigned)smem, ctx->stream, params, nullptr);
   GF_REQUIRE(r == 0, "cuLaunchKernel failed for the JIT kernel (error " + std::to_string(r) + ")");

@@ -482,6 +482,14 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
       out = {"par[" + std::to_string(k) + "]", 0};
       return true;
     }
+    case GA_NODE_X:  // the position: the whole vector (nbc1 == 0) or one coordinate
+      if (n->nbc1 == 0) { out = {"X", 1}; return true; }
+      if (int(n->nbc1) > N) return false;
+      out = {"X.v[" + std::to_string(int(n->nbc1) - 1) + "]", 0};
+      return true;
+    case GA_NODE_NORMAL:  // the unit outward normal of a boundary face (the term refuses a region of convexes)
+      out = {"Normal", 1};
+      return true;
     case GA_NODE_GRAD:
       if (n->name != v) return false;
       out = {"gu", rv + 1};
@@ -1515,6 +1523,11 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
                                   int64_t(ndof), &e.fem));
       GFGPU_CALL(gfgpu_tables_create(ctx_, dim, int(nq), int(ng), int(nd), w.data(), gtg.data(), phi.data(), gphi.data(),
                                      &e.tab));
+      // shape values of the geometric transformation at the Gauss points: the position X of run-time compiled integrands
+      std::vector<double> gtv(nq * ng);
+      for (size_type q = 0; q < nq; ++q)
+        for (size_type i = 0; i < ng; ++i) gtv[q * ng + i] = pgp->val(q)[i];
+      GFGPU_CALL(gfgpu_tables_set_gt_values(e.tab, gtv.data(), nullptr));
       if (rg_faces) {
         // tables at the face points (they follow the volume points in the method's point table, face after face:
         // approx_integration::valid_method, getfem_integration.cc:353-368) and the reference normals
@@ -1539,9 +1552,15 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
         }
         GFGPU_CALL(gfgpu_tables_set_faces(e.tab, int(nf), int(nqf), fn.data(), fw.data(), fgtg.data(), fphi.data(),
                                           fgphi.data()));
+        std::vector<double> fgtv(nf * nqf * ng);
+        for (size_type f = 0; f < nf; ++f)
+          for (size_type q = 0; q < nqf; ++q) {
+            const size_type ip = pai->ind_first_point_on_face(getfem::short_type(f)) + q;
+            for (size_type i = 0; i < ng; ++i) fgtv[((f * nqf + q) * ng) + i] = pgp->val(ip)[i];
+          }
+        GFGPU_CALL(gfgpu_tables_set_gt_values(e.tab, gtv.data(), fgtv.data()));
       }
       if (rt.family == GFGPU_JIT) {
-        GMM_ASSERT1(!rg_faces, "gfgpu: run-time compiled terms are volume terms");
         const bool vdep = rt.jit_form2.find("u") != std::string::npos;  // "u" or "gu" in the tangent: its pattern may move
         GFGPU_CALL(gfgpu_term_create_jit(ctx_, e.mesh, e.fem, e.tab, rt.jit_form1.c_str(), rt.jit_form2.c_str(), rt.params.data(),
                                          int(rt.params.size()), 1.0, vdep ? 1 : 0, &e.term));
@@ -1667,7 +1686,8 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
       if (V.size() < I.first() + ndof) V.resize(std::max<size_type>(nprim, I.first() + ndof), 0.0);
       for (size_type d = 0; d < ndof; ++d) V[I.first() + d] += R[d];
       t_fill += now_s() - t2;
-    } else if (rt.family == GFGPU_SOURCE || rt.family == GFGPU_NORMAL_SOURCE || rt.no_tangent) {
+    } else if (rt.family == GFGPU_SOURCE || rt.family == GFGPU_NORMAL_SOURCE || rt.no_tangent ||
+               (rt.family == GFGPU_JIT && rt.jit_form2 == "(0.0)")) {  // (a run-time compiled LOAD: no order-2 tree exists)
       // an order-1 term contributes nothing to the tangent; K only gets its size (workspace.cc:805-812)
       getfem::model_real_sparse_matrix &K = ws.assembled_matrix();
       const size_type need = std::max<size_type>(nprim, I.first() + ndof);

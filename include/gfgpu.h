@@ -139,6 +139,10 @@ int gfgpu_tables_create(gfgpu_ctx *ctx, int dim, int nq, int ng, int nd, const d
  * (bgeot_geometric_trans.h:141).  nf faces with nqf points each (the classical rules carry the same method on every face):
  *   normals[nf][dim] (reference normals as the reference stores them, not necessarily unit);
  *   w[nf][nqf]; gt_grad[nf][nqf][ng][dim]; phi[nf][nqf][nd]; gphi[nf][nqf][nd][dim] */
+/* optional: values of the geometric transformation's shape functions at the volume points, [nq][ng] (geotrans_precomp_::val,
+ * bgeot_geometric_trans.h), and -- NULL or, after gfgpu_tables_set_faces, [nf][nqf][ng] -- at the face points: the position
+ * X = sum_g G_g N_g(q) of a Gauss point, for JIT integrands that mention X (gmm::mult(G, pgp->val(ii)), C&E.cc ga_instruction_X) */
+int gfgpu_tables_set_gt_values(gfgpu_tables *t, const double *gt_val_host, const double *face_gt_val_host);
 int gfgpu_tables_set_faces(gfgpu_tables *t, int nf, int nqf, const double *normals_host, const double *w_host,
                            const double *gt_grad_host, const double *phi_host, const double *gphi_host);
 int gfgpu_tables_destroy(gfgpu_tables *t);
@@ -203,7 +207,9 @@ int gfgpu_term_potential_host(gfgpu_term *t, const double *U_host, double *E_hos
  * reference's analysis and symbolic differentiation the order-1 tree of an expression is linear in the test function and the
  * order-2 tree bilinear in (Test, Test2) (ga_exec interprets exactly those trees, C&E.cc:8750-9047); the caller hands them over
  * as C expressions in the identifiers
- *     u (double), gu (vec, Grad_u), par[k] (the term's parameters), tv / tg (Test_u / Grad_Test_u), t2v / t2g (Test2)
+ *     u (double), gu (vec, Grad_u), X (vec, the position: needs gfgpu_tables_set_gt_values), Normal (vec, the unit outward normal:
+ *     needs a region of faces, gfgpu_term_set_region; J and Normal as C&E.cc:8836-8847), par[k] (the term's parameters),
+ *     tv / tg (Test_u / Grad_Test_u), t2v / t2g (Test2)
  * with the helpers dot(a,b), normsqr(v), gnorm(v), mkvec(a,b,c), sqr, pos_part, neg_part, Heaviside, sign and the CUDA math
  * library.  form1 must be linear in (tv, tg), form2 bilinear in (tv, tg) x (t2v, t2g): the kernel extracts their coefficients
  * with unit probes.  Example, "(1+sqr(u))*Grad_u.Grad_Test_u + sin(u)*Test_u":

@@ -68,6 +68,10 @@ void ga_workspace::assembly(size_type order, bool condensation) {
       std::fprintf(stderr, "[gfgpu dryrun] order %d (assembly order %d) region %ld: %s -> %s%s %s\n", int(td.order), int(order),
                    long(td.rg->id()), ga_tree_to_string(*td.ptree).c_str(), ok ? "recognised" : "NOT recognised", fam.c_str(),
                    why.c_str());
+      for (const auto &rt : rts)  // the translated forms of a run-time compiled term: tests/test_shim_probe.py compiles them (NVRTC, no GPU)
+        if (ok && order == 2 && rt.family == GFGPU_JIT && associated_mf(rt.varname))
+          std::fprintf(stderr, "[gfgpu dryrun jit] dim=%d qdim=%d\t%s\t%s\n", int(associated_mf(rt.varname)->linked_mesh().dim()),
+                       int(associated_mf(rt.varname)->get_qdim()), rt.jit_form1.c_str(), rt.jit_form2.c_str());
     }
     getfem_b200::reference_assembly(*this, order, condensation);
     return;

@@ -182,6 +182,29 @@ def test_general_scalar_expressions_run_on_the_device(mesh, expr):
     assert 0 <= r["rel_K"] < 1e-12 and r["rel_V"] < 1e-12 and r["norm_V"] > 0, r
 
 
+JIT_X = [  # the position X and, on boundary faces, the unit normal: space-dependent coefficients / loads, nonlinear Robin conditions
+    ("dim=3 n=3 gt=pk k=2 q=1", "(1+X.X)*Grad_u.Grad_Test_u + X(3)*sin(u)*Test_u"),
+    ("dim=2 n=6 gt=qk k=2 q=1", "exp(X(1)*u)*Grad_u.Grad_Test_u - X(2)*Test_u"),
+    ("dim=3 n=2 gt=qk k=2", "(1+X(2))*Grad_u:Grad_Test_u - X.Test_u + (u.u)*(u.Test_u)"),
+    ("dim=3 n=3 gt=pk k=2 q=1 region=2", "X(1)*sin(u)*Test_u + (u*u*u*u)*Test_u"),
+    ("dim=3 n=3 gt=pk k=2 region=2", "(u.Normal)*(Test_u.Normal)*(1+X(1)) + exp(u(1))*Test_u(2)"),
+    ("dim=2 n=6 gt=qk k=2 region=2", "(u.Normal)*(Test_u.Normal)*(1+X(1)) + exp(u(1))*Test_u(2)"),
+    ("dim=3 n=2 gt=qk k=1 q=1 region=2", "(X.Normal)*u*Test_u + Normal(1)*Test_u"),
+]
+
+
+@pytest.mark.parametrize("mesh,expr", JIT_X)
+def test_expressions_of_the_position_and_the_normal_run_on_the_device(mesh, expr):
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN, "model=expr"] + mesh.split() + ["expr=" + expr], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["device_workspace_calls"] >= 2, r
+    assert r["pattern_ok"] and r["nnz_ref"] == r["nnz_gpu"], r
+    assert 0 <= r["rel_K"] < 1e-12 and r["rel_V"] < 1e-12 and r["norm_V"] > 0, r
+
+
 JIT_VECTOR = [  # vector variables (qdim = mesh dimension): matrices in the translator, 12 x 12 probe slots per Gauss point in 3D
     # a COMPOUND form: two bilinear forms summed on one region are thresholded together by the reference (C&E.cc:4889) --
     # refused in round 1, now one run-time compiled term
@@ -192,6 +215,8 @@ JIT_VECTOR = [  # vector variables (qdim = mesh dimension): matrices in the tran
      "((Id(3)+Grad_u)*(lambda*Trace(0.5*(Grad_u+Grad_u'+Grad_u'*Grad_u))*Id(3)+2*mu*(0.5*(Grad_u+Grad_u'+Grad_u'*Grad_u)))):Grad_Test_u"),
     ("dim=3 n=3 gt=pk k=1", "(1+Norm_sqr(u))*Grad_u:Grad_Test_u + (u.u)*(u.Test_u)"),
     ("dim=2 n=6 gt=qk k=2", "Sym(Grad_u):Grad_Test_u + Trace(Grad_u)*Trace(Grad_Test_u) + exp(u(1))*Test_u(2)"),
+    # a load summed into the tree of a linear form: one run-time compiled term (the probe alone must not take it for K u)
+    ("dim=3 n=2 gt=pk k=2", "lambda*Trace(Grad_u)*Trace(Grad_Test_u) + mu*(Grad_u'+Grad_u):Grad_Test_u + [1;2;3].Test_u"),
 ]
 
 

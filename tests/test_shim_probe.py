@@ -126,15 +126,16 @@ def test_derived_spellings_are_recognised(mesh, expr, family, params):
 
 
 def test_a_load_mixed_into_the_tree_is_not_taken_for_the_linear_form():
-    """r = K u must hold for the order-1 tree: with a source term summed into the same tree the printed forms decide (they
-    split the sum) or the expression is refused -- the probe alone never accepts it."""
+    """r = K u must hold for the order-1 tree: with a source term summed into the same tree the probe alone never accepts it
+    as a linear family -- the tree is refused, or (vector variables, round 2) translated as it stands into ONE run-time
+    compiled term (family 11) whose first form keeps the load and whose second form is the reference's own order-2 tree."""
     if not os.path.exists(BIN):
         pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
     expr = "lambda*Trace(Grad_u)*Trace(Grad_Test_u) + mu*(Grad_u'+Grad_u):Grad_Test_u + [1;2;3].Test_u"
     out = subprocess.run([BIN, "model=expr", "dim=3", "n=2", "gt=pk", "k=2", "expr=" + expr], capture_output=True, text=True,
                          timeout=300, env=dict(os.environ, GFGPU_DRYRUN="1"))
     lines = [l for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun] order 1")]
-    assert lines and all("NOT recognised" in l for l in lines), out.stderr[-1500:]
+    assert lines and all("NOT recognised" in l or "recognised family 11 " in l for l in lines), out.stderr[-1500:]
 
 
 SOURCE = 6
@@ -145,8 +146,6 @@ LOAD_CASES = [  # constant loads in spellings the printed forms do not know -> f
     ("dim=3 n=2 gt=qk k=2 region=1", "[0;mu;-lambda].Test_u*2", (0, 4, -6)),   # a Neumann load on the faces x = 1
 ]
 REFUSED = [  # the probe sees two items only: anything that may vary over the region is not its business
-    ("dim=3 n=2 gt=pk k=2", "X(1)*Test_u(1)"),
-    ("dim=3 n=2 gt=pk k=2 region=2", "Test_u.(lambda*Normal)*2"),                 # normal load on a non-planar boundary
     ("dim=3 n=2 gt=pk k=2 q=1", "Grad_Test_u.(c0*Grad_Test2_u)*2"),               # fem-data material: constant on the probe convexes only
     ("dim=3 n=2 gt=pk k=2 q=1", "c0*Test_u*3"),                                   # fem-data load
 ]
@@ -243,8 +242,46 @@ def test_general_scalar_expressions_take_the_nvrtc_route(expr):
     assert "recognised family 11" in line, line
 
 
+X_EXPRS = [  # the position X (whole vector or one coordinate): x = sum_g G_g N_g(q) from the geometric transformation's values
+    ("dim=3 n=2 gt=pk k=2 q=1", "X(1)*sin(u)*Test_u"),
+    ("dim=3 n=2 gt=pk k=2 q=1", "(1+X.X)*Grad_u.Grad_Test_u + X(3)*Test_u"),
+    ("dim=3 n=2 gt=pk k=2", "X(1)*Test_u(1)"),                                    # a body load that varies in space: no order-2 tree
+    ("dim=2 n=4 gt=qk k=2", "(1+X(2))*Grad_u:Grad_Test_u - X.Test_u"),
+    # boundary faces: the probe sees two items only, so what varies over the region (X, Normal on a non-planar boundary, the
+    # state) is compiled as it stands -- the run-time kernel takes the face tables and the unit normal (C&E.cc:8836-8847)
+    ("dim=3 n=2 gt=pk k=2 region=2", "X(1)*Test_u(1)"),
+    ("dim=3 n=2 gt=pk k=2 region=2", "Test_u.(lambda*Normal)*2"),
+    ("dim=3 n=2 gt=pk k=2 q=1 region=2", "X(1)*sin(u)*Test_u + (u*u*u*u)*Test_u"),             # radiation-like Robin condition
+    ("dim=2 n=4 gt=qk k=2 region=2", "(u.Normal)*(Test_u.Normal)*(1+X(1)) + exp(u(1))*Test_u(2)"),
+]
+
+
+@pytest.mark.parametrize("mesh,expr", X_EXPRS)
+def test_expressions_of_the_position_take_the_nvrtc_route(mesh, expr):
+    line = _dryrun_order1(mesh, expr)
+    assert "recognised family 11" in line, line
+
+
+@pytest.mark.parametrize("mesh,expr", X_EXPRS + [("dim=3 n=2 gt=pk k=2 q=1", e) for e in JIT_EXPRS])
+def test_the_translated_forms_compile(mesh, expr):
+    """CPU: what the translator emits for the reference's order-1 / order-2 trees is valid source for the run-time kernel
+    (NVRTC targets sm_100a without a GPU) -- position, unit normal, parameters and probes included."""
+    from getfem_b200 import capi
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN, "model=expr"] + mesh.split() + ["expr=" + expr], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, GFGPU_DRYRUN="1"))
+    assert out.returncode == 0, out.stderr[-1500:]
+    forms = [l.split("\t") for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun jit]")]
+    assert forms, out.stderr[-1500:]
+    for head, f1, f2 in forms:
+        m = re.search(r"dim=(\d) qdim=(\d)", head)
+        capi.jit_check(int(m.group(1)), f1, f2, qdim=int(m.group(2)))
+
+
 def test_the_nvrtc_route_refuses_what_it_cannot_express():
-    """vector variables, X, other variables: no silent approximation -- the tree is reported as not recognised"""
-    for mesh, expr in (("dim=3 n=2 gt=pk k=2", "sqr(Norm(u))*Grad_u:Grad_Test_u"), ("dim=3 n=2 gt=pk k=2 q=1", "X(1)*sin(u)*Test_u")):
+    """operators outside the translator's language, fem-data coefficients: no silent approximation -- the tree is reported as not
+    recognised"""
+    for mesh, expr in (("dim=3 n=2 gt=pk k=2", "sqr(Norm(u))*Grad_u:Grad_Test_u"), ("dim=3 n=2 gt=pk k=2 q=1", "c0*sin(u)*Test_u")):
         line = _dryrun_order1(mesh, expr)
         assert "NOT recognised" in line, line
