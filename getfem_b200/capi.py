@@ -88,6 +88,13 @@ SIGNATURES = {
     "gfgpu_term_residual_add_dev": (C.c_int, [_P, C.c_double, _P, _i64]),
     "gfgpu_rect_create": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_double, C.c_double, _PP]),
     "gfgpu_rect_destroy": (C.c_int, [_P]),
+    "gfgpu_rect_set_region": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "gfgpu_reduction_create": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _PP]),
+    "gfgpu_reduction_destroy": (C.c_int, [_P]),
+    "gfgpu_reduction_extend_host": (C.c_int, [_P, _P, _P]),
+    "gfgpu_reduction_restrict_add_host": (C.c_int, [_P, C.c_double, _P, _P]),
+    "gfgpu_matrix_add_term_reduced": (C.c_int, [_P, _P, _P, C.c_double, C.c_int64, C.c_int64]),
+    "gfgpu_matrix_add_rect_reduced": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_double, C.c_int64, C.c_int64]),
     "gfgpu_rect_assemble_dev": (C.c_int, [_P]),
     "gfgpu_rect_nnz": (_i64, [_P]),
     "gfgpu_rect_export_csc_host": (C.c_int, [_P, C.c_int, _P, _P, _P]),
@@ -497,6 +504,14 @@ class DeviceMatrix(_Handle):
     def add_term(self, term, alpha=1.0, row_off=0, col_off=0):
         check(lib().gfgpu_matrix_add_term(self.h, term.h, float(alpha), int(row_off), int(col_off)))
 
+    def add_term_reduced(self, term, E, alpha=1.0, row_off=0, col_off=0):
+        """K += alpha E^T K_term E (a term assembled on the basic dofs of a reduced mesh_fem, workspace.cc:861-935)"""
+        check(lib().gfgpu_matrix_add_term_reduced(self.h, term.h, E.h, float(alpha), int(row_off), int(col_off)))
+
+    def add_rect_reduced(self, rect, E_rows=None, E_cols=None, transposed=False, alpha=1.0, row_off=0, col_off=0):
+        check(lib().gfgpu_matrix_add_rect_reduced(self.h, rect.h, 1 if transposed else 0, E_rows.h if E_rows else None,
+                                                  E_cols.h if E_cols else None, float(alpha), int(row_off), int(col_off)))
+
     @property
     def nnz(self):
         return int(lib().gfgpu_matrix_nnz(self.h))
@@ -560,6 +575,7 @@ class DeviceMatrix(_Handle):
 
 
 RECT_DIV_PRESSURE = 0
+RECT_MASS = 1
 
 
 def jit_check(dim, form1, form2, qdim=1):
@@ -577,6 +593,12 @@ class DeviceRect(_Handle):
         self._keep = (mesh, fem_rows, tab_rows, fem_cols, tab_cols)
         check(lib().gfgpu_rect_create(ctx.h, mesh.h, fem_rows.h, tab_rows.h, fem_cols.h, tab_cols.h, int(family), float(coef),
                                       float(alpha), C.byref(self.h)))
+
+    def set_region(self, cv, face=None):
+        cv = None if cv is None else np.ascontiguousarray(cv, np.int32)
+        face = None if face is None else np.ascontiguousarray(face, np.int32)
+        check(lib().gfgpu_rect_set_region(self.h, 0 if cv is None else len(cv), ptr(cv) if cv is not None else None,
+                                          ptr(face) if face is not None else None))
 
     def assemble(self):
         check(lib().gfgpu_rect_assemble_dev(self.h))
@@ -598,6 +620,32 @@ class DeviceRect(_Handle):
         nout = self.ncols if transposed else self.nrows
         y = np.zeros(nout) if y is None else np.ascontiguousarray(y, np.float64).copy()
         check(lib().gfgpu_rect_mult_host(self.h, 1 if transposed else 0, float(alpha), ptr(x), float(beta), ptr(y)))
+        return y
+
+
+class DeviceReduction(_Handle):
+    """The extension matrix E (nb_basic_dof x nb_dof) of a reduced mesh_fem, given as a scipy CSR matrix or (rowptr, col, val)."""
+    _destroy = "gfgpu_reduction_destroy"
+
+    def __init__(self, ctx, n_basic, n_dof, rowptr, col, val):
+        super().__init__()
+        self.ctx, self.n_basic, self.n_dof = ctx, int(n_basic), int(n_dof)
+        rowptr = np.ascontiguousarray(rowptr, np.int64)
+        col = np.ascontiguousarray(col, np.int32)
+        val = np.ascontiguousarray(val, np.float64)
+        assert len(rowptr) == self.n_basic + 1
+        check(lib().gfgpu_reduction_create(ctx.h, self.n_basic, self.n_dof, ptr(rowptr), ptr(col), ptr(val), C.byref(self.h)))
+
+    def extend(self, x):
+        x = np.ascontiguousarray(x, np.float64)
+        y = np.empty(self.n_basic)
+        check(lib().gfgpu_reduction_extend_host(self.h, ptr(x), ptr(y)))
+        return y
+
+    def restrict_add(self, x, y, alpha=1.0):
+        x = np.ascontiguousarray(x, np.float64)
+        y = np.ascontiguousarray(y, np.float64).copy()
+        check(lib().gfgpu_reduction_restrict_add_host(self.h, float(alpha), ptr(x), ptr(y)))
         return y
 
 

@@ -146,6 +146,15 @@ struct gfgpu_tables {
 
 // A COUPLED bilinear term: test functions on one fem (rows), trial functions on another (columns), same mesh and
 // quadrature -- the off-diagonal blocks of mixed formulations (rect.cu).
+// extension matrix E of a reduced mesh_fem (nb_basic_dof x nb_dof), CSR, and its transpose (matrix.cu)
+struct gfgpu_reduction {
+  gfgpu_ctx *ctx;
+  int64_t n_basic, n_dof, nnz;
+  gf::DevBuf<int64_t> rp, trp;
+  gf::DevBuf<int32_t> col, tcol;
+  gf::DevBuf<double> val, tval;
+};
+
 struct gfgpu_rect {
   gfgpu_ctx *ctx;
   gfgpu_mesh *mesh;
@@ -165,6 +174,10 @@ struct gfgpu_rect {
   gf::DevBuf<int32_t> ir, irt;
   gf::DevBuf<double> pr, prt;
   gf::DevBuf<uint32_t> tperm;    // entry k of the transpose = entry tperm[k] of the block
+  // mesh region (gfgpu_rect_set_region): region-ordered copies of the connectivity and of the two dof tables, face of every item
+  bool region = false, region_faces = false;
+  gf::DevBuf<int32_t> r_conn, r_edr, r_edc;
+  gf::DevBuf<int8_t> r_face;
 };
 
 struct gfgpu_term {

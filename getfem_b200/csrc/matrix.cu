@@ -370,6 +370,185 @@ static void mat_build_csr(gfgpu_matrix *m) {
   m->csr_generation = m->generation;
 }
 
+
+// ---------------------------------------------------------------- reduced mesh_fem: K += E^T K_basic E, V += E^T V_basic
+// A reduced mesh_fem (mesh_fem::is_reduced(): partial_mesh_fem -- the multiplier spaces of the Dirichlet bricks --, periodic or
+// enriched spaces) is assembled by the reference on its BASIC dofs into unreduced matrices and then projected with the
+// extension matrix E (nb_basic_dof x nb_dof): K(I1, I2) += E1^T K_basic E2, V(I1) += E1^T V_basic (workspace.cc:861-935,
+// gmm::mult of sparse matrices).  Here each side is one expand-sort-compress pass on the device:
+//   rows pass  A = E^T S : every stored (j, k, v) of S and every stored (r, a) of row j of E gives (r, k, a v)
+//   cols pass  M = A E   : every stored (r, k, v) of A and every stored (c, b) of row k of E gives (r, c, v b)
+// products are expanded in the CSC order of the source, radix-sorted (CUB, stable) by (column, row) and summed per entry in
+// that order -- ascending inner index, the order of gmm's column / rank-one products -- by one thread per entry; sums that are
+// exactly 0.0 are not stored (rsvector::w removes them).  No atomics on values, bitwise reproducible.
+__global__ void k_red_count(const int64_t *__restrict__ jc, const int32_t *__restrict__ ir, int64_t ncols, const int64_t *__restrict__ erp,
+                            int side, int64_t *__restrict__ cnt) {
+  // one warp per source column
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int64_t k = warp; k < ncols; k += nw) {
+    const int64_t lenk = side ? erp[k + 1] - erp[k] : 0;
+    for (int64_t e = jc[k] + lane; e < jc[k + 1]; e += 32) cnt[e] = side ? lenk : erp[ir[e] + 1] - erp[ir[e]];
+  }
+}
+
+__global__ void k_red_expand(const int64_t *__restrict__ jc, const int32_t *__restrict__ ir, const double *__restrict__ pr, int64_t ncols,
+                             const int64_t *__restrict__ erp, const int32_t *__restrict__ ecol, const double *__restrict__ eval,
+                             int side, int64_t out_nrows, const int64_t *__restrict__ off, unsigned long long *__restrict__ key,
+                             double *__restrict__ val) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int64_t k = warp; k < ncols; k += nw) {
+    for (int64_t e = jc[k] + lane; e < jc[k + 1]; e += 32) {
+      const int64_t j = ir[e], o = off[e];
+      const double v = pr[e];
+      if (!side) {  // rows pass: (r, k) for every (r, a) of E's row j
+        for (int64_t q = erp[j]; q < erp[j + 1]; ++q) {
+          key[o + q - erp[j]] = (unsigned long long)k * (unsigned long long)out_nrows + (unsigned long long)ecol[q];
+          val[o + q - erp[j]] = eval[q] * v;
+        }
+      } else {      // cols pass: (j, c) for every (c, b) of E's row k
+        for (int64_t q = erp[k]; q < erp[k + 1]; ++q) {
+          key[o + q - erp[k]] = (unsigned long long)ecol[q] * (unsigned long long)out_nrows + (unsigned long long)j;
+          val[o + q - erp[k]] = v * eval[q];
+        }
+      }
+    }
+  }
+}
+
+// thread per sorted product: the first product of an entry sums its run in order and flags a nonzero result
+__global__ void k_red_sum(const unsigned long long *__restrict__ key, const double *__restrict__ val, int64_t n,
+                          double *__restrict__ sum, int64_t *__restrict__ keep) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t kp = 0;
+    if (i == 0 || key[i] != key[i - 1]) {
+      double s = val[i];
+      for (int64_t q = i + 1; q < n && key[q] == key[i]; ++q) s += val[q];
+      sum[i] = s;
+      kp = s != 0.0 ? 1 : 0;
+    }
+    keep[i] = kp;
+  }
+}
+
+__global__ void k_red_compact(const unsigned long long *__restrict__ key, const double *__restrict__ sum, const int64_t *__restrict__ keep,
+                              const int64_t *__restrict__ pos, int64_t n, int64_t out_nrows, int32_t *__restrict__ ir,
+                              double *__restrict__ pr, unsigned long long *__restrict__ colcnt) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (!keep[i]) continue;
+    const unsigned long long c = key[i] / (unsigned long long)out_nrows;
+    ir[pos[i]] = (int32_t)(key[i] % (unsigned long long)out_nrows);
+    pr[pos[i]] = sum[i];
+    atomicAdd(colcnt + c, 1ull);  // a count, not a value: order does not matter
+  }
+}
+
+__global__ void k_red_extend(const int64_t *__restrict__ erp, const int32_t *__restrict__ ecol, const double *__restrict__ eval, int64_t n,
+                             const double *__restrict__ x, double *__restrict__ y) {  // y = E x, thread per basic dof
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int64_t q = erp[j]; q < erp[j + 1]; ++q) s += eval[q] * x[ecol[q]];
+    y[j] = s;
+  }
+}
+
+__global__ void k_red_restrict(const int64_t *__restrict__ trp, const int32_t *__restrict__ tcol, const double *__restrict__ tval, int64_t n,
+                               double alpha, const double *__restrict__ x, double *__restrict__ y) {  // y += alpha E^T x, thread per dof
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int64_t q = trp[r]; q < trp[r + 1]; ++q) s += tval[q] * x[tcol[q]];
+    y[r] += alpha * s;
+  }
+}
+
+struct CscBuf {
+  DevBuf<int64_t> jc;
+  DevBuf<int32_t> ir;
+  DevBuf<double> pr;
+  int64_t nrows = 0, ncols = 0, nnz = 0;
+};
+
+// one pass: out = E^T S (side 0) or S E (side 1); S is nrows_in x ncols_in in CSC
+static void red_pass(gfgpu_ctx *ctx, const int64_t *jc, const int32_t *ir, const double *pr, int64_t nrows_in, int64_t ncols_in,
+                     int64_t nnz_in, const gfgpu_reduction *E, int side, CscBuf &out) {
+  cudaStream_t s = ctx->stream;
+  GF_REQUIRE((side ? ncols_in : nrows_in) == E->n_basic, "the extension matrix does not match the block");
+  out.nrows = side ? nrows_in : E->n_dof;
+  out.ncols = side ? E->n_dof : ncols_in;
+  out.jc.alloc(ctx, out.ncols + 1);
+  out.jc.zero();
+  out.nnz = 0;
+  if (!nnz_in) return;
+  const int B = 256;
+  DevBuf<int64_t> cnt, off;
+  cnt.alloc(ctx, nnz_in + 1);
+  off.alloc(ctx, nnz_in + 1);
+  GF_CUDA(cudaMemsetAsync(cnt.p + nnz_in, 0, sizeof(int64_t), s));
+  k_red_count<<<mgrid(ncols_in * 32, B), B, 0, s>>>(jc, ir, ncols_in, E->rp.p, side, cnt.p);
+  GF_LAUNCH_CHECK();
+  scan_counts(ctx, cnt.p, off.p, nnz_in + 1);
+  int64_t T = 0;
+  GF_CUDA(cudaMemcpyAsync(&T, off.p + nnz_in, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  GF_CUDA(cudaStreamSynchronize(s));
+  cnt.release();
+  if (!T) return;
+  DevBuf<unsigned long long> key, key2;
+  DevBuf<double> val, val2;
+  key.alloc(ctx, T); key2.alloc(ctx, T); val.alloc(ctx, T); val2.alloc(ctx, T);
+  k_red_expand<<<mgrid(ncols_in * 32, B), B, 0, s>>>(jc, ir, pr, ncols_in, E->rp.p, E->col.p, E->val.p, side, out.nrows, off.p, key.p,
+                                                    val.p);
+  GF_LAUNCH_CHECK();
+  off.release();
+  int bits = 1;
+  while (bits < 64 && ((unsigned long long)out.nrows * (unsigned long long)out.ncols) >> bits) ++bits;
+  size_t tb = 0;
+  GF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, key.p, key2.p, val.p, val2.p, T, 0, bits, s));
+  void *tmp = cub_scratch(ctx, tb);
+  GF_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, key.p, key2.p, val.p, val2.p, T, 0, bits, s));  // stable: products stay in order
+  count_launch(3);
+  key.release();
+  DevBuf<int64_t> keep, pos;
+  keep.alloc(ctx, T + 1);
+  pos.alloc(ctx, T + 1);
+  GF_CUDA(cudaMemsetAsync(keep.p + T, 0, sizeof(int64_t), s));
+  k_red_sum<<<mgrid(T, B), B, 0, s>>>(key2.p, val2.p, T, val.p, keep.p);
+  GF_LAUNCH_CHECK();
+  scan_counts(ctx, keep.p, pos.p, T + 1);
+  GF_CUDA(cudaMemcpyAsync(&out.nnz, pos.p + T, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  GF_CUDA(cudaStreamSynchronize(s));
+  if (!out.nnz) return;
+  out.ir.alloc(ctx, out.nnz);
+  out.pr.alloc(ctx, out.nnz);
+  DevBuf<int64_t> colcnt;
+  colcnt.alloc(ctx, out.ncols + 1);
+  colcnt.zero();
+  k_red_compact<<<mgrid(T, B), B, 0, s>>>(key2.p, val.p, keep.p, pos.p, T, out.nrows, out.ir.p, out.pr.p,
+                                                   reinterpret_cast<unsigned long long *>(colcnt.p));
+  GF_LAUNCH_CHECK();
+  scan_counts(ctx, colcnt.p, out.jc.p, out.ncols + 1);
+  GF_CUDA(cudaStreamSynchronize(s));
+}
+
+// m(row_off.., col_off..) += alpha * Er^T S Ec  (a null extension matrix = that side is not reduced)
+static void mat_add_projected(gfgpu_matrix *m, const int64_t *jc, const int32_t *ir, const double *pr, int64_t nrows, int64_t ncols,
+                              int64_t nnz, const gfgpu_reduction *Er, const gfgpu_reduction *Ec, double alpha, int64_t row_off,
+                              int64_t col_off) {
+  gfgpu_ctx *ctx = m->ctx;
+  CscBuf a, b;
+  if (Er) {
+    red_pass(ctx, jc, ir, pr, nrows, ncols, nnz, Er, 0, a);
+    jc = a.jc.p; ir = a.ir.p; pr = a.pr.p; nrows = a.nrows; ncols = a.ncols; nnz = a.nnz;
+  }
+  if (Ec) {
+    red_pass(ctx, jc, ir, pr, nrows, ncols, nnz, Ec, 1, b);
+    jc = b.jc.p; ir = b.ir.p; pr = b.pr.p; nrows = b.nrows; ncols = b.ncols; nnz = b.nnz;
+  }
+  GF_REQUIRE(row_off >= 0 && col_off >= 0 && row_off + nrows <= m->nrows && col_off + ncols <= m->ncols,
+             "the projected block does not fit the matrix");
+  mat_add(m, jc, ir, pr, ncols, nnz, alpha, row_off, col_off);
+}
+
 }  // namespace gf
 
 namespace gf { void set_last_error(const std::string &); }  // api.cu
@@ -668,6 +847,102 @@ int gfgpu_matrix_add_rect(gfgpu_matrix *m, gfgpu_rect *r, int transposed, double
   GF_CUDA(cudaSetDevice(m->ctx->device));
   if (transposed) gf::mat_add(m, r->jct.p, r->irt.p, r->prt.p, nc, r->nnz, alpha, row_off, col_off);
   else gf::mat_add(m, r->jc.p, r->ir.p, r->pr.p, nc, r->nnz, alpha, row_off, col_off);
+  GFM_END
+}
+
+
+int gfgpu_reduction_create(gfgpu_ctx *ctx, int64_t n_basic, int64_t n_dof, const int64_t *rowptr, const int32_t *col, const double *val,
+                           gfgpu_reduction **out) {
+  GFM_BEGIN
+  GF_REQUIRE(ctx && rowptr && out && n_basic >= 0 && n_dof >= 0, "bad argument");
+  const int64_t nnz = rowptr[n_basic];
+  GF_REQUIRE(nnz == 0 || (col && val), "null argument");
+  for (int64_t j = 0; j < n_basic; ++j) {
+    GF_REQUIRE(rowptr[j] <= rowptr[j + 1], "row pointers must ascend");
+    for (int64_t q = rowptr[j]; q < rowptr[j + 1]; ++q)
+      GF_REQUIRE(col[q] >= 0 && col[q] < n_dof && (q == rowptr[j] || col[q - 1] < col[q]), "columns out of range or not ascending");
+  }
+  GF_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<gfgpu_reduction> E(new gfgpu_reduction);
+  E->ctx = ctx; E->n_basic = n_basic; E->n_dof = n_dof; E->nnz = nnz;
+  E->rp.alloc(ctx, n_basic + 1); E->rp.upload(rowptr);
+  E->col.alloc(ctx, nnz); E->col.upload(col);
+  E->val.alloc(ctx, nnz); E->val.upload(val);
+  // the transpose (rows = dofs, ascending basic dof inside a row): V += E^T V_basic as an ordered gather
+  std::vector<int64_t> trp(n_dof + 1, 0);
+  for (int64_t q = 0; q < nnz; ++q) ++trp[col[q] + 1];
+  for (int64_t r = 0; r < n_dof; ++r) trp[r + 1] += trp[r];
+  std::vector<int32_t> tcol(nnz);
+  std::vector<double> tval(nnz);
+  std::vector<int64_t> fill(trp.begin(), trp.end() - 1);
+  for (int64_t j = 0; j < n_basic; ++j)
+    for (int64_t q = rowptr[j]; q < rowptr[j + 1]; ++q) { tcol[fill[col[q]]] = (int32_t)j; tval[fill[col[q]]++] = val[q]; }
+  E->trp.alloc(ctx, n_dof + 1); E->trp.upload(trp.data());
+  E->tcol.alloc(ctx, nnz); E->tcol.upload(tcol.data());
+  E->tval.alloc(ctx, nnz); E->tval.upload(tval.data());
+  GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = E.release();
+  GFM_END
+}
+
+int gfgpu_reduction_destroy(gfgpu_reduction *E) {
+  GFM_BEGIN
+  if (E) { cudaSetDevice(E->ctx->device); delete E; }
+  GFM_END
+}
+
+int gfgpu_reduction_extend_host(gfgpu_reduction *E, const double *x_host, double *y_host) {
+  GFM_BEGIN
+  GF_REQUIRE(E && x_host && y_host, "null argument");
+  gfgpu_ctx *ctx = E->ctx;
+  GF_CUDA(cudaSetDevice(ctx->device));
+  gf::DevBuf<double> x, y;
+  x.alloc(ctx, E->n_dof); y.alloc(ctx, E->n_basic);
+  x.upload(x_host);
+  if (E->n_basic) gf::k_red_extend<<<gf::mgrid(E->n_basic, 256), 256, 0, ctx->stream>>>(E->rp.p, E->col.p, E->val.p, E->n_basic, x.p, y.p);
+  GF_LAUNCH_CHECK();
+  y.download(y_host);
+  GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  GFM_END
+}
+
+int gfgpu_reduction_restrict_add_host(gfgpu_reduction *E, double alpha, const double *x_host, double *y_host) {
+  GFM_BEGIN
+  GF_REQUIRE(E && x_host && y_host, "null argument");
+  gfgpu_ctx *ctx = E->ctx;
+  GF_CUDA(cudaSetDevice(ctx->device));
+  gf::DevBuf<double> x, y;
+  x.alloc(ctx, E->n_basic); y.alloc(ctx, E->n_dof);
+  x.upload(x_host); y.upload(y_host);
+  if (E->n_dof) gf::k_red_restrict<<<gf::mgrid(E->n_dof, 256), 256, 0, ctx->stream>>>(E->trp.p, E->tcol.p, E->tval.p, E->n_dof, alpha, x.p, y.p);
+  GF_LAUNCH_CHECK();
+  y.download(y_host);
+  GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  GFM_END
+}
+
+int gfgpu_matrix_add_term_reduced(gfgpu_matrix *m, gfgpu_term *t, gfgpu_reduction *E, double alpha, int64_t row_off, int64_t col_off) {
+  GFM_BEGIN
+  GF_REQUIRE(m && t && E, "null argument");
+  GF_REQUIRE(m->ctx == t->ctx && m->ctx == E->ctx, "matrix, term and extension matrix live on different contexts");
+  GF_REQUIRE(t->pat_valid, "the term has no assembled tangent");
+  gf::term_settle_pending(t);
+  GF_CUDA(cudaSetDevice(m->ctx->device));
+  gf::mat_add_projected(m, t->jc.p, t->ir.p, t->pr.p, t->fem->ndof, t->fem->ndof, t->nnz, E, E, alpha, row_off, col_off);
+  GFM_END
+}
+
+int gfgpu_matrix_add_rect_reduced(gfgpu_matrix *m, gfgpu_rect *r, int transposed, gfgpu_reduction *E_rows, gfgpu_reduction *E_cols,
+                                  double alpha, int64_t row_off, int64_t col_off) {
+  GFM_BEGIN
+  GF_REQUIRE(m && r, "null argument");
+  GF_REQUIRE(m->ctx == r->ctx && (!E_rows || E_rows->ctx == m->ctx) && (!E_cols || E_cols->ctx == m->ctx),
+             "matrix, term and extension matrices live on different contexts");
+  GF_REQUIRE(r->pat_valid, "the coupled term has no assembled block");
+  const int64_t nr = transposed ? r->ncols : r->nrows, nc = transposed ? r->nrows : r->ncols;
+  GF_CUDA(cudaSetDevice(m->ctx->device));
+  if (transposed) gf::mat_add_projected(m, r->jct.p, r->irt.p, r->prt.p, nr, nc, r->nnz, E_rows, E_cols, alpha, row_off, col_off);
+  else gf::mat_add_projected(m, r->jc.p, r->ir.p, r->pr.p, nr, nc, r->nnz, E_rows, E_cols, alpha, row_off, col_off);
   GFM_END
 }
 

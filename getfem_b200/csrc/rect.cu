@@ -23,7 +23,10 @@ void set_last_error(const std::string &s);
 struct RectArgs {
   const double *x, *y, *z;
   const int32_t *conn, *edr, *edc;
-  const double *w, *gt_grad, *gphi_r, *phi_c;
+  const double *w, *gt_grad, *gphi_r, *phi_r, *phi_c;
+  const int8_t *face;      // face of every item (region of faces), or nullptr; the tables are then the face tables, face after face
+  const double *fnormal;   // nf x 3 reference normals
+  int family;
   int ng, nq, ndr, ndc, qr, qc;
   int64_t ne;
   double coef;
@@ -42,27 +45,42 @@ __global__ void __launch_bounds__(128) k_rect_div(const RectArgs a) {
   constexpr int GEO = N * N + 1 + N;
   const int tid = threadIdx.x;
   for (int64_t e = blockIdx.x; e < a.ne; e += gridDim.x) {
+    // tables of this item: the volume points, or the nq points of its face (C&E.cc:8827-8848)
+    const int fc = a.face ? a.face[e] : 0;
+    const double *tw = a.w + (size_t)fc * a.nq, *tgt = a.gt_grad + (size_t)fc * a.nq * a.ng * N;
+    const double *tgr = a.gphi_r + (size_t)fc * a.nq * a.ndr * N, *tpr = a.phi_r + (size_t)fc * a.nq * a.ndr;
+    const double *tpc = a.phi_c + (size_t)fc * a.nq * a.ndc;
+    const double *nref = a.face ? a.fnormal + fc * 3 : nullptr;
     for (int k = tid; k < N * a.ng; k += blockDim.x) {
       const int i = k / N, d = k % N;
       const int32_t p = a.conn[e * a.ng + i];
       sG[d + N * i] = (d == 0 ? a.x : d == 1 ? a.y : a.z)[p];
     }
     __syncthreads();
-    for (int q = tid; q < a.nq; q += blockDim.x) geometry<N>(sG, a.gt_grad + (size_t)q * a.ng * N, a.ng, sGeo + q * GEO);
+    for (int q = tid; q < a.nq; q += blockDim.x) geometry<N>(sG, tgt + (size_t)q * a.ng * N, a.ng, sGeo + q * GEO, nref);
     __syncthreads();
     double vmax = 0.0;
     for (int k = tid; k < sr * sc; k += blockDim.x) {  // k = row + sr * column, row = i * qr + a
-      const int row = k % sr, col = k / sr, i = row / a.qr, c = row % a.qr, j = col / a.qc;
+      const int row = k % sr, col = k / sr, i = row / a.qr, c = row % a.qr, j = col / a.qc, d = col % a.qc;
       double s = 0.0;
-      for (int q = 0; q < a.nq; ++q) {
-        const double wq = a.w[q];
-        if (wq == 0.0) continue;  // zero-weight points are skipped (C&E.cc:8852)
-        const double *geo = sGeo + q * GEO;
-        const double *g = a.gphi_r + ((size_t)q * a.ndr + i) * N;
-        double dv = 0.0;  // (B ghat_i)_c = d phi_i / d x_c
+      if (a.family == GFGPU_RECT_MASS) {  // E[(i,c), (j,d)] = delta_cd sum_q w_q J phi_i psi_j
+        if (c == d)
+          for (int q = 0; q < a.nq; ++q) {
+            const double wq = tw[q];
+            if (wq == 0.0) continue;
+            s += (wq * sGeo[q * GEO + N * N]) * tpr[(size_t)q * a.ndr + i] * tpc[(size_t)q * a.ndc + j];
+          }
+      } else {
+        for (int q = 0; q < a.nq; ++q) {
+          const double wq = tw[q];
+          if (wq == 0.0) continue;  // zero-weight points are skipped (C&E.cc:8852)
+          const double *geo = sGeo + q * GEO;
+          const double *g = tgr + ((size_t)q * a.ndr + i) * N;
+          double dv = 0.0;  // (B ghat_i)_c = d phi_i / d x_c
 #pragma unroll
-        for (int p = 0; p < N; ++p) dv += geo[c + N * p] * g[p];
-        s += (wq * geo[N * N]) * a.phi_c[(size_t)q * a.ndc + j] * dv;
+          for (int p = 0; p < N; ++p) dv += geo[c + N * p] * g[p];
+          s += (wq * geo[N * N]) * tpc[(size_t)q * a.ndc + j] * dv;
+        }
       }
       s *= a.coef;
       sE[k] = s;
@@ -183,13 +201,22 @@ static void rect_elements(gfgpu_rect *r) {
   RectArgs a;
   const int64_t np = r->mesh->npts;
   a.x = r->mesh->xyz.p; a.y = a.x + np; a.z = a.y + np;
-  a.conn = r->mesh->conn.p; a.edr = r->fr->edof.p; a.edc = r->fc->edof.p;
-  a.w = r->tr->w.p; a.gt_grad = r->tr->gt_grad.p; a.gphi_r = r->tr->gphi.p; a.phi_c = r->tc->phi.p;
-  a.ng = r->mesh->ng; a.nq = r->tr->nq; a.ndr = r->fr->nd; a.ndc = r->fc->nd; a.qr = r->fr->qdim; a.qc = r->fc->qdim;
+  a.conn = r->region ? r->r_conn.p : r->mesh->conn.p;
+  a.edr = r->region ? r->r_edr.p : r->fr->edof.p;
+  a.edc = r->region ? r->r_edc.p : r->fc->edof.p;
+  a.family = r->family;
+  if (r->region_faces) {
+    a.w = r->tr->fw.p; a.gt_grad = r->tr->fgt_grad.p; a.gphi_r = r->tr->fgphi.p; a.phi_r = r->tr->fphi.p; a.phi_c = r->tc->fphi.p;
+    a.face = r->r_face.p; a.fnormal = r->tr->fnormal.p;
+  } else {
+    a.w = r->tr->w.p; a.gt_grad = r->tr->gt_grad.p; a.gphi_r = r->tr->gphi.p; a.phi_r = r->tr->phi.p; a.phi_c = r->tc->phi.p;
+    a.face = nullptr; a.fnormal = nullptr;
+  }
+  a.ng = r->mesh->ng; a.nq = r->region_faces ? r->tr->nqf : r->tr->nq; a.ndr = r->fr->nd; a.ndc = r->fc->nd; a.qr = r->fr->qdim; a.qc = r->fc->qdim;
   a.ne = r->ne; a.coef = r->coef;
   a.stage = r->stage.p; a.keep = r->keep.p;
   const int N = r->mesh->dim;
-  const size_t smem = ((size_t)N * a.ng + (size_t)a.nq * (N * N + 1 + N) + (size_t)r->sr * r->sc + 2) * 8;
+  const size_t smem = ((size_t)N * a.ng + (size_t)a.nq * (N * N + 1 + N) + (size_t)r->sr * r->sc + 2) * 8;  // (a.nq: volume or face points)
   GF_REQUIRE(smem <= 200 * 1024, "coupled term: element matrix too large for shared memory");
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(r->ne, (int64_t)ctx->sm_count * 8));
   if (N == 2) {
@@ -211,7 +238,7 @@ static void rect_pattern(gfgpu_rect *r) {
   DevBuf<uint32_t> val0, head, scan;
   key0.alloc(ctx, nct); key1.alloc(ctx, nct); val0.alloc(ctx, nct); head.alloc(ctx, nct); scan.alloc(ctx, nct);
   r->perm.alloc(ctx, nct);
-  k_rect_keys<<<rgrid(nct, B), B, 0, s>>>(r->fr->edof.p, r->fc->edof.p, r->keep.p, r->fr->nd, r->fr->qdim, r->fc->nd, r->fc->qdim, nct,
+  k_rect_keys<<<rgrid(nct, B), B, 0, s>>>(r->region ? r->r_edr.p : r->fr->edof.p, r->region ? r->r_edc.p : r->fc->edof.p, r->keep.p, r->fr->nd, r->fr->qdim, r->fc->nd, r->fc->qdim, nct,
                                         r->nrows, key0.p, val0.p);
   GF_LAUNCH_CHECK();
   size_t tb = 0;
@@ -318,8 +345,11 @@ int gfgpu_rect_create(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem_rows, gfg
   GF_REQUIRE(tab_rows->nq == tab_cols->nq && tab_rows->ng == tab_cols->ng && tab_rows->dim == mesh->dim,
              "the two table sets must share the quadrature points");
   GF_REQUIRE(tab_rows->nd == fem_rows->nd && tab_cols->nd == fem_cols->nd, "tables do not match the fems");
-  GF_REQUIRE(family == GFGPU_RECT_DIV_PRESSURE, "unknown coupled family");
-  GF_REQUIRE(fem_rows->qdim == mesh->dim && fem_cols->qdim == 1, "div-pressure coupling: vector rows (qdim = mesh dimension), scalar columns");
+  GF_REQUIRE(family == GFGPU_RECT_DIV_PRESSURE || family == GFGPU_RECT_MASS, "unknown coupled family");
+  if (family == GFGPU_RECT_DIV_PRESSURE)
+    GF_REQUIRE(fem_rows->qdim == mesh->dim && fem_cols->qdim == 1, "div-pressure coupling: vector rows (qdim = mesh dimension), scalar columns");
+  else
+    GF_REQUIRE(fem_rows->qdim == fem_cols->qdim, "coupled mass term: both fems must have the same qdim");
   GF_REQUIRE(mesh->dim == 2 || mesh->dim == 3, "coupled terms: 2D and 3D meshes");
   std::unique_ptr<gfgpu_rect> r(new gfgpu_rect);
   r->ctx = ctx; r->mesh = mesh; r->fr = fem_rows; r->fc = fem_cols; r->tr = tab_rows; r->tc = tab_cols;
@@ -327,6 +357,57 @@ int gfgpu_rect_create(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem_rows, gfg
   r->nrows = fem_rows->ndof; r->ncols = fem_cols->ndof; r->ne = mesh->ne;
   r->sr = fem_rows->nd * fem_rows->qdim; r->sc = fem_cols->nd * fem_cols->qdim;
   *out = r.release();
+  GFR_END
+}
+
+int gfgpu_rect_set_region(gfgpu_rect *r, int64_t n_items, const int32_t *cv, const int32_t *face) {
+  GFR_BEGIN
+  GF_REQUIRE(r, "null term");
+  GF_REQUIRE(n_items >= 0 && (cv || n_items == 0), "bad region");
+  gfgpu_ctx *ctx = r->ctx;
+  GF_CUDA(cudaSetDevice(ctx->device));
+  r->pat_valid = false;  // another set of elements: another pattern
+  r->stage.release(); r->keep.release();
+  if (!cv) {
+    r->region = r->region_faces = false;
+    r->r_conn.release(); r->r_edr.release(); r->r_edc.release(); r->r_face.release();
+    r->ne = r->mesh->ne;
+    return 0;
+  }
+  const int ng = r->mesh->ng, ndr = r->fr->nd, ndc = r->fc->nd;
+  int64_t nfaces = 0;
+  for (int64_t k = 0; k < n_items; ++k) {
+    GF_REQUIRE(cv[k] >= 0 && cv[k] < r->mesh->ne, "region refers to a convex outside the mesh");
+    GF_REQUIRE(k == 0 || cv[k] > cv[k - 1] || (cv[k] == cv[k - 1] && face && face[k] > face[k - 1]),
+               "region items must come in mr_visitor order (ascending convex, then face)");
+    if (face && face[k] >= 0) ++nfaces;
+  }
+  GF_REQUIRE(nfaces == 0 || nfaces == n_items, "a region must hold either convexes or faces, not both");
+  if (nfaces) {
+    GF_REQUIRE(r->tr->nf > 0 && r->tc->nf == r->tr->nf && r->tc->nqf == r->tr->nqf, "a region of faces needs gfgpu_tables_set_faces on both table sets");
+    for (int64_t k = 0; k < n_items; ++k) GF_REQUIRE(face[k] < r->tr->nf, "face number outside the reference element");
+  }
+  std::vector<int32_t> hc((size_t)r->mesh->ne * ng), hr((size_t)r->mesh->ne * ndr), hcol((size_t)r->mesh->ne * ndc);
+  r->mesh->conn.download(hc.data());
+  r->fr->edof.download(hr.data());
+  r->fc->edof.download(hcol.data());
+  GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<int32_t> rc((size_t)n_items * ng), rr((size_t)n_items * ndr), rcc((size_t)n_items * ndc);
+  std::vector<int8_t> rf((size_t)n_items);
+  for (int64_t k = 0; k < n_items; ++k) {
+    std::copy(hc.begin() + (size_t)cv[k] * ng, hc.begin() + (size_t)(cv[k] + 1) * ng, rc.begin() + (size_t)k * ng);
+    std::copy(hr.begin() + (size_t)cv[k] * ndr, hr.begin() + (size_t)(cv[k] + 1) * ndr, rr.begin() + (size_t)k * ndr);
+    std::copy(hcol.begin() + (size_t)cv[k] * ndc, hcol.begin() + (size_t)(cv[k] + 1) * ndc, rcc.begin() + (size_t)k * ndc);
+    rf[k] = (int8_t)(nfaces ? face[k] : -1);
+  }
+  r->r_conn.alloc(ctx, rc.size()); r->r_conn.upload(rc.data());
+  r->r_edr.alloc(ctx, rr.size()); r->r_edr.upload(rr.data());
+  r->r_edc.alloc(ctx, rcc.size()); r->r_edc.upload(rcc.data());
+  if (nfaces) { r->r_face.alloc(ctx, rf.size()); r->r_face.upload(rf.data()); } else r->r_face.release();
+  GF_CUDA(cudaStreamSynchronize(ctx->stream));
+  r->region = true;
+  r->region_faces = nfaces > 0;
+  r->ne = n_items;
   GFR_END
 }
 

@@ -661,6 +661,25 @@ static bool recognise_coupled(const getfem::ga_workspace &ws, const std::string 
   // capture 1 = the scalar variable (A), capture 2 = the vector variable (B)
   std::string A, B;
   bool found = false;
+  if (order == 2) {  // coupled mass: "Test_a:Test2_b" (asm_mass_matrix on two fems), also with '.', '*' and the factors swapped
+    std::string ta, tb;
+    if (std::regex_match(s, m, std::regex("Test_" + ID + "[.:*]Test2_" + ID))) { ta = m[1]; tb = m[2]; }
+    else if (std::regex_match(s, m, std::regex("Test2_" + ID + "[.:*]Test_" + ID))) { ta = m[2]; tb = m[1]; }
+    if (!ta.empty() && ta == test1 && tb == test2 && ta != tb && ws.variable_exists(ta) && ws.variable_exists(tb)) {
+      const getfem::mesh_fem *mfa = ws.associated_mf(ta), *mfb = ws.associated_mf(tb);
+      if (mfa && mfb && &mfa->linked_mesh() == &mfb->linked_mesh() && mfa->get_qdim() == mfb->get_qdim()) {
+        out.family = GFGPU_SHIM_COUPLED_MASS;
+        out.varname = test1;
+        out.varname_u = ta;  // rows
+        out.varname_p = tb;  // columns
+        out.transposed = false;
+        out.sign = 1.0;
+        out.params.clear();
+        out.field_names.clear();
+        return true;
+      }
+    }
+  }
   if (order == 2) {
     const std::vector<std::pair<std::string, double>> fu = {{"\\(-Test2_" + ID + "\\)\\*Div_Test_" + ID, -1.0},
                                                             {"-\\(Test2_" + ID + "\\*Div_Test_" + ID + "\\)", -1.0},
@@ -779,9 +798,9 @@ static bool recognise_string(const getfem::ga_workspace &ws, const std::string &
   {  // volumic source term (add_source_term_brick, getfem_models.cc:4124-): "(-f)*Test_u", "(-f).Test_u", "-(f.Test_u)", "f.Test_u"
     double sign = 0;
     std::string name;
-    if (std::regex_match(s, m, std::regex("\\(-" + ID + "\\)[.*]Test_" + v))) { sign = -1; name = m[1]; }
-    else if (std::regex_match(s, m, std::regex("-\\(" + ID + "[.*]Test_" + v + "\\)"))) { sign = -1; name = m[1]; }
-    else if (std::regex_match(s, m, std::regex(ID + "[.*]Test_" + v))) { sign = 1; name = m[1]; }
+    if (std::regex_match(s, m, std::regex("\\(-" + ID + "\\)[.*:]Test_" + v))) { sign = -1; name = m[1]; }
+    else if (std::regex_match(s, m, std::regex("-\\(" + ID + "[.*:]Test_" + v + "\\)"))) { sign = -1; name = m[1]; }
+    else if (std::regex_match(s, m, std::regex(ID + "[.*:]Test_" + v))) { sign = 1; name = m[1]; }  // (":" = asm_source_term)
     if (sign != 0 && name != v && ws.is_constant(name) && !ws.variable_group_exists(name)) {
       const getfem::mesh_fem *pmf = ws.associated_mf(v);
       out.family = GFGPU_SOURCE;
@@ -893,7 +912,7 @@ struct device_assembler::rect_entry {
   gfgpu_tables *tu = nullptr, *tp = nullptr;
   gfgpu_rect *rect = nullptr;
   bool assembled = false;
-  size_type nu = 0, np = 0;
+  size_type nu = 0, np = 0;  // BASIC dofs of the two fems (what the device block is indexed by)
   ~rect_entry() {
     gfgpu_rect_destroy(rect);
     gfgpu_tables_destroy(tu);
@@ -903,6 +922,40 @@ struct device_assembler::rect_entry {
     gfgpu_mesh_destroy(mesh);
   }
 };
+
+// extension matrix of a reduced mesh_fem on the device (mesh_fem::extension_matrix(), a gmm::csr_matrix)
+struct device_assembler::reduction_entry {
+  context_watcher watch;
+  gfgpu_reduction *E = nullptr;
+  ~reduction_entry() { gfgpu_reduction_destroy(E); }
+};
+
+gfgpu_reduction *device_assembler::reduction_of(const getfem::mesh_fem &mf) {
+  if (!mf.is_reduced()) return nullptr;
+  std::unique_ptr<reduction_entry> &pe = reductions_[(const void *)&mf];
+  if (pe && !pe->watch.still_valid()) pe.reset();
+  if (pe) return pe->E;
+  if (reductions_.size() > 16)
+    for (auto jt = reductions_.begin(); jt != reductions_.end();) jt = (&jt->second == &pe) ? std::next(jt) : reductions_.erase(jt);
+  pe.reset(new reduction_entry);
+  pe->watch.add_dependency(mf);
+  const size_type nb = mf.nb_basic_dof(), nr = mf.nb_dof();
+  const auto &E = mf.extension_matrix();  // nb x nr, rows = basic dofs
+  GMM_ASSERT1(gmm::mat_nrows(E) == nb && gmm::mat_ncols(E) == nr, "gfgpu: unexpected size of the extension matrix");
+  std::vector<int64_t> rp(nb + 1, 0);
+  std::vector<int32_t> col;
+  std::vector<double> val;
+  for (size_type j = 0; j < nb; ++j) {
+    std::vector<std::pair<size_type, double>> row;
+    auto r = gmm::mat_const_row(E, j);
+    for (auto it = gmm::vect_const_begin(r); it != gmm::vect_const_end(r); ++it) row.emplace_back(it.index(), *it);
+    std::sort(row.begin(), row.end());
+    for (const auto &cv : row) { col.push_back(int32_t(cv.first)); val.push_back(cv.second); }
+    rp[j + 1] = int64_t(col.size());
+  }
+  GFGPU_CALL(gfgpu_reduction_create(ctx_, int64_t(nb), int64_t(nr), rp.data(), col.data(), val.data(), &pe->E));
+  return pe->E;
+}
 
 struct device_assembler::entry {
   context_watcher watch;
@@ -941,6 +994,7 @@ device_assembler::~device_assembler() {
   tangent_.reset();
   cache_.clear();
   rect_cache_.clear();
+  reductions_.clear();
   gfgpu_ctx_destroy(ctx_);
 }
 
@@ -1024,14 +1078,29 @@ static bool recognise_potential(const getfem::ga_workspace &ws, size_type itree,
 // one classical Lagrange fem each on every convex, one approximate integration method), created once and watched through
 // GetFEM's context_dependencies like every other cached entry.
 device_assembler::rect_entry &device_assembler::coupled_entry(getfem::ga_workspace &ws, const getfem::mesh_im &mim,
-                                                             const std::string &vu, const std::string &vp) {
+                                                             const std::string &vu, const std::string &vp, int family,
+                                                             const std::vector<int32_t> *rg_cv, const std::vector<int32_t> *rg_f) {
   const getfem::mesh_fem *pmu = ws.associated_mf(vu), *pmp = ws.associated_mf(vp);
-  GMM_ASSERT1(pmu && pmp && !pmu->is_reduced() && !pmp->is_reduced(), "gfgpu: coupled terms need two non-reduced fem variables");
+  GMM_ASSERT1(pmu && pmp, "gfgpu: coupled terms need two fem variables");
+  // (a reduced mesh_fem -- the multiplier space of a Dirichlet brick -- is mirrored on its BASIC dofs; the block is projected
+  //  with the extension matrices when it is added to the tangent, workspace.cc:861-935)
+  GMM_ASSERT1(family == GFGPU_RECT_MASS || (!pmu->is_reduced() && !pmp->is_reduced()),
+              "gfgpu: div-pressure terms need two non-reduced fem variables");
   const getfem::mesh_fem &mfu = *pmu, &mfp = *pmp;
   const getfem::mesh &m = mfu.linked_mesh();
   GMM_ASSERT1(&mfp.linked_mesh() == &m && &mim.linked_mesh() == &m, "gfgpu: coupled variables must share the mesh");
   std::ostringstream key;
-  key << &m << "/" << &mfu << "/" << &mfp << "/" << &mim << "/" << mfu.nb_dof() << "/" << mfp.nb_dof();
+  key << &m << "/" << &mfu << "/" << &mfp << "/" << &mim << "/" << mfu.nb_basic_dof() << "/" << mfp.nb_basic_dof() << "/f" << family;
+  size_type rg_faces = 0;
+  if (rg_cv) {  // the region's content is part of the key (FNV-1a over the items)
+    uint64_t h = 1469598103934665603ull;
+    for (size_t k = 0; k < rg_cv->size(); ++k) {
+      h = (h ^ uint64_t(uint32_t((*rg_cv)[k]))) * 1099511628211ull;
+      h = (h ^ uint64_t(uint32_t((*rg_f)[k]))) * 1099511628211ull;
+      rg_faces += (*rg_f)[k] >= 0;
+    }
+    key << "/rg" << rg_cv->size() << ":" << h;
+  }
   std::unique_ptr<rect_entry> &pe = rect_cache_[key.str()];
   if (pe && !pe->watch.still_valid()) pe.reset();
   if (pe) return *pe;
@@ -1066,8 +1135,8 @@ device_assembler::rect_entry &device_assembler::coupled_entry(getfem::ga_workspa
   const size_type ndu = pfu->nb_dof(cv0), ndp = pfp->nb_dof(cv0), ng = pgt->nb_points();
   getfem::papprox_integration pai = pim->approx_method();
   const size_type nq = pai->nb_points_on_convex();
-  e.nu = mfu.nb_dof();
-  e.np = mfp.nb_dof();
+  e.nu = mfu.nb_basic_dof();
+  e.np = mfp.nb_basic_dof();
   const size_type npts = m.points_index().last_true() + 1;
   std::vector<double> pts(npts * dim, 0.0);
   for (dal::bv_visitor p(m.points_index()); !p.finished(); ++p)
@@ -1101,14 +1170,39 @@ device_assembler::rect_entry &device_assembler::coupled_entry(getfem::ga_workspa
       }
     }
     GFGPU_CALL(gfgpu_tables_create(ctx_, dim, int(nq), int(ng), int(nd), w.data(), gtg.data(), phi.data(), gphi.data(), out));
+    if (rg_faces) {  // tables at the face points, face after face (approx_integration::valid_method, getfem_integration.cc:353-368)
+      const size_type nf = pgt->structure()->nb_faces(), nqf = pai->nb_points_on_face(0);
+      std::vector<double> fn(nf * dim), fw(nf * nqf), fgtg(nf * nqf * ng * dim), fphi(nf * nqf * nd), fgphi(nf * nqf * nd * dim);
+      for (size_type f = 0; f < nf; ++f) {
+        GMM_ASSERT1(pai->nb_points_on_face(getfem::short_type(f)) == nqf,
+                    "gfgpu: faces with different numbers of integration points are not handled");
+        for (int d = 0; d < dim; ++d) fn[f * dim + d] = pgt->normals()[f][d];
+        for (size_type q = 0; q < nqf; ++q) {
+          const size_type ip = pai->ind_first_point_on_face(getfem::short_type(f)) + q, o = f * nqf + q;
+          fw[o] = pai->coeff(ip);
+          const bgeot::base_matrix &pc = pgp->grad(ip);
+          for (size_type i = 0; i < ng; ++i)
+            for (int d = 0; d < dim; ++d) fgtg[(o * ng + i) * dim + d] = pc(i, d);
+          const bgeot::base_tensor &bv = pfp2->val(ip), &bg = pfp2->grad(ip);
+          for (size_type i = 0; i < nd; ++i) {
+            fphi[o * nd + i] = bv[i];
+            for (int d = 0; d < dim; ++d) fgphi[(o * nd + i) * dim + d] = bg[i + nd * d];
+          }
+        }
+      }
+      GFGPU_CALL(gfgpu_tables_set_faces(*out, int(nf), int(nqf), fn.data(), fw.data(), fgtg.data(), fphi.data(), fgphi.data()));
+    }
   };
   GFGPU_CALL(gfgpu_mesh_create(ctx_, dim, int64_t(npts), pts.data(), int64_t(ne), int(ng), conn.data(), gqk ? GFGPU_GT_QK : GFGPU_GT_PK,
                                &e.mesh));
-  GFGPU_CALL(gfgpu_fem_create(ctx_, e.mesh, uqk ? GFGPU_FEM_QK : GFGPU_FEM_PK, udeg, dim, int(ndu), edu.data(), int64_t(e.nu), &e.fu));
-  GFGPU_CALL(gfgpu_fem_create(ctx_, e.mesh, pqk ? GFGPU_FEM_QK : GFGPU_FEM_PK, pdeg, 1, int(ndp), edp.data(), int64_t(e.np), &e.fp));
+  GFGPU_CALL(gfgpu_fem_create(ctx_, e.mesh, uqk ? GFGPU_FEM_QK : GFGPU_FEM_PK, udeg, int(mfu.get_qdim()), int(ndu), edu.data(),
+                              int64_t(e.nu), &e.fu));
+  GFGPU_CALL(gfgpu_fem_create(ctx_, e.mesh, pqk ? GFGPU_FEM_QK : GFGPU_FEM_PK, pdeg, int(mfp.get_qdim()), int(ndp), edp.data(),
+                              int64_t(e.np), &e.fp));
   tables(pfu, ndu, &e.tu);
   tables(pfp, ndp, &e.tp);
-  GFGPU_CALL(gfgpu_rect_create(ctx_, e.mesh, e.fu, e.tu, e.fp, e.tp, GFGPU_RECT_DIV_PRESSURE, 1.0, 1.0, &e.rect));
+  GFGPU_CALL(gfgpu_rect_create(ctx_, e.mesh, e.fu, e.tu, e.fp, e.tp, family, 1.0, 1.0, &e.rect));
+  if (rg_cv) GFGPU_CALL(gfgpu_rect_set_region(e.rect, int64_t(rg_cv->size()), rg_cv->data(), rg_faces ? rg_f->data() : nullptr));
   return e;
 }
 
@@ -1280,7 +1374,10 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
   // only the VALUES come back to the host (jc / ir, 8.8 GB for BASELINE config 3, are downloaded once).
   struct { gfgpu_matrix *m = nullptr; } dK;
   std::string terms_sig;
-  struct pending_add { gfgpu_term *term; double alpha; int64_t off; gfgpu_rect *rect = nullptr; int transposed = 0; int64_t coff = 0; };
+  struct pending_add {
+    gfgpu_term *term; double alpha; int64_t off; gfgpu_rect *rect = nullptr; int transposed = 0; int64_t coff = 0;
+    gfgpu_reduction *Er = nullptr, *Ec = nullptr;  // reduced mesh_fems: the block is projected, E_rows^T S E_cols
+  };
   std::vector<pending_add> pending_adds;
   if (order == 2) {
     if (tangent_ && tangent_->n != need_all) tangent_.reset();
@@ -1292,9 +1389,74 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     dK.m = tangent_->m;
   }
   size_type n_added = 0;  // tangents accumulated into dK
+  // integration region in mr_visitor order (the order ga_exec walks it, C&E.cc:8789): all convexes (returns true), a set of
+  // convexes, or a set of faces
+  auto walk_region = [&](const getfem::ga_workspace::tree_description &td, const getfem::mesh &m, std::vector<int32_t> &rg_cv,
+                         std::vector<int32_t> &rg_f, size_type &rg_faces) -> bool {
+    GMM_ASSERT1(td.rg, "gfgpu: no region");
+    const bool all_cv = td.rg->id() == getfem::mesh_region::all_convexes().id();
+    rg_cv.clear(); rg_f.clear();
+    rg_faces = 0;
+    if (!all_cv) {
+      // Inside GETFEM_OMP_PARALLEL with several partitions mr_visitor walks only the calling thread's slice
+      // (getfem_mesh_region.cc:186-200, 503-540), and a copy of a mesh-owned region SHARES its implementation (operator=,
+      // getfem_mesh_region.cc:100-106), partition caches included.  The device assembles the WHOLE region in one call (made by
+      // the thread of partition 0 alone, see the dispatch patch): there the item list is rebuilt from the membership test,
+      // which ignores the partition -- ascending convexes, whole convex first, then faces: the visitor's order.
+      if (getfem::me_is_multithreaded_now() && getfem::partition_master::get().get_nb_partitions() > 1) {
+        for (dal::bv_visitor cv(m.convex_index()); !cv.finished(); ++cv) {
+          if (td.rg->is_in(cv, getfem::short_type(-1), m)) { rg_cv.push_back(int32_t(cv)); rg_f.push_back(-1); }
+          const getfem::short_type nf = m.structure_of_convex(cv)->nb_faces();
+          for (getfem::short_type f = 0; f < nf; ++f)
+            if (td.rg->is_in(cv, f, m)) { rg_cv.push_back(int32_t(cv)); rg_f.push_back(int32_t(f)); ++rg_faces; }
+        }
+      } else {
+        for (getfem::mr_visitor v(*td.rg, m); !v.finished(); ++v) {
+          rg_cv.push_back(int32_t(v.cv()));
+          const bool isf = v.f() != getfem::short_type(-1);
+          rg_f.push_back(isf ? int32_t(v.f()) : -1);
+          rg_faces += isf;
+        }
+      }
+      GMM_ASSERT1(rg_faces == 0 || rg_faces == rg_cv.size(), "gfgpu: a region must hold either convexes or faces");
+    }
+    return all_cv;
+  };
   for (auto &it : terms) {
     const auto &td = ws.tree_info(it.first);
     const recognised_term &rt = it.second;
+    if (rt.family == GFGPU_SHIM_COUPLED_MASS) {
+      // "Test_a:Test2_b" on two fems (asm_mass_matrix(M, mim, mf1, mf2, rg); the constraint matrix of the Dirichlet bricks with
+      // multipliers, getfem_models.cc:4386-4421): a directly written bilinear form, so order 2 only; rows = a, columns = b
+      if (order != 2) continue;
+      GMM_ASSERT1(!(getfem::me_is_multithreaded_now() && getfem::partition_master::get().get_nb_partitions() > 1) ||
+                      getfem::partition_master::get().get_current_partition() == 0, "gfgpu: internal error (partition)");
+      const getfem::mesh_fem &mfa = *ws.associated_mf(rt.varname_u), &mfb = *ws.associated_mf(rt.varname_p);
+      std::vector<int32_t> rg_cv, rg_f;
+      size_type rg_faces = 0;
+      const bool all_cv = walk_region(td, mfa.linked_mesh(), rg_cv, rg_f, rg_faces);
+      if (!all_cv && rg_cv.empty()) continue;
+      rect_entry &re = coupled_entry(ws, *td.mim, rt.varname_u, rt.varname_p, GFGPU_RECT_MASS, all_cv ? nullptr : &rg_cv,
+                                     all_cv ? nullptr : &rg_f);
+      const gmm::sub_interval &Ia = ws.interval_of_variable(rt.varname_u), &Ib = ws.interval_of_variable(rt.varname_p);
+      double t1 = now_s();
+      t_extract += t1 - t0;
+      if (!re.assembled) {
+        GFGPU_CALL(gfgpu_rect_assemble_dev(re.rect));
+        re.assembled = true;
+      }
+      pending_add pa{nullptr, rt.sign * ws.factor_of_variable(rt.varname_u) * ws.factor_of_variable(rt.varname_p), int64_t(Ia.first())};
+      pa.rect = re.rect; pa.transposed = 0; pa.coff = int64_t(Ib.first());
+      pa.Er = reduction_of(mfa); pa.Ec = reduction_of(mfb);
+      std::ostringstream sg;
+      sg << "rectM" << (const void *)re.rect << "@" << pa.off << "," << pa.coff << "/" << (const void *)pa.Er << "/" << (const void *)pa.Ec << ";";
+      terms_sig += sg.str();
+      pending_adds.push_back(pa);
+      ++n_added;
+      t_device += now_s() - t1;
+      t0 = now_s();
+      continue;
+    }
     if (rt.family == GFGPU_SHIM_COUPLED_DIV) {
       GMM_ASSERT1(td.rg && td.rg->id() == getfem::mesh_region::all_convexes().id(),
                   "gfgpu: coupled terms are handled on the whole mesh (no region)");
@@ -1338,43 +1500,24 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
       continue;
     }
     const getfem::mesh_fem *pmf = ws.associated_mf(rt.varname);
-    GMM_ASSERT1(pmf && !pmf->is_reduced(), "gfgpu: the variable must live on a non-reduced mesh_fem");
+    GMM_ASSERT1(pmf, "gfgpu: the variable must be a fem variable");
     const getfem::mesh_fem &mf = *pmf;
+    // A REDUCED mesh_fem (partial_mesh_fem: multiplier spaces; periodic / enriched spaces) is assembled on its basic dofs and
+    // projected with its extension matrix: K(I, I) += E^T K_basic E, V(I) += E^T V_basic, state U_basic = E U
+    // (workspace.cc:861-935).  `ndof` below counts the BASIC dofs (what the device term is indexed by), `nred` the variable's.
+    gfgpu_reduction *Ered = reduction_of(mf);
     const getfem::mesh_im &mim = *td.mim;
     const getfem::mesh &m = mf.linked_mesh();
     // integration region in mr_visitor order (the order ga_exec walks it, C&E.cc:8789): all convexes, a set of
     // convexes, or a set of faces
-    GMM_ASSERT1(td.rg, "gfgpu: no region");
-    const bool all_cv = td.rg->id() == getfem::mesh_region::all_convexes().id();
     std::vector<int32_t> rg_cv, rg_f;
     size_type rg_faces = 0;
-    if (!all_cv) {
-      // Inside GETFEM_OMP_PARALLEL with several partitions mr_visitor walks only the calling thread's slice
-      // (getfem_mesh_region.cc:186-200, 503-540), and a copy of a mesh-owned region SHARES its implementation (operator=,
-      // getfem_mesh_region.cc:100-106), partition caches included.  The device assembles the WHOLE region in one call (made by
-      // the thread of partition 0 alone, see the dispatch patch): there the item list is rebuilt from the membership test,
-      // which ignores the partition -- ascending convexes, whole convex first, then faces: the visitor's order.
-      if (getfem::me_is_multithreaded_now() && getfem::partition_master::get().get_nb_partitions() > 1) {
-        for (dal::bv_visitor cv(m.convex_index()); !cv.finished(); ++cv) {
-          if (td.rg->is_in(cv, getfem::short_type(-1), m)) { rg_cv.push_back(int32_t(cv)); rg_f.push_back(-1); }
-          const getfem::short_type nf = m.structure_of_convex(cv)->nb_faces();
-          for (getfem::short_type f = 0; f < nf; ++f)
-            if (td.rg->is_in(cv, f, m)) { rg_cv.push_back(int32_t(cv)); rg_f.push_back(int32_t(f)); ++rg_faces; }
-        }
-      } else {
-        for (getfem::mr_visitor v(*td.rg, m); !v.finished(); ++v) {
-          rg_cv.push_back(int32_t(v.cv()));
-          const bool isf = v.f() != getfem::short_type(-1);
-          rg_f.push_back(isf ? int32_t(v.f()) : -1);
-          rg_faces += isf;
-        }
-      }
-      if (rg_cv.empty()) continue;  // an empty region assembles nothing: ga_exec walks zero elements (C&E.cc:8789-8866)
-      GMM_ASSERT1(rg_faces == 0 || rg_faces == rg_cv.size(), "gfgpu: a region must hold either convexes or faces");
-    }
+    const bool all_cv = walk_region(td, m, rg_cv, rg_f, rg_faces);
+    if (!all_cv && rg_cv.empty()) continue;  // an empty region assembles nothing: ga_exec walks zero elements (C&E.cc:8789-8866)
     mark("region walked");
     const gmm::sub_interval &I = ws.interval_of_variable(rt.varname);
-    const size_type ndof = mf.nb_dof();  // triggers enumerate_dof
+    const size_type nred = mf.nb_dof();  // triggers enumerate_dof
+    const size_type ndof = mf.nb_basic_dof();
     mark("nb_dof");
     GMM_ASSERT1(m.convex_index().card() > 0 && m.convex_index().card() == m.convex_index().last_true() + 1,
                 "gfgpu: convex ids must be contiguous (call mesh::optimize_structure)");
@@ -1666,8 +1809,15 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     e.used = true;
     e.last_use = ++use_clock_;
     // the variable's values, in the fem's own numbering (the workspace interval only offsets the result)
-    const getfem::model_real_plain_vector &U = ws.value(rt.varname);
-    GMM_ASSERT1(U.size() == ndof, "gfgpu: bad size of the variable's value vector");
+    const getfem::model_real_plain_vector &Ured = ws.value(rt.varname);
+    GMM_ASSERT1(Ured.size() == nred, "gfgpu: bad size of the variable's value vector");
+    std::vector<double> Ubasic;
+    if (Ered) {
+      Ubasic.resize(ndof);
+      GFGPU_CALL(gfgpu_reduction_extend_host(Ered, Ured.data(), Ubasic.data()));
+    }
+    const double *Udata = Ered ? Ubasic.data() : Ured.data();
+    struct { const double *p; const double *data() const { return p; } } U{Udata};
     mark("entry ready");
     double t1 = now_s();
     t_extract += t1 - t0;
@@ -1683,20 +1833,27 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
       double t2 = now_s();
       t_device += t2 - t1;
       getfem::base_vector &V = ws.assembled_vector();
-      if (V.size() < I.first() + ndof) V.resize(std::max<size_type>(nprim, I.first() + ndof), 0.0);
-      for (size_type d = 0; d < ndof; ++d) V[I.first() + d] += R[d];
+      if (V.size() < I.first() + nred) V.resize(std::max<size_type>(nprim, I.first() + nred), 0.0);
+      if (Ered) {
+        std::vector<double> Vr(nred, 0.0);
+        GFGPU_CALL(gfgpu_reduction_restrict_add_host(Ered, 1.0, R.data(), Vr.data()));
+        for (size_type d = 0; d < nred; ++d) V[I.first() + d] += Vr[d];
+      } else {
+        for (size_type d = 0; d < ndof; ++d) V[I.first() + d] += R[d];
+      }
       t_fill += now_s() - t2;
     } else if (rt.family == GFGPU_SOURCE || rt.family == GFGPU_NORMAL_SOURCE || rt.no_tangent ||
                (rt.family == GFGPU_JIT && rt.jit_form2 == "(0.0)")) {  // (a run-time compiled LOAD: no order-2 tree exists)
       // an order-1 term contributes nothing to the tangent; K only gets its size (workspace.cc:805-812)
       getfem::model_real_sparse_matrix &K = ws.assembled_matrix();
-      const size_type need = std::max<size_type>(nprim, I.first() + ndof);
+      const size_type need = std::max<size_type>(nprim, I.first() + nred);
       if (gmm::mat_nrows(K) < need || gmm::mat_ncols(K) < need) gmm::resize(K, need, need);
     } else {
       GFGPU_CALL(gfgpu_term_assemble_host(e.term, U.data(), GFGPU_TANGENT, nullptr, nullptr));
       const double alpha = ws.factor_of_variable(rt.varname);  // alpha1 * alpha2 of the matrix assembly instructions
       terms_sig += key.str() + "@" + std::to_string(I.first()) + ";";
       pending_adds.push_back(pending_add{e.term, alpha * alpha, int64_t(I.first())});
+      pending_adds.back().Er = pending_adds.back().Ec = Ered;
       ++n_added;
       t_device += now_s() - t1;
     }
@@ -1705,7 +1862,7 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
   }
   if (order == 2 && n_added == 0) {  // only order-1 terms / empty regions: K just gets its size (workspace.cc:805-812)
     getfem::model_real_sparse_matrix &K = ws.assembled_matrix();
-    if (gmm::mat_nrows(K) < need_all || gmm::mat_ncols(K) < need_all) gmm::resize(K, need_all, need_all);
+    if (gmm::mat_nrows(K) == gmm::mat_ncols(K) && gmm::mat_nrows(K) < need_all) gmm::resize(K, need_all, need_all);
     return;
   }
   if (order == 2) {
@@ -1715,8 +1872,12 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     GFGPU_CALL(gfgpu_matrix_clear(tc.m, tc.sig == terms_sig ? 1 : 0));
     if (tc.sig != terms_sig) { tc.sig = terms_sig; tc.gen = -1; }
     for (const pending_add &pa : pending_adds) {
-      if (pa.rect) {
+      if (pa.rect && (pa.Er || pa.Ec)) {
+        GFGPU_CALL(gfgpu_matrix_add_rect_reduced(tc.m, pa.rect, pa.transposed, pa.Er, pa.Ec, pa.alpha, pa.off, pa.coff));
+      } else if (pa.rect) {
         GFGPU_CALL(gfgpu_matrix_add_rect(tc.m, pa.rect, pa.transposed, pa.alpha, pa.off, pa.coff));
+      } else if (pa.Er) {
+        GFGPU_CALL(gfgpu_matrix_add_term_reduced(tc.m, pa.term, pa.Er, pa.alpha, pa.off, pa.off));
       } else {
         GFGPU_CALL(gfgpu_matrix_add_term(tc.m, pa.term, pa.alpha, pa.off, pa.off));
       }
@@ -1735,8 +1896,15 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     double t2 = now_s();
     t_device += t2 - t1;
     getfem::model_real_sparse_matrix &K = ws.assembled_matrix();
-    if (gmm::mat_nrows(K) < need_all || gmm::mat_ncols(K) < need_all) gmm::resize(K, need_all, need_all);
-    fill_col_matrix(K, need_all, tc.jc.data(), tc.ir.data(), tc.pr.data());
+    if (gmm::mat_nrows(K) != gmm::mat_ncols(K)) {
+      // a RECTANGULAR matrix given by the caller -- asm_mass_matrix(B, mim, mf_mult, mf_u, rg) sets overlapping intervals
+      // (0, n_mult) and (0, n_u) and a n_mult x n_u matrix (getfem_assembling.h:743-755): the reference trusts the caller with
+      // the size (workspace.cc:807-811); every entry must fit
+      for (size_type j = gmm::mat_ncols(K); j < need_all; ++j)
+        GMM_ASSERT1(tc.jc[j] == tc.jc[j + 1], "gfgpu: the assembled matrix is too small for the terms (columns)");
+      for (int32_t r : tc.ir) GMM_ASSERT1(size_type(r) < gmm::mat_nrows(K), "gfgpu: the assembled matrix is too small for the terms (rows)");
+    } else if (gmm::mat_nrows(K) < need_all || gmm::mat_ncols(K) < need_all) gmm::resize(K, need_all, need_all);
+    fill_col_matrix(K, std::min<size_type>(need_all, gmm::mat_ncols(K)), tc.jc.data(), tc.ir.data(), tc.pr.data());
     t_fill += now_s() - t2;
   }
 }

@@ -41,7 +41,9 @@ struct recognised_term {
   std::string jit_form1, jit_form2;
   std::vector<std::string> jit_params;
 };
-enum { GFGPU_SHIM_COUPLED_DIV = 1000 };
+// GFGPU_SHIM_COUPLED_MASS: "Test_a:Test2_b" on two variables of the same qdim (asm_mass_matrix(M, mim, mf1, mf2, rg), the
+// constraint matrix of the Dirichlet bricks with multipliers): rows = varname_u (Test), columns = varname_p (Test2), factor sign
+enum { GFGPU_SHIM_COUPLED_DIV = 1000, GFGPU_SHIM_COUPLED_MASS = 1001 };
 
 // Matches the ORDER-1 tree of `ws` number `itree` (as printed by ga_tree_to_string after the
 // reference's semantic analysis) against the families of include/gfgpu.h.  Returns false if unknown.
@@ -84,7 +86,11 @@ class device_assembler {
   gfgpu_ctx *ctx_ = nullptr;
   std::map<std::string, std::unique_ptr<entry>> cache_;  // bounded (LRU); entries die with the getfem objects they mirror
   std::map<std::string, std::unique_ptr<rect_entry>> rect_cache_;  // coupled terms: two fems on one mesh
-  rect_entry &coupled_entry(getfem::ga_workspace &ws, const getfem::mesh_im &mim, const std::string &vu, const std::string &vp);
+  rect_entry &coupled_entry(getfem::ga_workspace &ws, const getfem::mesh_im &mim, const std::string &vu, const std::string &vp,
+                            int family = 0, const std::vector<int32_t> *rg_cv = nullptr, const std::vector<int32_t> *rg_f = nullptr);
+  struct reduction_entry;
+  std::map<const void *, std::unique_ptr<reduction_entry>> reductions_;  // extension matrices of reduced mesh_fems
+  gfgpu_reduction *reduction_of(const getfem::mesh_fem &mf);  // nullptr for a non-reduced mesh_fem
   std::map<std::string, std::pair<bool, std::vector<recognised_term>>> recognised_;  // recognition results across calls
   std::map<std::string, std::unique_ptr<grouping>> groupings_;  // convex groups per (mesh, mesh_fem, mesh_im)
   uint64_t use_clock_ = 0;

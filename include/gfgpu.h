@@ -292,6 +292,27 @@ int gfgpu_matrix_cg_dev(gfgpu_matrix *m, const double *b_dev, double *x_dev, dou
                         double *relres_out);
 int gfgpu_term_residual_add_dev(gfgpu_term *t, double alpha, double *rhs_dev, int64_t row_off);
 
+/* ---- reduced mesh_fem (mesh_fem::is_reduced(): partial_mesh_fem -- the multiplier spaces of the Dirichlet bricks --, periodic
+ * or enriched spaces).  The reference assembles such a variable on its BASIC dofs into unreduced containers and projects them
+ * with the extension matrix E (nb_basic_dof x nb_dof, mesh_fem::extension_matrix()): K(I1, I2) += E1^T K_basic E2 and
+ * V(I1) += E1^T V_basic; the state of the variable is extended first, U_basic = E U (workspace.cc:861-935,
+ * getfem_mesh_fem.h extend_vector).  Device terms are therefore created on the basic dof table (gfgpu_fem_create with
+ * ndof = nb_basic_dof) and their results pass through a gfgpu_reduction:
+ *   create            E in CSR: rowptr[n_basic + 1], ascending columns inside a row (gmm::csr_matrix layout)
+ *   extend            y[n_basic] = E x[n_dof]
+ *   restrict_add      y[n_dof] += alpha E^T x[n_basic]              (ordered gather, no atomics)
+ *   gfgpu_matrix_add_term_reduced / add_rect_reduced
+ *                     K(row_off.., col_off..) += alpha Er^T S Ec, one expand-sort-compress pass per reduced side, products
+ *                     summed in ascending inner index (the order of gmm's sparse products), exact zeros not stored
+ *                     (rsvector::w); a NULL extension matrix = that side is not reduced. */
+typedef struct gfgpu_reduction gfgpu_reduction;
+int gfgpu_reduction_create(gfgpu_ctx *ctx, int64_t n_basic, int64_t n_dof, const int64_t *rowptr_host, const int32_t *col_host,
+                           const double *val_host, gfgpu_reduction **out);
+int gfgpu_reduction_destroy(gfgpu_reduction *E);
+int gfgpu_reduction_extend_host(gfgpu_reduction *E, const double *x_host, double *y_host);
+int gfgpu_reduction_restrict_add_host(gfgpu_reduction *E, double alpha, const double *x_host, double *y_host);
+int gfgpu_matrix_add_term_reduced(gfgpu_matrix *m, gfgpu_term *t, gfgpu_reduction *E, double alpha, int64_t row_off, int64_t col_off);
+
 /* ---- coupled bilinear terms: Test on one fem (rows), Test2 on another (columns) -- the off-diagonal blocks of mixed
  * formulations.  ga_workspace::assembly(2) adds an order-2 tree whose test functions belong to two variables into the block
  * (interval of Test's variable) x (interval of Test2's variable), element matrix by element matrix through add_elem_matrix and
@@ -306,10 +327,17 @@ int gfgpu_term_residual_add_dev(gfgpu_term *t, double alpha, double *rhs_dev, in
  *               with the test functions swapped).
  *   mult        y = beta y + alpha B x (transposed == 0) or alpha B^T x: the residual parts R_u = B p, R_p = B^T u.
  *   gfgpu_matrix_add_rect   K(row_off.., col_off..) += alpha * block (or its transpose), union pattern like add_term. */
-enum { GFGPU_RECT_DIV_PRESSURE = 0 };
+enum { GFGPU_RECT_DIV_PRESSURE = 0,
+       /* block((i,a), (j,b)) = alpha * coef * delta_ab int phi_i psi_j: "Test_u1:Test2_u2" on two fems of the same qdim --
+        * asm_mass_matrix(M, mim, mf1, mf2, rg) (getfem_assembling.h:743-755), the constraint matrix of the Dirichlet bricks
+        * with multipliers (getfem_models.cc:4386-4421), usually on a region of faces */
+       GFGPU_RECT_MASS = 1 };
 typedef struct gfgpu_rect gfgpu_rect;
 int gfgpu_rect_create(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem_rows, gfgpu_tables *tab_rows, gfgpu_fem *fem_cols,
                       gfgpu_tables *tab_cols, int family, double coef, double alpha, gfgpu_rect **out);
+/* restricts the coupled term to a mesh region: items in mr_visitor order, face_host NULL / -1 for convexes, or all faces (both
+ * table sets then need gfgpu_tables_set_faces); cv_host NULL = back to all convexes.  Same meaning as gfgpu_term_set_region. */
+int gfgpu_rect_set_region(gfgpu_rect *r, int64_t n_items, const int32_t *cv_host, const int32_t *face_host);
 int gfgpu_rect_destroy(gfgpu_rect *r);
 int gfgpu_rect_assemble_dev(gfgpu_rect *r);
 int64_t gfgpu_rect_nnz(gfgpu_rect *r);
@@ -317,6 +345,8 @@ int gfgpu_rect_export_csc_host(gfgpu_rect *r, int transposed, int64_t *jc_host, 
 int gfgpu_rect_mult_dev(gfgpu_rect *r, int transposed, double alpha, const double *x_dev, double beta, double *y_dev);
 int gfgpu_rect_mult_host(gfgpu_rect *r, int transposed, double alpha, const double *x_host, double beta, double *y_host);
 int gfgpu_matrix_add_rect(gfgpu_matrix *m, gfgpu_rect *r, int transposed, double alpha, int64_t row_off, int64_t col_off);
+int gfgpu_matrix_add_rect_reduced(gfgpu_matrix *m, gfgpu_rect *r, int transposed, gfgpu_reduction *E_rows, gfgpu_reduction *E_cols,
+                                  double alpha, int64_t row_off, int64_t col_off);
 
 /* ---- multi-GPU: element blocks per rank, column-owned CSC slabs, one halo exchange per assembly.
  * Replaces the reference's MPI scheme (per-rank partial matrices summed with MPI_SUM_SPARSE_MATRIX /

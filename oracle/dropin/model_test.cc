@@ -14,6 +14,7 @@
 #include "getfem/getfem_models.h"
 #include "getfem/getfem_nonlinear_elasticity.h"
 #include "getfem/getfem_omp.h"
+#include "getfem/getfem_partial_mesh_fem.h"
 #include "getfem/getfem_regular_meshes.h"
 #include "gmm/gmm_kernel.h"
 
@@ -57,6 +58,20 @@ int main(int argc, char **argv) {
   }
   getfem::mesh_fem mf(m, getfem::dim_type(Q));
   mf.set_classical_finite_element(getfem::dim_type(K));
+  if (geti("reduced", 0) == 1) {
+    // a REDUCED mesh_fem by selection of basic dofs (what partial_mesh_fem / the multiplier filters do)
+    dal::bit_vector kept;
+    for (size_type d = 0; d < mf.nb_basic_dof(); ++d) if (d % 5 != 1) kept.add(d);
+    mf.reduce_to_basic_dof(kept);
+  } else if (geti("reduced", 0) == 2) {
+    // a GENERAL extension matrix (periodic / constrained spaces, mesh_fem::set_reduction_matrices): the last quarter of the
+    // basic dofs are combinations of two reduced dofs each, so E^T K E sums several products per entry
+    const size_type nb = mf.nb_basic_dof(), nr = nb - nb / 4;
+    gmm::row_matrix<gmm::rsvector<double>> R(nr, nb), E(nb, nr);
+    for (size_type j = 0; j < nr; ++j) { R(j, j) = 1.0; E(j, j) = 1.0; }
+    for (size_type j = nr; j < nb; ++j) { E(j, j - nr) = 0.5; E(j, (7 * (j - nr) + 3) % nr) = -0.25; }
+    mf.set_reduction_matrices(R, E);
+  }
   getfem::mesh_im mim(m);
   mim.set_integration_method(getfem::dim_type(qk ? 2 * K + 2 : 2 * K));
   getfem::mesh_fem mf_d(m, 1);  // fem data: heterogeneous coefficient
@@ -215,10 +230,23 @@ int main(int argc, char **argv) {
       LAMBDA[d] = 1.3 * (1.0 + 0.25 * std::cos(1.1 * P[0] - 0.7 * P[1]));
       MU[d] = 0.7 * (1.0 + 0.2 * std::cos(1.3 * P[0] - P[dim - 1]));
     }
+    // a multiplier space: the fem of one degree less, whole (asm_mass_rect) or restricted to the dofs of the Robin boundary
+    // through a partial_mesh_fem (asm_mass_rect_partial: a REDUCED mesh_fem, what model::add_multiplier builds)
+    getfem::mesh_fem mf_l(m, getfem::dim_type(Q));
+    mf_l.set_classical_finite_element(getfem::dim_type(K > 1 ? K - 1 : 1));
+    getfem::partial_mesh_fem mf_lp(mf_l);
+    mf_lp.adapt(mf_l.basic_dof_on_region(m.region(2)));
+    getfem::partial_mesh_fem mf_up(mf);  // the unknown itself restricted to the dofs of the Neumann boundary
+    mf_up.adapt(mf.basic_dof_on_region(m.region(1)));
     auto run = [&](bool device, gmm::csc_matrix<double> &C) {
       getfem_b200::gfgpu_enable(device);
       getfem::model_real_sparse_matrix M(mf.nb_dof(), mf.nb_dof());
-      if (kind == "asm_mass") getfem::asm_mass_matrix(M, mim, mf);
+      if (kind == "asm_mass_rect") { gmm::resize(M, mf_l.nb_dof(), mf.nb_dof()); getfem::asm_mass_matrix(M, mim, mf_l, mf, m.region(2)); }
+      else if (kind == "asm_mass_rect_volume") { gmm::resize(M, mf_l.nb_dof(), mf.nb_dof()); getfem::asm_mass_matrix(M, mim, mf_l, mf); }
+      else if (kind == "asm_mass_rect_partial") { gmm::resize(M, mf_lp.nb_dof(), mf.nb_dof()); getfem::asm_mass_matrix(M, mim, mf_lp, mf, m.region(2)); }
+      else if (kind == "asm_mass_partial") { gmm::resize(M, mf_up.nb_dof(), mf_up.nb_dof()); getfem::asm_mass_matrix(M, mim, mf_up, m.region(1)); }
+      else if (kind == "asm_mass_partial_both") { gmm::resize(M, mf_lp.nb_dof(), mf_up.nb_dof()); getfem::asm_mass_matrix(M, mim, mf_lp, mf_up); }
+      else if (kind == "asm_mass") getfem::asm_mass_matrix(M, mim, mf);
       else if (kind == "asm_laplacian") getfem::asm_stiffness_matrix_for_homogeneous_laplacian(M, mim, mf);
       else if (kind == "asm_elasticity") getfem::asm_stiffness_matrix_for_linear_elasticity(M, mim, mf, mf_d, LAMBDA, MU);
       else if (kind == "asm_mass_boundary") getfem::asm_mass_matrix(M, mim, mf, m.region(2));
@@ -296,6 +324,20 @@ int main(int argc, char **argv) {
   getfem::add_source_term_brick(md, mim, "u", "F");          // volumic load
   getfem::add_source_term_brick(md, mim, "u", "G", 1);       // Neumann load on x = 1
   getfem::add_linear_term(md, mim, "robin*u.Test_u", 2);     // Robin condition on the rest of the boundary
+  if (gets("dirichlet", "") == "mult") {
+    // the standard Dirichlet brick: a multiplier on a REDUCED mesh_fem (model::add_multiplier filters the dofs of the region
+    // through a partial_mesh_fem), constraint matrix = asm_mass_matrix(B, mim, mf_mult, mf_u, region), right-hand side
+    // asm_source_term on the multiplier space (getfem_models.cc:4386-4450)
+    std::vector<double> D(Q);
+    for (int k = 0; k < Q; ++k) D[k] = 0.25 * (k + 1);
+    md.add_initialized_fixed_size_data("Dd", D);
+    getfem::add_Dirichlet_condition_with_multipliers(md, mim, "u", getfem::dim_type(K > 1 ? K - 1 : 1), 1, "Dd");
+  } else if (gets("dirichlet", "") == "penal") {
+    std::vector<double> D(Q);
+    for (int k = 0; k < Q; ++k) D[k] = 0.25 * (k + 1);
+    md.add_initialized_fixed_size_data("Dd", D);
+    getfem::add_Dirichlet_condition_with_penalization(md, mim, "u", 1e6, 1, "Dd");
+  }
   if (geti("empty_region", 0)) {  // bricks on regions without any element: ga_exec walks nothing, the device path must do the same
     getfem::add_source_term_brick(md, mim, "u", "G", 77);
     getfem::add_linear_term(md, mim, "robin*u.Test_u", 78);

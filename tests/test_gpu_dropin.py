@@ -74,6 +74,87 @@ def test_legacy_asm_wrappers_run_on_the_device_unchanged(case):
     assert 0 <= r["rel_K"] < 1e-12, r
 
 
+MULT_ASM_CASES = [
+    # asm_mass_matrix(B, mim, mf_mult, mf_u, rg) -- "Test_u1:Test2_u2" on two fems, overlapping intervals and a RECTANGULAR
+    # caller-provided matrix (getfem_assembling.h:743-755): the constraint matrix of the Dirichlet bricks
+    "model=asm_mass_rect dim=3 n=3 gt=pk k=2",            # multiplier fem of degree 1 against u of degree 2, boundary faces
+    "model=asm_mass_rect dim=2 n=8 gt=qk k=2",
+    "model=asm_mass_rect dim=3 n=2 gt=qk k=2",
+    "model=asm_mass_rect_volume dim=3 n=3 gt=pk k=2",     # the same on the whole mesh
+    # ... with the multiplier space REDUCED to the dofs of the boundary (partial_mesh_fem, what model::add_multiplier builds):
+    # assembled on the basic dofs, rows projected with the extension matrix (workspace.cc:861-935)
+    "model=asm_mass_rect_partial dim=3 n=3 gt=pk k=2",
+    "model=asm_mass_rect_partial dim=2 n=8 gt=pk k=2",
+    "model=asm_mass_rect_partial dim=3 n=2 gt=qk k=2",
+    "model=asm_mass_partial dim=3 n=3 gt=pk k=2",         # one reduced fem on both sides: E^T M E
+    "model=asm_mass_partial_both dim=2 n=8 gt=pk k=2",    # two different reduced fems: E1^T M E2
+    "model=asm_mass_partial_both dim=3 n=3 gt=pk k=2",
+]
+
+
+@pytest.mark.parametrize("case", MULT_ASM_CASES)
+def test_multiplier_mass_matrices_run_on_the_device(case):
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN] + case.split(), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["device_workspace_calls"] >= 1, r
+    assert r["pattern_ok"] and r["nnz_ref"] == r["nnz_gpu"] and r["nnz_ref"] > 0, r
+    assert 0 <= r["rel_K"] < 1e-12, r
+
+
+DIRICHLET_CASES = [
+    # add_Dirichlet_condition_with_multipliers (getfem_models.cc:4316-4450), the standard way to impose u = g in GetFEM: a
+    # multiplier variable on a reduced mesh_fem, B = asm_mass_matrix(mf_mult, mf_u, region), right-hand side
+    # asm_source_term on the multiplier space ("A:Test_u" on the reduced fem), and -- inside model::actualize_sizes -- the
+    # inf-sup filter's own mass matrices: every one of those workspaces goes through the device
+    "model=poisson dim=2 n=12 gt=pk k=2 dirichlet=mult",
+    "model=poisson dim=3 n=3 gt=qk k=2 dirichlet=mult",
+    "model=elasticity dim=3 n=3 gt=pk k=2 dirichlet=mult",
+    "model=elasticity dim=2 n=8 gt=qk k=2 dirichlet=mult",
+    "model=finite_strain dim=3 n=2 gt=pk k=2 dirichlet=mult",
+    "model=elasticity dim=3 n=3 gt=pk k=2 dirichlet=penal",   # add_Dirichlet_condition_with_penalization
+]
+
+
+@pytest.mark.parametrize("case", DIRICHLET_CASES)
+def test_dirichlet_bricks_run_on_the_device(case):
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN] + case.split(), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["device_workspace_calls"] >= 6 and r["nnz_ref"] == r["nnz_gpu"], r
+    assert r["max_one_sided_rel"] < 1e-14, r
+    assert 0 <= r["rel_K"] < 1e-12 and r["rel_rhs"] < 1e-12, r
+
+
+REDUCED = [  # the VARIABLE itself on a reduced mesh_fem (model_test reduced=1: a selection of basic dofs, reduced=2: a general
+             # extension matrix with sums): K = E^T K_basic E, V = E^T V_basic at the state U_basic = E U
+    ("dim=3 n=3 gt=pk k=2 reduced=1", "lambda*Div_u*Div_Test_u + mu*(Grad_u+Grad_u'):Grad_Test_u"),
+    ("dim=2 n=8 gt=qk k=2 reduced=2", "lambda*Div_u*Div_Test_u + mu*(Grad_u+Grad_u'):Grad_Test_u"),
+    ("dim=3 n=3 gt=pk k=2 reduced=2", "lambda*Div_u*Div_Test_u + mu*(Grad_u+Grad_u'):Grad_Test_u + [1;2;3].Test_u"),
+    ("dim=3 n=3 gt=pk k=2 q=1 reduced=2", "(1+sqr(u))*Grad_u.Grad_Test_u + sin(u)*Test_u"),            # the NVRTC route, reduced
+    ("dim=2 n=8 gt=pk k=1 q=1 reduced=2", "a*Grad_u.Grad_Test_u + u*Test_u"),
+    ("dim=3 n=2 gt=qk k=2 reduced=1 uscale=0.02", "Saint_Venant_Kirchhoff_potential(Grad_u,params)"),    # order 0, 1 and 2
+]
+
+
+@pytest.mark.parametrize("mesh,expr", REDUCED)
+def test_reduced_mesh_fems_run_on_the_device(mesh, expr):
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN, "model=expr"] + mesh.split() + ["expr=" + expr], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["device_workspace_calls"] >= 2, r
+    assert r["pattern_ok"] and r["nnz_ref"] == r["nnz_gpu"], r
+    assert 0 <= r["rel_K"] < 1e-12 and r["rel_V"] < 1e-12 and r["norm_V"] > 0, r
+    if "potential" in expr:
+        assert r["E_ref"] != 0 and abs(r["E_gpu"] - r["E_ref"]) <= 1e-12 * abs(r["E_ref"]), r
+
+
 @pytest.mark.parametrize("case", ["model=elasticity dim=3 n=4 gt=pk k=2 threads=3", "model=poisson dim=2 n=16 gt=pk k=1 threads=8",
                                   "model=finite_strain dim=3 n=2 gt=qk k=2 threads=4"])
 def test_multithreaded_models_run_on_the_device(case):
