@@ -463,8 +463,9 @@ int gfgpu_term_set_fields(gfgpu_term *t, int nfields, gfgpu_fem *dfem, const dou
   GF_REQUIRE(dfem && phi && vals0, "null argument");
   GF_REQUIRE(dfem->mesh == t->mesh, "the data fem was built on another mesh");
   const int fam = t->family;
-  const int maxf = (fam == GFGPU_LAPLACE || fam == GFGPU_MASS || fam == GFGPU_SOURCE) ? 1 : fam == GFGPU_ELASTICITY ? 2 : 0;
-  GF_REQUIRE(maxf > 0, "fem-data coefficients are handled for the Laplace, mass, elasticity and source families");
+  const int maxf = (fam == GFGPU_LAPLACE || fam == GFGPU_MASS || fam == GFGPU_SOURCE) ? 1
+                   : (fam == GFGPU_ELASTICITY || fam == GFGPU_JIT) ? 2 : 0;  // JIT terms: fld[0], fld[1] in the integrand
+  GF_REQUIRE(maxf > 0, "fem-data coefficients are handled for the Laplace, mass, elasticity, source and JIT families");
   GF_REQUIRE(nfields >= 1 && nfields <= maxf, "wrong number of coefficient fields for this family");
   GF_REQUIRE(nfields < 2 || vals1, "null argument");
   GF_REQUIRE(dfem->qdim == (fam == GFGPU_SOURCE ? t->fem->qdim : 1),
@@ -682,7 +683,6 @@ static void term_assemble(gfgpu_term *t, const double *U_dev, int order_mask) {
     tic(0);
     const bool affine = t->mesh->gt_kind == GFGPU_GT_PK;
     if (t->family == GFGPU_JIT) {
-      GF_REQUIRE(!t->nfields, "JIT terms: constant parameters");
       gf::launch_jit_kernel(t, a);
     }
     bool ok = t->family == GFGPU_JIT ||

@@ -440,12 +440,12 @@ static bool recognise_by_probe(const getfem::ga_workspace &ws, size_type itree, 
 struct jit_value { std::string code; int rank; };  // rank 0 scalar, 1 vector of the mesh dimension, 2 matrix N x N
 
 static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node &n, const std::string &v, int N, int Q,
-                     std::vector<std::string> &params, jit_value &out) {
+                     std::vector<std::string> &params, std::vector<std::string> &fields, jit_value &out) {
   using namespace getfem;
   if (!n) return false;
   auto num = [](double x) { char b[48]; std::snprintf(b, sizeof b, "(%.17g)", x); std::string r(b);
                             if (r.find_first_of(".eEn") == std::string::npos) r.insert(r.size() - 1, ".0"); return r; };
-  auto child = [&](size_t k, jit_value &o) { return k < n->children.size() && jit_emit(ws, n->children[k], v, N, Q, params, o); };
+  auto child = [&](size_t k, jit_value &o) { return k < n->children.size() && jit_emit(ws, n->children[k], v, N, Q, params, fields, o); };
   const int rv = Q == 1 ? 0 : 1;  // rank of the variable's value; its gradient has one more
   auto tensor_const = [&](const base_tensor &t, jit_value &o) {
     if (t.size() == 1) { o = {num(t[0]), 0}; return true; }
@@ -473,6 +473,21 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
       return tensor_const(n->tensor(), out);
     case GA_NODE_VAL: {
       if (n->name == v) { out = {"u", rv}; return true; }
+      if (ws.variable_exists(n->name) && ws.is_constant(n->name) && !ws.variable_group_exists(n->name) &&
+          (ws.associated_mf(n->name) || ws.associated_im_data(n->name))) {
+        // a SCALAR fem-data / im-data coefficient (add_fem_constant, add_im_data): fld[k], evaluated at the Gauss point on its
+        // own fem (ga_instruction_val, C&E.cc:636-690); at most two, all on one data mesh_fem (checked when the term is built)
+        const getfem::mesh_fem *pmd = ws.associated_mf(n->name);
+        const getfem::im_data *pid = ws.associated_im_data(n->name);
+        if (pmd ? pmd->get_qdim() != 1 : pid->nb_tensor_elem() != 1) return false;
+        size_t k = 0;
+        while (k < fields.size() && fields[k] != n->name) ++k;
+        if (k == fields.size()) fields.push_back(n->name);
+        if (fields.size() > 2) return false;
+        if (pmd ? ws.associated_mf(fields[0]) != pmd : ws.associated_im_data(fields[0]) != pid) return false;
+        out = {"fld[" + std::to_string(k) + "]", 0};
+        return true;
+      }
       if (!ws.variable_exists(n->name) || !ws.is_constant(n->name) || ws.associated_mf(n->name) || ws.associated_im_data(n->name)) return false;
       if (ws.value(n->name).size() != 1) return false;  // scalar fixed-size constants
       size_t k = 0;
@@ -628,13 +643,13 @@ static bool recognise_jit(const getfem::ga_workspace &ws, size_type i1, recognis
   if (!pmf || ws.is_constant(v)) return false;
   const int N = int(pmf->linked_mesh().dim()), Q = int(pmf->get_qdim());
   if ((N != 2 && N != 3) || (Q != 1 && Q != N)) return false;
-  std::vector<std::string> params;
+  std::vector<std::string> params, fields;
   jit_value f1, f2{"(0.0)", 0};
-  if (!td.ptree || !jit_emit(ws, td.ptree->root, v, N, Q, params, f1) || f1.rank != 0) return false;
+  if (!td.ptree || !jit_emit(ws, td.ptree->root, v, N, Q, params, fields, f1) || f1.rank != 0) return false;
   for (size_type j = 0; j < ws.nb_trees(); ++j) {
     const auto &t2 = ws.tree_info(j);
     if (t2.order == 2 && t2.mim == td.mim && t2.rg == td.rg && t2.name_test1 == v && t2.name_test2 == v) {
-      if (!t2.ptree || !jit_emit(ws, t2.ptree->root, v, N, Q, params, f2) || f2.rank != 0) return false;
+      if (!t2.ptree || !jit_emit(ws, t2.ptree->root, v, N, Q, params, fields, f2) || f2.rank != 0) return false;
     } else if (t2.order == 2 && t2.mim == td.mim && t2.rg == td.rg && (t2.name_test1 == v) != (t2.name_test2 == v)) {
       return false;  // coupled to another variable: not this route
     }
@@ -645,6 +660,8 @@ static bool recognise_jit(const getfem::ga_workspace &ws, size_type i1, recognis
   out.jit_form1 = f1.code;
   out.jit_form2 = f2.code;
   out.jit_params = params;
+  out.field_names = fields;
+  out.field_sign = 1.0;
   for (const std::string &pn : params) out.params.push_back(ws.value(pn)[0]);
   return true;
 }

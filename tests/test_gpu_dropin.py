@@ -125,7 +125,9 @@ def test_dirichlet_bricks_run_on_the_device(case):
     out = subprocess.run([BIN] + case.split(), capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     r = json.loads(out.stdout.strip().splitlines()[-1])
-    assert r["device_workspace_calls"] >= 6 and r["nnz_ref"] == r["nnz_gpu"], r
+    assert r["device_workspace_calls"] >= 6, r
+    # (entries that cancel to round-off on one side and to 0.0 on the other are stored by one model tangent only: the bricks'
+    # gmm::copy drops exact zeros -- the criterion of test_model_assembly_runs_on_the_device_unchanged)
     assert r["max_one_sided_rel"] < 1e-14, r
     assert 0 <= r["rel_K"] < 1e-12 and r["rel_rhs"] < 1e-12, r
 
@@ -149,7 +151,9 @@ def test_reduced_mesh_fems_run_on_the_device(mesh, expr):
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     r = json.loads(out.stdout.strip().splitlines()[-1])
     assert r["device_workspace_calls"] >= 2, r
-    assert r["pattern_ok"] and r["nnz_ref"] == r["nnz_gpu"], r
+    # gmm's sparse products remove entries whose sum is EXACTLY 0.0, so an entry of K_basic that cancels to round-off on one path
+    # and to 0.0 on the other is stored on one side only: union comparison, one-sided entries must be round-off (model_test.cc)
+    assert r["pattern_ok"] and r["max_one_sided_rel"] < 1e-14, r
     assert 0 <= r["rel_K"] < 1e-12 and r["rel_V"] < 1e-12 and r["norm_V"] > 0, r
     if "potential" in expr:
         assert r["E_ref"] != 0 and abs(r["E_gpu"] - r["E_ref"]) <= 1e-12 * abs(r["E_ref"]), r
@@ -271,6 +275,10 @@ JIT_X = [  # the position X and, on boundary faces, the unit normal: space-depen
     ("dim=3 n=3 gt=pk k=2 region=2", "(u.Normal)*(Test_u.Normal)*(1+X(1)) + exp(u(1))*Test_u(2)"),
     ("dim=2 n=6 gt=qk k=2 region=2", "(u.Normal)*(Test_u.Normal)*(1+X(1)) + exp(u(1))*Test_u(2)"),
     ("dim=3 n=2 gt=qk k=1 q=1 region=2", "(X.Normal)*u*Test_u + Normal(1)*Test_u"),
+    # scalar fem-data coefficients inside a translated tree (a heterogeneous material times a nonlinear function of the state)
+    ("dim=3 n=3 gt=pk k=2 q=1", "c0*sin(u)*Test_u + (1+c0)*Grad_u.Grad_Test_u"),
+    ("dim=3 n=2 gt=qk k=2", "c0*(1+Norm_sqr(u))*Grad_u:Grad_Test_u + c0*X.Test_u"),
+    ("dim=2 n=6 gt=pk k=2 q=1 region=2", "c0*u*u*u*Test_u + c0*Test_u"),
 ]
 
 
