@@ -442,6 +442,34 @@ def main():
     checks = {"pr_norm": float(np.linalg.norm(pr_host.numpy()[: min(pr_host.numel(), 10_000_000)])),
               "R_norm": float(np.linalg.norm(R_host.numpy()))}
 
+    if plan is None:
+        # Size-independent properties of the FULL-SIZE result of the timed path (oracle comparisons stop at sizes the CPU finishes
+        # in seconds): the residual, which a separate kernel path computes, against K U through the assembled CSC (linear symmetric
+        # forms: R = K U = K^T U); symmetry of the tangent in the bilinear sense; rigid translations / constants in the kernel of K.
+        with torch.cuda.stream(stream):
+            dev = "cuda:%d" % local
+            y = torch.empty(ndof, dtype=torch.float64, device=dev)
+            Rv = capi._dev_tensor(term.residual_view(), ndof, local)
+            if family in ("laplace", "elast", "mass"):
+                term.tmult_dev(U_dev.data_ptr(), y.data_ptr())
+                checks["rel_R_minus_KU"] = float(((y - Rv).norm() / Rv.norm()).item())
+            g = torch.Generator(device=dev)
+            g.manual_seed(7)
+            x1 = torch.rand(ndof, dtype=torch.float64, device=dev, generator=g) - 0.5
+            x2 = torch.rand(ndof, dtype=torch.float64, device=dev, generator=g) - 0.5
+            term.tmult_dev(x1.data_ptr(), y.data_ptr())
+            a12 = float(torch.dot(x2, y).item())
+            ny = float(y.norm().item())
+            term.tmult_dev(x2.data_ptr(), y.data_ptr())
+            a21 = float(torch.dot(x1, y).item())
+            checks["symmetry_defect"] = abs(a12 - a21) / max(ny * float(x2.norm().item()), 1e-300)
+            if family != "mass":
+                t0v = torch.zeros(ndof, dtype=torch.float64, device=dev)
+                t0v[0::Q] = 1.0  # a rigid translation along the first axis (scalar forms: the constant)
+                term.tmult_dev(t0v.data_ptr(), y.data_ptr())
+                checks["rigid_translation_defect"] = float(y.abs().max().item()) / max(ny, 1e-300)
+            stream.synchronize()
+
     multi = None
     if world > 1:
         # parity of THIS multi-GPU path (same processes, same communicator) at a size every rank can also assemble alone, and

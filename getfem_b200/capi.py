@@ -89,6 +89,7 @@ SIGNATURES = {
     "gfgpu_rect_create": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_double, C.c_double, _PP]),
     "gfgpu_rect_destroy": (C.c_int, [_P]),
     "gfgpu_rect_set_region": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "gfgpu_term_tmult_dev": (C.c_int, [_P, C.c_double, _P, C.c_double, _P]),
     "gfgpu_reduction_create": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _PP]),
     "gfgpu_reduction_destroy": (C.c_int, [_P]),
     "gfgpu_reduction_extend_host": (C.c_int, [_P, _P, _P]),
@@ -380,6 +381,10 @@ class DeviceTerm(_Handle):
         jc, ir, pr = C.c_void_p(), C.c_void_p(), C.c_void_p()
         check(lib().gfgpu_term_csc_view(self.h, C.byref(jc), C.byref(ir), C.byref(pr)))
         return jc.value, ir.value, pr.value
+
+    def tmult_dev(self, x_dev_ptr, y_dev_ptr, alpha=1.0, beta=0.0):
+        """y = beta y + alpha K^T x on the device (the term's own CSC)"""
+        check(lib().gfgpu_term_tmult_dev(self.h, float(alpha), C.c_void_p(x_dev_ptr), float(beta), C.c_void_p(y_dev_ptr)))
 
     def residual_view(self):
         r = C.c_void_p()

@@ -837,6 +837,18 @@ int gfgpu_term_residual_add_dev(gfgpu_term *t, double alpha, double *rhs_dev, in
   GFM_END
 }
 
+int gfgpu_term_tmult_dev(gfgpu_term *t, double alpha, const double *x_dev, double beta, double *y_dev) {
+  GFM_BEGIN
+  GF_REQUIRE(t && x_dev && y_dev, "null argument");
+  GF_REQUIRE(t->pat_valid, "the term has no assembled tangent");
+  gf::term_settle_pending(t);
+  GF_CUDA(cudaSetDevice(t->ctx->device));
+  const int64_t n = t->fem->ndof;
+  if (n) gf::k_mat_tmult<<<gf::mgrid(n * 32, 256), 256, 0, t->ctx->stream>>>(t->jc.p, t->ir.p, t->pr.p, n, x_dev, alpha, beta, y_dev);
+  GF_LAUNCH_CHECK();
+  GFM_END
+}
+
 int gfgpu_matrix_add_rect(gfgpu_matrix *m, gfgpu_rect *r, int transposed, double alpha, int64_t row_off, int64_t col_off) {
   GFM_BEGIN
   GF_REQUIRE(m && r, "null argument");

@@ -293,6 +293,10 @@ int gfgpu_matrix_export_csr_dev(gfgpu_matrix *m, int64_t *rowptr_dev, int32_t *c
 int gfgpu_matrix_cg_dev(gfgpu_matrix *m, const double *b_dev, double *x_dev, double rtol, int max_iter, int *iters_out,
                         double *relres_out);
 int gfgpu_term_residual_add_dev(gfgpu_term *t, double alpha, double *rhs_dev, int64_t row_off);
+/* y = beta y + alpha K^T x on the term's own CSC (warp per column, fixed order): for the symmetric families K^T x = K x, which is
+ * how linear bricks form their residual (getfem_models.cc:2536-2620); bench.py uses it for its full-size property checks
+ * (R = K U, K t = 0 for rigid translations, x2.K x1 = x1.K x2). */
+int gfgpu_term_tmult_dev(gfgpu_term *t, double alpha, const double *x_dev, double beta, double *y_dev);
 
 /* ---- reduced mesh_fem (mesh_fem::is_reduced(): partial_mesh_fem -- the multiplier spaces of the Dirichlet bricks --, periodic
  * or enriched spaces).  The reference assembles such a variable on its BASIC dofs into unreduced containers and projects them

@@ -53,6 +53,15 @@ def test_term_projected_with_the_extension_matrix(kind):
     # tangent: K(off.., off..) += alpha E^T K_basic E, twice (the second call finds its pattern in place)
     jc, ir, pr = term.export_csc()
     Kb = sp.csc_matrix((pr, ir, jc), shape=(nb, nb))
+    # y = K^T x on the term's own CSC (gfgpu_term_tmult_dev: what bench.py's full-size property checks are made of)
+    import torch
+    xt = torch.from_numpy(rng.uniform(-1, 1, nb)).cuda()
+    yt = torch.full((nb,), 3.0, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    term.tmult_dev(xt.data_ptr(), yt.data_ptr(), alpha=2.0, beta=0.5)
+    term.ctx_synchronize()
+    want_y = 1.5 + 2.0 * (Kb.T @ xt.cpu().numpy())
+    assert np.linalg.norm(yt.cpu().numpy() - want_y) <= 1e-13 * np.linalg.norm(want_y)
     off, alpha = 5, 1.0  # (v + v = 2 v exactly: the selection case compares bit for bit)
     K = capi.DeviceMatrix(ctx, nr + off + 3)
     K.add_term_reduced(term, dE, alpha=alpha, row_off=off, col_off=off)
