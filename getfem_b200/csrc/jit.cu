@@ -168,6 +168,23 @@ __device__ __forceinline__ mat mkmat(double a0, double a1, double a2, double a3,
   return r;
 }
 
+// Saint-Venant Kirchhoff, the law the reference defines in any dimension (getfem_nonlinear_elasticity.cc:503-540):
+// E = (G + G' + G'G)/2, S = lambda tr(E) I + 2 mu E; dS[H] with dE = (H + H' + G'H + H'G)/2
+__device__ __forceinline__ mat svk_pk2(mat g, double lam, double mu) {
+  const mat gt = transp(g), E = 0.5 * (g + gt + gt * g);
+  mat r = (2.0 * mu) * E;
+  const double t = lam * trace(E);
+  for (int i = 0; i < GF_N; ++i) r.m[i][i] += t;
+  return r;
+}
+__device__ __forceinline__ mat svk_dpk2(mat g, double lam, double mu, mat h) {
+  const mat gt = transp(g), ht = transp(h), dE = 0.5 * (h + ht + gt * h + ht * g);
+  mat r = (2.0 * mu) * dE;
+  const double t = lam * trace(dE);
+  for (int i = 0; i < GF_N; ++i) r.m[i][i] += t;
+  return r;
+}
+
 #if GF_Q == 1
 __device__ __forceinline__ double gf_form1(double u, vec gu, vec X, vec Normal, const double *fld, const double *par, double tv, vec tg) { return GF_FORM1; }
 __device__ __forceinline__ double gf_form2(double u, vec gu, vec X, vec Normal, const double *fld, const double *par, double tv, vec tg, double t2v, vec t2g) {

@@ -461,6 +461,34 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
     }
     return false;
   };
+  // "Saint_Venant_Kirchhoff_PK2(G, params)" (AHL_wrapper_sigma with the SVK law, getfem_nonlinear_elasticity.cc:503-540, 1781-1827:
+  // E = (G + G' + G'G)/2, S = lambda tr(E) I + 2 mu E -- the one law the reference defines in ANY dimension, so this is also its
+  // 2D finite strain) and its first derivative contracted with a direction H: args = "G,lambda,mu"
+  auto svk_args = [&](const pga_tree_node &pn, size_type der1, std::string &args) {
+    if (pn->node_type != GA_NODE_PARAMS || pn->children.size() != 3) return false;
+    const pga_tree_node &f = pn->children[0];
+    if (f->node_type != GA_NODE_OPERATOR || f->name != "Saint_Venant_Kirchhoff_PK2" || f->der1 != der1 || f->der2 != 0) return false;
+    jit_value g;
+    if (!jit_emit(ws, pn->children[1], v, N, Q, params, fields, g) || g.rank != 2) return false;
+    const pga_tree_node &pp = pn->children[2];
+    std::string lam, mu;
+    if (pp->node_type == GA_NODE_CONSTANT && pp->tensor().size() == 2) {
+      lam = num(pp->tensor()[0]); mu = num(pp->tensor()[1]);
+    } else if (pp->node_type == GA_NODE_VAL && ws.variable_exists(pp->name) && ws.is_constant(pp->name) && !ws.associated_mf(pp->name) &&
+               !ws.associated_im_data(pp->name) && ws.value(pp->name).size() == 2) {
+      std::string *dst[2] = {&lam, &mu};
+      for (int c = 0; c < 2; ++c) {  // component c of a fixed-size constant vector: the parameter "name#c"
+        const std::string key = pp->name + "#" + std::to_string(c);
+        size_t k = 0;
+        while (k < params.size() && params[k] != key) ++k;
+        if (k == params.size()) params.push_back(key);
+        if (params.size() > size_t(GFGPU_MAX_PARAMS)) return false;
+        *dst[c] = "par[" + std::to_string(k) + "]";
+      }
+    } else return false;
+    args = g.code + "," + lam + "," + mu;
+    return true;
+  };
   switch (n->node_type) {
     case GA_NODE_ZERO: {
       if (n->test_function_type != 0 && n->test_function_type != size_type(-1)) return false;
@@ -566,7 +594,14 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
           if (!child(0, a) || !child(1, b)) return false;
           out = {"dot(" + a.code + "," + b.code + ")", (a.rank && b.rank) ? a.rank + b.rank - 2 : a.rank + b.rank};
           return true;
-        case GA_COLON:
+        case GA_COLON: {
+          std::string sa;  // Derivative_1_Saint_Venant_Kirchhoff_PK2(G, params):H = the directional derivative dS[H]
+          if (n->children.size() == 2 && svk_args(n->children[0], 1, sa)) {
+            if (!child(1, b) || b.rank != 2) return false;
+            out = {"svk_dpk2(" + sa + "," + b.code + ")", 2};
+            return true;
+          }
+        }
           if (!child(0, a) || !child(1, b) || a.rank != b.rank) return false;
           out = {"ddot(" + a.code + "," + b.code + ")", 0};
           return true;
@@ -604,6 +639,10 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
         }
         out = {code + ")", 0};
         return true;
+      }
+      {
+        std::string sa;
+        if (svk_args(n, 0, sa)) { out = {"svk_pk2(" + sa + ")", 2}; return true; }
       }
       if (f->node_type == GA_NODE_OPERATOR && (f->name == "Norm_sqr" || f->name == "Norm") && n->children.size() == 2) {
         jit_value a;
@@ -662,7 +701,10 @@ static bool recognise_jit(const getfem::ga_workspace &ws, size_type i1, recognis
   out.jit_params = params;
   out.field_names = fields;
   out.field_sign = 1.0;
-  for (const std::string &pn : params) out.params.push_back(ws.value(pn)[0]);
+  for (const std::string &pn : params) {  // "name" = a scalar constant, "name#c" = component c of a fixed-size vector constant
+    const size_t h = pn.find('#');
+    out.params.push_back(h == std::string::npos ? ws.value(pn)[0] : ws.value(pn.substr(0, h))[std::stoul(pn.substr(h + 1))]);
+  }
   return true;
 }
 

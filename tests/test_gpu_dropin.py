@@ -28,6 +28,10 @@ CASES = [
     "model=poisson dim=3 n=3 gt=qk k=2",
     "model=finite_strain dim=3 n=3 gt=pk k=2",
     "model=finite_strain dim=3 n=3 gt=qk k=2",
+    # 2D finite strain: the brick uses the law operator on 2 x 2 tensors, which the reference defines for Saint-Venant Kirchhoff
+    # only; its trees (operator and Derivative_1_ operator) are translated for the NVRTC route (svk_pk2 / svk_dpk2)
+    "model=finite_strain dim=2 n=8 gt=pk k=2",
+    "model=finite_strain dim=2 n=6 gt=qk k=2",
     # mixed formulation: add_linear_incompressibility (getfem_models.cc:6373-6409) -- coupled trees (Test_u, Test2_p) and
     # (Test_p, Test2_u) go to the device as one rectangular block and its transpose (gfgpu_rect_*)
     "model=incompressible dim=3 n=3 gt=pk k=2",
@@ -304,6 +308,9 @@ JIT_VECTOR = [  # vector variables (qdim = mesh dimension): matrices in the tran
      "((Id(3)+Grad_u)*(lambda*Trace(0.5*(Grad_u+Grad_u'+Grad_u'*Grad_u))*Id(3)+2*mu*(0.5*(Grad_u+Grad_u'+Grad_u'*Grad_u)))):Grad_Test_u"),
     ("dim=3 n=3 gt=pk k=1", "(1+Norm_sqr(u))*Grad_u:Grad_Test_u + (u.u)*(u.Test_u)"),
     ("dim=2 n=6 gt=qk k=2", "Sym(Grad_u):Grad_Test_u + Trace(Grad_u)*Trace(Grad_Test_u) + exp(u(1))*Test_u(2)"),
+    # the law operator inside a compound form, 3D: the translated svk_pk2 / svk_dpk2 against the reference's AHL wrapper
+    ("dim=3 n=2 gt=pk k=2 uscale=0.1", "((Id(3)+Grad_u)*Saint_Venant_Kirchhoff_PK2(Grad_u,params)):Grad_Test_u + a*u.Test_u"),
+    ("dim=2 n=6 gt=qk k=2 uscale=0.1", "((Id(2)+Grad_u)*Saint_Venant_Kirchhoff_PK2(Grad_u,[1.3;0.7])):Grad_Test_u"),
     # a load summed into the tree of a linear form: one run-time compiled term (the probe alone must not take it for K u)
     ("dim=3 n=2 gt=pk k=2", "lambda*Trace(Grad_u)*Trace(Grad_Test_u) + mu*(Grad_u'+Grad_u):Grad_Test_u + [1;2;3].Test_u"),
 ]

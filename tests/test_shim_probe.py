@@ -255,6 +255,9 @@ X_EXPRS = [  # the position X (whole vector or one coordinate): x = sum_g G_g N_
     ("dim=3 n=2 gt=pk k=2 region=2", "Test_u.(lambda*Normal)*2"),
     ("dim=3 n=2 gt=pk k=2 q=1 region=2", "X(1)*sin(u)*Test_u + (u*u*u*u)*Test_u"),             # radiation-like Robin condition
     ("dim=2 n=4 gt=qk k=2 region=2", "(u.Normal)*(Test_u.Normal)*(1+X(1)) + exp(u(1))*Test_u(2)"),
+    # the Saint-Venant Kirchhoff operator and its derivative (the one law the reference defines in any dimension: 2D finite strain)
+    ("dim=2 n=4 gt=pk k=2", "((Id(2)+Grad_u)*Saint_Venant_Kirchhoff_PK2(Grad_u,params)):Grad_Test_u"),
+    ("dim=3 n=2 gt=pk k=2", "((Id(3)+Grad_u)*Saint_Venant_Kirchhoff_PK2(Grad_u,[1.3;0.7])):Grad_Test_u + a*u.Test_u"),
     # scalar fem-data coefficients inside a translated tree: fld[k], evaluated on the data fem at every Gauss point
     ("dim=3 n=2 gt=pk k=2 q=1", "c0*sin(u)*Test_u + (1+c0)*Grad_u.Grad_Test_u"),
     ("dim=3 n=2 gt=pk k=2", "c0*(1+Norm_sqr(u))*Grad_u:Grad_Test_u + c0*X.Test_u"),
