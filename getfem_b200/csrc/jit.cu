@@ -168,6 +168,40 @@ __device__ __forceinline__ mat mkmat(double a0, double a1, double a2, double a3,
   return r;
 }
 
+// nonlinear operators of one square matrix and their first derivatives in a direction h (the reference's Det, Inv,
+// Right/Left_Cauchy_Green, Green_Lagrangian, Matrix_i2: getfem_generic_assembly_functions_and_operators.cc,
+// getfem_nonlinear_elasticity.cc:1930-2040)
+__device__ __forceinline__ double det(mat a) {
+  if (GF_N == 2) return a.m[0][0] * a.m[1][1] - a.m[0][1] * a.m[1][0];
+  return a.m[0][0] * (a.m[1][1] * a.m[GF_N - 1][GF_N - 1] - a.m[1][GF_N - 1] * a.m[GF_N - 1][1]) -
+         a.m[0][1] * (a.m[1][0] * a.m[GF_N - 1][GF_N - 1] - a.m[1][GF_N - 1] * a.m[GF_N - 1][0]) +
+         a.m[0][GF_N - 1] * (a.m[1][0] * a.m[GF_N - 1][1] - a.m[1][1] * a.m[GF_N - 1][0]);
+}
+__device__ __forceinline__ mat inv(mat a) {
+  mat r;
+  const double id = 1.0 / det(a);
+  if (GF_N == 2) {
+    r.m[0][0] = a.m[1][1] * id; r.m[0][1] = -a.m[0][1] * id; r.m[1][0] = -a.m[1][0] * id; r.m[1][1] = a.m[0][0] * id;
+  } else {
+    for (int i = 0; i < GF_N; ++i)
+      for (int j = 0; j < GF_N; ++j) {  // r(i,j) = cofactor(j,i) / det, cyclic indices
+        const int j1 = (j + 1) % GF_N, j2 = (j + 2) % GF_N, i1 = (i + 1) % GF_N, i2 = (i + 2) % GF_N;
+        r.m[i][j] = (a.m[j1][i1] * a.m[j2][i2] - a.m[j1][i2] * a.m[j2][i1]) * id;
+      }
+  }
+  return r;
+}
+__device__ __forceinline__ double ddet(mat a, mat h) { return det(a) * trace(inv(a) * h); }
+__device__ __forceinline__ mat dinv(mat a, mat h) { const mat ia = inv(a); return -(ia * h * ia); }
+__device__ __forceinline__ mat rcg(mat f) { return transp(f) * f; }
+__device__ __forceinline__ mat drcg(mat f, mat h) { return transp(h) * f + transp(f) * h; }
+__device__ __forceinline__ mat lcg(mat f) { return f * transp(f); }
+__device__ __forceinline__ mat dlcg(mat f, mat h) { return h * transp(f) + f * transp(h); }
+__device__ __forceinline__ mat glag(mat f) { mat r = 0.5 * (transp(f) * f); for (int i = 0; i < GF_N; ++i) r.m[i][i] -= 0.5; return r; }
+__device__ __forceinline__ mat dglag(mat f, mat h) { return 0.5 * (transp(h) * f + transp(f) * h); }
+__device__ __forceinline__ double mat_i2(mat a) { const double t = trace(a); return 0.5 * (t * t - trace(a * a)); }
+__device__ __forceinline__ double dmat_i2(mat a, mat h) { return trace(a) * trace(h) - trace(a * h); }
+
 // Saint-Venant Kirchhoff, the law the reference defines in any dimension (getfem_nonlinear_elasticity.cc:503-540):
 // E = (G + G' + G'G)/2, S = lambda tr(E) I + 2 mu E; dS[H] with dE = (H + H' + G'H + H'G)/2
 __device__ __forceinline__ mat svk_pk2(mat g, double lam, double mu) {

@@ -489,6 +489,30 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
     args = g.code + "," + lam + "," + mu;
     return true;
   };
+  // nonlinear operators of ONE square-matrix argument (getfem_generic_assembly_functions_and_operators.cc, the large-strain
+  // helpers of getfem_nonlinear_elasticity.cc:1930-2040): value, and first derivative contracted with a direction H --
+  // "Derivative_1_Op(A):H", the only way the reference's symbolic differentiation uses them in an order-2 tree
+  struct mat_operator { const char *name, *value; int rank; const char *deriv; };
+  static const mat_operator mat_ops[] = {
+      {"Det", "det", 0, "ddet"},                                  // d det[H] = det(A) tr(A^-1 H)
+      {"Inv", "inv", 2, "dinv"},                                  // d inv[H] = -A^-1 H A^-1
+      {"Right_Cauchy_Green", "rcg", 2, "drcg"},                   // F'F ; H'F + F'H
+      {"Left_Cauchy_Green", "lcg", 2, "dlcg"},                    // FF' ; HF' + FH'
+      {"Green_Lagrangian", "glag", 2, "dglag"},                   // (F'F - I)/2 ; (H'F + F'H)/2
+      {"Matrix_i2", "mat_i2", 0, "dmat_i2"},                      // ((tr A)^2 - tr(A^2))/2 ; tr A tr H - tr(A H)
+  };
+  auto mat_op_args = [&](const pga_tree_node &pn, size_type der1, const mat_operator *&op, std::string &args) {
+    if (pn->node_type != GA_NODE_PARAMS || pn->children.size() != 2) return false;
+    const pga_tree_node &f = pn->children[0];
+    if (f->node_type != GA_NODE_OPERATOR || f->der1 != der1 || f->der2 != 0) return false;
+    op = nullptr;
+    for (const mat_operator &o : mat_ops) if (f->name == o.name) op = &o;
+    if (!op) return false;
+    jit_value g;
+    if (!jit_emit(ws, pn->children[1], v, N, Q, params, fields, g) || g.rank != 2) return false;
+    args = g.code;
+    return true;
+  };
   switch (n->node_type) {
     case GA_NODE_ZERO: {
       if (n->test_function_type != 0 && n->test_function_type != size_type(-1)) return false;
@@ -601,6 +625,12 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
             out = {"svk_dpk2(" + sa + "," + b.code + ")", 2};
             return true;
           }
+          const mat_operator *mop = nullptr;
+          if (n->children.size() == 2 && mat_op_args(n->children[0], 1, mop, sa)) {
+            if (!child(1, b) || b.rank != 2) return false;
+            out = {std::string(mop->deriv) + "(" + sa + "," + b.code + ")", mop->rank};
+            return true;
+          }
         }
           if (!child(0, a) || !child(1, b) || a.rank != b.rank) return false;
           out = {"ddot(" + a.code + "," + b.code + ")", 0};
@@ -643,6 +673,8 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
       {
         std::string sa;
         if (svk_args(n, 0, sa)) { out = {"svk_pk2(" + sa + ")", 2}; return true; }
+        const mat_operator *mop = nullptr;
+        if (mat_op_args(n, 0, mop, sa)) { out = {std::string(mop->value) + "(" + sa + ")", mop->rank}; return true; }
       }
       if (f->node_type == GA_NODE_OPERATOR && (f->name == "Norm_sqr" || f->name == "Norm") && n->children.size() == 2) {
         jit_value a;

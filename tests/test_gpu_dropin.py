@@ -311,6 +311,15 @@ JIT_VECTOR = [  # vector variables (qdim = mesh dimension): matrices in the tran
     # the law operator inside a compound form, 3D: the translated svk_pk2 / svk_dpk2 against the reference's AHL wrapper
     ("dim=3 n=2 gt=pk k=2 uscale=0.1", "((Id(3)+Grad_u)*Saint_Venant_Kirchhoff_PK2(Grad_u,params)):Grad_Test_u + a*u.Test_u"),
     ("dim=2 n=6 gt=qk k=2 uscale=0.1", "((Id(2)+Grad_u)*Saint_Venant_Kirchhoff_PK2(Grad_u,[1.3;0.7])):Grad_Test_u"),
+    # nonlinear matrix operators with their Derivative_1_ forms: a compressible neo-Hookean law written out with Det / Inv
+    # (P = mu (F - F^-T) + lambda log(J) F^-T), 3D and 2D; SVK through Green_Lagrangian; invariants and Cauchy-Green tensors
+    ("dim=3 n=2 gt=pk k=2 uscale=0.1",
+     "(mu*((Id(3)+Grad_u) - Inv(Id(3)+Grad_u)') + lambda*log(Det(Id(3)+Grad_u))*Inv(Id(3)+Grad_u)'):Grad_Test_u"),
+    ("dim=2 n=6 gt=qk k=2 uscale=0.1",
+     "(mu*((Id(2)+Grad_u) - Inv(Id(2)+Grad_u)') + lambda*log(Det(Id(2)+Grad_u))*Inv(Id(2)+Grad_u)'):Grad_Test_u"),
+    ("dim=3 n=2 gt=qk k=2 uscale=0.1",
+     "((Id(3)+Grad_u)*(lambda*Trace(Green_Lagrangian(Id(3)+Grad_u))*Id(3)+2*mu*Green_Lagrangian(Id(3)+Grad_u))):Grad_Test_u"),
+    ("dim=3 n=2 gt=pk k=2 uscale=0.1", "(Matrix_i2(Right_Cauchy_Green(Id(3)+Grad_u))*Left_Cauchy_Green(Id(3)+Grad_u)):Grad_Test_u"),
     # a load summed into the tree of a linear form: one run-time compiled term (the probe alone must not take it for K u)
     ("dim=3 n=2 gt=pk k=2", "lambda*Trace(Grad_u)*Trace(Grad_Test_u) + mu*(Grad_u'+Grad_u):Grad_Test_u + [1;2;3].Test_u"),
 ]

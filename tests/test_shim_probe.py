@@ -258,6 +258,12 @@ X_EXPRS = [  # the position X (whole vector or one coordinate): x = sum_g G_g N_
     # the Saint-Venant Kirchhoff operator and its derivative (the one law the reference defines in any dimension: 2D finite strain)
     ("dim=2 n=4 gt=pk k=2", "((Id(2)+Grad_u)*Saint_Venant_Kirchhoff_PK2(Grad_u,params)):Grad_Test_u"),
     ("dim=3 n=2 gt=pk k=2", "((Id(3)+Grad_u)*Saint_Venant_Kirchhoff_PK2(Grad_u,[1.3;0.7])):Grad_Test_u + a*u.Test_u"),
+    # nonlinear matrix operators and their derivatives: a compressible neo-Hookean law WRITTEN OUT with Det / Inv, the
+    # large-strain helpers
+    ("dim=3 n=2 gt=pk k=2", "(mu*((Id(3)+Grad_u) - Inv(Id(3)+Grad_u)') + lambda*log(Det(Id(3)+Grad_u))*Inv(Id(3)+Grad_u)'):Grad_Test_u"),
+    ("dim=2 n=4 gt=qk k=2", "(mu*((Id(2)+Grad_u) - Inv(Id(2)+Grad_u)') + lambda*log(Det(Id(2)+Grad_u))*Inv(Id(2)+Grad_u)'):Grad_Test_u"),
+    ("dim=3 n=2 gt=pk k=2", "((Id(3)+Grad_u)*(lambda*Trace(Green_Lagrangian(Id(3)+Grad_u))*Id(3)+2*mu*Green_Lagrangian(Id(3)+Grad_u))):Grad_Test_u"),
+    ("dim=3 n=2 gt=pk k=2", "(Matrix_i2(Right_Cauchy_Green(Id(3)+Grad_u))*Left_Cauchy_Green(Id(3)+Grad_u)):Grad_Test_u"),
     # scalar fem-data coefficients inside a translated tree: fld[k], evaluated on the data fem at every Gauss point
     ("dim=3 n=2 gt=pk k=2 q=1", "c0*sin(u)*Test_u + (1+c0)*Grad_u.Grad_Test_u"),
     ("dim=3 n=2 gt=pk k=2", "c0*(1+Norm_sqr(u))*Grad_u:Grad_Test_u + c0*X.Test_u"),
@@ -291,6 +297,6 @@ def test_the_translated_forms_compile(mesh, expr):
 def test_the_nvrtc_route_refuses_what_it_cannot_express():
     """operators outside the translator's language: no silent approximation -- the tree is reported as not
     recognised"""
-    for mesh, expr in (("dim=3 n=2 gt=pk k=2", "sqr(Norm(u))*Grad_u:Grad_Test_u"), ("dim=3 n=2 gt=pk k=2", "Det(Id(3)+Grad_u)*(u.Test_u)")):
+    for mesh, expr in (("dim=3 n=2 gt=pk k=2", "sqr(Norm(u))*Grad_u:Grad_Test_u"), ("dim=3 n=2 gt=pk k=2", "Expm(Grad_u):Grad_Test_u")):
         line = _dryrun_order1(mesh, expr)
         assert "NOT recognised" in line, line
