@@ -313,9 +313,9 @@ JIT_VECTOR = [  # vector variables (qdim = mesh dimension): matrices in the tran
     ("dim=2 n=6 gt=qk k=2 uscale=0.1", "((Id(2)+Grad_u)*Saint_Venant_Kirchhoff_PK2(Grad_u,[1.3;0.7])):Grad_Test_u"),
     # nonlinear matrix operators with their Derivative_1_ forms: a compressible neo-Hookean law written out with Det / Inv
     # (P = mu (F - F^-T) + lambda log(J) F^-T), 3D and 2D; SVK through Green_Lagrangian; invariants and Cauchy-Green tensors
-    ("dim=3 n=2 gt=pk k=2 uscale=0.1",
+    ("dim=3 n=2 gt=pk k=2 uscale=0.02",   # (a state with det F > 0 everywhere: log(Det(F)) is NaN otherwise, in the reference too)
      "(mu*((Id(3)+Grad_u) - Inv(Id(3)+Grad_u)') + lambda*log(Det(Id(3)+Grad_u))*Inv(Id(3)+Grad_u)'):Grad_Test_u"),
-    ("dim=2 n=6 gt=qk k=2 uscale=0.1",
+    ("dim=2 n=6 gt=qk k=2 uscale=0.01",
      "(mu*((Id(2)+Grad_u) - Inv(Id(2)+Grad_u)') + lambda*log(Det(Id(2)+Grad_u))*Inv(Id(2)+Grad_u)'):Grad_Test_u"),
     ("dim=3 n=2 gt=qk k=2 uscale=0.1",
      "((Id(3)+Grad_u)*(lambda*Trace(Green_Lagrangian(Id(3)+Grad_u))*Id(3)+2*mu*Green_Lagrangian(Id(3)+Grad_u))):Grad_Test_u"),
