@@ -468,8 +468,11 @@ int gfgpu_term_set_fields(gfgpu_term *t, int nfields, gfgpu_fem *dfem, const dou
   GF_REQUIRE(maxf > 0, "fem-data coefficients are handled for the Laplace, mass, elasticity, source and JIT families");
   GF_REQUIRE(nfields >= 1 && nfields <= maxf, "wrong number of coefficient fields for this family");
   GF_REQUIRE(nfields < 2 || vals1, "null argument");
-  GF_REQUIRE(dfem->qdim == (fam == GFGPU_SOURCE ? t->fem->qdim : 1),
-             "the data fem must be scalar (the source term's: qdim of the variable)");
+  if (fam == GFGPU_JIT && dfem->qdim != 1)  // JIT terms: scalar fields fld[k], or ONE vector field vfld of the mesh dimension
+    GF_REQUIRE(dfem->qdim == t->mesh->dim && nfields == 1, "JIT terms: 1-2 scalar fields, or one vector field of the mesh dimension");
+  else
+    GF_REQUIRE(dfem->qdim == (fam == GFGPU_SOURCE ? t->fem->qdim : 1),
+               "the data fem must be scalar (the source term's: qdim of the variable)");
   GF_REQUIRE(t->strategy_asked != GFGPU_STRATEGY_RECOMPUTE, "fem-data coefficients use strategy STAGED");
   const int ndd = dfem->nd, nq = t->tab->nq;
   t->dphi.alloc(ctx, (size_t)nq * ndd); t->dphi.upload(phi);

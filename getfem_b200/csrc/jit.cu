@@ -220,8 +220,8 @@ __device__ __forceinline__ mat svk_dpk2(mat g, double lam, double mu, mat h) {
 }
 
 #if GF_Q == 1
-__device__ __forceinline__ double gf_form1(double u, vec gu, vec X, vec Normal, const double *fld, const double *par, double tv, vec tg) { return GF_FORM1; }
-__device__ __forceinline__ double gf_form2(double u, vec gu, vec X, vec Normal, const double *fld, const double *par, double tv, vec tg, double t2v, vec t2g) {
+__device__ __forceinline__ double gf_form1(double u, vec gu, vec X, vec Normal, const double *fld, vec vfld, const double *par, double tv, vec tg) { return GF_FORM1; }
+__device__ __forceinline__ double gf_form2(double u, vec gu, vec X, vec Normal, const double *fld, vec vfld, const double *par, double tv, vec tg, double t2v, vec t2g) {
   return GF_FORM2;
 }
 
@@ -231,7 +231,7 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
             const double *__restrict__ phi, const double *__restrict__ gphi, const double *__restrict__ gt_val,
             const signed char *__restrict__ face, const double *__restrict__ fnormal,
             const int *__restrict__ dedof, const double *__restrict__ dphi, const double *__restrict__ dvals0,
-            const double *__restrict__ dvals1, int nfields, int nd_d,
+            const double *__restrict__ dvals1, int nfields, int nd_d, int fqdim,
             const double *__restrict__ par, int ng, int nq, int nd,
             long long e0, long long ne, double alpha, double *__restrict__ stage, unsigned short *__restrict__ emask,
             double *__restrict__ rstage) {
@@ -323,21 +323,26 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
         for (int i = 0; i < ng; ++i)
           for (int k = 0; k < N; ++k) Xq.v[k] += sG[k + N * i] * gtvE[(size_t)q * ng + i];
       double fq[2] = {0.0, 0.0};
+      vec vq = zero;  // ONE vector-valued field (a data fem of qdim = mesh dimension, e.g. an advection velocity) instead of scalars
       for (int i = 0; i < (nfields ? nd_d : 0); ++i) {
         const double ph = dpE[(size_t)q * nd_d + i];
-        fq[0] += dvals0[ddE[i]] * ph;
-        if (nfields > 1) fq[1] += dvals1[ddE[i]] * ph;
+        if (fqdim > 1) {
+          for (int c = 0; c < N; ++c) vq.v[c] += dvals0[ddE[i] + c] * ph;
+        } else {
+          fq[0] += dvals0[ddE[i]] * ph;
+          if (nfields > 1) fq[1] += dvals1[ddE[i]] * ph;
+        }
       }
 #pragma unroll
       for (int a = 0; a < NA; ++a) {
         const double tv = a == 0 ? 1.0 : 0.0;
         const vec tg = a == 0 ? zero : unit(a - 1);
-        sC1[q * NA + a] = cw == 0.0 ? 0.0 : cw * gf_form1(uq, guq, Xq, Nq, fq, par, tv, tg);
+        sC1[q * NA + a] = cw == 0.0 ? 0.0 : cw * gf_form1(uq, guq, Xq, Nq, fq, vq, par, tv, tg);
 #pragma unroll
         for (int b = 0; b < NA; ++b) {
           const double t2v = b == 0 ? 1.0 : 0.0;
           const vec t2g = b == 0 ? zero : unit(b - 1);
-          sC2[(q * NA + a) * NA + b] = cw == 0.0 ? 0.0 : cw * gf_form2(uq, guq, Xq, Nq, fq, par, tv, tg, t2v, t2g);
+          sC2[(q * NA + a) * NA + b] = cw == 0.0 ? 0.0 : cw * gf_form2(uq, guq, Xq, Nq, fq, vq, par, tv, tg, t2v, t2g);
         }
       }
     }
@@ -383,8 +388,8 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
   }
 }
 #else  // ---------------------------------------------------------------- vector variable, qdim = mesh dimension
-__device__ __forceinline__ double gf_form1(vec u, mat gu, vec X, vec Normal, const double *fld, const double *par, vec tv, mat tg) { return GF_FORM1; }
-__device__ __forceinline__ double gf_form2(vec u, mat gu, vec X, vec Normal, const double *fld, const double *par, vec tv, mat tg, vec t2v, mat t2g) { return GF_FORM2; }
+__device__ __forceinline__ double gf_form1(vec u, mat gu, vec X, vec Normal, const double *fld, vec vfld, const double *par, vec tv, mat tg) { return GF_FORM1; }
+__device__ __forceinline__ double gf_form2(vec u, mat gu, vec X, vec Normal, const double *fld, vec vfld, const double *par, vec tv, mat tg, vec t2v, mat t2g) { return GF_FORM2; }
 
 // probe slot s = c * (N+1) + a: a = 0 -> the value of component c, a = 1 + k -> d/dx_k of component c
 __device__ __forceinline__ void gf_probe(int s, vec &tv, mat &tg) {
@@ -399,7 +404,7 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
             const double *__restrict__ phi, const double *__restrict__ gphi, const double *__restrict__ gt_val,
             const signed char *__restrict__ face, const double *__restrict__ fnormal,
             const int *__restrict__ dedof, const double *__restrict__ dphi, const double *__restrict__ dvals0,
-            const double *__restrict__ dvals1, int nfields, int nd_d,
+            const double *__restrict__ dvals1, int nfields, int nd_d, int fqdim,
             const double *__restrict__ par, int ng, int nq, int nd,
             long long e0, long long ne, double alpha, double *__restrict__ stage, unsigned short *__restrict__ emask,
             double *__restrict__ rstage) {
@@ -409,7 +414,7 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
   double *sG = sm;                               // N x ng
   double *sU = sG + N * ng;                      // nd x Q
   double *sT = sU + s1;                          // nq x nd x NA
-  constexpr int SS = Q + Q * N + 1 + 2 * N + 2;  // per point: u, Grad u, weight w J alpha, position X, unit normal, two fem-data fields
+  constexpr int SS = Q + Q * N + 1 + 3 * N + 2;  // per point: u, Grad u, weight w J alpha, position X, unit normal, two scalar fields, one vector field
   double *sS = sT + (size_t)nq * nd * NA;        // nq x SS
   double *sC1 = sS + (size_t)nq * SS;            // nq x NS
   double *sC2 = sC1 + (size_t)nq * NS;           // nq x NS x NS
@@ -476,8 +481,12 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
       for (int k = 0; k < N; ++k) S[Q + Q * N + 1 + N + k] = Nq.v[k];
       for (int i = 0; i < (nfields ? nd_d : 0); ++i) {
         const double ph = dpE[(size_t)q * nd_d + i];
-        S[Q + Q * N + 1 + 2 * N] += dvals0[ddE[i]] * ph;
-        if (nfields > 1) S[Q + Q * N + 2 + 2 * N] += dvals1[ddE[i]] * ph;
+        if (fqdim > 1) {
+          for (int c = 0; c < N; ++c) S[Q + Q * N + 3 + 2 * N + c] += dvals0[ddE[i] + c] * ph;
+        } else {
+          S[Q + Q * N + 1 + 2 * N] += dvals0[ddE[i]] * ph;
+          if (nfields > 1) S[Q + Q * N + 2 + 2 * N] += dvals1[ddE[i]] * ph;
+        }
       }
       double *T = sT + (size_t)q * nd * NA;
       for (int i = 0; i < nd; ++i) {
@@ -504,13 +513,15 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
       vec uq, Xq, Nq; mat guq;
       for (int k = 0; k < N; ++k) { Xq.v[k] = S[Q + Q * N + 1 + k]; Nq.v[k] = S[Q + Q * N + 1 + N + k]; }
       const double *fq = S + Q + Q * N + 1 + 2 * N;
+      vec vq;
+      for (int k = 0; k < N; ++k) vq.v[k] = S[Q + Q * N + 3 + 2 * N + k];
       for (int c = 0; c < Q; ++c) { uq.v[c] = S[c]; for (int k = 0; k < N; ++k) guq.m[c][k] = S[Q + c * N + k]; }
       vec tv, t2v; mat tg, t2g;
       gf_probe(s, tv, tg);
-      sC1[q * NS + s] = cw == 0.0 ? 0.0 : cw * gf_form1(uq, guq, Xq, Nq, fq, par, tv, tg);
+      sC1[q * NS + s] = cw == 0.0 ? 0.0 : cw * gf_form1(uq, guq, Xq, Nq, fq, vq, par, tv, tg);
       for (int s2 = 0; s2 < NS; ++s2) {
         gf_probe(s2, t2v, t2g);
-        sC2[((size_t)q * NS + s) * NS + s2] = cw == 0.0 ? 0.0 : cw * gf_form2(uq, guq, Xq, Nq, fq, par, tv, tg, t2v, t2g);
+        sC2[((size_t)q * NS + s) * NS + s2] = cw == 0.0 ? 0.0 : cw * gf_form2(uq, guq, Xq, Nq, fq, vq, par, tv, tg, t2v, t2g);
       }
     }
     __syncthreads();
@@ -642,7 +653,7 @@ void launch_jit_kernel(gfgpu_term *t, const ElemArgs &a) {
   GF_REQUIRE(Q == 1 || Q == N, "JIT terms: scalar variables, or vector variables of the mesh dimension");
   const size_t NS = (size_t)Q * NA, s1 = (size_t)nd * Q;
   const size_t smem = Q == 1 ? ((size_t)N * ng + nd + (size_t)nq * nd * NA + (size_t)nq * NA + (size_t)nq * NA * NA + (size_t)nd * nd + 2) * 8
-                             : ((size_t)N * ng + s1 + (size_t)nq * nd * NA + (size_t)nq * (Q + Q * N + 1 + 2 * N + 2) + (size_t)nq * NS +
+                             : ((size_t)N * ng + s1 + (size_t)nq * nd * NA + (size_t)nq * (Q + Q * N + 1 + 3 * N + 2) + (size_t)nq * NS +
                                 (size_t)nq * NS * NS + s1 * s1 + 2) * 8;
   GF_REQUIRE(smem <= 220 * 1024, "JIT terms: element too large for the run-time kernel (nq x nd x (N+1) doubles of shared memory)");
   if (t->jit_par.n != (size_t)GFGPU_MAX_PARAMS) {
@@ -662,7 +673,7 @@ void launch_jit_kernel(gfgpu_term *t, const ElemArgs &a) {
   const double *fnormal = a.fnormal;
   const int32_t *dedof = a.nfields ? a.dedof : nullptr;
   const double *dphi = a.nfields ? a.dphi : nullptr, *dv0 = a.dvals0, *dv1 = a.dvals1;
-  int nfields = a.nfields, nd_d = a.nd_d;
+  int nfields = a.nfields, nd_d = a.nd_d, fqdim = (a.nfields && t->dfem) ? t->dfem->qdim : 1;
   if (face) {  // boundary faces: the kernel indexes the face tables by the item's face
     w = a.fw; gt = a.fgt_grad; phi = a.fphi; gphi = a.fgphi;
     gtv = t->tab->fgt_val.n ? t->tab->fgt_val.p : nullptr;
@@ -694,7 +705,7 @@ void launch_jit_kernel(gfgpu_term *t, const ElemArgs &a) {
   const int32_t *conn = a.conn, *edof = a.edof;
   double *stage = a.stage, *rstage = a.rstage;
   uint16_t *emask = a.emask;
-  void *params[] = {&x, &y, &z, &conn, &edof, &U, &w, &gt, &phi, &gphi, &gtv, &face, &fnormal, &dedof, &dphi, &dv0, &dv1, &nfields, &nd_d, &par, &ing, &inq, &ind, &e0, &ne, &alpha, &stage, &emask, &rstage};
+  void *params[] = {&x, &y, &z, &conn, &edof, &U, &w, &gt, &phi, &gphi, &gtv, &face, &fnormal, &dedof, &dphi, &dv0, &dv1, &nfields, &nd_d, &fqdim, &par, &ing, &inq, &ind, &e0, &ne, &alpha, &stage, &emask, &rstage};
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ne, (long long)ctx->sm_count * 4));
   const int r = api.LaunchKernel(k->fn, grid, 1, 1, 128, 1, 1, (unsigned)smem, ctx->stream, params, nullptr);
   GF_REQUIRE(r == 0, "cuLaunchKernel failed for the JIT kernel (error " + std::to_string(r) + ")");

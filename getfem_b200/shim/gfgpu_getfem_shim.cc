@@ -531,7 +531,14 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
         // own fem (ga_instruction_val, C&E.cc:636-690); at most two, all on one data mesh_fem (checked when the term is built)
         const getfem::mesh_fem *pmd = ws.associated_mf(n->name);
         const getfem::im_data *pid = ws.associated_im_data(n->name);
+        if (pmd && int(pmd->get_qdim()) == N && N > 1) {  // ONE vector-valued fem-data field (an advection velocity, a body force direction)
+          if (!fields.empty() && fields[0] != n->name) return false;
+          if (fields.empty()) fields.push_back(n->name);
+          out = {"vfld", 1};
+          return true;
+        }
         if (pmd ? pmd->get_qdim() != 1 : pid->nb_tensor_elem() != 1) return false;
+        if (!fields.empty() && ws.associated_mf(fields[0]) && int(ws.associated_mf(fields[0])->get_qdim()) != 1) return false;
         size_t k = 0;
         while (k < fields.size() && fields[k] != n->name) ++k;
         if (k == fields.size()) fields.push_back(n->name);

@@ -169,7 +169,7 @@ int gfgpu_term_set_region(gfgpu_term *t, int64_t n_items, const int32_t *cv_host
  * of the elasticity brick, the distributed load F(x) of add_source_term_brick (getfem_models.cc:4124-).
  *   LAPLACE, MASS: 1 field (a), scalar data fem; ELASTICITY: 1 or 2 (lambda[, mu]), scalar data fem;
  *   SOURCE: 1 field of qdim components (data fem of the variable's qdim), vals0 already carrying the sign of the expression;
- *   JIT terms: 1 or 2 scalar fields, the integrand's fld[0], fld[1].
+ *   JIT terms: 1 or 2 scalar fields, the integrand's fld[0], fld[1]; or one vector field (data fem of qdim = mesh dimension), vfld.
  *   data_fem: a gfgpu_fem on the same mesh; phi_host[nq][nd_d]: its basis at the volume quadrature points
  *   (fem_precomp_::val); phi_faces_host[nf][nqf][nd_d] (or NULL): the same at the face points, for regions of faces;
  *   vals*_host: nodal values (data_fem ndof).  nfields = 0 removes the fields.  Such terms use strategy STAGED.
@@ -211,6 +211,8 @@ int gfgpu_term_potential_host(gfgpu_term *t, const double *U_host, double *E_hos
  *     u (double), gu (vec, Grad_u), X (vec, the position: needs gfgpu_tables_set_gt_values), Normal (vec, the unit outward normal:
  *     needs a region of faces, gfgpu_term_set_region; J and Normal as C&E.cc:8836-8847), par[k] (the term's parameters),
  *     fld[0], fld[1] (scalar fem-data coefficients at the Gauss point: gfgpu_term_set_fields with 1 or 2 fields),
+ *     vfld (vec: ONE vector-valued fem-data field of the mesh dimension, e.g. an advection velocity: gfgpu_term_set_fields
+ *     with a data fem of qdim = mesh dimension),
  *     tv / tg (Test_u / Grad_Test_u), t2v / t2g (Test2)
  * with the helpers dot(a,b), normsqr(v), gnorm(v), mkvec(a,b,c), sqr, pos_part, neg_part, Heaviside, sign and the CUDA math
  * library.  form1 must be linear in (tv, tg), form2 bilinear in (tv, tg) x (t2v, t2g): the kernel extracts their coefficients

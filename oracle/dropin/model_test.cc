@@ -105,6 +105,13 @@ int main(int argc, char **argv) {
     }
     double Er = 0, Eg = 0;
     C0.back() = 5.0;
+    getfem::mesh_fem mf_dv(m, getfem::dim_type(dim));
+    mf_dv.set_classical_finite_element(1);
+    std::vector<double> W0(mf_dv.nb_dof());
+    for (size_type d = 0; d < mf_dv.nb_dof(); ++d) {
+      bgeot::base_node P = mf_dv.point_of_basic_dof(d);
+      W0[d] = (d % dim == 0 ? 1.0 : -0.5) + 0.3 * std::sin(2.0 * P[0] + 1.3 * P[dim - 1] + double(d % dim));
+    }
     auto run = [&](bool device, gmm::csc_matrix<double> &C) {
       getfem_b200::gfgpu_enable(device);
       getfem::ga_workspace ws;
@@ -115,6 +122,7 @@ int main(int argc, char **argv) {
       ws.add_fixed_size_constant("a", A);
       ws.add_fixed_size_constant("params", PARAMS);
       ws.add_fem_constant("c0", mf_d, C0);  // a material that is 1 on the first convexes and 5 in a far corner
+      ws.add_fem_constant("w0", mf_dv, W0);  // a vector-valued field (an advection velocity)
       if (a.count("region")) ws.add_expression(expr, mim, m.region(size_type(geti("region", 1))));
       else ws.add_expression(expr, mim);
       const size_type ntot = mf.nb_dof() + (with_p ? mf_p.nb_dof() : 0);

@@ -283,6 +283,10 @@ JIT_X = [  # the position X and, on boundary faces, the unit normal: space-depen
     ("dim=3 n=3 gt=pk k=2 q=1", "c0*sin(u)*Test_u + (1+c0)*Grad_u.Grad_Test_u"),
     ("dim=3 n=2 gt=qk k=2", "c0*(1+Norm_sqr(u))*Grad_u:Grad_Test_u + c0*X.Test_u"),
     ("dim=2 n=6 gt=pk k=2 q=1 region=2", "c0*u*u*u*Test_u + c0*Test_u"),
+    # ONE vector-valued fem-data field: advection-diffusion by a data velocity (unsymmetric tangent), convection of a vector unknown
+    ("dim=3 n=3 gt=pk k=2 q=1", "(w0.Grad_u)*Test_u + 0.1*Grad_u.Grad_Test_u"),
+    ("dim=2 n=6 gt=qk k=2", "(Grad_u*w0).Test_u + (1+Norm_sqr(w0))*Grad_u:Grad_Test_u - w0.Test_u"),
+    ("dim=3 n=2 gt=qk k=1 q=1 region=2", "(w0.Normal)*u*Test_u"),
 ]
 
 

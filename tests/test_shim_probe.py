@@ -268,6 +268,9 @@ X_EXPRS = [  # the position X (whole vector or one coordinate): x = sum_g G_g N_
     ("dim=3 n=2 gt=pk k=2 q=1", "c0*sin(u)*Test_u + (1+c0)*Grad_u.Grad_Test_u"),
     ("dim=3 n=2 gt=pk k=2", "c0*(1+Norm_sqr(u))*Grad_u:Grad_Test_u + c0*X.Test_u"),
     ("dim=2 n=4 gt=qk k=2 q=1 region=2", "c0*u*u*u*Test_u"),
+    # ONE vector-valued fem-data field (vfld): advection by a data velocity
+    ("dim=3 n=2 gt=pk k=2 q=1", "(w0.Grad_u)*Test_u + 0.1*Grad_u.Grad_Test_u"),
+    ("dim=2 n=4 gt=qk k=2", "(Grad_u*w0).Test_u + (1+Norm_sqr(w0))*Grad_u:Grad_Test_u - w0.Test_u"),
 ]
 
 
