@@ -90,6 +90,7 @@ SIGNATURES = {
     "gfgpu_rect_destroy": (C.c_int, [_P]),
     "gfgpu_rect_set_region": (C.c_int, [_P, C.c_int64, _P, _P]),
     "gfgpu_term_tmult_dev": (C.c_int, [_P, C.c_double, _P, C.c_double, _P]),
+    "gfgpu_term_set_jit_potential": (C.c_int, [_P, C.c_char_p]),
     "gfgpu_reduction_create": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _PP]),
     "gfgpu_reduction_destroy": (C.c_int, [_P]),
     "gfgpu_reduction_extend_host": (C.c_int, [_P, _P, _P]),

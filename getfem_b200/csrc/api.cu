@@ -412,6 +412,19 @@ int gfgpu_term_set_params(gfgpu_term *t, const double *params, int nparams) {
   GF_API_END
 }
 
+int gfgpu_term_set_jit_potential(gfgpu_term *t, const char *form0) {
+  GF_API_BEGIN
+  GF_REQUIRE(t && form0, "null argument");
+  GF_REQUIRE(t->family == GFGPU_JIT, "only JIT terms take an order-0 form");
+  if (t->jit_form0 != form0) {
+    GF_CUDA(cudaSetDevice(t->ctx->device));
+    GF_CUDA(cudaStreamSynchronize(t->ctx->stream));
+    gf::jit_release(t);  // compiled again, with the potential, at the next launch
+    t->jit_form0 = form0;
+  }
+  GF_API_END
+}
+
 int gfgpu_jit_check(int dim, int qdim, const char *form1, const char *form2) {
   GF_API_BEGIN
   GF_REQUIRE(form1 && form2 && (dim == 2 || dim == 3) && (qdim == 1 || qdim == dim), "bad argument");

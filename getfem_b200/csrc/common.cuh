@@ -235,7 +235,8 @@ struct gfgpu_term {
   int direct_ok = 0;  // 0 unknown, 1 yes, -1 no
   gf::DevBuf<double> Ubuf;      // ndof (host path)
   // JIT family (jit.cu): the two forms as C expressions, the compiled kernel, the parameters on the device
-  std::string jit_form1, jit_form2;
+  std::string jit_form1, jit_form2, jit_form0;  // jit_form0: the order-0 integrand (gfgpu_term_set_jit_potential), may be empty
+  double *jit_epot = nullptr;                    // set while a potential is computed: per-element shares, ne doubles
   void *jit_kernel = nullptr;
   gf::DevBuf<double> jit_par;
   bool jit_value_dependent = true;

@@ -126,6 +126,21 @@ __device__ __forceinline__ double DER_PDFUNC2_ATAN2(double t, double v) { return
 __device__ __forceinline__ double DER_PDFUNC_ERF(double t) { return exp(-t * t) * 1.1283791670955126; }
 __device__ __forceinline__ double DER_PDFUNC_ERFC(double t) { return -exp(-t * t) * 1.1283791670955126; }
 __device__ __forceinline__ double Heaviside(double x) { return x < 0 ? 0.0 : 1.0; }
+// second derivatives, under the names the reference gives the derivative of a derivative that is defined by an expression
+// (getfem_generic_assembly_functions_and_operators.cc:418-490: "-0.25/(t*sqrt(t))", "-1/sqr(t)", ...)
+__device__ __forceinline__ double DER_PDFUNC_DER_PDFUNC_SQRT(double t) { return -0.25 / (t * sqrt(t)); }
+__device__ __forceinline__ double DER_PDFUNC_DER_PDFUNC_LOG(double t) { return -1.0 / (t * t); }
+__device__ __forceinline__ double DER_PDFUNC_DER_PDFUNC_LOG10(double t) { return -1.0 / (t * t * log(10.0)); }
+__device__ __forceinline__ double DER_PDFUNC_DER_PDFUNC_TANH(double t) { const double h = tanh(t); return 2.0 * h * (h * h - 1.0); }
+__device__ __forceinline__ double DER_PDFUNC_DER_PDFUNC_ASINH(double t) { return -t / pow(t * t + 1.0, 1.5); }
+__device__ __forceinline__ double DER_PDFUNC_DER_PDFUNC_ACOSH(double t) { return -t / pow(t * t - 1.0, 1.5); }
+__device__ __forceinline__ double DER_PDFUNC_DER_PDFUNC_ATANH(double t) { return 2.0 * t / ((1.0 - t * t) * (1.0 - t * t)); }
+__device__ __forceinline__ double DER_PDFUNC_DER_PDFUNC_COS(double t) { return -cos(t); }
+__device__ __forceinline__ double DER_PDFUNC_DER_PDFUNC_TAN(double t) { const double c = cos(t); return 2.0 * tan(t) / (c * c); }
+__device__ __forceinline__ double DER_PDFUNC_DER_PDFUNC_ASIN(double t) { return t / pow(1.0 - t * t, 1.5); }
+__device__ __forceinline__ double DER_PDFUNC_DER_PDFUNC_ACOS(double t) { return -t / pow(1.0 - t * t, 1.5); }
+__device__ __forceinline__ double DER_PDFUNC_DER_PDFUNC_ATAN(double t) { return -2.0 * t / ((1.0 + t * t) * (1.0 + t * t)); }
+__device__ __forceinline__ double DER_PDFUNC_NEG_PART(double t) { return -Heaviside(-t); }
 __device__ __forceinline__ double sign(double x) { return x < 0 ? -1.0 : (x > 0 ? 1.0 : 0.0); }
 
 // matrices of the mesh dimension: m[c][k] (for Grad_u: component c, direction k, the GWFL convention)
@@ -201,6 +216,16 @@ __device__ __forceinline__ mat glag(mat f) { mat r = 0.5 * (transp(f) * f); for 
 __device__ __forceinline__ mat dglag(mat f, mat h) { return 0.5 * (transp(h) * f + transp(f) * h); }
 __device__ __forceinline__ double mat_i2(mat a) { const double t = trace(a); return 0.5 * (t * t - trace(a * a)); }
 __device__ __forceinline__ double dmat_i2(mat a, mat h) { return trace(a) * trace(h) - trace(a * h); }
+// second derivatives in two directions (symmetric in h, k): "(Derivative_1_1_Op(A):H2):H1" of an order-2 tree derived from a potential
+__device__ __forceinline__ double d2det(mat a, mat h, mat k) {
+  const mat ia = inv(a), ih = ia * h, ik = ia * k;
+  return det(a) * (trace(ih) * trace(ik) - trace(ih * ik));
+}
+__device__ __forceinline__ mat d2inv(mat a, mat h, mat k) { const mat ia = inv(a), ih = ia * h, ik = ia * k; return ih * ik * ia + ik * ih * ia; }
+__device__ __forceinline__ mat d2rcg(mat f, mat h, mat k) { return transp(h) * k + transp(k) * h; }
+__device__ __forceinline__ mat d2lcg(mat f, mat h, mat k) { return h * transp(k) + k * transp(h); }
+__device__ __forceinline__ mat d2glag(mat f, mat h, mat k) { return 0.5 * (transp(h) * k + transp(k) * h); }
+__device__ __forceinline__ double d2mat_i2(mat a, mat h, mat k) { return trace(h) * trace(k) - trace(h * k); }
 
 // Saint-Venant Kirchhoff, the law the reference defines in any dimension (getfem_nonlinear_elasticity.cc:503-540):
 // E = (G + G' + G'G)/2, S = lambda tr(E) I + 2 mu E; dS[H] with dE = (H + H' + G'H + H'G)/2
@@ -220,6 +245,7 @@ __device__ __forceinline__ mat svk_dpk2(mat g, double lam, double mu, mat h) {
 }
 
 #if GF_Q == 1
+__device__ __forceinline__ double gf_form0(double u, vec gu, vec X, vec Normal, const double *fld, vec vfld, const double *par) { return GF_FORM0; }
 __device__ __forceinline__ double gf_form1(double u, vec gu, vec X, vec Normal, const double *fld, vec vfld, const double *par, double tv, vec tg) { return GF_FORM1; }
 __device__ __forceinline__ double gf_form2(double u, vec gu, vec X, vec Normal, const double *fld, vec vfld, const double *par, double tv, vec tg, double t2v, vec t2g) {
   return GF_FORM2;
@@ -234,7 +260,7 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
             const double *__restrict__ dvals1, int nfields, int nd_d, int fqdim,
             const double *__restrict__ par, int ng, int nq, int nd,
             long long e0, long long ne, double alpha, double *__restrict__ stage, unsigned short *__restrict__ emask,
-            double *__restrict__ rstage) {
+            double *__restrict__ rstage, double *__restrict__ epot) {
   constexpr int N = GF_N, NA = GF_N + 1;
   extern __shared__ double sm[];
   double *sG = sm;                       // N x ng
@@ -243,6 +269,7 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
   double *sC1 = sT + (size_t)nq * nd * NA;   // nq x NA      (w J folded in)
   double *sC2 = sC1 + (size_t)nq * NA;       // nq x NA x NA
   double *sK = sC2 + (size_t)nq * NA * NA;   // nd x nd
+  double *sP0 = sK + (size_t)nd * nd;        // nq: the order-0 integrand (w J folded in)
   __shared__ double sRed[4];
   const int tid = threadIdx.x;
   for (long long el = blockIdx.x; el < ne; el += gridDim.x) {
@@ -333,6 +360,7 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
           if (nfields > 1) fq[1] += dvals1[ddE[i]] * ph;
         }
       }
+      if (epot) sP0[q] = cw == 0.0 ? 0.0 : cw * gf_form0(uq, guq, Xq, Nq, fq, vq, par);
 #pragma unroll
       for (int a = 0; a < NA; ++a) {
         const double tv = a == 0 ? 1.0 : 0.0;
@@ -347,6 +375,11 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
       }
     }
     __syncthreads();
+    if (epot && tid == 0) {  // order 0: the element's share of the potential, Gauss points in order (ga_instruction_scalar_assembly)
+      double s = 0.0;
+      for (int q = 0; q < nq; ++q) s += sP0[q];
+      epot[el] = s;
+    }
     if (rstage)
       for (int i = tid; i < nd; i += blockDim.x) {
         double s = 0.0;
@@ -388,6 +421,7 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
   }
 }
 #else  // ---------------------------------------------------------------- vector variable, qdim = mesh dimension
+__device__ __forceinline__ double gf_form0(vec u, mat gu, vec X, vec Normal, const double *fld, vec vfld, const double *par) { return GF_FORM0; }
 __device__ __forceinline__ double gf_form1(vec u, mat gu, vec X, vec Normal, const double *fld, vec vfld, const double *par, vec tv, mat tg) { return GF_FORM1; }
 __device__ __forceinline__ double gf_form2(vec u, mat gu, vec X, vec Normal, const double *fld, vec vfld, const double *par, vec tv, mat tg, vec t2v, mat t2g) { return GF_FORM2; }
 
@@ -407,7 +441,7 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
             const double *__restrict__ dvals1, int nfields, int nd_d, int fqdim,
             const double *__restrict__ par, int ng, int nq, int nd,
             long long e0, long long ne, double alpha, double *__restrict__ stage, unsigned short *__restrict__ emask,
-            double *__restrict__ rstage) {
+            double *__restrict__ rstage, double *__restrict__ epot) {
   constexpr int N = GF_N, NA = GF_N + 1, Q = GF_N, NS = Q * NA;
   extern __shared__ double sm[];
   const int s1 = nd * Q;
@@ -419,6 +453,7 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
   double *sC1 = sS + (size_t)nq * SS;            // nq x NS
   double *sC2 = sC1 + (size_t)nq * NS;           // nq x NS x NS
   double *sK = sC2 + (size_t)nq * NS * NS;       // s1 x s1
+  double *sP0 = sK + (size_t)s1 * s1;            // nq: the order-0 integrand (w J folded in)
   __shared__ double sRed[4];
   const int tid = threadIdx.x;
   for (long long el = blockIdx.x; el < ne; el += gridDim.x) {
@@ -517,6 +552,7 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
       for (int k = 0; k < N; ++k) vq.v[k] = S[Q + Q * N + 3 + 2 * N + k];
       for (int c = 0; c < Q; ++c) { uq.v[c] = S[c]; for (int k = 0; k < N; ++k) guq.m[c][k] = S[Q + c * N + k]; }
       vec tv, t2v; mat tg, t2g;
+      if (epot && s == 0) sP0[q] = cw == 0.0 ? 0.0 : cw * gf_form0(uq, guq, Xq, Nq, fq, vq, par);
       gf_probe(s, tv, tg);
       sC1[q * NS + s] = cw == 0.0 ? 0.0 : cw * gf_form1(uq, guq, Xq, Nq, fq, vq, par, tv, tg);
       for (int s2 = 0; s2 < NS; ++s2) {
@@ -525,6 +561,11 @@ gf_jit_elem(const double *__restrict__ x, const double *__restrict__ y, const do
       }
     }
     __syncthreads();
+    if (epot && tid == 0) {
+      double p0 = 0.0;
+      for (int q = 0; q < nq; ++q) p0 += sP0[q];
+      epot[el] = p0;
+    }
     if (rstage)
       for (int k = tid; k < s1; k += blockDim.x) {
         const int i = k / Q, c = k % Q;
@@ -597,7 +638,8 @@ void jit_release(gfgpu_term *t) {
 static JitKernel *jit_compile(gfgpu_term *t) {
   JitApi &api = jit_api();
   const int N = t->mesh->dim;
-  std::string src = "#define GF_N " + std::to_string(N) + "\n#define GF_Q " + std::to_string(t->fem->qdim) + "\n#define GF_FORM1 (" +
+  std::string src = "#define GF_N " + std::to_string(N) + "\n#define GF_Q " + std::to_string(t->fem->qdim) + "\n#define GF_FORM0 (" +
+                    (t->jit_form0.empty() ? std::string("0.0") : t->jit_form0) + ")\n#define GF_FORM1 (" +
                     t->jit_form1 + ")\n#define GF_FORM2 (" + t->jit_form2 + ")\n" + kJitSource;
   nvrtcProgram_t prog = nullptr;
   GF_REQUIRE(api.CreateProgram(&prog, src.c_str(), "gfgpu_jit.cu", 0, nullptr, nullptr) == 0, "nvrtcCreateProgram failed");
@@ -629,7 +671,7 @@ static JitKernel *jit_compile(gfgpu_term *t) {
 // compile-only check (no GPU needed): used by the CPU tests and by gfgpu_term_create_jit to fail early
 std::string jit_check_source(int N, int Q, const std::string &form1, const std::string &form2) {
   JitApi &api = jit_api(false);
-  std::string src = "#define GF_N " + std::to_string(N) + "\n#define GF_Q " + std::to_string(Q) + "\n#define GF_FORM1 (" + form1 +
+  std::string src = "#define GF_N " + std::to_string(N) + "\n#define GF_Q " + std::to_string(Q) + "\n#define GF_FORM0 (0.0)\n#define GF_FORM1 (" + form1 +
                     ")\n#define GF_FORM2 (" + form2 + ")\n" + kJitSource;
   nvrtcProgram_t prog = nullptr;
   if (api.CreateProgram(&prog, src.c_str(), "gfgpu_jit.cu", 0, nullptr, nullptr) != 0) return "nvrtcCreateProgram failed";
@@ -652,9 +694,9 @@ void launch_jit_kernel(gfgpu_term *t, const ElemArgs &a) {
   const int Q = t->fem->qdim;
   GF_REQUIRE(Q == 1 || Q == N, "JIT terms: scalar variables, or vector variables of the mesh dimension");
   const size_t NS = (size_t)Q * NA, s1 = (size_t)nd * Q;
-  const size_t smem = Q == 1 ? ((size_t)N * ng + nd + (size_t)nq * nd * NA + (size_t)nq * NA + (size_t)nq * NA * NA + (size_t)nd * nd + 2) * 8
+  const size_t smem = Q == 1 ? ((size_t)N * ng + nd + (size_t)nq * nd * NA + (size_t)nq * NA + (size_t)nq * NA * NA + (size_t)nd * nd + nq + 2) * 8
                              : ((size_t)N * ng + s1 + (size_t)nq * nd * NA + (size_t)nq * (Q + Q * N + 1 + 3 * N + 2) + (size_t)nq * NS +
-                                (size_t)nq * NS * NS + s1 * s1 + 2) * 8;
+                                (size_t)nq * NS * NS + s1 * s1 + nq + 2) * 8;
   GF_REQUIRE(smem <= 220 * 1024, "JIT terms: element too large for the run-time kernel (nq x nd x (N+1) doubles of shared memory)");
   if (t->jit_par.n != (size_t)GFGPU_MAX_PARAMS) {
     t->jit_par.alloc(ctx, GFGPU_MAX_PARAMS);
@@ -705,7 +747,8 @@ void launch_jit_kernel(gfgpu_term *t, const ElemArgs &a) {
   const int32_t *conn = a.conn, *edof = a.edof;
   double *stage = a.stage, *rstage = a.rstage;
   uint16_t *emask = a.emask;
-  void *params[] = {&x, &y, &z, &conn, &edof, &U, &w, &gt, &phi, &gphi, &gtv, &face, &fnormal, &dedof, &dphi, &dv0, &dv1, &nfields, &nd_d, &fqdim, &par, &ing, &inq, &ind, &e0, &ne, &alpha, &stage, &emask, &rstage};
+  double *epot = t->jit_epot;
+  void *params[] = {&x, &y, &z, &conn, &edof, &U, &w, &gt, &phi, &gphi, &gtv, &face, &fnormal, &dedof, &dphi, &dv0, &dv1, &nfields, &nd_d, &fqdim, &par, &ing, &inq, &ind, &e0, &ne, &alpha, &stage, &emask, &rstage, &epot};
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ne, (long long)ctx->sm_count * 4));
   const int r = api.LaunchKernel(k->fn, grid, 1, 1, 128, 1, 1, (unsigned)smem, ctx->stream, params, nullptr);
   GF_REQUIRE(r == 0, "cuLaunchKernel failed for the JIT kernel (error " + std::to_string(r) + ")");

@@ -131,7 +131,20 @@ void term_assemble_for_potential(gfgpu_term *t, const double *U_dev);  // api.cu
 double term_potential(gfgpu_term *t, const double *U_dev) {
   gfgpu_ctx *ctx = t->ctx;
   const int fam = t->family;
-  GF_REQUIRE(fam != GFGPU_JIT, "JIT terms carry no order-0 form: the potential is not available");
+  if (fam == GFGPU_JIT) {
+    // run-time compiled term: the order-0 integrand is evaluated by the same kernel, next to the element residuals; the
+    // elements' shares are summed in one reduction (ga_instruction_scalar_assembly, C&E.cc:4628-4640)
+    GF_REQUIRE(!t->jit_form0.empty(), "this JIT term carries no order-0 form (gfgpu_term_set_jit_potential)");
+    const int64_t ne = t->e1 - t->e0;
+    if (ne <= 0) return 0.0;
+    DevBuf<double> out;
+    out.alloc(ctx, ne);
+    out.zero();
+    t->jit_epot = out.p;
+    try { term_assemble_for_potential(t, U_dev); } catch (...) { t->jit_epot = nullptr; throw; }
+    t->jit_epot = nullptr;
+    return device_sum(ctx, out.p, ne);
+  }
   const bool hyper = fam == GFGPU_SVK || fam == GFGPU_NEOHOOKEAN_CIARLET || fam == GFGPU_NEOHOOKEAN_BONET || fam >= GFGPU_MOONEY_RIVLIN;
   if (!hyper) {
     GF_REQUIRE(U_dev, "the potential of a linear or quadratic form needs the state vector");

@@ -492,19 +492,20 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
   // nonlinear operators of ONE square-matrix argument (getfem_generic_assembly_functions_and_operators.cc, the large-strain
   // helpers of getfem_nonlinear_elasticity.cc:1930-2040): value, and first derivative contracted with a direction H --
   // "Derivative_1_Op(A):H", the only way the reference's symbolic differentiation uses them in an order-2 tree
-  struct mat_operator { const char *name, *value; int rank; const char *deriv; };
+  struct mat_operator { const char *name, *value; int rank; const char *deriv, *deriv2; };
   static const mat_operator mat_ops[] = {
-      {"Det", "det", 0, "ddet"},                                  // d det[H] = det(A) tr(A^-1 H)
-      {"Inv", "inv", 2, "dinv"},                                  // d inv[H] = -A^-1 H A^-1
-      {"Right_Cauchy_Green", "rcg", 2, "drcg"},                   // F'F ; H'F + F'H
-      {"Left_Cauchy_Green", "lcg", 2, "dlcg"},                    // FF' ; HF' + FH'
-      {"Green_Lagrangian", "glag", 2, "dglag"},                   // (F'F - I)/2 ; (H'F + F'H)/2
-      {"Matrix_i2", "mat_i2", 0, "dmat_i2"},                      // ((tr A)^2 - tr(A^2))/2 ; tr A tr H - tr(A H)
+      {"Det", "det", 0, "ddet", "d2det"},                         // d det[H] = det(A) tr(A^-1 H)
+      {"Inv", "inv", 2, "dinv", "d2inv"},                         // d inv[H] = -A^-1 H A^-1
+      {"Right_Cauchy_Green", "rcg", 2, "drcg", "d2rcg"},          // F'F ; H'F + F'H
+      {"Left_Cauchy_Green", "lcg", 2, "dlcg", "d2lcg"},           // FF' ; HF' + FH'
+      {"Green_Lagrangian", "glag", 2, "dglag", "d2glag"},         // (F'F - I)/2 ; (H'F + F'H)/2
+      {"Matrix_i2", "mat_i2", 0, "dmat_i2", "d2mat_i2"},          // ((tr A)^2 - tr(A^2))/2 ; tr A tr H - tr(A H)
   };
-  auto mat_op_args = [&](const pga_tree_node &pn, size_type der1, const mat_operator *&op, std::string &args) {
+  // der = 0: the value; 1: Derivative_1_Op; 2: Derivative_1_1_Op (an order-2 tree derived from a potential)
+  auto mat_op_args = [&](const pga_tree_node &pn, size_type der, const mat_operator *&op, std::string &args) {
     if (pn->node_type != GA_NODE_PARAMS || pn->children.size() != 2) return false;
     const pga_tree_node &f = pn->children[0];
-    if (f->node_type != GA_NODE_OPERATOR || f->der1 != der1 || f->der2 != 0) return false;
+    if (f->node_type != GA_NODE_OPERATOR || f->der1 != (der ? 1 : 0) || f->der2 != (der == 2 ? 1 : 0)) return false;
     op = nullptr;
     for (const mat_operator &o : mat_ops) if (f->name == o.name) op = &o;
     if (!op) return false;
@@ -638,6 +639,15 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
             out = {std::string(mop->deriv) + "(" + sa + "," + b.code + ")", mop->rank};
             return true;
           }
+          // "(Derivative_1_1_Op(A):H2):H1": the second derivative in two directions
+          if (n->children.size() == 2 && n->children[0]->node_type == GA_NODE_OP && n->children[0]->op_type == GA_COLON &&
+              n->children[0]->children.size() == 2 && mat_op_args(n->children[0]->children[0], 2, mop, sa)) {
+            jit_value h2;
+            if (!jit_emit(ws, n->children[0]->children[1], v, N, Q, params, fields, h2) || h2.rank != 2) return false;
+            if (!child(1, b) || b.rank != 2) return false;
+            out = {std::string(mop->deriv2) + "(" + sa + "," + h2.code + "," + b.code + ")", mop->rank};
+            return true;
+          }
         }
           if (!child(0, a) || !child(1, b) || a.rank != b.rank) return false;
           out = {"ddot(" + a.code + "," + b.code + ")", 0};
@@ -665,7 +675,15 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
             {"DER_PDFUNC_ASINH", "DER_PDFUNC_ASINH"}, {"DER_PDFUNC_ACOSH", "DER_PDFUNC_ACOSH"}, {"DER_PDFUNC_ATANH", "DER_PDFUNC_ATANH"},
             {"DER_PDFUNC_COS", "DER_PDFUNC_COS"}, {"DER_PDFUNC_TAN", "DER_PDFUNC_TAN"}, {"DER_PDFUNC_ASIN", "DER_PDFUNC_ASIN"},
             {"DER_PDFUNC_ACOS", "DER_PDFUNC_ACOS"}, {"DER_PDFUNC_ATAN", "DER_PDFUNC_ATAN"}, {"DER_PDFUNC1_ATAN2", "DER_PDFUNC1_ATAN2"},
-            {"DER_PDFUNC2_ATAN2", "DER_PDFUNC2_ATAN2"}, {"DER_PDFUNC_ERF", "DER_PDFUNC_ERF"}, {"DER_PDFUNC_ERFC", "DER_PDFUNC_ERFC"}};
+            {"DER_PDFUNC2_ATAN2", "DER_PDFUNC2_ATAN2"}, {"DER_PDFUNC_ERF", "DER_PDFUNC_ERF"}, {"DER_PDFUNC_ERFC", "DER_PDFUNC_ERFC"},
+            {"DER_PDFUNC_NEG_PART", "DER_PDFUNC_NEG_PART"},
+            // second derivatives (the derivative of a derivative the reference defines by an expression)
+            {"DER_PDFUNC_DER_PDFUNC_SQRT", "DER_PDFUNC_DER_PDFUNC_SQRT"}, {"DER_PDFUNC_DER_PDFUNC_LOG", "DER_PDFUNC_DER_PDFUNC_LOG"},
+            {"DER_PDFUNC_DER_PDFUNC_LOG10", "DER_PDFUNC_DER_PDFUNC_LOG10"}, {"DER_PDFUNC_DER_PDFUNC_TANH", "DER_PDFUNC_DER_PDFUNC_TANH"},
+            {"DER_PDFUNC_DER_PDFUNC_ASINH", "DER_PDFUNC_DER_PDFUNC_ASINH"}, {"DER_PDFUNC_DER_PDFUNC_ACOSH", "DER_PDFUNC_DER_PDFUNC_ACOSH"},
+            {"DER_PDFUNC_DER_PDFUNC_ATANH", "DER_PDFUNC_DER_PDFUNC_ATANH"}, {"DER_PDFUNC_DER_PDFUNC_COS", "DER_PDFUNC_DER_PDFUNC_COS"},
+            {"DER_PDFUNC_DER_PDFUNC_TAN", "DER_PDFUNC_DER_PDFUNC_TAN"}, {"DER_PDFUNC_DER_PDFUNC_ASIN", "DER_PDFUNC_DER_PDFUNC_ASIN"},
+            {"DER_PDFUNC_DER_PDFUNC_ACOS", "DER_PDFUNC_DER_PDFUNC_ACOS"}, {"DER_PDFUNC_DER_PDFUNC_ATAN", "DER_PDFUNC_DER_PDFUNC_ATAN"}};
         auto it = fn.find(f->name);
         if (it == fn.end() || n->children.size() < 2 || n->children.size() > 3) return false;
         std::string code = it->second + "(";
@@ -732,9 +750,20 @@ static bool recognise_jit(const getfem::ga_workspace &ws, size_type i1, recognis
       return false;  // coupled to another variable: not this route
     }
   }
+  // the order-0 tree the two were derived from (add_expression of a potential): same integration method and region; it must
+  // translate too, without test functions -- then assembly(0) runs on the device as well
+  jit_value f0{"", 0};
+  for (size_type j = 0; j < ws.nb_trees(); ++j) {
+    const auto &t0 = ws.tree_info(j);
+    if (t0.order != 0 || t0.mim != td.mim || t0.rg != td.rg || t0.operation != getfem::ga_workspace::ASSEMBLY) continue;
+    jit_value g;
+    if (!f0.code.empty() || !t0.ptree || !jit_emit(ws, t0.ptree->root, v, N, Q, params, fields, g) || g.rank != 0) { f0.code.clear(); break; }
+    f0 = g;
+  }
   out = recognised_term();
   out.family = GFGPU_JIT;
   out.varname = v;
+  out.jit_form0 = f0.code;
   out.jit_form1 = f1.code;
   out.jit_form2 = f2.code;
   out.jit_params = params;
@@ -1372,8 +1401,16 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     if (order == 0) {  // only the order-0 trees contribute to assembled_potential() (workspace.cc:791-803)
       if (td.order != 0) continue;
       recognised_term rt;
-      GMM_ASSERT1(recognise_potential(ws, i, recognise_memo, rt),
-                  "gfgpu: potential not handled by the device path (no CPU fallback): " << getfem::ga_tree_to_string(*td.ptree));
+      bool ok0 = recognise_potential(ws, i, recognise_memo, rt);
+      if (!ok0) {  // the NVRTC route: the order-1 tree derived from this potential is a run-time compiled term that carries it
+        for (size_type j = 0; j < ws.nb_trees() && !ok0; ++j) {
+          const auto &t1 = ws.tree_info(j);
+          std::vector<recognised_term> r1;
+          if (t1.order != 1 || t1.mim != td.mim || t1.rg != td.rg || !recognise_memo(j, r1)) continue;
+          if (r1.size() == 1 && r1[0].family == GFGPU_JIT && !r1[0].jit_form0.empty()) { rt = r1[0]; ok0 = true; }
+        }
+      }
+      GMM_ASSERT1(ok0, "gfgpu: potential not handled by the device path (no CPU fallback): " << getfem::ga_tree_to_string(*td.ptree));
       terms.emplace_back(i, rt);
       continue;
     }
@@ -1691,7 +1728,7 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
     {  // parameters bit for bit (a load that changes by 1e-9 is another term), and the family's own scale stays 1:
        // factor_of_variable enters at gfgpu_matrix_add_term for order 2 only, like the reference (C&E.cc:5359-5418 vs 4669-4735)
       char hb[40];
-      if (rt.family == GFGPU_JIT) key << "/jit:" << rt.jit_form1 << "|" << rt.jit_form2;  // parameters are refreshed at every call
+      if (rt.family == GFGPU_JIT) key << "/jit:" << rt.jit_form0 << "|" << rt.jit_form1 << "|" << rt.jit_form2;  // parameters are refreshed at every call
       else for (double p : rt.params) { std::snprintf(hb, sizeof hb, "/%a", p); key << hb; }
     }
     for (const std::string &fn : rt.field_names)
@@ -1805,6 +1842,7 @@ void device_assembler::assembly(getfem::ga_workspace &ws, size_type order) {
         const bool vdep = rt.jit_form2.find("u") != std::string::npos;  // "u" or "gu" in the tangent: its pattern may move
         GFGPU_CALL(gfgpu_term_create_jit(ctx_, e.mesh, e.fem, e.tab, rt.jit_form1.c_str(), rt.jit_form2.c_str(), rt.params.data(),
                                          int(rt.params.size()), 1.0, vdep ? 1 : 0, &e.term));
+        if (!rt.jit_form0.empty()) GFGPU_CALL(gfgpu_term_set_jit_potential(e.term, rt.jit_form0.c_str()));
       } else {
         GFGPU_CALL(gfgpu_term_create(ctx_, e.mesh, e.fem, e.tab, rt.family, rt.params.data(), int(rt.params.size()), 1.0,
                                      GFGPU_STRATEGY_AUTO, &e.term));

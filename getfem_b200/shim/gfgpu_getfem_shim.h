@@ -39,6 +39,7 @@ struct recognised_term {
   // JIT terms (family GFGPU_JIT, the NVRTC route): the order-1 / order-2 trees translated into C expressions
   // (include/gfgpu.h, gfgpu_term_create_jit) and the names of the scalar constants behind par[k]
   std::string jit_form1, jit_form2;
+  std::string jit_form0;  // the order-0 tree on the same (integration method, region), when there is one and it translates
   std::vector<std::string> jit_params;
 };
 // GFGPU_SHIM_COUPLED_MASS: "Test_a:Test2_b" on two variables of the same qdim (asm_mass_matrix(M, mim, mf1, mf2, rg), the

@@ -226,6 +226,9 @@ int gfgpu_term_potential_host(gfgpu_term *t, const double *U_host, double *E_hos
 int gfgpu_term_create_jit(gfgpu_ctx *ctx, gfgpu_mesh *mesh, gfgpu_fem *fem, gfgpu_tables *tab, const char *form1, const char *form2,
                           const double *params, int nparams, double alpha, int value_dependent, gfgpu_term **out);
 int gfgpu_jit_check(int dim, int qdim, const char *form1, const char *form2);
+/* order 0 of a JIT term: the scalar integrand of the potential in the same identifiers, without test functions
+ * (ga_workspace::assembly(0), workspace.cc:791-803); gfgpu_term_potential_* then returns its integral. */
+int gfgpu_term_set_jit_potential(gfgpu_term *t, const char *form0);
 /* new values of par[] for the next assemblies of a JIT term (constants of the expression may change between calls) */
 int gfgpu_term_set_params(gfgpu_term *t, const double *params, int nparams);
 

@@ -70,8 +70,8 @@ void ga_workspace::assembly(size_type order, bool condensation) {
                    why.c_str());
       for (const auto &rt : rts)  // the translated forms of a run-time compiled term: tests/test_shim_probe.py compiles them (NVRTC, no GPU)
         if (ok && order == 2 && rt.family == GFGPU_JIT && associated_mf(rt.varname))
-          std::fprintf(stderr, "[gfgpu dryrun jit] dim=%d qdim=%d\t%s\t%s\n", int(associated_mf(rt.varname)->linked_mesh().dim()),
-                       int(associated_mf(rt.varname)->get_qdim()), rt.jit_form1.c_str(), rt.jit_form2.c_str());
+          std::fprintf(stderr, "[gfgpu dryrun jit] dim=%d qdim=%d\t%s\t%s\t%s\n", int(associated_mf(rt.varname)->linked_mesh().dim()),
+                       int(associated_mf(rt.varname)->get_qdim()), rt.jit_form1.c_str(), rt.jit_form2.c_str(), rt.jit_form0.c_str());
     }
     getfem_b200::reference_assembly(*this, order, condensation);
     return;

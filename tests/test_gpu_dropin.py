@@ -206,6 +206,14 @@ POTENTIALS = [  # order 0 through the dispatch patch: ws.assembly(0) / assembled
     ("dim=2 n=8 gt=pk k=2 q=1", "a*u*u/2"),
     ("dim=3 n=2 gt=qk k=2 uscale=0.02", "Compressible_Neo_Hookean_Ciarlet_potential(Grad_u,params)"),
     ("dim=3 n=2 gt=pk k=2 uscale=0.02", "Saint_Venant_Kirchhoff_potential(Grad_u,params)"),
+    # potentials that are no registered law: the NVRTC route carries the order-0 integrand next to the two forms the reference
+    # derives from it (second derivatives of Det, log, the Cauchy-Green tensor): a compressible neo-Hookean energy written out
+    ("dim=3 n=2 gt=pk k=2 uscale=0.02",
+     "mu/2*(Trace(Right_Cauchy_Green(Id(3)+Grad_u))-3) - mu*log(Det(Id(3)+Grad_u)) + lambda/2*sqr(log(Det(Id(3)+Grad_u)))"),
+    ("dim=2 n=6 gt=qk k=2 uscale=0.01",
+     "mu/2*(Trace(Right_Cauchy_Green(Id(2)+Grad_u))-2) - mu*log(Det(Id(2)+Grad_u)) + lambda/2*sqr(log(Det(Id(2)+Grad_u)))"),
+    ("dim=3 n=3 gt=pk k=2 q=1", "(1+sqr(u))*Norm_sqr(Grad_u)/2 + cos(u) + a*u"),
+    ("dim=3 n=2 gt=qk k=2 uscale=0.05", "Matrix_i2(Green_Lagrangian(Id(3)+Grad_u)) + sqr(Trace(Green_Lagrangian(Id(3)+Grad_u))) + tanh(u.u)"),
 ]
 
 

@@ -264,6 +264,9 @@ X_EXPRS = [  # the position X (whole vector or one coordinate): x = sum_g G_g N_
     ("dim=2 n=4 gt=qk k=2", "(mu*((Id(2)+Grad_u) - Inv(Id(2)+Grad_u)') + lambda*log(Det(Id(2)+Grad_u))*Inv(Id(2)+Grad_u)'):Grad_Test_u"),
     ("dim=3 n=2 gt=pk k=2", "((Id(3)+Grad_u)*(lambda*Trace(Green_Lagrangian(Id(3)+Grad_u))*Id(3)+2*mu*Green_Lagrangian(Id(3)+Grad_u))):Grad_Test_u"),
     ("dim=3 n=2 gt=pk k=2", "(Matrix_i2(Right_Cauchy_Green(Id(3)+Grad_u))*Left_Cauchy_Green(Id(3)+Grad_u)):Grad_Test_u"),
+    # a POTENTIAL: the reference differentiates it twice; orders 0, 1 and 2 are translated (second derivatives of Det / log, ...)
+    ("dim=3 n=2 gt=pk k=2", "mu/2*(Trace(Right_Cauchy_Green(Id(3)+Grad_u))-3) - mu*log(Det(Id(3)+Grad_u)) + lambda/2*sqr(log(Det(Id(3)+Grad_u)))"),
+    ("dim=2 n=4 gt=pk k=2 q=1", "(1+sqr(u))*Norm_sqr(Grad_u)/2 + cos(u) + a*u"),
     # scalar fem-data coefficients inside a translated tree: fld[k], evaluated on the data fem at every Gauss point
     ("dim=3 n=2 gt=pk k=2 q=1", "c0*sin(u)*Test_u + (1+c0)*Grad_u.Grad_Test_u"),
     ("dim=3 n=2 gt=pk k=2", "c0*(1+Norm_sqr(u))*Grad_u:Grad_Test_u + c0*X.Test_u"),
@@ -292,9 +295,13 @@ def test_the_translated_forms_compile(mesh, expr):
     assert out.returncode == 0, out.stderr[-1500:]
     forms = [l.split("\t") for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun jit]")]
     assert forms, out.stderr[-1500:]
-    for head, f1, f2 in forms:
+    for head, f1, f2, f0 in forms:
         m = re.search(r"dim=(\d) qdim=(\d)", head)
         capi.jit_check(int(m.group(1)), f1, f2, qdim=int(m.group(2)))
+        if f0:  # the order-0 integrand (a scalar without test functions), compiled in the place of the first form
+            capi.jit_check(int(m.group(1)), "(" + f0 + ")*dot(tv,tv)", f2, qdim=int(m.group(2)))
+    if "potential:" in expr or expr.startswith("mu/2*("):
+        assert all(f[3] for f in forms), forms
 
 
 def test_the_nvrtc_route_refuses_what_it_cannot_express():
