@@ -639,6 +639,16 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
             out = {std::string(mop->deriv) + "(" + sa + "," + b.code + ")", mop->rank};
             return true;
           }
+          // "X:(Derivative_1_1_Op(A):Y)" with a SCALAR-valued operator (the chain rule of f(G(F)) puts the second derivative of f
+          // between the two first derivatives of G): D2f[X, Y], symmetric
+          if (n->children.size() == 2 && n->children[1]->node_type == GA_NODE_OP && n->children[1]->op_type == GA_COLON &&
+              n->children[1]->children.size() == 2 && mat_op_args(n->children[1]->children[0], 2, mop, sa) && mop->rank == 0) {
+            jit_value y;
+            if (!jit_emit(ws, n->children[1]->children[1], v, N, Q, params, fields, y) || y.rank != 2) return false;
+            if (!child(0, a) || a.rank != 2) return false;
+            out = {std::string(mop->deriv2) + "(" + sa + "," + a.code + "," + y.code + ")", 0};
+            return true;
+          }
           // "(Derivative_1_1_Op(A):H2):H1": the second derivative in two directions
           if (n->children.size() == 2 && n->children[0]->node_type == GA_NODE_OP && n->children[0]->op_type == GA_COLON &&
               n->children[0]->children.size() == 2 && mat_op_args(n->children[0]->children[0], 2, mop, sa)) {

@@ -267,6 +267,7 @@ X_EXPRS = [  # the position X (whole vector or one coordinate): x = sum_g G_g N_
     # a POTENTIAL: the reference differentiates it twice; orders 0, 1 and 2 are translated (second derivatives of Det / log, ...)
     ("dim=3 n=2 gt=pk k=2", "mu/2*(Trace(Right_Cauchy_Green(Id(3)+Grad_u))-3) - mu*log(Det(Id(3)+Grad_u)) + lambda/2*sqr(log(Det(Id(3)+Grad_u)))"),
     ("dim=2 n=4 gt=pk k=2 q=1", "(1+sqr(u))*Norm_sqr(Grad_u)/2 + cos(u) + a*u"),
+    ("dim=3 n=2 gt=qk k=2", "Matrix_i2(Green_Lagrangian(Id(3)+Grad_u)) + sqr(Trace(Green_Lagrangian(Id(3)+Grad_u))) + tanh(u.u)"),
     # scalar fem-data coefficients inside a translated tree: fld[k], evaluated on the data fem at every Gauss point
     ("dim=3 n=2 gt=pk k=2 q=1", "c0*sin(u)*Test_u + (1+c0)*Grad_u.Grad_Test_u"),
     ("dim=3 n=2 gt=pk k=2", "c0*(1+Norm_sqr(u))*Grad_u:Grad_Test_u + c0*X.Test_u"),
