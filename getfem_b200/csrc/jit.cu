@@ -244,6 +244,29 @@ __device__ __forceinline__ mat svk_dpk2(mat g, double lam, double mu, mat h) {
   return r;
 }
 
+// compressible neo-Hookean laws (Neo_Hookean_hyperelastic_law::sigma / grad_sigma, getfem_nonlinear_elasticity.cc:612-702) on
+// GF_N x GF_N tensors -- in 2D this is the plane-strain wrapper (:906-945: C33 = 1, so det C and the 2 x 2 block of C^-1 are
+// those of the 2 x 2 tensor): S = mu I + k(i3) C^-1, i3 = det C, k = lambda/2 (i3 - 1) - mu (Ciarlet), lambda/2 log(i3) - mu
+// (Bonet); + 1e200 C where det F <= 0 (the reference's penalty on inverted elements)
+__device__ __forceinline__ mat nh_pk2(mat g, double lam, double mu, int bonet) {
+  mat f = g;
+  for (int i = 0; i < GF_N; ++i) f.m[i][i] += 1.0;
+  const mat c = transp(f) * f, ci = inv(c);
+  const double i3 = det(c), k = bonet ? 0.5 * lam * log(i3) - mu : 0.5 * lam * (i3 - 1.0) - mu;
+  mat r = k * ci;
+  for (int i = 0; i < GF_N; ++i) r.m[i][i] += mu;
+  if (det(f) <= 0.0) r = r + 1e200 * c;
+  return r;
+}
+__device__ __forceinline__ mat nh_dpk2(mat g, double lam, double mu, int bonet, mat h) {
+  mat f = g;
+  for (int i = 0; i < GF_N; ++i) f.m[i][i] += 1.0;
+  const mat c = transp(f) * f, ci = inv(c), dc = transp(h) * f + transp(f) * h;
+  const double i3 = det(c), k = bonet ? 0.5 * lam * log(i3) - mu : 0.5 * lam * (i3 - 1.0) - mu;
+  const double di3 = i3 * trace(ci * dc), dk = bonet ? 0.5 * lam * di3 / i3 : 0.5 * lam * di3;
+  return dk * ci - k * (ci * dc * ci);
+}
+
 #if GF_Q == 1
 __device__ __forceinline__ double gf_form0(double u, vec gu, vec X, vec Normal, const double *fld, vec vfld, const double *par) { return GF_FORM0; }
 __device__ __forceinline__ double gf_form1(double u, vec gu, vec X, vec Normal, const double *fld, vec vfld, const double *par, double tv, vec tg) { return GF_FORM1; }

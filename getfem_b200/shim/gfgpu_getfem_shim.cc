@@ -464,10 +464,22 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
   // "Saint_Venant_Kirchhoff_PK2(G, params)" (AHL_wrapper_sigma with the SVK law, getfem_nonlinear_elasticity.cc:503-540, 1781-1827:
   // E = (G + G' + G'G)/2, S = lambda tr(E) I + 2 mu E -- the one law the reference defines in ANY dimension, so this is also its
   // 2D finite strain) and its first derivative contracted with a direction H: args = "G,lambda,mu"
-  auto svk_args = [&](const pga_tree_node &pn, size_type der1, std::string &args) {
+  // The same for the compressible neo-Hookean laws (Neo_Hookean_hyperelastic_law, :612-702: S = mu I + k(det C) C^-1,
+  // k = lambda/2 (i3 - 1) - mu (Ciarlet) or lambda/2 log(i3) - mu (Bonet), + 1e200 C where det F <= 0), which the reference
+  // defines on 3 x 3 tensors, and for the PLANE STRAIN wrappers of the three laws (plane_strain_hyperelastic_law, :906-945: the
+  // 2 x 2 strain embedded in a 3 x 3 one with zeros; with C33 = 1 the 2 x 2 block of S is the SAME formula on 2 x 2 tensors).
+  // `fn` receives the device helper: svk_pk2 / nh_pk2 (+ a bonet flag folded into `args`).
+  auto svk_args = [&](const pga_tree_node &pn, size_type der1, std::string &args, std::string *fn = nullptr) {
     if (pn->node_type != GA_NODE_PARAMS || pn->children.size() != 3) return false;
     const pga_tree_node &f = pn->children[0];
-    if (f->node_type != GA_NODE_OPERATOR || f->name != "Saint_Venant_Kirchhoff_PK2" || f->der1 != der1 || f->der2 != 0) return false;
+    if (f->node_type != GA_NODE_OPERATOR || f->der1 != der1 || f->der2 != 0) return false;
+    std::string lawfn, tail;
+    const std::string ps = N == 2 ? "Plane_Strain_" : "";
+    if (f->name == "Saint_Venant_Kirchhoff_PK2" || (N == 2 && f->name == "Plane_Strain_Saint_Venant_Kirchhoff_PK2")) lawfn = "svk";
+    else if (f->name == ps + "Compressible_Neo_Hookean_Ciarlet_PK2") { lawfn = "nh"; tail = ",0"; }
+    else if (f->name == ps + "Compressible_Neo_Hookean_Bonet_PK2") { lawfn = "nh"; tail = ",1"; }
+    else return false;
+    if (fn) *fn = lawfn;
     jit_value g;
     if (!jit_emit(ws, pn->children[1], v, N, Q, params, fields, g) || g.rank != 2) return false;
     const pga_tree_node &pp = pn->children[2];
@@ -486,7 +498,7 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
         *dst[c] = "par[" + std::to_string(k) + "]";
       }
     } else return false;
-    args = g.code + "," + lam + "," + mu;
+    args = g.code + "," + lam + "," + mu + tail;
     return true;
   };
   // nonlinear operators of ONE square-matrix argument (getfem_generic_assembly_functions_and_operators.cc, the large-strain
@@ -628,9 +640,10 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
           return true;
         case GA_COLON: {
           std::string sa;  // Derivative_1_Saint_Venant_Kirchhoff_PK2(G, params):H = the directional derivative dS[H]
-          if (n->children.size() == 2 && svk_args(n->children[0], 1, sa)) {
+          std::string lawfn;
+          if (n->children.size() == 2 && svk_args(n->children[0], 1, sa, &lawfn)) {
             if (!child(1, b) || b.rank != 2) return false;
-            out = {"svk_dpk2(" + sa + "," + b.code + ")", 2};
+            out = {lawfn + "_dpk2(" + sa + "," + b.code + ")", 2};
             return true;
           }
           const mat_operator *mop = nullptr;
@@ -707,7 +720,8 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
       }
       {
         std::string sa;
-        if (svk_args(n, 0, sa)) { out = {"svk_pk2(" + sa + ")", 2}; return true; }
+        std::string lawfn;
+        if (svk_args(n, 0, sa, &lawfn)) { out = {lawfn + "_pk2(" + sa + ")", 2}; return true; }
         const mat_operator *mop = nullptr;
         if (mat_op_args(n, 0, mop, sa)) { out = {std::string(mop->value) + "(" + sa + ")", mop->rank}; return true; }
       }

@@ -350,7 +350,7 @@ int main(int argc, char **argv) {
   } else {
     std::vector<double> params{1.3, 0.7};
     md.add_initialized_fixed_size_data("params", params);
-    getfem::add_finite_strain_elasticity_brick(md, mim, "Saint_Venant_Kirchhoff", "u", "params");
+    getfem::add_finite_strain_elasticity_brick(md, mim, gets("law", "Saint_Venant_Kirchhoff"), "u", "params");
   }
   getfem::add_source_term_brick(md, mim, "u", "F");          // volumic load
   getfem::add_source_term_brick(md, mim, "u", "G", 1);       // Neumann load on x = 1
