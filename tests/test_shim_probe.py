@@ -313,3 +313,32 @@ def test_the_nvrtc_route_refuses_what_it_cannot_express():
     for mesh, expr in (("dim=3 n=2 gt=pk k=2", "sqr(Norm(u))*Grad_u:Grad_Test_u"), ("dim=3 n=2 gt=pk k=2", "Expm(Grad_u):Grad_Test_u")):
         line = _dryrun_order1(mesh, expr)
         assert "NOT recognised" in line, line
+
+
+def test_the_trees_of_the_dirichlet_brick_with_multipliers_are_recognised():
+    """CPU (dry run): add_Dirichlet_condition_with_multipliers makes three kinds of workspaces -- the inf-sup filter's
+    asm_mass_matrix inside model::actualize_sizes, the constraint matrix asm_mass_matrix(B, mim, mf_mult, mf_u, region) on the
+    REDUCED multiplier fem, and asm_source_term on it ("A:Test_u"): the coupled tree is the rectangular mass family (shim tag 1001),
+    the load a source term or a run-time compiled term; nothing is left to the "not recognised" path."""
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    for case in ("model=poisson dim=2 n=3 gt=pk k=2 dirichlet=mult", "model=elasticity dim=3 n=2 gt=pk k=2 dirichlet=mult"):
+        out = subprocess.run([BIN] + case.split(), capture_output=True, text=True, timeout=300, env=dict(os.environ, GFGPU_DRYRUN="1"))
+        assert out.returncode == 0, out.stderr[-1500:]
+        lines = [l for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun] order")]
+        coupled = [l for l in lines if "Test_u1:Test2_u2" in l]
+        assert len(coupled) >= 2 and all("recognised family 1001" in l for l in coupled), coupled
+        loads = [l for l in lines if "A:Test_u" in l]
+        assert loads and all("recognised family 6 " in l or "recognised family 11 " in l for l in loads), loads
+        assert not [l for l in lines if "NOT recognised" in l and "order 1 " in l], lines
+
+
+@pytest.mark.parametrize("kind", ["asm_mass_rect", "asm_mass_rect_volume", "asm_mass_rect_partial", "asm_mass_partial_both"])
+def test_mass_matrices_on_two_fems_are_the_rectangular_family(kind):
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN, "model=" + kind, "dim=2", "n=3", "gt=pk", "k=2"], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, GFGPU_DRYRUN="1"))
+    assert out.returncode == 0, out.stderr[-1500:]
+    lines = [l for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun] order 2")]
+    assert lines and all("recognised family 1001" in l for l in lines), lines
