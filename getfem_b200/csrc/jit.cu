@@ -267,6 +267,73 @@ __device__ __forceinline__ mat nh_dpk2(mat g, double lam, double mu, int bonet, 
   return dk * ci - k * (ci * dc * ci);
 }
 
+// Isotropic laws given through the invariants of C = F'F (compute_invariants, getfem_nonlinear_elasticity.cc:45-262):
+//   law 0  compressible Mooney-Rivlin (:503-607)  W = c1 (j1 - 3) + c2 (j2 - 3) + d1 (sqrt(i3) - 1)^2, j1 = i1 i3^(-1/3), j2 = i2 i3^(-2/3)
+//   law 1  Ciarlet-Geymonat (:817-888)            W = a i1 + b i2 + c i3 - d/2 log(i3) + e  (a, b, c, d from lambda, mu, a)
+//   law 2  generalized Blatz-Ko (:706-815)        W = z^n, z = a i1 + b sqrt(i3) + c i2 / i3 + d
+// S = 2 sum_a W_a di_a, dS[H] = 2 sum_a [(sum_b W_ab (di_b : dC)) di_a + W_a d2i_a[dC]], dC = H'F + F'H, with
+// di1 = I, di2 = i1 I - C, di3 = i3 C^-1; d2i2[dC] = tr(dC) I - dC, d2i3[dC] = i3 (tr(C^-1 dC) C^-1 - C^-1 dC C^-1).
+// On 2 x 2 tensors this is the PLANE STRAIN wrapper (plane_strain_hyperelastic_law, :906-945: the strain embedded in a 3 x 3 one
+// with zeros, C33 = 1): i1 and i2 are those of the embedded tensor, i3 and the 2 x 2 blocks of the gradients follow from C itself.
+__device__ __forceinline__ void iso_law_w(int law, double i1, double i2, double i3, const double *p, double *Wa, double *Wab) {
+  // Wab: 11, 12, 13, 22, 23, 33
+  for (int k = 0; k < 6; ++k) Wab[k] = 0.0;
+  if (law == 0) {
+    const double c1 = p[0], c2 = p[1], d1 = p[2], r13 = pow(i3, -1.0 / 3.0), r23 = r13 * r13;
+    Wa[0] = c1 * r13;
+    Wa[1] = c2 * r23;
+    Wa[2] = -c1 * i1 * r13 / (3.0 * i3) - 2.0 * c2 * i2 * r23 / (3.0 * i3) + d1 * (1.0 - 1.0 / sqrt(i3));
+    Wab[2] = -c1 * r13 / (3.0 * i3);
+    Wab[4] = -2.0 * c2 * r23 / (3.0 * i3);
+    Wab[5] = 4.0 * c1 * i1 * r13 / (9.0 * i3 * i3) + 10.0 * c2 * i2 * r23 / (9.0 * i3 * i3) + 0.5 * d1 / (i3 * sqrt(i3));
+  } else if (law == 1) {
+    const double a = p[2], b = 0.5 * p[1] - p[2], c = 0.25 * p[0] - 0.5 * p[1] + p[2], d = 0.5 * p[0] + p[1];
+    Wa[0] = a;
+    Wa[1] = b;
+    Wa[2] = c - 0.5 * d / i3;
+    Wab[5] = 0.5 * d / (i3 * i3);
+  } else {
+    const double a = p[0], b = p[1], c = p[2], d = p[3], n = p[4], s3 = sqrt(i3);
+    const double z = a * i1 + b * s3 + c * i2 / i3 + d;
+    const double za[3] = {a, c / i3, 0.5 * b / s3 - c * i2 / (i3 * i3)};
+    const double zab[6] = {0.0, 0.0, 0.0, 0.0, -c / (i3 * i3), -0.25 * b / (i3 * s3) + 2.0 * c * i2 / (i3 * i3 * i3)};
+    const double w1 = n * pow(z, n - 1.0), w2 = n * (n - 1.0) * pow(z, n - 2.0);
+    for (int k = 0; k < 3; ++k) Wa[k] = w1 * za[k];
+    const int ia[6] = {0, 0, 0, 1, 1, 2}, ib[6] = {0, 1, 2, 1, 2, 2};
+    for (int k = 0; k < 6; ++k) Wab[k] = w2 * za[ia[k]] * za[ib[k]] + w1 * zab[k];
+  }
+}
+__device__ __forceinline__ mat iso_pk2(mat g, int law, double p0, double p1, double p2, double p3, double p4) {
+  const double p[5] = {p0, p1, p2, p3, p4};
+  mat f = g;
+  for (int i = 0; i < GF_N; ++i) f.m[i][i] += 1.0;
+  const mat c = transp(f) * f, ci = inv(c);
+  const double emb = 3.0 - GF_N, i1 = trace(c) + emb, i2 = 0.5 * (i1 * i1 - trace(c * c) - emb), i3 = det(c);
+  double Wa[3], Wab[6];
+  iso_law_w(law, i1, i2, i3, p, Wa, Wab);
+  mat r = (2.0 * Wa[2] * i3) * ci - (2.0 * Wa[1]) * c;
+  for (int i = 0; i < GF_N; ++i) r.m[i][i] += 2.0 * (Wa[0] + Wa[1] * i1);
+  if (det(f) <= 0.0) r = r + 1e200 * c;  // the reference's penalty on inverted elements
+  return r;
+}
+__device__ __forceinline__ mat iso_dpk2(mat g, int law, double p0, double p1, double p2, double p3, double p4, mat h) {
+  const double p[5] = {p0, p1, p2, p3, p4};
+  mat f = g;
+  for (int i = 0; i < GF_N; ++i) f.m[i][i] += 1.0;
+  const mat c = transp(f) * f, ci = inv(c), dc = transp(h) * f + transp(f) * h, cidc = ci * dc;
+  const double emb = 3.0 - GF_N, i1 = trace(c) + emb, i2 = 0.5 * (i1 * i1 - trace(c * c) - emb), i3 = det(c);
+  double Wa[3], Wab[6];
+  iso_law_w(law, i1, i2, i3, p, Wa, Wab);
+  // di_b : dC
+  const double t = trace(dc), q1 = t, q2 = i1 * t - trace(c * dc), q3 = i3 * trace(cidc);
+  const double s1 = Wab[0] * q1 + Wab[1] * q2 + Wab[2] * q3, s2 = Wab[1] * q1 + Wab[3] * q2 + Wab[4] * q3,
+               s3 = Wab[2] * q1 + Wab[4] * q2 + Wab[5] * q3;
+  // sum_a s_a di_a + W_2 d2i2[dC] + W_3 d2i3[dC]
+  mat r = (2.0 * (s3 * i3 + Wa[2] * q3)) * ci - (2.0 * s2) * c - (2.0 * Wa[1]) * dc - (2.0 * Wa[2] * i3) * (cidc * ci);
+  for (int i = 0; i < GF_N; ++i) r.m[i][i] += 2.0 * (s1 + s2 * i1 + Wa[1] * t);
+  return r;
+}
+
 #if GF_Q == 1
 __device__ __forceinline__ double gf_form0(double u, vec gu, vec X, vec Normal, const double *fld, vec vfld, const double *par) { return GF_FORM0; }
 __device__ __forceinline__ double gf_form1(double u, vec gu, vec X, vec Normal, const double *fld, vec vfld, const double *par, double tv, vec tg) { return GF_FORM1; }

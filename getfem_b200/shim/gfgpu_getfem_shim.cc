@@ -473,32 +473,38 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
     if (pn->node_type != GA_NODE_PARAMS || pn->children.size() != 3) return false;
     const pga_tree_node &f = pn->children[0];
     if (f->node_type != GA_NODE_OPERATOR || f->der1 != der1 || f->der2 != 0) return false;
-    std::string lawfn, tail;
+    std::string lawfn, tail, head;
+    size_t np = 2;  // parameters of the law
     const std::string ps = N == 2 ? "Plane_Strain_" : "";
     if (f->name == "Saint_Venant_Kirchhoff_PK2" || (N == 2 && f->name == "Plane_Strain_Saint_Venant_Kirchhoff_PK2")) lawfn = "svk";
     else if (f->name == ps + "Compressible_Neo_Hookean_Ciarlet_PK2") { lawfn = "nh"; tail = ",0"; }
     else if (f->name == ps + "Compressible_Neo_Hookean_Bonet_PK2") { lawfn = "nh"; tail = ",1"; }
+    // the laws given through the invariants of C (iso_pk2 / iso_dpk2: law id first, five parameter slots)
+    else if (f->name == ps + "Compressible_Mooney_Rivlin_PK2") { lawfn = "iso"; head = "0,"; np = 3; }
+    else if (f->name == ps + "Ciarlet_Geymonat_PK2") { lawfn = "iso"; head = "1,"; np = 3; }
+    else if (f->name == ps + "Generalized_Blatz_Ko_PK2") { lawfn = "iso"; head = "2,"; np = 5; }
     else return false;
     if (fn) *fn = lawfn;
     jit_value g;
     if (!jit_emit(ws, pn->children[1], v, N, Q, params, fields, g) || g.rank != 2) return false;
     const pga_tree_node &pp = pn->children[2];
-    std::string lam, mu;
-    if (pp->node_type == GA_NODE_CONSTANT && pp->tensor().size() == 2) {
-      lam = num(pp->tensor()[0]); mu = num(pp->tensor()[1]);
+    std::vector<std::string> pv(np);
+    if (pp->node_type == GA_NODE_CONSTANT && pp->tensor().size() == np) {
+      for (size_t c = 0; c < np; ++c) pv[c] = num(pp->tensor()[c]);
     } else if (pp->node_type == GA_NODE_VAL && ws.variable_exists(pp->name) && ws.is_constant(pp->name) && !ws.associated_mf(pp->name) &&
-               !ws.associated_im_data(pp->name) && ws.value(pp->name).size() == 2) {
-      std::string *dst[2] = {&lam, &mu};
-      for (int c = 0; c < 2; ++c) {  // component c of a fixed-size constant vector: the parameter "name#c"
+               !ws.associated_im_data(pp->name) && ws.value(pp->name).size() == np) {
+      for (size_t c = 0; c < np; ++c) {  // component c of a fixed-size constant vector: the parameter "name#c"
         const std::string key = pp->name + "#" + std::to_string(c);
         size_t k = 0;
         while (k < params.size() && params[k] != key) ++k;
         if (k == params.size()) params.push_back(key);
         if (params.size() > size_t(GFGPU_MAX_PARAMS)) return false;
-        *dst[c] = "par[" + std::to_string(k) + "]";
+        pv[c] = "par[" + std::to_string(k) + "]";
       }
     } else return false;
-    args = g.code + "," + lam + "," + mu + tail;
+    args = g.code + "," + head;
+    for (size_t c = 0; c < (lawfn == "iso" ? 5 : np); ++c) args += (c ? "," : "") + (c < np ? pv[c] : std::string("0.0"));
+    args += tail;
     return true;
   };
   // nonlinear operators of ONE square-matrix argument (getfem_generic_assembly_functions_and_operators.cc, the large-strain

@@ -349,6 +349,10 @@ int main(int argc, char **argv) {
     getfem::add_generic_elliptic_brick(md, mim, "u", "a");
   } else {
     std::vector<double> params{1.3, 0.7};
+    const std::string lawn = gets("law", "Saint_Venant_Kirchhoff");
+    if (lawn == "Compressible_Mooney_Rivlin") params = {0.8, 0.3, 2.0};
+    else if (lawn == "Ciarlet_Geymonat") params = {1.3, 0.7, 0.25};
+    else if (lawn == "Generalized_Blatz_Ko") params = {1.0, 1.0, 1.5, -0.5, 1.5};
     md.add_initialized_fixed_size_data("params", params);
     getfem::add_finite_strain_elasticity_brick(md, mim, gets("law", "Saint_Venant_Kirchhoff"), "u", "params");
   }

@@ -32,10 +32,7 @@ CASES = [
     # only; its trees (operator and Derivative_1_ operator) are translated for the NVRTC route (svk_pk2 / svk_dpk2)
     "model=finite_strain dim=2 n=8 gt=pk k=2",
     "model=finite_strain dim=2 n=6 gt=qk k=2",
-    # ... and the PLANE STRAIN wrappers the brick picks in 2D for the neo-Hookean laws (adapt_law_name,
-    # getfem_nonlinear_elasticity.cc:2271-2298; plane_strain_hyperelastic_law :906-945): nh_pk2 / nh_dpk2 on 2 x 2 tensors
-    "model=finite_strain dim=2 n=8 gt=pk k=2 law=Compressible_Neo_Hookean_Ciarlet",
-    "model=finite_strain dim=2 n=6 gt=qk k=2 law=Compressible_Neo_Hookean_Bonet",
+    # (the plane-strain wrappers of the other laws: tests/test_gpu_zz_law_operators.py)
     # mixed formulation: add_linear_incompressibility (getfem_models.cc:6373-6409) -- coupled trees (Test_u, Test2_p) and
     # (Test_p, Test2_u) go to the device as one rectangular block and its transpose (gfgpu_rect_*)
     "model=incompressible dim=3 n=3 gt=pk k=2",
@@ -336,10 +333,6 @@ JIT_VECTOR = [  # vector variables (qdim = mesh dimension): matrices in the tran
     ("dim=3 n=2 gt=qk k=2 uscale=0.1",
      "((Id(3)+Grad_u)*(lambda*Trace(Green_Lagrangian(Id(3)+Grad_u))*Id(3)+2*mu*Green_Lagrangian(Id(3)+Grad_u))):Grad_Test_u"),
     ("dim=3 n=2 gt=pk k=2 uscale=0.1", "(Matrix_i2(Right_Cauchy_Green(Id(3)+Grad_u))*Left_Cauchy_Green(Id(3)+Grad_u)):Grad_Test_u"),
-    # the 3D neo-Hookean operators inside a compound form (alone they are closed-form families): the translated nh_pk2 / nh_dpk2
-    # against the reference's AHL wrapper
-    ("dim=3 n=2 gt=pk k=2 uscale=0.02", "((Id(3)+Grad_u)*Compressible_Neo_Hookean_Ciarlet_PK2(Grad_u,params)):Grad_Test_u + a*u.Test_u"),
-    ("dim=3 n=2 gt=qk k=2 uscale=0.02", "((Id(3)+Grad_u)*Compressible_Neo_Hookean_Bonet_PK2(Grad_u,[1.3;0.7])):Grad_Test_u + a*u.Test_u"),
     # a load summed into the tree of a linear form: one run-time compiled term (the probe alone must not take it for K u)
     ("dim=3 n=2 gt=pk k=2", "lambda*Trace(Grad_u)*Trace(Grad_Test_u) + mu*(Grad_u'+Grad_u):Grad_Test_u + [1;2;3].Test_u"),
 ]

@@ -69,6 +69,10 @@ void t_law(int law, const double *g, double lam, double mu, const double *h, dou
   if (law == 0) { st(svk_pk2(ld(g), lam, mu), S); st(svk_dpk2(ld(g), lam, mu, ld(h)), dS); }
   else { st(nh_pk2(ld(g), lam, mu, law - 1), S); st(nh_dpk2(ld(g), lam, mu, law - 1, ld(h)), dS); }
 }
+void t_iso(int law, const double *g, const double *p, const double *h, double *S, double *dS) {
+  st(iso_pk2(ld(g), law, p[0], p[1], p[2], p[3], p[4]), S);
+  st(iso_dpk2(ld(g), law, p[0], p[1], p[2], p[3], p[4], ld(h)), dS);
+}
 void t_ops(const double *a, const double *h, const double *k, double *sc, double *m) {
   // scalars: det, ddet, d2det, mat_i2, dmat_i2, d2mat_i2 ; matrices: inv, dinv, d2inv, rcg, drcg, d2rcg, lcg, dlcg, d2lcg, glag, dglag, d2glag
   const mat A = ld(a), H = ld(h), K = ld(k);
@@ -128,6 +132,18 @@ def test_device_helper_text_on_the_host(n, tmp_path):
             dr = np.einsum("ijkl,kl->ij", dSr, h3)
             assert np.abs(S - Sr[:n, :n]).max() <= 1e-13 * np.abs(Sr).max(), fam
             assert np.abs(dS - dr[:n, :n]).max() <= 1e-13 * np.abs(dr).max(), fam
+        # the invariant-based laws (compressible Mooney-Rivlin, Ciarlet-Geymonat, generalized Blatz-Ko) and their plane-strain wrappers
+        L.t_iso.argtypes = [C.c_int] + [C.c_void_p] * 5
+        for law, (fam, par) in enumerate((("mooney_rivlin", [0.8, 0.3, 2.0]), ("ciarlet_geymonat", [1.3, 0.7, 0.25]),
+                                          ("blatz_ko", [1.0, 1.0, 1.5, -0.5, 1.5]))):
+            p5 = np.zeros(5)
+            p5[:len(par)] = par
+            S, dS = np.zeros((n, n)), np.zeros((n, n))
+            L.t_iso(law, P(g), P(p5), P(h), P(S), P(dS))
+            Sr, dSr = oracle.hyper_law(fam, g3, par)
+            dr = np.einsum("ijkl,kl->ij", dSr, h3)
+            assert np.abs(S - Sr[:n, :n]).max() <= 1e-12 * np.abs(Sr).max(), (fam, n)
+            assert np.abs(dS - dr[:n, :n]).max() <= 1e-12 * np.abs(dr).max(), (fam, n)
         # the matrix operators: values against numpy, derivatives against central differences of the values
         a = np.ascontiguousarray(np.eye(n) + g)
         sc, m = np.zeros(6), np.zeros((12, n, n))

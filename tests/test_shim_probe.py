@@ -260,6 +260,9 @@ X_EXPRS = [  # the position X (whole vector or one coordinate): x = sum_g G_g N_
     ("dim=3 n=2 gt=pk k=2", "((Id(3)+Grad_u)*Saint_Venant_Kirchhoff_PK2(Grad_u,[1.3;0.7])):Grad_Test_u + a*u.Test_u"),
     ("dim=2 n=4 gt=pk k=2", "((Id(2)+Grad_u)*Plane_Strain_Compressible_Neo_Hookean_Ciarlet_PK2(Grad_u,params)):Grad_Test_u"),
     ("dim=3 n=2 gt=pk k=2", "((Id(3)+Grad_u)*Compressible_Neo_Hookean_Bonet_PK2(Grad_u,params)):Grad_Test_u + a*u.Test_u"),
+    ("dim=2 n=4 gt=qk k=2", "((Id(2)+Grad_u)*Plane_Strain_Compressible_Mooney_Rivlin_PK2(Grad_u,[0.8;0.3;2.0])):Grad_Test_u"),
+    ("dim=3 n=2 gt=pk k=2", "((Id(3)+Grad_u)*Ciarlet_Geymonat_PK2(Grad_u,[1.3;0.7;0.25])):Grad_Test_u + a*u.Test_u"),
+    ("dim=2 n=4 gt=pk k=2", "((Id(2)+Grad_u)*Plane_Strain_Generalized_Blatz_Ko_PK2(Grad_u,[1.0;1.0;1.5;-0.5;1.5])):Grad_Test_u"),
     # nonlinear matrix operators and their derivatives: a compressible neo-Hookean law WRITTEN OUT with Det / Inv, the
     # large-strain helpers
     ("dim=3 n=2 gt=pk k=2", "(mu*((Id(3)+Grad_u) - Inv(Id(3)+Grad_u)') + lambda*log(Det(Id(3)+Grad_u))*Inv(Id(3)+Grad_u)'):Grad_Test_u"),
