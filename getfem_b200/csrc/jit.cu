@@ -141,6 +141,10 @@ __device__ __forceinline__ double DER_PDFUNC_DER_PDFUNC_ASIN(double t) { return 
 __device__ __forceinline__ double DER_PDFUNC_DER_PDFUNC_ACOS(double t) { return -t / pow(1.0 - t * t, 1.5); }
 __device__ __forceinline__ double DER_PDFUNC_DER_PDFUNC_ATAN(double t) { return -2.0 * t / ((1.0 + t * t) * (1.0 + t * t)); }
 __device__ __forceinline__ double DER_PDFUNC_NEG_PART(double t) { return -Heaviside(-t); }
+__device__ __forceinline__ double DER_PDFUNC1_DER_PDFUNC1_POW(double t, double e) { return e * (e - 1.0) * pow(t, e - 2.0); }
+__device__ __forceinline__ double DER_PDFUNC2_DER_PDFUNC1_POW(double t, double e) { return pow(t, e - 1.0) * (e * log(t) + 1.0); }
+__device__ __forceinline__ double DER_PDFUNC1_DER_PDFUNC2_POW(double t, double e) { return pow(t, e - 1.0) * (e * log(t) + 1.0); }
+__device__ __forceinline__ double DER_PDFUNC2_DER_PDFUNC2_POW(double t, double e) { const double l = log(t); return pow(t, e) * l * l; }
 __device__ __forceinline__ double sign(double x) { return x < 0 ? -1.0 : (x > 0 ? 1.0 : 0.0); }
 
 // matrices of the mesh dimension: m[c][k] (for Grad_u: component c, direction k, the GWFL convention)
@@ -181,6 +185,19 @@ __device__ __forceinline__ mat mkmat(double a0, double a1, double a2, double a3,
   mat r;
   for (int j = 0; j < GF_N; ++j) for (int i = 0; i < GF_N; ++i) r.m[i][j] = a[i + GF_N * j];
   return r;
+}
+
+// Norm (norm_operator, getfem_generic_assembly_functions_and_operators.cc:181-218): derivative x/|x| (0 at x = 0), second
+// derivative (|x|^2 Id - x (x) x)/|x|^3 in two directions (the reference clamps |x| at 1e-25 in the 1/|x| term only)
+__device__ __forceinline__ vec dnorm(vec x) { const double n = gnorm(x); return n == 0.0 ? 0.0 * x : x / n; }
+__device__ __forceinline__ mat dnorm(mat x) { const double n = gnorm(x); return n == 0.0 ? 0.0 * x : x / n; }
+__device__ __forceinline__ double d2norm(vec x, vec h, vec k) {
+  const double n = gnorm(x), n3 = n * n * n;
+  return ddot(h, k) / (n < 1e-25 ? 1e-25 : n) - ddot(x, h) * ddot(x, k) / n3;
+}
+__device__ __forceinline__ double d2norm(mat x, mat h, mat k) {
+  const double n = gnorm(x), n3 = n * n * n;
+  return ddot(h, k) / (n < 1e-25 ? 1e-25 : n) - ddot(x, h) * ddot(x, k) / n3;
 }
 
 // nonlinear operators of one square matrix and their first derivatives in a direction h (the reference's Det, Inv,

@@ -532,6 +532,18 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
     args = g.code;
     return true;
   };
+  // "(Derivative_1_1_Norm(x) op H2) op H1" with op = "." (vector x) or ":" (matrix x): the second derivative of the norm in two
+  // directions; fills x and H2 when node `nd` has that shape
+  auto norm_second = [&](const pga_tree_node &nd, int op, jit_value &x, jit_value &h2) {
+    if (nd->children.size() != 2) return false;
+    const pga_tree_node &l = nd->children[0];
+    if (l->node_type != GA_NODE_OP || int(l->op_type) != op || l->children.size() != 2) return false;
+    const pga_tree_node &pn = l->children[0];
+    if (pn->node_type != GA_NODE_PARAMS || pn->children.size() != 2) return false;
+    const pga_tree_node &f = pn->children[0];
+    if (f->node_type != GA_NODE_OPERATOR || f->name != "Norm" || f->der1 != 1 || f->der2 != 1) return false;
+    return jit_emit(ws, pn->children[1], v, N, Q, params, fields, x) && jit_emit(ws, l->children[1], v, N, Q, params, fields, h2);
+  };
   switch (n->node_type) {
     case GA_NODE_ZERO: {
       if (n->test_function_type != 0 && n->test_function_type != size_type(-1)) return false;
@@ -641,10 +653,26 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
           out = {"(" + a.code + "/" + b.code + ")", a.rank};
           return true;
         case GA_DOT:  // contraction of the last index of a with the first of b
+          {
+            jit_value x, h2;
+            if (norm_second(n, GA_DOT, x, h2)) {
+              if (!child(1, b) || b.rank != 1 || x.rank != 1 || h2.rank != 1) return false;
+              out = {"d2norm(" + x.code + "," + h2.code + "," + b.code + ")", 0};
+              return true;
+            }
+          }
           if (!child(0, a) || !child(1, b)) return false;
           out = {"dot(" + a.code + "," + b.code + ")", (a.rank && b.rank) ? a.rank + b.rank - 2 : a.rank + b.rank};
           return true;
         case GA_COLON: {
+          {
+            jit_value x, h2;
+            if (norm_second(n, GA_COLON, x, h2)) {
+              if (!child(1, b) || b.rank != 2 || x.rank != 2 || h2.rank != 2) return false;
+              out = {"d2norm(" + x.code + "," + h2.code + "," + b.code + ")", 0};
+              return true;
+            }
+          }
           std::string sa;  // Derivative_1_Saint_Venant_Kirchhoff_PK2(G, params):H = the directional derivative dS[H]
           std::string lawfn;
           if (n->children.size() == 2 && svk_args(n->children[0], 1, sa, &lawfn)) {
@@ -706,6 +734,8 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
             {"DER_PDFUNC_ACOS", "DER_PDFUNC_ACOS"}, {"DER_PDFUNC_ATAN", "DER_PDFUNC_ATAN"}, {"DER_PDFUNC1_ATAN2", "DER_PDFUNC1_ATAN2"},
             {"DER_PDFUNC2_ATAN2", "DER_PDFUNC2_ATAN2"}, {"DER_PDFUNC_ERF", "DER_PDFUNC_ERF"}, {"DER_PDFUNC_ERFC", "DER_PDFUNC_ERFC"},
             {"DER_PDFUNC_NEG_PART", "DER_PDFUNC_NEG_PART"},
+            {"DER_PDFUNC1_DER_PDFUNC1_POW", "DER_PDFUNC1_DER_PDFUNC1_POW"}, {"DER_PDFUNC2_DER_PDFUNC1_POW", "DER_PDFUNC2_DER_PDFUNC1_POW"},
+            {"DER_PDFUNC1_DER_PDFUNC2_POW", "DER_PDFUNC1_DER_PDFUNC2_POW"}, {"DER_PDFUNC2_DER_PDFUNC2_POW", "DER_PDFUNC2_DER_PDFUNC2_POW"},
             // second derivatives (the derivative of a derivative the reference defines by an expression)
             {"DER_PDFUNC_DER_PDFUNC_SQRT", "DER_PDFUNC_DER_PDFUNC_SQRT"}, {"DER_PDFUNC_DER_PDFUNC_LOG", "DER_PDFUNC_DER_PDFUNC_LOG"},
             {"DER_PDFUNC_DER_PDFUNC_LOG10", "DER_PDFUNC_DER_PDFUNC_LOG10"}, {"DER_PDFUNC_DER_PDFUNC_TANH", "DER_PDFUNC_DER_PDFUNC_TANH"},
@@ -731,7 +761,15 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
         const mat_operator *mop = nullptr;
         if (mat_op_args(n, 0, mop, sa)) { out = {std::string(mop->value) + "(" + sa + ")", mop->rank}; return true; }
       }
-      if (f->node_type == GA_NODE_OPERATOR && (f->name == "Norm_sqr" || f->name == "Norm") && n->children.size() == 2) {
+      if (f->node_type == GA_NODE_OPERATOR && (f->name == "Norm_sqr" || f->name == "Norm") && n->children.size() == 2 &&
+          f->der1 == 1 && f->der2 == 0) {  // Derivative_1_Norm(x) = x/|x| (0 at 0), Derivative_1_Norm_sqr(x) = 2 x: same rank as x
+        jit_value a;
+        if (!child(1, a) || a.rank < 1) return false;
+        out = {f->name == "Norm" ? "dnorm(" + a.code + ")" : "((2.0)*" + a.code + ")", a.rank};
+        return true;
+      }
+      if (f->node_type == GA_NODE_OPERATOR && (f->name == "Norm_sqr" || f->name == "Norm") && n->children.size() == 2 &&
+          f->der1 == 0 && f->der2 == 0) {
         jit_value a;
         if (!child(1, a)) return false;
         out = {(f->name == "Norm" ? "gnorm(" : "normsqr(") + a.code + ")", 0};

@@ -57,3 +57,22 @@ def test_law_operators_inside_compound_forms(mesh, expr):
     assert r["device_workspace_calls"] >= 2, r
     assert r["pattern_ok"] and r["nnz_ref"] == r["nnz_gpu"], r
     assert 0 <= r["rel_K"] < 1e-12 and r["rel_V"] < 1e-12 and r["norm_V"] > 0, r
+
+
+NORM_POTENTIALS = [  # p-Laplacian-like energies: Norm / Norm_sqr with their first and second derivatives, the second derivatives of pow
+    ("dim=3 n=3 gt=pk k=2 q=1", "pow(Norm_sqr(Grad_u),1.5)/3 + pow(Norm(Grad_u),2.5)/2.5"),
+    ("dim=3 n=2 gt=qk k=2", "pow(Norm(Grad_u),2.5)/2.5 + Norm(u)"),
+    ("dim=2 n=6 gt=pk k=2", "pow(1+Norm_sqr(Grad_u),0.75) + sqr(Norm(u))/2"),
+]
+
+
+@pytest.mark.parametrize("mesh,expr", NORM_POTENTIALS)
+def test_norm_potentials_run_on_the_device(mesh, expr):
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN, "model=expr"] + mesh.split() + ["expr=" + expr], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["device_workspace_calls"] >= 3, r
+    assert r["pattern_ok"] and r["rel_K"] < 1e-12 and r["rel_V"] < 1e-12, r
+    assert r["E_ref"] != 0 and abs(r["E_gpu"] - r["E_ref"]) <= 1e-12 * abs(r["E_ref"]), r

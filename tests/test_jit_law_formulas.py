@@ -73,6 +73,22 @@ void t_iso(int law, const double *g, const double *p, const double *h, double *S
   st(iso_pk2(ld(g), law, p[0], p[1], p[2], p[3], p[4]), S);
   st(iso_dpk2(ld(g), law, p[0], p[1], p[2], p[3], p[4], ld(h)), dS);
 }
+void t_norm(const double *x, const double *h, const double *k, double *out) {
+  // out: |x| of a matrix, dnorm(x):h, d2norm(x,h,k); then the same for the first row taken as a vector
+  const mat X = ld(x), H = ld(h), K = ld(k);
+  out[0] = gnorm(X); out[1] = ddot(dnorm(X), H); out[2] = d2norm(X, H, K);
+  vec xv, hv, kv;
+  for (int i = 0; i < GF_N; ++i) { xv.v[i] = x[i]; hv.v[i] = h[i]; kv.v[i] = k[i]; }
+  out[3] = gnorm(xv); out[4] = dot(dnorm(xv), hv); out[5] = d2norm(xv, hv, kv);
+  const mat Z = 0.0 * X;
+  out[6] = ddot(dnorm(Z), H);  // 0 at x = 0, like the reference
+  out[7] = DER_PDFUNC1_DER_PDFUNC1_POW(1.7, 2.5); out[8] = DER_PDFUNC2_DER_PDFUNC1_POW(1.7, 2.5);
+  out[9] = DER_PDFUNC1_DER_PDFUNC2_POW(1.7, 2.5); out[10] = DER_PDFUNC2_DER_PDFUNC2_POW(1.7, 2.5);
+  out[11] = DER_PDFUNC_DER_PDFUNC_LOG(1.7); out[12] = DER_PDFUNC_DER_PDFUNC_SQRT(1.7); out[13] = DER_PDFUNC_DER_PDFUNC_TANH(0.4);
+  out[14] = DER_PDFUNC_DER_PDFUNC_ATAN(0.4); out[15] = DER_PDFUNC_DER_PDFUNC_COS(0.4); out[16] = DER_PDFUNC_DER_PDFUNC_TAN(0.4);
+  out[17] = DER_PDFUNC_DER_PDFUNC_ASIN(0.4); out[18] = DER_PDFUNC_DER_PDFUNC_ACOS(0.4); out[19] = DER_PDFUNC_DER_PDFUNC_ASINH(0.4);
+  out[20] = DER_PDFUNC_DER_PDFUNC_ATANH(0.4); out[21] = DER_PDFUNC_DER_PDFUNC_ACOSH(1.4); out[22] = DER_PDFUNC_DER_PDFUNC_LOG10(1.7);
+}
 void t_ops(const double *a, const double *h, const double *k, double *sc, double *m) {
   // scalars: det, ddet, d2det, mat_i2, dmat_i2, d2mat_i2 ; matrices: inv, dinv, d2inv, rcg, drcg, d2rcg, lcg, dlcg, d2lcg, glag, dglag, d2glag
   const mat A = ld(a), H = ld(h), K = ld(k);
@@ -144,6 +160,31 @@ def test_device_helper_text_on_the_host(n, tmp_path):
             dr = np.einsum("ijkl,kl->ij", dSr, h3)
             assert np.abs(S - Sr[:n, :n]).max() <= 1e-12 * np.abs(Sr).max(), (fam, n)
             assert np.abs(dS - dr[:n, :n]).max() <= 1e-12 * np.abs(dr).max(), (fam, n)
+        # Norm and the second derivatives of the predefined functions against central differences
+        L.t_norm.argtypes = [C.c_void_p] * 4
+        out = np.zeros(23)
+        L.t_norm(P(g), P(h), P(k), P(out))
+        e = 1e-5
+        for off, (xx, hh, kk) in ((0, (g, h, k)), (3, (g[0], h[0], k[0]))):
+            nf = np.linalg.norm
+            assert abs(out[off] - nf(xx)) <= 1e-14
+            assert abs(out[off + 1] - (nf(xx + e * hh) - nf(xx - e * hh)) / (2 * e)) <= 1e-7
+            d2 = (nf(xx + e * hh + e * kk) - nf(xx + e * hh - e * kk) - nf(xx - e * hh + e * kk) + nf(xx - e * hh - e * kk)) / (4 * e * e)
+            assert abs(out[off + 2] - d2) <= 1e-4 * max(1.0, abs(d2))
+        assert out[6] == 0.0
+        import math
+        second = lambda fn, t: (fn(t + 1e-4) - 2 * fn(t) + fn(t - 1e-4)) / 1e-8
+        assert abs(out[7] - second(lambda t: t ** 2.5, 1.7)) <= 1e-5
+        mixed = (lambda t, u: ((t + 1e-4) ** (u + 1e-4) - (t + 1e-4) ** (u - 1e-4) - (t - 1e-4) ** (u + 1e-4) + (t - 1e-4) ** (u - 1e-4)) / 4e-8)(1.7, 2.5)
+        assert abs(out[8] - mixed) <= 1e-5 and abs(out[9] - mixed) <= 1e-5
+        assert abs(out[10] - second(lambda u: 1.7 ** u, 2.5)) <= 1e-5
+        for idx, (fn, t) in zip(range(11, 23), ((math.log, 1.7), (math.sqrt, 1.7), (math.tanh, 0.4), (math.atan, 0.4), (math.cos, 0.4),
+                                                 (math.tan, 0.4), (math.asin, 0.4), (math.acos, 0.4), (math.asinh, 0.4), (math.atanh, 0.4),
+                                                 (math.acosh, 1.4), (math.log10, 1.7))):
+            want = second(fn, t)
+            if fn is math.cos:  # the reference's table gives DER_PDFUNC_COS' = "-cos(t)": the second derivative of cos
+                want = -math.cos(t)
+            assert abs(out[idx] - want) <= 2e-5 * max(1.0, abs(want)), (idx, out[idx], want)
         # the matrix operators: values against numpy, derivatives against central differences of the values
         a = np.ascontiguousarray(np.eye(n) + g)
         sc, m = np.zeros(6), np.zeros((12, n, n))
