@@ -233,6 +233,33 @@ __device__ __forceinline__ mat glag(mat f) { mat r = 0.5 * (transp(f) * f); for 
 __device__ __forceinline__ mat dglag(mat f, mat h) { return 0.5 * (transp(h) * f + transp(f) * h); }
 __device__ __forceinline__ double mat_i2(mat a) { const double t = trace(a); return 0.5 * (t * t - trace(a * a)); }
 __device__ __forceinline__ double dmat_i2(mat a, mat h) { return trace(a) * trace(h) - trace(a * h); }
+__device__ __forceinline__ double d2mat_i2(mat a, mat h, mat k);
+// Matrix_j1(A) = tr(A) det(A)^(-1/3), Matrix_j2(A) = i2(A) det(A)^(-2/3) (getfem_nonlinear_elasticity.cc:1351-1500; 1e200 where det <= 0)
+__device__ __forceinline__ double mat_j1(mat a) { const double d = det(a); return d > 0.0 ? trace(a) * pow(d, -1.0 / 3.0) : 1e200; }
+__device__ __forceinline__ double dmat_j1(mat a, mat h) {
+  const double d = det(a);
+  if (!(d > 0.0)) return 1e200;
+  return pow(d, -1.0 / 3.0) * (trace(h) - trace(a) * trace(inv(a) * h) / 3.0);
+}
+__device__ __forceinline__ double d2mat_j1(mat a, mat h, mat k) {
+  const mat ia = inv(a), ih = ia * h, ik = ia * k;
+  const double r = pow(det(a), -1.0 / 3.0), i1 = trace(a), th = trace(ih), tk = trace(ik);
+  const double t = trace(h) - i1 * th / 3.0, dt = -trace(k) * th / 3.0 + i1 * trace(ik * ih) / 3.0;
+  return r * (dt - tk * t / 3.0);
+}
+__device__ __forceinline__ double mat_j2(mat a) { const double d = det(a); return d > 0.0 ? mat_i2(a) * pow(d, -2.0 / 3.0) : 1e200; }
+__device__ __forceinline__ double dmat_j2(mat a, mat h) {
+  const double d = det(a);
+  if (!(d > 0.0)) return 1e200;
+  return pow(d, -2.0 / 3.0) * (dmat_i2(a, h) - 2.0 * mat_i2(a) * trace(inv(a) * h) / 3.0);
+}
+__device__ __forceinline__ double d2mat_j2(mat a, mat h, mat k) {
+  const mat ia = inv(a), ih = ia * h, ik = ia * k;
+  const double r2 = pow(det(a), -2.0 / 3.0), i2 = mat_i2(a), th = trace(ih), tk = trace(ik);
+  const double sh = dmat_i2(a, h) - 2.0 * i2 * th / 3.0;
+  const double ds = d2mat_i2(a, h, k) - 2.0 * dmat_i2(a, k) * th / 3.0 + 2.0 * i2 * trace(ik * ih) / 3.0;
+  return r2 * (ds - 2.0 * tk * sh / 3.0);
+}
 // second derivatives in two directions (symmetric in h, k): "(Derivative_1_1_Op(A):H2):H1" of an order-2 tree derived from a potential
 __device__ __forceinline__ double d2det(mat a, mat h, mat k) {
   const mat ia = inv(a), ih = ia * h, ik = ia * k;

@@ -518,6 +518,8 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
       {"Left_Cauchy_Green", "lcg", 2, "dlcg", "d2lcg"},           // FF' ; HF' + FH'
       {"Green_Lagrangian", "glag", 2, "dglag", "d2glag"},         // (F'F - I)/2 ; (H'F + F'H)/2
       {"Matrix_i2", "mat_i2", 0, "dmat_i2", "d2mat_i2"},          // ((tr A)^2 - tr(A^2))/2 ; tr A tr H - tr(A H)
+      {"Matrix_j1", "mat_j1", 0, "dmat_j1", "d2mat_j1"},          // tr(A) det(A)^(-1/3)
+      {"Matrix_j2", "mat_j2", 0, "dmat_j2", "d2mat_j2"},          // i2(A) det(A)^(-2/3)
   };
   // der = 0: the value; 1: Derivative_1_Op; 2: Derivative_1_1_Op (an order-2 tree derived from a potential)
   auto mat_op_args = [&](const pga_tree_node &pn, size_type der, const mat_operator *&op, std::string &args) {

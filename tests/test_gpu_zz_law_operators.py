@@ -63,6 +63,11 @@ NORM_POTENTIALS = [  # p-Laplacian-like energies: Norm / Norm_sqr with their fir
     ("dim=3 n=3 gt=pk k=2 q=1", "pow(Norm_sqr(Grad_u),1.5)/3 + pow(Norm(Grad_u),2.5)/2.5"),
     ("dim=3 n=2 gt=qk k=2", "pow(Norm(Grad_u),2.5)/2.5 + Norm(u)"),
     ("dim=2 n=6 gt=pk k=2", "pow(1+Norm_sqr(Grad_u),0.75) + sqr(Norm(u))/2"),
+    # the compressible Mooney-Rivlin energy WRITTEN OUT with Matrix_j1 / Matrix_j2 / Det of the Cauchy-Green tensor (the same value
+    # as Compressible_Mooney_Rivlin_potential(Grad_u,[0.8;0.3;2.0])): chain rule through two operators, second derivatives of both
+    ("dim=3 n=2 gt=pk k=2 uscale=0.02",
+     "0.8*(Matrix_j1(Right_Cauchy_Green(Id(3)+Grad_u))-3) + 0.3*(Matrix_j2(Right_Cauchy_Green(Id(3)+Grad_u))-3)"
+     " + 2.0*sqr(sqrt(Det(Right_Cauchy_Green(Id(3)+Grad_u)))-1)"),
 ]
 
 

@@ -90,9 +90,10 @@ void t_norm(const double *x, const double *h, const double *k, double *out) {
   out[20] = DER_PDFUNC_DER_PDFUNC_ATANH(0.4); out[21] = DER_PDFUNC_DER_PDFUNC_ACOSH(1.4); out[22] = DER_PDFUNC_DER_PDFUNC_LOG10(1.7);
 }
 void t_ops(const double *a, const double *h, const double *k, double *sc, double *m) {
-  // scalars: det, ddet, d2det, mat_i2, dmat_i2, d2mat_i2 ; matrices: inv, dinv, d2inv, rcg, drcg, d2rcg, lcg, dlcg, d2lcg, glag, dglag, d2glag
+  // scalars: det, ddet, d2det, mat_i2, dmat_i2, d2mat_i2, then the same for mat_j1 and mat_j2 ; matrices: inv, dinv, d2inv, rcg, drcg, d2rcg, lcg, dlcg, d2lcg, glag, dglag, d2glag
   const mat A = ld(a), H = ld(h), K = ld(k);
   sc[0] = det(A); sc[1] = ddet(A, H); sc[2] = d2det(A, H, K); sc[3] = mat_i2(A); sc[4] = dmat_i2(A, H); sc[5] = d2mat_i2(A, H, K);
+  sc[6] = mat_j1(A); sc[7] = dmat_j1(A, H); sc[8] = d2mat_j1(A, H, K); sc[9] = mat_j2(A); sc[10] = dmat_j2(A, H); sc[11] = d2mat_j2(A, H, K);
   const int s = GF_N * GF_N;
   st(inv(A), m); st(dinv(A, H), m + s); st(d2inv(A, H, K), m + 2 * s);
   st(rcg(A), m + 3 * s); st(drcg(A, H), m + 4 * s); st(d2rcg(A, H, K), m + 5 * s);
@@ -187,14 +188,16 @@ def test_device_helper_text_on_the_host(n, tmp_path):
             assert abs(out[idx] - want) <= 2e-5 * max(1.0, abs(want)), (idx, out[idx], want)
         # the matrix operators: values against numpy, derivatives against central differences of the values
         a = np.ascontiguousarray(np.eye(n) + g)
-        sc, m = np.zeros(6), np.zeros((12, n, n))
+        sc, m = np.zeros(12), np.zeros((12, n, n))
         L.t_ops(P(a), P(h), P(k), P(sc), P(m))
         f = {"det": np.linalg.det, "i2": lambda x: 0.5 * (np.trace(x) ** 2 - np.trace(x @ x)), "inv": np.linalg.inv,
+             "j1": lambda x: np.trace(x) * np.linalg.det(x) ** (-1.0 / 3.0),
+             "j2": lambda x: 0.5 * (np.trace(x) ** 2 - np.trace(x @ x)) * np.linalg.det(x) ** (-2.0 / 3.0),
              "rcg": lambda x: x.T @ x, "lcg": lambda x: x @ x.T, "glag": lambda x: 0.5 * (x.T @ x - np.eye(n))}
         e = 1e-5
         d1 = lambda fn: (fn(a + e * h) - fn(a - e * h)) / (2 * e)
         d2 = lambda fn: (fn(a + e * h + e * k) - fn(a + e * h - e * k) - fn(a - e * h + e * k) + fn(a - e * h - e * k)) / (4 * e * e)
-        for j, name in enumerate(("det", "i2")):
+        for j, name in enumerate(("det", "i2", "j1", "j2")):
             assert abs(sc[3 * j] - f[name](a)) <= 1e-13 * max(1.0, abs(f[name](a)))
             assert abs(sc[3 * j + 1] - d1(f[name])) <= 1e-7 * max(1.0, abs(sc[3 * j + 1]))
             assert abs(sc[3 * j + 2] - d2(f[name])) <= 1e-4 * max(1.0, abs(sc[3 * j + 2]))

@@ -276,6 +276,8 @@ X_EXPRS = [  # the position X (whole vector or one coordinate): x = sum_g G_g N_
     ("dim=3 n=2 gt=pk k=2 q=1", "pow(Norm_sqr(Grad_u),1.5)/3 + pow(Norm(Grad_u),2.5)/2.5"),
     ("dim=3 n=2 gt=pk k=2", "pow(Norm(Grad_u),2.5)/2.5 + Norm(u)"),
     ("dim=3 n=2 gt=pk k=2", "sqr(Norm(u))*Grad_u:Grad_Test_u"),
+    ("dim=3 n=2 gt=pk k=2", "0.8*(Matrix_j1(Right_Cauchy_Green(Id(3)+Grad_u))-3) + 0.3*(Matrix_j2(Right_Cauchy_Green(Id(3)+Grad_u))-3)"
+                            " + 2.0*sqr(sqrt(Det(Right_Cauchy_Green(Id(3)+Grad_u)))-1)"),
     ("dim=3 n=2 gt=qk k=2", "Matrix_i2(Green_Lagrangian(Id(3)+Grad_u)) + sqr(Trace(Green_Lagrangian(Id(3)+Grad_u))) + tanh(u.u)"),
     # scalar fem-data coefficients inside a translated tree: fld[k], evaluated on the data fem at every Gauss point
     ("dim=3 n=2 gt=pk k=2 q=1", "c0*sin(u)*Test_u + (1+c0)*Grad_u.Grad_Test_u"),
@@ -317,7 +319,7 @@ def test_the_translated_forms_compile(mesh, expr):
 def test_the_nvrtc_route_refuses_what_it_cannot_express():
     """operators outside the translator's language: no silent approximation -- the tree is reported as not
     recognised"""
-    for mesh, expr in (("dim=3 n=2 gt=pk k=2", "Matrix_j1(Id(3)+Grad_u)*(u.Test_u)"), ("dim=3 n=2 gt=pk k=2", "Expm(Grad_u):Grad_Test_u")):
+    for mesh, expr in (("dim=3 n=2 gt=pk k=2", "Cross_product(u,[1;2;3]).Test_u"), ("dim=3 n=2 gt=pk k=2", "Expm(Grad_u):Grad_Test_u")):
         line = _dryrun_order1(mesh, expr)
         assert "NOT recognised" in line, line
 
