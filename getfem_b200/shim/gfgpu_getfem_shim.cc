@@ -581,7 +581,30 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
         return true;
       }
       if (!ws.variable_exists(n->name) || !ws.is_constant(n->name) || ws.associated_mf(n->name) || ws.associated_im_data(n->name)) return false;
-      if (ws.value(n->name).size() != 1) return false;  // scalar fixed-size constants
+      if (ws.value(n->name).size() != 1) {
+        // a fixed-size VECTOR (N entries) or MATRIX (N x N, first index fastest like every GetFEM tensor) constant -- a load
+        // direction, an anisotropic diffusion tensor "(A*Grad_u).Grad_Test_u": its components are the parameters "name#c"
+        const bgeot::multi_index &sz = n->tensor().sizes();
+        const bool isvec = sz.size() == 1 && sz[0] == size_type(N), ismat = sz.size() == 2 && sz[0] == size_type(N) && sz[1] == size_type(N);
+        if ((!isvec && !ismat) || ws.value(n->name).size() != (isvec ? size_t(N) : size_t(N * N))) return false;
+        std::vector<std::string> pv;
+        for (size_t c = 0; c < ws.value(n->name).size(); ++c) {
+          const std::string key = n->name + "#" + std::to_string(c);
+          size_t k = 0;
+          while (k < params.size() && params[k] != key) ++k;
+          if (k == params.size()) params.push_back(key);
+          if (params.size() > size_t(GFGPU_MAX_PARAMS)) return false;
+          pv.push_back("par[" + std::to_string(k) + "]");
+        }
+        if (isvec) {
+          out = {"mkvec(" + pv[0] + "," + pv[1] + "," + (N > 2 ? pv[2] : std::string("0.0")) + ")", 1};
+        } else {
+          std::string c = "mkmat(";
+          for (int k = 0; k < 9; ++k) c += (k ? "," : "") + (k < N * N ? pv[k] : std::string("0.0"));
+          out = {c + ")", 2};
+        }
+        return true;
+      }
       size_t k = 0;
       while (k < params.size() && params[k] != n->name) ++k;
       if (k == params.size()) params.push_back(n->name);
@@ -754,6 +777,32 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
           code += (k > 1 ? "," : "") + a.code;
         }
         out = {code + ")", 0};
+        return true;
+      }
+      if (f->node_type == GA_NODE_RESHAPE && n->children.size() == 4 && n->children[1]->node_type == GA_NODE_VAL) {
+        // "Reshape(A, N, N)" of a fixed-size constant with N x N entries (first index fastest): a matrix of parameters
+        const pga_tree_node &pv0 = n->children[1];
+        auto cst = [&](size_t k) {
+          return n->children[k]->node_type == GA_NODE_CONSTANT && n->children[k]->tensor().size() == 1 &&
+                 int(n->children[k]->tensor()[0]) == N;
+        };
+        if (!cst(2) || !cst(3) || !ws.variable_exists(pv0->name) || !ws.is_constant(pv0->name) || ws.associated_mf(pv0->name) ||
+            ws.associated_im_data(pv0->name) || ws.value(pv0->name).size() != size_t(N * N))
+          return false;
+        std::string c = "mkmat(";
+        for (int k = 0; k < 9; ++k) {
+          std::string e = "0.0";
+          if (k < N * N) {
+            const std::string key = pv0->name + "#" + std::to_string(k);
+            size_t q = 0;
+            while (q < params.size() && params[q] != key) ++q;
+            if (q == params.size()) params.push_back(key);
+            if (params.size() > size_t(GFGPU_MAX_PARAMS)) return false;
+            e = "par[" + std::to_string(q) + "]";
+          }
+          c += (k ? "," : "") + e;
+        }
+        out = {c + ")", 2};
         return true;
       }
       {

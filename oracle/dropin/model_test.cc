@@ -96,6 +96,9 @@ int main(int argc, char **argv) {
         if (nz < 0 || long(k) < nz) U[k] = 0.0;
     }
     std::vector<double> Vr, Vg, C0(mf_d.nb_dof(), 1.0), PARAMS{1.3, 0.7};
+    std::vector<double> DVEC(dim), AMAT(dim * dim);
+    for (int k = 0; k < dim; ++k) DVEC[k] = 0.5 * (k + 1);
+    for (int k = 0; k < dim * dim; ++k) AMAT[k] = (k % (dim + 1) == 0 ? 2.0 : 0.0) + 0.1 * k;
     const bool with_p = geti("pvar", 0) != 0;
     std::vector<double> Pv(mf_p.nb_dof());
     {
@@ -121,6 +124,8 @@ int main(int argc, char **argv) {
       ws.add_fixed_size_constant("mu", MU);
       ws.add_fixed_size_constant("a", A);
       ws.add_fixed_size_constant("params", PARAMS);
+      ws.add_fixed_size_constant("dvec", DVEC);  // a vector constant of the mesh dimension
+      ws.add_fixed_size_constant("amat", AMAT);  // N x N entries (an anisotropic diffusion tensor through Reshape(amat,N,N)), not symmetric
       ws.add_fem_constant("c0", mf_d, C0);  // a material that is 1 on the first convexes and 5 in a far corner
       ws.add_fem_constant("w0", mf_dv, W0);  // a vector-valued field (an advection velocity)
       if (a.count("region")) ws.add_expression(expr, mim, m.region(size_type(geti("region", 1))));

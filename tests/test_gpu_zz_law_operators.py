@@ -81,3 +81,22 @@ def test_norm_potentials_run_on_the_device(mesh, expr):
     assert r["device_workspace_calls"] >= 3, r
     assert r["pattern_ok"] and r["rel_K"] < 1e-12 and r["rel_V"] < 1e-12, r
     assert r["E_ref"] != 0 and abs(r["E_gpu"] - r["E_ref"]) <= 1e-12 * abs(r["E_ref"]), r
+
+
+CONSTANTS = [  # fixed-size vector / matrix constants as parameters of a run-time compiled term (anisotropic diffusion, advection)
+    ("dim=3 n=3 gt=pk k=2 q=1", "(Reshape(amat,3,3)*Grad_u).Grad_Test_u + (dvec.Grad_u)*Test_u"),
+    ("dim=2 n=6 gt=qk k=2", "(Grad_u*Reshape(amat,2,2)):Grad_Test_u + sin(u.dvec)*(dvec.Test_u)"),
+    ("dim=3 n=2 gt=qk k=2", "sqr(Norm(u))*Grad_u:Grad_Test_u + (dvec.u)*(dvec.Test_u)"),
+]
+
+
+@pytest.mark.parametrize("mesh,expr", CONSTANTS)
+def test_vector_and_matrix_constants(mesh, expr):
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN, "model=expr"] + mesh.split() + ["expr=" + expr], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["device_workspace_calls"] >= 2, r
+    assert r["pattern_ok"] and r["nnz_ref"] == r["nnz_gpu"], r
+    assert 0 <= r["rel_K"] < 1e-12 and r["rel_V"] < 1e-12 and r["norm_V"] > 0, r

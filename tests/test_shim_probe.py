@@ -279,6 +279,9 @@ X_EXPRS = [  # the position X (whole vector or one coordinate): x = sum_g G_g N_
     ("dim=3 n=2 gt=pk k=2", "0.8*(Matrix_j1(Right_Cauchy_Green(Id(3)+Grad_u))-3) + 0.3*(Matrix_j2(Right_Cauchy_Green(Id(3)+Grad_u))-3)"
                             " + 2.0*sqr(sqrt(Det(Right_Cauchy_Green(Id(3)+Grad_u)))-1)"),
     ("dim=3 n=2 gt=qk k=2", "Matrix_i2(Green_Lagrangian(Id(3)+Grad_u)) + sqr(Trace(Green_Lagrangian(Id(3)+Grad_u))) + tanh(u.u)"),
+    # fixed-size VECTOR and MATRIX constants (an anisotropic diffusion tensor through Reshape(A,N,N), an advection direction)
+    ("dim=3 n=2 gt=pk k=2 q=1", "(Reshape(amat,3,3)*Grad_u).Grad_Test_u + (dvec.Grad_u)*Test_u"),
+    ("dim=2 n=4 gt=qk k=2", "(Grad_u*Reshape(amat,2,2)):Grad_Test_u + sin(u.dvec)*(dvec.Test_u)"),
     # scalar fem-data coefficients inside a translated tree: fld[k], evaluated on the data fem at every Gauss point
     ("dim=3 n=2 gt=pk k=2 q=1", "c0*sin(u)*Test_u + (1+c0)*Grad_u.Grad_Test_u"),
     ("dim=3 n=2 gt=pk k=2", "c0*(1+Norm_sqr(u))*Grad_u:Grad_Test_u + c0*X.Test_u"),
