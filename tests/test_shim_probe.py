@@ -354,3 +354,37 @@ def test_mass_matrices_on_two_fems_are_the_rectangular_family(kind):
     assert out.returncode == 0, out.stderr[-1500:]
     lines = [l for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun] order 2")]
     assert lines and all("recognised family 1001" in l for l in lines), lines
+
+
+def _zz_cases():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("zz_law_operators", os.path.join(ROOT, "tests", "test_gpu_zz_law_operators.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cases = [(["model=expr"] + m.split() + ["expr=" + e]) for m, e in mod.COMPOUND + mod.NORM_POTENTIALS + mod.CONSTANTS]
+    return cases + [c.split() for c in mod.MODELS]
+
+
+@pytest.mark.parametrize("args", _zz_cases(), ids=lambda a: " ".join(a)[:60])
+def test_every_case_of_the_last_gpu_file_translates_and_compiles(args):
+    """CPU: the end-to-end GPU cases that could not be run on a B200 in this round (tests/test_gpu_zz_law_operators.py) at least
+    take the NVRTC route in the dry run, and every form the translator emits for them compiles for sm_100a."""
+    from getfem_b200 import capi
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/model_test not built (needs the reference sources)")
+    out = subprocess.run([BIN] + args, capture_output=True, text=True, timeout=300, env=dict(os.environ, GFGPU_DRYRUN="1"))
+    assert out.returncode == 0, out.stderr[-1500:]
+    forms = [l.split("\t") for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun jit]")]
+    assert forms, out.stderr[-1500:]
+    assert not [l for l in out.stderr.splitlines() if l.startswith("[gfgpu dryrun] order 1") and "NOT recognised" in l]
+    seen = set()
+    for head, f1, f2, f0 in forms:
+        if (f1, f2, f0) in seen:
+            continue
+        seen.add((f1, f2, f0))
+        m = re.search(r"dim=(\d) qdim=(\d)", head)
+        capi.jit_check(int(m.group(1)), f1, f2, qdim=int(m.group(2)))
+        if f0:
+            capi.jit_check(int(m.group(1)), "(" + f0 + ")*dot(tv,tv)", f2, qdim=int(m.group(2)))
+    if args[0] == "model=expr" and ("potential" in " ".join(args) or any(a.startswith("expr=pow(") or a.startswith("expr=0.8*(Matrix_j1") for a in args)):
+        assert all(f[3] for f in forms), "the order-0 form is missing"
