@@ -140,12 +140,24 @@ __device__ __forceinline__ double DER_PDFUNC_DER_PDFUNC_TAN(double t) { const do
 __device__ __forceinline__ double DER_PDFUNC_DER_PDFUNC_ASIN(double t) { return t / pow(1.0 - t * t, 1.5); }
 __device__ __forceinline__ double DER_PDFUNC_DER_PDFUNC_ACOS(double t) { return -t / pow(1.0 - t * t, 1.5); }
 __device__ __forceinline__ double DER_PDFUNC_DER_PDFUNC_ATAN(double t) { return -2.0 * t / ((1.0 + t * t) * (1.0 + t * t)); }
-__device__ __forceinline__ double DER_PDFUNC_NEG_PART(double t) { return -Heaviside(-t); }
+__device__ __forceinline__ double DER_PDFUNC_NEG_PART(double t) { return t >= 0 ? 0.0 : -1.0; }  // ga_der_neg_part (:163)
 __device__ __forceinline__ double DER_PDFUNC1_DER_PDFUNC1_POW(double t, double e) { return e * (e - 1.0) * pow(t, e - 2.0); }
 __device__ __forceinline__ double DER_PDFUNC2_DER_PDFUNC1_POW(double t, double e) { return pow(t, e - 1.0) * (e * log(t) + 1.0); }
 __device__ __forceinline__ double DER_PDFUNC1_DER_PDFUNC2_POW(double t, double e) { return pow(t, e - 1.0) * (e * log(t) + 1.0); }
 __device__ __forceinline__ double DER_PDFUNC2_DER_PDFUNC2_POW(double t, double e) { const double l = log(t); return pow(t, e) * l * l; }
-__device__ __forceinline__ double sign(double x) { return x < 0 ? -1.0 : (x > 0 ? 1.0 : 0.0); }
+__device__ __forceinline__ double sign(double x) { return x >= 0 ? 1.0 : -1.0; }  // ga_sign: +1 at 0 (functions_and_operators.cc:110)
+// sinc with the reference's series below 1e-4 (:96-127), max / min derivatives (:165-168: ties go to BOTH arguments)
+__device__ __forceinline__ double sinc(double t) { const double t2 = t * t; return fabs(t) < 1e-4 ? 1.0 - t2 / 6.0 + t2 * t2 / 120.0 : sin(t) / t; }
+__device__ __forceinline__ double DER_PDFUNC_SINC(double t) {
+  const double t2 = t * t;
+  return fabs(t) < 1e-4 ? -t / 3.0 + t * t2 / 30.0 - t * t2 * t2 / 840.0 : (t * cos(t) - sin(t)) / (t * t);
+}
+__device__ __forceinline__ double DER2_PDFUNC_SINC(double t) {
+  const double t2 = t * t;
+  return fabs(t) < 1e-4 ? -1.0 / 3.0 + t2 / 10.0 - t2 * t2 / 168.0 : ((2.0 - t * t) * sin(t) - 2.0 * t * cos(t)) / (t * t * t);
+}
+__device__ __forceinline__ double DER_PDFUNC1_MAX(double t, double u) { return t - u >= 0 ? 1.0 : 0.0; }
+__device__ __forceinline__ double DER_PDFUNC2_MAX(double t, double u) { return u - t >= 0 ? 1.0 : 0.0; }
 
 // matrices of the mesh dimension: m[c][k] (for Grad_u: component c, direction k, the GWFL convention)
 struct mat { double m[GF_N][GF_N]; };

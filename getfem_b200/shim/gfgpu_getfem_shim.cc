@@ -759,6 +759,8 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
             {"DER_PDFUNC_ACOS", "DER_PDFUNC_ACOS"}, {"DER_PDFUNC_ATAN", "DER_PDFUNC_ATAN"}, {"DER_PDFUNC1_ATAN2", "DER_PDFUNC1_ATAN2"},
             {"DER_PDFUNC2_ATAN2", "DER_PDFUNC2_ATAN2"}, {"DER_PDFUNC_ERF", "DER_PDFUNC_ERF"}, {"DER_PDFUNC_ERFC", "DER_PDFUNC_ERFC"},
             {"DER_PDFUNC_NEG_PART", "DER_PDFUNC_NEG_PART"},
+            {"sinc", "sinc"}, {"DER_PDFUNC_SINC", "DER_PDFUNC_SINC"}, {"DER2_PDFUNC_SINC", "DER2_PDFUNC_SINC"},
+            {"DER_PDFUNC1_MAX", "DER_PDFUNC1_MAX"}, {"DER_PDFUNC2_MAX", "DER_PDFUNC2_MAX"},
             {"DER_PDFUNC1_DER_PDFUNC1_POW", "DER_PDFUNC1_DER_PDFUNC1_POW"}, {"DER_PDFUNC2_DER_PDFUNC1_POW", "DER_PDFUNC2_DER_PDFUNC1_POW"},
             {"DER_PDFUNC1_DER_PDFUNC2_POW", "DER_PDFUNC1_DER_PDFUNC2_POW"}, {"DER_PDFUNC2_DER_PDFUNC2_POW", "DER_PDFUNC2_DER_PDFUNC2_POW"},
             // second derivatives (the derivative of a derivative the reference defines by an expression)
