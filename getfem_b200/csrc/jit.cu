@@ -97,6 +97,11 @@ __device__ __forceinline__ double normsqr(vec a) { return dot(a, a); }
 __device__ __forceinline__ double normsqr(double a) { return a * a; }
 __device__ __forceinline__ double gnorm(vec a) { return sqrt(dot(a, a)); }
 __device__ __forceinline__ double gnorm(double a) { return fabs(a); }
+__device__ __forceinline__ vec cross(vec a, vec b) {  // Cross_product of two 3D vectors (bilinear: its derivatives are written inline)
+  vec r;
+  for (int i = 0; i < GF_N; ++i) r.v[i] = a.v[(i + 1) % GF_N] * b.v[(i + 2) % GF_N] - a.v[(i + 2) % GF_N] * b.v[(i + 1) % GF_N];
+  return r;
+}
 __device__ __forceinline__ vec mkvec(double a, double b, double c) { vec r; r.v[0] = a; r.v[1] = b; if (GF_N > 2) r.v[GF_N - 1] = c; return r; }
 __device__ __forceinline__ vec unit(int k) { vec r; for (int j = 0; j < GF_N; ++j) r.v[j] = j == k ? 1.0 : 0.0; return r; }
 __device__ __forceinline__ double sqr(double x) { return x * x; }

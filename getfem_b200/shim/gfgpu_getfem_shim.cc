@@ -814,6 +814,12 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
         const mat_operator *mop = nullptr;
         if (mat_op_args(n, 0, mop, sa)) { out = {std::string(mop->value) + "(" + sa + ")", mop->rank}; return true; }
       }
+      if (f->node_type == GA_NODE_CROSS_PRODUCT && n->children.size() == 3 && N == 3) {
+        jit_value a, b;  // bilinear: the reference's differentiation writes Cross_product(Test2_u, b) inline
+        if (!child(1, a) || !child(2, b) || a.rank != 1 || b.rank != 1) return false;
+        out = {"cross(" + a.code + "," + b.code + ")", 1};
+        return true;
+      }
       if (f->node_type == GA_NODE_OPERATOR && (f->name == "Norm_sqr" || f->name == "Norm") && n->children.size() == 2 &&
           f->der1 == 1 && f->der2 == 0) {  // Derivative_1_Norm(x) = x/|x| (0 at 0), Derivative_1_Norm_sqr(x) = 2 x: same rank as x
         jit_value a;

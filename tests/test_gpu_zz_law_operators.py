@@ -87,6 +87,8 @@ CONSTANTS = [  # fixed-size vector / matrix constants as parameters of a run-tim
     ("dim=3 n=3 gt=pk k=2 q=1", "(Reshape(amat,3,3)*Grad_u).Grad_Test_u + (dvec.Grad_u)*Test_u"),
     ("dim=2 n=6 gt=qk k=2", "(Grad_u*Reshape(amat,2,2)):Grad_Test_u + sin(u.dvec)*(dvec.Test_u)"),
     ("dim=3 n=2 gt=qk k=2", "sqr(Norm(u))*Grad_u:Grad_Test_u + (dvec.u)*(dvec.Test_u)"),
+    ("dim=3 n=2 gt=pk k=2", "Cross_product(u,dvec).Test_u + Norm_sqr(Cross_product(u,dvec))*(u.Test_u) + Grad_u:Grad_Test_u"),
+    ("dim=3 n=2 gt=pk k=2 q=1", "max(u,0.2)*Grad_u.Grad_Test_u + min(u,a)*Test_u + sinc(u)*Test_u + abs(u)*Test_u + neg_part(u)*Test_u"),
 ]
 
 

@@ -91,6 +91,7 @@ void t_norm(const double *x, const double *h, const double *k, double *out) {
   // the piecewise functions at their kinks, as the reference's C functions define them (functions_and_operators.cc:77-168)
   out[23] = sign(0.0); out[24] = Heaviside(0.0); out[25] = DER_PDFUNC_NEG_PART(0.0); out[26] = DER_PDFUNC1_MAX(1.0, 1.0);
   out[27] = DER_PDFUNC2_MAX(1.0, 1.0); out[28] = DER_PDFUNC1_MAX(0.0, 1.0); out[29] = sinc(1e-5); out[30] = sinc(0.7);
+  { const vec c = cross(xv, hv); for (int i = 0; i < GF_N; ++i) out[35 + i] = c.v[i]; }
   out[31] = DER_PDFUNC_SINC(0.7); out[32] = DER2_PDFUNC_SINC(0.7); out[33] = DER_PDFUNC_SINC(1e-5); out[34] = DER2_PDFUNC_SINC(1e-5);
 }
 void t_ops(const double *a, const double *h, const double *k, double *sc, double *m) {
@@ -167,7 +168,7 @@ def test_device_helper_text_on_the_host(n, tmp_path):
             assert np.abs(dS - dr[:n, :n]).max() <= 1e-12 * np.abs(dr).max(), (fam, n)
         # Norm and the second derivatives of the predefined functions against central differences
         L.t_norm.argtypes = [C.c_void_p] * 4
-        out = np.zeros(35)
+        out = np.zeros(38)
         L.t_norm(P(g), P(h), P(k), P(out))
         e = 1e-5
         for off, (xx, hh, kk) in ((0, (g, h, k)), (3, (g[0], h[0], k[0]))):
@@ -195,6 +196,8 @@ def test_device_helper_text_on_the_host(n, tmp_path):
         assert abs(out[29] - 1.0) <= 1e-10 and abs(out[30] - sincf(0.7)) <= 1e-15
         assert abs(out[31] - (sincf(0.7 + 1e-6) - sincf(0.7 - 1e-6)) / 2e-6) <= 1e-8 and abs(out[32] - second(sincf, 0.7)) <= 1e-5
         assert abs(out[33] + 1e-5 / 3.0) <= 1e-12 and abs(out[34] + 1.0 / 3.0) <= 1e-9
+        if n == 3:
+            assert np.abs(out[35:38] - np.cross(g[0], h[0])).max() <= 1e-15
         # the matrix operators: values against numpy, derivatives against central differences of the values
         a = np.ascontiguousarray(np.eye(n) + g)
         sc, m = np.zeros(12), np.zeros((12, n, n))

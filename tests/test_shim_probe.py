@@ -276,6 +276,7 @@ X_EXPRS = [  # the position X (whole vector or one coordinate): x = sum_g G_g N_
     ("dim=3 n=2 gt=pk k=2 q=1", "pow(Norm_sqr(Grad_u),1.5)/3 + pow(Norm(Grad_u),2.5)/2.5"),
     ("dim=3 n=2 gt=pk k=2", "pow(Norm(Grad_u),2.5)/2.5 + Norm(u)"),
     ("dim=3 n=2 gt=pk k=2", "sqr(Norm(u))*Grad_u:Grad_Test_u"),
+    ("dim=3 n=2 gt=pk k=2", "Cross_product(u,dvec).Test_u + Norm_sqr(Cross_product(u,dvec))*(u.Test_u)"),
     ("dim=3 n=2 gt=pk k=2 q=1", "max(u,0.2)*Grad_u.Grad_Test_u + min(u,a)*Test_u + sinc(u)*Test_u + abs(u)*Test_u + neg_part(u)*Test_u"),
     ("dim=3 n=2 gt=pk k=2", "0.8*(Matrix_j1(Right_Cauchy_Green(Id(3)+Grad_u))-3) + 0.3*(Matrix_j2(Right_Cauchy_Green(Id(3)+Grad_u))-3)"
                             " + 2.0*sqr(sqrt(Det(Right_Cauchy_Green(Id(3)+Grad_u)))-1)"),
@@ -323,7 +324,7 @@ def test_the_translated_forms_compile(mesh, expr):
 def test_the_nvrtc_route_refuses_what_it_cannot_express():
     """operators outside the translator's language: no silent approximation -- the tree is reported as not
     recognised"""
-    for mesh, expr in (("dim=3 n=2 gt=pk k=2", "Cross_product(u,[1;2;3]).Test_u"), ("dim=3 n=2 gt=pk k=2", "Expm(Grad_u):Grad_Test_u")):
+    for mesh, expr in (("dim=3 n=2 gt=pk k=2 q=1", "Hess_u:Hess_Test_u"), ("dim=3 n=2 gt=pk k=2", "Expm(Grad_u):Grad_Test_u")):
         line = _dryrun_order1(mesh, expr)
         assert "NOT recognised" in line, line
 
