@@ -612,6 +612,28 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
       out = {"par[" + std::to_string(k) + "]", 0};
       return true;
     }
+    case GA_NODE_C_MATRIX: {
+      // an explicit vector "[a; b; c]" or matrix "[a, b; c, d]" of scalar expressions (test functions included: they are values
+      // here): children in tensor storage order, first index fastest (ga_instruction_c_matrix_with_tests) -- mkmat's convention
+      const size_t nc = n->children.size();
+      const bgeot::multi_index &sz = n->tensor().sizes();
+      const size_t nb = size_t(n->nbc1);
+      if (nb < 1 || nb > 2 || sz.size() < nb) return false;
+      bool shape_ok = true;
+      for (size_t k = 0; k < nb; ++k) shape_ok = shape_ok && sz[sz.size() - nb + k] == size_type(N);
+      if (!shape_ok || nc != (nb == 1 ? size_t(N) : size_t(N * N))) return false;
+      std::vector<jit_value> ch(nc);
+      for (size_t k = 0; k < nc; ++k)
+        if (!child(k, ch[k]) || ch[k].rank != 0) return false;
+      if (nb == 1) {
+        out = {"mkvec(" + ch[0].code + "," + ch[1].code + "," + (N > 2 ? ch[2].code : std::string("0.0")) + ")", 1};
+      } else {
+        std::string c = "mkmat(";
+        for (int k = 0; k < 9; ++k) c += (k ? "," : "") + (k < N * N ? ch[k].code : std::string("0.0"));
+        out = {c + ")", 2};
+      }
+      return true;
+    }
     case GA_NODE_X:  // the position: the whole vector (nbc1 == 0) or one coordinate
       if (n->nbc1 == 0) { out = {"X", 1}; return true; }
       if (int(n->nbc1) > N) return false;

@@ -276,6 +276,7 @@ X_EXPRS = [  # the position X (whole vector or one coordinate): x = sum_g G_g N_
     ("dim=3 n=2 gt=pk k=2 q=1", "pow(Norm_sqr(Grad_u),1.5)/3 + pow(Norm(Grad_u),2.5)/2.5"),
     ("dim=3 n=2 gt=pk k=2", "pow(Norm(Grad_u),2.5)/2.5 + Norm(u)"),
     ("dim=3 n=2 gt=pk k=2", "sqr(Norm(u))*Grad_u:Grad_Test_u"),
+    ("dim=2 n=4 gt=pk k=2 q=1", "([1+u*u,0.3*u;0.1*u,2+sin(u)]*Grad_u).Grad_Test_u + [Grad_u(2);-Grad_u(1)].Grad_Test_u"),
     ("dim=3 n=2 gt=pk k=2", "Cross_product(u,dvec).Test_u + Norm_sqr(Cross_product(u,dvec))*(u.Test_u)"),
     ("dim=3 n=2 gt=pk k=2 q=1", "max(u,0.2)*Grad_u.Grad_Test_u + min(u,a)*Test_u + sinc(u)*Test_u + abs(u)*Test_u + neg_part(u)*Test_u"),
     ("dim=3 n=2 gt=pk k=2", "0.8*(Matrix_j1(Right_Cauchy_Green(Id(3)+Grad_u))-3) + 0.3*(Matrix_j2(Right_Cauchy_Green(Id(3)+Grad_u))-3)"
