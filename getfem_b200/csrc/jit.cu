@@ -189,6 +189,8 @@ __device__ __forceinline__ double ddot(double a, double b) { return a * b; }
 __device__ __forceinline__ mat transp(mat a) { mat r; for (int i = 0; i < GF_N; ++i) for (int j = 0; j < GF_N; ++j) r.m[i][j] = a.m[j][i]; return r; }
 __device__ __forceinline__ vec transp(vec a) { return a; }
 __device__ __forceinline__ double transp(double a) { return a; }
+__device__ __forceinline__ vec mcol(mat a, int j) { vec r; for (int i = 0; i < GF_N; ++i) r.v[i] = a.m[i][j]; return r; }  // M(:,j)
+__device__ __forceinline__ vec mrow(mat a, int i) { vec r; for (int j = 0; j < GF_N; ++j) r.v[j] = a.m[i][j]; return r; }  // M(i,:)
 __device__ __forceinline__ double trace(mat a) { double t = 0; for (int i = 0; i < GF_N; ++i) t += a.m[i][i]; return t; }
 __device__ __forceinline__ mat sym(mat a) { return 0.5 * (a + transp(a)); }
 __device__ __forceinline__ mat skew(mat a) { return 0.5 * (a - transp(a)); }

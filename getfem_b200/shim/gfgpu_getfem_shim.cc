@@ -868,6 +868,16 @@ static bool jit_emit(const getfem::ga_workspace &ws, const getfem::pga_tree_node
         out = {"(" + a.code + ").v[" + std::to_string(i1 - 1) + "]", 0};
         return true;
       }
+      // slices of a matrix: M(:,j) (column j) and M(i,:) (row i)
+      auto all_idx = [&](size_t k) { return k < n->children.size() && n->children[k]->node_type == GA_NODE_ALLINDICES; };
+      if (n->children.size() == 3 && all_idx(1) && index(2, i2) && child(0, a) && a.rank == 2) {
+        out = {"mcol(" + a.code + "," + std::to_string(i2 - 1) + ")", 1};
+        return true;
+      }
+      if (n->children.size() == 3 && index(1, i1) && all_idx(2) && child(0, a) && a.rank == 2) {
+        out = {"mrow(" + a.code + "," + std::to_string(i1 - 1) + ")", 1};
+        return true;
+      }
       if (n->children.size() == 3 && index(1, i1) && index(2, i2) && child(0, a) && a.rank == 2) {
         out = {"(" + a.code + ").m[" + std::to_string(i1 - 1) + "][" + std::to_string(i2 - 1) + "]", 0};
         return true;

@@ -88,6 +88,8 @@ CONSTANTS = [  # fixed-size vector / matrix constants as parameters of a run-tim
     ("dim=2 n=6 gt=qk k=2", "(Grad_u*Reshape(amat,2,2)):Grad_Test_u + sin(u.dvec)*(dvec.Test_u)"),
     ("dim=3 n=2 gt=qk k=2", "sqr(Norm(u))*Grad_u:Grad_Test_u + (dvec.u)*(dvec.Test_u)"),
     ("dim=3 n=2 gt=pk k=2", "Cross_product(u,dvec).Test_u + Norm_sqr(Cross_product(u,dvec))*(u.Test_u) + Grad_u:Grad_Test_u"),
+    # slices of a matrix, M(:,j) and M(i,:) (the spellings of tests/test_assembly.cc with a state-dependent coefficient)
+    ("dim=3 n=2 gt=pk k=2", "(1+u.u)*(Grad_u(:,1).Grad_Test_u(:,1) + 2*Grad_u(2,:).Grad_Test_u(2,:)) + Grad_u:Grad_Test_u"),
     # explicit vectors / matrices of expressions (GA_NODE_C_MATRIX): a state-dependent anisotropic tensor, a rotated gradient
     ("dim=2 n=6 gt=pk k=2 q=1", "([1+u*u,0.3*u;0.1*u,2+sin(u)]*Grad_u).Grad_Test_u + [Grad_u(2);-Grad_u(1)].Grad_Test_u"),
     ("dim=3 n=2 gt=qk k=2", "([u(1),0,0;0,u(2),0;0,0,1+u(3)*u(3)]*Grad_u):Grad_Test_u + [u(2);u(3);u(1)].Test_u + Grad_u:Grad_Test_u"),
